@@ -1,0 +1,22 @@
+"""numpy views of the C records declared in include/bsgpu.h (which mirror the reference's include/bs_call.h)."""
+import numpy as np
+
+PILEUP = np.dtype([("counts", "<u4", (2, 8)), ("n", "<u4"), ("quality", "<f4", (8,)), ("mapq2", "<f4")])
+GT_METH = np.dtype([("counts", "<u8", (8,)), ("qual", "<i4", (8,)), ("gt_prob", "<f8", (10,)),
+                    ("fisher_strand", "<f8"), ("mq", "<i4"), ("aq", "<i4"), ("max_gt", "u1"), ("pad", "u1", (7,))])
+GT_VCF = np.dtype([("gtm", GT_METH), ("ready", "u1"), ("skip", "u1"), ("pad", "u1", (6,))])
+SEG = np.dtype([("pos", "<u4"), ("off", "<u4"), ("len", "<u2"), ("mapq", "u1"), ("flags", "u1"), ("pad", "<u4")])
+TEMPLATE = np.dtype([("forward_position", "<u4"), ("reverse_position", "<u4"), ("reference_span", "<u4", (2,)),
+                     ("read_off", "<u4", (2,)), ("read_len", "<u4", (2,)), ("mm_off", "<u4", (2,)),
+                     ("mm_n", "<u4", (2,)), ("present", "u1", (2,)), ("mapq", "u1", (2,)),
+                     ("orientation", "u1"), ("bs_strand", "u1"), ("pad", "u1", (2,))])
+MISMS = np.dtype([("type", "<u4"), ("position", "<u4"), ("size", "<u4")])
+
+assert PILEUP.itemsize == 104
+assert GT_METH.itemsize == 200
+assert GT_VCF.itemsize == 208
+assert SEG.itemsize == 16
+assert TEMPLATE.itemsize == 56
+assert MISMS.itemsize == 12
+
+GENOTYPES = ("AA", "AC", "AG", "AT", "CC", "CG", "CT", "GG", "GT", "TT")

@@ -1,0 +1,179 @@
+/*
+ * bsgpu.h -- C ABI of libbsgpu: the B200 (sm_100a) pileup + bisulfite genotype-likelihood path of bs_call.
+ *
+ * Plain pointers and sizes only.  Every entry point returns BSGPU_OK (1) or BSGPU_FAIL (-1), the values of the
+ * reference's gt_status (gt/include/gt_error.h:23-24); bsgpu_last_error() gives the reason.  There is no CPU
+ * fallback: if no sm_100 device can be opened bsgpu_init fails.
+ *
+ * Record layouts are the reference's own (include/bs_call.h) so that host code can hand its arrays over
+ * unchanged:
+ *     bsgpu_pileup   = pileup    include/bs_call.h:174-182   (104 B)
+ *     bsgpu_gt_meth  = gt_meth   include/bs_call.h:152-160   (200 B)
+ *     bsgpu_gt_vcf   = gt_vcf    include/bs_call.h:162-166   (208 B)
+ *
+ * Which reference interface each entry point replaces:
+ *     bsgpu_init / bsgpu_destroy     init_calc_threads / join_calc_threads     src/call_genotypes.c:124-153
+ *                                    + fill_base_prob_table src/genotype_model.c:10, lfact_store_init src/stats_utils.c:14
+ *     bsgpu_call_sites[_dev]         the per-site body of call_thread           src/call_genotypes.c:43-115
+ *                                    (summarise, calc_gt_prob src/genotype_model.c:44, fisher src/stats_utils.c:25)
+ *     bsgpu_pileup_block[_dev]       the pileup loop of call_genotypes_ML       src/call_genotypes.c:172-226
+ *     bsgpu_call_block[_dev]         call_genotypes_ML + call_thread, fused     src/call_genotypes.c:155-272, 21-122
+ *     bsgpu_stage_templates          the (position, read bytes, mapq, strand) walk at the top of that loop,
+ *                                    src/call_genotypes.c:181-212, turned into sorted segments
+ *     bsgpu_process_block            process_template_vector                    src/process_template.c:18-126
+ *                                    (trim_read, trim_soft_clips, handle_overlap, indel normalisation on device)
+ * The link-compatible replacements for the three reference symbols themselves (call_genotypes_ML,
+ * init_calc_threads, join_calc_threads; include/bs_call.h:358-360) are in bs_call_b200/csrc/bsgpu_dropin.c and
+ * are built on top of this ABI; see INTEGRATION.md.
+ */
+#ifndef BSGPU_H
+#define BSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSGPU_OK 1
+#define BSGPU_FAIL (-1)
+
+#define BSGPU_MAX_QUAL 43      /* include/bs_call.h:25 */
+#define BSGPU_FLT_QUAL 63      /* include/bs_call.h:28 */
+
+typedef struct {
+	uint32_t counts[2][8];     /* [orientation][class]; classes 0-3 non-informative ACGT, 4-7 informative ACGT */
+	uint32_t n;
+	float quality[8];          /* sum of base qualities per class (integer valued) */
+	float mapq2;               /* sum of MAPQ^2 */
+} bsgpu_pileup;
+
+typedef struct {
+	uint64_t counts[8];
+	int32_t qual[8];
+	double gt_prob[10];        /* log10 posteriors: AA AC AG AT CC CG CT GG GT TT */
+	double fisher_strand;
+	int32_t mq;
+	int32_t aq;
+	uint8_t max_gt;
+	uint8_t pad_[7];
+} bsgpu_gt_meth;
+
+typedef struct {
+	bsgpu_gt_meth gtm;
+	uint8_t ready;             /* C99 bool in the reference */
+	uint8_t skip;
+	uint8_t pad_[6];
+} bsgpu_gt_vcf;
+
+/* One mate of one template after normalisation: `len` packed bytes (base | qual<<2, src/input_sam.c:76-86),
+ * one per reference position starting at `pos` (1-based).  flags: bit0 = strand index `ori` this mate is
+ * counted under (src/call_genotypes.c:185,221,224), bits1-2 = bisulfite strand (0 none, 1 C2T, 2 G2A). */
+typedef struct {
+	uint32_t pos;
+	uint32_t off;              /* offset of the first byte in bases[] */
+	uint16_t len;              /* <= BSGPU_MAX_SEG_LEN; longer mates are split by the stager */
+	uint8_t mapq;
+	uint8_t flags;
+	uint32_t pad_;
+} bsgpu_seg;                   /* 16 bytes */
+
+#define BSGPU_MAX_SEG_LEN 512
+
+/* Flat template record for the raw-template entry points (what the reference keeps in align_details,
+ * include/bs_call.h:64-73, with the two gt_vectors flattened into offset/length pairs). */
+typedef struct {
+	uint32_t forward_position, reverse_position;
+	uint32_t reference_span[2];
+	uint32_t read_off[2];      /* into bases[] */
+	uint32_t read_len[2];
+	uint32_t mm_off[2];        /* into misms[] */
+	uint32_t mm_n[2];
+	uint8_t present[2];        /* read[k] != NULL */
+	uint8_t mapq[2];
+	uint8_t orientation;       /* 0 FORWARD, 1 REVERSE */
+	uint8_t bs_strand;         /* 0 NON_CONVERTED, 1 STRAND_C2T, 2 STRAND_G2A */
+	uint8_t pad_[2];
+} bsgpu_template;              /* 56 bytes */
+
+/* gt_misms flattened (include/bs_call.h:53-62); type codes are the reference's enum: 1 INS, 2 DEL, 3 SOFT */
+typedef struct { uint32_t type, position, size; } bsgpu_misms;
+
+typedef struct {
+	double under_conv;         /* -c, default 0.01  (include/bs_call.h:16) */
+	double over_conv;          /*     default 0.05 */
+	double ref_bias;           /*     default 2 */
+	uint32_t left_trim[2];     /* -L */
+	uint32_t right_trim[2];    /* -R */
+	uint8_t min_qual;          /* -Q, default 20 */
+	int32_t device;            /* CUDA device ordinal */
+} bsgpu_params;
+
+typedef struct bsgpu_ctx bsgpu_ctx;
+
+/* counters a context keeps; all monotonically increasing */
+typedef struct {
+	uint64_t kernel_launches;  /* kernels of this library launched so far */
+	uint64_t sites;            /* sites processed */
+	uint64_t sites_called;     /* sites with n > 0 */
+	uint64_t h2d_bytes, d2h_bytes;
+	uint64_t qsum_overflow;    /* sites whose integer quality / mapq^2 sums left the float-exact envelope (2^24) */
+} bsgpu_stats;
+
+void bsgpu_default_params(bsgpu_params *p);
+int bsgpu_init(const bsgpu_params *p, bsgpu_ctx **out);
+void bsgpu_destroy(bsgpu_ctx *ctx);
+const char *bsgpu_last_error(void);
+int bsgpu_get_stats(bsgpu_ctx *ctx, bsgpu_stats *out);
+int bsgpu_version(void);
+
+/* ---- host-buffer entry points: H2D, kernels, D2H all inside the call (chunked and double buffered) ---- */
+
+/* pileup[] + ref codes -> gt_meth[] + skip[] */
+int bsgpu_call_sites(bsgpu_ctx *ctx, const bsgpu_pileup *pileup, const uint8_t *ref, size_t n,
+		bsgpu_gt_meth *out, uint8_t *skip);
+
+/* sorted segments -> pileup[] for the window [x, x+sz) */
+int bsgpu_pileup_block(bsgpu_ctx *ctx, const bsgpu_seg *segs, size_t nseg, const uint8_t *bases, size_t nbases,
+		uint32_t x, uint32_t sz, bsgpu_pileup *out);
+
+/* sorted segments + ref codes for [x, x+sz) -> gt_vcf[] (ready = 1 everywhere) */
+int bsgpu_call_block(bsgpu_ctx *ctx, const bsgpu_seg *segs, size_t nseg, const uint8_t *bases, size_t nbases,
+		const uint8_t *ref, uint32_t x, uint32_t sz, bsgpu_gt_vcf *out);
+
+/* normalised templates -> segments sorted by pos (host side; pure function, no device work).
+ * segs must have room for bsgpu_stage_bound(templates, n) entries.  *nseg receives the count. */
+size_t bsgpu_stage_bound(const bsgpu_template *t, size_t n);
+int bsgpu_stage_templates(const bsgpu_template *t, size_t n, const uint8_t *bases, uint32_t x, uint32_t y,
+		bsgpu_seg *segs, size_t *nseg);
+
+/* raw templates -> gt_vcf[]: normalisation, pileup and model all on the device.
+ * ref holds codes for [x, y] where x = max(first template start - 2, 1) (src/process_template.c:24-28);
+ * *x_out receives x; out must hold y - x + 1 records. */
+int bsgpu_process_block(bsgpu_ctx *ctx, const bsgpu_template *t, size_t n, const uint8_t *bases, size_t nbases,
+		const bsgpu_misms *misms, size_t nmisms, const uint8_t *ref, uint32_t y,
+		uint32_t *x_out, bsgpu_gt_vcf *out);
+
+/* ---- device-pointer entry points: everything already resident in HBM, asynchronous on `stream`
+ *      (a cudaStream_t passed as void*; NULL = the context's own stream) ---- */
+int bsgpu_call_sites_dev(bsgpu_ctx *ctx, const void *d_pileup, const void *d_ref, size_t n,
+		void *d_out, void *d_skip, void *stream);
+int bsgpu_pileup_block_dev(bsgpu_ctx *ctx, const void *d_segs, size_t nseg, const void *d_bases,
+		uint32_t x, uint32_t sz, void *d_pileup_out, void *stream);
+int bsgpu_call_block_dev(bsgpu_ctx *ctx, const void *d_segs, size_t nseg, const void *d_bases, const void *d_ref,
+		uint32_t x, uint32_t sz, void *d_vcf_out, void *stream);
+
+/* ---- synthetic workloads generated on the device (counter-based RNG; seed + index -> record) ---- */
+/* config 2 of BASELINE.json: per-site count vectors.  Writes n pileup records and n ref codes. */
+int bsgpu_synth_sites_dev(bsgpu_ctx *ctx, uint64_t seed, uint64_t first_site, size_t n, double mean_depth,
+		void *d_pileup, void *d_ref, void *stream);
+/* simulated WGBS reads over a window: sorted segments + packed bases + ref codes */
+int bsgpu_synth_block_dev(bsgpu_ctx *ctx, uint64_t seed, uint32_t x, uint32_t sz, uint32_t read_len, double depth,
+		void *d_segs, size_t seg_cap, void *d_bases, size_t base_cap, void *d_ref, size_t *nseg, size_t *nbases,
+		void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

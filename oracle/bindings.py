@@ -1,0 +1,237 @@
+"""ctypes bindings for the two CPU checkers.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module; the product package (bs_call_b200) never does.
+
+  Oracle     -> oracle/liboracle.so      the restatement in oracle/bs_oracle.c
+  Reference  -> oracle/_ref/libbsref.so  the reference's own compiled sources behind oracle/ref_harness.c
+                (built in the authoring container where /root/reference exists; travels prebuilt to GPU boxes)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# numpy views of the C records (layouts asserted against sizeof in the loaders)
+PILEUP = np.dtype([("counts", "<u4", (2, 8)), ("n", "<u4"), ("quality", "<f4", (8,)), ("mapq2", "<f4")])
+GT_METH = np.dtype([("counts", "<u8", (8,)), ("qual", "<i4", (8,)), ("gt_prob", "<f8", (10,)),
+                    ("fisher_strand", "<f8"), ("mq", "<i4"), ("aq", "<i4"), ("max_gt", "u1"), ("pad", "u1", (7,))])
+GT_VCF = np.dtype([("gtm", GT_METH), ("ready", "u1"), ("skip", "u1"), ("pad", "u1", (6,))])
+TEMPLATE = np.dtype([("forward_position", "<u4"), ("reverse_position", "<u4"), ("reference_span", "<u4", (2,)),
+                     ("read_off", "<u4", (2,)), ("read_len", "<u4", (2,)), ("mm_off", "<u4", (2,)),
+                     ("mm_n", "<u4", (2,)), ("present", "u1", (2,)), ("mapq", "u1", (2,)),
+                     ("orientation", "u1"), ("bs_strand", "u1"), ("pad", "u1", (2,))])
+MISMS = np.dtype([("type", "<u4"), ("position", "<u4"), ("size", "<u4")])
+assert PILEUP.itemsize == 104 and GT_METH.itemsize == 200 and GT_VCF.itemsize == 208
+assert TEMPLATE.itemsize == 56 and MISMS.itemsize == 12
+
+
+class BsoParams(C.Structure):
+    _fields_ = [("under_conv", C.c_double), ("over_conv", C.c_double), ("ref_bias", C.c_double),
+                ("left_trim", C.c_uint32 * 2), ("right_trim", C.c_uint32 * 2), ("min_qual", C.c_uint8)]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _c(a, dt):
+    a = np.ascontiguousarray(a, dtype=dt)
+    return a
+
+
+def build_oracle():
+    """(Re)build liboracle.so and, when the reference tree is present, _ref/libbsref.so."""
+    subprocess.run(["make", "-s", "-C", HERE], check=True, stdout=subprocess.DEVNULL)
+
+
+class Oracle:
+    """The C restatement (oracle/bs_oracle.c)."""
+
+    def __init__(self, under_conv=0.01, over_conv=0.05, ref_bias=2.0, min_qual=20,
+                 left_trim=(0, 0), right_trim=(0, 0)):
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        self.lib = C.CDLL(path)
+        self.lib.bso_fisher.restype = C.c_double
+        self.params = BsoParams(under_conv, over_conv, ref_bias, (C.c_uint32 * 2)(*left_trim),
+                                (C.c_uint32 * 2)(*right_trim), min_qual)
+
+    def qprob_table(self):
+        t = np.zeros((44, 5), dtype=np.float64)
+        self.lib.bso_qprob_table(_p(t))
+        return t
+
+    def lfact_table(self):
+        t = np.zeros(256, dtype=np.float64)
+        self.lib.bso_lfact_table(_p(t))
+        return t
+
+    def calc_gt_prob(self, counts, qual, rf):
+        g = np.zeros(1, dtype=GT_METH)
+        g["counts"][0] = counts
+        g["qual"][0] = qual
+        self.lib.bso_calc_gt_prob(_p(g), C.byref(self.params), C.c_int(int(rf)))
+        return g[0]
+
+    def fisher(self, tab):
+        t = np.ascontiguousarray(tab, dtype=np.int32)
+        return float(self.lib.bso_fisher(_p(t)))
+
+    def call_sites(self, pileup, ref, nthreads=1):
+        pileup = _c(pileup, PILEUP)
+        ref = _c(ref, np.uint8)
+        n = len(pileup)
+        out = np.zeros(n, dtype=GT_METH)
+        skip = np.zeros(n, dtype=np.uint8)
+        self.lib.bso_call_sites(_p(pileup), _p(ref), C.c_size_t(n), C.byref(self.params), _p(out), _p(skip),
+                                C.c_int(nthreads))
+        return out, skip
+
+    def pileup_block(self, templates, bases, x, y):
+        templates = _c(templates, TEMPLATE)
+        bases = _c(bases, np.uint8)
+        out = np.zeros(y - x + 1, dtype=PILEUP)
+        self.lib.bso_pileup_block(_p(templates), C.c_size_t(len(templates)), _p(bases), C.c_uint32(x), C.c_uint32(y),
+                                  C.byref(self.params), _p(out))
+        return out
+
+    def normalise_block(self, templates, bases, misms):
+        templates = _c(templates, TEMPLATE)
+        bases = _c(bases, np.uint8)
+        misms = _c(misms, MISMS)
+        cap = int(len(bases) + (misms["size"].sum() if len(misms) else 0) + 64)
+        out_t = np.zeros(len(templates), dtype=TEMPLATE)
+        out_b = np.zeros(cap, dtype=np.uint8)
+        used = C.c_size_t(0)
+        rc = self.lib.bso_normalise_block(_p(templates), C.c_size_t(len(templates)), _p(bases), _p(misms),
+                                          C.byref(self.params), _p(out_t), _p(out_b), C.c_size_t(cap), C.byref(used))
+        if rc:
+            raise RuntimeError("bso_normalise_block failed: %d" % rc)
+        return out_t, out_b[:used.value].copy()
+
+    def process_block(self, templates, bases, misms, refcodes, y):
+        """refcodes: codes for positions [x, y] where x = max(first-2, 1)."""
+        templates = _c(templates, TEMPLATE)
+        bases = _c(bases, np.uint8)
+        misms = _c(misms, MISMS)
+        refcodes = _c(refcodes, np.uint8)
+        first = int(templates[0]["forward_position"]) or int(templates[0]["reverse_position"])
+        x = first - 2 if first > 2 else 1
+        sz = y - x + 1
+        assert len(refcodes) >= sz
+        pile = np.zeros(sz, dtype=PILEUP)
+        vcf = np.zeros(sz, dtype=GT_VCF)
+        xo = C.c_uint32(0)
+        rc = self.lib.bso_process_block(_p(templates), C.c_size_t(len(templates)), _p(bases), _p(misms), _p(refcodes),
+                                        C.c_uint32(y), C.byref(self.params), C.byref(xo), _p(pile), _p(vcf))
+        if rc:
+            raise RuntimeError("bso_process_block failed: %d" % rc)
+        return xo.value, pile, vcf
+
+
+_REF_SINGLETON = None
+
+
+def reference_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "libbsref.so"))
+
+
+class Reference:
+    """The reference's own compiled hot path (process-wide singleton: it owns global thread state)."""
+
+    def __new__(cls, *a, **k):
+        global _REF_SINGLETON
+        if _REF_SINGLETON is None:
+            _REF_SINGLETON = super().__new__(cls)
+            _REF_SINGLETON._started = False
+        return _REF_SINGLETON
+
+    def __init__(self, under_conv=0.01, over_conv=0.05, ref_bias=2.0, min_qual=20, calc_threads=1,
+                 left_trim=(0, 0), right_trim=(0, 0)):
+        lt = (C.c_uint32 * 2)(*left_trim)
+        rt = (C.c_uint32 * 2)(*right_trim)
+        if not self._started:
+            path = os.path.join(HERE, "_ref", "libbsref.so")
+            if not os.path.exists(path):
+                raise FileNotFoundError(path)
+            self.lib = C.CDLL(path)
+            self.lib.bsref_fisher.restype = C.c_double
+            assert self.lib.bsref_sizeof(0) == PILEUP.itemsize
+            assert self.lib.bsref_sizeof(1) == GT_METH.itemsize
+            assert self.lib.bsref_sizeof(2) == GT_VCF.itemsize
+            assert self.lib.bsref_sizeof(3) == TEMPLATE.itemsize
+            rc = self.lib.bsref_init(C.c_double(under_conv), C.c_double(over_conv), C.c_double(ref_bias),
+                                     C.c_int(min_qual), C.c_int(max(calc_threads - 1, 0)), lt, rt)
+            assert rc == 0
+            self._started = True
+        else:
+            self.lib.bsref_set_params(C.c_double(under_conv), C.c_double(over_conv), C.c_double(ref_bias),
+                                      C.c_int(min_qual), lt, rt)
+
+    def calc_gt_prob(self, counts, qual, rf):
+        g = np.zeros(1, dtype=GT_METH)
+        c = np.ascontiguousarray(counts, dtype=np.uint64)
+        q = np.ascontiguousarray(qual, dtype=np.int32)
+        self.lib.bsref_calc_gt_prob(_p(c), _p(q), C.c_int(int(rf)), _p(g))
+        return g[0]
+
+    def calc_gt_prob_batch(self, counts, qual, rf):
+        c = np.ascontiguousarray(counts, dtype=np.uint64)
+        q = np.ascontiguousarray(qual, dtype=np.int32)
+        r = np.ascontiguousarray(rf, dtype=np.uint8)
+        g = np.zeros(len(r), dtype=GT_METH)
+        self.lib.bsref_calc_gt_prob_batch(_p(c), _p(q), _p(r), C.c_size_t(len(r)), _p(g))
+        return g
+
+    def fisher(self, tab):
+        t = np.ascontiguousarray(tab, dtype=np.int32)
+        return float(self.lib.bsref_fisher(_p(t)))
+
+    def lfact_table(self):
+        t = np.zeros(256, dtype=np.float64)
+        self.lib.bsref_lfact_table(_p(t))
+        return t
+
+    def call_block(self, templates, bases, refcodes, x, y):
+        """Normalised templates -> (pileup[], gt_vcf[]) via call_genotypes_ML.  refcodes covers [x, y+2]."""
+        templates = _c(templates, TEMPLATE)
+        bases = _c(bases, np.uint8)
+        sz = y - x + 1
+        rc_ = np.zeros(sz + 2, dtype=np.uint8)
+        rc_[:min(len(refcodes), sz + 2)] = refcodes[:sz + 2]
+        pile = np.zeros(sz, dtype=PILEUP)
+        vcf = np.zeros(sz, dtype=GT_VCF)
+        rc = self.lib.bsref_call_block(_p(templates), C.c_size_t(len(templates)), _p(bases), _p(rc_),
+                                       C.c_uint32(x), C.c_uint32(y), _p(pile), _p(vcf))
+        if rc:
+            raise RuntimeError("bsref_call_block failed: %d" % rc)
+        return pile, vcf
+
+    def process_block(self, templates, bases, misms, ctg_codes, y):
+        """Raw templates -> (x, pileup[], gt_vcf[], ref[], normalised templates, normalised bases)."""
+        templates = _c(templates, TEMPLATE)
+        bases = _c(bases, np.uint8)
+        misms = _c(misms, MISMS)
+        ctg_codes = _c(ctg_codes, np.uint8)
+        first = int(templates[0]["forward_position"]) or int(templates[0]["reverse_position"])
+        x = first - 2 if first > 2 else 1
+        sz = y - x + 1
+        pile = np.zeros(sz, dtype=PILEUP)
+        vcf = np.zeros(sz, dtype=GT_VCF)
+        ref = np.zeros(sz, dtype=np.uint8)
+        cap = int(len(bases) + (misms["size"].sum() if len(misms) else 0) + 64)
+        nt = np.zeros(len(templates), dtype=TEMPLATE)
+        nb = np.zeros(cap, dtype=np.uint8)
+        xo = C.c_uint32(0)
+        rc = self.lib.bsref_process_block(_p(templates), C.c_size_t(len(templates)), _p(bases), _p(misms),
+                                          _p(ctg_codes), C.c_uint32(len(ctg_codes)), C.c_uint32(y), C.byref(xo),
+                                          _p(pile), _p(vcf), _p(ref), _p(nt), _p(nb), C.c_size_t(cap))
+        if rc:
+            raise RuntimeError("bsref_process_block failed: %d" % rc)
+        used = int(nt["read_len"].sum())
+        return xo.value, pile, vcf, ref, nt, nb[:used].copy()

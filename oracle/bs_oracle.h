@@ -1,0 +1,107 @@
+/*
+ * bs_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement ("port") of the bs_call 2.1.7 pileup + genotype-likelihood hot path, written from the
+ * behaviour of the reference sources (cited per function in bs_oracle.c).  It exists so that the CUDA path
+ * can be checked on machines where /root/reference is absent (the GPU boxes).  Only tests/, the smoke check
+ * and bench.py's cpu_baseline / --impl reference legs may load it; the product (libbsgpu) never does.
+ *
+ * PARITY PINNING: the reference ships no tests or golden vectors, so this restatement is
+ * pinned against the reference's own compiled objects (oracle/_ref/libbsref.so, built by oracle/Makefile
+ * from the sources where they lie under /root/reference) by tests/test_oracle_vs_reference.py, and against
+ * the golden fixtures under tests/golden/ that were captured from those objects
+ * (tests/golden/make_golden.py).
+ */
+#ifndef BS_ORACLE_H
+#define BS_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same layouts as the reference's pileup / gt_meth / gt_vcf (include/bs_call.h:174-182, 152-160, 162-166) */
+typedef struct {
+	uint32_t counts[2][8];
+	uint32_t n;
+	float quality[8];
+	float mapq2;
+} bso_pileup;              /* 104 bytes */
+
+typedef struct {
+	uint64_t counts[8];
+	int32_t qual[8];
+	double gt_prob[10];
+	double fisher_strand;
+	int32_t mq;
+	int32_t aq;
+	uint8_t max_gt;
+	uint8_t pad[7];
+} bso_gt_meth;             /* 200 bytes */
+
+typedef struct {
+	bso_gt_meth gtm;
+	uint8_t ready;
+	uint8_t skip;
+	uint8_t pad[6];
+} bso_gt_vcf;              /* 208 bytes */
+
+/* Flat template record (identical to bsref_template in ref_harness.c) */
+typedef struct {
+	uint32_t forward_position, reverse_position;
+	uint32_t reference_span[2];
+	uint32_t read_off[2];
+	uint32_t read_len[2];
+	uint32_t mm_off[2];
+	uint32_t mm_n[2];
+	uint8_t present[2];
+	uint8_t mapq[2];
+	uint8_t orientation;
+	uint8_t bs_strand;
+	uint8_t pad[2];
+} bso_template;            /* 56 bytes */
+
+/* misms type codes follow the reference enum gt_misms_t {MISMS, INS, DEL, SOFT} (include/bs_call.h:53);
+ * note the naming inversion: CIGAR 'D' -> INS (zero-fill), CIGAR 'I' -> DEL (drop) (src/input_sam.c:117-130) */
+enum { BSO_MISMS = 0, BSO_INS = 1, BSO_DEL = 2, BSO_SOFT = 3 };
+typedef struct { uint32_t type, position, size; } bso_misms;
+
+typedef struct {
+	double under_conv, over_conv, ref_bias;
+	uint32_t left_trim[2], right_trim[2];
+	uint8_t min_qual;
+} bso_params;
+
+void bso_default_params(bso_params *p);
+
+/* model pieces */
+void bso_qprob_table(double *out /* 44 x {e,k,ln_k,ln_k_half,ln_k_one} */);
+void bso_lfact_table(double *out /* 256 */);
+void bso_calc_gt_prob(bso_gt_meth *gt, const bso_params *p, int rf);
+double bso_fisher(const int c_in[4]);
+
+/* per-site body of call_thread */
+void bso_summarise(const bso_pileup *tp, bso_gt_meth *tg);
+int  bso_strand_table(const bso_pileup *tp, int max_gt, int ftab[4]);
+void bso_call_site(const bso_pileup *tp, int rf, const bso_params *p, bso_gt_meth *out, uint8_t *skip);
+void bso_call_sites(const bso_pileup *tp, const uint8_t *ref, size_t n, const bso_params *p,
+		bso_gt_meth *out, uint8_t *skip, int nthreads);
+
+/* pileup loop over normalised templates */
+void bso_pileup_block(const bso_template *t, size_t n, const uint8_t *bases, uint32_t x, uint32_t y,
+		const bso_params *p, bso_pileup *out /* y-x+1, zeroed here */);
+
+/* template normalisation: returns 0, or <0 on the conditions where the reference calls gt_fatal_error_msg */
+int bso_normalise_block(const bso_template *t, size_t n, const uint8_t *bases, const bso_misms *mm,
+		const bso_params *p, bso_template *out_t, uint8_t *out_bases, size_t out_cap, size_t *out_used);
+
+/* whole path: raw templates -> gt_vcf[] */
+int bso_process_block(const bso_template *t, size_t n, const uint8_t *bases, const bso_misms *mm,
+		const uint8_t *refcodes /* codes for [x, y] */, uint32_t y, const bso_params *p,
+		uint32_t *x_out, bso_pileup *pile_out, bso_gt_vcf *vcf_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,143 @@
+"""Pins the restatement (oracle/bs_oracle.c) against the reference's own compiled objects
+(oracle/_ref/libbsref.so = unmodified /root/reference sources behind oracle/ref_harness.c).
+
+Both run on the same CPU with the same libm, so every field -- including the doubles -- must be
+bit-identical.  Skipped where the prebuilt reference library is absent.
+"""
+import numpy as np
+import pytest
+
+from tests import blockgen
+
+pytestmark = pytest.mark.reference
+
+
+def _same_records(a, b, what):
+    assert a.dtype == b.dtype and a.shape == b.shape
+    if a.tobytes() != b.tobytes():
+        for name in a.dtype.names:
+            if name.startswith("pad"):
+                continue
+            if a[name].tobytes() != b[name].tobytes():
+                bad = np.nonzero(np.any((a[name] != b[name]).reshape(len(a), -1), axis=1))[0]
+                raise AssertionError("%s: field %s differs at %d sites, first %d: %r vs %r"
+                                     % (what, name, len(bad), bad[0], a[name][bad[0]], b[name][bad[0]]))
+
+
+def test_kat_from_survey(oracle, reference):
+    # captured from the reference with defaults
+    c = [0, 14, 0, 0, 0, 10, 0, 5]
+    q = [35 if v else 0 for v in c]
+    want = [-111.48773751377976, -8.8528005438194999, -111.48773751377976, -93.107739053342456,
+            -6.5076274832880412e-06, -8.8528005438194999, -4.8244462420618976, -111.48773751377976,
+            -93.107739053342456, -91.602818028647008]
+    for impl in (oracle, reference):
+        g = impl.calc_gt_prob(c, q, 2)
+        assert g["max_gt"] == 4
+        np.testing.assert_allclose(g["gt_prob"], want, rtol=1e-13)
+        assert abs(impl.fisher([12, 3, 4, 11]) - 0.0092205703133985545) < 1e-16
+
+
+def test_tables(oracle, reference):
+    assert oracle.lfact_table().tobytes() == reference.lfact_table().tobytes()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_calc_gt_prob_random(oracle, reference, seed):
+    rng = np.random.default_rng(seed)
+    n = 4000
+    counts = np.zeros((n, 8), dtype=np.uint64)
+    for i in range(n):
+        k = rng.integers(0, 6)
+        cls = rng.choice(8, size=k, replace=False) if k else []
+        for c in cls:
+            counts[i, c] = int(rng.integers(1, 60)) if rng.random() < 0.95 else int(rng.integers(60, 5000))
+    qual = np.where(counts > 0, rng.integers(1, 44, size=(n, 8)), 0).astype(np.int32)
+    rf = rng.integers(0, 5, size=n).astype(np.uint8)
+    want = reference.calc_gt_prob_batch(counts, qual, rf)
+    for i in range(n):
+        got = oracle.calc_gt_prob(counts[i], qual[i], rf[i])
+        assert got["max_gt"] == want[i]["max_gt"], (i, counts[i], qual[i], rf[i])
+        assert got["gt_prob"].tobytes() == want[i]["gt_prob"].tobytes(), (i, counts[i], qual[i], rf[i])
+
+
+def test_calc_gt_prob_other_params(reference):
+    from oracle.bindings import Oracle, Reference
+    o = Oracle(under_conv=0.02, over_conv=0.1, ref_bias=1.0)
+    r = Reference(under_conv=0.02, over_conv=0.1, ref_bias=1.0)
+    try:
+        rng = np.random.default_rng(7)
+        for _ in range(500):
+            c = rng.integers(0, 30, size=8) * (rng.random(8) < 0.5)
+            q = np.where(c > 0, rng.integers(1, 44, size=8), 0)
+            rf = int(rng.integers(0, 5))
+            a, b = o.calc_gt_prob(c, q, rf), r.calc_gt_prob(c, q, rf)
+            assert a["max_gt"] == b["max_gt"] and a["gt_prob"].tobytes() == b["gt_prob"].tobytes()
+    finally:
+        Reference()  # restore defaults for the other tests
+
+
+def test_fisher_random(oracle, reference):
+    rng = np.random.default_rng(11)
+    tabs = [rng.integers(0, 40, size=4) for _ in range(3000)]
+    tabs += [rng.integers(0, 400, size=4) for _ in range(1000)]       # margins >= 256 -> lgamma path
+    tabs += [np.array(t) for t in ([0, 0, 0, 0], [5, 0, 0, 5], [0, 7, 7, 0], [1, 0, 0, 0], [300, 2, 1, 280])]
+    for t in tabs:
+        a, b = oracle.fisher(t), reference.fisher(t)
+        assert a == b or (np.isnan(a) and np.isnan(b)), (t, a, b)
+
+
+CASES = [
+    dict(depth=30, read_len=100, paired=True),
+    dict(depth=30, read_len=100, paired=True, indel_frac=0.3, clip_frac=0.3),
+    dict(depth=12, read_len=75, paired=True, frag_mean=110, frag_sd=30, indel_frac=0.5, clip_frac=0.2),
+    dict(depth=60, read_len=50, paired=False, indel_frac=0.2, clip_frac=0.2, nonconv_frac=0.3),
+    dict(depth=20, read_len=100, paired=True, single_mate_frac=0.3, indel_frac=0.2, n_frac=0.05),
+]
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("trims", [((0, 0), (0, 0)), ((5, 3), (2, 4))])
+def test_process_block(reference, case, trims):
+    from oracle.bindings import Oracle, Reference
+    lt, rt = trims
+    rng = np.random.default_rng(100 + case)
+    ref = blockgen.random_reference(rng, 6000, n_runs=2)
+    T, B, M, y = blockgen.make_block(rng, ref, 200, 4800, **CASES[case])
+    o = Oracle(left_trim=lt, right_trim=rt)
+    r = Reference(left_trim=lt, right_trim=rt)
+    try:
+        x, pile_r, vcf_r, ref_r, nt_r, nb_r = r.process_block(T, B, M, ref, y)
+    finally:
+        Reference()
+    nt_o, nb_o = o.normalise_block(T, B, M)
+    # the normalised reads
+    assert nb_o.tobytes() == nb_r.tobytes()
+    for f in ("forward_position", "reverse_position", "read_len", "read_off", "present"):
+        assert (nt_o[f] == nt_r[f]).all(), f
+    # ref window the reference decoded (last contig base reads as N, src/get_sequence.c:41)
+    sz = y - x + 1
+    np.testing.assert_array_equal(ref_r, ref[x - 1:x - 1 + sz])
+    xo, pile_o, vcf_o = o.process_block(T, B, M, ref_r, y)
+    assert xo == x
+    _same_records(pile_o, pile_r, "pileup")
+    _same_records(vcf_o, vcf_r, "gt_vcf")
+    assert (vcf_r["skip"] == 0).sum() > 1000
+    # the reference gives the same answer through call_genotypes_ML alone on the normalised block
+    pile_c, vcf_c = r.call_block(nt_r, nb_r, np.concatenate([ref_r, [0, 0]]).astype(np.uint8), x, y)
+    _same_records(pile_c, pile_r, "pileup via call_block")
+    _same_records(vcf_c, vcf_r, "gt_vcf via call_block")
+
+
+def test_deep_block_uses_lgamma(reference):
+    """500x single-end panel (config 4): strand tables with margins >= 256."""
+    from oracle.bindings import Oracle
+    rng = np.random.default_rng(5)
+    ref = blockgen.random_reference(rng, 1500)
+    T, B, M, y = blockgen.make_block(rng, ref, 100, 900, depth=500, read_len=150, paired=False, snp_rate=0.02)
+    x, pile_r, vcf_r, ref_r, nt_r, nb_r = reference.process_block(T, B, M, ref, y)
+    xo, pile_o, vcf_o = Oracle().process_block(T, B, M, ref_r, y)
+    _same_records(pile_o, pile_r, "pileup")
+    _same_records(vcf_o, vcf_r, "gt_vcf")
+    het = np.isin(vcf_r["gtm"]["max_gt"], [1, 2, 3, 5, 6, 8]) & (vcf_r["skip"] == 0)
+    assert het.sum() > 0 and pile_r["n"].max() >= 256
