@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- genome sites called per second on N B200s (BASELINE.json metric), next to the host-CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload at every N (config.workload): BASELINE.json configs[1] -- the likelihood-kernel microbench: 1e9 synthetic
+per-site count vectors PER GPU fed straight to the genotype / methylation model (weak scaling: rank r owns sites
+[r*1e9, (r+1)*1e9) of the same counter-based stream, no data-path collective).  A step = one pass of the hot path
+over the rank's 1e9 resident sites (16 launches of k_call_sites over 62.5 M-site slabs; outputs go to one slab-sized
+ring in HBM because 1e9 x 200 B does not fit beside the 105 GB of input).
+
+  value     sites/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e       same metric through the C ABI with HOST (pinned) buffers: H2D + kernel + D2H inside the timed region
+  roofline  k_call_sites: 306 algorithmic B/site (104 pileup + 1 ref + 200 gt_meth + 1 skip) / event time, against the
+            measured HBM copy bandwidth in MEASURED_PEAKS.json
+  fused     the fused pileup->likelihood kernel (k_pileup_tile) on a synthetic 30x WGBS window (config 3 shape),
+            reported beside the headline with its own roofline
+  cpu_baseline / --impl reference: the reference's own calc_gt_prob()/fisher() objects (oracle/_ref, else the oracle
+            port) on all host cores over a bounded sample of the same site stream
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20261018
+MEAN_DEPTH = 30.0
+BYTES_PER_SITE = 104 + 1 + 200 + 1
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[4 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_path(n_sample, nthreads):
+    """The CPU implementation of the path over sites [0, n_sample) of the stream; returns (seconds, kind, sample)."""
+    from oracle.bindings import Oracle, Reference, reference_available
+    o = Oracle()
+    p, r = o.synth_sites(SEED, 0, n_sample, MEAN_DEPTH, nthreads=nthreads)
+    if reference_available():
+        impl, kind = Reference(), "reference"
+        what = "reference calc_gt_prob()/fisher() objects (oracle/_ref) + summarise glue"
+    else:
+        impl, kind = o, "port"
+        what = "oracle port (oracle/bs_oracle.c)"
+    t0 = time.perf_counter()
+    out, skip = impl.call_sites(p, r, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    called = int((skip == 0).sum())
+    return dt, kind, "%d sites (%d called) of the same counter-based stream, %s, %d threads strided like the reference's calc threads" % (
+        n_sample, called, what, nthreads), called, (p, r, out, skip)
+
+
+def calibrate_cpu_sample(nthreads, target_s):
+    dt, _, _, _, _ = cpu_path(200000, nthreads)
+    rate = 200000 / max(dt, 1e-6)
+    n = int(min(max(rate * target_s, 1e6), 3.2e7))        # <= 10 GB of host records
+    return n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    nthreads = os.cpu_count() or 1
+    n = calibrate_cpu_sample(nthreads, 4.0)
+    for _ in range(args.warmup):
+        cpu_path(min(n, 2000000), nthreads)
+    tot_t, tot_n, kind, sample = 0.0, 0, None, None
+    for _ in range(args.steps):
+        dt, kind, sample, called, _ = cpu_path(n, nthreads)
+        tot_t += dt
+        tot_n += called
+    value = tot_n / tot_t
+    line = {"impl": "reference", "metric": "genome sites called/sec", "value": value, "unit": "sites/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[1]: likelihood microbench, synthetic per-site count vectors; CPU arm runs a bounded sample per step",
+                       "sites_per_step": n, "mean_depth": MEAN_DEPTH, "seed": SEED},
+            "cpu_baseline": {"value": value, "unit": "sites/s", "cores": nthreads, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="bsgpu")
+    ap.add_argument("--sites", type=float, default=1e9, help="resident sites per GPU (config 2: 1e9)")
+    ap.add_argument("--e2e-sites", type=float, default=8e6, help="sites per e2e step (host buffers)")
+    ap.add_argument("--fused-sites", type=float, default=50e6, help="window of the fused pileup->likelihood measurement")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from bs_call_b200 import lib as bslib
+    from bs_call_b200.records import GT_METH, PILEUP
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gpu = bslib.BsGpu(device=local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    n_sites = int(args.sites)
+    n_slab = 16
+    slab = (n_sites + n_slab - 1) // n_slab
+    slab += slab & 1                                 # even -> every slab starts 16-byte aligned (104 B records)
+    d_pile = torch.empty(n_sites * 104 + 16, dtype=torch.uint8, device="cuda")
+    d_ref = torch.empty(n_sites + 16, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(slab * 200 + 16, dtype=torch.uint8, device="cuda")
+    d_skip = torch.empty(slab + 16, dtype=torch.uint8, device="cuda")
+    first_site = rank * n_sites
+    for s in range(n_slab):
+        a = s * slab
+        m = min(slab, n_sites - a)
+        if m > 0:
+            gpu.synth_sites_dev(SEED, first_site + a, m, MEAN_DEPTH, d_pile.data_ptr() + a * 104, d_ref.data_ptr() + a, stream)
+    torch.cuda.synchronize()
+    called_total = int((d_pile.view(torch.int32)[16:n_sites * 26:26] > 0).sum().item())      # pileup.n > 0
+
+    def step():
+        for s in range(n_slab):
+            a = s * slab
+            m = min(slab, n_sites - a)
+            if m > 0:
+                gpu.call_sites_dev(d_pile.data_ptr() + a * 104, d_ref.data_ptr() + a, m, d_out.data_ptr(), d_skip.data_ptr(), stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = gpu.stats()["kernel_launches"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = gpu.stats()["kernel_launches"] - l0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    tot_called = torch.tensor([called_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_called, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = float(tot_called.item()) / (ms_per_step * 1e-3)
+
+    # spot check of the last slab against the oracle (not timed): the numbers above are for a path that is right
+    parity = None
+    if rank == 0:
+        from oracle.bindings import Oracle
+        from tests import util
+        a = (n_slab - 1) * slab
+        m = min(min(slab, n_sites - a), 20000)
+        p = d_pile[a * 104:(a + m) * 104].cpu().numpy().view(PILEUP)
+        r = d_ref[a:a + m].cpu().numpy()
+        got = d_out[:m * 200].cpu().numpy().view(GT_METH)
+        gskip = d_skip[:m].cpu().numpy()
+        wout, wskip = Oracle().call_sites(p, r, nthreads=4)
+        parity = {"sites_checked": util.assert_gt_meth_close(got, gskip, wout, wskip), "against": "oracle"}
+
+    # ---- roofline of the dominant kernel (k_call_sites): per launch, all sites of the slab move 306 B each
+    peak, peak_kind = measured_peaks()
+    launch_ms = ms / (args.steps * n_slab)
+    achieved = BYTES_PER_SITE * slab / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj["k_call_sites"]["dram_bytes_per_site"] * slab
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "k_call_sites", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                "algorithmic_bytes_per_site": BYTES_PER_SITE, "sites_per_launch": slab, "launch_ms": launch_ms}
+
+    # ---- e2e: the same metric through the C ABI with host buffers (H2D + kernel + D2H inside the timed region)
+    n_e2e = int(min(args.e2e_sites, n_sites))
+    hp = bslib.HostBuffer(n_e2e, PILEUP)
+    hr = bslib.HostBuffer(n_e2e, np.uint8)
+    ho = bslib.HostBuffer(n_e2e, GT_METH)
+    hs = bslib.HostBuffer(n_e2e, np.uint8)
+    hp.array.view(np.uint8)[:] = d_pile[:n_e2e * 104].cpu().numpy()
+    hr.array[:] = d_ref[:n_e2e].cpu().numpy()
+    e2e_called = int((hp.array["n"] > 0).sum())
+    for _ in range(2):
+        gpu.call_sites(hp.array, hr.array, out=ho.array, skip=hs.array)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        gpu.call_sites(hp.array, hr.array, out=ho.array, skip=hs.array)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    ce = torch.tensor([e2e_called], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ce, op=dist.ReduceOp.SUM)
+    e2e = {"value": float(ce.item()) * args.steps / float(te.item()), "unit": "sites/s", "h2d_bytes_per_step": n_e2e * 105,
+           "d2h_bytes_per_step": n_e2e * 201, "sites_per_step": n_e2e,
+           "note": "bsgpu_call_sites on pinned host arrays; 1 Mi-site chunks ping-pong on two streams"}
+    assert (hs.array == (hp.array["n"] == 0)).all()
+    for b in (hp, hr, ho, hs):
+        b.free()
+
+    # ---- fused pileup -> likelihood kernel on a synthetic 30x window (config 3 shape), device resident
+    fused = None
+    del d_out, d_skip
+    torch.cuda.empty_cache()
+    try:
+        fsz = int(args.fused_sites)
+        L, depth = 150, 30.0
+        ns = gpu.synth_block_nseg(fsz, L, depth)
+        d_seg = torch.empty(ns * 16 + 16, dtype=torch.uint8, device="cuda")
+        d_b = torch.empty(ns * L + 16, dtype=torch.uint8, device="cuda")
+        d_r = torch.empty(fsz + 16, dtype=torch.uint8, device="cuda")
+        d_v = torch.empty(fsz * 208 + 16, dtype=torch.uint8, device="cuda")
+        gpu.synth_block_dev(SEED + rank, 1000, fsz, L, depth, d_seg.data_ptr(), ns, d_b.data_ptr(), ns * L, d_r.data_ptr(), stream)
+        for _ in range(3):
+            gpu.call_block_dev(d_seg.data_ptr(), ns, d_b.data_ptr(), d_r.data_ptr(), 1000, fsz, d_v.data_ptr(), stream)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            gpu.call_block_dev(d_seg.data_ptr(), ns, d_b.data_ptr(), d_r.data_ptr(), 1000, fsz, d_v.data_ptr(), stream)
+        f1.record()
+        barrier()
+        fms = f0.elapsed_time(f1) / args.steps
+        fcalled = int((d_v.view(torch.uint8)[201::208][:fsz] == 0).sum().item())
+        fbytes = ns * (L + 16) + fsz * (1 + 208)
+        fused = {"kernel": "k_pileup_tile<fused> (+3 binning kernels)", "workload": "synthetic %dx PE-like %d-bp reads over a %d-site window" % (int(depth), L, fsz),
+                 "sites_per_s": fcalled / (fms * 1e-3), "ms": fms, "sites_called": fcalled,
+                 "roofline": {"bound": "hbm", "achieved": fbytes / (fms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": fbytes / (fms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_site": fbytes / fsz}}
+        del d_seg, d_b, d_r, d_v
+    except Exception as e:            # reported, never hidden
+        fused = {"error": str(e)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        nthreads = os.cpu_count() or 1
+        n_cpu = calibrate_cpu_sample(nthreads, 12.0)
+        dt, kind, sample, called, _ = cpu_path(n_cpu, nthreads)
+        cpu = {"value": called / dt, "unit": "sites/s", "cores": nthreads, "kind": kind, "sample": sample}
+
+    if rank == 0:
+        line = {"metric": "genome sites called/sec", "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE.json configs[1]: likelihood microbench, 1e9 synthetic per-site count vectors per GPU",
+                           "sites_per_gpu": n_sites, "sites_called_per_gpu": called_total, "mean_depth": MEAN_DEPTH, "seed": SEED,
+                           "parallelism": "sites sharded over %d rank(s), no collective" % world,
+                           "l2": "inputs larger than L2: each step streams %.1f GB of distinct records" % (n_sites * 105 / 1e9)},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "fused": fused, "parity_spot_check": parity}
+        print(json.dumps(line))
+    gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

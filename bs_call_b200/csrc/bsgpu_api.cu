@@ -1,0 +1,408 @@
+// bsgpu_api.cu -- the C ABI declared in include/bsgpu.h: context, staging, pipelines.  No CPU compute path:
+// every entry point that produces results launches kernels, and bsgpu_init fails if no sm_100 device opens.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "bsgpu.h"
+#include "bsgpu_device.cuh"
+#include "bsgpu_launch.h"
+
+static_assert(sizeof(bsgpu_pileup) == 104, "pileup layout (include/bs_call.h:174-182)");
+static_assert(sizeof(bsgpu_gt_meth) == 200, "gt_meth layout (include/bs_call.h:152-160)");
+static_assert(sizeof(bsgpu_gt_vcf) == 208, "gt_vcf layout (include/bs_call.h:162-166)");
+static_assert(sizeof(bsgpu_seg) == 16, "segment layout");
+static_assert(sizeof(bsgpu_template) == 56, "template layout");
+static_assert(offsetof(bsgpu_gt_meth, gt_prob) == 96 && offsetof(bsgpu_gt_meth, fisher_strand) == 176 &&
+		offsetof(bsgpu_gt_meth, mq) == 184 && offsetof(bsgpu_gt_meth, max_gt) == 192, "gt_meth offsets");
+static_assert(offsetof(bsgpu_pileup, n) == 64 && offsetof(bsgpu_pileup, quality) == 68 && offsetof(bsgpu_pileup, mapq2) == 100, "pileup offsets");
+
+using namespace bsgpu;
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return BSGPU_FAIL;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// grow-on-demand device / pinned buffers
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t bytes) {
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Slot {                  // one stage of the host-buffer pipelines
+	cudaStream_t stream = nullptr;
+	cudaEvent_t done = nullptr;
+	DevBuf in, ref, out, skip;
+};
+
+struct bsgpu_ctx {
+	int device = 0;
+	bsgpu_params params;
+	DevConst *d_const = nullptr;
+	unsigned long long *d_counters = nullptr;    // [0] sites called by the fused kernel, [1] envelope overflows
+	cudaStream_t stream = nullptr;               // context stream (block path, _dev default)
+	cudaStream_t copy_stream = nullptr;          // D2H of finished windows
+	Slot slot[2];
+	DevBuf segs, bases, ref, scratch, vcf, tmpl, misms;
+	std::vector<cudaEvent_t> win_events;
+	bsgpu_stats stats;
+	int launches = 0;
+};
+
+extern "C" {
+
+int bsgpu_version(void) { return 100; }
+
+const char *bsgpu_last_error(void) { return g_err; }
+
+void bsgpu_default_params(bsgpu_params *p) {
+	memset(p, 0, sizeof(*p));
+	p->under_conv = 0.01;      // include/bs_call.h:16-18
+	p->over_conv = 0.05;
+	p->ref_bias = 2.0;
+	p->min_qual = 20;          // include/bs_call.h:26
+	p->device = 0;
+}
+
+int bsgpu_init(const bsgpu_params *p, bsgpu_ctx **out) {
+	if (!p || !out) return fail("bsgpu_init: null argument");
+	if (p->min_qual < 1 || p->min_qual > BSGPU_MAX_QUAL) return fail("bsgpu_init: min_qual must be in [1,%d]", BSGPU_MAX_QUAL);
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) return fail("bsgpu_init: no CUDA device (%s); there is no CPU fallback", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+	if (p->device < 0 || p->device >= ndev) return fail("bsgpu_init: device %d out of range (have %d)", p->device, ndev);
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, p->device));
+	if (prop.major != 10) return fail("bsgpu_init: device %d is sm_%d%d; this library carries sm_100a code only", p->device, prop.major, prop.minor);
+	CU(cudaSetDevice(p->device));
+	bsgpu_ctx *c = new bsgpu_ctx();
+	c->device = p->device;
+	c->params = *p;
+	memset(&c->stats, 0, sizeof(c->stats));
+	// host-side tables, computed with the C library exactly as the reference does
+	DevConst h;
+	memset(&h, 0, sizeof(h));
+	for (int q = 0; q <= kMaxQual; q++) {          // src/genotype_model.c:10-21
+		double er = exp(-.1 * (double)q * kLn10);
+		if (er > .5) er = .5;
+		const double k = er / (3.0 - 4.0 * er);
+		h.qp[q][0] = k;
+		h.qp[q][1] = log(k);
+		h.qp[q][2] = log(0.5 + k);
+		h.qp[q][3] = log(1.0 + k);
+	}
+	double acc = 0.0;                              // src/stats_utils.c:14-21
+	h.lfact[0] = h.lfact[1] = 0.0;
+	for (int i = 2; i < 256; i++) { acc += log((double)i); h.lfact[i] = acc; }
+	h.l = 1.0 - p->under_conv;                     // src/genotype_model.c:47-48
+	h.t = p->over_conv;
+	h.lrb = log(p->ref_bias);                      // src/genotype_model.c:88-89
+	h.lrb1 = log(0.5 * (1.0 + p->ref_bias));
+	h.min_qual = p->min_qual;
+	CU(cudaMalloc(&c->d_const, sizeof(DevConst)));
+	CU(cudaMemcpy(c->d_const, &h, sizeof(h), cudaMemcpyHostToDevice));
+	CU(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
+	CU(cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long)));
+	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; i++) {
+		CU(cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking));
+		CU(cudaEventCreateWithFlags(&c->slot[i].done, cudaEventDisableTiming));
+	}
+	CU(configure_kernels());
+	*out = c;
+	return BSGPU_OK;
+}
+
+void bsgpu_destroy(bsgpu_ctx *c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaDeviceSynchronize();
+	for (int i = 0; i < 2; i++) {
+		c->slot[i].in.release(); c->slot[i].ref.release(); c->slot[i].out.release(); c->slot[i].skip.release();
+		if (c->slot[i].stream) cudaStreamDestroy(c->slot[i].stream);
+		if (c->slot[i].done) cudaEventDestroy(c->slot[i].done);
+	}
+	for (cudaEvent_t ev : c->win_events) cudaEventDestroy(ev);
+	c->segs.release(); c->bases.release(); c->ref.release(); c->scratch.release(); c->vcf.release(); c->tmpl.release(); c->misms.release();
+	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	if (c->d_const) cudaFree(c->d_const);
+	if (c->d_counters) cudaFree(c->d_counters);
+	delete c;
+}
+
+int bsgpu_get_stats(bsgpu_ctx *c, bsgpu_stats *out) {
+	if (!c || !out) return fail("bsgpu_get_stats: null argument");
+	CU(cudaSetDevice(c->device));
+	unsigned long long h[4];
+	CU(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+	c->stats.kernel_launches = (uint64_t)c->launches;
+	c->stats.sites_called = h[0];
+	c->stats.qsum_overflow = h[1];
+	*out = c->stats;
+	return BSGPU_OK;
+}
+
+void *bsgpu_host_alloc(size_t bytes) {
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { fail("bsgpu_host_alloc(%zu) failed", bytes); return nullptr; }
+	return p;
+}
+
+void bsgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------------
+// device-pointer entry points
+// ------------------------------------------------------------------------------------------------
+int bsgpu_call_sites_dev(bsgpu_ctx *c, const void *d_pileup, const void *d_ref, size_t n, void *d_out, void *d_skip, void *stream) {
+	if (!c) return fail("bsgpu_call_sites_dev: null context");
+	if (n && (!d_pileup || !d_ref || !d_out || !d_skip)) return fail("bsgpu_call_sites_dev: null buffer");
+	if (((uintptr_t)d_pileup | (uintptr_t)d_out) & 7u) return fail("bsgpu_call_sites_dev: record arrays must be 8-byte aligned");
+	CU(cudaSetDevice(c->device));
+	CU(launch_call_sites(d_pileup, d_ref, n, d_out, d_skip, false, c->d_const, stream ? (cudaStream_t)stream : c->stream, &c->launches));
+	c->stats.sites += n;
+	return BSGPU_OK;
+}
+
+int bsgpu_call_sites_vcf_dev(bsgpu_ctx *c, const void *d_pileup, const void *d_ref, size_t n, void *d_vcf, void *stream) {
+	if (!c) return fail("bsgpu_call_sites_vcf_dev: null context");
+	if (n && (!d_pileup || !d_ref || !d_vcf)) return fail("bsgpu_call_sites_vcf_dev: null buffer");
+	if (((uintptr_t)d_pileup | (uintptr_t)d_vcf) & 7u) return fail("bsgpu_call_sites_vcf_dev: record arrays must be 8-byte aligned");
+	CU(cudaSetDevice(c->device));
+	CU(launch_call_sites(d_pileup, d_ref, n, d_vcf, nullptr, true, c->d_const, stream ? (cudaStream_t)stream : c->stream, &c->launches));
+	c->stats.sites += n;
+	return BSGPU_OK;
+}
+
+size_t bsgpu_block_scratch_bytes(size_t nseg, uint32_t sz) { return pileup_scratch_bytes(nseg, sz); }
+
+static int block_dev(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *d_bases, const void *d_ref, uint32_t x, uint32_t sz,
+		void *d_out, int mode, void *d_scratch, void *stream) {
+	if (!c) return fail("bsgpu block: null context");
+	if (!sz) return BSGPU_OK;
+	if (!d_out || (nseg && (!d_segs || !d_bases)) || (mode && !d_ref)) return fail("bsgpu block: null buffer");
+	if ((uintptr_t)d_out & 15u) return fail("bsgpu block: output array must be 16-byte aligned");
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+	void *scratch = d_scratch;
+	if (!scratch) {
+		// growing the context's scratch frees the old allocation: make sure nothing queued earlier still uses it
+		if (pileup_scratch_bytes(nseg, sz) > c->scratch.cap) CU(cudaDeviceSynchronize());
+		CU(c->scratch.reserve(pileup_scratch_bytes(nseg, sz)));
+		scratch = c->scratch.p;
+	}
+	CU(launch_bin_segments(d_segs, nseg, x, sz, scratch, st, &c->launches));
+	const uint32_t ntiles = (sz + kPileTileSites - 1) / kPileTileSites;
+	CU(launch_pileup_tiles(scratch, nseg, d_bases, d_ref, x, sz, 0, ntiles, d_out, mode, c->d_const, c->d_counters, st, &c->launches));
+	c->stats.sites += sz;
+	return BSGPU_OK;
+}
+
+int bsgpu_pileup_block_dev(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *d_bases, uint32_t x, uint32_t sz, void *d_pileup_out, void *stream) {
+	return block_dev(c, d_segs, nseg, d_bases, nullptr, x, sz, d_pileup_out, 0, nullptr, stream);
+}
+
+int bsgpu_call_block_dev(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *d_bases, const void *d_ref, uint32_t x, uint32_t sz, void *d_vcf_out, void *stream) {
+	return block_dev(c, d_segs, nseg, d_bases, d_ref, x, sz, d_vcf_out, 1, nullptr, stream);
+}
+
+int bsgpu_synth_sites_dev(bsgpu_ctx *c, uint64_t seed, uint64_t first_site, size_t n, double mean_depth, void *d_pileup, void *d_ref, void *stream) {
+	if (!c) return fail("bsgpu_synth_sites_dev: null context");
+	CU(cudaSetDevice(c->device));
+	CU(launch_synth_sites(seed, first_site, n, mean_depth, d_pileup, d_ref, stream ? (cudaStream_t)stream : c->stream, &c->launches));
+	return BSGPU_OK;
+}
+
+size_t bsgpu_synth_block_nseg(uint32_t sz, uint32_t read_len, double depth) { return synth_block_nseg(sz, read_len, depth); }
+
+int bsgpu_synth_block_dev(bsgpu_ctx *c, uint64_t seed, uint32_t x, uint32_t sz, uint32_t read_len, double depth,
+		void *d_segs, size_t seg_cap, void *d_bases, size_t base_cap, void *d_ref, size_t *nseg, size_t *nbases, void *stream) {
+	if (!c) return fail("bsgpu_synth_block_dev: null context");
+	if (read_len < 16 || read_len > BSGPU_MAX_SEG_LEN) return fail("bsgpu_synth_block_dev: read_len must be in [16,%d]", BSGPU_MAX_SEG_LEN);
+	const size_t ns = synth_block_nseg(sz, read_len, depth);
+	if (ns > seg_cap || ns * read_len > base_cap) return fail("bsgpu_synth_block_dev: need %zu segments / %zu bases", ns, ns * read_len);
+	if (ns * (size_t)read_len > 0xffffffffull) return fail("bsgpu_synth_block_dev: more than 4 GiB of bases in one block");
+	CU(cudaSetDevice(c->device));
+	CU(launch_synth_block(seed, x, sz, read_len, depth, d_segs, d_bases, d_ref, stream ? (cudaStream_t)stream : c->stream, &c->launches));
+	if (nseg) *nseg = ns;
+	if (nbases) *nbases = ns * read_len;
+	return BSGPU_OK;
+}
+
+int bsgpu_sync(bsgpu_ctx *c) {
+	if (!c) return fail("bsgpu_sync: null context");
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());
+	return BSGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer entry points
+// ------------------------------------------------------------------------------------------------
+// pileup[] -> gt_meth[] + skip[]: chunks ping-pong between two slots, each with its own stream, so the H2D of chunk
+// i+1 and the D2H of chunk i-1 overlap the kernel of chunk i (PCIe is full duplex).
+int bsgpu_call_sites(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t *ref, size_t n, bsgpu_gt_meth *out, uint8_t *skip) {
+	if (!c) return fail("bsgpu_call_sites: null context");
+	if (!n) return BSGPU_OK;
+	if (!pileup || !ref || !out || !skip) return fail("bsgpu_call_sites: null buffer");
+	CU(cudaSetDevice(c->device));
+	const size_t chunk = 1u << 20;
+	size_t ci = 0;
+	for (size_t first = 0; first < n; first += chunk, ci++) {
+		Slot &s = c->slot[ci & 1];
+		const size_t m = n - first < chunk ? n - first : chunk;
+		CU(cudaStreamSynchronize(s.stream));      // the slot's previous chunk has fully left the device
+		CU(s.in.reserve(m * sizeof(bsgpu_pileup)));
+		CU(s.ref.reserve(m));
+		CU(s.out.reserve(m * sizeof(bsgpu_gt_meth)));
+		CU(s.skip.reserve(m));
+		CU(cudaMemcpyAsync(s.in.p, pileup + first, m * sizeof(bsgpu_pileup), cudaMemcpyHostToDevice, s.stream));
+		CU(cudaMemcpyAsync(s.ref.p, ref + first, m, cudaMemcpyHostToDevice, s.stream));
+		CU(launch_call_sites(s.in.p, s.ref.p, m, s.out.p, s.skip.p, false, c->d_const, s.stream, &c->launches));
+		CU(cudaMemcpyAsync(out + first, s.out.p, m * sizeof(bsgpu_gt_meth), cudaMemcpyDeviceToHost, s.stream));
+		CU(cudaMemcpyAsync(skip + first, s.skip.p, m, cudaMemcpyDeviceToHost, s.stream));
+		c->stats.h2d_bytes += m * (sizeof(bsgpu_pileup) + 1);
+		c->stats.d2h_bytes += m * (sizeof(bsgpu_gt_meth) + 1);
+	}
+	CU(cudaStreamSynchronize(c->slot[0].stream));
+	CU(cudaStreamSynchronize(c->slot[1].stream));
+	c->stats.sites += n;
+	return BSGPU_OK;
+}
+
+// segments + bases (+ ref) -> pileup[] or gt_vcf[].  Inputs go up in one piece (they are ~1/6 of the output volume);
+// the window is then processed in slabs of tiles so that the D2H of slab i overlaps the kernel of slab i+1.
+static int block_host(bsgpu_ctx *c, const bsgpu_seg *segs, size_t nseg, const uint8_t *bases, size_t nbases, const uint8_t *ref,
+		uint32_t x, uint32_t sz, void *out, int mode) {
+	if (!c) return fail("bsgpu block: null context");
+	if (!sz) return BSGPU_OK;
+	if (!out || (nseg && (!segs || !bases)) || (mode && !ref)) return fail("bsgpu block: null buffer");
+	if (nbases > 0xffffffffull) return fail("bsgpu block: more than 4 GiB of bases in one block; split the window");
+	for (size_t i = 0; i < nseg; i++) {
+		if (segs[i].len > BSGPU_MAX_SEG_LEN) return fail("bsgpu block: segment %zu longer than %d (use bsgpu_stage_templates)", i, BSGPU_MAX_SEG_LEN);
+		if ((size_t)segs[i].off + segs[i].len > nbases) return fail("bsgpu block: segment %zu points outside bases[]", i);
+	}
+	CU(cudaSetDevice(c->device));
+	const size_t rec = mode ? sizeof(bsgpu_gt_vcf) : sizeof(bsgpu_pileup);
+	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->copy_stream));
+	CU(c->segs.reserve(nseg * sizeof(bsgpu_seg) + 16));
+	CU(c->bases.reserve(nbases + 16));
+	CU(c->ref.reserve((size_t)sz + 16));
+	CU(c->scratch.reserve(pileup_scratch_bytes(nseg, sz)));
+	if (nseg) {
+		CU(cudaMemcpyAsync(c->segs.p, segs, nseg * sizeof(bsgpu_seg), cudaMemcpyHostToDevice, c->stream));
+		CU(cudaMemcpyAsync(c->bases.p, bases, nbases, cudaMemcpyHostToDevice, c->stream));
+	}
+	if (mode) CU(cudaMemcpyAsync(c->ref.p, ref, sz, cudaMemcpyHostToDevice, c->stream));
+	c->stats.h2d_bytes += nseg * sizeof(bsgpu_seg) + nbases + (mode ? sz : 0);
+	CU(launch_bin_segments(c->segs.p, nseg, x, sz, c->scratch.p, c->stream, &c->launches));
+	const uint32_t ntiles = (sz + kPileTileSites - 1) / kPileTileSites;
+	const uint32_t slab = 8192;                    // tiles per slab = 2 Mi sites = 436 MB of gt_vcf
+	const uint32_t nslab = (ntiles + slab - 1) / slab;
+	const uint32_t resident = nslab < 3 ? nslab : 3;      // ring of output slabs on the device
+	CU(c->vcf.reserve((size_t)resident * slab * kPileTileSites * rec));
+	while (c->win_events.size() < 2 * (size_t)resident) {
+		cudaEvent_t ev;
+		CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+		c->win_events.push_back(ev);
+	}
+	for (uint32_t si = 0; si < nslab; si++) {
+		const uint32_t r = si % resident;
+		cudaEvent_t computed = c->win_events[2 * r], copied = c->win_events[2 * r + 1];
+		const uint32_t t0 = si * slab, nt = ntiles - t0 < slab ? ntiles - t0 : slab;
+		const size_t site0 = (size_t)t0 * kPileTileSites;
+		const size_t nsite = (size_t)sz - site0 < (size_t)nt * kPileTileSites ? (size_t)sz - site0 : (size_t)nt * kPileTileSites;
+		uint8_t *dslab = (uint8_t *)c->vcf.p + (size_t)r * slab * kPileTileSites * rec;
+		if (si >= resident) CU(cudaStreamWaitEvent(c->stream, copied, 0));      // ring slot drained
+		CU(launch_pileup_tiles(c->scratch.p, nseg, c->bases.p, c->ref.p, x, sz, t0, nt, dslab, mode, c->d_const, c->d_counters, c->stream, &c->launches));
+		CU(cudaEventRecord(computed, c->stream));
+		CU(cudaStreamWaitEvent(c->copy_stream, computed, 0));
+		CU(cudaMemcpyAsync((uint8_t *)out + site0 * rec, dslab, nsite * rec, cudaMemcpyDeviceToHost, c->copy_stream));
+		CU(cudaEventRecord(copied, c->copy_stream));
+		c->stats.d2h_bytes += nsite * rec;
+	}
+	CU(cudaStreamSynchronize(c->copy_stream));
+	CU(cudaStreamSynchronize(c->stream));
+	c->stats.sites += sz;
+	return BSGPU_OK;
+}
+
+int bsgpu_pileup_block(bsgpu_ctx *c, const bsgpu_seg *segs, size_t nseg, const uint8_t *bases, size_t nbases, uint32_t x, uint32_t sz, bsgpu_pileup *out) {
+	return block_host(c, segs, nseg, bases, nbases, nullptr, x, sz, out, 0);
+}
+
+int bsgpu_call_block(bsgpu_ctx *c, const bsgpu_seg *segs, size_t nseg, const uint8_t *bases, size_t nbases, const uint8_t *ref, uint32_t x, uint32_t sz, bsgpu_gt_vcf *out) {
+	return block_host(c, segs, nseg, bases, nbases, ref, x, sz, out, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host staging: normalised templates -> segments.  Mirrors the walk at the top of the reference's pileup loop
+// (src/call_genotypes.c:181-212, 224): a mate is emitted when it is present, non-empty and holds at least one base
+// with 0 < q != 63; only such a mate flips the strand index for the next one.
+// ------------------------------------------------------------------------------------------------
+size_t bsgpu_stage_bound(const bsgpu_template *t, size_t n) {
+	size_t b = 0;
+	for (size_t i = 0; i < n; i++) for (int k = 0; k < 2; k++)
+		if (t[i].present[k]) b += (t[i].read_len[k] + BSGPU_MAX_SEG_LEN - 1) / BSGPU_MAX_SEG_LEN;
+	return b;
+}
+
+int bsgpu_stage_templates(const bsgpu_template *t, size_t n, const uint8_t *bases, uint32_t x, uint32_t y, bsgpu_seg *segs, size_t *nseg) {
+	if (!nseg || (n && (!t || !bases || !segs))) return fail("bsgpu_stage_templates: null argument");
+	size_t ns = 0;
+	for (size_t i = 0; i < n; i++) {
+		uint32_t ori = t[i].orientation & 1u;
+		const uint32_t st = t[i].bs_strand;
+		if (st > 2) return fail("bsgpu_stage_templates: template %zu has bs_strand %u", i, st);
+		for (int k = 0; k < 2; k++) {
+			if (!t[i].present[k] || !t[i].read_len[k]) continue;
+			const uint8_t *sp = bases + t[i].read_off[k];
+			const uint32_t rl = t[i].read_len[k];
+			uint32_t first = 0, last = rl;
+			while (first < rl) { const uint8_t q = sp[first] >> 2; if (q > 0 && q != BSGPU_FLT_QUAL) break; first++; }
+			if (first == rl) continue;
+			while (true) { const uint8_t q = sp[last - 1] >> 2; if (q > 0 && q != BSGPU_FLT_QUAL) break; last--; }
+			uint32_t pos = (k ? t[i].reverse_position : t[i].forward_position) + first;
+			if (pos < x) return fail("bsgpu_stage_templates: template %zu starts before the window (%u < %u)", i, pos, x);
+			uint32_t off = t[i].read_off[k] + first, len = last - first;
+			if (pos <= y) {
+				if ((uint64_t)pos + len > (uint64_t)y + 1) len = y + 1 - pos;          // pos <= y clip (:213)
+				while (len) {
+					const uint32_t l = len > BSGPU_MAX_SEG_LEN ? BSGPU_MAX_SEG_LEN : len;
+					bsgpu_seg &s = segs[ns++];
+					s.pos = pos; s.off = off; s.len = (uint16_t)l; s.mapq = t[i].mapq[k]; s.flags = (uint8_t)(ori | (st << 1)); s.pad_ = 0;
+					pos += l; off += l; len -= l;
+				}
+			}
+			ori ^= 1u;
+		}
+	}
+	*nseg = ns;
+	return BSGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,38 @@
+// bsgpu_launch.h -- launcher prototypes shared between bsgpu_kernels.cu and bsgpu_api.cu (internal).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bsgpu {
+
+struct DevConst;
+
+cudaError_t configure_kernels();
+
+cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, void *out, void *skip, bool vcf,
+		const DevConst *dc, cudaStream_t stream, int *launches);
+
+// scratch needed by the segment binning of one block
+size_t pileup_scratch_bytes(size_t nseg, uint32_t sz);
+
+// bins the segments of a block by 256-site tile (count, scan, scatter) into `scratch`
+cudaError_t launch_bin_segments(const void *segs, size_t nseg, uint32_t x, uint32_t sz, void *scratch,
+		cudaStream_t stream, int *launches);
+
+// pileup (mode 0 -> pileup[]) or fused pileup + model (mode 1 -> gt_vcf[]) for tiles [tile0, tile0 + ntiles) of a
+// block previously binned into `scratch`; `out` points at the record of site tile0 * 256
+cudaError_t launch_pileup_tiles(const void *scratch, size_t nseg, const void *bases, const void *ref, uint32_t x,
+		uint32_t sz, uint32_t tile0, uint32_t ntiles, void *out, int mode, const DevConst *dc,
+		unsigned long long *counters, cudaStream_t stream, int *launches);
+
+cudaError_t launch_synth_sites(uint64_t seed, uint64_t first, size_t n, double mean_depth, void *pileup, void *ref,
+		cudaStream_t stream, int *launches);
+
+size_t synth_block_nseg(uint32_t sz, uint32_t read_len, double depth);
+cudaError_t launch_synth_block(uint64_t seed, uint32_t x, uint32_t sz, uint32_t read_len, double depth,
+		void *segs, void *bases, void *ref, cudaStream_t stream, int *launches);
+
+constexpr int kPileTileSites = 256;
+
+}  // namespace bsgpu

@@ -1,0 +1,233 @@
+"""ctypes binding of the C ABI in include/bsgpu.h (libbsgpu.so, built in-tree by bs_call_b200/csrc/Makefile).
+
+This is the host-side mirror used by the tests and by bench.py: numpy arrays in the reference's record layouts
+go in and come out, exactly what a C host would hand to the same entry points.  There is no fallback of any
+kind: a missing library or a missing sm_100 device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .records import PILEUP, GT_METH, GT_VCF, SEG, TEMPLATE, MISMS
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbsgpu.so")
+
+BSGPU_OK = 1
+BSGPU_FAIL = -1
+
+# every symbol include/bsgpu.h declares (tests/test_abi.py checks the header and this list against the .so)
+EXPORTS = [
+    "bsgpu_default_params", "bsgpu_init", "bsgpu_destroy", "bsgpu_last_error", "bsgpu_get_stats", "bsgpu_version",
+    "bsgpu_sync", "bsgpu_host_alloc", "bsgpu_host_free",
+    "bsgpu_call_sites", "bsgpu_pileup_block", "bsgpu_call_block", "bsgpu_stage_bound", "bsgpu_stage_templates",
+    "bsgpu_process_block",
+    "bsgpu_call_sites_dev", "bsgpu_call_sites_vcf_dev", "bsgpu_pileup_block_dev", "bsgpu_call_block_dev",
+    "bsgpu_synth_sites_dev", "bsgpu_synth_block_nseg", "bsgpu_synth_block_dev",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [("under_conv", C.c_double), ("over_conv", C.c_double), ("ref_bias", C.c_double),
+                ("left_trim", C.c_uint32 * 2), ("right_trim", C.c_uint32 * 2), ("min_qual", C.c_uint8),
+                ("device", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("sites", C.c_uint64), ("sites_called", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("qsum_overflow", C.c_uint64)]
+
+
+class BsGpuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libbsgpu.so; raises if it has not been built (run `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BsGpuError("libbsgpu.so is missing at %s: build it with bs_call_b200/csrc/Makefile "
+                         "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.bsgpu_last_error.restype = C.c_char_p
+    lib.bsgpu_host_alloc.restype = C.c_void_p
+    lib.bsgpu_host_alloc.argtypes = [C.c_size_t]
+    lib.bsgpu_host_free.argtypes = [C.c_void_p]
+    lib.bsgpu_stage_bound.restype = C.c_size_t
+    lib.bsgpu_synth_block_nseg.restype = C.c_size_t
+    lib.bsgpu_synth_block_nseg.argtypes = [C.c_uint32, C.c_uint32, C.c_double]
+    lib.bsgpu_init.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
+    lib.bsgpu_destroy.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(int(a))         # raw device / host address
+
+
+class HostBuffer:
+    """Page-locked host array (bsgpu_host_alloc) viewed as a numpy array of `dtype`."""
+
+    def __init__(self, n, dtype):
+        lib = load()
+        self.dtype = np.dtype(dtype)
+        self.nbytes = max(int(n) * self.dtype.itemsize, 16)
+        self.addr = lib.bsgpu_host_alloc(C.c_size_t(self.nbytes))
+        if not self.addr:
+            raise BsGpuError(lib.bsgpu_last_error().decode())
+        buf = (C.c_uint8 * self.nbytes).from_address(self.addr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(n))
+
+    def free(self):
+        if self.addr:
+            self.array = None
+            load().bsgpu_host_free(C.c_void_p(self.addr))
+            self.addr = None
+
+
+class BsGpu:
+    """One context = one device.  Methods map one-to-one onto the C entry points."""
+
+    def __init__(self, under_conv=0.01, over_conv=0.05, ref_bias=2.0, min_qual=20, left_trim=(0, 0),
+                 right_trim=(0, 0), device=0):
+        self.lib = load()
+        self.params = Params(under_conv, over_conv, ref_bias, (C.c_uint32 * 2)(*left_trim),
+                             (C.c_uint32 * 2)(*right_trim), min_qual, device)
+        self.ctx = C.c_void_p()
+        self._check(self.lib.bsgpu_init(C.byref(self.params), C.byref(self.ctx)))
+
+    def _check(self, rc):
+        if rc != BSGPU_OK:
+            raise BsGpuError(self.lib.bsgpu_last_error().decode())
+
+    def close(self):
+        if self.ctx:
+            self.lib.bsgpu_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._check(self.lib.bsgpu_sync(self.ctx))
+
+    def stats(self):
+        s = Stats()
+        self._check(self.lib.bsgpu_get_stats(self.ctx, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+    # ---- host-buffer entry points -------------------------------------------------------------
+    def call_sites(self, pileup, ref, out=None, skip=None):
+        pileup = np.ascontiguousarray(pileup, dtype=PILEUP)
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        n = len(pileup)
+        assert len(ref) == n
+        out = np.empty(n, dtype=GT_METH) if out is None else out
+        skip = np.empty(n, dtype=np.uint8) if skip is None else skip
+        self._check(self.lib.bsgpu_call_sites(self.ctx, _ptr(pileup), _ptr(ref), C.c_size_t(n), _ptr(out), _ptr(skip)))
+        return out, skip
+
+    def pileup_block(self, segs, bases, x, sz, out=None):
+        segs = np.ascontiguousarray(segs, dtype=SEG)
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        out = np.empty(sz, dtype=PILEUP) if out is None else out
+        self._check(self.lib.bsgpu_pileup_block(self.ctx, _ptr(segs), C.c_size_t(len(segs)), _ptr(bases),
+                                                C.c_size_t(len(bases)), C.c_uint32(x), C.c_uint32(sz), _ptr(out)))
+        return out
+
+    def call_block(self, segs, bases, ref, x, sz, out=None):
+        segs = np.ascontiguousarray(segs, dtype=SEG)
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        assert len(ref) >= sz
+        out = np.empty(sz, dtype=GT_VCF) if out is None else out
+        self._check(self.lib.bsgpu_call_block(self.ctx, _ptr(segs), C.c_size_t(len(segs)), _ptr(bases),
+                                              C.c_size_t(len(bases)), _ptr(ref), C.c_uint32(x), C.c_uint32(sz), _ptr(out)))
+        return out
+
+    def process_block(self, templates, bases, misms, ref, y, out=None):
+        templates = np.ascontiguousarray(templates, dtype=TEMPLATE)
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        misms = np.ascontiguousarray(misms, dtype=MISMS)
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        first = int(templates[0]["forward_position"]) or int(templates[0]["reverse_position"])
+        x = first - 2 if first > 2 else 1
+        sz = y - x + 1
+        assert len(ref) >= sz
+        out = np.empty(sz, dtype=GT_VCF) if out is None else out
+        xo = C.c_uint32(0)
+        self._check(self.lib.bsgpu_process_block(self.ctx, _ptr(templates), C.c_size_t(len(templates)), _ptr(bases),
+                                                 C.c_size_t(len(bases)), _ptr(misms), C.c_size_t(len(misms)), _ptr(ref),
+                                                 C.c_uint32(y), C.byref(xo), _ptr(out)))
+        return xo.value, out
+
+    # ---- device-pointer entry points (addresses as ints, e.g. torch.Tensor.data_ptr()) --------
+    def call_sites_dev(self, d_pileup, d_ref, n, d_out, d_skip, stream=0):
+        self._check(self.lib.bsgpu_call_sites_dev(self.ctx, _ptr(d_pileup), _ptr(d_ref), C.c_size_t(n), _ptr(d_out),
+                                                  _ptr(d_skip), C.c_void_p(stream)))
+
+    def call_sites_vcf_dev(self, d_pileup, d_ref, n, d_vcf, stream=0):
+        self._check(self.lib.bsgpu_call_sites_vcf_dev(self.ctx, _ptr(d_pileup), _ptr(d_ref), C.c_size_t(n), _ptr(d_vcf),
+                                                      C.c_void_p(stream)))
+
+    def pileup_block_dev(self, d_segs, nseg, d_bases, x, sz, d_out, stream=0):
+        self._check(self.lib.bsgpu_pileup_block_dev(self.ctx, _ptr(d_segs), C.c_size_t(nseg), _ptr(d_bases), C.c_uint32(x),
+                                                    C.c_uint32(sz), _ptr(d_out), C.c_void_p(stream)))
+
+    def call_block_dev(self, d_segs, nseg, d_bases, d_ref, x, sz, d_out, stream=0):
+        self._check(self.lib.bsgpu_call_block_dev(self.ctx, _ptr(d_segs), C.c_size_t(nseg), _ptr(d_bases), _ptr(d_ref),
+                                                  C.c_uint32(x), C.c_uint32(sz), _ptr(d_out), C.c_void_p(stream)))
+
+    def synth_sites_dev(self, seed, first_site, n, mean_depth, d_pileup, d_ref, stream=0):
+        self._check(self.lib.bsgpu_synth_sites_dev(self.ctx, C.c_uint64(seed), C.c_uint64(first_site), C.c_size_t(n),
+                                                   C.c_double(mean_depth), _ptr(d_pileup), _ptr(d_ref), C.c_void_p(stream)))
+
+    def synth_block_nseg(self, sz, read_len, depth):
+        return int(self.lib.bsgpu_synth_block_nseg(C.c_uint32(sz), C.c_uint32(read_len), C.c_double(depth)))
+
+    def synth_block_dev(self, seed, x, sz, read_len, depth, d_segs, seg_cap, d_bases, base_cap, d_ref, stream=0):
+        ns, nb = C.c_size_t(0), C.c_size_t(0)
+        self._check(self.lib.bsgpu_synth_block_dev(self.ctx, C.c_uint64(seed), C.c_uint32(x), C.c_uint32(sz),
+                                                   C.c_uint32(read_len), C.c_double(depth), _ptr(d_segs), C.c_size_t(seg_cap),
+                                                   _ptr(d_bases), C.c_size_t(base_cap), _ptr(d_ref), C.byref(ns), C.byref(nb),
+                                                   C.c_void_p(stream)))
+        return ns.value, nb.value
+
+    # ---- host staging --------------------------------------------------------------------------
+    def stage_templates(self, templates, bases, x, y):
+        templates = np.ascontiguousarray(templates, dtype=TEMPLATE)
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        bound = int(self.lib.bsgpu_stage_bound(_ptr(templates), C.c_size_t(len(templates))))
+        segs = np.zeros(max(bound, 1), dtype=SEG)
+        ns = C.c_size_t(0)
+        self._check(self.lib.bsgpu_stage_templates(_ptr(templates), C.c_size_t(len(templates)), _ptr(bases), C.c_uint32(x),
+                                                   C.c_uint32(y), _ptr(segs), C.byref(ns)))
+        return segs[:ns.value]
+
+
+def stage_templates_host(templates, bases, x, y):
+    """bsgpu_stage_templates without a device context (pure host function of the ABI)."""
+    lib = load()
+    templates = np.ascontiguousarray(templates, dtype=TEMPLATE)
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    bound = int(lib.bsgpu_stage_bound(_ptr(templates), C.c_size_t(len(templates))))
+    segs = np.zeros(max(bound, 1), dtype=SEG)
+    ns = C.c_size_t(0)
+    if lib.bsgpu_stage_templates(_ptr(templates), C.c_size_t(len(templates)), _ptr(bases), C.c_uint32(x), C.c_uint32(y),
+                                 _ptr(segs), C.byref(ns)) != BSGPU_OK:
+        raise BsGpuError(lib.bsgpu_last_error().decode())
+    return segs[:ns.value]

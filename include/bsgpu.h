@@ -79,7 +79,7 @@ typedef struct {
 	uint32_t pad_;
 } bsgpu_seg;                   /* 16 bytes */
 
-#define BSGPU_MAX_SEG_LEN 512
+#define BSGPU_MAX_SEG_LEN 256
 
 /* Flat template record for the raw-template entry points (what the reference keeps in align_details,
  * include/bs_call.h:64-73, with the two gt_vectors flattened into offset/length pairs). */
@@ -127,6 +127,12 @@ void bsgpu_destroy(bsgpu_ctx *ctx);
 const char *bsgpu_last_error(void);
 int bsgpu_get_stats(bsgpu_ctx *ctx, bsgpu_stats *out);
 int bsgpu_version(void);
+int bsgpu_sync(bsgpu_ctx *ctx);              /* wait for everything queued on the context's device */
+
+/* page-locked host memory: arrays handed to the host-buffer entry points copy at full PCIe rate when they
+ * come from here (any host pointer is accepted, pageable ones just copy slower) */
+void *bsgpu_host_alloc(size_t bytes);
+void bsgpu_host_free(void *p);
 
 /* ---- host-buffer entry points: H2D, kernels, D2H all inside the call (chunked and double buffered) ---- */
 
@@ -159,6 +165,9 @@ int bsgpu_process_block(bsgpu_ctx *ctx, const bsgpu_template *t, size_t n, const
  *      (a cudaStream_t passed as void*; NULL = the context's own stream) ---- */
 int bsgpu_call_sites_dev(bsgpu_ctx *ctx, const void *d_pileup, const void *d_ref, size_t n,
 		void *d_out, void *d_skip, void *stream);
+/* same, writing gt_vcf[] (208-byte records with ready = 1 and the skip flag inside) */
+int bsgpu_call_sites_vcf_dev(bsgpu_ctx *ctx, const void *d_pileup, const void *d_ref, size_t n,
+		void *d_vcf, void *stream);
 int bsgpu_pileup_block_dev(bsgpu_ctx *ctx, const void *d_segs, size_t nseg, const void *d_bases,
 		uint32_t x, uint32_t sz, void *d_pileup_out, void *stream);
 int bsgpu_call_block_dev(bsgpu_ctx *ctx, const void *d_segs, size_t nseg, const void *d_bases, const void *d_ref,
@@ -168,7 +177,9 @@ int bsgpu_call_block_dev(bsgpu_ctx *ctx, const void *d_segs, size_t nseg, const 
 /* config 2 of BASELINE.json: per-site count vectors.  Writes n pileup records and n ref codes. */
 int bsgpu_synth_sites_dev(bsgpu_ctx *ctx, uint64_t seed, uint64_t first_site, size_t n, double mean_depth,
 		void *d_pileup, void *d_ref, void *stream);
-/* simulated WGBS reads over a window: sorted segments + packed bases + ref codes */
+/* simulated WGBS reads over a window: segments + packed bases (read i at offset i*read_len) + ref codes;
+ * bsgpu_synth_block_nseg gives the number of reads the generator emits for (sz, read_len, depth) */
+size_t bsgpu_synth_block_nseg(uint32_t sz, uint32_t read_len, double depth);
 int bsgpu_synth_block_dev(bsgpu_ctx *ctx, uint64_t seed, uint32_t x, uint32_t sz, uint32_t read_len, double depth,
 		void *d_segs, size_t seg_cap, void *d_bases, size_t base_cap, void *d_ref, size_t *nseg, size_t *nbases,
 		void *stream);

@@ -92,6 +92,13 @@ class Oracle:
                                 C.c_int(nthreads))
         return out, skip
 
+    def synth_sites(self, seed, first, n, mean_depth=30.0, nthreads=1):
+        p = np.zeros(n, dtype=PILEUP)
+        r = np.zeros(n, dtype=np.uint8)
+        self.lib.bso_synth_sites(C.c_uint64(seed), C.c_uint64(first), C.c_size_t(n), C.c_double(mean_depth), _p(p), _p(r),
+                                 C.c_int(nthreads))
+        return p, r
+
     def pileup_block(self, templates, bases, x, y):
         templates = _c(templates, TEMPLATE)
         bases = _c(bases, np.uint8)
@@ -191,6 +198,17 @@ class Reference:
     def fisher(self, tab):
         t = np.ascontiguousarray(tab, dtype=np.int32)
         return float(self.lib.bsref_fisher(_p(t)))
+
+    def call_sites(self, pileup, ref, nthreads=1):
+        """pileup[] -> gt_meth[] through the reference's calc_gt_prob()/fisher() (see ref_harness.c)."""
+        pileup = _c(pileup, PILEUP)
+        ref = _c(ref, np.uint8)
+        n = len(pileup)
+        out = np.zeros(n, dtype=GT_METH)
+        skip = np.zeros(n, dtype=np.uint8)
+        rc = self.lib.bsref_call_sites_mt(_p(pileup), _p(ref), C.c_size_t(n), _p(out), _p(skip), C.c_int(nthreads))
+        assert rc == 0
+        return out, skip
 
     def lfact_table(self):
         t = np.zeros(256, dtype=np.float64)

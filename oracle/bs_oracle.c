@@ -641,3 +641,76 @@ int bso_process_block(const bso_template *t, size_t n, const uint8_t *bases, con
 	free(nb);
 	return ret;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Host twin of the device generator k_synth_sites (bs_call_b200/csrc/bsgpu_kernels.cu): the same counter-based
+ * draws in the same order, so record i is the same on both sides (config 2 of BASELINE.json; distribution in
+ * SURVEY.md section 8d).  Used by the CPU baseline / reference arm of bench.py, which must not launch kernels.
+ * ------------------------------------------------------------------------------------------------ */
+static inline uint64_t mix64(uint64_t z) {
+	z += 0x9e3779b97f4a7c15ull;
+	z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+	z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+	return z ^ (z >> 31);
+}
+typedef struct { uint64_t s; } rng_t;
+static inline uint64_t rng_next(rng_t *r) { r->s += 0x9e3779b97f4a7c15ull; uint64_t z = r->s; z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31); }
+static inline float rng_unif(rng_t *r) { return (float)(rng_next(r) >> 40) * (1.0f / 16777216.0f); }
+
+static void synth_one(uint64_t seed, uint64_t idx, float mean_depth, bso_pileup *out, uint8_t *ref) {
+	rng_t r = { mix64(seed ^ mix64(idx)) };
+	float u = rng_unif(&r);
+	const int rb = u < 0.295f ? 0 : (u < 0.5f ? 1 : (u < 0.705f ? 2 : 3));
+	int a0 = rb, a1 = rb;
+	u = rng_unif(&r);
+	if (u < 0.001f) a1 = (rb + 1 + (int)(rng_next(&r) % 3)) & 3;
+	else if (u < 0.0015f) a0 = a1 = (rb + 1 + (int)(rng_next(&r) % 3)) & 3;
+	const float meth = rng_unif(&r) < 0.02f ? 0.7f : 0.01f;
+	int depth = 0;
+	if (rng_unif(&r) >= 0.03f) {
+		double p = exp(-(double)mean_depth), c = p;
+		const double uu = (double)(rng_next(&r) >> 11) * (1.0 / 9007199254740992.0);
+		while (uu > c && depth < 1000) { depth++; p *= (double)mean_depth / depth; c += p; }
+	}
+	uint32_t qs[8] = {0};
+	memset(out, 0, sizeof(*out));
+	for (int k = 0; k < depth; k++) {
+		const uint64_t bits = rng_next(&r);
+		int b = (bits & 1) ? a1 : a0;
+		const int st = 1 + (int)((bits >> 1) & 1), ori = (int)((bits >> 2) & 1);
+		const float uc = (float)((bits >> 8) & 0xffffff) * (1.0f / 16777216.0f);
+		const int converts = uc >= meth && uc < meth + (1.0f - meth) * 0.99f;
+		if (st == 1 && b == 1 && converts) b = 3;
+		if (st == 2 && b == 2 && converts) b = 0;
+		if (((bits >> 32) & 0x3ff) < 3) b = (b + 1 + (int)((bits >> 42) % 3)) & 3;
+		const int q = 20 + (int)((bits >> 48) % 24);
+		const int cl = st == 1 ? (b == 1 ? 5 : (b == 3 ? 7 : b)) : (b == 0 ? 4 : (b == 2 ? 6 : b));
+		out->counts[ori][cl]++;
+		qs[cl] += q;
+	}
+	for (int j = 0; j < 8; j++) out->quality[j] = (float)qs[j];
+	out->n = (uint32_t)depth;
+	out->mapq2 = 3600.0f * (float)depth;
+	*ref = (uint8_t)(rb + 1);
+}
+
+typedef struct { uint64_t seed, first; size_t n, t0, step; float mean; bso_pileup *p; uint8_t *ref; } synth_job;
+static void *synth_worker(void *arg) {
+	synth_job *j = arg;
+	for (size_t i = j->t0; i < j->n; i += j->step) synth_one(j->seed, j->first + i, j->mean, j->p + i, j->ref + i);
+	return NULL;
+}
+
+void bso_synth_sites(uint64_t seed, uint64_t first, size_t n, double mean_depth, bso_pileup *out, uint8_t *ref, int nthreads) {
+	if (nthreads < 1) nthreads = 1;
+	synth_job *jobs = malloc(sizeof(synth_job) * nthreads);
+	pthread_t *thr = malloc(sizeof(pthread_t) * nthreads);
+	for (int i = 0; i < nthreads; i++) {
+		jobs[i] = (synth_job){ seed, first, n, (size_t)i, (size_t)nthreads, (float)mean_depth, out, ref };
+		if (i) pthread_create(thr + i, NULL, synth_worker, jobs + i);
+	}
+	synth_worker(jobs);
+	for (int i = 1; i < nthreads; i++) pthread_join(thr[i], NULL);
+	free(jobs);
+	free(thr);
+}

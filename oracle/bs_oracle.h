@@ -101,6 +101,9 @@ int bso_process_block(const bso_template *t, size_t n, const uint8_t *bases, con
 		const uint8_t *refcodes /* codes for [x, y] */, uint32_t y, const bso_params *p,
 		uint32_t *x_out, bso_pileup *pile_out, bso_gt_vcf *vcf_out);
 
+/* host twin of the device generator of per-site count vectors (same draws, same records) */
+void bso_synth_sites(uint64_t seed, uint64_t first, size_t n, double mean_depth, bso_pileup *out, uint8_t *ref, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -338,8 +338,49 @@ int bsref_process_block(const bsref_template *t, size_t n, const uint8_t *bases,
 	return ret;
 }
 
-/* Timed run of the reference's per-site body over pre-built pileup records: used as the CPU baseline of the
- * likelihood microbench (config 2).  The reference has no entry point that takes pileup[] directly
- * (call_thread reads the function-static vector), so this feeds each record through the reference's
- * calc_gt_prob()/fisher() with the summarise arithmetic of src/call_genotypes.c:43-59 restated around
- * them -- see oracle/bs_oracle.c, which is the restatement actually used; nothing here duplicates it. */
+/* CPU baseline of the likelihood microbench (config 2): pre-built pileup records through the reference's model.
+ * The reference has no entry point that takes pileup[] directly (call_thread reads the function-static vector
+ * that call_genotypes_ML fills from reads), so each record goes through the reference's own calc_gt_prob() and
+ * fisher() objects, with the thin summarise / strand-table glue of src/call_genotypes.c:45-59,62-104 supplied by
+ * the restatement (bso_summarise, bso_strand_table in bs_oracle.c).  Sites are strided over `nthreads` threads the
+ * way the reference strides them over its calc threads (src/call_genotypes.c:259-270). */
+#include "bs_oracle.h"
+
+typedef struct { const bso_pileup *tp; const uint8_t *ref; size_t n, first, step; gt_meth *out; uint8_t *skip; } mt_job;
+
+static void *mt_worker(void *arg) {
+	mt_job *j = arg;
+	for (size_t i = j->first; i < j->n; i += j->step) {
+		gt_meth *tg = j->out + i;
+		memset(tg, 0, sizeof(*tg));
+		if (!j->tp[i].n) { j->skip[i] = 1; continue; }
+		bso_summarise(j->tp + i, (bso_gt_meth *)tg);
+		calc_gt_prob(tg, &par, (char)j->ref[i]);
+		double fs = 0.0;
+		int ftab[4];
+		if (par.defs.gt_het[tg->max_gt] && bso_strand_table(j->tp + i, tg->max_gt, ftab)) {
+			double z = fisher(ftab, par.defs.lfact_store);
+			if (z < 1.0e-20) z = 1.0e-20;
+			fs = log(z) / LOG10;
+		}
+		tg->fisher_strand = fs;
+		j->skip[i] = 0;
+	}
+	return NULL;
+}
+
+int bsref_call_sites_mt(const void *pile, const uint8_t *ref, size_t n, gt_meth *out, uint8_t *skip, int nthreads) {
+	if (!inited) return -1;
+	if (nthreads < 1) nthreads = 1;
+	mt_job *jobs = malloc(sizeof(mt_job) * nthreads);
+	pthread_t *thr = malloc(sizeof(pthread_t) * nthreads);
+	for (int i = 0; i < nthreads; i++) {
+		jobs[i] = (mt_job){ (const bso_pileup *)pile, ref, n, (size_t)i, (size_t)nthreads, out, skip };
+		if (i) pthread_create(thr + i, NULL, mt_worker, jobs + i);
+	}
+	mt_worker(jobs);
+	for (int i = 1; i < nthreads; i++) pthread_join(thr[i], NULL);
+	free(jobs);
+	free(thr);
+	return 0;
+}

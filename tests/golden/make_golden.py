@@ -1,0 +1,93 @@
+"""Generates the golden fixtures under tests/golden/ by RUNNING THE REFERENCE'S OWN CODE
+(oracle/_ref/libbsref.so = unmodified /root/reference sources, see oracle/Makefile and oracle/ref_harness.c).
+
+Run in the authoring container (where /root/reference exists):  python tests/golden/make_golden.py
+The GPU boxes have no reference tree; they check against these committed files.
+
+  sites_v1.npz   per-site model goldens: pileup[] + ref -> gt_meth[] + skip[]   (call_thread body through
+                 call_genotypes_ML on blocks built from synthetic reads, plus direct calc_gt_prob/fisher KATs)
+  block_*.npz    block goldens: raw templates -> normalised templates, pileup[], gt_vcf[]
+                 (process_template_vector -> call_genotypes_ML)
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.bindings import Reference  # noqa: E402
+from tests import blockgen  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+BLOCK_CASES = {
+    "block_pe_plain": dict(seed=11, reflen=5000, start=150, end=4200, trims=((0, 0), (0, 0)),
+                           kw=dict(depth=30, read_len=100, paired=True)),
+    "block_pe_indel_clip_trim": dict(seed=12, reflen=5000, start=150, end=4200, trims=((5, 0), (3, 2)),
+                                     kw=dict(depth=25, read_len=100, paired=True, indel_frac=0.3, clip_frac=0.3, frag_mean=150)),
+    "block_se_deep": dict(seed=13, reflen=1200, start=100, end=700, trims=((0, 0), (0, 0)),
+                          kw=dict(depth=500, read_len=150, paired=False, snp_rate=0.02)),
+    "block_mixed": dict(seed=14, reflen=4000, start=50, end=3300, trims=((2, 2), (2, 2)),
+                        kw=dict(depth=15, read_len=75, paired=True, single_mate_frac=0.3, indel_frac=0.2,
+                                clip_frac=0.1, nonconv_frac=0.2, n_frac=0.03, frag_mean=120, frag_sd=40)),
+}
+
+
+def make_blocks():
+    for name, c in BLOCK_CASES.items():
+        rng = np.random.default_rng(c["seed"])
+        ref = blockgen.random_reference(rng, c["reflen"], n_runs=2)
+        T, B, M, y = blockgen.make_block(rng, ref, c["start"], c["end"], **c["kw"])
+        lt, rt = c["trims"]
+        r = Reference(left_trim=lt, right_trim=rt)
+        x, pile, vcf, refw, nt, nb = r.process_block(T, B, M, ref, y)
+        Reference()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), templates=T, bases=B, misms=M, y=np.uint32(y), x=np.uint32(x),
+                            left_trim=np.array(lt, dtype=np.uint32), right_trim=np.array(rt, dtype=np.uint32),
+                            ref=refw, pileup=pile, vcf=vcf, norm_templates=nt, norm_bases=nb)
+        print(name, "sites", len(vcf), "called", int((vcf["skip"] == 0).sum()), "templates", len(T))
+
+
+def make_sites():
+    r = Reference()
+    piles, refs, outs = [], [], []
+    # (1) site records harvested from reference-built pileups of random blocks: realistic count structure
+    for seed, kw in ((21, dict(depth=30, read_len=100, paired=True)),
+                     (22, dict(depth=8, read_len=100, paired=True, snp_rate=0.01)),
+                     (23, dict(depth=400, read_len=150, paired=False, snp_rate=0.03)),
+                     (24, dict(depth=60, read_len=100, paired=True, nonconv_frac=0.5, snp_rate=0.02))):
+        rng = np.random.default_rng(seed)
+        ref = blockgen.random_reference(rng, 3000, n_runs=1)
+        T, B, M, y = blockgen.make_block(rng, ref, 100, 2300 if kw["depth"] < 100 else 500, **kw)
+        x, pile, vcf, refw, nt, nb = r.process_block(T, B, M, ref, y)
+        piles.append(pile)
+        refs.append(refw)
+        outs.append(vcf)
+    pile = np.concatenate(piles)
+    ref = np.concatenate(refs)
+    vcf = np.concatenate(outs)
+    # (2) direct KATs for calc_gt_prob / fisher on adversarial count vectors
+    rng = np.random.default_rng(99)
+    n = 3000
+    counts = np.zeros((n, 8), dtype=np.uint64)
+    for i in range(n):
+        k = int(rng.integers(0, 7))
+        for c in (rng.choice(8, size=k, replace=False) if k else []):
+            counts[i, c] = int(rng.integers(1, 80)) if rng.random() < 0.9 else int(rng.integers(80, 20000))
+    qual = np.where(counts > 0, rng.integers(1, 44, size=(n, 8)), 0).astype(np.int32)
+    rf = rng.integers(0, 5, size=n).astype(np.uint8)
+    kat = r.calc_gt_prob_batch(counts, qual, rf)
+    tabs = np.concatenate([rng.integers(0, 40, size=(1500, 4)), rng.integers(0, 600, size=(500, 4)),
+                           np.array([[0, 0, 0, 0], [5, 0, 0, 5], [0, 7, 7, 0], [1, 0, 0, 0], [300, 2, 1, 280], [12, 3, 4, 11]])]).astype(np.int32)
+    fis = np.array([r.fisher(t) for t in tabs])
+    np.savez_compressed(os.path.join(HERE, "sites_v1.npz"), pileup=pile, ref=ref, gt_meth=vcf["gtm"], skip=vcf["skip"],
+                        kat_counts=counts, kat_qual=qual, kat_rf=rf, kat_out=kat, fisher_tabs=tabs, fisher_p=fis)
+    print("sites", len(pile), "called", int((vcf["skip"] == 0).sum()), "het",
+          int(np.isin(vcf["gtm"]["max_gt"], [1, 2, 3, 5, 6, 8])[vcf["skip"] == 0].sum()))
+
+
+if __name__ == "__main__":
+    make_blocks()
+    make_sites()

@@ -1,0 +1,120 @@
+"""CPU-side checks (run with -m "not gpu"): oracle against the committed golden fixtures (captured from the
+reference's own code by tests/golden/make_golden.py), the C-ABI surface of libbsgpu.so, and the host staging logic."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from bs_call_b200 import lib as bslib
+from bs_call_b200 import records
+from tests import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BLOCKS = ["block_pe_plain", "block_pe_indel_clip_trim", "block_se_deep", "block_mixed"]
+
+
+def test_record_layouts_match_oracle():
+    from oracle import bindings
+    for name in ("PILEUP", "GT_METH", "GT_VCF", "TEMPLATE", "MISMS"):
+        assert getattr(records, name) == getattr(bindings, name), name
+
+
+def test_oracle_sites_golden(oracle):
+    g = util.load_golden("sites_v1")
+    out, skip = oracle.call_sites(g["pileup"], g["ref"], nthreads=2)
+    n = util.assert_gt_meth_close(out, skip, g["gt_meth"], g["skip"])
+    assert n > 7000
+    # same machine family as the one that made the fixtures -> normally bit-identical; tolerance covers libm versions
+    for i in range(len(g["kat_rf"])):
+        got = oracle.calc_gt_prob(g["kat_counts"][i], g["kat_qual"][i], g["kat_rf"][i])
+        want = g["kat_out"][i]
+        if not util.near_tie(want["gt_prob"][None])[0]:
+            assert got["max_gt"] == want["max_gt"]
+        np.testing.assert_allclose(got["gt_prob"], want["gt_prob"], rtol=util.PROB_RTOL, atol=util.PROB_ATOL)
+    for t, p in zip(g["fisher_tabs"], g["fisher_p"]):
+        assert oracle.fisher(t) == pytest.approx(p, rel=1e-10, abs=1e-300)
+
+
+@pytest.mark.parametrize("name", BLOCKS)
+def test_oracle_block_golden(name):
+    from oracle.bindings import Oracle
+    g = util.load_golden(name)
+    o = Oracle(left_trim=tuple(g["left_trim"]), right_trim=tuple(g["right_trim"]))
+    nt, nb = o.normalise_block(g["templates"], g["bases"], g["misms"])
+    assert nb.tobytes() == g["norm_bases"].tobytes()
+    for f in ("forward_position", "reverse_position", "read_len", "read_off", "present"):
+        assert (nt[f] == g["norm_templates"][f]).all(), f
+    x, pile, vcf = o.process_block(g["templates"], g["bases"], g["misms"], g["ref"], int(g["y"]))
+    assert x == int(g["x"])
+    util.assert_pileup_equal(pile, g["pileup"])
+    util.assert_vcf_close(vcf, g["vcf"])
+    # pileup straight from the golden normalised templates
+    pile2 = o.pileup_block(g["norm_templates"], g["norm_bases"], x, int(g["y"]))
+    util.assert_pileup_equal(pile2, g["pileup"])
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "bsgpu.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(bsgpu_[a-z0-9_]+)\s*\(", body))
+    assert declared == set(bslib.EXPORTS), (declared ^ set(bslib.EXPORTS))
+    so = C.CDLL(bslib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(so, name), "libbsgpu.so does not export %s" % name
+    assert so.bsgpu_version() >= 100
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(bslib.BsGpuError):
+        bslib.BsGpu()
+
+
+@pytest.mark.parametrize("name", BLOCKS)
+def test_stage_templates_reproduces_pileup(name, oracle):
+    """Segments staged by the ABI's host function, accumulated naively in numpy, give the golden pileup: checks the
+    mate walk / strand-index flip / window clip logic without a GPU."""
+    g = util.load_golden(name)
+    x, y = int(g["x"]), int(g["y"])
+    segs = bslib.stage_templates_host(g["norm_templates"], g["norm_bases"], x, y)
+    assert (segs["len"] <= 256).all() and (segs["len"] > 0).all()
+    sz = y - x + 1
+    cls = np.array([[0, 1, 2, 3], [0, 5, 2, 7], [4, 1, 6, 3]])
+    counts = np.zeros((sz, 2, 8), dtype=np.uint32)
+    qsum = np.zeros((sz, 8), dtype=np.float64)
+    mq2 = np.zeros(sz, dtype=np.float64)
+    nb = g["norm_bases"]
+    for s in segs:
+        b = nb[s["off"]:s["off"] + s["len"]]
+        q = b >> 2
+        ok = (q >= 20) & (q != 63)
+        site = np.arange(s["pos"] - x, s["pos"] - x + s["len"])
+        assert site.max() < sz
+        c = cls[(s["flags"] >> 1) & 3][b & 3]
+        np.add.at(counts, (site[ok], s["flags"] & 1, c[ok]), 1)
+        np.add.at(qsum, (site[ok], c[ok]), q[ok])
+        np.add.at(mq2, site[ok], float(s["mapq"]) ** 2)
+    want = g["pileup"]
+    assert (counts == want["counts"]).all()
+    assert (qsum.astype(np.float32) == want["quality"]).all()
+    assert (mq2.astype(np.float32) == want["mapq2"]).all()
+    assert (counts.sum(axis=(1, 2)) == want["n"]).all()
+
+
+def test_stage_rejects_bad_input():
+    t = np.zeros(1, dtype=records.TEMPLATE)
+    t["present"][0, 0] = 1
+    t["read_len"][0, 0] = 4
+    t["forward_position"] = 5
+    t["bs_strand"] = 3
+    with pytest.raises(bslib.BsGpuError):
+        bslib.stage_templates_host(t, np.full(4, 37 << 2, dtype=np.uint8), 1, 100)
+    t["bs_strand"] = 1
+    with pytest.raises(bslib.BsGpuError):      # starts before the window
+        bslib.stage_templates_host(t, np.full(4, 37 << 2, dtype=np.uint8), 10, 100)
+    segs = bslib.stage_templates_host(t, np.full(4, 37 << 2, dtype=np.uint8), 1, 6)     # clipped at y
+    assert len(segs) == 1 and segs[0]["len"] == 2

@@ -1,0 +1,63 @@
+"""Shared comparison helpers for the parity tests."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# Tolerances.  Integer / byte / index fields are bit-exact.  The doubles (gt_prob[], fisher_strand) go through
+# log/exp/lgamma, where glibc (reference) and the CUDA math library may differ in the last ulp: BASELINE.json's
+# north_star allows 1e-6 relative in log-likelihood; we hold the path to a much tighter 1e-9 relative with an
+# absolute floor of 1e-12 (log10 units).
+PROB_RTOL = 1e-9
+PROB_ATOL = 1e-12
+
+INT_FIELDS = ("counts", "qual", "mq", "aq")
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def assert_pileup_equal(got, want):
+    for f in ("counts", "n", "quality", "mapq2"):
+        if got[f].tobytes() != want[f].tobytes():
+            bad = np.nonzero(np.any((got[f] != want[f]).reshape(len(got), -1), axis=1))[0]
+            raise AssertionError("pileup field %s differs at %d sites; first %d: got %r want %r"
+                                 % (f, len(bad), bad[0], got[f][bad[0]], want[f][bad[0]]))
+
+
+def near_tie(want_prob):
+    """sites whose two best log10 posteriors are closer than 1e-9: an ulp-level libm difference may flip them"""
+    s = np.sort(want_prob, axis=1)
+    return (s[:, -1] - s[:, -2]) < 1e-9
+
+
+def assert_gt_meth_close(got, got_skip, want, want_skip, exact_doubles=False):
+    """got/want: GT_METH arrays; skip flags compared exactly; called sites compared field by field."""
+    assert got_skip.tobytes() == np.asarray(want_skip, dtype=np.uint8).tobytes(), "skip flags differ"
+    m = np.asarray(want_skip) == 0
+    g, w = got[m], want[m]
+    for f in INT_FIELDS:
+        if g[f].tobytes() != w[f].tobytes():
+            bad = np.nonzero(np.any((g[f] != w[f]).reshape(len(g), -1), axis=1))[0]
+            raise AssertionError("field %s differs at %d sites; first: got %r want %r" % (f, len(bad), g[f][bad[0]], w[f][bad[0]]))
+    tie = near_tie(w["gt_prob"])
+    diff = (g["max_gt"] != w["max_gt"]) & ~tie
+    assert not diff.any(), "max_gt differs at %d non-tied sites, first got %r want %r (probs %r)" % (
+        diff.sum(), g["max_gt"][diff][0], w["max_gt"][diff][0], w["gt_prob"][diff][0])
+    if exact_doubles:
+        assert g["gt_prob"].tobytes() == w["gt_prob"].tobytes()
+        assert g["fisher_strand"].tobytes() == w["fisher_strand"].tobytes()
+    else:
+        np.testing.assert_allclose(g["gt_prob"], w["gt_prob"], rtol=PROB_RTOL, atol=PROB_ATOL)
+        same_gt = g["max_gt"] == w["max_gt"]
+        np.testing.assert_allclose(g["fisher_strand"][same_gt], w["fisher_strand"][same_gt], rtol=1e-8, atol=1e-10)
+    # skipped sites carry an all-zero record
+    assert not got[~m].tobytes().strip(b"\0"), "skipped sites must be zero records"
+    return int(m.sum())
+
+
+def assert_vcf_close(got, want):
+    assert (got["ready"] == 1).all()
+    return assert_gt_meth_close(got["gtm"], got["skip"], want["gtm"], want["skip"])
