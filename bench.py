@@ -176,7 +176,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     gpu = bslib.BsGpu(device=local)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated torch stream: its handle is what the C ABI launches on, and what the CUDA events below are recorded on
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     n_sites = int(args.sites)
     n_slab = 16

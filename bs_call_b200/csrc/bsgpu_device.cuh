@@ -34,11 +34,24 @@ struct SiteCounts {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// Closed-form ML conversion fraction.  src/genotype_model.c:23-42
+// Exact division helpers.  a / b is computed as q = a*r, q' = fma(fma(-q, b, a), r, q) with r = RN(1/b) (Markstein):
+// correctly rounded, i.e. bit-identical to the IEEE quotient the reference computes, at 3 FP64 issues instead of the
+// ~35 of the generic division sequence (checked against a/b on 3e8 random operands).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double div_by(double a, double b, double r) {
+	const double q = a * r;
+	return fma(fma(-q, b, a), r, q);
+}
+constexpr double kInvLn10 = 1.0 / kLn10;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Closed-form ML conversion fraction.  src/genotype_model.c:23-42.  Z is garbage (NaN) when a + b == 0; the caller
+// only uses it for classes that have counts, exactly like the reference.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void conv_ml(double a, double b, double ka, double kb, double l, double t, double *Z) {
 	const double lpt = l + t, lmt = l - t;
 	const double d = (a + b) * lmt;
+	const double r = __drcp_rn(d);
 	const double two_m = 2.0 - lpt;
 	double num[3];
 	num[0] = a * (lpt + 2.0 * kb) - b * (two_m + 2.0 * ka);
@@ -46,7 +59,7 @@ __device__ __forceinline__ void conv_ml(double a, double b, double ka, double kb
 	num[2] = a * (lpt + 4.0 * kb) - b * (two_m + 4.0 * ka);
 #pragma unroll
 	for (int i = 0; i < 3; i++) {
-		double s = num[i] / d;
+		double s = div_by(num[i], d, r);
 		s = s < -1.0 ? -1.0 : (s > 1.0 ? 1.0 : s);
 		Z[i] = 0.5 * (lmt * s + 2.0 - lpt);
 	}
@@ -59,13 +72,32 @@ __host__ __device__ constexpr int gt_hits(int g, int b) {
 	return (a0[g] == b) + (a1[g] == b);
 }
 
+// exclusive prefix sum of a small per-lane count over the warp; *total = warp sum
+__device__ __forceinline__ int warp_offsets(int c, int lane, int *total) {
+	int incl = c;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+	*total = __shfl_sync(0xffffffffu, incl, 31);
+	return incl - c;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // 10 genotype log-likelihoods + reference prior + normalisation.  src/genotype_model.c:44-246
-// Each ll[g] receives the prior and then one addend per non-empty class, classes in order 0..7, exactly as the
-// reference does; returns max_gt and writes log10 posteriors to prob[10].
+//
+// Warp-cooperative: all 32 lanes of a warp call this together, one site per lane.  Each ll[g] receives the prior and
+// then one addend per non-empty class, classes in order 0..7, exactly as the reference does.  The transcendental
+// calls are what the per-site cost is made of, and which of them a site needs depends on which classes it has counts
+// in (3 logs for a typical A/T site, 6 for C/G, up to 12; 2-4 of the 10 exps are not vanishing).  Evaluating them
+// under per-lane branches makes every warp pay for the union.  Instead the lanes pool their arguments in a per-warp
+// shared-memory list (`wbuf`, 32 x 12 doubles), the warp evaluates the list 32 at a time fully converged, and each
+// lane reads its results back.  Values and order of every addition are unchanged.
+//   * exp(x) with x < -45 is replaced by 0: such a term (< 3e-20) cannot change a double sum that contains the
+//     exp(0) = 1 of the best genotype, so the result is the same double.
+// Returns max_gt and writes log10 posteriors to prob[10].
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int qual[8], int rf,
-		const DevConst *__restrict__ dc, const double (*__restrict__ qp)[4], double prob[10]) {
+		const DevConst *__restrict__ dc, const double (*__restrict__ qp)[4], double prob[10],
+		double *__restrict__ wbuf, int lane) {
 	double ll[10];
 	const double l = dc->l, t = dc->t;
 #pragma unroll
@@ -78,68 +110,103 @@ __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int q
 		}
 		ll[g] = v;
 	}
-	// classes 0-3 (:109-164)
+	// classes 0-3 (:109-164).  Branch-free: an empty class has n = 0 and qual 0, so its three products are signed zeros
+	// and the additions leave ll untouched.
 #pragma unroll
 	for (int j = 0; j < 4; j++) {
-		if (cnt[j]) {
-			const double n = (double)cnt[j];
-			const double *q = qp[qual[j]];
-			const double v0 = n * q[1], v1 = n * q[2], v2 = n * q[3];
+		const double n = (double)cnt[j];
+		const double *q = qp[qual[j]];
+		const double v0 = n * q[1], v1 = n * q[2], v2 = n * q[3];
 #pragma unroll
-			for (int g = 0; g < 10; g++) ll[g] += gt_hits(g, j) == 2 ? v2 : (gt_hits(g, j) == 1 ? v1 : v0);
-		}
+		for (int g = 0; g < 10; g++) ll[g] += gt_hits(g, j) == 2 ? v2 : (gt_hits(g, j) == 1 ? v1 : v0);
 	}
 	// :165-171
 	double Z[6];
 	const double n4 = (double)cnt[4], n5 = (double)cnt[5], n6 = (double)cnt[6], n7 = (double)cnt[7];
-	const double k4 = qp[qual[4]][0], k5 = qp[qual[5]][0], k6 = qp[qual[6]][0], k7 = qp[qual[7]][0];
-	if (cnt[5] | cnt[7]) conv_ml(n5, n7, k5, k7, l, t, Z);
-	if (cnt[4] | cnt[6]) conv_ml(n6, n4, k6, k4, l, t, Z + 3);
-	if (cnt[4]) {   // informative A (:173-187)
-		const double *q = qp[qual[4]];
-		const double kk = n4 * q[1], half = n4 * q[2], one = n4 * q[3];
-		const double ag = log(1.0 - 0.5 * Z[4] + k4) * n4;
-		const double gg = log(1.0 - Z[3] + k4) * n4;
-		const double mix = log(0.5 * (1.0 - Z[5]) + k4) * n4;
-		ll[0] += one; ll[2] += ag; ll[7] += gg; ll[5] += mix; ll[8] += mix;
-		ll[1] += half; ll[3] += half; ll[4] += kk; ll[6] += kk; ll[9] += kk;
+	const double *q4 = qp[qual[4]], *q5 = qp[qual[5]], *q6 = qp[qual[6]], *q7 = qp[qual[7]];
+	const double k4 = q4[0], k5 = q5[0], k6 = q6[0], k7 = q7[0];
+	conv_ml(n5, n7, k5, k7, l, t, Z);
+	conv_ml(n6, n4, k6, k4, l, t, Z + 3);
+
+	// ---- pooled log() of the informative-class arguments (:173-230)
+	const int nlog = 3 * ((cnt[4] != 0) + (cnt[5] != 0) + (cnt[6] != 0) + (cnt[7] != 0));
+	int total;
+	const int off = warp_offsets(nlog, lane, &total);
+	{
+		double *w = wbuf + off;
+		if (cnt[4]) { w[0] = 1.0 - 0.5 * Z[4] + k4; w[1] = 1.0 - Z[3] + k4; w[2] = 0.5 * (1.0 - Z[5]) + k4; w += 3; }
+		if (cnt[5]) { w[0] = Z[0] + k5; w[1] = 0.5 * Z[2] + k5; w[2] = 0.5 * Z[1] + k5; w += 3; }
+		if (cnt[6]) { w[0] = Z[3] + k6; w[1] = 0.5 * Z[5] + k6; w[2] = 0.5 * Z[4] + k6; w += 3; }
+		if (cnt[7]) { w[0] = 1.0 - Z[0] + k7; w[1] = 1.0 - 0.5 * Z[1] + k7; w[2] = 0.5 * (1.0 - Z[2]) + k7; }
 	}
-	if (cnt[5]) {   // informative C (:188-201)
-		const double kk = n5 * qp[qual[5]][1];
-		const double cc = log(Z[0] + k5) * n5;
-		const double mix = log(0.5 * Z[2] + k5) * n5;
-		const double ct = log(0.5 * Z[1] + k5) * n5;
-		ll[4] += cc; ll[1] += mix; ll[5] += mix; ll[6] += ct;
-		ll[0] += kk; ll[2] += kk; ll[3] += kk; ll[7] += kk; ll[8] += kk; ll[9] += kk;
+	__syncwarp();
+	for (int i = lane; i < total; i += 32) wbuf[i] = log(wbuf[i]);
+	__syncwarp();
+	{
+		const double *w = wbuf + off;
+		if (cnt[4]) {   // informative A
+			const double kk = n4 * q4[1], half = n4 * q4[2], one = n4 * q4[3];
+			const double ag = w[0] * n4, gg = w[1] * n4, mix = w[2] * n4;
+			ll[0] += one; ll[2] += ag; ll[7] += gg; ll[5] += mix; ll[8] += mix;
+			ll[1] += half; ll[3] += half; ll[4] += kk; ll[6] += kk; ll[9] += kk;
+			w += 3;
+		}
+		if (cnt[5]) {   // informative C
+			const double kk = n5 * q5[1];
+			const double cc = w[0] * n5, mix = w[1] * n5, ct = w[2] * n5;
+			ll[4] += cc; ll[1] += mix; ll[5] += mix; ll[6] += ct;
+			ll[0] += kk; ll[2] += kk; ll[3] += kk; ll[7] += kk; ll[8] += kk; ll[9] += kk;
+			w += 3;
+		}
+		if (cnt[6]) {   // informative G
+			const double kk = n6 * q6[1];
+			const double gg = w[0] * n6, mix = w[1] * n6, ag = w[2] * n6;
+			ll[7] += gg; ll[5] += mix; ll[8] += mix; ll[2] += ag;
+			ll[0] += kk; ll[1] += kk; ll[3] += kk; ll[4] += kk; ll[6] += kk; ll[9] += kk;
+			w += 3;
+		}
+		if (cnt[7]) {   // informative T
+			const double kk = n7 * q7[1], half = n7 * q7[2], one = n7 * q7[3];
+			const double cc = w[0] * n7, ct = w[1] * n7, mix = w[2] * n7;
+			ll[9] += one; ll[4] += cc; ll[6] += ct; ll[1] += mix; ll[5] += mix;
+			ll[3] += half; ll[8] += half; ll[0] += kk; ll[2] += kk; ll[7] += kk;
+		}
 	}
-	if (cnt[6]) {   // informative G (:202-215)
-		const double kk = n6 * qp[qual[6]][1];
-		const double gg = log(Z[3] + k6) * n6;
-		const double mix = log(0.5 * Z[5] + k6) * n6;
-		const double ag = log(0.5 * Z[4] + k6) * n6;
-		ll[7] += gg; ll[5] += mix; ll[8] += mix; ll[2] += ag;
-		ll[0] += kk; ll[1] += kk; ll[3] += kk; ll[4] += kk; ll[6] += kk; ll[9] += kk;
-	}
-	if (cnt[7]) {   // informative T (:216-230)
-		const double *q = qp[qual[7]];
-		const double kk = n7 * q[1], half = n7 * q[2], one = n7 * q[3];
-		const double cc = log(1.0 - Z[0] + k7) * n7;
-		const double ct = log(1.0 - 0.5 * Z[1] + k7) * n7;
-		const double mix = log(0.5 * (1.0 - Z[2]) + k7) * n7;
-		ll[9] += one; ll[4] += cc; ll[6] += ct; ll[1] += mix; ll[5] += mix;
-		ll[3] += half; ll[8] += half; ll[0] += kk; ll[2] += kk; ll[7] += kk;
-	}
+	__syncwarp();
 	// first strict maximum (:231-239)
 	double top = ll[0];
 	int best = 0;
 #pragma unroll
 	for (int g = 1; g < 10; g++) if (ll[g] > top) { top = ll[g]; best = g; }
-	double sum = 0.0;
+	// ---- pooled exp() of the non-vanishing differences (:240-242)
+	uint32_t need = 0;
 #pragma unroll
-	for (int g = 0; g < 10; g++) sum += exp(ll[g] - top);
+	for (int g = 0; g < 10; g++) { const double x = ll[g] - top; if (x >= -45.0 && x != 0.0) need |= 1u << g; }
+	const int nexp = __popc(need);
+	const int eoff = warp_offsets(nexp, lane, &total);
+	{
+		double *w = wbuf + eoff;
+#pragma unroll
+		for (int g = 0; g < 10; g++) if (need >> g & 1) *w++ = ll[g] - top;
+	}
+	__syncwarp();
+	for (int i = lane; i < total; i += 32) wbuf[i] = exp(wbuf[i]);
+	__syncwarp();
+	double sum = 0.0;
+	{
+		const double *w = wbuf + eoff;
+#pragma unroll
+		for (int g = 0; g < 10; g++) {
+			const double x = ll[g] - top;
+			double e = x == 0.0 ? 1.0 : 0.0;
+			if (need >> g & 1) e = *w++;
+			sum += e;
+		}
+	}
+	__syncwarp();
 	sum = log(sum);
 #pragma unroll
-	for (int g = 0; g < 10; g++) prob[g] = (ll[g] - top - sum) / kLn10;
+	for (int g = 0; g < 10; g++) prob[g] = div_by(ll[g] - top - sum, kLn10, kInvLn10);
 	return best;
 }
 
@@ -218,7 +285,7 @@ __device__ __forceinline__ double strand_bias(const SiteCounts &s, int max_gt, c
 	if (max_gt == 8) f2 = (int)(s.cnt[1][2] + s.cnt[1][4] + s.cnt[0][6]);
 	double z = fisher_exact(lfact_tab, f0, f1, f2, f3);
 	if (z < 1.0e-20) z = 1.0e-20;
-	return log(z) / kLn10;
+	return div_by(log(z), kLn10, kInvLn10);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -227,12 +294,8 @@ __device__ __forceinline__ double strand_bias(const SiteCounts &s, int max_gt, c
 // Returns false for a site with no counted base (record zeroed, the caller sets skip).
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool call_site(const SiteCounts &s, int rf, const DevConst *__restrict__ dc,
-		const double (*__restrict__ qp)[4], const double *__restrict__ lfact_tab, uint64_t *rec) {
-	if (!s.n) {
-#pragma unroll
-		for (int i = 0; i < 25; i++) rec[i] = 0;
-		return false;
-	}
+		const double (*__restrict__ qp)[4], const double *__restrict__ lfact_tab, uint64_t *rec,
+		double *__restrict__ wbuf, int lane) {
 	uint32_t tot[8];
 	int qual[8];
 	float tq = 0.0f;
@@ -246,10 +309,17 @@ __device__ __forceinline__ bool call_site(const SiteCounts &s, int rf, const Dev
 			qual[j] = (int)floorf((float)(0.5 + (double)(s.qsum[j] / nn)));
 		} else qual[j] = 0;
 	}
+	// the whole warp runs the model together (a lane without counts contributes nothing to the pooled lists)
+	double prob[10];
+	const int best = genotype_model(tot, qual, rf, dc, qp, prob, wbuf, lane);
+	__syncwarp();                      // wbuf may alias this warp's output rows: everyone is done with it
+	if (!s.n) {
+#pragma unroll
+		for (int i = 0; i < 25; i++) rec[i] = 0;
+		return false;
+	}
 	const int aq = (int)floorf((float)(0.5 + (double)(tq / (float)s.n)));
 	const int mq = (int)(0.5 + sqrt((double)(s.mapq2 / (float)s.n)));
-	double prob[10];
-	const int best = genotype_model(tot, qual, rf, dc, qp, prob);
 	const double fs = strand_bias(s, best, lfact_tab);
 #pragma unroll
 	for (int j = 0; j < 8; j++) rec[j] = tot[j];

@@ -142,7 +142,14 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 	} else s.n = 0;
 	__syncthreads();                       // every thread holds its input: the tile buffer can now take the output
 	uint64_t *rec = stage + tid * RW;
-	const bool called = call_site(s, rf, dc, tabs->qp, tabs->lfact, rec);
+	// pooled-argument list of this warp: the (still unused) output rows of its own 32 sites
+	double *wbuf = (double *)(stage + (tid & ~31) * RW);
+	if (tid >= nrec) {
+#pragma unroll
+		for (int j = 0; j < 8; j++) { s.cnt[0][j] = s.cnt[1][j] = 0; s.qsum[j] = 0.0f; }
+		s.mapq2 = 0.0f;
+	}
+	const bool called = call_site(s, rf, dc, tabs->qp, tabs->lfact, rec, wbuf, tid & 31);
 	if (VCF) rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
 	else if (tid < nrec) skip[first + tid] = called ? 0 : 1;
 	store_tile<REC>(out + first * REC, stage, nrec, bulk_ok, tid, kCallTile);
@@ -205,8 +212,8 @@ __global__ void k_bin_scatter(const Seg *__restrict__ segs, size_t nseg, uint32_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pileup by gather.  CTA = 256 threads = 256 consecutive sites.  Candidate segments are the two bins [t-1, t]
-// (a segment is at most 256 long).  Each warp filters 32 candidates at a time with one ballot, then walks the
+// Pileup by gather.  CTA = 128 threads = 128 consecutive sites (half a bin).  Candidate segments are the two bins
+// [t-1, t] (a segment is at most 256 long).  Each warp filters 32 candidates at a time with one ballot, then walks the
 // hits; a lane adds the byte at its own site into byte/halfword-packed register counters keyed by
 // (strand index, bisulfite strand), which are widened every 255 hits.
 //   MODE 0: write pileup[] (104 B / site)       MODE 1: run the model and write gt_vcf[] (208 B / site)
@@ -232,8 +239,10 @@ __device__ __forceinline__ void widen(Packed &p, uint32_t cnt[2][8], uint32_t qs
 	}
 }
 
+constexpr int kPileThreads = 128;     // one CTA = 128 consecutive sites = half a bin
+
 template <int MODE>
-__global__ void __launch_bounds__(kPileTile)
+__global__ void __launch_bounds__(kPileThreads)
 k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_start, const uint8_t *__restrict__ bases,
 		const uint8_t *__restrict__ ref, uint32_t x, uint32_t sz, uint32_t tile0, uint8_t *__restrict__ out,
 		const DevConst *__restrict__ dc, unsigned long long *__restrict__ counters) {
@@ -241,17 +250,17 @@ k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_sta
 	constexpr int RW = REC / 8;
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	uint64_t *stage = (uint64_t *)smem_raw;
-	SmemTables *tabs = (SmemTables *)(smem_raw + kPileTile * REC);
-	__shared__ Seg cand[kPileTile];
+	SmemTables *tabs = (SmemTables *)(smem_raw + kPileThreads * REC);
+	__shared__ Seg cand[kPileThreads];
 
 	const int tid = threadIdx.x, lane = tid & 31;
-	const uint32_t tile = tile0 + blockIdx.x;
-	const uint32_t site0 = tile * kPileTile;
-	const int nrec = (int)min((uint32_t)kPileTile, sz - site0);
+	const uint32_t site0 = tile0 * kPileTile + blockIdx.x * kPileThreads;     // first site of this CTA
+	const uint32_t bin = site0 / kPileTile;
+	const int nrec = (int)min((uint32_t)kPileThreads, sz - site0);
 	const uint32_t mypos = x + site0 + tid;                        // 1-based reference position of this thread's site
 	const uint32_t wpos0 = x + site0 + (tid & ~31);                // first position of this warp's 32 sites
 	const uint32_t min_qual = (uint32_t)dc->min_qual;
-	if (MODE) load_tables(tabs, dc, tid, kPileTile);
+	if (MODE) load_tables(tabs, dc, tid, kPileThreads);
 
 	uint32_t cnt[2][8], qs[8], mq2 = 0;
 #pragma unroll
@@ -261,9 +270,10 @@ k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_sta
 	for (int st = 0; st < 3; st++) { pk.c[0][st] = pk.c[1][st] = 0; pk.q[st] = 0; }
 	uint32_t since_widen = 0;
 
-	const uint32_t c_lo = bin_start[tile ? tile - 1 : 0], c_hi = bin_start[tile + 1];
-	for (uint32_t base = c_lo; base < c_hi; base += kPileTile) {
-		const uint32_t nc = min((uint32_t)kPileTile, c_hi - base);
+	// candidates: segments that start in the previous bin or in this one (a segment is at most one bin long)
+	const uint32_t c_lo = bin_start[bin ? bin - 1 : 0], c_hi = bin_start[bin + 1];
+	for (uint32_t base = c_lo; base < c_hi; base += kPileThreads) {
+		const uint32_t nc = min((uint32_t)kPileThreads, c_hi - base);
 		__syncthreads();
 		if ((uint32_t)tid < nc) cand[tid] = segs[base + tid];
 		__syncthreads();
@@ -275,15 +285,27 @@ k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_sta
 			}
 			uint32_t m = __ballot_sync(0xffffffffu, hit);
 			while (m) {
-				const int b = __ffs(m) - 1;
-				m &= m - 1;
-				const uint4 raw = *(const uint4 *)&cand[g + b];      // broadcast read
-				const uint32_t pos = raw.x, off = raw.y, len = raw.z & 0xffffu, mapq = (raw.z >> 16) & 0xffu, flags = raw.z >> 24;
-				const uint32_t d = mypos - pos;
-				if (d < len) {
-					const uint32_t byte = __ldg(bases + (size_t)off + d);
-					const uint32_t q = byte >> 2, bs = byte & 3u;
-					const uint32_t ok = (q >= min_qual) & (q != (uint32_t)kFltQual);
+				// four hits per trip: their byte loads are issued back to back before any is consumed
+				uint4 raw[4];
+				uint32_t byte[4];
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const bool valid = m != 0;
+					const int b = valid ? __ffs(m) - 1 : 0;
+					m &= m - 1;                                       // 0 stays 0
+					raw[u] = *(const uint4 *)&cand[g + b];            // broadcast read
+					if (!valid) raw[u].z = 0;                         // len 0: contributes nothing
+				}
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const uint32_t d = mypos - raw[u].x, len = raw[u].z & 0xffffu;
+					byte[u] = d < len ? (uint32_t)__ldg(bases + (size_t)raw[u].y + d) : 0u;
+				}
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const uint32_t mapq = (raw[u].z >> 16) & 0xffu, flags = raw[u].z >> 24;
+					const uint32_t q = byte[u] >> 2, bs = byte[u] & 3u;
+					const uint32_t ok = (q >= min_qual) & (q != (uint32_t)kFltQual);       // q = 0 for "no byte"
 					const uint32_t st = (flags >> 1) & 3u, ori = flags & 1u;
 					const uint32_t inc = ok << (8 * bs);
 					const uint64_t qinc = (uint64_t)(ok ? q : 0u) << (16 * bs);
@@ -293,7 +315,8 @@ k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_sta
 					else { pk.q[2] += qinc; if (ori) pk.c[1][2] += inc; else pk.c[0][2] += inc; }
 					mq2 += ok ? mapq * mapq : 0u;
 				}
-				if (++since_widen == 255) { widen(pk, cnt, qs); since_widen = 0; }
+				since_widen += 4;
+				if (since_widen > 251) { widen(pk, cnt, qs); since_widen = 0; }      // 8-bit fields hold 255
 			}
 		}
 	}
@@ -323,12 +346,13 @@ k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_sta
 	} else {
 		const int rf = tid < nrec ? ref[site0 + tid] : 0;
 		__syncthreads();                    // tables loaded
-		const bool called = call_site(s, rf, dc, tabs->qp, tabs->lfact, rec);
+		double *wbuf = (double *)(stage + (tid & ~31) * RW);
+		const bool called = call_site(s, rf, dc, tabs->qp, tabs->lfact, rec, wbuf, lane);
 		rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
 		const uint32_t nc = __syncthreads_count(called);
 		if (tid == 0 && nc) atomicAdd(counters, (unsigned long long)nc);
 	}
-	store_tile<REC>(out + (size_t)blockIdx.x * kPileTile * REC, stage, nrec, true, tid, kPileTile);
+	store_tile<REC>(out + (size_t)blockIdx.x * kPileThreads * REC, stage, nrec, true, tid, kPileThreads);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -457,7 +481,7 @@ __global__ void k_synth_reads(uint64_t seed, uint32_t x, uint32_t sz, uint32_t r
 #define LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
 static size_t call_smem(bool vcf) { return (size_t)kCallTile * (vcf ? 208 : 200) + sizeof(SmemTables); }
-static size_t pile_smem(int mode) { return (size_t)kPileTile * (mode ? 208 : 104) + sizeof(SmemTables); }
+static size_t pile_smem(int mode) { return (size_t)kPileThreads * (mode ? 208 : 104) + sizeof(SmemTables); }
 
 cudaError_t configure_kernels() {
 	cudaError_t e;
@@ -522,8 +546,12 @@ cudaError_t launch_pileup_tiles(const void *scratch, size_t nseg, const void *ba
 	const uint32_t all_tiles = (sz + kPileTile - 1) / kPileTile;
 	const Seg *sorted = (const Seg *)scratch;
 	const uint32_t *start = (const uint32_t *)((const uint8_t *)scratch + seg_area(nseg)) + all_tiles;
-	if (mode) k_pileup_tile<1><<<ntiles, kPileTile, pile_smem(1), stream>>>(sorted, start, (const uint8_t *)bases, (const uint8_t *)ref, x, sz, tile0, (uint8_t *)out, dc, counters);
-	else k_pileup_tile<0><<<ntiles, kPileTile, pile_smem(0), stream>>>(sorted, start, (const uint8_t *)bases, (const uint8_t *)ref, x, sz, tile0, (uint8_t *)out, dc, counters);
+	// sites covered by this launch: bins [tile0, tile0 + ntiles) clipped to the window; one CTA per 128 sites
+	const uint32_t first_site = tile0 * kPileTile;
+	const uint32_t nsite = min(ntiles * (uint32_t)kPileTile, sz - first_site);
+	const unsigned grid = (nsite + kPileThreads - 1) / kPileThreads;
+	if (mode) k_pileup_tile<1><<<grid, kPileThreads, pile_smem(1), stream>>>(sorted, start, (const uint8_t *)bases, (const uint8_t *)ref, x, sz, tile0, (uint8_t *)out, dc, counters);
+	else k_pileup_tile<0><<<grid, kPileThreads, pile_smem(0), stream>>>(sorted, start, (const uint8_t *)bases, (const uint8_t *)ref, x, sz, tile0, (uint8_t *)out, dc, counters);
 	*launches += 1;
 	LAUNCH_CHECK();
 	return cudaSuccess;

@@ -189,7 +189,9 @@ def test_synthetic_generators_and_device_entry_points(gpu, oracle):
     d_r = torch.empty(n, dtype=torch.uint8, device="cuda")
     d_o = torch.empty(n * 200, dtype=torch.uint8, device="cuda")
     d_s = torch.empty(n, dtype=torch.uint8, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    st = ts.cuda_stream
     gpu.synth_sites_dev(20261018, 0, n, 30.0, d_p.data_ptr(), d_r.data_ptr(), st)
     gpu.call_sites_dev(d_p.data_ptr(), d_r.data_ptr(), n, d_o.data_ptr(), d_s.data_ptr(), st)
     torch.cuda.synchronize()
@@ -198,6 +200,10 @@ def test_synthetic_generators_and_device_entry_points(gpu, oracle):
     out = d_o.cpu().numpy().view(GT_METH)
     skip = d_s.cpu().numpy()
     assert 25 < p["n"].mean() < 32 and 0.02 < (p["n"] == 0).mean() < 0.04
+    # the host twin of the generator (oracle/bs_oracle.c, used by the CPU arm of bench.py) draws the same records
+    hp, hr = oracle.synth_sites(20261018, 0, n, 30.0, nthreads=4)
+    same = (hp.view(np.uint8).reshape(n, 104) == p.view(np.uint8).reshape(n, 104)).all(axis=1)
+    assert same.mean() > 0.9999 and (hr == r).all()
     wout, wskip = oracle.call_sites(p, r, nthreads=4)
     util.assert_gt_meth_close(out, skip, wout, wskip)
     # same seed -> same records; vcf-layout variant agrees with the gt_meth variant
@@ -221,7 +227,9 @@ def test_synthetic_block_fused_vs_oracle(gpu, oracle):
     d_r = torch.empty(sz, dtype=torch.uint8, device="cuda")
     d_v = torch.empty(sz * 208, dtype=torch.uint8, device="cuda")
     d_p = torch.empty(sz * 104, dtype=torch.uint8, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    st = ts.cuda_stream
     nseg, nb = gpu.synth_block_dev(7, x, sz, L, depth, d_seg.data_ptr(), ns, d_b.data_ptr(), ns * L, d_r.data_ptr(), st)
     assert nseg == ns
     gpu.call_block_dev(d_seg.data_ptr(), nseg, d_b.data_ptr(), d_r.data_ptr(), x, sz, d_v.data_ptr(), st)
