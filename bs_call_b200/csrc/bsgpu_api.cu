@@ -65,7 +65,7 @@ struct bsgpu_ctx {
 	cudaStream_t stream = nullptr;               // context stream (block path, _dev default)
 	cudaStream_t copy_stream = nullptr;          // D2H of finished windows
 	Slot slot[2];
-	DevBuf segs, bases, ref, scratch, vcf, tmpl, misms;
+	DevBuf segs, bases, ref, scratch, vcf, tmpl, misms, obases, ooff;
 	std::vector<cudaEvent_t> win_events;
 	bsgpu_stats stats;
 	int launches = 0;
@@ -102,17 +102,18 @@ int bsgpu_init(const bsgpu_params *p, bsgpu_ctx **out) {
 	c->params = *p;
 	memset(&c->stats, 0, sizeof(c->stats));
 	// host-side tables, computed with the C library exactly as the reference does
-	DevConst h;
+	static DevConst h;
 	memset(&h, 0, sizeof(h));
 	for (int q = 0; q <= kMaxQual; q++) {          // src/genotype_model.c:10-21
 		double er = exp(-.1 * (double)q * kLn10);
 		if (er > .5) er = .5;
 		const double k = er / (3.0 - 4.0 * er);
-		h.qp[q][0] = k;
-		h.qp[q][1] = log(k);
-		h.qp[q][2] = log(0.5 + k);
-		h.qp[q][3] = log(1.0 + k);
+		h.tab.qp[q][0] = k;
+		h.tab.qp[q][1] = log(k);
+		h.tab.qp[q][2] = log(0.5 + k);
+		h.tab.qp[q][3] = log(1.0 + k);
 	}
+	build_math_tables(&h.tab.math);
 	double acc = 0.0;                              // src/stats_utils.c:14-21
 	h.lfact[0] = h.lfact[1] = 0.0;
 	for (int i = 2; i < 256; i++) { acc += log((double)i); h.lfact[i] = acc; }
@@ -146,7 +147,7 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 		if (c->slot[i].done) cudaEventDestroy(c->slot[i].done);
 	}
 	for (cudaEvent_t ev : c->win_events) cudaEventDestroy(ev);
-	c->segs.release(); c->bases.release(); c->ref.release(); c->scratch.release(); c->vcf.release(); c->tmpl.release(); c->misms.release();
+	c->segs.release(); c->bases.release(); c->ref.release(); c->scratch.release(); c->vcf.release(); c->tmpl.release(); c->misms.release(); c->obases.release(); c->ooff.release();
 	if (c->stream) cudaStreamDestroy(c->stream);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->d_const) cudaFree(c->d_const);
@@ -252,6 +253,18 @@ int bsgpu_synth_block_dev(bsgpu_ctx *c, uint64_t seed, uint32_t x, uint32_t sz, 
 	return BSGPU_OK;
 }
 
+// host evaluation of the device's table-driven log / exp (same source, both FMA-exact): lets CPU tests measure them
+int bsgpu_math_probe(const double *x, size_t n, double *out_log, double *out_exp) {
+	static MathTables mt;
+	static bool built = false;
+	if (!built) { build_math_tables(&mt); built = true; }
+	for (size_t i = 0; i < n; i++) {
+		if (out_log) out_log[i] = fast_log(x[i], &mt);
+		if (out_exp) out_exp[i] = fast_exp(x[i], &mt);
+	}
+	return BSGPU_OK;
+}
+
 int bsgpu_sync(bsgpu_ctx *c) {
 	if (!c) return fail("bsgpu_sync: null context");
 	CU(cudaSetDevice(c->device));
@@ -293,38 +306,19 @@ int bsgpu_call_sites(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t *re
 	return BSGPU_OK;
 }
 
-// segments + bases (+ ref) -> pileup[] or gt_vcf[].  Inputs go up in one piece (they are ~1/6 of the output volume);
-// the window is then processed in slabs of tiles so that the D2H of slab i overlaps the kernel of slab i+1.
-static int block_host(bsgpu_ctx *c, const bsgpu_seg *segs, size_t nseg, const uint8_t *bases, size_t nbases, const uint8_t *ref,
+// Device-resident segments / bases / ref -> host pileup[] or gt_vcf[].  The window is processed in slabs of tiles so
+// that the D2H of slab i (copy stream) overlaps the kernel of slab i+1 (context stream); outputs are ~6x the inputs.
+static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *d_bases, const void *d_ref,
 		uint32_t x, uint32_t sz, void *out, int mode) {
-	if (!c) return fail("bsgpu block: null context");
-	if (!sz) return BSGPU_OK;
-	if (!out || (nseg && (!segs || !bases)) || (mode && !ref)) return fail("bsgpu block: null buffer");
-	if (nbases > 0xffffffffull) return fail("bsgpu block: more than 4 GiB of bases in one block; split the window");
-	for (size_t i = 0; i < nseg; i++) {
-		if (segs[i].len > BSGPU_MAX_SEG_LEN) return fail("bsgpu block: segment %zu longer than %d (use bsgpu_stage_templates)", i, BSGPU_MAX_SEG_LEN);
-		if ((size_t)segs[i].off + segs[i].len > nbases) return fail("bsgpu block: segment %zu points outside bases[]", i);
-	}
-	CU(cudaSetDevice(c->device));
 	const size_t rec = mode ? sizeof(bsgpu_gt_vcf) : sizeof(bsgpu_pileup);
-	CU(cudaStreamSynchronize(c->stream));
-	CU(cudaStreamSynchronize(c->copy_stream));
-	CU(c->segs.reserve(nseg * sizeof(bsgpu_seg) + 16));
-	CU(c->bases.reserve(nbases + 16));
-	CU(c->ref.reserve((size_t)sz + 16));
 	CU(c->scratch.reserve(pileup_scratch_bytes(nseg, sz)));
-	if (nseg) {
-		CU(cudaMemcpyAsync(c->segs.p, segs, nseg * sizeof(bsgpu_seg), cudaMemcpyHostToDevice, c->stream));
-		CU(cudaMemcpyAsync(c->bases.p, bases, nbases, cudaMemcpyHostToDevice, c->stream));
-	}
-	if (mode) CU(cudaMemcpyAsync(c->ref.p, ref, sz, cudaMemcpyHostToDevice, c->stream));
-	c->stats.h2d_bytes += nseg * sizeof(bsgpu_seg) + nbases + (mode ? sz : 0);
-	CU(launch_bin_segments(c->segs.p, nseg, x, sz, c->scratch.p, c->stream, &c->launches));
+	CU(launch_bin_segments(d_segs, nseg, x, sz, c->scratch.p, c->stream, &c->launches));
 	const uint32_t ntiles = (sz + kPileTileSites - 1) / kPileTileSites;
 	const uint32_t slab = 8192;                    // tiles per slab = 2 Mi sites = 436 MB of gt_vcf
 	const uint32_t nslab = (ntiles + slab - 1) / slab;
 	const uint32_t resident = nslab < 3 ? nslab : 3;      // ring of output slabs on the device
-	CU(c->vcf.reserve((size_t)resident * slab * kPileTileSites * rec));
+	const uint32_t slab_tiles = ntiles < slab ? ntiles : slab;
+	CU(c->vcf.reserve((size_t)resident * slab_tiles * kPileTileSites * rec));
 	while (c->win_events.size() < 2 * (size_t)resident) {
 		cudaEvent_t ev;
 		CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -336,9 +330,9 @@ static int block_host(bsgpu_ctx *c, const bsgpu_seg *segs, size_t nseg, const ui
 		const uint32_t t0 = si * slab, nt = ntiles - t0 < slab ? ntiles - t0 : slab;
 		const size_t site0 = (size_t)t0 * kPileTileSites;
 		const size_t nsite = (size_t)sz - site0 < (size_t)nt * kPileTileSites ? (size_t)sz - site0 : (size_t)nt * kPileTileSites;
-		uint8_t *dslab = (uint8_t *)c->vcf.p + (size_t)r * slab * kPileTileSites * rec;
+		uint8_t *dslab = (uint8_t *)c->vcf.p + (size_t)r * slab_tiles * kPileTileSites * rec;
 		if (si >= resident) CU(cudaStreamWaitEvent(c->stream, copied, 0));      // ring slot drained
-		CU(launch_pileup_tiles(c->scratch.p, nseg, c->bases.p, c->ref.p, x, sz, t0, nt, dslab, mode, c->d_const, c->d_counters, c->stream, &c->launches));
+		CU(launch_pileup_tiles(c->scratch.p, nseg, d_bases, d_ref, x, sz, t0, nt, dslab, mode, c->d_const, c->d_counters, c->stream, &c->launches));
 		CU(cudaEventRecord(computed, c->stream));
 		CU(cudaStreamWaitEvent(c->copy_stream, computed, 0));
 		CU(cudaMemcpyAsync((uint8_t *)out + site0 * rec, dslab, nsite * rec, cudaMemcpyDeviceToHost, c->copy_stream));
@@ -349,6 +343,91 @@ static int block_host(bsgpu_ctx *c, const bsgpu_seg *segs, size_t nseg, const ui
 	CU(cudaStreamSynchronize(c->stream));
 	c->stats.sites += sz;
 	return BSGPU_OK;
+}
+
+// host segments + bases (+ ref) -> pileup[] or gt_vcf[]: inputs go up in one piece, then block_run
+static int block_host(bsgpu_ctx *c, const bsgpu_seg *segs, size_t nseg, const uint8_t *bases, size_t nbases, const uint8_t *ref,
+		uint32_t x, uint32_t sz, void *out, int mode) {
+	if (!c) return fail("bsgpu block: null context");
+	if (!sz) return BSGPU_OK;
+	if (!out || (nseg && (!segs || !bases)) || (mode && !ref)) return fail("bsgpu block: null buffer");
+	if (nbases > 0xffffffffull) return fail("bsgpu block: more than 4 GiB of bases in one block; split the window");
+	for (size_t i = 0; i < nseg; i++) {
+		if (segs[i].len > BSGPU_MAX_SEG_LEN) return fail("bsgpu block: segment %zu longer than %d (use bsgpu_stage_templates)", i, BSGPU_MAX_SEG_LEN);
+		if ((size_t)segs[i].off + segs[i].len > nbases) return fail("bsgpu block: segment %zu points outside bases[]", i);
+	}
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->copy_stream));
+	CU(c->segs.reserve(nseg * sizeof(bsgpu_seg) + 16));
+	CU(c->bases.reserve(nbases + 16));
+	CU(c->ref.reserve((size_t)sz + 16));
+	if (nseg) {
+		CU(cudaMemcpyAsync(c->segs.p, segs, nseg * sizeof(bsgpu_seg), cudaMemcpyHostToDevice, c->stream));
+		CU(cudaMemcpyAsync(c->bases.p, bases, nbases, cudaMemcpyHostToDevice, c->stream));
+	}
+	if (mode) CU(cudaMemcpyAsync(c->ref.p, ref, sz, cudaMemcpyHostToDevice, c->stream));
+	c->stats.h2d_bytes += nseg * sizeof(bsgpu_seg) + nbases + (mode ? sz : 0);
+	return block_run(c, c->segs.p, nseg, c->bases.p, c->ref.p, x, sz, out, mode);
+}
+
+// raw templates -> gt_vcf[]: normalisation, mate walk, pileup and model on the device (src/process_template.c:18-126)
+int bsgpu_process_block(bsgpu_ctx *c, const bsgpu_template *t, size_t n, const uint8_t *bases, size_t nbases,
+		const bsgpu_misms *misms, size_t nmisms, const uint8_t *ref, uint32_t y, uint32_t *x_out, bsgpu_gt_vcf *out) {
+	if (!c) return fail("bsgpu_process_block: null context");
+	if (!n) return fail("bsgpu_process_block: empty template list");       // the reference asserts ix > 0 (:22)
+	if (!t || !bases || !ref || !out || (nmisms && !misms)) return fail("bsgpu_process_block: null buffer");
+	// window: two positions before the first template's start (:24-28)
+	uint32_t x = t[0].forward_position ? t[0].forward_position : t[0].reverse_position;
+	if (!x || x > y) return fail("bsgpu_process_block: first template starts at %u, block ends at %u", x, y);
+	x = x > 2 ? x - 2 : 1;
+	const uint32_t sz = y - x + 1;
+	// per-mate output slots: read length + reference bases the read lacks (CIGAR D -> INS events)
+	std::vector<uint32_t> off(2 * n + 1);
+	uint64_t tot = 0;
+	uint32_t maxcap = 1;
+	for (size_t i = 0; i < n; i++) for (int k = 0; k < 2; k++) {
+		off[2 * i + k] = (uint32_t)tot;
+		if (!t[i].present[k]) continue;
+		if ((size_t)t[i].read_off[k] + t[i].read_len[k] > nbases) return fail("bsgpu_process_block: template %zu read outside bases[]", i);
+		if ((size_t)t[i].mm_off[k] + t[i].mm_n[k] > nmisms) return fail("bsgpu_process_block: template %zu events outside misms[]", i);
+		if (t[i].bs_strand > 2) return fail("bsgpu_process_block: template %zu has bs_strand %u", i, t[i].bs_strand);
+		uint64_t cap = t[i].read_len[k];
+		for (uint32_t z = 0; z < t[i].mm_n[k]; z++) if (misms[t[i].mm_off[k] + z].type == 1) cap += misms[t[i].mm_off[k] + z].size;
+		tot += cap;
+		if (cap > maxcap) maxcap = (uint32_t)(cap > 0xffffffu ? 0xffffffu : cap);
+	}
+	off[2 * n] = (uint32_t)tot;
+	if (tot > 0xffffffffull) return fail("bsgpu_process_block: more than 4 GiB of bases in one block; split the window");
+	const uint32_t spm = (maxcap + BSGPU_MAX_SEG_LEN - 1) / BSGPU_MAX_SEG_LEN;
+	const size_t nseg = n * 2 * (size_t)spm;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->copy_stream));
+	CU(c->tmpl.reserve(n * sizeof(bsgpu_template)));
+	CU(c->misms.reserve(nmisms * sizeof(bsgpu_misms) + 16));
+	CU(c->bases.reserve(nbases + 16));
+	CU(c->obases.reserve(tot + 16));
+	CU(c->ooff.reserve((2 * n + 1) * sizeof(uint32_t)));
+	CU(c->segs.reserve(nseg * sizeof(bsgpu_seg) + 16));
+	CU(c->ref.reserve((size_t)sz + 16));
+	CU(cudaMemcpyAsync(c->tmpl.p, t, n * sizeof(bsgpu_template), cudaMemcpyHostToDevice, c->stream));
+	if (nmisms) CU(cudaMemcpyAsync(c->misms.p, misms, nmisms * sizeof(bsgpu_misms), cudaMemcpyHostToDevice, c->stream));
+	if (nbases) CU(cudaMemcpyAsync(c->bases.p, bases, nbases, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->ooff.p, off.data(), (2 * n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->ref.p, ref, sz, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaStreamSynchronize(c->stream));          // `off` is a pageable temporary: the copy must finish before it dies
+	c->stats.h2d_bytes += n * sizeof(bsgpu_template) + nmisms * sizeof(bsgpu_misms) + nbases + (2 * n + 1) * 4 + sz;
+	unsigned long long before[4], after[4];
+	CU(cudaMemcpy(before, c->d_counters, sizeof(before), cudaMemcpyDeviceToHost));
+	CU(launch_normalise(c->tmpl.p, n, c->bases.p, c->misms.p, c->ooff.p, c->obases.p, c->segs.p, spm, x, y,
+			c->params.left_trim, c->params.right_trim, c->d_counters, c->stream, &c->launches));
+	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaMemcpy(after, c->d_counters, sizeof(after), cudaMemcpyDeviceToHost));
+	if (after[2] != before[2]) return fail("bsgpu_process_block: Error in CIGAR - illegal soft clip in %llu template(s)", after[2] - before[2]);
+	if (after[3] != before[3]) return fail("bsgpu_process_block: %llu mate(s) start before the block window", after[3] - before[3]);
+	if (x_out) *x_out = x;
+	return block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, out, 1);
 }
 
 int bsgpu_pileup_block(bsgpu_ctx *c, const bsgpu_seg *segs, size_t nseg, const uint8_t *bases, size_t nbases, uint32_t x, uint32_t sz, bsgpu_pileup *out) {

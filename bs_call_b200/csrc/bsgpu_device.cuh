@@ -7,6 +7,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "bsgpu_math.cuh"
 
 namespace bsgpu {
 
@@ -16,9 +17,13 @@ constexpr double kLn10 = 2.30258509299404568402;
 
 // Tables and constants computed once on the host with the C library (so they are bit-identical to what the
 // reference computes, src/genotype_model.c:10-21, src/stats_utils.c:14-21) and uploaded at bsgpu_init.
-struct DevConst {
+struct Tables {                   // copied into shared memory once per CTA
 	double qp[kMaxQual + 1][4];   // k, ln k, ln(1/2 + k), ln(1 + k)
-	double lfact[256];
+	MathTables math;              // reduction tables of fast_log / fast_exp (bsgpu_math.cuh)
+};
+struct DevConst {
+	Tables tab;
+	double lfact[256];            // log-factorials for the Fisher test (het sites only: read through L1, not staged)
 	double l, t;                  // 1 - under_conv, over_conv
 	double lrb, lrb1;             // ln(ref_bias), ln((1 + ref_bias) / 2)
 	int min_qual;
@@ -96,8 +101,10 @@ __device__ __forceinline__ int warp_offsets(int c, int lane, int *total) {
 // Returns max_gt and writes log10 posteriors to prob[10].
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int qual[8], int rf,
-		const DevConst *__restrict__ dc, const double (*__restrict__ qp)[4], double prob[10],
+		const DevConst *__restrict__ dc, const Tables *__restrict__ tb, double prob[10],
 		double *__restrict__ wbuf, int lane) {
+	const double (*__restrict__ qp)[4] = tb->qp;
+	const MathTables *__restrict__ mt = &tb->math;
 	double ll[10];
 	const double l = dc->l, t = dc->t;
 #pragma unroll
@@ -129,48 +136,54 @@ __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int q
 	conv_ml(n6, n4, k6, k4, l, t, Z + 3);
 
 	// ---- pooled log() of the informative-class arguments (:173-230)
-	const int nlog = 3 * ((cnt[4] != 0) + (cnt[5] != 0) + (cnt[6] != 0) + (cnt[7] != 0));
+	const bool c4 = cnt[4] != 0, c5 = cnt[5] != 0, c6 = cnt[6] != 0, c7 = cnt[7] != 0;
+	const int nlog = 3 * ((int)c4 + (int)c5 + (int)c6 + (int)c7);
 	int total;
-	const int off = warp_offsets(nlog, lane, &total);
-	{
-		double *w = wbuf + off;
-		if (cnt[4]) { w[0] = 1.0 - 0.5 * Z[4] + k4; w[1] = 1.0 - Z[3] + k4; w[2] = 0.5 * (1.0 - Z[5]) + k4; w += 3; }
-		if (cnt[5]) { w[0] = Z[0] + k5; w[1] = 0.5 * Z[2] + k5; w[2] = 0.5 * Z[1] + k5; w += 3; }
-		if (cnt[6]) { w[0] = Z[3] + k6; w[1] = 0.5 * Z[5] + k6; w[2] = 0.5 * Z[4] + k6; w += 3; }
-		if (cnt[7]) { w[0] = 1.0 - Z[0] + k7; w[1] = 1.0 - 0.5 * Z[1] + k7; w[2] = 0.5 * (1.0 - Z[2]) + k7; }
+	const int o4 = warp_offsets(nlog, lane, &total);
+	const int o5 = o4 + (c4 ? 3 : 0), o6 = o5 + (c5 ? 3 : 0), o7 = o6 + (c6 ? 3 : 0);
+	if (c4) { wbuf[o4] = 1.0 - 0.5 * Z[4] + k4; wbuf[o4 + 1] = 1.0 - Z[3] + k4; wbuf[o4 + 2] = 0.5 * (1.0 - Z[5]) + k4; }
+	if (c5) { wbuf[o5] = Z[0] + k5; wbuf[o5 + 1] = 0.5 * Z[2] + k5; wbuf[o5 + 2] = 0.5 * Z[1] + k5; }
+	if (c6) { wbuf[o6] = Z[3] + k6; wbuf[o6 + 1] = 0.5 * Z[5] + k6; wbuf[o6 + 2] = 0.5 * Z[4] + k6; }
+	if (c7) { wbuf[o7] = 1.0 - Z[0] + k7; wbuf[o7 + 1] = 1.0 - 0.5 * Z[1] + k7; wbuf[o7 + 2] = 0.5 * (1.0 - Z[2]) + k7; }
+	__syncwarp();
+	// two independent evaluations per trip for instruction-level parallelism
+	for (int i = lane; i < total; i += 64) {
+		const bool two = i + 32 < total;
+		const double a = wbuf[i], b = two ? wbuf[i + 32] : 1.0;
+		const double la = fast_log(a, mt), lb = fast_log(b, mt);
+		wbuf[i] = la;
+		if (two) wbuf[i + 32] = lb;
 	}
 	__syncwarp();
-	for (int i = lane; i < total; i += 32) wbuf[i] = log(wbuf[i]);
-	__syncwarp();
-	{
-		const double *w = wbuf + off;
-		if (cnt[4]) {   // informative A
-			const double kk = n4 * q4[1], half = n4 * q4[2], one = n4 * q4[3];
-			const double ag = w[0] * n4, gg = w[1] * n4, mix = w[2] * n4;
-			ll[0] += one; ll[2] += ag; ll[7] += gg; ll[5] += mix; ll[8] += mix;
-			ll[1] += half; ll[3] += half; ll[4] += kk; ll[6] += kk; ll[9] += kk;
-			w += 3;
-		}
-		if (cnt[5]) {   // informative C
-			const double kk = n5 * q5[1];
-			const double cc = w[0] * n5, mix = w[1] * n5, ct = w[2] * n5;
-			ll[4] += cc; ll[1] += mix; ll[5] += mix; ll[6] += ct;
-			ll[0] += kk; ll[2] += kk; ll[3] += kk; ll[7] += kk; ll[8] += kk; ll[9] += kk;
-			w += 3;
-		}
-		if (cnt[6]) {   // informative G
-			const double kk = n6 * q6[1];
-			const double gg = w[0] * n6, mix = w[1] * n6, ag = w[2] * n6;
-			ll[7] += gg; ll[5] += mix; ll[8] += mix; ll[2] += ag;
-			ll[0] += kk; ll[1] += kk; ll[3] += kk; ll[4] += kk; ll[6] += kk; ll[9] += kk;
-			w += 3;
-		}
-		if (cnt[7]) {   // informative T
-			const double kk = n7 * q7[1], half = n7 * q7[2], one = n7 * q7[3];
-			const double cc = w[0] * n7, ct = w[1] * n7, mix = w[2] * n7;
-			ll[9] += one; ll[4] += cc; ll[6] += ct; ll[1] += mix; ll[5] += mix;
-			ll[3] += half; ll[8] += half; ll[0] += kk; ll[2] += kk; ll[7] += kk;
-		}
+	// Add the four informative classes, in class order.  Branch-free: a class without counts has n = 0 and reads 0 for
+	// its logs, so every addend is a signed zero and ll is unchanged.
+	{   // informative A
+		const double a0 = c4 ? wbuf[o4] : 0.0, a1 = c4 ? wbuf[o4 + 1] : 0.0, a2 = c4 ? wbuf[o4 + 2] : 0.0;
+		const double kk = n4 * q4[1], half = n4 * q4[2], one = n4 * q4[3];
+		const double ag = a0 * n4, gg = a1 * n4, mix = a2 * n4;
+		ll[0] += one; ll[2] += ag; ll[7] += gg; ll[5] += mix; ll[8] += mix;
+		ll[1] += half; ll[3] += half; ll[4] += kk; ll[6] += kk; ll[9] += kk;
+	}
+	{   // informative C
+		const double a0 = c5 ? wbuf[o5] : 0.0, a1 = c5 ? wbuf[o5 + 1] : 0.0, a2 = c5 ? wbuf[o5 + 2] : 0.0;
+		const double kk = n5 * q5[1];
+		const double cc = a0 * n5, mix = a1 * n5, ct = a2 * n5;
+		ll[4] += cc; ll[1] += mix; ll[5] += mix; ll[6] += ct;
+		ll[0] += kk; ll[2] += kk; ll[3] += kk; ll[7] += kk; ll[8] += kk; ll[9] += kk;
+	}
+	{   // informative G
+		const double a0 = c6 ? wbuf[o6] : 0.0, a1 = c6 ? wbuf[o6 + 1] : 0.0, a2 = c6 ? wbuf[o6 + 2] : 0.0;
+		const double kk = n6 * q6[1];
+		const double gg = a0 * n6, mix = a1 * n6, ag = a2 * n6;
+		ll[7] += gg; ll[5] += mix; ll[8] += mix; ll[2] += ag;
+		ll[0] += kk; ll[1] += kk; ll[3] += kk; ll[4] += kk; ll[6] += kk; ll[9] += kk;
+	}
+	{   // informative T
+		const double a0 = c7 ? wbuf[o7] : 0.0, a1 = c7 ? wbuf[o7 + 1] : 0.0, a2 = c7 ? wbuf[o7 + 2] : 0.0;
+		const double kk = n7 * q7[1], half = n7 * q7[2], one = n7 * q7[3];
+		const double cc = a0 * n7, ct = a1 * n7, mix = a2 * n7;
+		ll[9] += one; ll[4] += cc; ll[6] += ct; ll[1] += mix; ll[5] += mix;
+		ll[3] += half; ll[8] += half; ll[0] += kk; ll[2] += kk; ll[7] += kk;
 	}
 	__syncwarp();
 	// first strict maximum (:231-239)
@@ -184,27 +197,26 @@ __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int q
 	for (int g = 0; g < 10; g++) { const double x = ll[g] - top; if (x >= -45.0 && x != 0.0) need |= 1u << g; }
 	const int nexp = __popc(need);
 	const int eoff = warp_offsets(nexp, lane, &total);
-	{
-		double *w = wbuf + eoff;
 #pragma unroll
-		for (int g = 0; g < 10; g++) if (need >> g & 1) *w++ = ll[g] - top;
-	}
+	for (int g = 0; g < 10; g++) if (need >> g & 1) wbuf[eoff + __popc(need & ((1u << g) - 1u))] = ll[g] - top;
 	__syncwarp();
-	for (int i = lane; i < total; i += 32) wbuf[i] = exp(wbuf[i]);
+	for (int i = lane; i < total; i += 64) {
+		const bool two = i + 32 < total;
+		const double a = wbuf[i], b = two ? wbuf[i + 32] : 0.0;
+		const double ea = fast_exp(a, mt), eb = fast_exp(b, mt);
+		wbuf[i] = ea;
+		if (two) wbuf[i + 32] = eb;
+	}
 	__syncwarp();
 	double sum = 0.0;
-	{
-		const double *w = wbuf + eoff;
 #pragma unroll
-		for (int g = 0; g < 10; g++) {
-			const double x = ll[g] - top;
-			double e = x == 0.0 ? 1.0 : 0.0;
-			if (need >> g & 1) e = *w++;
-			sum += e;
-		}
+	for (int g = 0; g < 10; g++) {
+		const double x = ll[g] - top;
+		const double e0 = x == 0.0 ? 1.0 : 0.0;
+		sum += (need >> g & 1) ? wbuf[eoff + __popc(need & ((1u << g) - 1u))] : e0;
 	}
 	__syncwarp();
-	sum = log(sum);
+	sum = fast_log(sum, mt);          // sum is in [1, 10]
 #pragma unroll
 	for (int g = 0; g < 10; g++) prob[g] = div_by(ll[g] - top - sum, kLn10, kInvLn10);
 	return best;
@@ -294,33 +306,33 @@ __device__ __forceinline__ double strand_bias(const SiteCounts &s, int max_gt, c
 // Returns false for a site with no counted base (record zeroed, the caller sets skip).
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool call_site(const SiteCounts &s, int rf, const DevConst *__restrict__ dc,
-		const double (*__restrict__ qp)[4], const double *__restrict__ lfact_tab, uint64_t *rec,
-		double *__restrict__ wbuf, int lane) {
+		const Tables *__restrict__ tb, uint64_t *rec, double *__restrict__ wbuf, int lane) {
 	uint32_t tot[8];
 	int qual[8];
 	float tq = 0.0f;
 #pragma unroll
 	for (int j = 0; j < 8; j++) {
 		tot[j] = s.cnt[0][j] + s.cnt[1][j];
-		const float nn = (float)tot[j];
-		if (nn > 0) {
-			tq += s.qsum[j];
-			// float divide, double add, narrowed to float, floorf  (:50)
-			qual[j] = (int)floorf((float)(0.5 + (double)(s.qsum[j] / nn)));
-		} else qual[j] = 0;
+		// float divide, double add, narrowed to float, floorf (:50).  Branch-free: an empty class divides by 1 instead of
+		// 0 (0/0 would send the FP32 division into its special-case subroutine) and its result is discarded.
+		const float nn = tot[j] ? (float)tot[j] : 1.0f;
+		const int qj = (int)floorf((float)(0.5 + (double)(s.qsum[j] / nn)));
+		qual[j] = tot[j] ? qj : 0;
+		tq += tot[j] ? s.qsum[j] : 0.0f;
 	}
 	// the whole warp runs the model together (a lane without counts contributes nothing to the pooled lists)
 	double prob[10];
-	const int best = genotype_model(tot, qual, rf, dc, qp, prob, wbuf, lane);
+	const int best = genotype_model(tot, qual, rf, dc, tb, prob, wbuf, lane);
 	__syncwarp();                      // wbuf may alias this warp's output rows: everyone is done with it
 	if (!s.n) {
 #pragma unroll
 		for (int i = 0; i < 25; i++) rec[i] = 0;
 		return false;
 	}
-	const int aq = (int)floorf((float)(0.5 + (double)(tq / (float)s.n)));
-	const int mq = (int)(0.5 + sqrt((double)(s.mapq2 / (float)s.n)));
-	const double fs = strand_bias(s, best, lfact_tab);
+	const float fn = (float)s.n;
+	const int aq = (int)floorf((float)(0.5 + (double)(tq / fn)));
+	const int mq = (int)(0.5 + sqrt((double)(s.mapq2 / fn)));
+	const double fs = strand_bias(s, best, dc->lfact);
 #pragma unroll
 	for (int j = 0; j < 8; j++) rec[j] = tot[j];
 #pragma unroll

@@ -15,6 +15,7 @@
 //     inside the 2^24 envelope).
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "bsgpu_device.cuh"
 #include "bsgpu_launch.h"
@@ -56,31 +57,24 @@ __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory tables: q -> {k, ln k, ln(1/2+k), ln(1+k)} and log-factorials
+// shared-memory copy of the lookup tables (q -> {k, ln k, ln(1/2+k), ln(1+k)}, log/exp reduction tables)
 // ------------------------------------------------------------------------------------------------
-struct SmemTables {
-	double qp[kMaxQual + 1][4];
-	double lfact[256];
-};
-
-__device__ __forceinline__ void load_tables(SmemTables *st, const DevConst *__restrict__ dc, int tid, int nthr) {
-	const double *src = &dc->qp[0][0];
-	double *dst = &st->qp[0][0];
-	constexpr int nq = (kMaxQual + 1) * 4;
-	for (int i = tid; i < nq + 256; i += nthr) dst[i] = src[i];     // qp then lfact are contiguous in both structs
+__device__ __forceinline__ void load_tables(Tables *st, const DevConst *__restrict__ dc, int tid, int nthr) {
+	const double *src = (const double *)&dc->tab;
+	double *dst = (double *)st;
+	for (int i = tid; i < (int)(sizeof(Tables) / sizeof(double)); i += nthr) dst[i] = src[i];
 }
 
-// Write the CTA's staged output tile (nrec records of REC bytes, contiguous in smem) to global memory.
+// Write the CTA's staged output tile (nrec records of REC bytes, contiguous in smem) to global memory.  With the bulk
+// engine the copy is asynchronous: the issuing thread (tid 0) must call tma_store_wait() before the tile buffer is
+// written again or the CTA exits.
 template <int REC>
 __device__ __forceinline__ void store_tile(void *gdst, const uint64_t *stage, int nrec, bool bulk_ok, int tid, int nthr) {
 	const uint32_t bytes = (uint32_t)nrec * REC;
 	if (bulk_ok && (bytes & 15u) == 0) {
 		fence_async_smem();
 		__syncthreads();
-		if (tid == 0) {
-			tma_store_1d(gdst, stage, bytes);
-			tma_store_wait();
-		}
+		if (tid == 0) tma_store_1d(gdst, stage, bytes);
 	} else {
 		__syncthreads();
 		uint64_t *g = (uint64_t *)gdst;
@@ -89,70 +83,89 @@ __device__ __forceinline__ void store_tile(void *gdst, const uint64_t *stage, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// Likelihood kernel: one site per thread, kTileSites sites per CTA.
+// Likelihood kernel: one site per thread, kCallTile sites per tile, persistent CTAs striding over the tiles.
 //   in : pileup[n] (104 B each), ref[n] (codes 0..4)
 //   out: VCF ? gt_vcf[n] (208 B, ready = 1) : gt_meth[n] (200 B) + skip[n]
+// Per tile: the input records arrive by one TMA bulk copy that was issued while the previous tile was being computed;
+// threads lift their record into registers, the next tile's copy is issued, the warp-cooperative model runs, records
+// are staged in shared memory and leave by one TMA bulk store that drains while the next tile computes.
 // ------------------------------------------------------------------------------------------------
 constexpr int kCallTile = 128;
 
-template <bool VCF>
-__global__ void __launch_bounds__(kCallTile)
+template <bool VCF, int MINB>
+__global__ void __launch_bounds__(kCallTile, MINB)
 k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref, size_t n,
 		uint8_t *__restrict__ out, uint8_t *__restrict__ skip, const DevConst *__restrict__ dc, int bulk_ok) {
 	constexpr int REC = VCF ? 208 : 200;
 	constexpr int RW = REC / 8;
 	extern __shared__ __align__(128) uint8_t smem_raw[];
-	uint64_t *stage = (uint64_t *)smem_raw;                              // kCallTile * RW words (input tile aliases its head)
-	SmemTables *tabs = (SmemTables *)(smem_raw + kCallTile * REC);
+	uint64_t *stage = (uint64_t *)smem_raw;                              // kCallTile output records
+	uint8_t *inbuf = smem_raw + kCallTile * REC;                         // kCallTile input records
+	Tables *tabs = (Tables *)(inbuf + kCallTile * 104);
 	__shared__ uint64_t bar;
 
 	const int tid = threadIdx.x;
-	const size_t first = (size_t)blockIdx.x * kCallTile;
-	const int nrec = (int)min((size_t)kCallTile, n - first);
-	const uint32_t in_bytes = (uint32_t)nrec * 104u;
-	const bool bulk_in = bulk_ok && (in_bytes & 15u) == 0;
-	const uint8_t *gin = pileup + first * 104;
-
-	if (bulk_in) {
-		if (tid == 0) {
-			mbar_init(&bar, 1);
-			mbar_expect_tx(&bar, in_bytes);
-			tma_load_1d(stage, gin, in_bytes, &bar);
-		}
-	} else {
-		const uint32_t *g = (const uint32_t *)gin;
-		uint32_t *s = (uint32_t *)stage;
-		for (uint32_t i = tid; i < in_bytes / 4; i += kCallTile) s[i] = g[i];
-	}
+	const size_t ntiles = (n + kCallTile - 1) / kCallTile;
 	load_tables(tabs, dc, tid, kCallTile);
-	const int rf = tid < nrec ? ref[first + tid] : 0;
+	if (tid == 0) mbar_init(&bar, 1);
 	__syncthreads();
-	if (bulk_in) mbar_wait(&bar, 0);
 
-	SiteCounts s;
-	if (tid < nrec) {
-		const uint2 *rec = (const uint2 *)(smem_raw + tid * 104);
-		uint32_t w[26];
+	auto tile_bulk = [&](size_t tile) {          // can this tile's input travel by the bulk engine?
+		const size_t first = tile * kCallTile;
+		const uint32_t bytes = (uint32_t)min((size_t)kCallTile, n - first) * 104u;
+		return bulk_ok && (bytes & 15u) == 0;
+	};
+	auto issue = [&](size_t tile) {
+		const size_t first = tile * kCallTile;
+		const uint32_t bytes = (uint32_t)min((size_t)kCallTile, n - first) * 104u;
+		mbar_expect_tx(&bar, bytes);
+		tma_load_1d(inbuf, pileup + first * 104, bytes, &bar);
+	};
+	size_t tile = blockIdx.x;
+	if (tile < ntiles && tid == 0 && tile_bulk(tile)) issue(tile);
+	uint32_t phase = 0;
+	for (; tile < ntiles; tile += gridDim.x) {
+		const size_t first = tile * kCallTile;
+		const int nrec = (int)min((size_t)kCallTile, n - first);
+		const int rf = tid < nrec ? ref[first + tid] : 0;
+		if (tile_bulk(tile)) {
+			mbar_wait(&bar, phase);
+			phase ^= 1;
+		} else {
+			const uint32_t *g = (const uint32_t *)(pileup + first * 104);
+			uint32_t *sm = (uint32_t *)inbuf;
+			for (int i = tid; i < nrec * 26; i += kCallTile) sm[i] = g[i];
+			__syncthreads();
+		}
+		SiteCounts s;
+		if (tid < nrec) {
+			const uint2 *rec = (const uint2 *)(inbuf + tid * 104);
+			uint32_t w[26];
 #pragma unroll
-		for (int i = 0; i < 13; i++) { const uint2 v = rec[i]; w[2 * i] = v.x; w[2 * i + 1] = v.y; }
+			for (int i = 0; i < 13; i++) { const uint2 v = rec[i]; w[2 * i] = v.x; w[2 * i + 1] = v.y; }
 #pragma unroll
-		for (int j = 0; j < 8; j++) { s.cnt[0][j] = w[j]; s.cnt[1][j] = w[8 + j]; s.qsum[j] = __uint_as_float(w[17 + j]); }
-		s.n = w[16];
-		s.mapq2 = __uint_as_float(w[25]);
-	} else s.n = 0;
-	__syncthreads();                       // every thread holds its input: the tile buffer can now take the output
-	uint64_t *rec = stage + tid * RW;
-	// pooled-argument list of this warp: the (still unused) output rows of its own 32 sites
-	double *wbuf = (double *)(stage + (tid & ~31) * RW);
-	if (tid >= nrec) {
+			for (int j = 0; j < 8; j++) { s.cnt[0][j] = w[j]; s.cnt[1][j] = w[8 + j]; s.qsum[j] = __uint_as_float(w[17 + j]); }
+			s.n = w[16];
+			s.mapq2 = __uint_as_float(w[25]);
+		} else {
 #pragma unroll
-		for (int j = 0; j < 8; j++) { s.cnt[0][j] = s.cnt[1][j] = 0; s.qsum[j] = 0.0f; }
-		s.mapq2 = 0.0f;
+			for (int j = 0; j < 8; j++) { s.cnt[0][j] = s.cnt[1][j] = 0; s.qsum[j] = 0.0f; }
+			s.n = 0;
+			s.mapq2 = 0.0f;
+		}
+		if (tid == 0) tma_store_wait();        // the previous tile's output has left the staging buffer
+		__syncthreads();                       // every thread holds its input; staging buffer free
+		const size_t next = tile + gridDim.x;
+		if (next < ntiles && tid == 0 && tile_bulk(next)) issue(next);
+		uint64_t *rec = stage + tid * RW;
+		// pooled-argument list of this warp: the (not yet written) output rows of its own 32 sites
+		double *wbuf = (double *)(stage + (tid & ~31) * RW);
+		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, tid & 31);
+		if (VCF) rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
+		else if (tid < nrec) skip[first + tid] = called ? 0 : 1;
+		store_tile<REC>(out + first * REC, stage, nrec, bulk_ok, tid, kCallTile);
 	}
-	const bool called = call_site(s, rf, dc, tabs->qp, tabs->lfact, rec, wbuf, tid & 31);
-	if (VCF) rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
-	else if (tid < nrec) skip[first + tid] = called ? 0 : 1;
-	store_tile<REC>(out + first * REC, stage, nrec, bulk_ok, tid, kCallTile);
+	if (tid == 0) tma_store_wait();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -160,12 +173,11 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 // ------------------------------------------------------------------------------------------------
 constexpr int kPileTile = 256;
 
-struct Seg { uint32_t pos, off; uint16_t len; uint8_t mapq, flags; uint32_t pad; };
-static_assert(sizeof(Seg) == 16, "segment record is 16 bytes");
 
 __global__ void k_bin_count(const Seg *__restrict__ segs, size_t nseg, uint32_t x, uint32_t ntiles, uint32_t *__restrict__ counts) {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= nseg) return;
+	if (!segs[i].len) return;                 // empty slots (the normaliser leaves them for absent mates)
 	const uint32_t pos = segs[i].pos;
 	// a segment that starts before the window still contributes to tile 0 (clipped there)
 	uint32_t t = pos >= x ? (pos - x) / kPileTile : 0;
@@ -207,6 +219,7 @@ __global__ void k_bin_scatter(const Seg *__restrict__ segs, size_t nseg, uint32_
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= nseg) return;
 	const Seg s = segs[i];
+	if (!s.len) return;
 	uint32_t t = s.pos >= x ? (s.pos - x) / kPileTile : 0;
 	if (t < ntiles) sorted[atomicAdd(cursor + t, 1u)] = s;
 }
@@ -214,14 +227,15 @@ __global__ void k_bin_scatter(const Seg *__restrict__ segs, size_t nseg, uint32_
 // ------------------------------------------------------------------------------------------------
 // Pileup by gather.  CTA = 128 threads = 128 consecutive sites (half a bin).  Candidate segments are the two bins
 // [t-1, t] (a segment is at most 256 long).  Each warp filters 32 candidates at a time with one ballot, then walks the
-// hits; a lane adds the byte at its own site into byte/halfword-packed register counters keyed by
-// (strand index, bisulfite strand), which are widened every 255 hits.
+// hits; a lane adds the byte at its own site into halfword-packed 64-bit register counters keyed by
+// (strand index, bisulfite strand), which are widened every 1500 hits.
 //   MODE 0: write pileup[] (104 B / site)       MODE 1: run the model and write gt_vcf[] (208 B / site)
 // ------------------------------------------------------------------------------------------------
 struct Packed {
-	uint32_t c[2][3];      // [ori][bs_strand] : 4 x 8-bit counters indexed by base
-	uint64_t q[3];         // [bs_strand]      : 4 x 16-bit quality sums indexed by base
+	uint64_t c[2][3];      // [ori][bs_strand] : 4 x 16-bit counters indexed by base
+	uint64_t q[3];         // [bs_strand]      : 4 x 16-bit quality sums indexed by base (q <= 43: good for 1524 hits)
 };
+constexpr uint32_t kWidenEvery = 1500;
 
 __device__ __forceinline__ void widen(Packed &p, uint32_t cnt[2][8], uint32_t qs[8]) {
 	// class of (bs_strand, base): st0 {0,1,2,3}  st1=C2T {0,5,2,7}  st2=G2A {4,1,6,3}   (src/call_genotypes.c:17-19)
@@ -231,7 +245,7 @@ __device__ __forceinline__ void widen(Packed &p, uint32_t cnt[2][8], uint32_t qs
 #pragma unroll
 		for (int b = 0; b < 4; b++) {
 #pragma unroll
-			for (int o = 0; o < 2; o++) cnt[o][cls[st][b]] += (p.c[o][st] >> (8 * b)) & 0xffu;
+			for (int o = 0; o < 2; o++) cnt[o][cls[st][b]] += (uint32_t)(p.c[o][st] >> (16 * b)) & 0xffffu;
 			qs[cls[st][b]] += (uint32_t)(p.q[st] >> (16 * b)) & 0xffffu;
 		}
 		p.c[0][st] = p.c[1][st] = 0;
@@ -250,8 +264,8 @@ k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_sta
 	constexpr int RW = REC / 8;
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	uint64_t *stage = (uint64_t *)smem_raw;
-	SmemTables *tabs = (SmemTables *)(smem_raw + kPileThreads * REC);
-	__shared__ Seg cand[kPileThreads];
+	Tables *tabs = (Tables *)(smem_raw + kPileThreads * REC);
+	__shared__ uint4 cand[kPileThreads];      // {pos, off, len, mapq^2 | st << 16 | ori << 18}
 
 	const int tid = threadIdx.x, lane = tid & 31;
 	const uint32_t site0 = tile0 * kPileTile + blockIdx.x * kPileThreads;     // first site of this CTA
@@ -275,13 +289,17 @@ k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_sta
 	for (uint32_t base = c_lo; base < c_hi; base += kPileThreads) {
 		const uint32_t nc = min((uint32_t)kPileThreads, c_hi - base);
 		__syncthreads();
-		if ((uint32_t)tid < nc) cand[tid] = segs[base + tid];
+		if ((uint32_t)tid < nc) {
+			const Seg sg = segs[base + tid];
+			const uint32_t mq = sg.mapq;
+			cand[tid] = make_uint4(sg.pos, sg.off, sg.len, mq * mq | ((uint32_t)(sg.flags >> 1) & 3u) << 16 | ((uint32_t)sg.flags & 1u) << 18);
+		}
 		__syncthreads();
 		for (uint32_t g = 0; g < nc; g += 32) {
 			bool hit = false;
 			if (g + lane < nc) {
-				const Seg &c = cand[g + lane];
-				hit = c.pos < wpos0 + 32 && c.pos + c.len > wpos0;
+				const uint4 c = cand[g + lane];
+				hit = c.x < wpos0 + 32 && c.x + c.z > wpos0;
 			}
 			uint32_t m = __ballot_sync(0xffffffffu, hit);
 			while (m) {
@@ -293,30 +311,31 @@ k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_sta
 					const bool valid = m != 0;
 					const int b = valid ? __ffs(m) - 1 : 0;
 					m &= m - 1;                                       // 0 stays 0
-					raw[u] = *(const uint4 *)&cand[g + b];            // broadcast read
+					raw[u] = cand[g + b];                             // broadcast read
 					if (!valid) raw[u].z = 0;                         // len 0: contributes nothing
 				}
 #pragma unroll
 				for (int u = 0; u < 4; u++) {
-					const uint32_t d = mypos - raw[u].x, len = raw[u].z & 0xffffu;
-					byte[u] = d < len ? (uint32_t)__ldg(bases + (size_t)raw[u].y + d) : 0u;
+					const uint32_t d = mypos - raw[u].x;
+					byte[u] = d < raw[u].z ? (uint32_t)__ldg(bases + (size_t)raw[u].y + d) : 0u;
 				}
 #pragma unroll
 				for (int u = 0; u < 4; u++) {
-					const uint32_t mapq = (raw[u].z >> 16) & 0xffu, flags = raw[u].z >> 24;
 					const uint32_t q = byte[u] >> 2, bs = byte[u] & 3u;
 					const uint32_t ok = (q >= min_qual) & (q != (uint32_t)kFltQual);       // q = 0 for "no byte"
-					const uint32_t st = (flags >> 1) & 3u, ori = flags & 1u;
-					const uint32_t inc = ok << (8 * bs);
-					const uint64_t qinc = (uint64_t)(ok ? q : 0u) << (16 * bs);
-					// (ori, st) are warp-uniform: a uniform branch picks the packed register
-					if (st == 0) { pk.q[0] += qinc; if (ori) pk.c[1][0] += inc; else pk.c[0][0] += inc; }
-					else if (st == 1) { pk.q[1] += qinc; if (ori) pk.c[1][1] += inc; else pk.c[0][1] += inc; }
-					else { pk.q[2] += qinc; if (ori) pk.c[1][2] += inc; else pk.c[0][2] += inc; }
-					mq2 += ok ? mapq * mapq : 0u;
+					const uint64_t cinc = (uint64_t)ok << (16 * bs);                      // +1 in the 16-bit field of this base
+					const uint64_t qinc = cinc * q;
+					const uint32_t meta = raw[u].w;
+					// (st, ori) are warp-uniform: uniform branches pick the packed registers
+					switch ((meta >> 16) & 3u) {
+					case 0: pk.q[0] += qinc; if (meta >> 18) pk.c[1][0] += cinc; else pk.c[0][0] += cinc; break;
+					case 1: pk.q[1] += qinc; if (meta >> 18) pk.c[1][1] += cinc; else pk.c[0][1] += cinc; break;
+					default: pk.q[2] += qinc; if (meta >> 18) pk.c[1][2] += cinc; else pk.c[0][2] += cinc; break;
+					}
+					mq2 += ok * (meta & 0xffffu);
 				}
 				since_widen += 4;
-				if (since_widen > 251) { widen(pk, cnt, qs); since_widen = 0; }      // 8-bit fields hold 255
+				if (since_widen > kWidenEvery) { widen(pk, cnt, qs); since_widen = 0; }
 			}
 		}
 	}
@@ -347,12 +366,13 @@ k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_sta
 		const int rf = tid < nrec ? ref[site0 + tid] : 0;
 		__syncthreads();                    // tables loaded
 		double *wbuf = (double *)(stage + (tid & ~31) * RW);
-		const bool called = call_site(s, rf, dc, tabs->qp, tabs->lfact, rec, wbuf, lane);
+		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, lane);
 		rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
 		const uint32_t nc = __syncthreads_count(called);
 		if (tid == 0 && nc) atomicAdd(counters, (unsigned long long)nc);
 	}
 	store_tile<REC>(out + (size_t)blockIdx.x * kPileThreads * REC, stage, nrec, true, tid, kPileThreads);
+	if (tid == 0) tma_store_wait();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -480,15 +500,35 @@ __global__ void k_synth_reads(uint64_t seed, uint32_t x, uint32_t sz, uint32_t r
 // ------------------------------------------------------------------------------------------------
 #define LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
-static size_t call_smem(bool vcf) { return (size_t)kCallTile * (vcf ? 208 : 200) + sizeof(SmemTables); }
-static size_t pile_smem(int mode) { return (size_t)kPileThreads * (mode ? 208 : 104) + sizeof(SmemTables); }
+static size_t call_smem(bool vcf) { return (size_t)kCallTile * ((vcf ? 208 : 200) + 104) + sizeof(Tables); }
+static size_t pile_smem(int mode) { return (size_t)kPileThreads * (mode ? 208 : 104) + sizeof(Tables); }
+
+static int g_sms = 148;
+static int g_call_minb = 4;          // resident CTAs per SM the likelihood kernel is compiled for (4 or 5)
+static int g_call_ctas[2][2];        // [minb == 5][vcf] measured occupancy
+
+template <typename K>
+static cudaError_t prep(K kernel, size_t smem, int threads, int *ctas_per_sm) {
+	cudaError_t e;
+	if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+	if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+	if (ctas_per_sm) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, threads, smem);
+	return cudaSuccess;
+}
 
 cudaError_t configure_kernels() {
 	cudaError_t e;
-	if ((e = cudaFuncSetAttribute(k_call_sites<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)call_smem(false))) != cudaSuccess) return e;
-	if ((e = cudaFuncSetAttribute(k_call_sites<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)call_smem(true))) != cudaSuccess) return e;
-	if ((e = cudaFuncSetAttribute(k_pileup_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pile_smem(0))) != cudaSuccess) return e;
-	if ((e = cudaFuncSetAttribute(k_pileup_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pile_smem(1))) != cudaSuccess) return e;
+	int dev = 0;
+	if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+	if ((e = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+	const char *env = getenv("BSGPU_CALL_MINB");          // tuning knob: 4 (default) or 5 resident CTAs per SM
+	if (env && atoi(env) == 5) g_call_minb = 5;
+	if ((e = prep(k_call_sites<false, 4>, call_smem(false), kCallTile, &g_call_ctas[0][0])) != cudaSuccess) return e;
+	if ((e = prep(k_call_sites<true, 4>, call_smem(true), kCallTile, &g_call_ctas[0][1])) != cudaSuccess) return e;
+	if ((e = prep(k_call_sites<false, 5>, call_smem(false), kCallTile, &g_call_ctas[1][0])) != cudaSuccess) return e;
+	if ((e = prep(k_call_sites<true, 5>, call_smem(true), kCallTile, &g_call_ctas[1][1])) != cudaSuccess) return e;
+	if ((e = prep(k_pileup_tile<0>, pile_smem(0), kPileThreads, nullptr)) != cudaSuccess) return e;
+	if ((e = prep(k_pileup_tile<1>, pile_smem(1), kPileThreads, nullptr)) != cudaSuccess) return e;
 	return cudaSuccess;
 }
 
@@ -496,9 +536,19 @@ cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, voi
 		const DevConst *dc, cudaStream_t stream, int *launches) {
 	if (!n) return cudaSuccess;
 	const bool bulk_ok = (((uintptr_t)pileup | (uintptr_t)out) & 15u) == 0;
-	const unsigned grid = (unsigned)((n + kCallTile - 1) / kCallTile);
-	if (vcf) k_call_sites<true><<<grid, kCallTile, call_smem(true), stream>>>((const uint8_t *)pileup, (const uint8_t *)ref, n, (uint8_t *)out, nullptr, dc, bulk_ok);
-	else k_call_sites<false><<<grid, kCallTile, call_smem(false), stream>>>((const uint8_t *)pileup, (const uint8_t *)ref, n, (uint8_t *)out, (uint8_t *)skip, dc, bulk_ok);
+	const size_t ntiles = (n + kCallTile - 1) / kCallTile;
+	const int five = g_call_minb == 5;
+	const size_t resident = (size_t)g_sms * (size_t)(g_call_ctas[five][vcf] > 0 ? g_call_ctas[five][vcf] : 1);
+	const unsigned grid = (unsigned)(ntiles < resident ? ntiles : resident);       // persistent: one CTA per resident slot
+	const uint8_t *p = (const uint8_t *)pileup, *r = (const uint8_t *)ref;
+	uint8_t *o = (uint8_t *)out, *sk = (uint8_t *)skip;
+	if (vcf) {
+		if (five) k_call_sites<true, 5><<<grid, kCallTile, call_smem(true), stream>>>(p, r, n, o, nullptr, dc, bulk_ok);
+		else k_call_sites<true, 4><<<grid, kCallTile, call_smem(true), stream>>>(p, r, n, o, nullptr, dc, bulk_ok);
+	} else {
+		if (five) k_call_sites<false, 5><<<grid, kCallTile, call_smem(false), stream>>>(p, r, n, o, sk, dc, bulk_ok);
+		else k_call_sites<false, 4><<<grid, kCallTile, call_smem(false), stream>>>(p, r, n, o, sk, dc, bulk_ok);
+	}
 	*launches += 1;
 	LAUNCH_CHECK();
 	return cudaSuccess;

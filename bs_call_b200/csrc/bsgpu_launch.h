@@ -8,6 +8,10 @@ namespace bsgpu {
 
 struct DevConst;
 
+// device-side view of bsgpu_seg (include/bsgpu.h)
+struct Seg { uint32_t pos, off; uint16_t len; uint8_t mapq, flags; uint32_t pad; };
+static_assert(sizeof(Seg) == 16, "segment record is 16 bytes");
+
 cudaError_t configure_kernels();
 
 cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, void *out, void *skip, bool vcf,
@@ -32,6 +36,11 @@ cudaError_t launch_synth_sites(uint64_t seed, uint64_t first, size_t n, double m
 size_t synth_block_nseg(uint32_t sz, uint32_t read_len, double depth);
 cudaError_t launch_synth_block(uint64_t seed, uint32_t x, uint32_t sz, uint32_t read_len, double depth,
 		void *segs, void *bases, void *ref, cudaStream_t stream, int *launches);
+
+// raw templates -> reads in reference coordinates + segment records (bsgpu_normalise.cu)
+cudaError_t launch_normalise(const void *tmpl, size_t n, const void *bases, void *ev_work, const void *out_off, void *obases,
+		void *segs, uint32_t segs_per_mate, uint32_t x, uint32_t y, const uint32_t left_trim[2], const uint32_t right_trim[2],
+		unsigned long long *counters, cudaStream_t stream, int *launches);
 
 constexpr int kPileTileSites = 256;
 

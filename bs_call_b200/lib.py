@@ -25,6 +25,7 @@ EXPORTS = [
     "bsgpu_process_block",
     "bsgpu_call_sites_dev", "bsgpu_call_sites_vcf_dev", "bsgpu_pileup_block_dev", "bsgpu_call_block_dev",
     "bsgpu_synth_sites_dev", "bsgpu_synth_block_nseg", "bsgpu_synth_block_dev",
+    "bsgpu_math_probe",
 ]
 
 
@@ -217,6 +218,15 @@ class BsGpu:
         self._check(self.lib.bsgpu_stage_templates(_ptr(templates), C.c_size_t(len(templates)), _ptr(bases), C.c_uint32(x),
                                                    C.c_uint32(y), _ptr(segs), C.byref(ns)))
         return segs[:ns.value]
+
+
+def math_probe(x):
+    """(log, exp) of the kernels' table-driven routines, evaluated on the host (bsgpu_math_probe)."""
+    lib = load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    lo, ex = np.zeros_like(x), np.zeros_like(x)
+    lib.bsgpu_math_probe(_ptr(x), C.c_size_t(len(x)), _ptr(lo), _ptr(ex))
+    return lo, ex
 
 
 def stage_templates_host(templates, bases, x, y):

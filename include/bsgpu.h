@@ -184,6 +184,11 @@ int bsgpu_synth_block_dev(bsgpu_ctx *ctx, uint64_t seed, uint32_t x, uint32_t sz
 		void *d_segs, size_t seg_cap, void *d_bases, size_t base_cap, void *d_ref, size_t *nseg, size_t *nbases,
 		void *stream);
 
+/* ---- diagnostics ---- */
+/* Evaluates, on the host, the table-driven log / exp the kernels use (same source; both sides are FMA-exact, so
+ * these are the device's values).  out_log / out_exp may be NULL.  log: x positive normal; exp: x in [-700, 0]. */
+int bsgpu_math_probe(const double *x, size_t n, double *out_log, double *out_exp);
+
 #ifdef __cplusplus
 }
 #endif

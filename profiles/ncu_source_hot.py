@@ -4,6 +4,7 @@ instructions executed, samples, dominant stall reasons.  usage: ncu_source_hot.p
 import csv, io, subprocess, sys, collections
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+SORTKEY = sys.argv[3] if len(sys.argv) > 3 else "samples"
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 # the dump is a sequence of per-file sections: ("File Path", p), ("Function Name", f), header row, data rows
@@ -37,6 +38,6 @@ for r in rows:
 # rows repeat per kernel instance of the same function; totals are still proportional
 tot_inst = sum(a["inst"] for a in agg.values()); tot_s = sum(a["samples"] for a in agg.values())
 print("total inst %.3g samples %d" % (tot_inst, tot_s))
-for key, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
+for key, a in sorted(agg.items(), key=lambda kv: -kv[1][SORTKEY])[:top]:
     st = ", ".join("%s %.0f%%" % (k[6:], 100 * v / max(a["samples"], 1)) for k, v in a["stalls"].most_common(3))
     print("%-22s:%-4d inst %5.1f%% thr/inst %4.1f samples %5.1f%%  [%s]  %s" % (key[0], key[1], 100 * a["inst"] / max(tot_inst, 1), a["tinst"] / max(a["inst"], 1), 100 * a["samples"] / max(tot_s, 1), st, a["src"].strip()[:70]))

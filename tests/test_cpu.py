@@ -118,3 +118,25 @@ def test_stage_rejects_bad_input():
         bslib.stage_templates_host(t, np.full(4, 37 << 2, dtype=np.uint8), 10, 100)
     segs = bslib.stage_templates_host(t, np.full(4, 37 << 2, dtype=np.uint8), 1, 6)     # clipped at y
     assert len(segs) == 1 and segs[0]["len"] == 2
+
+
+def test_fast_math_accuracy():
+    """The kernels' table-driven log/exp (bsgpu_math.cuh), evaluated by the host build of the same source, against
+    long double.  Domains are the ones the genotype model produces."""
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(1e-6, 3.0, 400000), np.exp(rng.uniform(np.log(1e-6), np.log(3.0), 400000)),
+                        1.0 + np.exp(rng.uniform(np.log(1e-16), np.log(9.0), 400000)), [1.0, 2.0, 0.5, 1.375, 0.6875]])
+    lo, _ = bslib.math_probe(x)
+    want = np.log(x.astype(np.longdouble))
+    err = np.abs(lo.astype(np.longdouble) - want)
+    assert lo[-5] == 0.0                                     # log(1) is exactly 0
+    assert float(err.max()) < 2.5e-15                        # absolute, at |log| ~ 14
+    big = np.abs(lo) > 0.01
+    assert float((err / np.spacing(np.abs(lo)))[big].max()) < 2.0      # ulps
+    m = (x >= 1.0) & (want > 0)
+    assert float((err[m] / want[m]).max()) < 4e-16           # log-sum-exp arguments keep relative accuracy down to 1+eps
+    xe = np.concatenate([rng.uniform(-45.5, 0.0, 800000), [0.0, -45.0]])
+    _, ex = bslib.math_probe(xe)
+    we = np.exp(xe.astype(np.longdouble))
+    assert float(np.abs((ex.astype(np.longdouble) - we) / we).max()) < 2.3e-16      # about 1 ulp
+    assert ex[-2] == 1.0

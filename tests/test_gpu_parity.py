@@ -256,3 +256,53 @@ def test_synthetic_block_fused_vs_oracle(gpu, oracle):
     v = d_v.cpu().numpy().view(GT_VCF)
     n = util.assert_gt_meth_close(v["gtm"], v["skip"], wout, wskip)
     assert n > 0.99 * sz - 400
+
+
+@pytest.mark.parametrize("name", BLOCKS)
+def test_process_block_golden(name):
+    """raw templates -> gt_vcf[] with trimming, soft clips, mate overlap and indel normalisation done on the device,
+    against what the reference's process_template_vector -> call_genotypes_ML produced"""
+    g = util.load_golden(name)
+    gpu = bslib.BsGpu(left_trim=tuple(int(v) for v in g["left_trim"]), right_trim=tuple(int(v) for v in g["right_trim"]))
+    x, vcf = gpu.process_block(g["templates"], g["bases"], g["misms"], g["ref"], int(g["y"]))
+    assert x == int(g["x"])
+    util.assert_vcf_close(vcf, g["vcf"])
+    gpu.close()
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_process_block_random_vs_oracle(case):
+    from oracle.bindings import Oracle
+    kw = [dict(depth=30, read_len=150, paired=True, frag_mean=220, indel_frac=0.3, clip_frac=0.3),
+          dict(depth=10, read_len=100, paired=True, frag_mean=120, frag_sd=40, indel_frac=0.6, clip_frac=0.4),
+          dict(depth=80, read_len=75, paired=False, indel_frac=0.3, clip_frac=0.3, nonconv_frac=0.3),
+          dict(depth=25, read_len=250, paired=True, frag_mean=300, single_mate_frac=0.2, indel_frac=0.4, n_frac=0.05)][case]
+    trims = [((0, 0), (0, 0)), ((5, 5), (3, 3)), ((10, 0), (0, 10)), ((1, 2), (3, 4))][case]
+    rng = np.random.default_rng(300 + case)
+    ref = blockgen.random_reference(rng, 40000, n_runs=3)
+    T, B, M, y = blockgen.make_block(rng, ref, 300, 36000, **kw)
+    o = Oracle(left_trim=trims[0], right_trim=trims[1])
+    gpu = bslib.BsGpu(left_trim=trims[0], right_trim=trims[1])
+    first = int(T[0]["forward_position"]) or int(T[0]["reverse_position"])
+    x = first - 2 if first > 2 else 1
+    refw = ref[x - 1:x - 1 + (y - x + 1)]
+    xo, pile, want = o.process_block(T, B, M, refw, y)
+    xg, vcf = gpu.process_block(T, B, M, refw, y)
+    assert xg == xo == x
+    n = util.assert_vcf_close(vcf, want)
+    assert n > 30000
+    gpu.close()
+
+
+def test_process_block_rejects_bad_cigar(gpu):
+    from bs_call_b200.records import MISMS, TEMPLATE
+    t = np.zeros(1, dtype=TEMPLATE)
+    t["forward_position"] = 10
+    t["present"][0, 0] = 1
+    t["read_len"][0, 0] = 20
+    t["reference_span"][0, 0] = 20
+    t["mm_n"][0, 0] = 1
+    m = np.zeros(1, dtype=MISMS)
+    m[0] = (3, 0, 25)                                     # soft clip longer than the read: fatal in the reference
+    with pytest.raises(bslib.BsGpuError):
+        gpu.process_block(t, np.full(20, 37 << 2, dtype=np.uint8), m, np.ones(64, dtype=np.uint8), 30)
