@@ -325,6 +325,30 @@ def main():
                  "sites_per_s": fcalled / (fms * 1e-3), "ms": fms, "sites_called": fcalled,
                  "roofline": {"bound": "hbm", "achieved": fbytes / (fms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": fbytes / (fms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_site": fbytes / fsz}}
+        # the same block as two kernels: pileup[] to HBM, then the likelihood kernel over it
+        d_p = torch.empty(fsz * 104 + 16, dtype=torch.uint8, device="cuda")
+        def two():
+            gpu.pileup_block_dev(d_seg.data_ptr(), ns, d_b.data_ptr(), 1000, fsz, d_p.data_ptr(), stream)
+            gpu.call_sites_vcf_dev(d_p.data_ptr(), d_r.data_ptr(), fsz, d_v.data_ptr(), stream)
+        for _ in range(3):
+            two()
+        barrier()
+        p0, p1, p2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        p0.record()
+        for _ in range(args.steps):
+            gpu.pileup_block_dev(d_seg.data_ptr(), ns, d_b.data_ptr(), 1000, fsz, d_p.data_ptr(), stream)
+        p1.record()
+        for _ in range(args.steps):
+            two()
+        p2.record()
+        barrier()
+        pms, tms = p0.elapsed_time(p1) / args.steps, p1.elapsed_time(p2) / args.steps
+        pbytes = ns * (L + 16) + fsz * 104
+        fused["pileup_only"] = {"kernel": "k_pileup_tile<pileup> (+3 binning kernels)", "ms": pms, "sites_per_s": fcalled / (pms * 1e-3),
+                                "roofline": {"bound": "hbm", "achieved": pbytes / (pms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                             "frac": pbytes / (pms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_site": pbytes / fsz}}
+        fused["two_kernel"] = {"ms": tms, "sites_per_s": fcalled / (tms * 1e-3)}
+        del d_p
         del d_seg, d_b, d_r, d_v
     except Exception as e:            # reported, never hidden
         fused = {"error": str(e)}

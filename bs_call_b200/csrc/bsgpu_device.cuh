@@ -313,10 +313,11 @@ __device__ __forceinline__ bool call_site(const SiteCounts &s, int rf, const Dev
 #pragma unroll
 	for (int j = 0; j < 8; j++) {
 		tot[j] = s.cnt[0][j] + s.cnt[1][j];
-		// float divide, double add, narrowed to float, floorf (:50).  Branch-free: an empty class divides by 1 instead of
-		// 0 (0/0 would send the FP32 division into its special-case subroutine) and its result is discarded.
+		// float divide, double add, narrowed to float, floorf (:50).  Branch-free: an empty class computes 1/1 instead of
+		// 0/0 (a zero or NaN operand sends the FP32 division into its special-case subroutine) and is discarded.
 		const float nn = tot[j] ? (float)tot[j] : 1.0f;
-		const int qj = (int)floorf((float)(0.5 + (double)(s.qsum[j] / nn)));
+		const float qs = tot[j] ? s.qsum[j] : 1.0f;
+		const int qj = (int)floorf((float)(0.5 + (double)(qs / nn)));
 		qual[j] = tot[j] ? qj : 0;
 		tq += tot[j] ? s.qsum[j] : 0.0f;
 	}
@@ -331,7 +332,7 @@ __device__ __forceinline__ bool call_site(const SiteCounts &s, int rf, const Dev
 	}
 	const float fn = (float)s.n;
 	const int aq = (int)floorf((float)(0.5 + (double)(tq / fn)));
-	const int mq = (int)(0.5 + sqrt((double)(s.mapq2 / fn)));
+	const int mq = (int)(0.5 + sqrt((double)(s.mapq2 / fn)));      // MAPQ 0 reads make this 0/n: rare, takes the slow path
 	const double fs = strand_bias(s, best, dc->lfact);
 #pragma unroll
 	for (int j = 0; j < 8; j++) rec[j] = tot[j];

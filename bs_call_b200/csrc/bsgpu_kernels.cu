@@ -95,7 +95,8 @@ constexpr int kCallTile = 128;
 template <bool VCF, int MINB>
 __global__ void __launch_bounds__(kCallTile, MINB)
 k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref, size_t n,
-		uint8_t *__restrict__ out, uint8_t *__restrict__ skip, const DevConst *__restrict__ dc, int bulk_ok) {
+		uint8_t *__restrict__ out, uint8_t *__restrict__ skip, const DevConst *__restrict__ dc, int bulk_ok,
+		unsigned long long *__restrict__ counters) {
 	constexpr int REC = VCF ? 208 : 200;
 	constexpr int RW = REC / 8;
 	extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -123,7 +124,7 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 	};
 	size_t tile = blockIdx.x;
 	if (tile < ntiles && tid == 0 && tile_bulk(tile)) issue(tile);
-	uint32_t phase = 0;
+	uint32_t phase = 0, ncalled = 0;
 	for (; tile < ntiles; tile += gridDim.x) {
 		const size_t first = tile * kCallTile;
 		const int nrec = (int)min((size_t)kCallTile, n - first);
@@ -161,11 +162,14 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 		// pooled-argument list of this warp: the (not yet written) output rows of its own 32 sites
 		double *wbuf = (double *)(stage + (tid & ~31) * RW);
 		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, tid & 31);
+		ncalled += called;
 		if (VCF) rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
 		else if (tid < nrec) skip[first + tid] = called ? 0 : 1;
 		store_tile<REC>(out + first * REC, stage, nrec, bulk_ok, tid, kCallTile);
 	}
 	if (tid == 0) tma_store_wait();
+	ncalled = __reduce_add_sync(0xffffffffu, ncalled);
+	if ((tid & 31) == 0 && ncalled) atomicAdd(counters, (unsigned long long)ncalled);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -533,7 +537,7 @@ cudaError_t configure_kernels() {
 }
 
 cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, void *out, void *skip, bool vcf,
-		const DevConst *dc, cudaStream_t stream, int *launches) {
+		const DevConst *dc, unsigned long long *counters, cudaStream_t stream, int *launches) {
 	if (!n) return cudaSuccess;
 	const bool bulk_ok = (((uintptr_t)pileup | (uintptr_t)out) & 15u) == 0;
 	const size_t ntiles = (n + kCallTile - 1) / kCallTile;
@@ -543,11 +547,11 @@ cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, voi
 	const uint8_t *p = (const uint8_t *)pileup, *r = (const uint8_t *)ref;
 	uint8_t *o = (uint8_t *)out, *sk = (uint8_t *)skip;
 	if (vcf) {
-		if (five) k_call_sites<true, 5><<<grid, kCallTile, call_smem(true), stream>>>(p, r, n, o, nullptr, dc, bulk_ok);
-		else k_call_sites<true, 4><<<grid, kCallTile, call_smem(true), stream>>>(p, r, n, o, nullptr, dc, bulk_ok);
+		if (five) k_call_sites<true, 5><<<grid, kCallTile, call_smem(true), stream>>>(p, r, n, o, nullptr, dc, bulk_ok, counters);
+		else k_call_sites<true, 4><<<grid, kCallTile, call_smem(true), stream>>>(p, r, n, o, nullptr, dc, bulk_ok, counters);
 	} else {
-		if (five) k_call_sites<false, 5><<<grid, kCallTile, call_smem(false), stream>>>(p, r, n, o, sk, dc, bulk_ok);
-		else k_call_sites<false, 4><<<grid, kCallTile, call_smem(false), stream>>>(p, r, n, o, sk, dc, bulk_ok);
+		if (five) k_call_sites<false, 5><<<grid, kCallTile, call_smem(false), stream>>>(p, r, n, o, sk, dc, bulk_ok, counters);
+		else k_call_sites<false, 4><<<grid, kCallTile, call_smem(false), stream>>>(p, r, n, o, sk, dc, bulk_ok, counters);
 	}
 	*launches += 1;
 	LAUNCH_CHECK();

@@ -15,7 +15,7 @@ static_assert(sizeof(Seg) == 16, "segment record is 16 bytes");
 cudaError_t configure_kernels();
 
 cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, void *out, void *skip, bool vcf,
-		const DevConst *dc, cudaStream_t stream, int *launches);
+		const DevConst *dc, unsigned long long *counters, cudaStream_t stream, int *launches);
 
 // scratch needed by the segment binning of one block
 size_t pileup_scratch_bytes(size_t nseg, uint32_t sz);

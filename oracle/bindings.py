@@ -142,28 +142,36 @@ class Oracle:
 
 
 _REF_SINGLETON = None
+_REF_LIBNAME = "libbsref.so"
 
 
 def reference_available():
     return os.path.exists(os.path.join(HERE, "_ref", "libbsref.so"))
 
 
+def dropin_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "libbsref_gpu.so"))
+
+
 class Reference:
-    """The reference's own compiled hot path (process-wide singleton: it owns global thread state)."""
+    """The reference's own compiled hot path (one instance per library: it owns global thread state)."""
+    LIBNAME = "libbsref.so"
+    _instances = {}
 
     def __new__(cls, *a, **k):
-        global _REF_SINGLETON
-        if _REF_SINGLETON is None:
-            _REF_SINGLETON = super().__new__(cls)
-            _REF_SINGLETON._started = False
-        return _REF_SINGLETON
+        inst = Reference._instances.get(cls.LIBNAME)
+        if inst is None:
+            inst = super().__new__(cls)
+            inst._started = False
+            Reference._instances[cls.LIBNAME] = inst
+        return inst
 
     def __init__(self, under_conv=0.01, over_conv=0.05, ref_bias=2.0, min_qual=20, calc_threads=1,
                  left_trim=(0, 0), right_trim=(0, 0)):
         lt = (C.c_uint32 * 2)(*left_trim)
         rt = (C.c_uint32 * 2)(*right_trim)
         if not self._started:
-            path = os.path.join(HERE, "_ref", "libbsref.so")
+            path = os.path.join(HERE, "_ref", self.LIBNAME)
             if not os.path.exists(path):
                 raise FileNotFoundError(path)
             self.lib = C.CDLL(path)
@@ -253,3 +261,9 @@ class Reference:
             raise RuntimeError("bsref_process_block failed: %d" % rc)
         used = int(nt["read_len"].sum())
         return xo.value, pile, vcf, ref, nt, nb[:used].copy()
+
+
+class ReferenceWithGpuDropin(Reference):
+    """The reference's process_template_vector etc. with src/call_genotypes.c replaced by the product's drop-in
+    (bs_call_b200/csrc/bsgpu_dropin.c over libbsgpu.so): oracle/_ref/libbsref_gpu.so.  Needs a GPU."""
+    LIBNAME = "libbsref_gpu.so"
