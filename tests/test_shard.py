@@ -1,0 +1,94 @@
+"""Multi-rank host logic on CPU: sharding plans, and a world_size-2 gloo run in which each rank calls the (CPU) oracle
+on its shard of the site stream and rank 0 merges in coordinate order -- the N>1 plumbing of bench.py without GPUs."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from bs_call_b200 import shard
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_lpt_balances_hg38_over_8():
+    owner = shard.lpt_assign(shard.HG38_CONTIGS, 8)
+    load = np.zeros(8)
+    for ln, o in zip(shard.HG38_CONTIGS, owner):
+        load[o] += ln
+    assert load.max() / load.mean() < 1.05          # within a few %
+    assert sorted(set(owner)) == list(range(8))
+
+
+def test_plan_covers_everything_once():
+    for n in (1, 2, 4, 8):
+        for lengths in (shard.HG38_CONTIGS, [50_000_000], [1000, 7, 5_000_000, 12]):
+            p = shard.plan(lengths, n)
+            assert len(p) == n
+            seen = {c: [] for c in range(len(lengths))}
+            for lst in p:
+                for r in lst:
+                    seen[r.contig].append((r.start, r.stop))
+            for c, ln in enumerate(lengths):
+                iv = sorted(seen[c])
+                assert iv[0][0] == 1 and iv[-1][1] == ln
+                for a, b in zip(iv, iv[1:]):
+                    assert a[1] + 1 == b[0]
+    p = shard.plan([50_000_000], 8)                    # one contig on 8 GPUs is split (level 2)
+    assert all(len(lst) == 1 for lst in p)
+
+
+def test_split_respects_block_boundaries():
+    bounds = [1, 900, 2500, 2600, 7000, 9100]
+    regs = shard.split_contig(0, 10000, 4, bounds)
+    for r in regs[1:]:
+        assert r.start in bounds
+    assert regs[0].start == 1 and regs[-1].stop == 10000
+
+
+def test_site_range():
+    for n in (0, 1, 10, 1_000_000_007):
+        for w in (1, 2, 3, 8):
+            rs = [shard.site_range(r, w, n) for r in range(w)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+import torch.distributed as dist
+from bs_call_b200 import shard
+from oracle.bindings import Oracle
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+o = Oracle()
+N = 60000
+first, last = shard.site_range(rank, world, N)
+p, r = o.synth_sites(20261018, first, last - first, 30.0)
+out, skip = o.call_sites(p, r)
+mine = [(shard.Region(0, first + 1, last), (out.tobytes(), skip.tobytes()))]
+gathered = [None] * world
+dist.all_gather_object(gathered, mine)
+dist.barrier()
+if rank == 0:
+    merged = shard.merge_in_coordinate_order(gathered)
+    whole_p, whole_r = o.synth_sites(20261018, 0, N, 30.0)
+    wout, wskip = o.call_sites(whole_p, whole_r)
+    assert b"".join(m[0] for m in merged) == wout.tobytes()
+    assert b"".join(m[1] for m in merged) == wskip.tobytes()
+    print("MERGE_OK", world)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_shard_and_merge(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "MERGE_OK 2" in res.stdout
