@@ -14,8 +14,8 @@ ring in HBM because 1e9 x 200 B does not fit beside the 105 GB of input).
   e2e       same metric through the C ABI with HOST (pinned) buffers: H2D + kernel + D2H inside the timed region
   roofline  k_call_sites: 306 algorithmic B/site (104 pileup + 1 ref + 200 gt_meth + 1 skip) / event time, against the
             measured HBM copy bandwidth in MEASURED_PEAKS.json
-  fused     the fused pileup->likelihood kernel (k_pileup_tile) on a synthetic 30x WGBS window (config 3 shape),
-            reported beside the headline with its own roofline
+  block_path  segments -> pileup -> model on a synthetic 30x WGBS window (config 3 shape): the default two-kernel
+            path, the pileup kernel alone, and the single fused kernel, each with its own roofline
   cpu_baseline / --impl reference: the reference's own calc_gt_prob()/fisher() objects (oracle/_ref, else the oracle
             port) on all host cores over a bounded sample of the same site stream
 """
@@ -152,7 +152,7 @@ def main():
     ap.add_argument("--impl", default="bsgpu")
     ap.add_argument("--sites", type=float, default=1e9, help="resident sites per GPU (config 2: 1e9)")
     ap.add_argument("--e2e-sites", type=float, default=8e6, help="sites per e2e step (host buffers)")
-    ap.add_argument("--fused-sites", type=float, default=50e6, help="window of the fused pileup->likelihood measurement")
+    ap.add_argument("--fused-sites", type=float, default=50e6, help="window of the block-path (pileup + model) measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -296,8 +296,8 @@ def main():
     for b in (hp, hr, ho, hs):
         b.free()
 
-    # ---- fused pileup -> likelihood kernel on a synthetic 30x window (config 3 shape), device resident
-    fused = None
+    # ---- block path (segments -> pileup -> model) on a synthetic 30x window (config 3 shape), device resident
+    block = None
     del d_out, d_skip
     torch.cuda.empty_cache()
     try:
@@ -308,50 +308,46 @@ def main():
         d_b = torch.empty(ns * L + 16, dtype=torch.uint8, device="cuda")
         d_r = torch.empty(fsz + 16, dtype=torch.uint8, device="cuda")
         d_v = torch.empty(fsz * 208 + 16, dtype=torch.uint8, device="cuda")
-        gpu.synth_block_dev(SEED + rank, 1000, fsz, L, depth, d_seg.data_ptr(), ns, d_b.data_ptr(), ns * L, d_r.data_ptr(), stream)
-        for _ in range(3):
-            gpu.call_block_dev(d_seg.data_ptr(), ns, d_b.data_ptr(), d_r.data_ptr(), 1000, fsz, d_v.data_ptr(), stream)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(args.steps):
-            gpu.call_block_dev(d_seg.data_ptr(), ns, d_b.data_ptr(), d_r.data_ptr(), 1000, fsz, d_v.data_ptr(), stream)
-        f1.record()
-        barrier()
-        fms = f0.elapsed_time(f1) / args.steps
-        fcalled = int((d_v.view(torch.uint8)[201::208][:fsz] == 0).sum().item())
-        fbytes = ns * (L + 16) + fsz * (1 + 208)
-        fused = {"kernel": "k_pileup_tile<fused> (+3 binning kernels)", "workload": "synthetic %dx PE-like %d-bp reads over a %d-site window" % (int(depth), L, fsz),
-                 "sites_per_s": fcalled / (fms * 1e-3), "ms": fms, "sites_called": fcalled,
-                 "roofline": {"bound": "hbm", "achieved": fbytes / (fms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                              "frac": fbytes / (fms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_site": fbytes / fsz}}
-        # the same block as two kernels: pileup[] to HBM, then the likelihood kernel over it
         d_p = torch.empty(fsz * 104 + 16, dtype=torch.uint8, device="cuda")
-        def two():
-            gpu.pileup_block_dev(d_seg.data_ptr(), ns, d_b.data_ptr(), 1000, fsz, d_p.data_ptr(), stream)
-            gpu.call_sites_vcf_dev(d_p.data_ptr(), d_r.data_ptr(), fsz, d_v.data_ptr(), stream)
-        for _ in range(3):
-            two()
-        barrier()
-        p0, p1, p2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        p0.record()
-        for _ in range(args.steps):
-            gpu.pileup_block_dev(d_seg.data_ptr(), ns, d_b.data_ptr(), 1000, fsz, d_p.data_ptr(), stream)
-        p1.record()
-        for _ in range(args.steps):
-            two()
-        p2.record()
-        barrier()
-        pms, tms = p0.elapsed_time(p1) / args.steps, p1.elapsed_time(p2) / args.steps
-        pbytes = ns * (L + 16) + fsz * 104
-        fused["pileup_only"] = {"kernel": "k_pileup_tile<pileup> (+3 binning kernels)", "ms": pms, "sites_per_s": fcalled / (pms * 1e-3),
-                                "roofline": {"bound": "hbm", "achieved": pbytes / (pms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                             "frac": pbytes / (pms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_site": pbytes / fsz}}
-        fused["two_kernel"] = {"ms": tms, "sites_per_s": fcalled / (tms * 1e-3)}
-        del d_p
-        del d_seg, d_b, d_r, d_v
+        gpu.synth_block_dev(SEED + rank, 1000, fsz, L, depth, d_seg.data_ptr(), ns, d_b.data_ptr(), ns * L, d_r.data_ptr(), stream)
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.steps):
+                fn()
+            b.record()
+            barrier()
+            return a.elapsed_time(b) / args.steps
+
+        bms = timed(lambda: gpu.call_block_dev(d_seg.data_ptr(), ns, d_b.data_ptr(), d_r.data_ptr(), 1000, fsz, d_v.data_ptr(), stream))
+        fcalled = int((d_v.view(torch.uint8)[201::208][:fsz] == 0).sum().item())
+        pms = timed(lambda: gpu.pileup_block_dev(d_seg.data_ptr(), ns, d_b.data_ptr(), 1000, fsz, d_p.data_ptr(), stream))
+        os.environ["BSGPU_FUSED"] = "1"
+        gfused = bslib.BsGpu(device=local)
+        del os.environ["BSGPU_FUSED"]
+        fms = timed(lambda: gfused.call_block_dev(d_seg.data_ptr(), ns, d_b.data_ptr(), d_r.data_ptr(), 1000, fsz, d_v.data_ptr(), stream))
+        gfused.close()
+        in_bytes = ns * (L + 16)
+
+        def roof(nbytes, ms_):
+            return {"bound": "hbm", "achieved": nbytes / (ms_ * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": nbytes / (ms_ * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_site": nbytes / fsz}
+
+        block = {"workload": "synthetic %dx %d-bp bisulfite reads over a %d-site window (config 3 shape), device resident" % (int(depth), L, fsz),
+                 "sites_called": fcalled,
+                 "default": {"kernels": "k_bin_* + k_pileup_tile<pileup> -> pileup[] in HBM -> k_call_sites<vcf>", "ms": bms,
+                             "sites_per_s": fcalled / (bms * 1e-3), "roofline": roof(in_bytes + fsz * (104 + 104 + 1 + 208), bms)},
+                 "pileup_only": {"kernels": "k_bin_* + k_pileup_tile<pileup>", "ms": pms, "sites_per_s": fcalled / (pms * 1e-3),
+                                 "roofline": roof(in_bytes + fsz * 104, pms)},
+                 "fused_variant": {"kernels": "k_bin_* + k_pileup_tile<fused> (BSGPU_FUSED=1)", "ms": fms, "sites_per_s": fcalled / (fms * 1e-3),
+                                   "roofline": roof(in_bytes + fsz * (1 + 208), fms)}}
+        del d_seg, d_b, d_r, d_v, d_p
     except Exception as e:            # reported, never hidden
-        fused = {"error": str(e)}
+        block = {"error": repr(e)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -369,7 +365,7 @@ def main():
                            "parallelism": "sites sharded over %d rank(s), no collective" % world,
                            "l2": "inputs larger than L2: each step streams %.1f GB of distinct records" % (n_sites * 105 / 1e9)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "fused": fused, "parity_spot_check": parity}
+                "block_path": block, "parity_spot_check": parity}
         print(json.dumps(line))
     gpu.close()
     if world > 1:

@@ -508,7 +508,7 @@ static size_t call_smem(bool vcf) { return (size_t)kCallTile * ((vcf ? 208 : 200
 static size_t pile_smem(int mode) { return (size_t)kPileThreads * (mode ? 208 : 104) + sizeof(Tables); }
 
 static int g_sms = 148;
-static int g_call_minb = 4;          // resident CTAs per SM the likelihood kernel is compiled for (4 or 5)
+static int g_call_minb = 5;          // resident CTAs per SM the likelihood kernel is compiled for (5: 96 regs; 4: 120 regs)
 static int g_call_ctas[2][2];        // [minb == 5][vcf] measured occupancy
 
 template <typename K>
@@ -525,8 +525,8 @@ cudaError_t configure_kernels() {
 	int dev = 0;
 	if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
 	if ((e = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-	const char *env = getenv("BSGPU_CALL_MINB");          // tuning knob: 4 (default) or 5 resident CTAs per SM
-	if (env && atoi(env) == 5) g_call_minb = 5;
+	const char *env = getenv("BSGPU_CALL_MINB");          // tuning knob: 5 (default, measured faster) or 4 resident CTAs per SM
+	if (env && atoi(env) == 4) g_call_minb = 4;
 	if ((e = prep(k_call_sites<false, 4>, call_smem(false), kCallTile, &g_call_ctas[0][0])) != cudaSuccess) return e;
 	if ((e = prep(k_call_sites<true, 4>, call_smem(true), kCallTile, &g_call_ctas[0][1])) != cudaSuccess) return e;
 	if ((e = prep(k_call_sites<false, 5>, call_smem(false), kCallTile, &g_call_ctas[1][0])) != cudaSuccess) return e;
