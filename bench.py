@@ -345,9 +345,76 @@ def main():
                                  "roofline": roof(in_bytes + fsz * 104, pms)},
                  "fused_variant": {"kernels": "k_bin_* + k_pileup_tile<fused> (BSGPU_FUSED=1)", "ms": fms, "sites_per_s": fcalled / (fms * 1e-3),
                                    "roofline": roof(in_bytes + fsz * (1 + 208), fms)}}
+        # end to end through the host-buffer entry point (what the drop-in calls): pinned host segments / bases / ref in,
+        # gt_vcf[] out, H2D + binning + pileup + model + D2H inside the timed region; a 16 Mi-site window of the same data
+        from bs_call_b200.records import GT_VCF, SEG, TEMPLATE
+        esz = int(min(fsz, 16 * 1024 * 1024))
+        ens = gpu.synth_block_nseg(esz, L, depth)
+        gpu.synth_block_dev(SEED + rank, 1000, esz, L, depth, d_seg.data_ptr(), ens, d_b.data_ptr(), ens * L, d_r.data_ptr(), stream)
+        torch.cuda.synchronize()
+        hseg = bslib.HostBuffer(ens, SEG)
+        hb = bslib.HostBuffer(ens * L, np.uint8)
+        hr = bslib.HostBuffer(esz, np.uint8)
+        hv = bslib.HostBuffer(esz, GT_VCF)
+        hseg.array.view(np.uint8)[:] = d_seg[:ens * 16].cpu().numpy()
+        hb.array[:] = d_b[:ens * L].cpu().numpy()
+        hr.array[:] = d_r[:esz].cpu().numpy()
+        for _ in range(2):
+            gpu.call_block(hseg.array, hb.array, hr.array, 1000, esz, out=hv.array)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            gpu.call_block(hseg.array, hb.array, hr.array, 1000, esz, out=hv.array)
+        torch.cuda.synchronize()
+        es = (time.perf_counter() - t0) / args.steps
+        ecalled = int((hv.array["skip"] == 0).sum())
+        block["e2e"] = {"value": ecalled / es, "unit": "sites/s", "sites_per_step": esz, "h2d_bytes_per_step": ens * (16 + L) + esz,
+                        "d2h_bytes_per_step": esz * 208, "note": "bsgpu_call_block on pinned host arrays (what the drop-in call_genotypes_ML calls)"}
+        # the reference's own call_genotypes_ML (serial pileup + calc threads on all cores) on a bounded slice of that block
+        if rank == 0 and world == 1 and not args.no_cpu:
+            from oracle.bindings import Reference, reference_available
+            csz = 1_500_000
+            segs_h = hseg.array
+            m = (segs_h["pos"] >= 1000) & (segs_h["pos"] + segs_h["len"] <= 1000 + csz)
+            sub = segs_h[m]
+            T = np.zeros(len(sub), dtype=TEMPLATE)
+            T["forward_position"] = sub["pos"]
+            T["read_off"][:, 0] = sub["off"]
+            T["read_len"][:, 0] = sub["len"]
+            T["present"][:, 0] = 1
+            T["mapq"][:, 0] = sub["mapq"]
+            T["orientation"] = sub["flags"] & 1
+            T["bs_strand"] = (sub["flags"] >> 1) & 3
+            refc = np.concatenate([hr.array[:csz], np.zeros(2, np.uint8)])
+            ncores = os.cpu_count() or 1
+            if reference_available():
+                R = Reference(calc_threads=ncores)
+                R.call_block(T[:2000], hb.array, refc, 1000, 1000 + csz - 1)          # warm-up (allocations)
+                t0 = time.perf_counter()
+                pile_c, vcf_c = R.call_block(T, hb.array, refc, 1000, 1000 + csz - 1)
+                cs = R.last_call_seconds()          # call_genotypes_ML until all sites ready; harness set-up excluded
+                kind, what = "reference", "reference call_genotypes_ML + call_thread (oracle/_ref/libbsref.so), harness threads as built"
+            else:
+                from oracle.bindings import Oracle
+                o = Oracle()
+                t0 = time.perf_counter()
+                pile_c = o.pileup_block(T, hb.array, 1000, 1000 + csz - 1)
+                out_c, skip_c = o.call_sites(pile_c, refc[:csz], nthreads=ncores)
+                cs = time.perf_counter() - t0
+                vcf_c = None
+                kind, what = "port", "oracle pileup (1 thread, as the reference) + model on all cores"
+            ccalled = int((pile_c["n"] > 0).sum())
+            block["cpu_baseline"] = {"value": ccalled / cs, "unit": "sites/s", "cores": ncores, "kind": kind,
+                                     "sample": "%d sites (%d called, %d segments) of the same block; %s" % (csz, ccalled, len(sub), what)}
+            if vcf_c is not None:
+                from tests import util
+                block["cpu_baseline"]["parity_sites_checked"] = util.assert_vcf_close(hv.array[:csz - 300], vcf_c[:csz - 300])
+        for hb_ in (hseg, hb, hr, hv):
+            hb_.free()
         del d_seg, d_b, d_r, d_v, d_p
     except Exception as e:            # reported, never hidden
-        block = {"error": repr(e)}
+        import traceback
+        block = {"error": repr(e), "trace": traceback.format_exc()[-800:]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

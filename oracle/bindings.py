@@ -176,6 +176,7 @@ class Reference:
                 raise FileNotFoundError(path)
             self.lib = C.CDLL(path)
             self.lib.bsref_fisher.restype = C.c_double
+            self.lib.bsref_last_call_seconds.restype = C.c_double
             assert self.lib.bsref_sizeof(0) == PILEUP.itemsize
             assert self.lib.bsref_sizeof(1) == GT_METH.itemsize
             assert self.lib.bsref_sizeof(2) == GT_VCF.itemsize
@@ -222,6 +223,10 @@ class Reference:
         t = np.zeros(256, dtype=np.float64)
         self.lib.bsref_lfact_table(_p(t))
         return t
+
+    def last_call_seconds(self):
+        """wall time of the last call_genotypes_ML / process_template_vector until every site was ready"""
+        return float(self.lib.bsref_last_call_seconds())
 
     def call_block(self, templates, bases, refcodes, x, y):
         """Normalised templates -> (pileup[], gt_vcf[]) via call_genotypes_ML.  refcodes covers [x, y+2]."""

@@ -51,6 +51,10 @@ static pthread_t drain_thr;
 static int inited = 0;
 static gt_vector *captured_pileup = NULL;
 static gt_vector *align_list = NULL;
+static double last_call_seconds = 0.0;    /* wall time of the last call_genotypes_ML + all sites ready (harness set-up excluded) */
+
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+double bsref_last_call_seconds(void) { return last_call_seconds; }
 
 /* ---- link-time interposition to observe the function-static pileup vector ---- */
 gt_vector *__real_gt_vector_new(size_t n, size_t es);
@@ -222,6 +226,7 @@ static void drop_list(void) {
 }
 
 /* Stand-in for print_thread (src/process.c:74-110) without the print_vcf_entry call */
+static double call_t0;
 static void consume(uint32_t sz, pileup *pile_out, gt_vcf *vcf_out, uint8_t *ref_out) {
 	work_t * const w = &par.work;
 	for (int i = 0; i < w->vcf_n; i++) {
@@ -247,6 +252,7 @@ static void consume(uint32_t sz, pileup *pile_out, gt_vcf *vcf_out, uint8_t *ref
 		pthread_cond_timedwait(&w->calc_cond2, &w->calc_mutex, &ts);
 	}
 	pthread_mutex_unlock(&w->calc_mutex);
+	last_call_seconds = now_s() - call_t0;
 	if (vcf_out) {
 		for (uint32_t i = 0; i < sz; i++) {
 			/* a skipped site's gtm is never written by the reference (src/call_genotypes.c:112): report zeros */
@@ -272,6 +278,7 @@ int bsref_call_block(const bsref_template *t, size_t n, const uint8_t *bases, co
 	memcpy(par.work.ref1->buffer, refcodes, sz + 2);
 	par.work.ref1->buffer[sz + 2] = 0;
 	par.work.ref1->length = sz + 3;
+	call_t0 = now_s();
 	call_genotypes_ML(&ctg, align_list, x, y, &par);
 	consume(sz, pile_out, vcf_out, NULL);
 	drop_list();
@@ -298,6 +305,7 @@ int bsref_process_block(const bsref_template *t, size_t n, const uint8_t *bases,
 	build_list(t, n, bases, mm);
 	uint32_t x = t[0].forward_position ? t[0].forward_position : t[0].reverse_position;
 	x = x > 2 ? x - 2 : 1;
+	call_t0 = now_s();
 	gt_status st = process_template_vector(align_list, &ctg, y, &par);
 	int ret = 0;
 	if (st != GT_STATUS_OK) ret = -2;
