@@ -55,7 +55,8 @@ constexpr double kInvLn10 = 1.0 / kLn10;
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void conv_ml(double a, double b, double ka, double kb, double l, double t, double *Z) {
 	const double lpt = l + t, lmt = l - t;
-	const double d = (a + b) * lmt;
+	const double d0 = (a + b) * lmt;
+	const double d = d0 != 0.0 ? d0 : 1.0;      // empty pair: result unused; keeps the reciprocal off its special-case path
 	const double r = __drcp_rn(d);
 	const double two_m = 2.0 - lpt;
 	double num[3];
@@ -330,9 +331,11 @@ __device__ __forceinline__ bool call_site(const SiteCounts &s, int rf, const Dev
 		for (int i = 0; i < 25; i++) rec[i] = 0;
 		return false;
 	}
-	const float fn = (float)s.n;
-	const int aq = (int)floorf((float)(0.5 + (double)(tq / fn)));
-	const int mq = (int)(0.5 + sqrt((double)(s.mapq2 / fn)));      // MAPQ 0 reads make this 0/n: rare, takes the slow path
+	// a lane without counts computes 1/1 (discarded) instead of 0/0, which would drag its whole warp through the FP32
+	// division's special-case subroutine
+	const float fn = s.n ? (float)s.n : 1.0f;
+	const int aq = (int)floorf((float)(0.5 + (double)((s.n ? tq : 1.0f) / fn)));
+	const int mq = (int)(0.5 + sqrt((double)((s.n ? s.mapq2 : 1.0f) / fn)));
 	const double fs = strand_bias(s, best, dc->lfact);
 #pragma unroll
 	for (int j = 0; j < 8; j++) rec[j] = tot[j];

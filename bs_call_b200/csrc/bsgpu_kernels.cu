@@ -236,8 +236,10 @@ __global__ void k_bin_scatter(const Seg *__restrict__ segs, size_t nseg, uint32_
 //   MODE 0: write pileup[] (104 B / site)       MODE 1: run the model and write gt_vcf[] (208 B / site)
 // ------------------------------------------------------------------------------------------------
 struct Packed {
-	uint64_t c[2][3];      // [ori][bs_strand] : 4 x 16-bit counters indexed by base
-	uint64_t q[3];         // [bs_strand]      : 4 x 16-bit quality sums indexed by base (q <= 43: good for 1524 hits)
+	// four 16-bit fields indexed by base, kept as two 32-bit halves (bases A,C | G,T) so that adds and multiply-adds
+	// never need a carry across the halves
+	uint32_t c[2][3][2];   // [ori][bs_strand][half] : counts
+	uint32_t q[3][2];      // [bs_strand][half]      : quality sums (q <= 43: good for 1524 hits)
 };
 constexpr uint32_t kWidenEvery = 1500;
 
@@ -249,11 +251,11 @@ __device__ __forceinline__ void widen(Packed &p, uint32_t cnt[2][8], uint32_t qs
 #pragma unroll
 		for (int b = 0; b < 4; b++) {
 #pragma unroll
-			for (int o = 0; o < 2; o++) cnt[o][cls[st][b]] += (uint32_t)(p.c[o][st] >> (16 * b)) & 0xffffu;
-			qs[cls[st][b]] += (uint32_t)(p.q[st] >> (16 * b)) & 0xffffu;
+			for (int o = 0; o < 2; o++) cnt[o][cls[st][b]] += (p.c[o][st][b >> 1] >> (16 * (b & 1))) & 0xffffu;
+			qs[cls[st][b]] += (p.q[st][b >> 1] >> (16 * (b & 1))) & 0xffffu;
 		}
-		p.c[0][st] = p.c[1][st] = 0;
-		p.q[st] = 0;
+		p.c[0][st][0] = p.c[0][st][1] = p.c[1][st][0] = p.c[1][st][1] = 0;
+		p.q[st][0] = p.q[st][1] = 0;
 	}
 }
 
@@ -269,7 +271,7 @@ k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_sta
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	uint64_t *stage = (uint64_t *)smem_raw;
 	Tables *tabs = (Tables *)(smem_raw + kPileThreads * REC);
-	__shared__ uint4 cand[kPileThreads];      // {pos, off, len, mapq^2 | st << 16 | ori << 18}
+	__shared__ uint4 cand[kPileThreads];      // {pos, off, len | st << 16 | ori << 18, mapq^2}
 
 	const int tid = threadIdx.x, lane = tid & 31;
 	const uint32_t site0 = tile0 * kPileTile + blockIdx.x * kPileThreads;     // first site of this CTA
@@ -285,7 +287,7 @@ k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_sta
 	for (int j = 0; j < 8; j++) cnt[0][j] = cnt[1][j] = qs[j] = 0;
 	Packed pk;
 #pragma unroll
-	for (int st = 0; st < 3; st++) { pk.c[0][st] = pk.c[1][st] = 0; pk.q[st] = 0; }
+	for (int st = 0; st < 3; st++) { pk.c[0][st][0] = pk.c[0][st][1] = pk.c[1][st][0] = pk.c[1][st][1] = 0; pk.q[st][0] = pk.q[st][1] = 0; }
 	uint32_t since_widen = 0;
 
 	// candidates: segments that start in the previous bin or in this one (a segment is at most one bin long)
@@ -296,14 +298,14 @@ k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_sta
 		if ((uint32_t)tid < nc) {
 			const Seg sg = segs[base + tid];
 			const uint32_t mq = sg.mapq;
-			cand[tid] = make_uint4(sg.pos, sg.off, sg.len, mq * mq | ((uint32_t)(sg.flags >> 1) & 3u) << 16 | ((uint32_t)sg.flags & 1u) << 18);
+			cand[tid] = make_uint4(sg.pos, sg.off, (uint32_t)sg.len | ((uint32_t)(sg.flags >> 1) & 3u) << 16 | ((uint32_t)sg.flags & 1u) << 18, mq * mq);
 		}
 		__syncthreads();
 		for (uint32_t g = 0; g < nc; g += 32) {
 			bool hit = false;
 			if (g + lane < nc) {
 				const uint4 c = cand[g + lane];
-				hit = c.x < wpos0 + 32 && c.x + c.z > wpos0;
+				hit = c.x < wpos0 + 32 && c.x + (c.z & 0xffffu) > wpos0;
 			}
 			uint32_t m = __ballot_sync(0xffffffffu, hit);
 			while (m) {
@@ -321,22 +323,31 @@ k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_sta
 #pragma unroll
 				for (int u = 0; u < 4; u++) {
 					const uint32_t d = mypos - raw[u].x;
-					byte[u] = d < raw[u].z ? (uint32_t)__ldg(bases + (size_t)raw[u].y + d) : 0u;
+					byte[u] = d < (raw[u].z & 0xffffu) ? (uint32_t)__ldg(bases + (size_t)raw[u].y + d) : 0u;
 				}
 #pragma unroll
 				for (int u = 0; u < 4; u++) {
-					const uint32_t q = byte[u] >> 2, bs = byte[u] & 3u;
-					const uint32_t ok = (q >= min_qual) & (q != (uint32_t)kFltQual);       // q = 0 for "no byte"
-					const uint64_t cinc = (uint64_t)ok << (16 * bs);                      // +1 in the 16-bit field of this base
-					const uint64_t qinc = cinc * q;
-					const uint32_t meta = raw[u].w;
+					const uint32_t q = byte[u] >> 2;
+					const uint32_t ok = (q - min_qual) < ((uint32_t)kFltQual - min_qual) ? 1u : 0u;   // min_qual <= q < 63 (q = 0: no byte)
+					const uint32_t v = ok << ((byte[u] & 1u) << 4);                   // +1 in the 16-bit field of this base ...
+					const uint32_t lo = (byte[u] & 2u) ? 0u : v, hi = v - lo;         // ... of the half that holds it
+					const uint32_t meta = raw[u].z;
 					// (st, ori) are warp-uniform: uniform branches pick the packed registers
 					switch ((meta >> 16) & 3u) {
-					case 0: pk.q[0] += qinc; if (meta >> 18) pk.c[1][0] += cinc; else pk.c[0][0] += cinc; break;
-					case 1: pk.q[1] += qinc; if (meta >> 18) pk.c[1][1] += cinc; else pk.c[0][1] += cinc; break;
-					default: pk.q[2] += qinc; if (meta >> 18) pk.c[1][2] += cinc; else pk.c[0][2] += cinc; break;
+					case 0:
+						pk.q[0][0] += lo * q; pk.q[0][1] += hi * q;
+						if (meta >> 18) { pk.c[1][0][0] += lo; pk.c[1][0][1] += hi; } else { pk.c[0][0][0] += lo; pk.c[0][0][1] += hi; }
+						break;
+					case 1:
+						pk.q[1][0] += lo * q; pk.q[1][1] += hi * q;
+						if (meta >> 18) { pk.c[1][1][0] += lo; pk.c[1][1][1] += hi; } else { pk.c[0][1][0] += lo; pk.c[0][1][1] += hi; }
+						break;
+					default:
+						pk.q[2][0] += lo * q; pk.q[2][1] += hi * q;
+						if (meta >> 18) { pk.c[1][2][0] += lo; pk.c[1][2][1] += hi; } else { pk.c[0][2][0] += lo; pk.c[0][2][1] += hi; }
+						break;
 					}
-					mq2 += ok * (meta & 0xffffu);
+					mq2 += ok * raw[u].w;
 				}
 				since_widen += 4;
 				if (since_widen > kWidenEvery) { widen(pk, cnt, qs); since_widen = 0; }

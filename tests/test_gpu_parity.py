@@ -306,3 +306,39 @@ def test_process_block_rejects_bad_cigar(gpu):
     m[0] = (3, 0, 25)                                     # soft clip longer than the read: fatal in the reference
     with pytest.raises(bslib.BsGpuError):
         gpu.process_block(t, np.full(20, 37 << 2, dtype=np.uint8), m, np.ones(64, dtype=np.uint8), 30)
+
+
+def test_pileup_very_deep_widens_more_than_once(oracle):
+    """> 1500 reads over one tile: the 16-bit packed counters are widened repeatedly"""
+    rng = np.random.default_rng(79)
+    ref = blockgen.random_reference(rng, 1200)
+    T, B, M, y = blockgen.make_block(rng, ref, 100, 500, depth=2500, read_len=100, paired=False, snp_rate=0.01, lowmapq_frac=0.0)
+    nt, nb = oracle.normalise_block(T, B, M)
+    x = int(T[0]["forward_position"]) - 2
+    sz = y - x + 1
+    want = oracle.pileup_block(nt, nb, x, y)
+    assert want["n"].max() > 1600
+    g = bslib.BsGpu()
+    segs = g.stage_templates(nt, nb, x, y)
+    util.assert_pileup_equal(g.pileup_block(segs, nb, x, sz), want)
+    assert g.stats()["qsum_overflow"] == 0
+    refw = ref[x - 1:x - 1 + sz]
+    vcf = g.call_block(segs, nb, refw, x, sz)
+    wout, wskip = oracle.call_sites(want, refw, nthreads=4)
+    util.assert_gt_meth_close(vcf["gtm"], vcf["skip"], wout, wskip)
+    g.close()
+
+
+def test_fused_variant_agrees(oracle):
+    """the single fused pileup+model kernel (BSGPU_FUSED=1) stays correct"""
+    import os
+    g0 = util.load_golden("block_mixed")
+    x, y = int(g0["x"]), int(g0["y"])
+    for var in ("BSGPU_FUSED",):
+        os.environ[var] = "1"
+        g = bslib.BsGpu()
+        del os.environ[var]
+        segs = g.stage_templates(g0["norm_templates"], g0["norm_bases"], x, y)
+        util.assert_pileup_equal(g.pileup_block(segs, g0["norm_bases"], x, y - x + 1), g0["pileup"])
+        util.assert_vcf_close(g.call_block(segs, g0["norm_bases"], g0["ref"], x, y - x + 1), g0["vcf"])
+        g.close()
