@@ -16,6 +16,7 @@ static_assert(sizeof(bsgpu_pileup) == 104, "pileup layout (include/bs_call.h:174
 static_assert(sizeof(bsgpu_gt_meth) == 200, "gt_meth layout (include/bs_call.h:152-160)");
 static_assert(sizeof(bsgpu_gt_vcf) == 208, "gt_vcf layout (include/bs_call.h:162-166)");
 static_assert(sizeof(bsgpu_seg) == 16, "segment layout");
+static_assert(BSGPU_MAX_SEG_LEN == bsgpu::kMaxSegLen, "segment length limit");
 static_assert(sizeof(bsgpu_template) == 56, "template layout");
 static_assert(offsetof(bsgpu_gt_meth, gt_prob) == 96 && offsetof(bsgpu_gt_meth, fisher_strand) == 176 &&
 		offsetof(bsgpu_gt_meth, mq) == 184 && offsetof(bsgpu_gt_meth, max_gt) == 192, "gt_meth offsets");
@@ -123,6 +124,12 @@ int bsgpu_init(const bsgpu_params *p, bsgpu_ctx **out) {
 	h.lrb = log(p->ref_bias);                      // src/genotype_model.c:88-89
 	h.lrb1 = log(0.5 * (1.0 + p->ref_bias));
 	h.min_qual = p->min_qual;
+	for (int b = 0; b < 256; b++) {                // a base counts iff min_qual <= q != 63 (src/call_genotypes.c:217)
+		const uint32_t q = (uint32_t)b >> 2, base = (uint32_t)b & 3u;
+		const uint32_t inc = (q >= p->min_qual && q != BSGPU_FLT_QUAL) ? (1u | q << 5) << (16 * (base & 1u)) : 0u;
+		h.pile_lut[b][0] = base < 2 ? inc : 0u;
+		h.pile_lut[b][1] = base < 2 ? 0u : inc;
+	}
 	CU(cudaMalloc(&c->d_const, sizeof(DevConst)));
 	CU(cudaMemcpy(c->d_const, &h, sizeof(h), cudaMemcpyHostToDevice));
 	CU(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
@@ -342,7 +349,7 @@ static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *
 	CU(c->scratch.reserve(pileup_scratch_bytes(nseg, sz)));
 	CU(launch_bin_segments(d_segs, nseg, x, sz, c->scratch.p, c->stream, &c->launches));
 	const uint32_t ntiles = (sz + kPileTileSites - 1) / kPileTileSites;
-	const uint32_t slab = 8192;                    // tiles per slab = 2 Mi sites = 436 MB of gt_vcf
+	const uint32_t slab = (2u << 20) / kPileTileSites;      // tiles per slab = 2 Mi sites = 436 MB of gt_vcf
 	const uint32_t nslab = (ntiles + slab - 1) / slab;
 	const uint32_t resident = nslab < 3 ? nslab : 3;      // ring of output slabs on the device
 	const uint32_t slab_tiles = ntiles < slab ? ntiles : slab;

@@ -28,6 +28,9 @@ struct DevConst {
 	double lrb, lrb1;             // ln(ref_bias), ln((1 + ref_bias) / 2)
 	int min_qual;
 	int pad_;
+	// gather kernel: packed base byte -> increment of the narrow accumulators {bases A,C | bases G,T}; each half-word is
+	// 5-bit count | 11-bit quality; zero for a byte that does not count (q < min_qual, q = 63)
+	uint32_t pile_lut[256][2];
 };
 
 // What a thread holds for its site before the model runs: the reference's pileup record in registers.

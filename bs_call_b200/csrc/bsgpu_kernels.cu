@@ -173,213 +173,268 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 }
 
 // ------------------------------------------------------------------------------------------------
-// Segment binning: counting sort of segments by the 256-site tile their start falls in.
+// Segment binning: counting sort of segments by the 128-site tile their start falls in (count, 3-phase exclusive scan,
+// scatter).  The scatter writes the pre-digested candidate record the gather kernel consumes.
 // ------------------------------------------------------------------------------------------------
-constexpr int kPileTile = 256;
+constexpr int kPileTile = kPileTileSites;      // 128 sites = one CTA of the gather kernel
+constexpr int kBinsBack = (kMaxSegLen + kPileTile - 2) / kPileTile;   // bins before tile T that can reach into it
 
+// {pos, off - pos (mod 2^32), len | combo << 16, mapq^2}; combo = 2 * bisulfite strand + strand index (0..5)
+struct Cand { uint32_t pos, offd, meta, mq2; };
+
+__device__ __forceinline__ uint32_t seg_bin(uint32_t pos, uint32_t x) { return pos >= x ? (pos - x) / kPileTile : 0; }
 
 __global__ void k_bin_count(const Seg *__restrict__ segs, size_t nseg, uint32_t x, uint32_t ntiles, uint32_t *__restrict__ counts) {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= nseg) return;
-	if (!segs[i].len) return;                 // empty slots (the normaliser leaves them for absent mates)
-	const uint32_t pos = segs[i].pos;
-	// a segment that starts before the window still contributes to tile 0 (clipped there)
-	uint32_t t = pos >= x ? (pos - x) / kPileTile : 0;
+	const Seg s = segs[i];
+	if (!s.len) return;                       // empty slots (the normaliser leaves them for absent mates)
+	// a segment that starts before the window still contributes to the first tiles (clipped there)
+	const uint32_t t = seg_bin(s.pos, x);
 	if (t < ntiles) atomicAdd(counts + t, 1u);
 }
 
-// single-CTA exclusive scan (ntiles is at most a few hundred thousand per launch; runs once per block of sites)
-__global__ void __launch_bounds__(1024) k_bin_scan(const uint32_t *__restrict__ counts, uint32_t ntiles, uint32_t *__restrict__ start, uint32_t *__restrict__ cursor) {
-	__shared__ uint32_t warp_tot[32];
-	__shared__ uint32_t carry;
-	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	if (tid == 0) carry = 0;
+// exclusive scan of counts[0..n) in three phases: per-CTA scan of 1024 items, single-CTA scan of the CTA totals, add.
+__device__ __forceinline__ uint32_t cta_scan_1024(uint32_t v, uint32_t *warp_tot, int tid, uint32_t *total) {
+	const int lane = tid & 31, wid = tid >> 5;
+	uint32_t incl = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+	if (lane == 31) warp_tot[wid] = incl;
 	__syncthreads();
-	for (uint32_t base = 0; base < ntiles; base += 1024) {
-		const uint32_t i = base + tid;
-		const uint32_t v = i < ntiles ? counts[i] : 0;
-		uint32_t incl = v;
+	if (wid == 0) {
+		uint32_t w = warp_tot[lane];
 #pragma unroll
-		for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-		if (lane == 31) warp_tot[wid] = incl;
-		__syncthreads();
-		if (wid == 0) {
-			uint32_t w = warp_tot[lane];
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += o; }
-			warp_tot[lane] = w;
-		}
-		__syncthreads();
-		const uint32_t excl = carry + (wid ? warp_tot[wid - 1] : 0) + incl - v;
-		if (i < ntiles) { start[i] = excl; cursor[i] = excl; }
-		__syncthreads();
-		if (tid == 1023) carry = excl + v;
-		__syncthreads();
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += o; }
+		warp_tot[lane] = w;
 	}
-	if (tid == 0) start[ntiles] = carry;
+	__syncthreads();
+	const uint32_t excl = (wid ? warp_tot[wid - 1] : 0) + incl - v;
+	*total = warp_tot[31];
+	__syncthreads();
+	return excl;
 }
 
-__global__ void k_bin_scatter(const Seg *__restrict__ segs, size_t nseg, uint32_t x, uint32_t ntiles, uint32_t *__restrict__ cursor, Seg *__restrict__ sorted) {
+__global__ void __launch_bounds__(1024) k_scan_local(const uint32_t *__restrict__ counts, uint32_t n, uint32_t *__restrict__ start, uint32_t *__restrict__ partial) {
+	__shared__ uint32_t warp_tot[32];
+	const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+	uint32_t total;
+	const uint32_t excl = cta_scan_1024(i < n ? counts[i] : 0, warp_tot, threadIdx.x, &total);
+	if (i < n) start[i] = excl;
+	if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_partials(uint32_t *__restrict__ partial, uint32_t nb) {
+	__shared__ uint32_t warp_tot[32];
+	uint32_t carry = 0;
+	for (uint32_t base = 0; base < nb; base += 1024) {
+		const uint32_t i = base + threadIdx.x;
+		uint32_t total;
+		const uint32_t excl = cta_scan_1024(i < nb ? partial[i] : 0, warp_tot, threadIdx.x, &total);
+		if (i < nb) partial[i] = carry + excl;
+		carry += total;
+	}
+	if (threadIdx.x == 0) partial[nb] = carry;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(uint32_t *__restrict__ start, uint32_t *__restrict__ cursor, uint32_t n, const uint32_t *__restrict__ partial, uint32_t nb) {
+	const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+	if (i < n) { const uint32_t v = start[i] + partial[blockIdx.x]; start[i] = v; cursor[i] = v; }
+	if (i == 0) start[n] = partial[nb];
+}
+
+__global__ void k_bin_scatter(const Seg *__restrict__ segs, size_t nseg, uint32_t x, uint32_t ntiles, uint32_t *__restrict__ cursor, Cand *__restrict__ sorted) {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= nseg) return;
 	const Seg s = segs[i];
 	if (!s.len) return;
-	uint32_t t = s.pos >= x ? (s.pos - x) / kPileTile : 0;
-	if (t < ntiles) sorted[atomicAdd(cursor + t, 1u)] = s;
+	const uint32_t t = seg_bin(s.pos, x);
+	if (t >= ntiles) return;
+	const uint32_t mq = s.mapq, combo = ((uint32_t)(s.flags >> 1) & 3u) * 2u + ((uint32_t)s.flags & 1u);
+	Cand c;
+	c.pos = s.pos; c.offd = s.off - s.pos; c.meta = (uint32_t)s.len | combo << 16; c.mq2 = mq * mq;
+	sorted[atomicAdd(cursor + t, 1u)] = c;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pileup by gather.  CTA = 128 threads = 128 consecutive sites (half a bin).  Candidate segments are the two bins
-// [t-1, t] (a segment is at most 256 long).  Each warp filters 32 candidates at a time with one ballot, then walks the
-// hits; a lane adds the byte at its own site into halfword-packed 64-bit register counters keyed by
-// (strand index, bisulfite strand), which are widened every 1500 hits.
+// Pileup by gather.  CTA = 128 threads = 128 consecutive sites (one bin); one thread owns one site and pulls the one
+// byte each overlapping segment contributes: no atomics on the counts, integer sums, order independent.
+//
+// Candidates are the bins [T - 2, T] (a segment is at most 256 long).  They are taken 128 at a time, one per thread,
+// and dealt to the warps whose 32-site window they overlap, sorted by `combo` = (bisulfite strand, strand index): a
+// counting sort in shared memory (24 counters).  A warp then walks its own hit list combo by combo, so inside the
+// hit loop the class mapping is fixed and the per-hit work is: broadcast LDS of the candidate, one byte load, one LDS
+// from a 256-entry table byte -> packed increment, two adds and a predicated add for mapq^2.
+//
+// Narrow accumulators: four 16-bit fields (one per base; 5-bit count | 11-bit quality sum) in two registers,
+// flushed into the wide per-class registers at the end of a combo run or after 28 hits.
 //   MODE 0: write pileup[] (104 B / site)       MODE 1: run the model and write gt_vcf[] (208 B / site)
 // ------------------------------------------------------------------------------------------------
-struct Packed {
-	// four 16-bit fields indexed by base, kept as two 32-bit halves (bases A,C | G,T) so that adds and multiply-adds
-	// never need a carry across the halves
-	uint32_t c[2][3][2];   // [ori][bs_strand][half] : counts
-	uint32_t q[3][2];      // [bs_strand][half]      : quality sums (q <= 43: good for 1524 hits)
-};
-constexpr uint32_t kWidenEvery = 1500;
+constexpr int kPileThreads = kPileTile;
+constexpr int kHitTrip = 28;                   // hits between flushes: 5-bit counts hold 31, multiple of the unroll
 
-__device__ __forceinline__ void widen(Packed &p, uint32_t cnt[2][8], uint32_t qs[8]) {
+struct WideAcc {
+	uint32_t cnt[8];           // per class: strand index 0 in the low half-word, 1 in the high one
+	uint32_t qs[8];            // per class quality sums
+	uint32_t mq2;
+};
+
+template <int K>
+__device__ __forceinline__ void flush_combo(uint32_t &lo, uint32_t &hi, WideAcc &w) {
 	// class of (bs_strand, base): st0 {0,1,2,3}  st1=C2T {0,5,2,7}  st2=G2A {4,1,6,3}   (src/call_genotypes.c:17-19)
 	constexpr int cls[3][4] = {{0, 1, 2, 3}, {0, 5, 2, 7}, {4, 1, 6, 3}};
+	constexpr int st = K >> 1, ori = K & 1;
 #pragma unroll
-	for (int st = 0; st < 3; st++) {
+	for (int b = 0; b < 4; b++) {
+		const uint32_t half = b < 2 ? lo : hi;
+		const uint32_t f = (b & 1) ? half >> 16 : half & 0xffffu;
+		w.cnt[cls[st][b]] += (f & 31u) << (16 * ori);
+		w.qs[cls[st][b]] += f >> 5;
+	}
+	lo = hi = 0;
+}
+
+// hit record in shared memory: {pos, len, t, mapq^2}; the byte of reference position p sits at lanebase[t] where
+// lanebase = bases + p - (tile end) is a per-lane pointer, so the address costs one 64-bit add of a 32-bit offset
+__device__ __forceinline__ void hit_one(const uint4 c, uint32_t mypos, const uint8_t *__restrict__ lanebase, const uint2 *__restrict__ lut,
+		uint32_t &lo, uint32_t &hi, uint32_t &mq2) {
+	const uint32_t byte = (mypos - c.x) < c.y ? (uint32_t)__ldg(lanebase + c.z) : 0u;
+	const uint2 e = lut[byte];
+	lo += e.x; hi += e.y;
+	if (e.x | e.y) mq2 += c.w;
+}
+
+template <int K>
+__device__ __forceinline__ void run_combo(const uint4 *__restrict__ hits, uint32_t hs, uint32_t he, uint32_t mypos,
+		const uint8_t *__restrict__ lanebase, const uint2 *__restrict__ lut, WideAcc &w) {
+	uint32_t lo = 0, hi = 0;
+	for (uint32_t h0 = hs; h0 < he; h0 += kHitTrip) {
+		const uint32_t h1 = min(h0 + (uint32_t)kHitTrip, he);
+		uint32_t h = h0;
+		for (; h + 4 <= h1; h += 4) {
+			// four hits per trip: their byte loads are issued back to back before any is consumed
+			uint4 c[4];
+			uint32_t byte[4];
 #pragma unroll
-		for (int b = 0; b < 4; b++) {
+			for (int u = 0; u < 4; u++) c[u] = hits[h + u];
 #pragma unroll
-			for (int o = 0; o < 2; o++) cnt[o][cls[st][b]] += (p.c[o][st][b >> 1] >> (16 * (b & 1))) & 0xffffu;
-			qs[cls[st][b]] += (p.q[st][b >> 1] >> (16 * (b & 1))) & 0xffffu;
+			for (int u = 0; u < 4; u++) byte[u] = (mypos - c[u].x) < c[u].y ? (uint32_t)__ldg(lanebase + c[u].z) : 0u;
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const uint2 e = lut[byte[u]];
+				lo += e.x; hi += e.y;
+				if (e.x | e.y) w.mq2 += c[u].w;
+			}
 		}
-		p.c[0][st][0] = p.c[0][st][1] = p.c[1][st][0] = p.c[1][st][1] = 0;
-		p.q[st][0] = p.q[st][1] = 0;
+		for (; h < h1; h++) hit_one(hits[h], mypos, lanebase, lut, lo, hi, w.mq2);
+		flush_combo<K>(lo, hi, w);
 	}
 }
 
-constexpr int kPileThreads = 128;     // one CTA = 128 consecutive sites = half a bin
-
 template <int MODE>
 __global__ void __launch_bounds__(kPileThreads)
-k_pileup_tile(const Seg *__restrict__ segs, const uint32_t *__restrict__ bin_start, const uint8_t *__restrict__ bases,
+k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_start, const uint8_t *__restrict__ bases,
 		const uint8_t *__restrict__ ref, uint32_t x, uint32_t sz, uint32_t tile0, uint8_t *__restrict__ out,
 		const DevConst *__restrict__ dc, unsigned long long *__restrict__ counters) {
 	constexpr int REC = MODE ? 208 : 104;
 	constexpr int RW = REC / 8;
 	extern __shared__ __align__(128) uint8_t smem_raw[];
-	uint64_t *stage = (uint64_t *)smem_raw;
-	Tables *tabs = (Tables *)(smem_raw + kPileThreads * REC);
-	__shared__ uint4 cand[kPileThreads];      // {pos, off, len | st << 16 | ori << 18, mapq^2}
+	uint64_t *stage = (uint64_t *)smem_raw;                      // output tile; before that, the four warps' hit lists
+	uint4 *whits = (uint4 *)smem_raw;                            // [4][kPileThreads]
+	uint2 *lut = (uint2 *)(smem_raw + kPileThreads * REC);       // byte -> {low, high} packed increment
+	Tables *tabs = (Tables *)(smem_raw + kPileThreads * REC + 256 * sizeof(uint2));
+	__shared__ uint32_t cnt[32], cur[32], rs[32], re[32];        // [warp][combo (8 slots)]
 
-	const int tid = threadIdx.x, lane = tid & 31;
-	const uint32_t site0 = tile0 * kPileTile + blockIdx.x * kPileThreads;     // first site of this CTA
-	const uint32_t bin = site0 / kPileTile;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const uint32_t tile = tile0 + blockIdx.x;
+	const uint32_t site0 = tile * kPileTile;                     // first site of this CTA
 	const int nrec = (int)min((uint32_t)kPileThreads, sz - site0);
-	const uint32_t mypos = x + site0 + tid;                        // 1-based reference position of this thread's site
-	const uint32_t wpos0 = x + site0 + (tid & ~31);                // first position of this warp's 32 sites
-	const uint32_t min_qual = (uint32_t)dc->min_qual;
+	const uint32_t tpos0 = x + site0;                            // 1-based reference position of the CTA's first site
+	const uint32_t mypos = tpos0 + tid;
+	const uint8_t *lanebase = bases - (kPileThreads - tid);     // + (off - pos + tpos0 + 128) = the byte of this lane's position
+	asm volatile("" : "+l"(lanebase));                          // keep it in a register pair: one 64-bit add per byte address
+	{
+		const uint2 *src = (const uint2 *)dc->pile_lut;
+		lut[tid] = src[tid];
+		lut[tid + kPileThreads] = src[tid + kPileThreads];
+	}
 	if (MODE) load_tables(tabs, dc, tid, kPileThreads);
 
-	uint32_t cnt[2][8], qs[8], mq2 = 0;
+	WideAcc w;
 #pragma unroll
-	for (int j = 0; j < 8; j++) cnt[0][j] = cnt[1][j] = qs[j] = 0;
-	Packed pk;
-#pragma unroll
-	for (int st = 0; st < 3; st++) { pk.c[0][st][0] = pk.c[0][st][1] = pk.c[1][st][0] = pk.c[1][st][1] = 0; pk.q[st][0] = pk.q[st][1] = 0; }
-	uint32_t since_widen = 0;
+	for (int j = 0; j < 8; j++) w.cnt[j] = w.qs[j] = 0;
+	w.mq2 = 0;
+	uint32_t warp_hits = 0;
 
-	// candidates: segments that start in the previous bin or in this one (a segment is at most one bin long)
-	const uint32_t c_lo = bin_start[bin ? bin - 1 : 0], c_hi = bin_start[bin + 1];
+	const uint32_t c_lo = bin_start[tile > (uint32_t)kBinsBack ? tile - kBinsBack : 0], c_hi = bin_start[tile + 1];
 	for (uint32_t base = c_lo; base < c_hi; base += kPileThreads) {
-		const uint32_t nc = min((uint32_t)kPileThreads, c_hi - base);
+		if (tid < 32) cnt[tid] = 0;
 		__syncthreads();
-		if ((uint32_t)tid < nc) {
-			const Seg sg = segs[base + tid];
-			const uint32_t mq = sg.mapq;
-			cand[tid] = make_uint4(sg.pos, sg.off, (uint32_t)sg.len | ((uint32_t)(sg.flags >> 1) & 3u) << 16 | ((uint32_t)sg.flags & 1u) << 18, mq * mq);
+		// deal: which warps does my candidate overlap?
+		uint4 c = make_uint4(0, 0, 0, 0);
+		int w_lo = 1, w_hi = 0;
+		uint32_t k = 0;
+		if (base + tid < c_hi) {
+			c = *(const uint4 *)(cands + base + tid);
+			const int rel = (int)(c.x - tpos0);                 // start relative to the tile (negative: starts before it)
+			const int s_lo = max(rel, 0), s_hi = min(rel + (int)(c.z & 0xffffu) - 1, kPileThreads - 1);
+			k = c.z >> 16;
+			if (s_hi >= s_lo && k < 6) { w_lo = s_lo >> 5; w_hi = s_hi >> 5; }
+		}
+		for (int ww = w_lo; ww <= w_hi; ww++) atomicAdd(&cnt[ww * 8 + k], 1u);
+		__syncthreads();
+		if (tid < 32) {
+			const uint32_t v = cnt[tid];
+			uint32_t incl = v;
+#pragma unroll
+			for (int d = 1; d < 8; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d, 8); if ((tid & 7) >= d) incl += o; }
+			const uint32_t first = (uint32_t)(tid >> 3) * kPileThreads + incl - v;
+			rs[tid] = first; cur[tid] = first; re[tid] = first + v;
 		}
 		__syncthreads();
-		for (uint32_t g = 0; g < nc; g += 32) {
-			bool hit = false;
-			if (g + lane < nc) {
-				const uint4 c = cand[g + lane];
-				hit = c.x < wpos0 + 32 && c.x + (c.z & 0xffffu) > wpos0;
-			}
-			uint32_t m = __ballot_sync(0xffffffffu, hit);
-			while (m) {
-				// four hits per trip: their byte loads are issued back to back before any is consumed
-				uint4 raw[4];
-				uint32_t byte[4];
-#pragma unroll
-				for (int u = 0; u < 4; u++) {
-					const bool valid = m != 0;
-					const int b = valid ? __ffs(m) - 1 : 0;
-					m &= m - 1;                                       // 0 stays 0
-					raw[u] = cand[g + b];                             // broadcast read
-					if (!valid) raw[u].z = 0;                         // len 0: contributes nothing
-				}
-#pragma unroll
-				for (int u = 0; u < 4; u++) {
-					const uint32_t d = mypos - raw[u].x;
-					byte[u] = d < (raw[u].z & 0xffffu) ? (uint32_t)__ldg(bases + (size_t)raw[u].y + d) : 0u;
-				}
-#pragma unroll
-				for (int u = 0; u < 4; u++) {
-					const uint32_t q = byte[u] >> 2;
-					const uint32_t ok = (q - min_qual) < ((uint32_t)kFltQual - min_qual) ? 1u : 0u;   // min_qual <= q < 63 (q = 0: no byte)
-					const uint32_t v = ok << ((byte[u] & 1u) << 4);                   // +1 in the 16-bit field of this base ...
-					const uint32_t lo = (byte[u] & 2u) ? 0u : v, hi = v - lo;         // ... of the half that holds it
-					const uint32_t meta = raw[u].z;
-					// (st, ori) are warp-uniform: uniform branches pick the packed registers
-					switch ((meta >> 16) & 3u) {
-					case 0:
-						pk.q[0][0] += lo * q; pk.q[0][1] += hi * q;
-						if (meta >> 18) { pk.c[1][0][0] += lo; pk.c[1][0][1] += hi; } else { pk.c[0][0][0] += lo; pk.c[0][0][1] += hi; }
-						break;
-					case 1:
-						pk.q[1][0] += lo * q; pk.q[1][1] += hi * q;
-						if (meta >> 18) { pk.c[1][1][0] += lo; pk.c[1][1][1] += hi; } else { pk.c[0][1][0] += lo; pk.c[0][1][1] += hi; }
-						break;
-					default:
-						pk.q[2][0] += lo * q; pk.q[2][1] += hi * q;
-						if (meta >> 18) { pk.c[1][2][0] += lo; pk.c[1][2][1] += hi; } else { pk.c[0][2][0] += lo; pk.c[0][2][1] += hi; }
-						break;
-					}
-					mq2 += ok * raw[u].w;
-				}
-				since_widen += 4;
-				if (since_widen > kWidenEvery) { widen(pk, cnt, qs); since_widen = 0; }
-			}
+		{
+			// {pos, len, offset of the byte of position tpos0 + 128 relative to bases (never negative), mapq^2}
+			const uint4 hrec = make_uint4(c.x, c.z & 0xffffu, c.y + tpos0 + (uint32_t)kPileThreads, c.w);
+			for (int ww = w_lo; ww <= w_hi; ww++) whits[atomicAdd(&cur[ww * 8 + k], 1u)] = hrec;
 		}
+		__syncthreads();
+		// walk this warp's hits, combo by combo
+		warp_hits += re[wid * 8 + 5] - rs[wid * 8];
+		run_combo<0>(whits, rs[wid * 8 + 0], re[wid * 8 + 0], mypos, lanebase, lut, w);
+		run_combo<1>(whits, rs[wid * 8 + 1], re[wid * 8 + 1], mypos, lanebase, lut, w);
+		run_combo<2>(whits, rs[wid * 8 + 2], re[wid * 8 + 2], mypos, lanebase, lut, w);
+		run_combo<3>(whits, rs[wid * 8 + 3], re[wid * 8 + 3], mypos, lanebase, lut, w);
+		run_combo<4>(whits, rs[wid * 8 + 4], re[wid * 8 + 4], mypos, lanebase, lut, w);
+		run_combo<5>(whits, rs[wid * 8 + 5], re[wid * 8 + 5], mypos, lanebase, lut, w);
+		__syncthreads();
 	}
-	widen(pk, cnt, qs);
 
 	SiteCounts s;
-	uint32_t n = 0, qmax = 0;
+	uint32_t nsum = 0, qmax = 0;
 #pragma unroll
 	for (int j = 0; j < 8; j++) {
-		s.cnt[0][j] = cnt[0][j]; s.cnt[1][j] = cnt[1][j];
-		n += cnt[0][j] + cnt[1][j];
-		s.qsum[j] = (float)qs[j];
-		qmax = max(qmax, qs[j]);
+		s.cnt[0][j] = w.cnt[j] & 0xffffu; s.cnt[1][j] = w.cnt[j] >> 16;
+		nsum += w.cnt[j];
+		s.qsum[j] = (float)w.qs[j];
+		qmax = max(qmax, w.qs[j]);
 	}
+	const uint32_t n = (nsum & 0xffffu) + (nsum >> 16);
 	s.n = tid < nrec ? n : 0;
-	s.mapq2 = (float)mq2;
-	// integer sums equal the reference's float sums only below 2^24: count the sites that leave the envelope
-	if (s.n && (qmax >= (1u << 24) || mq2 >= (1u << 24))) atomicAdd(counters + 1, 1ull);
+	s.mapq2 = (float)w.mq2;
+	// integer sums equal the reference's float sums only below 2^24, and the half-word counts hold 65535:
+	// count the sites that leave the envelope
+	if (s.n && (qmax >= (1u << 24) || w.mq2 >= (1u << 24) || warp_hits >= 65535u)) atomicAdd(counters + 1, 1ull);
 
 	uint64_t *rec = stage + tid * RW;
 	if (MODE == 0) {
-		uint32_t *w = (uint32_t *)rec;
+		uint32_t *o = (uint32_t *)rec;
 #pragma unroll
-		for (int j = 0; j < 8; j++) { w[j] = s.cnt[0][j]; w[8 + j] = s.cnt[1][j]; w[17 + j] = __float_as_uint(s.qsum[j]); }
-		w[16] = s.n;
-		w[25] = __float_as_uint(s.mapq2);
+		for (int j = 0; j < 8; j++) { o[j] = s.cnt[0][j]; o[8 + j] = s.cnt[1][j]; o[17 + j] = __float_as_uint(s.qsum[j]); }
+		o[16] = s.n;
+		o[25] = __float_as_uint(s.mapq2);
 	} else {
 		const int rf = tid < nrec ? ref[site0 + tid] : 0;
-		__syncthreads();                    // tables loaded
+		__syncthreads();                    // tables loaded (the candidate loop may not have run)
 		double *wbuf = (double *)(stage + (tid & ~31) * RW);
 		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, lane);
 		rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
@@ -516,7 +571,7 @@ __global__ void k_synth_reads(uint64_t seed, uint32_t x, uint32_t sz, uint32_t r
 #define LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
 static size_t call_smem(bool vcf) { return (size_t)kCallTile * ((vcf ? 208 : 200) + 104) + sizeof(Tables); }
-static size_t pile_smem(int mode) { return (size_t)kPileThreads * (mode ? 208 : 104) + sizeof(Tables); }
+static size_t pile_smem(int mode) { return (size_t)kPileThreads * (mode ? 208 : 104) + 256 * sizeof(uint2) + (mode ? sizeof(Tables) : 0); }
 
 static int g_sms = 148;
 static int g_call_minb = 5;          // resident CTAs per SM the likelihood kernel is compiled for (5: 96 regs; 4: 120 regs)
@@ -569,22 +624,24 @@ cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, voi
 	return cudaSuccess;
 }
 
-static size_t seg_area(size_t nseg) { return (nseg * sizeof(Seg) + 255) & ~(size_t)255; }
+static size_t seg_area(size_t nseg) { return (nseg * sizeof(Cand) + 255) & ~(size_t)255; }
+static uint32_t scan_ctas(uint32_t ntiles) { return (ntiles + 1023) / 1024; }
 
 size_t pileup_scratch_bytes(size_t nseg, uint32_t sz) {
 	const size_t ntiles = (sz + kPileTile - 1) / kPileTile;
-	return seg_area(nseg) + (3 * ntiles + 8) * sizeof(uint32_t) + 256;
+	return seg_area(nseg) + (3 * ntiles + scan_ctas((uint32_t)ntiles) + 16) * sizeof(uint32_t) + 256;
 }
 
-// scratch layout: sorted segs | counts[ntiles] | start[ntiles+1] | cursor[ntiles]
+// scratch layout: sorted candidates | counts[ntiles] | start[ntiles+1] | cursor[ntiles] | partial[ctas+1]
 cudaError_t launch_bin_segments(const void *segs, size_t nseg, uint32_t x, uint32_t sz, void *scratch,
 		cudaStream_t stream, int *launches) {
 	if (!sz) return cudaSuccess;
 	const uint32_t ntiles = (sz + kPileTile - 1) / kPileTile;
-	Seg *sorted = (Seg *)scratch;
+	Cand *sorted = (Cand *)scratch;
 	uint32_t *counts = (uint32_t *)((uint8_t *)scratch + seg_area(nseg));
 	uint32_t *start = counts + ntiles;
 	uint32_t *cursor = start + ntiles + 1;
+	uint32_t *partial = cursor + ntiles;
 	cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(uint32_t) * ntiles, stream);
 	if (e != cudaSuccess) return e;
 	const unsigned g = (unsigned)((nseg + 255) / 256);
@@ -593,8 +650,11 @@ cudaError_t launch_bin_segments(const void *segs, size_t nseg, uint32_t x, uint3
 		*launches += 1;
 		LAUNCH_CHECK();
 	}
-	k_bin_scan<<<1, 1024, 0, stream>>>(counts, ntiles, start, cursor);
-	*launches += 1;
+	const uint32_t nb = scan_ctas(ntiles);
+	k_scan_local<<<nb, 1024, 0, stream>>>(counts, ntiles, start, partial);
+	k_scan_partials<<<1, 1024, 0, stream>>>(partial, nb);
+	k_scan_add<<<nb, 1024, 0, stream>>>(start, cursor, ntiles, partial, nb);
+	*launches += 3;
 	LAUNCH_CHECK();
 	if (nseg) {
 		k_bin_scatter<<<g, 256, 0, stream>>>((const Seg *)segs, nseg, x, ntiles, cursor, sorted);
@@ -609,12 +669,10 @@ cudaError_t launch_pileup_tiles(const void *scratch, size_t nseg, const void *ba
 		unsigned long long *counters, cudaStream_t stream, int *launches) {
 	if (!ntiles) return cudaSuccess;
 	const uint32_t all_tiles = (sz + kPileTile - 1) / kPileTile;
-	const Seg *sorted = (const Seg *)scratch;
+	const Cand *sorted = (const Cand *)scratch;
 	const uint32_t *start = (const uint32_t *)((const uint8_t *)scratch + seg_area(nseg)) + all_tiles;
-	// sites covered by this launch: bins [tile0, tile0 + ntiles) clipped to the window; one CTA per 128 sites
-	const uint32_t first_site = tile0 * kPileTile;
-	const uint32_t nsite = min(ntiles * (uint32_t)kPileTile, sz - first_site);
-	const unsigned grid = (nsite + kPileThreads - 1) / kPileThreads;
+	// sites covered by this launch: tiles [tile0, tile0 + ntiles) clipped to the window; one CTA per tile
+	const unsigned grid = min(ntiles, all_tiles - tile0);
 	if (mode) k_pileup_tile<1><<<grid, kPileThreads, pile_smem(1), stream>>>(sorted, start, (const uint8_t *)bases, (const uint8_t *)ref, x, sz, tile0, (uint8_t *)out, dc, counters);
 	else k_pileup_tile<0><<<grid, kPileThreads, pile_smem(0), stream>>>(sorted, start, (const uint8_t *)bases, (const uint8_t *)ref, x, sz, tile0, (uint8_t *)out, dc, counters);
 	*launches += 1;

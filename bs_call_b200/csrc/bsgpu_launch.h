@@ -20,12 +20,12 @@ cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, voi
 // scratch needed by the segment binning of one block
 size_t pileup_scratch_bytes(size_t nseg, uint32_t sz);
 
-// bins the segments of a block by 256-site tile (count, scan, scatter) into `scratch`
+// bins the segments of a block by 128-site tile (count, scan, scatter) into `scratch`
 cudaError_t launch_bin_segments(const void *segs, size_t nseg, uint32_t x, uint32_t sz, void *scratch,
 		cudaStream_t stream, int *launches);
 
 // pileup (mode 0 -> pileup[]) or fused pileup + model (mode 1 -> gt_vcf[]) for tiles [tile0, tile0 + ntiles) of a
-// block previously binned into `scratch`; `out` points at the record of site tile0 * 256
+// block previously binned into `scratch`; `out` points at the record of site tile0 * kPileTileSites
 cudaError_t launch_pileup_tiles(const void *scratch, size_t nseg, const void *bases, const void *ref, uint32_t x,
 		uint32_t sz, uint32_t tile0, uint32_t ntiles, void *out, int mode, const DevConst *dc,
 		unsigned long long *counters, cudaStream_t stream, int *launches);
@@ -42,6 +42,7 @@ cudaError_t launch_normalise(const void *tmpl, size_t n, const void *bases, void
 		void *segs, uint32_t segs_per_mate, uint32_t x, uint32_t y, const uint32_t left_trim[2], const uint32_t right_trim[2],
 		unsigned long long *counters, cudaStream_t stream, int *launches);
 
-constexpr int kPileTileSites = 256;
+constexpr int kPileTileSites = 128;      // sites per tile of the gather kernel (= its CTA size)
+constexpr int kMaxSegLen = 256;          // BSGPU_MAX_SEG_LEN
 
 }  // namespace bsgpu
