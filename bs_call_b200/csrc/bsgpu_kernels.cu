@@ -49,6 +49,10 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 		::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_load_1d_s32(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes) {
 	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -294,31 +298,28 @@ __device__ __forceinline__ void flush_combo(uint32_t &lo, uint32_t &hi, WideAcc 
 	lo = hi = 0;
 }
 
-// hit record in shared memory: {pos, len, t, mapq^2}; the byte of reference position p sits at lanebase[t] where
-// lanebase = bases + p - (tile end) is a per-lane pointer, so the address costs one 64-bit add of a 32-bit offset
-__device__ __forceinline__ void hit_one(const uint4 c, uint32_t mypos, const uint8_t *__restrict__ lanebase, const uint2 *__restrict__ lut,
-		uint32_t &lo, uint32_t &hi, uint32_t &mq2) {
-	const uint32_t byte = (mypos - c.x) < c.y ? (uint32_t)__ldg(lanebase + c.z) : 0u;
-	const uint2 e = lut[byte];
-	lo += e.x; hi += e.y;
-	if (e.x | e.y) mq2 += c.w;
+// hit record in shared memory: {pos, len, t, mapq^2}; the byte of reference position p was staged at shared address
+// t + p (32-bit shared-window arithmetic), so the per-hit address is one add
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+	uint32_t v;
+	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
 }
 
+// Runs are padded to a multiple of four with empty records (len 0), so the hit loop has no remainder path.
 template <int K>
 __device__ __forceinline__ void run_combo(const uint4 *__restrict__ hits, uint32_t hs, uint32_t he, uint32_t mypos,
-		const uint8_t *__restrict__ lanebase, const uint2 *__restrict__ lut, WideAcc &w) {
+		const uint2 *__restrict__ lut, WideAcc &w) {
 	uint32_t lo = 0, hi = 0;
 	for (uint32_t h0 = hs; h0 < he; h0 += kHitTrip) {
 		const uint32_t h1 = min(h0 + (uint32_t)kHitTrip, he);
-		uint32_t h = h0;
-		for (; h + 4 <= h1; h += 4) {
-			// four hits per trip: their byte loads are issued back to back before any is consumed
+		for (uint32_t h = h0; h < h1; h += 4) {
 			uint4 c[4];
 			uint32_t byte[4];
 #pragma unroll
 			for (int u = 0; u < 4; u++) c[u] = hits[h + u];
 #pragma unroll
-			for (int u = 0; u < 4; u++) byte[u] = (mypos - c[u].x) < c[u].y ? (uint32_t)__ldg(lanebase + c[u].z) : 0u;
+			for (int u = 0; u < 4; u++) byte[u] = (mypos - c[u].x) < c[u].y ? lds_u8(c[u].z + mypos) : 0u;
 #pragma unroll
 			for (int u = 0; u < 4; u++) {
 				const uint2 e = lut[byte[u]];
@@ -326,9 +327,20 @@ __device__ __forceinline__ void run_combo(const uint4 *__restrict__ hits, uint32
 				if (e.x | e.y) w.mq2 += c[u].w;
 			}
 		}
-		for (; h < h1; h++) hit_one(hits[h], mypos, lanebase, lut, lo, hi, w.mq2);
 		flush_combo<K>(lo, hi, w);
 	}
+}
+
+constexpr int kDeal = 96;                      // candidates dealt per round (three warps' worth)
+constexpr int kHitCap = kDeal + 24;            // a warp's hit list: kDeal hits + padding of its six runs
+constexpr int kSlotBytes = 144;
+__host__ __device__ constexpr size_t pile_work_bytes(int rec) {
+	const size_t a = (size_t)kPileTile * rec, b = (size_t)4 * kHitCap * 16 + (size_t)kDeal * kSlotBytes;
+	return ((a > b ? a : b) + 127) & ~(size_t)127;
+}                // 128 bytes of a segment inside the tile + 16-byte alignment slack on both sides
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 template <int MODE>
@@ -339,11 +351,14 @@ k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_s
 	constexpr int REC = MODE ? 208 : 104;
 	constexpr int RW = REC / 8;
 	extern __shared__ __align__(128) uint8_t smem_raw[];
-	uint64_t *stage = (uint64_t *)smem_raw;                      // output tile; before that, the four warps' hit lists
-	uint4 *whits = (uint4 *)smem_raw;                            // [4][kPileThreads]
-	uint2 *lut = (uint2 *)(smem_raw + kPileThreads * REC);       // byte -> {low, high} packed increment
-	Tables *tabs = (Tables *)(smem_raw + kPileThreads * REC + 256 * sizeof(uint2));
+	// the output tile is staged where the hit lists and the staged read bytes lived (they are dead by then)
+	uint64_t *stage = (uint64_t *)smem_raw;
+	uint4 *whits = (uint4 *)smem_raw;                            // [4][kHitCap]
+	uint8_t *slots = smem_raw + 4 * kHitCap * sizeof(uint4);     // [kDeal][kSlotBytes] staged read bytes
+	uint2 *lut = (uint2 *)(smem_raw + pile_work_bytes(REC));     // byte -> {low, high} packed increment
+	Tables *tabs = (Tables *)(smem_raw + pile_work_bytes(REC) + 256 * sizeof(uint2));
 	__shared__ uint32_t cnt[32], cur[32], rs[32], re[32];        // [warp][combo (8 slots)]
+	__shared__ uint64_t bar;
 
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const uint32_t tile = tile0 + blockIdx.x;
@@ -351,61 +366,76 @@ k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_s
 	const int nrec = (int)min((uint32_t)kPileThreads, sz - site0);
 	const uint32_t tpos0 = x + site0;                            // 1-based reference position of the CTA's first site
 	const uint32_t mypos = tpos0 + tid;
-	const uint8_t *lanebase = bases - (kPileThreads - tid);     // + (off - pos + tpos0 + 128) = the byte of this lane's position
-	asm volatile("" : "+l"(lanebase));                          // keep it in a register pair: one 64-bit add per byte address
+	const uint32_t myslot = smem_u32(slots + tid * kSlotBytes);
 	{
 		const uint2 *src = (const uint2 *)dc->pile_lut;
 		lut[tid] = src[tid];
 		lut[tid + kPileThreads] = src[tid + kPileThreads];
 	}
 	if (MODE) load_tables(tabs, dc, tid, kPileThreads);
+	if (tid == 0) mbar_init(&bar, kPileThreads);
 
 	WideAcc w;
 #pragma unroll
 	for (int j = 0; j < 8; j++) w.cnt[j] = w.qs[j] = 0;
 	w.mq2 = 0;
-	uint32_t warp_hits = 0;
+	uint32_t warp_hits = 0, phase = 0;
 
 	const uint32_t c_lo = bin_start[tile > (uint32_t)kBinsBack ? tile - kBinsBack : 0], c_hi = bin_start[tile + 1];
-	for (uint32_t base = c_lo; base < c_hi; base += kPileThreads) {
+	for (uint32_t base = c_lo; base < c_hi; base += kDeal) {
 		if (tid < 32) cnt[tid] = 0;
 		__syncthreads();
-		// deal: which warps does my candidate overlap?
+		// deal: which warps does my candidate overlap?  Its bytes inside the tile start their way to shared memory now.
 		uint4 c = make_uint4(0, 0, 0, 0);
 		int w_lo = 1, w_hi = 0;
-		uint32_t k = 0;
-		if (base + tid < c_hi) {
+		uint32_t k = 0, t = 0;
+		if (tid < kDeal && base + tid < c_hi) {
 			c = *(const uint4 *)(cands + base + tid);
 			const int rel = (int)(c.x - tpos0);                 // start relative to the tile (negative: starts before it)
 			const int s_lo = max(rel, 0), s_hi = min(rel + (int)(c.z & 0xffffu) - 1, kPileThreads - 1);
 			k = c.z >> 16;
-			if (s_hi >= s_lo && k < 6) { w_lo = s_lo >> 5; w_hi = s_hi >> 5; }
+			if (s_hi >= s_lo && k < 6) {
+				w_lo = s_lo >> 5; w_hi = s_hi >> 5;
+				// byte of position p is bases[c.y + p]; copy the 16-byte aligned cover of positions [s_lo, s_hi]
+				const uint8_t *g0 = bases + (uint32_t)(c.y + tpos0 + (uint32_t)s_lo);
+				const uint8_t *a0 = (const uint8_t *)((uintptr_t)g0 & ~(uintptr_t)15);
+				const uint32_t bytes = (uint32_t)(((uintptr_t)g0 + (uint32_t)(s_hi - s_lo) + 16) & ~(uintptr_t)15) - (uint32_t)(uintptr_t)a0;
+				mbar_expect_tx(&bar, bytes);
+				tma_load_1d_s32(myslot, a0, bytes, &bar);
+				t = myslot + (uint32_t)(g0 - a0) - (tpos0 + (uint32_t)s_lo);
+			}
 		}
-		for (int ww = w_lo; ww <= w_hi; ww++) atomicAdd(&cnt[ww * 8 + k], 1u);
+		if (w_hi < w_lo) mbar_arrive(&bar);
+#pragma unroll
+		for (int ww = 0; ww < 4; ww++) if (ww >= w_lo && ww <= w_hi) atomicAdd(&cnt[ww * 8 + k], 1u);
 		__syncthreads();
 		if (tid < 32) {
-			const uint32_t v = cnt[tid];
-			uint32_t incl = v;
+			// runs start on multiples of four and are padded with empty records
+			const uint32_t v = cnt[tid], v4 = (v + 3u) & ~3u;
+			uint32_t incl = v4;
 #pragma unroll
 			for (int d = 1; d < 8; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d, 8); if ((tid & 7) >= d) incl += o; }
-			const uint32_t first = (uint32_t)(tid >> 3) * kPileThreads + incl - v;
-			rs[tid] = first; cur[tid] = first; re[tid] = first + v;
+			const uint32_t first = (uint32_t)(tid >> 3) * kHitCap + incl - v4;
+			rs[tid] = first; cur[tid] = first; re[tid] = first + v4;
+			for (uint32_t i = first + v; i < first + v4; i++) whits[i] = make_uint4(0, 0, 0, 0);
 		}
 		__syncthreads();
 		{
-			// {pos, len, offset of the byte of position tpos0 + 128 relative to bases (never negative), mapq^2}
-			const uint4 hrec = make_uint4(c.x, c.z & 0xffffu, c.y + tpos0 + (uint32_t)kPileThreads, c.w);
-			for (int ww = w_lo; ww <= w_hi; ww++) whits[atomicAdd(&cur[ww * 8 + k], 1u)] = hrec;
+			const uint4 hrec = make_uint4(c.x, c.z & 0xffffu, t, c.w);
+#pragma unroll
+			for (int ww = 0; ww < 4; ww++) if (ww >= w_lo && ww <= w_hi) whits[atomicAdd(&cur[ww * 8 + k], 1u)] = hrec;
 		}
 		__syncthreads();
+		mbar_wait(&bar, phase);            // the staged bytes have landed
+		phase ^= 1;
 		// walk this warp's hits, combo by combo
-		warp_hits += re[wid * 8 + 5] - rs[wid * 8];
-		run_combo<0>(whits, rs[wid * 8 + 0], re[wid * 8 + 0], mypos, lanebase, lut, w);
-		run_combo<1>(whits, rs[wid * 8 + 1], re[wid * 8 + 1], mypos, lanebase, lut, w);
-		run_combo<2>(whits, rs[wid * 8 + 2], re[wid * 8 + 2], mypos, lanebase, lut, w);
-		run_combo<3>(whits, rs[wid * 8 + 3], re[wid * 8 + 3], mypos, lanebase, lut, w);
-		run_combo<4>(whits, rs[wid * 8 + 4], re[wid * 8 + 4], mypos, lanebase, lut, w);
-		run_combo<5>(whits, rs[wid * 8 + 5], re[wid * 8 + 5], mypos, lanebase, lut, w);
+		warp_hits += re[wid * 8 + 5] - rs[wid * 8];      // includes padding: an upper bound is all the envelope check needs
+		run_combo<0>(whits, rs[wid * 8 + 0], re[wid * 8 + 0], mypos, lut, w);
+		run_combo<1>(whits, rs[wid * 8 + 1], re[wid * 8 + 1], mypos, lut, w);
+		run_combo<2>(whits, rs[wid * 8 + 2], re[wid * 8 + 2], mypos, lut, w);
+		run_combo<3>(whits, rs[wid * 8 + 3], re[wid * 8 + 3], mypos, lut, w);
+		run_combo<4>(whits, rs[wid * 8 + 4], re[wid * 8 + 4], mypos, lut, w);
+		run_combo<5>(whits, rs[wid * 8 + 5], re[wid * 8 + 5], mypos, lut, w);
 		__syncthreads();
 	}
 
@@ -427,11 +457,13 @@ k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_s
 
 	uint64_t *rec = stage + tid * RW;
 	if (MODE == 0) {
-		uint32_t *o = (uint32_t *)rec;
+		uint32_t o[26];
 #pragma unroll
 		for (int j = 0; j < 8; j++) { o[j] = s.cnt[0][j]; o[8 + j] = s.cnt[1][j]; o[17 + j] = __float_as_uint(s.qsum[j]); }
 		o[16] = s.n;
 		o[25] = __float_as_uint(s.mapq2);
+#pragma unroll
+		for (int j = 0; j < 13; j++) rec[j] = (uint64_t)o[2 * j] | (uint64_t)o[2 * j + 1] << 32;
 	} else {
 		const int rf = tid < nrec ? ref[site0 + tid] : 0;
 		__syncthreads();                    // tables loaded (the candidate loop may not have run)
@@ -571,7 +603,7 @@ __global__ void k_synth_reads(uint64_t seed, uint32_t x, uint32_t sz, uint32_t r
 #define LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
 static size_t call_smem(bool vcf) { return (size_t)kCallTile * ((vcf ? 208 : 200) + 104) + sizeof(Tables); }
-static size_t pile_smem(int mode) { return (size_t)kPileThreads * (mode ? 208 : 104) + 256 * sizeof(uint2) + (mode ? sizeof(Tables) : 0); }
+static size_t pile_smem(int mode) { return pile_work_bytes(mode ? 208 : 104) + 256 * sizeof(uint2) + (mode ? sizeof(Tables) : 0); }
 
 static int g_sms = 148;
 static int g_call_minb = 5;          // resident CTAs per SM the likelihood kernel is compiled for (5: 96 regs; 4: 120 regs)
