@@ -305,30 +305,52 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
 	return v;
 }
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+	uint2 v;
+	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+	return v;
+}
 
-// Runs are padded to a multiple of four with empty records (len 0), so the hit loop has no remainder path.
-template <int K>
-__device__ __forceinline__ void run_combo(const uint4 *__restrict__ hits, uint32_t hs, uint32_t he, uint32_t mypos,
-		const uint2 *__restrict__ lut, WideAcc &w) {
+// One run = the hits of one combo of this warp, padded to a multiple of four with empty records (len 0) so the loop
+// has no remainder path.  Records carry (mapq^2 - the tile's reference value): a run in which that is zero throughout
+// (COMMON) needs no per-hit mapq work -- reference x (bases counted) is added once per site at the end.
+template <int K, bool COMMON>
+__device__ __forceinline__ void run_hits(uint32_t hits, uint32_t hend, uint32_t mypos, uint32_t lut, WideAcc &w) {
 	uint32_t lo = 0, hi = 0;
-	for (uint32_t h0 = hs; h0 < he; h0 += kHitTrip) {
-		const uint32_t h1 = min(h0 + (uint32_t)kHitTrip, he);
-		for (uint32_t h = h0; h < h1; h += 4) {
+	while (hits < hend) {
+		const uint32_t trip_end = min(hits + (uint32_t)kHitTrip * 16u, hend);
+#pragma unroll 1
+		do {
 			uint4 c[4];
 			uint32_t byte[4];
 #pragma unroll
-			for (int u = 0; u < 4; u++) c[u] = hits[h + u];
+			for (int u = 0; u < 4; u++) c[u] = lds_v4(hits + 16 * u);
 #pragma unroll
 			for (int u = 0; u < 4; u++) byte[u] = (mypos - c[u].x) < c[u].y ? lds_u8(c[u].z + mypos) : 0u;
 #pragma unroll
 			for (int u = 0; u < 4; u++) {
-				const uint2 e = lut[byte[u]];
+				const uint2 e = lds_v2(lut + 8 * byte[u]);
 				lo += e.x; hi += e.y;
-				if (e.x | e.y) w.mq2 += c[u].w;
+				if (!COMMON) { if (e.x | e.y) w.mq2 += c[u].w; }
 			}
-		}
+			hits += 64;
+		} while (hits < trip_end);
 		flush_combo<K>(lo, hi, w);
 	}
+}
+
+template <int K>
+__device__ __forceinline__ void run_combo(const uint32_t *__restrict__ rs, const uint32_t *__restrict__ re, int wid,
+		uint32_t whits_s, uint32_t mypos, uint32_t lut_s, WideAcc &w) {
+	const uint32_t hs = rs[wid * 8 + K], he = re[wid * 8 + K];       // bit 31 of `he`: some record of the run has odd mapq
+	if (hs == (he & 0x7fffffffu)) return;
+	if (he >> 31) run_hits<K, false>(whits_s + 16 * hs, whits_s + 16 * (he & 0x7fffffffu), mypos, lut_s, w);
+	else run_hits<K, true>(whits_s + 16 * hs, whits_s + 16 * he, mypos, lut_s, w);
 }
 
 constexpr int kDeal = 96;                      // candidates dealt per round (three warps' worth)
@@ -344,7 +366,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kPileThreads)
+__global__ void __launch_bounds__(kPileThreads, MODE ? 4 : 9)
 k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_start, const uint8_t *__restrict__ bases,
 		const uint8_t *__restrict__ ref, uint32_t x, uint32_t sz, uint32_t tile0, uint8_t *__restrict__ out,
 		const DevConst *__restrict__ dc, unsigned long long *__restrict__ counters) {
@@ -357,7 +379,7 @@ k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_s
 	uint8_t *slots = smem_raw + 4 * kHitCap * sizeof(uint4);     // [kDeal][kSlotBytes] staged read bytes
 	uint2 *lut = (uint2 *)(smem_raw + pile_work_bytes(REC));     // byte -> {low, high} packed increment
 	Tables *tabs = (Tables *)(smem_raw + pile_work_bytes(REC) + 256 * sizeof(uint2));
-	__shared__ uint32_t cnt[32], cur[32], rs[32], re[32];        // [warp][combo (8 slots)]
+	__shared__ uint32_t cnt[32], cur[32], rs[32], re[32];        // [warp][combo (8 slots)]; cnt bit 31: odd mapq seen
 	__shared__ uint64_t bar;
 
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -382,6 +404,8 @@ k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_s
 	uint32_t warp_hits = 0, phase = 0;
 
 	const uint32_t c_lo = bin_start[tile > (uint32_t)kBinsBack ? tile - kBinsBack : 0], c_hi = bin_start[tile + 1];
+	const uint32_t mq_ref = c_lo < c_hi ? cands[c_lo].mq2 : 0u;       // the tile's reference mapq^2 (any value is correct)
+	const uint32_t whits_s = smem_u32(whits), lut_s = smem_u32(lut);
 	for (uint32_t base = c_lo; base < c_hi; base += kDeal) {
 		if (tid < 32) cnt[tid] = 0;
 		__syncthreads();
@@ -395,6 +419,7 @@ k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_s
 			const int s_lo = max(rel, 0), s_hi = min(rel + (int)(c.z & 0xffffu) - 1, kPileThreads - 1);
 			k = c.z >> 16;
 			if (s_hi >= s_lo && k < 6) {
+				c.w -= mq_ref;
 				w_lo = s_lo >> 5; w_hi = s_hi >> 5;
 				// byte of position p is bases[c.y + p]; copy the 16-byte aligned cover of positions [s_lo, s_hi]
 				const uint8_t *g0 = bases + (uint32_t)(c.y + tpos0 + (uint32_t)s_lo);
@@ -407,16 +432,20 @@ k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_s
 		}
 		if (w_hi < w_lo) mbar_arrive(&bar);
 #pragma unroll
-		for (int ww = 0; ww < 4; ww++) if (ww >= w_lo && ww <= w_hi) atomicAdd(&cnt[ww * 8 + k], 1u);
+#pragma unroll
+		for (int ww = 0; ww < 4; ww++) if (ww >= w_lo && ww <= w_hi) {
+			atomicAdd(&cnt[ww * 8 + k], 1u);
+			if (c.w) atomicOr(&cnt[ww * 8 + k], 0x80000000u);      // "odd mapq" flag of the run (rare)
+		}
 		__syncthreads();
 		if (tid < 32) {
 			// runs start on multiples of four and are padded with empty records
-			const uint32_t v = cnt[tid], v4 = (v + 3u) & ~3u;
+			const uint32_t vv = cnt[tid], v = vv & 0xffffu, v4 = (v + 3u) & ~3u;
 			uint32_t incl = v4;
 #pragma unroll
 			for (int d = 1; d < 8; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d, 8); if ((tid & 7) >= d) incl += o; }
 			const uint32_t first = (uint32_t)(tid >> 3) * kHitCap + incl - v4;
-			rs[tid] = first; cur[tid] = first; re[tid] = first + v4;
+			rs[tid] = first; cur[tid] = first; re[tid] = (first + v4) | (vv & 0x80000000u);
 			for (uint32_t i = first + v; i < first + v4; i++) whits[i] = make_uint4(0, 0, 0, 0);
 		}
 		__syncthreads();
@@ -429,13 +458,13 @@ k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_s
 		mbar_wait(&bar, phase);            // the staged bytes have landed
 		phase ^= 1;
 		// walk this warp's hits, combo by combo
-		warp_hits += re[wid * 8 + 5] - rs[wid * 8];      // includes padding: an upper bound is all the envelope check needs
-		run_combo<0>(whits, rs[wid * 8 + 0], re[wid * 8 + 0], mypos, lut, w);
-		run_combo<1>(whits, rs[wid * 8 + 1], re[wid * 8 + 1], mypos, lut, w);
-		run_combo<2>(whits, rs[wid * 8 + 2], re[wid * 8 + 2], mypos, lut, w);
-		run_combo<3>(whits, rs[wid * 8 + 3], re[wid * 8 + 3], mypos, lut, w);
-		run_combo<4>(whits, rs[wid * 8 + 4], re[wid * 8 + 4], mypos, lut, w);
-		run_combo<5>(whits, rs[wid * 8 + 5], re[wid * 8 + 5], mypos, lut, w);
+		warp_hits += (re[wid * 8 + 5] & 0x7fffffffu) - rs[wid * 8];      // includes padding: an upper bound is all the envelope check needs
+		run_combo<0>(rs, re, wid, whits_s, mypos, lut_s, w);
+		run_combo<1>(rs, re, wid, whits_s, mypos, lut_s, w);
+		run_combo<2>(rs, re, wid, whits_s, mypos, lut_s, w);
+		run_combo<3>(rs, re, wid, whits_s, mypos, lut_s, w);
+		run_combo<4>(rs, re, wid, whits_s, mypos, lut_s, w);
+		run_combo<5>(rs, re, wid, whits_s, mypos, lut_s, w);
 		__syncthreads();
 	}
 
@@ -450,6 +479,7 @@ k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_s
 	}
 	const uint32_t n = (nsum & 0xffffu) + (nsum >> 16);
 	s.n = tid < nrec ? n : 0;
+	w.mq2 += mq_ref * n;               // the common runs' share (exact modulo 2^32, like the sum itself)
 	s.mapq2 = (float)w.mq2;
 	// integer sums equal the reference's float sums only below 2^24, and the half-word counts hold 65535:
 	// count the sites that leave the envelope
