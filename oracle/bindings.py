@@ -25,8 +25,65 @@ TEMPLATE = np.dtype([("forward_position", "<u4"), ("reverse_position", "<u4"), (
                      ("mm_n", "<u4", (2,)), ("present", "u1", (2,)), ("mapq", "u1", (2,)),
                      ("orientation", "u1"), ("bs_strand", "u1"), ("pad", "u1", (2,))])
 MISMS = np.dtype([("type", "<u4"), ("position", "<u4"), ("size", "<u4")])
+# reader side: what get_next_align_details() produces per BAM record, and one block as read_input() hands it over
+RECORD = np.dtype([("ret", "<i4"), ("filtered", "<u4"), ("forward_position", "<u4"), ("reverse_position", "<u4"),
+                   ("alignment_flag", "<u4"), ("align_length", "<u4"), ("reference_span", "<u4"),
+                   ("read_off", "<u4"), ("read_len", "<u4"), ("mm_off", "<u4"), ("mm_n", "<u4"),
+                   ("reverse", "u1"), ("orientation", "u1"), ("bs_strand", "u1"), ("mapq", "u1")])
+BLOCK = np.dtype([("tid", "<u4"), ("x", "<u4"), ("y", "<u4"), ("first_template", "<u4"), ("n_templates", "<u4"),
+                  ("pad", "<u4"), ("vcf_off", "<u8")])
 assert PILEUP.itemsize == 104 and GT_METH.itemsize == 200 and GT_VCF.itemsize == 208
-assert TEMPLATE.itemsize == 56 and MISMS.itemsize == 12
+assert TEMPLATE.itemsize == 56 and MISMS.itemsize == 12 and RECORD.itemsize == 48 and BLOCK.itemsize == 32
+
+
+def _reader_caps(bam, nrec):
+    """generous output capacities for the reader entry points"""
+    return dict(tmpl=nrec + 8, bases=len(bam) + 64, misms=len(bam) // 4 + 64, blocks=nrec + 8)
+
+
+def _decode_records(fn, bam, mapq_thresh, max_template_len, keep_unmatched, ignore_dup):
+    bam = _c(bam, np.uint8)
+    cap = max(len(bam) // 36 + 8, 8)
+    rec = np.zeros(cap, dtype=RECORD)
+    bases = np.zeros(len(bam) + 64, dtype=np.uint8)
+    misms = np.zeros(len(bam) // 4 + 64, dtype=MISMS)
+    n, nb, nm = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    rc = fn(_p(bam), C.c_size_t(len(bam)), C.c_int(mapq_thresh), C.c_uint32(max_template_len), C.c_int(keep_unmatched),
+            C.c_int(ignore_dup), _p(rec), C.c_size_t(cap), C.byref(n), _p(bases), C.c_size_t(len(bases)), C.byref(nb),
+            _p(misms), C.c_size_t(len(misms)), C.byref(nm))
+    if rc:
+        raise RuntimeError("decode_records failed: %d" % rc)
+    return rec[:n.value].copy(), bases[:nb.value].copy(), misms[:nm.value].copy()
+
+
+def _read_input(fn, bam, target_len, ctg_codes, mapq_thresh, max_template_len, keep_unmatched, ignore_duplicates,
+                keep_duplicates, run_chain):
+    bam = _c(bam, np.uint8)
+    target_len = _c(target_len, np.uint32)
+    nt = len(target_len)
+    nrec = max(len(bam) // 36 + 8, 8)
+    caps = _reader_caps(bam, nrec)
+    blocks = np.zeros(caps["blocks"], dtype=BLOCK)
+    tmpl = np.zeros(caps["tmpl"], dtype=TEMPLATE)
+    bases = np.zeros(caps["bases"], dtype=np.uint8)
+    misms = np.zeros(caps["misms"], dtype=MISMS)
+    vcf_cap = int(target_len.sum()) + 8 if run_chain else 8
+    vcf = np.zeros(vcf_cap, dtype=GT_VCF)
+    codes = None
+    ptrs = None
+    if run_chain:
+        codes = [_c(c, np.uint8) for c in ctg_codes]
+        ptrs = (C.c_void_p * nt)(*[c.ctypes.data for c in codes])
+    nbk, ntm, nb, nm, nv = (C.c_size_t(0) for _ in range(5))
+    rc = fn(_p(bam), C.c_size_t(len(bam)), C.c_int(nt), _p(target_len), ptrs, C.c_int(mapq_thresh), C.c_uint32(max_template_len),
+            C.c_int(keep_unmatched), C.c_int(ignore_duplicates), C.c_int(keep_duplicates), C.c_int(run_chain),
+            _p(blocks), C.c_size_t(len(blocks)), C.byref(nbk), _p(tmpl), C.c_size_t(len(tmpl)), C.byref(ntm),
+            _p(bases), C.c_size_t(len(bases)), C.byref(nb), _p(misms), C.c_size_t(len(misms)), C.byref(nm),
+            _p(vcf), C.c_size_t(len(vcf)), C.byref(nv))
+    if rc:
+        raise RuntimeError("read_input failed: %d" % rc)
+    return (blocks[:nbk.value].copy(), tmpl[:ntm.value].copy(), bases[:nb.value].copy(), misms[:nm.value].copy(),
+            vcf[:nv.value].copy())
 
 
 class BsoParams(C.Structure):
@@ -120,6 +177,18 @@ class Oracle:
         if rc:
             raise RuntimeError("bso_normalise_block failed: %d" % rc)
         return out_t, out_b[:used.value].copy()
+
+    def decode_records(self, bam, mapq_thresh=20, max_template_len=1000, keep_unmatched=False, ignore_dup=False):
+        """raw BAM records -> (RECORD[], packed bases, misms): the restatement of get_next_align_details()"""
+        return _decode_records(self.lib.bso_decode_records, bam, mapq_thresh, max_template_len, keep_unmatched, ignore_dup)
+
+    def read_input(self, bam, target_len, ctg_codes=None, mapq_thresh=20, max_template_len=1000, keep_unmatched=False,
+                   ignore_duplicates=False, keep_duplicates=False, run_chain=False):
+        """raw BAM records -> (BLOCK[], TEMPLATE[], bases, misms, gt_vcf[]): the restatement of read_input(); with
+        run_chain the blocks also go through the restated process_template_vector / call_genotypes_ML"""
+        self.lib.bso_set_params(C.byref(self.params))
+        return _read_input(self.lib.bso_read_input, bam, target_len, ctg_codes, mapq_thresh, max_template_len,
+                           keep_unmatched, ignore_duplicates, keep_duplicates, run_chain)
 
     def process_block(self, templates, bases, misms, refcodes, y):
         """refcodes: codes for positions [x, y] where x = max(first-2, 1)."""
@@ -242,6 +311,17 @@ class Reference:
         if rc:
             raise RuntimeError("bsref_call_block failed: %d" % rc)
         return pile, vcf
+
+    def decode_records(self, bam, mapq_thresh=20, max_template_len=1000, keep_unmatched=False, ignore_dup=False):
+        """raw BAM records through the reference's get_next_align_details() (src/input_sam.c:222)"""
+        return _decode_records(self.lib.bsref_decode_records, bam, mapq_thresh, max_template_len, keep_unmatched, ignore_dup)
+
+    def read_input(self, bam, target_len, ctg_codes=None, mapq_thresh=20, max_template_len=1000, keep_unmatched=False,
+                   ignore_duplicates=False, keep_duplicates=False, run_chain=False):
+        """raw BAM records through the reference's read_input() (src/get_template_vector.c:49); with run_chain every
+        block continues through process_template_vector() and call_genotypes_ML() as in the reference binary"""
+        return _read_input(self.lib.bsref_read_input, bam, target_len, ctg_codes, mapq_thresh, max_template_len,
+                           keep_unmatched, ignore_duplicates, keep_duplicates, run_chain)
 
     def process_block(self, templates, bases, misms, ctg_codes, y):
         """Raw templates -> (x, pileup[], gt_vcf[], ref[], normalised templates, normalised bases)."""

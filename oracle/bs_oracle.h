@@ -101,6 +101,32 @@ int bso_process_block(const bso_template *t, size_t n, const uint8_t *bases, con
 		const uint8_t *refcodes /* codes for [x, y] */, uint32_t y, const bso_params *p,
 		uint32_t *x_out, bso_pileup *pile_out, bso_gt_vcf *vcf_out);
 
+/* ---- reader side (bs_oracle_reader.c) ---- */
+/* what get_next_align_details() yields for one BAM record (src/input_sam.c:222-312) */
+typedef struct {
+	int32_t ret;                 /* 0 keep, 1 filtered */
+	uint32_t filtered;           /* gt_filter_reason, include/bs_call.h:50 */
+	uint32_t forward_position, reverse_position;
+	uint32_t alignment_flag, align_length;
+	uint32_t reference_span;     /* of the mate this record is */
+	uint32_t read_off, read_len; /* into the packed-base output (ret == 0 only) */
+	uint32_t mm_off, mm_n;       /* into the event output */
+	uint8_t reverse, orientation, bs_strand, mapq;
+} bso_record;                  /* 48 bytes */
+
+/* one block as read_input() hands it to process_template_vector(): templates [first, first + n), window [x, y] */
+typedef struct { uint32_t tid, x, y, first_template, n_templates, pad; uint64_t vcf_off; } bso_block;
+
+int bso_decode_records(const uint8_t *bam, size_t nbytes, int mapq_thresh, uint32_t max_template_len, int keep_unmatched,
+		int ignore_dup, bso_record *out, size_t cap, size_t *nrec, uint8_t *bases_out, size_t bases_cap, size_t *nbases,
+		bso_misms *misms_out, size_t misms_cap, size_t *nmisms);
+void bso_set_params(const bso_params *p);      /* model parameters used when bso_read_input runs the whole chain */
+int bso_read_input(const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len, const uint8_t *const *ctg_codes,
+		int mapq_thresh, uint32_t max_template_len, int keep_unmatched, int ignore_duplicates, int keep_duplicates, int run_chain,
+		bso_block *blocks, size_t block_cap, size_t *nblocks, bso_template *tmpl, size_t tmpl_cap, size_t *ntmpl,
+		uint8_t *bases, size_t bases_cap, size_t *nbases, bso_misms *misms, size_t misms_cap, size_t *nmisms,
+		bso_gt_vcf *vcf, size_t vcf_cap, size_t *nvcf);
+
 /* host twin of the device generator of per-site count vectors (same draws, same records) */
 void bso_synth_sites(uint64_t seed, uint64_t first, size_t n, double mean_depth, bso_pileup *out, uint8_t *ref, int nthreads);
 

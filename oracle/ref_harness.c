@@ -392,3 +392,254 @@ int bsref_call_sites_mt(const void *pile, const uint8_t *ref, size_t n, gt_meth 
 	free(thr);
 	return 0;
 }
+
+/* =====================================================================================================
+ * Reader side: the reference's own BAM-record decode (src/input_sam.c) and block builder
+ * (read_input, src/get_template_vector.c), both compiled unmodified.  htslib is replaced by a memory-backed
+ * sam_read1() over a buffer of raw BAM alignment records (the byte stream that follows the header in an
+ * uncompressed BAM: int32 block_size, 32 bytes of fixed fields, then qname | cigar | seq | qual | aux).
+ * ===================================================================================================== */
+#include <htslib/sam.h>
+
+static const uint8_t *mem_bam;
+static size_t mem_len, mem_pos;
+
+static int32_t rd_i32(const uint8_t *p) { int32_t v; memcpy(&v, p, 4); return v; }
+static uint16_t rd_u16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+int sam_read1(htsFile *fp, bam_hdr_t *h, bam1_t *b) {
+	if (mem_pos == mem_len) return -1;
+	if (mem_pos + 4 > mem_len) return -2;
+	const int32_t bs = rd_i32(mem_bam + mem_pos);
+	if (bs < 32 || mem_pos + 4 + (size_t)bs > mem_len) return -2;
+	const uint8_t *p = mem_bam + mem_pos + 4;
+	bam1_core_t *c = &b->core;
+	c->tid = rd_i32(p);
+	c->pos = rd_i32(p + 4);
+	c->l_qname = p[8];
+	c->qual = p[9];
+	c->bin = rd_u16(p + 10);
+	c->n_cigar = rd_u16(p + 12);
+	c->flag = rd_u16(p + 14);
+	c->l_qseq = rd_i32(p + 16);
+	c->mtid = rd_i32(p + 20);
+	c->mpos = rd_i32(p + 24);
+	c->isize = rd_i32(p + 28);
+	c->l_extranul = 0;
+	b->l_data = bs - 32;
+	if ((uint32_t)b->l_data > b->m_data) { b->m_data = b->l_data + 64; b->data = realloc(b->data, b->m_data); }
+	memcpy(b->data, p + 32, b->l_data);
+	mem_pos += 4 + (size_t)bs;
+	return b->l_data;
+}
+int sam_itr_next(htsFile *fp, hts_itr_t *itr, bam1_t *b) { return -1; }
+hts_itr_t *sam_itr_queryi(const hts_idx_t *idx, int tid, hts_pos_t beg, hts_pos_t end) { return NULL; }
+void hts_itr_destroy(hts_itr_t *itr) { }
+bam1_t *bam_init1(void) { return calloc(1, sizeof(bam1_t)); }
+void bam_destroy1(bam1_t *b) { if (b) { free(b->data); free(b); } }
+
+int get_next_align_details(htsFile * const sam_input, bam_hdr_t *hdr, hts_itr_t *itr, bam1_t *b, align_details * const al, const uint64_t thresh,
+		const uint64_t max_template_len, bool keep_unmatched, bool ignore_dup, bool *reverse, gt_filter_reason * const filtered,
+		uint32_t * const align_length, uint32_t * const alignment_flag);
+
+/* per-record view of what get_next_align_details() produced (src/input_sam.c:222-312) */
+typedef struct {
+	int32_t ret;                 /* 0 keep, 1 filtered */
+	uint32_t filtered;           /* gt_filter_reason */
+	uint32_t forward_position, reverse_position;
+	uint32_t alignment_flag, align_length;
+	uint32_t reference_span;     /* of the mate this record is (index = reverse) */
+	uint32_t read_off, read_len; /* into bases_out (only when ret == 0) */
+	uint32_t mm_off, mm_n;       /* into misms_out */
+	uint8_t reverse, orientation, bs_strand, mapq;
+} bsref_record;
+
+int bsref_decode_records(const uint8_t *bam, size_t nbytes, int mapq_thresh, uint32_t max_template_len,
+		int keep_unmatched, int ignore_dup, bsref_record *out, size_t cap, size_t *nrec,
+		uint8_t *bases_out, size_t bases_cap, size_t *nbases, bsref_misms *misms_out, size_t misms_cap, size_t *nmisms) {
+	mem_bam = bam; mem_len = nbytes; mem_pos = 0;
+	bam1_t *b = bam_init1();
+	gt_vector *fl = gt_vector_new(4, sizeof(align_details *));
+	size_t n = 0, nb = 0, nm = 0;
+	int rc = 0;
+	for (;;) {
+		align_details *al = get_new_align_details(fl);
+		bool reverse = false;
+		gt_filter_reason flt;
+		uint32_t alen = 0, aflag = 0;
+		int ret = get_next_align_details(NULL, NULL, NULL, b, al, mapq_thresh, max_template_len, keep_unmatched, ignore_dup, &reverse, &flt, &alen, &aflag);
+		if (ret < 0) { if (ret != -1) rc = -2; break; }
+		if (n >= cap) { rc = -3; break; }
+		bsref_record *o = out + n++;
+		memset(o, 0, sizeof(*o));
+		o->ret = ret; o->filtered = flt;
+		o->forward_position = al->forward_position; o->reverse_position = al->reverse_position;
+		o->alignment_flag = aflag;
+		o->reverse = reverse; o->orientation = (uint8_t)al->orientation;
+		const int ix = reverse ? 1 : 0;
+		o->mapq = al->mapq[ix];
+		if (ret == 0) {
+			o->align_length = alen;
+			o->bs_strand = (uint8_t)al->bs_strand;
+			o->reference_span = al->reference_span[ix];
+			o->read_off = (uint32_t)nb; o->read_len = (uint32_t)gt_vector_get_used(al->read[ix]);
+			if (nb + o->read_len > bases_cap) { rc = -3; break; }
+			memcpy(bases_out + nb, al->read[ix]->memory, o->read_len);
+			nb += o->read_len;
+			o->mm_off = (uint32_t)nm; o->mm_n = (uint32_t)gt_vector_get_used(al->mismatches[ix]);
+			if (nm + o->mm_n > misms_cap) { rc = -3; break; }
+			gt_misms *mp = gt_vector_get_mem(al->mismatches[ix], gt_misms);
+			for (uint32_t z = 0; z < o->mm_n; z++) { misms_out[nm].type = mp[z].misms_type; misms_out[nm].position = mp[z].position; misms_out[nm].size = mp[z].size; nm++; }
+		}
+		for (int k = 0; k < 2; k++) { if (al->read[k]) gt_vector_delete(al->read[k]); gt_vector_delete(al->mismatches[k]); }
+		free(al);
+	}
+	bam_destroy1(b);
+	gt_vector_delete(fl);
+	*nrec = n; *nbases = nb; *nmisms = nm;
+	return rc;
+}
+
+/* ---- read_input() with a stand-in for process_thread (src/process.c:43-72) that snapshots every block ---- */
+typedef struct { uint32_t tid, x, y, first_template, n_templates, pad; uint64_t vcf_off; } bsref_block;
+
+typedef struct {
+	bsref_block *blocks; size_t block_cap, nblocks;
+	bsref_template *tmpl; size_t tmpl_cap, ntmpl;
+	uint8_t *bases; size_t bases_cap, nbases;
+	bsref_misms *misms; size_t misms_cap, nmisms;
+	gt_vcf *vcf; size_t vcf_cap, nvcf;
+	int run_chain;               /* also run process_template_vector + call_genotypes_ML on each block */
+	int err;
+} reader_out;
+
+static reader_out rdr;
+
+static void snapshot_block(gt_vector *alist, ctg_t *c, uint32_t y) {
+	const size_t n = gt_vector_get_used(alist);
+	align_details **p = gt_vector_get_mem(alist, align_details *);
+	if (rdr.nblocks >= rdr.block_cap || rdr.ntmpl + n > rdr.tmpl_cap) { rdr.err = -3; return; }
+	bsref_block *bk = rdr.blocks + rdr.nblocks++;
+	memset(bk, 0, sizeof(*bk));
+	bk->tid = (uint32_t)c->bam_tid; bk->y = y; bk->first_template = (uint32_t)rdr.ntmpl; bk->n_templates = (uint32_t)n;
+	uint32_t x = p[0]->forward_position ? p[0]->forward_position : p[0]->reverse_position;
+	bk->x = x > 2 ? x - 2 : 1;
+	bk->vcf_off = rdr.nvcf;
+	for (size_t i = 0; i < n; i++) {
+		align_details *al = p[i];
+		bsref_template *o = rdr.tmpl + rdr.ntmpl++;
+		memset(o, 0, sizeof(*o));
+		o->forward_position = al->forward_position; o->reverse_position = al->reverse_position;
+		o->orientation = (uint8_t)al->orientation; o->bs_strand = (uint8_t)al->bs_strand;
+		for (int k = 0; k < 2; k++) {
+			o->reference_span[k] = al->reference_span[k];
+			o->mapq[k] = al->mapq[k];
+			o->present[k] = al->read[k] != NULL;
+			const uint32_t rl = al->read[k] ? (uint32_t)gt_vector_get_used(al->read[k]) : 0;
+			const uint32_t nm = rl ? (uint32_t)gt_vector_get_used(al->mismatches[k]) : 0;
+			if (rdr.nbases + rl > rdr.bases_cap || rdr.nmisms + nm > rdr.misms_cap) { rdr.err = -3; return; }
+			o->read_off[k] = (uint32_t)rdr.nbases; o->read_len[k] = rl;
+			if (rl) memcpy(rdr.bases + rdr.nbases, al->read[k]->memory, rl);
+			rdr.nbases += rl;
+			o->mm_off[k] = (uint32_t)rdr.nmisms; o->mm_n[k] = nm;
+			gt_misms *mp = gt_vector_get_mem(al->mismatches[k], gt_misms);
+			for (uint32_t z = 0; z < nm; z++) { rdr.misms[rdr.nmisms].type = mp[z].misms_type; rdr.misms[rdr.nmisms].position = mp[z].position; rdr.misms[rdr.nmisms].size = mp[z].size; rdr.nmisms++; }
+		}
+	}
+	if (rdr.run_chain) {
+		const uint32_t sz = y - bk->x + 1;
+		if (rdr.nvcf + sz > rdr.vcf_cap) { rdr.err = -3; return; }
+		par.work.vcf_ctg = c;
+		call_t0 = now_s();
+		if (process_template_vector(alist, c, y, &par) != GT_STATUS_OK) { rdr.err = -2; return; }
+		consume(sz, NULL, rdr.vcf + rdr.nvcf, NULL);
+		rdr.nvcf += sz;
+	}
+}
+
+static void *reader_process_thread(void *arg) {
+	gt_vector *prev_align = NULL;
+	work_t * const work = &par.work;
+	while (true) {
+		pthread_mutex_lock(&work->process_mutex);
+		while (!work->align_list_waiting && !work->process_end) {
+			struct timespec ts;
+			clock_gettime(CLOCK_REALTIME, &ts);
+			ts.tv_sec += 1;
+			pthread_cond_timedwait(&work->process_cond1, &work->process_mutex, &ts);
+		}
+		pthread_mutex_unlock(&work->process_mutex);
+		gt_vector *alist = work->align_list_waiting;
+		if (alist == NULL) break;
+		ctg_t *c = work->ctg_waiting;
+		const uint32_t pos = work->y_waiting;
+		work->ctg_waiting = NULL;
+		work->free_list_waiting = prev_align;
+		work->align_list_waiting = NULL;
+		pthread_mutex_lock(&work->process_mutex);
+		pthread_cond_signal(&work->process_cond2);
+		pthread_mutex_unlock(&work->process_mutex);
+		if (!rdr.err) snapshot_block(alist, c, pos);
+		prev_align = alist;
+	}
+	return NULL;
+}
+
+gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param);
+
+/* ctg_codes[tid] (may be NULL when run_chain == 0): reference codes 0..4 for positions 1..target_len[tid] */
+int bsref_read_input(const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len, const uint8_t *const *ctg_codes,
+		int mapq_thresh, uint32_t max_template_len, int keep_unmatched, int ignore_duplicates, int keep_duplicates, int run_chain,
+		bsref_block *blocks, size_t block_cap, size_t *nblocks, bsref_template *tmpl, size_t tmpl_cap, size_t *ntmpl,
+		uint8_t *bases, size_t bases_cap, size_t *nbases, bsref_misms *misms, size_t misms_cap, size_t *nmisms,
+		gt_vcf *vcf, size_t vcf_cap, size_t *nvcf) {
+	if (!inited) return -1;
+	mem_bam = bam; mem_len = nbytes; mem_pos = 0;
+	memset(&rdr, 0, sizeof(rdr));
+	rdr.blocks = blocks; rdr.block_cap = block_cap; rdr.tmpl = tmpl; rdr.tmpl_cap = tmpl_cap; rdr.bases = bases; rdr.bases_cap = bases_cap;
+	rdr.misms = misms; rdr.misms_cap = misms_cap; rdr.vcf = vcf; rdr.vcf_cap = vcf_cap; rdr.run_chain = run_chain;
+	work_t * const w = &par.work;
+	bam_hdr_t hdr;
+	memset(&hdr, 0, sizeof(hdr));
+	hdr.n_targets = n_targets;
+	hdr.target_len = (uint32_t *)target_len;
+	hdr.target_name = calloc(n_targets, sizeof(char *));
+	ctg_t *ctgs = calloc(n_targets, sizeof(ctg_t));
+	w->contigs = calloc(n_targets, sizeof(ctg_t *));
+	w->tid2id = calloc(n_targets, sizeof(int));
+	for (int i = 0; i < n_targets; i++) {
+		char nm[32];
+		snprintf(nm, sizeof(nm), "ctg%d", i);
+		hdr.target_name[i] = strdup(nm);
+		ctgs[i].name = hdr.target_name[i];
+		ctgs[i].bam_tid = i;
+		if (run_chain) {
+			const uint32_t len = target_len[i];
+			const size_t nw = ((size_t)len + 9) / 5;
+			ctgs[i].seq = calloc(nw + 1, sizeof(uint16_t));
+			for (uint32_t j = 0; j < len; j++) ctgs[i].seq[j / 5] |= (uint16_t)(ctg_codes[i][j] & 7) << (3 * (4 - (j % 5)));
+			ctgs[i].start_pos = 1; ctgs[i].end_pos = len; ctgs[i].seq_len = len;
+		}
+		w->contigs[i] = ctgs + i;
+		w->tid2id[i] = i;
+	}
+	w->n_contigs = n_targets; w->n_regions = 0; w->sam_idx = NULL; w->sam_header = &hdr; w->curr_region = NULL;
+	w->process_end = false; w->align_list_waiting = NULL; w->free_list_waiting = NULL; w->ctg_waiting = NULL;
+	par.mapq_thresh = (uint8_t)mapq_thresh; par.max_template_len = max_template_len;
+	par.keep_unmatched = keep_unmatched; par.ignore_duplicates = ignore_duplicates; par.keep_duplicates = keep_duplicates;
+	pthread_t thr;
+	pthread_create(&thr, NULL, reader_process_thread, NULL);
+	gt_vector *al_list = gt_vector_new(32, sizeof(align_details *));
+	gt_status st = read_input(NULL, al_list, &par);
+	w->process_end = true;
+	pthread_mutex_lock(&w->process_mutex);
+	pthread_cond_broadcast(&w->process_cond1);
+	pthread_mutex_unlock(&w->process_mutex);
+	pthread_join(thr, NULL);
+	*nblocks = rdr.nblocks; *ntmpl = rdr.ntmpl; *nbases = rdr.nbases; *nmisms = rdr.nmisms; *nvcf = rdr.nvcf;
+	for (int i = 0; i < n_targets; i++) { free(hdr.target_name[i]); free(ctgs[i].seq); }
+	free(hdr.target_name); free(w->contigs); free(w->tid2id); free(ctgs);
+	w->contigs = NULL; w->tid2id = NULL; w->sam_header = NULL;
+	if (st != GT_STATUS_OK) return -2;
+	return rdr.err;
+}

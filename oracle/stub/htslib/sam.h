@@ -8,8 +8,14 @@
 #include <stdint.h>
 
 typedef struct htsFile htsFile;
-typedef struct bam_hdr_t bam_hdr_t;
 typedef struct hts_idx_t hts_idx_t;
+/* the fields of the header the hot path reads (src/get_template_vector.c:123: target_name) */
+typedef struct bam_hdr_t {
+	int32_t n_targets;
+	uint32_t *target_len;
+	char **target_name;
+	char *text;
+} bam_hdr_t;
 typedef struct hts_itr_t hts_itr_t;
 typedef int64_t hts_pos_t;
 
@@ -64,4 +70,8 @@ typedef struct {
 
 int sam_read1(htsFile *fp, bam_hdr_t *h, bam1_t *b);
 int sam_itr_next(htsFile *fp, hts_itr_t *itr, bam1_t *b);
+hts_itr_t *sam_itr_queryi(const hts_idx_t *idx, int tid, hts_pos_t beg, hts_pos_t end);
+void hts_itr_destroy(hts_itr_t *itr);
+bam1_t *bam_init1(void);
+void bam_destroy1(bam1_t *b);
 #endif
