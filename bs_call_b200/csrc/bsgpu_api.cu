@@ -24,6 +24,15 @@ static_assert(offsetof(bsgpu_pileup, n) == 64 && offsetof(bsgpu_pileup, quality)
 
 using namespace bsgpu;
 
+namespace bsgpu {      // host helpers of bsgpu_reader.cu
+int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_off, std::vector<uint32_t> &read_off,
+		std::vector<uint32_t> &mm_off, uint64_t *nbases, uint64_t *nmisms);
+int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
+		bool keep_duplicates, std::vector<bsgpu_block> &blocks, std::vector<bsgpu_template> &tmpl);
+}
+static_assert(sizeof(bsgpu_record) == 56, "record descriptor layout");
+static_assert(sizeof(bsgpu_block) == 32, "block layout");
+
 static thread_local char g_err[512] = "";
 
 static int fail(const char *fmt, ...) {
@@ -67,6 +76,8 @@ struct bsgpu_ctx {
 	cudaStream_t copy_stream = nullptr;          // D2H of finished windows
 	Slot slot[2];
 	DevBuf segs, bases, ref, scratch, vcf, tmpl, misms, obases, ooff, pile;
+	DevBuf rd_bam, rd_recoff, rd_readoff, rd_mmoff, rd_rec, rd_bases, rd_misms;      // reader side: stream, framing, decoded arrays
+	std::vector<uint64_t> rec_off;               // framing of the last decoded stream
 	bool fused = false;                          // BSGPU_FUSED=1: one fused pileup+model kernel instead of two kernels
 	std::vector<cudaEvent_t> win_events;
 	bsgpu_stats stats;
@@ -156,6 +167,7 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 		if (c->slot[i].done) cudaEventDestroy(c->slot[i].done);
 	}
 	for (cudaEvent_t ev : c->win_events) cudaEventDestroy(ev);
+	c->rd_bam.release(); c->rd_recoff.release(); c->rd_readoff.release(); c->rd_mmoff.release(); c->rd_rec.release(); c->rd_bases.release(); c->rd_misms.release();
 	c->segs.release(); c->bases.release(); c->ref.release(); c->scratch.release(); c->vcf.release(); c->tmpl.release(); c->misms.release(); c->obases.release(); c->ooff.release(); c->pile.release();
 	if (c->stream) cudaStreamDestroy(c->stream);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -465,6 +477,168 @@ int bsgpu_process_block(bsgpu_ctx *c, const bsgpu_template *t, size_t n, const u
 	if (after[3] != before[3]) return fail("bsgpu_process_block: %llu mate(s) start before the block window", after[3] - before[3]);
 	if (x_out) *x_out = x;
 	return block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, out, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// reader side
+// ------------------------------------------------------------------------------------------------
+void bsgpu_default_reader_params(bsgpu_reader_params *p) {
+	memset(p, 0, sizeof(*p));
+	p->max_template_len = 1000;     // include/bs_call.h:20
+	p->mapq_thresh = 20;            // include/bs_call.h:14
+}
+
+// frame + upload + decode; leaves descriptors, packed reads and events resident; *nb / *nm = sizes of the decoded arrays
+static int decode_resident(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const bsgpu_reader_params *rp, size_t *nrec, uint64_t *nb, uint64_t *nm) {
+	std::vector<uint32_t> read_off, mm_off;
+	c->rec_off.clear();
+	const int fr = frame_records(bam, nbytes, c->rec_off, read_off, mm_off, nb, nm);
+	if (fr == -1) return fail("bsgpu reader: truncated or malformed BAM record stream");
+	if (fr == -2) return fail("bsgpu reader: more than 4 Gi bases in one stream; split the input");
+	const size_t n = c->rec_off.size();
+	*nrec = n;
+	if (!n) return BSGPU_OK;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->copy_stream));
+	CU(c->rd_bam.reserve(nbytes + 16));
+	CU(c->rd_recoff.reserve(n * 8));
+	CU(c->rd_readoff.reserve(n * 4));
+	CU(c->rd_mmoff.reserve(n * 4));
+	CU(c->rd_rec.reserve(n * sizeof(bsgpu_record)));
+	CU(c->rd_bases.reserve(*nb + 16));
+	CU(c->rd_misms.reserve((*nm + 1) * sizeof(bsgpu_misms)));
+	CU(cudaMemcpyAsync(c->rd_bam.p, bam, nbytes, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->rd_recoff.p, c->rec_off.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->rd_readoff.p, read_off.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->rd_mmoff.p, mm_off.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+	c->stats.h2d_bytes += nbytes + n * 16;
+	CU(launch_decode_records(c->rd_bam.p, c->rd_recoff.p, c->rd_readoff.p, c->rd_mmoff.p, n, rp->mapq_thresh, rp->max_template_len,
+			rp->keep_unmatched, rp->ignore_duplicates, c->rd_rec.p, c->rd_bases.p, c->rd_misms.p, c->stream, &c->launches));
+	CU(cudaStreamSynchronize(c->stream));      // read_off / mm_off are temporaries
+	return BSGPU_OK;
+}
+
+int bsgpu_decode_records(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const bsgpu_reader_params *rp,
+		bsgpu_record *rec_out, size_t rec_cap, size_t *nrec, uint8_t *bases_out, size_t bases_cap, size_t *nbases,
+		bsgpu_misms *misms_out, size_t misms_cap, size_t *nmisms) {
+	if (!c || !rp || !nrec || (nbytes && !bam)) return fail("bsgpu_decode_records: null argument");
+	size_t n = 0;
+	uint64_t nb = 0, nm = 0;
+	if (decode_resident(c, bam, nbytes, rp, &n, &nb, &nm) != BSGPU_OK) return BSGPU_FAIL;
+	if (n > rec_cap || (bases_out && nb > bases_cap) || (misms_out && nm > misms_cap)) return fail("bsgpu_decode_records: need room for %zu records, %llu bases, %llu events", n, (unsigned long long)nb, (unsigned long long)nm);
+	if (n) {
+		if (rec_out) CU(cudaMemcpyAsync(rec_out, c->rd_rec.p, n * sizeof(bsgpu_record), cudaMemcpyDeviceToHost, c->stream));
+		// events of dropped records are never written: clear what the caller will see
+		if (bases_out && nb) CU(cudaMemcpyAsync(bases_out, c->rd_bases.p, nb, cudaMemcpyDeviceToHost, c->stream));
+		if (misms_out && nm) CU(cudaMemcpyAsync(misms_out, c->rd_misms.p, nm * sizeof(bsgpu_misms), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		c->stats.d2h_bytes += n * sizeof(bsgpu_record) + (bases_out ? nb : 0) + (misms_out ? nm * sizeof(bsgpu_misms) : 0);
+	}
+	*nrec = n;
+	if (nbases) *nbases = nb;
+	if (nmisms) *nmisms = nm;
+	return BSGPU_OK;
+}
+
+int bsgpu_build_blocks(const uint8_t *bam, size_t nbytes, const bsgpu_record *rec, size_t nrec, const bsgpu_reader_params *rp,
+		bsgpu_block *blocks, size_t block_cap, size_t *nblocks, bsgpu_template *tmpl, size_t tmpl_cap, size_t *ntmpl) {
+	if (!rp || !nblocks || !ntmpl || (nrec && (!bam || !rec))) return fail("bsgpu_build_blocks: null argument");
+	std::vector<uint64_t> rec_off;
+	std::vector<uint32_t> ro, mo;
+	uint64_t nb, nm;
+	if (frame_records(bam, nbytes, rec_off, ro, mo, &nb, &nm) || rec_off.size() != nrec) return fail("bsgpu_build_blocks: the record stream does not frame into %zu records", nrec);
+	std::vector<bsgpu_block> b;
+	std::vector<bsgpu_template> t;
+	const int rc = build_blocks_host(bam, rec_off.data(), rec, nrec, rp->keep_unmatched, rp->keep_duplicates, b, t);
+	if (rc == -4) return fail("bsgpu_build_blocks: duplicate read name among waiting mates");
+	if (rc) return fail("bsgpu_build_blocks: failed (%d)", rc);
+	if (b.size() > block_cap || t.size() > tmpl_cap) return fail("bsgpu_build_blocks: need room for %zu blocks, %zu templates", b.size(), t.size());
+	if (!b.empty()) memcpy(blocks, b.data(), b.size() * sizeof(bsgpu_block));
+	if (!t.empty()) memcpy(tmpl, t.data(), t.size() * sizeof(bsgpu_template));
+	*nblocks = b.size();
+	*ntmpl = t.size();
+	return BSGPU_OK;
+}
+
+static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *d_bases, const void *d_ref,
+		uint32_t x, uint32_t sz, void *out, int mode);
+
+int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len,
+		const uint8_t *const *ctg_codes, const bsgpu_reader_params *rp, bsgpu_block *blocks, size_t block_cap, size_t *nblocks,
+		bsgpu_gt_vcf *vcf, size_t vcf_cap, size_t *nvcf) {
+	if (!c || !rp || !nblocks || !nvcf || !target_len || !ctg_codes || (nbytes && !bam)) return fail("bsgpu_call_bam: null argument");
+	size_t n = 0;
+	uint64_t nb = 0, nm = 0;
+	*nblocks = 0; *nvcf = 0;
+	if (decode_resident(c, bam, nbytes, rp, &n, &nb, &nm) != BSGPU_OK) return BSGPU_FAIL;
+	if (!n) return BSGPU_OK;
+	std::vector<bsgpu_record> rec(n);
+	CU(cudaMemcpy(rec.data(), c->rd_rec.p, n * sizeof(bsgpu_record), cudaMemcpyDeviceToHost));
+	c->stats.d2h_bytes += n * sizeof(bsgpu_record);
+	std::vector<bsgpu_block> bl;
+	std::vector<bsgpu_template> tm;
+	const int rc = build_blocks_host(bam, c->rec_off.data(), rec.data(), n, rp->keep_unmatched, rp->keep_duplicates, bl, tm);
+	if (rc == -4) return fail("bsgpu_call_bam: duplicate read name among waiting mates");
+	if (rc) return fail("bsgpu_call_bam: block builder failed (%d)", rc);
+	if (bl.size() > block_cap) return fail("bsgpu_call_bam: need room for %zu blocks", bl.size());
+	size_t ov = 0;
+	// blocks of one contig are disjoint windows in increasing order: process each contig as ONE window.  Pileup counts
+	// are additive per site and the model is per site, so every block's records are exactly what a per-block run gives.
+	for (size_t b0 = 0; b0 < bl.size();) {
+		size_t b1 = b0;
+		while (b1 < bl.size() && bl[b1].tid == bl[b0].tid) b1++;
+		const uint32_t tid = bl[b0].tid, x = bl[b0].x, y = bl[b1 - 1].y, sz = y - x + 1;
+		if ((int)tid >= n_targets) return fail("bsgpu_call_bam: record on contig %u, only %d contigs given", tid, n_targets);
+		if (ov + sz > vcf_cap) return fail("bsgpu_call_bam: vcf[] too small (contig %u needs %u more records)", tid, sz);
+		const size_t t0 = bl[b0].first_template, nt = (size_t)bl[b1 - 1].first_template + bl[b1 - 1].n_templates - t0;
+		// per-mate output slots: read length + reference span bounds the read in reference coordinates
+		std::vector<uint32_t> off(2 * nt + 1);
+		uint64_t tot = 0;
+		uint32_t maxcap = 1;
+		for (size_t i = 0; i < nt; i++) for (int k = 0; k < 2; k++) {
+			off[2 * i + k] = (uint32_t)tot;
+			const bsgpu_template &t = tm[t0 + i];
+			if (!t.present[k]) continue;
+			const uint64_t cap = (uint64_t)t.read_len[k] + t.reference_span[k];
+			tot += cap;
+			if (cap > maxcap) maxcap = (uint32_t)(cap > 0xffffffu ? 0xffffffu : cap);
+		}
+		off[2 * nt] = (uint32_t)tot;
+		if (tot > 0xffffffffull) return fail("bsgpu_call_bam: more than 4 GiB of bases on contig %u; split the input", tid);
+		const uint32_t spm = (maxcap + BSGPU_MAX_SEG_LEN - 1) / BSGPU_MAX_SEG_LEN;
+		const size_t nseg = nt * 2 * (size_t)spm;
+		// reference window [x, y]: N beyond the contig end (src/get_sequence.c:36-41)
+		std::vector<uint8_t> refw(sz);
+		for (uint32_t i = 0; i < sz; i++) { const uint32_t pos = x + i; refw[i] = pos < target_len[tid] ? ctg_codes[tid][pos - 1] : 0; }
+		CU(cudaStreamSynchronize(c->stream));
+		CU(cudaStreamSynchronize(c->copy_stream));
+		CU(c->tmpl.reserve(nt * sizeof(bsgpu_template)));
+		CU(c->obases.reserve(tot + 16));
+		CU(c->ooff.reserve((2 * nt + 1) * sizeof(uint32_t)));
+		CU(c->segs.reserve(nseg * sizeof(bsgpu_seg) + 16));
+		CU(c->ref.reserve((size_t)sz + 16));
+		CU(cudaMemcpyAsync(c->tmpl.p, tm.data() + t0, nt * sizeof(bsgpu_template), cudaMemcpyHostToDevice, c->stream));
+		CU(cudaMemcpyAsync(c->ooff.p, off.data(), (2 * nt + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+		CU(cudaMemcpyAsync(c->ref.p, refw.data(), sz, cudaMemcpyHostToDevice, c->stream));
+		c->stats.h2d_bytes += nt * sizeof(bsgpu_template) + (2 * nt + 1) * 4 + sz;
+		unsigned long long before[4], after[4];
+		CU(cudaMemcpyAsync(before, c->d_counters, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
+		CU(launch_normalise(c->tmpl.p, nt, c->rd_bases.p, c->rd_misms.p, c->ooff.p, c->obases.p, c->segs.p, spm, x, y,
+				c->params.left_trim, c->params.right_trim, c->d_counters, c->stream, &c->launches));
+		CU(cudaMemcpyAsync(after, c->d_counters, sizeof(after), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		if (after[2] != before[2]) return fail("bsgpu_call_bam: Error in CIGAR - illegal soft clip in %llu template(s)", after[2] - before[2]);
+		if (after[3] != before[3]) return fail("bsgpu_call_bam: %llu mate(s) start before their contig window", after[3] - before[3]);
+		if (block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, vcf + ov, 1) != BSGPU_OK) return BSGPU_FAIL;
+		for (size_t b = b0; b < b1; b++) bl[b].vcf_off = ov + (bl[b].x - x);
+		ov += sz;
+		b0 = b1;
+	}
+	memcpy(blocks, bl.data(), bl.size() * sizeof(bsgpu_block));
+	*nblocks = bl.size();
+	*nvcf = ov;
+	return BSGPU_OK;
 }
 
 int bsgpu_pileup_block(bsgpu_ctx *c, const bsgpu_seg *segs, size_t nseg, const uint8_t *bases, size_t nbases, uint32_t x, uint32_t sz, bsgpu_pileup *out) {

@@ -42,6 +42,11 @@ cudaError_t launch_normalise(const void *tmpl, size_t n, const void *bases, void
 		void *segs, uint32_t segs_per_mate, uint32_t x, uint32_t y, const uint32_t left_trim[2], const uint32_t right_trim[2],
 		unsigned long long *counters, cudaStream_t stream, int *launches);
 
+// reader side (bsgpu_reader.cu)
+cudaError_t launch_decode_records(const void *bam, const void *rec_off, const void *read_off, const void *mm_off, size_t nrec,
+		uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup, void *out, void *bases, void *misms,
+		cudaStream_t stream, int *launches);
+
 constexpr int kPileTileSites = 128;      // sites per tile of the gather kernel (= its CTA size)
 constexpr int kMaxSegLen = 256;          // BSGPU_MAX_SEG_LEN
 

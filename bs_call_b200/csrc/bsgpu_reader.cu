@@ -1,0 +1,497 @@
+// bsgpu_reader.cu -- the reader side of the path: BAM alignment records -> templates grouped into blocks.
+//
+//   k_decode_records      one warp per record: flag / MAPQ / insert-size / orientation filters, positions, CIGAR ->
+//                         event list, bisulfite strand tag, 4-bit sequence + qualities -> packed bytes
+//                         (what get_next_align_details does per record, src/input_sam.c:222-312)
+//   frame_records         host: walks the block_size chain of the record stream (what sam_read1 does per call)
+//   BlockBuilder          host: mate pairing by read name, positional duplicate removal, block cutting
+//                         (read_input, src/get_template_vector.c:49-389).  Order dependent over a coordinate-sorted
+//                         stream, so it runs on the host over the 52-byte descriptors the kernel produced; the
+//                         decoded reads themselves stay in HBM and templates refer to them by offset.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cuda_runtime.h>
+#include "bsgpu.h"
+#include "bsgpu_launch.h"
+
+namespace bsgpu {
+
+namespace {
+
+enum : uint32_t { F_PAIRED = 1, F_PROPER = 2, F_UNMAP = 4, F_MUNMAP = 8, F_REVERSE = 16, F_READ2 = 128, F_SECONDARY = 256,
+	F_QCFAIL = 512, F_DUP = 1024, F_SUPP = 2048 };
+// gt_filter_reason (include/bs_call.h:50)
+enum : uint32_t { FLT_NONE = 0, FLT_UNMAPPED, FLT_QC, FLT_SECONDARY, FLT_MATE_UNMAPPED, FLT_DUPLICATE, FLT_NOPOS, FLT_NOMATEPOS,
+	FLT_MISMATCH_CHR, FLT_ORIENTATION, FLT_INSERT_SIZE, FLT_NOSEQ, FLT_MAPQ, FLT_NOT_CORRECTLY_ALIGNED };
+
+// records are not aligned in the stream: fields are assembled from bytes
+__host__ __device__ __forceinline__ uint32_t ld_u16(const uint8_t *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8; }
+__host__ __device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
+
+// bisulfite strand from the aligner's tag (src/input_sam.c:144-220): GEM XB:A, Bowtie/Bismark XG:Z, Novoalign ZB:Z,
+// BSMAP ZS:Z, bwa-meth YD:Z.  The walk keeps the reference's treatment of malformed tags (unknown type letters
+// consume nothing, array sizes multiply in 32 bits).
+__device__ uint32_t strand_from_tags(const uint8_t *s, const uint8_t *end) {
+	enum { UNK, GEM, BOWTIE, NOVO, BSMAP, BWAMETH };
+	uint32_t strand = 0;
+	bool ok = true;
+	while (ok && s + 4 <= end) {
+		int al = UNK;
+		const uint8_t t0 = s[0], t1 = s[1];
+		if (t0 == 'Z') al = t1 == 'B' ? NOVO : (t1 == 'S' ? BSMAP : UNK);
+		else if (t0 == 'X') al = t1 == 'G' ? BOWTIE : (t1 == 'B' ? GEM : UNK);
+		else if (t0 == 'Y' && t1 == 'D') al = BWAMETH;
+		const uint8_t type = s[2];
+		s += 3;
+		switch (type) {
+		case 'A':
+			if (al == GEM) { if (*s == 'C') strand = 1; else if (*s == 'G') strand = 2; }
+			s++;
+			break;
+		case 'C': case 'c': s++; break;
+		case 'S': case 's': if (s + 2 <= end) s += 2; else ok = false; break;
+		case 'I': case 'i': case 'f': if (s + 4 <= end) s += 4; else ok = false; break;
+		case 'd': if (s + 8 <= end) s += 8; else ok = false; break;
+		case 'Z': {
+			const uint8_t c = *s;
+			if (al == BOWTIE || al == NOVO) { if (c == 'C') strand = 1; else if (c == 'G') strand = 2; }
+			else if (al == BSMAP) { if (c == '+') strand = 1; else if (c == '-') strand = 2; }
+			else if (al == BWAMETH) { if (c == 'f') strand = 1; else if (c == 'r') strand = 2; }
+		}   // a string either way: skip to its terminator
+		case 'H':
+			while (s < end && *s) s++;
+			if (s < end) s++; else ok = false;
+			break;
+		case 'B': {
+			const uint8_t sub = *s++;
+			uint32_t sz;
+			switch (sub) {
+			case 'A': case 'C': case 'c': sz = 1; break;
+			case 's': case 'S': sz = 2; break;
+			case 'i': case 'I': case 'f': sz = 4; break;
+			case 'd': sz = 8; break;
+			case 'Z': case 'H': case 'B': sz = sub; break;       // the reference's table holds the letter itself
+			default: sz = 0;
+			}
+			if (s + 4 <= end && sz != 0) {
+				const uint32_t bytes = ld_u32(s) * sz;
+				s += 4;
+				if (s + bytes <= end) s += bytes; else ok = false;
+			} else ok = false;
+			break; }
+		default: break;
+		}
+	}
+	return strand;
+}
+
+constexpr int kDecodeWarps = 8;
+
+__global__ void __launch_bounds__(kDecodeWarps * 32)
+k_decode_records(const uint8_t *__restrict__ bam, const uint64_t *__restrict__ rec_off, const uint32_t *__restrict__ read_off,
+		const uint32_t *__restrict__ mm_off, size_t nrec, uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup,
+		bsgpu_record *__restrict__ out, uint8_t *__restrict__ bases, bsgpu_misms *__restrict__ misms) {
+	const size_t w = (size_t)blockIdx.x * kDecodeWarps + (threadIdx.x >> 5);
+	const int lane = threadIdx.x & 31;
+	if (w >= nrec) return;
+	const uint8_t *rec = bam + rec_off[w];
+	const uint32_t block_size = ld_u32(rec);
+	const uint8_t *p = rec + 4;
+	const int32_t tid = (int32_t)ld_u32(p), pos = (int32_t)ld_u32(p + 4), mtid = (int32_t)ld_u32(p + 20), mpos = (int32_t)ld_u32(p + 24),
+		isize = (int32_t)ld_u32(p + 28), l_qseq = (int32_t)ld_u32(p + 16);
+	const uint32_t l_qname = p[8], mapq = p[9], n_cigar = ld_u16(p + 12), flag = ld_u16(p + 14);
+
+	// ---- filters and positions (src/input_sam.c:231-300); every lane computes them, lane 0 writes
+	uint32_t flt = FLT_NONE;
+	if ((flag & F_PAIRED) && !keep_unmatched) {
+		if ((flag & (F_PROPER | F_UNMAP | F_MUNMAP | F_QCFAIL | F_SECONDARY | F_SUPP | F_DUP)) != F_PROPER) {
+			if (flag & (F_SECONDARY | F_SUPP)) flt = FLT_SECONDARY;
+			else if (flag & F_UNMAP) flt = FLT_UNMAPPED;
+			else if (flag & F_MUNMAP) flt = FLT_MATE_UNMAPPED;
+			else if (flag & F_QCFAIL) flt = FLT_QC;
+			else if (flag & F_DUP) { if (!ignore_dup) flt = FLT_DUPLICATE; }
+			else flt = FLT_NOT_CORRECTLY_ALIGNED;
+		}
+	} else if (flag & (F_UNMAP | F_QCFAIL | F_SECONDARY | F_SUPP | F_DUP)) {
+		if (flag & (F_SECONDARY | F_SUPP)) flt = FLT_SECONDARY;
+		else if (flag & F_UNMAP) flt = FLT_UNMAPPED;
+		else if (flag & F_QCFAIL) flt = FLT_QC;
+		else if (flag & F_DUP) flt = FLT_DUPLICATE;
+	}
+	bool mis_matched = (flag & (F_MUNMAP | F_PROPER)) != F_PROPER;
+	const bool reverse = flag & F_REVERSE, second = flag & F_READ2;
+	const bool mult_seg = (flag & (F_PAIRED | F_MUNMAP)) == F_PAIRED;
+	uint32_t fwd = reverse ? (uint32_t)(mpos + 1) : (uint32_t)(pos + 1);
+	uint32_t rev = reverse ? (uint32_t)(pos + 1) : (uint32_t)(mpos + 1);
+	if (mapq < mapq_thresh && !flt) flt = FLT_MAPQ;
+	if (mult_seg) {
+		if (tid != mtid) { if (!flt) flt = FLT_MISMATCH_CHR; if (keep_unmatched) mis_matched = true; }
+		if (!flt) {
+			const uint64_t is = (uint64_t)(isize < 0 ? -(int64_t)isize : (int64_t)isize);
+			if (is > (uint64_t)max_tlen) { flt = FLT_INSERT_SIZE; if (keep_unmatched) mis_matched = true; }
+		}
+		if (reverse ? pos < mpos : pos > mpos) { if (!flt) flt = FLT_ORIENTATION; if (keep_unmatched) mis_matched = true; }
+		if (mis_matched) { if (reverse) fwd = 0; else rev = 0; }
+	}
+	const bool dropped = flt && !(keep_unmatched && (flt == FLT_INSERT_SIZE || flt == FLT_MISMATCH_CHR || flt == FLT_ORIENTATION));
+
+	const uint8_t *cigar = p + 32 + l_qname;
+	const uint8_t *seq = cigar + 4 * (size_t)n_cigar;
+	const uint8_t *qual = seq + (((size_t)l_qseq + 1) >> 1);
+	const uint8_t *aux = qual + l_qseq, *end = p + block_size;
+	const uint32_t boff = read_off[w], moff = mm_off[w];
+
+	if (!dropped) {
+		// ---- sequence and qualities (src/input_sam.c:61-88): lanes stride over the bases
+		uint8_t *dst = bases + boff;
+		for (int32_t k = lane; k < l_qseq; k += 32) {
+			const uint32_t byte = seq[k >> 1];
+			const uint32_t nib = (k & 1) ? (byte & 15u) : (byte >> 4);
+			// 1 2 4 8 -> A C G T; everything else is N and becomes the zero byte
+			const uint32_t base = nib == 1 ? 0u : (nib == 2 ? 1u : (nib == 4 ? 2u : 3u));
+			const bool known = nib == 1 || nib == 2 || nib == 4 || nib == 8;
+			const uint32_t q = min((uint32_t)qual[k], (uint32_t)BSGPU_MAX_QUAL);
+			dst[k] = known ? (uint8_t)(base | q << 2) : (uint8_t)0;
+		}
+	}
+	if (lane) return;
+
+	bsgpu_record r;
+	memset(&r, 0, sizeof(r));
+	r.ret = dropped ? 1 : 0;
+	r.filtered = flt;
+	r.forward_position = fwd;
+	r.reverse_position = rev;
+	r.alignment_flag = (!mult_seg || mis_matched) ? flag & ~F_PAIRED : flag;
+	r.reverse = reverse;
+	r.orientation = ((second && reverse) || !(second || reverse)) ? 0 : 1;
+	r.mapq = (uint8_t)mapq;
+	r.tid = tid;
+	if (!dropped) {
+		// ---- CIGAR -> events (src/input_sam.c:90-136); note CIGAR I -> DEL, D -> INS, P treated like S
+		uint32_t position = 0, span = 0, n = 0;
+		for (uint32_t i = 0; i < n_cigar; i++) {
+			const uint32_t c = ld_u32(cigar + 4 * (size_t)i), len = c >> 4, op = c & 15u;
+			uint32_t type = 0;
+			switch (op) {
+			case 0: case 7: case 8: position += len; span += len; break;
+			case 4: case 6: type = 3; break;
+			case 1: type = 2; break;
+			case 2: type = 1; break;
+			default: break;
+			}
+			if (type) {
+				bsgpu_misms m;
+				m.type = type; m.position = position; m.size = len;
+				misms[moff + n++] = m;
+				if (type == 1) span += len; else position += len;
+			}
+		}
+		r.align_length = position;
+		r.reference_span = span;
+		r.mm_off = moff;
+		r.mm_n = n;
+		r.read_off = boff;
+		r.read_len = (uint32_t)l_qseq;
+		r.bs_strand = (uint8_t)strand_from_tags(aux, end);
+		// the qualities get_al_qual looks at: byte k of mate k (src/al_utils.c:26)
+		for (int k = 0; k < 2 && k < l_qseq; k++) {
+			const uint32_t byte = seq[k >> 1], nib = k ? (byte & 15u) : (byte >> 4);
+			const bool known = nib == 1 || nib == 2 || nib == 4 || nib == 8;
+			r.q01[k] = known ? (uint8_t)min((uint32_t)qual[k], (uint32_t)BSGPU_MAX_QUAL) : (uint8_t)0;
+		}
+	}
+	out[w] = r;
+}
+
+}  // namespace
+
+cudaError_t launch_decode_records(const void *bam, const void *rec_off, const void *read_off, const void *mm_off, size_t nrec,
+		uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup, void *out, void *bases, void *misms,
+		cudaStream_t stream, int *launches) {
+	if (!nrec) return cudaSuccess;
+	const unsigned grid = (unsigned)((nrec + kDecodeWarps - 1) / kDecodeWarps);
+	k_decode_records<<<grid, kDecodeWarps * 32, 0, stream>>>((const uint8_t *)bam, (const uint64_t *)rec_off, (const uint32_t *)read_off,
+		(const uint32_t *)mm_off, nrec, mapq_thresh, max_tlen, keep_unmatched, ignore_dup, (bsgpu_record *)out, (uint8_t *)bases, (bsgpu_misms *)misms);
+	*launches += 1;
+	return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host: framing
+// ---------------------------------------------------------------------------------------------------------------
+int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_off, std::vector<uint32_t> &read_off,
+		std::vector<uint32_t> &mm_off, uint64_t *nbases, uint64_t *nmisms) {
+	size_t at = 0;
+	uint64_t nb = 0, nm = 0;
+	while (at < nbytes) {
+		if (at + 36 > nbytes) return -1;
+		const uint32_t bs = ld_u32(bam + at);
+		if (bs < 32 || at + 4 + (size_t)bs > nbytes) return -1;
+		const uint8_t *p = bam + at + 4;
+		const uint32_t l_qname = p[8], n_cigar = ld_u16(p + 12), l_qseq = ld_u32(p + 16);
+		if ((int32_t)l_qseq < 0 || 32 + (uint64_t)l_qname + 4ull * n_cigar + ((uint64_t)l_qseq + 1) / 2 + l_qseq > bs) return -1;
+		rec_off.push_back(at);
+		read_off.push_back((uint32_t)nb);
+		mm_off.push_back((uint32_t)nm);
+		nb += l_qseq;
+		nm += n_cigar;
+		at += 4 + (size_t)bs;
+	}
+	if (nb > 0xffffffffull || nm > 0xffffffffull) return -2;
+	*nbases = nb;
+	*nmisms = nm;
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host: block builder.  Follows read_input (src/get_template_vector.c:49-389) decision by decision; a template is a
+// slot in `list` holding positions and, per mate, the index of the decoded record.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Tmpl {
+	uint32_t fwd, rev, span[2];
+	int64_t rec[2];
+	uint8_t mapq[2], orientation, bs_strand;
+};
+
+// open-addressing table of waiting mates keyed by read name; cleared in O(1) at block ends by bumping `gen`
+struct NameTable {
+	struct Ent { uint64_t hash; uint32_t name_rec, ix, flag, gen; };     // gen: 0 never used, odd = live, even = deleted
+	std::vector<Ent> tab;
+	uint32_t gen = 1, used = 0;
+	const uint8_t *bam;
+	const uint64_t *rec_off;
+	NameTable() : tab(1024) {}
+	static uint64_t hash_name(const uint8_t *s, uint32_t n) {
+		uint64_t h = 1469598103934665603ull;
+		for (uint32_t i = 0; i < n; i++) h = (h ^ s[i]) * 1099511628211ull;
+		return h ^ (h >> 29);
+	}
+	const uint8_t *name_of(uint32_t rec, uint32_t *len) const { const uint8_t *p = bam + rec_off[rec] + 4; *len = p[8]; return p + 32; }
+	void clear() { gen += 2; used = 0; if (gen > 0xfffffff0u) { for (auto &e : tab) e.gen = 0; gen = 1; } }
+	Ent *find(const uint8_t *s, uint32_t n, uint64_t h) {
+		const size_t mask = tab.size() - 1;
+		for (size_t i = h & mask;; i = (i + 1) & mask) {
+			Ent &e = tab[i];
+			if (e.gen != gen && e.gen != gen + 1) return nullptr;          // slot untouched in this block: end of the probe chain
+			if (e.gen == gen && e.hash == h) {
+				uint32_t l;
+				const uint8_t *nm = name_of(e.name_rec, &l);
+				if (l == n && !memcmp(nm, s, n)) return &e;
+			}
+		}
+	}
+	void grow() {
+		std::vector<Ent> old;
+		old.swap(tab);
+		tab.assign(old.size() * 2, Ent{0, 0, 0, 0, 0});
+		used = 0;
+		for (const Ent &e : old) if (e.gen == gen) insert_raw(e);
+	}
+	Ent *insert_raw(const Ent &v) {
+		const size_t mask = tab.size() - 1;
+		for (size_t i = v.hash & mask;; i = (i + 1) & mask) {
+			Ent &e = tab[i];
+			if (e.gen != gen && e.gen != gen + 1) { e = v; e.gen = gen; used++; return &e; }
+		}
+	}
+	// returns the index of the new entry's slot (stable until the next grow): callers keep indices, not pointers
+	void add(uint32_t name_rec, uint64_t h, uint32_t flag, uint32_t ix) {
+		if ((size_t)(used + 1) * 2 > tab.size()) grow();
+		insert_raw(Ent{h, name_rec, ix, flag, gen});
+	}
+	static void kill(Ent *e) { e->gen += 1; }
+};
+
+}  // namespace
+
+struct BlockBuilder {
+	const uint8_t *bam;
+	const uint64_t *rec_off;
+	const bsgpu_record *rec;
+	std::vector<Tmpl> list;
+	std::vector<int64_t> list_name;      // per slot: record whose name keys the slot's live table entry, -1 = none ("alh_p[ix]")
+	std::vector<uint32_t> list_flag;
+	size_t used = 0;
+	NameTable names;
+	std::vector<bsgpu_block> *blocks;
+	std::vector<bsgpu_template> *tmpl;
+
+	uint32_t al_qual(const Tmpl &t) const {          // get_al_qual with its sq[k] indexing (src/al_utils.c:19-35)
+		uint32_t qual = 0, n = 0;
+		for (int k = 0; k < 2; k++) {
+			if (t.rec[k] < 0) continue;
+			const bsgpu_record &r = rec[t.rec[k]];
+			const uint32_t q = r.q01[k];
+			if (q != BSGPU_FLT_QUAL) { qual += q * r.read_len; n += r.read_len; }
+		}
+		return n ? qual / n : 0;
+	}
+	void put(size_t ix, const Tmpl &t, int64_t name_rec, uint32_t flag) {
+		if (ix >= list.size()) { list.resize(ix + 1); list_name.resize(ix + 1); list_flag.resize(ix + 1); }
+		list[ix] = t; list_name[ix] = name_rec; list_flag[ix] = flag;
+		if (used <= ix) used = ix + 1;
+	}
+	void publish(uint32_t tid, uint32_t y) {
+		if (!used) return;
+		bsgpu_block b;
+		memset(&b, 0, sizeof(b));
+		const uint32_t first = list[0].fwd ? list[0].fwd : list[0].rev;
+		b.tid = tid; b.y = y; b.x = first > 2 ? first - 2 : 1;            // src/process_template.c:24-28
+		b.first_template = (uint32_t)tmpl->size(); b.n_templates = (uint32_t)used;
+		blocks->push_back(b);
+		for (size_t i = 0; i < used; i++) {
+			const Tmpl &t = list[i];
+			bsgpu_template d;
+			memset(&d, 0, sizeof(d));
+			d.forward_position = t.fwd; d.reverse_position = t.rev; d.orientation = t.orientation; d.bs_strand = t.bs_strand;
+			for (int k = 0; k < 2; k++) {
+				d.mapq[k] = t.mapq[k];
+				if (t.rec[k] < 0) continue;
+				const bsgpu_record &r = rec[t.rec[k]];
+				d.present[k] = 1; d.reference_span[k] = t.span[k];
+				d.read_off[k] = r.read_off; d.read_len[k] = r.read_len; d.mm_off[k] = r.mm_off; d.mm_n[k] = r.mm_n;
+			}
+			tmpl->push_back(d);
+		}
+		used = 0;
+	}
+
+	int run(size_t nrec, bool keep_unmatched, bool keep_duplicates) {
+		names.bam = bam; names.rec_off = rec_off;
+		int curr_tid = -1, old_tid = -1;
+		uint32_t max_pos = 0, start_pos = 0, read_idx = 0, curr_pos = 0, start_idx = 0;
+		for (size_t ri = 0; ri < nrec; ri++) {
+			const bsgpu_record &r = rec[ri];
+			if (r.ret > 0) continue;
+			const int ix = r.reverse ? 1 : 0;
+			Tmpl al;
+			memset(&al, 0, sizeof(al));
+			al.fwd = r.forward_position; al.rev = r.reverse_position; al.orientation = r.orientation; al.bs_strand = r.bs_strand;
+			al.rec[0] = al.rec[1] = -1; al.rec[ix] = (int64_t)ri; al.mapq[ix] = r.mapq; al.span[ix] = r.reference_span;
+			uint32_t nlen;
+			const uint8_t *name = names.name_of((uint32_t)ri, &nlen);
+			const bool paired = r.alignment_flag & F_PAIRED;
+			uint64_t nh = 0;
+			NameTable::Ent *waiting = nullptr;
+			bool new_block = false, new_contig = false;
+			if (curr_tid < 0 || curr_tid != r.tid) { new_contig = new_block = true; old_tid = curr_tid; curr_tid = r.tid; }
+			if (paired) nh = NameTable::hash_name(name, nlen);
+			bool insert = true;
+			if (!new_contig) {
+				if (paired && al.fwd > 0 && al.rev > 0) {
+					if (al.fwd == al.rev) insert = names.find(name, nlen, nh) == nullptr;
+					else insert = r.reverse ? al.fwd > al.rev : al.fwd < al.rev;
+				}
+				if (insert && start_pos > 0) {
+					if (al.fwd > 0) {
+						if (al.fwd > max_pos && (al.rev > max_pos || al.rev == 0) && al.fwd - max_pos > 1) new_block = true;
+					} else if (al.rev > max_pos && al.rev - max_pos > 1) new_block = true;
+				}
+			}
+			if (new_block) {
+				names.clear();
+				read_idx = start_idx = curr_pos = 0;
+				publish((uint32_t)(new_contig ? old_tid : curr_tid), max_pos);
+				max_pos = start_pos = 0;
+			}
+			{
+				const uint32_t s0 = r.reverse ? al.rev : al.fwd, ml = s0 + r.reference_span;
+				if (ml > max_pos) max_pos = ml;
+				if (start_pos == 0 || start_pos > s0) start_pos = s0;
+			}
+			if (paired) {
+				if (!insert) {
+					waiting = names.find(name, nlen, nh);
+					if (waiting) {
+						Tmpl &t = list[waiting->ix];
+						t.rec[ix] = (int64_t)ri; t.mapq[ix] = r.mapq; t.span[ix] = r.reference_span;
+						list_name[waiting->ix] = -1;
+						NameTable::kill(waiting);
+					} else {
+						bool skip = false;
+						if (!keep_duplicates) { const uint32_t xx = r.reverse ? al.rev : al.fwd; if (xx >= start_pos) skip = true; }
+						if (!skip && keep_unmatched) {
+							const uint32_t xx = (al.fwd > 0 ? al.fwd : al.rev) + r.align_length;
+							if (xx > max_pos) max_pos = xx;
+							put(read_idx++, al, -1, 0);
+						}
+					}
+				} else {
+					bool skip = false;
+					if (!keep_duplicates) {
+						const uint32_t pos = al.fwd > 0 ? al.fwd : al.rev;
+						if (pos == curr_pos) {
+							for (uint32_t i = start_idx; i < read_idx; i++) {
+								Tmpl &a1 = list[i];
+								if (al.fwd != a1.fwd || al.rev != a1.rev || al.bs_strand != a1.bs_strand) continue;
+								int maxq = 0, maxq1 = 0, kn = 0, kn1 = 0;
+								for (int k = 0; k < 2; k++) {
+									if (al.rec[k] >= 0 && rec[al.rec[k]].read_len > 0) { maxq += al.mapq[k]; kn++; }
+									if (a1.rec[k] >= 0 && rec[a1.rec[k]].read_len > 0) { maxq1 += a1.mapq[k]; kn1++; }
+								}
+								maxq /= kn; maxq1 /= kn1;
+								if (maxq1 < maxq || (maxq == maxq1 && al_qual(a1) < al_qual(al))) {
+									// the newcomer takes the slot; the slot's table entry is re-keyed to the newcomer's name
+									NameTable::Ent *h = names.find(name, nlen, nh);
+									if (h && list_name[i] >= 0) return -4;            // duplicate read name (fatal in the reference)
+									const bool from_slot = !h && list_name[i] >= 0;
+									if (from_slot) {
+										uint32_t ol;
+										const uint8_t *on = names.name_of((uint32_t)list_name[i], &ol);
+										h = names.find(on, ol, NameTable::hash_name(on, ol));
+									}
+									const Tmpl old = a1;
+									a1 = al;
+									if (h) NameTable::kill(h);
+									names.add((uint32_t)ri, nh, r.alignment_flag, i);
+									if (from_slot) { list_name[i] = (int64_t)ri; list_flag[i] = r.alignment_flag; }
+									al = old;
+								}
+								skip = true;
+							}
+						} else { curr_pos = pos; start_idx = read_idx; }
+					}
+					if (!skip) {
+						if (names.find(name, nlen, nh)) return -4;
+						names.add((uint32_t)ri, nh, r.alignment_flag, read_idx);
+						put(read_idx, al, (int64_t)ri, r.alignment_flag);
+						read_idx++;
+					}
+				}
+			} else {
+				bool skip = false;
+				if (!keep_duplicates) {
+					const uint32_t pos = al.fwd > 0 ? al.fwd : al.rev;
+					if (pos == curr_pos) {
+						for (uint32_t i = start_idx; i < read_idx; i++) {
+							Tmpl &a1 = list[i];
+							const bool lone = list_name[i] < 0 || (list_flag[i] & 9u) == 9u || (list_flag[i] & 9u) == 0u;
+							if (al.fwd == a1.fwd && al.rev == a1.rev && al.bs_strand == a1.bs_strand && lone) {
+								// mapq[0] on both sides whichever strand the reads are on (reference behaviour)
+								if (a1.mapq[0] < al.mapq[0] || (a1.mapq[0] == al.mapq[0] && al_qual(a1) < al_qual(al))) { const Tmpl old = a1; a1 = al; al = old; }
+								skip = true;
+							}
+						}
+					} else { curr_pos = pos; start_idx = read_idx; }
+				}
+				if (!skip) put(read_idx++, al, -1, 0);
+			}
+		}
+		if (curr_tid >= 0) publish((uint32_t)curr_tid, max_pos);
+		return 0;
+	}
+};
+
+int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
+		bool keep_duplicates, std::vector<bsgpu_block> &blocks, std::vector<bsgpu_template> &tmpl) {
+	BlockBuilder b;
+	b.bam = bam; b.rec_off = rec_off; b.rec = rec; b.blocks = &blocks; b.tmpl = &tmpl;
+	return b.run(nrec, keep_unmatched, keep_duplicates);
+}
+
+}  // namespace bsgpu

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from .records import PILEUP, GT_METH, GT_VCF, SEG, TEMPLATE, MISMS
+from .records import PILEUP, GT_METH, GT_VCF, SEG, TEMPLATE, MISMS, RECORD, BLOCK
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbsgpu.so")
@@ -23,6 +23,7 @@ EXPORTS = [
     "bsgpu_sync", "bsgpu_host_alloc", "bsgpu_host_free",
     "bsgpu_call_sites", "bsgpu_pileup_block", "bsgpu_call_block", "bsgpu_stage_bound", "bsgpu_stage_templates",
     "bsgpu_process_block",
+    "bsgpu_default_reader_params", "bsgpu_decode_records", "bsgpu_build_blocks", "bsgpu_call_bam",
     "bsgpu_call_sites_dev", "bsgpu_call_sites_vcf_dev", "bsgpu_pileup_block_dev", "bsgpu_call_block_dev",
     "bsgpu_synth_sites_dev", "bsgpu_synth_block_nseg", "bsgpu_synth_block_dev",
     "bsgpu_math_probe",
@@ -33,6 +34,16 @@ class Params(C.Structure):
     _fields_ = [("under_conv", C.c_double), ("over_conv", C.c_double), ("ref_bias", C.c_double),
                 ("left_trim", C.c_uint32 * 2), ("right_trim", C.c_uint32 * 2), ("min_qual", C.c_uint8),
                 ("device", C.c_int32)]
+
+
+class ReaderParams(C.Structure):
+    _fields_ = [("max_template_len", C.c_uint32), ("mapq_thresh", C.c_uint8), ("keep_unmatched", C.c_uint8),
+                ("ignore_duplicates", C.c_uint8), ("keep_duplicates", C.c_uint8)]
+
+
+def reader_params(mapq_thresh=20, max_template_len=1000, keep_unmatched=False, ignore_duplicates=False, keep_duplicates=False):
+    return ReaderParams(int(max_template_len), int(mapq_thresh), int(bool(keep_unmatched)), int(bool(ignore_duplicates)),
+                        int(bool(keep_duplicates)))
 
 
 class Stats(C.Structure):
@@ -176,6 +187,41 @@ class BsGpu:
                                                  C.c_uint32(y), C.byref(xo), _ptr(out)))
         return xo.value, out
 
+    # ---- reader side ----------------------------------------------------------------------------
+    def decode_records(self, bam, rp=None, want_reads=True):
+        """raw BAM records -> (RECORD[], packed bases, events); the decoded arrays also stay resident in the context"""
+        bam = np.ascontiguousarray(bam, dtype=np.uint8)
+        rp = rp or reader_params()
+        cap = len(bam) // 36 + 8
+        rec = np.zeros(cap, dtype=RECORD)
+        bases = np.zeros(len(bam) + 64, dtype=np.uint8) if want_reads else None
+        misms = np.zeros(len(bam) // 4 + 64, dtype=MISMS) if want_reads else None
+        n, nb, nm = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        self._check(self.lib.bsgpu_decode_records(self.ctx, _ptr(bam), C.c_size_t(len(bam)), C.byref(rp), _ptr(rec), C.c_size_t(cap),
+                                                  C.byref(n), _ptr(bases), C.c_size_t(len(bases) if want_reads else 0), C.byref(nb),
+                                                  _ptr(misms), C.c_size_t(len(misms) if want_reads else 0), C.byref(nm)))
+        if not want_reads:
+            return rec[:n.value], None, None
+        return rec[:n.value], bases[:nb.value], misms[:nm.value]
+
+    def call_bam(self, bam, target_len, ctg_codes, rp=None, vcf=None):
+        """raw BAM records + per-contig reference codes -> (BLOCK[], gt_vcf[]); the whole path on the device except the
+        block builder"""
+        bam = np.ascontiguousarray(bam, dtype=np.uint8)
+        target_len = np.ascontiguousarray(target_len, dtype=np.uint32)
+        rp = rp or reader_params()
+        codes = [np.ascontiguousarray(c, dtype=np.uint8) for c in ctg_codes]
+        ptrs = (C.c_void_p * len(codes))(*[c.ctypes.data for c in codes])
+        bcap = len(bam) // 36 + 8
+        blocks = np.zeros(bcap, dtype=BLOCK)
+        if vcf is None:
+            vcf = np.zeros(int(target_len.sum()) + 8, dtype=GT_VCF)
+        nb, nv = C.c_size_t(0), C.c_size_t(0)
+        self._check(self.lib.bsgpu_call_bam(self.ctx, _ptr(bam), C.c_size_t(len(bam)), C.c_int(len(codes)), _ptr(target_len), ptrs,
+                                            C.byref(rp), _ptr(blocks), C.c_size_t(bcap), C.byref(nb), _ptr(vcf), C.c_size_t(len(vcf)),
+                                            C.byref(nv)))
+        return blocks[:nb.value], vcf[:nv.value]
+
     # ---- device-pointer entry points (addresses as ints, e.g. torch.Tensor.data_ptr()) --------
     def call_sites_dev(self, d_pileup, d_ref, n, d_out, d_skip, stream=0):
         self._check(self.lib.bsgpu_call_sites_dev(self.ctx, _ptr(d_pileup), _ptr(d_ref), C.c_size_t(n), _ptr(d_out),
@@ -227,6 +273,21 @@ def math_probe(x):
     lo, ex = np.zeros_like(x), np.zeros_like(x)
     lib.bsgpu_math_probe(_ptr(x), C.c_size_t(len(x)), _ptr(lo), _ptr(ex))
     return lo, ex
+
+
+def build_blocks(bam, rec, rp=None):
+    """bsgpu_build_blocks: descriptors of decode_records -> (BLOCK[], TEMPLATE[]).  Pure host function of the ABI."""
+    lib = load()
+    bam = np.ascontiguousarray(bam, dtype=np.uint8)
+    rec = np.ascontiguousarray(rec, dtype=RECORD)
+    rp = rp or reader_params()
+    blocks = np.zeros(len(rec) + 8, dtype=BLOCK)
+    tmpl = np.zeros(len(rec) + 8, dtype=TEMPLATE)
+    nb, nt = C.c_size_t(0), C.c_size_t(0)
+    if lib.bsgpu_build_blocks(_ptr(bam), C.c_size_t(len(bam)), _ptr(rec), C.c_size_t(len(rec)), C.byref(rp), _ptr(blocks),
+                              C.c_size_t(len(blocks)), C.byref(nb), _ptr(tmpl), C.c_size_t(len(tmpl)), C.byref(nt)) != BSGPU_OK:
+        raise BsGpuError(lib.bsgpu_last_error().decode())
+    return blocks[:nb.value], tmpl[:nt.value]
 
 
 def stage_templates_host(templates, bases, x, y):

@@ -12,6 +12,16 @@ TEMPLATE = np.dtype([("forward_position", "<u4"), ("reverse_position", "<u4"), (
                      ("orientation", "u1"), ("bs_strand", "u1"), ("pad", "u1", (2,))])
 MISMS = np.dtype([("type", "<u4"), ("position", "<u4"), ("size", "<u4")])
 
+# reader side (include/bsgpu.h: bsgpu_record, bsgpu_block)
+RECORD = np.dtype([("ret", "<i4"), ("filtered", "<u4"), ("forward_position", "<u4"), ("reverse_position", "<u4"),
+                   ("alignment_flag", "<u4"), ("align_length", "<u4"), ("reference_span", "<u4"),
+                   ("read_off", "<u4"), ("read_len", "<u4"), ("mm_off", "<u4"), ("mm_n", "<u4"), ("tid", "<i4"),
+                   ("reverse", "u1"), ("orientation", "u1"), ("bs_strand", "u1"), ("mapq", "u1"),
+                   ("q01", "u1", (2,)), ("pad", "u1", (2,))])
+BLOCK = np.dtype([("tid", "<u4"), ("x", "<u4"), ("y", "<u4"), ("first_template", "<u4"), ("n_templates", "<u4"),
+                  ("pad", "<u4"), ("vcf_off", "<u8")])
+assert RECORD.itemsize == 56 and BLOCK.itemsize == 32
+
 assert PILEUP.itemsize == 104
 assert GT_METH.itemsize == 200
 assert GT_VCF.itemsize == 208

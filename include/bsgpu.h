@@ -22,6 +22,10 @@
  *                                    src/call_genotypes.c:181-212, turned into sorted segments
  *     bsgpu_process_block            process_template_vector                    src/process_template.c:18-126
  *                                    (trim_read, trim_soft_clips, handle_overlap, indel normalisation on device)
+ *     bsgpu_decode_records           get_next_align_details                     src/input_sam.c:222-312
+ *                                    (get_seq_and_qual :61, get_bam_misms :90, get_bs_strand :144, the filters :234-300)
+ *     bsgpu_build_blocks             read_input                                 src/get_template_vector.c:49-389
+ *     bsgpu_call_bam                 read_input -> process_thread -> call_genotypes_ML chained (src/process.c:43-72, 172)
  * The link-compatible replacements for the three reference symbols themselves (call_genotypes_ML,
  * init_calc_threads, join_calc_threads; include/bs_call.h:358-360) are in bs_call_b200/csrc/bsgpu_dropin.c and
  * are built on top of this ABI; see INTEGRATION.md.
@@ -110,6 +114,41 @@ typedef struct {
 	int32_t device;            /* CUDA device ordinal */
 } bsgpu_params;
 
+/* ---- reader side ---- */
+/* What get_next_align_details() yields for one BAM alignment record (src/input_sam.c:222-312): the filter verdict,
+ * positions and flags always; the decoded read (read_off / read_len into the packed-base array), CIGAR events
+ * (mm_off / mm_n), reference span and bisulfite strand only for records that are kept (ret == 0). */
+typedef struct {
+	int32_t ret;               /* 0 keep, 1 dropped by the filters */
+	uint32_t filtered;         /* gt_filter_reason (include/bs_call.h:50) */
+	uint32_t forward_position, reverse_position;
+	uint32_t alignment_flag;   /* BAM flag, BAM_FPAIRED cleared when the mate cannot be used */
+	uint32_t align_length;     /* read length the CIGAR implies */
+	uint32_t reference_span;
+	uint32_t read_off, read_len;
+	uint32_t mm_off, mm_n;
+	int32_t tid;
+	uint8_t reverse, orientation, bs_strand, mapq;
+	uint8_t q01[2];            /* qualities of the first two packed bytes (what get_al_qual reads, src/al_utils.c:26) */
+	uint8_t pad_[2];
+} bsgpu_record;                /* 56 bytes */
+
+/* One block as read_input() hands it to process_template_vector() (src/get_template_vector.c:170-189):
+ * templates [first_template, first_template + n_templates), window [x, y] on contig tid;
+ * vcf_off = index of the record of position x in the gt_vcf[] array bsgpu_call_bam returns. */
+typedef struct {
+	uint32_t tid, x, y, first_template, n_templates, pad_;
+	uint64_t vcf_off;
+} bsgpu_block;                 /* 32 bytes */
+
+typedef struct {
+	uint32_t max_template_len; /* -l, default 1000 (include/bs_call.h:20) */
+	uint8_t mapq_thresh;       /* -q, default 20 */
+	uint8_t keep_unmatched;    /* -k */
+	uint8_t ignore_duplicates; /* ignore the BAM duplicate flag */
+	uint8_t keep_duplicates;   /* -d: no positional duplicate removal */
+} bsgpu_reader_params;
+
 typedef struct bsgpu_ctx bsgpu_ctx;
 
 /* counters a context keeps; all monotonically increasing */
@@ -160,6 +199,30 @@ int bsgpu_stage_templates(const bsgpu_template *t, size_t n, const uint8_t *base
 int bsgpu_process_block(bsgpu_ctx *ctx, const bsgpu_template *t, size_t n, const uint8_t *bases, size_t nbases,
 		const bsgpu_misms *misms, size_t nmisms, const uint8_t *ref, uint32_t y,
 		uint32_t *x_out, bsgpu_gt_vcf *out);
+
+/* ---- reader side: `bam` is the byte stream that follows the header of an uncompressed BAM file (what remains of the
+ *      file after BGZF inflation: int32 block_size + record, repeated), coordinate sorted ---- */
+void bsgpu_default_reader_params(bsgpu_reader_params *p);
+
+/* get_next_align_details() for every record, on the device (src/input_sam.c:222-312).  rec_out receives one
+ * descriptor per record; the decoded reads and CIGAR events stay resident in the context for bsgpu_call_bam and are
+ * also copied to bases_out / misms_out when those are not NULL (tests, host-side consumers). */
+int bsgpu_decode_records(bsgpu_ctx *ctx, const uint8_t *bam, size_t nbytes, const bsgpu_reader_params *rp,
+		bsgpu_record *rec_out, size_t rec_cap, size_t *nrec, uint8_t *bases_out, size_t bases_cap, size_t *nbases,
+		bsgpu_misms *misms_out, size_t misms_cap, size_t *nmisms);
+
+/* read_input(): mate pairing, positional duplicate removal, block cutting (src/get_template_vector.c:49-389) over the
+ * descriptors of bsgpu_decode_records.  Host side (order dependent over the sorted stream); templates refer to the
+ * decoded arrays by offset. */
+int bsgpu_build_blocks(const uint8_t *bam, size_t nbytes, const bsgpu_record *rec, size_t nrec, const bsgpu_reader_params *rp,
+		bsgpu_block *blocks, size_t block_cap, size_t *nblocks, bsgpu_template *tmpl, size_t tmpl_cap, size_t *ntmpl);
+
+/* The whole path: BAM records -> decode -> blocks -> normalisation -> pileup -> model.  ctg_codes[tid] holds the
+ * reference codes 0..4 of positions 1..target_len[tid].  vcf receives, per contig that has blocks, one gt_vcf record for
+ * every position from the first block's x to the last block's y; blocks[b].vcf_off locates block b's window in it. */
+int bsgpu_call_bam(bsgpu_ctx *ctx, const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len,
+		const uint8_t *const *ctg_codes, const bsgpu_reader_params *rp, bsgpu_block *blocks, size_t block_cap, size_t *nblocks,
+		bsgpu_gt_vcf *vcf, size_t vcf_cap, size_t *nvcf);
 
 /* ---- device-pointer entry points: everything already resident in HBM, asynchronous on `stream`
  *      (a cudaStream_t passed as void*; NULL = the context's own stream) ---- */

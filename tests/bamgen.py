@@ -178,3 +178,48 @@ def concat_sorted(rec_lists):
     order = sorted(range(len(allr)), key=lambda i: (allr[i][0][0], allr[i][0][1]))
     buf = b"".join(allr[i][1] for i in order)
     return np.frombuffer(buf, dtype=np.uint8).copy(), len(allr)
+
+
+def make_stream(seed, n_contigs=None, dup=0.15, junk=0.1, depth=None, read_len=None, paired=None, contig_len=None):
+    """A small multi-contig, multi-block coordinate-sorted record stream.
+    -> (bam uint8[], number of records, target_len[], [reference codes per contig])"""
+    from tests import blockgen
+    rng = np.random.default_rng(seed)
+    nctg = int(rng.integers(1, 4)) if n_contigs is None else n_contigs
+    lists, refs, tl = [], [], []
+    for tid in range(nctg):
+        L = int(rng.integers(3000, 9000)) if contig_len is None else contig_len
+        ref = blockgen.random_reference(rng, L, n_runs=2)
+        refs.append(ref)
+        tl.append(L)
+        a = 50
+        while a < L - 900:
+            b = min(a + int(rng.integers(300, 2500)), L - 600)
+            T, B, M, _ = blockgen.make_block(
+                rng, ref, a, b, depth=int(rng.integers(4, 40)) if depth is None else depth,
+                read_len=int(rng.integers(30, 120)) if read_len is None else read_len,
+                paired=(rng.random() < 0.75) if paired is None else paired, indel_frac=0.1, clip_frac=0.1,
+                single_mate_frac=0.15, frag_mean=int(rng.integers(60, 300)), nonconv_frac=0.05)
+            lists.append(records_from_block(rng, T, B, M, tid=tid, name_prefix="s%d_%d_" % (seed, a), dup_frac=dup,
+                                            junk_frac=junk, qual_over=0.02, single_flag_paired=rng.random() < 0.2))
+            a = b + int(rng.integers(1, 400))
+    bam, n = concat_sorted(lists)
+    return bam, n, np.array(tl, dtype=np.uint32), refs
+
+
+def template_keys(tm, bases, misms):
+    """canonical, layout-independent view of a template list: positions, orientation, strand and per mate
+    (length, span, mapq, packed bytes, events); a mate without bytes only keeps its mapq"""
+    out = []
+    for t in tm:
+        mates = []
+        for k in (0, 1):
+            rl = int(t["read_len"][k]) if t["present"][k] else 0
+            if rl == 0:
+                mates.append((0, int(t["mapq"][k])))
+                continue
+            o = int(t["read_off"][k])
+            ev = tuple(tuple(int(v) for v in misms[int(t["mm_off"][k]) + z]) for z in range(int(t["mm_n"][k])))
+            mates.append((rl, int(t["reference_span"][k]), int(t["mapq"][k]), bytes(bases[o:o + rl]), ev))
+        out.append((int(t["forward_position"]), int(t["reverse_position"]), int(t["orientation"]), int(t["bs_strand"]), tuple(mates)))
+    return out

@@ -8,6 +8,8 @@ The GPU boxes have no reference tree; they check against these committed files.
                  call_genotypes_ML on blocks built from synthetic reads, plus direct calc_gt_prob/fisher KATs)
   block_*.npz    block goldens: raw templates -> normalised templates, pileup[], gt_vcf[]
                  (process_template_vector -> call_genotypes_ML)
+  reader_*.npz   reader goldens: raw BAM records -> per-record descriptors (get_next_align_details), blocks and
+                 templates (read_input), gt_vcf[] of every block (the whole chain)
 """
 import os
 import sys
@@ -88,6 +90,38 @@ def make_sites():
           int(np.isin(vcf["gtm"]["max_gt"], [1, 2, 3, 5, 6, 8])[vcf["skip"] == 0].sum()))
 
 
+READER_CASES = {
+    # paired-end, default options; mixed: singles + pairs, keep_unmatched, its own thresholds
+    "reader_pe": dict(seed=31, stream=dict(n_contigs=2, paired=True, depth=14, read_len=70, contig_len=4000),
+                      opts=dict(mapq_thresh=20, max_template_len=1000, keep_unmatched=False, ignore_duplicates=False, keep_duplicates=False)),
+    "reader_mixed": dict(seed=32, stream=dict(n_contigs=3, dup=0.25, contig_len=3500),
+                         opts=dict(mapq_thresh=10, max_template_len=600, keep_unmatched=True, ignore_duplicates=True, keep_duplicates=False)),
+}
+
+
+def make_reader():
+    """reader goldens: raw BAM records -> get_next_align_details() per record, read_input() blocks and templates, and the
+    gt_vcf[] of every block from the reference's chain read_input -> process_template_vector -> call_genotypes_ML"""
+    from tests import bamgen
+    r = Reference()
+    for name, c in READER_CASES.items():
+        bam, n, tl, refs = bamgen.make_stream(c["seed"], **c["stream"])
+        o = c["opts"]
+        rec, rbases, rmisms = r.decode_records(bam, o["mapq_thresh"], o["max_template_len"], o["keep_unmatched"], o["ignore_duplicates"])
+        blocks, tm, bases, misms, vcf = r.read_input(bam, tl, refs, run_chain=True, **o)
+        extra = {"ref%d" % i: refs[i] for i in range(len(refs))}
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), bam=bam, target_len=tl, rec=rec, rec_bases=rbases, rec_misms=rmisms,
+                            blocks=blocks, templates=tm, bases=bases, misms=misms, vcf=vcf,
+                            **{k: np.array(v) for k, v in o.items()}, **extra)
+        print(name, "records", n, "kept", int((rec["ret"] == 0).sum()), "blocks", len(blocks), "templates", len(tm),
+              "sites", len(vcf), "called", int((vcf["skip"] == 0).sum()))
+
+
 if __name__ == "__main__":
-    make_blocks()
-    make_sites()
+    which = sys.argv[1:] or ["blocks", "sites", "reader"]
+    if "blocks" in which:
+        make_blocks()
+    if "sites" in which:
+        make_sites()
+    if "reader" in which:
+        make_reader()

@@ -1,0 +1,73 @@
+"""CPU checks of the reader side that need no GPU: the product's host block builder (bsgpu_build_blocks, a pure host
+function of the ABI) against the oracle's restatement of read_input(), and the committed reader golden (captured
+from the reference's own read_input / process_template_vector / call_genotypes_ML) against the oracle."""
+import numpy as np
+import pytest
+
+from bs_call_b200 import lib
+from bs_call_b200.records import RECORD
+from tests import bamgen, util
+
+
+def descriptors_from_oracle(orec, obases, bam):
+    """the oracle's per-record view widened to the product's descriptor (adds the contig id and the two qualities the
+    duplicate tie-break reads)"""
+    r = np.zeros(len(orec), dtype=RECORD)
+    for f in orec.dtype.names:
+        r[f] = orec[f]
+    at = 0
+    for i in range(len(orec)):
+        bs = int(bam[at:at + 4].view("<i4")[0])
+        r["tid"][i] = int(bam[at + 4:at + 8].view("<i4")[0])
+        at += 4 + bs
+        if orec["ret"][i] == 0:
+            for k in range(min(2, int(orec["read_len"][i]))):
+                r["q01"][i, k] = obases[int(orec["read_off"][i]) + k] >> 2
+    return r
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_build_blocks_matches_oracle(oracle, seed):
+    bam, n, tl, _ = bamgen.make_stream(seed, dup=0.2)
+    kd, ku = seed % 5 == 3, seed % 7 == 5
+    orec, ob, om = oracle.decode_records(bam, 20, 1000, ku, False)
+    rec = descriptors_from_oracle(orec, ob, bam)
+    blocks, tm = lib.build_blocks(bam, rec, lib.reader_params(keep_unmatched=ku, keep_duplicates=kd))
+    wbk, wt, wb, wm, _ = oracle.read_input(bam, tl, None, keep_unmatched=ku, keep_duplicates=kd)
+    assert len(blocks) == len(wbk) > 0
+    for f in ("tid", "x", "y", "first_template", "n_templates"):
+        assert (blocks[f] == wbk[f]).all(), f
+    assert bamgen.template_keys(tm, ob, om) == bamgen.template_keys(wt, wb, wm)
+
+
+def test_build_blocks_rejects_bad_stream():
+    bam, n, _, _ = bamgen.make_stream(1)
+    rec = np.zeros(n, dtype=RECORD)
+    with pytest.raises(lib.BsGpuError):
+        lib.build_blocks(bam[:-7], rec)
+
+
+def test_empty_stream(oracle):
+    blocks, tm = lib.build_blocks(np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=RECORD))
+    assert len(blocks) == 0 and len(tm) == 0
+    r, b, m = oracle.decode_records(np.zeros(0, dtype=np.uint8))
+    assert len(r) == 0
+
+
+@pytest.mark.parametrize("name", ["reader_pe", "reader_mixed"])
+def test_oracle_matches_reader_golden(oracle, name):
+    g = util.load_golden(name)
+    o = dict(mapq_thresh=int(g["mapq_thresh"]), max_template_len=int(g["max_template_len"]), keep_unmatched=bool(g["keep_unmatched"]),
+             ignore_duplicates=bool(g["ignore_duplicates"]), keep_duplicates=bool(g["keep_duplicates"]))
+    refs = [g["ref%d" % i] for i in range(len(g["target_len"]))]
+    rec, rb, rm = oracle.decode_records(g["bam"], o["mapq_thresh"], o["max_template_len"], o["keep_unmatched"], o["ignore_duplicates"])
+    kept = g["rec"]["ret"] == 0
+    for f in g["rec"].dtype.names:
+        a, b = (g["rec"][f][kept], rec[f][kept]) if f in ("bs_strand", "align_length", "reference_span", "read_off", "read_len", "mm_off", "mm_n") else (g["rec"][f], rec[f])
+        assert (a == b).all(), f
+    assert rb.tobytes() == g["rec_bases"].tobytes()
+    wbk, wt, wb, wm, wv = oracle.read_input(g["bam"], g["target_len"], refs, run_chain=True, **o)
+    for f in ("tid", "x", "y", "first_template", "n_templates", "vcf_off"):
+        assert (wbk[f] == g["blocks"][f]).all(), f
+    assert bamgen.template_keys(wt, wb, wm) == bamgen.template_keys(g["templates"], g["bases"], g["misms"])
+    util.assert_gt_meth_close(wv["gtm"], wv["skip"], g["vcf"]["gtm"], g["vcf"]["skip"], exact_doubles=True)

@@ -1,0 +1,127 @@
+"""Reader-side parity (-m gpu): BAM record decode on the device (bsgpu_decode_records), the block builder over its
+descriptors, and the whole chain raw records -> gt_vcf[] (bsgpu_call_bam), against the goldens captured from the
+reference's own get_next_align_details / read_input / process_template_vector / call_genotypes_ML and against the
+oracle on seeded streams.  Everything on the reader side is integer / byte work: bit-exact."""
+import numpy as np
+import pytest
+
+from bs_call_b200 import lib as bslib
+from tests import bamgen, util
+
+pytestmark = pytest.mark.gpu
+
+KEPT_ONLY = ("bs_strand", "align_length", "reference_span", "read_len", "mm_n")
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    g = bslib.BsGpu()
+    yield g
+    g.close()
+
+
+def _rp(o):
+    return bslib.reader_params(mapq_thresh=o["mapq_thresh"], max_template_len=o["max_template_len"], keep_unmatched=o["keep_unmatched"],
+                               ignore_duplicates=o["ignore_duplicates"], keep_duplicates=o["keep_duplicates"])
+
+
+def _check_records(rec, bases, misms, want, wbases, wmisms):
+    assert len(rec) == len(want)
+    kept = want["ret"] == 0
+    for f in ("ret", "filtered", "forward_position", "reverse_position", "alignment_flag", "reverse", "orientation", "mapq"):
+        assert (rec[f] == want[f]).all(), f
+    for f in KEPT_ONLY:
+        assert (rec[f][kept] == want[f][kept]).all(), f
+    # decoded reads and events, record by record (the two sides lay them out differently)
+    for i in np.nonzero(kept)[0]:
+        a = bases[int(rec["read_off"][i]):int(rec["read_off"][i]) + int(rec["read_len"][i])]
+        b = wbases[int(want["read_off"][i]):int(want["read_off"][i]) + int(want["read_len"][i])]
+        assert a.tobytes() == b.tobytes(), "read of record %d" % i
+        a = misms[int(rec["mm_off"][i]):int(rec["mm_off"][i]) + int(rec["mm_n"][i])]
+        b = wmisms[int(want["mm_off"][i]):int(want["mm_off"][i]) + int(want["mm_n"][i])]
+        assert a.tobytes() == b.tobytes(), "events of record %d" % i
+        for k in range(min(2, int(rec["read_len"][i]))):
+            assert rec["q01"][i, k] == b"".join([bases[int(rec["read_off"][i]) + k:int(rec["read_off"][i]) + k + 1].tobytes()])[0] >> 2
+
+
+def _golden_opts(g):
+    return dict(mapq_thresh=int(g["mapq_thresh"]), max_template_len=int(g["max_template_len"]), keep_unmatched=bool(g["keep_unmatched"]),
+                ignore_duplicates=bool(g["ignore_duplicates"]), keep_duplicates=bool(g["keep_duplicates"]))
+
+
+@pytest.mark.parametrize("name", ["reader_pe", "reader_mixed"])
+def test_decode_records_golden(gpu, name):
+    g = util.load_golden(name)
+    before = gpu.stats()["kernel_launches"]
+    rec, bases, misms = gpu.decode_records(g["bam"], _rp(_golden_opts(g)))
+    assert gpu.stats()["kernel_launches"] == before + 1
+    _check_records(rec, bases, misms, g["rec"], g["rec_bases"], g["rec_misms"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_decode_records_oracle(gpu, oracle, seed):
+    bam, n, _, _ = bamgen.make_stream(100 + seed)
+    ku, ig = seed % 3 == 1, seed % 2 == 1
+    want, wb, wm = oracle.decode_records(bam, 20 - seed, 400 + 150 * seed, ku, ig)
+    rec, bases, misms = gpu.decode_records(bam, bslib.reader_params(mapq_thresh=20 - seed, max_template_len=400 + 150 * seed,
+                                                                  keep_unmatched=ku, ignore_duplicates=ig))
+    assert len(rec) == n
+    _check_records(rec, bases, misms, want, wb, wm)
+
+
+@pytest.mark.parametrize("name", ["reader_pe", "reader_mixed"])
+def test_blocks_from_device_descriptors_golden(gpu, name):
+    """decode on the device, build blocks on the host from the device's descriptors: the reference's blocks"""
+    g = util.load_golden(name)
+    o = _golden_opts(g)
+    rec, bases, misms = gpu.decode_records(g["bam"], _rp(o))
+    blocks, tm = bslib.build_blocks(g["bam"], rec, _rp(o))
+    for f in ("tid", "x", "y", "first_template", "n_templates"):
+        assert (blocks[f] == g["blocks"][f]).all(), f
+    assert bamgen.template_keys(tm, bases, misms) == bamgen.template_keys(g["templates"], g["bases"], g["misms"])
+
+
+@pytest.mark.parametrize("name", ["reader_pe", "reader_mixed"])
+def test_call_bam_golden(gpu, name):
+    """raw records in, gt_vcf[] of every block out: what the reference's whole chain produced"""
+    g = util.load_golden(name)
+    refs = [g["ref%d" % i] for i in range(len(g["target_len"]))]
+    blocks, vcf = gpu.call_bam(g["bam"], g["target_len"], refs, _rp(_golden_opts(g)))
+    want_b, want_v = g["blocks"], g["vcf"]
+    assert len(blocks) == len(want_b)
+    ncalled = 0
+    for b, w in zip(blocks, want_b):
+        assert (b["tid"], b["x"], b["y"], b["n_templates"]) == (w["tid"], w["x"], w["y"], w["n_templates"])
+        sz = int(w["y"]) - int(w["x"]) + 1
+        got = vcf[int(b["vcf_off"]):int(b["vcf_off"]) + sz]
+        ncalled += util.assert_vcf_close(got, want_v[int(w["vcf_off"]):int(w["vcf_off"]) + sz])
+    assert ncalled > 5000
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_call_bam_oracle(gpu, oracle, seed):
+    bam, n, tl, refs = bamgen.make_stream(200 + seed, dup=0.2)
+    o = dict(mapq_thresh=15, max_template_len=800, keep_unmatched=seed == 2, ignore_duplicates=False, keep_duplicates=seed == 3)
+    wbk, wt, wb, wm, wv = oracle.read_input(bam, tl, refs, run_chain=True, **o)
+    blocks, vcf = gpu.call_bam(bam, tl, refs, _rp(o))
+    assert len(blocks) == len(wbk) > 0
+    for b, w in zip(blocks, wbk):
+        assert (b["tid"], b["x"], b["y"], b["n_templates"]) == (w["tid"], w["x"], w["y"], w["n_templates"])
+        sz = int(w["y"]) - int(w["x"]) + 1
+        util.assert_vcf_close(vcf[int(b["vcf_off"]):int(b["vcf_off"]) + sz], wv[int(w["vcf_off"]):int(w["vcf_off"]) + sz])
+    # positions between blocks of a contig are uncovered: skip records
+    covered = np.zeros(len(vcf), dtype=bool)
+    for b in blocks:
+        covered[int(b["vcf_off"]):int(b["vcf_off"]) + int(b["y"]) - int(b["x"]) + 1] = True
+    assert (vcf["skip"][~covered] == 1).all()
+
+
+def test_reader_rejects_truncated_stream(gpu):
+    bam, n, tl, refs = bamgen.make_stream(7)
+    with pytest.raises(bslib.BsGpuError):
+        gpu.decode_records(bam[:-5])
+
+
+def test_reader_empty_stream(gpu):
+    rec, bases, misms = gpu.decode_records(np.zeros(0, dtype=np.uint8))
+    assert len(rec) == 0

@@ -141,3 +141,51 @@ def test_deep_block_uses_lgamma(reference):
     _same_records(vcf_o, vcf_r, "gt_vcf")
     het = np.isin(vcf_r["gtm"]["max_gt"], [1, 2, 3, 5, 6, 8]) & (vcf_r["skip"] == 0)
     assert het.sum() > 0 and pile_r["n"].max() >= 256
+
+
+# ---- reader side: record decode (src/input_sam.c) and read_input (src/get_template_vector.c) ----------------------
+KEPT_ONLY = ("bs_strand", "align_length", "reference_span", "read_off", "read_len", "mm_off", "mm_n")
+
+
+def _reader_opts(seed):
+    rng = np.random.default_rng(1000 + seed)
+    return dict(mapq_thresh=int(rng.integers(0, 30)), max_template_len=int(rng.integers(300, 1200)),
+                keep_unmatched=seed % 7 == 5, ignore_duplicates=bool(rng.random() < 0.3), keep_duplicates=seed % 5 == 3)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_decode_records(oracle, reference, seed):
+    """every field get_next_align_details() produces, the packed reads and the CIGAR events: identical"""
+    from tests import bamgen
+    bam, n, _, _ = bamgen.make_stream(seed)
+    o = _reader_opts(seed)
+    args = (bam, o["mapq_thresh"], o["max_template_len"], o["keep_unmatched"], o["ignore_duplicates"])
+    r, rb, rm = reference.decode_records(*args)
+    w, wb, wm = oracle.decode_records(*args)
+    assert len(r) == len(w) == n
+    kept = r["ret"] == 0
+    assert kept.sum() > 0 and (~kept).sum() > 0
+    for f in r.dtype.names:
+        a, b = (r[f][kept], w[f][kept]) if f in KEPT_ONLY else (r[f], w[f])
+        assert (a == b).all(), f
+    assert rb.tobytes() == wb.tobytes() and rm.tobytes() == wm.tobytes()
+    assert set(np.unique(r["bs_strand"][kept])) == {0, 1, 2}
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_read_input(oracle, reference, seed):
+    """blocks (contig, window, template ranges) and every template with its mates' bytes and events: identical;
+    every fourth seed also runs the chain read_input -> process_template_vector -> call_genotypes_ML on both sides"""
+    from tests import bamgen, util
+    bam, n, tl, refs = bamgen.make_stream(seed)
+    o = _reader_opts(seed)
+    chain = seed % 4 == 0
+    rbk, rt, rb, rm, rv = reference.read_input(bam, tl, refs, run_chain=chain, **o)
+    wbk, wt, wb, wm, wv = oracle.read_input(bam, tl, refs, run_chain=chain, **o)
+    assert len(rbk) == len(wbk) and len(rbk) > 0
+    for f in ("tid", "x", "y", "first_template", "n_templates", "vcf_off"):
+        assert (rbk[f] == wbk[f]).all(), f
+    assert bamgen.template_keys(rt, rb, rm) == bamgen.template_keys(wt, wb, wm)
+    if chain:
+        assert len(rv) == len(wv) and (rv["skip"] == 0).sum() > 0
+        util.assert_gt_meth_close(wv["gtm"], wv["skip"], rv["gtm"], rv["skip"], exact_doubles=True)
