@@ -144,6 +144,105 @@ def run_reference(args):
     return 0
 
 
+def bam_path(args, gpu, bslib, torch, np, stream, rank, world, local):
+    """Synthetic coordinate-sorted paired-end WGBS record stream (30x, 150 bp, 5 % positional duplicates, coverage gaps
+    every ~100 kb so that the reader cuts blocks) through bsgpu_call_bam with pinned host buffers: H2D of the records,
+    decode, block building, normalisation, pileup, model and D2H of gt_vcf[] all inside the timed region."""
+    from bs_call_b200.records import GT_VCF
+    L, depth, frag, tpb, gap = 150, 30.0, 300, 10000, 400
+    sz = int(args.bam_sites)
+    nt = int(sz * depth / (2 * L))
+    step = 2 * L / depth
+    dev = torch.device("cuda", local)
+    t = torch.arange(nt, device=dev, dtype=torch.int64)
+    p = 101 + torch.floor(t.double() * step).long() + (t // tpb) * gap
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + 17 + rank)
+    dup = (torch.rand(nt, device=dev, generator=g) < 0.05) & (t > 0)
+    src = torch.where(dup, t - 1, t)
+    dlen = (frag - L) + ((src * 2654435761) >> 7) % 41 - 20
+    pos_f = p[src]
+    pos_r = pos_f + dlen
+    order = torch.argsort(torch.cat([pos_f, pos_r]), stable=True)
+    rank_of = torch.empty_like(order)
+    rank_of[order] = torch.arange(2 * nt, device=dev)
+    ctg_len = int(pos_r.max().item()) + L + 600
+    nbytes = gpu.synth_bam_bytes(nt, L)
+    d_bam = torch.empty(nbytes + 16, dtype=torch.uint8, device=dev)
+    d_ref = torch.empty(ctg_len + 16, dtype=torch.uint8, device=dev)
+    u32 = lambda a: a.to(torch.int32).contiguous()
+    a_f, a_r, a_s, a_k = u32(pos_f), u32(pos_r), u32(src), u32(rank_of)
+    gpu.synth_bam_dev(SEED, nt, L, a_f.data_ptr(), a_r.data_ptr(), a_s.data_ptr(), a_k.data_ptr(), d_bam.data_ptr(), stream)
+    gpu.synth_ref_dev(SEED, 1, ctg_len, d_ref.data_ptr(), stream)
+    torch.cuda.synchronize()
+    hbam = bslib.HostBuffer(nbytes, np.uint8)
+    hvcf = bslib.HostBuffer(ctg_len + 8, GT_VCF)
+    hbam.array[:] = d_bam[:nbytes].cpu().numpy()
+    href = d_ref[:ctg_len].cpu().numpy()
+    del d_bam, d_ref
+    tl = np.array([ctg_len], dtype=np.uint32)
+    for _ in range(2):
+        blocks, vcf = gpu.call_bam(hbam.array, tl, [href], vcf=hvcf.array)
+    s0 = gpu.stats()
+    steps = max(1, min(args.steps, 3))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        blocks, vcf = gpu.call_bam(hbam.array, tl, [href], vcf=hvcf.array)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    s1 = gpu.stats()
+    called = int((vcf["skip"] == 0).sum())
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    cc = torch.tensor([called], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+    out = {"workload": "synthetic %dx paired-end %d-bp WGBS record stream over %d sites (config 3 shape): %d records, %d blocks, 5 %% duplicates" % (
+               int(depth), L, sz, 2 * nt, len(blocks)),
+           "e2e": {"value": float(cc.item()) / float(tt.item()), "unit": "sites/s", "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // steps,
+                   "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // steps, "sites_called_per_step": called,
+                   "records_per_s": 2 * nt / dt, "note": "bsgpu_call_bam on pinned host buffers, per rank work fixed"},
+           "stage_s_per_step": {"frame_h2d_decode": (s1["bam_decode_s"] - s0["bam_decode_s"]) / steps,
+                                "descriptors_d2h_block_builder_host": (s1["bam_build_s"] - s0["bam_build_s"]) / steps,
+                                "normalise_pileup_model_d2h": (s1["bam_call_s"] - s0["bam_call_s"]) / steps},
+           "gpu_launches_per_step": (s1["kernel_launches"] - s0["kernel_launches"]) // steps}
+    # the reference's own chain (read_input -> process_template_vector -> call_genotypes_ML, all its threads) on a bounded
+    # prefix of the same stream
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle.bindings import Oracle, Reference, reference_available
+        from tests import util
+        rb = nbytes // (2 * nt)
+        nrec_c = int(min(2 * nt, 260000))
+        prefix = hbam.array[:nrec_c * rb]
+        last_pos = int(prefix[(nrec_c - 1) * rb + 8:(nrec_c - 1) * rb + 12].view("<i4")[0]) + 1
+        clen = last_pos + 2 * L + 1200
+        ncores = os.cpu_count() or 1
+        if reference_available():
+            impl, kind = Reference(calc_threads=ncores), "reference"
+            what = "reference read_input -> process_template_vector -> call_genotypes_ML (oracle/_ref/libbsref.so)"
+        else:
+            impl, kind = Oracle(), "port"
+            what = "oracle port of the same chain (1 thread)"
+        t0 = time.perf_counter()
+        cb, ct, _, _, cv = impl.read_input(prefix, [clen], [href[:clen]], run_chain=True)
+        cs = time.perf_counter() - t0
+        ccalled = int((cv["skip"] == 0).sum())
+        out["cpu_baseline"] = {"value": ccalled / cs, "unit": "sites/s", "cores": ncores, "kind": kind,
+                               "sample": "first %d records (%d sites called, %d blocks) of the same stream; %s" % (nrec_c, ccalled, len(cb), what)}
+        # parity on every complete block of the prefix
+        checked = 0
+        for b, w in zip(blocks[:len(cb) - 1], cb[:len(cb) - 1]):
+            assert (b["x"], b["y"], b["n_templates"]) == (w["x"], w["y"], w["n_templates"])
+            n_ = int(w["y"]) - int(w["x"]) + 1
+            checked += util.assert_vcf_close(vcf[int(b["vcf_off"]):int(b["vcf_off"]) + n_], cv[int(w["vcf_off"]):int(w["vcf_off"]) + n_])
+        out["cpu_baseline"]["parity_sites_checked"] = checked
+    hbam.free()
+    hvcf.free()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +252,7 @@ def main():
     ap.add_argument("--sites", type=float, default=1e9, help="resident sites per GPU (config 2: 1e9)")
     ap.add_argument("--e2e-sites", type=float, default=8e6, help="sites per e2e step (host buffers)")
     ap.add_argument("--fused-sites", type=float, default=50e6, help="window of the block-path (pileup + model) measurement")
+    ap.add_argument("--bam-sites", type=float, default=8e6, help="window of the BAM-records-to-calls measurement (bsgpu_call_bam)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -416,6 +516,14 @@ def main():
         import traceback
         block = {"error": repr(e), "trace": traceback.format_exc()[-800:]}
 
+    # ---- the whole path from BAM records: decode -> blocks -> normalise -> pileup -> model (bsgpu_call_bam), host buffers
+    bam = None
+    try:
+        bam = bam_path(args, gpu, bslib, torch, np, stream, rank, world, local)
+    except Exception as e:
+        import traceback
+        bam = {"error": repr(e), "trace": traceback.format_exc()[-800:]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         nthreads = os.cpu_count() or 1
@@ -432,7 +540,7 @@ def main():
                            "parallelism": "sites sharded over %d rank(s), no collective" % world,
                            "l2": "inputs larger than L2: each step streams %.1f GB of distinct records" % (n_sites * 105 / 1e9)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "block_path": block, "parity_spot_check": parity}
+                "block_path": block, "bam_path": bam, "parity_spot_check": parity}
         print(json.dumps(line))
     gpu.close()
     if world > 1:

@@ -1,5 +1,6 @@
 // bsgpu_api.cu -- the C ABI declared in include/bsgpu.h: context, staging, pipelines.  No CPU compute path:
 // every entry point that produces results launches kernels, and bsgpu_init fails if no sm_100 device opens.
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -61,6 +62,21 @@ struct DevBuf {
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+struct PinBuf {                // grow-on-demand page-locked host buffer
+	void *p = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t bytes) {
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFreeHost(p);
+		p = nullptr; cap = 0;
+		const size_t want = bytes + bytes / 8 + 256;
+		cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct Slot {                  // one stage of the host-buffer pipelines
 	cudaStream_t stream = nullptr;
 	cudaEvent_t done = nullptr;
@@ -78,6 +94,7 @@ struct bsgpu_ctx {
 	DevBuf segs, bases, ref, scratch, vcf, tmpl, misms, obases, ooff, pile;
 	DevBuf rd_bam, rd_recoff, rd_readoff, rd_mmoff, rd_rec, rd_bases, rd_misms;      // reader side: stream, framing, decoded arrays
 	std::vector<uint64_t> rec_off;               // framing of the last decoded stream
+	PinBuf h_rec, h_off;                         // pinned staging: descriptors coming back, offset tables going up
 	bool fused = false;                          // BSGPU_FUSED=1: one fused pileup+model kernel instead of two kernels
 	std::vector<cudaEvent_t> win_events;
 	bsgpu_stats stats;
@@ -167,6 +184,7 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 		if (c->slot[i].done) cudaEventDestroy(c->slot[i].done);
 	}
 	for (cudaEvent_t ev : c->win_events) cudaEventDestroy(ev);
+	c->h_rec.release(); c->h_off.release();
 	c->rd_bam.release(); c->rd_recoff.release(); c->rd_readoff.release(); c->rd_mmoff.release(); c->rd_rec.release(); c->rd_bases.release(); c->rd_misms.release();
 	c->segs.release(); c->bases.release(); c->ref.release(); c->scratch.release(); c->vcf.release(); c->tmpl.release(); c->misms.release(); c->obases.release(); c->ooff.release(); c->pile.release();
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -269,6 +287,25 @@ int bsgpu_synth_sites_dev(bsgpu_ctx *c, uint64_t seed, uint64_t first_site, size
 }
 
 size_t bsgpu_synth_block_nseg(uint32_t sz, uint32_t read_len, double depth) { return synth_block_nseg(sz, read_len, depth); }
+
+size_t bsgpu_synth_bam_bytes(size_t ntemplates, uint32_t read_len) { return synth_bam_bytes(ntemplates, read_len); }
+
+int bsgpu_synth_bam_dev(bsgpu_ctx *c, uint64_t seed, size_t ntemplates, uint32_t read_len, const void *d_pos_f, const void *d_pos_r,
+		const void *d_src, const void *d_rank, void *d_out, void *stream) {
+	if (!c) return fail("bsgpu_synth_bam_dev: null context");
+	if (read_len < 16 || read_len > BSGPU_MAX_SEG_LEN) return fail("bsgpu_synth_bam_dev: read_len must be in [16,%d]", BSGPU_MAX_SEG_LEN);
+	if (ntemplates && (!d_pos_f || !d_pos_r || !d_src || !d_rank || !d_out)) return fail("bsgpu_synth_bam_dev: null buffer");
+	CU(cudaSetDevice(c->device));
+	CU(launch_synth_bam(seed, ntemplates, read_len, d_pos_f, d_pos_r, d_src, d_rank, d_out, stream ? (cudaStream_t)stream : c->stream, &c->launches));
+	return BSGPU_OK;
+}
+
+int bsgpu_synth_ref_dev(bsgpu_ctx *c, uint64_t seed, uint32_t x, uint32_t sz, void *d_ref, void *stream) {
+	if (!c) return fail("bsgpu_synth_ref_dev: null context");
+	CU(cudaSetDevice(c->device));
+	CU(launch_synth_ref(seed, x, sz, d_ref, stream ? (cudaStream_t)stream : c->stream, &c->launches));
+	return BSGPU_OK;
+}
 
 int bsgpu_synth_block_dev(bsgpu_ctx *c, uint64_t seed, uint32_t x, uint32_t sz, uint32_t read_len, double depth,
 		void *d_segs, size_t seg_cap, void *d_bases, size_t base_cap, void *d_ref, size_t *nseg, size_t *nbases, void *stream) {
@@ -509,9 +546,15 @@ static int decode_resident(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, cons
 	CU(c->rd_bases.reserve(*nb + 16));
 	CU(c->rd_misms.reserve((*nm + 1) * sizeof(bsgpu_misms)));
 	CU(cudaMemcpyAsync(c->rd_bam.p, bam, nbytes, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->rd_recoff.p, c->rec_off.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->rd_readoff.p, read_off.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->rd_mmoff.p, mm_off.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+	// the offset tables go up from pinned staging (pageable vectors would serialise the copies behind the big one)
+	CU(c->h_off.reserve(n * 16));
+	uint8_t *ho = (uint8_t *)c->h_off.p;
+	memcpy(ho, c->rec_off.data(), n * 8);
+	memcpy(ho + n * 8, read_off.data(), n * 4);
+	memcpy(ho + n * 12, mm_off.data(), n * 4);
+	CU(cudaMemcpyAsync(c->rd_recoff.p, ho, n * 8, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->rd_readoff.p, ho + n * 8, n * 4, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->rd_mmoff.p, ho + n * 12, n * 4, cudaMemcpyHostToDevice, c->stream));
 	c->stats.h2d_bytes += nbytes + n * 16;
 	CU(launch_decode_records(c->rd_bam.p, c->rd_recoff.p, c->rd_readoff.p, c->rd_mmoff.p, n, rp->mapq_thresh, rp->max_template_len,
 			rp->keep_unmatched, rp->ignore_duplicates, c->rd_rec.p, c->rd_bases.p, c->rd_misms.p, c->stream, &c->launches));
@@ -571,14 +614,22 @@ int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_target
 	size_t n = 0;
 	uint64_t nb = 0, nm = 0;
 	*nblocks = 0; *nvcf = 0;
+	auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double t0 = now();
 	if (decode_resident(c, bam, nbytes, rp, &n, &nb, &nm) != BSGPU_OK) return BSGPU_FAIL;
+	const double t1 = now();
+	c->stats.bam_decode_s += t1 - t0;
 	if (!n) return BSGPU_OK;
-	std::vector<bsgpu_record> rec(n);
-	CU(cudaMemcpy(rec.data(), c->rd_rec.p, n * sizeof(bsgpu_record), cudaMemcpyDeviceToHost));
+	CU(c->h_rec.reserve(n * sizeof(bsgpu_record)));
+	const bsgpu_record *rec = (const bsgpu_record *)c->h_rec.p;
+	CU(cudaMemcpyAsync(c->h_rec.p, c->rd_rec.p, n * sizeof(bsgpu_record), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
 	c->stats.d2h_bytes += n * sizeof(bsgpu_record);
 	std::vector<bsgpu_block> bl;
 	std::vector<bsgpu_template> tm;
-	const int rc = build_blocks_host(bam, c->rec_off.data(), rec.data(), n, rp->keep_unmatched, rp->keep_duplicates, bl, tm);
+	const int rc = build_blocks_host(bam, c->rec_off.data(), rec, n, rp->keep_unmatched, rp->keep_duplicates, bl, tm);
+	const double t2 = now();
+	c->stats.bam_build_s += t2 - t1;
 	if (rc == -4) return fail("bsgpu_call_bam: duplicate read name among waiting mates");
 	if (rc) return fail("bsgpu_call_bam: block builder failed (%d)", rc);
 	if (bl.size() > block_cap) return fail("bsgpu_call_bam: need room for %zu blocks", bl.size());
@@ -638,6 +689,7 @@ int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_target
 	memcpy(blocks, bl.data(), bl.size() * sizeof(bsgpu_block));
 	*nblocks = bl.size();
 	*nvcf = ov;
+	c->stats.bam_call_s += now() - t2;
 	return BSGPU_OK;
 }
 

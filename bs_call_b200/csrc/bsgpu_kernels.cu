@@ -627,6 +627,84 @@ __global__ void k_synth_reads(uint64_t seed, uint32_t x, uint32_t sz, uint32_t r
 	}
 }
 
+// Synthetic coordinate-sorted BAM record stream (config 3 shape) written straight into HBM: one warp per record.
+// Records are fixed size (qname of 15 characters + NUL, one CIGAR op, GEM strand tag XB:A), so record i of the sorted
+// stream sits at i * record_bytes; `rank` (computed by the caller with a sort over the start positions) says where the
+// record of (template, mate) goes.  Template t copies the reads of template src[t] (a positional duplicate when
+// src[t] != t) under its own name.
+__host__ __device__ constexpr uint32_t synth_bam_record_bytes(uint32_t read_len) { return 4 + 32 + 16 + 4 + (read_len + 1) / 2 + read_len + 4; }
+
+__global__ void k_synth_bam(uint64_t seed, size_t ntemplates, uint32_t read_len, const uint32_t *__restrict__ pos_f,
+		const uint32_t *__restrict__ pos_r, const uint32_t *__restrict__ src, const uint32_t *__restrict__ rank, uint8_t *__restrict__ out) {
+	const size_t wi = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (wi >= 2 * ntemplates) return;
+	const uint32_t k = wi >= ntemplates ? 1u : 0u;                 // 0: forward-strand mate, 1: reverse-strand mate
+	const size_t t = wi - (k ? ntemplates : 0), ts = src[t];
+	const uint32_t rb = synth_bam_record_bytes(read_len);
+	uint8_t *rec = out + (size_t)rank[wi] * rb;
+	Rng r(seed ^ 0x51ed27fULL, ts);
+	const uint64_t h = r.next();
+	const uint32_t st = 1 + (uint32_t)((h >> 24) & 1);             // C2T: top-strand fragment, G2A: bottom strand
+	const uint32_t hap = (uint32_t)((h >> 26) & 1);
+	const uint32_t fpos = pos_f[t], rpos = pos_r[t], pos = k ? rpos : fpos, mpos = k ? fpos : rpos;
+	const uint32_t mapq = ((h >> 28) & 0x1f) ? 60 : 5 + (uint32_t)((h >> 34) % 50);
+	const int32_t tlen = (int32_t)(rpos + read_len - fpos);
+	// directional library: read 1 is the forward mate of a top-strand fragment, the reverse mate of a bottom-strand one
+	const bool read1 = (k == 0) == (st == 1);
+	const uint32_t flag = 1u | 2u | (k ? 16u : 32u) | (read1 ? 64u : 128u);
+	if (lane == 0) {
+		auto put32 = [&](uint32_t o, uint32_t v) { rec[o] = (uint8_t)v; rec[o + 1] = (uint8_t)(v >> 8); rec[o + 2] = (uint8_t)(v >> 16); rec[o + 3] = (uint8_t)(v >> 24); };
+		put32(0, rb - 4);
+		put32(4, 0);                                  // refID
+		put32(8, pos - 1);
+		rec[12] = 16; rec[13] = (uint8_t)mapq; rec[14] = 0x48; rec[15] = 0x12;      // l_read_name, mapq, bin (unused)
+		rec[16] = 1; rec[17] = 0; rec[18] = (uint8_t)flag; rec[19] = (uint8_t)(flag >> 8);
+		put32(20, read_len);
+		put32(24, 0);                                 // next refID
+		put32(28, mpos - 1);
+		put32(32, (uint32_t)(k ? -tlen : tlen));
+		uint64_t id = t;
+		rec[36] = 't';
+		for (int i = 14; i >= 1; i--) { rec[36 + i] = (uint8_t)('0' + id % 10); id /= 10; }
+		rec[51] = 0;
+		put32(52, read_len << 4);                     // <read_len>M
+		uint8_t *aux = rec + 56 + (read_len + 1) / 2 + read_len;
+		aux[0] = 'X'; aux[1] = 'B'; aux[2] = 'A'; aux[3] = st == 1 ? 'C' : 'G';
+	}
+	uint8_t *seq = rec + 56, *qual = seq + (read_len + 1) / 2;
+	for (uint32_t j2 = lane; j2 < (read_len + 1) / 2; j2 += 32) {
+		uint32_t nibs = 0;
+		for (uint32_t u = 0; u < 2; u++) {
+			const uint32_t j = 2 * j2 + u;
+			uint32_t nib = 0, q = 0;
+			if (j < read_len) {
+				const uint32_t p = pos + j;
+				const int rc = synth_ref_code(seed, p);
+				const uint64_t g = mix64(seed ^ 0x77aa55ull ^ ((uint64_t)p << 20));            // site genotype
+				int b = rc ? rc - 1 : (int)(g & 3);
+				const uint32_t gsel = (uint32_t)(g >> 40) % 3000u;
+				if (gsel < 2) { if (gsel == 0 || hap) b = (b + 1 + (int)((g >> 8) % 3)) & 3; }
+				const uint64_t e = mix64(h ^ ((uint64_t)(j + 1000 * k) * 0x9e3779b97f4a7c15ull));
+				const float uc = (float)(e >> 40) * (1.0f / 16777216.0f);
+				const bool cpg = st == 1 ? (rc == 2 && synth_ref_code(seed, p + 1) == 3) : (rc == 3 && synth_ref_code(seed, p - 1) == 2);
+				const float meth = cpg ? 0.7f : 0.01f;
+				const bool converts = uc >= meth && uc < meth + (1.0f - meth) * 0.99f;
+				if (st == 1 && b == 1 && converts) b = 3;
+				if (st == 2 && b == 2 && converts) b = 0;
+				q = ((e >> 8) & 0xff) < 218 ? 37u : 10u + (uint32_t)((e >> 16) % 31);
+				const float perr = __expf(-0.2302585f * (float)q);
+				if ((float)((e >> 24) & 0xffff) * (1.0f / 65536.0f) < perr) b = (b + 1 + (int)((e >> 4) % 3)) & 3;
+				nib = 1u << b;
+				if (((e >> 44) & 0x3ff) == 0) nib = 15;                                    // N
+				qual[j] = (uint8_t)q;
+			}
+			nibs = (nibs << 4) | nib;
+		}
+		seq[j2] = (uint8_t)nibs;
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // launchers (called from bsgpu_api.cpp; all asynchronous on `stream`)
 // ------------------------------------------------------------------------------------------------
@@ -746,6 +824,26 @@ cudaError_t launch_synth_sites(uint64_t seed, uint64_t first, size_t n, double m
 		cudaStream_t stream, int *launches) {
 	if (!n) return cudaSuccess;
 	k_synth_sites<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(seed, first, n, (float)mean_depth, (uint8_t *)pileup, (uint8_t *)ref);
+	*launches += 1;
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+
+cudaError_t launch_synth_ref(uint64_t seed, uint32_t x, uint32_t sz, void *ref, cudaStream_t stream, int *launches) {
+	if (!sz) return cudaSuccess;
+	k_synth_ref<<<(sz + 255) / 256, 256, 0, stream>>>(seed, x, sz, (uint8_t *)ref);
+	*launches += 1;
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+
+size_t synth_bam_bytes(size_t ntemplates, uint32_t read_len) { return 2 * ntemplates * (size_t)synth_bam_record_bytes(read_len); }
+
+cudaError_t launch_synth_bam(uint64_t seed, size_t ntemplates, uint32_t read_len, const void *pos_f, const void *pos_r, const void *src,
+		const void *rank, void *out, cudaStream_t stream, int *launches) {
+	if (!ntemplates) return cudaSuccess;
+	k_synth_bam<<<(unsigned)((2 * ntemplates * 32 + 255) / 256), 256, 0, stream>>>(seed, ntemplates, read_len, (const uint32_t *)pos_f,
+		(const uint32_t *)pos_r, (const uint32_t *)src, (const uint32_t *)rank, (uint8_t *)out);
 	*launches += 1;
 	LAUNCH_CHECK();
 	return cudaSuccess;

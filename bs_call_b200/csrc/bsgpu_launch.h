@@ -37,6 +37,11 @@ size_t synth_block_nseg(uint32_t sz, uint32_t read_len, double depth);
 cudaError_t launch_synth_block(uint64_t seed, uint32_t x, uint32_t sz, uint32_t read_len, double depth,
 		void *segs, void *bases, void *ref, cudaStream_t stream, int *launches);
 
+size_t synth_bam_bytes(size_t ntemplates, uint32_t read_len);
+cudaError_t launch_synth_bam(uint64_t seed, size_t ntemplates, uint32_t read_len, const void *pos_f, const void *pos_r, const void *src,
+		const void *rank, void *out, cudaStream_t stream, int *launches);
+cudaError_t launch_synth_ref(uint64_t seed, uint32_t x, uint32_t sz, void *ref, cudaStream_t stream, int *launches);
+
 // raw templates -> reads in reference coordinates + segment records (bsgpu_normalise.cu)
 cudaError_t launch_normalise(const void *tmpl, size_t n, const void *bases, void *ev_work, const void *out_off, void *obases,
 		void *segs, uint32_t segs_per_mate, uint32_t x, uint32_t y, const uint32_t left_trim[2], const uint32_t right_trim[2],

@@ -226,6 +226,8 @@ int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_
 		std::vector<uint32_t> &mm_off, uint64_t *nbases, uint64_t *nmisms) {
 	size_t at = 0;
 	uint64_t nb = 0, nm = 0;
+	const size_t guess = nbytes / 200 + 16;          // typical short-read records are 250-400 bytes
+	rec_off.reserve(guess); read_off.reserve(guess); mm_off.reserve(guess);
 	while (at < nbytes) {
 		if (at + 36 > nbytes) return -1;
 		const uint32_t bs = ld_u32(bam + at);
@@ -233,6 +235,9 @@ int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_
 		const uint8_t *p = bam + at + 4;
 		const uint32_t l_qname = p[8], n_cigar = ld_u16(p + 12), l_qseq = ld_u32(p + 16);
 		if ((int32_t)l_qseq < 0 || 32 + (uint64_t)l_qname + 4ull * n_cigar + ((uint64_t)l_qseq + 1) / 2 + l_qseq > bs) return -1;
+		// the chain is a dependent load per record: ask for the header a few records ahead, where it will be if sizes stay similar
+		__builtin_prefetch(bam + at + 12 * (size_t)(bs + 4));
+		__builtin_prefetch(bam + at + 12 * (size_t)(bs + 4) + 64);
 		rec_off.push_back(at);
 		read_off.push_back((uint32_t)nb);
 		mm_off.push_back((uint32_t)nm);
@@ -267,8 +272,10 @@ struct NameTable {
 	const uint64_t *rec_off;
 	NameTable() : tab(1024) {}
 	static uint64_t hash_name(const uint8_t *s, uint32_t n) {
-		uint64_t h = 1469598103934665603ull;
-		for (uint32_t i = 0; i < n; i++) h = (h ^ s[i]) * 1099511628211ull;
+		uint64_t h = 0x9e3779b97f4a7c15ull ^ n;
+		uint32_t i = 0;
+		for (; i + 8 <= n; i += 8) { uint64_t w; memcpy(&w, s + i, 8); h = (h ^ w) * 0xff51afd7ed558ccdull; h ^= h >> 32; }
+		if (i < n) { uint64_t w = 0; memcpy(&w, s + i, n - i); h = (h ^ w) * 0xc4ceb9fe1a85ec53ull; h ^= h >> 32; }
 		return h ^ (h >> 29);
 	}
 	const uint8_t *name_of(uint32_t rec, uint32_t *len) const { const uint8_t *p = bam + rec_off[rec] + 4; *len = p[8]; return p + 32; }
@@ -489,6 +496,7 @@ struct BlockBuilder {
 
 int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
 		bool keep_duplicates, std::vector<bsgpu_block> &blocks, std::vector<bsgpu_template> &tmpl) {
+	tmpl.reserve(nrec / 2 + nrec / 8 + 16);
 	BlockBuilder b;
 	b.bam = bam; b.rec_off = rec_off; b.rec = rec; b.blocks = &blocks; b.tmpl = &tmpl;
 	return b.run(nrec, keep_unmatched, keep_duplicates);

@@ -26,6 +26,7 @@ EXPORTS = [
     "bsgpu_default_reader_params", "bsgpu_decode_records", "bsgpu_build_blocks", "bsgpu_call_bam",
     "bsgpu_call_sites_dev", "bsgpu_call_sites_vcf_dev", "bsgpu_pileup_block_dev", "bsgpu_call_block_dev",
     "bsgpu_synth_sites_dev", "bsgpu_synth_block_nseg", "bsgpu_synth_block_dev",
+    "bsgpu_synth_bam_bytes", "bsgpu_synth_bam_dev", "bsgpu_synth_ref_dev",
     "bsgpu_math_probe",
 ]
 
@@ -48,7 +49,8 @@ def reader_params(mapq_thresh=20, max_template_len=1000, keep_unmatched=False, i
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("sites", C.c_uint64), ("sites_called", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("qsum_overflow", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("qsum_overflow", C.c_uint64),
+                ("bam_decode_s", C.c_double), ("bam_build_s", C.c_double), ("bam_call_s", C.c_double)]
 
 
 class BsGpuError(RuntimeError):
@@ -72,6 +74,8 @@ def load():
     lib.bsgpu_host_alloc.argtypes = [C.c_size_t]
     lib.bsgpu_host_free.argtypes = [C.c_void_p]
     lib.bsgpu_stage_bound.restype = C.c_size_t
+    lib.bsgpu_synth_bam_bytes.restype = C.c_size_t
+    lib.bsgpu_synth_bam_bytes.argtypes = [C.c_size_t, C.c_uint32]
     lib.bsgpu_synth_block_nseg.restype = C.c_size_t
     lib.bsgpu_synth_block_nseg.argtypes = [C.c_uint32, C.c_uint32, C.c_double]
     lib.bsgpu_init.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
@@ -140,7 +144,7 @@ class BsGpu:
     def stats(self):
         s = Stats()
         self._check(self.lib.bsgpu_get_stats(self.ctx, C.byref(s)))
-        return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+        return {k: (float(getattr(s, k)) if t is C.c_double else int(getattr(s, k))) for k, t in Stats._fields_}
 
     # ---- host-buffer entry points -------------------------------------------------------------
     def call_sites(self, pileup, ref, out=None, skip=None):
@@ -253,6 +257,16 @@ class BsGpu:
                                                    _ptr(d_bases), C.c_size_t(base_cap), _ptr(d_ref), C.byref(ns), C.byref(nb),
                                                    C.c_void_p(stream)))
         return ns.value, nb.value
+
+    def synth_bam_bytes(self, ntemplates, read_len):
+        return int(self.lib.bsgpu_synth_bam_bytes(C.c_size_t(ntemplates), C.c_uint32(read_len)))
+
+    def synth_bam_dev(self, seed, ntemplates, read_len, d_pos_f, d_pos_r, d_src, d_rank, d_out, stream=0):
+        self._check(self.lib.bsgpu_synth_bam_dev(self.ctx, C.c_uint64(seed), C.c_size_t(ntemplates), C.c_uint32(read_len), _ptr(d_pos_f),
+                                                 _ptr(d_pos_r), _ptr(d_src), _ptr(d_rank), _ptr(d_out), C.c_void_p(stream)))
+
+    def synth_ref_dev(self, seed, x, sz, d_ref, stream=0):
+        self._check(self.lib.bsgpu_synth_ref_dev(self.ctx, C.c_uint64(seed), C.c_uint32(x), C.c_uint32(sz), _ptr(d_ref), C.c_void_p(stream)))
 
     # ---- host staging --------------------------------------------------------------------------
     def stage_templates(self, templates, bases, x, y):

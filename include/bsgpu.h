@@ -158,6 +158,9 @@ typedef struct {
 	uint64_t sites_called;     /* sites with n > 0 */
 	uint64_t h2d_bytes, d2h_bytes;
 	uint64_t qsum_overflow;    /* sites whose integer quality / mapq^2 sums left the float-exact envelope (2^24) */
+	/* wall time bsgpu_call_bam spent, accumulated: framing + H2D + record decode | descriptors D2H + block builder |
+	 * normalisation + pileup + model + D2H of gt_vcf[] */
+	double bam_decode_s, bam_build_s, bam_call_s;
 } bsgpu_stats;
 
 void bsgpu_default_params(bsgpu_params *p);
@@ -246,6 +249,16 @@ size_t bsgpu_synth_block_nseg(uint32_t sz, uint32_t read_len, double depth);
 int bsgpu_synth_block_dev(bsgpu_ctx *ctx, uint64_t seed, uint32_t x, uint32_t sz, uint32_t read_len, double depth,
 		void *d_segs, size_t seg_cap, void *d_bases, size_t base_cap, void *d_ref, size_t *nseg, size_t *nbases,
 		void *stream);
+
+/* synthetic coordinate-sorted BAM record stream (paired-end, fixed-size records: bsgpu_synth_bam_bytes(n, read_len) bytes
+ * for n templates).  d_pos_f / d_pos_r: 1-based start of the forward / reverse mate of every template; d_src[t]: the
+ * template whose reads template t carries (t itself, or an earlier one for a positional duplicate); d_rank[i]: index in
+ * the sorted stream of record i (i < n: forward mate of template i, else reverse mate of template i - n).  Reads are
+ * drawn from the same synthetic genome as bsgpu_synth_block_dev; bsgpu_synth_ref_dev writes its codes for [x, x+sz). */
+size_t bsgpu_synth_bam_bytes(size_t ntemplates, uint32_t read_len);
+int bsgpu_synth_bam_dev(bsgpu_ctx *ctx, uint64_t seed, size_t ntemplates, uint32_t read_len, const void *d_pos_f,
+		const void *d_pos_r, const void *d_src, const void *d_rank, void *d_out, void *stream);
+int bsgpu_synth_ref_dev(bsgpu_ctx *ctx, uint64_t seed, uint32_t x, uint32_t sz, void *d_ref, void *stream);
 
 /* ---- diagnostics ---- */
 /* Evaluates, on the host, the table-driven log / exp the kernels use (same source; both sides are FMA-exact, so
