@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turn the scratch outputs of profiles/run_profile.sh (gpurun_out/) into the tracked, per-round summaries here.
-usage: python profiles/summarise.py r01"""
+usage: python profiles/summarise.py r01b      (reads gpurun_out/<tag>_*; the first round's files had no tag prefix)"""
 import collections
 import csv
 import io
@@ -17,7 +17,7 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 
 
 def launches():
-    rows = [r for r in csv.reader(open(os.path.join(G, "launches.csv"))) if len(r) > 10 and r[0].isdigit()]
+    rows = [r for r in csv.reader(open(os.path.join(G, tag + "_launches.csv"))) if len(r) > 10 and r[0].isdigit()]
     agg = collections.OrderedDict()
     for r in rows:
         name = r[4].split("(")[0].replace("bsgpu::", "").replace("void ", "")
@@ -25,13 +25,13 @@ def launches():
         a[0] += 1
         a[1] += float(r[-1]) / 1e3
     tot = sum(a[1] for a in agg.values())
-    lines = ["# kernel launches of `python bench.py --sites 3.2e7 --steps 1 --no-cpu --e2e-sites 1e6 --fused-sites 8e6` under",
+    lines = ["# kernel launches of `python bench.py --sites 3.2e7 --steps 1 --no-cpu --e2e-sites 1e6 --fused-sites 8e6 --bam-sites 2e6` under",
              "# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES, not absolutes)",
              "", "| kernel | launches | total us | share | grid | block |", "|---|---:|---:|---:|---|---|"]
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append("| %s | %d | %.1f | %.1f%% | %s | %s |" % (k, a[0], a[1], 100 * a[1] / tot, a[2], a[3]))
     open(os.path.join(HERE, tag + "_launches.md"), "w").write("\n".join(lines) + "\n")
-    shutil.copy(os.path.join(G, "launches.csv"), os.path.join(HERE, tag + "_launches.csv"))
+    shutil.copy(os.path.join(G, tag + "_launches.csv"), os.path.join(HERE, tag + "_launches.csv"))
 
 
 def kernel(rep, name, per_site_n):
@@ -58,11 +58,14 @@ def kernel(rep, name, per_site_n):
 
 
 launches()
-traffic = {"k_call_sites": kernel("prof_call.ncu-rep", "k_call_sites", 2_000_000),
-           "k_pileup_tile": kernel("prof_pile.ncu-rep", "k_pileup_tile", 8_000_000)}
+traffic = {"k_call_sites": kernel(tag + "_prof_call.ncu-rep", "k_call_sites", 2_000_000),
+           "k_pileup_tile": kernel(tag + "_prof_pile.ncu-rep", "k_pileup_tile", 8_000_000)}
+if os.path.exists(os.path.join(G, tag + "_prof_reader.ncu-rep")):
+    kernel(tag + "_prof_reader.ncu-rep", "reader_kernels", 1)
+traffic["round"] = tag
 json.dump(traffic, open(os.path.join(HERE, "traffic.json"), "w"), indent=1)
 for f in ("bench_full.json", "bench_reference.json"):
-    if os.path.exists(os.path.join(G, f)):
-        shutil.copy(os.path.join(G, f), os.path.join(HERE, "%s_%s" % (tag, f)))
+    if os.path.exists(os.path.join(G, tag + "_" + f)):
+        shutil.copy(os.path.join(G, tag + "_" + f), os.path.join(HERE, "%s_%s" % (tag, f)))
 print(open(os.path.join(HERE, tag + "_launches.md")).read())
 print(json.dumps(traffic, indent=1))
