@@ -26,10 +26,19 @@ static_assert(offsetof(bsgpu_pileup, n) == 64 && offsetof(bsgpu_pileup, quality)
 using namespace bsgpu;
 
 namespace bsgpu {      // host helpers of bsgpu_reader.cu
+struct FrameScratch;
+FrameScratch *frame_scratch_new();
+void frame_scratch_free(FrameScratch *s);
 int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_off, std::vector<uint32_t> &read_off,
-		std::vector<uint32_t> &mm_off, uint64_t *nbases, uint64_t *nmisms);
+		std::vector<uint32_t> &mm_off, uint64_t *nbases, uint64_t *nmisms, FrameScratch *scratch);
 int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
-		bool keep_duplicates, std::vector<bsgpu_block> &blocks, std::vector<bsgpu_template> &tmpl);
+		bool keep_duplicates, std::vector<bsgpu_block> &blocks, bsgpu_template *tmpl, size_t *ntmpl);
+struct BuildJob;
+BuildJob *build_blocks_start(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
+		bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread);
+size_t build_blocks_pieces(const BuildJob *job);
+int build_blocks_piece(BuildJob *job, size_t p, const std::vector<bsgpu_block> **blocks, size_t *tmpl_base, size_t *ntmpl);
+void build_blocks_finish(BuildJob *job);
 }
 static_assert(sizeof(bsgpu_record) == 56, "record descriptor layout");
 static_assert(sizeof(bsgpu_block) == 32, "block layout");
@@ -94,9 +103,13 @@ struct bsgpu_ctx {
 	DevBuf segs, bases, ref, scratch, vcf, tmpl, misms, obases, ooff, pile;
 	DevBuf rd_bam, rd_recoff, rd_readoff, rd_mmoff, rd_rec, rd_bases, rd_misms;      // reader side: stream, framing, decoded arrays
 	std::vector<uint64_t> rec_off;               // framing of the last decoded stream
-	PinBuf h_rec, h_off;                         // pinned staging: descriptors coming back, offset tables going up
+	std::vector<uint32_t> read_off, mm_off, off_tmp;
+	std::vector<uint8_t> ref_tmp;
+	FrameScratch *frame_scratch = nullptr;
+	PinBuf h_rec, h_off, h_tmpl;                 // pinned staging: descriptors coming back, offset tables and templates going up
 	bool fused = false;                          // BSGPU_FUSED=1: one fused pileup+model kernel instead of two kernels
 	std::vector<cudaEvent_t> win_events;
+	bool ring_busy[3] = {false, false, false};   // output ring slot may still be copying out (deferred block_run)
 	bsgpu_stats stats;
 	int launches = 0;
 };
@@ -184,7 +197,8 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 		if (c->slot[i].done) cudaEventDestroy(c->slot[i].done);
 	}
 	for (cudaEvent_t ev : c->win_events) cudaEventDestroy(ev);
-	c->h_rec.release(); c->h_off.release();
+	if (c->frame_scratch) frame_scratch_free(c->frame_scratch);
+	c->h_rec.release(); c->h_off.release(); c->h_tmpl.release();
 	c->rd_bam.release(); c->rd_recoff.release(); c->rd_readoff.release(); c->rd_mmoff.release(); c->rd_rec.release(); c->rd_bases.release(); c->rd_misms.release();
 	c->segs.release(); c->bases.release(); c->ref.release(); c->scratch.release(); c->vcf.release(); c->tmpl.release(); c->misms.release(); c->obases.release(); c->ooff.release(); c->pile.release();
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -392,8 +406,10 @@ static int call_bins(bsgpu_ctx *c, size_t nseg, const void *d_bases, const void 
 
 // Device-resident segments / bases / ref -> host pileup[] or gt_vcf[].  The window is processed in slabs of tiles so
 // that the D2H of slab i (copy stream) overlaps the kernel of slab i+1 (context stream); outputs are ~6x the inputs.
+// `defer`: return without waiting for the device (the caller synchronises both streams before it touches `out` or lets
+// go of the inputs); successive deferred runs overlap the D2H of one window with the kernels of the next
 static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *d_bases, const void *d_ref,
-		uint32_t x, uint32_t sz, void *out, int mode) {
+		uint32_t x, uint32_t sz, void *out, int mode, bool defer) {
 	const size_t rec = mode ? sizeof(bsgpu_gt_vcf) : sizeof(bsgpu_pileup);
 	CU(c->scratch.reserve(pileup_scratch_bytes(nseg, sz)));
 	CU(launch_bin_segments(d_segs, nseg, x, sz, c->scratch.p, c->stream, &c->launches));
@@ -416,18 +432,21 @@ static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *
 		const size_t site0 = (size_t)t0 * kPileTileSites;
 		const size_t nsite = (size_t)sz - site0 < (size_t)nt * kPileTileSites ? (size_t)sz - site0 : (size_t)nt * kPileTileSites;
 		uint8_t *dslab = (uint8_t *)c->vcf.p + (size_t)r * slab_tiles * kPileTileSites * rec;
-		if (si >= resident) CU(cudaStreamWaitEvent(c->stream, copied, 0));      // ring slot drained
+		// ring slot drained: by this run, or by an earlier deferred run whose copy may still be in flight
+		if (si >= resident || c->ring_busy[r]) CU(cudaStreamWaitEvent(c->stream, copied, 0));
 		if (mode) { if (call_bins(c, nseg, d_bases, d_ref, x, sz, t0, nt, dslab, c->stream) != BSGPU_OK) return BSGPU_FAIL; }
 		else CU(launch_pileup_tiles(c->scratch.p, nseg, d_bases, d_ref, x, sz, t0, nt, dslab, 0, c->d_const, c->d_counters, c->stream, &c->launches));
 		CU(cudaEventRecord(computed, c->stream));
 		CU(cudaStreamWaitEvent(c->copy_stream, computed, 0));
 		CU(cudaMemcpyAsync((uint8_t *)out + site0 * rec, dslab, nsite * rec, cudaMemcpyDeviceToHost, c->copy_stream));
 		CU(cudaEventRecord(copied, c->copy_stream));
+		c->ring_busy[r] = defer;
 		c->stats.d2h_bytes += nsite * rec;
 	}
+	c->stats.sites += sz;
+	if (defer) return BSGPU_OK;
 	CU(cudaStreamSynchronize(c->copy_stream));
 	CU(cudaStreamSynchronize(c->stream));
-	c->stats.sites += sz;
 	return BSGPU_OK;
 }
 
@@ -454,7 +473,7 @@ static int block_host(bsgpu_ctx *c, const bsgpu_seg *segs, size_t nseg, const ui
 	}
 	if (mode) CU(cudaMemcpyAsync(c->ref.p, ref, sz, cudaMemcpyHostToDevice, c->stream));
 	c->stats.h2d_bytes += nseg * sizeof(bsgpu_seg) + nbases + (mode ? sz : 0);
-	return block_run(c, c->segs.p, nseg, c->bases.p, c->ref.p, x, sz, out, mode);
+	return block_run(c, c->segs.p, nseg, c->bases.p, c->ref.p, x, sz, out, mode, false);
 }
 
 // raw templates -> gt_vcf[]: normalisation, mate walk, pileup and model on the device (src/process_template.c:18-126)
@@ -513,7 +532,7 @@ int bsgpu_process_block(bsgpu_ctx *c, const bsgpu_template *t, size_t n, const u
 	if (after[2] != before[2]) return fail("bsgpu_process_block: Error in CIGAR - illegal soft clip in %llu template(s)", after[2] - before[2]);
 	if (after[3] != before[3]) return fail("bsgpu_process_block: %llu mate(s) start before the block window", after[3] - before[3]);
 	if (x_out) *x_out = x;
-	return block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, out, 1);
+	return block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, out, 1, false);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -527,25 +546,27 @@ void bsgpu_default_reader_params(bsgpu_reader_params *p) {
 
 // frame + upload + decode; leaves descriptors, packed reads and events resident; *nb / *nm = sizes of the decoded arrays
 static int decode_resident(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const bsgpu_reader_params *rp, size_t *nrec, uint64_t *nb, uint64_t *nm) {
-	std::vector<uint32_t> read_off, mm_off;
-	c->rec_off.clear();
-	const int fr = frame_records(bam, nbytes, c->rec_off, read_off, mm_off, nb, nm);
+	std::vector<uint32_t> &read_off = c->read_off, &mm_off = c->mm_off;
+	if (!c->frame_scratch) c->frame_scratch = frame_scratch_new();
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->copy_stream));
+	// the stream itself can start its way up while the host frames it
+	CU(c->rd_bam.reserve(nbytes + 16));
+	if (nbytes) CU(cudaMemcpyAsync(c->rd_bam.p, bam, nbytes, cudaMemcpyHostToDevice, c->stream));
+	const int fr = frame_records(bam, nbytes, c->rec_off, read_off, mm_off, nb, nm, c->frame_scratch);
+	if (fr) cudaStreamSynchronize(c->stream);
 	if (fr == -1) return fail("bsgpu reader: truncated or malformed BAM record stream");
 	if (fr == -2) return fail("bsgpu reader: more than 4 Gi bases in one stream; split the input");
 	const size_t n = c->rec_off.size();
 	*nrec = n;
-	if (!n) return BSGPU_OK;
-	CU(cudaSetDevice(c->device));
-	CU(cudaStreamSynchronize(c->stream));
-	CU(cudaStreamSynchronize(c->copy_stream));
-	CU(c->rd_bam.reserve(nbytes + 16));
+	if (!n) { CU(cudaStreamSynchronize(c->stream)); return BSGPU_OK; }
 	CU(c->rd_recoff.reserve(n * 8));
 	CU(c->rd_readoff.reserve(n * 4));
 	CU(c->rd_mmoff.reserve(n * 4));
 	CU(c->rd_rec.reserve(n * sizeof(bsgpu_record)));
 	CU(c->rd_bases.reserve(*nb + 16));
 	CU(c->rd_misms.reserve((*nm + 1) * sizeof(bsgpu_misms)));
-	CU(cudaMemcpyAsync(c->rd_bam.p, bam, nbytes, cudaMemcpyHostToDevice, c->stream));
 	// the offset tables go up from pinned staging (pageable vectors would serialise the copies behind the big one)
 	CU(c->h_off.reserve(n * 16));
 	uint8_t *ho = (uint8_t *)c->h_off.p;
@@ -590,22 +611,70 @@ int bsgpu_build_blocks(const uint8_t *bam, size_t nbytes, const bsgpu_record *re
 	std::vector<uint64_t> rec_off;
 	std::vector<uint32_t> ro, mo;
 	uint64_t nb, nm;
-	if (frame_records(bam, nbytes, rec_off, ro, mo, &nb, &nm) || rec_off.size() != nrec) return fail("bsgpu_build_blocks: the record stream does not frame into %zu records", nrec);
+	if (frame_records(bam, nbytes, rec_off, ro, mo, &nb, &nm, nullptr) || rec_off.size() != nrec) return fail("bsgpu_build_blocks: the record stream does not frame into %zu records", nrec);
 	std::vector<bsgpu_block> b;
-	std::vector<bsgpu_template> t;
-	const int rc = build_blocks_host(bam, rec_off.data(), rec, nrec, rp->keep_unmatched, rp->keep_duplicates, b, t);
-	if (rc == -4) return fail("bsgpu_build_blocks: duplicate read name among waiting mates");
-	if (rc) return fail("bsgpu_build_blocks: failed (%d)", rc);
-	if (b.size() > block_cap || t.size() > tmpl_cap) return fail("bsgpu_build_blocks: need room for %zu blocks, %zu templates", b.size(), t.size());
-	if (!b.empty()) memcpy(blocks, b.data(), b.size() * sizeof(bsgpu_block));
-	if (!t.empty()) memcpy(tmpl, t.data(), t.size() * sizeof(bsgpu_template));
-	*nblocks = b.size();
-	*ntmpl = t.size();
-	return BSGPU_OK;
+	bsgpu_template *t = tmpl_cap >= nrec ? tmpl : (bsgpu_template *)malloc((nrec + 1) * sizeof(bsgpu_template));      // build in place when there is room
+	if (!t) return fail("bsgpu_build_blocks: out of memory");
+	size_t nt = 0;
+	const int rc = build_blocks_host(bam, rec_off.data(), rec, nrec, rp->keep_unmatched, rp->keep_duplicates, b, t, &nt);
+	int ret = BSGPU_OK;
+	if (rc == -4) ret = fail("bsgpu_build_blocks: duplicate read name among waiting mates");
+	else if (rc) ret = fail("bsgpu_build_blocks: failed (%d)", rc);
+	else if (b.size() > block_cap || nt > tmpl_cap) ret = fail("bsgpu_build_blocks: need room for %zu blocks, %zu templates", b.size(), nt);
+	else {
+		if (!b.empty()) memcpy(blocks, b.data(), b.size() * sizeof(bsgpu_block));
+		if (t != tmpl && nt) memcpy(tmpl, t, nt * sizeof(bsgpu_template));
+		*nblocks = b.size();
+		*ntmpl = nt;
+	}
+	if (t != tmpl) free(t);
+	return ret;
 }
 
 static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *d_bases, const void *d_ref,
-		uint32_t x, uint32_t sz, void *out, int mode);
+		uint32_t x, uint32_t sz, void *out, int mode, bool defer);
+
+// templates [tm, tm + nt) of ONE contig (their reads and events are resident from the decode) -> gt_vcf[] of window [x, y]
+static int call_window(bsgpu_ctx *c, const bsgpu_template *tm, size_t nt, uint32_t tid, uint32_t ctg_len, const uint8_t *codes,
+		uint32_t x, uint32_t y, bsgpu_gt_vcf *out) {
+	const uint32_t sz = y - x + 1;
+	// per-mate output slots: read length + reference span bounds the read in reference coordinates
+	std::vector<uint32_t> &off = c->off_tmp;
+	off.resize(2 * nt + 1);
+	uint64_t tot = 0;
+	uint32_t maxcap = 1;
+	for (size_t i = 0; i < nt; i++) for (int k = 0; k < 2; k++) {
+		off[2 * i + k] = (uint32_t)tot;
+		const bsgpu_template &t = tm[i];
+		if (!t.present[k]) continue;
+		const uint64_t cap = (uint64_t)t.read_len[k] + t.reference_span[k];
+		tot += cap;
+		if (cap > maxcap) maxcap = (uint32_t)(cap > 0xffffffu ? 0xffffffu : cap);
+	}
+	off[2 * nt] = (uint32_t)tot;
+	if (tot > 0xffffffffull) return fail("bsgpu_call_bam: more than 4 GiB of bases in one window of contig %u; split the input", tid);
+	const uint32_t spm = (maxcap + BSGPU_MAX_SEG_LEN - 1) / BSGPU_MAX_SEG_LEN;
+	const size_t nseg = nt * 2 * (size_t)spm;
+	// reference window [x, y]: N beyond the contig end (src/get_sequence.c:36-41)
+	std::vector<uint8_t> &refw = c->ref_tmp;
+	refw.resize(sz);
+	for (uint32_t i = 0; i < sz; i++) { const uint32_t pos = x + i; refw[i] = pos < ctg_len ? codes[pos - 1] : 0; }
+	// Everything below is queued behind the previous window on the context stream; nothing waits on the host.  (Growing a
+	// device buffer frees the old one, which synchronises the device; `off` / `refw` are pageable, so their copies are
+	// staged before cudaMemcpyAsync returns and the vectors can be refilled for the next window.)
+	CU(c->tmpl.reserve(nt * sizeof(bsgpu_template)));
+	CU(c->obases.reserve(tot + 16));
+	CU(c->ooff.reserve((2 * nt + 1) * sizeof(uint32_t)));
+	CU(c->segs.reserve(nseg * sizeof(bsgpu_seg) + 16));
+	CU(c->ref.reserve((size_t)sz + 16));
+	CU(cudaMemcpyAsync(c->tmpl.p, tm, nt * sizeof(bsgpu_template), cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->ooff.p, off.data(), (2 * nt + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->ref.p, refw.data(), sz, cudaMemcpyHostToDevice, c->stream));
+	c->stats.h2d_bytes += nt * sizeof(bsgpu_template) + (2 * nt + 1) * 4 + sz;
+	CU(launch_normalise(c->tmpl.p, nt, c->rd_bases.p, c->rd_misms.p, c->ooff.p, c->obases.p, c->segs.p, spm, x, y,
+			c->params.left_trim, c->params.right_trim, c->d_counters, c->stream, &c->launches));
+	return block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, out, 1, true);
+}
 
 int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len,
 		const uint8_t *const *ctg_codes, const bsgpu_reader_params *rp, bsgpu_block *blocks, size_t block_cap, size_t *nblocks,
@@ -625,71 +694,70 @@ int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_target
 	CU(cudaMemcpyAsync(c->h_rec.p, c->rd_rec.p, n * sizeof(bsgpu_record), cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	c->stats.d2h_bytes += n * sizeof(bsgpu_record);
-	std::vector<bsgpu_block> bl;
-	std::vector<bsgpu_template> tm;
-	const int rc = build_blocks_host(bam, c->rec_off.data(), rec, n, rp->keep_unmatched, rp->keep_duplicates, bl, tm);
-	const double t2 = now();
-	c->stats.bam_build_s += t2 - t1;
-	if (rc == -4) return fail("bsgpu_call_bam: duplicate read name among waiting mates");
-	if (rc) return fail("bsgpu_call_bam: block builder failed (%d)", rc);
-	if (bl.size() > block_cap) return fail("bsgpu_call_bam: need room for %zu blocks", bl.size());
-	size_t ov = 0;
-	// blocks of one contig are disjoint windows in increasing order: process each contig as ONE window.  Pileup counts
-	// are additive per site and the model is per site, so every block's records are exactly what a per-block run gives.
-	for (size_t b0 = 0; b0 < bl.size();) {
-		size_t b1 = b0;
-		while (b1 < bl.size() && bl[b1].tid == bl[b0].tid) b1++;
-		const uint32_t tid = bl[b0].tid, x = bl[b0].x, y = bl[b1 - 1].y, sz = y - x + 1;
-		if ((int)tid >= n_targets) return fail("bsgpu_call_bam: record on contig %u, only %d contigs given", tid, n_targets);
-		if (ov + sz > vcf_cap) return fail("bsgpu_call_bam: vcf[] too small (contig %u needs %u more records)", tid, sz);
-		const size_t t0 = bl[b0].first_template, nt = (size_t)bl[b1 - 1].first_template + bl[b1 - 1].n_templates - t0;
-		// per-mate output slots: read length + reference span bounds the read in reference coordinates
-		std::vector<uint32_t> off(2 * nt + 1);
-		uint64_t tot = 0;
-		uint32_t maxcap = 1;
-		for (size_t i = 0; i < nt; i++) for (int k = 0; k < 2; k++) {
-			off[2 * i + k] = (uint32_t)tot;
-			const bsgpu_template &t = tm[t0 + i];
-			if (!t.present[k]) continue;
-			const uint64_t cap = (uint64_t)t.read_len[k] + t.reference_span[k];
-			tot += cap;
-			if (cap > maxcap) maxcap = (uint32_t)(cap > 0xffffffu ? 0xffffffu : cap);
+	CU(c->h_tmpl.reserve((n + 1) * sizeof(bsgpu_template)));
+	bsgpu_template *tm = (bsgpu_template *)c->h_tmpl.p;
+	// The block builder runs on a pool of host threads over pieces of the stream (cut where read_input is certain to
+	// start a block); pieces are taken over in order, so the device works on the first ones while the rest are built.
+	// A piece is processed as one window per contig it touches; the windows of a contig tile the span from its first
+	// block's x to its last block's y.  Pileup counts are additive per site and the model is per site, so every block's
+	// records are exactly what a per-block run gives; positions between blocks come back as skip records.
+	unsigned long long before[4], after[4];       // normalisation failures are counted on the device: compared at the end
+	CU(cudaMemcpy(before, c->d_counters, sizeof(before), cudaMemcpyDeviceToHost));
+	BuildJob *job = build_blocks_start(bam, c->rec_off.data(), rec, n, rp->keep_unmatched, rp->keep_duplicates, tm, 2);
+	const size_t np = build_blocks_pieces(job);
+	size_t ov = 0, nbk = 0, ntm = 0;
+	int cur_tid = -1;
+	uint32_t ctg_x0 = 0, ctg_end = 0;       // current contig: x of its first block, last position already written
+	size_t ctg_ov = 0;                      // vcf index of position ctg_x0
+	int ret = BSGPU_OK;
+	double t_wait = 0;
+	for (size_t p = 0; p < np && ret == BSGPU_OK; p++) {
+		const std::vector<bsgpu_block> *pb;
+		size_t base, nt_piece;
+		const double w0 = now();
+		const int rc = build_blocks_piece(job, p, &pb, &base, &nt_piece);
+		t_wait += now() - w0;
+		if (rc == -4) { ret = fail("bsgpu_call_bam: duplicate read name among waiting mates"); break; }
+		if (rc) { ret = fail("bsgpu_call_bam: block builder failed (%d)", rc); break; }
+		if (nbk + pb->size() > block_cap) { ret = fail("bsgpu_call_bam: blocks[] too small"); break; }
+		for (size_t b0 = 0; b0 < pb->size() && ret == BSGPU_OK;) {
+			size_t b1 = b0;
+			while (b1 < pb->size() && (*pb)[b1].tid == (*pb)[b0].tid) b1++;
+			const uint32_t tid = (*pb)[b0].tid;
+			if ((int)tid >= n_targets) { ret = fail("bsgpu_call_bam: record on contig %u, only %d contigs given", tid, n_targets); break; }
+			if ((int)tid != cur_tid) { cur_tid = (int)tid; ctg_x0 = (*pb)[b0].x; ctg_end = ctg_x0 - 1; ctg_ov = ov; }
+			const uint32_t x = ctg_end + 1, y = (*pb)[b1 - 1].y;
+			const size_t t_lo = base + (*pb)[b0].first_template, t_n = (size_t)(*pb)[b1 - 1].first_template + (*pb)[b1 - 1].n_templates - (*pb)[b0].first_template;
+			if (y >= x) {
+				const uint32_t sz = y - x + 1;
+				if (ov + sz > vcf_cap) { ret = fail("bsgpu_call_bam: vcf[] too small (contig %u needs %u more records)", tid, sz); break; }
+				ret = call_window(c, tm + t_lo, t_n, tid, target_len[tid], ctg_codes[tid], x, y, vcf + ov);
+				ov += sz;
+				ctg_end = y;
+			}
+			for (size_t b = b0; b < b1; b++) {
+				bsgpu_block o = (*pb)[b];
+				o.first_template = (uint32_t)(ntm + o.first_template);
+				o.vcf_off = ctg_ov + (o.x - ctg_x0);
+				blocks[nbk++] = o;
+			}
+			b0 = b1;
 		}
-		off[2 * nt] = (uint32_t)tot;
-		if (tot > 0xffffffffull) return fail("bsgpu_call_bam: more than 4 GiB of bases on contig %u; split the input", tid);
-		const uint32_t spm = (maxcap + BSGPU_MAX_SEG_LEN - 1) / BSGPU_MAX_SEG_LEN;
-		const size_t nseg = nt * 2 * (size_t)spm;
-		// reference window [x, y]: N beyond the contig end (src/get_sequence.c:36-41)
-		std::vector<uint8_t> refw(sz);
-		for (uint32_t i = 0; i < sz; i++) { const uint32_t pos = x + i; refw[i] = pos < target_len[tid] ? ctg_codes[tid][pos - 1] : 0; }
-		CU(cudaStreamSynchronize(c->stream));
-		CU(cudaStreamSynchronize(c->copy_stream));
-		CU(c->tmpl.reserve(nt * sizeof(bsgpu_template)));
-		CU(c->obases.reserve(tot + 16));
-		CU(c->ooff.reserve((2 * nt + 1) * sizeof(uint32_t)));
-		CU(c->segs.reserve(nseg * sizeof(bsgpu_seg) + 16));
-		CU(c->ref.reserve((size_t)sz + 16));
-		CU(cudaMemcpyAsync(c->tmpl.p, tm.data() + t0, nt * sizeof(bsgpu_template), cudaMemcpyHostToDevice, c->stream));
-		CU(cudaMemcpyAsync(c->ooff.p, off.data(), (2 * nt + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-		CU(cudaMemcpyAsync(c->ref.p, refw.data(), sz, cudaMemcpyHostToDevice, c->stream));
-		c->stats.h2d_bytes += nt * sizeof(bsgpu_template) + (2 * nt + 1) * 4 + sz;
-		unsigned long long before[4], after[4];
-		CU(cudaMemcpyAsync(before, c->d_counters, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
-		CU(launch_normalise(c->tmpl.p, nt, c->rd_bases.p, c->rd_misms.p, c->ooff.p, c->obases.p, c->segs.p, spm, x, y,
-				c->params.left_trim, c->params.right_trim, c->d_counters, c->stream, &c->launches));
-		CU(cudaMemcpyAsync(after, c->d_counters, sizeof(after), cudaMemcpyDeviceToHost, c->stream));
-		CU(cudaStreamSynchronize(c->stream));
-		if (after[2] != before[2]) return fail("bsgpu_call_bam: Error in CIGAR - illegal soft clip in %llu template(s)", after[2] - before[2]);
-		if (after[3] != before[3]) return fail("bsgpu_call_bam: %llu mate(s) start before their contig window", after[3] - before[3]);
-		if (block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, vcf + ov, 1) != BSGPU_OK) return BSGPU_FAIL;
-		for (size_t b = b0; b < b1; b++) bl[b].vcf_off = ov + (bl[b].x - x);
-		ov += sz;
-		b0 = b1;
+		ntm += nt_piece;
 	}
-	memcpy(blocks, bl.data(), bl.size() * sizeof(bsgpu_block));
-	*nblocks = bl.size();
+	build_blocks_finish(job);
+	cudaStreamSynchronize(c->stream);
+	cudaStreamSynchronize(c->copy_stream);
+	for (bool &b : c->ring_busy) b = false;
+	if (ret != BSGPU_OK) return ret;
+	CU(cudaMemcpy(after, c->d_counters, sizeof(after), cudaMemcpyDeviceToHost));
+	if (after[2] != before[2]) return fail("bsgpu_call_bam: Error in CIGAR - illegal soft clip in %llu template(s)", after[2] - before[2]);
+	if (after[3] != before[3]) return fail("bsgpu_call_bam: %llu mate(s) start before their contig window", after[3] - before[3]);
+	*nblocks = nbk;
 	*nvcf = ov;
-	c->stats.bam_call_s += now() - t2;
+	const double t2 = now();
+	c->stats.bam_build_s += t_wait;
+	c->stats.bam_call_s += t2 - t1 - t_wait;
 	return BSGPU_OK;
 }
 

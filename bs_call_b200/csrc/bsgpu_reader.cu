@@ -10,7 +10,10 @@
 //                         decoded reads themselves stay in HBM and templates refer to them by offset.
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <thread>
 #include <vector>
 #include <cuda_runtime.h>
 #include "bsgpu.h"
@@ -222,29 +225,139 @@ cudaError_t launch_decode_records(const void *bam, const void *rec_off, const vo
 // ---------------------------------------------------------------------------------------------------------------
 // host: framing
 // ---------------------------------------------------------------------------------------------------------------
-int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_off, std::vector<uint32_t> &read_off,
-		std::vector<uint32_t> &mm_off, uint64_t *nbases, uint64_t *nmisms) {
-	size_t at = 0;
-	uint64_t nb = 0, nm = 0;
-	const size_t guess = nbytes / 200 + 16;          // typical short-read records are 250-400 bytes
-	rec_off.reserve(guess); read_off.reserve(guess); mm_off.reserve(guess);
-	while (at < nbytes) {
-		if (at + 36 > nbytes) return -1;
-		const uint32_t bs = ld_u32(bam + at);
-		if (bs < 32 || at + 4 + (size_t)bs > nbytes) return -1;
+namespace {
+
+// one record header at `at`: 0 ok (sizes in *bs, *lseq, *ncig), -1 malformed / truncated
+inline int frame_one(const uint8_t *bam, size_t nbytes, size_t at, uint32_t *bs, uint32_t *lseq, uint32_t *ncig) {
+	if (at + 36 > nbytes) return -1;
+	*bs = ld_u32(bam + at);
+	if (*bs < 32 || at + 4 + (size_t)*bs > nbytes) return -1;
+	const uint8_t *p = bam + at + 4;
+	const uint32_t l_qname = p[8];
+	*ncig = ld_u16(p + 12);
+	*lseq = ld_u32(p + 16);
+	if ((int32_t)*lseq < 0 || 32 + (uint64_t)l_qname + 4ull * *ncig + ((uint64_t)*lseq + 1) / 2 + *lseq > *bs) return -1;
+	return 0;
+}
+
+// does a record plausibly start at `at`?  Only used to GUESS where a worker starts; the stitch below never trusts it.
+bool plausible_record(const uint8_t *bam, size_t nbytes, size_t at, int depth) {
+	for (int d = 0; d < depth; d++) {
+		if (at == nbytes) return true;
+		uint32_t bs, lseq, ncig;
+		if (frame_one(bam, nbytes, at, &bs, &lseq, &ncig)) return false;
 		const uint8_t *p = bam + at + 4;
-		const uint32_t l_qname = p[8], n_cigar = ld_u16(p + 12), l_qseq = ld_u32(p + 16);
-		if ((int32_t)l_qseq < 0 || 32 + (uint64_t)l_qname + 4ull * n_cigar + ((uint64_t)l_qseq + 1) / 2 + l_qseq > bs) return -1;
+		const int32_t tid = (int32_t)ld_u32(p), pos = (int32_t)ld_u32(p + 4), mtid = (int32_t)ld_u32(p + 20);
+		const uint32_t l_qname = p[8];
+		if (tid < -1 || tid > (1 << 24) || mtid < -1 || mtid > (1 << 24) || pos < -1 || l_qname < 2 || bs > (1u << 24)) return false;
+		if (p[32 + l_qname - 1] != 0) return false;
+		for (uint32_t i = 0; i + 1 < l_qname && i < 12; i++) if (p[32 + i] < 33 || p[32 + i] > 126) return false;
+		at += 4 + (size_t)bs;
+	}
+	return true;
+}
+
+}  // namespace
+
+struct FramePiece {
+	size_t start = 0, end = 0;          // first offset walked, offset after the last good record
+	bool bad = false;                   // the walk stopped at a malformed record at `end`
+	std::vector<uint64_t> off;
+	std::vector<uint32_t> rbase, rmm;   // bases / CIGAR ops before each record, counted from the start of the piece
+	uint64_t nb = 0, nm = 0;
+};
+struct FrameScratch { std::vector<FramePiece> piece; };      // kept by the caller between streams: no fresh pages per call
+
+FrameScratch *frame_scratch_new() { return new FrameScratch(); }
+void frame_scratch_free(FrameScratch *s) { delete s; }
+
+namespace {
+
+void walk_piece(const uint8_t *bam, size_t nbytes, size_t from, size_t until, FramePiece &fp) {
+	size_t at = from;
+	fp.start = from; fp.bad = false; fp.nb = fp.nm = 0;
+	fp.off.clear(); fp.rbase.clear(); fp.rmm.clear();
+	const size_t guess = (until > from ? until - from : 0) / 200 + 16;      // typical short-read records are 250-400 bytes
+	fp.off.reserve(guess); fp.rbase.reserve(guess); fp.rmm.reserve(guess);
+	uint64_t nb = 0, nm = 0;
+	while (at < until) {
+		uint32_t bs, lseq, ncig;
+		if (frame_one(bam, nbytes, at, &bs, &lseq, &ncig)) { fp.bad = true; break; }
 		// the chain is a dependent load per record: ask for the header a few records ahead, where it will be if sizes stay similar
 		__builtin_prefetch(bam + at + 12 * (size_t)(bs + 4));
 		__builtin_prefetch(bam + at + 12 * (size_t)(bs + 4) + 64);
-		rec_off.push_back(at);
-		read_off.push_back((uint32_t)nb);
-		mm_off.push_back((uint32_t)nm);
-		nb += l_qseq;
-		nm += n_cigar;
+		fp.off.push_back(at); fp.rbase.push_back((uint32_t)nb); fp.rmm.push_back((uint32_t)nm);
+		nb += lseq; nm += ncig;
 		at += 4 + (size_t)bs;
 	}
+	fp.end = at; fp.nb = nb; fp.nm = nm;
+}
+
+}  // namespace
+
+// Framing = walking the block_size chain, a dependent load per record.  Large streams are walked by several host
+// threads: worker k guesses a record boundary near k/K of the stream (a plausible header followed by plausible headers)
+// and walks its piece; the pieces are then stitched from the front -- a piece is taken over only from an offset the
+// chain walked so far actually lands on, otherwise the stitcher keeps walking itself until it does.  The result is the
+// sequential chain whatever the guesses were.
+int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_off, std::vector<uint32_t> &read_off,
+		std::vector<uint32_t> &mm_off, uint64_t *nbases, uint64_t *nmisms, FrameScratch *scratch) {
+	unsigned want = std::thread::hardware_concurrency();
+	if (const char *e = getenv("BSGPU_FRAMER_THREADS")) want = (unsigned)atoi(e);
+	want = std::max(1u, std::min(want, 32u));
+	size_t min_bytes = 16u << 20;
+	if (const char *e = getenv("BSGPU_FRAMER_MIN_BYTES")) min_bytes = (size_t)atoll(e);
+	const unsigned K = nbytes >= min_bytes ? want : 1;
+	FrameScratch local;
+	std::vector<FramePiece> &piece = scratch ? scratch->piece : local.piece;
+	if (piece.size() < K) piece.resize(K);
+	if (K == 1) walk_piece(bam, nbytes, 0, nbytes, piece[0]);
+	else {
+		std::vector<std::thread> thr;
+		for (unsigned k = 0; k < K; k++) thr.emplace_back([&, k] {
+			const size_t lo = nbytes * k / K, hi = nbytes * (k + 1) / K;
+			size_t from = lo;
+			// BSGPU_FRAMER_BLIND (tests): start at the raw byte offset, i.e. with a wrong guess almost every time
+			if (k && !getenv("BSGPU_FRAMER_BLIND")) { while (from < hi && !plausible_record(bam, nbytes, from, 4)) from++; }
+			walk_piece(bam, nbytes, from, hi, piece[k]);
+		});
+		for (auto &t : thr) t.join();
+	}
+	// stitch
+	size_t total = 0;
+	for (unsigned k = 0; k < K; k++) total += piece[k].off.size();
+	rec_off.clear(); read_off.clear(); mm_off.clear();
+	rec_off.reserve(total + 16); read_off.reserve(total + 16); mm_off.reserve(total + 16);
+	uint64_t nb = 0, nm = 0;
+	size_t at = 0;
+	for (unsigned k = 0; k < K; k++) {
+		const FramePiece &p = piece[k];
+		const size_t hi = nbytes * (k + 1) / K;
+		// walk on our own until we stand on an offset the piece has (at once when the guess was right), or pass the piece
+		size_t idx = 0;
+		bool joined = false;
+		while (at < hi) {
+			const auto it = std::lower_bound(p.off.begin() + idx, p.off.end(), (uint64_t)at);
+			idx = (size_t)(it - p.off.begin());
+			if (it != p.off.end() && *it == at) { joined = true; break; }
+			uint32_t bs, lseq, ncig;
+			if (frame_one(bam, nbytes, at, &bs, &lseq, &ncig)) return -1;
+			rec_off.push_back(at); read_off.push_back((uint32_t)nb); mm_off.push_back((uint32_t)nm);
+			nb += lseq; nm += ncig;
+			at += 4 + (size_t)bs;
+		}
+		if (joined) {
+			const size_t m = p.off.size() - idx, o = rec_off.size();
+			const uint64_t db = nb - p.rbase[idx], dm = nm - p.rmm[idx];
+			rec_off.insert(rec_off.end(), p.off.begin() + idx, p.off.end());
+			read_off.resize(o + m); mm_off.resize(o + m);
+			for (size_t i = 0; i < m; i++) { read_off[o + i] = (uint32_t)(p.rbase[idx + i] + db); mm_off[o + i] = (uint32_t)(p.rmm[idx + i] + dm); }
+			nb = p.nb + db; nm = p.nm + dm;
+			at = p.end;
+			if (p.bad) return -1;
+		}
+	}
+	if (at != nbytes) return -1;
 	if (nb > 0xffffffffull || nm > 0xffffffffull) return -2;
 	*nbases = nb;
 	*nmisms = nm;
@@ -326,7 +439,8 @@ struct BlockBuilder {
 	size_t used = 0;
 	NameTable names;
 	std::vector<bsgpu_block> *blocks;
-	std::vector<bsgpu_template> *tmpl;
+	bsgpu_template *out = nullptr;       // templates of this builder, in publication order (room for one per record)
+	size_t nout = 0;
 
 	uint32_t al_qual(const Tmpl &t) const {          // get_al_qual with its sq[k] indexing (src/al_utils.c:19-35)
 		uint32_t qual = 0, n = 0;
@@ -349,7 +463,7 @@ struct BlockBuilder {
 		memset(&b, 0, sizeof(b));
 		const uint32_t first = list[0].fwd ? list[0].fwd : list[0].rev;
 		b.tid = tid; b.y = y; b.x = first > 2 ? first - 2 : 1;            // src/process_template.c:24-28
-		b.first_template = (uint32_t)tmpl->size(); b.n_templates = (uint32_t)used;
+		b.first_template = (uint32_t)nout; b.n_templates = (uint32_t)used;
 		blocks->push_back(b);
 		for (size_t i = 0; i < used; i++) {
 			const Tmpl &t = list[i];
@@ -363,16 +477,34 @@ struct BlockBuilder {
 				d.present[k] = 1; d.reference_span[k] = t.span[k];
 				d.read_off[k] = r.read_off; d.read_len[k] = r.read_len; d.mm_off[k] = r.mm_off; d.mm_n[k] = r.mm_n;
 			}
-			tmpl->push_back(d);
+			out[nout++] = d;
 		}
 		used = 0;
 	}
 
-	int run(size_t nrec, bool keep_unmatched, bool keep_duplicates) {
+	// records [rbeg, nrec): rbeg must be the start of the stream or a point where read_input is certain to start a new block
+	int run(size_t rbeg, size_t nrec, bool keep_unmatched, bool keep_duplicates) {
 		names.bam = bam; names.rec_off = rec_off;
 		int curr_tid = -1, old_tid = -1;
 		uint32_t max_pos = 0, start_pos = 0, read_idx = 0, curr_pos = 0, start_idx = 0;
-		for (size_t ri = 0; ri < nrec; ri++) {
+		// The loop is a chain of dependent cache misses (record -> name in the stream -> table slot).  Names are hashed a few
+		// records ahead and the lines they will touch are requested early.
+		constexpr size_t kAhead = 12;
+		uint64_t ring[16];
+		auto look_ahead = [&](size_t j) {
+			if (j >= nrec) return;
+			const bsgpu_record &q = rec[j];
+			if (q.ret > 0 || !(q.alignment_flag & F_PAIRED)) return;
+			uint32_t l;
+			const uint8_t *nm = names.name_of((uint32_t)j, &l);
+			const uint64_t h = NameTable::hash_name(nm, l);
+			ring[j & 15] = h;
+			__builtin_prefetch(&names.tab[h & (names.tab.size() - 1)]);
+		};
+		for (size_t j = rbeg; j < rbeg + kAhead; j++) look_ahead(j);
+		for (size_t ri = rbeg; ri < nrec; ri++) {
+			if (ri + kAhead + 8 < nrec) __builtin_prefetch(bam + rec_off[ri + kAhead + 8] + 36);      // the name of a record further ahead
+			look_ahead(ri + kAhead);
 			const bsgpu_record &r = rec[ri];
 			if (r.ret > 0) continue;
 			const int ix = r.reverse ? 1 : 0;
@@ -387,7 +519,7 @@ struct BlockBuilder {
 			NameTable::Ent *waiting = nullptr;
 			bool new_block = false, new_contig = false;
 			if (curr_tid < 0 || curr_tid != r.tid) { new_contig = new_block = true; old_tid = curr_tid; curr_tid = r.tid; }
-			if (paired) nh = NameTable::hash_name(name, nlen);
+			if (paired) nh = ring[ri & 15];
 			bool insert = true;
 			if (!new_contig) {
 				if (paired && al.fwd > 0 && al.rev > 0) {
@@ -494,12 +626,122 @@ struct BlockBuilder {
 	}
 };
 
+// Records at which read_input is CERTAIN to start a new block whatever its state (src/get_template_vector.c:111-149):
+// the first kept record of a contig, or a record that is inserted by its flags alone and whose positions all lie more
+// than one base beyond the end of every kept record before it on the contig.  The builder's state is reset there
+// (:151-207), so the stream can be cut at such records and the pieces built independently.  (A conservative subset of
+// the block starts: the running end is never reset, and mates at equal positions -- whose insertion depends on the
+// name table -- are not used.)
+static void certain_block_starts(const bsgpu_record *rec, size_t nrec, std::vector<size_t> &starts) {
+	int tid = -1;
+	uint64_t maxend = 0;
+	for (size_t i = 0; i < nrec; i++) {
+		const bsgpu_record &r = rec[i];
+		if (r.ret > 0) continue;
+		const uint32_t fwd = r.forward_position, rev = r.reverse_position, own = r.reverse ? rev : fwd;
+		if (r.tid != tid) { tid = r.tid; maxend = 0; starts.push_back(i); }
+		else {
+			bool insert = true;
+			if ((r.alignment_flag & F_PAIRED) && fwd > 0 && rev > 0) insert = fwd == rev ? false : (r.reverse ? fwd > rev : fwd < rev);
+			if (insert && (fwd == 0 || (uint64_t)fwd > maxend + 1) && (rev == 0 || (uint64_t)rev > maxend + 1) && (fwd | rev)) starts.push_back(i);
+		}
+		const uint64_t e1 = (uint64_t)own + r.reference_span, e2 = (uint64_t)(fwd > 0 ? fwd : rev) + r.align_length;
+		if (e1 > maxend) maxend = e1;
+		if (e2 > maxend) maxend = e2;
+	}
+}
+
+// A build in flight: the stream cut into pieces at certain block starts, pieces built by a pool of host threads in
+// order.  Piece p's templates sit at tmpl + cuts[p] (a piece has no more templates than records) and its blocks number
+// their templates from the start of the piece, so a consumer can take pieces over one by one while later ones are
+// still being built.
+struct BuildJob {
+	std::vector<size_t> cuts;
+	std::vector<std::vector<bsgpu_block>> pb;
+	std::vector<size_t> pn;
+	std::vector<int> rc;
+	std::vector<std::atomic<int>> done;
+	std::vector<std::thread> thr;
+	std::atomic<size_t> next{0};
+	explicit BuildJob(size_t np) : pb(np), pn(np, 0), rc(np, 0), done(np) { for (auto &d : done) d.store(0); }
+};
+
+BuildJob *build_blocks_start(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
+		bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread) {
+	unsigned want = std::thread::hardware_concurrency();
+	if (const char *e = getenv("BSGPU_BUILDER_THREADS")) want = (unsigned)atoi(e);
+	want = std::max(1u, std::min(want, 32u));
+	size_t min_rec = 50000;                              // below this one thread is faster than starting several
+	if (const char *e = getenv("BSGPU_BUILDER_MIN_RECORDS")) min_rec = (size_t)atoll(e);
+	std::vector<size_t> cuts{0};
+	if (want > 1 && nrec >= min_rec) {
+		std::vector<size_t> starts;
+		certain_block_starts(rec, nrec, starts);
+		const size_t npw = (size_t)want * std::max(1u, pieces_per_thread);
+		size_t si = 0;
+		for (size_t k = 1; k < npw; k++) {
+			const size_t target = nrec * k / npw;
+			while (si < starts.size() && starts[si] < target) si++;
+			if (si < starts.size() && starts[si] > cuts.back()) cuts.push_back(starts[si]);
+		}
+	}
+	cuts.push_back(nrec);
+	const size_t np = cuts.size() - 1;
+	BuildJob *job = new BuildJob(np);
+	job->cuts = cuts;
+	const unsigned nthr = (unsigned)std::min<size_t>(want, np);
+	for (unsigned t = 0; t < nthr; t++) job->thr.emplace_back([=] {
+		for (;;) {
+			const size_t p = job->next.fetch_add(1);
+			if (p >= np) break;
+			BlockBuilder b;
+			b.bam = bam; b.rec_off = rec_off; b.rec = rec; b.blocks = &job->pb[p];
+			b.out = tmpl + job->cuts[p];
+			job->rc[p] = b.run(job->cuts[p], job->cuts[p + 1], keep_unmatched, keep_duplicates);
+			job->pn[p] = b.nout;
+			job->done[p].store(1, std::memory_order_release);
+		}
+	});
+	return job;
+}
+
+size_t build_blocks_pieces(const BuildJob *job) { return job->pb.size(); }
+
+// waits for piece p; returns its status, its blocks (templates numbered from the start of the piece), the index of its
+// first template in the template array and its number of templates
+int build_blocks_piece(BuildJob *job, size_t p, const std::vector<bsgpu_block> **blocks, size_t *tmpl_base, size_t *ntmpl) {
+	while (!job->done[p].load(std::memory_order_acquire)) std::this_thread::yield();
+	*blocks = &job->pb[p];
+	*tmpl_base = job->cuts[p];
+	*ntmpl = job->pn[p];
+	return job->rc[p];
+}
+
+void build_blocks_finish(BuildJob *job) {
+	for (auto &t : job->thr) t.join();
+	delete job;
+}
+
+// the whole build at once: `tmpl` must have room for nrec templates; *ntmpl receives the count, templates compacted
 int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
-		bool keep_duplicates, std::vector<bsgpu_block> &blocks, std::vector<bsgpu_template> &tmpl) {
-	tmpl.reserve(nrec / 2 + nrec / 8 + 16);
-	BlockBuilder b;
-	b.bam = bam; b.rec_off = rec_off; b.rec = rec; b.blocks = &blocks; b.tmpl = &tmpl;
-	return b.run(nrec, keep_unmatched, keep_duplicates);
+		bool keep_duplicates, std::vector<bsgpu_block> &blocks, bsgpu_template *tmpl, size_t *ntmpl) {
+	BuildJob *job = build_blocks_start(bam, rec_off, rec, nrec, keep_unmatched, keep_duplicates, tmpl, 1);
+	const size_t np = build_blocks_pieces(job);
+	size_t at = 0;
+	int rc = 0;
+	for (size_t p = 0; p < np; p++) {
+		const std::vector<bsgpu_block> *pb;
+		size_t base, n;
+		const int r = build_blocks_piece(job, p, &pb, &base, &n);
+		if (r && !rc) rc = r;
+		if (rc) continue;
+		for (bsgpu_block b : *pb) { b.first_template += (uint32_t)at; blocks.push_back(b); }
+		if (n && at != base) memmove(tmpl + at, tmpl + base, n * sizeof(bsgpu_template));      // close the gap (earlier pieces are done)
+		at += n;
+	}
+	build_blocks_finish(job);
+	*ntmpl = at;
+	return rc;
 }
 
 }  // namespace bsgpu

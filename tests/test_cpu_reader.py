@@ -71,3 +71,43 @@ def test_oracle_matches_reader_golden(oracle, name):
         assert (wbk[f] == g["blocks"][f]).all(), f
     assert bamgen.template_keys(wt, wb, wm) == bamgen.template_keys(g["templates"], g["bases"], g["misms"])
     util.assert_gt_meth_close(wv["gtm"], wv["skip"], g["vcf"]["gtm"], g["vcf"]["skip"], exact_doubles=True)
+
+
+def test_parallel_builder_equals_sequential(oracle, monkeypatch):
+    """the stream is cut at records where read_input is certain to start a new block and the pieces are built on
+    separate host threads: same blocks, same templates as one thread"""
+    bam, n, tl, _ = bamgen.make_stream(77, n_contigs=3, dup=0.2, contig_len=9000)
+    orec, ob, om = oracle.decode_records(bam, 20, 1000, False, False)
+    rec = descriptors_from_oracle(orec, ob, bam)
+    monkeypatch.setenv("BSGPU_BUILDER_THREADS", "1")
+    b1, t1 = lib.build_blocks(bam, rec)
+    monkeypatch.setenv("BSGPU_BUILDER_THREADS", "7")
+    monkeypatch.setenv("BSGPU_BUILDER_MIN_RECORDS", "1")
+    b7, t7 = lib.build_blocks(bam, rec)
+    assert len(b1) > 3
+    assert b1.tobytes() == b7.tobytes() and t1.tobytes() == t7.tobytes()
+    wbk, wt, wb, wm, _ = oracle.read_input(bam, tl, None)
+    assert (b7["y"] == wbk["y"]).all() and bamgen.template_keys(t7, ob, om) == bamgen.template_keys(wt, wb, wm)
+
+
+@pytest.mark.parametrize("blind", [False, True])
+def test_parallel_framer_equals_sequential(oracle, monkeypatch, blind):
+    """several host threads walk the block_size chain from guessed record boundaries; the stitch only takes a piece over
+    from an offset the true chain lands on.  With BSGPU_FRAMER_BLIND the guesses are raw byte offsets (wrong almost
+    every time) and the result must still be the sequential chain."""
+    bam, n, tl, _ = bamgen.make_stream(78, n_contigs=2, contig_len=8000)
+    orec, ob, om = oracle.decode_records(bam, 20, 1000, False, False)
+    rec = descriptors_from_oracle(orec, ob, bam)
+    monkeypatch.setenv("BSGPU_FRAMER_THREADS", "1")
+    b1, t1 = lib.build_blocks(bam, rec)
+    monkeypatch.setenv("BSGPU_FRAMER_THREADS", "6")
+    monkeypatch.setenv("BSGPU_FRAMER_MIN_BYTES", "1")
+    if blind:
+        monkeypatch.setenv("BSGPU_FRAMER_BLIND", "1")
+    b6, t6 = lib.build_blocks(bam, rec)
+    assert b1.tobytes() == b6.tobytes() and t1.tobytes() == t6.tobytes()
+    # a truncated stream is rejected by the parallel framer too
+    with pytest.raises(lib.BsGpuError):
+        lib.build_blocks(bam[:-9], rec)
+    with pytest.raises(lib.BsGpuError):
+        lib.build_blocks(bam, rec[:-1])

@@ -125,3 +125,23 @@ def test_reader_rejects_truncated_stream(gpu):
 def test_reader_empty_stream(gpu):
     rec, bases, misms = gpu.decode_records(np.zeros(0, dtype=np.uint8))
     assert len(rec) == 0
+
+
+def test_call_bam_pieces_tile_the_contigs(gpu, oracle, monkeypatch):
+    """the block builder cut into many pieces on a thread pool, pieces consumed in order by the device stages: the windows
+    of successive pieces tile each contig and every block's records are those of the single-piece run"""
+    bam, n, tl, refs = bamgen.make_stream(300, n_contigs=3, dup=0.2, contig_len=9000)
+    o = dict(mapq_thresh=20, max_template_len=1000, keep_unmatched=False, ignore_duplicates=False, keep_duplicates=False)
+    wbk, wt, wb, wm, wv = oracle.read_input(bam, tl, refs, run_chain=True, **o)
+    monkeypatch.setenv("BSGPU_BUILDER_THREADS", "5")
+    monkeypatch.setenv("BSGPU_BUILDER_MIN_RECORDS", "1")
+    blocks, vcf = gpu.call_bam(bam, tl, refs, _rp(o))
+    assert len(blocks) == len(wbk) > 6
+    for b, w in zip(blocks, wbk):
+        assert (b["tid"], b["x"], b["y"], b["n_templates"], b["first_template"]) == (w["tid"], w["x"], w["y"], w["n_templates"], w["first_template"])
+        sz = int(w["y"]) - int(w["x"]) + 1
+        util.assert_vcf_close(vcf[int(b["vcf_off"]):int(b["vcf_off"]) + sz], wv[int(w["vcf_off"]):int(w["vcf_off"]) + sz])
+    covered = np.zeros(len(vcf), dtype=bool)
+    for b in blocks:
+        covered[int(b["vcf_off"]):int(b["vcf_off"]) + int(b["y"]) - int(b["x"]) + 1] = True
+    assert (vcf["skip"][~covered] == 1).all() and (vcf["ready"] == 1).all()
