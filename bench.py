@@ -275,6 +275,11 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1:
+        # the reader's host stages (framer, block builder) run thread pools: share the cores between the ranks of the box
+        per_rank = str(max(2, (os.cpu_count() or 2) // world))
+        os.environ.setdefault("BSGPU_BUILDER_THREADS", per_rank)
+        os.environ.setdefault("BSGPU_FRAMER_THREADS", per_rank)
     gpu = bslib.BsGpu(device=local)
     # a dedicated torch stream: its handle is what the C ABI launches on, and what the CUDA events below are recorded on
     tstream = torch.cuda.Stream()
