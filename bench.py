@@ -450,6 +450,25 @@ def main():
                                  "roofline": roof(in_bytes + fsz * 104, pms)},
                  "fused_variant": {"kernels": "k_bin_* + k_pileup_tile<fused> (BSGPU_FUSED=1)", "ms": fms, "sites_per_s": fcalled / (fms * 1e-3),
                                    "roofline": roof(in_bytes + fsz * (1 + 208), fms)}}
+        # deep targeted panel (config 4 shape): 500x single-end 150-bp reads, the stress case for pileup accumulation
+        try:
+            dsz, ddepth = int(min(fsz, 2_000_000)), 500.0
+            dns = gpu.synth_block_nseg(dsz, L, ddepth)
+            dd_seg = torch.empty(dns * 16 + 16, dtype=torch.uint8, device="cuda")
+            dd_b = torch.empty(dns * L + 16, dtype=torch.uint8, device="cuda")
+            gpu.synth_block_dev(SEED + 99 + rank, 1000, dsz, L, ddepth, dd_seg.data_ptr(), dns, dd_b.data_ptr(), dns * L, d_r.data_ptr(), stream)
+            dpms = timed(lambda: gpu.pileup_block_dev(dd_seg.data_ptr(), dns, dd_b.data_ptr(), 1000, dsz, d_p.data_ptr(), stream))
+            dbms = timed(lambda: gpu.call_block_dev(dd_seg.data_ptr(), dns, dd_b.data_ptr(), d_r.data_ptr(), 1000, dsz, d_v.data_ptr(), stream))
+            dbytes = dns * (L + 16) + dsz * 104
+            block["deep_panel"] = {"workload": "synthetic %dx %d-bp reads over %d sites (config 4 shape), device resident" % (int(ddepth), L, dsz),
+                                   "pileup_only": {"ms": dpms, "sites_per_s": dsz / (dpms * 1e-3), "bases_per_s": dns * L / (dpms * 1e-3),
+                                                   "roofline": {"bound": "hbm", "achieved": dbytes / (dpms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                                                "frac": dbytes / (dpms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_site": dbytes / dsz}},
+                                   "default": {"ms": dbms, "sites_per_s": dsz / (dbms * 1e-3)},
+                                   "envelope_overflow_sites": gpu.stats()["qsum_overflow"]}
+            del dd_seg, dd_b
+        except Exception as e:
+            block["deep_panel"] = {"error": repr(e)}
         # end to end through the host-buffer entry point (what the drop-in calls): pinned host segments / bases / ref in,
         # gt_vcf[] out, H2D + binning + pileup + model + D2H inside the timed region; a 16 Mi-site window of the same data
         from bs_call_b200.records import GT_VCF, SEG, TEMPLATE
