@@ -188,14 +188,19 @@ struct Cand { uint32_t pos, offd, meta, mq2; };
 
 __device__ __forceinline__ uint32_t seg_bin(uint32_t pos, uint32_t x) { return pos >= x ? (pos - x) / kPileTile : 0; }
 
+// Input segments usually arrive in coordinate order, so the lanes of a warp mostly fall into one or two tiles: lanes
+// with the same tile are grouped with match.any and one of them does the atomic for the group (a deep panel puts
+// hundreds of segments into every tile).
 __global__ void k_bin_count(const Seg *__restrict__ segs, size_t nseg, uint32_t x, uint32_t ntiles, uint32_t *__restrict__ counts) {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= nseg) return;
-	const Seg s = segs[i];
-	if (!s.len) return;                       // empty slots (the normaliser leaves them for absent mates)
-	// a segment that starts before the window still contributes to the first tiles (clipped there)
-	const uint32_t t = seg_bin(s.pos, x);
-	if (t < ntiles) atomicAdd(counts + t, 1u);
+	uint32_t t = 0xffffffffu;                 // no contribution: out of range, empty slot (the normaliser leaves them for absent mates)
+	if (i < nseg) {
+		const Seg s = segs[i];
+		// a segment that starts before the window still contributes to the first tiles (clipped there)
+		if (s.len) { const uint32_t b = seg_bin(s.pos, x); if (b < ntiles) t = b; }
+	}
+	const uint32_t peers = __match_any_sync(0xffffffffu, t);
+	if (t != 0xffffffffu && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(counts + t, (uint32_t)__popc(peers));
 }
 
 // exclusive scan of counts[0..n) in three phases: per-CTA scan of 1024 items, single-CTA scan of the CTA totals, add.
@@ -249,15 +254,24 @@ __global__ void __launch_bounds__(1024) k_scan_add(uint32_t *__restrict__ start,
 
 __global__ void k_bin_scatter(const Seg *__restrict__ segs, size_t nseg, uint32_t x, uint32_t ntiles, uint32_t *__restrict__ cursor, Cand *__restrict__ sorted) {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= nseg) return;
-	const Seg s = segs[i];
-	if (!s.len) return;
-	const uint32_t t = seg_bin(s.pos, x);
-	if (t >= ntiles) return;
+	uint32_t t = 0xffffffffu;
+	Seg s;
+	s.pos = 0; s.off = 0; s.len = 0; s.mapq = 0; s.flags = 0; s.pad = 0;
+	if (i < nseg) {
+		s = segs[i];
+		if (s.len) { const uint32_t b = seg_bin(s.pos, x); if (b < ntiles) t = b; }
+	}
+	// one atomic per group of lanes that share a tile; the leader's old value is the group's first slot
+	const uint32_t peers = __match_any_sync(0xffffffffu, t);
+	const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+	uint32_t first = 0;
+	if (t != 0xffffffffu && lane == leader) first = atomicAdd(cursor + t, (uint32_t)__popc(peers));
+	first = __shfl_sync(0xffffffffu, first, leader);
+	if (t == 0xffffffffu) return;
 	const uint32_t mq = s.mapq, combo = ((uint32_t)(s.flags >> 1) & 3u) * 2u + ((uint32_t)s.flags & 1u);
 	Cand c;
 	c.pos = s.pos; c.offd = s.off - s.pos; c.meta = (uint32_t)s.len | combo << 16; c.mq2 = mq * mq;
-	sorted[atomicAdd(cursor + t, 1u)] = c;
+	sorted[first + __popc(peers & ((1u << lane) - 1u))] = c;
 }
 
 // ------------------------------------------------------------------------------------------------
