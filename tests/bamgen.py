@@ -75,6 +75,52 @@ def _other_tags(rng):
     return out
 
 
+def exotic_cigar(rng, cigar):
+    """the same alignment written with the operators aligners rarely use: = / X for M, hard clips at the ends, and now
+    and then an N (skipped region: ignored by the reference) or a P (padding: treated like a soft clip) in the middle"""
+    out = []
+    for op, ln in cigar:
+        if op == CIGAR_M and ln > 3 and rng.random() < 0.5:
+            a = int(rng.integers(1, ln - 1))
+            out += [(7, a), (8, 1), (7, ln - a - 1)] if ln - a - 1 > 0 else [(7, a), (8, ln - a)]
+        else:
+            out.append((op, ln))
+        if rng.random() < 0.05:
+            out.append((3, int(rng.integers(1, 50))))
+        if rng.random() < 0.03:
+            out.append((6, int(rng.integers(1, 4))))
+    if rng.random() < 0.3:
+        out.insert(0, (CIGAR_H, int(rng.integers(1, 30))))
+    if rng.random() < 0.3:
+        out.append((CIGAR_H, int(rng.integers(1, 30))))
+    if rng.random() < 0.02:
+        out.append((9, 3))          # 'B': no case in the reference's switch
+    return out
+
+
+def exotic_stream(seed, n=600):
+    """records for the decode-only tests: unusual CIGAR operators, every flag combination, empty tag lists"""
+    rng = np.random.default_rng(seed)
+    recs = []
+    pos = 10
+    for i in range(n):
+        pos += int(rng.integers(0, 30))
+        l = int(rng.integers(1, 90))
+        packed = (rng.integers(0, 4, size=l) | (rng.integers(1, 44, size=l) << 2)).astype(np.uint8)
+        packed[rng.random(l) < 0.05] = 0
+        quals = np.where(rng.random(l) < 0.1, rng.integers(44, 255, size=l), packed >> 2)
+        cig = exotic_cigar(rng, [(CIGAR_S, 2), (CIGAR_M, max(l - 2, 1))] if l > 4 and rng.random() < 0.3 else [(CIGAR_M, l)])
+        flag = int(rng.integers(0, 4096)) if rng.random() < 0.5 else int(rng.choice([0, 16, 99, 147, 83, 163, 65, 129, 73, 137]))
+        mtid = 0 if rng.random() < 0.9 else 1
+        mpos = pos + int(rng.integers(-300, 300))
+        tl = int(rng.integers(-1500, 1500))
+        aux = b"" if rng.random() < 0.2 else _other_tags(rng) + _strand_tag(rng, int(rng.integers(0, 3)), int(rng.integers(0, 5))) + _other_tags(rng)
+        if rng.random() < 0.05:
+            aux += b"Q?x"             # a tag type the reference's switch has no case for
+        recs.append(pack_record(0, pos, int(rng.integers(0, 61)), flag, mtid, max(mpos, 0), tl, ("x%d" % i).encode(), cig, packed, quals, aux))
+    return np.frombuffer(b"".join(recs), dtype=np.uint8).copy(), n
+
+
 def pack_record(tid, pos0, mapq, flag, mtid, mpos0, tlen, qname, cigar, packed, quals, aux):
     """one BAM alignment record (with its leading block_size)"""
     l_seq = len(packed)

@@ -69,6 +69,18 @@ def test_decode_records_oracle(gpu, oracle, seed):
     _check_records(rec, bases, misms, want, wb, wm)
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_decode_exotic_records(gpu, oracle, seed):
+    """= / X / H / N / P / B operators, arbitrary flag words, unknown tag types, qualities up to 254"""
+    bam, n = bamgen.exotic_stream(40 + seed)
+    for ku in (False, True):
+        want, wb, wm = oracle.decode_records(bam, 10, 700, ku, seed == 1)
+        rec, bases, misms = gpu.decode_records(bam, bslib.reader_params(mapq_thresh=10, max_template_len=700, keep_unmatched=ku,
+                                                                      ignore_duplicates=seed == 1))
+        assert len(rec) == n
+        _check_records(rec, bases, misms, want, wb, wm)
+
+
 @pytest.mark.parametrize("name", ["reader_pe", "reader_mixed"])
 def test_blocks_from_device_descriptors_golden(gpu, name):
     """decode on the device, build blocks on the host from the device's descriptors: the reference's blocks"""

@@ -172,6 +172,22 @@ def test_decode_records(oracle, reference, seed):
     assert set(np.unique(r["bs_strand"][kept])) == {0, 1, 2}
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_decode_exotic_records(oracle, reference, seed):
+    """= / X / H / N / P / B operators, arbitrary flag words, unknown tag types, qualities up to 254"""
+    from tests import bamgen
+    bam, n = bamgen.exotic_stream(seed)
+    for ku in (False, True):
+        r, rb, rm = reference.decode_records(bam, 10, 700, ku, seed % 2 == 0)
+        w, wb, wm = oracle.decode_records(bam, 10, 700, ku, seed % 2 == 0)
+        kept = r["ret"] == 0
+        assert len(r) == n and kept.sum() > 50
+        for f in r.dtype.names:
+            a, b = (r[f][kept], w[f][kept]) if f in KEPT_ONLY else (r[f], w[f])
+            assert (a == b).all(), f
+        assert rb.tobytes() == wb.tobytes() and rm.tobytes() == wm.tobytes()
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_read_input(oracle, reference, seed):
     """blocks (contig, window, template ranges) and every template with its mates' bytes and events: identical;
