@@ -1,5 +1,6 @@
 // bsgpu_api.cu -- the C ABI declared in include/bsgpu.h: context, staging, pipelines.  No CPU compute path:
 // every entry point that produces results launches kernels, and bsgpu_init fails if no sm_100 device opens.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -34,6 +35,10 @@ int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_
 int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
 		bool keep_duplicates, std::vector<bsgpu_block> &blocks, bsgpu_template *tmpl, size_t *ntmpl);
 struct BuildJob;
+struct CertainState { int tid = -1; uint64_t maxend = 0; };
+void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts);
+BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t rbeg, size_t rend,
+		const std::vector<size_t> &starts, bool keep_unmatched, bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread);
 BuildJob *build_blocks_start(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
 		bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread);
 size_t build_blocks_pieces(const BuildJob *job);
@@ -108,7 +113,8 @@ struct bsgpu_ctx {
 	FrameScratch *frame_scratch = nullptr;
 	PinBuf h_rec, h_off, h_tmpl;                 // pinned staging: descriptors coming back, offset tables and templates going up
 	bool fused = false;                          // BSGPU_FUSED=1: one fused pileup+model kernel instead of two kernels
-	std::vector<cudaEvent_t> win_events;
+	std::vector<cudaEvent_t> win_events, rd_up, rd_done;      // output ring; reader: byte piece uploaded, chunk descriptors home
+	uint32_t ring_pos = 0;                       // next output ring slot of the deferred runs
 	bool ring_busy[3] = {false, false, false};   // output ring slot may still be copying out (deferred block_run)
 	bsgpu_stats stats;
 	int launches = 0;
@@ -197,6 +203,8 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 		if (c->slot[i].done) cudaEventDestroy(c->slot[i].done);
 	}
 	for (cudaEvent_t ev : c->win_events) cudaEventDestroy(ev);
+	for (cudaEvent_t ev : c->rd_up) cudaEventDestroy(ev);
+	for (cudaEvent_t ev : c->rd_done) cudaEventDestroy(ev);
 	if (c->frame_scratch) frame_scratch_free(c->frame_scratch);
 	c->h_rec.release(); c->h_off.release(); c->h_tmpl.release();
 	c->rd_bam.release(); c->rd_recoff.release(); c->rd_readoff.release(); c->rd_mmoff.release(); c->rd_rec.release(); c->rd_bases.release(); c->rd_misms.release();
@@ -416,17 +424,19 @@ static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *
 	const uint32_t ntiles = (sz + kPileTileSites - 1) / kPileTileSites;
 	const uint32_t slab = (2u << 20) / kPileTileSites;      // tiles per slab = 2 Mi sites = 436 MB of gt_vcf
 	const uint32_t nslab = (ntiles + slab - 1) / slab;
-	const uint32_t resident = nslab < 3 ? nslab : 3;      // ring of output slabs on the device
-	const uint32_t slab_tiles = ntiles < slab ? ntiles : slab;
+	// ring of output slabs on the device.  Deferred runs rotate through all three slots with a fixed slot size, so the
+	// kernels of one window never wait for the copy-out of the window before it.
+	const uint32_t resident = defer ? 3 : (nslab < 3 ? nslab : 3);
+	const uint32_t slab_tiles = defer ? slab : (ntiles < slab ? ntiles : slab);
 	CU(c->vcf.reserve((size_t)resident * slab_tiles * kPileTileSites * rec));
-	if (mode && !c->fused) CU(c->pile.reserve((size_t)slab_tiles * kPileTileSites * sizeof(bsgpu_pileup) + 16));
-	while (c->win_events.size() < 2 * (size_t)resident) {
+	if (mode && !c->fused) CU(c->pile.reserve((size_t)(defer || ntiles >= slab ? slab : ntiles) * kPileTileSites * sizeof(bsgpu_pileup) + 16));
+	while (c->win_events.size() < 6) {
 		cudaEvent_t ev;
 		CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 		c->win_events.push_back(ev);
 	}
 	for (uint32_t si = 0; si < nslab; si++) {
-		const uint32_t r = si % resident;
+		const uint32_t r = defer ? (c->ring_pos + si) % 3 : si % resident;
 		cudaEvent_t computed = c->win_events[2 * r], copied = c->win_events[2 * r + 1];
 		const uint32_t t0 = si * slab, nt = ntiles - t0 < slab ? ntiles - t0 : slab;
 		const size_t site0 = (size_t)t0 * kPileTileSites;
@@ -443,6 +453,7 @@ static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *
 		c->ring_busy[r] = defer;
 		c->stats.d2h_bytes += nsite * rec;
 	}
+	if (defer) c->ring_pos = (c->ring_pos + nslab) % 3;
 	c->stats.sites += sz;
 	if (defer) return BSGPU_OK;
 	CU(cudaStreamSynchronize(c->copy_stream));
@@ -544,42 +555,94 @@ void bsgpu_default_reader_params(bsgpu_reader_params *p) {
 	p->mapq_thresh = 20;            // include/bs_call.h:14
 }
 
-// frame + upload + decode; leaves descriptors, packed reads and events resident; *nb / *nm = sizes of the decoded arrays
-static int decode_resident(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const bsgpu_reader_params *rp, size_t *nrec, uint64_t *nb, uint64_t *nm) {
+// frame + upload + decode, in chunks: the stream goes up in byte pieces on the upload stream while the host frames it;
+// chunk k = the records that end inside pieces 0..k, decoded on the decode stream as soon as piece k has landed, its
+// descriptors copied back to the pinned array h_rec.  On return everything is queued; chunk_end[k] = one past the last
+// record of chunk k and c->rd_done[k] fires when its descriptors are on the host.  Descriptors, packed reads and events
+// stay resident.  *nb / *nm = sizes of the decoded arrays.
+static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const bsgpu_reader_params *rp, unsigned want_chunks,
+		size_t *nrec, uint64_t *nb, uint64_t *nm, std::vector<size_t> &chunk_end) {
 	std::vector<uint32_t> &read_off = c->read_off, &mm_off = c->mm_off;
 	if (!c->frame_scratch) c->frame_scratch = frame_scratch_new();
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
 	CU(cudaStreamSynchronize(c->copy_stream));
-	// the stream itself can start its way up while the host frames it
+	cudaStream_t up = c->slot[0].stream, dec = c->slot[1].stream;
+	CU(cudaStreamSynchronize(up));
+	CU(cudaStreamSynchronize(dec));
+	const unsigned K = nbytes >= (64u << 20) ? std::max(1u, std::min(want_chunks, 8u)) : 1;
+	while (c->rd_up.size() < K) {
+		cudaEvent_t e1, e2;
+		CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+		c->rd_up.push_back(e1); c->rd_done.push_back(e2);
+	}
+	// the stream itself starts its way up while the host frames it
 	CU(c->rd_bam.reserve(nbytes + 16));
-	if (nbytes) CU(cudaMemcpyAsync(c->rd_bam.p, bam, nbytes, cudaMemcpyHostToDevice, c->stream));
+	std::vector<size_t> piece_end(K);
+	for (unsigned k = 0; k < K; k++) {
+		const size_t lo = nbytes * k / K, hi = nbytes * (k + 1) / K;
+		piece_end[k] = hi;
+		if (hi > lo) CU(cudaMemcpyAsync((uint8_t *)c->rd_bam.p + lo, bam + lo, hi - lo, cudaMemcpyHostToDevice, up));
+		CU(cudaEventRecord(c->rd_up[k], up));
+	}
 	const int fr = frame_records(bam, nbytes, c->rec_off, read_off, mm_off, nb, nm, c->frame_scratch);
-	if (fr) cudaStreamSynchronize(c->stream);
+	if (fr) cudaStreamSynchronize(up);
 	if (fr == -1) return fail("bsgpu reader: truncated or malformed BAM record stream");
 	if (fr == -2) return fail("bsgpu reader: more than 4 Gi bases in one stream; split the input");
 	const size_t n = c->rec_off.size();
 	*nrec = n;
-	if (!n) { CU(cudaStreamSynchronize(c->stream)); return BSGPU_OK; }
+	chunk_end.clear();
+	if (!n) { CU(cudaStreamSynchronize(up)); return BSGPU_OK; }
 	CU(c->rd_recoff.reserve(n * 8));
 	CU(c->rd_readoff.reserve(n * 4));
 	CU(c->rd_mmoff.reserve(n * 4));
 	CU(c->rd_rec.reserve(n * sizeof(bsgpu_record)));
 	CU(c->rd_bases.reserve(*nb + 16));
 	CU(c->rd_misms.reserve((*nm + 1) * sizeof(bsgpu_misms)));
-	// the offset tables go up from pinned staging (pageable vectors would serialise the copies behind the big one)
+	CU(c->h_rec.reserve(n * sizeof(bsgpu_record)));
+	// the offset tables go up from pinned staging (pageable vectors would serialise the copies behind the big ones)
 	CU(c->h_off.reserve(n * 16));
 	uint8_t *ho = (uint8_t *)c->h_off.p;
 	memcpy(ho, c->rec_off.data(), n * 8);
 	memcpy(ho + n * 8, read_off.data(), n * 4);
 	memcpy(ho + n * 12, mm_off.data(), n * 4);
-	CU(cudaMemcpyAsync(c->rd_recoff.p, ho, n * 8, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->rd_readoff.p, ho + n * 8, n * 4, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->rd_mmoff.p, ho + n * 12, n * 4, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->rd_recoff.p, ho, n * 8, cudaMemcpyHostToDevice, dec));
+	CU(cudaMemcpyAsync(c->rd_readoff.p, ho + n * 8, n * 4, cudaMemcpyHostToDevice, dec));
+	CU(cudaMemcpyAsync(c->rd_mmoff.p, ho + n * 12, n * 4, cudaMemcpyHostToDevice, dec));
 	c->stats.h2d_bytes += nbytes + n * 16;
-	CU(launch_decode_records(c->rd_bam.p, c->rd_recoff.p, c->rd_readoff.p, c->rd_mmoff.p, n, rp->mapq_thresh, rp->max_template_len,
-			rp->keep_unmatched, rp->ignore_duplicates, c->rd_rec.p, c->rd_bases.p, c->rd_misms.p, c->stream, &c->launches));
-	CU(cudaStreamSynchronize(c->stream));      // read_off / mm_off are temporaries
+	size_t r0 = 0;
+	for (unsigned k = 0; k < K; k++) {
+		// records that end inside pieces 0..k (the last chunk takes the rest)
+		size_t r1 = n;
+		if (k + 1 < K) {
+			const auto it = std::upper_bound(c->rec_off.begin() + r0, c->rec_off.end(), (uint64_t)piece_end[k]);
+			r1 = (size_t)(it - c->rec_off.begin());
+			if (r1 > r0) r1--;                          // the record that starts before the boundary may end after it
+			while (r1 > r0 && c->rec_off[r1 - 1] + 4 + (uint64_t)(bam[c->rec_off[r1 - 1]] | bam[c->rec_off[r1 - 1] + 1] << 8 | bam[c->rec_off[r1 - 1] + 2] << 16 | (uint64_t)bam[c->rec_off[r1 - 1] + 3] << 24) > piece_end[k]) r1--;
+		}
+		CU(cudaStreamWaitEvent(dec, c->rd_up[k], 0));
+		if (r1 > r0) {
+			CU(launch_decode_records(c->rd_bam.p, (const uint64_t *)c->rd_recoff.p + r0, (const uint32_t *)c->rd_readoff.p + r0,
+					(const uint32_t *)c->rd_mmoff.p + r0, r1 - r0, rp->mapq_thresh, rp->max_template_len, rp->keep_unmatched,
+					rp->ignore_duplicates, (bsgpu_record *)c->rd_rec.p + r0, c->rd_bases.p, c->rd_misms.p, dec, &c->launches));
+			CU(cudaMemcpyAsync((bsgpu_record *)c->h_rec.p + r0, (const bsgpu_record *)c->rd_rec.p + r0, (r1 - r0) * sizeof(bsgpu_record),
+					cudaMemcpyDeviceToHost, dec));
+		}
+		CU(cudaEventRecord(c->rd_done[k], dec));
+		chunk_end.push_back(r1);
+		r0 = r1;
+	}
+	c->stats.d2h_bytes += n * sizeof(bsgpu_record);
+	return BSGPU_OK;
+}
+
+// the whole stream decoded and its descriptors on the host (h_rec)
+static int decode_resident(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const bsgpu_reader_params *rp, size_t *nrec, uint64_t *nb, uint64_t *nm) {
+	std::vector<size_t> chunk_end;
+	if (decode_queue(c, bam, nbytes, rp, 1, nrec, nb, nm, chunk_end) != BSGPU_OK) return BSGPU_FAIL;
+	CU(cudaStreamSynchronize(c->slot[0].stream));
+	CU(cudaStreamSynchronize(c->slot[1].stream));
 	return BSGPU_OK;
 }
 
@@ -592,12 +655,12 @@ int bsgpu_decode_records(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const 
 	if (decode_resident(c, bam, nbytes, rp, &n, &nb, &nm) != BSGPU_OK) return BSGPU_FAIL;
 	if (n > rec_cap || (bases_out && nb > bases_cap) || (misms_out && nm > misms_cap)) return fail("bsgpu_decode_records: need room for %zu records, %llu bases, %llu events", n, (unsigned long long)nb, (unsigned long long)nm);
 	if (n) {
-		if (rec_out) CU(cudaMemcpyAsync(rec_out, c->rd_rec.p, n * sizeof(bsgpu_record), cudaMemcpyDeviceToHost, c->stream));
+		if (rec_out) memcpy(rec_out, c->h_rec.p, n * sizeof(bsgpu_record));
 		// events of dropped records are never written: clear what the caller will see
 		if (bases_out && nb) CU(cudaMemcpyAsync(bases_out, c->rd_bases.p, nb, cudaMemcpyDeviceToHost, c->stream));
 		if (misms_out && nm) CU(cudaMemcpyAsync(misms_out, c->rd_misms.p, nm * sizeof(bsgpu_misms), cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
-		c->stats.d2h_bytes += n * sizeof(bsgpu_record) + (bases_out ? nb : 0) + (misms_out ? nm * sizeof(bsgpu_misms) : 0);
+		c->stats.d2h_bytes += (bases_out ? nb : 0) + (misms_out ? nm * sizeof(bsgpu_misms) : 0);
 	}
 	*nrec = n;
 	if (nbases) *nbases = nb;
@@ -685,32 +748,52 @@ int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_target
 	*nblocks = 0; *nvcf = 0;
 	auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	const double t0 = now();
-	if (decode_resident(c, bam, nbytes, rp, &n, &nb, &nm) != BSGPU_OK) return BSGPU_FAIL;
+	std::vector<size_t> chunk_end;
+	if (decode_queue(c, bam, nbytes, rp, 4, &n, &nb, &nm, chunk_end) != BSGPU_OK) return BSGPU_FAIL;
 	const double t1 = now();
 	c->stats.bam_decode_s += t1 - t0;
 	if (!n) return BSGPU_OK;
-	CU(c->h_rec.reserve(n * sizeof(bsgpu_record)));
 	const bsgpu_record *rec = (const bsgpu_record *)c->h_rec.p;
-	CU(cudaMemcpyAsync(c->h_rec.p, c->rd_rec.p, n * sizeof(bsgpu_record), cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaStreamSynchronize(c->stream));
-	c->stats.d2h_bytes += n * sizeof(bsgpu_record);
 	CU(c->h_tmpl.reserve((n + 1) * sizeof(bsgpu_template)));
 	bsgpu_template *tm = (bsgpu_template *)c->h_tmpl.p;
-	// The block builder runs on a pool of host threads over pieces of the stream (cut where read_input is certain to
-	// start a block); pieces are taken over in order, so the device works on the first ones while the rest are built.
-	// A piece is processed as one window per contig it touches; the windows of a contig tile the span from its first
-	// block's x to its last block's y.  Pileup counts are additive per site and the model is per site, so every block's
-	// records are exactly what a per-block run gives; positions between blocks come back as skip records.
 	unsigned long long before[4], after[4];       // normalisation failures are counted on the device: compared at the end
 	CU(cudaMemcpy(before, c->d_counters, sizeof(before), cudaMemcpyDeviceToHost));
-	BuildJob *job = build_blocks_start(bam, c->rec_off.data(), rec, n, rp->keep_unmatched, rp->keep_duplicates, tm, 2);
-	const size_t np = build_blocks_pieces(job);
-	size_t ov = 0, nbk = 0, ntm = 0;
+	// Chunk by chunk, as the descriptors come home: the part of the stream up to the last CERTAIN block start seen so far
+	// is cut into pieces that a pool of host threads builds (read_input's state is reset at such records); the caller's
+	// thread takes the pieces over in order and queues their device work, so the upload and decode of later chunks, the
+	// builders, the kernels and the D2H of earlier windows all overlap.  A piece is processed as one window per contig it
+	// touches; the windows of a contig tile the span from its first block's x to its last block's y.  Pileup counts are
+	// additive per site and the model is per site, so every block's records are exactly what a per-block run gives;
+	// positions between blocks come back as skip records.
+	size_t ov = 0, nbk = 0, ntm = 0, built = 0, scanned = 0;
 	int cur_tid = -1;
 	uint32_t ctg_x0 = 0, ctg_end = 0;       // current contig: x of its first block, last position already written
 	size_t ctg_ov = 0;                      // vcf index of position ctg_x0
 	int ret = BSGPU_OK;
 	double t_wait = 0;
+	CertainState cst;
+	std::vector<size_t> starts;
+	BuildJob *job = nullptr;
+	for (size_t ck = 0; ck < chunk_end.size() && ret == BSGPU_OK; ck++) {
+		const double w0 = now();
+		CU(cudaEventSynchronize(c->rd_done[ck]));
+		t_wait += now() - w0;
+		const size_t avail = chunk_end[ck];
+		certain_block_starts(rec, scanned, avail, &cst, starts);
+		scanned = avail;
+		const bool last = ck + 1 == chunk_end.size();
+		// build up to the last certain start (everything when the stream is complete); starts[] holds those > built
+		size_t upto = last ? n : built;
+		if (!last) for (size_t i = starts.size(); i-- > 0;) if (starts[i] > built) { upto = starts[i]; break; }
+		if (upto <= built) continue;
+		std::vector<size_t> inside;
+		for (size_t v : starts) if (v > built && v < upto) inside.push_back(v);
+		job = build_blocks_start_range(bam, c->rec_off.data(), rec, built, upto, inside, rp->keep_unmatched, rp->keep_duplicates, tm, 2);
+		std::vector<size_t> keep;
+		for (size_t v : starts) if (v >= upto) keep.push_back(v);
+		starts.swap(keep);
+		built = upto;
+		const size_t np = build_blocks_pieces(job);
 	for (size_t p = 0; p < np && ret == BSGPU_OK; p++) {
 		const std::vector<bsgpu_block> *pb;
 		size_t base, nt_piece;
@@ -745,7 +828,11 @@ int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_target
 		}
 		ntm += nt_piece;
 	}
-	build_blocks_finish(job);
+		build_blocks_finish(job);
+		job = nullptr;
+	}
+	cudaStreamSynchronize(c->slot[0].stream);
+	cudaStreamSynchronize(c->slot[1].stream);
 	cudaStreamSynchronize(c->stream);
 	cudaStreamSynchronize(c->copy_stream);
 	for (bool &b : c->ring_busy) b = false;

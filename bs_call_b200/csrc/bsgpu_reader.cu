@@ -626,16 +626,19 @@ struct BlockBuilder {
 	}
 };
 
+struct CertainState { int tid = -1; uint64_t maxend = 0; };
+
 // Records at which read_input is CERTAIN to start a new block whatever its state (src/get_template_vector.c:111-149):
 // the first kept record of a contig, or a record that is inserted by its flags alone and whose positions all lie more
 // than one base beyond the end of every kept record before it on the contig.  The builder's state is reset there
-// (:151-207), so the stream can be cut at such records and the pieces built independently.  (A conservative subset of
+// (:151-207), so the stream can be cut at such records and the pieces built independently.  The scan keeps its state
+// in `st`, so a stream whose descriptors arrive in chunks can be scanned chunk by chunk.  (A conservative subset of
 // the block starts: the running end is never reset, and mates at equal positions -- whose insertion depends on the
 // name table -- are not used.)
-static void certain_block_starts(const bsgpu_record *rec, size_t nrec, std::vector<size_t> &starts) {
-	int tid = -1;
-	uint64_t maxend = 0;
-	for (size_t i = 0; i < nrec; i++) {
+void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts) {
+	int tid = st->tid;
+	uint64_t maxend = st->maxend;
+	for (size_t i = rbeg; i < rend; i++) {
 		const bsgpu_record &r = rec[i];
 		if (r.ret > 0) continue;
 		const uint32_t fwd = r.forward_position, rev = r.reverse_position, own = r.reverse ? rev : fwd;
@@ -649,6 +652,7 @@ static void certain_block_starts(const bsgpu_record *rec, size_t nrec, std::vect
 		if (e1 > maxend) maxend = e1;
 		if (e2 > maxend) maxend = e2;
 	}
+	st->tid = tid; st->maxend = maxend;
 }
 
 // A build in flight: the stream cut into pieces at certain block starts, pieces built by a pool of host threads in
@@ -666,26 +670,27 @@ struct BuildJob {
 	explicit BuildJob(size_t np) : pb(np), pn(np, 0), rc(np, 0), done(np) { for (auto &d : done) d.store(0); }
 };
 
-BuildJob *build_blocks_start(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
-		bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread) {
+// records [rbeg, rend); rbeg is the start of the stream or a certain block start; `starts` = the certain block starts
+// inside the range (ascending), from which the cuts between pieces are chosen
+BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t rbeg, size_t rend,
+		const std::vector<size_t> &starts, bool keep_unmatched, bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread) {
 	unsigned want = std::thread::hardware_concurrency();
 	if (const char *e = getenv("BSGPU_BUILDER_THREADS")) want = (unsigned)atoi(e);
 	want = std::max(1u, std::min(want, 32u));
 	size_t min_rec = 50000;                              // below this one thread is faster than starting several
 	if (const char *e = getenv("BSGPU_BUILDER_MIN_RECORDS")) min_rec = (size_t)atoll(e);
-	std::vector<size_t> cuts{0};
+	const size_t nrec = rend - rbeg;
+	std::vector<size_t> cuts{rbeg};
 	if (want > 1 && nrec >= min_rec) {
-		std::vector<size_t> starts;
-		certain_block_starts(rec, nrec, starts);
 		const size_t npw = (size_t)want * std::max(1u, pieces_per_thread);
 		size_t si = 0;
 		for (size_t k = 1; k < npw; k++) {
-			const size_t target = nrec * k / npw;
+			const size_t target = rbeg + nrec * k / npw;
 			while (si < starts.size() && starts[si] < target) si++;
-			if (si < starts.size() && starts[si] > cuts.back()) cuts.push_back(starts[si]);
+			if (si < starts.size() && starts[si] > cuts.back() && starts[si] < rend) cuts.push_back(starts[si]);
 		}
 	}
-	cuts.push_back(nrec);
+	cuts.push_back(rend);
 	const size_t np = cuts.size() - 1;
 	BuildJob *job = new BuildJob(np);
 	job->cuts = cuts;
@@ -703,6 +708,14 @@ BuildJob *build_blocks_start(const uint8_t *bam, const uint64_t *rec_off, const 
 		}
 	});
 	return job;
+}
+
+BuildJob *build_blocks_start(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
+		bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread) {
+	std::vector<size_t> starts;
+	CertainState st;
+	certain_block_starts(rec, 0, nrec, &st, starts);
+	return build_blocks_start_range(bam, rec_off, rec, 0, nrec, starts, keep_unmatched, keep_duplicates, tmpl, pieces_per_thread);
 }
 
 size_t build_blocks_pieces(const BuildJob *job) { return job->pb.size(); }
