@@ -570,7 +570,9 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 	cudaStream_t up = c->slot[0].stream, dec = c->slot[1].stream;
 	CU(cudaStreamSynchronize(up));
 	CU(cudaStreamSynchronize(dec));
-	const unsigned K = nbytes >= (64u << 20) ? std::max(1u, std::min(want_chunks, 8u)) : 1;
+	size_t chunk_min = 64u << 20;                       // smaller streams go up and are decoded in one piece
+	if (const char *e = getenv("BSGPU_READER_CHUNK_MIN_BYTES")) chunk_min = (size_t)atoll(e);
+	const unsigned K = nbytes >= chunk_min ? std::max(1u, std::min(want_chunks, 8u)) : 1;
 	while (c->rd_up.size() < K) {
 		cudaEvent_t e1, e2;
 		CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));

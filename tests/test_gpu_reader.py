@@ -128,6 +128,26 @@ def test_call_bam_oracle(gpu, oracle, seed):
     assert (vcf["skip"][~covered] == 1).all()
 
 
+def test_call_bam_chunked_upload_and_decode(gpu, oracle, monkeypatch):
+    """the stream uploaded in four byte pieces, decoded chunk by chunk, blocks built up to the last certain block start of
+    each chunk: same result as in one piece"""
+    bam, n, tl, refs = bamgen.make_stream(301, n_contigs=3, dup=0.2, contig_len=9000)
+    o = dict(mapq_thresh=20, max_template_len=1000, keep_unmatched=False, ignore_duplicates=False, keep_duplicates=False)
+    wbk, wt, wb, wm, wv = oracle.read_input(bam, tl, refs, run_chain=True, **o)
+    monkeypatch.setenv("BSGPU_READER_CHUNK_MIN_BYTES", "1")
+    monkeypatch.setenv("BSGPU_BUILDER_THREADS", "3")
+    monkeypatch.setenv("BSGPU_BUILDER_MIN_RECORDS", "1")
+    blocks, vcf = gpu.call_bam(bam, tl, refs, _rp(o))
+    assert len(blocks) == len(wbk) >= 4
+    for b, w in zip(blocks, wbk):
+        assert (b["tid"], b["x"], b["y"], b["n_templates"], b["first_template"]) == (w["tid"], w["x"], w["y"], w["n_templates"], w["first_template"])
+        sz = int(w["y"]) - int(w["x"]) + 1
+        util.assert_vcf_close(vcf[int(b["vcf_off"]):int(b["vcf_off"]) + sz], wv[int(w["vcf_off"]):int(w["vcf_off"]) + sz])
+    rec, bases, misms = gpu.decode_records(bam, _rp(o))
+    want, wb2, wm2 = oracle.decode_records(bam, 20, 1000, False, False)
+    _check_records(rec, bases, misms, want, wb2, wm2)
+
+
 def test_reader_rejects_truncated_stream(gpu):
     bam, n, tl, refs = bamgen.make_stream(7)
     with pytest.raises(bslib.BsGpuError):
