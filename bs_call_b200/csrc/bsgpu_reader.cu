@@ -1,7 +1,8 @@
 // bsgpu_reader.cu -- the reader side of the path: BAM alignment records -> templates grouped into blocks.
 //
-//   k_decode_records      one warp per record: flag / MAPQ / insert-size / orientation filters, positions, CIGAR ->
-//                         event list, bisulfite strand tag, 4-bit sequence + qualities -> packed bytes
+//   k_decode_records      one lane per record for the scalar part (flag / MAPQ / insert-size / orientation filters,
+//                         positions, CIGAR -> event list, bisulfite strand tag), one warp per record for the bytes
+//                         (4-bit sequence + qualities -> packed bytes)
 //                         (what get_next_align_details does per record, src/input_sam.c:222-312)
 //   frame_records         host: walks the block_size chain of the record stream (what sam_read1 does per call)
 //   BlockBuilder          host: mate pairing by read name, positional duplicate removal, block cutting
@@ -92,121 +93,140 @@ __device__ uint32_t strand_from_tags(const uint8_t *s, const uint8_t *end) {
 
 constexpr int kDecodeWarps = 8;
 
+// A warp takes 32 consecutive records.  Phase 1, one record per LANE: the fixed fields, the filter cascade, the CIGAR
+// walk, the tag walk and the descriptor -- short scalar work whose cost is shared by 32 records.  Phase 2, one record
+// per TRIP with all lanes: the 4-bit sequence and the qualities become packed bytes, lanes striding over the bases
+// (coalesced byte stores).
 __global__ void __launch_bounds__(kDecodeWarps * 32)
 k_decode_records(const uint8_t *__restrict__ bam, const uint64_t *__restrict__ rec_off, const uint32_t *__restrict__ read_off,
 		const uint32_t *__restrict__ mm_off, size_t nrec, uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup,
 		bsgpu_record *__restrict__ out, uint8_t *__restrict__ bases, bsgpu_misms *__restrict__ misms) {
-	const size_t w = (size_t)blockIdx.x * kDecodeWarps + (threadIdx.x >> 5);
+	const size_t w0 = ((size_t)blockIdx.x * kDecodeWarps + (threadIdx.x >> 5)) * 32;
 	const int lane = threadIdx.x & 31;
-	if (w >= nrec) return;
-	const uint8_t *rec = bam + rec_off[w];
-	const uint32_t block_size = ld_u32(rec);
-	const uint8_t *p = rec + 4;
-	const int32_t tid = (int32_t)ld_u32(p), pos = (int32_t)ld_u32(p + 4), mtid = (int32_t)ld_u32(p + 20), mpos = (int32_t)ld_u32(p + 24),
-		isize = (int32_t)ld_u32(p + 28), l_qseq = (int32_t)ld_u32(p + 16);
-	const uint32_t l_qname = p[8], mapq = p[9], n_cigar = ld_u16(p + 12), flag = ld_u16(p + 14);
+	if (w0 >= nrec) return;
+	const size_t w = w0 + lane;
+	// ---- phase 1: my record
+	const uint8_t *seq = nullptr;
+	int32_t l_qseq = 0;
+	uint32_t boff = 0;
+	bool decode = false;
+	if (w < nrec) {
+		const uint8_t *rec = bam + rec_off[w];
+		const uint32_t block_size = ld_u32(rec);
+		const uint8_t *p = rec + 4;
+		const int32_t tid = (int32_t)ld_u32(p), pos = (int32_t)ld_u32(p + 4), mtid = (int32_t)ld_u32(p + 20), mpos = (int32_t)ld_u32(p + 24),
+			isize = (int32_t)ld_u32(p + 28);
+		l_qseq = (int32_t)ld_u32(p + 16);
+		const uint32_t l_qname = p[8], mapq = p[9], n_cigar = ld_u16(p + 12), flag = ld_u16(p + 14);
 
-	// ---- filters and positions (src/input_sam.c:231-300); every lane computes them, lane 0 writes
-	uint32_t flt = FLT_NONE;
-	if ((flag & F_PAIRED) && !keep_unmatched) {
-		if ((flag & (F_PROPER | F_UNMAP | F_MUNMAP | F_QCFAIL | F_SECONDARY | F_SUPP | F_DUP)) != F_PROPER) {
+		// filters and positions (src/input_sam.c:231-300)
+		uint32_t flt = FLT_NONE;
+		if ((flag & F_PAIRED) && !keep_unmatched) {
+			if ((flag & (F_PROPER | F_UNMAP | F_MUNMAP | F_QCFAIL | F_SECONDARY | F_SUPP | F_DUP)) != F_PROPER) {
+				if (flag & (F_SECONDARY | F_SUPP)) flt = FLT_SECONDARY;
+				else if (flag & F_UNMAP) flt = FLT_UNMAPPED;
+				else if (flag & F_MUNMAP) flt = FLT_MATE_UNMAPPED;
+				else if (flag & F_QCFAIL) flt = FLT_QC;
+				else if (flag & F_DUP) { if (!ignore_dup) flt = FLT_DUPLICATE; }
+				else flt = FLT_NOT_CORRECTLY_ALIGNED;
+			}
+		} else if (flag & (F_UNMAP | F_QCFAIL | F_SECONDARY | F_SUPP | F_DUP)) {
 			if (flag & (F_SECONDARY | F_SUPP)) flt = FLT_SECONDARY;
 			else if (flag & F_UNMAP) flt = FLT_UNMAPPED;
-			else if (flag & F_MUNMAP) flt = FLT_MATE_UNMAPPED;
 			else if (flag & F_QCFAIL) flt = FLT_QC;
-			else if (flag & F_DUP) { if (!ignore_dup) flt = FLT_DUPLICATE; }
-			else flt = FLT_NOT_CORRECTLY_ALIGNED;
+			else if (flag & F_DUP) flt = FLT_DUPLICATE;
 		}
-	} else if (flag & (F_UNMAP | F_QCFAIL | F_SECONDARY | F_SUPP | F_DUP)) {
-		if (flag & (F_SECONDARY | F_SUPP)) flt = FLT_SECONDARY;
-		else if (flag & F_UNMAP) flt = FLT_UNMAPPED;
-		else if (flag & F_QCFAIL) flt = FLT_QC;
-		else if (flag & F_DUP) flt = FLT_DUPLICATE;
-	}
-	bool mis_matched = (flag & (F_MUNMAP | F_PROPER)) != F_PROPER;
-	const bool reverse = flag & F_REVERSE, second = flag & F_READ2;
-	const bool mult_seg = (flag & (F_PAIRED | F_MUNMAP)) == F_PAIRED;
-	uint32_t fwd = reverse ? (uint32_t)(mpos + 1) : (uint32_t)(pos + 1);
-	uint32_t rev = reverse ? (uint32_t)(pos + 1) : (uint32_t)(mpos + 1);
-	if (mapq < mapq_thresh && !flt) flt = FLT_MAPQ;
-	if (mult_seg) {
-		if (tid != mtid) { if (!flt) flt = FLT_MISMATCH_CHR; if (keep_unmatched) mis_matched = true; }
-		if (!flt) {
-			const uint64_t is = (uint64_t)(isize < 0 ? -(int64_t)isize : (int64_t)isize);
-			if (is > (uint64_t)max_tlen) { flt = FLT_INSERT_SIZE; if (keep_unmatched) mis_matched = true; }
+		bool mis_matched = (flag & (F_MUNMAP | F_PROPER)) != F_PROPER;
+		const bool reverse = flag & F_REVERSE, second = flag & F_READ2;
+		const bool mult_seg = (flag & (F_PAIRED | F_MUNMAP)) == F_PAIRED;
+		uint32_t fwd = reverse ? (uint32_t)(mpos + 1) : (uint32_t)(pos + 1);
+		uint32_t rev = reverse ? (uint32_t)(pos + 1) : (uint32_t)(mpos + 1);
+		if (mapq < mapq_thresh && !flt) flt = FLT_MAPQ;
+		if (mult_seg) {
+			if (tid != mtid) { if (!flt) flt = FLT_MISMATCH_CHR; if (keep_unmatched) mis_matched = true; }
+			if (!flt) {
+				const uint64_t is = (uint64_t)(isize < 0 ? -(int64_t)isize : (int64_t)isize);
+				if (is > (uint64_t)max_tlen) { flt = FLT_INSERT_SIZE; if (keep_unmatched) mis_matched = true; }
+			}
+			if (reverse ? pos < mpos : pos > mpos) { if (!flt) flt = FLT_ORIENTATION; if (keep_unmatched) mis_matched = true; }
+			if (mis_matched) { if (reverse) fwd = 0; else rev = 0; }
 		}
-		if (reverse ? pos < mpos : pos > mpos) { if (!flt) flt = FLT_ORIENTATION; if (keep_unmatched) mis_matched = true; }
-		if (mis_matched) { if (reverse) fwd = 0; else rev = 0; }
+		const bool dropped = flt && !(keep_unmatched && (flt == FLT_INSERT_SIZE || flt == FLT_MISMATCH_CHR || flt == FLT_ORIENTATION));
+
+		const uint8_t *cigar = p + 32 + l_qname;
+		seq = cigar + 4 * (size_t)n_cigar;
+		const uint8_t *qual = seq + (((size_t)l_qseq + 1) >> 1);
+		const uint8_t *aux = qual + l_qseq, *end = p + block_size;
+		boff = read_off[w];
+		const uint32_t moff = mm_off[w];
+		decode = !dropped;
+
+		bsgpu_record r;
+		memset(&r, 0, sizeof(r));
+		r.ret = dropped ? 1 : 0;
+		r.filtered = flt;
+		r.forward_position = fwd;
+		r.reverse_position = rev;
+		r.alignment_flag = (!mult_seg || mis_matched) ? flag & ~F_PAIRED : flag;
+		r.reverse = reverse;
+		r.orientation = ((second && reverse) || !(second || reverse)) ? 0 : 1;
+		r.mapq = (uint8_t)mapq;
+		r.tid = tid;
+		if (!dropped) {
+			// CIGAR -> events (src/input_sam.c:90-136); note CIGAR I -> DEL, D -> INS, P treated like S
+			uint32_t position = 0, span = 0, n = 0;
+			for (uint32_t i = 0; i < n_cigar; i++) {
+				const uint32_t c = ld_u32(cigar + 4 * (size_t)i), len = c >> 4, op = c & 15u;
+				uint32_t type = 0;
+				switch (op) {
+				case 0: case 7: case 8: position += len; span += len; break;
+				case 4: case 6: type = 3; break;
+				case 1: type = 2; break;
+				case 2: type = 1; break;
+				default: break;
+				}
+				if (type) {
+					bsgpu_misms m;
+					m.type = type; m.position = position; m.size = len;
+					misms[moff + n++] = m;
+					if (type == 1) span += len; else position += len;
+				}
+			}
+			r.align_length = position;
+			r.reference_span = span;
+			r.mm_off = moff;
+			r.mm_n = n;
+			r.read_off = boff;
+			r.read_len = (uint32_t)l_qseq;
+			r.bs_strand = (uint8_t)strand_from_tags(aux, end);
+			// the qualities get_al_qual looks at: byte k of mate k (src/al_utils.c:26)
+			for (int k = 0; k < 2 && k < l_qseq; k++) {
+				const uint32_t byte = seq[k >> 1], nib = k ? (byte & 15u) : (byte >> 4);
+				const bool known = nib == 1 || nib == 2 || nib == 4 || nib == 8;
+				r.q01[k] = known ? (uint8_t)min((uint32_t)qual[k], (uint32_t)BSGPU_MAX_QUAL) : (uint8_t)0;
+			}
+		}
+		out[w] = r;
 	}
-	const bool dropped = flt && !(keep_unmatched && (flt == FLT_INSERT_SIZE || flt == FLT_MISMATCH_CHR || flt == FLT_ORIENTATION));
-
-	const uint8_t *cigar = p + 32 + l_qname;
-	const uint8_t *seq = cigar + 4 * (size_t)n_cigar;
-	const uint8_t *qual = seq + (((size_t)l_qseq + 1) >> 1);
-	const uint8_t *aux = qual + l_qseq, *end = p + block_size;
-	const uint32_t boff = read_off[w], moff = mm_off[w];
-
-	if (!dropped) {
-		// ---- sequence and qualities (src/input_sam.c:61-88): lanes stride over the bases
-		uint8_t *dst = bases + boff;
-		for (int32_t k = lane; k < l_qseq; k += 32) {
-			const uint32_t byte = seq[k >> 1];
+	// ---- phase 2: sequence and qualities (src/input_sam.c:61-88), record by record with the whole warp
+	const uint32_t todo = __ballot_sync(0xffffffffu, decode);
+	const unsigned long long seq_bits = (unsigned long long)(uintptr_t)seq;
+	for (uint32_t m = todo; m; m &= m - 1) {
+		const int j = __ffs(m) - 1;
+		const uint8_t *sq = (const uint8_t *)(uintptr_t)__shfl_sync(0xffffffffu, seq_bits, j);
+		const int32_t ls = __shfl_sync(0xffffffffu, l_qseq, j);
+		const uint8_t *ql = sq + (((size_t)ls + 1) >> 1);
+		uint8_t *dst = bases + __shfl_sync(0xffffffffu, boff, j);
+		for (int32_t k = lane; k < ls; k += 32) {
+			const uint32_t byte = sq[k >> 1];
 			const uint32_t nib = (k & 1) ? (byte & 15u) : (byte >> 4);
 			// 1 2 4 8 -> A C G T; everything else is N and becomes the zero byte
 			const uint32_t base = nib == 1 ? 0u : (nib == 2 ? 1u : (nib == 4 ? 2u : 3u));
 			const bool known = nib == 1 || nib == 2 || nib == 4 || nib == 8;
-			const uint32_t q = min((uint32_t)qual[k], (uint32_t)BSGPU_MAX_QUAL);
+			const uint32_t q = min((uint32_t)ql[k], (uint32_t)BSGPU_MAX_QUAL);
 			dst[k] = known ? (uint8_t)(base | q << 2) : (uint8_t)0;
 		}
 	}
-	if (lane) return;
-
-	bsgpu_record r;
-	memset(&r, 0, sizeof(r));
-	r.ret = dropped ? 1 : 0;
-	r.filtered = flt;
-	r.forward_position = fwd;
-	r.reverse_position = rev;
-	r.alignment_flag = (!mult_seg || mis_matched) ? flag & ~F_PAIRED : flag;
-	r.reverse = reverse;
-	r.orientation = ((second && reverse) || !(second || reverse)) ? 0 : 1;
-	r.mapq = (uint8_t)mapq;
-	r.tid = tid;
-	if (!dropped) {
-		// ---- CIGAR -> events (src/input_sam.c:90-136); note CIGAR I -> DEL, D -> INS, P treated like S
-		uint32_t position = 0, span = 0, n = 0;
-		for (uint32_t i = 0; i < n_cigar; i++) {
-			const uint32_t c = ld_u32(cigar + 4 * (size_t)i), len = c >> 4, op = c & 15u;
-			uint32_t type = 0;
-			switch (op) {
-			case 0: case 7: case 8: position += len; span += len; break;
-			case 4: case 6: type = 3; break;
-			case 1: type = 2; break;
-			case 2: type = 1; break;
-			default: break;
-			}
-			if (type) {
-				bsgpu_misms m;
-				m.type = type; m.position = position; m.size = len;
-				misms[moff + n++] = m;
-				if (type == 1) span += len; else position += len;
-			}
-		}
-		r.align_length = position;
-		r.reference_span = span;
-		r.mm_off = moff;
-		r.mm_n = n;
-		r.read_off = boff;
-		r.read_len = (uint32_t)l_qseq;
-		r.bs_strand = (uint8_t)strand_from_tags(aux, end);
-		// the qualities get_al_qual looks at: byte k of mate k (src/al_utils.c:26)
-		for (int k = 0; k < 2 && k < l_qseq; k++) {
-			const uint32_t byte = seq[k >> 1], nib = k ? (byte & 15u) : (byte >> 4);
-			const bool known = nib == 1 || nib == 2 || nib == 4 || nib == 8;
-			r.q01[k] = known ? (uint8_t)min((uint32_t)qual[k], (uint32_t)BSGPU_MAX_QUAL) : (uint8_t)0;
-		}
-	}
-	out[w] = r;
 }
 
 }  // namespace
@@ -215,7 +235,7 @@ cudaError_t launch_decode_records(const void *bam, const void *rec_off, const vo
 		uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup, void *out, void *bases, void *misms,
 		cudaStream_t stream, int *launches) {
 	if (!nrec) return cudaSuccess;
-	const unsigned grid = (unsigned)((nrec + kDecodeWarps - 1) / kDecodeWarps);
+	const unsigned grid = (unsigned)((nrec + kDecodeWarps * 32 - 1) / (kDecodeWarps * 32));
 	k_decode_records<<<grid, kDecodeWarps * 32, 0, stream>>>((const uint8_t *)bam, (const uint64_t *)rec_off, (const uint32_t *)read_off,
 		(const uint32_t *)mm_off, nrec, mapq_thresh, max_tlen, keep_unmatched, ignore_dup, (bsgpu_record *)out, (uint8_t *)bases, (bsgpu_misms *)misms);
 	*launches += 1;
