@@ -775,7 +775,18 @@ int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_target
 	double t_wait = 0;
 	CertainState cst;
 	std::vector<size_t> starts;
-	BuildJob *job = nullptr;
+	// the builder threads of a job read the pinned arrays of the context: whatever way this function is left, the job is
+	// joined first and the device is quiet
+	struct JobGuard {
+		bsgpu_ctx *c; BuildJob *job = nullptr;
+		~JobGuard() {
+			if (job) build_blocks_finish(job);
+			cudaStreamSynchronize(c->slot[0].stream); cudaStreamSynchronize(c->slot[1].stream);
+			cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
+			for (bool &b : c->ring_busy) b = false;
+		}
+	} guard{c};
+	BuildJob *&job = guard.job;
 	for (size_t ck = 0; ck < chunk_end.size() && ret == BSGPU_OK; ck++) {
 		const double w0 = now();
 		CU(cudaEventSynchronize(c->rd_done[ck]));
@@ -833,11 +844,10 @@ int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_target
 		build_blocks_finish(job);
 		job = nullptr;
 	}
-	cudaStreamSynchronize(c->slot[0].stream);
-	cudaStreamSynchronize(c->slot[1].stream);
-	cudaStreamSynchronize(c->stream);
-	cudaStreamSynchronize(c->copy_stream);
-	for (bool &b : c->ring_busy) b = false;
+	CU(cudaStreamSynchronize(c->slot[0].stream));
+	CU(cudaStreamSynchronize(c->slot[1].stream));
+	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->copy_stream));
 	if (ret != BSGPU_OK) return ret;
 	CU(cudaMemcpy(after, c->d_counters, sizeof(after), cudaMemcpyDeviceToHost));
 	if (after[2] != before[2]) return fail("bsgpu_call_bam: Error in CIGAR - illegal soft clip in %llu template(s)", after[2] - before[2]);
