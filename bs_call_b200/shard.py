@@ -85,6 +85,30 @@ def merge_in_coordinate_order(per_rank):
     return [p for _, p in flat]
 
 
+def split_records_by_contig(bam, owner_of_contig: Sequence[int], n_ranks: int):
+    """Level 1 for a coordinate-sorted BAM record stream (the bytes after the header of an uncompressed BAM): records of
+    contig c go to rank owner_of_contig[c], order preserved, so every rank's stream is itself coordinate sorted and holds
+    whole contigs -- each can be handed to bsgpu_call_bam as it is.  Records without a contig (refID < 0) are dropped
+    (read_input asserts curr_tid >= 0, src/get_template_vector.c:119).  Returns one uint8 array per rank."""
+    import numpy as np
+    bam = np.ascontiguousarray(bam, dtype=np.uint8)
+    parts = [[] for _ in range(n_ranks)]
+    at, n = 0, len(bam)
+    run_start, run_owner = 0, None
+    while at < n:
+        bs = int(bam[at:at + 4].view("<i4")[0])
+        tid = int(bam[at + 4:at + 8].view("<i4")[0])
+        owner = owner_of_contig[tid] if 0 <= tid < len(owner_of_contig) else None
+        if owner != run_owner:
+            if run_owner is not None:
+                parts[run_owner].append(bam[run_start:at])
+            run_start, run_owner = at, owner
+        at += 4 + bs
+    if run_owner is not None:
+        parts[run_owner].append(bam[run_start:at])
+    return [np.concatenate(p) if p else np.zeros(0, dtype=np.uint8) for p in parts]
+
+
 HG38_CONTIGS = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
                 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
                 58617616, 64444167, 46709983, 50818468, 156040895, 57227415]

@@ -92,3 +92,50 @@ def test_two_rank_gloo_shard_and_merge(tmp_path):
                          capture_output=True, text=True, timeout=300, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert "MERGE_OK 2" in res.stdout
+
+
+BAM_WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+import torch.distributed as dist
+from bs_call_b200 import shard
+from oracle.bindings import Oracle
+from tests import bamgen
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+o = Oracle()
+bam, n, tl, refs = bamgen.make_stream(55, n_contigs=3, contig_len=4000)
+owner = shard.lpt_assign([int(v) for v in tl], world)
+mine = shard.split_records_by_contig(bam, owner, world)[rank]
+blocks, tm, b, m, vcf = o.read_input(mine, tl, refs, run_chain=True)
+out = [(shard.Region(int(k["tid"]), int(k["x"]), int(k["y"])),
+        vcf[int(k["vcf_off"]):int(k["vcf_off"]) + int(k["y"]) - int(k["x"]) + 1].tobytes()) for k in blocks]
+gathered = [None] * world
+dist.all_gather_object(gathered, out)
+dist.barrier()
+if rank == 0:
+    # consecutive blocks of a contig may share one (uncovered) position: merge on (contig, start) without the overlap check
+    flat = sorted((it for lst in gathered for it in lst), key=lambda it: (it[0].contig, it[0].start))
+    wb, wt, wbb, wm, wv = o.read_input(bam, tl, refs, run_chain=True)
+    assert len(flat) == len(wb)
+    for (reg, payload), k in zip(flat, wb):
+        assert (reg.contig, reg.start, reg.stop) == (int(k["tid"]), int(k["x"]), int(k["y"]))
+        assert payload == wv[int(k["vcf_off"]):int(k["vcf_off"]) + int(k["y"]) - int(k["x"]) + 1].tobytes()
+    assert sorted(set(owner)) == list(range(world))
+    print("BAM_MERGE_OK", world, len(flat))
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_bam_stream_sharded_by_contig(tmp_path):
+    """level-1 sharding of a BAM record stream: each rank runs the whole chain (the CPU oracle stands in for the device)
+    on the contigs it owns; merged in coordinate order the blocks are those of the single-process run"""
+    script = tmp_path / "bam_worker.py"
+    script.write_text(BAM_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29534", str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "BAM_MERGE_OK 2" in res.stdout
