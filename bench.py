@@ -144,6 +144,28 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Run this rank (and so the pinned buffers it allocates and the reader's host threads it starts) on the CPUs of the
+    NUMA node its GPU hangs off.  Best effort: returns a note for the JSON line."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "gpu %s reports no numa node" % bus
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no allowed cpu on numa node %d" % node
+        os.sched_setaffinity(0, cpus)
+        return "bound to numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:
+        return "not bound (%s)" % type(e).__name__
+
+
 def bam_path(args, gpu, bslib, torch, np, stream, rank, world, local):
     """Synthetic coordinate-sorted paired-end WGBS record stream (30x, 150 bp, 5 % positional duplicates, coverage gaps
     every ~100 kb so that the reader cuts blocks) through bsgpu_call_bam with pinned host buffers: H2D of the records,
@@ -275,9 +297,10 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    numa_note = bind_to_gpu_numa_node(torch, local) if world > 1 else "single rank: not bound"
     if world > 1:
         # the reader's host stages (framer, block builder) run thread pools: share the cores between the ranks of the box
-        per_rank = str(max(2, (os.cpu_count() or 2) // world))
+        per_rank = str(max(2, min(len(os.sched_getaffinity(0)), (os.cpu_count() or 2) // world)))
         os.environ.setdefault("BSGPU_BUILDER_THREADS", per_rank)
         os.environ.setdefault("BSGPU_FRAMER_THREADS", per_rank)
     gpu = bslib.BsGpu(device=local)
@@ -561,7 +584,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "BASELINE.json configs[1]: likelihood microbench, 1e9 synthetic per-site count vectors per GPU",
                            "sites_per_gpu": n_sites, "sites_called_per_gpu": called_total, "mean_depth": MEAN_DEPTH, "seed": SEED,
-                           "parallelism": "sites sharded over %d rank(s), no collective" % world,
+                           "parallelism": "sites sharded over %d rank(s), no collective" % world, "host": numa_note,
                            "l2": "inputs larger than L2: each step streams %.1f GB of distinct records" % (n_sites * 105 / 1e9)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "block_path": block, "bam_path": bam, "parity_spot_check": parity}
