@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Randomised stress of the reader path on a GPU box (not collected by pytest): many seeded record streams with random
+reader options and random host-pipeline settings (chunked upload, builder pieces, framer threads) through bsgpu_call_bam,
+block by block against the oracle chain.   usage: python tests/fuzz_reader.py [first_seed] [n_seeds]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+from bs_call_b200 import lib as bslib  # noqa: E402
+from oracle.bindings import Oracle  # noqa: E402
+from tests import bamgen, util  # noqa: E402
+
+first = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+count = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+gpu, oracle = bslib.BsGpu(), Oracle()
+sites = 0
+for seed in range(first, first + count):
+    rng = np.random.default_rng(seed)
+    bam, n, tl, refs = bamgen.make_stream(seed, dup=float(rng.choice([0.0, 0.1, 0.3])), junk=float(rng.choice([0.0, 0.1, 0.3])))
+    o = dict(mapq_thresh=int(rng.integers(0, 40)), max_template_len=int(rng.integers(200, 1500)), keep_unmatched=bool(rng.random() < 0.3),
+             ignore_duplicates=bool(rng.random() < 0.3), keep_duplicates=bool(rng.random() < 0.3))
+    for k, v in (("BSGPU_READER_CHUNK_MIN_BYTES", rng.choice(["1", "1000000000"])), ("BSGPU_BUILDER_THREADS", str(int(rng.integers(1, 9)))),
+                 ("BSGPU_BUILDER_MIN_RECORDS", rng.choice(["1", "1000000000"])), ("BSGPU_FRAMER_THREADS", str(int(rng.integers(1, 9)))),
+                 ("BSGPU_FRAMER_MIN_BYTES", rng.choice(["1", "1000000000"]))):
+        os.environ[k] = str(v)
+    wbk, wt, wb, wm, wv = oracle.read_input(bam, tl, refs, run_chain=True, **o)
+    blocks, vcf = gpu.call_bam(bam, tl, refs, bslib.reader_params(**o))
+    assert len(blocks) == len(wbk), (seed, len(blocks), len(wbk))
+    for b, w in zip(blocks, wbk):
+        assert (b["tid"], b["x"], b["y"], b["n_templates"], b["first_template"]) == (w["tid"], w["x"], w["y"], w["n_templates"], w["first_template"]), seed
+        sz = int(w["y"]) - int(w["x"]) + 1
+        sites += util.assert_vcf_close(vcf[int(b["vcf_off"]):int(b["vcf_off"]) + sz], wv[int(w["vcf_off"]):int(w["vcf_off"]) + sz])
+print("fuzz ok: seeds %d..%d, %d called sites compared" % (first, first + count - 1, sites))
