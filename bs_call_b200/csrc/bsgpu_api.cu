@@ -684,6 +684,7 @@ int bsgpu_build_blocks(const uint8_t *bam, size_t nbytes, const bsgpu_record *re
 	const int rc = build_blocks_host(bam, rec_off.data(), rec, nrec, rp->keep_unmatched, rp->keep_duplicates, b, t, &nt);
 	int ret = BSGPU_OK;
 	if (rc == -4) ret = fail("bsgpu_build_blocks: duplicate read name among waiting mates");
+	else if (rc == -5) ret = fail("bsgpu_build_blocks: the two mates of a template disagree about their positions");
 	else if (rc) ret = fail("bsgpu_build_blocks: failed (%d)", rc);
 	else if (b.size() > block_cap || nt > tmpl_cap) ret = fail("bsgpu_build_blocks: need room for %zu blocks, %zu templates", b.size(), nt);
 	else {
@@ -814,6 +815,7 @@ int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_target
 		const int rc = build_blocks_piece(job, p, &pb, &base, &nt_piece);
 		t_wait += now() - w0;
 		if (rc == -4) { ret = fail("bsgpu_call_bam: duplicate read name among waiting mates"); break; }
+		if (rc == -5) { ret = fail("bsgpu_call_bam: the two mates of a template disagree about their positions"); break; }
 		if (rc) { ret = fail("bsgpu_call_bam: block builder failed (%d)", rc); break; }
 		if (nbk + pb->size() > block_cap) { ret = fail("bsgpu_call_bam: blocks[] too small"); break; }
 		for (size_t b0 = 0; b0 < pb->size() && ret == BSGPU_OK;) {

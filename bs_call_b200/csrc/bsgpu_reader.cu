@@ -568,6 +568,7 @@ struct BlockBuilder {
 					waiting = names.find(name, nlen, nh);
 					if (waiting) {
 						Tmpl &t = list[waiting->ix];
+						if (al.fwd != t.fwd || al.rev != t.rev) return -5;      // the reference asserts here (src/get_template_vector.c:239)
 						t.rec[ix] = (int64_t)ri; t.mapq[ix] = r.mapq; t.span[ix] = r.reference_span;
 						list_name[waiting->ix] = -1;
 						NameTable::kill(waiting);

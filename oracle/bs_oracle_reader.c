@@ -351,6 +351,7 @@ static int build_blocks(const uint8_t *bam, size_t nbytes, const bso_record *rec
 				hent *h = h_find(hash, v.qname, v.l_qname);
 				if (h) {
 					tmpl_s *t = st.list + h->ix;
+					if (al.fwd != t->fwd || al.rev != t->rev) { o->err = -5; break; }      /* assert() in the reference (:239) */
 					t->rec[ix] = (int64_t)ri; t->mapq[ix] = r->mapq; t->span[ix] = r->reference_span;
 					st.list_h[h->ix] = NULL;
 					h->live = 0;

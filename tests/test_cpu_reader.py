@@ -111,3 +111,21 @@ def test_parallel_framer_equals_sequential(oracle, monkeypatch, blind):
         lib.build_blocks(bam[:-9], rec)
     with pytest.raises(lib.BsGpuError):
         lib.build_blocks(bam, rec[:-1])
+
+
+@pytest.mark.parametrize("seed,code", [(2002, "positions"), (2017, "duplicate read name")])
+def test_streams_the_reference_aborts_on_are_errors(oracle, seed, code):
+    """read_input() asserts that a mate agrees with its waiting partner about both positions
+    (src/get_template_vector.c:239) and treats a read name that is already waiting as fatal (:327-328): the oracle and
+    the product's builder return an error on exactly those streams (found by fuzzing against the compiled reference,
+    which aborts the process there)"""
+    rng = np.random.default_rng(seed)
+    bam, n, tl, refs = bamgen.make_stream(seed, dup=float(rng.choice([0.0, 0.1, 0.3])), junk=float(rng.choice([0.0, 0.1, 0.3])))
+    o = dict(mapq_thresh=int(rng.integers(0, 40)), max_template_len=int(rng.integers(200, 1500)), keep_unmatched=bool(rng.random() < 0.3),
+             ignore_duplicates=bool(rng.random() < 0.3), keep_duplicates=bool(rng.random() < 0.3))
+    with pytest.raises(RuntimeError):
+        oracle.read_input(bam, tl, refs, **o)
+    orec, ob, om = oracle.decode_records(bam, o["mapq_thresh"], o["max_template_len"], o["keep_unmatched"], o["ignore_duplicates"])
+    rec = descriptors_from_oracle(orec, ob, bam)
+    with pytest.raises(lib.BsGpuError, match=code):
+        lib.build_blocks(bam, rec, lib.reader_params(**o))
