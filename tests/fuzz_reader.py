@@ -14,7 +14,7 @@ from tests import bamgen, util  # noqa: E402
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 count = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 gpu, oracle = bslib.BsGpu(), Oracle()
-sites = 0
+sites = refused = 0
 for seed in range(first, first + count):
     rng = np.random.default_rng(seed)
     bam, n, tl, refs = bamgen.make_stream(seed, dup=float(rng.choice([0.0, 0.1, 0.3])), junk=float(rng.choice([0.0, 0.1, 0.3])))
@@ -24,11 +24,21 @@ for seed in range(first, first + count):
                  ("BSGPU_BUILDER_MIN_RECORDS", rng.choice(["1", "1000000000"])), ("BSGPU_FRAMER_THREADS", str(int(rng.integers(1, 9)))),
                  ("BSGPU_FRAMER_MIN_BYTES", rng.choice(["1", "1000000000"]))):
         os.environ[k] = str(v)
-    wbk, wt, wb, wm, wv = oracle.read_input(bam, tl, refs, run_chain=True, **o)
+    try:
+        wbk, wt, wb, wm, wv = oracle.read_input(bam, tl, refs, run_chain=True, **o)
+    except RuntimeError:
+        # a stream on which the reference aborts (duplicate waiting read name, mates that disagree, a mate before its
+        # block window): the product must refuse it as well
+        try:
+            gpu.call_bam(bam, tl, refs, bslib.reader_params(**o))
+        except bslib.BsGpuError:
+            refused += 1
+            continue
+        raise AssertionError("seed %d: the oracle refuses the stream, the product does not" % seed)
     blocks, vcf = gpu.call_bam(bam, tl, refs, bslib.reader_params(**o))
     assert len(blocks) == len(wbk), (seed, len(blocks), len(wbk))
     for b, w in zip(blocks, wbk):
         assert (b["tid"], b["x"], b["y"], b["n_templates"], b["first_template"]) == (w["tid"], w["x"], w["y"], w["n_templates"], w["first_template"]), seed
         sz = int(w["y"]) - int(w["x"]) + 1
         sites += util.assert_vcf_close(vcf[int(b["vcf_off"]):int(b["vcf_off"]) + sz], wv[int(w["vcf_off"]):int(w["vcf_off"]) + sz])
-print("fuzz ok: seeds %d..%d, %d called sites compared" % (first, first + count - 1, sites))
+print("fuzz ok: seeds %d..%d, %d called sites compared, %d streams refused by both sides" % (first, first + count - 1, sites, refused))
