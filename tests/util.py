@@ -61,3 +61,31 @@ def assert_gt_meth_close(got, got_skip, want, want_skip, exact_doubles=False):
 def assert_vcf_close(got, want):
     assert (got["ready"] == 1).all()
     return assert_gt_meth_close(got["gtm"], got["skip"], want["gtm"], want["skip"])
+
+
+def writer_fields(gtm, skip):
+    """The integer fields the reference's writer derives from a gt_meth record (src/print_vcf.c:140-217, 584-591):
+    genotype (first strict maximum of gt_prob[]), QUAL / GQ phred, FS, QD and the FILTER bits q20 / qd2 / fs60 / mq40 /
+    mac1.  numpy restatement used to check that ulp-level differences in the doubles never reach the VCF."""
+    m = np.asarray(skip) == 0
+    g = gtm[m]
+    prob = g["gt_prob"]
+    gt = np.argmax(prob, axis=1)                      # first maximum, like the strict '>' scan of the writer
+    z = prob[np.arange(len(g)), gt]
+    z1 = np.exp(z * np.log(10.0))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ph = np.where(z1 >= 1.0, 255, np.minimum((-10.0 * np.log(1.0 - np.minimum(z1, 1.0 - 1e-300)) / np.log(10.0)), 255.0)).astype(np.int64)
+    ph = np.where(z1 >= 1.0, 255, ph)
+    fs = (-g["fisher_strand"] * 10.0 + 0.5).astype(np.int64)
+    c = g["counts"].astype(np.int64)
+    dp1 = c[:, :4].sum(axis=1)
+    qd = np.where(dp1 > 0, ph // np.maximum(dp1, 1), ph)
+    flt = (ph < 20) * 1 + (qd < 2) * 2 + (fs > 60) * 4 + (g["mq"] < 40) * 8
+    a = {1: (c[:, 1] + c[:, 5] + c[:, 7], c[:, 0] + c[:, 4]), 2: (c[:, 2] + c[:, 6], c[:, 0]), 3: (c[:, 3] + c[:, 7], c[:, 0] + c[:, 4]),
+         5: (c[:, 2] + c[:, 6] + c[:, 4], c[:, 1] + c[:, 5] + c[:, 7]), 6: (c[:, 3], c[:, 1] + c[:, 5]),
+         8: (c[:, 3] + c[:, 7], c[:, 2] + c[:, 6] + c[:, 4])}
+    mac1 = np.zeros(len(g), dtype=bool)
+    for k, (u, v) in a.items():
+        mac1 |= (gt == k) & ((u <= 1) | (v <= 1))
+    flt = np.where((flt == 0) & mac1, 128, flt)
+    return {"gt": gt, "phred": ph, "fs": fs, "qd": qd, "flt": flt}
