@@ -118,7 +118,32 @@ struct bsgpu_ctx {
 	bool ring_busy[3] = {false, false, false};   // output ring slot may still be copying out (deferred block_run)
 	bsgpu_stats stats;
 	int launches = 0;
+	// --report-file side channels (bsgpu_profile_enable)
+	bool profile_on = false;
+	ProfDev *d_prof = nullptr;
+	DevBuf prof_scratch;                         // used16 | cand | chunkmax of the window being normalised
+	int prof_parity = 0;                         // which ProfDev::used[] holds the running value
+	ProfArgs prof_args;
 };
+
+// profile arguments of a normalise launch over n templates and a window of sz sites (NULL while the profile is off)
+static const ProfArgs *profile_for(bsgpu_ctx *c, size_t n, uint32_t sz, cudaError_t *err) {
+	*err = cudaSuccess;
+	if (!c->profile_on || !n) return nullptr;
+	const size_t nchunks = (n + kProfChunk - 1) / kProfChunk;
+	const size_t a = (n * 2 + 15) & ~(size_t)15, b = (n + 15) & ~(size_t)15;
+	*err = c->prof_scratch.reserve(a + b + nchunks * 4);
+	if (*err != cudaSuccess) return nullptr;
+	ProfArgs &pa = c->prof_args;
+	pa.ref = (const uint8_t *)c->ref.p;
+	pa.refn = sz + 1;
+	pa.min_qual = c->params.min_qual;
+	pa.prof = c->d_prof;
+	pa.used16 = (uint16_t *)c->prof_scratch.p;
+	pa.cand = (uint8_t *)c->prof_scratch.p + a;
+	pa.chunkmax = (uint32_t *)((uint8_t *)c->prof_scratch.p + a + b);
+	return &pa;
+}
 
 extern "C" {
 
@@ -213,6 +238,8 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->d_const) cudaFree(c->d_const);
 	if (c->d_counters) cudaFree(c->d_counters);
+	if (c->d_prof) cudaFree(c->d_prof);
+	c->prof_scratch.release();
 	delete c;
 }
 
@@ -531,19 +558,61 @@ int bsgpu_process_block(bsgpu_ctx *c, const bsgpu_template *t, size_t n, const u
 	if (nmisms) CU(cudaMemcpyAsync(c->misms.p, misms, nmisms * sizeof(bsgpu_misms), cudaMemcpyHostToDevice, c->stream));
 	if (nbases) CU(cudaMemcpyAsync(c->bases.p, bases, nbases, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->ooff.p, off.data(), (2 * n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->ref.p, ref, sz, cudaMemcpyHostToDevice, c->stream));
+	const size_t nref = (size_t)sz + (c->profile_on ? 1 : 0);      // the profile looks one code past the block (src/meth_profile.c:70)
+	CU(cudaMemcpyAsync(c->ref.p, ref, nref, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaStreamSynchronize(c->stream));          // `off` is a pageable temporary: the copy must finish before it dies
-	c->stats.h2d_bytes += n * sizeof(bsgpu_template) + nmisms * sizeof(bsgpu_misms) + nbases + (2 * n + 1) * 4 + sz;
+	c->stats.h2d_bytes += n * sizeof(bsgpu_template) + nmisms * sizeof(bsgpu_misms) + nbases + (2 * n + 1) * 4 + nref;
 	unsigned long long before[4], after[4];
 	CU(cudaMemcpy(before, c->d_counters, sizeof(before), cudaMemcpyDeviceToHost));
+	cudaError_t perr;
+	const ProfArgs *pa = profile_for(c, n, sz, &perr);
+	CU(perr);
 	CU(launch_normalise(c->tmpl.p, n, c->bases.p, c->misms.p, c->ooff.p, c->obases.p, c->segs.p, spm, x, y,
-			c->params.left_trim, c->params.right_trim, c->d_counters, c->stream, &c->launches));
+			c->params.left_trim, c->params.right_trim, c->d_counters, pa, c->prof_parity, c->stream, &c->launches));
+	if (pa) c->prof_parity ^= 1;
 	CU(cudaStreamSynchronize(c->stream));
 	CU(cudaMemcpy(after, c->d_counters, sizeof(after), cudaMemcpyDeviceToHost));
 	if (after[2] != before[2]) return fail("bsgpu_process_block: Error in CIGAR - illegal soft clip in %llu template(s)", after[2] - before[2]);
 	if (after[3] != before[3]) return fail("bsgpu_process_block: %llu mate(s) start before the block window", after[3] - before[3]);
 	if (x_out) *x_out = x;
 	return block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, out, 1, false);
+}
+
+// ------------------------------------------------------------------------------------------------
+// --report-file side channels
+// ------------------------------------------------------------------------------------------------
+int bsgpu_profile_enable(bsgpu_ctx *c, int on) {
+	if (!c) return fail("bsgpu_profile_enable: null context");
+	CU(cudaSetDevice(c->device));
+	if (on && !c->d_prof) {
+		CU(cudaMalloc(&c->d_prof, sizeof(ProfDev)));
+		CU(cudaMemset(c->d_prof, 0, sizeof(ProfDev)));
+		c->prof_parity = 0;
+	}
+	c->profile_on = on != 0;
+	return BSGPU_OK;
+}
+
+int bsgpu_profile_read(bsgpu_ctx *c, bsgpu_profile *out, int reset) {
+	if (!c || !out) return fail("bsgpu_profile_read: null argument");
+	if (!c->d_prof) return fail("bsgpu_profile_read: the profile was never enabled");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	static ProfDev h;
+	CU(cudaMemcpy(&h, c->d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+	c->stats.d2h_bytes += sizeof(h);
+	if (h.too_long) return fail("bsgpu profile: %llu template(s) reach beyond original read position %d", h.too_long, BSGPU_PROFILE_MAX - 2);
+	memset(out, 0, sizeof(*out));
+	out->used = h.used[c->prof_parity];
+	for (uint32_t i = 0; i < out->used && i < BSGPU_PROFILE_MAX; i++) for (int k = 0; k < 4; k++) out->conv_cts[i][k] = h.conv[i][k];
+	for (int k = 0; k < 5; k++) out->base_filter[k] = h.base_filter[k];
+	out->reads = h.reads;
+	out->read_bases = h.read_bases;
+	if (reset) {
+		CU(cudaMemset(c->d_prof, 0, sizeof(ProfDev)));
+		c->prof_parity = 0;
+	}
+	return BSGPU_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -723,8 +792,8 @@ static int call_window(bsgpu_ctx *c, const bsgpu_template *tm, size_t nt, uint32
 	const size_t nseg = nt * 2 * (size_t)spm;
 	// reference window [x, y]: N beyond the contig end (src/get_sequence.c:36-41)
 	std::vector<uint8_t> &refw = c->ref_tmp;
-	refw.resize(sz);
-	for (uint32_t i = 0; i < sz; i++) { const uint32_t pos = x + i; refw[i] = pos < ctg_len ? codes[pos - 1] : 0; }
+	refw.resize((size_t)sz + 1);               // one code past the window for the conversion profile (src/meth_profile.c:70)
+	for (uint32_t i = 0; i <= sz; i++) { const uint32_t pos = x + i; refw[i] = pos < ctg_len ? codes[pos - 1] : 0; }
 	// Everything below is queued behind the previous window on the context stream; nothing waits on the host.  (Growing a
 	// device buffer frees the old one, which synchronises the device; `off` / `refw` are pageable, so their copies are
 	// staged before cudaMemcpyAsync returns and the vectors can be refilled for the next window.)
@@ -735,10 +804,14 @@ static int call_window(bsgpu_ctx *c, const bsgpu_template *tm, size_t nt, uint32
 	CU(c->ref.reserve((size_t)sz + 16));
 	CU(cudaMemcpyAsync(c->tmpl.p, tm, nt * sizeof(bsgpu_template), cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->ooff.p, off.data(), (2 * nt + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->ref.p, refw.data(), sz, cudaMemcpyHostToDevice, c->stream));
-	c->stats.h2d_bytes += nt * sizeof(bsgpu_template) + (2 * nt + 1) * 4 + sz;
+	CU(cudaMemcpyAsync(c->ref.p, refw.data(), (size_t)sz + 1, cudaMemcpyHostToDevice, c->stream));
+	c->stats.h2d_bytes += nt * sizeof(bsgpu_template) + (2 * nt + 1) * 4 + sz + 1;
+	cudaError_t perr;
+	const ProfArgs *pa = profile_for(c, nt, sz, &perr);
+	CU(perr);
 	CU(launch_normalise(c->tmpl.p, nt, c->rd_bases.p, c->rd_misms.p, c->ooff.p, c->obases.p, c->segs.p, spm, x, y,
-			c->params.left_trim, c->params.right_trim, c->d_counters, c->stream, &c->launches));
+			c->params.left_trim, c->params.right_trim, c->d_counters, pa, c->prof_parity, c->stream, &c->launches));
+	if (pa) c->prof_parity ^= 1;
 	return block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, out, 1, true);
 }
 

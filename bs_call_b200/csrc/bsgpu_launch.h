@@ -3,6 +3,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "bsgpu.h"
 
 namespace bsgpu {
 
@@ -42,10 +43,29 @@ cudaError_t launch_synth_bam(uint64_t seed, size_t ntemplates, uint32_t read_len
 		const void *rank, void *out, cudaStream_t stream, int *launches);
 cudaError_t launch_synth_ref(uint64_t seed, uint32_t x, uint32_t sz, void *ref, cudaStream_t stream, int *launches);
 
-// raw templates -> reads in reference coordinates + segment records (bsgpu_normalise.cu)
+// device-resident totals of the --report-file side channels (bsgpu_profile) and what a launch needs to add to them
+struct ProfDev {
+	unsigned long long conv[BSGPU_PROFILE_MAX][4];
+	unsigned long long base_filter[5];
+	unsigned long long reads, read_bases, too_long;
+	uint32_t used[2];                // running `used` of the profile vector, double buffered by launch parity
+};
+struct ProfArgs {
+	const uint8_t *ref;              // codes of the block window, index 0 = position x
+	uint32_t refn;                   // codes available (window size + 1)
+	uint32_t min_qual;
+	ProfDev *prof;
+	uint16_t *used16;                // per template: max_pos + 1
+	uint8_t *cand;                   // per template: 0, or 1 + counter of the byte that lands on entry `used`
+	uint32_t *chunkmax;              // maximum of used16 over every kProfChunk templates
+};
+constexpr uint32_t kProfChunk = 4096;
+
+// raw templates -> reads in reference coordinates + segment records (bsgpu_normalise.cu); prof != NULL: also the
+// profile (two more launches)
 cudaError_t launch_normalise(const void *tmpl, size_t n, const void *bases, void *ev_work, const void *out_off, void *obases,
 		void *segs, uint32_t segs_per_mate, uint32_t x, uint32_t y, const uint32_t left_trim[2], const uint32_t right_trim[2],
-		unsigned long long *counters, cudaStream_t stream, int *launches);
+		unsigned long long *counters, const ProfArgs *prof, int parity, cudaStream_t stream, int *launches);
 
 // reader side (bsgpu_reader.cu)
 cudaError_t launch_decode_records(const void *bam, const void *rec_off, const void *read_off, const void *mm_off, size_t nrec,

@@ -149,6 +149,18 @@ typedef struct {
 	uint8_t keep_duplicates;   /* -d: no positional duplicate removal */
 } bsgpu_reader_params;
 
+/* The read-level side channels of --report-file that the reference gathers inside the replaced functions (bs_stats,
+ * include/bs_call.h:124-146): the non-CpG conversion profile of meth_profile() (src/meth_profile.c:48-76) and the base /
+ * read tallies of process_template_vector() and its helpers (src/process_template.c:52-63, src/al_utils.c:141,150,308). */
+#define BSGPU_PROFILE_MAX 1024
+typedef struct {
+	uint64_t conv_cts[BSGPU_PROFILE_MAX][4]; /* stats->meth_profile: entry i holds meth_cts of original read position i - 1 */
+	uint32_t used;                           /* gt_vector_get_used(stats->meth_profile); entries >= used are zero */
+	uint32_t pad_;
+	uint64_t base_filter[5];                 /* stats->base_filter[base_none, base_trim, base_clip, base_overlap, base_lowqual] */
+	uint64_t reads, read_bases;              /* what process_template_vector adds to filter_cts / filter_bases[gt_flt_none] */
+} bsgpu_profile;
+
 typedef struct bsgpu_ctx bsgpu_ctx;
 
 /* counters a context keeps; all monotonically increasing */
@@ -202,6 +214,14 @@ int bsgpu_stage_templates(const bsgpu_template *t, size_t n, const uint8_t *base
 int bsgpu_process_block(bsgpu_ctx *ctx, const bsgpu_template *t, size_t n, const uint8_t *bases, size_t nbases,
 		const bsgpu_misms *misms, size_t nmisms, const uint8_t *ref, uint32_t y,
 		uint32_t *x_out, bsgpu_gt_vcf *out);
+
+/* Side channels of --report-file (stats != NULL in the reference).  While enabled, bsgpu_process_block and
+ * bsgpu_call_bam also gather a bsgpu_profile over every template they normalise, in call order; `ref` of
+ * bsgpu_process_block must then hold one more code (position y + 1; the reference's ref1 string has it,
+ * src/process_template.c:29-30).  bsgpu_profile_read waits for the queued work, copies the totals out and, if `reset`,
+ * starts again from zero. */
+int bsgpu_profile_enable(bsgpu_ctx *ctx, int on);
+int bsgpu_profile_read(bsgpu_ctx *ctx, bsgpu_profile *out, int reset);
 
 /* ---- reader side: `bam` is the byte stream that follows the header of an uncompressed BAM file (what remains of the
  *      file after BGZF inflation: int32 block_size + record, repeated), coordinate sorted ---- */

@@ -86,6 +86,20 @@ def _read_input(fn, bam, target_len, ctg_codes, mapq_thresh, max_template_len, k
             vcf[:nv.value].copy())
 
 
+PROFILE_MAX = 1024
+
+
+class BsoProfile(C.Structure):
+    _fields_ = [("conv_cts", (C.c_uint64 * 4) * PROFILE_MAX), ("used", C.c_uint32), ("pad", C.c_uint32),
+                ("base_filter", C.c_uint64 * 5), ("reads", C.c_uint64), ("read_bases", C.c_uint64)]
+
+
+def profile_dict(used, conv, base_filter, reads, read_bases):
+    """common shape of the --report-file side channels: conv[i] = meth_cts of original read position i - 1"""
+    return dict(used=int(used), conv=np.asarray(conv, dtype=np.uint64)[:int(used)].copy(),
+                base_filter=np.asarray(base_filter, dtype=np.uint64).copy(), reads=int(reads), read_bases=int(read_bases))
+
+
 class BsoParams(C.Structure):
     _fields_ = [("under_conv", C.c_double), ("over_conv", C.c_double), ("ref_bias", C.c_double),
                 ("left_trim", C.c_uint32 * 2), ("right_trim", C.c_uint32 * 2), ("min_qual", C.c_uint8)]
@@ -190,6 +204,20 @@ class Oracle:
         return _read_input(self.lib.bso_read_input, bam, target_len, ctg_codes, mapq_thresh, max_template_len,
                            keep_unmatched, ignore_duplicates, keep_duplicates, run_chain)
 
+    def profile_enable(self, on=True):
+        """--report-file side channels (process-wide in the library); process_block then wants codes for [x, y + 1]"""
+        self.lib.bso_profile_enable(C.c_int(1 if on else 0))
+        self._profile_on = bool(on)
+
+    def profile_reset(self):
+        self.lib.bso_profile_reset()
+
+    def profile_read(self):
+        pr = BsoProfile()
+        self.lib.bso_profile_read(C.byref(pr))
+        conv = np.ctypeslib.as_array(pr.conv_cts).reshape(PROFILE_MAX, 4)
+        return profile_dict(pr.used, conv, list(pr.base_filter), pr.reads, pr.read_bases)
+
     def process_block(self, templates, bases, misms, refcodes, y):
         """refcodes: codes for positions [x, y] where x = max(first-2, 1)."""
         templates = _c(templates, TEMPLATE)
@@ -199,7 +227,7 @@ class Oracle:
         first = int(templates[0]["forward_position"]) or int(templates[0]["reverse_position"])
         x = first - 2 if first > 2 else 1
         sz = y - x + 1
-        assert len(refcodes) >= sz
+        assert len(refcodes) >= sz + (1 if getattr(self, "_profile_on", False) else 0)
         pile = np.zeros(sz, dtype=PILEUP)
         vcf = np.zeros(sz, dtype=GT_VCF)
         xo = C.c_uint32(0)
@@ -311,6 +339,26 @@ class Reference:
         if rc:
             raise RuntimeError("bsref_call_block failed: %d" % rc)
         return pile, vcf
+
+    def stats_enable(self, on=True):
+        """give the reference a bs_stats (what --report-file does): meth_profile() and the tallies become live"""
+        self.lib.bsref_stats_enable(C.c_int(1 if on else 0))
+
+    def stats_reset(self):
+        self.lib.bsref_stats_reset()
+
+    def stats_read(self):
+        """-> profile_dict plus the raw filter_cts / filter_bases arrays of bs_stats"""
+        conv = np.zeros((1 << 16, 4), dtype=np.uint64)
+        bf = np.zeros(5, dtype=np.uint64)
+        fc = np.zeros(15, dtype=np.uint64)
+        fb = np.zeros(15, dtype=np.uint64)
+        self.lib.bsref_stats_read.restype = C.c_uint32
+        used = self.lib.bsref_stats_read(_p(conv), C.c_size_t(len(conv)), _p(bf), _p(fc), _p(fb))
+        d = profile_dict(used, conv, bf, fc[0], fb[0])
+        d["filter_cts"] = fc
+        d["filter_bases"] = fb
+        return d
 
     def decode_records(self, bam, mapq_thresh=20, max_template_len=1000, keep_unmatched=False, ignore_dup=False):
         """raw BAM records through the reference's get_next_align_details() (src/input_sam.c:222)"""

@@ -380,7 +380,70 @@ typedef struct {
 	int present[2];
 	bso_misms *mm[2];
 	uint32_t nmm[2];
+	uint32_t tl[2], tr[2];        /* trim_left / trim_right of src/process_template.c:42-45 */
+	int *orig[2];                 /* original read position of every byte (profile only) */
 } tmpl_w;
+
+/* ---- --report-file side channels gathered on this path (bs_stats, include/bs_call.h:124-146) ---- */
+#define PROF_ALLOC 70000
+static struct {
+	int on;
+	uint64_t (*mem)[4];           /* stats->meth_profile->memory */
+	size_t used;
+	uint64_t base_filter[5], reads, read_bases;
+} prof;
+
+void bso_profile_enable(int on) {
+	if (on && !prof.mem) prof.mem = calloc(PROF_ALLOC, sizeof(*prof.mem));
+	prof.on = on;
+}
+void bso_profile_reset(void) {
+	if (prof.mem) memset(prof.mem, 0, PROF_ALLOC * sizeof(*prof.mem));
+	prof.used = 0;
+	memset(prof.base_filter, 0, sizeof(prof.base_filter));
+	prof.reads = prof.read_bases = 0;
+}
+void bso_profile_read(bso_profile *out) {
+	memset(out, 0, sizeof(*out));
+	out->used = (uint32_t)prof.used;
+	for (size_t i = 0; i < prof.used && i < BSO_PROFILE_MAX; i++) memcpy(out->conv_cts[i], prof.mem[i], sizeof(prof.mem[i]));
+	memcpy(out->base_filter, prof.base_filter, sizeof(prof.base_filter));
+	out->reads = prof.reads;
+	out->read_bases = prof.read_bases;
+}
+
+/* meth_profile() for one normalised template (src/meth_profile.c:48-76).  refcodes[0] is position x. */
+static void profile_template(const tmpl_w *w, int bs_strand, int max_pos, const uint8_t *refcodes, uint32_t x) {
+	/* [prev][cur] -> 4: a C not followed by G or N (looked up one step ahead), 8: a G not preceded by C or N */
+	static const uint8_t ctx_tab[5][5] = {
+		{0, 0, 0, 0, 0}, {0, 0, 0, 8, 0}, {0, 4, 4, 0, 4}, {0, 0, 0, 8, 0}, {0, 0, 0, 8, 0} };
+	/* flt_tab rows (src/init_param.c:57-69): per strand, per base, for MIN_QUAL <= q < FLT_QUAL; low two bits pick the counter */
+	static const uint8_t row[3][4] = { {11, 6, 10, 7}, {11, 4, 10, 5}, {9, 6, 8, 7} };
+	if ((size_t)max_pos + 1 > prof.used) {
+		/* gt_vector_reserve(.., zero_mem = true) clears from the old `used` to the end of the allocation
+		 * (gt/src/gt_vector.c:34-37), then used is raised */
+		memset(prof.mem + prof.used, 0, (PROF_ALLOC - prof.used) * sizeof(*prof.mem));
+		prof.used = (size_t)max_pos + 1;
+	}
+	uint64_t (*mc)[4] = prof.mem + 1;
+	for (int k = 0; k < 2; k++) {
+		if (!w->present[k] || !w->len[k]) continue;
+		const uint32_t pos = w->pos[k];
+		const uint8_t *rf = refcodes + (pos - x);
+		uint32_t prev = 0, cur = 0;
+		if (pos > x) { prev = rf[-1]; cur = *rf++; }
+		uint32_t mask = prev < 5 && cur < 5 ? ctx_tab[prev][cur] : 0;
+		for (uint32_t j = 0; j < w->len[k]; j++) {
+			const uint8_t b = w->rd[k][j];
+			const uint32_t q = b >> 2;
+			const uint32_t xx = (q >= 20 && q < BSO_FLT_QUAL) ? row[bs_strand][b & 3] : 0;      /* MIN_QUAL, include/bs_call.h:28 */
+			const uint32_t carried = (xx & mask) >> 1;
+			prev = cur; cur = *rf++;
+			mask = prev < 5 && cur < 5 ? ctx_tab[prev][cur] : 0;
+			mc[w->orig[k][j]][xx & 3] += (((xx & mask) | carried) >> 2) & 1;
+		}
+	}
+}
 
 static void mark_trimmed(uint8_t *sp, uint32_t rl, uint32_t left, uint32_t right) {
 	for (uint32_t i = 0; i < left && i < rl; i++) sp[i] = (sp[i] & 3) | (BSO_FLT_QUAL << 2);
@@ -415,9 +478,13 @@ static int strip_soft_clips(tmpl_w *w) {
 					if (m.size >= rl) return -1;
 					shift = m.size;
 					cut_left(w, k, shift);
+					w->tl[k] = shift;
+					if (prof.on) prof.base_filter[2] += shift;
 				} else {
 					if (m.position + m.size != rl) return -1;
 					cut_right(w, k, m.size);
+					w->tr[k] = m.size;
+					if (prof.on) prof.base_filter[2] += m.size;
 				}
 			} else {
 				if (nclip) m.position -= shift;
@@ -444,11 +511,12 @@ static void drop_events(tmpl_w *w, int k, uint32_t z) {
 	w->nmm[k] -= z;
 }
 
-static void resolve_overlap(tmpl_w *w) {
-	if (!(w->present[0] && w->len[0] && w->present[1] && w->len[1])) return;
+/* returns -1 when nothing is shared, else (mate that was cut) | (cut at its right end) << 1 */
+static int overlap_cut(tmpl_w *w) {
+	if (!(w->present[0] && w->len[0] && w->present[1] && w->len[1])) return -1;
 	const int rev = !(w->pos[0] <= w->pos[1]);
 	const int32_t overlap = rev ? (int32_t)(w->span[1] + w->pos[1] - w->pos[0]) : (int32_t)(w->span[0] - w->pos[1] + w->pos[0]);
-	if (!(w->pos[0] + w->span[0] >= w->pos[1])) return;
+	if (!(w->pos[0] + w->span[0] >= w->pos[1])) return -1;
 	/* which mate loses the shared part: the one with the shorter reference span, else the lower mean quality,
 	 * else mate 0  (:185-202) */
 	int tr;
@@ -463,7 +531,7 @@ static void resolve_overlap(tmpl_w *w) {
 	if (!nmm) {
 		if (at_right) cut_right(w, tr, (uint32_t)overlap);
 		else cut_left(w, tr, (uint32_t)overlap);
-		return;
+		return tr | at_right << 1;
 	}
 	int done = 0;
 	int64_t adj = 0;
@@ -522,6 +590,19 @@ static void resolve_overlap(tmpl_w *w) {
 			w->nmm[tr] = 0;
 		}
 	}
+	return tr | at_right << 1;
+}
+
+/* handle_overlap including its bookkeeping (src/al_utils.c:304-314): what was cut is added to the base_overlap tally
+ * and to trim_right (cut at the right end) or trim_left of the mate that lost it */
+static void resolve_overlap(tmpl_w *w) {
+	const uint32_t before[2] = { w->len[0], w->len[1] };
+	const int c = overlap_cut(w);
+	if (c < 0) return;
+	const int tr = c & 1;
+	if (prof.on) prof.base_filter[3] += (before[0] - w->len[0]) + (before[1] - w->len[1]);
+	if (c >> 1) w->tr[tr] += before[tr] - w->len[tr];
+	else w->tl[tr] += before[tr] - w->len[tr];
 }
 
 /* rewrite mate k into reference coordinates: zero-fill INS (reference bases missing from the read), drop DEL */
@@ -532,19 +613,29 @@ static uint32_t to_ref_coords(tmpl_w *w, int k) {
 	for (uint32_t z = 0; z < w->nmm[k]; z++) {
 		const bso_misms *m = w->mm[k] + z;
 		const uint32_t at = m->position + adj;
+		int *og = w->orig[k];
 		if (m->type == BSO_INS) {
 			memmove(sp + at + m->size, sp + at, used - at);
 			memset(sp + at, 0, m->size);
+			if (og) {
+				memmove(og + at + m->size, og + at, sizeof(int) * (used - at));
+				for (uint32_t i = 0; i < m->size; i++) og[at + i] = -1;
+			}
 			adj += m->size;
 			used += m->size;
 		} else if (m->type == BSO_DEL) {
 			memmove(sp + at, sp + at + m->size, used - at - m->size);
+			if (og) memmove(og + at, og + at + m->size, sizeof(int) * (used - at - m->size));
 			adj -= m->size;
 			used -= m->size;
 		}
 	}
 	return used;
 }
+
+/* the block's reference window for the profile: set by bso_process_block around its call of bso_normalise_block */
+static const uint8_t *prof_ref;
+static uint32_t prof_x;
 
 int bso_normalise_block(const bso_template *t, size_t n, const uint8_t *bases, const bso_misms *mm,
 		const bso_params *p, bso_template *out_t, uint8_t *out_bases, size_t out_cap, size_t *out_used) {
@@ -578,7 +669,40 @@ int bso_normalise_block(const bso_template *t, size_t n, const uint8_t *bases, c
 		if (strip_soft_clips(&w) < 0) ret = -1;
 		else {
 			resolve_overlap(&w);
-			for (int k = 0; k < 2; k++) if (w.present[k]) w.len[k] = to_ref_coords(&w, k);
+			int max_pos = 0;
+			for (int k = 0; k < 2; k++) {
+				if (!w.present[k]) continue;
+				if (prof.on) {
+					/* tallies over the bytes that are left (src/process_template.c:52-62) and the map back to positions in
+					 * the original read: slot 0 counts up from trim_left, slot 1 down from rdl + trim_right - 1 (:80-91) */
+					const int rdl = (int)w.len[k];
+					for (int j = 0; j < rdl; j++) {
+						const uint8_t q = w.rd[k][j] >> 2;
+						if (q == BSO_FLT_QUAL) prof.base_filter[1]++;
+						else if (q < p->min_qual) prof.base_filter[4]++;
+						else prof.base_filter[0]++;
+					}
+					prof.reads++;
+					prof.read_bases += (uint64_t)rdl;
+					uint32_t grow = 0;
+					for (uint32_t z = 0; z < w.nmm[k]; z++) if (w.mm[k][z].type == BSO_INS) grow += w.mm[k][z].size;
+					w.orig[k] = malloc(sizeof(int) * ((size_t)rdl + grow + 8));
+					int mpos;
+					if (k) {
+						const int top = rdl + (int)w.tr[k] - 1;
+						for (int j = 0; j < rdl; j++) w.orig[k][j] = top - j;
+						mpos = top;
+					} else {
+						const int first = (int)w.tl[k];
+						for (int j = 0; j < rdl; j++) w.orig[k][j] = first + j;
+						mpos = first + rdl;
+					}
+					if (mpos > max_pos) max_pos = mpos;
+				}
+				w.len[k] = to_ref_coords(&w, k);
+			}
+			if (prof.on && prof_ref) profile_template(&w, t->bs_strand, max_pos, prof_ref, prof_x);
+			for (int k = 0; k < 2; k++) { free(w.orig[k]); w.orig[k] = NULL; }
 		}
 		bso_template *o = out_t + i;
 		memset(o, 0, sizeof(*o));
@@ -623,7 +747,9 @@ int bso_process_block(const bso_template *t, size_t n, const uint8_t *bases, con
 	bso_template *nt = malloc(sizeof(bso_template) * n);
 	uint8_t *nb = malloc(cap + 16);
 	size_t used = 0;
+	prof_ref = refcodes; prof_x = x;              /* with the profile on, refcodes holds one more code (y + 1) */
 	int ret = bso_normalise_block(t, n, bases, mm, p, nt, nb, cap + 16, &used);
+	prof_ref = NULL;
 	if (!ret) {
 		bso_pileup *pl = pile_out ? pile_out : malloc(sizeof(bso_pileup) * sz);
 		bso_pileup_block(nt, n, nb, x, y, p, pl);

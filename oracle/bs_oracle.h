@@ -101,6 +101,21 @@ int bso_process_block(const bso_template *t, size_t n, const uint8_t *bases, con
 		const uint8_t *refcodes /* codes for [x, y] */, uint32_t y, const bso_params *p,
 		uint32_t *x_out, bso_pileup *pile_out, bso_gt_vcf *vcf_out);
 
+/* --report-file side channels of this path (bs_stats, include/bs_call.h:124-146): the non-CpG conversion profile of
+ * meth_profile() (src/meth_profile.c:48-76) and the tallies of process_template_vector (src/process_template.c:52-63,
+ * src/al_utils.c:141,150,308).  While enabled, bso_process_block accumulates them (process-wide, in call order) and its
+ * refcodes must hold one more code (position y + 1). */
+#define BSO_PROFILE_MAX 1024
+typedef struct {
+	uint64_t conv_cts[BSO_PROFILE_MAX][4];
+	uint32_t used, pad;
+	uint64_t base_filter[5];
+	uint64_t reads, read_bases;
+} bso_profile;
+void bso_profile_enable(int on);
+void bso_profile_reset(void);
+void bso_profile_read(bso_profile *out);
+
 /* ---- reader side (bs_oracle_reader.c) ---- */
 /* what get_next_align_details() yields for one BAM record (src/input_sam.c:222-312) */
 typedef struct {

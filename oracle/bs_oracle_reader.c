@@ -476,7 +476,7 @@ int bso_read_input(const uint8_t *bam, size_t nbytes, int n_targets, const uint3
 			if (ov + sz > vcf_cap || (int)bk->tid >= n_targets) { rc = -3; break; }
 			/* reference window [x, y]: codes of the contig, N beyond its end (src/get_sequence.c:20-55) */
 			uint8_t *rc_ = calloc((size_t)sz + 4, 1);
-			for (uint32_t i = 0; i < sz; i++) { const uint32_t pos = bk->x + i; rc_[i] = pos < target_len[bk->tid] ? ctg_codes[bk->tid][pos - 1] : 0; }
+			for (uint32_t i = 0; i <= sz; i++) { const uint32_t pos = bk->x + i; rc_[i] = pos < target_len[bk->tid] ? ctg_codes[bk->tid][pos - 1] : 0; }      /* one past y: the profile looks ahead */
 			uint32_t xo = 0;
 			bso_pileup *pile = malloc(sizeof(bso_pileup) * sz);
 			const int e = bso_process_block(tmpl + bk->first_template, bk->n_templates, bases, misms, rc_, bk->y, &p, &xo, pile, vcf + ov);

@@ -68,8 +68,8 @@ gt_vector *__wrap_gt_vector_new(size_t n, size_t es) {
 bool load_sequence(ctg_t * const contig, faidx_t *idx, const bool calc_gc) { return contig->seq == NULL; }
 void free_sequence(ctg_t * const contig) { }
 
-/* meth-profile ring drainer: same hand-off protocol as src/process.c:20-41 (stats are NULL so
- * meth_profile() itself is a no-op, src/meth_profile.c:49) */
+/* meth-profile ring drainer: same hand-off protocol as src/process.c:20-41 (meth_profile() is a no-op
+ * unless bsref_stats_enable(1) was called, src/meth_profile.c:49) */
 static void *drain_mprof(void *arg) {
 	work_t * const w = &par.work;
 	pthread_mutex_lock(&w->mprof_mutex);
@@ -155,6 +155,37 @@ void bsref_shutdown(void) {
 	pthread_mutex_unlock(&par.work.mprof_mutex);
 	pthread_join(drain_thr, NULL);
 	inited = 0;
+}
+
+/* ---- --report-file side channels: give the reference a bs_stats the way init_stats does (src/stats.c:304-312; only the
+ * meth_profile vector is touched on this path) and read back what meth_profile(), process_template_vector(),
+ * trim_soft_clips(), handle_overlap() and read_input() put there ---- */
+static bs_stats ref_stats;
+void bsref_stats_enable(int on) {
+	if (on && !ref_stats.meth_profile) {
+		ref_stats.meth_profile = gt_vector_new(256, sizeof(meth_cts));
+		memset(ref_stats.meth_profile->memory, 0, sizeof(meth_cts) * ref_stats.meth_profile->elements_allocated);
+	}
+	par.work.stats = on ? &ref_stats : NULL;
+}
+void bsref_stats_reset(void) {
+	gt_vector *mp = ref_stats.meth_profile;
+	memset(&ref_stats, 0, sizeof(ref_stats));
+	ref_stats.meth_profile = mp;
+	if (mp) {
+		memset(mp->memory, 0, sizeof(meth_cts) * mp->elements_allocated);
+		gt_vector_set_used(mp, 0);
+	}
+}
+/* conv: room for cap entries of 4 counters; returns `used` of the profile vector */
+uint32_t bsref_stats_read(uint64_t *conv, size_t cap, uint64_t base_filter[5], uint64_t filter_cts[15], uint64_t filter_bases[15]) {
+	gt_vector *mp = ref_stats.meth_profile;
+	const size_t used = mp ? gt_vector_get_used(mp) : 0;
+	for (size_t i = 0; i < used && i < cap; i++) memcpy(conv + 4 * i, gt_vector_get_elm(mp, i, meth_cts)->conv_cts, 4 * sizeof(uint64_t));
+	memcpy(base_filter, ref_stats.base_filter, sizeof(ref_stats.base_filter));
+	memcpy(filter_cts, ref_stats.filter_cts, sizeof(ref_stats.filter_cts));
+	memcpy(filter_bases, ref_stats.filter_bases, sizeof(ref_stats.filter_bases));
+	return (uint32_t)used;
 }
 
 /* Direct calls into the model */

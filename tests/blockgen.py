@@ -21,6 +21,14 @@ def random_reference(rng, length, gc=0.41, n_runs=0):
     return ref
 
 
+def window_codes(ref, lo, hi):
+    """codes of positions [lo, hi] as get_sequence_string() hands them out: N from the contig's last position on
+    (src/get_sequence.c:41-48)"""
+    pos = np.arange(lo, hi + 1)
+    padded = np.concatenate([ref, np.zeros(max(0, hi - len(ref)) + 1, dtype=np.uint8)])
+    return np.where(pos < len(ref), padded[pos - 1], 0).astype(np.uint8)
+
+
 def _sample_genotypes(rng, ref, snp_rate):
     """two haplotypes as base indices 0..3 (N positions get A)."""
     base = np.where(ref > 0, ref - 1, 0).astype(np.uint8)

@@ -129,6 +129,75 @@ def test_process_block(reference, case, trims):
     _same_records(vcf_c, vcf_r, "gt_vcf via call_block")
 
 
+def same_profile(a, b, what=""):
+    assert a["used"] == b["used"], (what, a["used"], b["used"])
+    np.testing.assert_array_equal(a["conv"], b["conv"], err_msg=what)
+    np.testing.assert_array_equal(a["base_filter"], b["base_filter"], err_msg=what)
+    assert (a["reads"], a["read_bases"]) == (b["reads"], b["read_bases"]), what
+
+
+# the profile vector grows with the longest read seen so far and counts on its top entry are dropped (see
+# k_profile_resolve): the order of the blocks matters, so each run feeds several blocks of different shapes
+PROFILE_RUNS = [
+    [dict(depth=20, read_len=50, paired=False, nonconv_frac=0.2), dict(depth=20, read_len=100, paired=True), dict(depth=10, read_len=75, paired=False)],
+    [dict(depth=25, read_len=100, paired=True, indel_frac=0.4, clip_frac=0.4, frag_mean=130, frag_sd=40),
+     dict(depth=25, read_len=100, paired=True, single_mate_frac=0.5, clip_frac=0.3)],
+    [dict(depth=15, read_len=60, paired=True, frag_mean=90, frag_sd=20, indel_frac=0.5, clip_frac=0.5, n_frac=0.05, single_mate_frac=0.2)] * 3,
+]
+
+
+@pytest.mark.parametrize("run", range(len(PROFILE_RUNS)))
+@pytest.mark.parametrize("trims", [((0, 0), (0, 0)), ((5, 3), (2, 4))])
+def test_profile(reference, run, trims):
+    """--report-file side channels of the path (non-CpG conversion profile, base / read tallies): the restatement
+    against the reference's meth_profile() / process_template_vector() with stats switched on, block after block"""
+    from oracle.bindings import Oracle, Reference
+    lt, rt = trims
+    rng = np.random.default_rng(700 + run)
+    ref = blockgen.random_reference(rng, 4000, n_runs=2)
+    o = Oracle(left_trim=lt, right_trim=rt, min_qual=25 if run == 1 else 20)
+    r = Reference(left_trim=lt, right_trim=rt, min_qual=25 if run == 1 else 20)
+    r.stats_enable(True); r.stats_reset()
+    o.profile_enable(True); o.profile_reset()
+    try:
+        # last: a pile of reads at positions 1 and 2, where the FSM starts one code late (src/meth_profile.c:65)
+        blocks = [(150 + 40 * b, 2650 + 40 * b, case) for b, case in enumerate(PROFILE_RUNS[run])]
+        blocks.append((1, 3, dict(depth=4000, read_len=50, paired=run != 0, frag_mean=70, frag_sd=10, single_mate_frac=0.3 if run else 0.0)))
+        for b, (start, end, case) in enumerate(blocks):
+            T, B, M, y = blockgen.make_block(rng, ref, start, end, **case)
+            x, pile_r, vcf_r, ref_r, nt_r, nb_r = r.process_block(T, B, M, ref, y)
+            refw = blockgen.window_codes(ref, x, y + 1)
+            xo, pile_o, vcf_o = o.process_block(T, B, M, refw, y)
+            _same_records(vcf_o, vcf_r, "gt_vcf")
+            pr, po = r.stats_read(), o.profile_read()
+            same_profile(po, pr, "run %d block %d" % (run, b))
+        assert pr["conv"].sum() > 1000 and pr["base_filter"][0] > 0
+    finally:
+        r.stats_enable(False); o.profile_enable(False)
+        Reference()
+
+
+def test_profile_growth_drops_top_entry(reference):
+    """fresh profile, lone mates in either slot: whether the count of a slot-1 mate's first byte survives depends on
+    which templates came before it (gt_vector_reserve clears from the old `used` upwards, gt/src/gt_vector.c:34-37)"""
+    from oracle.bindings import Oracle, Reference
+    rng = np.random.default_rng(4242)
+    ref = blockgen.random_reference(rng, 3000)
+    o, r = Oracle(), Reference()
+    r.stats_enable(True); o.profile_enable(True)
+    try:
+        for b in range(40):
+            r.stats_reset(); o.profile_reset()
+            start = 20 + 60 * b
+            T, B, M, y = blockgen.make_block(rng, ref, start, start + 40, depth=30, read_len=int(rng.integers(30, 60)), paired=True,
+                                             single_mate_frac=1.0, clip_frac=0.3, conv=0.5)
+            x = r.process_block(T, B, M, ref, y)[0]
+            o.process_block(T, B, M, blockgen.window_codes(ref, x, y + 1), y)
+            same_profile(o.profile_read(), r.stats_read(), "block %d" % b)
+    finally:
+        r.stats_enable(False); o.profile_enable(False)
+
+
 def test_deep_block_uses_lgamma(reference):
     """500x single-end panel (config 4): strand tables with margins >= 256."""
     from oracle.bindings import Oracle
