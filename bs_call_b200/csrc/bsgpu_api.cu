@@ -33,14 +33,16 @@ void frame_scratch_free(FrameScratch *s);
 int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_off, std::vector<uint32_t> &read_off,
 		std::vector<uint32_t> &mm_off, uint64_t *nbases, uint64_t *nmisms, FrameScratch *scratch);
 int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
-		bool keep_duplicates, std::vector<bsgpu_block> &blocks, bsgpu_template *tmpl, size_t *ntmpl);
+		bool keep_duplicates, std::vector<bsgpu_block> &blocks, bsgpu_template *tmpl, size_t *ntmpl, uint64_t *tally);
 struct BuildJob;
 struct CertainState { int tid = -1; uint64_t maxend = 0; };
 void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts);
 BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t rbeg, size_t rend,
-		const std::vector<size_t> &starts, bool keep_unmatched, bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread);
+		const std::vector<size_t> &starts, bool keep_unmatched, bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread,
+		bool with_tally);
 BuildJob *build_blocks_start(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
-		bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread);
+		bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread, bool with_tally);
+const uint64_t *build_blocks_piece_tally(const BuildJob *job, size_t p);
 size_t build_blocks_pieces(const BuildJob *job);
 int build_blocks_piece(BuildJob *job, size_t p, const std::vector<bsgpu_block> **blocks, size_t *tmpl_base, size_t *ntmpl);
 void build_blocks_finish(BuildJob *job);
@@ -121,6 +123,7 @@ struct bsgpu_ctx {
 	// --report-file side channels (bsgpu_profile_enable)
 	bool profile_on = false;
 	ProfDev *d_prof = nullptr;
+	uint64_t reader_tally[30] = {0};             // read_input's filter_cts[15] | filter_bases[15] (host side, bsgpu_call_bam)
 	DevBuf prof_scratch;                         // used16 | cand | chunkmax of the window being normalised
 	int prof_parity = 0;                         // which ProfDev::used[] holds the running value
 	ProfArgs prof_args;
@@ -606,11 +609,13 @@ int bsgpu_profile_read(bsgpu_ctx *c, bsgpu_profile *out, int reset) {
 	out->used = h.used[c->prof_parity];
 	for (uint32_t i = 0; i < out->used && i < BSGPU_PROFILE_MAX; i++) for (int k = 0; k < 4; k++) out->conv_cts[i][k] = h.conv[i][k];
 	for (int k = 0; k < 5; k++) out->base_filter[k] = h.base_filter[k];
-	out->reads = h.reads;
-	out->read_bases = h.read_bases;
+	for (int k = 0; k < 15; k++) { out->filter_cts[k] = c->reader_tally[k]; out->filter_bases[k] = c->reader_tally[15 + k]; }
+	out->filter_cts[0] += h.reads;
+	out->filter_bases[0] += h.read_bases;
 	if (reset) {
 		CU(cudaMemset(c->d_prof, 0, sizeof(ProfDev)));
 		c->prof_parity = 0;
+		memset(c->reader_tally, 0, sizeof(c->reader_tally));
 	}
 	return BSGPU_OK;
 }
@@ -741,6 +746,14 @@ int bsgpu_decode_records(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const 
 
 int bsgpu_build_blocks(const uint8_t *bam, size_t nbytes, const bsgpu_record *rec, size_t nrec, const bsgpu_reader_params *rp,
 		bsgpu_block *blocks, size_t block_cap, size_t *nblocks, bsgpu_template *tmpl, size_t tmpl_cap, size_t *ntmpl) {
+	return bsgpu_build_blocks_tally(bam, nbytes, rec, nrec, rp, blocks, block_cap, nblocks, tmpl, tmpl_cap, ntmpl, nullptr, nullptr);
+}
+
+int bsgpu_build_blocks_tally(const uint8_t *bam, size_t nbytes, const bsgpu_record *rec, size_t nrec, const bsgpu_reader_params *rp,
+		bsgpu_block *blocks, size_t block_cap, size_t *nblocks, bsgpu_template *tmpl, size_t tmpl_cap, size_t *ntmpl,
+		uint64_t *filter_cts, uint64_t *filter_bases) {
+	if ((filter_cts == nullptr) != (filter_bases == nullptr)) return fail("bsgpu_build_blocks_tally: give both tally arrays or neither");
+	uint64_t tally[30] = {0};
 	if (!rp || !nblocks || !ntmpl || (nrec && (!bam || !rec))) return fail("bsgpu_build_blocks: null argument");
 	std::vector<uint64_t> rec_off;
 	std::vector<uint32_t> ro, mo;
@@ -750,7 +763,8 @@ int bsgpu_build_blocks(const uint8_t *bam, size_t nbytes, const bsgpu_record *re
 	bsgpu_template *t = tmpl_cap >= nrec ? tmpl : (bsgpu_template *)malloc((nrec + 1) * sizeof(bsgpu_template));      // build in place when there is room
 	if (!t) return fail("bsgpu_build_blocks: out of memory");
 	size_t nt = 0;
-	const int rc = build_blocks_host(bam, rec_off.data(), rec, nrec, rp->keep_unmatched, rp->keep_duplicates, b, t, &nt);
+	const int rc = build_blocks_host(bam, rec_off.data(), rec, nrec, rp->keep_unmatched, rp->keep_duplicates, b, t, &nt, filter_cts ? tally : nullptr);
+	if (!rc && filter_cts) for (int k = 0; k < 15; k++) { filter_cts[k] += tally[k]; filter_bases[k] += tally[15 + k]; }
 	int ret = BSGPU_OK;
 	if (rc == -4) ret = fail("bsgpu_build_blocks: duplicate read name among waiting mates");
 	else if (rc == -5) ret = fail("bsgpu_build_blocks: the two mates of a template disagree about their positions");
@@ -875,7 +889,7 @@ int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_target
 		if (upto <= built) continue;
 		std::vector<size_t> inside;
 		for (size_t v : starts) if (v > built && v < upto) inside.push_back(v);
-		job = build_blocks_start_range(bam, c->rec_off.data(), rec, built, upto, inside, rp->keep_unmatched, rp->keep_duplicates, tm, 2);
+		job = build_blocks_start_range(bam, c->rec_off.data(), rec, built, upto, inside, rp->keep_unmatched, rp->keep_duplicates, tm, 2, c->profile_on);
 		std::vector<size_t> keep;
 		for (size_t v : starts) if (v >= upto) keep.push_back(v);
 		starts.swap(keep);
@@ -891,6 +905,7 @@ int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_target
 		if (rc == -5) { ret = fail("bsgpu_call_bam: the two mates of a template disagree about their positions"); break; }
 		if (rc) { ret = fail("bsgpu_call_bam: block builder failed (%d)", rc); break; }
 		if (nbk + pb->size() > block_cap) { ret = fail("bsgpu_call_bam: blocks[] too small"); break; }
+		if (const uint64_t *pt = build_blocks_piece_tally(job, p)) for (int k = 0; k < 30; k++) c->reader_tally[k] += pt[k];
 		for (size_t b0 = 0; b0 < pb->size() && ret == BSGPU_OK;) {
 			size_t b1 = b0;
 			while (b1 < pb->size() && (*pb)[b1].tid == (*pb)[b0].tid) b1++;

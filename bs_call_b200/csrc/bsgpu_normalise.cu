@@ -355,8 +355,9 @@ __device__ void normalise_one(const NormArgs &a, const size_t i, const int lane,
 		}
 		const uint32_t row = t.bs_strand == 0 ? 0x7A6Bu : t.bs_strand == 1 ? 0x5A4Bu : 0x7869u;      // src/init_param.c:60-67
 		for (int k = 0; k < 2; k++) {
-			// the FSM starts one code late for a mate that begins at the window's first position (src/meth_profile.c:65)
-			pm[k].r0 = (int32_t)(pos[k] - a.x) - (pos[k] > a.x ? 0 : 1);
+			// the FSM starts one code late for a mate that begins at the block's first position (src/meth_profile.c:65),
+			// which only position 1 can be: blocks start two bases before their first template (src/process_template.c:27)
+			pm[k].r0 = (int32_t)(pos[k] - a.x) - (pos[k] == 1 ? 1 : 0);
 			pm[k].tab = row;
 			pm[k].k = (uint32_t)k;
 			pm[k].tl = mt[k].tl;

@@ -461,6 +461,9 @@ struct BlockBuilder {
 	std::vector<bsgpu_block> *blocks;
 	bsgpu_template *out = nullptr;       // templates of this builder, in publication order (room for one per record)
 	size_t nout = 0;
+	uint64_t *tally = nullptr;           // --report-file: filter_cts[15] then filter_bases[15] of read_input, or none
+	void count(int reason_cts, uint64_t cts, int reason_bases, uint64_t bases) { tally[reason_cts] += cts; tally[15 + reason_bases] += bases; }
+	uint32_t read_len_of(const Tmpl &t, int k) const { return t.rec[k] >= 0 ? rec[t.rec[k]].read_len : 0; }
 
 	uint32_t al_qual(const Tmpl &t) const {          // get_al_qual with its sq[k] indexing (src/al_utils.c:19-35)
 		uint32_t qual = 0, n = 0;
@@ -526,7 +529,14 @@ struct BlockBuilder {
 			if (ri + kAhead + 8 < nrec) __builtin_prefetch(bam + rec_off[ri + kAhead + 8] + 36);      // the name of a record further ahead
 			look_ahead(ri + kAhead);
 			const bsgpu_record &r = rec[ri];
-			if (r.ret > 0) continue;
+			if (r.ret > 0) {
+				if (tally) {                 // src/get_template_vector.c:104-107: l_seq of the record that was dropped
+					int32_t l_seq;
+					memcpy(&l_seq, bam + rec_off[ri] + 20, 4);
+					count((int)r.filtered, 1, (int)r.filtered, (uint64_t)(uint32_t)l_seq);
+				}
+				continue;
+			}
 			const int ix = r.reverse ? 1 : 0;
 			Tmpl al;
 			memset(&al, 0, sizeof(al));
@@ -573,6 +583,7 @@ struct BlockBuilder {
 						list_name[waiting->ix] = -1;
 						NameTable::kill(waiting);
 					} else {
+						if (tally) count(14, 1, 14, r.read_len);      // the partner never came (:243-246)
 						bool skip = false;
 						if (!keep_duplicates) { const uint32_t xx = r.reverse ? al.rev : al.fwd; if (xx >= start_pos) skip = true; }
 						if (!skip && keep_unmatched) {
@@ -612,6 +623,10 @@ struct BlockBuilder {
 									if (from_slot) { list_name[i] = (int64_t)ri; list_flag[i] = r.alignment_flag; }
 									al = old;
 								}
+								if (tally) {                 // the template that lost (:314-319)
+									const uint32_t len1 = read_len_of(al, 0), len2 = read_len_of(al, 1);
+									count(5, len1 && len2 ? 2 : 1, 5, (uint64_t)len1 + len2);
+								}
 								skip = true;
 							}
 						} else { curr_pos = pos; start_idx = read_idx; }
@@ -634,6 +649,7 @@ struct BlockBuilder {
 							if (al.fwd == a1.fwd && al.rev == a1.rev && al.bs_strand == a1.bs_strand && lone) {
 								// mapq[0] on both sides whichever strand the reads are on (reference behaviour)
 								if (a1.mapq[0] < al.mapq[0] || (a1.mapq[0] == al.mapq[0] && al_qual(a1) < al_qual(al))) { const Tmpl old = a1; a1 = al; al = old; }
+								if (tally) count(5, 1, 0, read_len_of(al, ix));      // a duplicate whose bases go under gt_flt_none (:361-364)
 								skip = true;
 							}
 						}
@@ -684,6 +700,7 @@ struct BuildJob {
 	std::vector<size_t> cuts;
 	std::vector<std::vector<bsgpu_block>> pb;
 	std::vector<size_t> pn;
+	std::vector<uint64_t> tally;         // 30 per piece when tallies were asked for
 	std::vector<int> rc;
 	std::vector<std::atomic<int>> done;
 	std::vector<std::thread> thr;
@@ -694,7 +711,8 @@ struct BuildJob {
 // records [rbeg, rend); rbeg is the start of the stream or a certain block start; `starts` = the certain block starts
 // inside the range (ascending), from which the cuts between pieces are chosen
 BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t rbeg, size_t rend,
-		const std::vector<size_t> &starts, bool keep_unmatched, bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread) {
+		const std::vector<size_t> &starts, bool keep_unmatched, bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread,
+		bool with_tally) {
 	unsigned want = std::thread::hardware_concurrency();
 	if (const char *e = getenv("BSGPU_BUILDER_THREADS")) want = (unsigned)atoi(e);
 	want = std::max(1u, std::min(want, 32u));
@@ -715,6 +733,7 @@ BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, 
 	const size_t np = cuts.size() - 1;
 	BuildJob *job = new BuildJob(np);
 	job->cuts = cuts;
+	if (with_tally) job->tally.assign(np * 30, 0);
 	const unsigned nthr = (unsigned)std::min<size_t>(want, np);
 	for (unsigned t = 0; t < nthr; t++) job->thr.emplace_back([=] {
 		for (;;) {
@@ -723,6 +742,7 @@ BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, 
 			BlockBuilder b;
 			b.bam = bam; b.rec_off = rec_off; b.rec = rec; b.blocks = &job->pb[p];
 			b.out = tmpl + job->cuts[p];
+			if (with_tally) b.tally = job->tally.data() + p * 30;
 			job->rc[p] = b.run(job->cuts[p], job->cuts[p + 1], keep_unmatched, keep_duplicates);
 			job->pn[p] = b.nout;
 			job->done[p].store(1, std::memory_order_release);
@@ -732,11 +752,11 @@ BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, 
 }
 
 BuildJob *build_blocks_start(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
-		bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread) {
+		bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread, bool with_tally) {
 	std::vector<size_t> starts;
 	CertainState st;
 	certain_block_starts(rec, 0, nrec, &st, starts);
-	return build_blocks_start_range(bam, rec_off, rec, 0, nrec, starts, keep_unmatched, keep_duplicates, tmpl, pieces_per_thread);
+	return build_blocks_start_range(bam, rec_off, rec, 0, nrec, starts, keep_unmatched, keep_duplicates, tmpl, pieces_per_thread, with_tally);
 }
 
 size_t build_blocks_pieces(const BuildJob *job) { return job->pb.size(); }
@@ -751,6 +771,9 @@ int build_blocks_piece(BuildJob *job, size_t p, const std::vector<bsgpu_block> *
 	return job->rc[p];
 }
 
+// read_input's tallies of piece p (valid once build_blocks_piece has returned it): 15 counts then 15 base sums, or NULL
+const uint64_t *build_blocks_piece_tally(const BuildJob *job, size_t p) { return job->tally.empty() ? nullptr : job->tally.data() + p * 30; }
+
 void build_blocks_finish(BuildJob *job) {
 	for (auto &t : job->thr) t.join();
 	delete job;
@@ -758,8 +781,8 @@ void build_blocks_finish(BuildJob *job) {
 
 // the whole build at once: `tmpl` must have room for nrec templates; *ntmpl receives the count, templates compacted
 int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
-		bool keep_duplicates, std::vector<bsgpu_block> &blocks, bsgpu_template *tmpl, size_t *ntmpl) {
-	BuildJob *job = build_blocks_start(bam, rec_off, rec, nrec, keep_unmatched, keep_duplicates, tmpl, 1);
+		bool keep_duplicates, std::vector<bsgpu_block> &blocks, bsgpu_template *tmpl, size_t *ntmpl, uint64_t *tally) {
+	BuildJob *job = build_blocks_start(bam, rec_off, rec, nrec, keep_unmatched, keep_duplicates, tmpl, 1, tally != nullptr);
 	const size_t np = build_blocks_pieces(job);
 	size_t at = 0;
 	int rc = 0;
@@ -769,6 +792,7 @@ int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_r
 		const int r = build_blocks_piece(job, p, &pb, &base, &n);
 		if (r && !rc) rc = r;
 		if (rc) continue;
+		if (tally) { const uint64_t *pt = build_blocks_piece_tally(job, p); for (int k = 0; k < 30; k++) tally[k] += pt[k]; }
 		for (bsgpu_block b : *pb) { b.first_template += (uint32_t)at; blocks.push_back(b); }
 		if (n && at != base) memmove(tmpl + at, tmpl + base, n * sizeof(bsgpu_template));      // close the gap (earlier pieces are done)
 		at += n;

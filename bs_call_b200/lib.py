@@ -22,7 +22,7 @@ EXPORTS = [
     "bsgpu_default_params", "bsgpu_init", "bsgpu_destroy", "bsgpu_last_error", "bsgpu_get_stats", "bsgpu_version",
     "bsgpu_sync", "bsgpu_host_alloc", "bsgpu_host_free",
     "bsgpu_call_sites", "bsgpu_pileup_block", "bsgpu_call_block", "bsgpu_stage_bound", "bsgpu_stage_templates",
-    "bsgpu_process_block",
+    "bsgpu_process_block", "bsgpu_profile_enable", "bsgpu_profile_read", "bsgpu_build_blocks_tally",
     "bsgpu_default_reader_params", "bsgpu_decode_records", "bsgpu_build_blocks", "bsgpu_call_bam",
     "bsgpu_call_sites_dev", "bsgpu_call_sites_vcf_dev", "bsgpu_pileup_block_dev", "bsgpu_call_block_dev",
     "bsgpu_synth_sites_dev", "bsgpu_synth_block_nseg", "bsgpu_synth_block_dev",
@@ -51,6 +51,15 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("sites", C.c_uint64), ("sites_called", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("qsum_overflow", C.c_uint64),
                 ("bam_decode_s", C.c_double), ("bam_build_s", C.c_double), ("bam_call_s", C.c_double)]
+
+
+PROFILE_MAX = 1024
+
+
+class Profile(C.Structure):
+    """bsgpu_profile (include/bsgpu.h): the --report-file side channels of the path"""
+    _fields_ = [("conv_cts", (C.c_uint64 * 4) * PROFILE_MAX), ("used", C.c_uint32), ("pad_", C.c_uint32),
+                ("base_filter", C.c_uint64 * 5), ("filter_cts", C.c_uint64 * 15), ("filter_bases", C.c_uint64 * 15)]
 
 
 class BsGpuError(RuntimeError):
@@ -183,13 +192,29 @@ class BsGpu:
         first = int(templates[0]["forward_position"]) or int(templates[0]["reverse_position"])
         x = first - 2 if first > 2 else 1
         sz = y - x + 1
-        assert len(ref) >= sz
+        assert len(ref) >= sz + (1 if getattr(self, "_profile_on", False) else 0)
         out = np.empty(sz, dtype=GT_VCF) if out is None else out
         xo = C.c_uint32(0)
         self._check(self.lib.bsgpu_process_block(self.ctx, _ptr(templates), C.c_size_t(len(templates)), _ptr(bases),
                                                  C.c_size_t(len(bases)), _ptr(misms), C.c_size_t(len(misms)), _ptr(ref),
                                                  C.c_uint32(y), C.byref(xo), _ptr(out)))
         return xo.value, out
+
+    # ---- --report-file side channels -------------------------------------------------------------
+    def profile_enable(self, on=True):
+        """gather the non-CpG conversion profile and the base / read tallies in process_block and call_bam
+        (process_block then wants reference codes for [x, y + 1])"""
+        self._check(self.lib.bsgpu_profile_enable(self.ctx, C.c_int(1 if on else 0)))
+        self._profile_on = bool(on)
+
+    def profile_read(self, reset=False):
+        """-> dict(used, conv[used, 4], base_filter[5], filter_cts[15], filter_bases[15]); conv[i] = counters of original read
+        position i - 1, the filter arrays are indexed by gt_filter_reason"""
+        pr = Profile()
+        self._check(self.lib.bsgpu_profile_read(self.ctx, C.byref(pr), C.c_int(1 if reset else 0)))
+        conv = np.ctypeslib.as_array(pr.conv_cts).reshape(PROFILE_MAX, 4)
+        return dict(used=int(pr.used), conv=conv[:pr.used].copy(), base_filter=np.array(list(pr.base_filter), dtype=np.uint64),
+                    filter_cts=np.array(list(pr.filter_cts), dtype=np.uint64), filter_bases=np.array(list(pr.filter_bases), dtype=np.uint64))
 
     # ---- reader side ----------------------------------------------------------------------------
     def decode_records(self, bam, rp=None, want_reads=True):
@@ -289,8 +314,9 @@ def math_probe(x):
     return lo, ex
 
 
-def build_blocks(bam, rec, rp=None):
-    """bsgpu_build_blocks: descriptors of decode_records -> (BLOCK[], TEMPLATE[]).  Pure host function of the ABI."""
+def build_blocks(bam, rec, rp=None, tally=False):
+    """bsgpu_build_blocks: descriptors of decode_records -> (BLOCK[], TEMPLATE[]).  Pure host function of the ABI.
+    tally: also return read_input's filter_cts[15] / filter_bases[15] (bsgpu_build_blocks_tally)."""
     lib = load()
     bam = np.ascontiguousarray(bam, dtype=np.uint8)
     rec = np.ascontiguousarray(rec, dtype=RECORD)
@@ -298,9 +324,17 @@ def build_blocks(bam, rec, rp=None):
     blocks = np.zeros(len(rec) + 8, dtype=BLOCK)
     tmpl = np.zeros(len(rec) + 8, dtype=TEMPLATE)
     nb, nt = C.c_size_t(0), C.c_size_t(0)
-    if lib.bsgpu_build_blocks(_ptr(bam), C.c_size_t(len(bam)), _ptr(rec), C.c_size_t(len(rec)), C.byref(rp), _ptr(blocks),
-                              C.c_size_t(len(blocks)), C.byref(nb), _ptr(tmpl), C.c_size_t(len(tmpl)), C.byref(nt)) != BSGPU_OK:
+    if tally:
+        fc, fb = np.zeros(15, dtype=np.uint64), np.zeros(15, dtype=np.uint64)
+        rc = lib.bsgpu_build_blocks_tally(_ptr(bam), C.c_size_t(len(bam)), _ptr(rec), C.c_size_t(len(rec)), C.byref(rp), _ptr(blocks),
+                                          C.c_size_t(len(blocks)), C.byref(nb), _ptr(tmpl), C.c_size_t(len(tmpl)), C.byref(nt), _ptr(fc), _ptr(fb))
+    else:
+        rc = lib.bsgpu_build_blocks(_ptr(bam), C.c_size_t(len(bam)), _ptr(rec), C.c_size_t(len(rec)), C.byref(rp), _ptr(blocks),
+                                    C.c_size_t(len(blocks)), C.byref(nb), _ptr(tmpl), C.c_size_t(len(tmpl)), C.byref(nt))
+    if rc != BSGPU_OK:
         raise BsGpuError(lib.bsgpu_last_error().decode())
+    if tally:
+        return blocks[:nb.value], tmpl[:nt.value], fc, fb
     return blocks[:nb.value], tmpl[:nt.value]
 
 

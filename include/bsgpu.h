@@ -150,15 +150,17 @@ typedef struct {
 } bsgpu_reader_params;
 
 /* The read-level side channels of --report-file that the reference gathers inside the replaced functions (bs_stats,
- * include/bs_call.h:124-146): the non-CpG conversion profile of meth_profile() (src/meth_profile.c:48-76) and the base /
- * read tallies of process_template_vector() and its helpers (src/process_template.c:52-63, src/al_utils.c:141,150,308). */
+ * include/bs_call.h:124-146): the non-CpG conversion profile of meth_profile() (src/meth_profile.c:48-76), the base /
+ * read tallies of process_template_vector() and its helpers (src/process_template.c:52-63, src/al_utils.c:141,150,308)
+ * and the per-reason tallies of read_input() (src/get_template_vector.c:104-107,243-246,314-319,361-364). */
 #define BSGPU_PROFILE_MAX 1024
 typedef struct {
 	uint64_t conv_cts[BSGPU_PROFILE_MAX][4]; /* stats->meth_profile: entry i holds meth_cts of original read position i - 1 */
 	uint32_t used;                           /* gt_vector_get_used(stats->meth_profile); entries >= used are zero */
 	uint32_t pad_;
 	uint64_t base_filter[5];                 /* stats->base_filter[base_none, base_trim, base_clip, base_overlap, base_lowqual] */
-	uint64_t reads, read_bases;              /* what process_template_vector adds to filter_cts / filter_bases[gt_flt_none] */
+	uint64_t filter_cts[15];                 /* stats->filter_cts / filter_bases, indexed by gt_filter_reason (include/bs_call.h:50); */
+	uint64_t filter_bases[15];               /* [0] = mates / bases that reached normalisation (+ the bases of src/get_template_vector.c:363) */
 } bsgpu_profile;
 
 typedef struct bsgpu_ctx bsgpu_ctx;
@@ -239,6 +241,11 @@ int bsgpu_decode_records(bsgpu_ctx *ctx, const uint8_t *bam, size_t nbytes, cons
  * decoded arrays by offset. */
 int bsgpu_build_blocks(const uint8_t *bam, size_t nbytes, const bsgpu_record *rec, size_t nrec, const bsgpu_reader_params *rp,
 		bsgpu_block *blocks, size_t block_cap, size_t *nblocks, bsgpu_template *tmpl, size_t tmpl_cap, size_t *ntmpl);
+/* same, also adding read_input's per-reason tallies (filtered records, mates whose partner never came, duplicates) to
+ * filter_cts[15] / filter_bases[15] */
+int bsgpu_build_blocks_tally(const uint8_t *bam, size_t nbytes, const bsgpu_record *rec, size_t nrec, const bsgpu_reader_params *rp,
+		bsgpu_block *blocks, size_t block_cap, size_t *nblocks, bsgpu_template *tmpl, size_t tmpl_cap, size_t *ntmpl,
+		uint64_t *filter_cts, uint64_t *filter_bases);
 
 /* The whole path: BAM records -> decode -> blocks -> normalisation -> pileup -> model.  ctg_codes[tid] holds the
  * reference codes 0..4 of positions 1..target_len[tid].  vcf receives, per contig that has blocks, one gt_vcf record for

@@ -91,13 +91,15 @@ PROFILE_MAX = 1024
 
 class BsoProfile(C.Structure):
     _fields_ = [("conv_cts", (C.c_uint64 * 4) * PROFILE_MAX), ("used", C.c_uint32), ("pad", C.c_uint32),
-                ("base_filter", C.c_uint64 * 5), ("reads", C.c_uint64), ("read_bases", C.c_uint64)]
+                ("base_filter", C.c_uint64 * 5), ("filter_cts", C.c_uint64 * 15), ("filter_bases", C.c_uint64 * 15)]
 
 
-def profile_dict(used, conv, base_filter, reads, read_bases):
-    """common shape of the --report-file side channels: conv[i] = meth_cts of original read position i - 1"""
+def profile_dict(used, conv, base_filter, filter_cts, filter_bases):
+    """common shape of the --report-file side channels: conv[i] = meth_cts of original read position i - 1;
+    filter_cts / filter_bases indexed by gt_filter_reason"""
     return dict(used=int(used), conv=np.asarray(conv, dtype=np.uint64)[:int(used)].copy(),
-                base_filter=np.asarray(base_filter, dtype=np.uint64).copy(), reads=int(reads), read_bases=int(read_bases))
+                base_filter=np.asarray(base_filter, dtype=np.uint64).copy(),
+                filter_cts=np.asarray(filter_cts, dtype=np.uint64).copy(), filter_bases=np.asarray(filter_bases, dtype=np.uint64).copy())
 
 
 class BsoParams(C.Structure):
@@ -216,7 +218,7 @@ class Oracle:
         pr = BsoProfile()
         self.lib.bso_profile_read(C.byref(pr))
         conv = np.ctypeslib.as_array(pr.conv_cts).reshape(PROFILE_MAX, 4)
-        return profile_dict(pr.used, conv, list(pr.base_filter), pr.reads, pr.read_bases)
+        return profile_dict(pr.used, conv, list(pr.base_filter), list(pr.filter_cts), list(pr.filter_bases))
 
     def process_block(self, templates, bases, misms, refcodes, y):
         """refcodes: codes for positions [x, y] where x = max(first-2, 1)."""
@@ -348,17 +350,14 @@ class Reference:
         self.lib.bsref_stats_reset()
 
     def stats_read(self):
-        """-> profile_dict plus the raw filter_cts / filter_bases arrays of bs_stats"""
+        """-> profile_dict of the reference's bs_stats"""
         conv = np.zeros((1 << 16, 4), dtype=np.uint64)
         bf = np.zeros(5, dtype=np.uint64)
         fc = np.zeros(15, dtype=np.uint64)
         fb = np.zeros(15, dtype=np.uint64)
         self.lib.bsref_stats_read.restype = C.c_uint32
         used = self.lib.bsref_stats_read(_p(conv), C.c_size_t(len(conv)), _p(bf), _p(fc), _p(fb))
-        d = profile_dict(used, conv, bf, fc[0], fb[0])
-        d["filter_cts"] = fc
-        d["filter_bases"] = fb
-        return d
+        return profile_dict(used, conv, bf, fc, fb)
 
     def decode_records(self, bam, mapq_thresh=20, max_template_len=1000, keep_unmatched=False, ignore_dup=False):
         """raw BAM records through the reference's get_next_align_details() (src/input_sam.c:222)"""

@@ -390,7 +390,7 @@ static struct {
 	int on;
 	uint64_t (*mem)[4];           /* stats->meth_profile->memory */
 	size_t used;
-	uint64_t base_filter[5], reads, read_bases;
+	uint64_t base_filter[5], filter_cts[15], filter_bases[15];
 } prof;
 
 void bso_profile_enable(int on) {
@@ -401,15 +401,22 @@ void bso_profile_reset(void) {
 	if (prof.mem) memset(prof.mem, 0, PROF_ALLOC * sizeof(*prof.mem));
 	prof.used = 0;
 	memset(prof.base_filter, 0, sizeof(prof.base_filter));
-	prof.reads = prof.read_bases = 0;
+	memset(prof.filter_cts, 0, sizeof(prof.filter_cts));
+	memset(prof.filter_bases, 0, sizeof(prof.filter_bases));
+}
+int bso_profile_is_on(void) { return prof.on; }
+void bso_profile_tally(int reason_cts, uint64_t cts, int reason_bases, uint64_t bases) {
+	if (!prof.on) return;
+	prof.filter_cts[reason_cts] += cts;
+	prof.filter_bases[reason_bases] += bases;
 }
 void bso_profile_read(bso_profile *out) {
 	memset(out, 0, sizeof(*out));
 	out->used = (uint32_t)prof.used;
 	for (size_t i = 0; i < prof.used && i < BSO_PROFILE_MAX; i++) memcpy(out->conv_cts[i], prof.mem[i], sizeof(prof.mem[i]));
 	memcpy(out->base_filter, prof.base_filter, sizeof(prof.base_filter));
-	out->reads = prof.reads;
-	out->read_bases = prof.read_bases;
+	memcpy(out->filter_cts, prof.filter_cts, sizeof(prof.filter_cts));
+	memcpy(out->filter_bases, prof.filter_bases, sizeof(prof.filter_bases));
 }
 
 /* meth_profile() for one normalised template (src/meth_profile.c:48-76).  refcodes[0] is position x. */
@@ -682,8 +689,8 @@ int bso_normalise_block(const bso_template *t, size_t n, const uint8_t *bases, c
 						else if (q < p->min_qual) prof.base_filter[4]++;
 						else prof.base_filter[0]++;
 					}
-					prof.reads++;
-					prof.read_bases += (uint64_t)rdl;
+					prof.filter_cts[0]++;
+					prof.filter_bases[0] += (uint64_t)rdl;
 					uint32_t grow = 0;
 					for (uint32_t z = 0; z < w.nmm[k]; z++) if (w.mm[k][z].type == BSO_INS) grow += w.mm[k][z].size;
 					w.orig[k] = malloc(sizeof(int) * ((size_t)rdl + grow + 8));

@@ -103,16 +103,18 @@ int bso_process_block(const bso_template *t, size_t n, const uint8_t *bases, con
 
 /* --report-file side channels of this path (bs_stats, include/bs_call.h:124-146): the non-CpG conversion profile of
  * meth_profile() (src/meth_profile.c:48-76) and the tallies of process_template_vector (src/process_template.c:52-63,
- * src/al_utils.c:141,150,308).  While enabled, bso_process_block accumulates them (process-wide, in call order) and its
+ * src/al_utils.c:141,150,308) and of read_input (src/get_template_vector.c:104-107,243-246,314-319,361-364).  While enabled, bso_process_block accumulates them (process-wide, in call order) and its
  * refcodes must hold one more code (position y + 1). */
 #define BSO_PROFILE_MAX 1024
 typedef struct {
 	uint64_t conv_cts[BSO_PROFILE_MAX][4];
 	uint32_t used, pad;
 	uint64_t base_filter[5];
-	uint64_t reads, read_bases;
+	uint64_t filter_cts[15], filter_bases[15];   /* indexed by gt_filter_reason; [0] also takes the reads / bases that reach normalisation */
 } bso_profile;
 void bso_profile_enable(int on);
+int bso_profile_is_on(void);
+void bso_profile_tally(int reason_cts, uint64_t cts, int reason_bases, uint64_t bases);      /* used by the reader restatement */
 void bso_profile_reset(void);
 void bso_profile_read(bso_profile *out);
 

@@ -314,7 +314,10 @@ static int build_blocks(const uint8_t *bam, size_t nbytes, const bso_record *rec
 		bam_view v;
 		if (next_record(bam, nbytes, &at, &v)) { o->err = -2; break; }
 		const bso_record *r = rec + ri;
-		if (r->ret > 0) continue;                                     /* filtered (:100-106) */
+		if (r->ret > 0) {                                             /* filtered (:100-106) */
+			bso_profile_tally((int)r->filtered, 1, (int)r->filtered, (uint64_t)(uint32_t)v.l_qseq);
+			continue;
+		}
 		const int reverse = r->reverse, ix = reverse ? 1 : 0;
 		tmpl_s al;                                                     /* the incoming alignment as a one-mate template */
 		memset(&al, 0, sizeof(al));
@@ -356,6 +359,7 @@ static int build_blocks(const uint8_t *bam, size_t nbytes, const bso_record *rec
 					st.list_h[h->ix] = NULL;
 					h->live = 0;
 				} else {
+					bso_profile_tally(14, 1, 14, r->read_len);           /* :243-246 */
 					int skip = 0;
 					if (!keep_duplicates) { const uint32_t xx = reverse ? al.rev : al.fwd; if (xx >= start_pos) skip = 1; }
 					if (!skip && keep_unmatched) {
@@ -395,6 +399,10 @@ static int build_blocks(const uint8_t *bam, size_t nbytes, const bso_record *rec
 								/* `al` is now the displaced template; its name is not needed again: a second match would
 								 * look it up under the NEWCOMER's tag, exactly as the reference does (tag is not swapped) */
 							}
+							if (bso_profile_is_on()) {                              /* the template that lost (:314-319) */
+								const uint32_t len1 = al.rec[0] >= 0 ? rec[al.rec[0]].read_len : 0, len2 = al.rec[1] >= 0 ? rec[al.rec[1]].read_len : 0;
+								bso_profile_tally(5, len1 && len2 ? 2 : 1, 5, (uint64_t)len1 + len2);
+							}
 							skip = 1;
 						}
 					} else { curr_pos = pos; start_idx = read_idx; }
@@ -420,6 +428,8 @@ static int build_blocks(const uint8_t *bam, size_t nbytes, const bso_record *rec
 							if (a1->mapq[0] < al.mapq[0] || (a1->mapq[0] == al.mapq[0] && al_qual(&st, a1) < al_qual(&st, &al))) {
 								const tmpl_s old = *a1; *a1 = al; al = old;
 							}
+							/* counted as a duplicate, its bases under gt_flt_none (reference behaviour, :361-364) */
+							bso_profile_tally(5, 1, 0, al.rec[ix] >= 0 ? rec[al.rec[ix]].read_len : 0);
 							skip = 1;
 						}
 					}

@@ -214,3 +214,13 @@ def random_pileups(rng, n, depth=30, het_frac=0.05, empty_frac=0.03, max_depth=N
             P["mapq2"][i] += float(int(rng.integers(20, 61)) ** 2)
             P["n"][i] += 1
     return P, ref
+
+
+# the profile vector grows with the longest read seen so far and counts on its top entry are dropped (see
+# k_profile_resolve): the order of the blocks matters, so each run feeds several blocks of different shapes
+PROFILE_RUNS = [
+    [dict(depth=20, read_len=50, paired=False, nonconv_frac=0.2), dict(depth=20, read_len=100, paired=True), dict(depth=10, read_len=75, paired=False)],
+    [dict(depth=25, read_len=100, paired=True, indel_frac=0.4, clip_frac=0.4, frag_mean=130, frag_sd=40),
+     dict(depth=25, read_len=100, paired=True, single_mate_frac=0.5, clip_frac=0.3)],
+    [dict(depth=15, read_len=60, paired=True, frag_mean=90, frag_sd=20, indel_frac=0.5, clip_frac=0.5, n_frac=0.05, single_mate_frac=0.2)] * 3,
+]

@@ -8,6 +8,7 @@ The GPU boxes have no reference tree; they check against these committed files.
                  call_genotypes_ML on blocks built from synthetic reads, plus direct calc_gt_prob/fisher KATs)
   block_*.npz    block goldens: raw templates -> normalised templates, pileup[], gt_vcf[]
                  (process_template_vector -> call_genotypes_ML)
+  profile_v1.npz --report-file side channels of the block and reader goldens (meth_profile, base / read tallies)
   reader_*.npz   reader goldens: raw BAM records -> per-record descriptors (get_next_align_details), blocks and
                  templates (read_input), gt_vcf[] of every block (the whole chain)
 """
@@ -117,8 +118,44 @@ def make_reader():
               "sites", len(vcf), "called", int((vcf["skip"] == 0).sum()))
 
 
+def make_profile():
+    """--report-file side channels (non-CpG conversion profile, base / read tallies) of the block and reader goldens,
+    from the reference with a live bs_stats; each case starts from a fresh profile"""
+    from tests import bamgen
+    out = {}
+
+    def keep(name, p):
+        for k in ("used", "conv", "base_filter", "filter_cts", "filter_bases"):
+            out[name + "__" + k] = np.asarray(p[k])
+
+    for name, c in BLOCK_CASES.items():
+        rng = np.random.default_rng(c["seed"])
+        ref = blockgen.random_reference(rng, c["reflen"], n_runs=2)
+        T, B, M, y = blockgen.make_block(rng, ref, c["start"], c["end"], **c["kw"])
+        lt, rt = c["trims"]
+        r = Reference(left_trim=lt, right_trim=rt)
+        r.stats_enable(True); r.stats_reset()
+        x = r.process_block(T, B, M, ref, y)[0]
+        keep(name, r.stats_read())
+        out[name + "__ref"] = blockgen.window_codes(ref, x, y + 1)          # the profile looks one code past the block
+        r.stats_enable(False)
+        Reference()
+        print(name, "profile used", int(out[name + "__used"]), "counts", int(out[name + "__conv"].sum()))
+    r = Reference()
+    for name, c in READER_CASES.items():
+        bam, n, tl, refs = bamgen.make_stream(c["seed"], **c["stream"])
+        r.stats_enable(True); r.stats_reset()
+        r.read_input(bam, tl, refs, run_chain=True, **c["opts"])
+        keep(name, r.stats_read())
+        r.stats_enable(False)
+        print(name, "profile used", int(out[name + "__used"]), "counts", int(out[name + "__conv"].sum()), "filter_cts", out[name + "__filter_cts"])
+    np.savez_compressed(os.path.join(HERE, "profile_v1.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["blocks", "sites", "reader"]
+    which = sys.argv[1:] or ["blocks", "sites", "reader", "profile"]
+    if "profile" in which:
+        make_profile()
     if "blocks" in which:
         make_blocks()
     if "sites" in which:

@@ -73,6 +73,35 @@ def test_oracle_matches_reader_golden(oracle, name):
     util.assert_gt_meth_close(wv["gtm"], wv["skip"], g["vcf"]["gtm"], g["vcf"]["skip"], exact_doubles=True)
 
 
+BLOCKS = ["block_pe_plain", "block_pe_indel_clip_trim", "block_se_deep", "block_mixed"]
+
+
+@pytest.mark.parametrize("name", BLOCKS + ["reader_pe", "reader_mixed"])
+def test_oracle_matches_profile_golden(name):
+    """--report-file side channels: the restatement against what the reference's meth_profile() / process_template_vector()
+    / read_input() left in bs_stats for the committed goldens"""
+    from oracle.bindings import Oracle
+    g = util.load_golden(name)
+    want, refw = util.golden_profile(name)
+    if name in BLOCKS:
+        o = Oracle(left_trim=tuple(int(v) for v in g["left_trim"]), right_trim=tuple(int(v) for v in g["right_trim"]))
+    else:
+        o = Oracle()
+    o.profile_enable(True); o.profile_reset()
+    try:
+        if name in BLOCKS:
+            o.process_block(g["templates"], g["bases"], g["misms"], refw, int(g["y"]))
+        else:
+            opts = dict(mapq_thresh=int(g["mapq_thresh"]), max_template_len=int(g["max_template_len"]), keep_unmatched=bool(g["keep_unmatched"]),
+                        ignore_duplicates=bool(g["ignore_duplicates"]), keep_duplicates=bool(g["keep_duplicates"]))
+            o.read_input(g["bam"], g["target_len"], [g["ref%d" % i] for i in range(len(g["target_len"]))], run_chain=True, **opts)
+        got = o.profile_read()
+    finally:
+        o.profile_enable(False)
+    util.same_profile(got, want, name, recycled_vectors=name not in BLOCKS)
+    assert want["conv"].sum() > 5000
+
+
 def test_parallel_builder_equals_sequential(oracle, monkeypatch):
     """the stream is cut at records where read_input is certain to start a new block and the pieces are built on
     separate host threads: same blocks, same templates as one thread"""

@@ -7,7 +7,7 @@ bit-identical.  Skipped where the prebuilt reference library is absent.
 import numpy as np
 import pytest
 
-from tests import blockgen
+from tests import blockgen, util
 
 pytestmark = pytest.mark.reference
 
@@ -129,21 +129,10 @@ def test_process_block(reference, case, trims):
     _same_records(vcf_c, vcf_r, "gt_vcf via call_block")
 
 
-def same_profile(a, b, what=""):
-    assert a["used"] == b["used"], (what, a["used"], b["used"])
-    np.testing.assert_array_equal(a["conv"], b["conv"], err_msg=what)
-    np.testing.assert_array_equal(a["base_filter"], b["base_filter"], err_msg=what)
-    assert (a["reads"], a["read_bases"]) == (b["reads"], b["read_bases"]), what
+same_profile = util.same_profile
 
 
-# the profile vector grows with the longest read seen so far and counts on its top entry are dropped (see
-# k_profile_resolve): the order of the blocks matters, so each run feeds several blocks of different shapes
-PROFILE_RUNS = [
-    [dict(depth=20, read_len=50, paired=False, nonconv_frac=0.2), dict(depth=20, read_len=100, paired=True), dict(depth=10, read_len=75, paired=False)],
-    [dict(depth=25, read_len=100, paired=True, indel_frac=0.4, clip_frac=0.4, frag_mean=130, frag_sd=40),
-     dict(depth=25, read_len=100, paired=True, single_mate_frac=0.5, clip_frac=0.3)],
-    [dict(depth=15, read_len=60, paired=True, frag_mean=90, frag_sd=20, indel_frac=0.5, clip_frac=0.5, n_frac=0.05, single_mate_frac=0.2)] * 3,
-]
+PROFILE_RUNS = blockgen.PROFILE_RUNS
 
 
 @pytest.mark.parametrize("run", range(len(PROFILE_RUNS)))
@@ -265,8 +254,19 @@ def test_read_input(oracle, reference, seed):
     bam, n, tl, refs = bamgen.make_stream(seed)
     o = _reader_opts(seed)
     chain = seed % 4 == 0
-    rbk, rt, rb, rm, rv = reference.read_input(bam, tl, refs, run_chain=chain, **o)
-    wbk, wt, wb, wm, wv = oracle.read_input(bam, tl, refs, run_chain=chain, **o)
+    # with --report-file's counters live on both sides: read_input's own tallies always, the conversion profile and the
+    # normalisation tallies when the chain runs
+    reference.stats_enable(True); reference.stats_reset()
+    oracle.profile_enable(True); oracle.profile_reset()
+    try:
+        rbk, rt, rb, rm, rv = reference.read_input(bam, tl, refs, run_chain=chain, **o)
+        wbk, wt, wb, wm, wv = oracle.read_input(bam, tl, refs, run_chain=chain, **o)
+        pr, po = reference.stats_read(), oracle.profile_read()
+    finally:
+        reference.stats_enable(False); oracle.profile_enable(False)
+    same_profile(po, pr, "seed %d" % seed, recycled_vectors=True)
+    assert not chain or po["filter_cts"][0] == wt["present"].sum()
+    assert pr["filter_cts"].sum() > 0 and (not chain or pr["conv"].sum() > 0)
     assert len(rbk) == len(wbk) and len(rbk) > 0
     for f in ("tid", "x", "y", "first_template", "n_templates", "vcf_off"):
         assert (rbk[f] == wbk[f]).all(), f

@@ -89,3 +89,28 @@ def writer_fields(gtm, skip):
         mac1 |= (gt == k) & ((u <= 1) | (v <= 1))
     flt = np.where((flt == 0) & mac1, 128, flt)
     return {"gt": gt, "phred": ph, "fs": fs, "qd": qd, "flt": flt}
+
+
+def same_profile(a, b, what="", recycled_vectors=False):
+    """a: restatement or product, b: reference.  recycled_vectors: b comes from read_input's recycled align_details, whose
+    absent mates are often EMPTY rather than NULL vectors (src/al_utils.c:52-63); process_template_vector counts those
+    as reads with no bases (src/process_template.c:49,61), so filter_cts[gt_flt_none] of the reference then depends on its
+    allocation history and can only be bounded from below by the number of mates that exist.  filter_bases[gt_flt_none]
+    is then also written by two threads without a lock (read_input at src/get_template_vector.c:363 and the process
+    thread at src/process_template.c:62), so the reference may lose updates: bounded from above by the exact sum."""
+    assert a["used"] == b["used"], (what, a["used"], b["used"])
+    np.testing.assert_array_equal(a["conv"], b["conv"], err_msg=what)
+    np.testing.assert_array_equal(a["base_filter"], b["base_filter"], err_msg=what)
+    np.testing.assert_array_equal(a["filter_cts"][1:], b["filter_cts"][1:], err_msg=what)
+    np.testing.assert_array_equal(a["filter_bases"][1:], b["filter_bases"][1:], err_msg=what)
+    if recycled_vectors:
+        assert a["filter_cts"][0] <= b["filter_cts"][0], what
+        assert a["filter_bases"][0] >= b["filter_bases"][0] >= 0.98 * a["filter_bases"][0], what
+    else:
+        assert a["filter_cts"][0] == b["filter_cts"][0] and a["filter_bases"][0] == b["filter_bases"][0], what
+
+
+def golden_profile(name):
+    """the reference's --report-file side channels for golden `name` (tests/golden/profile_v1.npz)"""
+    g = load_golden("profile_v1")
+    return {k: g[name + "__" + k] for k in ("used", "conv", "base_filter", "filter_cts", "filter_bases")}, g.get(name + "__ref")
