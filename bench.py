@@ -230,6 +230,24 @@ def bam_path(args, gpu, bslib, torch, np, stream, rank, world, local):
                                 "descriptors_d2h_block_builder_host": (s1["bam_build_s"] - s0["bam_build_s"]) / steps,
                                 "normalise_pileup_model_d2h": (s1["bam_call_s"] - s0["bam_call_s"]) / steps},
            "gpu_launches_per_step": (s1["kernel_launches"] - s0["kernel_launches"]) // steps}
+    # the same with the --report-file side channels on (conversion profile + base / read tallies by the normalisation
+    # kernel, read_input's tallies by the host builder)
+    gpu.profile_enable(True)
+    gpu.call_bam(hbam.array, tl, [href], vcf=hvcf.array)
+    gpu.profile_read(reset=True)
+    sp0 = gpu.stats()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        gpu.call_bam(hbam.array, tl, [href], vcf=hvcf.array)
+    torch.cuda.synchronize()
+    dtp = (time.perf_counter() - t0) / steps
+    sp1 = gpu.stats()
+    prof = gpu.profile_read(reset=True)
+    out["with_report_side_channels"] = {"value": called / dtp, "unit": "sites/s", "slowdown": dtp / dt,
+                                         "normalise_pileup_model_d2h_s": (sp1["bam_call_s"] - sp0["bam_call_s"]) / steps,
+                                         "gpu_launches_per_step": (sp1["kernel_launches"] - sp0["kernel_launches"]) // steps,
+                                         "profile_counts_per_step": int(prof["conv"].sum()) // steps, "profile_used": prof["used"]}
     # the reference's own chain (read_input -> process_template_vector -> call_genotypes_ML, all its threads) on a bounded
     # prefix of the same stream
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -250,6 +268,17 @@ def bam_path(args, gpu, bslib, torch, np, stream, rank, world, local):
         t0 = time.perf_counter()
         cb, ct, _, _, cv = impl.read_input(prefix, [clen], [href[:clen]], run_chain=True)
         cs = time.perf_counter() - t0
+        # once more with its stats live (what --report-file does), for the parity of the side channels below
+        if kind == "reference":
+            impl.stats_enable(True); impl.stats_reset()
+            impl.read_input(prefix, [clen], [href[:clen]], run_chain=True)
+            cprof = impl.stats_read()
+            impl.stats_enable(False)
+        else:
+            impl.profile_enable(True); impl.profile_reset()
+            impl.read_input(prefix, [clen], [href[:clen]], run_chain=True)
+            cprof = impl.profile_read()
+            impl.profile_enable(False)
         ccalled = int((cv["skip"] == 0).sum())
         out["cpu_baseline"] = {"value": ccalled / cs, "unit": "sites/s", "cores": ncores, "kind": kind,
                                "sample": "first %d records (%d sites called, %d blocks) of the same stream; %s" % (nrec_c, ccalled, len(cb), what)}
@@ -260,6 +289,10 @@ def bam_path(args, gpu, bslib, torch, np, stream, rank, world, local):
             n_ = int(w["y"]) - int(w["x"]) + 1
             checked += util.assert_vcf_close(vcf[int(b["vcf_off"]):int(b["vcf_off"]) + n_], cv[int(w["vcf_off"]):int(w["vcf_off"]) + n_])
         out["cpu_baseline"]["parity_sites_checked"] = checked
+        gpu.call_bam(prefix, [clen], [href[:clen]], vcf=hvcf.array)
+        util.same_profile(gpu.profile_read(reset=True), cprof, "bench prefix", recycled_vectors=kind == "reference")
+        out["with_report_side_channels"]["parity_profile_counts_checked"] = int(cprof["conv"].sum())
+    gpu.profile_enable(False)
     hbam.free()
     hvcf.free()
     return out
