@@ -102,6 +102,24 @@ def profile_dict(used, conv, base_filter, filter_cts, filter_bases):
                 filter_cts=np.asarray(filter_cts, dtype=np.uint64).copy(), filter_bases=np.asarray(filter_bases, dtype=np.uint64).copy())
 
 
+VCF_IDS = tuple(range(16))      # PASS fail mac1 CX GT FT GL GQ DP MQ QD MC8 AMQ CS CG FS: ids in header order
+
+
+def _print_block(fn, vcf, refcodes, x, rid, ctg_end, vcf_ids, all_positions):
+    vcf = _c(vcf, GT_VCF)
+    sz = len(vcf)
+    refcodes = _c(refcodes, np.uint8)
+    assert len(refcodes) >= sz + 2
+    ids = _c(VCF_IDS if vcf_ids is None else vcf_ids, np.int32)
+    out = np.zeros(sz * 256 + 1024, dtype=np.uint8)
+    nb, nr = C.c_size_t(0), C.c_size_t(0)
+    rc = fn(_p(vcf), C.c_uint32(sz), _p(refcodes), C.c_uint32(x), C.c_int(rid), C.c_uint32(ctg_end), _p(ids),
+            C.c_int(1 if all_positions else 0), _p(out), C.c_size_t(len(out)), C.byref(nb), C.byref(nr))
+    if rc:
+        raise RuntimeError("print_block failed: %d" % rc)
+    return out[:nb.value].copy(), nr.value
+
+
 class BsoParams(C.Structure):
     _fields_ = [("under_conv", C.c_double), ("over_conv", C.c_double), ("ref_bias", C.c_double),
                 ("left_trim", C.c_uint32 * 2), ("right_trim", C.c_uint32 * 2), ("min_qual", C.c_uint8)]
@@ -205,6 +223,10 @@ class Oracle:
         self.lib.bso_set_params(C.byref(self.params))
         return _read_input(self.lib.bso_read_input, bam, target_len, ctg_codes, mapq_thresh, max_template_len,
                            keep_unmatched, ignore_duplicates, keep_duplicates, run_chain)
+
+    def print_block(self, vcf, refcodes, x, rid=0, ctg_end=0xffffffff, vcf_ids=None, all_positions=False):
+        """the restatement of the reference's writer over one block of gt_vcf[] -> (BCF record bytes, number of records)"""
+        return _print_block(self.lib.bso_print_block, vcf, refcodes, x, rid, ctg_end, vcf_ids, all_positions)
 
     def profile_enable(self, on=True):
         """--report-file side channels (process-wide in the library); process_block then wants codes for [x, y + 1]"""
@@ -341,6 +363,11 @@ class Reference:
         if rc:
             raise RuntimeError("bsref_call_block failed: %d" % rc)
         return pile, vcf
+
+    def print_block(self, vcf, refcodes, x, rid=0, ctg_end=0xffffffff, vcf_ids=None, all_positions=False):
+        """one block of gt_vcf[] through the reference's print_vcf_entry / flush_vcf_entries (src/print_vcf.c) as the print
+        thread runs them; refcodes covers [x, x + len(vcf) + 1].  Returns (BCF record bytes, number of records)."""
+        return _print_block(self.lib.bsref_print_block, vcf, refcodes, x, rid, ctg_end, vcf_ids, all_positions)
 
     def stats_enable(self, on=True):
         """give the reference a bs_stats (what --report-file does): meth_profile() and the tallies become live"""

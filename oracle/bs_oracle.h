@@ -144,6 +144,16 @@ int bso_read_input(const uint8_t *bam, size_t nbytes, int n_targets, const uint3
 		uint8_t *bases, size_t bases_cap, size_t *nbases, bso_misms *misms, size_t misms_cap, size_t *nmisms,
 		bso_gt_vcf *vcf, size_t vcf_cap, size_t *nvcf);
 
+/* ---- writer side (bs_oracle_writer.c): what print_thread derives from a block of gt_vcf records and hands to bcf_write()
+ *      (src/print_vcf.c:32-381, 535-594; src/process.c:89-104).  refcodes: sz + 2 codes (positions x .. x + sz + 1);
+ *      vcf_ids: the 16 header dictionary ids in the order of include/bs_call.h:192-207; out receives the records in BCF
+ *      layout (l_shared, l_indiv, fixed fields, shared, indiv). ---- */
+#define BSO_BCF_MAX_RECORD 384
+size_t bso_print_site(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, uint32_t i, int rid, uint32_t ctg_end,
+		const int *ids, int all_positions, uint8_t *out);
+int bso_print_block(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, int rid, uint32_t ctg_end,
+		const int *vcf_ids, int all_positions, uint8_t *out, size_t cap, size_t *nbytes, size_t *nrec);
+
 /* host twin of the device generator of per-site count vectors (same draws, same records) */
 void bso_synth_sites(uint64_t seed, uint64_t first, size_t n, double mean_depth, bso_pileup *out, uint8_t *ref, int nthreads);
 

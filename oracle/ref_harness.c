@@ -674,3 +674,153 @@ int bsref_read_input(const uint8_t *bam, size_t nbytes, int n_targets, const uin
 	if (st != GT_STATUS_OK) return -2;
 	return rdr.err;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Writer side: the reference's print_vcf_entry() / flush_vcf_entries() / _print_vcf_entry() (src/print_vcf.c, compiled
+ * unmodified) driven over a block of gt_vcf records the way print_thread drives them (src/process.c:89-104), with the
+ * htslib functions that file calls supplied here.
+ *
+ * htslib is a system dependency of bs_call (configure.ac:9-14; any 1.x release with the bcf_enc_* API), not vendored
+ * under /root/reference and absent from this image.  What follows restates the part of its PUBLISHED behaviour the
+ * writer relies on -- the BCF2 typed-value encoding and record layout of the VCF/BCF specification v4.3, section 6.3
+ * -- under the API names print_vcf.c calls.  bcf_write() appends the record, laid out as in a BCF file, to a buffer.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#include <htslib/vcf.h>
+#include <htslib/khash.h>
+#include "dbSNP.h"
+
+void bcf_enc_size(kstring_t *s, int size, int type) {
+	if (size >= 15) {
+		kputc(15 << 4 | type, s);
+		if (size >= 128) {
+			if (size >= 32768) { int32_t x = size; kputc(1 << 4 | BCF_BT_INT32, s); kputsn((char *)&x, 4, s); }
+			else { int16_t x = (int16_t)size; kputc(1 << 4 | BCF_BT_INT16, s); kputsn((char *)&x, 2, s); }
+		} else { kputc(1 << 4 | BCF_BT_INT8, s); kputc(size, s); }
+	} else kputc(size << 4 | type, s);
+}
+void bcf_enc_int1(kstring_t *s, int32_t x) {
+	if (x == bcf_int32_vector_end) { bcf_enc_size(s, 1, BCF_BT_INT8); kputc(bcf_int8_vector_end, s); }
+	else if (x == bcf_int32_missing) { bcf_enc_size(s, 1, BCF_BT_INT8); kputc(bcf_int8_missing, s); }
+	else if (x <= BCF_MAX_BT_INT8 && x >= BCF_MIN_BT_INT8) { bcf_enc_size(s, 1, BCF_BT_INT8); kputc(x, s); }
+	else if (x <= BCF_MAX_BT_INT16 && x >= BCF_MIN_BT_INT16) { int16_t z = (int16_t)x; bcf_enc_size(s, 1, BCF_BT_INT16); kputsn((char *)&z, 2, s); }
+	else { int32_t z = x; bcf_enc_size(s, 1, BCF_BT_INT32); kputsn((char *)&z, 4, s); }
+}
+void bcf_enc_vint(kstring_t *s, int n, int32_t *a, int wsize) {
+	if (n <= 0) { bcf_enc_size(s, 0, BCF_BT_NULL); return; }
+	if (n == 1) { bcf_enc_int1(s, a[0]); return; }
+	int32_t max = INT32_MIN + 1, min = INT32_MAX;
+	if (wsize <= 0) wsize = n;
+	for (int i = 0; i < n; i++) {
+		if (a[i] == bcf_int32_missing || a[i] == bcf_int32_vector_end) continue;
+		if (max < a[i]) max = a[i];
+		if (min > a[i]) min = a[i];
+	}
+	if (max <= BCF_MAX_BT_INT8 && min >= BCF_MIN_BT_INT8) {
+		bcf_enc_size(s, wsize, BCF_BT_INT8);
+		for (int i = 0; i < n; i++) kputc(a[i] == bcf_int32_vector_end ? bcf_int8_vector_end : a[i] == bcf_int32_missing ? bcf_int8_missing : a[i], s);
+	} else if (max <= BCF_MAX_BT_INT16 && min >= BCF_MIN_BT_INT16) {
+		bcf_enc_size(s, wsize, BCF_BT_INT16);
+		for (int i = 0; i < n; i++) {
+			int16_t z = a[i] == bcf_int32_vector_end ? bcf_int16_vector_end : a[i] == bcf_int32_missing ? bcf_int16_missing : (int16_t)a[i];
+			kputsn((char *)&z, 2, s);
+		}
+	} else {
+		bcf_enc_size(s, wsize, BCF_BT_INT32);
+		for (int i = 0; i < n; i++) { int32_t z = a[i]; kputsn((char *)&z, 4, s); }
+	}
+}
+void bcf_enc_vfloat(kstring_t *s, int n, float *a) {
+	bcf_enc_size(s, n, BCF_BT_FLOAT);
+	kputsn((char *)a, (size_t)n << 2, s);          /* little-endian host */
+}
+void bcf_enc_vchar(kstring_t *s, int l, const char *a) {
+	bcf_enc_size(s, l, BCF_BT_CHAR);
+	kputsn(a, l, s);
+}
+bcf1_t *bcf_init(void) { return calloc(1, sizeof(bcf1_t)); }
+void bcf_clear(bcf1_t *v) {
+	v->rid = 0; v->pos = 0; v->rlen = 0;
+	{ uint32_t miss = 0x7F800001u; memcpy(&v->qual, &miss, 4); }          /* bcf_float_missing */
+	v->n_info = v->n_allele = v->n_fmt = v->n_sample = 0;
+	v->shared.l = v->indiv.l = 0;
+}
+
+/* capture buffer of bcf_write(): records as they lie in a BCF file (two length words, six fixed words, shared, indiv) */
+static uint8_t *pv_out;
+static size_t pv_cap, pv_len, pv_nrec;
+static int pv_overflow;
+int bcf_write(htsFile *fp, bcf_hdr_t *h, bcf1_t *v) {
+	uint32_t x[8];
+	x[0] = (uint32_t)v->shared.l + 24;
+	x[1] = (uint32_t)v->indiv.l;
+	x[2] = (uint32_t)v->rid;
+	x[3] = (uint32_t)v->pos;
+	x[4] = (uint32_t)v->rlen;
+	memcpy(x + 5, &v->qual, 4);
+	x[6] = (uint32_t)v->n_allele << 16 | v->n_info;
+	x[7] = (uint32_t)v->n_fmt << 24 | v->n_sample;
+	const size_t need = 32 + v->shared.l + v->indiv.l;
+	if (pv_len + need > pv_cap) { pv_overflow = 1; return 0; }
+	memcpy(pv_out + pv_len, x, 32);
+	memcpy(pv_out + pv_len + 32, v->shared.s, v->shared.l);
+	memcpy(pv_out + pv_len + 32 + v->shared.l, v->indiv.s, v->indiv.l);
+	pv_len += need;
+	pv_nrec++;
+	return 0;
+}
+
+/* header side and dbSNP: never reached from the harness (print_vcf_header is not called, par.work.dbSNP_hdr is NULL) */
+static void pv_unreachable(const char *what) { fprintf(stderr, "ref_harness: %s called\n", what); abort(); }
+bcf_hdr_t *bcf_hdr_init(const char *mode) { pv_unreachable("bcf_hdr_init"); return NULL; }
+int bcf_hdr_append(bcf_hdr_t *h, const char *line) { pv_unreachable("bcf_hdr_append"); return -1; }
+int bcf_hdr_printf(bcf_hdr_t *h, const char *format, ...) { pv_unreachable("bcf_hdr_printf"); return -1; }
+const char *bcf_hdr_get_version(const bcf_hdr_t *hdr) { pv_unreachable("bcf_hdr_get_version"); return NULL; }
+int bcf_hdr_add_sample(bcf_hdr_t *hdr, const char *sample) { pv_unreachable("bcf_hdr_add_sample"); return -1; }
+int bcf_hdr_write(htsFile *fp, bcf_hdr_t *h) { pv_unreachable("bcf_hdr_write"); return -1; }
+htsFile *hts_open(const char *fn, const char *mode) { pv_unreachable("hts_open"); return NULL; }
+int hts_set_threads(htsFile *fp, int n) { pv_unreachable("hts_set_threads"); return -1; }
+int bam_name2id(bam_hdr_t *h, const char *ref) { pv_unreachable("bam_name2id"); return -1; }
+khint_t bsstub_kh_get(const void *h, const char *key) { pv_unreachable("kh_get"); return 0; }
+khint_t bsstub_kh_end(const void *h) { pv_unreachable("kh_end"); return 0; }
+uint8_t dbSNP_lookup_name(const dbsnp_header_t *const hdr, const dbsnp_ctg_t *c, char *const rs, size_t *const rs_len, const uint32_t x) { pv_unreachable("dbSNP_lookup_name"); return 0; }
+bool load_dbSNP_ctg(const dbsnp_header_t *const hdr, dbsnp_ctg_t *const c) { pv_unreachable("load_dbSNP_ctg"); return false; }
+void unload_dbSNP_ctg(dbsnp_ctg_t *const c) { pv_unreachable("unload_dbSNP_ctg"); }
+
+void print_vcf_entry(bcf1_t *bcf, ctg_t * const ctg, gt_meth *gtm, const char *rf, const uint32_t x, const uint32_t xstart, bool skip, sr_param * const par);
+void flush_vcf_entries(bcf1_t *bcf, const sr_param * const par);
+
+/* One block through the reference's writer, as print_thread runs it (src/process.c:89-104).
+ * refcodes: sz + 2 codes (positions x .. x + sz + 1), the string get_sequence_string() leaves in work.ref.
+ * vcf_ids: the 16 dictionary ids print_vcf_header() looks up (include/bs_call.h:192-208).
+ * out receives the records bcf_write() was handed, in BCF layout; returns 0, or -3 when out is too small. */
+int bsref_print_block(const gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, int rid, uint32_t ctg_end,
+		const int *vcf_ids, int all_positions, uint8_t *out, size_t cap, size_t *nbytes, size_t *nrec) {
+	static ctg_t pv_ctg[2];
+	static int flip = 0;
+	static bcf1_t *bcf = NULL;
+	if (!inited) return -1;
+	if (!bcf) bcf = bcf_init();
+	/* a different ctg_t object every call: _print_vcf_entry then forgets the last position it printed (:117-127) */
+	ctg_t *c = pv_ctg + (flip ^= 1);
+	memset(c, 0, sizeof(*c));
+	c->name = "ctg"; c->vcf_rid = rid; c->start_pos = 1; c->end_pos = ctg_end; c->curr_reg = NULL;
+	bs_stats *saved = par.work.stats;
+	par.work.stats = NULL;                     /* the writer's own statistics are not part of this check */
+	par.work.vcf_ctg = c;
+	par.work.dbSNP_hdr = NULL;
+	par.all_positions = all_positions;
+	for (int i = 0; i < 16; i++) par.work.vcf_ids[i] = vcf_ids[i];
+	pv_out = out; pv_cap = cap; pv_len = 0; pv_nrec = 0; pv_overflow = 0;
+	char *rf = malloc((size_t)sz + 3);
+	memcpy(rf, refcodes, (size_t)sz + 2);
+	rf[sz + 2] = 0;
+	for (uint32_t i = 0; i < sz; i++) {
+		gt_vcf v = vcf[i];
+		print_vcf_entry(bcf, c, &v.gtm, rf, x + i, x, v.skip, &par);
+	}
+	flush_vcf_entries(bcf, &par);
+	free(rf);
+	par.work.stats = saved;
+	*nbytes = pv_len; *nrec = pv_nrec;
+	return pv_overflow ? -3 : 0;
+}

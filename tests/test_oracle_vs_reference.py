@@ -274,3 +274,49 @@ def test_read_input(oracle, reference, seed):
     if chain:
         assert len(rv) == len(wv) and (rv["skip"] == 0).sum() > 0
         util.assert_gt_meth_close(wv["gtm"], wv["skip"], rv["gtm"], rv["skip"], exact_doubles=True)
+
+
+# ---- writer side: print_vcf_entry / flush_vcf_entries / _print_vcf_entry (src/print_vcf.c) ------------------------------
+def _same_bcf(got, want, what):
+    if got[0].tobytes() != want[0].tobytes() or got[1] != want[1]:
+        a, b = util.split_bcf(got[0]), util.split_bcf(want[0])
+        for k, (ra, rb) in enumerate(zip(a, b)):
+            assert ra == rb, "%s: record %d differs\n%s\n%s" % (what, k, ra.hex(), rb.hex())
+        raise AssertionError("%s: %d records vs %d" % (what, len(a), len(b)))
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_print_block_on_called_blocks(oracle, reference, case):
+    """the BCF records the reference's writer emits for a block (its own compiled print_vcf.c behind a capturing
+    bcf_write) against the restatement, byte for byte, on blocks called by the reference itself"""
+    rng = np.random.default_rng(300 + case)
+    ref = blockgen.random_reference(rng, 6000, n_runs=6)
+    T, B, M, y = blockgen.make_block(rng, ref, 200, 4800, **CASES[case])
+    x, pile_r, vcf_r, ref_r, nt_r, nb_r = reference.process_block(T, B, M, ref, y)
+    refw = blockgen.window_codes(ref, x, y + 2)
+    for allp in (False, True):
+        for ctg_end in (0xffffffff, x + len(vcf_r) // 2):
+            want = reference.print_block(vcf_r, refw, x, rid=case, ctg_end=ctg_end, all_positions=allp)
+            got = oracle.print_block(vcf_r, refw, x, rid=case, ctg_end=ctg_end, all_positions=allp)
+            _same_bcf(got, want, "case %d all_positions %r" % (case, allp))
+    assert want[1] > 100
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_print_block_on_random_records(oracle, reference, seed):
+    """records built to reach every branch of the writer (any call on any reference base incl. N, two ALT alleles, deep
+    counts, all filter combinations, certain and hopeless posteriors), N runs in the reference window, blocks of every
+    small size, header ids that need one, two and four bytes"""
+    rng = np.random.default_rng(900 + seed)
+    ids = [list(range(16)), [3, 200, 5, 40000, 7, 100000, 9, 11, 127, 128, 13, 15, 17, 19, 21, 23]][seed % 2]
+    sizes = list(range(1, 9)) + [40, 333, 2000]
+    for sz in sizes:
+        vcf = util.random_gt_vcf(rng, sz, skip_frac=[0.0, 0.25, 0.6][seed % 3])
+        refw = rng.integers(1, 5, size=sz + 2).astype(np.uint8)
+        refw[rng.random(sz + 2) < [0.0, 0.03, 0.3][(seed // 2) % 3]] = 0
+        x = int(rng.integers(1, 1000))
+        ctg_end = x + sz - 1 - int(rng.integers(0, 3))
+        for allp in (False, True):
+            want = reference.print_block(vcf, refw, x, rid=3, ctg_end=ctg_end, vcf_ids=ids, all_positions=allp)
+            got = oracle.print_block(vcf, refw, x, rid=3, ctg_end=ctg_end, vcf_ids=ids, all_positions=allp)
+            _same_bcf(got, want, "seed %d size %d all_positions %r" % (seed, sz, allp))

@@ -114,3 +114,38 @@ def golden_profile(name):
     """the reference's --report-file side channels for golden `name` (tests/golden/profile_v1.npz)"""
     g = load_golden("profile_v1")
     return {k: g[name + "__" + k] for k in ("used", "conv", "base_filter", "filter_cts", "filter_bases")}, g.get(name + "__ref")
+
+
+def random_gt_vcf(rng, n, skip_frac=0.25, deep_frac=0.05):
+    """gt_vcf records that are not the output of any pileup but visit every branch of the writer: any call, any depth (one-
+    and two-byte integer vectors), posteriors from certain to hopeless, strand bias, low MQ, empty count slots"""
+    from bs_call_b200.records import GT_VCF
+    v = np.zeros(n, dtype=GT_VCF)
+    g = v["gtm"]
+    depth = np.where(rng.random(n) < deep_frac, rng.integers(100, 70000, size=n), rng.integers(0, 40, size=n))
+    for k in range(8):
+        g["counts"][:, k] = (rng.random(n) < 0.45) * rng.integers(0, 1 + depth // 3 + 1, size=n)
+    g["qual"] = rng.integers(0, 44, size=(n, 8))
+    lp = -np.abs(rng.normal(0, 1, size=(n, 10))) * rng.choice([0.01, 1.0, 30.0, 200.0], size=(n, 1))
+    best = rng.integers(0, 10, size=n)
+    lp[np.arange(n), best] = -np.abs(rng.normal(0, 1, size=n)) * rng.choice([0.0, 1e-9, 1e-3, 0.3], size=n)
+    g["gt_prob"] = lp
+    g["fisher_strand"] = -np.abs(rng.normal(0, 1, size=n)) * rng.choice([0.0, 0.5, 4.0, 9.0], size=n)
+    g["mq"] = rng.integers(0, 61, size=n)
+    g["aq"] = rng.integers(0, 44, size=n)
+    g["max_gt"] = best
+    v["ready"] = 1
+    v["skip"] = (rng.random(n) < skip_frac) | (g["counts"].sum(axis=1) == 0)
+    return v
+
+
+def split_bcf(buf):
+    """BCF record bytes -> list of per-record byte strings"""
+    out, at = [], 0
+    while at < len(buf):
+        l = 8 + int(buf[at:at + 4].view("<u4")[0]) + int(buf[at + 4:at + 8].view("<u4")[0])
+        out.append(buf[at:at + l].tobytes())
+        at += l
+    assert at == len(buf)
+    return out
+
