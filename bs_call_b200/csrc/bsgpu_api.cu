@@ -123,6 +123,10 @@ struct bsgpu_ctx {
 	// --report-file side channels (bsgpu_profile_enable)
 	bool profile_on = false;
 	ProfDev *d_prof = nullptr;
+	// writer side
+	DevBuf wr_site, wr_cta, wr_out, wr_vcf, wr_ref;
+	unsigned long long *d_wr_totals = nullptr;   // 8 slots of (bytes, records, oversized)
+	unsigned long long *h_wr_totals = nullptr;   // pinned mirror
 	uint64_t reader_tally[30] = {0};             // read_input's filter_cts[15] | filter_bases[15] (host side, bsgpu_call_bam)
 	DevBuf prof_scratch;                         // used16 | cand | chunkmax of the window being normalised
 	int prof_parity = 0;                         // which ProfDev::used[] holds the running value
@@ -216,6 +220,9 @@ int bsgpu_init(const bsgpu_params *p, bsgpu_ctx **out) {
 		CU(cudaEventCreateWithFlags(&c->slot[i].done, cudaEventDisableTiming));
 	}
 	CU(configure_kernels());
+	CU(configure_writer());
+	CU(cudaMalloc(&c->d_wr_totals, 8 * 3 * sizeof(unsigned long long)));
+	CU(cudaHostAlloc(&c->h_wr_totals, 8 * 3 * sizeof(unsigned long long), cudaHostAllocDefault));
 	{ const char *e = getenv("BSGPU_FUSED"); c->fused = e && atoi(e) == 1; }
 	*out = c;
 	return BSGPU_OK;
@@ -243,6 +250,9 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 	if (c->d_counters) cudaFree(c->d_counters);
 	if (c->d_prof) cudaFree(c->d_prof);
 	c->prof_scratch.release();
+	c->wr_site.release(); c->wr_cta.release(); c->wr_out.release(); c->wr_vcf.release(); c->wr_ref.release();
+	if (c->d_wr_totals) cudaFree(c->d_wr_totals);
+	if (c->h_wr_totals) cudaFreeHost(c->h_wr_totals);
 	delete c;
 }
 
@@ -579,6 +589,189 @@ int bsgpu_process_block(bsgpu_ctx *c, const bsgpu_template *t, size_t n, const u
 	if (after[3] != before[3]) return fail("bsgpu_process_block: %llu mate(s) start before the block window", after[3] - before[3]);
 	if (x_out) *x_out = x;
 	return block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, out, 1, false);
+}
+
+// ------------------------------------------------------------------------------------------------
+// writer side: gt_vcf[] -> BCF records
+// ------------------------------------------------------------------------------------------------
+void bsgpu_default_bcf_params(bsgpu_bcf_params *p) {
+	memset(p, 0, sizeof(*p));
+	for (int k = 0; k < 16; k++) p->ids[k] = k;      // the order print_vcf_header() adds them to an empty header
+	p->ctg_end = 0xffffffffu;
+}
+
+static int check_totals(const unsigned long long *t, size_t out_cap, const char *who) {
+	if (t[2]) return fail("%s: %llu record(s) longer than %d bytes", who, t[2], BSGPU_BCF_MAX_RECORD);
+	if (t[0] > out_cap) return fail("%s: output buffer too small (%llu bytes needed, %zu given)", who, t[0], out_cap);
+	return BSGPU_OK;
+}
+
+// one block, everything resident: records into d_out, sizes back through the pinned totals (slot 0); waits for `st`
+static int bcf_run(bsgpu_ctx *c, const void *d_vcf, const void *d_ref, uint32_t x, uint32_t sz, const bsgpu_bcf_params *p,
+		void *d_out, size_t out_cap, size_t *nbytes, size_t *nrec, cudaStream_t st, const char *who) {
+	if (bcf_site_scratch_bytes(sz) > c->wr_site.cap || bcf_cta_scratch_bytes(sz) > c->wr_cta.cap) CU(cudaDeviceSynchronize());
+	CU(c->wr_site.reserve(bcf_site_scratch_bytes(sz)));
+	CU(c->wr_cta.reserve(bcf_cta_scratch_bytes(sz)));
+	BcfJob j;
+	j.d_vcf = d_vcf; j.d_ref = d_ref; j.x = x; j.sz = sz; j.d_blocks = nullptr; j.nblocks = 0; j.p = *p; j.dc = c->d_const;
+	j.site_scratch = c->wr_site.p;
+	CU(launch_bcf_calls(j, 0, sz, st, &c->launches));
+	CU(launch_bcf_records(j, 0, sz, c->wr_cta.p, d_out, out_cap, c->d_wr_totals, st, &c->launches));
+	CU(cudaMemcpyAsync(c->h_wr_totals, c->d_wr_totals, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if (check_totals(c->h_wr_totals, out_cap, who) != BSGPU_OK) return BSGPU_FAIL;
+	*nbytes = (size_t)c->h_wr_totals[0];
+	*nrec = (size_t)c->h_wr_totals[1];
+	return BSGPU_OK;
+}
+
+int bsgpu_bcf_block_dev(bsgpu_ctx *c, const void *d_vcf, const void *d_ref, uint32_t x, uint32_t sz, const bsgpu_bcf_params *p,
+		void *d_out, size_t out_cap, size_t *nbytes, size_t *nrec, void *stream) {
+	if (!c || !p || !nbytes || !nrec) return fail("bsgpu_bcf_block_dev: null argument");
+	*nbytes = *nrec = 0;
+	if (!sz) return BSGPU_OK;
+	if (!d_vcf || !d_ref || !d_out) return fail("bsgpu_bcf_block_dev: null buffer");
+	if ((uintptr_t)d_vcf & 7u) return fail("bsgpu_bcf_block_dev: gt_vcf[] must be 8-byte aligned");
+	CU(cudaSetDevice(c->device));
+	return bcf_run(c, d_vcf, d_ref, x, sz, p, d_out, out_cap, nbytes, nrec, stream ? (cudaStream_t)stream : c->stream, "bsgpu_bcf_block_dev");
+}
+
+int bsgpu_bcf_block(bsgpu_ctx *c, const bsgpu_gt_vcf *vcf, const uint8_t *ref, uint32_t x, uint32_t sz, const bsgpu_bcf_params *p,
+		uint8_t *out, size_t out_cap, size_t *nbytes, size_t *nrec) {
+	if (!c || !p || !nbytes || !nrec) return fail("bsgpu_bcf_block: null argument");
+	*nbytes = *nrec = 0;
+	if (!sz) return BSGPU_OK;
+	if (!vcf || !ref || !out) return fail("bsgpu_bcf_block: null buffer");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	const size_t dcap = (size_t)sz * BSGPU_BCF_MAX_RECORD < out_cap ? (size_t)sz * BSGPU_BCF_MAX_RECORD : out_cap;
+	CU(c->wr_vcf.reserve((size_t)sz * sizeof(bsgpu_gt_vcf)));
+	CU(c->wr_ref.reserve((size_t)sz + 16));
+	CU(c->wr_out.reserve(dcap + 16));
+	CU(cudaMemcpyAsync(c->wr_vcf.p, vcf, (size_t)sz * sizeof(bsgpu_gt_vcf), cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->wr_ref.p, ref, (size_t)sz + 2, cudaMemcpyHostToDevice, c->stream));
+	c->stats.h2d_bytes += (size_t)sz * (sizeof(bsgpu_gt_vcf) + 1) + 2;
+	if (bcf_run(c, c->wr_vcf.p, c->wr_ref.p, x, sz, p, c->wr_out.p, dcap, nbytes, nrec, c->stream, "bsgpu_bcf_block") != BSGPU_OK) return BSGPU_FAIL;
+	if (*nbytes) CU(cudaMemcpy(out, c->wr_out.p, *nbytes, cudaMemcpyDeviceToHost));
+	c->stats.d2h_bytes += *nbytes + 24;
+	return BSGPU_OK;
+}
+
+static int block_dev(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *d_bases, const void *d_ref, uint32_t x, uint32_t sz,
+		void *d_out, int mode, void *d_scratch, void *stream);
+
+int bsgpu_call_block_bcf(bsgpu_ctx *c, const bsgpu_seg *segs, size_t nseg, const uint8_t *bases, size_t nbases, const uint8_t *ref,
+		uint32_t x, uint32_t sz, const bsgpu_bcf_params *p, uint8_t *out, size_t out_cap, size_t *nbytes, size_t *nrec) {
+	if (!c || !p || !nbytes || !nrec) return fail("bsgpu_call_block_bcf: null argument");
+	*nbytes = *nrec = 0;
+	if (!sz) return BSGPU_OK;
+	if (!ref || !out || (nseg && (!segs || !bases))) return fail("bsgpu_call_block_bcf: null buffer");
+	if (nbases > 0xffffffffull) return fail("bsgpu_call_block_bcf: more than 4 GiB of bases in one block; split the window");
+	for (size_t i = 0; i < nseg; i++) {
+		if (segs[i].len > BSGPU_MAX_SEG_LEN) return fail("bsgpu_call_block_bcf: segment %zu longer than %d (use bsgpu_stage_templates)", i, BSGPU_MAX_SEG_LEN);
+		if ((size_t)segs[i].off + segs[i].len > nbases) return fail("bsgpu_call_block_bcf: segment %zu points outside bases[]", i);
+	}
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->copy_stream));
+	const size_t dcap = (size_t)sz * BSGPU_BCF_MAX_RECORD < out_cap ? (size_t)sz * BSGPU_BCF_MAX_RECORD : out_cap;
+	CU(c->segs.reserve(nseg * sizeof(bsgpu_seg) + 16));
+	CU(c->bases.reserve(nbases + 16));
+	CU(c->wr_ref.reserve((size_t)sz + 16));
+	CU(c->wr_vcf.reserve((size_t)sz * sizeof(bsgpu_gt_vcf)));
+	CU(c->wr_out.reserve(dcap + 16));
+	if (nseg) {
+		CU(cudaMemcpyAsync(c->segs.p, segs, nseg * sizeof(bsgpu_seg), cudaMemcpyHostToDevice, c->stream));
+		CU(cudaMemcpyAsync(c->bases.p, bases, nbases, cudaMemcpyHostToDevice, c->stream));
+	}
+	CU(cudaMemcpyAsync(c->wr_ref.p, ref, (size_t)sz + 2, cudaMemcpyHostToDevice, c->stream));
+	c->stats.h2d_bytes += nseg * sizeof(bsgpu_seg) + nbases + sz + 2;
+	if (block_dev(c, c->segs.p, nseg, c->bases.p, c->wr_ref.p, x, sz, c->wr_vcf.p, 1, nullptr, c->stream) != BSGPU_OK) return BSGPU_FAIL;
+	if (bcf_run(c, c->wr_vcf.p, c->wr_ref.p, x, sz, p, c->wr_out.p, dcap, nbytes, nrec, c->stream, "bsgpu_call_block_bcf") != BSGPU_OK) return BSGPU_FAIL;
+	if (*nbytes) CU(cudaMemcpy(out, c->wr_out.p, *nbytes, cudaMemcpyDeviceToHost));
+	c->stats.d2h_bytes += *nbytes + 24;
+	return BSGPU_OK;
+}
+
+// pileup[] of one block of n sites -> BCF records.  Chunks of sites go up on one stream, through the model and the
+// writer on the context stream and down on the copy stream; the writer runs one chunk behind the model because a
+// site's record looks at the calls of the two sites after it.
+int bsgpu_call_sites_bcf(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t *ref, size_t n, uint32_t x, const bsgpu_bcf_params *p,
+		uint8_t *out, size_t out_cap, size_t *nbytes, size_t *nrec) {
+	if (!c || !p || !nbytes || !nrec) return fail("bsgpu_call_sites_bcf: null argument");
+	*nbytes = *nrec = 0;
+	if (!n) return BSGPU_OK;
+	if (!pileup || !ref || !out) return fail("bsgpu_call_sites_bcf: null buffer");
+	if (n > 0xfffffff0ull) return fail("bsgpu_call_sites_bcf: more than 2^32 sites in one block");
+	CU(cudaSetDevice(c->device));
+	cudaStream_t up = c->slot[0].stream, st = c->stream, down = c->copy_stream;
+	CU(cudaStreamSynchronize(up)); CU(cudaStreamSynchronize(st)); CU(cudaStreamSynchronize(down));
+	const size_t chunk = 1u << 20;
+	const size_t K = (n + chunk - 1) / chunk;
+	const size_t ocap = chunk * BSGPU_BCF_MAX_RECORD;          // one chunk's records at most
+	CU(c->slot[0].in.reserve(chunk * sizeof(bsgpu_pileup)));
+	CU(c->slot[1].in.reserve(chunk * sizeof(bsgpu_pileup)));
+	CU(c->wr_vcf.reserve(2 * chunk * sizeof(bsgpu_gt_vcf)));
+	CU(c->wr_out.reserve(2 * ocap + 16));
+	CU(c->wr_ref.reserve(n + 16));
+	CU(c->wr_site.reserve(bcf_site_scratch_bytes((uint32_t)n)));
+	CU(c->wr_cta.reserve(2 * bcf_cta_scratch_bytes((uint32_t)chunk)));
+	std::vector<cudaEvent_t> ev(4 * K);                         // per chunk: uploaded, modelled, records built, records copied out
+	for (auto &e : ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	auto E = [&](size_t k, int what) { return ev[4 * k + what]; };
+	BcfJob j;
+	j.d_ref = c->wr_ref.p; j.x = x; j.sz = (uint32_t)n; j.d_blocks = nullptr; j.nblocks = 0; j.p = *p; j.dc = c->d_const;
+	j.site_scratch = c->wr_site.p;
+	CU(cudaMemcpyAsync(c->wr_ref.p, ref, n + 2, cudaMemcpyHostToDevice, up));
+	size_t at = 0, recs = 0;
+	int ret = BSGPU_OK;
+	// build the records of chunk k (its model and that of chunk k + 1 are queued), start their way home when sized
+	auto queue_records = [&](size_t k) -> int {
+		const size_t lo = k * chunk, m = n - lo < chunk ? n - lo : chunk;
+		if (k >= 2) CU(cudaStreamWaitEvent(st, E(k - 2, 3), 0));      // the output buffer of chunk k - 2 has left
+		// a.vcf + i must address the ring slot of chunk k for the sites of chunk k (no other site's record is read)
+		j.d_vcf = (const uint8_t *)c->wr_vcf.p + (k & 1) * chunk * sizeof(bsgpu_gt_vcf) - lo * sizeof(bsgpu_gt_vcf);
+		CU(launch_bcf_records(j, (uint32_t)lo, (uint32_t)m, (uint8_t *)c->wr_cta.p + (k & 1) * bcf_cta_scratch_bytes((uint32_t)chunk),
+				(uint8_t *)c->wr_out.p + (k & 1) * ocap, ocap, c->d_wr_totals + 3 * (k & 7), st, &c->launches));
+		CU(cudaMemcpyAsync(c->h_wr_totals + 3 * (k & 7), c->d_wr_totals + 3 * (k & 7), 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		CU(cudaEventRecord(E(k, 2), st));
+		return BSGPU_OK;
+	};
+	auto collect = [&](size_t k) -> int {
+		CU(cudaEventSynchronize(E(k, 2)));
+		const unsigned long long *t = c->h_wr_totals + 3 * (k & 7);
+		if (t[2]) return fail("bsgpu_call_sites_bcf: %llu record(s) longer than %d bytes", t[2], BSGPU_BCF_MAX_RECORD);
+		if (at + t[0] > out_cap) return fail("bsgpu_call_sites_bcf: output buffer too small (%zu bytes given)", out_cap);
+		if (t[0]) CU(cudaMemcpyAsync(out + at, (uint8_t *)c->wr_out.p + (k & 1) * ocap, t[0], cudaMemcpyDeviceToHost, down));
+		CU(cudaEventRecord(E(k, 3), down));
+		at += t[0]; recs += t[1];
+		c->stats.d2h_bytes += t[0] + 24;
+		return BSGPU_OK;
+	};
+	for (size_t k = 0; k < K && ret == BSGPU_OK; k++) {
+		const size_t lo = k * chunk, m = n - lo < chunk ? n - lo : chunk;
+		if (k >= 2) CU(cudaStreamWaitEvent(up, E(k - 2, 1), 0));      // the model has consumed the input buffer
+		CU(cudaMemcpyAsync(c->slot[k & 1].in.p, pileup + lo, m * sizeof(bsgpu_pileup), cudaMemcpyHostToDevice, up));
+		CU(cudaEventRecord(E(k, 0), up));
+		c->stats.h2d_bytes += m * (sizeof(bsgpu_pileup) + 1);
+		CU(cudaStreamWaitEvent(st, E(k, 0), 0));
+		CU(launch_call_sites(c->slot[k & 1].in.p, (const uint8_t *)c->wr_ref.p + lo, m, (uint8_t *)c->wr_vcf.p + (k & 1) * chunk * sizeof(bsgpu_gt_vcf),
+				nullptr, true, c->d_const, c->d_counters, st, &c->launches));
+		CU(cudaEventRecord(E(k, 1), st));
+		j.d_vcf = (const uint8_t *)c->wr_vcf.p + (k & 1) * chunk * sizeof(bsgpu_gt_vcf) - lo * sizeof(bsgpu_gt_vcf);
+		CU(launch_bcf_calls(j, (uint32_t)lo, (uint32_t)m, st, &c->launches));
+		if (k >= 1) ret = queue_records(k - 1);
+		if (ret == BSGPU_OK && k >= 2) ret = collect(k - 2);
+	}
+	if (ret == BSGPU_OK) ret = queue_records(K - 1);
+	if (ret == BSGPU_OK && K >= 2) ret = collect(K - 2);
+	if (ret == BSGPU_OK) ret = collect(K - 1);
+	cudaStreamSynchronize(up); cudaStreamSynchronize(st); cudaStreamSynchronize(down);
+	for (auto &e : ev) cudaEventDestroy(e);
+	if (ret != BSGPU_OK) return ret;
+	c->stats.sites += n;
+	*nbytes = at; *nrec = recs;
+	return BSGPU_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -67,6 +67,24 @@ cudaError_t launch_normalise(const void *tmpl, size_t n, const void *bases, void
 		void *segs, uint32_t segs_per_mate, uint32_t x, uint32_t y, const uint32_t left_trim[2], const uint32_t right_trim[2],
 		unsigned long long *counters, const ProfArgs *prof, int parity, cudaStream_t stream, int *launches);
 
+// writer side (bsgpu_writer.cu): gt_vcf[] of a window -> BCF records
+struct BcfJob {
+	const void *d_vcf;               // gt_vcf[sz]
+	const void *d_ref;               // sz + 2 codes, index 0 = position x
+	uint32_t x, sz;
+	const void *d_blocks;            // (first, last) site index of every block, ascending; NULL = the window is one block
+	uint32_t nblocks;
+	bsgpu_bcf_params p;
+	const DevConst *dc;
+	void *site_scratch;              // bcf_site_scratch_bytes(sz)
+};
+size_t bcf_site_scratch_bytes(uint32_t sz);
+size_t bcf_cta_scratch_bytes(uint32_t cnt);
+cudaError_t configure_writer();
+cudaError_t launch_bcf_calls(const BcfJob &j, uint32_t i0, uint32_t cnt, cudaStream_t stream, int *launches);
+cudaError_t launch_bcf_records(const BcfJob &j, uint32_t i0, uint32_t cnt, void *cta_scratch, void *d_out, size_t out_cap,
+		unsigned long long *d_totals, cudaStream_t stream, int *launches);
+
 // reader side (bsgpu_reader.cu)
 cudaError_t launch_decode_records(const void *bam, const void *rec_off, const void *read_off, const void *mm_off, size_t nrec,
 		uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup, void *out, void *bases, void *misms,

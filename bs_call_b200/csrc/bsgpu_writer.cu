@@ -1,0 +1,461 @@
+// bsgpu_writer.cu -- the per-site derivations of the VCF/BCF writer on the device.
+//
+// What the reference's print thread does with a block of gt_vcf records (src/process.c:89-104 driving
+// print_vcf_entry / flush_vcf_entries / _print_vcf_entry, src/print_vcf.c:32-381, 535-594): pick the call of every
+// site, look at the calls and the reference codes two sites either side, derive QUAL / GQ, QD, FS, the filters, the
+// genotype likelihood subset, the CpG status, and serialise one BCF record per site that is not skipped.  There the
+// block is walked with a five-site sliding window on one thread; here every site is an independent function of the
+// block (the formulation of oracle/bs_oracle_writer.c, which is pinned against the reference's compiled print_vcf.c),
+// so the records are built by one thread per site, sized first, placed by a prefix sum, and leave the device as the
+// byte stream bcf_write() would have produced -- about a quarter of the bytes of the gt_vcf records they replace.
+//
+//   k_bcf_measure   call of every site (u8) + length of its record (u16) + per-CTA byte / record totals
+//   k_bcf_offsets   exclusive scan of the per-CTA totals (one CTA)
+//   k_bcf_emit      records built in shared memory at their offsets inside the CTA, copied out as aligned words
+//
+// The byte encoding is BCF2 (VCF/BCF specification v4.3 section 6.3) as htslib's bcf_enc_* helpers produce it.
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "bsgpu.h"
+#include "bsgpu_device.cuh"
+#include "bsgpu_launch.h"
+
+namespace bsgpu {
+
+namespace {
+
+constexpr int kWrThreads = 128;                       // sites per CTA
+constexpr int kMaxRec = BSGPU_BCF_MAX_RECORD;         // upper bound of one record (checked per site)
+constexpr double kLn10 = 2.30258509299404568402;     // LOG10, include/bs_call.h:36
+
+struct GtVcf {                 // bsgpu_gt_vcf as the kernels read it
+	unsigned long long counts[8];
+	int qual[8];
+	double gt_prob[10];
+	double fisher_strand;
+	int mq, aq;
+	uint8_t max_gt, pad0[7];
+	uint8_t ready, skip, pad1[6];
+};
+static_assert(sizeof(GtVcf) == 208, "gt_vcf layout");
+
+enum { T_INT8 = 1, T_INT16 = 2, T_INT32 = 3, T_FLOAT = 5, T_CHAR = 7 };
+
+struct Count { uint32_t n = 0; __device__ __forceinline__ void put(uint32_t) { n++; } };
+struct Store { uint8_t *p; uint32_t n = 0; __device__ __forceinline__ void put(uint32_t c) { p[n++] = (uint8_t)c; } };
+
+template <class W> __device__ __forceinline__ void put_le(W &w, uint32_t v, int bytes) { for (int b = 0; b < bytes; b++) w.put(v >> (8 * b)); }
+template <class W> __device__ void enc_size(W &w, int size, int type) {
+	if (size < 15) { w.put(size << 4 | type); return; }
+	w.put(15 << 4 | type);
+	if (size < 128) { w.put(1 << 4 | T_INT8); w.put(size); }
+	else if (size < 32768) { w.put(1 << 4 | T_INT16); put_le(w, (uint32_t)size, 2); }
+	else { w.put(1 << 4 | T_INT32); put_le(w, (uint32_t)size, 4); }
+}
+__device__ __forceinline__ int int_type(int32_t mn, int32_t mx) {          // narrowest type; the lowest eight values are reserved
+	if (mx <= 127 && mn >= -120) return T_INT8;
+	if (mx <= 32767 && mn >= -32760) return T_INT16;
+	return T_INT32;
+}
+template <class W> __device__ void enc_int1(W &w, int32_t x) {
+	const int t = int_type(x, x);
+	w.put(1 << 4 | t);
+	put_le(w, (uint32_t)x, t == T_INT8 ? 1 : t == T_INT16 ? 2 : 4);
+}
+template <class W> __device__ void enc_vint(W &w, int n, const int32_t *a) {
+	if (n == 1) { enc_int1(w, a[0]); return; }
+	int32_t mx = INT32_MIN + 1, mn = INT32_MAX;
+	for (int i = 0; i < n; i++) { mx = max(mx, a[i]); mn = min(mn, a[i]); }
+	const int t = int_type(mn, mx);
+	enc_size(w, n, t);
+	for (int i = 0; i < n; i++) put_le(w, (uint32_t)a[i], t == T_INT8 ? 1 : t == T_INT16 ? 2 : 4);
+}
+
+// genotype index 0..9 = AA AC AG AT CC CG CT GG GT TT -> its two alleles as reference codes 1..4
+__device__ __forceinline__ void alleles_of(int gt, int &a0, int &a1) {
+	a0 = gt < 4 ? 1 : gt < 7 ? 2 : gt < 9 ? 3 : 4;
+	a1 = gt < 4 ? 1 + gt : gt < 7 ? gt - 2 : gt < 9 ? gt - 4 : 4;
+}
+__device__ __forceinline__ int gl_index(int a, int b) { return a < b ? a * (9 - a) / 2 + b - 5 : b * (9 - b) / 2 + a - 5; }
+__device__ __forceinline__ bool has_c(int gt) { return (0x072u >> gt) & 1u; }          // AC CC CG CT
+__device__ __forceinline__ bool has_g(int gt) { return (0x1a4u >> gt) & 1u; }          // AG CG GG GT
+__device__ __forceinline__ bool is_het(int gt) { return (0x16eu >> gt) & 1u; }         // AC AG AT CG CT GT
+
+// the call the writer makes (src/print_vcf.c:579-588): first maximum of gt_prob, 0 for a skipped site
+__device__ __forceinline__ int site_call(const GtVcf *v) {
+	if (v->skip) return 0;
+	int gt = 0;
+	double z = v->gt_prob[0];
+#pragma unroll
+	for (int i = 1; i < 10; i++) { const double p = v->gt_prob[i]; if (p > z) { z = p; gt = i; } }
+	return gt + 1;
+}
+
+struct WrArgs {
+	const GtVcf *vcf;
+	const uint8_t *ref;              // codes of positions x .. x + sz + 1
+	uint32_t x, sz;                  // window: position of site 0, number of sites
+	uint32_t i0, i1;                 // sites [i0, i1) are handled by this launch
+	const uint2 *blocks;             // (first, last) site index of every block in the window, ascending; NULL = the window is one block
+	uint32_t nblocks;
+	int32_t ids[16];
+	int32_t rid;
+	uint32_t ctg_end;
+	int all_positions;
+	const DevConst *dc;
+	uint8_t *calls;                  // per site: 0, or 1 + genotype
+	uint16_t *len;                   // per site: bytes of its record
+	unsigned long long *cta_bytes;   // per CTA: bytes, then (after k_bcf_offsets) offset of the CTA's first byte
+	uint32_t *cta_recs;
+	unsigned long long *totals;      // [0] bytes, [1] records, [2] sites whose record exceeded kMaxRec
+	uint8_t *out;
+	unsigned long long out_cap;
+};
+
+// block of site i: first / last site index; false when the site lies between blocks.  A site shared by two touching
+// blocks is the earlier block's (the later visit is dropped by the x <= old_x test, src/print_vcf.c:127).
+__device__ bool block_of(const WrArgs &a, uint32_t i, uint32_t &first, uint32_t &last) {
+	if (!a.blocks) { first = 0; last = a.sz - 1; return true; }
+	uint32_t lo = 0, hi = a.nblocks;
+	while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a.blocks[mid].y < i) lo = mid + 1; else hi = mid; }
+	if (lo == a.nblocks || a.blocks[lo].x > i) return false;
+	first = a.blocks[lo].x; last = a.blocks[lo].y;
+	return true;
+}
+
+// One record.  `g` = calls of sites i-2 .. i+2 as the writer's window holds them.  Returns bytes written (0: no record).
+template <class W>
+__device__ uint32_t build_record(const WrArgs &a, uint32_t i, uint32_t first, uint32_t last, const int g[5], W &w) {
+	if (!g[2]) return 0;
+	const GtVcf *v = a.vcf + i;
+	uint32_t dp1 = 0, dinf = 0;
+#pragma unroll
+	for (int k = 0; k < 4; k++) { dp1 += (uint32_t)v->counts[k]; dinf += (uint32_t)v->counts[4 + k]; }
+	if (!(dp1 + dinf)) return 0;
+	// Reference context.  The reference fills its window with strncpy() from a string in which N is the terminator
+	// (src/print_vcf.c:572-578), so once an N has been copied everything after it reads as N; the window starts at
+	// site - 2, except for the last two sites of a block, which reuse the window of the block's last site
+	// (flush_vcf_entries only shifts it, :539-543): an N up to two codes further left wipes them too.  Codes before the
+	// block are N.
+	uint32_t rc[5];
+	{
+		const int64_t ii = i, f = first, l = last;
+		const int64_t wstart = ii + 2 <= l ? ii - 2 : l - 4;
+		bool wiped = false;
+		for (int64_t j = wstart < f ? f : wstart; j < ii - 2; j++) wiped |= a.ref[j] == 0;
+#pragma unroll
+		for (int k = 0; k < 5; k++) {
+			const int64_t j = ii + k - 2;
+			const uint32_t c = j >= f && !wiped ? a.ref[j] : 0u;
+			if (c == 0 && j >= f) wiped = true;
+			rc[k] = c;
+		}
+	}
+	const int rfix = (int)rc[2], gt = g[2] - 1;
+	if (!a.all_positions && ((gt == 0 && rfix == 1) || (gt == 9 && rfix == 4))) return 0;      // hom-ref A / T (gt_flag, :91-102)
+	if (a.x + i > a.ctg_end) return 0;
+	// QUAL / GQ: phred of the probability that the call is wrong (:140-148)
+	const MathTables *mt = &a.dc->tab.math;
+	const double lp = v->gt_prob[gt] * kLn10;
+	const double z1 = lp == 0.0 ? 1.0 : fast_exp(lp < -700.0 ? -700.0 : lp, mt);
+	int phred;
+	if (z1 >= 1.0) phred = 255;
+	else { phred = (int)(-10.0 * fast_log(1.0 - z1, mt) / kLn10); if (phred > 255) phred = 255; }
+	const int fs = (int)(-v->fisher_strand * 10.0 + 0.5);
+	const uint32_t qd = dp1 > 0 ? (uint32_t)phred / dp1 : (uint32_t)phred;
+	uint32_t flt = 0;
+	if (phred < 20) flt |= 1;
+	if (qd < 2) flt |= 2;
+	if (fs > 60) flt |= 4;
+	if (v->mq < 40) flt |= 8;
+	int32_t fid = a.ids[0];
+	if (!flt) {
+		const unsigned long long *c = v->counts;
+		bool mac1 = false;
+		switch (gt) {                                                                  // :190-210
+		case 1: mac1 = c[1] + c[5] + c[7] <= 1 || c[0] + c[4] <= 1; break;
+		case 2: mac1 = c[2] + c[6] <= 1 || c[0] <= 1; break;
+		case 3: mac1 = c[3] + c[7] <= 1 || c[0] + c[4] <= 1; break;
+		case 5: mac1 = c[2] + c[6] + c[4] <= 1 || c[1] + c[5] + c[7] <= 1; break;
+		case 6: mac1 = c[3] <= 1 || c[1] + c[5] <= 1; break;
+		case 8: mac1 = c[3] + c[7] <= 1 || c[2] + c[6] + c[4] <= 1; break;
+		}
+		if (mac1) fid = a.ids[2];
+	} else fid = a.ids[1];
+	// ALT: the alleles of the call that are not the reference base, in base order (ref_alt / all_idx, :34-45, 62-73)
+	int a0, a1;
+	alleles_of(gt, a0, a1);
+	int alts[2] = { 0, 0 }, n_alt = 0;
+	if (a0 != rfix) alts[n_alt++] = a0;
+	if (a1 != rfix && a1 != a0) alts[n_alt++] = a1;
+	const uint32_t base_char = 0x54474341u;            // "ACGT"
+	auto bchar = [&](uint32_t c) -> uint32_t { return c ? (base_char >> (8 * (c - 1))) & 0xffu : (uint32_t)'N'; };
+
+	// ---- the fixed part is written last (it holds the lengths); shared then indiv follow it
+	const uint32_t start = w.n;
+	for (int k = 0; k < 32; k++) w.put(0);
+	const uint32_t sh0 = w.n;
+	enc_size(w, 0, T_CHAR);                            // ID: none (no dbSNP index on this path)
+	w.put(1 << 4 | T_CHAR); w.put(bchar(rc[2]));       // REF
+	for (int k = 0; k < n_alt; k++) { w.put(1 << 4 | T_CHAR); w.put(bchar((uint32_t)alts[k])); }
+	enc_int1(w, fid);                                  // FILTER
+	enc_int1(w, a.ids[3]);                             // INFO CX: reference context
+	w.put(5 << 4 | T_CHAR);
+#pragma unroll
+	for (int k = 0; k < 5; k++) w.put(bchar(rc[k]));
+	const uint32_t l_shared = w.n - sh0;
+
+	const uint32_t in0 = w.n;
+	uint32_t n_fmt = 11;
+	// GT as the reference's gt_int table has it (:75-86): 2,2 hom-ref; 4,4 hom-alt; 2,4 het with the reference allele;
+	// 4,8 -- not 4,6 -- for a het of two ALT alleles
+	enc_int1(w, a.ids[4]);
+	w.put(2 << 4 | T_INT8);
+	if (a0 == a1) { const uint32_t c = a0 == rfix ? 2 : 4; w.put(c); w.put(c); }
+	else if (a0 == rfix || a1 == rfix) { w.put(2); w.put(4); }
+	else { w.put(4); w.put(8); }
+	// FT (:277-301): the names of the failed filters, each WITH its terminating NUL (the copy loop steps over it), ';' between
+	enc_int1(w, a.ids[5]);
+	if (flt & 15u) {
+		const uint32_t nl = ((flt & 1u) ? 4 : 0) + ((flt & 2u) ? 4 : 0) + ((flt & 4u) ? 5 : 0) + ((flt & 8u) ? 5 : 0) + __popc(flt & 15u) - 1;
+		enc_size(w, (int)nl, T_CHAR);
+		bool some = false;
+		if (flt & 1u) { w.put('q'); w.put('2'); w.put('0'); w.put(0); some = true; }
+		if (flt & 2u) { if (some) w.put(';'); w.put('q'); w.put('d'); w.put('2'); w.put(0); some = true; }
+		if (flt & 4u) { if (some) w.put(';'); w.put('f'); w.put('s'); w.put('6'); w.put('0'); w.put(0); some = true; }
+		if (flt & 8u) { if (some) w.put(';'); w.put('m'); w.put('q'); w.put('4'); w.put('0'); w.put(0); }
+	} else { w.put(4 << 4 | T_CHAR); w.put('P'); w.put('A'); w.put('S'); w.put('S'); }
+	enc_int1(w, a.ids[8]); enc_int1(w, (int32_t)dp1);  // DP
+	enc_int1(w, a.ids[9]); enc_int1(w, v->mq);         // MQ
+	enc_int1(w, a.ids[7]); enc_int1(w, phred);         // GQ
+	enc_int1(w, a.ids[10]); enc_int1(w, (int32_t)qd);  // QD
+	{                                                  // GL (:317-345): RR, then per ALT allele R/A (when the reference base is known) and A/A
+		enc_int1(w, a.ids[6]);
+		const int n = 1 + n_alt * (rfix ? 2 : 1);
+		w.put(n << 4 | T_FLOAT);
+		auto putf = [&](double z) { if (z < -99.999) z = -99.999; put_le(w, __float_as_uint((float)z), 4); };
+		putf(rfix ? v->gt_prob[gl_index(rfix, rfix)] : -99.999);
+		for (int k = 0; k < n_alt; k++) {
+			if (rfix) putf(v->gt_prob[gl_index(rfix, alts[k])]);
+			putf(v->gt_prob[gl_index(alts[k], alts[k])]);
+		}
+	}
+	{                                                  // MC8, AMQ (:347-358)
+		int32_t c8[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++) c8[k] = (int32_t)v->counts[k];
+		enc_int1(w, a.ids[11]);
+		enc_vint(w, 8, c8);
+		int32_t q8[8];
+		int n = 0;
+#pragma unroll
+		for (int k = 0; k < 8; k++) if (v->counts[k] > 0) q8[n++] = v->qual[k];
+		if (n) { enc_int1(w, a.ids[12]); enc_vint(w, n, q8); n_fmt++; }
+	}
+	enc_int1(w, a.ids[13]);                            // CS: strand(s) on which the call has a cytosine (:60-61)
+	if (has_c(gt)) { if (has_g(gt)) { w.put(2 << 4 | T_CHAR); w.put('+'); w.put('-'); } else { w.put(1 << 4 | T_CHAR); w.put('+'); } }
+	else if (has_g(gt)) { w.put(1 << 4 | T_CHAR); w.put('-'); }
+	else { w.put(2 << 4 | T_CHAR); w.put('N'); w.put('A'); }
+	{                                                  // CG: CpG status from the calls either side (:229-270); "CG" goes out as its first character
+		const int c0 = g[2], nx = g[3], pv = g[1];
+		uint32_t cg;
+		if ((c0 == 5 && nx == 8) || (c0 == 8 && pv == 5)) cg = 'C';
+		else if (c0 == 5) cg = nx ? (has_g(nx - 1) ? 'H' : 'N') : '?';
+		else if (c0 == 8) cg = pv ? (has_c(pv - 1) ? 'H' : 'N') : '?';
+		else if (has_c(c0 - 1)) cg = nx ? (has_g(nx - 1) ? 'H' : 'N') : '?';
+		else if (has_g(c0 - 1)) cg = pv ? (has_c(pv - 1) ? 'H' : 'N') : '.';
+		else cg = '.';
+		enc_int1(w, a.ids[14]);
+		w.put(1 << 4 | T_CHAR); w.put(cg);
+	}
+	enc_int1(w, a.ids[3]);                             // CX: context from the calls, IUPAC
+	w.put(5 << 4 | T_CHAR);
+#pragma unroll
+	for (int k = 0; k < 5; k++) w.put((uint32_t)"NAMRWCSYGKT"[g[k]]);
+	if (is_het(gt)) { enc_int1(w, a.ids[15]); enc_int1(w, fs); n_fmt++; }      // FS
+	const uint32_t l_indiv = w.n - in0;
+
+	// the eight words in front, as bcf_write lays a record out
+	const uint32_t end = w.n;
+	w.n = start;
+	put_le(w, l_shared + 24, 4);
+	put_le(w, l_indiv, 4);
+	put_le(w, (uint32_t)a.rid, 4);
+	put_le(w, a.x + i - 1, 4);
+	put_le(w, 1u, 4);
+	put_le(w, __float_as_uint((float)phred), 4);
+	put_le(w, (uint32_t)(1 + n_alt) << 16 | 1u, 4);
+	put_le(w, n_fmt << 24 | 1u, 4);
+	w.n = end;
+	return end - start;
+}
+
+__global__ void __launch_bounds__(256) k_bcf_calls(const WrArgs a) {
+	const uint32_t i = a.i0 + blockIdx.x * 256 + threadIdx.x;
+	if (i < a.i1) a.calls[i] = (uint8_t)site_call(a.vcf + i);
+}
+
+// the writer's window around site i: nothing before the block; beyond its end the last site's call is seen again
+// (flush_vcf_entries shifts the window without clearing the slot it vacates, src/print_vcf.c:538)
+__device__ __forceinline__ void window_calls(const WrArgs &a, uint32_t i, uint32_t first, uint32_t last, int g[5]) {
+#pragma unroll
+	for (int k = 0; k < 5; k++) {
+		const int64_t j = (int64_t)i + k - 2;
+		g[k] = j < (int64_t)first ? 0 : a.calls[j <= (int64_t)last ? j : (int64_t)last];
+	}
+}
+
+__global__ void __launch_bounds__(kWrThreads) k_bcf_measure(const WrArgs a) {
+	__shared__ uint32_t wsum[kWrThreads / 32][2];
+	const uint32_t i = a.i0 + blockIdx.x * kWrThreads + threadIdx.x;
+	uint32_t n = 0;
+	if (i < a.i1) {
+		uint32_t first, last;
+		if (block_of(a, i, first, last)) {
+			int g[5];
+			window_calls(a, i, first, last, g);
+			Count w;
+			n = build_record(a, i, first, last, g, w);
+			if (n > (uint32_t)kMaxRec) { atomicAdd(a.totals + 2, 1ull); n = 0; }
+		}
+		a.len[i] = (uint16_t)n;
+	}
+	const uint32_t bytes = __reduce_add_sync(0xffffffffu, n), recs = __reduce_add_sync(0xffffffffu, n ? 1u : 0u);
+	if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5][0] = bytes; wsum[threadIdx.x >> 5][1] = recs; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t b = 0, r = 0;
+		for (int k = 0; k < kWrThreads / 32; k++) { b += wsum[k][0]; r += wsum[k][1]; }
+		a.cta_bytes[blockIdx.x] = b;
+		a.cta_recs[blockIdx.x] = r;
+	}
+}
+
+// exclusive scan of the per-CTA byte totals, in place; totals[0] = bytes, totals[1] = records of the window
+__global__ void __launch_bounds__(1024) k_bcf_offsets(unsigned long long *cta_bytes, const uint32_t *cta_recs, uint32_t nctas, unsigned long long *totals) {
+	__shared__ unsigned long long wsum[32];
+	__shared__ unsigned long long carry_s;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	if (tid == 0) carry_s = 0;
+	unsigned long long recs = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < nctas; base += 1024) {
+		const uint32_t j = base + tid;
+		const unsigned long long v = j < nctas ? cta_bytes[j] : 0ull;
+		if (j < nctas) recs += cta_recs[j];
+		unsigned long long inc = v;
+		for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+		if (lane == 31) wsum[wid] = inc;
+		__syncthreads();
+		unsigned long long pre = carry_s;
+		for (int k = 0; k < wid; k++) pre += wsum[k];
+		if (j < nctas) cta_bytes[j] = pre + inc - v;
+		__syncthreads();
+		if (tid == 1023) carry_s = pre + inc;
+		__syncthreads();
+	}
+	for (int d = 16; d; d >>= 1) recs += __shfl_down_sync(0xffffffffu, recs, d);
+	if (lane == 0) wsum[wid] = recs;
+	__syncthreads();
+	if (tid == 0) {
+		unsigned long long r = 0;
+		for (int k = 0; k < 32; k++) r += wsum[k];
+		totals[0] = carry_s;
+		totals[1] = r;
+	}
+}
+
+__global__ void __launch_bounds__(kWrThreads) k_bcf_emit(const WrArgs a) {
+	extern __shared__ __align__(16) uint8_t stage[];          // the CTA's records, back to back
+	__shared__ uint32_t wsum[kWrThreads / 32];
+	const uint32_t i = a.i0 + blockIdx.x * kWrThreads + threadIdx.x;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t n = i < a.i1 ? a.len[i] : 0u;
+	uint32_t inc = n;
+	for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+	if (lane == 31) wsum[wid] = inc;
+	__syncthreads();
+	uint32_t off = inc - n, total = 0;
+	for (int k = 0; k < kWrThreads / 32; k++) { if (k < wid) off += wsum[k]; total += wsum[k]; }
+	if (n) {
+		uint32_t first, last;
+		block_of(a, i, first, last);
+		int g[5];
+		window_calls(a, i, first, last, g);
+		Store w;
+		w.p = stage + off;
+		build_record(a, i, first, last, g, w);
+	}
+	__syncthreads();
+	// copy out: bytes up to the first aligned word of the destination, aligned words (each stitched from two staged
+	// words), bytes after the last one
+	const unsigned long long dst0 = a.cta_bytes[blockIdx.x];
+	if (dst0 + total > a.out_cap) return;                   // the host compares totals[0] with the capacity and reports
+	uint8_t *dst = a.out + dst0;
+	const uint32_t head = min(total, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
+	if (threadIdx.x < head) dst[threadIdx.x] = stage[threadIdx.x];
+	const uint32_t nwords = (total - head) >> 2;
+	uint32_t *dw = (uint32_t *)(dst + head);
+	const uint32_t *sw = (const uint32_t *)stage;
+	const uint32_t sh = (head & 3) * 8;
+	for (uint32_t k = threadIdx.x; k < nwords; k += kWrThreads) {
+		const uint32_t b = head + 4 * k;                     // staged byte offset of this word
+		const uint32_t lo = sw[b >> 2], hi = sw[(b >> 2) + 1];
+		dw[k] = sh ? __funnelshift_r(lo, hi, sh) : lo;
+	}
+	const uint32_t tail0 = head + 4 * nwords;
+	if (threadIdx.x < total - tail0) dst[tail0 + threadIdx.x] = stage[tail0 + threadIdx.x];
+}
+
+}  // namespace
+
+// per-site scratch of a window (calls, lengths) and per-CTA scratch of one launch over `cnt` sites
+size_t bcf_site_scratch_bytes(uint32_t sz) { return (((size_t)sz + 15) & ~(size_t)15) + (((size_t)sz * 2 + 15) & ~(size_t)15); }
+size_t bcf_cta_scratch_bytes(uint32_t cnt) {
+	const size_t nctas = ((size_t)cnt + kWrThreads - 1) / kWrThreads;
+	return nctas * 8 + ((nctas * 4 + 15) & ~(size_t)15) + 16;
+}
+
+cudaError_t configure_writer() {
+	return cudaFuncSetAttribute(k_bcf_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, kWrThreads * kMaxRec + 16);
+}
+
+static WrArgs writer_args(const BcfJob &j, uint32_t i0, uint32_t cnt) {
+	WrArgs a;
+	a.vcf = (const GtVcf *)j.d_vcf; a.ref = (const uint8_t *)j.d_ref; a.x = j.x; a.sz = j.sz; a.i0 = i0; a.i1 = i0 + cnt;
+	a.blocks = (const uint2 *)j.d_blocks; a.nblocks = j.nblocks;
+	for (int k = 0; k < 16; k++) a.ids[k] = j.p.ids[k];
+	a.rid = j.p.rid; a.ctg_end = j.p.ctg_end; a.all_positions = j.p.all_positions; a.dc = j.dc;
+	a.calls = (uint8_t *)j.site_scratch;
+	a.len = (uint16_t *)((uint8_t *)j.site_scratch + (((size_t)j.sz + 15) & ~(size_t)15));
+	a.cta_bytes = nullptr; a.cta_recs = nullptr; a.totals = nullptr; a.out = nullptr; a.out_cap = 0;
+	return a;
+}
+
+// the writer's call of sites [i0, i0 + cnt): must have run for a site and its two neighbours either side before the
+// site's record is built
+cudaError_t launch_bcf_calls(const BcfJob &j, uint32_t i0, uint32_t cnt, cudaStream_t stream, int *launches) {
+	if (!cnt) return cudaSuccess;
+	k_bcf_calls<<<(cnt + 255) / 256, 256, 0, stream>>>(writer_args(j, i0, cnt));
+	*launches += 1;
+	return cudaGetLastError();
+}
+
+// records of sites [i0, i0 + cnt) -> d_out (back to back, in site order); d_totals: bytes, records, oversized records
+cudaError_t launch_bcf_records(const BcfJob &j, uint32_t i0, uint32_t cnt, void *cta_scratch, void *d_out, size_t out_cap,
+		unsigned long long *d_totals, cudaStream_t stream, int *launches) {
+	cudaError_t e = cudaMemsetAsync(d_totals, 0, 3 * sizeof(unsigned long long), stream);
+	if (e != cudaSuccess || !cnt) return e;
+	const uint32_t nctas = (cnt + kWrThreads - 1) / kWrThreads;
+	WrArgs a = writer_args(j, i0, cnt);
+	a.cta_bytes = (unsigned long long *)cta_scratch;
+	a.cta_recs = (uint32_t *)((uint8_t *)cta_scratch + (size_t)nctas * 8);
+	a.totals = d_totals; a.out = (uint8_t *)d_out; a.out_cap = out_cap;
+	k_bcf_measure<<<nctas, kWrThreads, 0, stream>>>(a);
+	k_bcf_offsets<<<1, 1024, 0, stream>>>(a.cta_bytes, a.cta_recs, nctas, d_totals);
+	k_bcf_emit<<<nctas, kWrThreads, kWrThreads * kMaxRec + 16, stream>>>(a);
+	*launches += 3;
+	return cudaGetLastError();
+}
+
+}  // namespace bsgpu

@@ -23,6 +23,7 @@ EXPORTS = [
     "bsgpu_sync", "bsgpu_host_alloc", "bsgpu_host_free",
     "bsgpu_call_sites", "bsgpu_pileup_block", "bsgpu_call_block", "bsgpu_stage_bound", "bsgpu_stage_templates",
     "bsgpu_process_block", "bsgpu_profile_enable", "bsgpu_profile_read", "bsgpu_build_blocks_tally",
+    "bsgpu_default_bcf_params", "bsgpu_bcf_block", "bsgpu_bcf_block_dev", "bsgpu_call_block_bcf", "bsgpu_call_sites_bcf",
     "bsgpu_default_reader_params", "bsgpu_decode_records", "bsgpu_build_blocks", "bsgpu_call_bam",
     "bsgpu_call_sites_dev", "bsgpu_call_sites_vcf_dev", "bsgpu_pileup_block_dev", "bsgpu_call_block_dev",
     "bsgpu_synth_sites_dev", "bsgpu_synth_block_nseg", "bsgpu_synth_block_dev",
@@ -60,6 +61,23 @@ class Profile(C.Structure):
     """bsgpu_profile (include/bsgpu.h): the --report-file side channels of the path"""
     _fields_ = [("conv_cts", (C.c_uint64 * 4) * PROFILE_MAX), ("used", C.c_uint32), ("pad_", C.c_uint32),
                 ("base_filter", C.c_uint64 * 5), ("filter_cts", C.c_uint64 * 15), ("filter_bases", C.c_uint64 * 15)]
+
+
+BCF_MAX_RECORD = 384
+
+
+class BcfParams(C.Structure):
+    """bsgpu_bcf_params (include/bsgpu.h): header dictionary ids, contig id and end, -A"""
+    _fields_ = [("ids", C.c_int32 * 16), ("rid", C.c_int32), ("ctg_end", C.c_uint32), ("all_positions", C.c_uint8), ("pad_", C.c_uint8 * 3)]
+
+
+def bcf_params(ids=None, rid=0, ctg_end=0xffffffff, all_positions=False):
+    p = BcfParams()
+    load().bsgpu_default_bcf_params(C.byref(p))
+    if ids is not None:
+        p.ids = (C.c_int32 * 16)(*[int(v) for v in ids])
+    p.rid, p.ctg_end, p.all_positions = int(rid), int(ctg_end), 1 if all_positions else 0
+    return p
 
 
 class BsGpuError(RuntimeError):
@@ -199,6 +217,46 @@ class BsGpu:
                                                  C.c_size_t(len(bases)), _ptr(misms), C.c_size_t(len(misms)), _ptr(ref),
                                                  C.c_uint32(y), C.byref(xo), _ptr(out)))
         return xo.value, out
+
+    # ---- writer side ------------------------------------------------------------------------------
+    def bcf_block(self, vcf, ref, x, params=None, out=None):
+        """gt_vcf[] of one block + reference codes of [x, x + len(vcf) + 1] -> (BCF record bytes, number of records)"""
+        vcf = np.ascontiguousarray(vcf, dtype=GT_VCF)
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        sz = len(vcf)
+        assert len(ref) >= sz + 2
+        p = params or bcf_params()
+        out = np.empty(sz * BCF_MAX_RECORD + 64, dtype=np.uint8) if out is None else out
+        nb, nr = C.c_size_t(0), C.c_size_t(0)
+        self._check(self.lib.bsgpu_bcf_block(self.ctx, _ptr(vcf), _ptr(ref), C.c_uint32(x), C.c_uint32(sz), C.byref(p), _ptr(out),
+                                             C.c_size_t(len(out)), C.byref(nb), C.byref(nr)))
+        return out[:nb.value], nr.value
+
+    def call_block_bcf(self, segs, bases, ref, x, sz, params=None, out=None):
+        """sorted segments + reference codes of [x, x + sz + 1] -> (BCF record bytes, number of records)"""
+        segs = np.ascontiguousarray(segs, dtype=SEG)
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        assert len(ref) >= sz + 2
+        p = params or bcf_params()
+        out = np.empty(sz * BCF_MAX_RECORD + 64, dtype=np.uint8) if out is None else out
+        nb, nr = C.c_size_t(0), C.c_size_t(0)
+        self._check(self.lib.bsgpu_call_block_bcf(self.ctx, _ptr(segs), C.c_size_t(len(segs)), _ptr(bases), C.c_size_t(len(bases)), _ptr(ref),
+                                                  C.c_uint32(x), C.c_uint32(sz), C.byref(p), _ptr(out), C.c_size_t(len(out)), C.byref(nb), C.byref(nr)))
+        return out[:nb.value], nr.value
+
+    def call_sites_bcf(self, pileup, ref, x, params=None, out=None):
+        """pileup[] of consecutive sites from position x (one block) + reference codes of [x, x + n + 1] -> (BCF bytes, records)"""
+        pileup = np.ascontiguousarray(pileup, dtype=PILEUP)
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        n = len(pileup)
+        assert len(ref) >= n + 2
+        p = params or bcf_params()
+        out = np.empty(n * BCF_MAX_RECORD + 64, dtype=np.uint8) if out is None else out
+        nb, nr = C.c_size_t(0), C.c_size_t(0)
+        self._check(self.lib.bsgpu_call_sites_bcf(self.ctx, _ptr(pileup), _ptr(ref), C.c_size_t(n), C.c_uint32(x), C.byref(p), _ptr(out),
+                                                  C.c_size_t(len(out)), C.byref(nb), C.byref(nr)))
+        return out[:nb.value], nr.value
 
     # ---- --report-file side channels -------------------------------------------------------------
     def profile_enable(self, on=True):

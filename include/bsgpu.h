@@ -163,6 +163,17 @@ typedef struct {
 	uint64_t filter_bases[15];               /* [0] = mates / bases that reached normalisation (+ the bases of src/get_template_vector.c:363) */
 } bsgpu_profile;
 
+/* ---- writer side: what the print thread needs besides the records to serialise a site (src/print_vcf.c) ---- */
+#define BSGPU_BCF_MAX_RECORD 384
+typedef struct {
+	int32_t ids[16];           /* BCF header dictionary ids of PASS fail mac1 CX GT FT GL GQ DP MQ QD MC8 AMQ CS CG FS: work.vcf_ids
+	                              as print_vcf_header() fills it (include/bs_call.h:192-207, src/print_vcf.c:751-764) */
+	int32_t rid;               /* ctg->vcf_rid */
+	uint32_t ctg_end;          /* ctg->end_pos: sites beyond it are not written (src/print_vcf.c:159) */
+	uint8_t all_positions;     /* -A: also write homozygous-reference A / T sites */
+	uint8_t pad_[3];
+} bsgpu_bcf_params;
+
 typedef struct bsgpu_ctx bsgpu_ctx;
 
 /* counters a context keeps; all monotonically increasing */
@@ -224,6 +235,24 @@ int bsgpu_process_block(bsgpu_ctx *ctx, const bsgpu_template *t, size_t n, const
  * starts again from zero. */
 int bsgpu_profile_enable(bsgpu_ctx *ctx, int on);
 int bsgpu_profile_read(bsgpu_ctx *ctx, bsgpu_profile *out, int reset);
+
+/* ---- writer side: a block of gt_vcf records -> the BCF records print_thread would hand to bcf_write()
+ *      (print_vcf_entry / flush_vcf_entries / _print_vcf_entry, src/print_vcf.c:32-381, 535-594, driven per block by
+ *      src/process.c:89-104), laid out as in a BCF file: l_shared, l_indiv, CHROM, POS, rlen, QUAL, n_allele|n_info,
+ *      n_fmt|n_sample, shared, indiv.  No dbSNP ids (ID is empty).  ref holds sz + 2 codes: positions x .. x + sz + 1, the
+ *      string get_sequence_string() leaves in work.ref.  *nbytes / *nrec receive the size of the output. ---- */
+void bsgpu_default_bcf_params(bsgpu_bcf_params *p);      /* ids 0..15 in header order, rid 0, no contig end, -A off */
+int bsgpu_bcf_block(bsgpu_ctx *ctx, const bsgpu_gt_vcf *vcf, const uint8_t *ref, uint32_t x, uint32_t sz, const bsgpu_bcf_params *p,
+		uint8_t *out, size_t out_cap, size_t *nbytes, size_t *nrec);
+/* sorted segments -> BCF records of the block: pileup, model and writer derivations on the device, only the records come back */
+int bsgpu_call_block_bcf(bsgpu_ctx *ctx, const bsgpu_seg *segs, size_t nseg, const uint8_t *bases, size_t nbases, const uint8_t *ref,
+		uint32_t x, uint32_t sz, const bsgpu_bcf_params *p, uint8_t *out, size_t out_cap, size_t *nbytes, size_t *nrec);
+/* pileup[] of n consecutive sites starting at position x (one block) -> BCF records; chunked and pipelined like bsgpu_call_sites */
+int bsgpu_call_sites_bcf(bsgpu_ctx *ctx, const bsgpu_pileup *pileup, const uint8_t *ref, size_t n, uint32_t x, const bsgpu_bcf_params *p,
+		uint8_t *out, size_t out_cap, size_t *nbytes, size_t *nrec);
+/* device-resident variant of bsgpu_bcf_block; waits for `stream` to return the sizes */
+int bsgpu_bcf_block_dev(bsgpu_ctx *ctx, const void *d_vcf, const void *d_ref, uint32_t x, uint32_t sz, const bsgpu_bcf_params *p,
+		void *d_out, size_t out_cap, size_t *nbytes, size_t *nrec, void *stream);
 
 /* ---- reader side: `bam` is the byte stream that follows the header of an uncompressed BAM file (what remains of the
  *      file after BGZF inflation: int32 block_size + record, repeated), coordinate sorted ---- */

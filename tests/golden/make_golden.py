@@ -9,6 +9,7 @@ The GPU boxes have no reference tree; they check against these committed files.
   block_*.npz    block goldens: raw templates -> normalised templates, pileup[], gt_vcf[]
                  (process_template_vector -> call_genotypes_ML)
   profile_v1.npz --report-file side channels of the block and reader goldens (meth_profile, base / read tallies)
+  writer_v1.npz  the BCF records of the reference's writer for the gt_vcf[] of the block goldens
   reader_*.npz   reader goldens: raw BAM records -> per-record descriptors (get_next_align_details), blocks and
                  templates (read_input), gt_vcf[] of every block (the whole chain)
 """
@@ -152,8 +153,32 @@ def make_profile():
     np.savez_compressed(os.path.join(HERE, "profile_v1.npz"), **out)
 
 
+def make_writer():
+    """writer goldens: the BCF records the reference's own print_vcf_entry / flush_vcf_entries / _print_vcf_entry
+    (src/print_vcf.c, compiled unmodified; bcf_write captured by oracle/ref_harness.c) emit for the gt_vcf[] of the block
+    goldens, without and with -A (all positions)"""
+    out = {}
+    r = Reference()
+    for name, c in BLOCK_CASES.items():
+        g = np.load(os.path.join(HERE, name + ".npz"))
+        rng = np.random.default_rng(c["seed"])
+        ref = blockgen.random_reference(rng, c["reflen"], n_runs=2)
+        x, sz = int(g["x"]), len(g["vcf"])
+        refw = blockgen.window_codes(ref, x, x + sz + 1)
+        assert (refw[:sz] == g["ref"]).all()
+        out[name + "__ref"] = refw
+        for allp in (0, 1):
+            b, n = r.print_block(g["vcf"], refw, x, rid=2, all_positions=bool(allp))
+            out["%s__all%d" % (name, allp)] = b
+            out["%s__n%d" % (name, allp)] = np.uint32(n)
+            print(name, "all_positions", allp, "records", n, "bytes", len(b))
+    np.savez_compressed(os.path.join(HERE, "writer_v1.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["blocks", "sites", "reader", "profile"]
+    which = sys.argv[1:] or ["blocks", "sites", "reader", "profile", "writer"]
+    if "writer" in which:
+        make_writer()
     if "profile" in which:
         make_profile()
     if "blocks" in which:

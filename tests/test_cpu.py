@@ -55,6 +55,19 @@ def test_oracle_block_golden(name):
     util.assert_pileup_equal(pile2, g["pileup"])
 
 
+@pytest.mark.parametrize("name", BLOCKS)
+def test_oracle_writer_matches_golden(name, oracle):
+    """the restated writer against the BCF records captured from the reference's compiled src/print_vcf.c"""
+    g = util.load_golden(name)
+    w = util.load_golden("writer_v1")
+    for allp in (0, 1):
+        b, n = oracle.print_block(g["vcf"], w[name + "__ref"], int(g["x"]), rid=2, all_positions=bool(allp))
+        assert n == int(w["%s__n%d" % (name, allp)]) and n > 300
+        assert b.tobytes() == w["%s__all%d" % (name, allp)].tobytes()
+    recs = util.split_bcf(b)
+    assert len(recs) == n and max(len(r) for r in recs) <= 384
+
+
 def test_abi_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "bsgpu.h")).read()
     body = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
