@@ -298,6 +298,89 @@ def bam_path(args, gpu, bslib, torch, np, stream, rank, world, local):
     return out
 
 
+def writer_path(args, gpu, bslib, torch, np, stream, rank, world, local):
+    """the writer's per-site derivations on the device.  (a) gt_vcf[] resident -> BCF records
+    resident (the three writer kernels alone); (b) count vectors on the host -> BCF records on the host
+    (bsgpu_call_sites_bcf: H2D, model, writer, D2H of the records only); (c) the reference's own writer
+    (print_vcf_entry / flush_vcf_entries, one thread as in the reference) on a bounded sample, with byte parity."""
+    from bs_call_b200.records import GT_VCF, PILEUP
+    n = int(args.e2e_sites)
+    dev = torch.device("cuda", local)
+    d_pile = torch.empty(n * 104 + 16, dtype=torch.uint8, device=dev)
+    d_ref = torch.empty(n + 16, dtype=torch.uint8, device=dev)
+    d_vcf = torch.empty(n * 208 + 16, dtype=torch.uint8, device=dev)
+    gpu.synth_sites_dev(SEED, rank * n, n, MEAN_DEPTH, d_pile.data_ptr(), d_ref.data_ptr(), stream)
+    d_ref[n:n + 2] = 1
+    gpu.call_sites_vcf_dev(d_pile.data_ptr(), d_ref.data_ptr(), n, d_vcf.data_ptr(), stream)
+    torch.cuda.synchronize()
+    cap = n * 160
+    d_out = torch.empty(cap + 16, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        nb, nr = gpu.bcf_block_dev(d_vcf.data_ptr(), d_ref.data_ptr(), 1, n, d_out.data_ptr(), cap, stream=stream)
+    steps = max(1, args.steps)
+    l0 = gpu.stats()["kernel_launches"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        nb, nr = gpu.bcf_block_dev(d_vcf.data_ptr(), d_ref.data_ptr(), 1, n, d_out.data_ptr(), cap, stream=stream)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    peak, peak_kind = measured_peaks()
+    alg = 208.0 * n + nb                              # every gt_vcf record read once, every record byte written once
+    out = {"workload": "%d sites of the config-2 stream as one block: gt_vcf[] -> BCF records (%d records, %.1f B each)" % (n, nr, nb / max(nr, 1)),
+           "resident": {"value": n / (ms * 1e-3), "unit": "sites/s", "ms": ms, "gpu_launches": (gpu.stats()["kernel_launches"] - l0) // steps,
+                        "roofline": {"kernel": "k_bcf_calls + k_bcf_measure + k_bcf_offsets + k_bcf_emit", "bound": "hbm",
+                                     "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                                     "algorithmic_bytes_per_site": alg / n}}}
+    # (b) host count vectors -> host records
+    hp = bslib.HostBuffer(n, PILEUP)
+    hr = bslib.HostBuffer(n + 2, np.uint8)
+    ho = bslib.HostBuffer(cap, np.uint8)
+    hp.array.view(np.uint8)[:] = d_pile[:n * 104].cpu().numpy()
+    hr.array[:] = d_ref[:n + 2].cpu().numpy()
+    called = int((hp.array["n"] > 0).sum())
+    for _ in range(2):
+        rb, rn = gpu.call_sites_bcf(hp.array, hr.array, 1, out=ho.array)
+    s0 = gpu.stats()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rb, rn = gpu.call_sites_bcf(hp.array, hr.array, 1, out=ho.array)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    s1 = gpu.stats()
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    cc = torch.tensor([called], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+    assert rn == nr and len(rb) == nb
+    out["e2e"] = {"value": float(cc.item()) / float(tt.item()), "unit": "sites/s", "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // steps,
+                  "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // steps, "records_per_step": rn,
+                  "note": "bsgpu_call_sites_bcf on pinned host arrays: count vectors up, BCF records down"}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle.bindings import Oracle, Reference, reference_available
+        m = int(min(n, 1500000))
+        vcf = d_vcf[:m * 208].cpu().numpy().view(GT_VCF)
+        refw = hr.array[:m + 2].copy()
+        if reference_available():
+            impl, kind, what = Reference(), "reference", "reference print_vcf_entry / flush_vcf_entries / _print_vcf_entry (oracle/_ref/libbsref.so), one thread as in bs_call"
+        else:
+            impl, kind, what = Oracle(), "port", "oracle port of the writer, one thread"
+        t0 = time.perf_counter()
+        wb, wn = impl.print_block(vcf, refw, 1)
+        cs = time.perf_counter() - t0
+        gb, gn = gpu.bcf_block(vcf, refw, 1)
+        assert gn == wn and gb.tobytes() == wb.tobytes(), "device writer differs from the %s" % kind
+        out["cpu_baseline"] = {"value": m / cs, "unit": "sites/s", "cores": 1, "kind": kind,
+                               "sample": "first %d sites (%d records): %s" % (m, wn, what), "parity_records_checked": wn, "parity_bytes_checked": len(wb)}
+    for b in (hp, hr, ho):
+        b.free()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -604,6 +687,16 @@ def main():
         import traceback
         bam = {"error": repr(e), "trace": traceback.format_exc()[-800:]}
 
+    # ---- the writer's derivations on the device: gt_vcf[] -> BCF records; count vectors -> BCF records end to end
+    writer = None
+    try:
+        del d_pile, d_ref
+        torch.cuda.empty_cache()
+        writer = writer_path(args, gpu, bslib, torch, np, stream, rank, world, local)
+    except Exception as e:
+        import traceback
+        writer = {"error": repr(e), "trace": traceback.format_exc()[-800:]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         nthreads = os.cpu_count() or 1
@@ -620,7 +713,7 @@ def main():
                            "parallelism": "sites sharded over %d rank(s), no collective" % world, "host": numa_note,
                            "l2": "inputs larger than L2: each step streams %.1f GB of distinct records" % (n_sites * 105 / 1e9)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "block_path": block, "bam_path": bam, "parity_spot_check": parity}
+                "block_path": block, "bam_path": bam, "writer_path": writer, "parity_spot_check": parity}
         print(json.dumps(line))
     gpu.close()
     if world > 1:

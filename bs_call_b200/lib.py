@@ -232,6 +232,14 @@ class BsGpu:
                                              C.c_size_t(len(out)), C.byref(nb), C.byref(nr)))
         return out[:nb.value], nr.value
 
+    def bcf_block_dev(self, d_vcf, d_ref, x, sz, d_out, out_cap, params=None, stream=0):
+        """device-resident gt_vcf[] -> records in device memory; returns (bytes, records) after waiting for the stream"""
+        p = params or bcf_params()
+        nb, nr = C.c_size_t(0), C.c_size_t(0)
+        self._check(self.lib.bsgpu_bcf_block_dev(self.ctx, C.c_void_p(d_vcf), C.c_void_p(d_ref), C.c_uint32(x), C.c_uint32(sz), C.byref(p),
+                                                 C.c_void_p(d_out), C.c_size_t(out_cap), C.byref(nb), C.byref(nr), C.c_void_p(stream)))
+        return nb.value, nr.value
+
     def call_block_bcf(self, segs, bases, ref, x, sz, params=None, out=None):
         """sorted segments + reference codes of [x, x + sz + 1] -> (BCF record bytes, number of records)"""
         segs = np.ascontiguousarray(segs, dtype=SEG)
