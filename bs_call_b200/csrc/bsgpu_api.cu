@@ -124,7 +124,8 @@ struct bsgpu_ctx {
 	bool profile_on = false;
 	ProfDev *d_prof = nullptr;
 	// writer side
-	DevBuf wr_site, wr_cta, wr_out, wr_vcf, wr_ref;
+	DevBuf wr_site, wr_cta, wr_out, wr_vcf, wr_ref, wr_blocks, wr_ring[3];
+	cudaEvent_t wr_built[3] = {nullptr, nullptr, nullptr}, wr_copied[3] = {nullptr, nullptr, nullptr};
 	unsigned long long *d_wr_totals = nullptr;   // 8 slots of (bytes, records, oversized)
 	unsigned long long *h_wr_totals = nullptr;   // pinned mirror
 	uint64_t reader_tally[30] = {0};             // read_input's filter_cts[15] | filter_bases[15] (host side, bsgpu_call_bam)
@@ -250,7 +251,8 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 	if (c->d_counters) cudaFree(c->d_counters);
 	if (c->d_prof) cudaFree(c->d_prof);
 	c->prof_scratch.release();
-	c->wr_site.release(); c->wr_cta.release(); c->wr_out.release(); c->wr_vcf.release(); c->wr_ref.release();
+	c->wr_site.release(); c->wr_cta.release(); c->wr_out.release(); c->wr_vcf.release(); c->wr_ref.release(); c->wr_blocks.release();
+	for (int i = 0; i < 3; i++) { c->wr_ring[i].release(); if (c->wr_built[i]) cudaEventDestroy(c->wr_built[i]); if (c->wr_copied[i]) cudaEventDestroy(c->wr_copied[i]); }
 	if (c->d_wr_totals) cudaFree(c->d_wr_totals);
 	if (c->h_wr_totals) cudaFreeHost(c->h_wr_totals);
 	delete c;
@@ -977,8 +979,35 @@ static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *
 		uint32_t x, uint32_t sz, void *out, int mode, bool defer);
 
 // templates [tm, tm + nt) of ONE contig (their reads and events are resident from the decode) -> gt_vcf[] of window [x, y]
+// where the records of bsgpu_call_bam_bcf go: windows are queued on the context stream, their sizes come home through
+// pinned memory, and the copy-out of window w is issued once its size is known -- by then window w + 1 is queued
+struct BcfSink {
+	bsgpu_bcf_params p;
+	const int32_t *vcf_rid;
+	uint8_t *out;
+	size_t out_cap, at = 0, recs = 0;
+	uint64_t queued = 0, collected = 0;
+	size_t ring_cap[3] = {0, 0, 0};
+};
+
+static int sink_collect(bsgpu_ctx *c, BcfSink *k) {
+	const int slot = (int)(k->collected % 3);
+	CU(cudaEventSynchronize(c->wr_built[slot]));
+	const unsigned long long *t = c->h_wr_totals + 3 * (k->collected & 7);
+	if (t[2]) return fail("bsgpu_call_bam_bcf: %llu record(s) longer than %d bytes", t[2], BSGPU_BCF_MAX_RECORD);
+	if (t[0] > k->ring_cap[slot]) return fail("bsgpu_call_bam_bcf: the records of one window (%llu bytes) exceed the device staging buffer", t[0]);
+	if (k->at + t[0] > k->out_cap) return fail("bsgpu_call_bam_bcf: output buffer too small (%zu bytes given)", k->out_cap);
+	if (t[0]) CU(cudaMemcpyAsync(k->out + k->at, c->wr_ring[slot].p, t[0], cudaMemcpyDeviceToHost, c->copy_stream));
+	CU(cudaEventRecord(c->wr_copied[slot], c->copy_stream));
+	k->at += t[0]; k->recs += t[1];
+	c->stats.d2h_bytes += t[0] + 24;
+	k->collected++;
+	return BSGPU_OK;
+}
+
+// wb[0 .. nwb): the blocks inside the window (BCF sink only)
 static int call_window(bsgpu_ctx *c, const bsgpu_template *tm, size_t nt, uint32_t tid, uint32_t ctg_len, const uint8_t *codes,
-		uint32_t x, uint32_t y, bsgpu_gt_vcf *out) {
+		uint32_t x, uint32_t y, bsgpu_gt_vcf *out, BcfSink *sink = nullptr, const bsgpu_block *wb = nullptr, size_t nwb = 0) {
 	const uint32_t sz = y - x + 1;
 	// per-mate output slots: read length + reference span bounds the read in reference coordinates
 	std::vector<uint32_t> &off = c->off_tmp;
@@ -999,8 +1028,8 @@ static int call_window(bsgpu_ctx *c, const bsgpu_template *tm, size_t nt, uint32
 	const size_t nseg = nt * 2 * (size_t)spm;
 	// reference window [x, y]: N beyond the contig end (src/get_sequence.c:36-41)
 	std::vector<uint8_t> &refw = c->ref_tmp;
-	refw.resize((size_t)sz + 1);               // one code past the window for the conversion profile (src/meth_profile.c:70)
-	for (uint32_t i = 0; i <= sz; i++) { const uint32_t pos = x + i; refw[i] = pos < ctg_len ? codes[pos - 1] : 0; }
+	refw.resize((size_t)sz + 2);               // one code past the window for the conversion profile (src/meth_profile.c:70), two for the writer
+	for (uint32_t i = 0; i < sz + 2; i++) { const uint64_t pos = (uint64_t)x + i; refw[i] = pos < ctg_len ? codes[pos - 1] : 0; }
 	// Everything below is queued behind the previous window on the context stream; nothing waits on the host.  (Growing a
 	// device buffer frees the old one, which synchronises the device; `off` / `refw` are pageable, so their copies are
 	// staged before cudaMemcpyAsync returns and the vectors can be refilled for the next window.)
@@ -1011,20 +1040,53 @@ static int call_window(bsgpu_ctx *c, const bsgpu_template *tm, size_t nt, uint32
 	CU(c->ref.reserve((size_t)sz + 16));
 	CU(cudaMemcpyAsync(c->tmpl.p, tm, nt * sizeof(bsgpu_template), cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->ooff.p, off.data(), (2 * nt + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->ref.p, refw.data(), (size_t)sz + 1, cudaMemcpyHostToDevice, c->stream));
-	c->stats.h2d_bytes += nt * sizeof(bsgpu_template) + (2 * nt + 1) * 4 + sz + 1;
+	CU(cudaMemcpyAsync(c->ref.p, refw.data(), (size_t)sz + 2, cudaMemcpyHostToDevice, c->stream));
+	c->stats.h2d_bytes += nt * sizeof(bsgpu_template) + (2 * nt + 1) * 4 + sz + 2;
 	cudaError_t perr;
 	const ProfArgs *pa = profile_for(c, nt, sz, &perr);
 	CU(perr);
 	CU(launch_normalise(c->tmpl.p, nt, c->rd_bases.p, c->rd_misms.p, c->ooff.p, c->obases.p, c->segs.p, spm, x, y,
 			c->params.left_trim, c->params.right_trim, c->d_counters, pa, c->prof_parity, c->stream, &c->launches));
 	if (pa) c->prof_parity ^= 1;
-	return block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, out, 1, true);
+	if (!sink) return block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, out, 1, true);
+	// ---- records instead of gt_vcf[]: the window's gt_vcf[] stays on the device, the writer kernels turn it into BCF
+	const int slot = (int)(sink->queued % 3);
+	for (int i = 0; i < 3; i++) if (!c->wr_built[i]) {
+		CU(cudaEventCreateWithFlags(&c->wr_built[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&c->wr_copied[i], cudaEventDisableTiming));
+	}
+	const size_t rcap = (size_t)sz * 256 + 4096;
+	const bool grow = (size_t)sz * sizeof(bsgpu_gt_vcf) > c->wr_vcf.cap || rcap + 16 > c->wr_ring[slot].cap || bcf_site_scratch_bytes(sz) > c->wr_site.cap ||
+			bcf_cta_scratch_bytes(sz) > c->wr_cta.cap || (nwb + 1) * 8 > c->wr_blocks.cap;
+	if (grow) CU(cudaDeviceSynchronize());          // growing frees buffers that queued work may still use
+	CU(c->wr_vcf.reserve((size_t)sz * sizeof(bsgpu_gt_vcf)));
+	CU(c->wr_ring[slot].reserve(rcap + 16));
+	CU(c->wr_site.reserve(bcf_site_scratch_bytes(sz)));
+	CU(c->wr_cta.reserve(bcf_cta_scratch_bytes(sz)));
+	CU(c->wr_blocks.reserve((nwb + 1) * 8));
+	sink->ring_cap[slot] = rcap;
+	std::vector<uint32_t> pairs(2 * nwb);
+	for (size_t b = 0; b < nwb; b++) { pairs[2 * b] = wb[b].x - x; pairs[2 * b + 1] = wb[b].y - x; }
+	CU(cudaMemcpyAsync(c->wr_blocks.p, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, c->stream));      // pageable: staged before the call returns
+	if (block_dev(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, c->wr_vcf.p, 1, nullptr, c->stream) != BSGPU_OK) return BSGPU_FAIL;
+	BcfJob j;
+	j.d_vcf = c->wr_vcf.p; j.d_ref = c->ref.p; j.x = x; j.sz = sz; j.d_blocks = c->wr_blocks.p; j.nblocks = (uint32_t)nwb;
+	j.p = sink->p; j.p.rid = sink->vcf_rid ? sink->vcf_rid[tid] : (int32_t)tid; j.p.ctg_end = ctg_len;
+	j.dc = c->d_const; j.site_scratch = c->wr_site.p;
+	if (sink->queued >= 3) CU(cudaStreamWaitEvent(c->stream, c->wr_copied[slot], 0));      // the slot's previous records have left
+	CU(launch_bcf_calls(j, 0, sz, c->stream, &c->launches));
+	CU(launch_bcf_records(j, 0, sz, c->wr_cta.p, c->wr_ring[slot].p, rcap, c->d_wr_totals + 3 * (sink->queued & 7), c->stream, &c->launches));
+	CU(cudaMemcpyAsync(c->h_wr_totals + 3 * (sink->queued & 7), c->d_wr_totals + 3 * (sink->queued & 7), 3 * sizeof(unsigned long long),
+			cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaEventRecord(c->wr_built[slot], c->stream));
+	sink->queued++;
+	while (sink->queued - sink->collected > 1) if (sink_collect(c, sink) != BSGPU_OK) return BSGPU_FAIL;
+	return BSGPU_OK;
 }
 
-int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len,
+static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len,
 		const uint8_t *const *ctg_codes, const bsgpu_reader_params *rp, bsgpu_block *blocks, size_t block_cap, size_t *nblocks,
-		bsgpu_gt_vcf *vcf, size_t vcf_cap, size_t *nvcf) {
+		bsgpu_gt_vcf *vcf, size_t vcf_cap, size_t *nvcf, BcfSink *sink) {
 	if (!c || !rp || !nblocks || !nvcf || !target_len || !ctg_codes || (nbytes && !bam)) return fail("bsgpu_call_bam: null argument");
 	size_t n = 0;
 	uint64_t nb = 0, nm = 0;
@@ -1105,19 +1167,22 @@ int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_target
 			const uint32_t tid = (*pb)[b0].tid;
 			if ((int)tid >= n_targets) { ret = fail("bsgpu_call_bam: record on contig %u, only %d contigs given", tid, n_targets); break; }
 			if ((int)tid != cur_tid) { cur_tid = (int)tid; ctg_x0 = (*pb)[b0].x; ctg_end = ctg_x0 - 1; ctg_ov = ov; }
-			const uint32_t x = ctg_end + 1, y = (*pb)[b1 - 1].y;
+			// windows tile the contig; a block may begin ON the last site of the block before it (its x is two before its
+			// first template, src/process_template.c:27), and the writer's context of its first sites reaches back there:
+			// the record windows then overlap by that one uncovered site
+			const uint32_t x = sink ? std::min(ctg_end + 1, (*pb)[b0].x) : ctg_end + 1, y = (*pb)[b1 - 1].y;
 			const size_t t_lo = base + (*pb)[b0].first_template, t_n = (size_t)(*pb)[b1 - 1].first_template + (*pb)[b1 - 1].n_templates - (*pb)[b0].first_template;
 			if (y >= x) {
 				const uint32_t sz = y - x + 1;
-				if (ov + sz > vcf_cap) { ret = fail("bsgpu_call_bam: vcf[] too small (contig %u needs %u more records)", tid, sz); break; }
-				ret = call_window(c, tm + t_lo, t_n, tid, target_len[tid], ctg_codes[tid], x, y, vcf + ov);
+				if (!sink && ov + sz > vcf_cap) { ret = fail("bsgpu_call_bam: vcf[] too small (contig %u needs %u more records)", tid, sz); break; }
+				ret = call_window(c, tm + t_lo, t_n, tid, target_len[tid], ctg_codes[tid], x, y, sink ? nullptr : vcf + ov, sink, pb->data() + b0, b1 - b0);
 				ov += sz;
 				ctg_end = y;
 			}
 			for (size_t b = b0; b < b1; b++) {
 				bsgpu_block o = (*pb)[b];
 				o.first_template = (uint32_t)(ntm + o.first_template);
-				o.vcf_off = ctg_ov + (o.x - ctg_x0);
+				o.vcf_off = sink ? 0 : ctg_ov + (o.x - ctg_x0);
 				blocks[nbk++] = o;
 			}
 			b0 = b1;
@@ -1127,6 +1192,7 @@ int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_target
 		build_blocks_finish(job);
 		job = nullptr;
 	}
+	while (ret == BSGPU_OK && sink && sink->collected < sink->queued) ret = sink_collect(c, sink);
 	CU(cudaStreamSynchronize(c->slot[0].stream));
 	CU(cudaStreamSynchronize(c->slot[1].stream));
 	CU(cudaStreamSynchronize(c->stream));
@@ -1140,6 +1206,25 @@ int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_target
 	const double t2 = now();
 	c->stats.bam_build_s += t_wait;
 	c->stats.bam_call_s += t2 - t1 - t_wait;
+	return BSGPU_OK;
+}
+
+int bsgpu_call_bam(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len,
+		const uint8_t *const *ctg_codes, const bsgpu_reader_params *rp, bsgpu_block *blocks, size_t block_cap, size_t *nblocks,
+		bsgpu_gt_vcf *vcf, size_t vcf_cap, size_t *nvcf) {
+	return call_bam_impl(c, bam, nbytes, n_targets, target_len, ctg_codes, rp, blocks, block_cap, nblocks, vcf, vcf_cap, nvcf, nullptr);
+}
+
+int bsgpu_call_bam_bcf(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len,
+		const uint8_t *const *ctg_codes, const bsgpu_reader_params *rp, const bsgpu_bcf_params *p, const int32_t *vcf_rid,
+		bsgpu_block *blocks, size_t block_cap, size_t *nblocks, uint8_t *out, size_t out_cap, size_t *nbytes_out, size_t *nrec) {
+	if (!p || !nbytes_out || !nrec || (out_cap && !out)) return fail("bsgpu_call_bam_bcf: null argument");
+	BcfSink sink;
+	sink.p = *p; sink.vcf_rid = vcf_rid; sink.out = out; sink.out_cap = out_cap;
+	size_t nvcf = 0;
+	*nbytes_out = *nrec = 0;
+	if (call_bam_impl(c, bam, nbytes, n_targets, target_len, ctg_codes, rp, blocks, block_cap, nblocks, nullptr, 0, &nvcf, &sink) != BSGPU_OK) return BSGPU_FAIL;
+	*nbytes_out = sink.at; *nrec = sink.recs;
 	return BSGPU_OK;
 }
 

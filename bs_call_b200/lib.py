@@ -23,7 +23,7 @@ EXPORTS = [
     "bsgpu_sync", "bsgpu_host_alloc", "bsgpu_host_free",
     "bsgpu_call_sites", "bsgpu_pileup_block", "bsgpu_call_block", "bsgpu_stage_bound", "bsgpu_stage_templates",
     "bsgpu_process_block", "bsgpu_profile_enable", "bsgpu_profile_read", "bsgpu_build_blocks_tally",
-    "bsgpu_default_bcf_params", "bsgpu_bcf_block", "bsgpu_bcf_block_dev", "bsgpu_call_block_bcf", "bsgpu_call_sites_bcf",
+    "bsgpu_call_bam_bcf", "bsgpu_default_bcf_params", "bsgpu_bcf_block", "bsgpu_bcf_block_dev", "bsgpu_call_block_bcf", "bsgpu_call_sites_bcf",
     "bsgpu_default_reader_params", "bsgpu_decode_records", "bsgpu_build_blocks", "bsgpu_call_bam",
     "bsgpu_call_sites_dev", "bsgpu_call_sites_vcf_dev", "bsgpu_pileup_block_dev", "bsgpu_call_block_dev",
     "bsgpu_synth_sites_dev", "bsgpu_synth_block_nseg", "bsgpu_synth_block_dev",
@@ -318,6 +318,23 @@ class BsGpu:
         return blocks[:nb.value], vcf[:nv.value]
 
     # ---- device-pointer entry points (addresses as ints, e.g. torch.Tensor.data_ptr()) --------
+    def call_bam_bcf(self, bam, target_len, ctg_codes, rp=None, params=None, vcf_rid=None, out=None):
+        """raw BAM records + per-contig reference codes -> (BLOCK[], BCF record bytes, number of records)"""
+        bam = np.ascontiguousarray(bam, dtype=np.uint8)
+        target_len = np.ascontiguousarray(target_len, dtype=np.uint32)
+        rp = rp or reader_params()
+        p = params or bcf_params()
+        codes = [np.ascontiguousarray(c, dtype=np.uint8) for c in ctg_codes]
+        ptrs = (C.c_void_p * len(codes))(*[c.ctypes.data for c in codes])
+        rid = None if vcf_rid is None else np.ascontiguousarray(vcf_rid, dtype=np.int32)
+        blocks = np.zeros(len(bam) // 36 + 8, dtype=BLOCK)
+        out = np.empty(int(target_len.sum()) * 160 + 4096, dtype=np.uint8) if out is None else out
+        nbk, nb, nr = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        self._check(self.lib.bsgpu_call_bam_bcf(self.ctx, _ptr(bam), C.c_size_t(len(bam)), C.c_int(len(codes)), _ptr(target_len), ptrs,
+                                                C.byref(rp), C.byref(p), _ptr(rid), _ptr(blocks), C.c_size_t(len(blocks)), C.byref(nbk),
+                                                _ptr(out), C.c_size_t(len(out)), C.byref(nb), C.byref(nr)))
+        return blocks[:nbk.value], out[:nb.value], nr.value
+
     def call_sites_dev(self, d_pileup, d_ref, n, d_out, d_skip, stream=0):
         self._check(self.lib.bsgpu_call_sites_dev(self.ctx, _ptr(d_pileup), _ptr(d_ref), C.c_size_t(n), _ptr(d_out),
                                                   _ptr(d_skip), C.c_void_p(stream)))

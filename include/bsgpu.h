@@ -250,6 +250,13 @@ int bsgpu_call_block_bcf(bsgpu_ctx *ctx, const bsgpu_seg *segs, size_t nseg, con
 /* pileup[] of n consecutive sites starting at position x (one block) -> BCF records; chunked and pipelined like bsgpu_call_sites */
 int bsgpu_call_sites_bcf(bsgpu_ctx *ctx, const bsgpu_pileup *pileup, const uint8_t *ref, size_t n, uint32_t x, const bsgpu_bcf_params *p,
 		uint8_t *out, size_t out_cap, size_t *nbytes, size_t *nrec);
+/* The whole path with the writer's derivations included: BAM records -> BCF records.  As bsgpu_call_bam, except that what
+ * comes back is the record stream of every block in stream order (blocks[b].vcf_off is 0).  p gives the header ids and
+ * -A; CHROM of a record is vcf_rid[tid] (tid itself when vcf_rid is NULL) and sites from position target_len[tid] on are not
+ * written (ctg->end_pos, src/print_vcf.c:159). */
+int bsgpu_call_bam_bcf(bsgpu_ctx *ctx, const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len,
+		const uint8_t *const *ctg_codes, const bsgpu_reader_params *rp, const bsgpu_bcf_params *p, const int32_t *vcf_rid,
+		bsgpu_block *blocks, size_t block_cap, size_t *nblocks, uint8_t *out, size_t out_cap, size_t *nbytes_out, size_t *nrec);
 /* device-resident variant of bsgpu_bcf_block; waits for `stream` to return the sizes */
 int bsgpu_bcf_block_dev(bsgpu_ctx *ctx, const void *d_vcf, const void *d_ref, uint32_t x, uint32_t sz, const bsgpu_bcf_params *p,
 		void *d_out, size_t out_cap, size_t *nbytes, size_t *nrec, void *stream);

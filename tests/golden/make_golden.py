@@ -172,6 +172,21 @@ def make_writer():
             out["%s__all%d" % (name, allp)] = b
             out["%s__n%d" % (name, allp)] = np.uint32(n)
             print(name, "all_positions", allp, "records", n, "bytes", len(b))
+    # the reader goldens: every block of the reference's chain through the reference's writer, concatenated in stream order
+    from tests import bamgen
+    for name, c in READER_CASES.items():
+        g = np.load(os.path.join(HERE, name + ".npz"))
+        _, _, tl, refs = bamgen.make_stream(c["seed"], **c["stream"])
+        parts, total = [], 0
+        for b in g["blocks"]:
+            x, y, tid = int(b["x"]), int(b["y"]), int(b["tid"])
+            sz = y - x + 1
+            v = g["vcf"][int(b["vcf_off"]):int(b["vcf_off"]) + sz]
+            rb, n = r.print_block(v, blockgen.window_codes(refs[tid], x, y + 2), x, rid=tid, ctg_end=int(tl[tid]))
+            parts.append(rb); total += n
+        out[name + "__bcf"] = np.concatenate(parts)
+        out[name + "__nrec"] = np.uint32(total)
+        print(name, "records", total, "bytes", len(out[name + "__bcf"]))
     np.savez_compressed(os.path.join(HERE, "writer_v1.npz"), **out)
 
 

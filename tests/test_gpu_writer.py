@@ -107,3 +107,70 @@ def test_output_too_small_is_an_error(gpu):
     refw = util.load_golden("writer_v1")["block_pe_plain__ref"]
     with pytest.raises(bslib.BsGpuError):
         gpu.bcf_block(g["vcf"], refw, int(g["x"]), out=np.empty(1000, dtype=np.uint8))
+
+
+def _reader_opts(g):
+    return dict(mapq_thresh=int(g["mapq_thresh"]), max_template_len=int(g["max_template_len"]), keep_unmatched=bool(g["keep_unmatched"]),
+                ignore_duplicates=bool(g["ignore_duplicates"]), keep_duplicates=bool(g["keep_duplicates"]))
+
+
+def oracle_bcf_of_stream(oracle, bam, tl, refs, opts, all_positions=False):
+    """the oracle's chain read_input -> process_template_vector -> call_genotypes_ML, then its writer block by block"""
+    bk, _, _, _, vcf = oracle.read_input(bam, tl, refs, run_chain=True, **opts)
+    parts, total = [], 0
+    for b in bk:
+        x, y, tid = int(b["x"]), int(b["y"]), int(b["tid"])
+        sz = y - x + 1
+        v = vcf[int(b["vcf_off"]):int(b["vcf_off"]) + sz]
+        rb, n = oracle.print_block(v, blockgen.window_codes(refs[tid], x, y + 2), x, rid=tid, ctg_end=int(tl[tid]), all_positions=all_positions)
+        parts.append(rb)
+        total += n
+    return bk, (np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)), total
+
+
+@pytest.mark.parametrize("name", ["reader_pe", "reader_mixed"])
+def test_bam_to_records_goldens(gpu, name):
+    """raw BAM records -> BCF records, everything between on the device except the block builder, against the records of
+    the reference's own chain read_input -> process_template_vector -> call_genotypes_ML -> print_vcf_entry"""
+    g = util.load_golden(name)
+    w = util.load_golden("writer_v1")
+    refs = [g["ref%d" % i] for i in range(len(g["target_len"]))]
+    blocks, out, n = gpu.call_bam_bcf(g["bam"], g["target_len"], refs, bslib.reader_params(**_reader_opts(g)))
+    assert len(blocks) == len(g["blocks"])
+    got, want = util.split_bcf(np.asarray(out)), util.split_bcf(w[name + "__bcf"])
+    assert n == len(got) == len(want) == int(w[name + "__nrec"])
+    # fixed fields (CHROM, POS, QUAL, allele and field counts) and everything that is not a float: identical; the GL floats
+    # carry the last bits of the device's posteriors
+    assert [r[:32] for r in got] == [r[:32] for r in want]
+    same = sum(a == b for a, b in zip(got, want))
+    assert same >= 0.98 * len(want), (same, len(want))
+
+
+@pytest.mark.parametrize("seed", [2, 5, 9, 14])
+def test_bam_to_records_streams(gpu, oracle, monkeypatch, seed):
+    """streams with duplicates, junk and gaps through bsgpu_call_bam_bcf (windows that hold several blocks, blocks that
+    touch, chunked upload, parallel builder) against the oracle's writer over the DEVICE's gt_vcf[] of the same stream"""
+    bam, n, tl, refs = bamgen_stream(seed)
+    opts = dict(mapq_thresh=20, max_template_len=1000, keep_unmatched=seed % 2 == 1, ignore_duplicates=False, keep_duplicates=False)
+    monkeypatch.setenv("BSGPU_READER_CHUNK_MIN_BYTES", "1")
+    monkeypatch.setenv("BSGPU_BUILDER_MIN_RECORDS", "1")
+    monkeypatch.setenv("BSGPU_BUILDER_THREADS", "3")
+    allp = seed % 4 == 1
+    blocks, vcf = gpu.call_bam(bam, tl, refs, bslib.reader_params(**opts))
+    parts, total = [], 0
+    for b in blocks:
+        x, y, tid = int(b["x"]), int(b["y"]), int(b["tid"])
+        v = vcf[int(b["vcf_off"]):int(b["vcf_off"]) + y - x + 1]
+        rb, k = oracle.print_block(v, blockgen.window_codes(refs[tid], x, y + 2), x, rid=tid + 7, ctg_end=int(tl[tid]), all_positions=allp)
+        parts.append(rb)
+        total += k
+    want = (np.concatenate(parts), total)
+    b2, out, nrec = gpu.call_bam_bcf(bam, tl, refs, bslib.reader_params(**opts), bslib.bcf_params(all_positions=allp),
+                                     vcf_rid=[t + 7 for t in range(len(tl))])
+    assert len(b2) == len(blocks) and total > 500
+    same_bcf((np.asarray(out), nrec), want, "seed %d" % seed)
+
+
+def bamgen_stream(seed):
+    from tests import bamgen
+    return bamgen.make_stream(seed, dup=0.2, junk=0.1)
