@@ -230,6 +230,33 @@ def bam_path(args, gpu, bslib, torch, np, stream, rank, world, local):
                                 "descriptors_d2h_block_builder_host": (s1["bam_build_s"] - s0["bam_build_s"]) / steps,
                                 "normalise_pileup_model_d2h": (s1["bam_call_s"] - s0["bam_call_s"]) / steps},
            "gpu_launches_per_step": (s1["kernel_launches"] - s0["kernel_launches"]) // steps}
+    # the same stream all the way to BCF records (the writer's derivations on the device): only the records come home
+    hbcf = bslib.HostBuffer(ctg_len * 96 + 4096, np.uint8)
+    for _ in range(2):
+        _, rb, rn = gpu.call_bam_bcf(hbam.array, tl, [href], out=hbcf.array)
+    sb0 = gpu.stats()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, rb, rn = gpu.call_bam_bcf(hbam.array, tl, [href], out=hbcf.array)
+    torch.cuda.synchronize()
+    dtb = (time.perf_counter() - t0) / steps
+    sb1 = gpu.stats()
+    tb_ = torch.tensor([dtb], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tb_, op=dist.ReduceOp.MAX)
+    out["to_bcf_records"] = {"value": float(cc.item()) / float(tb_.item()), "unit": "sites/s", "records_per_step": rn, "record_bytes_per_step": len(rb),
+                             "h2d_bytes_per_step": (sb1["h2d_bytes"] - sb0["h2d_bytes"]) // steps, "d2h_bytes_per_step": (sb1["d2h_bytes"] - sb0["d2h_bytes"]) // steps,
+                             "stage_s_per_step": {"frame_h2d_decode": (sb1["bam_decode_s"] - sb0["bam_decode_s"]) / steps,
+                                                  "descriptors_d2h_block_builder_host": (sb1["bam_build_s"] - sb0["bam_build_s"]) / steps,
+                                                  "normalise_pileup_model_writer_d2h": (sb1["bam_call_s"] - sb0["bam_call_s"]) / steps},
+                             "gpu_launches_per_step": (sb1["kernel_launches"] - sb0["kernel_launches"]) // steps,
+                             "note": "bsgpu_call_bam_bcf on pinned host buffers: BAM records up, BCF records down"}
+    bcf_first = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        bcf_first = rb.copy()
+    hbcf.free()
     # the same with the --report-file side channels on (conversion profile + base / read tallies by the normalisation
     # kernel, read_input's tallies by the host builder)
     gpu.profile_enable(True)
@@ -289,6 +316,26 @@ def bam_path(args, gpu, bslib, torch, np, stream, rank, world, local):
             n_ = int(w["y"]) - int(w["x"]) + 1
             checked += util.assert_vcf_close(vcf[int(b["vcf_off"]):int(b["vcf_off"]) + n_], cv[int(w["vcf_off"]):int(w["vcf_off"]) + n_])
         out["cpu_baseline"]["parity_sites_checked"] = checked
+        # the records: the reference's writer over the reference's own chain on every complete block of the prefix, against
+        # the leading records of the device's stream (fixed fields identical; GL floats carry the posteriors' last bits)
+        if kind == "reference":
+            from tests import blockgen
+            want = []
+            for w in cb[:len(cb) - 1]:
+                n_ = int(w["y"]) - int(w["x"]) + 1
+                wb_, _ = impl.print_block(cv[int(w["vcf_off"]):int(w["vcf_off"]) + n_], blockgen.window_codes(href[:clen], int(w["x"]), int(w["y"]) + 2),
+                                          int(w["x"]), rid=0, ctg_end=ctg_len)
+                want += util.split_bcf(wb_)
+            at, same, fixed = 0, 0, 0
+            for r in want:
+                l = 8 + int(bcf_first[at:at + 4].view("<u4")[0]) + int(bcf_first[at + 4:at + 8].view("<u4")[0])
+                g_ = bcf_first[at:at + l].tobytes()
+                fixed += g_[:32] == r[:32]
+                same += g_ == r
+                at += l
+            assert fixed == len(want), "device records differ from the reference writer's in their fixed fields"
+            out["to_bcf_records"]["parity_records_checked"] = len(want)
+            out["to_bcf_records"]["parity_records_byte_identical"] = same
         gpu.call_bam(prefix, [clen], [href[:clen]], vcf=hvcf.array)
         util.same_profile(gpu.profile_read(reset=True), cprof, "bench prefix", recycled_vectors=kind == "reference")
         out["with_report_side_channels"]["parity_profile_counts_checked"] = int(cprof["conv"].sum())
