@@ -1,6 +1,7 @@
 // bsgpu_api.cu -- the C ABI declared in include/bsgpu.h: context, staging, pipelines.  No CPU compute path:
 // every entry point that produces results launches kernels, and bsgpu_init fails if no sm_100 device opens.
 #include <algorithm>
+#include <functional>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -43,6 +44,7 @@ BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, 
 BuildJob *build_blocks_start(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
 		bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread, bool with_tally);
 const uint64_t *build_blocks_piece_tally(const BuildJob *job, size_t p);
+uint32_t build_blocks_piece_maxcap(const BuildJob *job, size_t p);
 size_t build_blocks_pieces(const BuildJob *job);
 int build_blocks_piece(BuildJob *job, size_t p, const std::vector<bsgpu_block> **blocks, size_t *tmpl_base, size_t *ntmpl);
 void build_blocks_finish(BuildJob *job);
@@ -128,6 +130,7 @@ struct bsgpu_ctx {
 	cudaEvent_t wr_built[3] = {nullptr, nullptr, nullptr}, wr_copied[3] = {nullptr, nullptr, nullptr};
 	unsigned long long *d_wr_totals = nullptr;   // 8 slots of (bytes, records, oversized)
 	unsigned long long *h_wr_totals = nullptr;   // pinned mirror
+	double tm_prep = 0, tm_queue = 0, tm_collect = 0;      // BSGPU_TIMING: host time of bsgpu_call_bam's window loop
 	uint64_t reader_tally[30] = {0};             // read_input's filter_cts[15] | filter_bases[15] (host side, bsgpu_call_bam)
 	DevBuf prof_scratch;                         // used16 | cand | chunkmax of the window being normalised
 	int prof_parity = 0;                         // which ProfDev::used[] holds the running value
@@ -992,7 +995,9 @@ struct BcfSink {
 
 static int sink_collect(bsgpu_ctx *c, BcfSink *k) {
 	const int slot = (int)(k->collected % 3);
+	const double tc0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 	CU(cudaEventSynchronize(c->wr_built[slot]));
+	c->tm_collect += std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - tc0;
 	const unsigned long long *t = c->h_wr_totals + 3 * (k->collected & 7);
 	if (t[2]) return fail("bsgpu_call_bam_bcf: %llu record(s) longer than %d bytes", t[2], BSGPU_BCF_MAX_RECORD);
 	if (t[0] > k->ring_cap[slot]) return fail("bsgpu_call_bam_bcf: the records of one window (%llu bytes) exceed the device staging buffer", t[0]);
@@ -1007,64 +1012,78 @@ static int sink_collect(bsgpu_ctx *c, BcfSink *k) {
 
 // wb[0 .. nwb): the blocks inside the window (BCF sink only)
 static int call_window(bsgpu_ctx *c, const bsgpu_template *tm, size_t nt, uint32_t tid, uint32_t ctg_len, const uint8_t *codes,
-		uint32_t x, uint32_t y, bsgpu_gt_vcf *out, BcfSink *sink = nullptr, const bsgpu_block *wb = nullptr, size_t nwb = 0) {
+		uint32_t x, uint32_t y, bsgpu_gt_vcf *out, uint32_t maxcap_hint = 0, BcfSink *sink = nullptr, const bsgpu_block *wb = nullptr, size_t nwb = 0) {
 	const uint32_t sz = y - x + 1;
-	// per-mate output slots: read length + reference span bounds the read in reference coordinates
+	auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double tp0 = now();
+	// Per-mate output slots: read length + reference span bounds a mate in reference coordinates.  The block builder
+	// reports the largest such bound of its piece; when that is moderate every mate simply gets a slot of that size and no
+	// offset table is built or uploaded.  Otherwise (a few very long spans) exact offsets are laid out here.
 	std::vector<uint32_t> &off = c->off_tmp;
-	off.resize(2 * nt + 1);
 	uint64_t tot = 0;
-	uint32_t maxcap = 1;
-	for (size_t i = 0; i < nt; i++) for (int k = 0; k < 2; k++) {
-		off[2 * i + k] = (uint32_t)tot;
-		const bsgpu_template &t = tm[i];
-		if (!t.present[k]) continue;
-		const uint64_t cap = (uint64_t)t.read_len[k] + t.reference_span[k];
-		tot += cap;
-		if (cap > maxcap) maxcap = (uint32_t)(cap > 0xffffffu ? 0xffffffu : cap);
+	uint32_t maxcap = 1, slot = 0;
+	if (maxcap_hint && maxcap_hint <= 1024 && 2ull * nt * ((maxcap_hint + 15u) & ~15u) <= 0xffffffffull) {
+		slot = (maxcap_hint + 15u) & ~15u;
+		maxcap = maxcap_hint;
+		tot = 2ull * nt * slot;
+	} else {
+		off.resize(2 * nt + 1);
+		for (size_t i = 0; i < nt; i++) for (int k = 0; k < 2; k++) {
+			off[2 * i + k] = (uint32_t)tot;
+			const bsgpu_template &t = tm[i];
+			if (!t.present[k]) continue;
+			const uint64_t cap = (uint64_t)t.read_len[k] + t.reference_span[k];
+			tot += cap;
+			if (cap > maxcap) maxcap = (uint32_t)(cap > 0xffffffu ? 0xffffffu : cap);
+		}
+		off[2 * nt] = (uint32_t)tot;
 	}
-	off[2 * nt] = (uint32_t)tot;
 	if (tot > 0xffffffffull) return fail("bsgpu_call_bam: more than 4 GiB of bases in one window of contig %u; split the input", tid);
 	const uint32_t spm = (maxcap + BSGPU_MAX_SEG_LEN - 1) / BSGPU_MAX_SEG_LEN;
 	const size_t nseg = nt * 2 * (size_t)spm;
-	// reference window [x, y]: N beyond the contig end (src/get_sequence.c:36-41)
-	std::vector<uint8_t> &refw = c->ref_tmp;
-	refw.resize((size_t)sz + 2);               // one code past the window for the conversion profile (src/meth_profile.c:70), two for the writer
-	for (uint32_t i = 0; i < sz + 2; i++) { const uint64_t pos = (uint64_t)x + i; refw[i] = pos < ctg_len ? codes[pos - 1] : 0; }
+	// reference window [x, y + 2] (one code past the window for the conversion profile, src/meth_profile.c:70, two for the
+	// writer): straight from the contig's codes, N from the contig's last position on (src/get_sequence.c:36-41)
+	const uint64_t navail = (uint64_t)x < ctg_len ? (uint64_t)ctg_len - x : 0;          // positions x .. ctg_len - 1
+	const size_t ncopy = (size_t)std::min<uint64_t>(navail, (uint64_t)sz + 2);
+	const double tp1 = now();
+	c->tm_prep += tp1 - tp0;
+	struct Acc { double &d; double t0; std::function<double()> f; ~Acc() { d += f() - t0; } } acc_{c->tm_queue, tp1, now};
 	// Everything below is queued behind the previous window on the context stream; nothing waits on the host.  (Growing a
 	// device buffer frees the old one, which synchronises the device; `off` / `refw` are pageable, so their copies are
 	// staged before cudaMemcpyAsync returns and the vectors can be refilled for the next window.)
 	CU(c->tmpl.reserve(nt * sizeof(bsgpu_template)));
 	CU(c->obases.reserve(tot + 16));
-	CU(c->ooff.reserve((2 * nt + 1) * sizeof(uint32_t)));
+	if (!slot) CU(c->ooff.reserve((2 * nt + 1) * sizeof(uint32_t)));
 	CU(c->segs.reserve(nseg * sizeof(bsgpu_seg) + 16));
 	CU(c->ref.reserve((size_t)sz + 16));
 	CU(cudaMemcpyAsync(c->tmpl.p, tm, nt * sizeof(bsgpu_template), cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->ooff.p, off.data(), (2 * nt + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->ref.p, refw.data(), (size_t)sz + 2, cudaMemcpyHostToDevice, c->stream));
-	c->stats.h2d_bytes += nt * sizeof(bsgpu_template) + (2 * nt + 1) * 4 + sz + 2;
+	if (!slot) CU(cudaMemcpyAsync(c->ooff.p, off.data(), (2 * nt + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+	if (ncopy) CU(cudaMemcpyAsync(c->ref.p, codes + x - 1, ncopy, cudaMemcpyHostToDevice, c->stream));
+	if (ncopy < (size_t)sz + 2) CU(cudaMemsetAsync((uint8_t *)c->ref.p + ncopy, 0, (size_t)sz + 2 - ncopy, c->stream));
+	c->stats.h2d_bytes += nt * sizeof(bsgpu_template) + (slot ? 0 : (2 * nt + 1) * 4) + ncopy;
 	cudaError_t perr;
 	const ProfArgs *pa = profile_for(c, nt, sz, &perr);
 	CU(perr);
-	CU(launch_normalise(c->tmpl.p, nt, c->rd_bases.p, c->rd_misms.p, c->ooff.p, c->obases.p, c->segs.p, spm, x, y,
-			c->params.left_trim, c->params.right_trim, c->d_counters, pa, c->prof_parity, c->stream, &c->launches));
+	CU(launch_normalise(c->tmpl.p, nt, c->rd_bases.p, c->rd_misms.p, slot ? nullptr : c->ooff.p, c->obases.p, c->segs.p, spm, x, y,
+			c->params.left_trim, c->params.right_trim, c->d_counters, pa, c->prof_parity, c->stream, &c->launches, slot));
 	if (pa) c->prof_parity ^= 1;
 	if (!sink) return block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, out, 1, true);
 	// ---- records instead of gt_vcf[]: the window's gt_vcf[] stays on the device, the writer kernels turn it into BCF
-	const int slot = (int)(sink->queued % 3);
+	const int rslot = (int)(sink->queued % 3);
 	for (int i = 0; i < 3; i++) if (!c->wr_built[i]) {
 		CU(cudaEventCreateWithFlags(&c->wr_built[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&c->wr_copied[i], cudaEventDisableTiming));
 	}
 	const size_t rcap = (size_t)sz * 256 + 4096;
-	const bool grow = (size_t)sz * sizeof(bsgpu_gt_vcf) > c->wr_vcf.cap || rcap + 16 > c->wr_ring[slot].cap || bcf_site_scratch_bytes(sz) > c->wr_site.cap ||
+	const bool grow = (size_t)sz * sizeof(bsgpu_gt_vcf) > c->wr_vcf.cap || rcap + 16 > c->wr_ring[rslot].cap || bcf_site_scratch_bytes(sz) > c->wr_site.cap ||
 			bcf_cta_scratch_bytes(sz) > c->wr_cta.cap || (nwb + 1) * 8 > c->wr_blocks.cap;
 	if (grow) CU(cudaDeviceSynchronize());          // growing frees buffers that queued work may still use
 	CU(c->wr_vcf.reserve((size_t)sz * sizeof(bsgpu_gt_vcf)));
-	CU(c->wr_ring[slot].reserve(rcap + 16));
+	CU(c->wr_ring[rslot].reserve(rcap + 16));
 	CU(c->wr_site.reserve(bcf_site_scratch_bytes(sz)));
 	CU(c->wr_cta.reserve(bcf_cta_scratch_bytes(sz)));
 	CU(c->wr_blocks.reserve((nwb + 1) * 8));
-	sink->ring_cap[slot] = rcap;
+	sink->ring_cap[rslot] = rcap;
 	std::vector<uint32_t> pairs(2 * nwb);
 	for (size_t b = 0; b < nwb; b++) { pairs[2 * b] = wb[b].x - x; pairs[2 * b + 1] = wb[b].y - x; }
 	CU(cudaMemcpyAsync(c->wr_blocks.p, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, c->stream));      // pageable: staged before the call returns
@@ -1073,12 +1092,12 @@ static int call_window(bsgpu_ctx *c, const bsgpu_template *tm, size_t nt, uint32
 	j.d_vcf = c->wr_vcf.p; j.d_ref = c->ref.p; j.x = x; j.sz = sz; j.d_blocks = c->wr_blocks.p; j.nblocks = (uint32_t)nwb;
 	j.p = sink->p; j.p.rid = sink->vcf_rid ? sink->vcf_rid[tid] : (int32_t)tid; j.p.ctg_end = ctg_len;
 	j.dc = c->d_const; j.site_scratch = c->wr_site.p;
-	if (sink->queued >= 3) CU(cudaStreamWaitEvent(c->stream, c->wr_copied[slot], 0));      // the slot's previous records have left
+	if (sink->queued >= 3) CU(cudaStreamWaitEvent(c->stream, c->wr_copied[rslot], 0));      // the slot's previous records have left
 	CU(launch_bcf_calls(j, 0, sz, c->stream, &c->launches));
-	CU(launch_bcf_records(j, 0, sz, c->wr_cta.p, c->wr_ring[slot].p, rcap, c->d_wr_totals + 3 * (sink->queued & 7), c->stream, &c->launches));
+	CU(launch_bcf_records(j, 0, sz, c->wr_cta.p, c->wr_ring[rslot].p, rcap, c->d_wr_totals + 3 * (sink->queued & 7), c->stream, &c->launches));
 	CU(cudaMemcpyAsync(c->h_wr_totals + 3 * (sink->queued & 7), c->d_wr_totals + 3 * (sink->queued & 7), 3 * sizeof(unsigned long long),
 			cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaEventRecord(c->wr_built[slot], c->stream));
+	CU(cudaEventRecord(c->wr_built[rslot], c->stream));
 	sink->queued++;
 	while (sink->queued - sink->collected > 1) if (sink_collect(c, sink) != BSGPU_OK) return BSGPU_FAIL;
 	return BSGPU_OK;
@@ -1130,12 +1149,17 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 		}
 	} guard{c};
 	BuildJob *&job = guard.job;
+	double tm_rd = 0, tm_cert = 0, tm_piece = 0, tm_win = 0;
+	c->tm_prep = c->tm_queue = c->tm_collect = 0;
 	for (size_t ck = 0; ck < chunk_end.size() && ret == BSGPU_OK; ck++) {
 		const double w0 = now();
 		CU(cudaEventSynchronize(c->rd_done[ck]));
 		t_wait += now() - w0;
+		tm_rd += now() - w0;
 		const size_t avail = chunk_end[ck];
+		const double w1 = now();
 		certain_block_starts(rec, scanned, avail, &cst, starts);
+		tm_cert += now() - w1;
 		scanned = avail;
 		const bool last = ck + 1 == chunk_end.size();
 		// build up to the last certain start (everything when the stream is complete); starts[] holds those > built
@@ -1156,6 +1180,9 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 		const double w0 = now();
 		const int rc = build_blocks_piece(job, p, &pb, &base, &nt_piece);
 		t_wait += now() - w0;
+		tm_piece += now() - w0;
+		const double w2 = now();
+		struct WinAcc { double &d; double t0; std::function<double()> f; ~WinAcc() { d += f() - t0; } } wacc_{tm_win, w2, now};
 		if (rc == -4) { ret = fail("bsgpu_call_bam: duplicate read name among waiting mates"); break; }
 		if (rc == -5) { ret = fail("bsgpu_call_bam: the two mates of a template disagree about their positions"); break; }
 		if (rc) { ret = fail("bsgpu_call_bam: block builder failed (%d)", rc); break; }
@@ -1175,7 +1202,8 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 			if (y >= x) {
 				const uint32_t sz = y - x + 1;
 				if (!sink && ov + sz > vcf_cap) { ret = fail("bsgpu_call_bam: vcf[] too small (contig %u needs %u more records)", tid, sz); break; }
-				ret = call_window(c, tm + t_lo, t_n, tid, target_len[tid], ctg_codes[tid], x, y, sink ? nullptr : vcf + ov, sink, pb->data() + b0, b1 - b0);
+				ret = call_window(c, tm + t_lo, t_n, tid, target_len[tid], ctg_codes[tid], x, y, sink ? nullptr : vcf + ov, build_blocks_piece_maxcap(job, p),
+						sink, pb->data() + b0, b1 - b0);
 				ov += sz;
 				ctg_end = y;
 			}
@@ -1204,6 +1232,9 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	*nblocks = nbk;
 	*nvcf = ov;
 	const double t2 = now();
+	if (getenv("BSGPU_TIMING"))
+		fprintf(stderr, "bsgpu_call_bam: decode_queue %.2f ms | wait descriptors %.2f, certain starts %.2f, wait pieces %.2f, windows %.2f (prep %.2f, queue %.2f, collect %.2f) | total %.2f ms\n",
+				(t1 - t0) * 1e3, tm_rd * 1e3, tm_cert * 1e3, tm_piece * 1e3, tm_win * 1e3, c->tm_prep * 1e3, c->tm_queue * 1e3, c->tm_collect * 1e3, (t2 - t0) * 1e3);
 	c->stats.bam_build_s += t_wait;
 	c->stats.bam_call_s += t2 - t1 - t_wait;
 	return BSGPU_OK;

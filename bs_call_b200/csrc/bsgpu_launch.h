@@ -62,10 +62,10 @@ struct ProfArgs {
 constexpr uint32_t kProfChunk = 4096;
 
 // raw templates -> reads in reference coordinates + segment records (bsgpu_normalise.cu); prof != NULL: also the
-// profile (two more launches)
+// profile (two more launches); out_off == NULL: every mate owns `slot` bytes of obases
 cudaError_t launch_normalise(const void *tmpl, size_t n, const void *bases, void *ev_work, const void *out_off, void *obases,
 		void *segs, uint32_t segs_per_mate, uint32_t x, uint32_t y, const uint32_t left_trim[2], const uint32_t right_trim[2],
-		unsigned long long *counters, const ProfArgs *prof, int parity, cudaStream_t stream, int *launches);
+		unsigned long long *counters, const ProfArgs *prof, int parity, cudaStream_t stream, int *launches, uint32_t slot = 0);
 
 // writer side (bsgpu_writer.cu): gt_vcf[] of a window -> BCF records
 struct BcfJob {

@@ -255,7 +255,10 @@ constexpr int kNormWarps = 8;
 struct NormArgs {
 	const bsgpu_template *tmpl; size_t n; const uint8_t *bases; bsgpu_misms *ev_work; const uint32_t *out_off; uint8_t *obases;
 	Seg *segs; uint32_t segs_per_mate, x, y, lt0, rt0, lt1, rt1; unsigned long long *counters;
+	uint32_t slot;               // out_off == NULL: mate j of the launch owns bytes [j * slot, (j + 1) * slot) of obases
 };
+__device__ __forceinline__ uint32_t out_begin(const NormArgs &a, size_t j) { return a.out_off ? a.out_off[j] : (uint32_t)(j * a.slot); }
+__device__ __forceinline__ uint32_t out_room(const NormArgs &a, size_t j) { return a.out_off ? a.out_off[j + 1] - a.out_off[j] : a.slot; }
 
 // One WARP per template.  The event-list surgery (soft clips, overlap) is a short sequential walk done by lane 0; what
 // touches every byte of the reads -- the quality means that break span ties, the rewrite into reference coordinates,
@@ -369,8 +372,8 @@ __device__ void normalise_one(const NormArgs &a, const size_t i, const int lane,
 	uint32_t ori = t.orientation & 1u;
 	for (int k = 0; k < 2; k++) {
 		if (!mt[k].present) continue;
-		uint8_t *out = a.obases + a.out_off[2 * i + k];
-		const uint32_t cap = a.out_off[2 * i + k + 1] - a.out_off[2 * i + k];
+		uint8_t *out = a.obases + out_begin(a, 2 * i + k);
+		const uint32_t cap = out_room(a, 2 * i + k);
 		const uint32_t rl = to_ref_coords<PROF>(mt[k], out, cap, lane, pa, pm[k], hist, i);
 		if (!rl) continue;
 		__syncwarp();
@@ -391,7 +394,7 @@ __device__ void normalise_one(const NormArgs &a, const size_t i, const int lane,
 			if (!b0) break;
 		}
 		if (lane == 0) {
-			uint32_t p = pos[k] + first, off = a.out_off[2 * i + k] + first, len = last - first;
+			uint32_t p = pos[k] + first, off = out_begin(a, 2 * i + k) + first, len = last - first;
 			if (p < a.x) { atomicAdd(a.counters + 3, 1ull); len = 0; }       // cannot happen for a well-formed block (assert at :186)
 			if (len && p <= a.y) {
 				if ((uint64_t)p + len > (uint64_t)a.y + 1) len = a.y + 1 - p;
@@ -504,12 +507,13 @@ __global__ void __launch_bounds__(kProfChunk / 4) k_profile_resolve(const uint16
 
 cudaError_t launch_normalise(const void *tmpl, size_t n, const void *bases, void *ev_work, const void *out_off, void *obases,
 		void *segs, uint32_t segs_per_mate, uint32_t x, uint32_t y, const uint32_t left_trim[2], const uint32_t right_trim[2],
-		unsigned long long *counters, const ProfArgs *prof, int parity, cudaStream_t stream, int *launches) {
+		unsigned long long *counters, const ProfArgs *prof, int parity, cudaStream_t stream, int *launches, uint32_t slot) {
 	if (!n) return cudaSuccess;
 	NormArgs a;
 	a.tmpl = (const bsgpu_template *)tmpl; a.n = n; a.bases = (const uint8_t *)bases; a.ev_work = (bsgpu_misms *)ev_work;
 	a.out_off = (const uint32_t *)out_off; a.obases = (uint8_t *)obases; a.segs = (Seg *)segs; a.segs_per_mate = segs_per_mate;
 	a.x = x; a.y = y; a.lt0 = left_trim[0]; a.rt0 = right_trim[0]; a.lt1 = left_trim[1]; a.rt1 = right_trim[1]; a.counters = counters;
+	a.slot = slot;
 	const size_t ctas = (n + kNormWarps - 1) / kNormWarps;
 	if (!prof) {
 		k_normalise<<<(unsigned)ctas, kNormWarps * 32, 0, stream>>>(a);

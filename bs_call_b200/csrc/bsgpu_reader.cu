@@ -461,6 +461,7 @@ struct BlockBuilder {
 	std::vector<bsgpu_block> *blocks;
 	bsgpu_template *out = nullptr;       // templates of this builder, in publication order (room for one per record)
 	size_t nout = 0;
+	uint32_t maxcap = 1;                 // largest read_len + reference span of a published mate: bounds a mate in reference coordinates
 	uint64_t *tally = nullptr;           // --report-file: filter_cts[15] then filter_bases[15] of read_input, or none
 	void count(int reason_cts, uint64_t cts, int reason_bases, uint64_t bases) { tally[reason_cts] += cts; tally[15 + reason_bases] += bases; }
 	uint32_t read_len_of(const Tmpl &t, int k) const { return t.rec[k] >= 0 ? rec[t.rec[k]].read_len : 0; }
@@ -499,6 +500,8 @@ struct BlockBuilder {
 				const bsgpu_record &r = rec[t.rec[k]];
 				d.present[k] = 1; d.reference_span[k] = t.span[k];
 				d.read_off[k] = r.read_off; d.read_len[k] = r.read_len; d.mm_off[k] = r.mm_off; d.mm_n[k] = r.mm_n;
+				const uint64_t cap = (uint64_t)r.read_len + t.span[k];
+				if (cap > maxcap) maxcap = (uint32_t)(cap > 0xffffffu ? 0xffffffu : cap);
 			}
 			out[nout++] = d;
 		}
@@ -672,7 +675,7 @@ struct CertainState { int tid = -1; uint64_t maxend = 0; };
 // in `st`, so a stream whose descriptors arrive in chunks can be scanned chunk by chunk.  (A conservative subset of
 // the block starts: the running end is never reset, and mates at equal positions -- whose insertion depends on the
 // name table -- are not used.)
-void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts) {
+static void certain_block_starts_seq(const bsgpu_record *rec, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts) {
 	int tid = st->tid;
 	uint64_t maxend = st->maxend;
 	for (size_t i = rbeg; i < rend; i++) {
@@ -692,6 +695,81 @@ void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, Cer
 	st->tid = tid; st->maxend = maxend;
 }
 
+// The scan above is a running maximum, so it splits: every host thread scans a segment from a blank state and keeps
+// the records that pass against its LOCAL running end, with the smaller of their positions; whether those before the
+// segment's first contig change really pass depends on the end carried in from the segments before, which a short
+// sequential pass supplies.  (The descriptors are 56 bytes each in pinned memory the device has just written: one thread
+// streams them at DRAM latency, 11 ms for 1.6 M records.)
+void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts) {
+	unsigned want = std::thread::hardware_concurrency();
+	if (const char *e = getenv("BSGPU_BUILDER_THREADS")) want = (unsigned)atoi(e);
+	want = std::max(1u, std::min(want, 16u));
+	const size_t n = rend - rbeg;
+	size_t min_rec = 50000;
+	if (const char *e = getenv("BSGPU_BUILDER_MIN_RECORDS")) min_rec = (size_t)atoll(e);
+	if (want == 1 || n < min_rec || n < want) { certain_block_starts_seq(rec, rbeg, rend, st, starts); return; }
+	struct Cand { size_t i; uint64_t minpos; };
+	struct SegOut {
+		bool any = false, changed = false;
+		size_t head = 0;                      // first kept record: decided by the carry
+		int head_tid = -1, tail_tid = -1;
+		uint64_t head_end = 0;                // running end of the head's contig up to the first contig change (or the segment end)
+		uint64_t tail_end = 0;                // running end of the last contig at the segment end
+		std::vector<Cand> pending;            // pass locally, before the first contig change: need the carried end
+		std::vector<size_t> fin;              // decided: contig changes and whatever passes after the first one
+	};
+	std::vector<SegOut> seg(want);
+	std::vector<std::thread> thr;
+	for (unsigned t = 0; t < want; t++) thr.emplace_back([&, t] {
+		SegOut &o = seg[t];
+		const size_t lo = rbeg + n * t / want, hi = rbeg + n * (t + 1) / want;
+		int tid = -1;
+		uint64_t maxend = 0;
+		for (size_t i = lo; i < hi; i++) {
+			const bsgpu_record &r = rec[i];
+			if (r.ret > 0) continue;
+			const uint32_t fwd = r.forward_position, rev = r.reverse_position, own = r.reverse ? rev : fwd;
+			if (!o.any) { o.any = true; o.head = i; o.head_tid = tid = r.tid; maxend = 0; }
+			else if (r.tid != tid) {
+				if (!o.changed) { o.changed = true; o.head_end = maxend; }
+				tid = r.tid; maxend = 0; o.fin.push_back(i);
+			} else {
+				bool insert = true;
+				if ((r.alignment_flag & F_PAIRED) && fwd > 0 && rev > 0) insert = fwd == rev ? false : (r.reverse ? fwd > rev : fwd < rev);
+				if (insert && (fwd == 0 || (uint64_t)fwd > maxend + 1) && (rev == 0 || (uint64_t)rev > maxend + 1) && (fwd | rev)) {
+					if (o.changed) o.fin.push_back(i);
+					else o.pending.push_back(Cand{i, (uint64_t)(fwd == 0 ? rev : rev == 0 ? fwd : std::min(fwd, rev))});
+				}
+			}
+			const uint64_t e1 = (uint64_t)own + r.reference_span, e2 = (uint64_t)(fwd > 0 ? fwd : rev) + r.align_length;
+			if (e1 > maxend) maxend = e1;
+			if (e2 > maxend) maxend = e2;
+		}
+		o.tail_tid = tid; o.tail_end = maxend;
+		if (!o.changed) o.head_end = maxend;
+	});
+	for (auto &t : thr) t.join();
+	int tid = st->tid;
+	uint64_t maxend = st->maxend;
+	for (const SegOut &o : seg) {
+		if (!o.any) continue;
+		if (o.head_tid != tid) { tid = o.head_tid; maxend = 0; starts.push_back(o.head); }
+		else {
+			const bsgpu_record &r = rec[o.head];
+			const uint32_t fwd = r.forward_position, rev = r.reverse_position;
+			bool insert = true;
+			if ((r.alignment_flag & F_PAIRED) && fwd > 0 && rev > 0) insert = fwd == rev ? false : (r.reverse ? fwd > rev : fwd < rev);
+			if (insert && (fwd == 0 || (uint64_t)fwd > maxend + 1) && (rev == 0 || (uint64_t)rev > maxend + 1) && (fwd | rev)) starts.push_back(o.head);
+		}
+		// a record that passed against the local end passes against the true one iff it also clears the carried end
+		for (const Cand &cd : o.pending) if (cd.minpos > maxend + 1) starts.push_back(cd.i);
+		starts.insert(starts.end(), o.fin.begin(), o.fin.end());
+		if (o.changed) { tid = o.tail_tid; maxend = o.tail_end; }
+		else if (o.head_end > maxend) maxend = o.head_end;
+	}
+	st->tid = tid; st->maxend = maxend;
+}
+
 // A build in flight: the stream cut into pieces at certain block starts, pieces built by a pool of host threads in
 // order.  Piece p's templates sit at tmpl + cuts[p] (a piece has no more templates than records) and its blocks number
 // their templates from the start of the piece, so a consumer can take pieces over one by one while later ones are
@@ -700,12 +778,13 @@ struct BuildJob {
 	std::vector<size_t> cuts;
 	std::vector<std::vector<bsgpu_block>> pb;
 	std::vector<size_t> pn;
+	std::vector<uint32_t> pmax;          // per piece: BlockBuilder::maxcap
 	std::vector<uint64_t> tally;         // 30 per piece when tallies were asked for
 	std::vector<int> rc;
 	std::vector<std::atomic<int>> done;
 	std::vector<std::thread> thr;
 	std::atomic<size_t> next{0};
-	explicit BuildJob(size_t np) : pb(np), pn(np, 0), rc(np, 0), done(np) { for (auto &d : done) d.store(0); }
+	explicit BuildJob(size_t np) : pb(np), pn(np, 0), pmax(np, 1), rc(np, 0), done(np) { for (auto &d : done) d.store(0); }
 };
 
 // records [rbeg, rend); rbeg is the start of the stream or a certain block start; `starts` = the certain block starts
@@ -745,6 +824,7 @@ BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, 
 			if (with_tally) b.tally = job->tally.data() + p * 30;
 			job->rc[p] = b.run(job->cuts[p], job->cuts[p + 1], keep_unmatched, keep_duplicates);
 			job->pn[p] = b.nout;
+			job->pmax[p] = b.maxcap;
 			job->done[p].store(1, std::memory_order_release);
 		}
 	});
@@ -770,6 +850,8 @@ int build_blocks_piece(BuildJob *job, size_t p, const std::vector<bsgpu_block> *
 	*ntmpl = job->pn[p];
 	return job->rc[p];
 }
+
+uint32_t build_blocks_piece_maxcap(const BuildJob *job, size_t p) { return job->pmax[p]; }
 
 // read_input's tallies of piece p (valid once build_blocks_piece has returned it): 15 counts then 15 base sums, or NULL
 const uint64_t *build_blocks_piece_tally(const BuildJob *job, size_t p) { return job->tally.empty() ? nullptr : job->tally.data() + p * 30; }
