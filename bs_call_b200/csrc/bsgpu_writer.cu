@@ -26,6 +26,8 @@ namespace {
 
 constexpr int kWrThreads = 128;                       // sites per CTA
 constexpr int kMaxRec = BSGPU_BCF_MAX_RECORD;         // upper bound of one record (checked per site)
+constexpr int kStageBytes = 20 * 1024;                // shared-memory staging of a CTA's records: 160 B per site, a few times the
+                                                      // typical load (45 B per site at 30x); a CTA with more writes straight to HBM
 constexpr double kLn10 = 2.30258509299404568402;     // LOG10, include/bs_call.h:36
 
 struct GtVcf {                 // bsgpu_gt_vcf as the kernels read it
@@ -377,21 +379,23 @@ __global__ void __launch_bounds__(kWrThreads) k_bcf_emit(const WrArgs a) {
 	__syncthreads();
 	uint32_t off = inc - n, total = 0;
 	for (int k = 0; k < kWrThreads / 32; k++) { if (k < wid) off += wsum[k]; total += wsum[k]; }
+	const unsigned long long dst0 = a.cta_bytes[blockIdx.x];
+	if (dst0 + total > a.out_cap) return;                   // the host compares totals[0] with the capacity and reports
+	uint8_t *dst = a.out + dst0;
+	const bool staged = total <= (uint32_t)kStageBytes;
 	if (n) {
 		uint32_t first, last;
 		block_of(a, i, first, last);
 		int g[5];
 		window_calls(a, i, first, last, g);
 		Store w;
-		w.p = stage + off;
+		w.p = (staged ? stage : dst) + off;
 		build_record(a, i, first, last, g, w);
 	}
+	if (!staged) return;
 	__syncthreads();
 	// copy out: bytes up to the first aligned word of the destination, aligned words (each stitched from two staged
 	// words), bytes after the last one
-	const unsigned long long dst0 = a.cta_bytes[blockIdx.x];
-	if (dst0 + total > a.out_cap) return;                   // the host compares totals[0] with the capacity and reports
-	uint8_t *dst = a.out + dst0;
 	const uint32_t head = min(total, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
 	if (threadIdx.x < head) dst[threadIdx.x] = stage[threadIdx.x];
 	const uint32_t nwords = (total - head) >> 2;
@@ -417,7 +421,7 @@ size_t bcf_cta_scratch_bytes(uint32_t cnt) {
 }
 
 cudaError_t configure_writer() {
-	return cudaFuncSetAttribute(k_bcf_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, kWrThreads * kMaxRec + 16);
+	return cudaFuncSetAttribute(k_bcf_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes + 16);
 }
 
 static WrArgs writer_args(const BcfJob &j, uint32_t i0, uint32_t cnt) {
@@ -453,7 +457,7 @@ cudaError_t launch_bcf_records(const BcfJob &j, uint32_t i0, uint32_t cnt, void 
 	a.totals = d_totals; a.out = (uint8_t *)d_out; a.out_cap = out_cap;
 	k_bcf_measure<<<nctas, kWrThreads, 0, stream>>>(a);
 	k_bcf_offsets<<<1, 1024, 0, stream>>>(a.cta_bytes, a.cta_recs, nctas, d_totals);
-	k_bcf_emit<<<nctas, kWrThreads, kWrThreads * kMaxRec + 16, stream>>>(a);
+	k_bcf_emit<<<nctas, kWrThreads, kStageBytes + 16, stream>>>(a);
 	*launches += 3;
 	return cudaGetLastError();
 }
