@@ -799,7 +799,8 @@ int bsgpu_profile_read(bsgpu_ctx *c, bsgpu_profile *out, int reset) {
 	if (!c->d_prof) return fail("bsgpu_profile_read: the profile was never enabled");
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
-	static ProfDev h;
+	std::vector<ProfDev> hbuf(1);
+	ProfDev &h = hbuf[0];
 	CU(cudaMemcpy(&h, c->d_prof, sizeof(h), cudaMemcpyDeviceToHost));
 	c->stats.d2h_bytes += sizeof(h);
 	if (h.too_long) return fail("bsgpu profile: %llu template(s) reach beyond original read position %d", h.too_long, BSGPU_PROFILE_MAX - 2);
@@ -1140,39 +1141,38 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	// the builder threads of a job read the pinned arrays of the context: whatever way this function is left, the job is
 	// joined first and the device is quiet
 	struct JobGuard {
-		bsgpu_ctx *c; BuildJob *job = nullptr;
+		bsgpu_ctx *c; std::vector<BuildJob *> jobs;
 		~JobGuard() {
-			if (job) build_blocks_finish(job);
+			for (BuildJob *j : jobs) if (j) build_blocks_finish(j);
 			cudaStreamSynchronize(c->slot[0].stream); cudaStreamSynchronize(c->slot[1].stream);
 			cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
 			for (bool &b : c->ring_busy) b = false;
 		}
 	} guard{c};
-	BuildJob *&job = guard.job;
+	// The certain block starts of every chunk are marked as its descriptors come home; then ONE job over the whole stream
+	// hands its pieces to the builder threads in stream order, and the caller's thread takes the pieces over in that order
+	// while later ones are still being built.
 	double tm_rd = 0, tm_cert = 0, tm_piece = 0, tm_win = 0;
 	c->tm_prep = c->tm_queue = c->tm_collect = 0;
-	for (size_t ck = 0; ck < chunk_end.size() && ret == BSGPU_OK; ck++) {
+	for (size_t ck = 0; ck < chunk_end.size(); ck++) {
 		const double w0 = now();
 		CU(cudaEventSynchronize(c->rd_done[ck]));
 		t_wait += now() - w0;
 		tm_rd += now() - w0;
-		const size_t avail = chunk_end[ck];
 		const double w1 = now();
-		certain_block_starts(rec, scanned, avail, &cst, starts);
+		certain_block_starts(rec, scanned, chunk_end[ck], &cst, starts);
 		tm_cert += now() - w1;
-		scanned = avail;
-		const bool last = ck + 1 == chunk_end.size();
-		// build up to the last certain start (everything when the stream is complete); starts[] holds those > built
-		size_t upto = last ? n : built;
-		if (!last) for (size_t i = starts.size(); i-- > 0;) if (starts[i] > built) { upto = starts[i]; break; }
-		if (upto <= built) continue;
+		scanned = chunk_end[ck];
+	}
+	{
+		static const unsigned ppt = [] { const char *e = getenv("BSGPU_BUILDER_PIECES"); const int v = e ? atoi(e) : 0; return v > 0 ? (unsigned)v : 2u; }();
 		std::vector<size_t> inside;
-		for (size_t v : starts) if (v > built && v < upto) inside.push_back(v);
-		job = build_blocks_start_range(bam, c->rec_off.data(), rec, built, upto, inside, rp->keep_unmatched, rp->keep_duplicates, tm, 2, c->profile_on);
-		std::vector<size_t> keep;
-		for (size_t v : starts) if (v >= upto) keep.push_back(v);
-		starts.swap(keep);
-		built = upto;
+		for (size_t v : starts) if (v > 0 && v < n) inside.push_back(v);
+		guard.jobs.push_back(build_blocks_start_range(bam, c->rec_off.data(), rec, 0, n, inside, rp->keep_unmatched, rp->keep_duplicates, tm, ppt, c->profile_on));
+		built = n;
+	}
+	for (size_t ji = 0; ji < guard.jobs.size() && ret == BSGPU_OK; ji++) {
+		BuildJob *&job = guard.jobs[ji];
 		const size_t np = build_blocks_pieces(job);
 	for (size_t p = 0; p < np && ret == BSGPU_OK; p++) {
 		const std::vector<bsgpu_block> *pb;
