@@ -1,6 +1,7 @@
 // bsgpu_api.cu -- the C ABI declared in include/bsgpu.h: context, staging, pipelines.  No CPU compute path:
 // every entry point that produces results launches kernels, and bsgpu_init fails if no sm_100 device opens.
 #include <algorithm>
+#include <thread>
 #include <functional>
 #include <chrono>
 #include <cmath>
@@ -38,6 +39,7 @@ int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_r
 struct BuildJob;
 struct CertainState { int tid = -1; uint64_t maxend = 0; };
 void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts);
+void certain_block_starts_keys(const uint32_t *keys, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts);
 BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t rbeg, size_t rend,
 		const std::vector<size_t> &starts, bool keep_unmatched, bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread,
 		bool with_tally);
@@ -110,12 +112,12 @@ struct bsgpu_ctx {
 	cudaStream_t copy_stream = nullptr;          // D2H of finished windows
 	Slot slot[2];
 	DevBuf segs, bases, ref, scratch, vcf, tmpl, misms, obases, ooff, pile;
-	DevBuf rd_bam, rd_recoff, rd_readoff, rd_mmoff, rd_rec, rd_bases, rd_misms;      // reader side: stream, framing, decoded arrays
+	DevBuf rd_bam, rd_recoff, rd_readoff, rd_mmoff, rd_rec, rd_bases, rd_misms, rd_key;      // reader side: stream, framing, decoded arrays
 	std::vector<uint64_t> rec_off;               // framing of the last decoded stream
 	std::vector<uint32_t> read_off, mm_off, off_tmp;
 	std::vector<uint8_t> ref_tmp;
 	FrameScratch *frame_scratch = nullptr;
-	PinBuf h_rec, h_off, h_tmpl;                 // pinned staging: descriptors coming back, offset tables and templates going up
+	PinBuf h_rec, h_off, h_tmpl, h_key;                 // pinned staging: descriptors coming back, offset tables and templates going up
 	bool fused = false;                          // BSGPU_FUSED=1: one fused pileup+model kernel instead of two kernels
 	std::vector<cudaEvent_t> win_events, rd_up, rd_done;      // output ring; reader: byte piece uploaded, chunk descriptors home
 	uint32_t ring_pos = 0;                       // next output ring slot of the deferred runs
@@ -245,7 +247,7 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 	for (cudaEvent_t ev : c->rd_up) cudaEventDestroy(ev);
 	for (cudaEvent_t ev : c->rd_done) cudaEventDestroy(ev);
 	if (c->frame_scratch) frame_scratch_free(c->frame_scratch);
-	c->h_rec.release(); c->h_off.release(); c->h_tmpl.release();
+	c->h_rec.release(); c->h_off.release(); c->h_tmpl.release(); c->h_key.release(); c->rd_key.release();
 	c->rd_bam.release(); c->rd_recoff.release(); c->rd_readoff.release(); c->rd_mmoff.release(); c->rd_rec.release(); c->rd_bases.release(); c->rd_misms.release();
 	c->segs.release(); c->bases.release(); c->ref.release(); c->scratch.release(); c->vcf.release(); c->tmpl.release(); c->misms.release(); c->obases.release(); c->ooff.release(); c->pile.release();
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -876,12 +878,27 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 	CU(c->rd_bases.reserve(*nb + 16));
 	CU(c->rd_misms.reserve((*nm + 1) * sizeof(bsgpu_misms)));
 	CU(c->h_rec.reserve(n * sizeof(bsgpu_record)));
+	CU(c->rd_key.reserve(n * 16));
+	CU(c->h_key.reserve(n * 16));
 	// the offset tables go up from pinned staging (pageable vectors would serialise the copies behind the big ones)
 	CU(c->h_off.reserve(n * 16));
 	uint8_t *ho = (uint8_t *)c->h_off.p;
-	memcpy(ho, c->rec_off.data(), n * 8);
-	memcpy(ho + n * 8, read_off.data(), n * 4);
-	memcpy(ho + n * 12, mm_off.data(), n * 4);
+	{
+		// 16 bytes per record into page-locked memory: a few threads, each a slice of the three tables
+		const unsigned T = n >= (1u << 18) ? std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1;
+		auto part = [&](unsigned t) {
+			const size_t lo = n * t / T, hi = n * (t + 1) / T;
+			memcpy(ho + lo * 8, c->rec_off.data() + lo, (hi - lo) * 8);
+			memcpy(ho + n * 8 + lo * 4, read_off.data() + lo, (hi - lo) * 4);
+			memcpy(ho + n * 12 + lo * 4, mm_off.data() + lo, (hi - lo) * 4);
+		};
+		if (T == 1) part(0);
+		else {
+			std::vector<std::thread> thr;
+			for (unsigned t = 0; t < T; t++) thr.emplace_back(part, t);
+			for (auto &t : thr) t.join();
+		}
+	}
 	CU(cudaMemcpyAsync(c->rd_recoff.p, ho, n * 8, cudaMemcpyHostToDevice, dec));
 	CU(cudaMemcpyAsync(c->rd_readoff.p, ho + n * 8, n * 4, cudaMemcpyHostToDevice, dec));
 	CU(cudaMemcpyAsync(c->rd_mmoff.p, ho + n * 12, n * 4, cudaMemcpyHostToDevice, dec));
@@ -900,7 +917,8 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 		if (r1 > r0) {
 			CU(launch_decode_records(c->rd_bam.p, (const uint64_t *)c->rd_recoff.p + r0, (const uint32_t *)c->rd_readoff.p + r0,
 					(const uint32_t *)c->rd_mmoff.p + r0, r1 - r0, rp->mapq_thresh, rp->max_template_len, rp->keep_unmatched,
-					rp->ignore_duplicates, (bsgpu_record *)c->rd_rec.p + r0, c->rd_bases.p, c->rd_misms.p, dec, &c->launches));
+					rp->ignore_duplicates, (bsgpu_record *)c->rd_rec.p + r0, c->rd_bases.p, c->rd_misms.p, dec, &c->launches, (uint8_t *)c->rd_key.p + r0 * 16));
+			CU(cudaMemcpyAsync((uint8_t *)c->h_key.p + r0 * 16, (const uint8_t *)c->rd_key.p + r0 * 16, (r1 - r0) * 16, cudaMemcpyDeviceToHost, dec));
 			CU(cudaMemcpyAsync((bsgpu_record *)c->h_rec.p + r0, (const bsgpu_record *)c->rd_rec.p + r0, (r1 - r0) * sizeof(bsgpu_record),
 					cudaMemcpyDeviceToHost, dec));
 		}
@@ -908,7 +926,7 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 		chunk_end.push_back(r1);
 		r0 = r1;
 	}
-	c->stats.d2h_bytes += n * sizeof(bsgpu_record);
+	c->stats.d2h_bytes += n * (sizeof(bsgpu_record) + 16);
 	return BSGPU_OK;
 }
 
@@ -1149,29 +1167,15 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 			for (bool &b : c->ring_busy) b = false;
 		}
 	} guard{c};
-	// The certain block starts of every chunk are marked as its descriptors come home; then ONE job over the whole stream
-	// hands its pieces to the builder threads in stream order, and the caller's thread takes the pieces over in that order
-	// while later ones are still being built.
+	// The certain block starts of every chunk are marked as its keys come home (all host threads over the 16-byte keys); then
+	// ONE job over the whole stream hands its pieces to the builder threads in stream order, and the caller's thread takes
+	// the pieces over in that order and queues their windows while later pieces are still being built.  (Measured against a
+	// job per chunk started as soon as the chunk is home: the builder threads then compete with the caller's thread for
+	// the cores while it queues windows, 33-36 ms per 1.6 M records against 31.)
 	double tm_rd = 0, tm_cert = 0, tm_piece = 0, tm_win = 0;
 	c->tm_prep = c->tm_queue = c->tm_collect = 0;
-	for (size_t ck = 0; ck < chunk_end.size(); ck++) {
-		const double w0 = now();
-		CU(cudaEventSynchronize(c->rd_done[ck]));
-		t_wait += now() - w0;
-		tm_rd += now() - w0;
-		const double w1 = now();
-		certain_block_starts(rec, scanned, chunk_end[ck], &cst, starts);
-		tm_cert += now() - w1;
-		scanned = chunk_end[ck];
-	}
-	{
-		static const unsigned ppt = [] { const char *e = getenv("BSGPU_BUILDER_PIECES"); const int v = e ? atoi(e) : 0; return v > 0 ? (unsigned)v : 2u; }();
-		std::vector<size_t> inside;
-		for (size_t v : starts) if (v > 0 && v < n) inside.push_back(v);
-		guard.jobs.push_back(build_blocks_start_range(bam, c->rec_off.data(), rec, 0, n, inside, rp->keep_unmatched, rp->keep_duplicates, tm, ppt, c->profile_on));
-		built = n;
-	}
-	for (size_t ji = 0; ji < guard.jobs.size() && ret == BSGPU_OK; ji++) {
+	static const unsigned ppt = [] { const char *e = getenv("BSGPU_BUILDER_PIECES"); const int v = e ? atoi(e) : 0; return v > 0 ? (unsigned)v : 2u; }();
+	auto consume = [&](size_t ji) -> int {
 		BuildJob *&job = guard.jobs[ji];
 		const size_t np = build_blocks_pieces(job);
 	for (size_t p = 0; p < np && ret == BSGPU_OK; p++) {
@@ -1219,7 +1223,25 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	}
 		build_blocks_finish(job);
 		job = nullptr;
+		return ret;
+	};
+	for (size_t ck = 0; ck < chunk_end.size(); ck++) {
+		const double w0 = now();
+		CU(cudaEventSynchronize(c->rd_done[ck]));
+		t_wait += now() - w0;
+		tm_rd += now() - w0;
+		const double w1 = now();
+		certain_block_starts_keys((const uint32_t *)c->h_key.p, scanned, chunk_end[ck], &cst, starts);
+		tm_cert += now() - w1;
+		scanned = chunk_end[ck];
 	}
+	{
+		std::vector<size_t> inside;
+		for (size_t v : starts) if (v > 0 && v < n) inside.push_back(v);
+		guard.jobs.push_back(build_blocks_start_range(bam, c->rec_off.data(), rec, 0, n, inside, rp->keep_unmatched, rp->keep_duplicates, tm, ppt, c->profile_on));
+		built = n;
+	}
+	ret = consume(0);
 	while (ret == BSGPU_OK && sink && sink->collected < sink->queued) ret = sink_collect(c, sink);
 	CU(cudaStreamSynchronize(c->slot[0].stream));
 	CU(cudaStreamSynchronize(c->slot[1].stream));

@@ -88,7 +88,7 @@ cudaError_t launch_bcf_records(const BcfJob &j, uint32_t i0, uint32_t cnt, void 
 // reader side (bsgpu_reader.cu)
 cudaError_t launch_decode_records(const void *bam, const void *rec_off, const void *read_off, const void *mm_off, size_t nrec,
 		uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup, void *out, void *bases, void *misms,
-		cudaStream_t stream, int *launches);
+		cudaStream_t stream, int *launches, void *keys = nullptr);
 
 constexpr int kPileTileSites = 128;      // sites per tile of the gather kernel (= its CTA size)
 constexpr int kMaxSegLen = 256;          // BSGPU_MAX_SEG_LEN

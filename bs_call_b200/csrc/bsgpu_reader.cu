@@ -100,7 +100,7 @@ constexpr int kDecodeWarps = 8;
 __global__ void __launch_bounds__(kDecodeWarps * 32)
 k_decode_records(const uint8_t *__restrict__ bam, const uint64_t *__restrict__ rec_off, const uint32_t *__restrict__ read_off,
 		const uint32_t *__restrict__ mm_off, size_t nrec, uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup,
-		bsgpu_record *__restrict__ out, uint8_t *__restrict__ bases, bsgpu_misms *__restrict__ misms) {
+		bsgpu_record *__restrict__ out, uint8_t *__restrict__ bases, bsgpu_misms *__restrict__ misms, uint4 *__restrict__ keys) {
 	const size_t w0 = ((size_t)blockIdx.x * kDecodeWarps + (threadIdx.x >> 5)) * 32;
 	const int lane = threadIdx.x & 31;
 	if (w0 >= nrec) return;
@@ -207,6 +207,19 @@ k_decode_records(const uint8_t *__restrict__ bam, const uint64_t *__restrict__ r
 			}
 		}
 		out[w] = r;
+		if (keys) {
+			// what the scan for certain block starts needs of a record (certain_block_starts): its contig (-1: dropped), the
+			// smaller of its positions if it is inserted by its flags alone (else 0), the furthest end it can give its block
+			uint32_t minnz = 0;
+			if (!dropped) {
+				bool insert = true;
+				if ((r.alignment_flag & F_PAIRED) && fwd > 0 && rev > 0) insert = fwd == rev ? false : (reverse ? fwd > rev : fwd < rev);
+				if (insert) minnz = fwd == 0 ? rev : rev == 0 ? fwd : min(fwd, rev);
+			}
+			const unsigned long long e1 = (unsigned long long)(reverse ? rev : fwd) + r.reference_span, e2 = (unsigned long long)(fwd > 0 ? fwd : rev) + r.align_length;
+			const unsigned long long e = max(e1, e2);
+			keys[w] = make_uint4(dropped ? 0xffffffffu : (uint32_t)tid, minnz, (uint32_t)min(e, 0xffffffffull), 0u);
+		}
 	}
 	// ---- phase 2: sequence and qualities (src/input_sam.c:61-88), record by record with the whole warp
 	const uint32_t todo = __ballot_sync(0xffffffffu, decode);
@@ -233,11 +246,11 @@ k_decode_records(const uint8_t *__restrict__ bam, const uint64_t *__restrict__ r
 
 cudaError_t launch_decode_records(const void *bam, const void *rec_off, const void *read_off, const void *mm_off, size_t nrec,
 		uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup, void *out, void *bases, void *misms,
-		cudaStream_t stream, int *launches) {
+		cudaStream_t stream, int *launches, void *keys) {
 	if (!nrec) return cudaSuccess;
 	const unsigned grid = (unsigned)((nrec + kDecodeWarps * 32 - 1) / (kDecodeWarps * 32));
 	k_decode_records<<<grid, kDecodeWarps * 32, 0, stream>>>((const uint8_t *)bam, (const uint64_t *)rec_off, (const uint32_t *)read_off,
-		(const uint32_t *)mm_off, nrec, mapq_thresh, max_tlen, keep_unmatched, ignore_dup, (bsgpu_record *)out, (uint8_t *)bases, (bsgpu_misms *)misms);
+		(const uint32_t *)mm_off, nrec, mapq_thresh, max_tlen, keep_unmatched, ignore_dup, (bsgpu_record *)out, (uint8_t *)bases, (bsgpu_misms *)misms, (uint4 *)keys);
 	*launches += 1;
 	return cudaGetLastError();
 }
@@ -343,13 +356,14 @@ int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_
 		});
 		for (auto &t : thr) t.join();
 	}
-	// stitch
-	size_t total = 0;
-	for (unsigned k = 0; k < K; k++) total += piece[k].off.size();
-	rec_off.clear(); read_off.clear(); mm_off.clear();
-	rec_off.reserve(total + 16); read_off.reserve(total + 16); mm_off.reserve(total + 16);
+	// stitch, in two steps: decide sequentially where every piece joins the chain (cheap: a binary search per piece, a few
+	// records walked by hand when a guess was wrong), then let the threads copy their pieces into place
+	struct Join { size_t idx, m, dest; uint64_t db, dm; };
+	struct Own { size_t dest; uint64_t off; uint32_t rb, rm; };
+	std::vector<Join> join(K, Join{0, 0, 0, 0, 0});
+	std::vector<Own> own;
 	uint64_t nb = 0, nm = 0;
-	size_t at = 0;
+	size_t at = 0, count = 0;
 	for (unsigned k = 0; k < K; k++) {
 		const FramePiece &p = piece[k];
 		const size_t hi = nbytes * (k + 1) / K;
@@ -362,20 +376,36 @@ int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_
 			if (it != p.off.end() && *it == at) { joined = true; break; }
 			uint32_t bs, lseq, ncig;
 			if (frame_one(bam, nbytes, at, &bs, &lseq, &ncig)) return -1;
-			rec_off.push_back(at); read_off.push_back((uint32_t)nb); mm_off.push_back((uint32_t)nm);
+			own.push_back(Own{count++, (uint64_t)at, (uint32_t)nb, (uint32_t)nm});
 			nb += lseq; nm += ncig;
 			at += 4 + (size_t)bs;
 		}
 		if (joined) {
-			const size_t m = p.off.size() - idx, o = rec_off.size();
-			const uint64_t db = nb - p.rbase[idx], dm = nm - p.rmm[idx];
-			rec_off.insert(rec_off.end(), p.off.begin() + idx, p.off.end());
-			read_off.resize(o + m); mm_off.resize(o + m);
-			for (size_t i = 0; i < m; i++) { read_off[o + i] = (uint32_t)(p.rbase[idx + i] + db); mm_off[o + i] = (uint32_t)(p.rmm[idx + i] + dm); }
-			nb = p.nb + db; nm = p.nm + dm;
+			Join &j = join[k];
+			j.idx = idx; j.m = p.off.size() - idx; j.dest = count;
+			j.db = nb - p.rbase[idx]; j.dm = nm - p.rmm[idx];
+			count += j.m;
+			nb = p.nb + j.db; nm = p.nm + j.dm;
 			at = p.end;
 			if (p.bad) return -1;
 		}
+	}
+	// (growing a vector value-initialises the new tail; a context's vectors keep their size from stream to stream)
+	rec_off.resize(count); read_off.resize(count); mm_off.resize(count);
+	for (const Own &o : own) { rec_off[o.dest] = o.off; read_off[o.dest] = o.rb; mm_off[o.dest] = o.rm; }
+	auto place = [&](unsigned k) {
+		const FramePiece &p = piece[k];
+		const Join &j = join[k];
+		if (!j.m) return;
+		memcpy(rec_off.data() + j.dest, p.off.data() + j.idx, j.m * sizeof(uint64_t));
+		uint32_t *ro = read_off.data() + j.dest, *mo = mm_off.data() + j.dest;
+		for (size_t i = 0; i < j.m; i++) { ro[i] = (uint32_t)(p.rbase[j.idx + i] + j.db); mo[i] = (uint32_t)(p.rmm[j.idx + i] + j.dm); }
+	};
+	if (K == 1) place(0);
+	else {
+		std::vector<std::thread> thr;
+		for (unsigned k = 0; k < K; k++) thr.emplace_back(place, k);
+		for (auto &t : thr) t.join();
 	}
 	if (at != nbytes) return -1;
 	if (nb > 0xffffffffull || nm > 0xffffffffull) return -2;
@@ -675,39 +705,61 @@ struct CertainState { int tid = -1; uint64_t maxend = 0; };
 // in `st`, so a stream whose descriptors arrive in chunks can be scanned chunk by chunk.  (A conservative subset of
 // the block starts: the running end is never reset, and mates at equal positions -- whose insertion depends on the
 // name table -- are not used.)
-static void certain_block_starts_seq(const bsgpu_record *rec, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts) {
+// What the scan needs of record i, from the 56-byte descriptor or from the 16-byte key k_decode_records writes next to it
+// ({contig or -1 for a dropped record, smaller position of a record inserted by its flags alone or 0, furthest end, 0})
+struct RecView {
+	const bsgpu_record *rec;
+	bool kept(size_t i) const { return rec[i].ret <= 0; }
+	int tid(size_t i) const { return rec[i].tid; }
+	uint64_t minnz(size_t i) const {
+		const bsgpu_record &r = rec[i];
+		const uint32_t fwd = r.forward_position, rev = r.reverse_position;
+		bool insert = true;
+		if ((r.alignment_flag & F_PAIRED) && fwd > 0 && rev > 0) insert = fwd == rev ? false : (r.reverse ? fwd > rev : fwd < rev);
+		return !insert ? 0 : fwd == 0 ? rev : rev == 0 ? fwd : std::min(fwd, rev);
+	}
+	uint64_t end(size_t i) const {
+		const bsgpu_record &r = rec[i];
+		const uint32_t fwd = r.forward_position, rev = r.reverse_position;
+		return std::max((uint64_t)(r.reverse ? rev : fwd) + r.reference_span, (uint64_t)(fwd > 0 ? fwd : rev) + r.align_length);
+	}
+};
+struct KeyView {
+	const uint32_t *key;
+	bool kept(size_t i) const { return key[4 * i] != 0xffffffffu; }
+	int tid(size_t i) const { return (int)key[4 * i]; }
+	uint64_t minnz(size_t i) const { return key[4 * i + 1]; }
+	uint64_t end(size_t i) const { return key[4 * i + 2]; }
+};
+
+template <class V>
+static void certain_scan_seq(const V &v, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts) {
 	int tid = st->tid;
 	uint64_t maxend = st->maxend;
 	for (size_t i = rbeg; i < rend; i++) {
-		const bsgpu_record &r = rec[i];
-		if (r.ret > 0) continue;
-		const uint32_t fwd = r.forward_position, rev = r.reverse_position, own = r.reverse ? rev : fwd;
-		if (r.tid != tid) { tid = r.tid; maxend = 0; starts.push_back(i); }
-		else {
-			bool insert = true;
-			if ((r.alignment_flag & F_PAIRED) && fwd > 0 && rev > 0) insert = fwd == rev ? false : (r.reverse ? fwd > rev : fwd < rev);
-			if (insert && (fwd == 0 || (uint64_t)fwd > maxend + 1) && (rev == 0 || (uint64_t)rev > maxend + 1) && (fwd | rev)) starts.push_back(i);
-		}
-		const uint64_t e1 = (uint64_t)own + r.reference_span, e2 = (uint64_t)(fwd > 0 ? fwd : rev) + r.align_length;
-		if (e1 > maxend) maxend = e1;
-		if (e2 > maxend) maxend = e2;
+		if (!v.kept(i)) continue;
+		if (v.tid(i) != tid) { tid = v.tid(i); maxend = 0; starts.push_back(i); }
+		else { const uint64_t m = v.minnz(i); if (m && m > maxend + 1) starts.push_back(i); }
+		const uint64_t e = v.end(i);
+		if (e > maxend) maxend = e;
 	}
 	st->tid = tid; st->maxend = maxend;
 }
 
-// The scan above is a running maximum, so it splits: every host thread scans a segment from a blank state and keeps
-// the records that pass against its LOCAL running end, with the smaller of their positions; whether those before the
+// The scan is a running maximum, so it splits: every host thread scans a segment from a blank state and keeps the
+// records that pass against its LOCAL running end, with the smaller of their positions; whether those before the
 // segment's first contig change really pass depends on the end carried in from the segments before, which a short
-// sequential pass supplies.  (The descriptors are 56 bytes each in pinned memory the device has just written: one thread
-// streams them at DRAM latency, 11 ms for 1.6 M records.)
-void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts) {
+// sequential pass supplies.  (Descriptors and keys lie in pinned memory the device has just written: one thread streams
+// them at 6-8 GB/s.)
+template <class V>
+static void certain_scan(const V &v, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts) {
 	unsigned want = std::thread::hardware_concurrency();
 	if (const char *e = getenv("BSGPU_BUILDER_THREADS")) want = (unsigned)atoi(e);
 	want = std::max(1u, std::min(want, 16u));
 	const size_t n = rend - rbeg;
 	size_t min_rec = 50000;
 	if (const char *e = getenv("BSGPU_BUILDER_MIN_RECORDS")) min_rec = (size_t)atoll(e);
-	if (want == 1 || n < min_rec || n < want) { certain_block_starts_seq(rec, rbeg, rend, st, starts); return; }
+	if (want == 1 || n < min_rec || n < want) { certain_scan_seq(v, rbeg, rend, st, starts); return; }
 	struct Cand { size_t i; uint64_t minpos; };
 	struct SegOut {
 		bool any = false, changed = false;
@@ -726,24 +778,21 @@ void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, Cer
 		int tid = -1;
 		uint64_t maxend = 0;
 		for (size_t i = lo; i < hi; i++) {
-			const bsgpu_record &r = rec[i];
-			if (r.ret > 0) continue;
-			const uint32_t fwd = r.forward_position, rev = r.reverse_position, own = r.reverse ? rev : fwd;
-			if (!o.any) { o.any = true; o.head = i; o.head_tid = tid = r.tid; maxend = 0; }
-			else if (r.tid != tid) {
+			if (!v.kept(i)) continue;
+			const int ti = v.tid(i);
+			if (!o.any) { o.any = true; o.head = i; o.head_tid = tid = ti; maxend = 0; }
+			else if (ti != tid) {
 				if (!o.changed) { o.changed = true; o.head_end = maxend; }
-				tid = r.tid; maxend = 0; o.fin.push_back(i);
+				tid = ti; maxend = 0; o.fin.push_back(i);
 			} else {
-				bool insert = true;
-				if ((r.alignment_flag & F_PAIRED) && fwd > 0 && rev > 0) insert = fwd == rev ? false : (r.reverse ? fwd > rev : fwd < rev);
-				if (insert && (fwd == 0 || (uint64_t)fwd > maxend + 1) && (rev == 0 || (uint64_t)rev > maxend + 1) && (fwd | rev)) {
+				const uint64_t m = v.minnz(i);
+				if (m && m > maxend + 1) {
 					if (o.changed) o.fin.push_back(i);
-					else o.pending.push_back(Cand{i, (uint64_t)(fwd == 0 ? rev : rev == 0 ? fwd : std::min(fwd, rev))});
+					else o.pending.push_back(Cand{i, m});
 				}
 			}
-			const uint64_t e1 = (uint64_t)own + r.reference_span, e2 = (uint64_t)(fwd > 0 ? fwd : rev) + r.align_length;
-			if (e1 > maxend) maxend = e1;
-			if (e2 > maxend) maxend = e2;
+			const uint64_t e = v.end(i);
+			if (e > maxend) maxend = e;
 		}
 		o.tail_tid = tid; o.tail_end = maxend;
 		if (!o.changed) o.head_end = maxend;
@@ -754,13 +803,7 @@ void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, Cer
 	for (const SegOut &o : seg) {
 		if (!o.any) continue;
 		if (o.head_tid != tid) { tid = o.head_tid; maxend = 0; starts.push_back(o.head); }
-		else {
-			const bsgpu_record &r = rec[o.head];
-			const uint32_t fwd = r.forward_position, rev = r.reverse_position;
-			bool insert = true;
-			if ((r.alignment_flag & F_PAIRED) && fwd > 0 && rev > 0) insert = fwd == rev ? false : (r.reverse ? fwd > rev : fwd < rev);
-			if (insert && (fwd == 0 || (uint64_t)fwd > maxend + 1) && (rev == 0 || (uint64_t)rev > maxend + 1) && (fwd | rev)) starts.push_back(o.head);
-		}
+		else { const uint64_t m = v.minnz(o.head); if (m && m > maxend + 1) starts.push_back(o.head); }
 		// a record that passed against the local end passes against the true one iff it also clears the carried end
 		for (const Cand &cd : o.pending) if (cd.minpos > maxend + 1) starts.push_back(cd.i);
 		starts.insert(starts.end(), o.fin.begin(), o.fin.end());
@@ -768,6 +811,13 @@ void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, Cer
 		else if (o.head_end > maxend) maxend = o.head_end;
 	}
 	st->tid = tid; st->maxend = maxend;
+}
+
+void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts) {
+	certain_scan(RecView{rec}, rbeg, rend, st, starts);
+}
+void certain_block_starts_keys(const uint32_t *keys, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts) {
+	certain_scan(KeyView{keys}, rbeg, rend, st, starts);
 }
 
 // A build in flight: the stream cut into pieces at certain block starts, pieces built by a pool of host threads in

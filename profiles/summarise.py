@@ -62,6 +62,8 @@ traffic = {"k_call_sites": kernel(tag + "_prof_call.ncu-rep", "k_call_sites", 2_
            "k_pileup_tile": kernel(tag + "_prof_pile.ncu-rep", "k_pileup_tile", 8_000_000)}
 if os.path.exists(os.path.join(G, tag + "_prof_reader.ncu-rep")):
     kernel(tag + "_prof_reader.ncu-rep", "reader_kernels", 1)
+if os.path.exists(os.path.join(G, tag + "_prof_writer.ncu-rep")):
+    kernel(tag + "_prof_writer.ncu-rep", "writer_kernels", 1)
 traffic["round"] = tag
 json.dump(traffic, open(os.path.join(HERE, "traffic.json"), "w"), indent=1)
 for f in ("bench_full.json", "bench_reference.json"):
