@@ -47,6 +47,7 @@ BuildJob *build_blocks_start(const uint8_t *bam, const uint64_t *rec_off, const 
 		bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread, bool with_tally);
 const uint64_t *build_blocks_piece_tally(const BuildJob *job, size_t p);
 uint32_t build_blocks_piece_maxcap(const BuildJob *job, size_t p);
+bool build_blocks_piece_ready(const BuildJob *job, size_t p);
 size_t build_blocks_pieces(const BuildJob *job);
 int build_blocks_piece(BuildJob *job, size_t p, const std::vector<bsgpu_block> **blocks, size_t *tmpl_base, size_t *ntmpl);
 void build_blocks_finish(BuildJob *job);
@@ -1029,8 +1030,10 @@ static int sink_collect(bsgpu_ctx *c, BcfSink *k) {
 	return BSGPU_OK;
 }
 
+struct TmSpan { const bsgpu_template *p; size_t n; };      // the templates of a window: runs in pinned host memory, in order
+
 // wb[0 .. nwb): the blocks inside the window (BCF sink only)
-static int call_window(bsgpu_ctx *c, const bsgpu_template *tm, size_t nt, uint32_t tid, uint32_t ctg_len, const uint8_t *codes,
+static int call_window(bsgpu_ctx *c, const TmSpan *span, size_t nspan, size_t nt, uint32_t tid, uint32_t ctg_len, const uint8_t *codes,
 		uint32_t x, uint32_t y, bsgpu_gt_vcf *out, uint32_t maxcap_hint = 0, BcfSink *sink = nullptr, const bsgpu_block *wb = nullptr, size_t nwb = 0) {
 	const uint32_t sz = y - x + 1;
 	auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1047,9 +1050,10 @@ static int call_window(bsgpu_ctx *c, const bsgpu_template *tm, size_t nt, uint32
 		tot = 2ull * nt * slot;
 	} else {
 		off.resize(2 * nt + 1);
-		for (size_t i = 0; i < nt; i++) for (int k = 0; k < 2; k++) {
+		size_t i = 0;
+		for (size_t sp = 0; sp < nspan; sp++) for (size_t j = 0; j < span[sp].n; j++, i++) for (int k = 0; k < 2; k++) {
 			off[2 * i + k] = (uint32_t)tot;
-			const bsgpu_template &t = tm[i];
+			const bsgpu_template &t = span[sp].p[j];
 			if (!t.present[k]) continue;
 			const uint64_t cap = (uint64_t)t.read_len[k] + t.reference_span[k];
 			tot += cap;
@@ -1075,7 +1079,13 @@ static int call_window(bsgpu_ctx *c, const bsgpu_template *tm, size_t nt, uint32
 	if (!slot) CU(c->ooff.reserve((2 * nt + 1) * sizeof(uint32_t)));
 	CU(c->segs.reserve(nseg * sizeof(bsgpu_seg) + 16));
 	CU(c->ref.reserve((size_t)sz + 16));
-	CU(cudaMemcpyAsync(c->tmpl.p, tm, nt * sizeof(bsgpu_template), cudaMemcpyHostToDevice, c->stream));
+	{
+		size_t at = 0;
+		for (size_t sp = 0; sp < nspan; sp++) {
+			if (span[sp].n) CU(cudaMemcpyAsync((bsgpu_template *)c->tmpl.p + at, span[sp].p, span[sp].n * sizeof(bsgpu_template), cudaMemcpyHostToDevice, c->stream));
+			at += span[sp].n;
+		}
+	}
 	if (!slot) CU(cudaMemcpyAsync(c->ooff.p, off.data(), (2 * nt + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
 	if (ncopy) CU(cudaMemcpyAsync(c->ref.p, codes + x - 1, ncopy, cudaMemcpyHostToDevice, c->stream));
 	if (ncopy < (size_t)sz + 2) CU(cudaMemsetAsync((uint8_t *)c->ref.p + ncopy, 0, (size_t)sz + 2 - ncopy, c->stream));
@@ -1174,53 +1184,77 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	// the cores while it queues windows, 33-36 ms per 1.6 M records against 31.)
 	double tm_rd = 0, tm_cert = 0, tm_piece = 0, tm_win = 0;
 	c->tm_prep = c->tm_queue = c->tm_collect = 0;
-	static const unsigned ppt = [] { const char *e = getenv("BSGPU_BUILDER_PIECES"); const int v = e ? atoi(e) : 0; return v > 0 ? (unsigned)v : 2u; }();
+	static const unsigned ppt = [] { const char *e = getenv("BSGPU_BUILDER_PIECES"); const int v = e ? atoi(e) : 0; return v > 0 ? (unsigned)v : 6u; }();
+	// Pieces are taken over in stream order; the pieces that are ALREADY built when the caller gets there go together (up to
+	// kGroup of them), so small pieces keep the builder's latency low without multiplying the windows and their launches.
 	auto consume = [&](size_t ji) -> int {
 		BuildJob *&job = guard.jobs[ji];
 		const size_t np = build_blocks_pieces(job);
-	for (size_t p = 0; p < np && ret == BSGPU_OK; p++) {
-		const std::vector<bsgpu_block> *pb;
-		size_t base, nt_piece;
-		const double w0 = now();
-		const int rc = build_blocks_piece(job, p, &pb, &base, &nt_piece);
-		t_wait += now() - w0;
-		tm_piece += now() - w0;
-		const double w2 = now();
-		struct WinAcc { double &d; double t0; std::function<double()> f; ~WinAcc() { d += f() - t0; } } wacc_{tm_win, w2, now};
-		if (rc == -4) { ret = fail("bsgpu_call_bam: duplicate read name among waiting mates"); break; }
-		if (rc == -5) { ret = fail("bsgpu_call_bam: the two mates of a template disagree about their positions"); break; }
-		if (rc) { ret = fail("bsgpu_call_bam: block builder failed (%d)", rc); break; }
-		if (nbk + pb->size() > block_cap) { ret = fail("bsgpu_call_bam: blocks[] too small"); break; }
-		if (const uint64_t *pt = build_blocks_piece_tally(job, p)) for (int k = 0; k < 30; k++) c->reader_tally[k] += pt[k];
-		for (size_t b0 = 0; b0 < pb->size() && ret == BSGPU_OK;) {
-			size_t b1 = b0;
-			while (b1 < pb->size() && (*pb)[b1].tid == (*pb)[b0].tid) b1++;
-			const uint32_t tid = (*pb)[b0].tid;
-			if ((int)tid >= n_targets) { ret = fail("bsgpu_call_bam: record on contig %u, only %d contigs given", tid, n_targets); break; }
-			if ((int)tid != cur_tid) { cur_tid = (int)tid; ctg_x0 = (*pb)[b0].x; ctg_end = ctg_x0 - 1; ctg_ov = ov; }
-			// windows tile the contig; a block may begin ON the last site of the block before it (its x is two before its
-			// first template, src/process_template.c:27), and the writer's context of its first sites reaches back there:
-			// the record windows then overlap by that one uncovered site
-			const uint32_t x = sink ? std::min(ctg_end + 1, (*pb)[b0].x) : ctg_end + 1, y = (*pb)[b1 - 1].y;
-			const size_t t_lo = base + (*pb)[b0].first_template, t_n = (size_t)(*pb)[b1 - 1].first_template + (*pb)[b1 - 1].n_templates - (*pb)[b0].first_template;
-			if (y >= x) {
-				const uint32_t sz = y - x + 1;
-				if (!sink && ov + sz > vcf_cap) { ret = fail("bsgpu_call_bam: vcf[] too small (contig %u needs %u more records)", tid, sz); break; }
-				ret = call_window(c, tm + t_lo, t_n, tid, target_len[tid], ctg_codes[tid], x, y, sink ? nullptr : vcf + ov, build_blocks_piece_maxcap(job, p),
-						sink, pb->data() + b0, b1 - b0);
-				ov += sz;
-				ctg_end = y;
+		constexpr size_t kGroup = 6;
+		std::vector<bsgpu_block> gb;                       // blocks of the group, templates numbered from the start of the group
+		std::vector<TmSpan> gs;                            // one run of templates per piece
+		std::vector<size_t> gs_first;                      // group number of the first template of every run
+		for (size_t p = 0; p < np && ret == BSGPU_OK;) {
+			gb.clear(); gs.clear(); gs_first.clear();
+			size_t gnt = 0;
+			uint32_t gmax = 1;
+			const size_t p0 = p;
+			while (p < np && p - p0 < kGroup && (p == p0 || build_blocks_piece_ready(job, p))) {
+				const std::vector<bsgpu_block> *pb;
+				size_t base, nt_piece;
+				const double w0 = now();
+				const int rc = build_blocks_piece(job, p, &pb, &base, &nt_piece);
+				t_wait += now() - w0;
+				tm_piece += now() - w0;
+				if (rc == -4) return fail("bsgpu_call_bam: duplicate read name among waiting mates");
+				if (rc == -5) return fail("bsgpu_call_bam: the two mates of a template disagree about their positions");
+				if (rc) return fail("bsgpu_call_bam: block builder failed (%d)", rc);
+				if (const uint64_t *pt = build_blocks_piece_tally(job, p)) for (int k = 0; k < 30; k++) c->reader_tally[k] += pt[k];
+				for (bsgpu_block o : *pb) { o.first_template += (uint32_t)gnt; gb.push_back(o); }
+				gs.push_back(TmSpan{tm + base, nt_piece});
+				gs_first.push_back(gnt);
+				gnt += nt_piece;
+				gmax = std::max(gmax, build_blocks_piece_maxcap(job, p));
+				p++;
 			}
-			for (size_t b = b0; b < b1; b++) {
-				bsgpu_block o = (*pb)[b];
-				o.first_template = (uint32_t)(ntm + o.first_template);
-				o.vcf_off = sink ? 0 : ctg_ov + (o.x - ctg_x0);
-				blocks[nbk++] = o;
+			const double w2 = now();
+			struct WinAcc { double &d; double t0; std::function<double()> f; ~WinAcc() { d += f() - t0; } } wacc_{tm_win, w2, now};
+			if (nbk + gb.size() > block_cap) return fail("bsgpu_call_bam: blocks[] too small");
+			for (size_t b0 = 0; b0 < gb.size() && ret == BSGPU_OK;) {
+				size_t b1 = b0;
+				while (b1 < gb.size() && gb[b1].tid == gb[b0].tid) b1++;
+				const uint32_t tid = gb[b0].tid;
+				if ((int)tid >= n_targets) return fail("bsgpu_call_bam: record on contig %u, only %d contigs given", tid, n_targets);
+				if ((int)tid != cur_tid) { cur_tid = (int)tid; ctg_x0 = gb[b0].x; ctg_end = ctg_x0 - 1; ctg_ov = ov; }
+				// windows tile the contig; a block may begin ON the last site of the block before it (its x is two before its
+				// first template, src/process_template.c:27), and the writer's context of its first sites reaches back there:
+				// the record windows then overlap by that one uncovered site
+				const uint32_t x = sink ? std::min(ctg_end + 1, gb[b0].x) : ctg_end + 1, y = gb[b1 - 1].y;
+				const size_t t_lo = gb[b0].first_template, t_hi = (size_t)gb[b1 - 1].first_template + gb[b1 - 1].n_templates;
+				if (y >= x) {
+					const uint32_t sz = y - x + 1;
+					if (!sink && ov + sz > vcf_cap) return fail("bsgpu_call_bam: vcf[] too small (contig %u needs %u more records)", tid, sz);
+					// the runs of the group that hold templates [t_lo, t_hi)
+					std::vector<TmSpan> ws;
+					for (size_t r = 0; r < gs.size(); r++) {
+						const size_t lo = std::max(t_lo, gs_first[r]), hi = std::min(t_hi, gs_first[r] + gs[r].n);
+						if (hi > lo) ws.push_back(TmSpan{gs[r].p + (lo - gs_first[r]), hi - lo});
+					}
+					ret = call_window(c, ws.data(), ws.size(), t_hi - t_lo, tid, target_len[tid], ctg_codes[tid], x, y, sink ? nullptr : vcf + ov, gmax,
+							sink, gb.data() + b0, b1 - b0);
+					ov += sz;
+					ctg_end = y;
+				}
+				for (size_t b = b0; b < b1; b++) {
+					bsgpu_block o = gb[b];
+					o.first_template = (uint32_t)(ntm + o.first_template);
+					o.vcf_off = sink ? 0 : ctg_ov + (o.x - ctg_x0);
+					blocks[nbk++] = o;
+				}
+				b0 = b1;
 			}
-			b0 = b1;
+			ntm += gnt;
 		}
-		ntm += nt_piece;
-	}
 		build_blocks_finish(job);
 		job = nullptr;
 		return ret;

@@ -902,6 +902,7 @@ int build_blocks_piece(BuildJob *job, size_t p, const std::vector<bsgpu_block> *
 }
 
 uint32_t build_blocks_piece_maxcap(const BuildJob *job, size_t p) { return job->pmax[p]; }
+bool build_blocks_piece_ready(const BuildJob *job, size_t p) { return job->done[p].load(std::memory_order_acquire) != 0; }
 
 // read_input's tallies of piece p (valid once build_blocks_piece has returned it): 15 counts then 15 base sums, or NULL
 const uint64_t *build_blocks_piece_tally(const BuildJob *job, size_t p) { return job->tally.empty() ? nullptr : job->tally.data() + p * 30; }

@@ -174,3 +174,62 @@ def test_bam_to_records_streams(gpu, oracle, monkeypatch, seed):
 def bamgen_stream(seed):
     from tests import bamgen
     return bamgen.make_stream(seed, dup=0.2, junk=0.1)
+
+
+def test_edge_cases(gpu, oracle):
+    """empty inputs, a stream without a single kept record, buffers that are too small in the middle of a pipeline"""
+    from bs_call_b200.records import GT_VCF, PILEUP
+    # nothing in, nothing out
+    b, n = gpu.bcf_block(np.zeros(0, dtype=GT_VCF), np.zeros(2, dtype=np.uint8), 1)
+    assert len(b) == 0 and n == 0
+    b, n = gpu.call_sites_bcf(np.zeros(0, dtype=PILEUP), np.zeros(2, dtype=np.uint8), 1)
+    assert len(b) == 0 and n == 0
+    # a block of skipped sites only
+    v = np.zeros(300, dtype=GT_VCF); v["skip"] = 1; v["ready"] = 1
+    b, n = gpu.bcf_block(v, np.ones(302, dtype=np.uint8), 10)
+    assert len(b) == 0 and n == 0
+    # every record of the stream filtered (unmapped): no blocks, no records, no error
+    from tests import bamgen
+    bam, _, tl, refs = bamgen.make_stream(4)
+    bad = bam.copy()
+    at = 0
+    while at < len(bad):
+        bs = int(bad[at:at + 4].view("<i4")[0])
+        bad[at + 4 + 14] |= 4                       # BAM_FUNMAP
+        at += 4 + bs
+    blocks, out, nrec = gpu.call_bam_bcf(bad, tl, refs)
+    assert len(blocks) == 0 and len(out) == 0 and nrec == 0
+    # output buffers too small: reported, and the context keeps working afterwards
+    pile, ref = oracle.synth_sites(9, 0, 2500000, nthreads=8)
+    refw = np.concatenate([ref, [1, 1]]).astype(np.uint8)
+    with pytest.raises(bslib.BsGpuError):
+        gpu.call_sites_bcf(pile, refw, 1, out=np.empty(40 << 20, dtype=np.uint8))          # room for about one chunk of three
+    with pytest.raises(bslib.BsGpuError):
+        gpu.call_bam_bcf(bam, tl, refs, out=np.empty(20000, dtype=np.uint8))
+    b1, n1 = gpu.call_sites_bcf(pile[:70000], refw[:70002], 1)
+    gtm, skip = gpu.call_sites(pile[:70000], ref[:70000])
+    v = np.zeros(70000, dtype=GT_VCF); v["gtm"] = gtm; v["skip"] = skip; v["ready"] = 1
+    same_bcf((b1, n1), oracle.print_block(v, refw[:70002], 1), "after the failed calls")
+
+
+def test_records_and_side_channels_together(gpu, oracle):
+    """--report-file side channels switched on while the records are produced: both as when each runs alone"""
+    from tests import bamgen
+    bam, _, tl, refs = bamgen.make_stream(11, dup=0.2, junk=0.1)
+    opts = dict(mapq_thresh=20, max_template_len=1000, keep_unmatched=False, ignore_duplicates=False, keep_duplicates=False)
+    _, plain, nplain = gpu.call_bam_bcf(bam, tl, refs, bslib.reader_params(**opts))
+    plain = np.asarray(plain).copy()
+    oracle.profile_enable(True); oracle.profile_reset()
+    try:
+        oracle.read_input(bam, tl, refs, run_chain=True, **opts)
+        want = oracle.profile_read()
+    finally:
+        oracle.profile_enable(False)
+    g2 = bslib.BsGpu()
+    try:
+        g2.profile_enable(True)
+        _, rec, nrec = g2.call_bam_bcf(bam, tl, refs, bslib.reader_params(**opts))
+        assert nrec == nplain and np.asarray(rec).tobytes() == plain.tobytes()
+        util.same_profile(g2.profile_read(), want, "records + side channels")
+    finally:
+        g2.close()
