@@ -623,7 +623,6 @@ static int bcf_run(bsgpu_ctx *c, const void *d_vcf, const void *d_ref, uint32_t 
 	BcfJob j;
 	j.d_vcf = d_vcf; j.d_ref = d_ref; j.x = x; j.sz = sz; j.d_blocks = nullptr; j.nblocks = 0; j.p = *p; j.dc = c->d_const;
 	j.site_scratch = c->wr_site.p;
-	CU(launch_bcf_calls(j, 0, sz, st, &c->launches));
 	CU(launch_bcf_records(j, 0, sz, c->wr_cta.p, d_out, out_cap, c->d_wr_totals, st, &c->launches));
 	CU(cudaMemcpyAsync(c->h_wr_totals, c->d_wr_totals, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
@@ -767,7 +766,9 @@ int bsgpu_call_sites_bcf(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t
 				nullptr, true, c->d_const, c->d_counters, st, &c->launches));
 		CU(cudaEventRecord(E(k, 1), st));
 		j.d_vcf = (const uint8_t *)c->wr_vcf.p + (k & 1) * chunk * sizeof(bsgpu_gt_vcf) - lo * sizeof(bsgpu_gt_vcf);
-		CU(launch_bcf_calls(j, (uint32_t)lo, (uint32_t)m, st, &c->launches));
+		// the records of chunk k - 1 look at the calls of the first two sites of this chunk (the rest of this chunk's calls are
+		// written when its own records are measured)
+		CU(launch_bcf_calls(j, (uint32_t)lo, (uint32_t)std::min<size_t>(m, 2), st, &c->launches));
 		if (k >= 1) ret = queue_records(k - 1);
 		if (ret == BSGPU_OK && k >= 2) ret = collect(k - 2);
 	}
@@ -1122,7 +1123,6 @@ static int call_window(bsgpu_ctx *c, const TmSpan *span, size_t nspan, size_t nt
 	j.p = sink->p; j.p.rid = sink->vcf_rid ? sink->vcf_rid[tid] : (int32_t)tid; j.p.ctg_end = ctg_len;
 	j.dc = c->d_const; j.site_scratch = c->wr_site.p;
 	if (sink->queued >= 3) CU(cudaStreamWaitEvent(c->stream, c->wr_copied[rslot], 0));      // the slot's previous records have left
-	CU(launch_bcf_calls(j, 0, sz, c->stream, &c->launches));
 	CU(launch_bcf_records(j, 0, sz, c->wr_cta.p, c->wr_ring[rslot].p, rcap, c->d_wr_totals + 3 * (sink->queued & 7), c->stream, &c->launches));
 	CU(cudaMemcpyAsync(c->h_wr_totals + 3 * (sink->queued & 7), c->d_wr_totals + 3 * (sink->queued & 7), 3 * sizeof(unsigned long long),
 			cudaMemcpyDeviceToHost, c->stream));

@@ -10,6 +10,7 @@
 // byte stream bcf_write() would have produced -- about a quarter of the bytes of the gt_vcf records they replace.
 //
 //   k_bcf_measure   call of every site (u8) + length of its record (u16) + per-CTA byte / record totals
+//   (k_bcf_calls    the calls alone: for the two sites a chunked caller needs from the chunk after the one it emits)
 //   k_bcf_offsets   exclusive scan of the per-CTA totals (one CTA)
 //   k_bcf_emit      records built in shared memory at their offsets inside the CTA, copied out as aligned words
 //
@@ -127,7 +128,7 @@ __device__ bool block_of(const WrArgs &a, uint32_t i, uint32_t &first, uint32_t 
 
 // One record.  `g` = calls of sites i-2 .. i+2 as the writer's window holds them.  Returns bytes written (0: no record).
 template <class W>
-__device__ uint32_t build_record(const WrArgs &a, uint32_t i, uint32_t first, uint32_t last, const int g[5], W &w) {
+__device__ __forceinline__ uint32_t build_record(const WrArgs &a, uint32_t i, uint32_t first, uint32_t last, const int g[5], W &w) {
 	if (!g[2]) return 0;
 	const GtVcf *v = a.vcf + i;
 	uint32_t dp1 = 0, dinf = 0;
@@ -312,10 +313,13 @@ __global__ void __launch_bounds__(kWrThreads) k_bcf_measure(const WrArgs a) {
 	const uint32_t i = a.i0 + blockIdx.x * kWrThreads + threadIdx.x;
 	uint32_t n = 0;
 	if (i < a.i1) {
+		// the site's own call is made here (and kept for the neighbours' records); a record's LENGTH does not depend on
+		// the calls around it, so the window is left empty for the count
+		const int own = site_call(a.vcf + i);
+		a.calls[i] = (uint8_t)own;
 		uint32_t first, last;
 		if (block_of(a, i, first, last)) {
-			int g[5];
-			window_calls(a, i, first, last, g);
+			const int g[5] = { 0, 0, own, 0, 0 };
 			Count w;
 			n = build_record(a, i, first, last, g, w);
 			if (n > (uint32_t)kMaxRec) { atomicAdd(a.totals + 2, 1ull); n = 0; }
@@ -388,9 +392,9 @@ __global__ void __launch_bounds__(kWrThreads) k_bcf_emit(const WrArgs a) {
 		block_of(a, i, first, last);
 		int g[5];
 		window_calls(a, i, first, last, g);
-		Store w;
-		w.p = (staged ? stage : dst) + off;
-		build_record(a, i, first, last, g, w);
+		// two instances on purpose: with the destination's address space known the byte stores are STS / STG, not generic
+		if (staged) { Store w; w.p = stage + off; build_record(a, i, first, last, g, w); }
+		else { Store w; w.p = dst + off; build_record(a, i, first, last, g, w); }
 	}
 	if (!staged) return;
 	__syncthreads();
