@@ -723,7 +723,13 @@ int bsgpu_call_sites_bcf(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t
 	CU(c->wr_ref.reserve(n + 16));
 	CU(c->wr_site.reserve(bcf_site_scratch_bytes((uint32_t)n)));
 	CU(c->wr_cta.reserve(2 * bcf_cta_scratch_bytes((uint32_t)chunk)));
-	std::vector<cudaEvent_t> ev(4 * K);                         // per chunk: uploaded, modelled, records built, records copied out
+	// per chunk: uploaded, modelled, records built, records copied out.  Whatever way the function is left, the three
+	// streams are drained before the events go
+	struct Events {
+		std::vector<cudaEvent_t> v; cudaStream_t s[3];
+		~Events() { for (cudaStream_t q : s) cudaStreamSynchronize(q); for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+	} evs{std::vector<cudaEvent_t>(4 * K, nullptr), {up, st, down}};
+	std::vector<cudaEvent_t> &ev = evs.v;
 	for (auto &e : ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	auto E = [&](size_t k, int what) { return ev[4 * k + what]; };
 	BcfJob j;
@@ -775,8 +781,7 @@ int bsgpu_call_sites_bcf(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t
 	if (ret == BSGPU_OK) ret = queue_records(K - 1);
 	if (ret == BSGPU_OK && K >= 2) ret = collect(K - 2);
 	if (ret == BSGPU_OK) ret = collect(K - 1);
-	cudaStreamSynchronize(up); cudaStreamSynchronize(st); cudaStreamSynchronize(down);
-	for (auto &e : ev) cudaEventDestroy(e);
+	CU(cudaStreamSynchronize(up)); CU(cudaStreamSynchronize(st)); CU(cudaStreamSynchronize(down));
 	if (ret != BSGPU_OK) return ret;
 	c->stats.sites += n;
 	*nbytes = at; *nrec = recs;
