@@ -861,15 +861,20 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 		CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
 		c->rd_up.push_back(e1); c->rd_done.push_back(e2);
 	}
-	// the stream itself starts its way up while the host frames it
+	// The stream itself starts its way up while the host frames it -- the first half only: the copy engine serves
+	// transfers in the order they were submitted, and the offset tables (known after framing) must not queue behind the
+	// whole stream, or the first chunk could not be decoded before the last byte has arrived.
 	CU(c->rd_bam.reserve(nbytes + 16));
 	std::vector<size_t> piece_end(K);
-	for (unsigned k = 0; k < K; k++) {
-		const size_t lo = nbytes * k / K, hi = nbytes * (k + 1) / K;
-		piece_end[k] = hi;
+	for (unsigned k = 0; k < K; k++) piece_end[k] = nbytes * (k + 1) / K;
+	auto upload_piece = [&](unsigned k) -> int {
+		const size_t lo = nbytes * k / K, hi = piece_end[k];
 		if (hi > lo) CU(cudaMemcpyAsync((uint8_t *)c->rd_bam.p + lo, bam + lo, hi - lo, cudaMemcpyHostToDevice, up));
 		CU(cudaEventRecord(c->rd_up[k], up));
-	}
+		return BSGPU_OK;
+	};
+	const unsigned k_early = (K + 1) / 2;
+	for (unsigned k = 0; k < k_early; k++) if (upload_piece(k) != BSGPU_OK) return BSGPU_FAIL;
 	const int fr = frame_records(bam, nbytes, c->rec_off, read_off, mm_off, nb, nm, c->frame_scratch);
 	if (fr) cudaStreamSynchronize(up);
 	if (fr == -1) return fail("bsgpu reader: truncated or malformed BAM record stream");
@@ -909,6 +914,7 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 	CU(cudaMemcpyAsync(c->rd_recoff.p, ho, n * 8, cudaMemcpyHostToDevice, dec));
 	CU(cudaMemcpyAsync(c->rd_readoff.p, ho + n * 8, n * 4, cudaMemcpyHostToDevice, dec));
 	CU(cudaMemcpyAsync(c->rd_mmoff.p, ho + n * 12, n * 4, cudaMemcpyHostToDevice, dec));
+	for (unsigned k = k_early; k < K; k++) if (upload_piece(k) != BSGPU_OK) return BSGPU_FAIL;
 	c->stats.h2d_bytes += nbytes + n * 16;
 	size_t r0 = 0;
 	for (unsigned k = 0; k < K; k++) {
@@ -1265,6 +1271,7 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 		job = nullptr;
 		return ret;
 	};
+	const bool trace = getenv("BSGPU_TIMING") != nullptr && atoi(getenv("BSGPU_TIMING")) > 1;
 	const bool per_chunk = getenv("BSGPU_SINGLE_JOB") == nullptr;      // default: a builder job per chunk, started as the chunk comes home
 	size_t consumed = 0;
 	for (size_t ck = 0; ck < chunk_end.size() && ret == BSGPU_OK; ck++) {
@@ -1290,9 +1297,14 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 			starts.swap(keep);
 			built = upto;
 		}
+		const double w3 = now();
 		while (ret == BSGPU_OK && consumed + 1 < guard.jobs.size()) ret = consume(consumed++);
+		if (trace) fprintf(stderr, "  chunk %zu: descriptors home %.2f ms, certain starts done %.2f, job started %.2f, earlier job consumed %.2f (records %zu)\n",
+				ck, (w1 - t0) * 1e3, (w1 - t0 + 0) * 1e3 + 0, (w3 - t0) * 1e3, (now() - t0) * 1e3, chunk_end[ck]);
 	}
+	const double w4 = now();
 	while (ret == BSGPU_OK && consumed < guard.jobs.size()) ret = consume(consumed++);
+	if (trace) fprintf(stderr, "  last job: consumed %.2f -> %.2f ms\n", (w4 - t0) * 1e3, (now() - t0) * 1e3);
 	while (ret == BSGPU_OK && sink && sink->collected < sink->queued) ret = sink_collect(c, sink);
 	CU(cudaStreamSynchronize(c->slot[0].stream));
 	CU(cudaStreamSynchronize(c->slot[1].stream));
