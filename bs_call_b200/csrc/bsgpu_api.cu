@@ -1,6 +1,7 @@
 // bsgpu_api.cu -- the C ABI declared in include/bsgpu.h: context, staging, pipelines.  No CPU compute path:
 // every entry point that produces results launches kernels, and bsgpu_init fails if no sm_100 device opens.
 #include <algorithm>
+#include <atomic>
 #include <thread>
 #include <functional>
 #include <chrono>
@@ -1180,8 +1181,9 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	// the builder threads of a job read the pinned arrays of the context: whatever way this function is left, the job is
 	// joined first and the device is quiet
 	struct JobGuard {
-		bsgpu_ctx *c; std::vector<BuildJob *> jobs;
+		bsgpu_ctx *c; std::vector<BuildJob *> jobs; std::thread scanner;
 		~JobGuard() {
+			if (scanner.joinable()) scanner.join();
 			for (BuildJob *j : jobs) if (j) build_blocks_finish(j);
 			cudaStreamSynchronize(c->slot[0].stream); cudaStreamSynchronize(c->slot[1].stream);
 			cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
@@ -1273,38 +1275,57 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	};
 	const bool trace = getenv("BSGPU_TIMING") != nullptr && atoi(getenv("BSGPU_TIMING")) > 1;
 	const bool per_chunk = getenv("BSGPU_SINGLE_JOB") == nullptr;      // default: a builder job per chunk, started as the chunk comes home
-	size_t consumed = 0;
-	for (size_t ck = 0; ck < chunk_end.size() && ret == BSGPU_OK; ck++) {
-		const double w0 = now();
-		CU(cudaEventSynchronize(c->rd_done[ck]));
-		t_wait += now() - w0;
-		tm_rd += now() - w0;
-		const double w1 = now();
-		certain_block_starts_keys((const uint32_t *)c->h_key.p, scanned, chunk_end[ck], &cst, starts);
-		tm_cert += now() - w1;
-		scanned = chunk_end[ck];
-		const bool last = ck + 1 == chunk_end.size();
-		if (!per_chunk && !last) continue;
-		// build up to the last certain start (everything when the stream is complete); starts[] holds those > built
-		size_t upto = last ? n : built;
-		if (!last) for (size_t i = starts.size(); i-- > 0;) if (starts[i] > built) { upto = starts[i]; break; }
-		if (upto > built) {
-			std::vector<size_t> inside;
-			for (size_t v : starts) if (v > built && v < upto) inside.push_back(v);
-			guard.jobs.push_back(build_blocks_start_range(bam, c->rec_off.data(), rec, built, upto, inside, rp->keep_unmatched, rp->keep_duplicates, tm, ppt, c->profile_on));
-			std::vector<size_t> keep;
-			for (size_t v : starts) if (v >= upto) keep.push_back(v);
-			starts.swap(keep);
-			built = upto;
+	// The scan for certain starts and the start of the builder jobs run on a thread of their own, chunk by chunk as the
+	// descriptors come home; the caller's thread does nothing but take finished pieces over and queue their windows.
+	guard.jobs.reserve(chunk_end.size() + 1);            // the scanner appends, the caller reads entries below njobs: no reallocation
+	std::atomic<size_t> njobs{0};
+	std::atomic<int> scan_state{0};                      // 0 running, 1 done, -1 a CUDA call failed
+	double sc_rd = 0, sc_cert = 0;
+	cudaError_t scan_err = cudaSuccess;
+	guard.scanner = std::thread([&] {
+		cudaSetDevice(c->device);
+		for (size_t ck = 0; ck < chunk_end.size(); ck++) {
+			const double w0 = now();
+			scan_err = cudaEventSynchronize(c->rd_done[ck]);
+			if (scan_err != cudaSuccess) { scan_state.store(-1, std::memory_order_release); return; }
+			const double w1 = now();
+			sc_rd += w1 - w0;
+			certain_block_starts_keys((const uint32_t *)c->h_key.p, scanned, chunk_end[ck], &cst, starts);
+			sc_cert += now() - w1;
+			scanned = chunk_end[ck];
+			const bool last = ck + 1 == chunk_end.size();
+			if (!per_chunk && !last) continue;
+			// build up to the last certain start (everything when the stream is complete); starts[] holds those > built
+			size_t upto = last ? n : built;
+			if (!last) for (size_t i = starts.size(); i-- > 0;) if (starts[i] > built) { upto = starts[i]; break; }
+			if (upto > built) {
+				std::vector<size_t> inside;
+				for (size_t v : starts) if (v > built && v < upto) inside.push_back(v);
+				guard.jobs.push_back(build_blocks_start_range(bam, c->rec_off.data(), rec, built, upto, inside, rp->keep_unmatched, rp->keep_duplicates, tm, ppt, c->profile_on));
+				njobs.store(guard.jobs.size(), std::memory_order_release);
+				std::vector<size_t> keep;
+				for (size_t v : starts) if (v >= upto) keep.push_back(v);
+				starts.swap(keep);
+				built = upto;
+			}
+			if (trace) fprintf(stderr, "  chunk %zu: descriptors home %.2f ms, job started %.2f ms (records %zu)\n", ck, (w1 - t0) * 1e3, (now() - t0) * 1e3, chunk_end[ck]);
 		}
-		const double w3 = now();
-		while (ret == BSGPU_OK && consumed + 1 < guard.jobs.size()) ret = consume(consumed++);
-		if (trace) fprintf(stderr, "  chunk %zu: descriptors home %.2f ms, certain starts done %.2f, job started %.2f, earlier job consumed %.2f (records %zu)\n",
-				ck, (w1 - t0) * 1e3, (w1 - t0 + 0) * 1e3 + 0, (w3 - t0) * 1e3, (now() - t0) * 1e3, chunk_end[ck]);
+		scan_state.store(1, std::memory_order_release);
+	});
+	for (size_t ji = 0; ret == BSGPU_OK;) {
+		const double w0 = now();
+		while (njobs.load(std::memory_order_acquire) <= ji && scan_state.load(std::memory_order_acquire) == 0) std::this_thread::yield();
+		t_wait += now() - w0;
+		tm_piece += now() - w0;
+		if (njobs.load(std::memory_order_acquire) > ji) {
+			ret = consume(ji++);
+			if (trace) fprintf(stderr, "  job %zu consumed at %.2f ms\n", ji - 1, (now() - t0) * 1e3);
+		}
+		else break;                                       // the scanner has finished (or failed) and every job is consumed
 	}
-	const double w4 = now();
-	while (ret == BSGPU_OK && consumed < guard.jobs.size()) ret = consume(consumed++);
-	if (trace) fprintf(stderr, "  last job: consumed %.2f -> %.2f ms\n", (w4 - t0) * 1e3, (now() - t0) * 1e3);
+	guard.scanner.join();
+	tm_rd += sc_rd; tm_cert += sc_cert;
+	if (scan_state.load() < 0) { CU(scan_err); }
 	while (ret == BSGPU_OK && sink && sink->collected < sink->queued) ret = sink_collect(c, sink);
 	CU(cudaStreamSynchronize(c->slot[0].stream));
 	CU(cudaStreamSynchronize(c->slot[1].stream));

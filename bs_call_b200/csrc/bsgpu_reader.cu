@@ -752,10 +752,10 @@ static void certain_scan_seq(const V &v, size_t rbeg, size_t rend, CertainState 
 // sequential pass supplies.  (Descriptors and keys lie in pinned memory the device has just written: one thread streams
 // them at 6-8 GB/s.)
 template <class V>
-static void certain_scan(const V &v, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts) {
+static void certain_scan(const V &v, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts, unsigned max_threads) {
 	unsigned want = std::thread::hardware_concurrency();
 	if (const char *e = getenv("BSGPU_BUILDER_THREADS")) want = (unsigned)atoi(e);
-	want = std::max(1u, std::min(want, 16u));
+	want = std::max(1u, std::min(want, max_threads));
 	const size_t n = rend - rbeg;
 	size_t min_rec = 50000;
 	if (const char *e = getenv("BSGPU_BUILDER_MIN_RECORDS")) min_rec = (size_t)atoll(e);
@@ -814,10 +814,12 @@ static void certain_scan(const V &v, size_t rbeg, size_t rend, CertainState *st,
 }
 
 void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts) {
-	certain_scan(RecView{rec}, rbeg, rend, st, starts);
+	certain_scan(RecView{rec}, rbeg, rend, st, starts, 16);
 }
 void certain_block_starts_keys(const uint32_t *keys, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts) {
-	certain_scan(KeyView{keys}, rbeg, rend, st, starts);
+	// a chunk's keys are a few MB and the builder threads of the chunk before are busy on the same cores: a few threads do
+	static const unsigned kt = [] { const char *e = getenv("BSGPU_SCAN_THREADS"); const int v = e ? atoi(e) : 0; return v > 0 ? (unsigned)v : 4u; }();
+	certain_scan(KeyView{keys}, rbeg, rend, st, starts, kt);
 }
 
 // A build in flight: the stream cut into pieces at certain block starts, pieces built by a pool of host threads in
