@@ -114,12 +114,13 @@ struct bsgpu_ctx {
 	cudaStream_t copy_stream = nullptr;          // D2H of finished windows
 	Slot slot[2];
 	DevBuf segs, bases, ref, scratch, vcf, tmpl, misms, obases, ooff, pile;
-	DevBuf rd_bam, rd_recoff, rd_readoff, rd_mmoff, rd_rec, rd_bases, rd_misms, rd_key;      // reader side: stream, framing, decoded arrays
+	DevBuf rd_bam, rd_recoff, rd_readoff, rd_mmoff, rd_rec, rd_bases, rd_misms, rd_key, rd_mask;
+	std::vector<size_t> mask_off;                // word offset of every chunk's certain-start mask in rd_mask / h_mask      // reader side: stream, framing, decoded arrays
 	std::vector<uint64_t> rec_off;               // framing of the last decoded stream
 	std::vector<uint32_t> read_off, mm_off, off_tmp;
 	std::vector<uint8_t> ref_tmp;
 	FrameScratch *frame_scratch = nullptr;
-	PinBuf h_rec, h_off, h_tmpl, h_key;                 // pinned staging: descriptors coming back, offset tables and templates going up
+	PinBuf h_rec, h_off, h_tmpl, h_key, h_mask;                 // pinned staging: descriptors coming back, offset tables and templates going up
 	bool fused = false;                          // BSGPU_FUSED=1: one fused pileup+model kernel instead of two kernels
 	std::vector<cudaEvent_t> win_events, rd_up, rd_done;      // output ring; reader: byte piece uploaded, chunk descriptors home
 	uint32_t ring_pos = 0;                       // next output ring slot of the deferred runs
@@ -249,7 +250,7 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 	for (cudaEvent_t ev : c->rd_up) cudaEventDestroy(ev);
 	for (cudaEvent_t ev : c->rd_done) cudaEventDestroy(ev);
 	if (c->frame_scratch) frame_scratch_free(c->frame_scratch);
-	c->h_rec.release(); c->h_off.release(); c->h_tmpl.release(); c->h_key.release(); c->rd_key.release();
+	c->h_rec.release(); c->h_off.release(); c->h_tmpl.release(); c->h_key.release(); c->rd_key.release(); c->h_mask.release(); c->rd_mask.release();
 	c->rd_bam.release(); c->rd_recoff.release(); c->rd_readoff.release(); c->rd_mmoff.release(); c->rd_rec.release(); c->rd_bases.release(); c->rd_misms.release();
 	c->segs.release(); c->bases.release(); c->ref.release(); c->scratch.release(); c->vcf.release(); c->tmpl.release(); c->misms.release(); c->obases.release(); c->ooff.release(); c->pile.release();
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -891,8 +892,18 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 	CU(c->rd_bases.reserve(*nb + 16));
 	CU(c->rd_misms.reserve((*nm + 1) * sizeof(bsgpu_misms)));
 	CU(c->h_rec.reserve(n * sizeof(bsgpu_record)));
+	// certain block starts: the keys the decode kernel writes come home and host threads scan them; BSGPU_DEVICE_SCAN=1
+	// uses the bit mask of the scan on the device instead (always computed), BSGPU_CHECK_SCAN=1 does both and compares
+	const bool host_scan = getenv("BSGPU_DEVICE_SCAN") == nullptr || getenv("BSGPU_CHECK_SCAN") != nullptr;
 	CU(c->rd_key.reserve(n * 16));
-	CU(c->h_key.reserve(n * 16));
+	if (host_scan) CU(c->h_key.reserve(n * 16));
+	CU(c->rd_mask.reserve((n / 32 + 2 * K + 8) * 4 + 16));
+	CU(c->h_mask.reserve((n / 32 + 2 * K + 8) * 4));
+	c->mask_off.assign(K + 1, 0);
+	uint32_t *d_carry = (uint32_t *)c->rd_mask.p;          // first four words of the buffer: {last contig, running end}
+	CU(cudaMemsetAsync(d_carry, 0xff, 4, dec));
+	CU(cudaMemsetAsync(d_carry + 1, 0, 12, dec));
+	size_t mask_words = 4;
 	// the offset tables go up from pinned staging (pageable vectors would serialise the copies behind the big ones)
 	CU(c->h_off.reserve(n * 16));
 	uint8_t *ho = (uint8_t *)c->h_off.p;
@@ -932,7 +943,12 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 			CU(launch_decode_records(c->rd_bam.p, (const uint64_t *)c->rd_recoff.p + r0, (const uint32_t *)c->rd_readoff.p + r0,
 					(const uint32_t *)c->rd_mmoff.p + r0, r1 - r0, rp->mapq_thresh, rp->max_template_len, rp->keep_unmatched,
 					rp->ignore_duplicates, (bsgpu_record *)c->rd_rec.p + r0, c->rd_bases.p, c->rd_misms.p, dec, &c->launches, (uint8_t *)c->rd_key.p + r0 * 16));
-			CU(cudaMemcpyAsync((uint8_t *)c->h_key.p + r0 * 16, (const uint8_t *)c->rd_key.p + r0 * 16, (r1 - r0) * 16, cudaMemcpyDeviceToHost, dec));
+			if (host_scan) CU(cudaMemcpyAsync((uint8_t *)c->h_key.p + r0 * 16, (const uint8_t *)c->rd_key.p + r0 * 16, (r1 - r0) * 16, cudaMemcpyDeviceToHost, dec));
+			const size_t words = (r1 - r0 + 31) / 32;
+			CU(launch_certain_starts((const uint8_t *)c->rd_key.p + r0 * 16, (uint32_t)(r1 - r0), d_carry, (uint32_t *)c->rd_mask.p + mask_words, dec, &c->launches));
+			CU(cudaMemcpyAsync((uint32_t *)c->h_mask.p + mask_words, (const uint32_t *)c->rd_mask.p + mask_words, words * 4, cudaMemcpyDeviceToHost, dec));
+			c->mask_off[k] = mask_words;
+			mask_words += words;
 			CU(cudaMemcpyAsync((bsgpu_record *)c->h_rec.p + r0, (const bsgpu_record *)c->rd_rec.p + r0, (r1 - r0) * sizeof(bsgpu_record),
 					cudaMemcpyDeviceToHost, dec));
 		}
@@ -940,7 +956,7 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 		chunk_end.push_back(r1);
 		r0 = r1;
 	}
-	c->stats.d2h_bytes += n * (sizeof(bsgpu_record) + 16);
+	c->stats.d2h_bytes += n * (sizeof(bsgpu_record) + (host_scan ? 16 : 0)) + mask_words * 4;
 	return BSGPU_OK;
 }
 
@@ -1282,6 +1298,8 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	std::atomic<int> scan_state{0};                      // 0 running, 1 done, -1 a CUDA call failed
 	double sc_rd = 0, sc_cert = 0;
 	cudaError_t scan_err = cudaSuccess;
+	const bool check_scan = getenv("BSGPU_CHECK_SCAN") != nullptr, use_host_scan = check_scan || getenv("BSGPU_DEVICE_SCAN") == nullptr;
+	std::atomic<int> scan_mismatch{0};
 	guard.scanner = std::thread([&] {
 		cudaSetDevice(c->device);
 		for (size_t ck = 0; ck < chunk_end.size(); ck++) {
@@ -1290,7 +1308,18 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 			if (scan_err != cudaSuccess) { scan_state.store(-1, std::memory_order_release); return; }
 			const double w1 = now();
 			sc_rd += w1 - w0;
-			certain_block_starts_keys((const uint32_t *)c->h_key.p, scanned, chunk_end[ck], &cst, starts);
+			if (use_host_scan) certain_block_starts_keys((const uint32_t *)c->h_key.p, scanned, chunk_end[ck], &cst, starts);
+			if (!use_host_scan || check_scan) {
+				// the device's mask of the chunk: bit i of word i / 32 <-> record scanned + i
+				std::vector<size_t> dev;
+				const uint32_t *mw = (const uint32_t *)c->h_mask.p + c->mask_off[ck];
+				const size_t cn = chunk_end[ck] - scanned;
+				for (size_t w = 0; w < (cn + 31) / 32; w++) for (uint32_t b = mw[w]; b; b &= b - 1) dev.push_back(scanned + w * 32 + (size_t)__builtin_ctz(b));
+				if (check_scan) {
+					const size_t had = starts.size() - dev.size();
+					if (starts.size() < dev.size() || !std::equal(dev.begin(), dev.end(), starts.begin() + had)) scan_mismatch.store(1);
+				} else starts.insert(starts.end(), dev.begin(), dev.end());
+			}
 			sc_cert += now() - w1;
 			scanned = chunk_end[ck];
 			const bool last = ck + 1 == chunk_end.size();
@@ -1326,6 +1355,7 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	guard.scanner.join();
 	tm_rd += sc_rd; tm_cert += sc_cert;
 	if (scan_state.load() < 0) { CU(scan_err); }
+	if (scan_mismatch.load()) return fail("bsgpu_call_bam: BSGPU_CHECK_SCAN: the device's certain block starts differ from the host scan");
 	while (ret == BSGPU_OK && sink && sink->collected < sink->queued) ret = sink_collect(c, sink);
 	CU(cudaStreamSynchronize(c->slot[0].stream));
 	CU(cudaStreamSynchronize(c->slot[1].stream));

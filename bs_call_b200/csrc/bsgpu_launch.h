@@ -90,6 +90,9 @@ cudaError_t launch_decode_records(const void *bam, const void *rec_off, const vo
 		uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup, void *out, void *bases, void *misms,
 		cudaStream_t stream, int *launches, void *keys = nullptr);
 
+// certain block starts of a chunk of records as a bit mask, from the keys launch_decode_records wrote (bsgpu_reader.cu)
+cudaError_t launch_certain_starts(const void *keys, uint32_t n, void *carry, void *mask, cudaStream_t stream, int *launches);
+
 constexpr int kPileTileSites = 128;      // sites per tile of the gather kernel (= its CTA size)
 constexpr int kMaxSegLen = 256;          // BSGPU_MAX_SEG_LEN
 

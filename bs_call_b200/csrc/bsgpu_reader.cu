@@ -244,6 +244,106 @@ k_decode_records(const uint8_t *__restrict__ bam, const uint64_t *__restrict__ r
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// device: certain block starts (see certain_block_starts below for what they are) as a bit per record.
+// The host formulation is a running maximum that is reset at every contig change: a segmented max-scan.  One CTA walks
+// the chunk in tiles of 4096 keys (four consecutive records per thread): a take-right scan gives every thread the contig
+// of the last kept record before its own, which decides where segments begin; a segmented max-scan of the records' ends
+// gives it the running end before its records; with those it replays its four records exactly as the host loop would.
+// The state at the end of a chunk is carried to the next launch through `carry` ({last contig, running end}).
+// One CTA on purpose: the chunk is 6 MB of keys, the scan runs beside the decode of the next chunk and off the host's
+// critical path; ~0.1 us per 1000 records.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr uint32_t kNoTid = 0xffffffffu;
+struct SegMax { uint32_t flag; uint32_t m; };      // flag: a segment begins inside; m: maximum since the last begin
+__device__ __forceinline__ SegMax seg_combine(SegMax a, SegMax b) { return SegMax{a.flag | b.flag, b.flag ? b.m : max(a.m, b.m)}; }
+
+__global__ void __launch_bounds__(1024) k_certain_starts(const uint4 *__restrict__ keys, uint32_t n, uint32_t *__restrict__ carry, uint32_t *__restrict__ mask) {
+	__shared__ uint32_t w_tid[32];
+	__shared__ SegMax w_seg[32];
+	__shared__ uint32_t c_tid, c_m;
+	const int tid_x = threadIdx.x, lane = tid_x & 31, wid = tid_x >> 5;
+	if (tid_x == 0) { c_tid = carry[0]; c_m = carry[1]; }
+	__syncthreads();
+	for (uint32_t base = 0; base < n; base += 4096) {
+		const uint32_t i0 = base + 4 * tid_x;
+		uint4 k[4];
+#pragma unroll
+		for (int e = 0; e < 4; e++) k[e] = i0 + e < n ? keys[i0 + e] : make_uint4(kNoTid, 0, 0, 0);
+		// ---- contig of the last kept record before my four: take-right scan
+		uint32_t mine = kNoTid;
+#pragma unroll
+		for (int e = 0; e < 4; e++) if (k[e].x != kNoTid) mine = k[e].x;
+		uint32_t inc = mine;
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d && inc == kNoTid) inc = o; }
+		if (lane == 31) w_tid[wid] = inc;
+		__syncthreads();
+		uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
+		if (lane == 0) prev = kNoTid;
+		if (prev == kNoTid) { for (int w = wid - 1; w >= 0 && prev == kNoTid; w--) prev = w_tid[w]; }
+		if (prev == kNoTid) prev = c_tid;
+		uint32_t tile_last = kNoTid;
+		if (tid_x == 1023) { tile_last = inc; for (int w = 30; w >= 0 && tile_last == kNoTid; w--) tile_last = w_tid[w]; }
+		// ---- my four records: where segments begin, and the running end since the last begin
+		SegMax agg{0u, 0u};
+		uint32_t pt = prev;
+#pragma unroll
+		for (int e = 0; e < 4; e++) {
+			if (k[e].x == kNoTid) continue;
+			const uint32_t f = k[e].x != pt;
+			agg = seg_combine(agg, SegMax{f, k[e].z});
+			pt = k[e].x;
+		}
+		SegMax sinc = agg;
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t of = __shfl_up_sync(0xffffffffu, sinc.flag, d), om = __shfl_up_sync(0xffffffffu, sinc.m, d);
+			if (lane >= d) sinc = seg_combine(SegMax{of, om}, sinc);
+		}
+		if (lane == 31) w_seg[wid] = sinc;
+		__syncthreads();
+		SegMax before{0u, c_m};                                   // everything before my records, the carry included
+		for (int w = 0; w < wid; w++) before = seg_combine(before, w_seg[w]);
+		{
+			const uint32_t of = __shfl_up_sync(0xffffffffu, sinc.flag, 1), om = __shfl_up_sync(0xffffffffu, sinc.m, 1);
+			if (lane) before = seg_combine(before, SegMax{of, om});
+		}
+		// ---- replay (src/get_template_vector.c:111-149 as certain_scan_seq has it)
+		uint32_t m = before.m, bits = 0;
+		pt = prev;
+#pragma unroll
+		for (int e = 0; e < 4; e++) {
+			if (k[e].x == kNoTid) continue;
+			if (k[e].x != pt) { bits |= 1u << e; m = 0; pt = k[e].x; }
+			else if (k[e].y && (unsigned long long)k[e].y > (unsigned long long)m + 1) bits |= 1u << e;
+			m = max(m, k[e].z);
+		}
+		// eight threads make one word of the mask
+		uint32_t word = bits << (4 * (lane & 7));
+		word |= __shfl_xor_sync(0xffffffffu, word, 1);
+		word |= __shfl_xor_sync(0xffffffffu, word, 2);
+		word |= __shfl_xor_sync(0xffffffffu, word, 4);
+		if ((lane & 7) == 0 && i0 < n) mask[i0 >> 5] = word;
+		__syncthreads();
+		if (tid_x == 1023) {
+			const SegMax total = seg_combine(before, agg);
+			c_m = total.m;
+			if (tile_last != kNoTid) c_tid = tile_last;
+		}
+		__syncthreads();
+	}
+	if (tid_x == 0) { carry[0] = c_tid; carry[1] = c_m; }
+}
+}  // namespace
+
+// mask: one bit per record of the chunk (bit i of word i / 32), (n + 31) / 32 words, 4096-record tiles start on word boundaries
+cudaError_t launch_certain_starts(const void *keys, uint32_t n, void *carry, void *mask, cudaStream_t stream, int *launches) {
+	if (!n) return cudaSuccess;
+	k_certain_starts<<<1, 1024, 0, stream>>>((const uint4 *)keys, n, (uint32_t *)carry, (uint32_t *)mask);
+	*launches += 1;
+	return cudaGetLastError();
+}
+
 cudaError_t launch_decode_records(const void *bam, const void *rec_off, const void *read_off, const void *mm_off, size_t nrec,
 		uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup, void *out, void *bases, void *misms,
 		cudaStream_t stream, int *launches, void *keys) {

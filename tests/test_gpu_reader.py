@@ -177,3 +177,20 @@ def test_call_bam_pieces_tile_the_contigs(gpu, oracle, monkeypatch):
     for b in blocks:
         covered[int(b["vcf_off"]):int(b["vcf_off"]) + int(b["y"]) - int(b["x"]) + 1] = True
     assert (vcf["skip"][~covered] == 1).all() and (vcf["ready"] == 1).all()
+
+
+@pytest.mark.parametrize("seed", [1, 6, 13, 27])
+def test_device_scan_of_certain_block_starts(monkeypatch, seed):
+    """the segmented max-scan on the device (k_certain_starts) marks exactly the records the host scan marks, chunk after
+    chunk with the state carried between launches: BSGPU_CHECK_SCAN makes bsgpu_call_bam run both and fail on a difference"""
+    bam, n, tl, refs = bamgen.make_stream(seed, n_contigs=3, dup=0.2, junk=0.2, contig_len=6000 + 700 * seed)
+    monkeypatch.setenv("BSGPU_CHECK_SCAN", "1")
+    monkeypatch.setenv("BSGPU_READER_CHUNK_MIN_BYTES", "1")
+    monkeypatch.setenv("BSGPU_BUILDER_MIN_RECORDS", "1")
+    g = bslib.BsGpu()
+    try:
+        for ku in (False, True):
+            blocks, vcf = g.call_bam(bam, tl, refs, bslib.reader_params(keep_unmatched=ku))
+            assert len(blocks) > 3
+    finally:
+        g.close()
