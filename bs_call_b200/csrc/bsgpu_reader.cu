@@ -14,6 +14,10 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <mutex>
+#include <functional>
+#include <deque>
+#include <condition_variable>
 #include <thread>
 #include <vector>
 #include <cuda_runtime.h>
@@ -922,6 +926,43 @@ void certain_block_starts_keys(const uint32_t *keys, size_t rbeg, size_t rend, C
 	certain_scan(KeyView{keys}, rbeg, rend, st, starts, kt);
 }
 
+// The builder's workers: a fixed pool (two cores are left to the thread that queues device work and to the driver's),
+// fed with pieces in the order the jobs were started, so the pieces of an earlier job -- the ones the caller waits for
+// first -- are always served first and several jobs in flight never oversubscribe the cores.
+class BuildPool {
+	std::mutex mu;
+	std::condition_variable cv;
+	std::deque<std::function<void()>> q;
+	std::vector<std::thread> workers;
+	BuildPool() {
+		unsigned n = std::thread::hardware_concurrency();
+		// BSGPU_BUILDER_THREADS is what a multi-rank launcher sets to share the box's cores between its ranks (bench.py)
+		if (const char *e = getenv("BSGPU_POOL_THREADS")) n = (unsigned)atoi(e);
+		else if (const char *e2 = getenv("BSGPU_BUILDER_THREADS")) n = (unsigned)atoi(e2);
+		else n = n > 4 ? n - 2 : n;
+		n = std::max(1u, std::min(n, 64u));
+		for (unsigned i = 0; i < n; i++) workers.emplace_back([this] {
+			for (;;) {
+				std::function<void()> f;
+				{
+					std::unique_lock<std::mutex> lk(mu);
+					cv.wait(lk, [this] { return !q.empty(); });
+					f = std::move(q.front());
+					q.pop_front();
+				}
+				f();
+			}
+		});
+		for (auto &t : workers) t.detach();              // the pool lives as long as the process
+	}
+public:
+	static BuildPool &get() { static BuildPool *p = new BuildPool(); return *p; }
+	void submit(std::function<void()> f) {
+		{ std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(f)); }
+		cv.notify_one();
+	}
+};
+
 // A build in flight: the stream cut into pieces at certain block starts, pieces built by a pool of host threads in
 // order.  Piece p's templates sit at tmpl + cuts[p] (a piece has no more templates than records) and its blocks number
 // their templates from the start of the piece, so a consumer can take pieces over one by one while later ones are
@@ -965,21 +1006,18 @@ BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, 
 	BuildJob *job = new BuildJob(np);
 	job->cuts = cuts;
 	if (with_tally) job->tally.assign(np * 30, 0);
-	const unsigned nthr = (unsigned)std::min<size_t>(want, np);
-	for (unsigned t = 0; t < nthr; t++) job->thr.emplace_back([=] {
-		for (;;) {
-			const size_t p = job->next.fetch_add(1);
-			if (p >= np) break;
-			BlockBuilder b;
-			b.bam = bam; b.rec_off = rec_off; b.rec = rec; b.blocks = &job->pb[p];
-			b.out = tmpl + job->cuts[p];
-			if (with_tally) b.tally = job->tally.data() + p * 30;
-			job->rc[p] = b.run(job->cuts[p], job->cuts[p + 1], keep_unmatched, keep_duplicates);
-			job->pn[p] = b.nout;
-			job->pmax[p] = b.maxcap;
-			job->done[p].store(1, std::memory_order_release);
-		}
-	});
+	auto build_piece = [=](size_t p) {
+		BlockBuilder b;
+		b.bam = bam; b.rec_off = rec_off; b.rec = rec; b.blocks = &job->pb[p];
+		b.out = tmpl + job->cuts[p];
+		if (with_tally) b.tally = job->tally.data() + p * 30;
+		job->rc[p] = b.run(job->cuts[p], job->cuts[p + 1], keep_unmatched, keep_duplicates);
+		job->pn[p] = b.nout;
+		job->pmax[p] = b.maxcap;
+		job->done[p].store(1, std::memory_order_release);
+	};
+	if (np == 1) build_piece(0);                          // small stream or one thread asked for: built here, now
+	else for (size_t p = 0; p < np; p++) BuildPool::get().submit([=] { build_piece(p); });
 	return job;
 }
 
@@ -1010,7 +1048,8 @@ bool build_blocks_piece_ready(const BuildJob *job, size_t p) { return job->done[
 const uint64_t *build_blocks_piece_tally(const BuildJob *job, size_t p) { return job->tally.empty() ? nullptr : job->tally.data() + p * 30; }
 
 void build_blocks_finish(BuildJob *job) {
-	for (auto &t : job->thr) t.join();
+	// every piece has been handed to the pool (or built): wait until the last one has reported before the job goes
+	for (auto &d : job->done) while (!d.load(std::memory_order_acquire)) std::this_thread::yield();
 	delete job;
 }
 
