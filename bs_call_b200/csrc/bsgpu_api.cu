@@ -893,7 +893,8 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 	CU(c->rd_misms.reserve((*nm + 1) * sizeof(bsgpu_misms)));
 	CU(c->h_rec.reserve(n * sizeof(bsgpu_record)));
 	// certain block starts: the keys the decode kernel writes come home and host threads scan them; BSGPU_DEVICE_SCAN=1
-	// uses the bit mask of the scan on the device instead (always computed), BSGPU_CHECK_SCAN=1 does both and compares
+	// uses the bit mask of the scan on the device instead, BSGPU_CHECK_SCAN=1 does both and compares
+	const bool dev_scan = getenv("BSGPU_DEVICE_SCAN") != nullptr || getenv("BSGPU_CHECK_SCAN") != nullptr;
 	const bool host_scan = getenv("BSGPU_DEVICE_SCAN") == nullptr || getenv("BSGPU_CHECK_SCAN") != nullptr;
 	CU(c->rd_key.reserve(n * 16));
 	if (host_scan) CU(c->h_key.reserve(n * 16));
@@ -944,11 +945,13 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 					(const uint32_t *)c->rd_mmoff.p + r0, r1 - r0, rp->mapq_thresh, rp->max_template_len, rp->keep_unmatched,
 					rp->ignore_duplicates, (bsgpu_record *)c->rd_rec.p + r0, c->rd_bases.p, c->rd_misms.p, dec, &c->launches, (uint8_t *)c->rd_key.p + r0 * 16));
 			if (host_scan) CU(cudaMemcpyAsync((uint8_t *)c->h_key.p + r0 * 16, (const uint8_t *)c->rd_key.p + r0 * 16, (r1 - r0) * 16, cudaMemcpyDeviceToHost, dec));
-			const size_t words = (r1 - r0 + 31) / 32;
-			CU(launch_certain_starts((const uint8_t *)c->rd_key.p + r0 * 16, (uint32_t)(r1 - r0), d_carry, (uint32_t *)c->rd_mask.p + mask_words, dec, &c->launches));
-			CU(cudaMemcpyAsync((uint32_t *)c->h_mask.p + mask_words, (const uint32_t *)c->rd_mask.p + mask_words, words * 4, cudaMemcpyDeviceToHost, dec));
-			c->mask_off[k] = mask_words;
-			mask_words += words;
+			if (dev_scan) {
+				const size_t words = (r1 - r0 + 31) / 32;
+				CU(launch_certain_starts((const uint8_t *)c->rd_key.p + r0 * 16, (uint32_t)(r1 - r0), d_carry, (uint32_t *)c->rd_mask.p + mask_words, dec, &c->launches));
+				CU(cudaMemcpyAsync((uint32_t *)c->h_mask.p + mask_words, (const uint32_t *)c->rd_mask.p + mask_words, words * 4, cudaMemcpyDeviceToHost, dec));
+				c->mask_off[k] = mask_words;
+				mask_words += words;
+			}
 			CU(cudaMemcpyAsync((bsgpu_record *)c->h_rec.p + r0, (const bsgpu_record *)c->rd_rec.p + r0, (r1 - r0) * sizeof(bsgpu_record),
 					cudaMemcpyDeviceToHost, dec));
 		}
