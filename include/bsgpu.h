@@ -26,6 +26,11 @@
  *                                    (get_seq_and_qual :61, get_bam_misms :90, get_bs_strand :144, the filters :234-300)
  *     bsgpu_build_blocks             read_input                                 src/get_template_vector.c:49-389
  *     bsgpu_call_bam                 read_input -> process_thread -> call_genotypes_ML chained (src/process.c:43-72, 172)
+ *     bsgpu_bcf_block[_dev], bsgpu_call_block_bcf, bsgpu_call_sites_bcf, bsgpu_call_bam_bcf
+ *                                    print_vcf_entry / flush_vcf_entries / _print_vcf_entry as print_thread drives them
+ *                                    (src/print_vcf.c:32-381, 535-594; src/process.c:89-104): the BCF records themselves
+ *     bsgpu_profile_enable / _read   meth_profile + mprof_thread (src/meth_profile.c:48-76, src/process.c:20-41) and the
+ *                                    bs_stats tallies of process_template_vector / read_input (--report-file)
  * The link-compatible replacements for the three reference symbols themselves (call_genotypes_ML,
  * init_calc_threads, join_calc_threads; include/bs_call.h:358-360) are in bs_call_b200/csrc/bsgpu_dropin.c and
  * are built on top of this ABI; see INTEGRATION.md.
