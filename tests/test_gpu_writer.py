@@ -87,7 +87,7 @@ def test_block_path_to_records(gpu, oracle):
         assert same == len(ref_recs)
 
 
-@pytest.mark.parametrize("n", [1, 5, 1000, (1 << 20) - 1, (1 << 20) + 3, 3 * (1 << 20) + 12345])
+@pytest.mark.parametrize("n", [1, 5, 1000, (1 << 18) - 1, (1 << 18) + 1, (1 << 18) + 2, 2 * (1 << 18) + 3, (1 << 20) + 3, 9 * (1 << 18) + 12345])
 def test_sites_to_records_pipeline(gpu, oracle, n):
     """count vectors -> records in chunks (the writer runs one chunk behind the model): the chunk seams must not show"""
     pile, ref = oracle.synth_sites(7, 1000, n, nthreads=8)
