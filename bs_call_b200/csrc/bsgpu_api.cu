@@ -1076,7 +1076,8 @@ static int call_window(bsgpu_ctx *c, const TmSpan *span, size_t nspan, size_t nt
 	std::vector<uint32_t> &off = c->off_tmp;
 	uint64_t tot = 0;
 	uint32_t maxcap = 1, slot = 0;
-	if (maxcap_hint && maxcap_hint <= 1024 && 2ull * nt * ((maxcap_hint + 15u) & ~15u) <= 0xffffffffull) {
+	static const bool exact_slots = getenv("BSGPU_EXACT_SLOTS") != nullptr;      // tests: force the offset-table path
+	if (!exact_slots && maxcap_hint && maxcap_hint <= 1024 && 2ull * nt * ((maxcap_hint + 15u) & ~15u) <= 0xffffffffull) {
 		slot = (maxcap_hint + 15u) & ~15u;
 		maxcap = maxcap_hint;
 		tot = 2ull * nt * slot;

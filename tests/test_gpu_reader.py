@@ -194,3 +194,26 @@ def test_device_scan_of_certain_block_starts(monkeypatch, seed):
             assert len(blocks) > 3
     finally:
         g.close()
+
+
+def test_exact_offset_table_path(monkeypatch):
+    """windows whose mates get exact offsets instead of uniform slots (what a piece with a very long reference span falls
+    back to; BSGPU_EXACT_SLOTS forces it): same records"""
+    bam, n, tl, refs = bamgen.make_stream(19, n_contigs=2, dup=0.2, junk=0.1)
+    g = bslib.BsGpu()
+    try:
+        b1, v1 = g.call_bam(bam, tl, refs)
+        v1 = v1.copy()
+    finally:
+        g.close()
+    monkeypatch.setenv("BSGPU_EXACT_SLOTS", "1")
+    import subprocess, sys, os, json
+    # the switch is read once per process: run the second pass in a fresh interpreter
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from bs_call_b200 import lib; from tests import bamgen; "
+            "bam, n, tl, refs = bamgen.make_stream(19, n_contigs=2, dup=0.2, junk=0.1); g = lib.BsGpu(); b, v = g.call_bam(bam, tl, refs); "
+            "import hashlib; print(len(b), hashlib.sha1(v.tobytes()).hexdigest())" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, BSGPU_EXACT_SLOTS="1"))
+    assert out.returncode == 0, out.stderr[-500:]
+    import hashlib
+    nb, digest = out.stdout.split()[-2:]
+    assert int(nb) == len(b1) and digest == hashlib.sha1(v1.tobytes()).hexdigest()
