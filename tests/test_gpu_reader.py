@@ -211,9 +211,10 @@ def test_exact_offset_table_path(monkeypatch):
     # the switch is read once per process: run the second pass in a fresh interpreter
     code = ("import sys, numpy as np; sys.path.insert(0, %r); from bs_call_b200 import lib; from tests import bamgen; "
             "bam, n, tl, refs = bamgen.make_stream(19, n_contigs=2, dup=0.2, junk=0.1); g = lib.BsGpu(); b, v = g.call_bam(bam, tl, refs); "
-            "import hashlib; print(len(b), hashlib.sha1(v.tobytes()).hexdigest())" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            "import hashlib; print(len(b), hashlib.sha1(b''.join(np.ascontiguousarray(v['gtm'][f]).tobytes() for f in ('counts', 'qual', 'gt_prob', 'fisher_strand', 'mq', 'aq', 'max_gt')) + v['skip'].tobytes()).hexdigest())" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, BSGPU_EXACT_SLOTS="1"))
     assert out.returncode == 0, out.stderr[-500:]
     import hashlib
     nb, digest = out.stdout.split()[-2:]
-    assert int(nb) == len(b1) and digest == hashlib.sha1(v1.tobytes()).hexdigest()
+    want = hashlib.sha1(b"".join(np.ascontiguousarray(v1["gtm"][f]).tobytes() for f in ("counts", "qual", "gt_prob", "fisher_strand", "mq", "aq", "max_gt")) + v1["skip"].tobytes()).hexdigest()
+    assert int(nb) == len(b1) and digest == want
