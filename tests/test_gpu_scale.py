@@ -95,3 +95,55 @@ def test_pileup_kernel_properties_at_50m_sites(gpu):
     counted = ((q >= 20) & (q != 63) & inside).sum()
     assert int(rec[:, 16].to(torch.int64).sum()) == int(counted)
     assert gpu.stats()["qsum_overflow"] == 0
+
+
+def test_record_stream_properties_at_8m_sites(gpu):
+    """8 M sites of the config-2 stream all the way to BCF records (bsgpu_call_sites_bcf, 31 chunks): the stream parses
+    into whole records; positions strictly increase; the sites that have a record, their QUAL, genotype filter and allele
+    counts are what an independent numpy derivation from the gt_meth records of the same sites gives
+    (tests/util.py:writer_fields, src/print_vcf.c:139-217); two runs are byte-identical"""
+    import struct
+    from tests import util
+    from bs_call_b200.records import PILEUP
+    n = 8_000_000
+    d_p = torch.empty(n * 104 + 16, dtype=torch.uint8, device="cuda")
+    d_r = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+    gpu.synth_sites_dev(SEED, 12345, n, 30.0, d_p.data_ptr(), d_r.data_ptr(), 0)
+    torch.cuda.synchronize()
+    pile = d_p[:n * 104].cpu().numpy().view(PILEUP)
+    ref = d_r[:n].cpu().numpy()
+    refw = np.concatenate([ref, [1, 1]]).astype(np.uint8)
+    x0 = 1000
+    b1, n1 = gpu.call_sites_bcf(pile, refw, x0)
+    b1 = np.asarray(b1).copy()
+    b2, n2 = gpu.call_sites_bcf(pile, refw, x0)
+    assert n1 == n2 and b1.tobytes() == np.asarray(b2).tobytes()
+    # walk the records
+    buf = memoryview(b1.tobytes())
+    pos = np.empty(n1, dtype=np.int64); qual = np.empty(n1, dtype=np.float32); nal = np.empty(n1, dtype=np.int32); nfmt = np.empty(n1, dtype=np.int32)
+    at, k = 0, 0
+    unpack = struct.Struct("<IIiiifII").unpack_from
+    while at < len(buf):
+        ls, li, rid, p, rlen, q, w6, w7 = unpack(buf, at)
+        assert ls >= 24 + 12 and li > 40 and rid == 0 and rlen == 1 and (w6 & 0xffff) == 1 and (w7 & 0xffffff) == 1
+        pos[k], qual[k], nal[k], nfmt[k] = p, q, w6 >> 16, w7 >> 24
+        at += 8 + ls + li
+        k += 1
+    assert at == len(buf) and k == n1
+    assert (np.diff(pos) > 0).all() and pos[0] >= x0 - 1 and pos[-1] <= x0 + n - 2
+    # the independent derivation
+    gtm, skip = gpu.call_sites(pile, ref)
+    f = util.writer_fields(gtm, skip)
+    called = np.nonzero(skip == 0)[0]
+    gt, rf = f["gt"], ref[called]
+    emitted = ~(((gt == 0) & (rf == 1)) | ((gt == 9) & (rf == 4)))          # hom-ref A / T is skipped without -A
+    want_pos = called[emitted] + x0 - 1
+    assert len(want_pos) == n1 and (want_pos == pos).all()
+    assert (qual.astype(np.int64) == f["phred"][emitted]).all()
+    a0 = np.array([1, 1, 1, 1, 2, 2, 2, 3, 3, 4])[gt[emitted]]
+    a1 = np.array([1, 2, 3, 4, 2, 3, 4, 3, 4, 4])[gt[emitted]]
+    r = rf[emitted]
+    n_alt = (a0 != r).astype(np.int32) + ((a1 != r) & (a1 != a0)).astype(np.int32)
+    assert (nal == 1 + n_alt).all()
+    het = np.isin(gt[emitted], [1, 2, 3, 5, 6, 8])
+    assert (nfmt == 12 + het).all()          # 11 + AMQ (a called site has a non-empty count slot) + FS for heterozygotes
