@@ -11,11 +11,16 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <deque>
+#include <mutex>
+#include <condition_variable>
+#include <string>
 #include <cuda_runtime.h>
 
 #include "bsgpu.h"
 #include "bsgpu_device.cuh"
 #include "bsgpu_launch.h"
+#include "bsgpu_session.h"
 
 static_assert(sizeof(bsgpu_pileup) == 104, "pileup layout (include/bs_call.h:174-182)");
 static_assert(sizeof(bsgpu_gt_meth) == 200, "gt_meth layout (include/bs_call.h:152-160)");
@@ -34,7 +39,7 @@ struct FrameScratch;
 FrameScratch *frame_scratch_new();
 void frame_scratch_free(FrameScratch *s);
 int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_off, std::vector<uint32_t> &read_off,
-		std::vector<uint32_t> &mm_off, uint64_t *nbases, uint64_t *nmisms, FrameScratch *scratch);
+		std::vector<uint32_t> &mm_off, uint64_t *nbases, uint64_t *nmisms, FrameScratch *scratch, size_t *framed = nullptr);
 int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
 		bool keep_duplicates, std::vector<bsgpu_block> &blocks, bsgpu_template *tmpl, size_t *ntmpl, uint64_t *tally);
 struct BuildJob;
@@ -845,7 +850,7 @@ void bsgpu_default_reader_params(bsgpu_reader_params *p) {
 // record of chunk k and c->rd_done[k] fires when its descriptors are on the host.  Descriptors, packed reads and events
 // stay resident.  *nb / *nm = sizes of the decoded arrays.
 static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const bsgpu_reader_params *rp, unsigned want_chunks,
-		size_t *nrec, uint64_t *nb, uint64_t *nm, std::vector<size_t> &chunk_end) {
+		size_t *nrec, uint64_t *nb, uint64_t *nm, std::vector<size_t> &chunk_end, size_t *framed = nullptr) {
 	std::vector<uint32_t> &read_off = c->read_off, &mm_off = c->mm_off;
 	if (!c->frame_scratch) c->frame_scratch = frame_scratch_new();
 	CU(cudaSetDevice(c->device));
@@ -877,7 +882,7 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 	};
 	const unsigned k_early = (K + 1) / 2;
 	for (unsigned k = 0; k < k_early; k++) if (upload_piece(k) != BSGPU_OK) return BSGPU_FAIL;
-	const int fr = frame_records(bam, nbytes, c->rec_off, read_off, mm_off, nb, nm, c->frame_scratch);
+	const int fr = frame_records(bam, nbytes, c->rec_off, read_off, mm_off, nb, nm, c->frame_scratch, framed);
 	if (fr) cudaStreamSynchronize(up);
 	if (fr == -1) return fail("bsgpu reader: truncated or malformed BAM record stream");
 	if (fr == -2) return fail("bsgpu reader: more than 4 Gi bases in one stream; split the input");
@@ -1033,6 +1038,18 @@ int bsgpu_build_blocks_tally(const uint8_t *bam, size_t nbytes, const bsgpu_reco
 static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *d_bases, const void *d_ref,
 		uint32_t x, uint32_t sz, void *out, int mode, bool defer);
 
+// What a streaming session (bsgpu_bam_*) asks of a run over the bytes it has staged so far
+struct BamRunOpts {
+	bool partial = false;                    // stop at the last CERTAIN block start of the buffer; a record cut off by its end is fine
+	size_t consumed = 0;                     // out: bytes of the buffer whose records were turned into results
+	size_t records = 0;                      // out: records in those bytes
+	std::vector<bsgpu_block> *blocks_vec = nullptr;      // blocks go here (grown as needed) instead of into blocks[]
+	// results go into a buffer the session owns; when it is too small `grow(user, keep, need)` returns a larger one that
+	// holds the first `keep` bytes of the old one (no copy into the old one is in flight when it is called)
+	uint8_t *(*grow)(void *user, size_t keep, size_t need, size_t *new_cap) = nullptr;
+	void *user = nullptr;
+};
+
 // templates [tm, tm + nt) of ONE contig (their reads and events are resident from the decode) -> gt_vcf[] of window [x, y]
 // where the records of bsgpu_call_bam_bcf go: windows are queued on the context stream, their sizes come home through
 // pinned memory, and the copy-out of window w is issued once its size is known -- by then window w + 1 is queued
@@ -1043,6 +1060,7 @@ struct BcfSink {
 	size_t out_cap, at = 0, recs = 0;
 	uint64_t queued = 0, collected = 0;
 	size_t ring_cap[3] = {0, 0, 0};
+	BamRunOpts *opts = nullptr;              // session runs: the output buffer can grow
 };
 
 static int sink_collect(bsgpu_ctx *c, BcfSink *k) {
@@ -1053,7 +1071,14 @@ static int sink_collect(bsgpu_ctx *c, BcfSink *k) {
 	const unsigned long long *t = c->h_wr_totals + 3 * (k->collected & 7);
 	if (t[2]) return fail("bsgpu_call_bam_bcf: %llu record(s) longer than %d bytes", t[2], BSGPU_BCF_MAX_RECORD);
 	if (t[0] > k->ring_cap[slot]) return fail("bsgpu_call_bam_bcf: the records of one window (%llu bytes) exceed the device staging buffer", t[0]);
-	if (k->at + t[0] > k->out_cap) return fail("bsgpu_call_bam_bcf: output buffer too small (%zu bytes given)", k->out_cap);
+	if (k->at + t[0] > k->out_cap) {
+		if (!k->opts || !k->opts->grow) return fail("bsgpu_call_bam_bcf: output buffer too small (%zu bytes given)", k->out_cap);
+		CU(cudaStreamSynchronize(c->copy_stream));      // earlier windows' records have landed in the old buffer
+		size_t ncap = 0;
+		uint8_t *nbuf = k->opts->grow(k->opts->user, k->at, k->at + t[0], &ncap);
+		if (!nbuf) return fail("bsgpu_bam: cannot grow the result buffer to %llu bytes", (unsigned long long)(k->at + t[0]));
+		k->out = nbuf; k->out_cap = ncap;
+	}
 	if (t[0]) CU(cudaMemcpyAsync(k->out + k->at, c->wr_ring[slot].p, t[0], cudaMemcpyDeviceToHost, c->copy_stream));
 	CU(cudaEventRecord(c->wr_copied[slot], c->copy_stream));
 	k->at += t[0]; k->recs += t[1];
@@ -1166,7 +1191,7 @@ static int call_window(bsgpu_ctx *c, const TmSpan *span, size_t nspan, size_t nt
 
 static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len,
 		const uint8_t *const *ctg_codes, const bsgpu_reader_params *rp, bsgpu_block *blocks, size_t block_cap, size_t *nblocks,
-		bsgpu_gt_vcf *vcf, size_t vcf_cap, size_t *nvcf, BcfSink *sink) {
+		bsgpu_gt_vcf *vcf, size_t vcf_cap, size_t *nvcf, BcfSink *sink, BamRunOpts *opts = nullptr) {
 	if (!c || !rp || !nblocks || !nvcf || !target_len || !ctg_codes || (nbytes && !bam)) return fail("bsgpu_call_bam: null argument");
 	size_t n = 0;
 	uint64_t nb = 0, nm = 0;
@@ -1174,7 +1199,11 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	const double t0 = now();
 	std::vector<size_t> chunk_end;
-	if (decode_queue(c, bam, nbytes, rp, 4, &n, &nb, &nm, chunk_end) != BSGPU_OK) return BSGPU_FAIL;
+	const bool partial = opts && opts->partial;
+	size_t framed = nbytes;
+	if (decode_queue(c, bam, nbytes, rp, 4, &n, &nb, &nm, chunk_end, opts ? &framed : nullptr) != BSGPU_OK) return BSGPU_FAIL;
+	if (opts && !partial && framed != nbytes) return fail("bsgpu_bam: the record stream ends inside a record (%zu bytes left over)", nbytes - framed);
+	if (sink) sink->opts = opts;
 	const double t1 = now();
 	c->stats.bam_decode_s += t1 - t0;
 	if (!n) return BSGPU_OK;
@@ -1253,7 +1282,8 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 			}
 			const double w2 = now();
 			struct WinAcc { double &d; double t0; std::function<double()> f; ~WinAcc() { d += f() - t0; } } wacc_{tm_win, w2, now};
-			if (nbk + gb.size() > block_cap) return fail("bsgpu_call_bam: blocks[] too small");
+			if (opts && opts->blocks_vec) { opts->blocks_vec->resize(nbk + gb.size()); blocks = opts->blocks_vec->data(); }
+			else if (nbk + gb.size() > block_cap) return fail("bsgpu_call_bam: blocks[] too small");
 			for (size_t b0 = 0; b0 < gb.size() && ret == BSGPU_OK;) {
 				size_t b1 = b0;
 				while (b1 < gb.size() && gb[b1].tid == gb[b0].tid) b1++;
@@ -1267,7 +1297,14 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 				const size_t t_lo = gb[b0].first_template, t_hi = (size_t)gb[b1 - 1].first_template + gb[b1 - 1].n_templates;
 				if (y >= x) {
 					const uint32_t sz = y - x + 1;
-					if (!sink && ov + sz > vcf_cap) return fail("bsgpu_call_bam: vcf[] too small (contig %u needs %u more records)", tid, sz);
+					if (!sink && ov + sz > vcf_cap) {
+						if (!opts || !opts->grow) return fail("bsgpu_call_bam: vcf[] too small (contig %u needs %u more records)", tid, sz);
+						CU(cudaStreamSynchronize(c->copy_stream));      // the windows queued so far have landed in the old buffer
+						size_t ncap = 0;
+						uint8_t *nbuf = opts->grow(opts->user, ov * sizeof(bsgpu_gt_vcf), (ov + sz) * sizeof(bsgpu_gt_vcf), &ncap);
+						if (!nbuf) return fail("bsgpu_bam: cannot grow the result buffer to %zu records", ov + sz);
+						vcf = (bsgpu_gt_vcf *)nbuf; vcf_cap = ncap / sizeof(bsgpu_gt_vcf);
+					}
 					// the runs of the group that hold templates [t_lo, t_hi)
 					std::vector<TmSpan> ws;
 					for (size_t r = 0; r < gs.size(); r++) {
@@ -1329,8 +1366,11 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 			const bool last = ck + 1 == chunk_end.size();
 			if (!per_chunk && !last) continue;
 			// build up to the last certain start (everything when the stream is complete); starts[] holds those > built
-			size_t upto = last ? n : built;
-			if (!last) for (size_t i = starts.size(); i-- > 0;) if (starts[i] > built) { upto = starts[i]; break; }
+			// (a session's run stops at the last certain start even when the buffer is complete: the records after it wait
+			// for the bytes that follow)
+			const bool to_end = last && !partial;
+			size_t upto = to_end ? n : built;
+			if (!to_end) for (size_t i = starts.size(); i-- > 0;) if (starts[i] > built) { upto = starts[i]; break; }
 			if (upto > built) {
 				std::vector<size_t> inside;
 				for (size_t v : starts) if (v > built && v < upto) inside.push_back(v);
@@ -1371,6 +1411,10 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	if (after[3] != before[3]) return fail("bsgpu_call_bam: %llu mate(s) start before their contig window", after[3] - before[3]);
 	*nblocks = nbk;
 	*nvcf = ov;
+	if (opts) {
+		opts->records = built;
+		opts->consumed = built == n ? framed : (size_t)c->rec_off[built];
+	}
 	const double t2 = now();
 	if (getenv("BSGPU_TIMING"))
 		fprintf(stderr, "bsgpu_call_bam: decode_queue %.2f ms | wait descriptors %.2f, certain starts %.2f, wait pieces %.2f, windows %.2f (prep %.2f, queue %.2f, collect %.2f) | total %.2f ms\n",
@@ -1396,6 +1440,150 @@ int bsgpu_call_bam_bcf(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_ta
 	*nbytes_out = *nrec = 0;
 	if (call_bam_impl(c, bam, nbytes, n_targets, target_len, ctg_codes, rp, blocks, block_cap, nblocks, nullptr, 0, &nvcf, &sink) != BSGPU_OK) return BSGPU_FAIL;
 	*nbytes_out = sink.at; *nrec = sink.recs;
+	return BSGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming session: read_input's O(block) memory behaviour for a stream of any length
+// (src/get_template_vector.c:86-110 reads one record at a time and hands blocks on as they close).
+// The host logic -- staging, batching, worker thread, hand-over of results -- is bsgpu_session.h; here are its hooks:
+// page-locked memory and the run of one batch through call_bam_impl.
+// ------------------------------------------------------------------------------------------------
+struct bsgpu_bam_session {
+	bsgpu_ctx *c = nullptr;
+	int n_targets = 0;
+	std::vector<uint32_t> target_len;
+	std::vector<const uint8_t *> codes;
+	bsgpu_reader_params rp;
+	bool bcf = false;
+	bsgpu_bcf_params bp;
+	std::vector<int32_t> rid;
+	Session core;
+};
+
+static uint8_t *sess_pin(size_t bytes) {
+	void *p = nullptr;
+	return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? (uint8_t *)p : nullptr;
+}
+static void sess_unpin(uint8_t *p) { cudaFreeHost(p); }
+static void sess_thread_init(void *user) { cudaSetDevice(((bsgpu_bam_session *)user)->c->device); }
+
+static int sess_run(void *user, const uint8_t *data, size_t len, bool whole, SessResult *r, size_t *consumed, size_t *records, std::string *err) {
+	bsgpu_bam_session *s = (bsgpu_bam_session *)user;
+	Session::GrowCtx g{&s->core, r};
+	BamRunOpts o;
+	o.partial = !whole; o.blocks_vec = &r->blocks; o.grow = Session::grow; o.user = &g;
+	size_t nblk = 0, nvcf = 0;
+	int rc;
+	if (s->bcf) {
+		BcfSink sink;
+		sink.p = s->bp; sink.vcf_rid = s->rid.empty() ? nullptr : s->rid.data(); sink.out = r->buf; sink.out_cap = r->cap;
+		rc = call_bam_impl(s->c, data, len, s->n_targets, s->target_len.data(), s->codes.data(), &s->rp, nullptr, 0, &nblk, nullptr, 0, &nvcf, &sink, &o);
+		r->nbytes = sink.at; r->nrec = sink.recs;
+	} else {
+		rc = call_bam_impl(s->c, data, len, s->n_targets, s->target_len.data(), s->codes.data(), &s->rp, nullptr, 0, &nblk, (bsgpu_gt_vcf *)r->buf,
+				r->cap / sizeof(bsgpu_gt_vcf), &nvcf, nullptr, &o);
+		r->nbytes = nvcf * sizeof(bsgpu_gt_vcf); r->nrec = nvcf;
+	}
+	r->blocks.resize(nblk);
+	*consumed = o.consumed; *records = o.records;
+	if (rc != BSGPU_OK) { *err = g_err; return -1; }
+	return 0;
+}
+
+int bsgpu_bam_open(bsgpu_ctx *c, int n_targets, const uint32_t *target_len, const uint8_t *const *ctg_codes, const bsgpu_reader_params *rp,
+		const bsgpu_bcf_params *bcf, const int32_t *vcf_rid, size_t batch_bytes, bsgpu_bam_session **out) {
+	if (!c || !rp || !out || n_targets <= 0 || !target_len || !ctg_codes) return fail("bsgpu_bam_open: null argument");
+	if (cudaSetDevice(c->device) != cudaSuccess) return fail("bsgpu_bam_open: cannot select device %d", c->device);
+	bsgpu_bam_session *s = new bsgpu_bam_session();
+	s->c = c; s->n_targets = n_targets; s->rp = *rp;
+	s->target_len.assign(target_len, target_len + n_targets);
+	s->codes.assign(ctg_codes, ctg_codes + n_targets);
+	s->bcf = bcf != nullptr;
+	if (bcf) s->bp = *bcf;
+	if (vcf_rid) s->rid.assign(vcf_rid, vcf_rid + n_targets);
+	if (!batch_bytes) { const char *e = getenv("BSGPU_BATCH_BYTES"); batch_bytes = e && atoll(e) > 0 ? (size_t)atoll(e) : (size_t)384 << 20; }
+	SessHooks hk;
+	hk.user = s; hk.alloc = sess_pin; hk.release = sess_unpin; hk.thread_init = sess_thread_init; hk.run = sess_run;
+	// first guess of a batch's results: BCF records are about as many bytes as the BAM records they come from, gt_vcf[] four times that
+	if (!s->core.open(hk, batch_bytes, s->bcf ? batch_bytes : 4 * batch_bytes)) {
+		s->core.close();
+		delete s;
+		return fail("bsgpu_bam_open: cannot allocate page-locked staging for batches of %zu bytes", batch_bytes);
+	}
+	*out = s;
+	return BSGPU_OK;
+}
+
+int bsgpu_bam_feed(bsgpu_bam_session *s, const uint8_t *bytes, size_t nbytes, size_t *accepted) {
+	if (!s || (nbytes && !bytes)) return fail("bsgpu_bam_feed: null argument");
+	std::string err;
+	size_t acc = 0;
+	const bool ok = s->core.feed(bytes, nbytes, accepted != nullptr, &acc, &err);
+	if (accepted) *accepted = acc;
+	return ok ? BSGPU_OK : fail("%s", err.c_str());
+}
+
+int bsgpu_bam_reserve(bsgpu_bam_session *s, uint8_t **ptr, size_t *avail, int wait) {
+	if (!s || !ptr || !avail) return fail("bsgpu_bam_reserve: null argument");
+	std::string err;
+	return s->core.reserve(ptr, avail, wait != 0, &err) ? BSGPU_OK : fail("%s", err.c_str());
+}
+
+int bsgpu_bam_commit(bsgpu_bam_session *s, size_t nbytes) {
+	if (!s) return fail("bsgpu_bam_commit: null argument");
+	std::string err;
+	return s->core.commit(nbytes, &err) ? BSGPU_OK : fail("%s", err.c_str());
+}
+
+int bsgpu_bam_finish(bsgpu_bam_session *s) {
+	if (!s) return fail("bsgpu_bam_finish: null argument");
+	std::string err;
+	return s->core.mark(true, &err) ? BSGPU_OK : fail("%s", err.c_str());
+}
+
+int bsgpu_bam_cut(bsgpu_bam_session *s) {
+	if (!s) return fail("bsgpu_bam_cut: null argument");
+	std::string err;
+	return s->core.mark(false, &err) ? BSGPU_OK : fail("%s", err.c_str());
+}
+
+int bsgpu_bam_rewind(bsgpu_bam_session *s) {
+	if (!s) return fail("bsgpu_bam_rewind: null argument");
+	std::string err;
+	return s->core.rewind(&err) ? BSGPU_OK : fail("%s", err.c_str());
+}
+
+int bsgpu_bam_drain(bsgpu_bam_session *s, int wait, bsgpu_bam_result *res) {
+	if (!s || !res) return fail("bsgpu_bam_drain: null argument");
+	memset(res, 0, sizeof(*res));
+	std::string err;
+	SessResult *r = nullptr;
+	bool done = false;
+	if (!s->core.drain(wait != 0, &r, &done, &err)) return fail("%s", err.c_str());
+	res->finished = done ? 1 : 0;
+	if (!r) return BSGPU_OK;
+	res->id = r->id; res->blocks = r->blocks.data(); res->nblocks = r->blocks.size();
+	res->data = r->buf; res->nbytes = r->nbytes; res->nrec = r->nrec; res->bytes_in = r->bytes_in; res->records_in = r->records_in;
+	return BSGPU_OK;
+}
+
+int bsgpu_bam_release(bsgpu_bam_session *s, uint64_t id) {
+	if (!s) return fail("bsgpu_bam_release: null argument");
+	return s->core.give_back(id) ? BSGPU_OK : fail("bsgpu_bam_release: no result %llu is lent out", (unsigned long long)id);
+}
+
+int bsgpu_bam_progress(bsgpu_bam_session *s, bsgpu_bam_progress_t *out) {
+	if (!s || !out) return fail("bsgpu_bam_progress: null argument");
+	s->core.progress(out);
+	return BSGPU_OK;
+}
+
+int bsgpu_bam_close(bsgpu_bam_session *s) {
+	if (!s) return BSGPU_OK;
+	cudaSetDevice(s->c->device);
+	s->core.close();
+	delete s;
 	return BSGPU_OK;
 }
 

@@ -437,8 +437,19 @@ void walk_piece(const uint8_t *bam, size_t nbytes, size_t from, size_t until, Fr
 // and walks its piece; the pieces are then stitched from the front -- a piece is taken over only from an offset the
 // chain walked so far actually lands on, otherwise the stitcher keeps walking itself until it does.  The result is the
 // sequential chain whatever the guesses were.
+// `framed` (may be NULL): a stream that ends inside a record is accepted and *framed receives the offset of that
+// incomplete record (nbytes when the stream ends on a record boundary) -- what a reader that feeds the stream in arbitrary
+// slices needs; without it a truncated stream is an error.
 int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_off, std::vector<uint32_t> &read_off,
-		std::vector<uint32_t> &mm_off, uint64_t *nbases, uint64_t *nmisms, FrameScratch *scratch) {
+		std::vector<uint32_t> &mm_off, uint64_t *nbases, uint64_t *nmisms, FrameScratch *scratch, size_t *framed) {
+	// is the record at `at` merely cut off by the end of the buffer (as opposed to malformed)?
+	auto cut_off = [&](size_t at) {
+		if (!framed) return false;
+		if (at + 4 > nbytes) return true;
+		const uint32_t bs = ld_u32(bam + at);
+		return bs >= 32 && at + 4 + (size_t)bs > nbytes;
+	};
+	bool stopped = false;
 	unsigned want = std::thread::hardware_concurrency();
 	if (const char *e = getenv("BSGPU_FRAMER_THREADS")) want = (unsigned)atoi(e);
 	want = std::max(1u, std::min(want, 32u));
@@ -468,7 +479,7 @@ int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_
 	std::vector<Own> own;
 	uint64_t nb = 0, nm = 0;
 	size_t at = 0, count = 0;
-	for (unsigned k = 0; k < K; k++) {
+	for (unsigned k = 0; k < K && !stopped; k++) {
 		const FramePiece &p = piece[k];
 		const size_t hi = nbytes * (k + 1) / K;
 		// walk on our own until we stand on an offset the piece has (at once when the guess was right), or pass the piece
@@ -479,7 +490,10 @@ int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_
 			idx = (size_t)(it - p.off.begin());
 			if (it != p.off.end() && *it == at) { joined = true; break; }
 			uint32_t bs, lseq, ncig;
-			if (frame_one(bam, nbytes, at, &bs, &lseq, &ncig)) return -1;
+			if (frame_one(bam, nbytes, at, &bs, &lseq, &ncig)) {
+				if (cut_off(at)) { stopped = true; break; }
+				return -1;
+			}
 			own.push_back(Own{count++, (uint64_t)at, (uint32_t)nb, (uint32_t)nm});
 			nb += lseq; nm += ncig;
 			at += 4 + (size_t)bs;
@@ -491,7 +505,10 @@ int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_
 			count += j.m;
 			nb = p.nb + j.db; nm = p.nm + j.dm;
 			at = p.end;
-			if (p.bad) return -1;
+			if (p.bad) {
+				if (cut_off(at)) stopped = true;
+				else return -1;
+			}
 		}
 	}
 	// (growing a vector value-initialises the new tail; a context's vectors keep their size from stream to stream)
@@ -511,7 +528,8 @@ int frame_records(const uint8_t *bam, size_t nbytes, std::vector<uint64_t> &rec_
 		for (unsigned k = 0; k < K; k++) thr.emplace_back(place, k);
 		for (auto &t : thr) t.join();
 	}
-	if (at != nbytes) return -1;
+	if (at != nbytes && !stopped) return -1;
+	if (framed) *framed = at;
 	if (nb > 0xffffffffull || nm > 0xffffffffull) return -2;
 	*nbases = nb;
 	*nmisms = nm;

@@ -25,6 +25,8 @@ EXPORTS = [
     "bsgpu_process_block", "bsgpu_profile_enable", "bsgpu_profile_read", "bsgpu_build_blocks_tally",
     "bsgpu_call_bam_bcf", "bsgpu_default_bcf_params", "bsgpu_bcf_block", "bsgpu_bcf_block_dev", "bsgpu_call_block_bcf", "bsgpu_call_sites_bcf",
     "bsgpu_default_reader_params", "bsgpu_decode_records", "bsgpu_build_blocks", "bsgpu_call_bam",
+    "bsgpu_bam_open", "bsgpu_bam_feed", "bsgpu_bam_reserve", "bsgpu_bam_commit", "bsgpu_bam_finish", "bsgpu_bam_cut", "bsgpu_bam_rewind", "bsgpu_bam_drain",
+    "bsgpu_bam_release", "bsgpu_bam_progress", "bsgpu_bam_close",
     "bsgpu_call_sites_dev", "bsgpu_call_sites_vcf_dev", "bsgpu_pileup_block_dev", "bsgpu_call_block_dev",
     "bsgpu_synth_sites_dev", "bsgpu_synth_block_nseg", "bsgpu_synth_block_dev",
     "bsgpu_synth_bam_bytes", "bsgpu_synth_bam_dev", "bsgpu_synth_ref_dev",
@@ -64,6 +66,17 @@ class Profile(C.Structure):
 
 
 BCF_MAX_RECORD = 384
+
+
+class BamResult(C.Structure):
+    """bsgpu_bam_result (include/bsgpu.h): the results of one batch of a streaming session, lent out in pinned memory"""
+    _fields_ = [("id", C.c_uint64), ("blocks", C.c_void_p), ("nblocks", C.c_size_t), ("data", C.c_void_p), ("nbytes", C.c_size_t),
+                ("nrec", C.c_size_t), ("bytes_in", C.c_size_t), ("records_in", C.c_size_t), ("finished", C.c_int), ("pad_", C.c_int)]
+
+
+class BamProgress(C.Structure):
+    _fields_ = [("bytes_fed", C.c_uint64), ("bytes_done", C.c_uint64), ("records_done", C.c_uint64), ("batches", C.c_uint64),
+                ("carry_bytes", C.c_uint64), ("empty_batches", C.c_uint64), ("pinned_bytes", C.c_uint64)]
 
 
 class BcfParams(C.Structure):
@@ -317,6 +330,10 @@ class BsGpu:
                                             C.byref(nv)))
         return blocks[:nb.value], vcf[:nv.value]
 
+    def bam_session(self, target_len, ctg_codes, rp=None, bcf=None, vcf_rid=None, batch_bytes=0):
+        """streaming session over this context (bsgpu_bam_open); bcf: None -> gt_vcf[] results, True / BcfParams -> BCF records"""
+        return BamSession(self, target_len, ctg_codes, rp, bcf, vcf_rid, batch_bytes)
+
     # ---- device-pointer entry points (addresses as ints, e.g. torch.Tensor.data_ptr()) --------
     def call_bam_bcf(self, bam, target_len, ctg_codes, rp=None, params=None, vcf_rid=None, out=None):
         """raw BAM records + per-contig reference codes -> (BLOCK[], BCF record bytes, number of records)"""
@@ -386,6 +403,141 @@ class BsGpu:
         self._check(self.lib.bsgpu_stage_templates(_ptr(templates), C.c_size_t(len(templates)), _ptr(bases), C.c_uint32(x),
                                                    C.c_uint32(y), _ptr(segs), C.byref(ns)))
         return segs[:ns.value]
+
+
+class BamSession:
+    """bsgpu_bam_open / _feed / _finish / _drain / _release / _close: the reader side in bounded memory.  Results come back
+    as (BLOCK[] view, data view, nrec, BamResult); the views alias the session's pinned memory until release(id)."""
+
+    def __init__(self, gpu, target_len, ctg_codes, rp=None, bcf=None, vcf_rid=None, batch_bytes=0):
+        self.gpu, self.lib = gpu, gpu.lib
+        self.target_len = np.ascontiguousarray(target_len, dtype=np.uint32)
+        self.codes = [None if c is None else np.ascontiguousarray(c, dtype=np.uint8) for c in ctg_codes]      # kept alive: the session reads them
+        ptrs = (C.c_void_p * len(self.codes))(*[None if c is None else c.ctypes.data for c in self.codes])
+        self.rp = rp or reader_params()
+        self.bcf = bcf_params() if bcf is True else bcf
+        self.rid = None if vcf_rid is None else np.ascontiguousarray(vcf_rid, dtype=np.int32)
+        self.s = C.c_void_p()
+        self.lib.bsgpu_bam_open.argtypes = None
+        gpu._check(self.lib.bsgpu_bam_open(gpu.ctx, C.c_int(len(self.codes)), _ptr(self.target_len), ptrs, C.byref(self.rp),
+                                           C.byref(self.bcf) if self.bcf is not None else None, _ptr(self.rid), C.c_size_t(int(batch_bytes)),
+                                           C.byref(self.s)))
+
+    def feed(self, data, nowait=False):
+        """returns the number of bytes taken (all of them unless nowait)"""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        acc = C.c_size_t(0)
+        self.gpu._check(self.lib.bsgpu_bam_feed(self.s, _ptr(data), C.c_size_t(len(data)), C.byref(acc) if nowait else None))
+        return acc.value if nowait else len(data)
+
+    def reserve(self, wait=True):
+        """-> numpy view of the staging area where the next bytes of the stream go (commit(n) afterwards)"""
+        ptr, avail = C.c_void_p(), C.c_size_t(0)
+        self.gpu._check(self.lib.bsgpu_bam_reserve(self.s, C.byref(ptr), C.byref(avail), C.c_int(1 if wait else 0)))
+        if not avail.value:
+            return np.zeros(0, dtype=np.uint8)
+        return np.frombuffer((C.c_uint8 * avail.value).from_address(ptr.value), dtype=np.uint8)
+
+    def commit(self, n):
+        self.gpu._check(self.lib.bsgpu_bam_commit(self.s, C.c_size_t(int(n))))
+
+    def finish(self):
+        self.gpu._check(self.lib.bsgpu_bam_finish(self.s))
+
+    def cut(self):
+        self.gpu._check(self.lib.bsgpu_bam_cut(self.s))
+
+    def rewind(self):
+        self.gpu._check(self.lib.bsgpu_bam_rewind(self.s))
+
+    def drain(self, wait=True):
+        """-> None when no result is ready (check .finished), else (blocks, data, nrec, result)"""
+        r = BamResult()
+        self.gpu._check(self.lib.bsgpu_bam_drain(self.s, C.c_int(1 if wait else 0), C.byref(r)))
+        self.finished = bool(r.finished)
+        if not r.id:
+            return None
+        blocks = np.frombuffer((C.c_uint8 * (r.nblocks * BLOCK.itemsize)).from_address(r.blocks), dtype=BLOCK) if r.nblocks else np.zeros(0, dtype=BLOCK)
+        if self.bcf is not None:
+            data = np.frombuffer((C.c_uint8 * r.nbytes).from_address(r.data), dtype=np.uint8) if r.nbytes else np.zeros(0, dtype=np.uint8)
+        else:
+            data = np.frombuffer((C.c_uint8 * r.nbytes).from_address(r.data), dtype=GT_VCF) if r.nbytes else np.zeros(0, dtype=GT_VCF)
+        return blocks, data, int(r.nrec), r
+
+    def release(self, r):
+        self.gpu._check(self.lib.bsgpu_bam_release(self.s, C.c_uint64(r.id if isinstance(r, BamResult) else int(r))))
+
+    def progress(self):
+        p = BamProgress()
+        self.gpu._check(self.lib.bsgpu_bam_progress(self.s, C.byref(p)))
+        return {k: int(getattr(p, k)) for k, _ in BamProgress._fields_}
+
+    def close(self):
+        if self.s:
+            self.lib.bsgpu_bam_close(self.s)
+            self.s = C.c_void_p()
+
+    def run(self, bam, slice_bytes=1 << 20, nowait=True, keep=True):
+        """convenience for tests: feeds `bam` in slices and collects the results as (blocks, data copy, nrec) per batch.
+        nowait: one thread, non-blocking feeds, draining whenever a feed comes up short.  Otherwise two threads as in the
+        reference: this one feeds (blocking), a second one drains."""
+        bam = np.ascontiguousarray(bam, dtype=np.uint8)
+        out = []
+
+        def collect(got):
+            b, d, n, r = got
+            out.append((b.copy(), d.copy() if keep else None, n))
+            self.release(r)
+
+        def drain_all():
+            while True:
+                got = self.drain(wait=True)
+                if got is not None:
+                    collect(got)
+                if self.finished:
+                    return
+
+        if nowait:
+            at = 0
+            while at < len(bam):
+                m = min(slice_bytes, len(bam) - at)
+                took = self.feed(bam[at:at + m], nowait=True)
+                at += took
+                if took < m:
+                    got = self.drain(wait=True)
+                    if got is not None:
+                        collect(got)
+            self.finish()
+            drain_all()
+            return out
+        import threading
+        err = []
+
+        def printer():
+            try:
+                while True:
+                    got = self.drain(wait=True)
+                    if got is not None:
+                        collect(got)
+                    elif not self.finished:
+                        import time
+                        time.sleep(0.0005)          # nothing in flight yet: the feeder has not filled a batch
+                    if self.finished:
+                        return
+            except Exception as e:        # noqa: BLE001 -- handed to the feeding thread
+                err.append(e)
+
+        t = threading.Thread(target=printer)
+        t.start()
+        try:
+            for at in range(0, len(bam), slice_bytes):
+                self.feed(bam[at:at + slice_bytes])
+            self.finish()
+        finally:
+            t.join()
+        if err:
+            raise err[0]
+        return out
 
 
 def math_probe(x):

@@ -11,7 +11,7 @@ collective is the final ordered merge of per-rank results on the host (what the 
   stream   the synthetic per-site stream of config 2 -> equal contiguous site ranges
 """
 from dataclasses import dataclass
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 
 def lpt_assign(weights: Sequence[float], n_ranks: int) -> List[int]:
@@ -50,15 +50,27 @@ def split_contig(contig: int, length: int, n_parts: int, boundaries: Sequence[in
     return [Region(contig, cuts[i], cuts[i + 1] - 1) for i in range(len(cuts) - 1)]
 
 
-def plan(contig_lengths: Sequence[int], n_ranks: int, split_over: float = 1.5) -> List[List[Region]]:
-    """Per-rank region lists.  A contig heavier than split_over x the ideal per-rank share is first split (level 2)."""
-    total = float(sum(contig_lengths))
+def plan(contig_lengths: Sequence[int], n_ranks: int, split_over: float = 1.5,
+         boundaries: Optional[Sequence[Sequence[int]]] = None, weights: Optional[Sequence[float]] = None) -> List[List[Region]]:
+    """Per-rank region lists.  A contig heavier than split_over x the ideal per-rank share is first split (level 2).
+
+    boundaries[c] = sorted positions at which a new block starts on contig c (block x; from the BAM index in a real run).
+    A contig is only ever cut AT such a position: a block that straddled a cut would be split between two ranks, which
+    changes mate pairing, duplicate removal and the pileup at the edge.  Without boundaries for a contig it is never split
+    (plan() then stays valid for reads; equal-size cuts are only right for the per-site stream, see site_range()).
+    weights[c] = work of contig c (its base count) when that is not proportional to its length."""
+    w = [float(x) for x in (weights if weights is not None else contig_lengths)]
+    total = float(sum(w))
     share = total / n_ranks
     regions: List[Region] = []
+    rw: List[float] = []
     for c, ln in enumerate(contig_lengths):
-        parts = max(1, int(round(ln / share))) if ln > split_over * share else 1
-        regions.extend(split_contig(c, ln, parts))
-    owner = lpt_assign([r.stop - r.start + 1 for r in regions], n_ranks)
+        bnd = boundaries[c] if boundaries is not None and c < len(boundaries) else None
+        parts = max(2, int(round(w[c] / share))) if n_ranks > 1 and w[c] > split_over * share and bnd else 1
+        rs = split_contig(c, ln, parts, bnd or ())
+        regions.extend(rs)
+        rw.extend(w[c] * (r.stop - r.start + 1) / max(ln, 1) for r in rs)
+    owner = lpt_assign(rw, n_ranks)
     out: List[List[Region]] = [[] for _ in range(n_ranks)]
     for r, o in zip(regions, owner):
         out[o].append(r)

@@ -29,6 +29,9 @@
  *     bsgpu_bcf_block[_dev], bsgpu_call_block_bcf, bsgpu_call_sites_bcf, bsgpu_call_bam_bcf
  *                                    print_vcf_entry / flush_vcf_entries / _print_vcf_entry as print_thread drives them
  *                                    (src/print_vcf.c:32-381, 535-594; src/process.c:89-104): the BCF records themselves
+ *     bsgpu_bam_open / _feed / _reserve / _commit / _finish / _drain / _release / _close
+ *                                    the same chain with read_input's streaming behaviour: one sam_read1() at a time in,
+ *                                    blocks out as they close, O(block) memory (src/get_template_vector.c:86-110, 140-189)
  *     bsgpu_profile_enable / _read   meth_profile + mprof_thread (src/meth_profile.c:48-76, src/process.c:20-41) and the
  *                                    bs_stats tallies of process_template_vector / read_input (--report-file)
  * The link-compatible replacements for the three reference symbols themselves (call_genotypes_ML,
@@ -294,6 +297,60 @@ int bsgpu_build_blocks_tally(const uint8_t *bam, size_t nbytes, const bsgpu_reco
 int bsgpu_call_bam(bsgpu_ctx *ctx, const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len,
 		const uint8_t *const *ctg_codes, const bsgpu_reader_params *rp, bsgpu_block *blocks, size_t block_cap, size_t *nblocks,
 		bsgpu_gt_vcf *vcf, size_t vcf_cap, size_t *nvcf);
+
+/* ---- streaming session: the reader side in bounded memory, for streams of any length ----
+ * read_input() reads one record at a time and hands a block on as soon as it closes (src/get_template_vector.c:86-110,
+ * 140-189), so bs_call's memory is O(block).  A session gives the same behaviour to the device path: the record stream is
+ * fed in arbitrary slices (a slice may end anywhere, also inside a record), the session cuts it at records where read_input
+ * is certain to start a new block, runs batches of about `batch_bytes` (0: 384 MiB, or BSGPU_BATCH_BYTES) through
+ * decode -> blocks -> normalisation -> pileup -> model (-> writer) on a worker thread while the caller feeds the next
+ * batch, and lends the results of every batch out in page-locked memory.  The three threads of the reference map onto it:
+ * the reader thread feeds (src/bs_call.c main -> read_input), the session's worker is process_thread (src/process.c:43-72),
+ * the print thread drains (src/process.c:74-110).  A single thread can drive it too: pass `accepted` to bsgpu_bam_feed
+ * (it then never blocks and may take fewer bytes than offered) and poll bsgpu_bam_drain.
+ *   bcf == NULL: results are gt_vcf[] records, block windows as in bsgpu_call_bam (blocks[b].vcf_off indexes the batch's array);
+ *   bcf != NULL: results are the BCF records of the batch's blocks in stream order, as in bsgpu_call_bam_bcf.
+ * ctg_codes[] must stay valid while the session is open; the context must not be used by other calls meanwhile.
+ * Limits: one block (not one stream) must stay below 4 Gi decoded bases. */
+typedef struct bsgpu_bam_session bsgpu_bam_session;
+typedef struct {
+	uint64_t id;               /* handle for bsgpu_bam_release; 0: no result was ready */
+	const bsgpu_block *blocks; /* the blocks of the batch, templates numbered within the batch */
+	size_t nblocks;
+	const uint8_t *data;       /* BCF record stream, or gt_vcf[] */
+	size_t nbytes;
+	size_t nrec;               /* BCF records, or gt_vcf records */
+	size_t bytes_in, records_in;   /* the part of the stream (bytes, BAM records) these results account for */
+	int finished;              /* 1: the stream was finished and no further result will come */
+	int pad_;
+} bsgpu_bam_result;
+typedef struct {
+	uint64_t bytes_fed, bytes_done, records_done, batches;
+	uint64_t carry_bytes;      /* bytes that were staged again because they followed a batch's last certain block start */
+	uint64_t empty_batches;    /* batches that held no certain block start (the staging buffer grew instead) */
+	uint64_t pinned_bytes;     /* page-locked memory the session holds right now */
+} bsgpu_bam_progress_t;
+int bsgpu_bam_open(bsgpu_ctx *ctx, int n_targets, const uint32_t *target_len, const uint8_t *const *ctg_codes, const bsgpu_reader_params *rp,
+		const bsgpu_bcf_params *bcf, const int32_t *vcf_rid, size_t batch_bytes, bsgpu_bam_session **out);
+/* copies the slice into the session's staging.  accepted == NULL: blocks while both staging buffers are full;
+ * accepted != NULL: never blocks, *accepted <= nbytes says how much was taken (drain, then offer the rest again) */
+int bsgpu_bam_feed(bsgpu_bam_session *s, const uint8_t *bytes, size_t nbytes, size_t *accepted);
+/* zero-copy feeding: *ptr = where the next bytes of the stream go, *avail = how many fit (0 when wait == 0 and both
+ * staging buffers are full); write there (an inflater's output buffer), then commit what was written */
+int bsgpu_bam_reserve(bsgpu_bam_session *s, uint8_t **ptr, size_t *avail, int wait);
+int bsgpu_bam_commit(bsgpu_bam_session *s, size_t nbytes);
+/* The bytes fed so far end where read_input would close a block whatever follows (end of a contig, end of a region cut at
+ * a block boundary): they run as a batch of their own, so no batch of results mixes two regions, while the session stays
+ * open and the next region can be fed at once. */
+int bsgpu_bam_cut(bsgpu_bam_session *s);
+int bsgpu_bam_finish(bsgpu_bam_session *s);       /* no more bytes: the staged rest runs as the last batch */
+int bsgpu_bam_rewind(bsgpu_bam_session *s);       /* after a finished, fully drained stream: ready for another stream (buffers kept) */
+/* next batch of results in stream order; wait != 0: blocks until one is ready or none can come.  res->data / res->blocks
+ * stay valid until bsgpu_bam_release(s, res->id), which returns the buffers for reuse */
+int bsgpu_bam_drain(bsgpu_bam_session *s, int wait, bsgpu_bam_result *res);
+int bsgpu_bam_release(bsgpu_bam_session *s, uint64_t id);
+int bsgpu_bam_progress(bsgpu_bam_session *s, bsgpu_bam_progress_t *out);
+int bsgpu_bam_close(bsgpu_bam_session *s);
 
 /* ---- device-pointer entry points: everything already resident in HBM, asynchronous on `stream`
  *      (a cudaStream_t passed as void*; NULL = the context's own stream) ---- */

@@ -34,8 +34,28 @@ def test_plan_covers_everything_once():
                 assert iv[0][0] == 1 and iv[-1][1] == ln
                 for a, b in zip(iv, iv[1:]):
                     assert a[1] + 1 == b[0]
-    p = shard.plan([50_000_000], 8)                    # one contig on 8 GPUs is split (level 2)
+    # one contig on 8 GPUs is split (level 2) -- at block boundaries, and only when they are known
+    bounds = list(range(1, 50_000_000, 99_371))
+    p = shard.plan([50_000_000], 8, boundaries=[bounds])
     assert all(len(lst) == 1 for lst in p)
+    for lst in p:
+        assert lst[0].start in bounds
+    loads = [lst[0].stop - lst[0].start + 1 for lst in p]
+    assert max(loads) / (50_000_000 / 8) < 1.05
+    p = shard.plan([50_000_000], 8)                    # no boundaries: never cut through a block
+    assert sum(len(lst) for lst in p) == 1
+
+
+def test_plan_hg38_level2_split_at_8():
+    """24 hg38-shaped contigs on 8 ranks with split_over = 0.4: the largest contigs are cut in two at block boundaries and
+    the plan balances within a few per cent"""
+    lens = shard.HG38_CONTIGS
+    bounds = [list(range(1, ln, 100_400)) for ln in lens]
+    p = shard.plan(lens, 8, split_over=0.4, boundaries=bounds)
+    load = [sum(r.stop - r.start + 1 for r in lst) for lst in p]
+    assert max(load) / (sum(lens) / 8) < 1.05
+    split = [r for lst in p for r in lst if not (r.start == 1 and r.stop == lens[r.contig])]
+    assert split and all(r.start == 1 or r.start in bounds[r.contig] for r in split)
 
 
 def test_split_respects_block_boundaries():
