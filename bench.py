@@ -35,6 +35,16 @@ MEAN_DEPTH = 30.0
 BYTES_PER_SITE = 104 + 1 + 200 + 1
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    """progress on stderr (the JSON line is the only thing on stdout)"""
+    if os.environ.get("RANK", "0") == "0":
+        sys.stderr.write("[bench %7.1fs] %s\n" % (time.time() - _T0, msg))
+        sys.stderr.flush()
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -230,6 +240,7 @@ def bam_path(args, gpu, bslib, torch, np, stream, rank, world, local):
                                 "descriptors_d2h_block_builder_host": (s1["bam_build_s"] - s0["bam_build_s"]) / steps,
                                 "normalise_pileup_model_d2h": (s1["bam_call_s"] - s0["bam_call_s"]) / steps},
            "gpu_launches_per_step": (s1["kernel_launches"] - s0["kernel_launches"]) // steps}
+    log("bam: gt_vcf %.3g sites/s; to BCF ..." % out["e2e"]["value"])
     # the same stream all the way to BCF records (the writer's derivations on the device): only the records come home
     hbcf = bslib.HostBuffer(ctg_len * 96 + 4096, np.uint8)
     for _ in range(2):
@@ -271,20 +282,22 @@ def bam_path(args, gpu, bslib, torch, np, stream, rank, world, local):
     dtp = (time.perf_counter() - t0) / steps
     sp1 = gpu.stats()
     prof = gpu.profile_read(reset=True)
-    out["with_report_side_channels"] = {"value": called / dtp, "unit": "sites/s", "slowdown": dtp / dt,
+    tp_ = torch.tensor([dtp], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tp_, op=dist.ReduceOp.MAX)
+    out["with_report_side_channels"] = {"value": float(cc.item()) / float(tp_.item()), "unit": "sites/s", "slowdown": dtp / dt,
                                          "normalise_pileup_model_d2h_s": (sp1["bam_call_s"] - sp0["bam_call_s"]) / steps,
                                          "gpu_launches_per_step": (sp1["kernel_launches"] - sp0["kernel_launches"]) // steps,
                                          "profile_counts_per_step": int(prof["conv"].sum()) // steps, "profile_used": prof["used"]}
-    # the reference's own chain (read_input -> process_template_vector -> call_genotypes_ML, all its threads) on a bounded
-    # prefix of the same stream
+    # The reference's own chain (read_input -> process_template_vector -> call_genotypes_ML, all its threads) and its writer:
+    # timed on a bounded prefix of the stream (cpu_baseline), then run over --cpu-diff-records of it (default: ALL, config 3
+    # "VCF/BCF diffed against the CPU run") with its stats live, and every block's gt_vcf[] records, every BCF record and the
+    # --report-file side channels compared with what the device produced for the same records.
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle.bindings import Oracle, Reference, reference_available
-        from tests import util
+        from oracle.bindings import Oracle, Reference, bcf_diff, reference_available
+        from tests import blockgen, util
         rb = nbytes // (2 * nt)
-        nrec_c = int(min(2 * nt, 260000))
-        prefix = hbam.array[:nrec_c * rb]
-        last_pos = int(prefix[(nrec_c - 1) * rb + 8:(nrec_c - 1) * rb + 12].view("<i4")[0]) + 1
-        clen = last_pos + 2 * L + 1200
         ncores = os.cpu_count() or 1
         if reference_available():
             impl, kind = Reference(calc_threads=ncores), "reference"
@@ -292,56 +305,285 @@ def bam_path(args, gpu, bslib, torch, np, stream, rank, world, local):
         else:
             impl, kind = Oracle(), "port"
             what = "oracle port of the same chain (1 thread)"
+
+        def prefix_of(nrec_c):
+            pre = hbam.array[:nrec_c * rb]
+            last_pos = int(pre[(nrec_c - 1) * rb + 8:(nrec_c - 1) * rb + 12].view("<i4")[0]) + 1
+            return pre, min(ctg_len, last_pos + 2 * L + 1200)
+
+        log("bam: BCF %.3g sites/s; CPU reference on a prefix, then the diff ..." % out["to_bcf_records"]["value"])
+        nrec_t = int(min(2 * nt, 400000))
+        pre, clen = prefix_of(nrec_t)
         t0 = time.perf_counter()
-        cb, ct, _, _, cv = impl.read_input(prefix, [clen], [href[:clen]], run_chain=True)
+        cb, ct, _, _, cv = impl.read_input(pre, [clen], [href[:clen]], run_chain=True)
         cs = time.perf_counter() - t0
-        # once more with its stats live (what --report-file does), for the parity of the side channels below
-        if kind == "reference":
-            impl.stats_enable(True); impl.stats_reset()
-            impl.read_input(prefix, [clen], [href[:clen]], run_chain=True)
-            cprof = impl.stats_read()
-            impl.stats_enable(False)
-        else:
-            impl.profile_enable(True); impl.profile_reset()
-            impl.read_input(prefix, [clen], [href[:clen]], run_chain=True)
-            cprof = impl.profile_read()
-            impl.profile_enable(False)
         ccalled = int((cv["skip"] == 0).sum())
         out["cpu_baseline"] = {"value": ccalled / cs, "unit": "sites/s", "cores": ncores, "kind": kind,
-                               "sample": "first %d records (%d sites called, %d blocks) of the same stream; %s" % (nrec_c, ccalled, len(cb), what)}
-        # parity on every complete block of the prefix
+                               "sample": "first %d records (%d sites called, %d blocks) of the same stream; %s" % (nrec_t, ccalled, len(cb), what)}
+        del cb, cv
+        nrec_c = int(min(2 * nt, args.cpu_diff_records if args.cpu_diff_records > 0 else 2 * nt))
+        whole = nrec_c == 2 * nt
+        pre, clen = prefix_of(nrec_c)
+        if kind == "reference":
+            impl.stats_enable(True); impl.stats_reset()
+        else:
+            impl.profile_enable(True); impl.profile_reset()
+        t0 = time.perf_counter()
+        cb, ct, _, _, cv = impl.read_input(pre, [clen], [href[:clen]], run_chain=True)
+        cs_all = time.perf_counter() - t0
+        if kind == "reference":
+            cprof = impl.stats_read(); impl.stats_enable(False)
+        else:
+            cprof = impl.profile_read(); impl.profile_enable(False)
+        log("bam: CPU chain over %d records took %.1f s; comparing ..." % (nrec_c, cs_all))
+        # every block of the whole stream (every complete block of a prefix: its last block is cut short)
+        nblk = len(cb) if whole else len(cb) - 1
+        assert whole is False or len(cb) == len(blocks)
         checked = 0
-        for b, w in zip(blocks[:len(cb) - 1], cb[:len(cb) - 1]):
+        for b, w in zip(blocks[:nblk], cb[:nblk]):
             assert (b["x"], b["y"], b["n_templates"]) == (w["x"], w["y"], w["n_templates"])
             n_ = int(w["y"]) - int(w["x"]) + 1
             checked += util.assert_vcf_close(vcf[int(b["vcf_off"]):int(b["vcf_off"]) + n_], cv[int(w["vcf_off"]):int(w["vcf_off"]) + n_])
-        out["cpu_baseline"]["parity_sites_checked"] = checked
-        # the records: the reference's writer over the reference's own chain on every complete block of the prefix, against
-        # the leading records of the device's stream (fixed fields identical; GL floats carry the posteriors' last bits)
+        out["cpu_diff"] = {"records_in": nrec_c, "whole_stream": whole, "blocks": nblk, "sites_called_checked": checked,
+                           "cpu_chain_s": cs_all, "against": what + ", stats live"}
+        # the records: the reference's writer over the reference's own chain, block by block, against the device's stream
         if kind == "reference":
-            from tests import blockgen
             want = []
-            for w in cb[:len(cb) - 1]:
+            t0 = time.perf_counter()
+            for w in cb[:nblk]:
                 n_ = int(w["y"]) - int(w["x"]) + 1
                 wb_, _ = impl.print_block(cv[int(w["vcf_off"]):int(w["vcf_off"]) + n_], blockgen.window_codes(href[:clen], int(w["x"]), int(w["y"]) + 2),
                                           int(w["x"]), rid=0, ctg_end=ctg_len)
-                want += util.split_bcf(wb_)
-            at, same, fixed = 0, 0, 0
-            for r in want:
-                l = 8 + int(bcf_first[at:at + 4].view("<u4")[0]) + int(bcf_first[at + 4:at + 8].view("<u4")[0])
-                g_ = bcf_first[at:at + l].tobytes()
-                fixed += g_[:32] == r[:32]
-                same += g_ == r
-                at += l
-            assert fixed == len(want), "device records differ from the reference writer's in their fixed fields"
-            out["to_bcf_records"]["parity_records_checked"] = len(want)
-            out["to_bcf_records"]["parity_records_byte_identical"] = same
-        gpu.call_bam(prefix, [clen], [href[:clen]], vcf=hvcf.array)
-        util.same_profile(gpu.profile_read(reset=True), cprof, "bench prefix", recycled_vectors=kind == "reference")
+                want.append(wb_)
+            ws = time.perf_counter() - t0
+            want = np.concatenate(want)
+            got = bcf_first if whole else bcf_first[:len(want)]
+            d = bcf_diff(got, want)
+            assert d["records_a"] == d["records_b"] == d["fixed_equal"] and d["order_violations"] == 0, d
+            out["cpu_diff"].update({"bcf_records": d["records_a"], "bcf_records_fixed_fields_equal": d["fixed_equal"],
+                                    "bcf_records_byte_identical": d["identical"], "bcf_bytes": len(want), "cpu_writer_s": ws})
+            out["to_bcf_records"]["parity_records_checked"] = d["records_a"]
+            out["to_bcf_records"]["parity_records_byte_identical"] = d["identical"]
+            del want
+        del cv
+        log("bam: records compared; side channels ...")
+        gpu.call_bam(pre, [clen], [href[:clen]], vcf=hvcf.array)
+        util.same_profile(gpu.profile_read(reset=True), cprof, "bench stream", recycled_vectors=kind == "reference")
         out["with_report_side_channels"]["parity_profile_counts_checked"] = int(cprof["conv"].sum())
     gpu.profile_enable(False)
     hbam.free()
     hvcf.free()
+    return out
+
+
+def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
+    """BASELINE.json configs[4] shape: a 24-contig hg38-shaped genome (contig lengths / --genome-scale), 30x paired-end
+    WGBS record streams, sharded over the ranks by shard.plan (level 1: contigs by longest-processing-time; level 2: the
+    heaviest contigs cut in two AT BLOCK BOUNDARIES) -- strong scaling, the genome is the same at every N.  Every rank
+    pushes its regions through ONE streaming session (bsgpu_bam_open / _feed / _cut / _drain): BAM records in pinned host
+    memory in, BCF records in pinned host memory out, H2D / D2H inside the timed region, a feeding thread and a printing
+    thread as in the reference.  Then the ordered merge: the per-batch extents of all ranks gathered on rank 0 and put in
+    coordinate order (the reference's workflow is one output per region, concatenated: src/process_sam_header.c:52-70)."""
+    import threading
+    import zlib
+    from bs_call_b200 import synthgenome as sg
+    import torch.distributed as dist
+    dev = torch.device("cuda", local)
+    scale = int(args.genome_scale)
+    rb = gpu.synth_bam_bytes(1, sg.READ_LEN) // 2          # bytes of one record (a template is two)
+    if scale <= 0:
+        # largest genome whose records (in) and BCF records (out) for ONE rank holding everything fit in a quarter of the host's free memory
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 64 << 30
+        scale = 64
+        for sc in (8, 16, 32):
+            nt_tot = sum(sg.n_templates(ln) for ln in sg.contig_lengths(sc))
+            if nt_tot * 2 * rb * 2.2 < avail / 4:
+                scale = sc
+                break
+    lens, plan = sg.plan(scale, world)
+    mine = [(r,) + sg.region_templates(r, lens[r.contig]) for r in plan[rank]]
+    mine = [(r, t0, t1) for r, t0, t1 in mine if t1 > t0]
+    nbytes_in = sum((t1 - t0) * 2 * rb for _, t0, t1 in mine)
+    hbam = bslib.HostBuffer(max(nbytes_in, 16), np.uint8)
+    contigs = sorted({r.contig for r, _, _ in mine})
+    href = {c: bslib.HostBuffer(lens[c], np.uint8) for c in contigs}
+    d_ref = torch.empty(max(lens) + 16, dtype=torch.uint8, device=dev)
+    for c in contigs:
+        gpu.synth_ref_dev(SEED + 1000003 * c, 1, lens[c], d_ref.data_ptr(), stream)
+        torch.cuda.synchronize()
+        torch.from_numpy(href[c].array).copy_(d_ref[:lens[c]])
+    del d_ref
+    spans, at = [], 0
+    max_reg = max([(t1 - t0) * 2 * rb for _, t0, t1 in mine] + [16])
+    d_out = torch.empty(max_reg + 16, dtype=torch.uint8, device=dev)
+    for r, t0, t1 in mine:
+        n = sg.region_stream_dev(gpu, torch, dev, SEED, r.contig, t0, t1, d_out, stream)
+        view = hbam.array[at:at + n]
+        torch.from_numpy(view).copy_(d_out[:n])
+        sg.patch_contig(view, r.contig, rb)
+        spans.append((r, at, at + n))
+        at += n
+    del d_out
+    torch.cuda.empty_cache()
+    log("genome: %d regions, %.2f GB of records on this rank, scale 1/%d" % (len(spans), nbytes_in / 1e9, scale))
+    codes = [href[c].array if c in href else None for c in range(len(lens))]
+    sess = gpu.bam_session(np.array(lens, dtype=np.uint32), codes, bcf=True, batch_bytes=int(args.genome_batch_mb) << 20)
+    SLICE = 32 << 20
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def one_pass(keep):
+        res, err = [], []
+
+        def printer():
+            try:
+                while True:
+                    got = sess.drain(wait=True)
+                    if got is not None:
+                        b, d, n, r = got
+                        res.append((b.copy(), d if keep else None, len(d), n, r))
+                        if not keep:
+                            sess.release(r)
+                    elif not sess.finished:
+                        time.sleep(0.0002)
+                    if sess.finished:
+                        return
+            except Exception as e:      # noqa: BLE001
+                err.append(e)
+
+        th = threading.Thread(target=printer)
+        barrier()
+        t0 = time.perf_counter()
+        th.start()
+        try:
+            for r, lo, hi in spans:
+                for off in range(lo, hi, SLICE):
+                    sess.feed(hbam.array[off:min(off + SLICE, hi)])
+                sess.cut()                       # a region ends where a block ends: no batch of results mixes two regions
+            sess.finish()
+        finally:
+            th.join()
+        dt = time.perf_counter() - t0
+        if err:
+            raise err[0]
+        return dt, res
+
+    def give_back(res):
+        for _, _, _, _, r in res:
+            sess.release(r)
+
+    # every pass keeps all its results lent out until it is over (they are the output of the run), so the session's pool of
+    # pinned result buffers reaches its final size during the warm-up passes
+    for _ in range(2):
+        dtw, res = one_pass(True)
+        log("genome: warm-up pass %.3f s, %d result batches" % (dtw, len(res)))
+        give_back(res)
+        sess.rewind()
+    s0 = gpu.stats()
+    steps = 3
+    dts = []
+    for k in range(steps):
+        dt, res = one_pass(True)
+        dts.append(dt)
+        if k < steps - 1:
+            give_back(res)
+            sess.rewind()
+    s1 = gpu.stats()
+    prog = sess.progress()
+    log("genome: timed passes %s s" % ", ".join("%.3f" % v for v in dts))
+    dt = sum(dts) / steps
+    called = (s1["sites_called"] - s0["sites_called"]) // steps
+    # ---- ordered merge (timed): every batch of results is an extent (contig, first block x, last block y, bytes, records)
+    barrier()
+    tm0 = time.perf_counter()
+    table = [(int(b[0]["tid"]), int(b[0]["x"]), int(b[-1]["y"]), nb, nr, rank, i) for i, (b, _, nb, nr, _) in enumerate(res) if len(b)]
+    if world > 1:
+        tables = [None] * world
+        dist.all_gather_object(tables, table)
+    else:
+        tables = [table]
+    merged = sorted(e for t in tables for e in t)
+    for a, b2 in zip(merged, merged[1:]):
+        assert a[0] < b2[0] or a[2] <= b2[1], "extents overlap: %r %r" % (a, b2)
+    merge_s = time.perf_counter() - tm0
+    # ---- what must be the same at every N: records and bytes of the whole genome, and the records of the two smallest contigs
+    small = sorted(range(len(lens)), key=lambda c: lens[c])[:2]
+    crc = {c: 0 for c in small}
+    keep_small = {}
+    for b, d, nb, nr, r in res:
+        if len(b) and int(b[0]["tid"]) in crc:
+            c = int(b[0]["tid"])
+            crc[c] = zlib.crc32(d, crc[c])
+            if rank == 0 and world == 1 and c == small[0]:
+                keep_small.setdefault(c, []).append(d.copy())
+    tot = torch.tensor([sum(nb for _, _, nb, _, _ in res), sum(nr for _, _, _, nr, _ in res), called, nbytes_in, len(res)] +
+                       [crc[c] for c in small], dtype=torch.int64, device=dev)
+    tmax = torch.tensor([dt, max(dts), min(dts)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)       # a contig's records all sit on one rank unless it was split: crc of a split contig is not comparable
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    split_contigs = sorted({r.contig for lst in plan for r in lst if not (r.start == 1 and r.stop == lens[r.contig])})
+    loads = [sum(sg.region_templates(r, lens[r.contig])[1] - sg.region_templates(r, lens[r.contig])[0] for r in lst) for lst in plan]
+    out = {"workload": "synthetic hg38-shaped genome, 24 contigs at 1/%d scale (%d positions), 30x paired-end %d-bp WGBS records with 5 %% duplicates and a "
+                       "coverage gap every ~100 kb; BASELINE.json configs[4] shape without dbSNP" % (scale, sum(lens), sg.READ_LEN),
+           "scaling": "strong", "value": float(tot[2].item()) / float(tmax[0].item()), "unit": "sites/s",
+           "pass_s": float(tmax[0].item()), "pass_s_minmax": [float(tmax[2].item()), float(tmax[1].item())], "passes_timed": steps,
+           "merge_s": merge_s, "value_with_merge": float(tot[2].item()) / (float(tmax[0].item()) + merge_s),
+           "sites_called": int(tot[2].item()), "records_in_bytes": int(tot[3].item()), "bcf_records": int(tot[1].item()), "bcf_bytes": int(tot[0].item()),
+           "result_batches": int(tot[4].item()), "extents_merged": len(merged),
+           "plan": {"regions": sum(len(lst) for lst in plan), "contigs_split_at_block_boundaries": split_contigs,
+                    "templates_per_rank": loads, "imbalance": max(loads) / (sum(loads) / len(loads))},
+           "invariants": {"crc32_contig_%d" % c: (int(tot[5 + i].item()) if c not in split_contigs else None) for i, c in enumerate(small)},
+           "session_rank0": {"batch_bytes": int(args.genome_batch_mb) << 20, "batches_per_pass": prog["batches"] // (steps + 2),
+                             "carry_bytes_per_pass": prog["carry_bytes"] // (steps + 2), "empty_batches": prog["empty_batches"],
+                             "pinned_bytes": prog["pinned_bytes"]},
+           "h2d_bytes_per_pass": (s1["h2d_bytes"] - s0["h2d_bytes"]) // steps, "d2h_bytes_per_pass": (s1["d2h_bytes"] - s0["d2h_bytes"]) // steps,
+           "gpu_launches_per_pass": (s1["kernel_launches"] - s0["kernel_launches"]) // steps,
+           "note": "per rank: bsgpu_bam_feed in 32 MiB slices from pinned host memory + bsgpu_bam_cut per region, results drained by a second thread; "
+                   "value = sites called on all ranks / max over ranks of the wall time of a pass"}
+    # ---- parity: the smallest contig against the reference's own chain + writer, record for record (rank 0 of a 1-GPU run)
+    if rank == 0 and world == 1 and not args.no_cpu and keep_small:
+        from oracle.bindings import Reference, bcf_diff, reference_available
+        from tests import blockgen
+        c = small[0]
+        r, lo, hi = [sp for sp in spans if sp[0].contig == c][0]
+        if reference_available():
+            ncores = os.cpu_count() or 1
+            impl = Reference(calc_threads=ncores)
+            sub = hbam.array[lo:hi].copy()
+            sg.patch_contig(sub, 0, rb)
+            hc = href[c].array
+            t0 = time.perf_counter()
+            cb, ct, _, _, cv = impl.read_input(sub, [lens[c]], [hc], run_chain=True)
+            cs = time.perf_counter() - t0
+            want = []
+            t0 = time.perf_counter()
+            for w in cb:
+                n_ = int(w["y"]) - int(w["x"]) + 1
+                wb_, _ = impl.print_block(cv[int(w["vcf_off"]):int(w["vcf_off"]) + n_], blockgen.window_codes(hc, int(w["x"]), int(w["y"]) + 2),
+                                          int(w["x"]), rid=c, ctg_end=lens[c])
+                want.append(wb_)
+            ws = time.perf_counter() - t0
+            diff = bcf_diff(np.concatenate(keep_small[c]), np.concatenate(want))
+            assert diff["records_a"] == diff["records_b"] == diff["fixed_equal"] and diff["order_violations"] == 0, diff
+            ccalled = int((cv["skip"] == 0).sum())
+            out["parity"] = {"contig": c, "positions": lens[c], "sites_called": ccalled, "blocks": len(cb), "records": diff["records_a"],
+                             "records_fixed_fields_equal": diff["fixed_equal"], "records_byte_identical": diff["identical"],
+                             "against": "reference read_input -> process_template_vector -> call_genotypes_ML -> print_vcf_entry (oracle/_ref/libbsref.so)"}
+            out["cpu_baseline"] = {"value": ccalled / (cs + ws), "unit": "sites/s", "cores": ncores, "kind": "reference",
+                                   "sample": "contig %d of the same genome (%d positions, %d sites called): the reference's chain on all cores (%.2f s) + its writer on one thread (%.2f s)" % (c, lens[c], ccalled, cs, ws)}
+    give_back(res)
+    sess.close()
+    hbam.free()
+    for h in href.values():
+        h.free()
     return out
 
 
@@ -437,13 +679,24 @@ def main():
     ap.add_argument("--sites", type=float, default=1e9, help="resident sites per GPU (config 2: 1e9)")
     ap.add_argument("--e2e-sites", type=float, default=8e6, help="sites per e2e step (host buffers)")
     ap.add_argument("--fused-sites", type=float, default=50e6, help="window of the block-path (pileup + model) measurement")
-    ap.add_argument("--bam-sites", type=float, default=8e6, help="window of the BAM-records-to-calls measurement (bsgpu_call_bam)")
+    ap.add_argument("--bam-sites", type=float, default=50e6, help="window of the BAM-records-to-calls measurement (bsgpu_call_bam): config 3 is 50 M")
+    ap.add_argument("--cpu-diff-records", type=float, default=0, help="records of that stream the CPU reference re-runs for the diff (0: all of them)")
+    ap.add_argument("--deep-sites", type=float, default=10e6, help="sites of the 500x panel (config 4: 10 Mb)")
+    ap.add_argument("--genome-scale", type=int, default=0, help="genome leg: hg38 contig lengths divided by this (0: by the host's free memory)")
+    ap.add_argument("--genome-batch-mb", type=int, default=384, help="genome leg: batch size of the streaming session")
+    ap.add_argument("--no-genome", action="store_true", help="skip the genome leg")
+    ap.add_argument("--legs", default="e2e,block,bam,writer,genome,cpu", help="secondary legs to run (comma separated)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.warmup < 3:
         args.warmup = 3
+    legs = set(args.legs.split(","))
+    import faulthandler
+    faulthandler.enable()
+    if os.environ.get("BENCH_WATCHDOG_S"):          # debugging aid: dump every thread's stack if the run takes longer than this
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG_S"]), exit=True)
 
     import numpy as np
     import torch
@@ -593,7 +846,10 @@ def main():
     block = None
     del d_out, d_skip
     torch.cuda.empty_cache()
+    log("headline %.3g sites/s, e2e %.3g sites/s; block path ..." % (value, e2e["value"]))
     try:
+        if "block" not in legs:
+            raise RuntimeError("leg skipped (--legs)")
         fsz = int(args.fused_sites)
         L, depth = 150, 30.0
         ns = gpu.synth_block_nseg(fsz, L, depth)
@@ -633,26 +889,42 @@ def main():
         block = {"workload": "synthetic %dx %d-bp bisulfite reads over a %d-site window (config 3 shape), device resident" % (int(depth), L, fsz),
                  "sites_called": fcalled,
                  "default": {"kernels": "k_bin_* + k_pileup_tile<pileup> -> pileup[] in HBM -> k_call_sites<vcf>", "ms": bms,
-                             "sites_per_s": fcalled / (bms * 1e-3), "roofline": roof(in_bytes + fsz * (104 + 104 + 1 + 208), bms)},
+                             "sites_per_s": fcalled / (bms * 1e-3), "roofline": dict(roof(in_bytes + fsz * (1 + 208), bms),
+                                 note="algorithmic bytes = SURVEY.md 8d fused figure (segments + bases + ref in, gt_vcf out); the pileup[] scratch between the two kernels "
+                                      "(104 B/site written and read back) is this implementation's own traffic and is not counted")},
                  "pileup_only": {"kernels": "k_bin_* + k_pileup_tile<pileup>", "ms": pms, "sites_per_s": fcalled / (pms * 1e-3),
                                  "roofline": roof(in_bytes + fsz * 104, pms)},
                  "fused_variant": {"kernels": "k_bin_* + k_pileup_tile<fused> (BSGPU_FUSED=1)", "ms": fms, "sites_per_s": fcalled / (fms * 1e-3),
                                    "roofline": roof(in_bytes + fsz * (1 + 208), fms)}}
-        # deep targeted panel (config 4 shape): 500x single-end 150-bp reads, the stress case for pileup accumulation
+        # deep targeted panel (config 4: 500x single-end 150-bp reads over 10 Mb), the stress case for pileup accumulation.  One
+        # window holds at most 4 Gi bases (32-bit offsets into bases[]), so the 10 Mb go through as windows of 2.5 Mb that
+        # share the device buffers; times are summed over the windows.
         try:
-            dsz, ddepth = int(min(fsz, 2_000_000)), 500.0
-            dns = gpu.synth_block_nseg(dsz, L, ddepth)
+            ddepth = 500.0
+            dtot = int(min(args.deep_sites, 10_000_000))
+            dwin = int(min(dtot, 2_500_000))
+            nwin = (dtot + dwin - 1) // dwin
+            dns = gpu.synth_block_nseg(dwin, L, ddepth)
             dd_seg = torch.empty(dns * 16 + 16, dtype=torch.uint8, device="cuda")
             dd_b = torch.empty(dns * L + 16, dtype=torch.uint8, device="cuda")
-            gpu.synth_block_dev(SEED + 99 + rank, 1000, dsz, L, ddepth, dd_seg.data_ptr(), dns, dd_b.data_ptr(), dns * L, d_r.data_ptr(), stream)
-            dpms = timed(lambda: gpu.pileup_block_dev(dd_seg.data_ptr(), dns, dd_b.data_ptr(), 1000, dsz, d_p.data_ptr(), stream))
-            dbms = timed(lambda: gpu.call_block_dev(dd_seg.data_ptr(), dns, dd_b.data_ptr(), d_r.data_ptr(), 1000, dsz, d_v.data_ptr(), stream))
-            dbytes = dns * (L + 16) + dsz * 104
-            block["deep_panel"] = {"workload": "synthetic %dx %d-bp reads over %d sites (config 4 shape), device resident" % (int(ddepth), L, dsz),
-                                   "pileup_only": {"ms": dpms, "sites_per_s": dsz / (dpms * 1e-3), "bases_per_s": dns * L / (dpms * 1e-3),
+            dpms = dbms = 0.0
+            dcalled = 0
+            for wi in range(nwin):
+                gpu.synth_block_dev(SEED + 99 + rank + 7 * wi, 1000, dwin, L, ddepth, dd_seg.data_ptr(), dns, dd_b.data_ptr(), dns * L, d_r.data_ptr(), stream)
+                dpms += timed(lambda: gpu.pileup_block_dev(dd_seg.data_ptr(), dns, dd_b.data_ptr(), 1000, dwin, d_p.data_ptr(), stream))
+                dbms += timed(lambda: gpu.call_block_dev(dd_seg.data_ptr(), dns, dd_b.data_ptr(), d_r.data_ptr(), 1000, dwin, d_v.data_ptr(), stream))
+                dcalled += int((d_v.view(torch.uint8)[201::208][:dwin] == 0).sum().item())
+            dsz = dwin * nwin
+            dbytes = nwin * (dns * (L + 16) + dwin * 104)
+            block["deep_panel"] = {"workload": "synthetic %dx %d-bp reads over %d sites in %d windows (config 4: 10 Mb panel), device resident" % (int(ddepth), L, dsz, nwin),
+                                   "sites_called": dcalled,
+                                   "pileup_only": {"ms": dpms, "sites_per_s": dsz / (dpms * 1e-3), "bases_per_s": nwin * dns * L / (dpms * 1e-3),
                                                    "roofline": {"bound": "hbm", "achieved": dbytes / (dpms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                                                 "frac": dbytes / (dpms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_site": dbytes / dsz}},
-                                   "default": {"ms": dbms, "sites_per_s": dsz / (dbms * 1e-3)},
+                                   "default": {"ms": dbms, "sites_per_s": dsz / (dbms * 1e-3),
+                                               "roofline": {"bound": "hbm", "achieved": (dbytes + dsz * 105) / (dbms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                                            "frac": (dbytes + dsz * 105) / (dbms * 1e-3) / 1e9 / peak,
+                                                            "algorithmic_bytes_per_site": (dbytes + dsz * 105) / dsz}},
                                    "envelope_overflow_sites": gpu.stats()["qsum_overflow"]}
             del dd_seg, dd_b
         except Exception as e:
@@ -730,7 +1002,10 @@ def main():
 
     # ---- the whole path from BAM records: decode -> blocks -> normalise -> pileup -> model (bsgpu_call_bam), host buffers
     bam = None
+    log("BAM records leg (config 3) ...")
     try:
+        if "bam" not in legs:
+            raise RuntimeError("leg skipped (--legs)")
         bam = bam_path(args, gpu, bslib, torch, np, stream, rank, world, local)
     except Exception as e:
         import traceback
@@ -738,16 +1013,31 @@ def main():
 
     # ---- the writer's derivations on the device: gt_vcf[] -> BCF records; count vectors -> BCF records end to end
     writer = None
+    log("writer leg ...")
     try:
         del d_pile, d_ref
         torch.cuda.empty_cache()
+        if "writer" not in legs:
+            raise RuntimeError("leg skipped (--legs)")
         writer = writer_path(args, gpu, bslib, torch, np, stream, rank, world, local)
     except Exception as e:
         import traceback
         writer = {"error": repr(e), "trace": traceback.format_exc()[-800:]}
 
+    # ---- the genome: 24 contigs sharded over the ranks, streaming sessions, ordered merge (strong scaling)
+    genome = None
+    log("genome leg (config 5 shape) ...")
+    if not args.no_genome and "genome" in legs:
+        try:
+            torch.cuda.empty_cache()
+            genome = genome_path(args, gpu, bslib, torch, np, stream, rank, world, local)
+        except Exception as e:
+            import traceback
+            genome = {"error": repr(e), "trace": traceback.format_exc()[-1200:]}
+
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    log("cpu baseline of the headline ...")
+    if rank == 0 and world == 1 and not args.no_cpu and "cpu" in legs:
         nthreads = os.cpu_count() or 1
         n_cpu = calibrate_cpu_sample(nthreads, 12.0)
         dt, kind, sample, called, _ = cpu_path(n_cpu, nthreads)
@@ -762,7 +1052,7 @@ def main():
                            "parallelism": "sites sharded over %d rank(s), no collective" % world, "host": numa_note,
                            "l2": "inputs larger than L2: each step streams %.1f GB of distinct records" % (n_sites * 105 / 1e9)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "block_path": block, "bam_path": bam, "writer_path": writer, "parity_spot_check": parity}
+                "block_path": block, "bam_path": bam, "writer_path": writer, "genome_path": genome, "parity_spot_check": parity}
         print(json.dumps(line))
     gpu.close()
     if world > 1:

@@ -131,6 +131,7 @@ struct bsgpu_ctx {
 	uint32_t ring_pos = 0;                       // next output ring slot of the deferred runs
 	bool ring_busy[3] = {false, false, false};   // output ring slot may still be copying out (deferred block_run)
 	bsgpu_stats stats;
+	uint64_t guard_base[4] = {0, 0, 0, 0};      // guard counters of the device before the last bsgpu_guard_read(reset)
 	int launches = 0;
 	// --report-file side channels (bsgpu_profile_enable)
 	bool profile_on = false;
@@ -225,8 +226,8 @@ int bsgpu_init(const bsgpu_params *p, bsgpu_ctx **out) {
 	}
 	CU(cudaMalloc(&c->d_const, sizeof(DevConst)));
 	CU(cudaMemcpy(c->d_const, &h, sizeof(h), cudaMemcpyHostToDevice));
-	CU(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
-	CU(cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long)));
+	CU(cudaMalloc(&c->d_counters, (kGuardList + kGuardCap) * sizeof(unsigned long long)));
+	CU(cudaMemset(c->d_counters, 0, (kGuardList + kGuardCap) * sizeof(unsigned long long)));
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 2; i++) {
@@ -274,11 +275,15 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 int bsgpu_get_stats(bsgpu_ctx *c, bsgpu_stats *out) {
 	if (!c || !out) return fail("bsgpu_get_stats: null argument");
 	CU(cudaSetDevice(c->device));
-	unsigned long long h[4];
+	unsigned long long h[8];
 	CU(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
 	c->stats.kernel_launches = (uint64_t)c->launches;
 	c->stats.sites_called = h[0];
 	c->stats.qsum_overflow = h[1];
+	c->stats.near_tie_sites = h[4] + c->guard_base[0];
+	c->stats.exact_tie_sites = h[5] + c->guard_base[1];
+	c->stats.near_qual_sites = h[6] + c->guard_base[2];
+	c->stats.near_fs_sites = h[7] + c->guard_base[3];
 	*out = c->stats;
 	return BSGPU_OK;
 }
@@ -410,6 +415,24 @@ int bsgpu_math_probe(const double *x, size_t n, double *out_log, double *out_exp
 	return BSGPU_OK;
 }
 
+// Sites whose result sits inside a guard band since the last reset: ids[k] = kind << 56 | site id, where the id is the
+// index of the site in the bsgpu_call_sites / _bcf call, or its position for the block and reader entry points.
+int bsgpu_guard_read(bsgpu_ctx *c, uint64_t *ids, size_t cap, size_t *n, int reset) {
+	if (!c || !n || (cap && !ids)) return fail("bsgpu_guard_read: null argument");
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());
+	unsigned long long h[kGuardList];
+	CU(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+	const size_t have = (size_t)std::min<unsigned long long>(h[8], (unsigned long long)kGuardCap);
+	*n = std::min(have, cap);
+	if (*n) CU(cudaMemcpy(ids, c->d_counters + kGuardList, *n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+	if (reset) {
+		for (int k = 0; k < 4; k++) c->guard_base[k] += h[4 + k];
+		CU(cudaMemset(c->d_counters + 4, 0, (kGuardList - 4) * sizeof(unsigned long long)));
+	}
+	return BSGPU_OK;
+}
+
 int bsgpu_sync(bsgpu_ctx *c) {
 	if (!c) return fail("bsgpu_sync: null context");
 	CU(cudaSetDevice(c->device));
@@ -439,7 +462,7 @@ int bsgpu_call_sites(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t *re
 		CU(s.skip.reserve(m));
 		CU(cudaMemcpyAsync(s.in.p, pileup + first, m * sizeof(bsgpu_pileup), cudaMemcpyHostToDevice, s.stream));
 		CU(cudaMemcpyAsync(s.ref.p, ref + first, m, cudaMemcpyHostToDevice, s.stream));
-		CU(launch_call_sites(s.in.p, s.ref.p, m, s.out.p, s.skip.p, false, c->d_const, c->d_counters, s.stream, &c->launches));
+		CU(launch_call_sites(s.in.p, s.ref.p, m, s.out.p, s.skip.p, false, c->d_const, c->d_counters, s.stream, &c->launches, first));
 		CU(cudaMemcpyAsync(out + first, s.out.p, m * sizeof(bsgpu_gt_meth), cudaMemcpyDeviceToHost, s.stream));
 		CU(cudaMemcpyAsync(skip + first, s.skip.p, m, cudaMemcpyDeviceToHost, s.stream));
 		c->stats.h2d_bytes += m * (sizeof(bsgpu_pileup) + 1);
@@ -463,7 +486,7 @@ static int call_bins(bsgpu_ctx *c, size_t nseg, const void *d_bases, const void 
 	const size_t site0 = (size_t)t0 * kPileTileSites;
 	const size_t nsite = (size_t)sz - site0 < (size_t)nt * kPileTileSites ? (size_t)sz - site0 : (size_t)nt * kPileTileSites;
 	CU(launch_pileup_tiles(c->scratch.p, nseg, d_bases, d_ref, x, sz, t0, nt, c->pile.p, 0, c->d_const, c->d_counters, st, &c->launches));
-	CU(launch_call_sites(c->pile.p, (const uint8_t *)d_ref + site0, nsite, dout, nullptr, true, c->d_const, c->d_counters, st, &c->launches));
+	CU(launch_call_sites(c->pile.p, (const uint8_t *)d_ref + site0, nsite, dout, nullptr, true, c->d_const, c->d_counters, st, &c->launches, (unsigned long long)x + site0));
 	return BSGPU_OK;
 }
 
@@ -628,7 +651,7 @@ static int bcf_run(bsgpu_ctx *c, const void *d_vcf, const void *d_ref, uint32_t 
 	CU(c->wr_site.reserve(bcf_site_scratch_bytes(sz)));
 	CU(c->wr_cta.reserve(bcf_cta_scratch_bytes(sz)));
 	BcfJob j;
-	j.d_vcf = d_vcf; j.d_ref = d_ref; j.x = x; j.sz = sz; j.d_blocks = nullptr; j.nblocks = 0; j.p = *p; j.dc = c->d_const;
+	j.d_vcf = d_vcf; j.d_ref = d_ref; j.x = x; j.sz = sz; j.d_blocks = nullptr; j.nblocks = 0; j.p = *p; j.dc = c->d_const; j.guard = c->d_counters;
 	j.site_scratch = c->wr_site.p;
 	CU(launch_bcf_records(j, 0, sz, c->wr_cta.p, d_out, out_cap, c->d_wr_totals, st, &c->launches));
 	CU(cudaMemcpyAsync(c->h_wr_totals, c->d_wr_totals, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -740,7 +763,7 @@ int bsgpu_call_sites_bcf(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t
 	for (auto &e : ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	auto E = [&](size_t k, int what) { return ev[4 * k + what]; };
 	BcfJob j;
-	j.d_ref = c->wr_ref.p; j.x = x; j.sz = (uint32_t)n; j.d_blocks = nullptr; j.nblocks = 0; j.p = *p; j.dc = c->d_const;
+	j.d_ref = c->wr_ref.p; j.x = x; j.sz = (uint32_t)n; j.d_blocks = nullptr; j.nblocks = 0; j.p = *p; j.dc = c->d_const; j.guard = c->d_counters;
 	j.site_scratch = c->wr_site.p;
 	CU(cudaMemcpyAsync(c->wr_ref.p, ref, n + 2, cudaMemcpyHostToDevice, up));
 	size_t at = 0, recs = 0;
@@ -1178,7 +1201,7 @@ static int call_window(bsgpu_ctx *c, const TmSpan *span, size_t nspan, size_t nt
 	BcfJob j;
 	j.d_vcf = c->wr_vcf.p; j.d_ref = c->ref.p; j.x = x; j.sz = sz; j.d_blocks = c->wr_blocks.p; j.nblocks = (uint32_t)nwb;
 	j.p = sink->p; j.p.rid = sink->vcf_rid ? sink->vcf_rid[tid] : (int32_t)tid; j.p.ctg_end = ctg_len;
-	j.dc = c->d_const; j.site_scratch = c->wr_site.p;
+	j.dc = c->d_const; j.guard = c->d_counters; j.site_scratch = c->wr_site.p;
 	if (sink->queued >= 3) CU(cudaStreamWaitEvent(c->stream, c->wr_copied[rslot], 0));      // the slot's previous records have left
 	CU(launch_bcf_records(j, 0, sz, c->wr_cta.p, c->wr_ring[rslot].p, rcap, c->d_wr_totals + 3 * (sink->queued & 7), c->stream, &c->launches));
 	CU(cudaMemcpyAsync(c->h_wr_totals + 3 * (sink->queued & 7), c->d_wr_totals + 3 * (sink->queued & 7), 3 * sizeof(unsigned long long),
@@ -1506,7 +1529,7 @@ int bsgpu_bam_open(bsgpu_ctx *c, int n_targets, const uint32_t *target_len, cons
 	SessHooks hk;
 	hk.user = s; hk.alloc = sess_pin; hk.release = sess_unpin; hk.thread_init = sess_thread_init; hk.run = sess_run;
 	// first guess of a batch's results: BCF records are about as many bytes as the BAM records they come from, gt_vcf[] four times that
-	if (!s->core.open(hk, batch_bytes, s->bcf ? batch_bytes : 4 * batch_bytes)) {
+	if (!s->core.open(hk, batch_bytes, s->bcf ? 1.0 : 4.2)) {
 		s->core.close();
 		delete s;
 		return fail("bsgpu_bam_open: cannot allocate page-locked staging for batches of %zu bytes", batch_bytes);

@@ -51,6 +51,14 @@ __device__ __forceinline__ double div_by(double a, double b, double r) {
 	return fma(fma(-q, b, a), r, q);
 }
 constexpr double kInvLn10 = 1.0 / kLn10;
+// Guard band of the genotype call: relative distance of the two best log-likelihoods below which the call is reported as
+// "may differ from the reference" (the parity bar on gt_prob[] itself is 1e-9 relative).  Entries of the guard list are
+// kind << 56 | site id; kinds: 1 the two best genotypes are closer than the band or EQUAL (the reference adds the same terms
+// in another order for some genotype pairs, so a tie here need not be a tie there), 2 QUAL / GQ within its band of an
+// integer, 3 FS within its band.
+constexpr double kTieBand = 1.0e-9;
+constexpr int kGuardCap = 65536;           // flagged sites listed per context between two reads (all of them are counted)
+constexpr int kGuardList = 16;             // d_counters[16 ..): the list; [8] = its length; [4] near ties, [5] exact ties, [6] QUAL, [7] FS
 
 // ---------------------------------------------------------------------------------------------------------------
 // Closed-form ML conversion fraction.  src/genotype_model.c:23-42.  Z is garbage (NaN) when a + b == 0; the caller
@@ -106,7 +114,7 @@ __device__ __forceinline__ int warp_offsets(int c, int lane, int *total) {
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int qual[8], int rf,
 		const DevConst *__restrict__ dc, const Tables *__restrict__ tb, double prob[10],
-		double *__restrict__ wbuf, int lane) {
+		double *__restrict__ wbuf, int lane, int *__restrict__ tie) {
 	const double (*__restrict__ qp)[4] = tb->qp;
 	const MathTables *__restrict__ mt = &tb->math;
 	double ll[10];
@@ -190,11 +198,20 @@ __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int q
 		ll[3] += half; ll[8] += half; ll[0] += kk; ll[2] += kk; ll[7] += kk;
 	}
 	__syncwarp();
-	// first strict maximum (:231-239)
-	double top = ll[0];
+	// first strict maximum (:231-239), and the runner-up for the guard band: the transcendental terms of ll[] are within
+	// 1.5 ulp of libm's, so the order of two genotypes whose likelihoods differ by less than kTieBand (relative) is not
+	// guaranteed to be the reference's.  Such sites are reported (bsgpu_stats.near_tie_sites, bsgpu_guard_read), not hidden.
+	double top = ll[0], second = -1.0e300;
 	int best = 0;
 #pragma unroll
-	for (int g = 1; g < 10; g++) if (ll[g] > top) { top = ll[g]; best = g; }
+	for (int g = 1; g < 10; g++) {
+		if (ll[g] > top) { second = top; top = ll[g]; best = g; }
+		else if (ll[g] > second) second = ll[g];
+	}
+	{
+		const double gap = top - second, mag = fabs(top) > 1.0 ? fabs(top) : 1.0;
+		*tie = gap == 0.0 ? 2 : gap <= kTieBand * mag ? 1 : 0;
+	}
 	// ---- exp() of the differences (:240-242), all ten evaluated straight: the table-driven exp is ~18 instructions, which is
 	// less than what pooling the 2-4 non-vanishing ones across the warp costs in mask / offset / shared-memory traffic
 	double sum = 0.0;
@@ -291,10 +308,11 @@ __device__ __forceinline__ double strand_bias(const SiteCounts &s, int max_gt, c
 // ---------------------------------------------------------------------------------------------------------------
 // Per-site body of call_thread (src/call_genotypes.c:43-115): summarise, model, strand bias; writes the 200-byte
 // gt_meth image as 25 eight-byte words into `rec` (a row of the CTA's staging tile in shared memory).
-// Returns false for a site with no counted base (record zeroed, the caller sets skip).
+// Returns false for a site with no counted base (record zeroed, the caller sets skip).  *tie: 0, 1 = the two best
+// genotypes are closer than the guard band (the call may differ from the reference's), 2 = they are exactly equal.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool call_site(const SiteCounts &s, int rf, const DevConst *__restrict__ dc,
-		const Tables *__restrict__ tb, uint64_t *rec, double *__restrict__ wbuf, int lane) {
+		const Tables *__restrict__ tb, uint64_t *rec, double *__restrict__ wbuf, int lane, int *__restrict__ tie) {
 	uint32_t tot[8];
 	int qual[8];
 	float tq = 0.0f;
@@ -311,9 +329,10 @@ __device__ __forceinline__ bool call_site(const SiteCounts &s, int rf, const Dev
 	}
 	// the whole warp runs the model together (a lane without counts contributes nothing to the pooled lists)
 	double prob[10];
-	const int best = genotype_model(tot, qual, rf, dc, tb, prob, wbuf, lane);
+	const int best = genotype_model(tot, qual, rf, dc, tb, prob, wbuf, lane, tie);
 	__syncwarp();                      // wbuf may alias this warp's output rows: everyone is done with it
 	if (!s.n) {
+		*tie = 0;
 #pragma unroll
 		for (int i = 0; i < 25; i++) rec[i] = 0;
 		return false;

@@ -96,11 +96,19 @@ __device__ __forceinline__ void store_tile(void *gdst, const uint64_t *stage, in
 // ------------------------------------------------------------------------------------------------
 constexpr int kCallTile = 128;
 
+// a site whose result sits inside a guard band: counted, and listed while the list has room
+// (tie: 1 = closer than the band, counted here; 2 = equal, counted by the caller per warp; both are listed as kind 1)
+__device__ __forceinline__ void guard_flag(unsigned long long *counters, int tie, unsigned long long id) {
+	if (tie == 1) atomicAdd(counters + 4, 1ull);
+	const unsigned long long k = atomicAdd(counters + 8, 1ull);
+	if (k < (unsigned long long)kGuardCap) counters[kGuardList + k] = 1ull << 56 | (id & 0x00ffffffffffffffull);
+}
+
 template <bool VCF, int MINB>
 __global__ void __launch_bounds__(kCallTile, MINB)
 k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref, size_t n,
 		uint8_t *__restrict__ out, uint8_t *__restrict__ skip, const DevConst *__restrict__ dc, int bulk_ok,
-		unsigned long long *__restrict__ counters) {
+		unsigned long long *__restrict__ counters, unsigned long long guard_base) {
 	constexpr int REC = VCF ? 208 : 200;
 	constexpr int RW = REC / 8;
 	extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -128,7 +136,7 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 	};
 	size_t tile = blockIdx.x;
 	if (tile < ntiles && tid == 0 && tile_bulk(tile)) issue(tile);
-	uint32_t phase = 0, ncalled = 0;
+	uint32_t phase = 0, ncalled = 0, nexact = 0;
 	for (; tile < ntiles; tile += gridDim.x) {
 		const size_t first = tile * kCallTile;
 		const int nrec = (int)min((size_t)kCallTile, n - first);
@@ -165,15 +173,20 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 		uint64_t *rec = stage + tid * RW;
 		// pooled-argument list of this warp: the (not yet written) output rows of its own 32 sites
 		double *wbuf = (double *)(stage + (tid & ~31) * RW);
-		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, tid & 31);
+		int tie;
+		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, tid & 31, &tie);
 		ncalled += called;
+		nexact += tie == 2;
+		if (tie) guard_flag(counters, tie, guard_base + first + tid);
 		if (VCF) rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
 		else if (tid < nrec) skip[first + tid] = called ? 0 : 1;
 		store_tile<REC>(out + first * REC, stage, nrec, bulk_ok, tid, kCallTile);
 	}
 	if (tid == 0) tma_store_wait();
 	ncalled = __reduce_add_sync(0xffffffffu, ncalled);
+	nexact = __reduce_add_sync(0xffffffffu, nexact);
 	if ((tid & 31) == 0 && ncalled) atomicAdd(counters, (unsigned long long)ncalled);
+	if ((tid & 31) == 0 && nexact) atomicAdd(counters + 5, (unsigned long long)nexact);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -512,7 +525,10 @@ k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_s
 		const int rf = tid < nrec ? ref[site0 + tid] : 0;
 		__syncthreads();                    // tables loaded (the candidate loop may not have run)
 		double *wbuf = (double *)(stage + (tid & ~31) * RW);
-		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, lane);
+		int tie;
+		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, lane, &tie);
+		if (tie) guard_flag(counters, tie, (unsigned long long)x + site0 + tid);
+		if (tie == 2) atomicAdd(counters + 5, 1ull);
 		rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
 		const uint32_t nc = __syncthreads_count(called);
 		if (tid == 0 && nc) atomicAdd(counters, (unsigned long long)nc);
@@ -757,7 +773,7 @@ cudaError_t configure_kernels() {
 }
 
 cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, void *out, void *skip, bool vcf,
-		const DevConst *dc, unsigned long long *counters, cudaStream_t stream, int *launches) {
+		const DevConst *dc, unsigned long long *counters, cudaStream_t stream, int *launches, unsigned long long guard_base) {
 	if (!n) return cudaSuccess;
 	const bool bulk_ok = (((uintptr_t)pileup | (uintptr_t)out) & 15u) == 0;
 	const size_t ntiles = (n + kCallTile - 1) / kCallTile;
@@ -767,11 +783,11 @@ cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, voi
 	const uint8_t *p = (const uint8_t *)pileup, *r = (const uint8_t *)ref;
 	uint8_t *o = (uint8_t *)out, *sk = (uint8_t *)skip;
 	if (vcf) {
-		if (five) k_call_sites<true, 5><<<grid, kCallTile, call_smem(true), stream>>>(p, r, n, o, nullptr, dc, bulk_ok, counters);
-		else k_call_sites<true, 4><<<grid, kCallTile, call_smem(true), stream>>>(p, r, n, o, nullptr, dc, bulk_ok, counters);
+		if (five) k_call_sites<true, 5><<<grid, kCallTile, call_smem(true), stream>>>(p, r, n, o, nullptr, dc, bulk_ok, counters, guard_base);
+		else k_call_sites<true, 4><<<grid, kCallTile, call_smem(true), stream>>>(p, r, n, o, nullptr, dc, bulk_ok, counters, guard_base);
 	} else {
-		if (five) k_call_sites<false, 5><<<grid, kCallTile, call_smem(false), stream>>>(p, r, n, o, sk, dc, bulk_ok, counters);
-		else k_call_sites<false, 4><<<grid, kCallTile, call_smem(false), stream>>>(p, r, n, o, sk, dc, bulk_ok, counters);
+		if (five) k_call_sites<false, 5><<<grid, kCallTile, call_smem(false), stream>>>(p, r, n, o, sk, dc, bulk_ok, counters, guard_base);
+		else k_call_sites<false, 4><<<grid, kCallTile, call_smem(false), stream>>>(p, r, n, o, sk, dc, bulk_ok, counters, guard_base);
 	}
 	*launches += 1;
 	LAUNCH_CHECK();

@@ -15,8 +15,9 @@ static_assert(sizeof(Seg) == 16, "segment record is 16 bytes");
 
 cudaError_t configure_kernels();
 
+// guard_base: id of site 0 of this launch in the guard list (bsgpu_guard_read)
 cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, void *out, void *skip, bool vcf,
-		const DevConst *dc, unsigned long long *counters, cudaStream_t stream, int *launches);
+		const DevConst *dc, unsigned long long *counters, cudaStream_t stream, int *launches, unsigned long long guard_base = 0);
 
 // scratch needed by the segment binning of one block
 size_t pileup_scratch_bytes(size_t nseg, uint32_t sz);
@@ -77,6 +78,7 @@ struct BcfJob {
 	bsgpu_bcf_params p;
 	const DevConst *dc;
 	void *site_scratch;              // bcf_site_scratch_bytes(sz)
+	unsigned long long *guard = nullptr;      // the context's counters: sites whose QUAL / FS sit inside their guard band are counted and listed
 };
 size_t bcf_site_scratch_bytes(uint32_t sz);
 size_t bcf_cta_scratch_bytes(uint32_t cnt);

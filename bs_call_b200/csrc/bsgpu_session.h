@@ -48,7 +48,8 @@ class Session {
 public:
 	struct Stage { uint8_t *p = nullptr; size_t cap = 0, head = 0, start = 0, fill = 0; };      // data = [start, fill); fed bytes from `head` on
 	SessHooks hk;
-	size_t batch_bytes = 0, first_result_cap = 0;
+	size_t batch_bytes = 0;
+	double result_ratio = 1.0;               // first guess of a batch's result bytes per input byte
 	Stage stage[2];
 	int w = 0;                               // staging buffer the caller fills
 	bool filling = false;                    // the caller is writing into stage[w] outside the lock
@@ -79,10 +80,10 @@ public:
 		return nb;
 	}
 
-	bool open(const SessHooks &hooks, size_t batch, size_t result_cap) {
+	bool open(const SessHooks &hooks, size_t batch, double ratio) {
 		hk = hooks;
 		batch_bytes = std::max<size_t>(batch, 4096);
-		first_result_cap = result_cap;
+		result_ratio = ratio;
 		for (int b = 0; b < 2; b++) if (!stage_fit(b, std::max<size_t>(batch_bytes / 8, 4096))) return false;
 		worker = std::thread([this] { run_worker(); });
 		return true;
@@ -288,16 +289,26 @@ private:
 			if (closing) return;
 			const int b = job_buf;
 			const bool final = job_final, whole = job_whole;
-			SessResult *r = nullptr;
-			if (!pool.empty()) { r = pool.back(); pool.pop_back(); }
 			const uint8_t *data = stage[b].p + stage[b].start;
 			const size_t len = stage[b].fill - stage[b].start;
+			// a result buffer from the pool: the smallest that holds the guess, else the largest there is (it grows)
+			const size_t guess = (size_t)((double)len * result_ratio) + 4096;
+			SessResult *r = nullptr;
+			{
+				size_t pick = pool.size();
+				for (size_t i = 0; i < pool.size(); i++) {
+					if (pick == pool.size()) { pick = i; continue; }
+					const size_t a = pool[i]->cap, c = pool[pick]->cap;
+					if (c >= guess ? (a >= guess && a < c) : a > c) pick = i;
+				}
+				if (pick < pool.size()) { r = pool[pick]; pool.erase(pool.begin() + pick); }
+			}
 			lk.unlock();
 			if (!r) r = new SessResult();
 			std::string err;
 			int rc = 0;
 			if (!r->buf) {
-				r->cap = first_result_cap + 4096;
+				r->cap = guess;
 				r->buf = hk.alloc(r->cap);
 				if (!r->buf) { r->cap = 0; rc = -1; err = "bsgpu_bam: cannot allocate page-locked result memory"; }
 			}

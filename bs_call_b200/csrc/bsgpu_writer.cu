@@ -44,8 +44,8 @@ static_assert(sizeof(GtVcf) == 208, "gt_vcf layout");
 
 enum { T_INT8 = 1, T_INT16 = 2, T_INT32 = 3, T_FLOAT = 5, T_CHAR = 7 };
 
-struct Count { uint32_t n = 0; __device__ __forceinline__ void put(uint32_t) { n++; } };
-struct Store { uint8_t *p; uint32_t n = 0; __device__ __forceinline__ void put(uint32_t c) { p[n++] = (uint8_t)c; } };
+struct Count { static constexpr bool kCounting = true; uint32_t n = 0; __device__ __forceinline__ void put(uint32_t) { n++; } };
+struct Store { static constexpr bool kCounting = false; uint8_t *p; uint32_t n = 0; __device__ __forceinline__ void put(uint32_t c) { p[n++] = (uint8_t)c; } };
 
 template <class W> __device__ __forceinline__ void put_le(W &w, uint32_t v, int bytes) { for (int b = 0; b < bytes; b++) w.put(v >> (8 * b)); }
 template <class W> __device__ void enc_size(W &w, int size, int type) {
@@ -113,7 +113,14 @@ struct WrArgs {
 	unsigned long long *totals;      // [0] bytes, [1] records, [2] sites whose record exceeded kMaxRec
 	uint8_t *out;
 	unsigned long long out_cap;
+	unsigned long long *guard;       // the context's counters (guard bands), or NULL
 };
+
+__device__ __forceinline__ void guard_note(unsigned long long *counters, int kind, unsigned long long id) {
+	atomicAdd(counters + 4 + kind, 1ull);
+	const unsigned long long k = atomicAdd(counters + 8, 1ull);
+	if (k < (unsigned long long)kGuardCap) counters[kGuardList + k] = (unsigned long long)kind << 56 | (id & 0x00ffffffffffffffull);
+}
 
 // block of site i: first / last site index; false when the site lies between blocks.  A site shared by two touching
 // blocks is the earlier block's (the later visit is dropped by the x <= old_x test, src/print_vcf.c:127).
@@ -163,8 +170,24 @@ __device__ __forceinline__ uint32_t build_record(const WrArgs &a, uint32_t i, ui
 	const double z1 = lp == 0.0 ? 1.0 : fast_exp(lp < -700.0 ? -700.0 : lp, mt);
 	int phred;
 	if (z1 >= 1.0) phred = 255;
-	else { phred = (int)(-10.0 * fast_log(1.0 - z1, mt) / kLn10); if (phred > 255) phred = 255; }
-	const int fs = (int)(-v->fisher_strand * 10.0 + 0.5);
+	else {
+		const double ph = -10.0 * fast_log(1.0 - z1, mt) / kLn10;
+		phred = (int)ph; if (phred > 255) phred = 255;
+		// Guard band (counted once, in the measuring pass): the posterior is within 1e-9 relative of the reference's, which
+		// moves 1 - z1 by |lp| 1e-9 + an ulp of 1 and ph by 10 / ln 10 times that relative change; a ph that close to an
+		// integer (below the 255 cap) may truncate differently.
+		if (W::kCounting && a.guard && ph < 255.5) {
+			const double band = 4.342944819 * (fabs(lp) * 1.0e-9 + 2.3e-16) / (1.0 - z1) + 1.0e-9 * ph + 1.0e-12;
+			const double fr = ph - floor(ph);
+			if (fr < band || 1.0 - fr < band) guard_note(a.guard, 2, (unsigned long long)a.x + i);
+		}
+	}
+	const double fsv = -v->fisher_strand * 10.0 + 0.5;
+	const int fs = (int)fsv;
+	if (W::kCounting && a.guard && is_het(gt)) {        // FS is only written for a het call; fisher_strand is within 1e-8 relative
+		const double band = fabs(fsv) * 1.0e-8 + 1.0e-12, fr = fsv - floor(fsv);
+		if (fr < band || 1.0 - fr < band) guard_note(a.guard, 3, (unsigned long long)a.x + i);
+	}
 	const uint32_t qd = dp1 > 0 ? (uint32_t)phred / dp1 : (uint32_t)phred;
 	uint32_t flt = 0;
 	if (phred < 20) flt |= 1;
@@ -437,6 +460,7 @@ static WrArgs writer_args(const BcfJob &j, uint32_t i0, uint32_t cnt) {
 	a.calls = (uint8_t *)j.site_scratch;
 	a.len = (uint16_t *)((uint8_t *)j.site_scratch + (((size_t)j.sz + 15) & ~(size_t)15));
 	a.cta_bytes = nullptr; a.cta_recs = nullptr; a.totals = nullptr; a.out = nullptr; a.out_cap = 0;
+	a.guard = j.guard;
 	return a;
 }
 

@@ -20,7 +20,7 @@ BSGPU_FAIL = -1
 # every symbol include/bsgpu.h declares (tests/test_abi.py checks the header and this list against the .so)
 EXPORTS = [
     "bsgpu_default_params", "bsgpu_init", "bsgpu_destroy", "bsgpu_last_error", "bsgpu_get_stats", "bsgpu_version",
-    "bsgpu_sync", "bsgpu_host_alloc", "bsgpu_host_free",
+    "bsgpu_sync", "bsgpu_guard_read", "bsgpu_host_alloc", "bsgpu_host_free",
     "bsgpu_call_sites", "bsgpu_pileup_block", "bsgpu_call_block", "bsgpu_stage_bound", "bsgpu_stage_templates",
     "bsgpu_process_block", "bsgpu_profile_enable", "bsgpu_profile_read", "bsgpu_build_blocks_tally",
     "bsgpu_call_bam_bcf", "bsgpu_default_bcf_params", "bsgpu_bcf_block", "bsgpu_bcf_block_dev", "bsgpu_call_block_bcf", "bsgpu_call_sites_bcf",
@@ -53,7 +53,8 @@ def reader_params(mapq_thresh=20, max_template_len=1000, keep_unmatched=False, i
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("sites", C.c_uint64), ("sites_called", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("qsum_overflow", C.c_uint64),
-                ("bam_decode_s", C.c_double), ("bam_build_s", C.c_double), ("bam_call_s", C.c_double)]
+                ("bam_decode_s", C.c_double), ("bam_build_s", C.c_double), ("bam_call_s", C.c_double),
+                ("near_tie_sites", C.c_uint64), ("exact_tie_sites", C.c_uint64), ("near_qual_sites", C.c_uint64), ("near_fs_sites", C.c_uint64)]
 
 
 PROFILE_MAX = 1024
@@ -180,6 +181,14 @@ class BsGpu:
 
     def sync(self):
         self._check(self.lib.bsgpu_sync(self.ctx))
+
+    def guard_read(self, reset=True):
+        """-> (kinds, ids) of the sites inside a guard band since the last reset (kind 1 call, 2 QUAL / GQ, 3 FS)"""
+        ids = np.zeros(65536, dtype=np.uint64)
+        n = C.c_size_t(0)
+        self._check(self.lib.bsgpu_guard_read(self.ctx, _ptr(ids), C.c_size_t(len(ids)), C.byref(n), C.c_int(1 if reset else 0)))
+        ids = ids[:n.value]
+        return (ids >> np.uint64(56)).astype(np.int64), (ids & np.uint64((1 << 56) - 1)).astype(np.int64)
 
     def stats(self):
         s = Stats()

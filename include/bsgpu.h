@@ -194,6 +194,15 @@ typedef struct {
 	/* wall time bsgpu_call_bam spent, accumulated: framing + H2D + record decode | descriptors D2H + block builder |
 	 * normalisation + pileup + model + D2H of gt_vcf[] */
 	double bam_decode_s, bam_build_s, bam_call_s;
+	/* Guard bands (hard part 1).  The device's log / exp are within 1.5 ulp of libm's, so a decision
+	 * that hangs on the last bits of a likelihood may fall the other way than in the reference.  Such sites are counted:
+	 * near_tie_sites   the two best genotype log-likelihoods differ by <= 1e-9 relative (src/genotype_model.c:231-239): max_gt,
+	 *                  hence GT, may differ; exact_tie_sites: they are EQUAL here (the reference sums the same terms in another
+	 *                  order for some genotype pairs, so it need not see a tie: listed as well)
+	 * near_qual_sites  QUAL / GQ before truncation lies within its error band of an integer (src/print_vcf.c:140-148)
+	 * near_fs_sites    FS before truncation lies within its error band of an integer (src/print_vcf.c:151)
+	 * bsgpu_guard_read lists them (up to 65536 between two resets). */
+	uint64_t near_tie_sites, exact_tie_sites, near_qual_sites, near_fs_sites;
 } bsgpu_stats;
 
 void bsgpu_default_params(bsgpu_params *p);
@@ -203,6 +212,9 @@ const char *bsgpu_last_error(void);
 int bsgpu_get_stats(bsgpu_ctx *ctx, bsgpu_stats *out);
 int bsgpu_version(void);
 int bsgpu_sync(bsgpu_ctx *ctx);              /* wait for everything queued on the context's device */
+/* the flagged sites since the last reset: ids[k] = kind << 56 | id; kind 1 near tie of the call, 2 QUAL / GQ, 3 FS; id = index
+ * of the site within the bsgpu_call_sites[_bcf] call, or its position for the block / reader entry points.  *n <= cap. */
+int bsgpu_guard_read(bsgpu_ctx *ctx, uint64_t *ids, size_t cap, size_t *n, int reset);
 
 /* page-locked host memory: arrays handed to the host-buffer entry points copy at full PCIe rate when they
  * come from here (any host pointer is accepted, pageable ones just copy slower) */

@@ -120,6 +120,21 @@ def _print_block(fn, vcf, refcodes, x, rid, ctg_end, vcf_ids, all_positions):
     return out[:nb.value].copy(), nr.value
 
 
+def bcf_diff(a, b):
+    """two BCF record streams -> dict(records_a, records_b, fixed_equal, identical, order_violations, first_diff)"""
+    path = os.path.join(HERE, "liboracle.so")
+    if not os.path.exists(path):
+        build_oracle()
+    lib = C.CDLL(path)
+    a = _c(a, np.uint8)
+    b = _c(b, np.uint8)
+    out = (C.c_longlong * 6)()
+    rc = lib.bso_bcf_diff(_p(a), C.c_size_t(len(a)), _p(b), C.c_size_t(len(b)), out)
+    if rc:
+        raise RuntimeError("bcf_diff: malformed record stream")
+    return dict(zip(("records_a", "records_b", "fixed_equal", "identical", "order_violations", "first_diff"), [int(v) for v in out]))
+
+
 class BsoParams(C.Structure):
     _fields_ = [("under_conv", C.c_double), ("over_conv", C.c_double), ("ref_bias", C.c_double),
                 ("left_trim", C.c_uint32 * 2), ("right_trim", C.c_uint32 * 2), ("min_qual", C.c_uint8)]

@@ -236,3 +236,45 @@ int bso_print_block(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes,
 	*nbytes = at; *nrec = n;
 	return 0;
 }
+
+/* Walks two BCF record streams side by side (test infrastructure for full-size diffs: Python cannot walk millions of
+ * records).  Counts records, records whose 32 leading bytes (lengths, CHROM, POS, rlen, QUAL, n_allele | n_info,
+ * n_fmt | n_sample) agree, records that agree byte for byte, and checks that POS never decreases within a CHROM in `a`.
+ * out[0] records in a, out[1] records in b, out[2] fixed part equal, out[3] identical, out[4] order violations in a,
+ * out[5] index of the first record that differs in its fixed part (or -1).  Returns 0, or -1 on a malformed stream. */
+int bso_bcf_diff(const uint8_t *a, size_t na, const uint8_t *b, size_t nb, long long *out) {
+	size_t ia = 0, ib = 0;
+	long long ra = 0, rb = 0, fixed = 0, same = 0, bad_order = 0, first_diff = -1;
+	int32_t last_chrom = -1, last_pos = -1;
+	while (ia < na || ib < nb) {
+		size_t la = 0, lb = 0;
+		if (ia < na) {
+			if (ia + 32 > na) return -1;
+			uint32_t s, i;
+			memcpy(&s, a + ia, 4); memcpy(&i, a + ia + 4, 4);
+			la = 8 + (size_t)s + i;
+			if (la < 32 || ia + la > na) return -1;
+			int32_t chrom, pos;
+			memcpy(&chrom, a + ia + 8, 4); memcpy(&pos, a + ia + 12, 4);
+			if (chrom == last_chrom && pos <= last_pos) bad_order++;
+			last_chrom = chrom; last_pos = pos;
+			ra++;
+		}
+		if (ib < nb) {
+			if (ib + 32 > nb) return -1;
+			uint32_t s, i;
+			memcpy(&s, b + ib, 4); memcpy(&i, b + ib + 4, 4);
+			lb = 8 + (size_t)s + i;
+			if (lb < 32 || ib + lb > nb) return -1;
+			rb++;
+		}
+		if (la && lb) {
+			if (!memcmp(a + ia, b + ib, 32)) fixed++;
+			else if (first_diff < 0) first_diff = ra - 1;
+			if (la == lb && !memcmp(a + ia, b + ib, la)) same++;
+		}
+		ia += la; ib += lb;
+	}
+	out[0] = ra; out[1] = rb; out[2] = fixed; out[3] = same; out[4] = bad_order; out[5] = first_diff;
+	return 0;
+}

@@ -160,7 +160,7 @@ int main(int argc, char **argv) {
 		rn.s = &s; rn.max_sleep_us = it % 2 ? 300 : 0;
 		SessHooks hk;
 		hk.user = &rn; hk.alloc = h_alloc; hk.release = h_free; hk.run = fake_run;
-		CHECK(s.open(hk, batch, it % 2 ? 100 : batch), "open");
+		CHECK(s.open(hk, batch, it % 2 ? 0.01 : 1.0), "open");
 		Collected c;
 		const size_t max_slice = (it % 3 == 0) ? 700 : (it % 3 == 1) ? 20000 : 1000000;
 		if (it % 2) drive_threads(s, v, rng, max_slice, cuts, c);
@@ -189,7 +189,7 @@ int main(int argc, char **argv) {
 		v.resize(v.size() - 3);
 		Runner rn; Session s; rn.s = &s;
 		SessHooks hk; hk.user = &rn; hk.alloc = h_alloc; hk.release = h_free; hk.run = fake_run;
-		CHECK(s.open(hk, 1 << 20, 1 << 20), "open");
+		CHECK(s.open(hk, 1 << 20, 1.0), "open");
 		std::string err; size_t took;
 		CHECK(s.feed(v.data(), v.size(), true, &took, &err) && took == v.size(), "feed");
 		CHECK(s.mark(true, &err), "finish");
@@ -202,7 +202,7 @@ int main(int argc, char **argv) {
 	{
 		Runner rn; Session s; rn.s = &s;
 		SessHooks hk; hk.user = &rn; hk.alloc = h_alloc; hk.release = h_free; hk.run = fake_run;
-		CHECK(s.open(hk, 4096, 4096), "open");
+		CHECK(s.open(hk, 4096, 1.0), "open");
 		std::string err; size_t took; uint8_t b[8] = {4, 0, 0, 0, 1, 2, 3, 4};
 		CHECK(!s.commit(1, &err), "commit without reserve");
 		CHECK(s.mark(true, &err), "finish");
