@@ -431,7 +431,18 @@ def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
     torch.cuda.empty_cache()
     log("genome: %d regions, %.2f GB of records on this rank, scale 1/%d" % (len(spans), nbytes_in / 1e9, scale))
     codes = [href[c].array if c in href else None for c in range(len(lens))]
-    sess = gpu.bam_session(np.array(lens, dtype=np.uint32), codes, bcf=True, batch_bytes=int(args.genome_batch_mb) << 20)
+    # Lanes: a session runs its batches one after the other (frame -> upload -> decode -> blocks -> windows), so ONE session
+    # leaves the device idle during the host stages of a batch.  --genome-sessions K opens K contexts + sessions on the GPU
+    # and deals the rank's regions out to them (longest first): the host stages of one lane run under the device stages of
+    # another.  Results stay per region, so the ordered merge is the same.
+    from bs_call_b200 import shard as _shard
+    nl = max(1, min(int(args.genome_sessions), len(spans)))
+    owner = _shard.lpt_assign([hi - lo for _, lo, hi in spans], nl)
+    lanes = []
+    for k in range(nl):
+        g = gpu if k == 0 else bslib.BsGpu(device=local)
+        lanes.append({"gpu": g, "spans": [sp for sp, o in zip(spans, owner) if o == k],
+                      "sess": g.bam_session(np.array(lens, dtype=np.uint32), codes, bcf=True, batch_bytes=int(args.genome_batch_mb) << 20)})
     SLICE = 32 << 20
 
     def barrier():
@@ -439,8 +450,8 @@ def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
         if world > 1:
             dist.barrier()
 
-    def one_pass(keep):
-        res, err = [], []
+    def lane_pass(lane, res, err):
+        sess = lane["sess"]
 
         def printer():
             try:
@@ -448,9 +459,7 @@ def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
                     got = sess.drain(wait=True)
                     if got is not None:
                         b, d, n, r = got
-                        res.append((b.copy(), d if keep else None, len(d), n, r))
-                        if not keep:
-                            sess.release(r)
+                        res.append((b.copy(), d, len(d), n, (sess, r)))
                     elif not sess.finished:
                         time.sleep(0.0002)
                     if sess.finished:
@@ -459,44 +468,59 @@ def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
                 err.append(e)
 
         th = threading.Thread(target=printer)
-        barrier()
-        t0 = time.perf_counter()
         th.start()
         try:
-            for r, lo, hi in spans:
+            for r, lo, hi in lane["spans"]:
                 for off in range(lo, hi, SLICE):
                     sess.feed(hbam.array[off:min(off + SLICE, hi)])
                 sess.cut()                       # a region ends where a block ends: no batch of results mixes two regions
             sess.finish()
+        except Exception as e:          # noqa: BLE001
+            err.append(e)
         finally:
             th.join()
+
+    def one_pass():
+        res, err = [[] for _ in lanes], []
+        barrier()
+        t0 = time.perf_counter()
+        ths = [threading.Thread(target=lane_pass, args=(ln, res[k], err)) for k, ln in enumerate(lanes)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
         dt = time.perf_counter() - t0
         if err:
             raise err[0]
-        return dt, res
+        return dt, [x for lst in res for x in lst]
 
     def give_back(res):
-        for _, _, _, _, r in res:
+        for _, _, _, _, (sess, r) in res:
             sess.release(r)
+        for ln in lanes:
+            ln["sess"].rewind()
 
-    # every pass keeps all its results lent out until it is over (they are the output of the run), so the session's pool of
-    # pinned result buffers reaches its final size during the warm-up passes
+    def all_stats():
+        st = [ln["gpu"].stats() for ln in lanes]
+        return {k: sum(x[k] for x in st) for k in st[0]}
+
+    # every pass keeps all its results lent out until it is over (they are the output of the run), so the sessions' pools of
+    # pinned result buffers reach their final size during the warm-up passes
     for _ in range(2):
-        dtw, res = one_pass(True)
+        dtw, res = one_pass()
         log("genome: warm-up pass %.3f s, %d result batches" % (dtw, len(res)))
         give_back(res)
-        sess.rewind()
-    s0 = gpu.stats()
+    s0 = all_stats()
     steps = 3
     dts = []
     for k in range(steps):
-        dt, res = one_pass(True)
+        dt, res = one_pass()
         dts.append(dt)
         if k < steps - 1:
             give_back(res)
-            sess.rewind()
-    s1 = gpu.stats()
-    prog = sess.progress()
+    s1 = all_stats()
+    progs = [ln["sess"].progress() for ln in lanes]
+    prog = {k: sum(x[k] for x in progs) for k in progs[0]}
     log("genome: timed passes %s s" % ", ".join("%.3f" % v for v in dts))
     dt = sum(dts) / steps
     called = (s1["sites_called"] - s0["sites_called"]) // steps
@@ -541,12 +565,12 @@ def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
            "plan": {"regions": sum(len(lst) for lst in plan), "contigs_split_at_block_boundaries": split_contigs,
                     "templates_per_rank": loads, "imbalance": max(loads) / (sum(loads) / len(loads))},
            "invariants": {"crc32_contig_%d" % c: (int(tot[5 + i].item()) if c not in split_contigs else None) for i, c in enumerate(small)},
-           "session_rank0": {"batch_bytes": int(args.genome_batch_mb) << 20, "batches_per_pass": prog["batches"] // (steps + 2),
+           "session_rank0": {"sessions_per_gpu": nl, "batch_bytes": int(args.genome_batch_mb) << 20, "batches_per_pass": prog["batches"] // (steps + 2),
                              "carry_bytes_per_pass": prog["carry_bytes"] // (steps + 2), "empty_batches": prog["empty_batches"],
                              "pinned_bytes": prog["pinned_bytes"]},
            "h2d_bytes_per_pass": (s1["h2d_bytes"] - s0["h2d_bytes"]) // steps, "d2h_bytes_per_pass": (s1["d2h_bytes"] - s0["d2h_bytes"]) // steps,
            "gpu_launches_per_pass": (s1["kernel_launches"] - s0["kernel_launches"]) // steps,
-           "note": "per rank: bsgpu_bam_feed in 32 MiB slices from pinned host memory + bsgpu_bam_cut per region, results drained by a second thread; "
+           "note": "per rank: %d session(s), each fed by bsgpu_bam_feed in 32 MiB slices from pinned host memory + bsgpu_bam_cut per region and drained by a thread of its own; " % nl +
                    "value = sites called on all ranks / max over ranks of the wall time of a pass"}
     # ---- parity: the smallest contig against the reference's own chain + writer, record for record (rank 0 of a 1-GPU run)
     if rank == 0 and world == 1 and not args.no_cpu and keep_small:
@@ -579,8 +603,12 @@ def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
                              "against": "reference read_input -> process_template_vector -> call_genotypes_ML -> print_vcf_entry (oracle/_ref/libbsref.so)"}
             out["cpu_baseline"] = {"value": ccalled / (cs + ws), "unit": "sites/s", "cores": ncores, "kind": "reference",
                                    "sample": "contig %d of the same genome (%d positions, %d sites called): the reference's chain on all cores (%.2f s) + its writer on one thread (%.2f s)" % (c, lens[c], ccalled, cs, ws)}
-    give_back(res)
-    sess.close()
+    for _, _, _, _, (sess, r) in res:
+        sess.release(r)
+    for k, ln in enumerate(lanes):
+        ln["sess"].close()
+        if k:
+            ln["gpu"].close()
     hbam.free()
     for h in href.values():
         h.free()
@@ -684,6 +712,7 @@ def main():
     ap.add_argument("--deep-sites", type=float, default=10e6, help="sites of the 500x panel (config 4: 10 Mb)")
     ap.add_argument("--genome-scale", type=int, default=0, help="genome leg: hg38 contig lengths divided by this (0: by the host's free memory)")
     ap.add_argument("--genome-batch-mb", type=int, default=384, help="genome leg: batch size of the streaming session")
+    ap.add_argument("--genome-sessions", type=int, default=1, help="genome leg: sessions (contexts) per GPU, regions dealt out between them (experimental: >1 needs BSGPU_SERIALIZE_SESSIONS=1 today)")
     ap.add_argument("--no-genome", action="store_true", help="skip the genome leg")
     ap.add_argument("--legs", default="e2e,block,bam,writer,genome,cpu", help="secondary legs to run (comma separated)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -1498,6 +1498,11 @@ static int sess_run(void *user, const uint8_t *data, size_t len, bool whole, Ses
 	o.partial = !whole; o.blocks_vec = &r->blocks; o.grow = Session::grow; o.user = &g;
 	size_t nblk = 0, nvcf = 0;
 	int rc;
+	// BSGPU_SERIALIZE_SESSIONS=1 (debugging aid): the batches of all sessions of the process run one at a time
+	static std::mutex serial;
+	static const bool serialize = getenv("BSGPU_SERIALIZE_SESSIONS") != nullptr;
+	std::unique_lock<std::mutex> sl(serial, std::defer_lock);
+	if (serialize) sl.lock();
 	if (s->bcf) {
 		BcfSink sink;
 		sink.p = s->bp; sink.vcf_rid = s->rid.empty() ? nullptr : s->rid.data(); sink.out = r->buf; sink.out_cap = r->cap;
