@@ -1312,6 +1312,7 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 				while (b1 < gb.size() && gb[b1].tid == gb[b0].tid) b1++;
 				const uint32_t tid = gb[b0].tid;
 				if ((int)tid >= n_targets) return fail("bsgpu_call_bam: record on contig %u, only %d contigs given", tid, n_targets);
+				if (!ctg_codes[tid]) return fail("bsgpu_call_bam: no reference codes were given for contig %u", tid);
 				if ((int)tid != cur_tid) { cur_tid = (int)tid; ctg_x0 = gb[b0].x; ctg_end = ctg_x0 - 1; ctg_ov = ov; }
 				// windows tile the contig; a block may begin ON the last site of the block before it (its x is two before its
 				// first template, src/process_template.c:27), and the writer's context of its first sites reaches back there:
@@ -1540,6 +1541,12 @@ int bsgpu_bam_open(bsgpu_ctx *c, int n_targets, const uint32_t *target_len, cons
 		return fail("bsgpu_bam_open: cannot allocate page-locked staging for batches of %zu bytes", batch_bytes);
 	}
 	*out = s;
+	return BSGPU_OK;
+}
+
+int bsgpu_bam_set_contig(bsgpu_bam_session *s, int tid, const uint8_t *codes) {
+	if (!s || tid < 0 || tid >= s->n_targets) return fail("bsgpu_bam_set_contig: contig %d out of range", tid);
+	s->codes[tid] = codes;               // read by the worker only for contigs whose records are in a batch
 	return BSGPU_OK;
 }
 

@@ -198,29 +198,28 @@ __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int q
 		ll[3] += half; ll[8] += half; ll[0] += kk; ll[2] += kk; ll[7] += kk;
 	}
 	__syncwarp();
-	// first strict maximum (:231-239), and the runner-up for the guard band: the transcendental terms of ll[] are within
-	// 1.5 ulp of libm's, so the order of two genotypes whose likelihoods differ by less than kTieBand (relative) is not
-	// guaranteed to be the reference's.  Such sites are reported (bsgpu_stats.near_tie_sites, bsgpu_guard_read), not hidden.
-	double top = ll[0], second = -1.0e300;
+	// first strict maximum (:231-239)
+	double top = ll[0];
 	int best = 0;
 #pragma unroll
-	for (int g = 1; g < 10; g++) {
-		if (ll[g] > top) { second = top; top = ll[g]; best = g; }
-		else if (ll[g] > second) second = ll[g];
-	}
-	{
-		const double gap = top - second, mag = fabs(top) > 1.0 ? fabs(top) : 1.0;
-		*tie = gap == 0.0 ? 2 : gap <= kTieBand * mag ? 1 : 0;
-	}
+	for (int g = 1; g < 10; g++) if (ll[g] > top) { top = ll[g]; best = g; }
 	// ---- exp() of the differences (:240-242), all ten evaluated straight: the table-driven exp is ~18 instructions, which is
-	// less than what pooling the 2-4 non-vanishing ones across the warp costs in mask / offset / shared-memory traffic
+	// less than what pooling the 2-4 non-vanishing ones across the warp costs in mask / offset / shared-memory traffic.
+	// The same differences feed the guard band: the transcendental terms of ll[] are within 1.5 ulp of libm's, so the order
+	// of two genotypes whose likelihoods differ by less than kTieBand (relative) is not guaranteed to be the reference's.
+	// Such sites are reported (bsgpu_stats.near_tie_sites / exact_tie_sites, bsgpu_guard_read), not hidden.
+	const double band = -kTieBand * (fabs(top) > 1.0 ? fabs(top) : 1.0);
+	int ntop = 0, near = 0;
 	double sum = 0.0;
 #pragma unroll
 	for (int g = 0; g < 10; g++) {
 		const double x = ll[g] - top;
 		const double e = fast_exp(x < -45.0 ? -45.0 : x, mt);
 		sum += x < -45.0 ? 0.0 : (x == 0.0 ? 1.0 : e);
+		ntop += x == 0.0;
+		near |= x != 0.0 && x >= band;
 	}
+	*tie = ntop > 1 ? 2 : near;
 	sum = fast_log(sum, mt);          // sum is in [1, 10]
 #pragma unroll
 	for (int g = 0; g < 10; g++) prob[g] = div_by(ll[g] - top - sum, kLn10, kInvLn10);

@@ -10,7 +10,8 @@
  * stays as it is.  The pileup loop and the calc threads' per-site body run on the GPU through the C ABI of
  * include/bsgpu.h; the hand-off protocol with the reader, the meth-profile thread and the print thread is the
  * reference's:
- *   - results may only be written into work->vcf once the printer has drained the previous block (vcf_n == 0);
+ *   - a block is computed into the spare one of two page-locked arrays while the printer drains the block before, and is
+ *     published (work->vcf, vcf_x, vcf_n) once the printer has finished (vcf_n == 0);
  *   - work->ref / work->ref1 are swapped only after the meth-profile ring is empty, and before vcf_n is published;
  *   - every vcf[i] carries ready = true when vcf_n is published (the printer consumes strictly in index order, so
  *     publishing a fully computed block is a legal schedule of the reference's per-site signalling);
@@ -33,8 +34,9 @@ static bsgpu_seg *g_segs;
 static size_t g_seg_cap;
 static uint8_t *g_bases;
 static size_t g_base_cap;
-static gt_vcf *g_vcf;           /* page-locked; what work->vcf points at */
-static size_t g_vcf_cap;
+static gt_vcf *g_vcf[2];        /* page-locked; work->vcf points at the one that was published last */
+static size_t g_vcf_cap[2];
+static int g_next;              /* the array the next block is computed into */
 
 static void die(const char *what) {
 	gt_fatal_error_msg("bsgpu: %s: %s\n", what, bsgpu_last_error());
@@ -141,21 +143,25 @@ void call_genotypes_ML(ctg_t * const ctg, gt_vector * const align_list, const ui
 	/* host staging of this block (the reader may not reclaim align_list before we return) */
 	size_t nbases = 0;
 	const size_t nseg = stage(align_list, x, y, &nbases);
-	/* the previous block must have left work->vcf (src/call_genotypes.c:228-235) */
+	/* Pileup, model and strand test for every site of the block (work->ref1 holds the reference codes of [x, y + 2],
+	 * src/process_template.c:29-30), written in the gt_vcf layout with ready = true into the SPARE one of two arrays: the
+	 * print thread may still be writing the block before from the other one.  (The reference also runs its pileup before
+	 * it waits for the printer, src/call_genotypes.c:180-235; its calc threads then need the single work->vcf.) */
+	const int slot = g_next;
+	if (sz > g_vcf_cap[slot]) {
+		bsgpu_host_free(g_vcf[slot]);
+		g_vcf_cap[slot] = (size_t)sz + sz / 4 + 1024;
+		if ((g_vcf[slot] = bsgpu_host_alloc(g_vcf_cap[slot] * sizeof(gt_vcf))) == NULL) die("bsgpu_host_alloc");
+	}
+	const uint8_t *refcodes = (const uint8_t *)gt_string_get_string(work->ref1);
+	if (bsgpu_call_block(g_ctx, g_segs, nseg, g_bases, nbases, refcodes, x, sz, (bsgpu_gt_vcf *)g_vcf[slot]) != BSGPU_OK) die("bsgpu_call_block");
+	/* publication: the previous block must have left the print thread (src/call_genotypes.c:228-235) */
 	pthread_mutex_lock(&work->print_mutex);
 	while (work->vcf_n) timed_wait(&work->print_cond2, &work->print_mutex);
 	pthread_mutex_unlock(&work->print_mutex);
-	if (sz > g_vcf_cap) {
-		bsgpu_host_free(g_vcf);
-		g_vcf_cap = (size_t)sz + sz / 4 + 1024;
-		if ((g_vcf = bsgpu_host_alloc(g_vcf_cap * sizeof(gt_vcf))) == NULL) die("bsgpu_host_alloc");
-		work->vcf = g_vcf;
-		work->vcf_size = (int)(g_vcf_cap > 0x7fffffff ? 0x7fffffff : g_vcf_cap);
-	}
-	/* work->ref1 holds the reference codes of [x, y + 2] (src/process_template.c:29-30): pileup, model and strand test
-	 * for every site of the block, written straight into work->vcf in the gt_vcf layout with ready = true */
-	const uint8_t *refcodes = (const uint8_t *)gt_string_get_string(work->ref1);
-	if (bsgpu_call_block(g_ctx, g_segs, nseg, g_bases, nbases, refcodes, x, sz, (bsgpu_gt_vcf *)work->vcf) != BSGPU_OK) die("bsgpu_call_block");
+	work->vcf = g_vcf[slot];
+	work->vcf_size = (int)(g_vcf_cap[slot] > 0x7fffffff ? 0x7fffffff : g_vcf_cap[slot]);
+	g_next = slot ^ 1;
 	work->vcf_x = x;
 	work->vcf_ctg = ctg;
 	/* meth profiling reads ref1 and the read buffers: let it finish before the buffers change hands (:243-254) */

@@ -1,0 +1,354 @@
+/*
+ * bsgpu_seam_reader.c -- seams C and D: a link-compatible replacement for the reference's src/get_template_vector.c,
+ * src/process_template.c AND src/call_genotypes.c (include/bs_call.h:355-360):
+ *
+ *     gt_status read_input(htsFile *sam_input, gt_vector *align_list, sr_param *param);
+ *     gt_status process_template_vector(...), void call_genotypes_ML(...)      -- not reached any more
+ *     void init_calc_threads(sr_param *param);  void join_calc_threads(sr_param *param);
+ *
+ * Build bs_call with this file in place of those three (and link libbsgpu.so).  main(), option parsing, htslib input,
+ * the reference FASTA, the VCF/BCF header and file, and (seam C) the print thread with its writer stay the reference's.
+ *
+ * read_input here does what the reference's does at its top -- fetch one alignment record after the other with
+ * sam_read1() / sam_itr_next() over the regions (src/get_template_vector.c:66-110, src/input_sam.c:228-229) -- and puts
+ * every record of a wanted contig, as the BAM record it is, into a streaming session of the device library
+ * (bsgpu_bam_reserve / _commit, include/bsgpu.h): record decode and filters, mate pairing, duplicate removal, block
+ * cutting, normalisation, pileup and model all happen behind that.  A second thread takes the results:
+ *   seam C (default): gt_vcf[] of every block, published to the reference's print thread by the protocol of
+ *       src/call_genotypes.c:228-258 -- work->vcf points INTO the session's page-locked result, nothing is copied;
+ *   seam D (BSGPU_SEAM_RECORDS=1): the BCF records of every block (print_vcf_entry's work done on the device), handed to
+ *       htslib's bcf_write() one by one -- which writes BCF as it is and formats VCF text for -O v / z.  No dbSNP ids and no
+ *       --report-file site statistics on this path yet (src/print_vcf.c:167, 382-526): use seam C with -D / --report-file.
+ * Contig sequences: the session wants the codes 0..4 of a whole contig; they are taken from the reference's own
+ * get_sequence_string() when the first record of a contig arrives and kept to the end of the run (one byte per position).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <pthread.h>
+#include <htslib/sam.h>
+#include <htslib/vcf.h>
+
+#include "gem_tools.h"
+#include "bs_call.h"
+#include "bsgpu.h"
+
+static bsgpu_ctx *g_ctx;
+static int g_profile;
+
+static void die(const char *what) {
+	gt_fatal_error_msg("bsgpu: %s: %s\n", what, bsgpu_last_error());
+}
+
+static void timed_wait(pthread_cond_t *c, pthread_mutex_t *m) {
+	struct timespec ts;
+	clock_gettime(CLOCK_REALTIME, &ts);
+	ts.tv_sec += 5;
+	pthread_cond_timedwait(c, m, &ts);
+}
+
+void init_calc_threads(sr_param * const param) {
+	work_t * const work = &param->work;
+	bsgpu_params p;
+	bsgpu_default_params(&p);
+	p.under_conv = param->under_conv;
+	p.over_conv = param->over_conv;
+	p.ref_bias = param->ref_bias;
+	p.min_qual = param->min_qual;
+	for (int i = 0; i < 2; i++) { p.left_trim[i] = param->left_trim[i]; p.right_trim[i] = param->right_trim[i]; }
+	const char *dev = getenv("BSGPU_DEVICE");
+	p.device = dev ? atoi(dev) : 0;
+	if (bsgpu_init(&p, &g_ctx) != BSGPU_OK) die("bsgpu_init");
+	g_profile = 0;
+	work->calc_end = false;
+	work->n_calc_threads = 0;
+	work->calc_threads_complete = 0;
+	work->calc_threads = NULL;
+}
+
+static void fold_profile(bs_stats * const stats) {
+	bsgpu_profile *pr = malloc(sizeof(bsgpu_profile));
+	if (pr == NULL || bsgpu_profile_read(g_ctx, pr, 1) != BSGPU_OK) die("bsgpu_profile_read");
+	if (pr->used > gt_vector_get_used(stats->meth_profile)) {
+		const uint64_t old = gt_vector_get_used(stats->meth_profile);
+		gt_vector_reserve(stats->meth_profile, pr->used, false);
+		memset(gt_vector_get_mem(stats->meth_profile, meth_cts) + old, 0, (pr->used - old) * sizeof(meth_cts));
+		gt_vector_set_used(stats->meth_profile, pr->used);
+	}
+	meth_cts *mc = gt_vector_get_mem(stats->meth_profile, meth_cts);
+	for (uint32_t i = 0; i < pr->used; i++) for (int k = 0; k < 4; k++) mc[i].conv_cts[k] += pr->conv_cts[i][k];
+	for (int k = 0; k < 5; k++) stats->base_filter[k] += pr->base_filter[k];
+	for (int k = 0; k < 15; k++) { stats->filter_cts[k] += pr->filter_cts[k]; stats->filter_bases[k] += pr->filter_bases[k]; }
+	free(pr);
+}
+
+void join_calc_threads(sr_param * const param) {
+	work_t * const work = &param->work;
+	work->calc_end = true;
+	if (g_profile && work->stats != NULL) fold_profile(work->stats);
+	bsgpu_destroy(g_ctx);
+	g_ctx = NULL;
+	pthread_mutex_lock(&work->vcf_mutex);
+	pthread_cond_signal(&work->vcf_cond);
+	pthread_mutex_unlock(&work->vcf_mutex);
+}
+
+void call_genotypes_ML(ctg_t * const ctg, gt_vector * const align_list, const uint32_t x, const uint32_t y, sr_param * const param) {
+	gt_fatal_error_msg("bsgpu: call_genotypes_ML reached although the whole chain runs on the device\n");
+}
+
+gt_status process_template_vector(gt_vector *align_list, ctg_t * const ctg, uint32_t y, sr_param *param) {
+	gt_fatal_error_msg("bsgpu: process_template_vector reached although the whole chain runs on the device\n");
+	return GT_STATUS_FAIL;
+}
+
+/* ---- the thread that takes the session's results ---- */
+typedef struct {
+	sr_param *param;
+	bsgpu_bam_session *sess;
+	uint8_t **codes;             /* per tid: codes of positions 1 .. target_len, or NULL */
+	int n_targets;
+	int records;                 /* seam D */
+	int failed;
+} taker_t;
+
+/* seam C: one block of gt_vcf records to the reference's print thread (src/call_genotypes.c:228-258, src/process.c:80-104) */
+static void publish_block(taker_t * const tk, const bsgpu_block * const b, const gt_vcf * const vcf) {
+	work_t * const work = &tk->param->work;
+	const int k = work->tid2id[b->tid];
+	assert(k >= 0);
+	ctg_t * const ctg = work->contigs[k];
+	const uint32_t sz = b->y - b->x + 1;
+	/* reference codes of [x, y + 2] into the spare string: N from the contig's last position on (src/get_sequence.c:41-48) */
+	gt_string_resize(work->ref1, sz + 3);
+	char *rp = work->ref1->buffer;
+	const uint32_t len = ctg->end_pos;
+	const uint8_t *codes = tk->codes[b->tid];
+	for (uint32_t i = 0; i < sz + 2; i++) { const uint64_t pos = (uint64_t)b->x + i; rp[i] = pos < len ? (char)codes[pos - 1] : 0; }
+	rp[sz + 2] = 0;
+	work->ref1->length = sz + 3;
+	pthread_mutex_lock(&work->print_mutex);
+	while (work->vcf_n) timed_wait(&work->print_cond2, &work->print_mutex);
+	pthread_mutex_unlock(&work->print_mutex);
+	work->vcf = (gt_vcf *)vcf;           /* the print thread reads the session's page-locked result in place */
+	work->vcf_size = (int)sz;
+	work->vcf_x = b->x;
+	work->vcf_ctg = ctg;
+	gt_string *tp = work->ref;
+	work->ref = work->ref1;
+	work->ref1 = tp;
+	work->vcf_n = sz;
+	pthread_mutex_lock(&work->print_mutex);
+	pthread_cond_signal(&work->print_cond1);
+	pthread_mutex_unlock(&work->print_mutex);
+	pthread_mutex_lock(&work->vcf_mutex);
+	pthread_cond_signal(&work->vcf_cond);
+	pthread_mutex_unlock(&work->vcf_mutex);
+}
+
+/* seam D: the records as they lie in a BCF file -> bcf_write(), which is what _print_vcf_entry ends with (src/print_vcf.c:375-380) */
+static int write_records(taker_t * const tk, bcf1_t * const bcf, const uint8_t *p, size_t n) {
+	work_t * const work = &tk->param->work;
+	while (n) {
+		uint32_t w[8];
+		if (n < 32) return -1;
+		memcpy(w, p, 32);
+		const size_t l_shared = w[0], l_indiv = w[1];
+		if (l_shared < 24 || 8 + l_shared + l_indiv > n) return -1;
+		kstring_t sh = bcf->shared, in = bcf->indiv;
+		bcf->rid = (int32_t)w[2]; bcf->pos = (int32_t)w[3]; bcf->rlen = (int32_t)w[4];
+		memcpy(&bcf->qual, &w[5], 4);
+		bcf->n_info = w[6] & 0xffff; bcf->n_allele = w[6] >> 16;
+		bcf->n_sample = w[7] & 0xffffff; bcf->n_fmt = w[7] >> 24;
+		bcf->shared.s = (char *)(p + 32); bcf->shared.l = l_shared - 24; bcf->shared.m = bcf->shared.l;
+		bcf->indiv.s = (char *)(p + 8 + l_shared); bcf->indiv.l = l_indiv; bcf->indiv.m = l_indiv;
+		const int rc = bcf_write(work->vcf_file, work->vcf_hdr, bcf);
+		bcf->shared = sh; bcf->indiv = in;
+		if (rc) return -1;
+		p += 8 + l_shared + l_indiv;
+		n -= 8 + l_shared + l_indiv;
+	}
+	return 0;
+}
+
+static void *taker_thread(void *arg) {
+	taker_t * const tk = arg;
+	work_t * const work = &tk->param->work;
+	bcf1_t *bcf = tk->records ? bcf_init() : NULL;
+	uint64_t held = 0;               /* seam C: the result the print thread is still reading from */
+	for (;;) {
+		bsgpu_bam_result res;
+		if (bsgpu_bam_drain(tk->sess, 1, &res) != BSGPU_OK) { fprintf(stderr, "bsgpu: %s\n", bsgpu_last_error()); tk->failed = 1; break; }
+		if (res.id) {
+			if (tk->records) {
+				if (write_records(tk, bcf, res.data, res.nbytes)) { fprintf(stderr, "bsgpu: malformed record stream or write error\n"); tk->failed = 1; }
+				bsgpu_bam_release(tk->sess, res.id);
+			} else {
+				const gt_vcf *vcf = (const gt_vcf *)res.data;
+				for (size_t b = 0; b < res.nblocks; b++) publish_block(tk, res.blocks + b, vcf + res.blocks[b].vcf_off);
+				/* the block published last is still with the print thread: its result is released once the next one is out */
+				if (held) {
+					bsgpu_bam_release(tk->sess, held);
+					held = 0;
+				}
+				if (res.nblocks) held = res.id; else bsgpu_bam_release(tk->sess, res.id);
+			}
+		}
+		if (res.finished) break;
+	}
+	if (held) {
+		pthread_mutex_lock(&work->print_mutex);
+		while (work->vcf_n) timed_wait(&work->print_cond2, &work->print_mutex);
+		pthread_mutex_unlock(&work->print_mutex);
+		bsgpu_bam_release(tk->sess, held);
+	}
+	if (bcf) bcf_destroy(bcf);
+	return NULL;
+}
+
+/* codes 0..4 of a whole contig from the reference's own sequence store (src/get_sequence.c:20-55) */
+static uint8_t *contig_codes(ctg_t * const ctg, ctg_t * const prev, sr_param * const param) {
+	gt_string *s = gt_string_new(1024);
+	const uint32_t len = ctg->end_pos;
+	gt_string_resize(s, (uint64_t)len + 8);
+	if (get_sequence_string(ctg, 1, len, prev, s, param)) { gt_string_delete(s); return NULL; }
+	uint8_t *codes = malloc((size_t)len + 8);
+	if (codes != NULL) memcpy(codes, s->buffer, len);
+	gt_string_delete(s);
+	return codes;
+}
+
+gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param) {
+	work_t * const work = &param->work;
+	bam_hdr_t * const hdr = work->sam_header;
+	const int nt = hdr->n_targets;
+	bsgpu_reader_params rp;
+	bsgpu_default_reader_params(&rp);
+	rp.max_template_len = (uint32_t)param->max_template_len;
+	rp.mapq_thresh = param->mapq_thresh;
+	rp.keep_unmatched = param->keep_unmatched;
+	rp.ignore_duplicates = param->ignore_duplicates;
+	rp.keep_duplicates = param->keep_duplicates;
+	taker_t tk;
+	memset(&tk, 0, sizeof(tk));
+	tk.param = param; tk.n_targets = nt;
+	tk.records = getenv("BSGPU_SEAM_RECORDS") != NULL && atoi(getenv("BSGPU_SEAM_RECORDS")) != 0;
+	tk.codes = calloc((size_t)nt, sizeof(uint8_t *));
+	if (work->stats != NULL) {
+		if (bsgpu_profile_enable(g_ctx, 1) != BSGPU_OK) die("bsgpu_profile_enable");
+		g_profile = 1;
+	}
+	bsgpu_bcf_params bp;
+	int32_t *rid = NULL;
+	if (tk.records) {
+		bsgpu_default_bcf_params(&bp);
+		for (int k = 0; k < 16; k++) bp.ids[k] = work->vcf_ids[k];
+		bp.all_positions = param->all_positions;
+		rid = calloc((size_t)nt, sizeof(int32_t));
+		for (int t = 0; t < nt; t++) { const int k = work->tid2id[t]; rid[t] = k >= 0 ? work->contigs[k]->vcf_rid : 0; }
+	}
+	const uint8_t **codes0 = calloc((size_t)nt, sizeof(uint8_t *));
+	if (bsgpu_bam_open(g_ctx, nt, hdr->target_len, codes0, &rp, tk.records ? &bp : NULL, rid, 0, &tk.sess) != BSGPU_OK) die("bsgpu_bam_open");
+	free(codes0);
+	pthread_t taker;
+	pthread_create(&taker, NULL, taker_thread, &tk);
+
+	const int n_reg = work->n_regions;
+	int reg_ix = 0;
+	hts_itr_t *itr = NULL;
+	if (n_reg > 0 && work->sam_idx) {
+		region_t * const reg = work->regions + reg_ix++;
+		itr = sam_itr_queryi(work->sam_idx, reg->ctg->bam_tid, reg->start - 1, reg->stop);
+		fprintf(stderr, "Processing region %s:%u-%u\n", reg->ctg->name, reg->start, reg->stop);
+		work->curr_region = reg;
+	}
+	bam1_t *b = bam_init1();
+	int curr_tid = -1;
+	bool chr_skip = false;
+	ctg_t *prev_ctg = NULL;
+	gt_status st = GT_STATUS_OK;
+	uint8_t *dst = NULL;
+	size_t avail = 0, used = 0;
+	for (;;) {
+		int ret = itr == NULL ? sam_read1(sam_input, hdr, b) : sam_itr_next(sam_input, itr, b);
+		if (ret < 0) {
+			if (ret != -1) { st = GT_STATUS_FAIL; break; }
+			if (itr != NULL) hts_itr_destroy(itr);
+			itr = NULL;
+			if (reg_ix < n_reg && work->sam_idx) {
+				region_t * const reg = work->regions + reg_ix++;
+				itr = sam_itr_queryi(work->sam_idx, reg->ctg->bam_tid, reg->start - 1, reg->stop);
+				fprintf(stderr, "Processing region %s:%u-%u\n", reg->ctg->name, reg->start, reg->stop);
+				work->curr_region = reg;
+				continue;
+			}
+			break;                                          /* end of input */
+		}
+		const bam1_core_t * const c = &b->core;
+		if (c->tid >= 0 && c->tid != curr_tid) {
+			curr_tid = c->tid;
+			const int k = c->tid < nt ? work->tid2id[curr_tid] : -1;
+			chr_skip = k < 0;
+			fprintf(stderr, "Processing chromosome %s (%s)\n", hdr->target_name[curr_tid], chr_skip ? "SKIP" : "OK");
+			if (!chr_skip) {
+				ctg_t * const ctg = work->contigs[k];
+				ctg->curr_reg = work->curr_region;
+				if (tk.codes[curr_tid] == NULL) tk.codes[curr_tid] = contig_codes(ctg, prev_ctg, param);
+				if (tk.codes[curr_tid] == NULL) {
+					fprintf(stderr, "Problem loading reference sequence for contig '%s'\n", ctg->name);
+					st = GT_STATUS_FAIL;
+					break;
+				}
+				prev_ctg = ctg;
+				if (bsgpu_bam_set_contig(tk.sess, curr_tid, tk.codes[curr_tid]) != BSGPU_OK) die("bsgpu_bam_set_contig");
+			}
+		}
+		if (chr_skip || c->tid < 0) continue;               /* records without a wanted contig never reach a block */
+		/* the record as it lies in a BAM file: block_size, the 32 fixed bytes, then qname | cigar | seq | qual | aux */
+		const size_t need = 36 + (size_t)b->l_data;
+		if (avail - used < need) {
+			if (dst != NULL && bsgpu_bam_commit(tk.sess, used) != BSGPU_OK) die("bsgpu_bam_commit");
+			dst = NULL; used = 0;
+			for (;;) {
+				if (bsgpu_bam_reserve(tk.sess, &dst, &avail, 1) != BSGPU_OK) die("bsgpu_bam_reserve");
+				if (avail >= need) break;
+				/* the tail of a staging buffer: fill it with the head of the record through the copying entry point */
+				if (bsgpu_bam_commit(tk.sess, 0) != BSGPU_OK) die("bsgpu_bam_commit");
+				dst = NULL;
+				break;
+			}
+		}
+		uint8_t hdr36[36];
+		const uint32_t bs = 32 + (uint32_t)b->l_data, bin_mq_nl = (uint32_t)c->bin << 16 | (uint32_t)c->qual << 8 | (uint32_t)c->l_qname;
+		const uint32_t flag_nc = (uint32_t)c->flag << 16 | (c->n_cigar & 0xffff);
+		const int32_t pos = (int32_t)c->pos, mpos = (int32_t)c->mpos, isize = (int32_t)c->isize, lq = c->l_qseq, tid = c->tid, mtid = c->mtid;
+		memcpy(hdr36, &bs, 4); memcpy(hdr36 + 4, &tid, 4); memcpy(hdr36 + 8, &pos, 4); memcpy(hdr36 + 12, &bin_mq_nl, 4);
+		memcpy(hdr36 + 16, &flag_nc, 4); memcpy(hdr36 + 20, &lq, 4); memcpy(hdr36 + 24, &mtid, 4); memcpy(hdr36 + 28, &mpos, 4);
+		memcpy(hdr36 + 32, &isize, 4);
+		if (dst != NULL) {
+			memcpy(dst + used, hdr36, 36);
+			memcpy(dst + used + 36, b->data, (size_t)b->l_data);
+			used += need;
+			/* an open reservation keeps the session from moving carried records in front of this buffer: commit every few MB */
+			if (used >= ((size_t)4 << 20)) {
+				if (bsgpu_bam_commit(tk.sess, used) != BSGPU_OK) die("bsgpu_bam_commit");
+				dst = NULL; avail = used = 0;
+			}
+		} else {
+			if (bsgpu_bam_feed(tk.sess, hdr36, 36, NULL) != BSGPU_OK || bsgpu_bam_feed(tk.sess, b->data, (size_t)b->l_data, NULL) != BSGPU_OK) die("bsgpu_bam_feed");
+			avail = used = 0;
+		}
+		if (tk.failed) { st = GT_STATUS_FAIL; break; }
+	}
+	if (dst != NULL && bsgpu_bam_commit(tk.sess, used) != BSGPU_OK) die("bsgpu_bam_commit");
+	if (bsgpu_bam_finish(tk.sess) != BSGPU_OK) { fprintf(stderr, "bsgpu: %s\n", bsgpu_last_error()); st = GT_STATUS_FAIL; }
+	pthread_join(taker, NULL);
+	if (tk.failed) st = GT_STATUS_FAIL;
+	bsgpu_bam_close(tk.sess);
+	bam_destroy1(b);
+	for (int t = 0; t < nt; t++) free(tk.codes[t]);
+	free(tk.codes);
+	free(rid);
+	return st;
+}

@@ -25,7 +25,7 @@ EXPORTS = [
     "bsgpu_process_block", "bsgpu_profile_enable", "bsgpu_profile_read", "bsgpu_build_blocks_tally",
     "bsgpu_call_bam_bcf", "bsgpu_default_bcf_params", "bsgpu_bcf_block", "bsgpu_bcf_block_dev", "bsgpu_call_block_bcf", "bsgpu_call_sites_bcf",
     "bsgpu_default_reader_params", "bsgpu_decode_records", "bsgpu_build_blocks", "bsgpu_call_bam",
-    "bsgpu_bam_open", "bsgpu_bam_feed", "bsgpu_bam_reserve", "bsgpu_bam_commit", "bsgpu_bam_finish", "bsgpu_bam_cut", "bsgpu_bam_rewind", "bsgpu_bam_drain",
+    "bsgpu_bam_open", "bsgpu_bam_set_contig", "bsgpu_bam_feed", "bsgpu_bam_reserve", "bsgpu_bam_commit", "bsgpu_bam_finish", "bsgpu_bam_cut", "bsgpu_bam_rewind", "bsgpu_bam_drain",
     "bsgpu_bam_release", "bsgpu_bam_progress", "bsgpu_bam_close",
     "bsgpu_call_sites_dev", "bsgpu_call_sites_vcf_dev", "bsgpu_pileup_block_dev", "bsgpu_call_block_dev",
     "bsgpu_synth_sites_dev", "bsgpu_synth_block_nseg", "bsgpu_synth_block_dev",

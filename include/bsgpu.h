@@ -344,6 +344,9 @@ typedef struct {
 } bsgpu_bam_progress_t;
 int bsgpu_bam_open(bsgpu_ctx *ctx, int n_targets, const uint32_t *target_len, const uint8_t *const *ctg_codes, const bsgpu_reader_params *rp,
 		const bsgpu_bcf_params *bcf, const int32_t *vcf_rid, size_t batch_bytes, bsgpu_bam_session **out);
+/* the reference codes of a contig that was NULL at bsgpu_bam_open (a host that loads contigs as the stream reaches them):
+ * call it before the first record of that contig is fed; the array must stay valid until the session is closed */
+int bsgpu_bam_set_contig(bsgpu_bam_session *s, int tid, const uint8_t *codes);
 /* copies the slice into the session's staging.  accepted == NULL: blocks while both staging buffers are full;
  * accepted != NULL: never blocks, *accepted <= nbytes says how much was taken (drain, then offer the rest again) */
 int bsgpu_bam_feed(bsgpu_bam_session *s, const uint8_t *bytes, size_t nbytes, size_t *accepted);

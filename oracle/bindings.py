@@ -441,3 +441,45 @@ class ReferenceWithGpuDropin(Reference):
     """The reference's process_template_vector etc. with src/call_genotypes.c replaced by the product's drop-in
     (bs_call_b200/csrc/bsgpu_dropin.c over libbsgpu.so): oracle/_ref/libbsref_gpu.so.  Needs a GPU."""
     LIBNAME = "libbsref_gpu.so"
+
+
+def seam_available(name):
+    return os.path.exists(os.path.join(HERE, "_ref", "libbsref_%s.so" % name))
+
+
+class ReferenceWithSeamB(Reference):
+    """The reference with src/process_template.c and src/call_genotypes.c replaced by the product's
+    bs_call_b200/csrc/bsgpu_seam_template.c (process_template_vector on the device): oracle/_ref/libbsref_seamB.so.
+    read_input, get_next_align_details and the rest are the reference's own objects.  Needs a GPU."""
+    LIBNAME = "libbsref_seamB.so"
+
+
+class ReferenceWithSeamC(Reference):
+    """The reference with src/get_template_vector.c, src/process_template.c and src/call_genotypes.c replaced by the product's
+    bs_call_b200/csrc/bsgpu_seam_reader.c (read_input feeding a streaming session of the device library):
+    oracle/_ref/libbsref_seamC.so.  get_next_align_details' record source (sam_read1), the sequence store, the print-thread
+    protocol and bcf_write are the harness's stand-ins for htslib / src/process.c.  Needs a GPU."""
+    LIBNAME = "libbsref_seamC.so"
+
+    def seam_read_input(self, bam, target_len, ctg_codes, mapq_thresh=20, max_template_len=1000, keep_unmatched=False,
+                        ignore_duplicates=False, keep_duplicates=False, vcf_ids=None, all_positions=False):
+        """the product's read_input() under the harness's print thread -> (blocks, gt_vcf[], BCF bytes, BCF records); which
+        of gt_vcf[] (seam C) or records (seam D) comes back is decided by BSGPU_SEAM_RECORDS in the environment"""
+        bam = _c(bam, np.uint8)
+        target_len = _c(target_len, np.uint32)
+        codes = [_c(c, np.uint8) for c in ctg_codes]
+        ptrs = (C.c_void_p * len(codes))(*[c.ctypes.data for c in codes])
+        ids = _c(VCF_IDS if vcf_ids is None else vcf_ids, np.int32)
+        nrec_max = len(bam) // 36 + 8
+        blocks = np.zeros(nrec_max, dtype=BLOCK)
+        vcf = np.zeros(int(target_len.sum()) + 8, dtype=GT_VCF)
+        out = np.zeros(int(target_len.sum()) * 160 + 4096, dtype=np.uint8)
+        nb, nv, ob, orec = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        rc = self.lib.bsref_seam_read_input(_p(bam), C.c_size_t(len(bam)), C.c_int(len(codes)), _p(target_len), ptrs,
+                                            C.c_int(mapq_thresh), C.c_uint32(max_template_len), C.c_int(int(keep_unmatched)),
+                                            C.c_int(int(ignore_duplicates)), C.c_int(int(keep_duplicates)), _p(ids), C.c_int(int(all_positions)),
+                                            _p(blocks), C.c_size_t(len(blocks)), C.byref(nb), _p(vcf), C.c_size_t(len(vcf)), C.byref(nv),
+                                            _p(out), C.c_size_t(len(out)), C.byref(ob), C.byref(orec))
+        if rc:
+            raise RuntimeError("bsref_seam_read_input failed: %d" % rc)
+        return blocks[:nb.value].copy(), vcf[:nv.value].copy(), out[:ob.value].copy(), orec.value

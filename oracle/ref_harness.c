@@ -675,6 +675,120 @@ int bsref_read_input(const uint8_t *bam, size_t nbytes, int n_targets, const uin
 	return rdr.err;
 }
 
+#ifdef BSREF_SEAM_READER
+/* ---- seams C / D (bs_call_b200/csrc/bsgpu_seam_reader.c linked in place of get_template_vector.c, process_template.c and
+ * call_genotypes.c): read_input() is the product's, fed by the memory-backed sam_read1() above.  The harness stands in for
+ * what src/process.c runs around it: a print thread that takes every published block off work->vcf (seam C), and the
+ * capture buffer behind bcf_write() (seam D, BSGPU_SEAM_RECORDS=1 in the environment). ---- */
+static uint8_t *pv_out;
+static size_t pv_cap, pv_len, pv_nrec;
+static int pv_overflow;
+static struct { bsref_block *blocks; size_t cap, n; gt_vcf *vcf; size_t vcf_cap, nvcf; int err; } seam;
+
+static void *seam_print_thread(void *arg) {
+	work_t * const w = &par.work;
+	for (;;) {
+		pthread_mutex_lock(&w->print_mutex);
+		while (!w->vcf_n && !w->print_end) {
+			struct timespec ts;
+			clock_gettime(CLOCK_REALTIME, &ts);
+			ts.tv_sec += 1;
+			pthread_cond_timedwait(&w->print_cond1, &w->print_mutex, &ts);
+		}
+		pthread_mutex_unlock(&w->print_mutex);
+		if (!w->vcf_n) break;
+		const uint32_t sz = (uint32_t)w->vcf_n;
+		if (seam.n >= seam.cap || seam.nvcf + sz > seam.vcf_cap) seam.err = -3;
+		else {
+			bsref_block *bk = seam.blocks + seam.n++;
+			memset(bk, 0, sizeof(*bk));
+			bk->tid = (uint32_t)w->vcf_ctg->bam_tid; bk->x = w->vcf_x; bk->y = w->vcf_x + sz - 1; bk->vcf_off = seam.nvcf;
+			/* the block's reference string must be the codes of [x, y + 2] (what the writer would read) */
+			const char *rf = gt_string_get_string(w->ref);
+			const ctg_t *c = w->vcf_ctg;
+			for (uint32_t i = 0; i < sz + 2 && !seam.err; i++) {
+				const uint64_t pos = (uint64_t)w->vcf_x + i;
+				char want = 0;
+				if (pos < c->end_pos) want = (char)((c->seq[(pos - 1) / 5] >> (3 * (4 - ((pos - 1) % 5)))) & 7);
+				if (rf[i] != want) seam.err = -7;
+			}
+			for (uint32_t i = 0; i < sz; i++) {
+				if (!w->vcf[i].ready) seam.err = -6;
+				if (w->vcf[i].skip) { memset(seam.vcf + seam.nvcf + i, 0, sizeof(gt_vcf)); seam.vcf[seam.nvcf + i].skip = true; seam.vcf[seam.nvcf + i].ready = true; }
+				else seam.vcf[seam.nvcf + i] = w->vcf[i];
+			}
+			seam.nvcf += sz;
+		}
+		pthread_mutex_lock(&w->print_mutex);
+		w->vcf_n = 0;
+		pthread_cond_signal(&w->print_cond2);
+		pthread_mutex_unlock(&w->print_mutex);
+	}
+	return NULL;
+}
+
+int bsref_seam_read_input(const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len, const uint8_t *const *ctg_codes,
+		int mapq_thresh, uint32_t max_template_len, int keep_unmatched, int ignore_duplicates, int keep_duplicates,
+		const int *vcf_ids, int all_positions,
+		bsref_block *blocks, size_t block_cap, size_t *nblocks, gt_vcf *vcf, size_t vcf_cap, size_t *nvcf,
+		uint8_t *bcf_out, size_t bcf_cap, size_t *bcf_bytes, size_t *bcf_nrec) {
+	if (!inited) return -1;
+	mem_bam = bam; mem_len = nbytes; mem_pos = 0;
+	memset(&seam, 0, sizeof(seam));
+	seam.blocks = blocks; seam.cap = block_cap; seam.vcf = vcf; seam.vcf_cap = vcf_cap;
+	pv_out = bcf_out; pv_cap = bcf_cap; pv_len = 0; pv_nrec = 0; pv_overflow = 0;
+	work_t * const w = &par.work;
+	bam_hdr_t hdr;
+	memset(&hdr, 0, sizeof(hdr));
+	hdr.n_targets = n_targets;
+	hdr.target_len = (uint32_t *)target_len;
+	hdr.target_name = calloc(n_targets, sizeof(char *));
+	ctg_t *ctgs = calloc(n_targets, sizeof(ctg_t));
+	w->contigs = calloc(n_targets, sizeof(ctg_t *));
+	w->tid2id = calloc(n_targets, sizeof(int));
+	for (int i = 0; i < n_targets; i++) {
+		char nm[32];
+		snprintf(nm, sizeof(nm), "ctg%d", i);
+		hdr.target_name[i] = strdup(nm);
+		ctgs[i].name = hdr.target_name[i];
+		ctgs[i].bam_tid = i;
+		ctgs[i].vcf_rid = i;
+		const uint32_t len = target_len[i];
+		const size_t nw = ((size_t)len + 9) / 5;
+		ctgs[i].seq = calloc(nw + 1, sizeof(uint16_t));
+		for (uint32_t j = 0; j < len; j++) ctgs[i].seq[j / 5] |= (uint16_t)(ctg_codes[i][j] & 7) << (3 * (4 - (j % 5)));
+		ctgs[i].start_pos = 1; ctgs[i].end_pos = len; ctgs[i].seq_len = len;
+		w->contigs[i] = ctgs + i;
+		w->tid2id[i] = i;
+	}
+	w->n_contigs = n_targets; w->n_regions = 0; w->sam_idx = NULL; w->sam_header = &hdr; w->curr_region = NULL;
+	w->process_end = false; w->print_end = false; w->vcf_n = 0; w->vcf_ctg = NULL;
+	gt_vcf * const saved_vcf = w->vcf;
+	const int saved_size = w->vcf_size;
+	par.mapq_thresh = (uint8_t)mapq_thresh; par.max_template_len = max_template_len;
+	par.keep_unmatched = keep_unmatched; par.ignore_duplicates = ignore_duplicates; par.keep_duplicates = keep_duplicates;
+	par.all_positions = all_positions;
+	for (int i = 0; i < 16; i++) w->vcf_ids[i] = vcf_ids[i];
+	pthread_t thr;
+	pthread_create(&thr, NULL, seam_print_thread, NULL);
+	gt_vector *al_list = gt_vector_new(32, sizeof(align_details *));
+	gt_status st = read_input(NULL, al_list, &par);
+	pthread_mutex_lock(&w->print_mutex);
+	w->print_end = true;
+	pthread_cond_signal(&w->print_cond1);
+	pthread_mutex_unlock(&w->print_mutex);
+	pthread_join(thr, NULL);
+	*nblocks = seam.n; *nvcf = seam.nvcf; *bcf_bytes = pv_len; *bcf_nrec = pv_nrec;
+	w->vcf = saved_vcf; w->vcf_size = saved_size;          /* work->vcf pointed into the session's results: gone now */
+	for (int i = 0; i < n_targets; i++) { free(hdr.target_name[i]); free(ctgs[i].seq); }
+	free(hdr.target_name); free(w->contigs); free(w->tid2id); free(ctgs);
+	w->contigs = NULL; w->tid2id = NULL; w->sam_header = NULL;
+	if (st != GT_STATUS_OK) return -2;
+	if (pv_overflow) return -3;
+	return seam.err;
+}
+#endif
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Writer side: the reference's print_vcf_entry() / flush_vcf_entries() / _print_vcf_entry() (src/print_vcf.c, compiled
  * unmodified) driven over a block of gt_vcf records the way print_thread drives them (src/process.c:89-104), with the
@@ -738,6 +852,7 @@ void bcf_enc_vchar(kstring_t *s, int l, const char *a) {
 	kputsn(a, l, s);
 }
 bcf1_t *bcf_init(void) { return calloc(1, sizeof(bcf1_t)); }
+void bcf_destroy(bcf1_t *v) { if (v) { free(v->shared.s); free(v->indiv.s); free(v); } }
 void bcf_clear(bcf1_t *v) {
 	v->rid = 0; v->pos = 0; v->rlen = 0;
 	{ uint32_t miss = 0x7F800001u; memcpy(&v->qual, &miss, 4); }          /* bcf_float_missing */
@@ -746,9 +861,11 @@ void bcf_clear(bcf1_t *v) {
 }
 
 /* capture buffer of bcf_write(): records as they lie in a BCF file (two length words, six fixed words, shared, indiv) */
+#ifndef BSREF_SEAM_READER
 static uint8_t *pv_out;
 static size_t pv_cap, pv_len, pv_nrec;
 static int pv_overflow;
+#endif
 int bcf_write(htsFile *fp, bcf_hdr_t *h, bcf1_t *v) {
 	uint32_t x[8];
 	x[0] = (uint32_t)v->shared.l + 24;

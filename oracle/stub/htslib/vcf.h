@@ -90,6 +90,7 @@ void bcf_enc_vfloat(kstring_t *s, int n, float *a);
 void bcf_enc_vchar(kstring_t *s, int l, const char *a);
 
 bcf1_t *bcf_init(void);
+void bcf_destroy(bcf1_t *v);
 void bcf_clear(bcf1_t *v);
 int bcf_write(htsFile *fp, bcf_hdr_t *h, bcf1_t *v);
 
