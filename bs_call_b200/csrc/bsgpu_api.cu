@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <map>
 #include <deque>
 #include <mutex>
 #include <condition_variable>
@@ -131,6 +132,10 @@ struct bsgpu_ctx {
 	uint32_t ring_pos = 0;                       // next output ring slot of the deferred runs
 	bool ring_busy[3] = {false, false, false};   // output ring slot may still be copying out (deferred block_run)
 	bsgpu_stats stats;
+	// dbSNP / region annotation: per contig (bsgpu_set_contig_annotation) and of the last single-contig call (params->dbsnp)
+	struct DbDev { DevBuf mask, fq, cum, off, names; uint32_t words = 0; uint32_t reg_start = 0, reg_stop = 0; uint64_t key[4] = {0, 0, 0, 0}; };
+	std::map<int, DbDev *> contig_ann;
+	DbDev call_db;
 	uint64_t guard_base[4] = {0, 0, 0, 0};      // guard counters of the device before the last bsgpu_guard_read(reset)
 	int launches = 0;
 	// --report-file side channels (bsgpu_profile_enable)
@@ -269,6 +274,8 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 	for (int i = 0; i < 3; i++) { c->wr_ring[i].release(); if (c->wr_built[i]) cudaEventDestroy(c->wr_built[i]); if (c->wr_copied[i]) cudaEventDestroy(c->wr_copied[i]); }
 	if (c->d_wr_totals) cudaFree(c->d_wr_totals);
 	if (c->h_wr_totals) cudaFreeHost(c->h_wr_totals);
+	for (auto &kv : c->contig_ann) if (kv.second) { for (DevBuf *b : {&kv.second->mask, &kv.second->fq, &kv.second->cum, &kv.second->off, &kv.second->names}) b->release(); delete kv.second; }
+	for (DevBuf *b : {&c->call_db.mask, &c->call_db.fq, &c->call_db.cum, &c->call_db.off, &c->call_db.names}) b->release();
 	delete c;
 }
 
@@ -644,6 +651,71 @@ static int check_totals(const unsigned long long *t, size_t out_cap, const char 
 	return BSGPU_OK;
 }
 
+// dbSNP entries of a contig -> the device tables of DbView (synchronous; done once per contig / per distinct table)
+static int db_upload(bsgpu_ctx *c, const bsgpu_dbsnp *db, bsgpu_ctx::DbDev &d, const char *who) {
+	d.words = 0;
+	if (!db || !db->n) return BSGPU_OK;
+	if (!db->pos || !db->flags || !db->name_off || !db->names) return fail("%s: dbSNP table with a null array", who);
+	const uint32_t n = db->n;
+	for (uint32_t k = 0; k < n; k++) {
+		if (!db->pos[k] || (k && db->pos[k] <= db->pos[k - 1])) return fail("%s: dbSNP positions must be 1-based, ascending and unique (entry %u)", who, k);
+		if (db->name_off[k + 1] < db->name_off[k] || db->name_off[k + 1] - db->name_off[k] > BSGPU_DBSNP_MAX_ID) return fail("%s: dbSNP entry %u has an ID longer than %d bytes", who, k, BSGPU_DBSNP_MAX_ID);
+	}
+	const uint32_t words = (db->pos[n - 1] >> 6) + 1;
+	std::vector<unsigned long long> mask(words, 0), fq(words, 0);
+	std::vector<uint32_t> cum(words + 1, 0);
+	for (uint32_t k = 0; k < n; k++) {
+		const uint32_t p = db->pos[k];
+		mask[p >> 6] |= 1ull << (p & 63);
+		if (db->flags[k] & 2) fq[p >> 6] |= 1ull << (p & 63);
+		cum[(p >> 6) + 1]++;
+	}
+	for (uint32_t w = 0; w < words; w++) cum[w + 1] += cum[w];
+	const size_t nbytes = db->name_off[n];
+	CU(cudaDeviceSynchronize());              // the old tables may still be in use
+	CU(d.mask.reserve(words * 8)); CU(d.fq.reserve(words * 8)); CU(d.cum.reserve((words + 1) * 4));
+	CU(d.off.reserve(((size_t)n + 1) * 4)); CU(d.names.reserve(nbytes + 16));
+	CU(cudaMemcpy(d.mask.p, mask.data(), words * 8, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(d.fq.p, fq.data(), words * 8, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(d.cum.p, cum.data(), (words + 1) * 4, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(d.off.p, db->name_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice));
+	if (nbytes) CU(cudaMemcpy(d.names.p, db->names, nbytes, cudaMemcpyHostToDevice));
+	c->stats.h2d_bytes += words * 20 + ((size_t)n + 1) * 4 + nbytes;
+	d.words = words;
+	return BSGPU_OK;
+}
+
+static DbView db_view(const bsgpu_ctx::DbDev &d) {
+	DbView v;
+	if (d.words) { v.mask = (const unsigned long long *)d.mask.p; v.fq = (const unsigned long long *)d.fq.p; v.cum = (const uint32_t *)d.cum.p; v.off = (const uint32_t *)d.off.p; v.names = (const uint8_t *)d.names.p; v.words = d.words; }
+	return v;
+}
+
+// region and dbSNP table of a single-contig call (params->reg_*, params->dbsnp) into the job; the table is uploaded again only
+// when it is not the one of the call before
+static int job_annotate(bsgpu_ctx *c, const bsgpu_bcf_params *p, BcfJob &j, const char *who) {
+	j.reg_start = p->reg_start; j.reg_stop = p->reg_stop;
+	j.db = DbView();
+	const bsgpu_dbsnp *db = p->dbsnp;
+	if (!db || !db->n) return BSGPU_OK;
+	const uint64_t key[4] = {(uint64_t)(uintptr_t)db->pos, db->n, (uint64_t)(uintptr_t)db->names, ((uint64_t)db->pos[0] << 32) | db->pos[db->n - 1]};
+	if (!c->call_db.words || memcmp(key, c->call_db.key, sizeof(key))) {
+		if (db_upload(c, db, c->call_db, who) != BSGPU_OK) return BSGPU_FAIL;
+		memcpy(c->call_db.key, key, sizeof(key));
+	}
+	j.db = db_view(c->call_db);
+	return BSGPU_OK;
+}
+
+int bsgpu_set_contig_annotation(bsgpu_ctx *c, int tid, uint32_t reg_start, uint32_t reg_stop, const bsgpu_dbsnp *db) {
+	if (!c || tid < 0) return fail("bsgpu_set_contig_annotation: bad argument");
+	CU(cudaSetDevice(c->device));
+	bsgpu_ctx::DbDev *&d = c->contig_ann[tid];
+	if (!d) d = new bsgpu_ctx::DbDev();
+	d->reg_start = reg_start; d->reg_stop = reg_stop;
+	return db_upload(c, db, *d, "bsgpu_set_contig_annotation");
+}
+
 // one block, everything resident: records into d_out, sizes back through the pinned totals (slot 0); waits for `st`
 static int bcf_run(bsgpu_ctx *c, const void *d_vcf, const void *d_ref, uint32_t x, uint32_t sz, const bsgpu_bcf_params *p,
 		void *d_out, size_t out_cap, size_t *nbytes, size_t *nrec, cudaStream_t st, const char *who) {
@@ -653,6 +725,7 @@ static int bcf_run(bsgpu_ctx *c, const void *d_vcf, const void *d_ref, uint32_t 
 	BcfJob j;
 	j.d_vcf = d_vcf; j.d_ref = d_ref; j.x = x; j.sz = sz; j.d_blocks = nullptr; j.nblocks = 0; j.p = *p; j.dc = c->d_const; j.guard = c->d_counters;
 	j.site_scratch = c->wr_site.p;
+	if (job_annotate(c, p, j, who) != BSGPU_OK) return BSGPU_FAIL;
 	CU(launch_bcf_records(j, 0, sz, c->wr_cta.p, d_out, out_cap, c->d_wr_totals, st, &c->launches));
 	CU(cudaMemcpyAsync(c->h_wr_totals, c->d_wr_totals, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
@@ -765,6 +838,7 @@ int bsgpu_call_sites_bcf(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t
 	BcfJob j;
 	j.d_ref = c->wr_ref.p; j.x = x; j.sz = (uint32_t)n; j.d_blocks = nullptr; j.nblocks = 0; j.p = *p; j.dc = c->d_const; j.guard = c->d_counters;
 	j.site_scratch = c->wr_site.p;
+	if (job_annotate(c, p, j, "bsgpu_call_sites_bcf") != BSGPU_OK) return BSGPU_FAIL;
 	CU(cudaMemcpyAsync(c->wr_ref.p, ref, n + 2, cudaMemcpyHostToDevice, up));
 	size_t at = 0, recs = 0;
 	int ret = BSGPU_OK;
@@ -1202,6 +1276,10 @@ static int call_window(bsgpu_ctx *c, const TmSpan *span, size_t nspan, size_t nt
 	j.d_vcf = c->wr_vcf.p; j.d_ref = c->ref.p; j.x = x; j.sz = sz; j.d_blocks = c->wr_blocks.p; j.nblocks = (uint32_t)nwb;
 	j.p = sink->p; j.p.rid = sink->vcf_rid ? sink->vcf_rid[tid] : (int32_t)tid; j.p.ctg_end = ctg_len;
 	j.dc = c->d_const; j.guard = c->d_counters; j.site_scratch = c->wr_site.p;
+	{
+		const auto it = c->contig_ann.find((int)tid);
+		if (it != c->contig_ann.end() && it->second) { j.db = db_view(*it->second); j.reg_start = it->second->reg_start; j.reg_stop = it->second->reg_stop; }
+	}
 	if (sink->queued >= 3) CU(cudaStreamWaitEvent(c->stream, c->wr_copied[rslot], 0));      // the slot's previous records have left
 	CU(launch_bcf_records(j, 0, sz, c->wr_cta.p, c->wr_ring[rslot].p, rcap, c->d_wr_totals + 3 * (sink->queued & 7), c->stream, &c->launches));
 	CU(cudaMemcpyAsync(c->h_wr_totals + 3 * (sink->queued & 7), c->d_wr_totals + 3 * (sink->queued & 7), 3 * sizeof(unsigned long long),

@@ -69,6 +69,15 @@ cudaError_t launch_normalise(const void *tmpl, size_t n, const void *bases, void
 		unsigned long long *counters, const ProfArgs *prof, int parity, cudaStream_t stream, int *launches, uint32_t slot = 0);
 
 // writer side (bsgpu_writer.cu): gt_vcf[] of a window -> BCF records
+// device view of a contig's dbSNP entries: one bit per position (bit pos & 63 of word pos >> 6) for "known" and for "always
+// written", the number of entries before each word, and the ID bytes of entry k at names[off[k] .. off[k + 1])
+struct DbView {
+	const unsigned long long *mask = nullptr, *fq = nullptr;
+	const uint32_t *cum = nullptr, *off = nullptr;
+	const uint8_t *names = nullptr;
+	uint32_t words = 0;
+};
+
 struct BcfJob {
 	const void *d_vcf;               // gt_vcf[sz]
 	const void *d_ref;               // sz + 2 codes, index 0 = position x
@@ -78,6 +87,8 @@ struct BcfJob {
 	bsgpu_bcf_params p;
 	const DevConst *dc;
 	void *site_scratch;              // bcf_site_scratch_bytes(sz)
+	DbView db;                       // dbSNP entries of the window's contig
+	uint32_t reg_start = 0, reg_stop = 0;    // ctg->curr_reg (0, 0: none -> the contig end clips)
 	unsigned long long *guard = nullptr;      // the context's counters: sites whose QUAL / FS sit inside their guard band are counted and listed
 };
 size_t bcf_site_scratch_bytes(uint32_t sz);

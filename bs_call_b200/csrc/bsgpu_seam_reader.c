@@ -48,18 +48,23 @@ static void timed_wait(pthread_cond_t *c, pthread_mutex_t *m) {
 	pthread_cond_timedwait(c, m, &ts);
 }
 
+static bsgpu_params g_params;
+
+static void params_of(const sr_param * const param, bsgpu_params * const p) {
+	bsgpu_default_params(p);
+	p->under_conv = param->under_conv;
+	p->over_conv = param->over_conv;
+	p->ref_bias = param->ref_bias;
+	p->min_qual = param->min_qual;
+	for (int i = 0; i < 2; i++) { p->left_trim[i] = param->left_trim[i]; p->right_trim[i] = param->right_trim[i]; }
+	const char *dev = getenv("BSGPU_DEVICE");
+	p->device = dev ? atoi(dev) : 0;
+}
+
 void init_calc_threads(sr_param * const param) {
 	work_t * const work = &param->work;
-	bsgpu_params p;
-	bsgpu_default_params(&p);
-	p.under_conv = param->under_conv;
-	p.over_conv = param->over_conv;
-	p.ref_bias = param->ref_bias;
-	p.min_qual = param->min_qual;
-	for (int i = 0; i < 2; i++) { p.left_trim[i] = param->left_trim[i]; p.right_trim[i] = param->right_trim[i]; }
-	const char *dev = getenv("BSGPU_DEVICE");
-	p.device = dev ? atoi(dev) : 0;
-	if (bsgpu_init(&p, &g_ctx) != BSGPU_OK) die("bsgpu_init");
+	params_of(param, &g_params);
+	if (bsgpu_init(&g_params, &g_ctx) != BSGPU_OK) die("bsgpu_init");
 	g_profile = 0;
 	work->calc_end = false;
 	work->n_calc_threads = 0;
@@ -235,6 +240,16 @@ gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param
 	tk.param = param; tk.n_targets = nt;
 	tk.records = getenv("BSGPU_SEAM_RECORDS") != NULL && atoi(getenv("BSGPU_SEAM_RECORDS")) != 0;
 	tk.codes = calloc((size_t)nt, sizeof(uint8_t *));
+	{   /* the options are fixed for a run of bs_call; a host that changed them since init_calc_threads gets a new context */
+		bsgpu_params now;
+		params_of(param, &now);
+		if (memcmp(&now, &g_params, sizeof(now))) {
+			bsgpu_destroy(g_ctx);
+			g_params = now;
+			if (bsgpu_init(&g_params, &g_ctx) != BSGPU_OK) die("bsgpu_init");
+			g_profile = 0;
+		}
+	}
 	if (work->stats != NULL) {
 		if (bsgpu_profile_enable(g_ctx, 1) != BSGPU_OK) die("bsgpu_profile_enable");
 		g_profile = 1;

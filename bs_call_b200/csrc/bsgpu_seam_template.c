@@ -65,18 +65,24 @@ static void *pinned_grow(void *old, size_t *cap, size_t need, size_t elem) {
 	return p;
 }
 
+static bsgpu_params g_params;
+static void fold_profile(bs_stats * const stats);
+
+static void params_of(const sr_param * const param, bsgpu_params * const p) {
+	bsgpu_default_params(p);
+	p->under_conv = param->under_conv;
+	p->over_conv = param->over_conv;
+	p->ref_bias = param->ref_bias;
+	p->min_qual = param->min_qual;
+	for (int i = 0; i < 2; i++) { p->left_trim[i] = param->left_trim[i]; p->right_trim[i] = param->right_trim[i]; }
+	const char *dev = getenv("BSGPU_DEVICE");
+	p->device = dev ? atoi(dev) : 0;
+}
+
 void init_calc_threads(sr_param * const param) {
 	work_t * const work = &param->work;
-	bsgpu_params p;
-	bsgpu_default_params(&p);
-	p.under_conv = param->under_conv;
-	p.over_conv = param->over_conv;
-	p.ref_bias = param->ref_bias;
-	p.min_qual = param->min_qual;
-	for (int i = 0; i < 2; i++) { p.left_trim[i] = param->left_trim[i]; p.right_trim[i] = param->right_trim[i]; }
-	const char *dev = getenv("BSGPU_DEVICE");
-	p.device = dev ? atoi(dev) : 0;
-	if (bsgpu_init(&p, &g_ctx) != BSGPU_OK) die("bsgpu_init");
+	params_of(param, &g_params);
+	if (bsgpu_init(&g_params, &g_ctx) != BSGPU_OK) die("bsgpu_init");
 	g_profile = 0;
 	work->calc_end = false;
 	work->n_calc_threads = 0;            /* no host calc threads exist */
@@ -132,6 +138,19 @@ gt_status process_template_vector(gt_vector *align_list, ctg_t * const ctg, uint
 	if (get_sequence_string(ctg, x, sz + 2, work->vcf_ctg, work->ref1, param)) {
 		fprintf(stderr, "Problem loading reference sequence for contig '%s' %" PRIu32 " %" PRIu32 "\n", ctg->name, x, sz);
 		return GT_STATUS_FAIL;
+	}
+	/* -L / -R, -Q and the conversion rates are fixed for a run of bs_call; a host that changes them between blocks (the
+	 * test harness does) gets a context for the new values */
+	{
+		bsgpu_params now;
+		params_of(param, &now);
+		if (memcmp(&now, &g_params, sizeof(now))) {
+			if (g_profile && work->stats != NULL) fold_profile(work->stats);
+			bsgpu_destroy(g_ctx);
+			g_params = now;
+			if (bsgpu_init(&g_params, &g_ctx) != BSGPU_OK) die("bsgpu_init");
+			g_profile = 0;
+		}
 	}
 	if (work->stats != NULL && !g_profile) {
 		if (bsgpu_profile_enable(g_ctx, 1) != BSGPU_OK) die("bsgpu_profile_enable");

@@ -114,6 +114,8 @@ struct WrArgs {
 	uint8_t *out;
 	unsigned long long out_cap;
 	unsigned long long *guard;       // the context's counters (guard bands), or NULL
+	DbView db;                       // dbSNP entries of the contig (words == 0: none)
+	uint32_t reg_start, reg_stop;    // ctg->curr_reg (0, 0: none)
 };
 
 __device__ __forceinline__ void guard_note(unsigned long long *counters, int kind, unsigned long long id) {
@@ -162,8 +164,22 @@ __device__ __forceinline__ uint32_t build_record(const WrArgs &a, uint32_t i, ui
 		}
 	}
 	const int rfix = (int)rc[2], gt = g[2] - 1;
-	if (!a.all_positions && ((gt == 0 && rfix == 1) || (gt == 9 && rfix == 4))) return 0;      // hom-ref A / T (gt_flag, :91-102)
-	if (a.x + i > a.ctg_end) return 0;
+	// dbSNP (:133): what dbSNP_lookup_name() answers for this position -- 0, 1 (known) or 3 (known, always written) and the ID
+	const uint32_t pos = a.x + i;
+	uint32_t rs_found = 0, rs_len = 0;
+	const uint8_t *rs = nullptr;
+	if ((pos >> 6) < a.db.words) {
+		const unsigned long long m = a.db.mask[pos >> 6], bit = 1ull << (pos & 63);
+		if (m & bit) {
+			rs_found = (a.db.fq[pos >> 6] & bit) ? 3u : 1u;
+			const uint32_t k = a.db.cum[pos >> 6] + (uint32_t)__popcll(m & (bit - 1));
+			rs = a.db.names + a.db.off[k];
+			rs_len = a.db.off[k + 1] - a.db.off[k];
+		}
+	}
+	if (!a.all_positions && !(rs_found & 2u) && ((gt == 0 && rfix == 1) || (gt == 9 && rfix == 4))) return 0;      // hom-ref A / T (gt_flag, :91-102, 139)
+	if (a.reg_start | a.reg_stop) { if (pos < a.reg_start || pos > a.reg_stop) return 0; }      // ctg->curr_reg clips, else the contig end (:154-157)
+	else if (pos > a.ctg_end) return 0;
 	// QUAL / GQ: phred of the probability that the call is wrong (:140-148)
 	const MathTables *mt = &a.dc->tab.math;
 	const double lp = v->gt_prob[gt] * kLn10;
@@ -221,7 +237,8 @@ __device__ __forceinline__ uint32_t build_record(const WrArgs &a, uint32_t i, ui
 	const uint32_t start = w.n;
 	for (int k = 0; k < 32; k++) w.put(0);
 	const uint32_t sh0 = w.n;
-	enc_size(w, 0, T_CHAR);                            // ID: none (no dbSNP index on this path)
+	enc_size(w, (int)rs_len, T_CHAR);                  // ID (:163-167): the dbSNP name, or none
+	for (uint32_t k = 0; k < rs_len; k++) w.put(rs[k]);
 	w.put(1 << 4 | T_CHAR); w.put(bchar(rc[2]));       // REF
 	for (int k = 0; k < n_alt; k++) { w.put(1 << 4 | T_CHAR); w.put(bchar((uint32_t)alts[k])); }
 	enc_int1(w, fid);                                  // FILTER
@@ -461,6 +478,7 @@ static WrArgs writer_args(const BcfJob &j, uint32_t i0, uint32_t cnt) {
 	a.len = (uint16_t *)((uint8_t *)j.site_scratch + (((size_t)j.sz + 15) & ~(size_t)15));
 	a.cta_bytes = nullptr; a.cta_recs = nullptr; a.totals = nullptr; a.out = nullptr; a.out_cap = 0;
 	a.guard = j.guard;
+	a.db = j.db; a.reg_start = j.reg_start; a.reg_stop = j.reg_stop;
 	return a;
 }
 

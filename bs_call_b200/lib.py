@@ -23,7 +23,7 @@ EXPORTS = [
     "bsgpu_sync", "bsgpu_guard_read", "bsgpu_host_alloc", "bsgpu_host_free",
     "bsgpu_call_sites", "bsgpu_pileup_block", "bsgpu_call_block", "bsgpu_stage_bound", "bsgpu_stage_templates",
     "bsgpu_process_block", "bsgpu_profile_enable", "bsgpu_profile_read", "bsgpu_build_blocks_tally",
-    "bsgpu_call_bam_bcf", "bsgpu_default_bcf_params", "bsgpu_bcf_block", "bsgpu_bcf_block_dev", "bsgpu_call_block_bcf", "bsgpu_call_sites_bcf",
+    "bsgpu_call_bam_bcf", "bsgpu_default_bcf_params", "bsgpu_set_contig_annotation", "bsgpu_bcf_block", "bsgpu_bcf_block_dev", "bsgpu_call_block_bcf", "bsgpu_call_sites_bcf",
     "bsgpu_default_reader_params", "bsgpu_decode_records", "bsgpu_build_blocks", "bsgpu_call_bam",
     "bsgpu_bam_open", "bsgpu_bam_set_contig", "bsgpu_bam_feed", "bsgpu_bam_reserve", "bsgpu_bam_commit", "bsgpu_bam_finish", "bsgpu_bam_cut", "bsgpu_bam_rewind", "bsgpu_bam_drain",
     "bsgpu_bam_release", "bsgpu_bam_progress", "bsgpu_bam_close",
@@ -82,15 +82,35 @@ class BamProgress(C.Structure):
 
 class BcfParams(C.Structure):
     """bsgpu_bcf_params (include/bsgpu.h): header dictionary ids, contig id and end, -A"""
-    _fields_ = [("ids", C.c_int32 * 16), ("rid", C.c_int32), ("ctg_end", C.c_uint32), ("all_positions", C.c_uint8), ("pad_", C.c_uint8 * 3)]
+    _fields_ = [("ids", C.c_int32 * 16), ("rid", C.c_int32), ("ctg_end", C.c_uint32), ("all_positions", C.c_uint8), ("pad_", C.c_uint8 * 3),
+                ("reg_start", C.c_uint32), ("reg_stop", C.c_uint32), ("dbsnp", C.c_void_p)]
 
 
-def bcf_params(ids=None, rid=0, ctg_end=0xffffffff, all_positions=False):
+class Dbsnp(C.Structure):
+    """bsgpu_dbsnp (include/bsgpu.h): what dbSNP_lookup_name() answers for the known positions of one contig"""
+    _fields_ = [("n", C.c_uint32), ("pos", C.c_void_p), ("flags", C.c_void_p), ("name_off", C.c_void_p), ("names", C.c_void_p)]
+
+
+def dbsnp(pos, flags, name_off, names):
+    """-> Dbsnp over numpy arrays (kept alive on the returned object)"""
+    a = [np.ascontiguousarray(pos, dtype=np.uint32), np.ascontiguousarray(flags, dtype=np.uint8),
+         np.ascontiguousarray(name_off, dtype=np.uint32), np.ascontiguousarray(names, dtype=np.uint8)]
+    d = Dbsnp(len(a[0]), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data)
+    d._keep = a
+    return d
+
+
+def bcf_params(ids=None, rid=0, ctg_end=0xffffffff, all_positions=False, region=None, dbsnp=None):
     p = BcfParams()
     load().bsgpu_default_bcf_params(C.byref(p))
     if ids is not None:
         p.ids = (C.c_int32 * 16)(*[int(v) for v in ids])
     p.rid, p.ctg_end, p.all_positions = int(rid), int(ctg_end), 1 if all_positions else 0
+    if region is not None:
+        p.reg_start, p.reg_stop = int(region[0]), int(region[1])
+    if dbsnp is not None:
+        p.dbsnp = C.addressof(dbsnp)
+        p._keep = dbsnp
     return p
 
 
@@ -289,6 +309,12 @@ class BsGpu:
         return out[:nb.value], nr.value
 
     # ---- --report-file side channels -------------------------------------------------------------
+    def set_contig_annotation(self, tid, region=None, dbsnp=None):
+        """region (start, stop) and / or Dbsnp of contig `tid` for call_bam_bcf and sessions (bsgpu_set_contig_annotation)"""
+        r0, r1 = region if region is not None else (0, 0)
+        self._check(self.lib.bsgpu_set_contig_annotation(self.ctx, C.c_int(int(tid)), C.c_uint32(int(r0)), C.c_uint32(int(r1)),
+                                                         C.byref(dbsnp) if dbsnp is not None else None))
+
     def profile_enable(self, on=True):
         """gather the non-CpG conversion profile and the base / read tallies in process_block and call_bam
         (process_block then wants reference codes for [x, y + 1])"""

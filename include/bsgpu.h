@@ -173,6 +173,19 @@ typedef struct {
 
 /* ---- writer side: what the print thread needs besides the records to serialise a site (src/print_vcf.c) ---- */
 #define BSGPU_BCF_MAX_RECORD 384
+#define BSGPU_DBSNP_MAX_ID 96
+/* The dbSNP entries of one contig as the writer sees them (-D; src/print_vcf.c:133 calls dbSNP_lookup_name(), src/dbSNP.c:305,
+ * once per site).  The index file and its reader stay with the host; the host hands over the ANSWERS: positions (1-based,
+ * ascending, unique), flags[k] = the return value (1 known, 3 known and "always written": the site gets a record even when it
+ * is homozygous reference A / T, src/print_vcf.c:139), and the ID bytes exactly as lookup leaves them in rs[0 .. rs_len)
+ * (at most BSGPU_DBSNP_MAX_ID each): names[name_off[k] .. name_off[k + 1]).  name_off has n + 1 entries. */
+typedef struct {
+	uint32_t n;
+	const uint32_t *pos;
+	const uint8_t *flags;
+	const uint32_t *name_off;
+	const uint8_t *names;
+} bsgpu_dbsnp;
 typedef struct {
 	int32_t ids[16];           /* BCF header dictionary ids of PASS fail mac1 CX GT FT GL GQ DP MQ QD MC8 AMQ CS CG FS: work.vcf_ids
 	                              as print_vcf_header() fills it (include/bs_call.h:192-207, src/print_vcf.c:751-764) */
@@ -180,6 +193,9 @@ typedef struct {
 	uint32_t ctg_end;          /* ctg->end_pos: sites beyond it are not written (src/print_vcf.c:159) */
 	uint8_t all_positions;     /* -A: also write homozygous-reference A / T sites */
 	uint8_t pad_[3];
+	uint32_t reg_start, reg_stop;  /* ctg->curr_reg (-C / region list): only sites inside are written, and the contig end no longer
+	                              clips (src/print_vcf.c:154-157); 0, 0 = no region */
+	const bsgpu_dbsnp *dbsnp;  /* -D: the contig's dbSNP entries, or NULL (single-contig entry points; see bsgpu_set_contig_annotation) */
 } bsgpu_bcf_params;
 
 typedef struct bsgpu_ctx bsgpu_ctx;
@@ -259,9 +275,12 @@ int bsgpu_profile_read(bsgpu_ctx *ctx, bsgpu_profile *out, int reset);
 /* ---- writer side: a block of gt_vcf records -> the BCF records print_thread would hand to bcf_write()
  *      (print_vcf_entry / flush_vcf_entries / _print_vcf_entry, src/print_vcf.c:32-381, 535-594, driven per block by
  *      src/process.c:89-104), laid out as in a BCF file: l_shared, l_indiv, CHROM, POS, rlen, QUAL, n_allele|n_info,
- *      n_fmt|n_sample, shared, indiv.  No dbSNP ids (ID is empty).  ref holds sz + 2 codes: positions x .. x + sz + 1, the
+ *      n_fmt|n_sample, shared, indiv.  ref holds sz + 2 codes: positions x .. x + sz + 1, the
  *      string get_sequence_string() leaves in work.ref.  *nbytes / *nrec receive the size of the output. ---- */
-void bsgpu_default_bcf_params(bsgpu_bcf_params *p);      /* ids 0..15 in header order, rid 0, no contig end, -A off */
+void bsgpu_default_bcf_params(bsgpu_bcf_params *p);      /* ids 0..15 in header order, rid 0, no contig end, -A off, no region, no dbSNP */
+/* region and dbSNP entries of contig `tid` for the entry points that see many contigs (bsgpu_call_bam_bcf, sessions opened on
+ * the context afterwards or before -- it is looked up per window).  db may be NULL (region only); the arrays are copied. */
+int bsgpu_set_contig_annotation(bsgpu_ctx *ctx, int tid, uint32_t reg_start, uint32_t reg_stop, const bsgpu_dbsnp *db);
 int bsgpu_bcf_block(bsgpu_ctx *ctx, const bsgpu_gt_vcf *vcf, const uint8_t *ref, uint32_t x, uint32_t sz, const bsgpu_bcf_params *p,
 		uint8_t *out, size_t out_cap, size_t *nbytes, size_t *nrec);
 /* sorted segments -> BCF records of the block: pileup, model and writer derivations on the device, only the records come back */

@@ -105,7 +105,22 @@ def profile_dict(used, conv, base_filter, filter_cts, filter_bases):
 VCF_IDS = tuple(range(16))      # PASS fail mac1 CX GT FT GL GQ DP MQ QD MC8 AMQ CS CG FS: ids in header order
 
 
-def _print_block(fn, vcf, refcodes, x, rid, ctg_end, vcf_ids, all_positions):
+class BsoDbsnp(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("pos", C.c_void_p), ("flags", C.c_void_p), ("name_off", C.c_void_p), ("names", C.c_void_p)]
+
+
+def dbsnp_arrays(entries):
+    """entries: iterable of (position, flags, id bytes), any order -> (pos u32[], flags u8[], name_off u32[n + 1], names u8[])"""
+    entries = sorted(entries, key=lambda e: e[0])
+    pos = np.array([e[0] for e in entries], dtype=np.uint32)
+    flags = np.array([e[1] for e in entries], dtype=np.uint8)
+    off = np.zeros(len(entries) + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(e[2]) for e in entries])
+    names = np.frombuffer(b"".join(bytes(e[2]) for e in entries) + b"\0", dtype=np.uint8).copy()
+    return pos, flags, off, names
+
+
+def _print_block(fn, vcf, refcodes, x, rid, ctg_end, vcf_ids, all_positions, region=None, dbsnp=None, ann_fn=None, flat_db=False):
     vcf = _c(vcf, GT_VCF)
     sz = len(vcf)
     refcodes = _c(refcodes, np.uint8)
@@ -113,8 +128,21 @@ def _print_block(fn, vcf, refcodes, x, rid, ctg_end, vcf_ids, all_positions):
     ids = _c(VCF_IDS if vcf_ids is None else vcf_ids, np.int32)
     out = np.zeros(sz * 256 + 1024, dtype=np.uint8)
     nb, nr = C.c_size_t(0), C.c_size_t(0)
-    rc = fn(_p(vcf), C.c_uint32(sz), _p(refcodes), C.c_uint32(x), C.c_int(rid), C.c_uint32(ctg_end), _p(ids),
-            C.c_int(1 if all_positions else 0), _p(out), C.c_size_t(len(out)), C.byref(nb), C.byref(nr))
+    if region is None and dbsnp is None:
+        rc = fn(_p(vcf), C.c_uint32(sz), _p(refcodes), C.c_uint32(x), C.c_int(rid), C.c_uint32(ctg_end), _p(ids),
+                C.c_int(1 if all_positions else 0), _p(out), C.c_size_t(len(out)), C.byref(nb), C.byref(nr))
+    else:
+        r0, r1 = region if region is not None else (0, 0)
+        pos, flags, off, names = dbsnp if dbsnp is not None else dbsnp_arrays([])
+        if flat_db:          # the harness takes the table as flat arguments
+            rc = ann_fn(_p(vcf), C.c_uint32(sz), _p(refcodes), C.c_uint32(x), C.c_int(rid), C.c_uint32(ctg_end), _p(ids),
+                        C.c_int(1 if all_positions else 0), C.c_uint32(r0), C.c_uint32(r1), C.c_uint32(len(pos)), _p(pos), _p(flags), _p(off), _p(names),
+                        _p(out), C.c_size_t(len(out)), C.byref(nb), C.byref(nr))
+        else:
+            db = BsoDbsnp(len(pos), pos.ctypes.data, flags.ctypes.data, off.ctypes.data, names.ctypes.data)
+            rc = ann_fn(_p(vcf), C.c_uint32(sz), _p(refcodes), C.c_uint32(x), C.c_int(rid), C.c_uint32(ctg_end), _p(ids),
+                        C.c_int(1 if all_positions else 0), C.c_uint32(r0), C.c_uint32(r1), C.byref(db) if len(pos) else None,
+                        _p(out), C.c_size_t(len(out)), C.byref(nb), C.byref(nr))
     if rc:
         raise RuntimeError("print_block failed: %d" % rc)
     return out[:nb.value].copy(), nr.value
@@ -239,9 +267,11 @@ class Oracle:
         return _read_input(self.lib.bso_read_input, bam, target_len, ctg_codes, mapq_thresh, max_template_len,
                            keep_unmatched, ignore_duplicates, keep_duplicates, run_chain)
 
-    def print_block(self, vcf, refcodes, x, rid=0, ctg_end=0xffffffff, vcf_ids=None, all_positions=False):
-        """the restatement of the reference's writer over one block of gt_vcf[] -> (BCF record bytes, number of records)"""
-        return _print_block(self.lib.bso_print_block, vcf, refcodes, x, rid, ctg_end, vcf_ids, all_positions)
+    def print_block(self, vcf, refcodes, x, rid=0, ctg_end=0xffffffff, vcf_ids=None, all_positions=False, region=None, dbsnp=None):
+        """the restatement of the reference's writer over one block of gt_vcf[] -> (BCF record bytes, number of records);
+        region = (start, stop) of ctg->curr_reg, dbsnp = dbsnp_arrays(...) of the contig's index entries"""
+        return _print_block(self.lib.bso_print_block, vcf, refcodes, x, rid, ctg_end, vcf_ids, all_positions, region, dbsnp,
+                            self.lib.bso_print_block_ann)
 
     def profile_enable(self, on=True):
         """--report-file side channels (process-wide in the library); process_block then wants codes for [x, y + 1]"""
@@ -379,10 +409,11 @@ class Reference:
             raise RuntimeError("bsref_call_block failed: %d" % rc)
         return pile, vcf
 
-    def print_block(self, vcf, refcodes, x, rid=0, ctg_end=0xffffffff, vcf_ids=None, all_positions=False):
+    def print_block(self, vcf, refcodes, x, rid=0, ctg_end=0xffffffff, vcf_ids=None, all_positions=False, region=None, dbsnp=None):
         """one block of gt_vcf[] through the reference's print_vcf_entry / flush_vcf_entries (src/print_vcf.c) as the print
         thread runs them; refcodes covers [x, x + len(vcf) + 1].  Returns (BCF record bytes, number of records)."""
-        return _print_block(self.lib.bsref_print_block, vcf, refcodes, x, rid, ctg_end, vcf_ids, all_positions)
+        return _print_block(self.lib.bsref_print_block, vcf, refcodes, x, rid, ctg_end, vcf_ids, all_positions, region, dbsnp,
+                            self.lib.bsref_print_block_ann, flat_db=True)
 
     def stats_enable(self, on=True):
         """give the reference a bs_stats (what --report-file does): meth_profile() and the tallies become live"""

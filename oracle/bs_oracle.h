@@ -149,6 +149,13 @@ int bso_read_input(const uint8_t *bam, size_t nbytes, int n_targets, const uint3
  *      vcf_ids: the 16 header dictionary ids in the order of include/bs_call.h:192-207; out receives the records in BCF
  *      layout (l_shared, l_indiv, fixed fields, shared, indiv). ---- */
 #define BSO_BCF_MAX_RECORD 384
+/* the dbSNP entries of one contig as the writer sees them through dbSNP_lookup_name() (src/dbSNP.c:305-346) */
+typedef struct { uint32_t n; const uint32_t *pos; const uint8_t *flags; const uint32_t *name_off; const uint8_t *names; } bso_dbsnp;
+size_t bso_print_site_ann(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, uint32_t i, int rid, uint32_t ctg_end,
+		const int *ids, int all_positions, uint32_t reg_start, uint32_t reg_stop, const bso_dbsnp *db, uint8_t *out);
+int bso_print_block_ann(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, int rid, uint32_t ctg_end,
+		const int *vcf_ids, int all_positions, uint32_t reg_start, uint32_t reg_stop, const bso_dbsnp *db,
+		uint8_t *out, size_t cap, size_t *nbytes, size_t *nrec);
 size_t bso_print_site(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, uint32_t i, int rid, uint32_t ctg_end,
 		const int *ids, int all_positions, uint8_t *out);
 int bso_print_block(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, int rid, uint32_t ctg_end,

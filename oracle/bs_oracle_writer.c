@@ -65,8 +65,26 @@ static int site_call(const bso_gt_vcf *v) {
 	return gt + 1;
 }
 
+/* dbSNP hit of position pos (what dbSNP_lookup_name() gives the writer, src/dbSNP.c:305-346): flags 0 / 1 / 3 and the ID bytes */
+static int db_lookup(const bso_dbsnp *db, uint32_t pos, const uint8_t **name, uint32_t *len) {
+	if (!db || !db->n) return 0;
+	uint32_t lo = 0, hi = db->n;
+	while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (db->pos[mid] < pos) lo = mid + 1; else hi = mid; }
+	if (lo == db->n || db->pos[lo] != pos) return 0;
+	*name = db->names + db->name_off[lo];
+	*len = db->name_off[lo + 1] - db->name_off[lo];
+	return db->flags[lo];
+}
+
 size_t bso_print_site(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, uint32_t i, int rid, uint32_t ctg_end,
 		const int *ids, int all_positions, uint8_t *out) {
+	return bso_print_site_ann(vcf, sz, refcodes, x, i, rid, ctg_end, ids, all_positions, 0, 0, NULL, out);
+}
+
+/* reg_start / reg_stop: ctg->curr_reg (0, 0: none -- then the contig end clips, src/print_vcf.c:154-157); db: the contig's
+ * dbSNP entries (NULL: no -D index) */
+size_t bso_print_site_ann(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, uint32_t i, int rid, uint32_t ctg_end,
+		const int *ids, int all_positions, uint32_t reg_start, uint32_t reg_stop, const bso_dbsnp *db, uint8_t *out) {
 	int g[5];
 	/* calls of the five sites around this one; before the block: none; beyond its end: flush_vcf_entries shifts the
 	 * window without clearing the slot it vacates (:538), so the last site's call is seen again */
@@ -97,8 +115,12 @@ size_t bso_print_site(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcode
 	}
 	const int rfix = rc[2], gt = g[2] - 1;
 	const int hom_ref_at = (gt == 0 && rfix == 1) || (gt == 9 && rfix == 4);      /* gt_flag, :91-102 */
-	if (!all_positions && hom_ref_at) return 0;
-	if (x + i > ctg_end) return 0;
+	const uint8_t *rs = NULL;
+	uint32_t rs_len = 0;
+	const int rs_found = db_lookup(db, x + i, &rs, &rs_len);                       /* :133 */
+	if (!all_positions && !(rs_found & 2) && hom_ref_at) return 0;                 /* :139: an "always output" dbSNP site is kept */
+	if (reg_start || reg_stop) { if (x + i < reg_start || x + i > reg_stop) return 0; }      /* :154-157 */
+	else if (x + i > ctg_end) return 0;
 	/* phred-scaled probability that the call is wrong (:140-148), quality by depth, strand bias, filters (:151-153, 184-187) */
 	const double z1 = exp(gtm->gt_prob[gt] * LN10);
 	int phred;
@@ -132,9 +154,10 @@ size_t bso_print_site(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcode
 	int alts[2] = { 0, 0 }, n_alt = 0;
 	for (int k = 0; k < 2; k++) { const int a = allele_of[gt][k]; if (a != rfix && (!n_alt || alts[0] != a)) alts[n_alt++] = a; }
 
-	uint8_t sh[64], in[256];
+	uint8_t sh[384], in[256];
 	wbuf S = { sh, 0 }, I = { in, 0 };
-	enc_size(&S, 0, T_CHAR);                                 /* ID: none (no dbSNP index on this path) */
+	if (!rs_found) enc_size(&S, 0, T_CHAR);                  /* ID (:163-167) */
+	else enc_chars(&S, (const char *)rs, (int)rs_len);
 	enc_chars(&S, ref_ctx + 2, 1);                           /* REF */
 	for (int k = 0; k < n_alt; k++) enc_chars(&S, base_char + alts[k], 1);
 	enc_int1(&S, fid);                                       /* FILTER */
@@ -227,10 +250,16 @@ size_t bso_print_site(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcode
 
 int bso_print_block(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, int rid, uint32_t ctg_end,
 		const int *vcf_ids, int all_positions, uint8_t *out, size_t cap, size_t *nbytes, size_t *nrec) {
+	return bso_print_block_ann(vcf, sz, refcodes, x, rid, ctg_end, vcf_ids, all_positions, 0, 0, NULL, out, cap, nbytes, nrec);
+}
+
+int bso_print_block_ann(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, int rid, uint32_t ctg_end,
+		const int *vcf_ids, int all_positions, uint32_t reg_start, uint32_t reg_stop, const bso_dbsnp *db,
+		uint8_t *out, size_t cap, size_t *nbytes, size_t *nrec) {
 	size_t at = 0, n = 0;
 	for (uint32_t i = 0; i < sz; i++) {
 		if (at + BSO_BCF_MAX_RECORD > cap) return -3;
-		const size_t l = bso_print_site(vcf, sz, refcodes, x, i, rid, ctg_end, vcf_ids, all_positions, out + at);
+		const size_t l = bso_print_site_ann(vcf, sz, refcodes, x, i, rid, ctg_end, vcf_ids, all_positions, reg_start, reg_stop, db, out + at);
 		if (l) { at += l; n++; }
 	}
 	*nbytes = at; *nrec = n;

@@ -899,9 +899,24 @@ int hts_set_threads(htsFile *fp, int n) { pv_unreachable("hts_set_threads"); ret
 int bam_name2id(bam_hdr_t *h, const char *ref) { pv_unreachable("bam_name2id"); return -1; }
 khint_t bsstub_kh_get(const void *h, const char *key) { pv_unreachable("kh_get"); return 0; }
 khint_t bsstub_kh_end(const void *h) { pv_unreachable("kh_end"); return 0; }
-uint8_t dbSNP_lookup_name(const dbsnp_header_t *const hdr, const dbsnp_ctg_t *c, char *const rs, size_t *const rs_len, const uint32_t x) { pv_unreachable("dbSNP_lookup_name"); return 0; }
-bool load_dbSNP_ctg(const dbsnp_header_t *const hdr, dbsnp_ctg_t *const c) { pv_unreachable("load_dbSNP_ctg"); return false; }
-void unload_dbSNP_ctg(dbsnp_ctg_t *const c) { pv_unreachable("unload_dbSNP_ctg"); }
+/* dbSNP: the index file and its reader (src/dbSNP.c) are host I/O outside the path; what the path's writer sees of them is
+ * the answer of dbSNP_lookup_name() per position -- flags (1 known, 3 known and always written) and the ID bytes -- which
+ * the harness serves from a table the test supplies (bsref_print_block_ann).  print_vcf.c's use of the answer
+ * (src/print_vcf.c:133, 139, 163-167) is the compiled reference's. */
+static struct { uint32_t n; const uint32_t *pos; const uint8_t *flags; const uint32_t *name_off; const uint8_t *names; } db_tab;
+uint8_t dbSNP_lookup_name(const dbsnp_header_t *const hdr, const dbsnp_ctg_t *c, char *const rs, size_t *const rs_len, const uint32_t x) {
+	rs[0] = 0;
+	uint32_t lo = 0, hi = db_tab.n;
+	while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (db_tab.pos[mid] < x) lo = mid + 1; else hi = mid; }
+	if (lo == db_tab.n || db_tab.pos[lo] != x) return 0;
+	const uint32_t l = db_tab.name_off[lo + 1] - db_tab.name_off[lo];
+	memcpy(rs, db_tab.names + db_tab.name_off[lo], l);
+	rs[l] = 0;
+	if (rs_len) *rs_len = l;
+	return db_tab.flags[lo];
+}
+bool load_dbSNP_ctg(const dbsnp_header_t *const hdr, dbsnp_ctg_t *const c) { return true; }
+void unload_dbSNP_ctg(dbsnp_ctg_t *const c) { }
 
 void print_vcf_entry(bcf1_t *bcf, ctg_t * const ctg, gt_meth *gtm, const char *rf, const uint32_t x, const uint32_t xstart, bool skip, sr_param * const par);
 void flush_vcf_entries(bcf1_t *bcf, const sr_param * const par);
@@ -910,21 +925,45 @@ void flush_vcf_entries(bcf1_t *bcf, const sr_param * const par);
  * refcodes: sz + 2 codes (positions x .. x + sz + 1), the string get_sequence_string() leaves in work.ref.
  * vcf_ids: the 16 dictionary ids print_vcf_header() looks up (include/bs_call.h:192-208).
  * out receives the records bcf_write() was handed, in BCF layout; returns 0, or -3 when out is too small. */
+int bsref_print_block_ann(const gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, int rid, uint32_t ctg_end,
+		const int *vcf_ids, int all_positions, uint32_t reg_start, uint32_t reg_stop,
+		uint32_t db_n, const uint32_t *db_pos, const uint8_t *db_flags, const uint32_t *db_name_off, const uint8_t *db_names,
+		uint8_t *out, size_t cap, size_t *nbytes, size_t *nrec);
+
 int bsref_print_block(const gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, int rid, uint32_t ctg_end,
 		const int *vcf_ids, int all_positions, uint8_t *out, size_t cap, size_t *nbytes, size_t *nrec) {
+	return bsref_print_block_ann(vcf, sz, refcodes, x, rid, ctg_end, vcf_ids, all_positions, 0, 0, 0, NULL, NULL, NULL, NULL, out, cap, nbytes, nrec);
+}
+
+/* the same with ctg->curr_reg = [reg_start, reg_stop] (0, 0: none; what -C / a region list sets, src/get_template_vector.c:123)
+ * and a dbSNP index that knows the db_n positions given (-D) */
+int bsref_print_block_ann(const gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, int rid, uint32_t ctg_end,
+		const int *vcf_ids, int all_positions, uint32_t reg_start, uint32_t reg_stop,
+		uint32_t db_n, const uint32_t *db_pos, const uint8_t *db_flags, const uint32_t *db_name_off, const uint8_t *db_names,
+		uint8_t *out, size_t cap, size_t *nbytes, size_t *nrec) {
 	static ctg_t pv_ctg[2];
+	static region_t pv_reg;
 	static int flip = 0;
 	static bcf1_t *bcf = NULL;
+	static dbsnp_header_t db_hdr;
+	static dbsnp_ctg_t db_ctg;
 	if (!inited) return -1;
 	if (!bcf) bcf = bcf_init();
 	/* a different ctg_t object every call: _print_vcf_entry then forgets the last position it printed (:117-127) */
 	ctg_t *c = pv_ctg + (flip ^= 1);
 	memset(c, 0, sizeof(*c));
 	c->name = "ctg"; c->vcf_rid = rid; c->start_pos = 1; c->end_pos = ctg_end; c->curr_reg = NULL;
+	if (reg_start || reg_stop) { pv_reg.ctg = c; pv_reg.start = reg_start; pv_reg.stop = reg_stop; c->curr_reg = &pv_reg; }
 	bs_stats *saved = par.work.stats;
 	par.work.stats = NULL;                     /* the writer's own statistics are not part of this check */
 	par.work.vcf_ctg = c;
 	par.work.dbSNP_hdr = NULL;
+	db_tab.n = 0;
+	if (db_n) {
+		db_tab.n = db_n; db_tab.pos = db_pos; db_tab.flags = db_flags; db_tab.name_off = db_name_off; db_tab.names = db_names;
+		if (db_hdr.dbSNP == NULL) { db_ctg.name = "ctg"; HASH_ADD_KEYPTR(hh, db_hdr.dbSNP, db_ctg.name, strlen(db_ctg.name), &db_ctg); }
+		par.work.dbSNP_hdr = &db_hdr;
+	}
 	par.all_positions = all_positions;
 	for (int i = 0; i < 16; i++) par.work.vcf_ids[i] = vcf_ids[i];
 	pv_out = out; pv_cap = cap; pv_len = 0; pv_nrec = 0; pv_overflow = 0;
@@ -938,6 +977,7 @@ int bsref_print_block(const gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, u
 	flush_vcf_entries(bcf, &par);
 	free(rf);
 	par.work.stats = saved;
+	par.work.dbSNP_hdr = NULL;
 	*nbytes = pv_len; *nrec = pv_nrec;
 	return pv_overflow ? -3 : 0;
 }

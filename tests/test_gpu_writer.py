@@ -233,3 +233,65 @@ def test_records_and_side_channels_together(gpu, oracle):
         util.same_profile(g2.profile_read(), want, "records + side channels")
     finally:
         g2.close()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_dbsnp_ids_and_regions(gpu, oracle, seed):
+    """-D and -C on the device (src/print_vcf.c:133, 139, 154-157, 163-167): dbSNP IDs in the record, "always written" sites,
+    clipping to the region instead of the contig end; the oracle's annotated writer is held to the compiled reference's in
+    tests/test_oracle_vs_reference.py"""
+    from tests.test_oracle_vs_reference import random_dbsnp
+    rng = np.random.default_rng(2900 + seed)
+    for sz in (1, 7, 129, 3000, 70001):
+        vcf = util.random_gt_vcf(rng, sz, skip_frac=[0.0, 0.3][seed % 2])
+        refw = rng.integers(1, 5, size=sz + 2).astype(np.uint8)
+        refw[rng.random(sz + 2) < 0.02] = 0
+        x = int(rng.integers(1, 100000))
+        ctg_end = x + sz - 1 - int(rng.integers(0, 3))
+        db = random_dbsnp(rng, max(1, x - 5), x + sz + 5)
+        for region in (None, (x + sz // 4, x + (3 * sz) // 4), (x + 2, x + sz + 100)):
+            for allp in (False, True):
+                for d in (None, db):
+                    want = oracle.print_block(vcf, refw, x, rid=2, ctg_end=ctg_end, all_positions=allp, region=region, dbsnp=d)
+                    p = bslib.bcf_params(rid=2, ctg_end=ctg_end, all_positions=allp, region=region, dbsnp=bslib.dbsnp(*d) if d is not None else None)
+                    got = gpu.bcf_block(vcf, refw, x, p)
+                    same_bcf(got, want, "seed %d size %d %r" % (seed, sz, (region, allp, d is not None)))
+
+
+def test_bam_to_records_with_contig_annotation(oracle, monkeypatch):
+    """bsgpu_set_contig_annotation: per-contig dbSNP entries and regions on the many-contig path (bsgpu_call_bam_bcf, and a
+    streaming session on the same context), against the oracle's annotated writer block by block"""
+    from tests import bamgen
+    from tests.test_oracle_vs_reference import random_dbsnp
+    bam, n, tl, refs = bamgen.make_stream(77, n_contigs=3, dup=0.1, contig_len=9000)
+    rng = np.random.default_rng(78)
+    dbs = [random_dbsnp(rng, 1, int(tl[t]), frac=0.1) for t in range(3)]
+    regions = [None, (1500, 7000), (1, int(tl[2]) + 50)]
+    g = bslib.BsGpu()
+    try:
+        blocks, vcf = g.call_bam(bam, tl, refs)
+        keep = []
+        for t in range(3):
+            d = bslib.dbsnp(*dbs[t]) if t != 1 else None
+            keep.append(d)
+            g.set_contig_annotation(t, region=regions[t], dbsnp=d)
+        parts, total = [], 0
+        for b in blocks:
+            x, y, tid = int(b["x"]), int(b["y"]), int(b["tid"])
+            v = vcf[int(b["vcf_off"]):int(b["vcf_off"]) + y - x + 1]
+            rb, k = oracle.print_block(v, blockgen.window_codes(refs[tid], x, y + 2), x, rid=tid, ctg_end=int(tl[tid]),
+                                       region=regions[tid], dbsnp=dbs[tid] if tid != 1 else None)
+            parts.append(rb)
+            total += k
+        want = (np.concatenate(parts), total)
+        _, out, nrec = g.call_bam_bcf(bam, tl, refs)
+        same_bcf((np.asarray(out).copy(), nrec), want, "call_bam_bcf")
+        s = g.bam_session(tl, refs, bcf=True, batch_bytes=30000)
+        try:
+            res = s.run(bam, slice_bytes=7777)
+        finally:
+            s.close()
+        same_bcf((np.concatenate([d for _, d, _ in res]), sum(k for _, _, k in res)), want, "session")
+        assert total > 300
+    finally:
+        g.close()

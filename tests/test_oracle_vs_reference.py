@@ -320,3 +320,40 @@ def test_print_block_on_random_records(oracle, reference, seed):
             want = reference.print_block(vcf, refw, x, rid=3, ctg_end=ctg_end, vcf_ids=ids, all_positions=allp)
             got = oracle.print_block(vcf, refw, x, rid=3, ctg_end=ctg_end, vcf_ids=ids, all_positions=allp)
             _same_bcf(got, want, "seed %d size %d all_positions %r" % (seed, sz, allp))
+
+
+def random_dbsnp(rng, lo, hi, frac=0.15):
+    """dbSNP answers for a random subset of [lo, hi): known / always-written flags, IDs of 3..14 bytes, some with the trailing
+    NUL an odd number of digits leaves behind (src/dbSNP.c:337-341)"""
+    from oracle.bindings import dbsnp_arrays
+    n = max(1, int((hi - lo) * frac))
+    ents = []
+    for p in rng.choice(np.arange(lo, hi), size=min(n, hi - lo), replace=False):
+        nm = b"rs%d" % int(rng.integers(1, 10 ** int(rng.integers(1, 11))))
+        if rng.random() < 0.3:
+            nm += b"\0"
+        ents.append((int(p), 3 if rng.random() < 0.4 else 1, nm))
+    return dbsnp_arrays(ents)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_print_block_with_dbsnp_and_regions(oracle, reference, seed):
+    """-D and -C as the writer sees them (src/print_vcf.c:133, 139, 154-157, 163-167): IDs, "always written" homozygous
+    reference A / T sites, clipping to ctg->curr_reg instead of the contig end -- restatement against the compiled writer fed
+    through its own dbSNP_lookup_name() interface"""
+    rng = np.random.default_rng(1900 + seed)
+    for sz in (1, 7, 300, 5000):
+        vcf = util.random_gt_vcf(rng, sz, skip_frac=[0.0, 0.3][seed % 2])
+        refw = rng.integers(1, 5, size=sz + 2).astype(np.uint8)
+        refw[rng.random(sz + 2) < 0.02] = 0
+        x = int(rng.integers(1, 1000))
+        ctg_end = x + sz - 1 - int(rng.integers(0, 3))
+        db = random_dbsnp(rng, max(1, x - 5), x + sz + 5)
+        regions = [None, (x + sz // 4, x + (3 * sz) // 4), (1, x + sz // 2), (x + 2, x + sz + 100)]
+        for region in regions:
+            for allp in (False, True):
+                for d in (None, db):
+                    kw = dict(rid=2, ctg_end=ctg_end, all_positions=allp, region=region, dbsnp=d)
+                    want = reference.print_block(vcf, refw, x, **kw)
+                    got = oracle.print_block(vcf, refw, x, **kw)
+                    _same_bcf(got, want, "seed %d size %d %r" % (seed, sz, (region, allp, d is not None)))
