@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <unordered_map>
 #include <map>
 #include <deque>
 #include <mutex>
@@ -47,11 +48,10 @@ struct BuildJob;
 struct CertainState { int tid = -1; uint64_t maxend = 0; };
 void certain_block_starts(const bsgpu_record *rec, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts);
 void certain_block_starts_keys(const uint32_t *keys, size_t rbeg, size_t rend, CertainState *st, std::vector<size_t> &starts);
-BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t rbeg, size_t rend,
+BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, const uint32_t *name_id, size_t rbeg, size_t rend,
 		const std::vector<size_t> &starts, bool keep_unmatched, bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread,
 		bool with_tally);
-BuildJob *build_blocks_start(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
-		bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread, bool with_tally);
+void host_name_ids(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, uint32_t *name_id);
 const uint64_t *build_blocks_piece_tally(const BuildJob *job, size_t p);
 uint32_t build_blocks_piece_maxcap(const BuildJob *job, size_t p);
 bool build_blocks_piece_ready(const BuildJob *job, size_t p);
@@ -120,7 +120,8 @@ struct bsgpu_ctx {
 	cudaStream_t copy_stream = nullptr;          // D2H of finished windows
 	Slot slot[2];
 	DevBuf segs, bases, ref, scratch, vcf, tmpl, misms, obases, ooff, pile;
-	DevBuf rd_bam, rd_recoff, rd_readoff, rd_mmoff, rd_rec, rd_bases, rd_misms, rd_key, rd_mask;
+	DevBuf rd_bam, rd_recoff, rd_readoff, rd_mmoff, rd_rec, rd_bases, rd_misms, rd_key, rd_mask, rd_names, rd_nameid;
+	PinBuf h_nameid;                             // name ids of the records coming home (QNAME join on the device)
 	std::vector<size_t> mask_off;                // word offset of every chunk's certain-start mask in rd_mask / h_mask      // reader side: stream, framing, decoded arrays
 	std::vector<uint64_t> rec_off;               // framing of the last decoded stream
 	std::vector<uint32_t> read_off, mm_off, off_tmp;
@@ -262,6 +263,7 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 	for (cudaEvent_t ev : c->rd_done) cudaEventDestroy(ev);
 	if (c->frame_scratch) frame_scratch_free(c->frame_scratch);
 	c->h_rec.release(); c->h_off.release(); c->h_tmpl.release(); c->h_key.release(); c->rd_key.release(); c->h_mask.release(); c->rd_mask.release();
+	c->rd_names.release(); c->rd_nameid.release(); c->h_nameid.release();
 	c->rd_bam.release(); c->rd_recoff.release(); c->rd_readoff.release(); c->rd_mmoff.release(); c->rd_rec.release(); c->rd_bases.release(); c->rd_misms.release();
 	c->segs.release(); c->bases.release(); c->ref.release(); c->scratch.release(); c->vcf.release(); c->tmpl.release(); c->misms.release(); c->obases.release(); c->ooff.release(); c->pile.release();
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -1000,6 +1002,14 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 	const bool host_scan = getenv("BSGPU_DEVICE_SCAN") == nullptr || getenv("BSGPU_CHECK_SCAN") != nullptr;
 	CU(c->rd_key.reserve(n * 16));
 	if (host_scan) CU(c->h_key.reserve(n * 16));
+	// QNAME join: table of kept paired records by name hash, name ids per record (+ one word: the overflow flag)
+	const size_t name_slots = name_table_slots(n);
+	CU(c->rd_names.reserve(name_table_bytes(n)));
+	CU(c->rd_nameid.reserve((n + 1) * 4));
+	CU(c->h_nameid.reserve((n + 1 + K) * 4));      // + the overflow flag as it stood after every chunk
+	memset((uint32_t *)c->h_nameid.p + n, 0, (1 + K) * 4);
+	CU(cudaMemsetAsync(c->rd_names.p, 0, name_table_bytes(n), dec));
+	CU(cudaMemsetAsync((uint32_t *)c->rd_nameid.p + n, 0, 4, dec));
 	CU(c->rd_mask.reserve((n / 32 + 2 * K + 8) * 4 + 16));
 	CU(c->h_mask.reserve((n / 32 + 2 * K + 8) * 4));
 	c->mask_off.assign(K + 1, 0);
@@ -1045,7 +1055,11 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 		if (r1 > r0) {
 			CU(launch_decode_records(c->rd_bam.p, (const uint64_t *)c->rd_recoff.p + r0, (const uint32_t *)c->rd_readoff.p + r0,
 					(const uint32_t *)c->rd_mmoff.p + r0, r1 - r0, rp->mapq_thresh, rp->max_template_len, rp->keep_unmatched,
-					rp->ignore_duplicates, (bsgpu_record *)c->rd_rec.p + r0, c->rd_bases.p, c->rd_misms.p, dec, &c->launches, (uint8_t *)c->rd_key.p + r0 * 16));
+					rp->ignore_duplicates, (bsgpu_record *)c->rd_rec.p + r0, c->rd_bases.p, c->rd_misms.p, dec, &c->launches, (uint8_t *)c->rd_key.p + r0 * 16,
+					c->rd_names.p, name_slots, (uint32_t)r0, (uint32_t *)c->rd_nameid.p + n));
+			CU(launch_name_ids(c->rd_bam.p, c->rd_recoff.p, c->rd_rec.p, (uint32_t)r0, (uint32_t)r1, c->rd_names.p, name_slots, c->rd_nameid.p, dec, &c->launches));
+			CU(cudaMemcpyAsync((uint32_t *)c->h_nameid.p + r0, (const uint32_t *)c->rd_nameid.p + r0, (r1 - r0) * 4, cudaMemcpyDeviceToHost, dec));
+			CU(cudaMemcpyAsync((uint32_t *)c->h_nameid.p + n + 1 + k, (const uint32_t *)c->rd_nameid.p + n, 4, cudaMemcpyDeviceToHost, dec));
 			if (host_scan) CU(cudaMemcpyAsync((uint8_t *)c->h_key.p + r0 * 16, (const uint8_t *)c->rd_key.p + r0 * 16, (r1 - r0) * 16, cudaMemcpyDeviceToHost, dec));
 			if (dev_scan) {
 				const size_t words = (r1 - r0 + 31) / 32;
@@ -1061,7 +1075,7 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 		chunk_end.push_back(r1);
 		r0 = r1;
 	}
-	c->stats.d2h_bytes += n * (sizeof(bsgpu_record) + (host_scan ? 16 : 0)) + mask_words * 4;
+	c->stats.d2h_bytes += n * (sizeof(bsgpu_record) + 4 + (host_scan ? 16 : 0)) + mask_words * 4;
 	return BSGPU_OK;
 }
 
@@ -1443,6 +1457,8 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	cudaError_t scan_err = cudaSuccess;
 	const bool check_scan = getenv("BSGPU_CHECK_SCAN") != nullptr, use_host_scan = check_scan || getenv("BSGPU_DEVICE_SCAN") == nullptr;
 	std::atomic<int> scan_mismatch{0};
+	std::unordered_map<std::string, uint32_t> host_names;
+	size_t host_names_done = 0, name_fallbacks = 0;
 	guard.scanner = std::thread([&] {
 		cudaSetDevice(c->device);
 		for (size_t ck = 0; ck < chunk_end.size(); ck++) {
@@ -1451,6 +1467,21 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 			if (scan_err != cudaSuccess) { scan_state.store(-1, std::memory_order_release); return; }
 			const double w1 = now();
 			sc_rd += w1 - w0;
+			// the device's name table overflowed (a read name on more than five kept records, or hashes colliding): from this
+			// chunk on the ids are computed here, over a map that first catches up with the records before
+			if (((const uint32_t *)c->h_nameid.p)[n + 1 + ck] && chunk_end[ck] > scanned) {
+				uint32_t *ids = (uint32_t *)c->h_nameid.p;
+				for (size_t i = host_names_done; i < chunk_end[ck]; i++) {
+					uint32_t id = 0xffffffffu;
+					if (rec[i].ret <= 0 && (rec[i].alignment_flag & 1u)) {
+						const uint8_t *p = bam + c->rec_off[i] + 4;
+						id = host_names.emplace(std::string((const char *)p + 32, p[8]), (uint32_t)i).first->second;
+					}
+					if (i >= scanned) ids[i] = id;
+				}
+				host_names_done = chunk_end[ck];
+				name_fallbacks++;
+			}
 			if (use_host_scan) certain_block_starts_keys((const uint32_t *)c->h_key.p, scanned, chunk_end[ck], &cst, starts);
 			if (!use_host_scan || check_scan) {
 				// the device's mask of the chunk: bit i of word i / 32 <-> record scanned + i
@@ -1476,7 +1507,7 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 			if (upto > built) {
 				std::vector<size_t> inside;
 				for (size_t v : starts) if (v > built && v < upto) inside.push_back(v);
-				guard.jobs.push_back(build_blocks_start_range(bam, c->rec_off.data(), rec, built, upto, inside, rp->keep_unmatched, rp->keep_duplicates, tm, ppt, c->profile_on));
+				guard.jobs.push_back(build_blocks_start_range(bam, c->rec_off.data(), rec, (const uint32_t *)c->h_nameid.p, built, upto, inside, rp->keep_unmatched, rp->keep_duplicates, tm, ppt, c->profile_on));
 				njobs.store(guard.jobs.size(), std::memory_order_release);
 				std::vector<size_t> keep;
 				for (size_t v : starts) if (v >= upto) keep.push_back(v);

@@ -101,7 +101,13 @@ cudaError_t launch_bcf_records(const BcfJob &j, uint32_t i0, uint32_t cnt, void 
 // reader side (bsgpu_reader.cu)
 cudaError_t launch_decode_records(const void *bam, const void *rec_off, const void *read_off, const void *mm_off, size_t nrec,
 		uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup, void *out, void *bases, void *misms,
-		cudaStream_t stream, int *launches, void *keys = nullptr);
+		cudaStream_t stream, int *launches, void *keys = nullptr, void *name_table = nullptr, size_t name_slots = 0, uint32_t rec_base = 0,
+		void *name_overflow = nullptr);
+// QNAME join (bsgpu_reader.cu): the table k_decode_records fills, and the kernel that turns it into per-record name ids
+size_t name_table_slots(size_t nrec);
+size_t name_table_bytes(size_t nrec);
+cudaError_t launch_name_ids(const void *bam, const void *rec_off, const void *rec, uint32_t r0, uint32_t r1, const void *table, size_t slots,
+		void *name_id, cudaStream_t stream, int *launches);
 
 // certain block starts of a chunk of records as a bit mask, from the keys launch_decode_records wrote (bsgpu_reader.cu)
 cudaError_t launch_certain_starts(const void *keys, uint32_t n, void *carry, void *mask, cudaStream_t stream, int *launches);

@@ -20,6 +20,8 @@
 #include <condition_variable>
 #include <thread>
 #include <vector>
+#include <unordered_map>
+#include <string>
 #include <cuda_runtime.h>
 #include "bsgpu.h"
 #include "bsgpu_launch.h"
@@ -97,6 +99,33 @@ __device__ uint32_t strand_from_tags(const uint8_t *s, const uint8_t *end) {
 
 constexpr int kDecodeWarps = 8;
 
+// ---- QNAME join on the device (the hash find / insert of read_input, src/get_template_vector.c:131-385, turned into a perfect
+// hash): every kept, paired record is entered into an open-addressing table under the 64-bit hash of its read name
+// (k_decode_records), then k_name_ids gives each such record the index of the FIRST record of the batch that carries exactly
+// the same name (names compared byte by byte).  The host's block builder indexes its waiting-mate entries by that id and
+// never hashes or even reads a name.  A slot keeps up to five record indices; more records under one hash (a name used by
+// more than five kept records, or colliding hashes) raise the overflow flag and the host computes the ids itself.
+struct NameSlot { unsigned long long key; uint32_t cnt; uint32_t idx[5]; };
+static_assert(sizeof(NameSlot) == 32, "name table slot");
+
+__host__ __device__ __forceinline__ unsigned long long name_hash(const uint8_t *s, uint32_t n) {
+	unsigned long long h = 0x9e3779b97f4a7c15ull ^ n;
+	for (uint32_t i = 0; i < n; i++) { h = (h ^ s[i]) * 0x100000001b3ull; }
+	h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+	return h | 1ull;                      // 0 marks an empty slot
+}
+
+__device__ __forceinline__ void name_insert(NameSlot *tab, uint32_t mask, unsigned long long key, uint32_t rec, uint32_t *overflow) {
+	for (uint32_t s = (uint32_t)(key >> 17) & mask;; s = (s + 1) & mask) {
+		const unsigned long long old = atomicCAS(&tab[s].key, 0ull, key);
+		if (old == 0ull || old == key) {
+			const uint32_t k = atomicAdd(&tab[s].cnt, 1u);
+			if (k < 5) tab[s].idx[k] = rec; else atomicExch(overflow, 1u);
+			return;
+		}
+	}
+}
+
 // A warp takes 32 consecutive records.  Phase 1, one record per LANE: the fixed fields, the filter cascade, the CIGAR
 // walk, the tag walk and the descriptor -- short scalar work whose cost is shared by 32 records.  Phase 2, one record
 // per TRIP with all lanes: the 4-bit sequence and the qualities become packed bytes, lanes striding over the bases
@@ -104,7 +133,8 @@ constexpr int kDecodeWarps = 8;
 __global__ void __launch_bounds__(kDecodeWarps * 32)
 k_decode_records(const uint8_t *__restrict__ bam, const uint64_t *__restrict__ rec_off, const uint32_t *__restrict__ read_off,
 		const uint32_t *__restrict__ mm_off, size_t nrec, uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup,
-		bsgpu_record *__restrict__ out, uint8_t *__restrict__ bases, bsgpu_misms *__restrict__ misms, uint4 *__restrict__ keys) {
+		bsgpu_record *__restrict__ out, uint8_t *__restrict__ bases, bsgpu_misms *__restrict__ misms, uint4 *__restrict__ keys,
+		NameSlot *__restrict__ names, uint32_t name_mask, uint32_t rec_base, uint32_t *__restrict__ name_overflow) {
 	const size_t w0 = ((size_t)blockIdx.x * kDecodeWarps + (threadIdx.x >> 5)) * 32;
 	const int lane = threadIdx.x & 31;
 	if (w0 >= nrec) return;
@@ -211,6 +241,7 @@ k_decode_records(const uint8_t *__restrict__ bam, const uint64_t *__restrict__ r
 			}
 		}
 		out[w] = r;
+		if (names && !dropped && (r.alignment_flag & F_PAIRED)) name_insert(names, name_mask, name_hash(p + 32, l_qname), rec_base + (uint32_t)w, name_overflow);
 		if (keys) {
 			// what the scan for certain block starts needs of a record (certain_block_starts): its contig (-1: dropped), the
 			// smaller of its positions if it is inserted by its flags alone (else 0), the furthest end it can give its block
@@ -338,7 +369,53 @@ __global__ void __launch_bounds__(1024) k_certain_starts(const uint4 *__restrict
 	}
 	if (tid_x == 0) { carry[0] = c_tid; carry[1] = c_m; }
 }
+// name_id[i] = the smallest record index of the batch whose read name is that of record i (i itself when it is the first), for
+// kept paired records; 0xffffffff for the others.  rec_off / rec / name_id are indexed by the batch-wide record number.
+__global__ void __launch_bounds__(256)
+k_name_ids(const uint8_t *__restrict__ bam, const uint64_t *__restrict__ rec_off, const bsgpu_record *__restrict__ rec, uint32_t r0, uint32_t r1,
+		const NameSlot *__restrict__ tab, uint32_t mask, uint32_t *__restrict__ name_id) {
+	const uint32_t i = r0 + blockIdx.x * 256 + threadIdx.x;
+	if (i >= r1) return;
+	uint32_t id = 0xffffffffu;
+	const bsgpu_record r = rec[i];
+	if (r.ret == 0 && (r.alignment_flag & F_PAIRED)) {
+		const uint8_t *p = bam + rec_off[i] + 4;
+		const uint32_t l = p[8];
+		const unsigned long long key = name_hash(p + 32, l);
+		id = i;
+		for (uint32_t s = (uint32_t)(key >> 17) & mask;; s = (s + 1) & mask) {
+			const unsigned long long k = tab[s].key;
+			if (k == key) {
+				const uint32_t cnt = min(tab[s].cnt, 5u);
+				for (uint32_t c = 0; c < cnt; c++) {
+					const uint32_t j = tab[s].idx[c];
+					if (j >= id) continue;
+					const uint8_t *q = bam + rec_off[j] + 4;
+					bool same = q[8] == l;
+					for (uint32_t b = 0; same && b < l; b++) same = q[32 + b] == p[32 + b];
+					if (same) id = j;
+				}
+				break;
+			}
+			if (k == 0ull) break;          // cannot happen for an inserted record
+		}
+	}
+	name_id[i] = id;
+}
+
 }  // namespace
+
+size_t name_table_slots(size_t nrec) { size_t s = 1024; while (s < 2 * nrec) s <<= 1; return s; }
+size_t name_table_bytes(size_t nrec) { return name_table_slots(nrec) * sizeof(NameSlot); }
+
+cudaError_t launch_name_ids(const void *bam, const void *rec_off, const void *rec, uint32_t r0, uint32_t r1, const void *table, size_t slots,
+		void *name_id, cudaStream_t stream, int *launches) {
+	if (r1 <= r0) return cudaSuccess;
+	k_name_ids<<<(r1 - r0 + 255) / 256, 256, 0, stream>>>((const uint8_t *)bam, (const uint64_t *)rec_off, (const bsgpu_record *)rec, r0, r1,
+		(const NameSlot *)table, (uint32_t)(slots - 1), (uint32_t *)name_id);
+	*launches += 1;
+	return cudaGetLastError();
+}
 
 // mask: one bit per record of the chunk (bit i of word i / 32), (n + 31) / 32 words, 4096-record tiles start on word boundaries
 cudaError_t launch_certain_starts(const void *keys, uint32_t n, void *carry, void *mask, cudaStream_t stream, int *launches) {
@@ -350,11 +427,12 @@ cudaError_t launch_certain_starts(const void *keys, uint32_t n, void *carry, voi
 
 cudaError_t launch_decode_records(const void *bam, const void *rec_off, const void *read_off, const void *mm_off, size_t nrec,
 		uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup, void *out, void *bases, void *misms,
-		cudaStream_t stream, int *launches, void *keys) {
+		cudaStream_t stream, int *launches, void *keys, void *name_table, size_t name_slots, uint32_t rec_base, void *name_overflow) {
 	if (!nrec) return cudaSuccess;
 	const unsigned grid = (unsigned)((nrec + kDecodeWarps * 32 - 1) / (kDecodeWarps * 32));
 	k_decode_records<<<grid, kDecodeWarps * 32, 0, stream>>>((const uint8_t *)bam, (const uint64_t *)rec_off, (const uint32_t *)read_off,
-		(const uint32_t *)mm_off, nrec, mapq_thresh, max_tlen, keep_unmatched, ignore_dup, (bsgpu_record *)out, (uint8_t *)bases, (bsgpu_misms *)misms, (uint4 *)keys);
+		(const uint32_t *)mm_off, nrec, mapq_thresh, max_tlen, keep_unmatched, ignore_dup, (bsgpu_record *)out, (uint8_t *)bases, (bsgpu_misms *)misms, (uint4 *)keys,
+		(NameSlot *)name_table, name_table ? (uint32_t)(name_slots - 1) : 0u, rec_base, (uint32_t *)name_overflow);
 	*launches += 1;
 	return cudaGetLastError();
 }
@@ -548,55 +626,24 @@ struct Tmpl {
 	uint8_t mapq[2], orientation, bs_strand;
 };
 
-// open-addressing table of waiting mates keyed by read name; cleared in O(1) at block ends by bumping `gen`
-struct NameTable {
-	struct Ent { uint64_t hash; uint32_t name_rec, ix, flag, gen; };     // gen: 0 never used, odd = live, even = deleted
-	std::vector<Ent> tab;
-	uint32_t gen = 1, used = 0;
-	const uint8_t *bam;
-	const uint64_t *rec_off;
-	NameTable() : tab(1024) {}
-	static uint64_t hash_name(const uint8_t *s, uint32_t n) {
-		uint64_t h = 0x9e3779b97f4a7c15ull ^ n;
-		uint32_t i = 0;
-		for (; i + 8 <= n; i += 8) { uint64_t w; memcpy(&w, s + i, 8); h = (h ^ w) * 0xff51afd7ed558ccdull; h ^= h >> 32; }
-		if (i < n) { uint64_t w = 0; memcpy(&w, s + i, n - i); h = (h ^ w) * 0xc4ceb9fe1a85ec53ull; h ^= h >> 32; }
-		return h ^ (h >> 29);
-	}
-	const uint8_t *name_of(uint32_t rec, uint32_t *len) const { const uint8_t *p = bam + rec_off[rec] + 4; *len = p[8]; return p + 32; }
-	void clear() { gen += 2; used = 0; if (gen > 0xfffffff0u) { for (auto &e : tab) e.gen = 0; gen = 1; } }
-	Ent *find(const uint8_t *s, uint32_t n, uint64_t h) {
-		const size_t mask = tab.size() - 1;
-		for (size_t i = h & mask;; i = (i + 1) & mask) {
-			Ent &e = tab[i];
-			if (e.gen != gen && e.gen != gen + 1) return nullptr;          // slot untouched in this block: end of the probe chain
-			if (e.gen == gen && e.hash == h) {
-				uint32_t l;
-				const uint8_t *nm = name_of(e.name_rec, &l);
-				if (l == n && !memcmp(nm, s, n)) return &e;
-			}
-		}
-	}
-	void grow() {
-		std::vector<Ent> old;
-		old.swap(tab);
-		tab.assign(old.size() * 2, Ent{0, 0, 0, 0, 0});
-		used = 0;
-		for (const Ent &e : old) if (e.gen == gen) insert_raw(e);
-	}
-	Ent *insert_raw(const Ent &v) {
-		const size_t mask = tab.size() - 1;
-		for (size_t i = v.hash & mask;; i = (i + 1) & mask) {
-			Ent &e = tab[i];
-			if (e.gen != gen && e.gen != gen + 1) { e = v; e.gen = gen; used++; return &e; }
-		}
-	}
-	// returns the index of the new entry's slot (stable until the next grow): callers keep indices, not pointers
-	void add(uint32_t name_rec, uint64_t h, uint32_t flag, uint32_t ix) {
-		if ((size_t)(used + 1) * 2 > tab.size()) grow();
-		insert_raw(Ent{h, name_rec, ix, flag, gen});
-	}
-	static void kill(Ent *e) { e->gen += 1; }
+// read_input's hash of waiting mates (uthash keyed by QNAME, src/get_template_vector.c:131-385) as an index: name_id[rec] is
+// the first record of the stream that carries rec's read name (computed on the device, k_name_ids, or by host_name_ids), so
+// the entry of a name is a slot of an array -- no hashing, no name bytes touched.  Entries are cleared in O(1) at block ends
+// by bumping `cur`.  A builder piece starts at a certain block start; the rare name whose first record lies before the
+// piece (a read name used twice on a contig) goes through a small map.
+struct NameIndex {
+	struct Ent { uint32_t gen = 0, ix = 0; };      // live iff gen == cur
+	const uint32_t *name_id = nullptr;
+	size_t base = 0;
+	std::vector<Ent> near;
+	std::unordered_map<uint32_t, Ent> far;
+	uint32_t cur = 1;
+	void init(const uint32_t *ids, size_t rbeg, size_t rend) { name_id = ids; base = rbeg; near.assign(rend - rbeg, Ent()); far.clear(); cur = 1; }
+	void clear() { cur++; }
+	Ent *slot(size_t rec) { const uint32_t r = name_id[rec]; return r >= base ? &near[r - base] : &far[r]; }
+	Ent *find(size_t rec) { Ent *e = slot(rec); return e->gen == cur ? e : nullptr; }
+	void add(size_t rec, uint32_t ix) { Ent *e = slot(rec); e->gen = cur; e->ix = ix; }
+	static void kill(Ent *e) { e->gen = 0; }
 };
 
 }  // namespace
@@ -609,7 +656,8 @@ struct BlockBuilder {
 	std::vector<int64_t> list_name;      // per slot: record whose name keys the slot's live table entry, -1 = none ("alh_p[ix]")
 	std::vector<uint32_t> list_flag;
 	size_t used = 0;
-	NameTable names;
+	NameIndex names;
+	const uint32_t *name_id = nullptr;
 	std::vector<bsgpu_block> *blocks;
 	bsgpu_template *out = nullptr;       // templates of this builder, in publication order (room for one per record)
 	size_t nout = 0;
@@ -662,26 +710,21 @@ struct BlockBuilder {
 
 	// records [rbeg, nrec): rbeg must be the start of the stream or a point where read_input is certain to start a new block
 	int run(size_t rbeg, size_t nrec, bool keep_unmatched, bool keep_duplicates) {
-		names.bam = bam; names.rec_off = rec_off;
+		names.init(name_id, rbeg, nrec);
 		int curr_tid = -1, old_tid = -1;
 		uint32_t max_pos = 0, start_pos = 0, read_idx = 0, curr_pos = 0, start_idx = 0;
-		// The loop is a chain of dependent cache misses (record -> name in the stream -> table slot).  Names are hashed a few
-		// records ahead and the lines they will touch are requested early.
+		// The loop is a chain of dependent loads (record -> its name id -> the entry of that name): the entry of a record a few
+		// places ahead is requested early.
 		constexpr size_t kAhead = 12;
-		uint64_t ring[16];
 		auto look_ahead = [&](size_t j) {
 			if (j >= nrec) return;
 			const bsgpu_record &q = rec[j];
 			if (q.ret > 0 || !(q.alignment_flag & F_PAIRED)) return;
-			uint32_t l;
-			const uint8_t *nm = names.name_of((uint32_t)j, &l);
-			const uint64_t h = NameTable::hash_name(nm, l);
-			ring[j & 15] = h;
-			__builtin_prefetch(&names.tab[h & (names.tab.size() - 1)]);
+			const uint32_t id = name_id[j];
+			if (id >= rbeg) __builtin_prefetch(&names.near[id - rbeg]);
 		};
 		for (size_t j = rbeg; j < rbeg + kAhead; j++) look_ahead(j);
 		for (size_t ri = rbeg; ri < nrec; ri++) {
-			if (ri + kAhead + 8 < nrec) __builtin_prefetch(bam + rec_off[ri + kAhead + 8] + 36);      // the name of a record further ahead
 			look_ahead(ri + kAhead);
 			const bsgpu_record &r = rec[ri];
 			if (r.ret > 0) {
@@ -697,18 +740,14 @@ struct BlockBuilder {
 			memset(&al, 0, sizeof(al));
 			al.fwd = r.forward_position; al.rev = r.reverse_position; al.orientation = r.orientation; al.bs_strand = r.bs_strand;
 			al.rec[0] = al.rec[1] = -1; al.rec[ix] = (int64_t)ri; al.mapq[ix] = r.mapq; al.span[ix] = r.reference_span;
-			uint32_t nlen;
-			const uint8_t *name = names.name_of((uint32_t)ri, &nlen);
 			const bool paired = r.alignment_flag & F_PAIRED;
-			uint64_t nh = 0;
-			NameTable::Ent *waiting = nullptr;
+			NameIndex::Ent *waiting = nullptr;
 			bool new_block = false, new_contig = false;
 			if (curr_tid < 0 || curr_tid != r.tid) { new_contig = new_block = true; old_tid = curr_tid; curr_tid = r.tid; }
-			if (paired) nh = ring[ri & 15];
 			bool insert = true;
 			if (!new_contig) {
 				if (paired && al.fwd > 0 && al.rev > 0) {
-					if (al.fwd == al.rev) insert = names.find(name, nlen, nh) == nullptr;
+					if (al.fwd == al.rev) insert = names.find(ri) == nullptr;
 					else insert = r.reverse ? al.fwd > al.rev : al.fwd < al.rev;
 				}
 				if (insert && start_pos > 0) {
@@ -730,13 +769,13 @@ struct BlockBuilder {
 			}
 			if (paired) {
 				if (!insert) {
-					waiting = names.find(name, nlen, nh);
+					waiting = names.find(ri);
 					if (waiting) {
 						Tmpl &t = list[waiting->ix];
 						if (al.fwd != t.fwd || al.rev != t.rev) return -5;      // the reference asserts here (src/get_template_vector.c:239)
 						t.rec[ix] = (int64_t)ri; t.mapq[ix] = r.mapq; t.span[ix] = r.reference_span;
 						list_name[waiting->ix] = -1;
-						NameTable::kill(waiting);
+						NameIndex::kill(waiting);
 					} else {
 						if (tally) count(14, 1, 14, r.read_len);      // the partner never came (:243-246)
 						bool skip = false;
@@ -763,18 +802,14 @@ struct BlockBuilder {
 								maxq /= kn; maxq1 /= kn1;
 								if (maxq1 < maxq || (maxq == maxq1 && al_qual(a1) < al_qual(al))) {
 									// the newcomer takes the slot; the slot's table entry is re-keyed to the newcomer's name
-									NameTable::Ent *h = names.find(name, nlen, nh);
+									NameIndex::Ent *h = names.find(ri);
 									if (h && list_name[i] >= 0) return -4;            // duplicate read name (fatal in the reference)
 									const bool from_slot = !h && list_name[i] >= 0;
-									if (from_slot) {
-										uint32_t ol;
-										const uint8_t *on = names.name_of((uint32_t)list_name[i], &ol);
-										h = names.find(on, ol, NameTable::hash_name(on, ol));
-									}
+									if (from_slot) h = names.find((size_t)list_name[i]);
 									const Tmpl old = a1;
 									a1 = al;
-									if (h) NameTable::kill(h);
-									names.add((uint32_t)ri, nh, r.alignment_flag, i);
+									if (h) NameIndex::kill(h);
+									names.add(ri, i);
 									if (from_slot) { list_name[i] = (int64_t)ri; list_flag[i] = r.alignment_flag; }
 									al = old;
 								}
@@ -787,8 +822,8 @@ struct BlockBuilder {
 						} else { curr_pos = pos; start_idx = read_idx; }
 					}
 					if (!skip) {
-						if (names.find(name, nlen, nh)) return -4;
-						names.add((uint32_t)ri, nh, r.alignment_flag, read_idx);
+						if (names.find(ri)) return -4;
+						names.add(ri, read_idx);
 						put(read_idx, al, (int64_t)ri, r.alignment_flag);
 						read_idx++;
 					}
@@ -817,6 +852,20 @@ struct BlockBuilder {
 		return 0;
 	}
 };
+
+// name_id[] on the host (what k_name_ids computes on the device): used by the host-only entry point bsgpu_build_blocks and
+// when the device table overflowed
+void host_name_ids(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, uint32_t *name_id) {
+	std::unordered_map<std::string, uint32_t> first;
+	first.reserve(nrec);
+	for (size_t i = 0; i < nrec; i++) {
+		name_id[i] = 0xffffffffu;
+		if (rec[i].ret > 0 || !(rec[i].alignment_flag & F_PAIRED)) continue;
+		const uint8_t *p = bam + rec_off[i] + 4;
+		const auto it = first.emplace(std::string((const char *)p + 32, p[8]), (uint32_t)i);
+		name_id[i] = it.first->second;
+	}
+}
 
 struct CertainState { int tid = -1; uint64_t maxend = 0; };
 
@@ -1000,7 +1049,7 @@ struct BuildJob {
 
 // records [rbeg, rend); rbeg is the start of the stream or a certain block start; `starts` = the certain block starts
 // inside the range (ascending), from which the cuts between pieces are chosen
-BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t rbeg, size_t rend,
+BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, const uint32_t *name_id, size_t rbeg, size_t rend,
 		const std::vector<size_t> &starts, bool keep_unmatched, bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread,
 		bool with_tally) {
 	unsigned want = std::thread::hardware_concurrency();
@@ -1026,7 +1075,7 @@ BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, 
 	if (with_tally) job->tally.assign(np * 30, 0);
 	auto build_piece = [=](size_t p) {
 		BlockBuilder b;
-		b.bam = bam; b.rec_off = rec_off; b.rec = rec; b.blocks = &job->pb[p];
+		b.bam = bam; b.rec_off = rec_off; b.rec = rec; b.name_id = name_id; b.blocks = &job->pb[p];
 		b.out = tmpl + job->cuts[p];
 		if (with_tally) b.tally = job->tally.data() + p * 30;
 		job->rc[p] = b.run(job->cuts[p], job->cuts[p + 1], keep_unmatched, keep_duplicates);
@@ -1039,12 +1088,12 @@ BuildJob *build_blocks_start_range(const uint8_t *bam, const uint64_t *rec_off, 
 	return job;
 }
 
-BuildJob *build_blocks_start(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
+BuildJob *build_blocks_start(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, const uint32_t *name_id, size_t nrec, bool keep_unmatched,
 		bool keep_duplicates, bsgpu_template *tmpl, unsigned pieces_per_thread, bool with_tally) {
 	std::vector<size_t> starts;
 	CertainState st;
 	certain_block_starts(rec, 0, nrec, &st, starts);
-	return build_blocks_start_range(bam, rec_off, rec, 0, nrec, starts, keep_unmatched, keep_duplicates, tmpl, pieces_per_thread, with_tally);
+	return build_blocks_start_range(bam, rec_off, rec, name_id, 0, nrec, starts, keep_unmatched, keep_duplicates, tmpl, pieces_per_thread, with_tally);
 }
 
 size_t build_blocks_pieces(const BuildJob *job) { return job->pb.size(); }
@@ -1074,7 +1123,9 @@ void build_blocks_finish(BuildJob *job) {
 // the whole build at once: `tmpl` must have room for nrec templates; *ntmpl receives the count, templates compacted
 int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_record *rec, size_t nrec, bool keep_unmatched,
 		bool keep_duplicates, std::vector<bsgpu_block> &blocks, bsgpu_template *tmpl, size_t *ntmpl, uint64_t *tally) {
-	BuildJob *job = build_blocks_start(bam, rec_off, rec, nrec, keep_unmatched, keep_duplicates, tmpl, 1, tally != nullptr);
+	std::vector<uint32_t> name_id(nrec + 1);
+	host_name_ids(bam, rec_off, rec, nrec, name_id.data());
+	BuildJob *job = build_blocks_start(bam, rec_off, rec, name_id.data(), nrec, keep_unmatched, keep_duplicates, tmpl, 1, tally != nullptr);
 	const size_t np = build_blocks_pieces(job);
 	size_t at = 0;
 	int rc = 0;

@@ -218,3 +218,43 @@ def test_exact_offset_table_path(monkeypatch):
     nb, digest = out.stdout.split()[-2:]
     want = hashlib.sha1(b"".join(np.ascontiguousarray(v1["gtm"][f]).tobytes() for f in ("counts", "qual", "gt_prob", "fisher_strand", "mq", "aq", "max_gt")) + v1["skip"].tobytes()).hexdigest()
     assert int(nb) == len(b1) and digest == want
+
+
+def _repeat_on_contigs(bam, copies):
+    """the records of a one-contig stream again on contigs 1 .. copies - 1 (same read names: legal, read_input's name table
+    is emptied at every block end)"""
+    out, at, n = [], 0, len(bam)
+    offs = []
+    while at < n:
+        bs = int(bam[at:at + 4].view("<i4")[0])
+        offs.append((at, 4 + bs))
+        at += 4 + bs
+    for t in range(copies):
+        b = bam.copy()
+        for o, l in offs:
+            b[o + 4:o + 8] = np.frombuffer(np.int32(t).tobytes(), dtype=np.uint8)
+            if int(bam[o + 24:o + 28].view("<i4")[0]) >= 0:
+                b[o + 24:o + 28] = np.frombuffer(np.int32(t).tobytes(), dtype=np.uint8)
+        out.append(b)
+    return np.concatenate(out), len(offs) * copies
+
+
+def test_name_join_overflow_falls_back_to_the_host(gpu, oracle, monkeypatch):
+    """every read name on eight kept records (four contigs x two mates): the device's name table keeps five per hash, raises
+    its overflow flag, and the host computes the name ids for the affected chunks -- same blocks, same records"""
+    bam1, n1, tl1, refs1 = bamgen.make_stream(611, n_contigs=1, dup=0.2, junk=0.1, contig_len=7000, paired=True)
+    bam, n = _repeat_on_contigs(bam1, 4)
+    tl, refs = np.repeat(tl1, 4), refs1 * 4
+    o = dict(mapq_thresh=20, max_template_len=1000, keep_unmatched=False, ignore_duplicates=False, keep_duplicates=False)
+    wbk, wt, wb, wm, wv = oracle.read_input(bam, tl, refs, run_chain=True, **o)
+    for chunked in (False, True):
+        if chunked:
+            monkeypatch.setenv("BSGPU_READER_CHUNK_MIN_BYTES", "1")
+            monkeypatch.setenv("BSGPU_BUILDER_MIN_RECORDS", "1")
+            monkeypatch.setenv("BSGPU_BUILDER_THREADS", "3")
+        blocks, vcf = gpu.call_bam(bam, tl, refs, _rp(o))
+        assert len(blocks) == len(wbk) > 4
+        for b, w in zip(blocks, wbk):
+            assert (b["tid"], b["x"], b["y"], b["n_templates"]) == (w["tid"], w["x"], w["y"], w["n_templates"])
+            sz = int(w["y"]) - int(w["x"]) + 1
+            util.assert_vcf_close(vcf[int(b["vcf_off"]):int(b["vcf_off"]) + sz], wv[int(w["vcf_off"]):int(w["vcf_off"]) + sz])
