@@ -72,7 +72,11 @@ static int fail(const char *fmt, ...) {
 	return BSGPU_FAIL;
 }
 
-#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+// BSGPU_SYNC_CHECK=1 (debugging aid; compute-sanitizer is not available on every pool): the device is synchronised after
+// every runtime call made through CU(), so that an asynchronous fault is reported at the call that caused it
+static const bool g_sync_check = getenv("BSGPU_SYNC_CHECK") != nullptr;
+#define CU(call) do { cudaError_t e_ = (call); if (e_ == cudaSuccess && g_sync_check) e_ = cudaDeviceSynchronize(); \
+	if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 // grow-on-demand device / pinned buffers
 struct DevBuf {
@@ -955,7 +959,11 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
 	CU(cudaStreamSynchronize(c->copy_stream));
-	cudaStream_t up = c->slot[0].stream, dec = c->slot[1].stream;
+	// debugging switches: BSGPU_ONE_STREAM=1 puts upload, decode and the windows on one stream (no kernel of the reader stage
+	// overlaps a kernel of the window stage); BSGPU_NO_NAME_JOIN=1 leaves the QNAME join to the host
+	static const bool one_stream = getenv("BSGPU_ONE_STREAM") != nullptr, no_join = getenv("BSGPU_NO_NAME_JOIN") != nullptr;
+	static const bool dec_own = getenv("BSGPU_DECODE_STREAM") != nullptr;      // decode kernels on a stream of their own (round-1 behaviour)
+	cudaStream_t up = one_stream ? c->stream : c->slot[0].stream, dec = one_stream || !dec_own ? c->stream : c->slot[1].stream;
 	CU(cudaStreamSynchronize(up));
 	CU(cudaStreamSynchronize(dec));
 	size_t chunk_min = 64u << 20;                       // smaller streams go up and are decoded in one piece
@@ -1056,8 +1064,9 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 			CU(launch_decode_records(c->rd_bam.p, (const uint64_t *)c->rd_recoff.p + r0, (const uint32_t *)c->rd_readoff.p + r0,
 					(const uint32_t *)c->rd_mmoff.p + r0, r1 - r0, rp->mapq_thresh, rp->max_template_len, rp->keep_unmatched,
 					rp->ignore_duplicates, (bsgpu_record *)c->rd_rec.p + r0, c->rd_bases.p, c->rd_misms.p, dec, &c->launches, (uint8_t *)c->rd_key.p + r0 * 16,
-					c->rd_names.p, name_slots, (uint32_t)r0, (uint32_t *)c->rd_nameid.p + n));
-			CU(launch_name_ids(c->rd_bam.p, c->rd_recoff.p, c->rd_rec.p, (uint32_t)r0, (uint32_t)r1, c->rd_names.p, name_slots, c->rd_nameid.p, dec, &c->launches));
+					no_join ? nullptr : c->rd_names.p, name_slots, (uint32_t)r0, (uint32_t *)c->rd_nameid.p + n));
+			if (no_join) CU(cudaMemsetAsync((uint32_t *)c->rd_nameid.p + n, 0xff, 4, dec));      // "overflow": the host computes the ids
+			else CU(launch_name_ids(c->rd_bam.p, c->rd_recoff.p, c->rd_rec.p, (uint32_t)r0, (uint32_t)r1, c->rd_names.p, name_slots, c->rd_nameid.p, dec, &c->launches));
 			CU(cudaMemcpyAsync((uint32_t *)c->h_nameid.p + r0, (const uint32_t *)c->rd_nameid.p + r0, (r1 - r0) * 4, cudaMemcpyDeviceToHost, dec));
 			CU(cudaMemcpyAsync((uint32_t *)c->h_nameid.p + n + 1 + k, (const uint32_t *)c->rd_nameid.p + n, 4, cudaMemcpyDeviceToHost, dec));
 			if (host_scan) CU(cudaMemcpyAsync((uint8_t *)c->h_key.p + r0 * 16, (const uint8_t *)c->rd_key.p + r0 * 16, (r1 - r0) * 16, cudaMemcpyDeviceToHost, dec));

@@ -208,18 +208,27 @@ __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int q
 	// The same differences feed the guard band: the transcendental terms of ll[] are within 1.5 ulp of libm's, so the order
 	// of two genotypes whose likelihoods differ by less than kTieBand (relative) is not guaranteed to be the reference's.
 	// Such sites are reported (bsgpu_stats.near_tie_sites / exact_tie_sites, bsgpu_guard_read), not hidden.
-	const double band = -kTieBand * (fabs(top) > 1.0 ? fabs(top) : 1.0);
-	int ntop = 0, near = 0;
 	double sum = 0.0;
 #pragma unroll
 	for (int g = 0; g < 10; g++) {
 		const double x = ll[g] - top;
 		const double e = fast_exp(x < -45.0 ? -45.0 : x, mt);
 		sum += x < -45.0 ? 0.0 : (x == 0.0 ? 1.0 : e);
-		ntop += x == 0.0;
-		near |= x != 0.0 && x >= band;
 	}
-	*tie = ntop > 1 ? 2 : near;
+	// A runner-up inside the band contributes e^x >= 1 - 1e-9 |top| to the sum, so only sites with sum >= 2 - 1e-6 (the call
+	// holds less than half of the posterior mass: rare at sequencing depth) are looked at genotype by genotype.
+	*tie = 0;
+	if (sum >= 2.0 - 1.0e-6) {
+		const double band = -kTieBand * (fabs(top) > 1.0 ? fabs(top) : 1.0);
+		int ntop = 0, near = 0;
+#pragma unroll
+		for (int g = 0; g < 10; g++) {
+			const double x = ll[g] - top;
+			ntop += x == 0.0;
+			near |= x != 0.0 && x >= band;
+		}
+		*tie = ntop > 1 ? 2 : near;
+	}
 	sum = fast_log(sum, mt);          // sum is in [1, 10]
 #pragma unroll
 	for (int g = 0; g < 10; g++) prob[g] = div_by(ll[g] - top - sum, kLn10, kInvLn10);
