@@ -215,11 +215,11 @@ __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int q
 		const double e = fast_exp(x < -45.0 ? -45.0 : x, mt);
 		sum += x < -45.0 ? 0.0 : (x == 0.0 ? 1.0 : e);
 	}
-	// A runner-up inside the band contributes e^x >= 1 - 1e-9 |top| to the sum, so only sites with sum >= 2 - 1e-6 (the call
-	// holds less than half of the posterior mass: rare at sequencing depth) are looked at genotype by genotype.
+	// A runner-up inside the band (x >= -band) contributes e^x >= 1 - band to the sum, so only sites with sum >= 2 - 2 band (the
+	// call holds less than half of the posterior mass: rare at sequencing depth) are looked at genotype by genotype.
 	*tie = 0;
-	if (sum >= 2.0 - 1.0e-6) {
-		const double band = -kTieBand * (fabs(top) > 1.0 ? fabs(top) : 1.0);
+	const double band = -kTieBand * (fabs(top) > 1.0 ? fabs(top) : 1.0);
+	if (sum >= 2.0 + 2.0 * band) {
 		int ntop = 0, near = 0;
 #pragma unroll
 		for (int g = 0; g < 10; g++) {
