@@ -496,10 +496,22 @@ static int call_bins(bsgpu_ctx *c, size_t nseg, const void *d_bases, const void 
 		CU(launch_pileup_tiles(c->scratch.p, nseg, d_bases, d_ref, x, sz, t0, nt, dout, 1, c->d_const, c->d_counters, st, &c->launches));
 		return BSGPU_OK;
 	}
-	const size_t site0 = (size_t)t0 * kPileTileSites;
-	const size_t nsite = (size_t)sz - site0 < (size_t)nt * kPileTileSites ? (size_t)sz - site0 : (size_t)nt * kPileTileSites;
-	CU(launch_pileup_tiles(c->scratch.p, nseg, d_bases, d_ref, x, sz, t0, nt, c->pile.p, 0, c->d_const, c->d_counters, st, &c->launches));
-	CU(launch_call_sites(c->pile.p, (const uint8_t *)d_ref + site0, nsite, dout, nullptr, true, c->d_const, c->d_counters, st, &c->launches, (unsigned long long)x + site0));
+	// The count vectors go from the pileup kernel to the model through an HBM scratch.  BSGPU_SUBSLAB_TILES=n hands them over in
+	// sub-slabs of n tiles that fit the L2 (126 MB), alternating between two halves of the scratch.  Measured (50 M sites, 30x):
+	// one launch each 5.54 ms, n = 8192: 6.59, 4096: 7.31, 2048: 8.95 -- the tails of the smaller launches cost more than the
+	// cached read-back saves (neither kernel is HBM-bound), so the default is 0: one launch each.
+	static const uint32_t sub = [] { const char *e = getenv("BSGPU_SUBSLAB_TILES"); const long v = e ? atol(e) : 0; return (uint32_t)(v < 0 ? 0 : v); }();
+	const uint32_t step = sub ? sub : nt;
+	for (uint32_t k = 0, a = 0; a < nt; a += step, k++) {
+		const uint32_t m = nt - a < step ? nt - a : step, ta = t0 + a;
+		const size_t site0 = (size_t)ta * kPileTileSites;
+		const size_t nsite = (size_t)sz - site0 < (size_t)m * kPileTileSites ? (size_t)sz - site0 : (size_t)m * kPileTileSites;
+		// the scratch holds a whole slab (c->pile is sized by the callers): sub-slab k uses half (k & 1) of its first 2 * step tiles
+		uint8_t *pile = (uint8_t *)c->pile.p + (sub ? (size_t)(k & 1) * step * kPileTileSites * sizeof(bsgpu_pileup) : 0);
+		CU(launch_pileup_tiles(c->scratch.p, nseg, d_bases, d_ref, x, sz, ta, m, pile, 0, c->d_const, c->d_counters, st, &c->launches));
+		CU(launch_call_sites(pile, (const uint8_t *)d_ref + site0, nsite, (uint8_t *)dout + (site0 - (size_t)t0 * kPileTileSites) * sizeof(bsgpu_gt_vcf), nullptr, true,
+				c->d_const, c->d_counters, st, &c->launches, (unsigned long long)x + site0));
+	}
 	return BSGPU_OK;
 }
 
@@ -1094,6 +1106,7 @@ static int decode_resident(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, cons
 	if (decode_queue(c, bam, nbytes, rp, 1, nrec, nb, nm, chunk_end) != BSGPU_OK) return BSGPU_FAIL;
 	CU(cudaStreamSynchronize(c->slot[0].stream));
 	CU(cudaStreamSynchronize(c->slot[1].stream));
+	CU(cudaStreamSynchronize(c->stream));          // the decode kernels run on the context stream
 	return BSGPU_OK;
 }
 

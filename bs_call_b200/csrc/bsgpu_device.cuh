@@ -218,8 +218,9 @@ __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int q
 	// A runner-up inside the band (x >= -band) contributes e^x >= 1 - band to the sum, so only sites with sum >= 2 - 2 band (the
 	// call holds less than half of the posterior mass: rare at sequencing depth) are looked at genotype by genotype.
 	*tie = 0;
-	const double band = -kTieBand * (fabs(top) > 1.0 ? fabs(top) : 1.0);
-	if (sum >= 2.0 + 2.0 * band) {
+#ifndef BSGPU_NO_GUARD
+	if (sum >= 1.99) {                 // (band <= 1e-9 |top|, far below 0.005 for any |top| a double sum of this model reaches)
+		const double band = -kTieBand * (fabs(top) > 1.0 ? fabs(top) : 1.0);
 		int ntop = 0, near = 0;
 #pragma unroll
 		for (int g = 0; g < 10; g++) {
@@ -229,6 +230,7 @@ __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int q
 		}
 		*tie = ntop > 1 ? 2 : near;
 	}
+#endif
 	sum = fast_log(sum, mt);          // sum is in [1, 10]
 #pragma unroll
 	for (int g = 0; g < 10; g++) prob[g] = div_by(ll[g] - top - sum, kLn10, kInvLn10);

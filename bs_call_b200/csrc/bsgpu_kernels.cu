@@ -97,9 +97,9 @@ __device__ __forceinline__ void store_tile(void *gdst, const uint64_t *stage, in
 constexpr int kCallTile = 128;
 
 // a site whose result sits inside a guard band: counted, and listed while the list has room
-// (tie: 1 = closer than the band, counted here; 2 = equal, counted by the caller per warp; both are listed as kind 1)
-__device__ __forceinline__ void guard_flag(unsigned long long *counters, int tie, unsigned long long id) {
-	if (tie == 1) atomicAdd(counters + 4, 1ull);
+// (tie: 1 = closer than the band, 2 = equal; both are listed as kind 1.  Rare: kept out of line)
+__device__ __noinline__ void guard_flag(unsigned long long *counters, int tie, unsigned long long id) {
+	atomicAdd(counters + (tie == 1 ? 4 : 5), 1ull);
 	const unsigned long long k = atomicAdd(counters + 8, 1ull);
 	if (k < (unsigned long long)kGuardCap) counters[kGuardList + k] = 1ull << 56 | (id & 0x00ffffffffffffffull);
 }
@@ -136,7 +136,7 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 	};
 	size_t tile = blockIdx.x;
 	if (tile < ntiles && tid == 0 && tile_bulk(tile)) issue(tile);
-	uint32_t phase = 0, ncalled = 0, nexact = 0;
+	uint32_t phase = 0, ncalled = 0;
 	for (; tile < ntiles; tile += gridDim.x) {
 		const size_t first = tile * kCallTile;
 		const int nrec = (int)min((size_t)kCallTile, n - first);
@@ -176,7 +176,6 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 		int tie;
 		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, tid & 31, &tie);
 		ncalled += called;
-		nexact += tie == 2;
 		if (tie) guard_flag(counters, tie, guard_base + first + tid);
 		if (VCF) rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
 		else if (tid < nrec) skip[first + tid] = called ? 0 : 1;
@@ -184,9 +183,7 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 	}
 	if (tid == 0) tma_store_wait();
 	ncalled = __reduce_add_sync(0xffffffffu, ncalled);
-	nexact = __reduce_add_sync(0xffffffffu, nexact);
 	if ((tid & 31) == 0 && ncalled) atomicAdd(counters, (unsigned long long)ncalled);
-	if ((tid & 31) == 0 && nexact) atomicAdd(counters + 5, (unsigned long long)nexact);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -331,6 +328,14 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 	uint32_t v;
 	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
 	return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
+	asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
 	uint4 v;
@@ -528,12 +533,147 @@ k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_s
 		int tie;
 		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, lane, &tie);
 		if (tie) guard_flag(counters, tie, (unsigned long long)x + site0 + tid);
-		if (tie == 2) atomicAdd(counters + 5, 1ull);
 		rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
 		const uint32_t nc = __syncthreads_count(called);
 		if (tid == 0 && nc) atomicAdd(counters, (unsigned long long)nc);
 	}
 	store_tile<REC>(out + (size_t)blockIdx.x * kPileThreads * REC, stage, nrec, true, tid, kPileThreads);
+	if (tid == 0) tma_store_wait();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pileup by scatter into shared memory (the formulation the reference itself uses, src/call_genotypes.c:213-222, made
+// parallel): CTA = one 128-site tile as above, but the lanes of a warp run ALONG a read.  A warp takes one candidate at a
+// time; every lane loads four consecutive bytes of the read's part inside the tile and adds each counted byte to its site's
+// cell with one shared-memory atomic: cell (strand index, class) of a site is one 32-bit word, count in the high and quality
+// sum in the low half-word, so "counts[ori][c]++, quality[c] += q" is a single add.  A 3 x 256-entry table in shared memory
+// maps (bisulfite strand, byte) to {increment, byte offset of the class plane}, zero for a byte that does not count.
+// Integer adds commute, so the result does not depend on the order the atomics land in: bit-identical to the gather.
+//   * columns are swizzled, col(site) = (site & 3) * 32 + (site >> 2): the four bytes of a lane go to four different
+//     32-column groups and, for each of them, the 32 lanes hit 32 consecutive words -- no bank conflicts;
+//   * MAPQ^2: the tile's first candidate gives a reference value that is added n times at the end; only candidates with
+//     another MAPQ pay a second atomic per counted base (the difference, modulo 2^32 like the sum itself);
+//   * a tile with more than kScNarrowMax candidates (a half-word cell holds 65535: 1400 bases of quality 43 are safe)
+//     keeps counts and quality sums in separate words (two atomics per base, 32-bit range).
+// Per counted base: ~8 instructions, against ~10 per (site, hit) pair plus the dealing of the gather.
+// ------------------------------------------------------------------------------------------------
+constexpr int kScNarrowMax = 1400;
+constexpr int kScWarps = 4;
+__host__ __device__ constexpr size_t scatter_smem_bytes() {
+	// cells [2 planes][16][128] (narrow uses the first plane) | mapq plane [128] | table [3][256]; the output tile (128 x 104 B)
+	// is staged over the cells once they have been read into registers
+	return (size_t)2 * 16 * 128 * 4 + 128 * 4 + 3 * 256 * 4;
+}
+
+template <bool WIDE>
+__device__ __forceinline__ void scatter_candidates(const Cand *__restrict__ cands, uint32_t c_lo, uint32_t c_hi, const uint8_t *__restrict__ bases,
+		uint32_t tpos0, uint32_t mq_ref, uint32_t cells_s, uint32_t mqd_s, uint32_t lut_s, int lane, int wid) {
+	for (uint32_t ci = c_lo + (uint32_t)wid; ci < c_hi; ci += kScWarps) {
+		const uint4 c = *(const uint4 *)(cands + ci);
+		const int rel = (int)(c.x - tpos0);
+		const int s_lo = max(rel, 0), s_hi = min(rel + (int)(c.z & 0xffffu) - 1, kPileTile - 1);
+		const uint32_t k = c.z >> 16;
+		if (s_hi < s_lo || k >= 6) continue;
+		const uint32_t lut = lut_s + (k >> 1) * 1024u;                 // table of this bisulfite strand
+		const uint32_t ori_off = (k & 1u) * 8u * 512u;                 // plane group of this strand index
+		const uint32_t dmq = c.w - mq_ref;
+		const uint8_t *g0 = bases + (uint32_t)(c.y + tpos0 + (uint32_t)s_lo);      // byte of site s_lo
+		const uint32_t d = (uint32_t)((uintptr_t)g0 & 3u);
+		const uint32_t *a0 = (const uint32_t *)(g0 - d);
+		const int n = s_hi - s_lo + 1;
+		// lane i, byte j of chunk q holds site s_lo + 128 q + 4 i + j - d
+		for (int q0 = 0; q0 < n + (int)d; q0 += 128) {
+			const int first = q0 + 4 * lane - (int)d;                   // site offset (from s_lo) of this lane's byte 0
+			if (first + 3 < 0 || first >= n) continue;
+			const uint32_t word = a0[(q0 >> 2) + lane];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const int so = first + j;
+				const uint32_t e = lds_u32(lut + ((word >> (8 * j)) & 0xffu) * 4u);
+				if ((unsigned)so < (unsigned)n && e) {
+					const uint32_t site = (uint32_t)(s_lo + so);
+					const uint32_t col = ((site & 3u) << 5) + (site >> 2);
+					const uint32_t addr = cells_s + ori_off + (e >> 20) + col * 4u;
+					if (WIDE) {
+						red_shared_add(addr, 1u);
+						red_shared_add(addr + 16u * 512u, e & 0xffffu);
+					} else red_shared_add(addr, e & 0xfffffu);
+					if (dmq) red_shared_add(mqd_s + col * 4u, dmq);
+				}
+			}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(kPileThreads, 8)
+k_pileup_scatter(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_start, const uint8_t *__restrict__ bases,
+		uint32_t x, uint32_t sz, uint32_t tile0, uint8_t *__restrict__ out, const DevConst *__restrict__ dc,
+		unsigned long long *__restrict__ counters) {
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	uint32_t *cells = (uint32_t *)smem_raw;                                  // [2][16][128]
+	uint32_t *mqd = cells + 2 * 16 * 128;                                    // [128]
+	uint32_t *lut = mqd + 128;                                               // [3][256]
+	uint64_t *stage = (uint64_t *)smem_raw;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const uint32_t tile = tile0 + blockIdx.x;
+	const uint32_t site0 = tile * kPileTile;
+	const int nrec = (int)min((uint32_t)kPileThreads, sz - site0);
+	const uint32_t tpos0 = x + site0;
+	const uint32_t c_lo = bin_start[tile > (uint32_t)kBinsBack ? tile - kBinsBack : 0], c_hi = bin_start[tile + 1];
+	const bool wide = c_hi - c_lo > (uint32_t)kScNarrowMax;
+	// table: (strand, byte) -> class plane offset << 20 | increment; narrow: 1 << 16 | q, wide: q (the count is a separate add)
+	{
+		const uint32_t minq = (uint32_t)dc->min_qual;
+		for (int i = tid; i < 3 * 256; i += kPileThreads) {
+			const uint32_t st = (uint32_t)i >> 8, b = (uint32_t)i & 255u, q = b >> 2, base = b & 3u;
+			// class of (bs_strand, base): st0 {0,1,2,3}  st1=C2T {0,5,2,7}  st2=G2A {4,1,6,3}   (src/call_genotypes.c:17-19)
+			const uint32_t cls = ((st == 0 ? 0x3210u : st == 1 ? 0x7250u : 0x3614u) >> (4 * base)) & 15u;
+			const bool counted = q >= minq && q != (uint32_t)BSGPU_FLT_QUAL;
+			lut[i] = counted ? (cls * 512u) << 20 | (wide ? q : (1u << 16 | q)) : 0u;
+		}
+		for (int i = tid; i < (wide ? 2 : 1) * 16 * 128; i += kPileThreads) cells[i] = 0;
+		mqd[tid] = 0;
+	}
+	__syncthreads();
+	const uint32_t mq_ref = c_lo < c_hi ? cands[c_lo].mq2 : 0u;
+	if (wide) scatter_candidates<true>(cands, c_lo, c_hi, bases, tpos0, mq_ref, smem_u32(cells), smem_u32(mqd), smem_u32(lut), lane, wid);
+	else scatter_candidates<false>(cands, c_lo, c_hi, bases, tpos0, mq_ref, smem_u32(cells), smem_u32(mqd), smem_u32(lut), lane, wid);
+	__syncthreads();
+	// my site's cells -> the reference's pileup record
+	uint32_t o[26];
+	{
+		const uint32_t col = (((uint32_t)tid & 3u) << 5) + ((uint32_t)tid >> 2);
+		uint32_t n = 0, qmax = 0;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			uint32_t c0, c1, qs;
+			if (wide) {
+				c0 = cells[j * 128 + col]; c1 = cells[(8 + j) * 128 + col];
+				qs = cells[(16 + j) * 128 + col] + cells[(24 + j) * 128 + col];
+			} else {
+				const uint32_t a = cells[j * 128 + col], b = cells[(8 + j) * 128 + col];
+				c0 = a >> 16; c1 = b >> 16; qs = (a & 0xffffu) + (b & 0xffffu);
+			}
+			o[j] = c0; o[8 + j] = c1; o[17 + j] = __float_as_uint((float)qs);
+			n += c0 + c1;
+			qmax = max(qmax, qs);
+		}
+		const uint32_t mq2 = mq_ref * n + mqd[col];          // exact modulo 2^32, like the sum itself
+		if (tid >= nrec) {
+#pragma unroll
+			for (int j = 0; j < 26; j++) o[j] = 0;
+			n = 0;
+		}
+		o[16] = n;
+		o[25] = __float_as_uint((float)mq2);
+		// integer sums equal the reference's float sums only below 2^24: count the sites that leave the envelope
+		if (n && (qmax >= (1u << 24) || mq2 >= (1u << 24))) atomicAdd(counters + 1, 1ull);
+	}
+	__syncthreads();                       // everybody has read its cells: the staging tile may overwrite them
+	uint64_t *rec = stage + tid * 13;
+#pragma unroll
+	for (int j = 0; j < 13; j++) rec[j] = (uint64_t)o[2 * j] | (uint64_t)o[2 * j + 1] << 32;
+	store_tile<104>(out + (size_t)blockIdx.x * kPileThreads * 104, stage, nrec, true, tid, kPileThreads);
 	if (tid == 0) tma_store_wait();
 }
 
@@ -769,6 +909,7 @@ cudaError_t configure_kernels() {
 	if ((e = prep(k_call_sites<true, 5>, call_smem(true), kCallTile, &g_call_ctas[1][1])) != cudaSuccess) return e;
 	if ((e = prep(k_pileup_tile<0>, pile_smem(0), kPileThreads, nullptr)) != cudaSuccess) return e;
 	if ((e = prep(k_pileup_tile<1>, pile_smem(1), kPileThreads, nullptr)) != cudaSuccess) return e;
+	if ((e = prep(k_pileup_scatter, scatter_smem_bytes(), kPileThreads, nullptr)) != cudaSuccess) return e;
 	return cudaSuccess;
 }
 
@@ -843,7 +984,12 @@ cudaError_t launch_pileup_tiles(const void *scratch, size_t nseg, const void *ba
 	const uint32_t *start = (const uint32_t *)((const uint8_t *)scratch + seg_area(nseg)) + all_tiles;
 	// sites covered by this launch: tiles [tile0, tile0 + ntiles) clipped to the window; one CTA per tile
 	const unsigned grid = min(ntiles, all_tiles - tile0);
+	// BSGPU_PILEUP=scatter: build pileup[] (mode 0) with the shared-memory-atomics formulation instead of the gather.  Measured
+	// on B200 (bit-identical results): 30x / 150 bp 4.62 ms per 50 M sites against 2.22 ms, 500x panel 15.0 ms per 10 M sites
+	// against 6.15 ms -- a RED.shared per counted base costs more than the gather's ten instructions per (site, hit) pair.
+	static const bool scatter = [] { const char *e = getenv("BSGPU_PILEUP"); return e ? e[0] == 's' : false; }();
 	if (mode) k_pileup_tile<1><<<grid, kPileThreads, pile_smem(1), stream>>>(sorted, start, (const uint8_t *)bases, (const uint8_t *)ref, x, sz, tile0, (uint8_t *)out, dc, counters);
+	else if (scatter) k_pileup_scatter<<<grid, kPileThreads, scatter_smem_bytes(), stream>>>(sorted, start, (const uint8_t *)bases, x, sz, tile0, (uint8_t *)out, dc, counters);
 	else k_pileup_tile<0><<<grid, kPileThreads, pile_smem(0), stream>>>(sorted, start, (const uint8_t *)bases, (const uint8_t *)ref, x, sz, tile0, (uint8_t *)out, dc, counters);
 	*launches += 1;
 	LAUNCH_CHECK();

@@ -12,7 +12,7 @@ import numpy as np
 from .records import PILEUP, GT_METH, GT_VCF, SEG, TEMPLATE, MISMS, RECORD, BLOCK
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbsgpu.so")
+LIB_PATH = os.environ.get("BSGPU_LIB_PATH") or os.path.join(_HERE, "libbsgpu.so")      # (the override is for A/B builds of the kernels)
 
 BSGPU_OK = 1
 BSGPU_FAIL = -1
