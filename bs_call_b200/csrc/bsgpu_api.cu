@@ -75,7 +75,11 @@ static int fail(const char *fmt, ...) {
 // BSGPU_SYNC_CHECK=1 (debugging aid; compute-sanitizer is not available on every pool): the device is synchronised after
 // every runtime call made through CU(), so that an asynchronous fault is reported at the call that caused it
 static const bool g_sync_check = getenv("BSGPU_SYNC_CHECK") != nullptr;
-#define CU(call) do { cudaError_t e_ = (call); if (e_ == cudaSuccess && g_sync_check) e_ = cudaDeviceSynchronize(); \
+// BSGPU_SYNC_AFTER=<text> (debugging aid): the device is synchronised BEFORE AND AFTER every launcher call whose source text
+// contains <text> (e.g. launch_pileup, launch_bcf), so that those kernels never run next to any other kernel of the process
+static const char *g_sync_after = getenv("BSGPU_SYNC_AFTER");
+#define CU(call) do { const bool iso_ = g_sync_after && strstr(#call, g_sync_after); if (iso_) cudaDeviceSynchronize(); \
+	cudaError_t e_ = (call); if (e_ == cudaSuccess && (g_sync_check || iso_)) e_ = cudaDeviceSynchronize(); \
 	if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 // grow-on-demand device / pinned buffers

@@ -110,11 +110,12 @@ __device__ __forceinline__ int warp_offsets(int c, int lane, int *total) {
 // lane reads its results back.  Values and order of every addition are unchanged.
 //   * exp(x) with x < -45 is replaced by 0: such a term (< 3e-20) cannot change a double sum that contains the
 //     exp(0) = 1 of the best genotype, so the result is the same double.
-// Returns max_gt and writes log10 posteriors to prob[10].
+// Returns max_gt | tie << 8 (tie: 0, 1 = runner-up inside the guard band, 2 = equal to the best) and writes log10 posteriors
+// to prob[10].
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int qual[8], int rf,
 		const DevConst *__restrict__ dc, const Tables *__restrict__ tb, double prob[10],
-		double *__restrict__ wbuf, int lane, int *__restrict__ tie) {
+		double *__restrict__ wbuf, int lane, bool covered) {
 	const double (*__restrict__ qp)[4] = tb->qp;
 	const MathTables *__restrict__ mt = &tb->math;
 	double ll[10];
@@ -217,9 +218,11 @@ __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int q
 	}
 	// A runner-up inside the band (x >= -band) contributes e^x >= 1 - band to the sum, so only sites with sum >= 2 - 2 band (the
 	// call holds less than half of the posterior mass: rare at sequencing depth) are looked at genotype by genotype.
-	*tie = 0;
+	int tie = 0;
 #ifndef BSGPU_NO_GUARD
-	if (sum >= 1.99) {                 // (band <= 1e-9 |top|, far below 0.005 for any |top| a double sum of this model reaches)
+	// (an uncovered site has ten equal likelihoods and no call: without `covered` its lane would drag most warps through the
+	// look, 3 % empty sites put one into 62 % of the warps; band <= 1e-9 |top| is far below the 0.005 of the first test)
+	if (covered && sum >= 1.99) {
 		const double band = -kTieBand * (fabs(top) > 1.0 ? fabs(top) : 1.0);
 		int ntop = 0, near = 0;
 #pragma unroll
@@ -228,13 +231,13 @@ __device__ __forceinline__ int genotype_model(const uint32_t cnt[8], const int q
 			ntop += x == 0.0;
 			near |= x != 0.0 && x >= band;
 		}
-		*tie = ntop > 1 ? 2 : near;
+		tie = ntop > 1 ? 2 : near;
 	}
 #endif
 	sum = fast_log(sum, mt);          // sum is in [1, 10]
 #pragma unroll
 	for (int g = 0; g < 10; g++) prob[g] = div_by(ll[g] - top - sum, kLn10, kInvLn10);
-	return best;
+	return best | tie << 8;          // the tie flag rides in the same register as the call (the model runs at the register limit)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -318,11 +321,12 @@ __device__ __forceinline__ double strand_bias(const SiteCounts &s, int max_gt, c
 // ---------------------------------------------------------------------------------------------------------------
 // Per-site body of call_thread (src/call_genotypes.c:43-115): summarise, model, strand bias; writes the 200-byte
 // gt_meth image as 25 eight-byte words into `rec` (a row of the CTA's staging tile in shared memory).
-// Returns false for a site with no counted base (record zeroed, the caller sets skip).  *tie: 0, 1 = the two best
-// genotypes are closer than the guard band (the call may differ from the reference's), 2 = they are exactly equal.
+// Returns false for a site with no counted base (record zeroed, the caller sets skip).  Byte 1 of the record's last word
+// (padding of gt_meth) carries the guard flag of the call -- 0, 1 = the two best genotypes are closer than the guard band
+// (the call may differ from the reference's), 2 = they are exactly equal -- for the caller to read and clear.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool call_site(const SiteCounts &s, int rf, const DevConst *__restrict__ dc,
-		const Tables *__restrict__ tb, uint64_t *rec, double *__restrict__ wbuf, int lane, int *__restrict__ tie) {
+		const Tables *__restrict__ tb, uint64_t *rec, double *__restrict__ wbuf, int lane) {
 	uint32_t tot[8];
 	int qual[8];
 	float tq = 0.0f;
@@ -339,10 +343,10 @@ __device__ __forceinline__ bool call_site(const SiteCounts &s, int rf, const Dev
 	}
 	// the whole warp runs the model together (a lane without counts contributes nothing to the pooled lists)
 	double prob[10];
-	const int best = genotype_model(tot, qual, rf, dc, tb, prob, wbuf, lane, tie);
+	const int best_tie = genotype_model(tot, qual, rf, dc, tb, prob, wbuf, lane, s.n != 0);
+	const int best = best_tie & 0xff;
 	__syncwarp();                      // wbuf may alias this warp's output rows: everyone is done with it
 	if (!s.n) {
-		*tie = 0;
 #pragma unroll
 		for (int i = 0; i < 25; i++) rec[i] = 0;
 		return false;
@@ -361,7 +365,7 @@ __device__ __forceinline__ bool call_site(const SiteCounts &s, int rf, const Dev
 	for (int g = 0; g < 10; g++) rec[12 + g] = (uint64_t)__double_as_longlong(prob[g]);
 	rec[22] = (uint64_t)__double_as_longlong(fs);
 	rec[23] = (uint64_t)(uint32_t)mq | ((uint64_t)(uint32_t)aq << 32);
-	rec[24] = (uint64_t)best;
+	rec[24] = (uint64_t)(uint32_t)best_tie;
 	return true;
 }
 

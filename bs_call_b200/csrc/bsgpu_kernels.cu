@@ -98,7 +98,7 @@ constexpr int kCallTile = 128;
 
 // a site whose result sits inside a guard band: counted, and listed while the list has room
 // (tie: 1 = closer than the band, 2 = equal; both are listed as kind 1.  Rare: kept out of line)
-__device__ __noinline__ void guard_flag(unsigned long long *counters, int tie, unsigned long long id) {
+__device__ __forceinline__ void guard_flag(unsigned long long *counters, int tie, unsigned long long id) {
 	atomicAdd(counters + (tie == 1 ? 4 : 5), 1ull);
 	const unsigned long long k = atomicAdd(counters + 8, 1ull);
 	if (k < (unsigned long long)kGuardCap) counters[kGuardList + k] = 1ull << 56 | (id & 0x00ffffffffffffffull);
@@ -173,10 +173,12 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 		uint64_t *rec = stage + tid * RW;
 		// pooled-argument list of this warp: the (not yet written) output rows of its own 32 sites
 		double *wbuf = (double *)(stage + (tid & ~31) * RW);
-		int tie;
-		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, tid & 31, &tie);
+		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, tid & 31);
 		ncalled += called;
-		if (tie) guard_flag(counters, tie, guard_base + first + tid);
+		if (called && (rec[24] >> 8)) {        // guard flag of the call (rare): report it, give the padding byte back
+			guard_flag(counters, (int)(rec[24] >> 8) & 3, guard_base + first + tid);
+			rec[24] &= 0xffull;
+		}
 		if (VCF) rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
 		else if (tid < nrec) skip[first + tid] = called ? 0 : 1;
 		store_tile<REC>(out + first * REC, stage, nrec, bulk_ok, tid, kCallTile);
@@ -530,9 +532,11 @@ k_pileup_tile(const Cand *__restrict__ cands, const uint32_t *__restrict__ bin_s
 		const int rf = tid < nrec ? ref[site0 + tid] : 0;
 		__syncthreads();                    // tables loaded (the candidate loop may not have run)
 		double *wbuf = (double *)(stage + (tid & ~31) * RW);
-		int tie;
-		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, lane, &tie);
-		if (tie) guard_flag(counters, tie, (unsigned long long)x + site0 + tid);
+		const bool called = call_site(s, rf, dc, tabs, rec, wbuf, lane);
+		if (called && (rec[24] >> 8)) {
+			guard_flag(counters, (int)(rec[24] >> 8) & 3, (unsigned long long)x + site0 + tid);
+			rec[24] &= 0xffull;
+		}
 		rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
 		const uint32_t nc = __syncthreads_count(called);
 		if (tid == 0 && nc) atomicAdd(counters, (unsigned long long)nc);
