@@ -788,7 +788,9 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
-    l0 = gpu.stats()["kernel_launches"]
+    gpu.guard_read(reset=True)
+    g0 = gpu.stats()
+    l0 = g0["kernel_launches"]
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -800,7 +802,13 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    launches = gpu.stats()["kernel_launches"] - l0
+    g1 = gpu.stats()
+    launches = g1["kernel_launches"] - l0
+    # guard bands (hard part 1): sites of the timed steps whose call hangs on the last bits of a likelihood
+    guard = {"sites_per_step": n_sites, "near_tie_sites_per_step": (g1["near_tie_sites"] - g0["near_tie_sites"]) // args.steps,
+             "exact_tie_sites_per_step": (g1["exact_tie_sites"] - g0["exact_tie_sites"]) // args.steps,
+             "note": "two best genotype log-likelihoods within 1e-9 relative (near) or equal (exact): the call may differ from the CPU's at these sites only; "
+                     "listed by bsgpu_guard_read, counted in bsgpu_stats"}
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     tot_called = torch.tensor([called_total], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -1081,7 +1089,7 @@ def main():
                            "parallelism": "sites sharded over %d rank(s), no collective" % world, "host": numa_note,
                            "l2": "inputs larger than L2: each step streams %.1f GB of distinct records" % (n_sites * 105 / 1e9)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "block_path": block, "bam_path": bam, "writer_path": writer, "genome_path": genome, "parity_spot_check": parity}
+                "block_path": block, "bam_path": bam, "writer_path": writer, "genome_path": genome, "guard_bands": guard, "parity_spot_check": parity}
         print(json.dumps(line))
     gpu.close()
     if world > 1:

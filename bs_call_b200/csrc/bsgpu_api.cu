@@ -145,6 +145,7 @@ struct bsgpu_ctx {
 	struct DbDev { DevBuf mask, fq, cum, off, names; uint32_t words = 0; uint32_t reg_start = 0, reg_stop = 0; uint64_t key[4] = {0, 0, 0, 0}; };
 	std::map<int, DbDev *> contig_ann;
 	DbDev call_db;
+	bool zero_decoded = false;                   // bsgpu_decode_records hands the decoded arrays out: slots of dropped records are cleared
 	uint64_t guard_base[4] = {0, 0, 0, 0};      // guard counters of the device before the last bsgpu_guard_read(reset)
 	int launches = 0;
 	// --report-file side channels (bsgpu_profile_enable)
@@ -207,12 +208,14 @@ int bsgpu_init(const bsgpu_params *p, bsgpu_ctx **out) {
 	CU(cudaGetDeviceProperties(&prop, p->device));
 	if (prop.major != 10) return fail("bsgpu_init: device %d is sm_%d%d; this library carries sm_100a code only", p->device, prop.major, prop.minor);
 	CU(cudaSetDevice(p->device));
+#define CUI(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { bsgpu_destroy(c); return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
 	bsgpu_ctx *c = new bsgpu_ctx();
 	c->device = p->device;
 	c->params = *p;
 	memset(&c->stats, 0, sizeof(c->stats));
 	// host-side tables, computed with the C library exactly as the reference does
-	static DevConst h;
+	std::vector<DevConst> hbuf(1);          // (48 KB: not on the stack, not shared between threads that initialise contexts)
+	DevConst &h = hbuf[0];
 	memset(&h, 0, sizeof(h));
 	for (int q = 0; q <= kMaxQual; q++) {          // src/genotype_model.c:10-21
 		double er = exp(-.1 * (double)q * kLn10);
@@ -238,21 +241,22 @@ int bsgpu_init(const bsgpu_params *p, bsgpu_ctx **out) {
 		h.pile_lut[b][0] = base < 2 ? inc : 0u;
 		h.pile_lut[b][1] = base < 2 ? 0u : inc;
 	}
-	CU(cudaMalloc(&c->d_const, sizeof(DevConst)));
-	CU(cudaMemcpy(c->d_const, &h, sizeof(h), cudaMemcpyHostToDevice));
-	CU(cudaMalloc(&c->d_counters, (kGuardList + kGuardCap) * sizeof(unsigned long long)));
-	CU(cudaMemset(c->d_counters, 0, (kGuardList + kGuardCap) * sizeof(unsigned long long)));
-	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	CUI(cudaMalloc(&c->d_const, sizeof(DevConst)));
+	CUI(cudaMemcpy(c->d_const, &h, sizeof(h), cudaMemcpyHostToDevice));
+	CUI(cudaMalloc(&c->d_counters, (kGuardList + kGuardCap) * sizeof(unsigned long long)));
+	CUI(cudaMemset(c->d_counters, 0, (kGuardList + kGuardCap) * sizeof(unsigned long long)));
+	CUI(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CUI(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 2; i++) {
-		CU(cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking));
-		CU(cudaEventCreateWithFlags(&c->slot[i].done, cudaEventDisableTiming));
+		CUI(cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking));
+		CUI(cudaEventCreateWithFlags(&c->slot[i].done, cudaEventDisableTiming));
 	}
-	CU(configure_kernels());
-	CU(configure_writer());
-	CU(cudaMalloc(&c->d_wr_totals, 8 * 3 * sizeof(unsigned long long)));
-	CU(cudaHostAlloc(&c->h_wr_totals, 8 * 3 * sizeof(unsigned long long), cudaHostAllocDefault));
+	CUI(configure_kernels());
+	CUI(configure_writer());
+	CUI(cudaMalloc(&c->d_wr_totals, 8 * 3 * sizeof(unsigned long long)));
+	CUI(cudaHostAlloc(&c->h_wr_totals, 8 * 3 * sizeof(unsigned long long), cudaHostAllocDefault));
 	{ const char *e = getenv("BSGPU_FUSED"); c->fused = e && atoi(e) == 1; }
+#undef CUI
 	*out = c;
 	return BSGPU_OK;
 }
@@ -292,8 +296,9 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 int bsgpu_get_stats(bsgpu_ctx *c, bsgpu_stats *out) {
 	if (!c || !out) return fail("bsgpu_get_stats: null argument");
 	CU(cudaSetDevice(c->device));
-	unsigned long long h[8];
+	unsigned long long h[16];
 	CU(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+	c->stats.long_segments = h[9];
 	c->stats.kernel_launches = (uint64_t)c->launches;
 	c->stats.sites_called = h[0];
 	c->stats.qsum_overflow = h[1];
@@ -347,6 +352,7 @@ static int block_dev(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *
 	if (!sz) return BSGPU_OK;
 	if (!d_out || (nseg && (!d_segs || !d_bases)) || (mode && !d_ref)) return fail("bsgpu block: null buffer");
 	if ((uintptr_t)d_out & 15u) return fail("bsgpu block: output array must be 16-byte aligned");
+	if (nseg && ((uintptr_t)d_bases & 15u)) return fail("bsgpu block: bases[] must be 16-byte aligned (and end with 16 readable bytes of slack)");
 	CU(cudaSetDevice(c->device));
 	cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
 	void *scratch = d_scratch;
@@ -356,7 +362,7 @@ static int block_dev(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *
 		CU(c->scratch.reserve(pileup_scratch_bytes(nseg, sz)));
 		scratch = c->scratch.p;
 	}
-	CU(launch_bin_segments(d_segs, nseg, x, sz, scratch, st, &c->launches));
+	CU(launch_bin_segments(d_segs, nseg, x, sz, scratch, st, &c->launches, c->d_counters));
 	const uint32_t ntiles = (sz + kPileTileSites - 1) / kPileTileSites;
 	if (mode && !c->fused) {
 		const size_t need = (size_t)sz * sizeof(bsgpu_pileup) + 16;
@@ -445,7 +451,7 @@ int bsgpu_guard_read(bsgpu_ctx *c, uint64_t *ids, size_t cap, size_t *n, int res
 	if (*n) CU(cudaMemcpy(ids, c->d_counters + kGuardList, *n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
 	if (reset) {
 		for (int k = 0; k < 4; k++) c->guard_base[k] += h[4 + k];
-		CU(cudaMemset(c->d_counters + 4, 0, (kGuardList - 4) * sizeof(unsigned long long)));
+		CU(cudaMemset(c->d_counters + 4, 0, 5 * sizeof(unsigned long long)));      // the four counters and the list length ([9]: long_segments stays)
 	}
 	return BSGPU_OK;
 }
@@ -527,7 +533,7 @@ static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *
 		uint32_t x, uint32_t sz, void *out, int mode, bool defer) {
 	const size_t rec = mode ? sizeof(bsgpu_gt_vcf) : sizeof(bsgpu_pileup);
 	CU(c->scratch.reserve(pileup_scratch_bytes(nseg, sz)));
-	CU(launch_bin_segments(d_segs, nseg, x, sz, c->scratch.p, c->stream, &c->launches));
+	CU(launch_bin_segments(d_segs, nseg, x, sz, c->scratch.p, c->stream, &c->launches, c->d_counters));
 	const uint32_t ntiles = (sz + kPileTileSites - 1) / kPileTileSites;
 	const uint32_t slab = (2u << 20) / kPileTileSites;      // tiles per slab = 2 Mi sites = 436 MB of gt_vcf
 	const uint32_t nslab = (ntiles + slab - 1) / slab;
@@ -1020,6 +1026,10 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 	CU(c->rd_bases.reserve(*nb + 16));
 	CU(c->rd_misms.reserve((*nm + 1) * sizeof(bsgpu_misms)));
 	CU(c->h_rec.reserve(n * sizeof(bsgpu_record)));
+	if (c->zero_decoded) {                          // k_decode_records skips dropped records: what the caller copies out is defined everywhere
+		CU(cudaMemsetAsync(c->rd_bases.p, 0, *nb + 16, dec));
+		CU(cudaMemsetAsync(c->rd_misms.p, 0, (*nm + 1) * sizeof(bsgpu_misms), dec));
+	}
 	// certain block starts: the keys the decode kernel writes come home and host threads scan them; BSGPU_DEVICE_SCAN=1
 	// uses the bit mask of the scan on the device instead, BSGPU_CHECK_SCAN=1 does both and compares
 	const bool dev_scan = getenv("BSGPU_DEVICE_SCAN") != nullptr || getenv("BSGPU_CHECK_SCAN") != nullptr;
@@ -1120,7 +1130,10 @@ int bsgpu_decode_records(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const 
 	if (!c || !rp || !nrec || (nbytes && !bam)) return fail("bsgpu_decode_records: null argument");
 	size_t n = 0;
 	uint64_t nb = 0, nm = 0;
-	if (decode_resident(c, bam, nbytes, rp, &n, &nb, &nm) != BSGPU_OK) return BSGPU_FAIL;
+	c->zero_decoded = bases_out != nullptr || misms_out != nullptr;
+	const int drc = decode_resident(c, bam, nbytes, rp, &n, &nb, &nm);
+	c->zero_decoded = false;
+	if (drc != BSGPU_OK) return BSGPU_FAIL;
 	if (n > rec_cap || (bases_out && nb > bases_cap) || (misms_out && nm > misms_cap)) return fail("bsgpu_decode_records: need room for %zu records, %llu bases, %llu events", n, (unsigned long long)nb, (unsigned long long)nm);
 	if (n) {
 		if (rec_out) memcpy(rec_out, c->h_rec.p, n * sizeof(bsgpu_record));

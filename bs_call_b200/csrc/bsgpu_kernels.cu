@@ -203,11 +203,13 @@ __device__ __forceinline__ uint32_t seg_bin(uint32_t pos, uint32_t x) { return p
 // Input segments usually arrive in coordinate order, so the lanes of a warp mostly fall into one or two tiles: lanes
 // with the same tile are grouped with match.any and one of them does the atomic for the group (a deep panel puts
 // hundreds of segments into every tile).
-__global__ void k_bin_count(const Seg *__restrict__ segs, size_t nseg, uint32_t x, uint32_t ntiles, uint32_t *__restrict__ counts) {
+__global__ void k_bin_count(const Seg *__restrict__ segs, size_t nseg, uint32_t x, uint32_t ntiles, uint32_t *__restrict__ counts,
+		unsigned long long *__restrict__ counters) {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t t = 0xffffffffu;                 // no contribution: out of range, empty slot (the normaliser leaves them for absent mates)
 	if (i < nseg) {
 		const Seg s = segs[i];
+		if (s.len > kMaxSegLen && counters) atomicAdd(counters + 9, 1ull);      // contract of the _dev entry points (bsgpu_stats.long_segments)
 		// a segment that starts before the window still contributes to the first tiles (clipped there)
 		if (s.len) { const uint32_t b = seg_bin(s.pos, x); if (b < ntiles) t = b; }
 	}
@@ -949,7 +951,7 @@ size_t pileup_scratch_bytes(size_t nseg, uint32_t sz) {
 
 // scratch layout: sorted candidates | counts[ntiles] | start[ntiles+1] | cursor[ntiles] | partial[ctas+1]
 cudaError_t launch_bin_segments(const void *segs, size_t nseg, uint32_t x, uint32_t sz, void *scratch,
-		cudaStream_t stream, int *launches) {
+		cudaStream_t stream, int *launches, unsigned long long *counters) {
 	if (!sz) return cudaSuccess;
 	const uint32_t ntiles = (sz + kPileTile - 1) / kPileTile;
 	Cand *sorted = (Cand *)scratch;
@@ -961,7 +963,7 @@ cudaError_t launch_bin_segments(const void *segs, size_t nseg, uint32_t x, uint3
 	if (e != cudaSuccess) return e;
 	const unsigned g = (unsigned)((nseg + 255) / 256);
 	if (nseg) {
-		k_bin_count<<<g, 256, 0, stream>>>((const Seg *)segs, nseg, x, ntiles, counts);
+		k_bin_count<<<g, 256, 0, stream>>>((const Seg *)segs, nseg, x, ntiles, counts, counters);
 		*launches += 1;
 		LAUNCH_CHECK();
 	}

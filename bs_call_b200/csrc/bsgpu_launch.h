@@ -24,7 +24,7 @@ size_t pileup_scratch_bytes(size_t nseg, uint32_t sz);
 
 // bins the segments of a block by 128-site tile (count, scan, scatter) into `scratch`
 cudaError_t launch_bin_segments(const void *segs, size_t nseg, uint32_t x, uint32_t sz, void *scratch,
-		cudaStream_t stream, int *launches);
+		cudaStream_t stream, int *launches, unsigned long long *counters = nullptr);
 
 // pileup (mode 0 -> pileup[]) or fused pileup + model (mode 1 -> gt_vcf[]) for tiles [tile0, tile0 + ntiles) of a
 // block previously binned into `scratch`; `out` points at the record of site tile0 * kPileTileSites

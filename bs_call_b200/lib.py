@@ -54,7 +54,8 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("sites", C.c_uint64), ("sites_called", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("qsum_overflow", C.c_uint64),
                 ("bam_decode_s", C.c_double), ("bam_build_s", C.c_double), ("bam_call_s", C.c_double),
-                ("near_tie_sites", C.c_uint64), ("exact_tie_sites", C.c_uint64), ("near_qual_sites", C.c_uint64), ("near_fs_sites", C.c_uint64)]
+                ("near_tie_sites", C.c_uint64), ("exact_tie_sites", C.c_uint64), ("near_qual_sites", C.c_uint64), ("near_fs_sites", C.c_uint64),
+                ("long_segments", C.c_uint64)]
 
 
 PROFILE_MAX = 1024

@@ -219,6 +219,7 @@ typedef struct {
 	 * near_fs_sites    FS before truncation lies within its error band of an integer (src/print_vcf.c:151)
 	 * bsgpu_guard_read lists them (up to 65536 between two resets). */
 	uint64_t near_tie_sites, exact_tie_sites, near_qual_sites, near_fs_sites;
+	uint64_t long_segments;    /* segments longer than BSGPU_MAX_SEG_LEN handed to a _dev entry point (contract violation) */
 } bsgpu_stats;
 
 void bsgpu_default_params(bsgpu_params *p);
@@ -387,7 +388,13 @@ int bsgpu_bam_progress(bsgpu_bam_session *s, bsgpu_bam_progress_t *out);
 int bsgpu_bam_close(bsgpu_bam_session *s);
 
 /* ---- device-pointer entry points: everything already resident in HBM, asynchronous on `stream`
- *      (a cudaStream_t passed as void*; NULL = the context's own stream) ---- */
+ *      (a cudaStream_t passed as void*; NULL = the context's own stream) ----
+ * Contract of the caller-owned arrays (the host-buffer entry points check or arrange all of this themselves):
+ *   d_bases   16-byte aligned, and readable for 16 bytes beyond its last base: the pileup kernel stages a segment with a bulk
+ *             copy of the 16-byte aligned cover of its bytes, so it reads up to 15 bytes either side of the segment
+ *   d_segs    every len <= BSGPU_MAX_SEG_LEN (a longer segment would be seen by the first three tiles it overlaps only);
+ *             segments that break this are counted in bsgpu_stats.long_segments and the results of the call are void
+ *   d_pileup / d_out / d_vcf   8-byte aligned (16 for the block entry points) */
 int bsgpu_call_sites_dev(bsgpu_ctx *ctx, const void *d_pileup, const void *d_ref, size_t n,
 		void *d_out, void *d_skip, void *stream);
 /* same, writing gt_vcf[] (208-byte records with ready = 1 and the skip flag inside) */
