@@ -841,7 +841,10 @@ def main():
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic = tj["k_call_sites"]["dram_bytes_per_site"] * slab
+            if "k_call_sites_bench" in tj and abs(tj["k_call_sites_bench"]["sites_per_launch"] - slab) <= 2:
+                traffic = tj["k_call_sites_bench"]["dram_bytes_per_launch"]          # measured on a launch of this very size
+            else:
+                traffic = tj["k_call_sites"]["dram_bytes_per_site"] * slab
         except Exception:
             traffic = None
     roofline = {"kernel": "k_call_sites", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -64,6 +64,21 @@ if os.path.exists(os.path.join(G, tag + "_prof_reader.ncu-rep")):
     kernel(tag + "_prof_reader.ncu-rep", "reader_kernels", 1)
 if os.path.exists(os.path.join(G, tag + "_prof_writer.ncu-rep")):
     kernel(tag + "_prof_writer.ncu-rep", "writer_kernels", 1)
+# the headline kernel at bench size: dram bytes of a 62.5 M-site launch (ncu --metrics, one pass; run_profile_r02.sh)
+tb = os.path.join(G, tag + "_traffic_call_bench.csv")
+if os.path.exists(tb):
+    rows = [r for r in csv.reader(open(tb)) if len(r) > 10 and r[0].isdigit()]
+    per = collections.defaultdict(dict)
+    for r in rows:
+        name, unit, val = r[-3], r[-2], float(r[-1].replace(",", ""))
+        per[r[0]][name] = val * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1, "ms": 1e3, "ns": 1e-3, "s": 1e6, "usecond": 1, "msecond": 1e3, "nsecond": 1e-3}.get(unit, 1)
+    launches_ = [v for v in per.values() if "dram__bytes_read.sum" in v]
+    if launches_:
+        b = sum(v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"] for v in launches_) / len(launches_)
+        traffic["k_call_sites_bench"] = {"dram_bytes_per_launch": b, "sites_per_launch": 62_500_000, "dram_bytes_per_site": b / 62_500_000,
+                                         "gpu_time_us": sum(v.get("gpu__time_duration.sum", 0.0) for v in launches_) / len(launches_), "launches_averaged": len(launches_),
+                                         "note": "dram__bytes_read.sum + dram__bytes_write.sum of bench-sized launches (python bench.py --sites 1e9), ncu --metrics, one pass"}
+        shutil.copy(tb, os.path.join(HERE, tag + "_traffic_call_bench.csv"))
 traffic["round"] = tag
 json.dump(traffic, open(os.path.join(HERE, "traffic.json"), "w"), indent=1)
 for f in ("bench_full.json", "bench_reference.json"):
