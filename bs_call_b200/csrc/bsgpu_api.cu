@@ -128,16 +128,28 @@ struct bsgpu_ctx {
 	cudaStream_t copy_stream = nullptr;          // D2H of finished windows
 	Slot slot[2];
 	DevBuf segs, bases, ref, scratch, vcf, tmpl, misms, obases, ooff, pile;
-	DevBuf rd_bam, rd_recoff, rd_readoff, rd_mmoff, rd_rec, rd_bases, rd_misms, rd_key, rd_mask, rd_names, rd_nameid;
-	PinBuf h_nameid;                             // name ids of the records coming home (QNAME join on the device)
-	std::vector<size_t> mask_off;                // word offset of every chunk's certain-start mask in rd_mask / h_mask      // reader side: stream, framing, decoded arrays
-	std::vector<uint64_t> rec_off;               // framing of the last decoded stream
-	std::vector<uint32_t> read_off, mm_off, off_tmp;
+	// Reader side of one run over a record stream: the stream itself, its framing, the decoded arrays, what comes home of them.
+	// Two sets, so that a streaming session can have the reader stage of batch k + 1 under way (framing, upload, decode,
+	// certain-start scan, block builder) while the windows of batch k are still being queued and run.
+	struct ReaderSet {
+		DevBuf rd_bam, rd_recoff, rd_readoff, rd_mmoff, rd_rec, rd_bases, rd_misms, rd_key, rd_mask, rd_names, rd_nameid;
+		PinBuf h_nameid;                         // name ids of the records coming home (QNAME join on the device)
+		std::vector<size_t> mask_off;            // word offset of every chunk's certain-start mask in rd_mask / h_mask
+		std::vector<uint64_t> rec_off;           // framing of the stream
+		std::vector<uint32_t> read_off, mm_off;
+		FrameScratch *frame_scratch = nullptr;
+		PinBuf h_rec, h_off, h_tmpl, h_key, h_mask;      // pinned staging: descriptors coming back, offset tables and templates going up
+		std::vector<cudaEvent_t> rd_up, rd_done;         // byte piece uploaded, chunk descriptors home
+		cudaStream_t up = nullptr;               // the set's upload stream
+	} rs[2];
+	// window stage turnstile of pipelined runs: run `ticket` queues its windows when win_done == ticket
+	std::mutex win_mu;
+	std::condition_variable win_cv;
+	uint64_t win_done = 0, next_ticket = 0;
+	std::vector<uint32_t> off_tmp;
 	std::vector<uint8_t> ref_tmp;
-	FrameScratch *frame_scratch = nullptr;
-	PinBuf h_rec, h_off, h_tmpl, h_key, h_mask;                 // pinned staging: descriptors coming back, offset tables and templates going up
 	bool fused = false;                          // BSGPU_FUSED=1: one fused pileup+model kernel instead of two kernels
-	std::vector<cudaEvent_t> win_events, rd_up, rd_done;      // output ring; reader: byte piece uploaded, chunk descriptors home
+	std::vector<cudaEvent_t> win_events;         // output ring
 	uint32_t ring_pos = 0;                       // next output ring slot of the deferred runs
 	bool ring_busy[3] = {false, false, false};   // output ring slot may still be copying out (deferred block_run)
 	bsgpu_stats stats;
@@ -271,12 +283,15 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 		if (c->slot[i].done) cudaEventDestroy(c->slot[i].done);
 	}
 	for (cudaEvent_t ev : c->win_events) cudaEventDestroy(ev);
-	for (cudaEvent_t ev : c->rd_up) cudaEventDestroy(ev);
-	for (cudaEvent_t ev : c->rd_done) cudaEventDestroy(ev);
-	if (c->frame_scratch) frame_scratch_free(c->frame_scratch);
-	c->h_rec.release(); c->h_off.release(); c->h_tmpl.release(); c->h_key.release(); c->rd_key.release(); c->h_mask.release(); c->rd_mask.release();
-	c->rd_names.release(); c->rd_nameid.release(); c->h_nameid.release();
-	c->rd_bam.release(); c->rd_recoff.release(); c->rd_readoff.release(); c->rd_mmoff.release(); c->rd_rec.release(); c->rd_bases.release(); c->rd_misms.release();
+	for (bsgpu_ctx::ReaderSet &R : c->rs) {
+		for (cudaEvent_t ev : R.rd_up) cudaEventDestroy(ev);
+		for (cudaEvent_t ev : R.rd_done) cudaEventDestroy(ev);
+		if (R.frame_scratch) frame_scratch_free(R.frame_scratch);
+		R.h_rec.release(); R.h_off.release(); R.h_tmpl.release(); R.h_key.release(); R.rd_key.release(); R.h_mask.release(); R.rd_mask.release();
+		R.rd_names.release(); R.rd_nameid.release(); R.h_nameid.release();
+		R.rd_bam.release(); R.rd_recoff.release(); R.rd_readoff.release(); R.rd_mmoff.release(); R.rd_rec.release(); R.rd_bases.release(); R.rd_misms.release();
+		if (R.up && R.up != c->slot[0].stream) cudaStreamDestroy(R.up);
+	}
 	c->segs.release(); c->bases.release(); c->ref.release(); c->scratch.release(); c->vcf.release(); c->tmpl.release(); c->misms.release(); c->obases.release(); c->ooff.release(); c->pile.release();
 	if (c->stream) cudaStreamDestroy(c->stream);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -327,7 +342,7 @@ int bsgpu_call_sites_dev(bsgpu_ctx *c, const void *d_pileup, const void *d_ref, 
 	if (((uintptr_t)d_pileup | (uintptr_t)d_out) & 7u) return fail("bsgpu_call_sites_dev: record arrays must be 8-byte aligned");
 	CU(cudaSetDevice(c->device));
 	CU(launch_call_sites(d_pileup, d_ref, n, d_out, d_skip, false, c->d_const, c->d_counters, stream ? (cudaStream_t)stream : c->stream, &c->launches));
-	c->stats.sites += n;
+	__atomic_fetch_add(&c->stats.sites, (uint64_t)(n), __ATOMIC_RELAXED);
 	return BSGPU_OK;
 }
 
@@ -337,7 +352,7 @@ int bsgpu_call_sites_vcf_dev(bsgpu_ctx *c, const void *d_pileup, const void *d_r
 	if (((uintptr_t)d_pileup | (uintptr_t)d_vcf) & 7u) return fail("bsgpu_call_sites_vcf_dev: record arrays must be 8-byte aligned");
 	CU(cudaSetDevice(c->device));
 	CU(launch_call_sites(d_pileup, d_ref, n, d_vcf, nullptr, true, c->d_const, c->d_counters, stream ? (cudaStream_t)stream : c->stream, &c->launches));
-	c->stats.sites += n;
+	__atomic_fetch_add(&c->stats.sites, (uint64_t)(n), __ATOMIC_RELAXED);
 	return BSGPU_OK;
 }
 
@@ -372,7 +387,7 @@ static int block_dev(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *
 	} else {
 		CU(launch_pileup_tiles(scratch, nseg, d_bases, d_ref, x, sz, 0, ntiles, d_out, mode, c->d_const, c->d_counters, st, &c->launches));
 	}
-	c->stats.sites += sz;
+	__atomic_fetch_add(&c->stats.sites, (uint64_t)(sz), __ATOMIC_RELAXED);
 	return BSGPU_OK;
 }
 
@@ -488,12 +503,12 @@ int bsgpu_call_sites(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t *re
 		CU(launch_call_sites(s.in.p, s.ref.p, m, s.out.p, s.skip.p, false, c->d_const, c->d_counters, s.stream, &c->launches, first));
 		CU(cudaMemcpyAsync(out + first, s.out.p, m * sizeof(bsgpu_gt_meth), cudaMemcpyDeviceToHost, s.stream));
 		CU(cudaMemcpyAsync(skip + first, s.skip.p, m, cudaMemcpyDeviceToHost, s.stream));
-		c->stats.h2d_bytes += m * (sizeof(bsgpu_pileup) + 1);
-		c->stats.d2h_bytes += m * (sizeof(bsgpu_gt_meth) + 1);
+		__atomic_fetch_add(&c->stats.h2d_bytes, (uint64_t)(m * (sizeof(bsgpu_pileup) + 1)), __ATOMIC_RELAXED);
+		__atomic_fetch_add(&c->stats.d2h_bytes, (uint64_t)(m * (sizeof(bsgpu_gt_meth) + 1)), __ATOMIC_RELAXED);
 	}
 	CU(cudaStreamSynchronize(c->slot[0].stream));
 	CU(cudaStreamSynchronize(c->slot[1].stream));
-	c->stats.sites += n;
+	__atomic_fetch_add(&c->stats.sites, (uint64_t)(n), __ATOMIC_RELAXED);
 	return BSGPU_OK;
 }
 
@@ -564,10 +579,10 @@ static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *
 		CU(cudaMemcpyAsync((uint8_t *)out + site0 * rec, dslab, nsite * rec, cudaMemcpyDeviceToHost, c->copy_stream));
 		CU(cudaEventRecord(copied, c->copy_stream));
 		c->ring_busy[r] = defer;
-		c->stats.d2h_bytes += nsite * rec;
+		__atomic_fetch_add(&c->stats.d2h_bytes, (uint64_t)(nsite * rec), __ATOMIC_RELAXED);
 	}
 	if (defer) c->ring_pos = (c->ring_pos + nslab) % 3;
-	c->stats.sites += sz;
+	__atomic_fetch_add(&c->stats.sites, (uint64_t)(sz), __ATOMIC_RELAXED);
 	if (defer) return BSGPU_OK;
 	CU(cudaStreamSynchronize(c->copy_stream));
 	CU(cudaStreamSynchronize(c->stream));
@@ -596,7 +611,7 @@ static int block_host(bsgpu_ctx *c, const bsgpu_seg *segs, size_t nseg, const ui
 		CU(cudaMemcpyAsync(c->bases.p, bases, nbases, cudaMemcpyHostToDevice, c->stream));
 	}
 	if (mode) CU(cudaMemcpyAsync(c->ref.p, ref, sz, cudaMemcpyHostToDevice, c->stream));
-	c->stats.h2d_bytes += nseg * sizeof(bsgpu_seg) + nbases + (mode ? sz : 0);
+	__atomic_fetch_add(&c->stats.h2d_bytes, (uint64_t)(nseg * sizeof(bsgpu_seg) + nbases + (mode ? sz : 0)), __ATOMIC_RELAXED);
 	return block_run(c, c->segs.p, nseg, c->bases.p, c->ref.p, x, sz, out, mode, false);
 }
 
@@ -647,7 +662,7 @@ int bsgpu_process_block(bsgpu_ctx *c, const bsgpu_template *t, size_t n, const u
 	const size_t nref = (size_t)sz + (c->profile_on ? 1 : 0);      // the profile looks one code past the block (src/meth_profile.c:70)
 	CU(cudaMemcpyAsync(c->ref.p, ref, nref, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaStreamSynchronize(c->stream));          // `off` is a pageable temporary: the copy must finish before it dies
-	c->stats.h2d_bytes += n * sizeof(bsgpu_template) + nmisms * sizeof(bsgpu_misms) + nbases + (2 * n + 1) * 4 + nref;
+	__atomic_fetch_add(&c->stats.h2d_bytes, (uint64_t)(n * sizeof(bsgpu_template) + nmisms * sizeof(bsgpu_misms) + nbases + (2 * n + 1) * 4 + nref), __ATOMIC_RELAXED);
 	unsigned long long before[4], after[4];
 	CU(cudaMemcpy(before, c->d_counters, sizeof(before), cudaMemcpyDeviceToHost));
 	cudaError_t perr;
@@ -708,7 +723,7 @@ static int db_upload(bsgpu_ctx *c, const bsgpu_dbsnp *db, bsgpu_ctx::DbDev &d, c
 	CU(cudaMemcpy(d.cum.p, cum.data(), (words + 1) * 4, cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(d.off.p, db->name_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice));
 	if (nbytes) CU(cudaMemcpy(d.names.p, db->names, nbytes, cudaMemcpyHostToDevice));
-	c->stats.h2d_bytes += words * 20 + ((size_t)n + 1) * 4 + nbytes;
+	__atomic_fetch_add(&c->stats.h2d_bytes, (uint64_t)(words * 20 + ((size_t)n + 1) * 4 + nbytes), __ATOMIC_RELAXED);
 	d.words = words;
 	return BSGPU_OK;
 }
@@ -788,10 +803,10 @@ int bsgpu_bcf_block(bsgpu_ctx *c, const bsgpu_gt_vcf *vcf, const uint8_t *ref, u
 	CU(c->wr_out.reserve(dcap + 16));
 	CU(cudaMemcpyAsync(c->wr_vcf.p, vcf, (size_t)sz * sizeof(bsgpu_gt_vcf), cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->wr_ref.p, ref, (size_t)sz + 2, cudaMemcpyHostToDevice, c->stream));
-	c->stats.h2d_bytes += (size_t)sz * (sizeof(bsgpu_gt_vcf) + 1) + 2;
+	__atomic_fetch_add(&c->stats.h2d_bytes, (uint64_t)((size_t)sz * (sizeof(bsgpu_gt_vcf) + 1) + 2), __ATOMIC_RELAXED);
 	if (bcf_run(c, c->wr_vcf.p, c->wr_ref.p, x, sz, p, c->wr_out.p, dcap, nbytes, nrec, c->stream, "bsgpu_bcf_block") != BSGPU_OK) return BSGPU_FAIL;
 	if (*nbytes) CU(cudaMemcpy(out, c->wr_out.p, *nbytes, cudaMemcpyDeviceToHost));
-	c->stats.d2h_bytes += *nbytes + 24;
+	__atomic_fetch_add(&c->stats.d2h_bytes, (uint64_t)(*nbytes + 24), __ATOMIC_RELAXED);
 	return BSGPU_OK;
 }
 
@@ -823,11 +838,11 @@ int bsgpu_call_block_bcf(bsgpu_ctx *c, const bsgpu_seg *segs, size_t nseg, const
 		CU(cudaMemcpyAsync(c->bases.p, bases, nbases, cudaMemcpyHostToDevice, c->stream));
 	}
 	CU(cudaMemcpyAsync(c->wr_ref.p, ref, (size_t)sz + 2, cudaMemcpyHostToDevice, c->stream));
-	c->stats.h2d_bytes += nseg * sizeof(bsgpu_seg) + nbases + sz + 2;
+	__atomic_fetch_add(&c->stats.h2d_bytes, (uint64_t)(nseg * sizeof(bsgpu_seg) + nbases + sz + 2), __ATOMIC_RELAXED);
 	if (block_dev(c, c->segs.p, nseg, c->bases.p, c->wr_ref.p, x, sz, c->wr_vcf.p, 1, nullptr, c->stream) != BSGPU_OK) return BSGPU_FAIL;
 	if (bcf_run(c, c->wr_vcf.p, c->wr_ref.p, x, sz, p, c->wr_out.p, dcap, nbytes, nrec, c->stream, "bsgpu_call_block_bcf") != BSGPU_OK) return BSGPU_FAIL;
 	if (*nbytes) CU(cudaMemcpy(out, c->wr_out.p, *nbytes, cudaMemcpyDeviceToHost));
-	c->stats.d2h_bytes += *nbytes + 24;
+	__atomic_fetch_add(&c->stats.d2h_bytes, (uint64_t)(*nbytes + 24), __ATOMIC_RELAXED);
 	return BSGPU_OK;
 }
 
@@ -890,7 +905,7 @@ int bsgpu_call_sites_bcf(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t
 		if (t[0]) CU(cudaMemcpyAsync(out + at, (uint8_t *)c->wr_out.p + (k & 1) * ocap, t[0], cudaMemcpyDeviceToHost, down));
 		CU(cudaEventRecord(E(k, 3), down));
 		at += t[0]; recs += t[1];
-		c->stats.d2h_bytes += t[0] + 24;
+		__atomic_fetch_add(&c->stats.d2h_bytes, (uint64_t)(t[0] + 24), __ATOMIC_RELAXED);
 		return BSGPU_OK;
 	};
 	for (size_t k = 0; k < K && ret == BSGPU_OK; k++) {
@@ -898,7 +913,7 @@ int bsgpu_call_sites_bcf(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t
 		if (k >= 2) CU(cudaStreamWaitEvent(up, E(k - 2, 1), 0));      // the model has consumed the input buffer
 		CU(cudaMemcpyAsync(c->slot[k & 1].in.p, pileup + lo, m * sizeof(bsgpu_pileup), cudaMemcpyHostToDevice, up));
 		CU(cudaEventRecord(E(k, 0), up));
-		c->stats.h2d_bytes += m * (sizeof(bsgpu_pileup) + 1);
+		__atomic_fetch_add(&c->stats.h2d_bytes, (uint64_t)(m * (sizeof(bsgpu_pileup) + 1)), __ATOMIC_RELAXED);
 		CU(cudaStreamWaitEvent(st, E(k, 0), 0));
 		CU(launch_call_sites(c->slot[k & 1].in.p, (const uint8_t *)c->wr_ref.p + lo, m, (uint8_t *)c->wr_vcf.p + (k & 1) * chunk * sizeof(bsgpu_gt_vcf),
 				nullptr, true, c->d_const, c->d_counters, st, &c->launches));
@@ -915,7 +930,7 @@ int bsgpu_call_sites_bcf(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t
 	if (ret == BSGPU_OK) ret = collect(K - 1);
 	CU(cudaStreamSynchronize(up)); CU(cudaStreamSynchronize(st)); CU(cudaStreamSynchronize(down));
 	if (ret != BSGPU_OK) return ret;
-	c->stats.sites += n;
+	__atomic_fetch_add(&c->stats.sites, (uint64_t)(n), __ATOMIC_RELAXED);
 	*nbytes = at; *nrec = recs;
 	return BSGPU_OK;
 }
@@ -943,7 +958,7 @@ int bsgpu_profile_read(bsgpu_ctx *c, bsgpu_profile *out, int reset) {
 	std::vector<ProfDev> hbuf(1);
 	ProfDev &h = hbuf[0];
 	CU(cudaMemcpy(&h, c->d_prof, sizeof(h), cudaMemcpyDeviceToHost));
-	c->stats.d2h_bytes += sizeof(h);
+	__atomic_fetch_add(&c->stats.d2h_bytes, (uint64_t)(sizeof(h)), __ATOMIC_RELAXED);
 	if (h.too_long) return fail("bsgpu profile: %llu template(s) reach beyond original read position %d", h.too_long, BSGPU_PROFILE_MAX - 2);
 	memset(out, 0, sizeof(*out));
 	out->used = h.used[c->prof_parity];
@@ -972,94 +987,102 @@ void bsgpu_default_reader_params(bsgpu_reader_params *p) {
 // frame + upload + decode, in chunks: the stream goes up in byte pieces on the upload stream while the host frames it;
 // chunk k = the records that end inside pieces 0..k, decoded on the decode stream as soon as piece k has landed, its
 // descriptors copied back to the pinned array h_rec.  On return everything is queued; chunk_end[k] = one past the last
-// record of chunk k and c->rd_done[k] fires when its descriptors are on the host.  Descriptors, packed reads and events
+// record of chunk k and R.rd_done[k] fires when its descriptors are on the host.  Descriptors, packed reads and events
 // stay resident.  *nb / *nm = sizes of the decoded arrays.
-static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const bsgpu_reader_params *rp, unsigned want_chunks,
-		size_t *nrec, uint64_t *nb, uint64_t *nm, std::vector<size_t> &chunk_end, size_t *framed = nullptr) {
-	std::vector<uint32_t> &read_off = c->read_off, &mm_off = c->mm_off;
-	if (!c->frame_scratch) c->frame_scratch = frame_scratch_new();
+static int decode_queue(bsgpu_ctx *c, bsgpu_ctx::ReaderSet &R, const uint8_t *bam, size_t nbytes, const bsgpu_reader_params *rp, unsigned want_chunks,
+		size_t *nrec, uint64_t *nb, uint64_t *nm, std::vector<size_t> &chunk_end, size_t *framed = nullptr, bool pipelined = false) {
+	std::vector<uint32_t> &read_off = R.read_off, &mm_off = R.mm_off;
+	if (!R.frame_scratch) R.frame_scratch = frame_scratch_new();
 	CU(cudaSetDevice(c->device));
-	CU(cudaStreamSynchronize(c->stream));
-	CU(cudaStreamSynchronize(c->copy_stream));
+	if (!R.up) {
+		if (&R == &c->rs[0]) R.up = c->slot[0].stream;
+		else CU(cudaStreamCreateWithFlags(&R.up, cudaStreamNonBlocking));
+	}
 	// debugging switches: BSGPU_ONE_STREAM=1 puts upload, decode and the windows on one stream (no kernel of the reader stage
 	// overlaps a kernel of the window stage); BSGPU_NO_NAME_JOIN=1 leaves the QNAME join to the host
 	static const bool one_stream = getenv("BSGPU_ONE_STREAM") != nullptr, no_join = getenv("BSGPU_NO_NAME_JOIN") != nullptr;
 	static const bool dec_own = getenv("BSGPU_DECODE_STREAM") != nullptr;      // decode kernels on a stream of their own (round-1 behaviour)
-	cudaStream_t up = one_stream ? c->stream : c->slot[0].stream, dec = one_stream || !dec_own ? c->stream : c->slot[1].stream;
+	cudaStream_t up = one_stream ? c->stream : R.up, dec = one_stream || !dec_own || pipelined ? c->stream : c->slot[1].stream;
+	if (!pipelined) {
+		// nothing of an earlier call is in flight any more.  (A pipelined run of a session starts while the run before it is
+		// still at its window stage: its reader set was last used two runs ago, and the session has waited for that one.)
+		CU(cudaStreamSynchronize(c->stream));
+		CU(cudaStreamSynchronize(c->copy_stream));
+		CU(cudaStreamSynchronize(dec));
+	}
 	CU(cudaStreamSynchronize(up));
-	CU(cudaStreamSynchronize(dec));
 	size_t chunk_min = 64u << 20;                       // smaller streams go up and are decoded in one piece
 	if (const char *e = getenv("BSGPU_READER_CHUNK_MIN_BYTES")) chunk_min = (size_t)atoll(e);
 	const unsigned K = nbytes >= chunk_min ? std::max(1u, std::min(want_chunks, 8u)) : 1;
-	while (c->rd_up.size() < K) {
+	while (R.rd_up.size() < K) {
 		cudaEvent_t e1, e2;
 		CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-		c->rd_up.push_back(e1); c->rd_done.push_back(e2);
+		R.rd_up.push_back(e1); R.rd_done.push_back(e2);
 	}
 	// The stream itself starts its way up while the host frames it -- the first half only: the copy engine serves
 	// transfers in the order they were submitted, and the offset tables (known after framing) must not queue behind the
 	// whole stream, or the first chunk could not be decoded before the last byte has arrived.
-	CU(c->rd_bam.reserve(nbytes + 16));
+	CU(R.rd_bam.reserve(nbytes + 16));
 	std::vector<size_t> piece_end(K);
 	for (unsigned k = 0; k < K; k++) piece_end[k] = nbytes * (k + 1) / K;
 	auto upload_piece = [&](unsigned k) -> int {
 		const size_t lo = nbytes * k / K, hi = piece_end[k];
-		if (hi > lo) CU(cudaMemcpyAsync((uint8_t *)c->rd_bam.p + lo, bam + lo, hi - lo, cudaMemcpyHostToDevice, up));
-		CU(cudaEventRecord(c->rd_up[k], up));
+		if (hi > lo) CU(cudaMemcpyAsync((uint8_t *)R.rd_bam.p + lo, bam + lo, hi - lo, cudaMemcpyHostToDevice, up));
+		CU(cudaEventRecord(R.rd_up[k], up));
 		return BSGPU_OK;
 	};
 	const unsigned k_early = (K + 1) / 2;
 	for (unsigned k = 0; k < k_early; k++) if (upload_piece(k) != BSGPU_OK) return BSGPU_FAIL;
-	const int fr = frame_records(bam, nbytes, c->rec_off, read_off, mm_off, nb, nm, c->frame_scratch, framed);
+	const int fr = frame_records(bam, nbytes, R.rec_off, read_off, mm_off, nb, nm, R.frame_scratch, framed);
 	if (fr) cudaStreamSynchronize(up);
 	if (fr == -1) return fail("bsgpu reader: truncated or malformed BAM record stream");
 	if (fr == -2) return fail("bsgpu reader: more than 4 Gi bases in one stream; split the input");
-	const size_t n = c->rec_off.size();
+	const size_t n = R.rec_off.size();
 	*nrec = n;
 	chunk_end.clear();
 	if (!n) { CU(cudaStreamSynchronize(up)); return BSGPU_OK; }
-	CU(c->rd_recoff.reserve(n * 8));
-	CU(c->rd_readoff.reserve(n * 4));
-	CU(c->rd_mmoff.reserve(n * 4));
-	CU(c->rd_rec.reserve(n * sizeof(bsgpu_record)));
-	CU(c->rd_bases.reserve(*nb + 16));
-	CU(c->rd_misms.reserve((*nm + 1) * sizeof(bsgpu_misms)));
-	CU(c->h_rec.reserve(n * sizeof(bsgpu_record)));
+	CU(R.rd_recoff.reserve(n * 8));
+	CU(R.rd_readoff.reserve(n * 4));
+	CU(R.rd_mmoff.reserve(n * 4));
+	CU(R.rd_rec.reserve(n * sizeof(bsgpu_record)));
+	CU(R.rd_bases.reserve(*nb + 16));
+	CU(R.rd_misms.reserve((*nm + 1) * sizeof(bsgpu_misms)));
+	CU(R.h_rec.reserve(n * sizeof(bsgpu_record)));
 	if (c->zero_decoded) {                          // k_decode_records skips dropped records: what the caller copies out is defined everywhere
-		CU(cudaMemsetAsync(c->rd_bases.p, 0, *nb + 16, dec));
-		CU(cudaMemsetAsync(c->rd_misms.p, 0, (*nm + 1) * sizeof(bsgpu_misms), dec));
+		CU(cudaMemsetAsync(R.rd_bases.p, 0, *nb + 16, dec));
+		CU(cudaMemsetAsync(R.rd_misms.p, 0, (*nm + 1) * sizeof(bsgpu_misms), dec));
 	}
 	// certain block starts: the keys the decode kernel writes come home and host threads scan them; BSGPU_DEVICE_SCAN=1
 	// uses the bit mask of the scan on the device instead, BSGPU_CHECK_SCAN=1 does both and compares
 	const bool dev_scan = getenv("BSGPU_DEVICE_SCAN") != nullptr || getenv("BSGPU_CHECK_SCAN") != nullptr;
 	const bool host_scan = getenv("BSGPU_DEVICE_SCAN") == nullptr || getenv("BSGPU_CHECK_SCAN") != nullptr;
-	CU(c->rd_key.reserve(n * 16));
-	if (host_scan) CU(c->h_key.reserve(n * 16));
+	CU(R.rd_key.reserve(n * 16));
+	if (host_scan) CU(R.h_key.reserve(n * 16));
 	// QNAME join: table of kept paired records by name hash, name ids per record (+ one word: the overflow flag)
 	const size_t name_slots = name_table_slots(n);
-	CU(c->rd_names.reserve(name_table_bytes(n)));
-	CU(c->rd_nameid.reserve((n + 1) * 4));
-	CU(c->h_nameid.reserve((n + 1 + K) * 4));      // + the overflow flag as it stood after every chunk
-	memset((uint32_t *)c->h_nameid.p + n, 0, (1 + K) * 4);
-	CU(cudaMemsetAsync(c->rd_names.p, 0, name_table_bytes(n), dec));
-	CU(cudaMemsetAsync((uint32_t *)c->rd_nameid.p + n, 0, 4, dec));
-	CU(c->rd_mask.reserve((n / 32 + 2 * K + 8) * 4 + 16));
-	CU(c->h_mask.reserve((n / 32 + 2 * K + 8) * 4));
-	c->mask_off.assign(K + 1, 0);
-	uint32_t *d_carry = (uint32_t *)c->rd_mask.p;          // first four words of the buffer: {last contig, running end}
+	CU(R.rd_names.reserve(name_table_bytes(n)));
+	CU(R.rd_nameid.reserve((n + 1) * 4));
+	CU(R.h_nameid.reserve((n + 1 + K) * 4));      // + the overflow flag as it stood after every chunk
+	memset((uint32_t *)R.h_nameid.p + n, 0, (1 + K) * 4);
+	CU(cudaMemsetAsync(R.rd_names.p, 0, name_table_bytes(n), dec));
+	CU(cudaMemsetAsync((uint32_t *)R.rd_nameid.p + n, 0, 4, dec));
+	CU(R.rd_mask.reserve((n / 32 + 2 * K + 8) * 4 + 16));
+	CU(R.h_mask.reserve((n / 32 + 2 * K + 8) * 4));
+	R.mask_off.assign(K + 1, 0);
+	uint32_t *d_carry = (uint32_t *)R.rd_mask.p;          // first four words of the buffer: {last contig, running end}
 	CU(cudaMemsetAsync(d_carry, 0xff, 4, dec));
 	CU(cudaMemsetAsync(d_carry + 1, 0, 12, dec));
 	size_t mask_words = 4;
 	// the offset tables go up from pinned staging (pageable vectors would serialise the copies behind the big ones)
-	CU(c->h_off.reserve(n * 16));
-	uint8_t *ho = (uint8_t *)c->h_off.p;
+	CU(R.h_off.reserve(n * 16));
+	uint8_t *ho = (uint8_t *)R.h_off.p;
 	{
 		// 16 bytes per record into page-locked memory: a few threads, each a slice of the three tables
 		const unsigned T = n >= (1u << 18) ? std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1;
 		auto part = [&](unsigned t) {
 			const size_t lo = n * t / T, hi = n * (t + 1) / T;
-			memcpy(ho + lo * 8, c->rec_off.data() + lo, (hi - lo) * 8);
+			memcpy(ho + lo * 8, R.rec_off.data() + lo, (hi - lo) * 8);
 			memcpy(ho + n * 8 + lo * 4, read_off.data() + lo, (hi - lo) * 4);
 			memcpy(ho + n * 12 + lo * 4, mm_off.data() + lo, (hi - lo) * 4);
 		};
@@ -1070,54 +1093,55 @@ static int decode_queue(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const b
 			for (auto &t : thr) t.join();
 		}
 	}
-	CU(cudaMemcpyAsync(c->rd_recoff.p, ho, n * 8, cudaMemcpyHostToDevice, dec));
-	CU(cudaMemcpyAsync(c->rd_readoff.p, ho + n * 8, n * 4, cudaMemcpyHostToDevice, dec));
-	CU(cudaMemcpyAsync(c->rd_mmoff.p, ho + n * 12, n * 4, cudaMemcpyHostToDevice, dec));
+	CU(cudaMemcpyAsync(R.rd_recoff.p, ho, n * 8, cudaMemcpyHostToDevice, dec));
+	CU(cudaMemcpyAsync(R.rd_readoff.p, ho + n * 8, n * 4, cudaMemcpyHostToDevice, dec));
+	CU(cudaMemcpyAsync(R.rd_mmoff.p, ho + n * 12, n * 4, cudaMemcpyHostToDevice, dec));
 	for (unsigned k = k_early; k < K; k++) if (upload_piece(k) != BSGPU_OK) return BSGPU_FAIL;
-	c->stats.h2d_bytes += nbytes + n * 16;
+	__atomic_fetch_add(&c->stats.h2d_bytes, (uint64_t)(nbytes + n * 16), __ATOMIC_RELAXED);
 	size_t r0 = 0;
 	for (unsigned k = 0; k < K; k++) {
 		// records that end inside pieces 0..k (the last chunk takes the rest)
 		size_t r1 = n;
 		if (k + 1 < K) {
-			const auto it = std::upper_bound(c->rec_off.begin() + r0, c->rec_off.end(), (uint64_t)piece_end[k]);
-			r1 = (size_t)(it - c->rec_off.begin());
+			const auto it = std::upper_bound(R.rec_off.begin() + r0, R.rec_off.end(), (uint64_t)piece_end[k]);
+			r1 = (size_t)(it - R.rec_off.begin());
 			if (r1 > r0) r1--;                          // the record that starts before the boundary may end after it
-			while (r1 > r0 && c->rec_off[r1 - 1] + 4 + (uint64_t)(bam[c->rec_off[r1 - 1]] | bam[c->rec_off[r1 - 1] + 1] << 8 | bam[c->rec_off[r1 - 1] + 2] << 16 | (uint64_t)bam[c->rec_off[r1 - 1] + 3] << 24) > piece_end[k]) r1--;
+			while (r1 > r0 && R.rec_off[r1 - 1] + 4 + (uint64_t)(bam[R.rec_off[r1 - 1]] | bam[R.rec_off[r1 - 1] + 1] << 8 | bam[R.rec_off[r1 - 1] + 2] << 16 | (uint64_t)bam[R.rec_off[r1 - 1] + 3] << 24) > piece_end[k]) r1--;
 		}
-		CU(cudaStreamWaitEvent(dec, c->rd_up[k], 0));
+		CU(cudaStreamWaitEvent(dec, R.rd_up[k], 0));
 		if (r1 > r0) {
-			CU(launch_decode_records(c->rd_bam.p, (const uint64_t *)c->rd_recoff.p + r0, (const uint32_t *)c->rd_readoff.p + r0,
-					(const uint32_t *)c->rd_mmoff.p + r0, r1 - r0, rp->mapq_thresh, rp->max_template_len, rp->keep_unmatched,
-					rp->ignore_duplicates, (bsgpu_record *)c->rd_rec.p + r0, c->rd_bases.p, c->rd_misms.p, dec, &c->launches, (uint8_t *)c->rd_key.p + r0 * 16,
-					no_join ? nullptr : c->rd_names.p, name_slots, (uint32_t)r0, (uint32_t *)c->rd_nameid.p + n));
-			if (no_join) CU(cudaMemsetAsync((uint32_t *)c->rd_nameid.p + n, 0xff, 4, dec));      // "overflow": the host computes the ids
-			else CU(launch_name_ids(c->rd_bam.p, c->rd_recoff.p, c->rd_rec.p, (uint32_t)r0, (uint32_t)r1, c->rd_names.p, name_slots, c->rd_nameid.p, dec, &c->launches));
-			CU(cudaMemcpyAsync((uint32_t *)c->h_nameid.p + r0, (const uint32_t *)c->rd_nameid.p + r0, (r1 - r0) * 4, cudaMemcpyDeviceToHost, dec));
-			CU(cudaMemcpyAsync((uint32_t *)c->h_nameid.p + n + 1 + k, (const uint32_t *)c->rd_nameid.p + n, 4, cudaMemcpyDeviceToHost, dec));
-			if (host_scan) CU(cudaMemcpyAsync((uint8_t *)c->h_key.p + r0 * 16, (const uint8_t *)c->rd_key.p + r0 * 16, (r1 - r0) * 16, cudaMemcpyDeviceToHost, dec));
+			CU(launch_decode_records(R.rd_bam.p, (const uint64_t *)R.rd_recoff.p + r0, (const uint32_t *)R.rd_readoff.p + r0,
+					(const uint32_t *)R.rd_mmoff.p + r0, r1 - r0, rp->mapq_thresh, rp->max_template_len, rp->keep_unmatched,
+					rp->ignore_duplicates, (bsgpu_record *)R.rd_rec.p + r0, R.rd_bases.p, R.rd_misms.p, dec, &c->launches, (uint8_t *)R.rd_key.p + r0 * 16,
+					no_join ? nullptr : R.rd_names.p, name_slots, (uint32_t)r0, (uint32_t *)R.rd_nameid.p + n));
+			if (no_join) CU(cudaMemsetAsync((uint32_t *)R.rd_nameid.p + n, 0xff, 4, dec));      // "overflow": the host computes the ids
+			else CU(launch_name_ids(R.rd_bam.p, R.rd_recoff.p, R.rd_rec.p, (uint32_t)r0, (uint32_t)r1, R.rd_names.p, name_slots, R.rd_nameid.p, dec, &c->launches));
+			CU(cudaMemcpyAsync((uint32_t *)R.h_nameid.p + r0, (const uint32_t *)R.rd_nameid.p + r0, (r1 - r0) * 4, cudaMemcpyDeviceToHost, dec));
+			CU(cudaMemcpyAsync((uint32_t *)R.h_nameid.p + n + 1 + k, (const uint32_t *)R.rd_nameid.p + n, 4, cudaMemcpyDeviceToHost, dec));
+			if (host_scan) CU(cudaMemcpyAsync((uint8_t *)R.h_key.p + r0 * 16, (const uint8_t *)R.rd_key.p + r0 * 16, (r1 - r0) * 16, cudaMemcpyDeviceToHost, dec));
 			if (dev_scan) {
 				const size_t words = (r1 - r0 + 31) / 32;
-				CU(launch_certain_starts((const uint8_t *)c->rd_key.p + r0 * 16, (uint32_t)(r1 - r0), d_carry, (uint32_t *)c->rd_mask.p + mask_words, dec, &c->launches));
-				CU(cudaMemcpyAsync((uint32_t *)c->h_mask.p + mask_words, (const uint32_t *)c->rd_mask.p + mask_words, words * 4, cudaMemcpyDeviceToHost, dec));
-				c->mask_off[k] = mask_words;
+				CU(launch_certain_starts((const uint8_t *)R.rd_key.p + r0 * 16, (uint32_t)(r1 - r0), d_carry, (uint32_t *)R.rd_mask.p + mask_words, dec, &c->launches));
+				CU(cudaMemcpyAsync((uint32_t *)R.h_mask.p + mask_words, (const uint32_t *)R.rd_mask.p + mask_words, words * 4, cudaMemcpyDeviceToHost, dec));
+				R.mask_off[k] = mask_words;
 				mask_words += words;
 			}
-			CU(cudaMemcpyAsync((bsgpu_record *)c->h_rec.p + r0, (const bsgpu_record *)c->rd_rec.p + r0, (r1 - r0) * sizeof(bsgpu_record),
+			CU(cudaMemcpyAsync((bsgpu_record *)R.h_rec.p + r0, (const bsgpu_record *)R.rd_rec.p + r0, (r1 - r0) * sizeof(bsgpu_record),
 					cudaMemcpyDeviceToHost, dec));
 		}
-		CU(cudaEventRecord(c->rd_done[k], dec));
+		CU(cudaEventRecord(R.rd_done[k], dec));
 		chunk_end.push_back(r1);
 		r0 = r1;
 	}
-	c->stats.d2h_bytes += n * (sizeof(bsgpu_record) + 4 + (host_scan ? 16 : 0)) + mask_words * 4;
+	__atomic_fetch_add(&c->stats.d2h_bytes, (uint64_t)(n * (sizeof(bsgpu_record) + 4 + (host_scan ? 16 : 0)) + mask_words * 4), __ATOMIC_RELAXED);
 	return BSGPU_OK;
 }
 
 // the whole stream decoded and its descriptors on the host (h_rec)
 static int decode_resident(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const bsgpu_reader_params *rp, size_t *nrec, uint64_t *nb, uint64_t *nm) {
 	std::vector<size_t> chunk_end;
-	if (decode_queue(c, bam, nbytes, rp, 1, nrec, nb, nm, chunk_end) != BSGPU_OK) return BSGPU_FAIL;
+	bsgpu_ctx::ReaderSet &R = c->rs[0];
+	if (decode_queue(c, R, bam, nbytes, rp, 1, nrec, nb, nm, chunk_end) != BSGPU_OK) return BSGPU_FAIL;
 	CU(cudaStreamSynchronize(c->slot[0].stream));
 	CU(cudaStreamSynchronize(c->slot[1].stream));
 	CU(cudaStreamSynchronize(c->stream));          // the decode kernels run on the context stream
@@ -1133,15 +1157,16 @@ int bsgpu_decode_records(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, const 
 	c->zero_decoded = bases_out != nullptr || misms_out != nullptr;
 	const int drc = decode_resident(c, bam, nbytes, rp, &n, &nb, &nm);
 	c->zero_decoded = false;
+	bsgpu_ctx::ReaderSet &R = c->rs[0];
 	if (drc != BSGPU_OK) return BSGPU_FAIL;
 	if (n > rec_cap || (bases_out && nb > bases_cap) || (misms_out && nm > misms_cap)) return fail("bsgpu_decode_records: need room for %zu records, %llu bases, %llu events", n, (unsigned long long)nb, (unsigned long long)nm);
 	if (n) {
-		if (rec_out) memcpy(rec_out, c->h_rec.p, n * sizeof(bsgpu_record));
+		if (rec_out) memcpy(rec_out, R.h_rec.p, n * sizeof(bsgpu_record));
 		// events of dropped records are never written: clear what the caller will see
-		if (bases_out && nb) CU(cudaMemcpyAsync(bases_out, c->rd_bases.p, nb, cudaMemcpyDeviceToHost, c->stream));
-		if (misms_out && nm) CU(cudaMemcpyAsync(misms_out, c->rd_misms.p, nm * sizeof(bsgpu_misms), cudaMemcpyDeviceToHost, c->stream));
+		if (bases_out && nb) CU(cudaMemcpyAsync(bases_out, R.rd_bases.p, nb, cudaMemcpyDeviceToHost, c->stream));
+		if (misms_out && nm) CU(cudaMemcpyAsync(misms_out, R.rd_misms.p, nm * sizeof(bsgpu_misms), cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
-		c->stats.d2h_bytes += (bases_out ? nb : 0) + (misms_out ? nm * sizeof(bsgpu_misms) : 0);
+		__atomic_fetch_add(&c->stats.d2h_bytes, (uint64_t)((bases_out ? nb : 0) + (misms_out ? nm * sizeof(bsgpu_misms) : 0)), __ATOMIC_RELAXED);
 	}
 	*nrec = n;
 	if (nbases) *nbases = nb;
@@ -1191,6 +1216,15 @@ static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *
 // What a streaming session (bsgpu_bam_*) asks of a run over the bytes it has staged so far
 struct BamRunOpts {
 	bool partial = false;                    // stop at the last CERTAIN block start of the buffer; a record cut off by its end is fine
+	// Pipelined runs of a session: run k + 1 may do its reader stage (reader set (k + 1) & 1) while run k is still queueing
+	// windows; it takes its turn at the window stage when run k has finished.  `ticket` numbers the runs of the context from
+	// the value of bsgpu_ctx::win_done at the first one; on_scanned is called (from the run's scanner thread) as soon as the
+	// bytes the run accounts for are known -- the staged bytes are not read by the run after that.
+	bool pipelined = false;
+	int reader_set = 0;
+	uint64_t ticket = 0;
+	void (*on_scanned)(void *user, size_t consumed, size_t records) = nullptr;
+	void *scan_user = nullptr;
 	size_t consumed = 0;                     // out: bytes of the buffer whose records were turned into results
 	size_t records = 0;                      // out: records in those bytes
 	std::vector<bsgpu_block> *blocks_vec = nullptr;      // blocks go here (grown as needed) instead of into blocks[]
@@ -1232,7 +1266,7 @@ static int sink_collect(bsgpu_ctx *c, BcfSink *k) {
 	if (t[0]) CU(cudaMemcpyAsync(k->out + k->at, c->wr_ring[slot].p, t[0], cudaMemcpyDeviceToHost, c->copy_stream));
 	CU(cudaEventRecord(c->wr_copied[slot], c->copy_stream));
 	k->at += t[0]; k->recs += t[1];
-	c->stats.d2h_bytes += t[0] + 24;
+	__atomic_fetch_add(&c->stats.d2h_bytes, (uint64_t)(t[0] + 24), __ATOMIC_RELAXED);
 	k->collected++;
 	return BSGPU_OK;
 }
@@ -1240,7 +1274,7 @@ static int sink_collect(bsgpu_ctx *c, BcfSink *k) {
 struct TmSpan { const bsgpu_template *p; size_t n; };      // the templates of a window: runs in pinned host memory, in order
 
 // wb[0 .. nwb): the blocks inside the window (BCF sink only)
-static int call_window(bsgpu_ctx *c, const TmSpan *span, size_t nspan, size_t nt, uint32_t tid, uint32_t ctg_len, const uint8_t *codes,
+static int call_window(bsgpu_ctx *c, bsgpu_ctx::ReaderSet &R, const TmSpan *span, size_t nspan, size_t nt, uint32_t tid, uint32_t ctg_len, const uint8_t *codes,
 		uint32_t x, uint32_t y, bsgpu_gt_vcf *out, uint32_t maxcap_hint = 0, BcfSink *sink = nullptr, const bsgpu_block *wb = nullptr, size_t nwb = 0) {
 	const uint32_t sz = y - x + 1;
 	auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1297,11 +1331,11 @@ static int call_window(bsgpu_ctx *c, const TmSpan *span, size_t nspan, size_t nt
 	if (!slot) CU(cudaMemcpyAsync(c->ooff.p, off.data(), (2 * nt + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
 	if (ncopy) CU(cudaMemcpyAsync(c->ref.p, codes + x - 1, ncopy, cudaMemcpyHostToDevice, c->stream));
 	if (ncopy < (size_t)sz + 2) CU(cudaMemsetAsync((uint8_t *)c->ref.p + ncopy, 0, (size_t)sz + 2 - ncopy, c->stream));
-	c->stats.h2d_bytes += nt * sizeof(bsgpu_template) + (slot ? 0 : (2 * nt + 1) * 4) + ncopy;
+	__atomic_fetch_add(&c->stats.h2d_bytes, (uint64_t)(nt * sizeof(bsgpu_template) + (slot ? 0 : (2 * nt + 1) * 4) + ncopy), __ATOMIC_RELAXED);
 	cudaError_t perr;
 	const ProfArgs *pa = profile_for(c, nt, sz, &perr);
 	CU(perr);
-	CU(launch_normalise(c->tmpl.p, nt, c->rd_bases.p, c->rd_misms.p, slot ? nullptr : c->ooff.p, c->obases.p, c->segs.p, spm, x, y,
+	CU(launch_normalise(c->tmpl.p, nt, R.rd_bases.p, R.rd_misms.p, slot ? nullptr : c->ooff.p, c->obases.p, c->segs.p, spm, x, y,
 			c->params.left_trim, c->params.right_trim, c->d_counters, pa, c->prof_parity, c->stream, &c->launches, slot));
 	if (pa) c->prof_parity ^= 1;
 	if (!sink) return block_run(c, c->segs.p, nseg, c->obases.p, c->ref.p, x, sz, out, 1, true);
@@ -1354,16 +1388,29 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	const double t0 = now();
 	std::vector<size_t> chunk_end;
 	const bool partial = opts && opts->partial;
+	const bool pipelined = opts && opts->pipelined;
+	bsgpu_ctx::ReaderSet &R = c->rs[opts ? opts->reader_set & 1 : 0];
+	// a pipelined run passes the window stage on to the next run whatever way it ends -- after it has had its own turn
+	struct Turn {
+		bsgpu_ctx *c; uint64_t ticket; bool on;
+		void wait() { if (!on) return; std::unique_lock<std::mutex> lk(c->win_mu); c->win_cv.wait(lk, [&] { return c->win_done >= ticket; }); }
+		~Turn() { if (!on) return; wait(); std::unique_lock<std::mutex> lk(c->win_mu); if (c->win_done == ticket) c->win_done = ticket + 1; c->win_cv.notify_all(); }
+	} turn{c, opts ? opts->ticket : 0, pipelined};
+	// the session is told how far the run goes as soon as that is known (the staged bytes are free from then on); with the
+	// --report-file tallies on the block builder still reads record lengths from the stream, so it is told at the very end
+	bool told = false;
+	auto tell = [&](size_t consumed_, size_t records_) { if (opts && opts->on_scanned && !told) { told = true; opts->on_scanned(opts->scan_user, consumed_, records_); } };
+	struct Teller { std::function<void()> f; ~Teller() { f(); } } teller{[&] { if (opts) tell(opts->consumed, opts->records); }};
 	size_t framed = nbytes;
-	if (decode_queue(c, bam, nbytes, rp, 4, &n, &nb, &nm, chunk_end, opts ? &framed : nullptr) != BSGPU_OK) return BSGPU_FAIL;
+	if (decode_queue(c, R, bam, nbytes, rp, 4, &n, &nb, &nm, chunk_end, opts ? &framed : nullptr, pipelined) != BSGPU_OK) return BSGPU_FAIL;
 	if (opts && !partial && framed != nbytes) return fail("bsgpu_bam: the record stream ends inside a record (%zu bytes left over)", nbytes - framed);
 	if (sink) sink->opts = opts;
 	const double t1 = now();
 	c->stats.bam_decode_s += t1 - t0;
 	if (!n) return BSGPU_OK;
-	const bsgpu_record *rec = (const bsgpu_record *)c->h_rec.p;
-	CU(c->h_tmpl.reserve((n + 1) * sizeof(bsgpu_template)));
-	bsgpu_template *tm = (bsgpu_template *)c->h_tmpl.p;
+	const bsgpu_record *rec = (const bsgpu_record *)R.h_rec.p;
+	CU(R.h_tmpl.reserve((n + 1) * sizeof(bsgpu_template)));
+	bsgpu_template *tm = (bsgpu_template *)R.h_tmpl.p;
 	unsigned long long before[4], after[4];       // normalisation failures are counted on the device: compared at the end
 	CU(cudaMemcpy(before, c->d_counters, sizeof(before), cudaMemcpyDeviceToHost));
 	// Chunk by chunk, as the descriptors come home: the part of the stream up to the last CERTAIN block start seen so far
@@ -1466,7 +1513,7 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 						const size_t lo = std::max(t_lo, gs_first[r]), hi = std::min(t_hi, gs_first[r] + gs[r].n);
 						if (hi > lo) ws.push_back(TmSpan{gs[r].p + (lo - gs_first[r]), hi - lo});
 					}
-					ret = call_window(c, ws.data(), ws.size(), t_hi - t_lo, tid, target_len[tid], ctg_codes[tid], x, y, sink ? nullptr : vcf + ov, gmax,
+					ret = call_window(c, R, ws.data(), ws.size(), t_hi - t_lo, tid, target_len[tid], ctg_codes[tid], x, y, sink ? nullptr : vcf + ov, gmax,
 							sink, gb.data() + b0, b1 - b0);
 					ov += sz;
 					ctg_end = y;
@@ -1502,18 +1549,18 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 		cudaSetDevice(c->device);
 		for (size_t ck = 0; ck < chunk_end.size(); ck++) {
 			const double w0 = now();
-			scan_err = cudaEventSynchronize(c->rd_done[ck]);
+			scan_err = cudaEventSynchronize(R.rd_done[ck]);
 			if (scan_err != cudaSuccess) { scan_state.store(-1, std::memory_order_release); return; }
 			const double w1 = now();
 			sc_rd += w1 - w0;
 			// the device's name table overflowed (a read name on more than five kept records, or hashes colliding): from this
 			// chunk on the ids are computed here, over a map that first catches up with the records before
-			if (((const uint32_t *)c->h_nameid.p)[n + 1 + ck] && chunk_end[ck] > scanned) {
-				uint32_t *ids = (uint32_t *)c->h_nameid.p;
+			if (((const uint32_t *)R.h_nameid.p)[n + 1 + ck] && chunk_end[ck] > scanned) {
+				uint32_t *ids = (uint32_t *)R.h_nameid.p;
 				for (size_t i = host_names_done; i < chunk_end[ck]; i++) {
 					uint32_t id = 0xffffffffu;
 					if (rec[i].ret <= 0 && (rec[i].alignment_flag & 1u)) {
-						const uint8_t *p = bam + c->rec_off[i] + 4;
+						const uint8_t *p = bam + R.rec_off[i] + 4;
 						id = host_names.emplace(std::string((const char *)p + 32, p[8]), (uint32_t)i).first->second;
 					}
 					if (i >= scanned) ids[i] = id;
@@ -1521,11 +1568,11 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 				host_names_done = chunk_end[ck];
 				name_fallbacks++;
 			}
-			if (use_host_scan) certain_block_starts_keys((const uint32_t *)c->h_key.p, scanned, chunk_end[ck], &cst, starts);
+			if (use_host_scan) certain_block_starts_keys((const uint32_t *)R.h_key.p, scanned, chunk_end[ck], &cst, starts);
 			if (!use_host_scan || check_scan) {
 				// the device's mask of the chunk: bit i of word i / 32 <-> record scanned + i
 				std::vector<size_t> dev;
-				const uint32_t *mw = (const uint32_t *)c->h_mask.p + c->mask_off[ck];
+				const uint32_t *mw = (const uint32_t *)R.h_mask.p + R.mask_off[ck];
 				const size_t cn = chunk_end[ck] - scanned;
 				for (size_t w = 0; w < (cn + 31) / 32; w++) for (uint32_t b = mw[w]; b; b &= b - 1) dev.push_back(scanned + w * 32 + (size_t)__builtin_ctz(b));
 				if (check_scan) {
@@ -1546,7 +1593,7 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 			if (upto > built) {
 				std::vector<size_t> inside;
 				for (size_t v : starts) if (v > built && v < upto) inside.push_back(v);
-				guard.jobs.push_back(build_blocks_start_range(bam, c->rec_off.data(), rec, (const uint32_t *)c->h_nameid.p, built, upto, inside, rp->keep_unmatched, rp->keep_duplicates, tm, ppt, c->profile_on));
+				guard.jobs.push_back(build_blocks_start_range(bam, R.rec_off.data(), rec, (const uint32_t *)R.h_nameid.p, built, upto, inside, rp->keep_unmatched, rp->keep_duplicates, tm, ppt, c->profile_on));
 				njobs.store(guard.jobs.size(), std::memory_order_release);
 				std::vector<size_t> keep;
 				for (size_t v : starts) if (v >= upto) keep.push_back(v);
@@ -1555,8 +1602,10 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 			}
 			if (trace) fprintf(stderr, "  chunk %zu: descriptors home %.2f ms, job started %.2f ms (records %zu)\n", ck, (w1 - t0) * 1e3, (now() - t0) * 1e3, chunk_end[ck]);
 		}
+		if (!c->profile_on) tell(built == n ? framed : (size_t)R.rec_off[built], built);
 		scan_state.store(1, std::memory_order_release);
 	});
+	turn.wait();                                          // pipelined: the run before this one has left the window stage
 	for (size_t ji = 0; ret == BSGPU_OK;) {
 		const double w0 = now();
 		while (njobs.load(std::memory_order_acquire) <= ji && scan_state.load(std::memory_order_acquire) == 0) std::this_thread::yield();
@@ -1585,7 +1634,7 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	*nvcf = ov;
 	if (opts) {
 		opts->records = built;
-		opts->consumed = built == n ? framed : (size_t)c->rec_off[built];
+		opts->consumed = built == n ? framed : (size_t)R.rec_off[built];
 	}
 	const double t2 = now();
 	if (getenv("BSGPU_TIMING"))
@@ -1640,11 +1689,23 @@ static uint8_t *sess_pin(size_t bytes) {
 static void sess_unpin(uint8_t *p) { cudaFreeHost(p); }
 static void sess_thread_init(void *user) { cudaSetDevice(((bsgpu_bam_session *)user)->c->device); }
 
-static int sess_run(void *user, const uint8_t *data, size_t len, bool whole, SessResult *r, size_t *consumed, size_t *records, std::string *err) {
+static int sess_run(void *user, const uint8_t *data, size_t len, bool whole, SessResult *r, uint64_t seq,
+		void (*scanned)(void *sess, uint64_t seq, size_t consumed, size_t records), void *sess,
+		size_t *consumed, size_t *records, std::string *err) {
 	bsgpu_bam_session *s = (bsgpu_bam_session *)user;
 	Session::GrowCtx g{&s->core, r};
+	struct Told { void (*f)(void *, uint64_t, size_t, size_t); void *sess; uint64_t seq; } told{scanned, sess, seq};
 	BamRunOpts o;
 	o.partial = !whole; o.blocks_vec = &r->blocks; o.grow = Session::grow; o.user = &g;
+	// runs of a session overlap: reader stage of this one under the window stage of the one before (BSGPU_SESSION_PIPELINE=0: one at a time)
+	static const bool pipeline = [] { const char *e = getenv("BSGPU_SESSION_PIPELINE"); return !e || atoi(e) != 0; }();
+	o.pipelined = true;
+	o.reader_set = (int)(seq & 1);
+	{ std::unique_lock<std::mutex> lk(s->c->win_mu); o.ticket = s->c->next_ticket++; }
+	if (pipeline) {
+		o.on_scanned = [](void *u, size_t consumed_, size_t records_) { Told *t = (Told *)u; t->f(t->sess, t->seq, consumed_, records_); };
+		o.scan_user = &told;
+	}
 	size_t nblk = 0, nvcf = 0;
 	int rc;
 	// BSGPU_SERIALIZE_SESSIONS=1 (debugging aid): the batches of all sessions of the process run one at a time

@@ -936,7 +936,7 @@ cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, voi
 		if (five) k_call_sites<false, 5><<<grid, kCallTile, call_smem(false), stream>>>(p, r, n, o, sk, dc, bulk_ok, counters, guard_base);
 		else k_call_sites<false, 4><<<grid, kCallTile, call_smem(false), stream>>>(p, r, n, o, sk, dc, bulk_ok, counters, guard_base);
 	}
-	*launches += 1;
+	__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 	LAUNCH_CHECK();
 	return cudaSuccess;
 }
@@ -964,18 +964,18 @@ cudaError_t launch_bin_segments(const void *segs, size_t nseg, uint32_t x, uint3
 	const unsigned g = (unsigned)((nseg + 255) / 256);
 	if (nseg) {
 		k_bin_count<<<g, 256, 0, stream>>>((const Seg *)segs, nseg, x, ntiles, counts, counters);
-		*launches += 1;
+		__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 		LAUNCH_CHECK();
 	}
 	const uint32_t nb = scan_ctas(ntiles);
 	k_scan_local<<<nb, 1024, 0, stream>>>(counts, ntiles, start, partial);
 	k_scan_partials<<<1, 1024, 0, stream>>>(partial, nb);
 	k_scan_add<<<nb, 1024, 0, stream>>>(start, cursor, ntiles, partial, nb);
-	*launches += 3;
+	__atomic_fetch_add(launches, 3, __ATOMIC_RELAXED);
 	LAUNCH_CHECK();
 	if (nseg) {
 		k_bin_scatter<<<g, 256, 0, stream>>>((const Seg *)segs, nseg, x, ntiles, cursor, sorted);
-		*launches += 1;
+		__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 		LAUNCH_CHECK();
 	}
 	return cudaSuccess;
@@ -997,7 +997,7 @@ cudaError_t launch_pileup_tiles(const void *scratch, size_t nseg, const void *ba
 	if (mode) k_pileup_tile<1><<<grid, kPileThreads, pile_smem(1), stream>>>(sorted, start, (const uint8_t *)bases, (const uint8_t *)ref, x, sz, tile0, (uint8_t *)out, dc, counters);
 	else if (scatter) k_pileup_scatter<<<grid, kPileThreads, scatter_smem_bytes(), stream>>>(sorted, start, (const uint8_t *)bases, x, sz, tile0, (uint8_t *)out, dc, counters);
 	else k_pileup_tile<0><<<grid, kPileThreads, pile_smem(0), stream>>>(sorted, start, (const uint8_t *)bases, (const uint8_t *)ref, x, sz, tile0, (uint8_t *)out, dc, counters);
-	*launches += 1;
+	__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 	LAUNCH_CHECK();
 	return cudaSuccess;
 }
@@ -1006,7 +1006,7 @@ cudaError_t launch_synth_sites(uint64_t seed, uint64_t first, size_t n, double m
 		cudaStream_t stream, int *launches) {
 	if (!n) return cudaSuccess;
 	k_synth_sites<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(seed, first, n, (float)mean_depth, (uint8_t *)pileup, (uint8_t *)ref);
-	*launches += 1;
+	__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 	LAUNCH_CHECK();
 	return cudaSuccess;
 }
@@ -1014,7 +1014,7 @@ cudaError_t launch_synth_sites(uint64_t seed, uint64_t first, size_t n, double m
 cudaError_t launch_synth_ref(uint64_t seed, uint32_t x, uint32_t sz, void *ref, cudaStream_t stream, int *launches) {
 	if (!sz) return cudaSuccess;
 	k_synth_ref<<<(sz + 255) / 256, 256, 0, stream>>>(seed, x, sz, (uint8_t *)ref);
-	*launches += 1;
+	__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 	LAUNCH_CHECK();
 	return cudaSuccess;
 }
@@ -1026,7 +1026,7 @@ cudaError_t launch_synth_bam(uint64_t seed, size_t ntemplates, uint32_t read_len
 	if (!ntemplates) return cudaSuccess;
 	k_synth_bam<<<(unsigned)((2 * ntemplates * 32 + 255) / 256), 256, 0, stream>>>(seed, ntemplates, read_len, (const uint32_t *)pos_f,
 		(const uint32_t *)pos_r, (const uint32_t *)src, (const uint32_t *)rank, (uint8_t *)out);
-	*launches += 1;
+	__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 	LAUNCH_CHECK();
 	return cudaSuccess;
 }
@@ -1040,12 +1040,12 @@ cudaError_t launch_synth_block(uint64_t seed, uint32_t x, uint32_t sz, uint32_t 
 		void *segs, void *bases, void *ref, cudaStream_t stream, int *launches) {
 	const size_t nseg = synth_block_nseg(sz, read_len, depth);
 	k_synth_ref<<<(sz + 255) / 256, 256, 0, stream>>>(seed, x, sz, (uint8_t *)ref);
-	*launches += 1;
+	__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 	LAUNCH_CHECK();
 	if (nseg) {
 		const double step = (double)read_len / depth;
 		k_synth_reads<<<(unsigned)((nseg * 32 + 255) / 256), 256, 0, stream>>>(seed, x, sz, read_len, step, nseg, (Seg *)segs, (uint8_t *)bases);
-		*launches += 1;
+		__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 		LAUNCH_CHECK();
 	}
 	return cudaSuccess;

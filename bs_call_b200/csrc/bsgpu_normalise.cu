@@ -517,7 +517,7 @@ cudaError_t launch_normalise(const void *tmpl, size_t n, const void *bases, void
 	const size_t ctas = (n + kNormWarps - 1) / kNormWarps;
 	if (!prof) {
 		k_normalise<<<(unsigned)ctas, kNormWarps * 32, 0, stream>>>(a);
-		*launches += 1;
+		__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 		return cudaGetLastError();
 	}
 	const size_t nchunks = (n + kProfChunk - 1) / kProfChunk;
@@ -527,7 +527,7 @@ cudaError_t launch_normalise(const void *tmpl, size_t n, const void *bases, void
 	if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
 	k_normalise_profile<<<(unsigned)std::min(ctas, (size_t)sms * 6), kNormWarps * 32, 0, stream>>>(a, *prof);
 	k_profile_resolve<<<(unsigned)nchunks, kProfChunk / 4, 0, stream>>>(prof->used16, prof->cand, prof->chunkmax, n, prof->prof, parity);
-	*launches += 2;
+	__atomic_fetch_add(launches, 2, __ATOMIC_RELAXED);
 	return cudaGetLastError();
 }
 

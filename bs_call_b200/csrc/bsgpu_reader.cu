@@ -413,7 +413,7 @@ cudaError_t launch_name_ids(const void *bam, const void *rec_off, const void *re
 	if (r1 <= r0) return cudaSuccess;
 	k_name_ids<<<(r1 - r0 + 255) / 256, 256, 0, stream>>>((const uint8_t *)bam, (const uint64_t *)rec_off, (const bsgpu_record *)rec, r0, r1,
 		(const NameSlot *)table, (uint32_t)(slots - 1), (uint32_t *)name_id);
-	*launches += 1;
+	__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 	return cudaGetLastError();
 }
 
@@ -421,7 +421,7 @@ cudaError_t launch_name_ids(const void *bam, const void *rec_off, const void *re
 cudaError_t launch_certain_starts(const void *keys, uint32_t n, void *carry, void *mask, cudaStream_t stream, int *launches) {
 	if (!n) return cudaSuccess;
 	k_certain_starts<<<1, 1024, 0, stream>>>((const uint4 *)keys, n, (uint32_t *)carry, (uint32_t *)mask);
-	*launches += 1;
+	__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 	return cudaGetLastError();
 }
 
@@ -433,7 +433,7 @@ cudaError_t launch_decode_records(const void *bam, const void *rec_off, const vo
 	k_decode_records<<<grid, kDecodeWarps * 32, 0, stream>>>((const uint8_t *)bam, (const uint64_t *)rec_off, (const uint32_t *)read_off,
 		(const uint32_t *)mm_off, nrec, mapq_thresh, max_tlen, keep_unmatched, ignore_dup, (bsgpu_record *)out, (uint8_t *)bases, (bsgpu_misms *)misms, (uint4 *)keys,
 		(NameSlot *)name_table, name_table ? (uint32_t)(name_slots - 1) : 0u, rec_base, (uint32_t *)name_overflow);
-	*launches += 1;
+	__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 	return cudaGetLastError();
 }
 

@@ -10,6 +10,10 @@
 // there on (read_input's state is blank at such a record, so nothing is lost by starting over there) are the `carry`,
 // copied in front of the bytes the caller has fed meanwhile.  Results of a batch sit in a buffer of the session that is
 // lent to the caller until it is released.  Memory: two batches + the results not yet released.
+//
+// Two runs can be in flight: a run reports how far it goes (`scanned`) as soon as its reader stage knows -- the staged bytes
+// are free from then on and the carry can be placed -- and the next batch starts its own reader stage while the run before
+// it is still at its window stage (the runner serialises the window stages and keeps them in order).
 #pragma once
 #include <algorithm>
 #include <condition_variable>
@@ -41,7 +45,12 @@ struct SessHooks {
 	// One batch.  `whole`: the bytes end where a block ends (end of stream / bsgpu_bam_cut) -- everything is processed and a
 	// record cut off by the end of the buffer is an error; otherwise the run stops at the last certain block start.  Fills
 	// r->buf (growing it with Session::grow) / nbytes / nrec / blocks, *consumed (bytes accounted for) and *records.
-	int (*run)(void *user, const uint8_t *data, size_t len, bool whole, SessResult *r, size_t *consumed, size_t *records, std::string *err) = nullptr;
+	// seq numbers the runs of the session; runs seq and seq + 1 may overlap as described above.  scanned(sess, seq, consumed,
+	// records) must be called exactly once per successful run, at the latest before it returns; after the call the run must not
+	// read data[] any more.
+	int (*run)(void *user, const uint8_t *data, size_t len, bool whole, SessResult *r, uint64_t seq,
+			void (*scanned)(void *sess, uint64_t seq, size_t consumed, size_t records), void *sess,
+			size_t *consumed, size_t *records, std::string *err) = nullptr;
 };
 
 class Session {
@@ -55,10 +64,14 @@ public:
 	bool filling = false;                    // the caller is writing into stage[w] outside the lock
 	std::mutex mu;
 	std::condition_variable cv;
-	std::thread worker;
-	int job_buf = -1;
-	bool job_final = false, job_whole = false, busy = false, finishing = false, final_submitted = false, finished = false, closing = false, failed = false;
+	struct Run { std::thread th; int buf = 0; bool final = false, whole = false, scanned = false, returned = false; uint64_t seq = 0; size_t len = 0; const uint8_t *data = nullptr; };
+	std::deque<Run *> runs;                  // in flight, oldest first
+	std::vector<Run *> dead;                 // returned: joined at the next opportunity
+	uint64_t next_seq = 0, next_result_seq = 0;
+	bool scan_pending = false;               // the newest run has not said how far it goes: the carry of the next batch is unknown
+	bool finishing = false, final_submitted = false, finished = false, closing = false, failed = false;
 	bool cut_pending = false;
+	size_t max_outstanding = 3;              // runs in flight + results not yet drained
 	std::string errmsg;
 	std::deque<SessResult *> ready;
 	std::vector<SessResult *> pool, lent;
@@ -85,7 +98,6 @@ public:
 		batch_bytes = std::max<size_t>(batch, 4096);
 		result_ratio = ratio;
 		for (int b = 0; b < 2; b++) if (!stage_fit(b, std::max<size_t>(batch_bytes / 8, 4096))) return false;
-		worker = std::thread([this] { run_worker(); });
 		return true;
 	}
 
@@ -93,6 +105,7 @@ public:
 	bool feed(const uint8_t *bytes, size_t nbytes, bool nowait, size_t *accepted, std::string *err) {
 		std::unique_lock<std::mutex> lk(mu);
 		*accepted = 0;
+		reap(lk);
 		if (finishing) { *err = "bsgpu_bam_feed: the stream was finished"; return false; }
 		if (filling) { *err = "bsgpu_bam_feed: a reservation is open"; return false; }
 		size_t off = 0;
@@ -158,7 +171,8 @@ public:
 	bool rewind(std::string *err) {
 		std::unique_lock<std::mutex> lk(mu);
 		if (failed) { *err = errmsg; return false; }
-		if (!finished || busy || !ready.empty()) { *err = "bsgpu_bam_rewind: the stream has not been finished and drained"; return false; }
+		if (!finished || !runs.empty() || !ready.empty()) { *err = "bsgpu_bam_rewind: the stream has not been finished and drained"; return false; }
+		reap(lk);
 		finishing = final_submitted = finished = false;
 		for (Stage &st : stage) st.start = st.fill = st.head;
 		return true;
@@ -168,8 +182,9 @@ public:
 	bool drain(bool wait, SessResult **out, bool *done, std::string *err) {
 		std::unique_lock<std::mutex> lk(mu);
 		*out = nullptr;
+		reap(lk);
 		// something will come as long as a batch is with the worker or is about to be handed to it
-		if (wait) cv.wait(lk, [&] { return !ready.empty() || failed || finished || !(busy || finishing || cut_pending); });
+		if (wait) cv.wait(lk, [&] { return !ready.empty() || failed || finished || !(!runs.empty() || finishing || cut_pending); });
 		if (ready.empty()) {
 			if (failed) { *err = errmsg; return false; }
 			*done = finished;
@@ -180,7 +195,8 @@ public:
 		lent.push_back(r);
 		*out = r;
 		*done = r->last && ready.empty();
-		cv.notify_all();                      // the worker may have been waiting for room in the ready queue
+		try_submit();                         // a batch may have been waiting for room among the outstanding results
+		cv.notify_all();
 		return true;
 	}
 
@@ -211,7 +227,11 @@ public:
 			closing = true;
 			cv.notify_all();
 		}
-		if (worker.joinable()) worker.join();      // a batch in flight runs to its end first
+		{                                         // batches in flight run to their end first
+			std::unique_lock<std::mutex> lk(mu);
+			cv.wait(lk, [&] { return runs.empty(); });
+			reap(lk);
+		}
 		for (Stage &st : stage) if (st.p) { hk.release(st.p); st.p = nullptr; }
 		for (auto *v : {&pool, &lent}) { for (SessResult *r : *v) { if (r->buf) hk.release(r->buf); delete r; } v->clear(); }
 		for (SessResult *r : ready) { if (r->buf) hk.release(r->buf); delete r; }
@@ -247,22 +267,44 @@ private:
 		return true;
 	}
 
-	// lock held: hand stage[w] to the worker when it is idle and the buffer is full (or a cut / the end of the stream is marked)
+	// lock held: joins the threads of runs that have returned
+	void reap(std::unique_lock<std::mutex> &lk) {
+		std::vector<Run *> d;
+		d.swap(dead);
+		if (d.empty()) return;
+		lk.unlock();
+		for (Run *r : d) { if (r->th.joinable()) r->th.join(); delete r; }
+		lk.lock();
+	}
+
+	// lock held: start a run over stage[w] when the buffer is full (or a cut / the end of the stream is marked), the run before
+	// it has said how far it goes, and there is room among the outstanding results
 	void try_submit() {
-		if (busy || final_submitted || failed || filling) return;
+		if (scan_pending || final_submitted || failed || filling || closing) return;
+		if (runs.size() >= 2 || runs.size() + ready.size() >= max_outstanding) return;
 		Stage &st = stage[w];
 		const bool full = st.fill - st.head >= batch_bytes;
 		if (!full && !finishing && !cut_pending) return;
 		const bool whole = finishing || cut_pending;      // the staged bytes end on a block boundary: nothing is carried over
 		if (finishing) {
+			if (st.fill == st.start) {               // nothing left to run: the stream is over once the runs in flight have returned
+				if (!runs.empty()) return;
+				final_submitted = true; finished = true; cut_pending = false;
+				cv.notify_all();
+				return;
+			}
 			final_submitted = true;
-			if (st.fill == st.start) { finished = true; cut_pending = false; cv.notify_all(); return; }
 		} else if (cut_pending && st.fill == st.start) { cut_pending = false; cv.notify_all(); return; }
 		cut_pending = false;
-		job_buf = w; job_final = finishing; job_whole = whole; busy = true;
+		Run *r = new Run();
+		r->buf = w; r->final = finishing; r->whole = whole; r->seq = next_seq++;
+		r->data = st.p + st.start; r->len = st.fill - st.start;
+		runs.push_back(r);
+		scan_pending = true;
 		w ^= 1;
 		Stage &nx = stage[w];
 		nx.start = nx.fill = nx.head;
+		r->th = std::thread([this, r] { run_batch(r); });
 		cv.notify_all();
 	}
 
@@ -281,64 +323,75 @@ private:
 		}
 	}
 
-	void run_worker() {
+	// the run says how far it goes: the carry moves in front of what the caller has fed into the other buffer meanwhile, and
+	// the run's own staging buffer is free
+	static void scanned_cb(void *sess, uint64_t seq, size_t consumed, size_t records) { ((Session *)sess)->on_scanned(seq, consumed, records); }
+	void on_scanned(uint64_t seq, size_t consumed, size_t records) {
+		std::unique_lock<std::mutex> lk(mu);
+		Run *r = nullptr;
+		for (Run *q : runs) if (q->seq == seq) r = q;
+		if (!r || r->scanned) return;
+		r->scanned = true;
+		const size_t carry = r->len - consumed;
+		Stage &nx = stage[r->buf ^ 1];
+		if (carry && !failed) {
+			cv.wait(lk, [&] { return !filling || closing; });
+			if (carry > nx.start && !stage_fit(r->buf ^ 1, carry + (nx.head - nx.start))) { failed = true; errmsg = "bsgpu_bam: cannot allocate staging memory for the carried records"; }
+			if (!failed) { memcpy(nx.p + nx.start - carry, r->data + consumed, carry); nx.start -= carry; }
+		}
+		if (r->whole && carry && !failed) { failed = true; errmsg = "bsgpu_bam: internal: a whole batch left records behind"; }
+		bytes_done += consumed; records_done += records; batches++; carry_bytes += carry;
+		if (!consumed) empty_batches++;
+		scan_pending = false;
+		try_submit();
+		cv.notify_all();
+	}
+
+	void run_batch(Run *run) {
 		if (hk.thread_init) hk.thread_init(hk.user);
 		std::unique_lock<std::mutex> lk(mu);
-		for (;;) {
-			cv.wait(lk, [&] { return closing || (job_buf >= 0 && ready.size() < max_ready); });
-			if (closing) return;
-			const int b = job_buf;
-			const bool final = job_final, whole = job_whole;
-			const uint8_t *data = stage[b].p + stage[b].start;
-			const size_t len = stage[b].fill - stage[b].start;
-			// a result buffer from the pool: the smallest that holds the guess, else the largest there is (it grows)
-			const size_t guess = (size_t)((double)len * result_ratio) + 4096;
-			SessResult *r = nullptr;
-			{
-				size_t pick = pool.size();
-				for (size_t i = 0; i < pool.size(); i++) {
-					if (pick == pool.size()) { pick = i; continue; }
-					const size_t a = pool[i]->cap, c = pool[pick]->cap;
-					if (c >= guess ? (a >= guess && a < c) : a > c) pick = i;
-				}
-				if (pick < pool.size()) { r = pool[pick]; pool.erase(pool.begin() + pick); }
+		// a result buffer from the pool: the smallest that holds the guess, else the largest there is (it grows)
+		const size_t guess = (size_t)((double)run->len * result_ratio) + 4096;
+		SessResult *r = nullptr;
+		{
+			size_t pick = pool.size();
+			for (size_t i = 0; i < pool.size(); i++) {
+				if (pick == pool.size()) { pick = i; continue; }
+				const size_t a = pool[i]->cap, c = pool[pick]->cap;
+				if (c >= guess ? (a >= guess && a < c) : a > c) pick = i;
 			}
-			lk.unlock();
-			if (!r) r = new SessResult();
-			std::string err;
-			int rc = 0;
-			if (!r->buf) {
-				r->cap = guess;
-				r->buf = hk.alloc(r->cap);
-				if (!r->buf) { r->cap = 0; rc = -1; err = "bsgpu_bam: cannot allocate page-locked result memory"; }
-			}
-			size_t consumed = 0, records = 0;
-			r->blocks.clear(); r->nbytes = r->nrec = 0;
-			if (!rc) rc = hk.run(hk.user, data, len, whole, r, &consumed, &records, &err);
-			lk.lock();
-			if (rc) {
-				failed = true; errmsg = err;
-				pool.push_back(r);
-			} else {
-				// the carry goes in front of what the caller has fed into the other buffer meanwhile
-				const size_t carry = len - consumed;
-				Stage &nx = stage[b ^ 1];
-				if (carry) {
-					cv.wait(lk, [&] { return !filling || closing; });
-					if (carry > nx.start && !stage_fit(b ^ 1, carry + (nx.head - nx.start))) { failed = true; errmsg = "bsgpu_bam: cannot allocate staging memory for the carried records"; }
-					if (!failed) { memcpy(nx.p + nx.start - carry, data + consumed, carry); nx.start -= carry; }
-				}
-				if (whole && carry && !failed) { failed = true; errmsg = "bsgpu_bam: internal: a whole batch left records behind"; }
-				r->bytes_in = consumed; r->records_in = records; r->id = next_id++; r->last = final;
-				bytes_done += consumed; records_done += records; batches++; carry_bytes += carry;
-				if (!consumed) empty_batches++;
-				if (consumed || whole) ready.push_back(r); else pool.push_back(r);      // no certain start in the batch: nothing to show yet
-				if (final) finished = true;
-			}
-			job_buf = -1; busy = false;
-			try_submit();
-			cv.notify_all();
+			if (pick < pool.size()) { r = pool[pick]; pool.erase(pool.begin() + pick); }
 		}
+		lk.unlock();
+		if (!r) r = new SessResult();
+		std::string err;
+		int rc = 0;
+		if (!r->buf) {
+			r->cap = guess;
+			r->buf = hk.alloc(r->cap);
+			if (!r->buf) { r->cap = 0; rc = -1; err = "bsgpu_bam: cannot allocate page-locked result memory"; }
+		}
+		size_t consumed = 0, records = 0;
+		r->blocks.clear(); r->nbytes = r->nrec = 0;
+		if (!rc) rc = hk.run(hk.user, run->data, run->len, run->whole, r, run->seq, scanned_cb, this, &consumed, &records, &err);
+		if (!rc) on_scanned(run->seq, consumed, records);      // (no-op when the run has told already)
+		lk.lock();
+		// results leave in the order of the runs
+		cv.wait(lk, [&] { return next_result_seq == run->seq; });
+		if (rc) {
+			if (!failed) { failed = true; errmsg = err; }
+			pool.push_back(r);
+			if (!run->scanned) { run->scanned = true; scan_pending = false; }
+		} else {
+			r->bytes_in = consumed; r->records_in = records; r->id = next_id++; r->last = run->final;
+			if (consumed || run->whole) ready.push_back(r); else pool.push_back(r);      // no certain start in the batch: nothing to show yet
+		}
+		next_result_seq++;
+		for (size_t i = 0; i < runs.size(); i++) if (runs[i] == run) { runs.erase(runs.begin() + i); break; }
+		dead.push_back(run);
+		if (run->final) finished = true;
+		try_submit();
+		cv.notify_all();
 	}
 };
 

@@ -487,7 +487,7 @@ static WrArgs writer_args(const BcfJob &j, uint32_t i0, uint32_t cnt) {
 cudaError_t launch_bcf_calls(const BcfJob &j, uint32_t i0, uint32_t cnt, cudaStream_t stream, int *launches) {
 	if (!cnt) return cudaSuccess;
 	k_bcf_calls<<<(cnt + 255) / 256, 256, 0, stream>>>(writer_args(j, i0, cnt));
-	*launches += 1;
+	__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
 	return cudaGetLastError();
 }
 
@@ -504,7 +504,7 @@ cudaError_t launch_bcf_records(const BcfJob &j, uint32_t i0, uint32_t cnt, void 
 	k_bcf_measure<<<nctas, kWrThreads, 0, stream>>>(a);
 	k_bcf_offsets<<<1, 1024, 0, stream>>>(a.cta_bytes, a.cta_recs, nctas, d_totals);
 	k_bcf_emit<<<nctas, kWrThreads, kStageBytes + 16, stream>>>(a);
-	*launches += 3;
+	__atomic_fetch_add(launches, 3, __ATOMIC_RELAXED);
 	return cudaGetLastError();
 }
 

@@ -27,7 +27,10 @@ struct Runner {
 	int max_sleep_us = 0;
 };
 
-static int fake_run(void *user, const uint8_t *data, size_t len, bool whole, SessResult *r, size_t *consumed, size_t *records, std::string *err) {
+static std::mutex g_run_mu;            // the stand-in serialises its "window stages" like the real runner does
+static int fake_run(void *user, const uint8_t *data, size_t len, bool whole, SessResult *r, uint64_t seq,
+		void (*scanned)(void *sess, uint64_t seq, size_t consumed, size_t records), void *sess,
+		size_t *consumed, size_t *records, std::string *err) {
 	Runner *rn = (Runner *)user;
 	size_t at = 0, nrec = 0, last_start = 0, rec_before_start = 0;
 	while (at + 4 <= len) {
@@ -47,10 +50,13 @@ static int fake_run(void *user, const uint8_t *data, size_t len, bool whole, Ses
 		size_t ncap;
 		if (!Session::grow(&g, 0, take, &ncap)) { *err = "grow failed"; return -1; }
 	}
-	memcpy(r->buf, data, take);
+	memcpy(r->buf, data, take);           // (the run reads the staged bytes BEFORE it tells how far it goes)
 	r->nbytes = take; r->nrec = nr;
 	*consumed = take; *records = nr;
-	if (rn->max_sleep_us) usleep(rn->rng() % rn->max_sleep_us);
+	unsigned coin;
+	{ std::lock_guard<std::mutex> lk(g_run_mu); coin = rn->rng(); }
+	if (coin % 3) scanned(sess, seq, take, nr);        // two runs in three tell early; the others leave it to their return
+	if (rn->max_sleep_us) usleep(coin % rn->max_sleep_us);
 	return 0;
 }
 
