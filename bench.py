@@ -548,7 +548,8 @@ def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
             if rank == 0 and world == 1 and c == small[0]:
                 keep_small.setdefault(c, []).append(d.copy())
     tot = torch.tensor([sum(nb for _, _, nb, _, _ in res), sum(nr for _, _, _, nr, _ in res), called, nbytes_in, len(res)] +
-                       [crc[c] for c in small], dtype=torch.int64, device=dev)
+                       [crc[c] for c in small] +
+                       [(s1[k] - s0[k]) // steps for k in ("h2d_bytes", "d2h_bytes", "kernel_launches")], dtype=torch.int64, device=dev)
     tmax = torch.tensor([dt, max(dts), min(dts)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)       # a contig's records all sit on one rank unless it was split: crc of a split contig is not comparable
@@ -568,8 +569,8 @@ def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
            "session_rank0": {"sessions_per_gpu": nl, "batch_bytes": int(args.genome_batch_mb) << 20, "batches_per_pass": prog["batches"] // (steps + 2),
                              "carry_bytes_per_pass": prog["carry_bytes"] // (steps + 2), "empty_batches": prog["empty_batches"],
                              "pinned_bytes": prog["pinned_bytes"]},
-           "h2d_bytes_per_pass": (s1["h2d_bytes"] - s0["h2d_bytes"]) // steps, "d2h_bytes_per_pass": (s1["d2h_bytes"] - s0["d2h_bytes"]) // steps,
-           "gpu_launches_per_pass": (s1["kernel_launches"] - s0["kernel_launches"]) // steps,
+           "h2d_bytes_per_pass": int(tot[5 + len(small)].item()), "d2h_bytes_per_pass": int(tot[6 + len(small)].item()),
+           "gpu_launches_per_pass": int(tot[7 + len(small)].item()),
            "note": "per rank: %d session(s), each fed by bsgpu_bam_feed in 32 MiB slices from pinned host memory + bsgpu_bam_cut per region and drained by a thread of its own; " % nl +
                    "value = sites called on all ranks / max over ranks of the wall time of a pass"}
     # ---- parity: the smallest contig against the reference's own chain + writer, record for record (rank 0 of a 1-GPU run)
@@ -748,6 +749,7 @@ def main():
         per_rank = str(max(2, min(len(os.sched_getaffinity(0)), (os.cpu_count() or 2) // world)))
         os.environ.setdefault("BSGPU_BUILDER_THREADS", per_rank)
         os.environ.setdefault("BSGPU_FRAMER_THREADS", per_rank)
+        os.environ.setdefault("BSGPU_FEED_THREADS", str(max(2, min(8, int(per_rank) // 2))))
     gpu = bslib.BsGpu(device=local)
     # a dedicated torch stream: its handle is what the C ABI launches on, and what the CUDA events below are recorded on
     tstream = torch.cuda.Stream()
