@@ -922,7 +922,8 @@ cudaError_t configure_kernels() {
 cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, void *out, void *skip, bool vcf,
 		const DevConst *dc, unsigned long long *counters, cudaStream_t stream, int *launches, unsigned long long guard_base) {
 	if (!n) return cudaSuccess;
-	const bool bulk_ok = (((uintptr_t)pileup | (uintptr_t)out) & 15u) == 0;
+	static const bool no_bulk = getenv("BSGPU_NO_BULK") != nullptr;      // debugging: plain loads / stores instead of the bulk-copy engine
+	const bool bulk_ok = !no_bulk && (((uintptr_t)pileup | (uintptr_t)out) & 15u) == 0;
 	const size_t ntiles = (n + kCallTile - 1) / kCallTile;
 	const int five = g_call_minb == 5;
 	const size_t resident = (size_t)g_sms * (size_t)(g_call_ctas[five][vcf] > 0 ? g_call_ctas[five][vcf] : 1);

@@ -105,6 +105,35 @@ def profile_dict(used, conv, base_filter, filter_cts, filter_bases):
 VCF_IDS = tuple(range(16))      # PASS fail mac1 CX GT FT GL GQ DP MQ QD MC8 AMQ CS CG FS: ids in header order
 
 
+# bso_site_stats / bsgpu_site_stats: the writer's --report-file statistics (src/print_vcf.c:382-526), flat
+STATS_FS_MAX = 4096
+STATS_COV_MAX = 4096
+COV_STATS = np.dtype([("var", "<u8"), ("CpG", "<u8", (2,)), ("CpG_inf", "<u8", (2,)), ("all", "<u8"), ("gc_pcent", "<u8", (101,))])
+SITE_STATS = np.dtype([
+    ("snps", "<u8", (2,)), ("multi", "<u8", (2,)), ("dbSNP_sites", "<u8", (2,)), ("dbSNP_var", "<u8", (2,)), ("CpG_ref", "<u8", (2,)), ("CpG_nonref", "<u8", (2,)),
+    ("mut_counts", "<u8", (12, 2)), ("dbSNP_mut_counts", "<u8", (12, 2)), ("qual", "<u8", (4, 256)), ("filter_counts", "<u8", (2, 32)),
+    ("CpG_ref_meth", "<f8", (2, 101)), ("CpG_nonref_meth", "<f8", (2, 101)),
+    ("qd_stats", "<u8", (256, 2)), ("mq_stats", "<u8", (256, 2)), ("fs_stats", "<u8", (STATS_FS_MAX, 2)),
+    ("fs_overflow", "<u8"), ("cov_overflow", "<u8"), ("cov", COV_STATS, (STATS_COV_MAX,))])
+assert COV_STATS.itemsize == 107 * 8
+
+
+def site_stats_equal(a, b, rtol=1e-9, what="site stats"):
+    """two SITE_STATS records: integer counters identical, the methylation posteriors (sums of doubles) within rtol"""
+    bad = []
+    for name in SITE_STATS.names:
+        if name in ("CpG_ref_meth", "CpG_nonref_meth"):
+            if not np.allclose(a[name], b[name], rtol=rtol, atol=1e-12):
+                bad.append(name)
+        elif name == "cov":
+            for f in COV_STATS.names:
+                if not np.array_equal(a["cov"][f], b["cov"][f]):
+                    bad.append("cov." + f)
+        elif not np.array_equal(a[name], b[name]):
+            bad.append(name)
+    assert not bad, "%s differ in %s" % (what, bad)
+
+
 class BsoDbsnp(C.Structure):
     _fields_ = [("n", C.c_uint32), ("pos", C.c_void_p), ("flags", C.c_void_p), ("name_off", C.c_void_p), ("names", C.c_void_p)]
 
@@ -273,6 +302,25 @@ class Oracle:
         return _print_block(self.lib.bso_print_block, vcf, refcodes, x, rid, ctg_end, vcf_ids, all_positions, region, dbsnp,
                             self.lib.bso_print_block_ann)
 
+    def stats_block(self, vcf, refcodes, x, ctg_end=0xffffffff, all_positions=False, region=None, dbsnp=None, gc=None, start_pos=1,
+                    stats=None, state=None):
+        """the writer's --report-file statistics of one block (restatement of src/print_vcf.c:382-526), added to `stats`
+        (a SITE_STATS record array of length 1; made when None).  state = [prev_cpg_x, prev_cpg_flt] carried between blocks."""
+        vcf = _c(vcf, GT_VCF)
+        refcodes = _c(refcodes, np.uint8)
+        if stats is None:
+            stats = np.zeros(1, dtype=SITE_STATS)
+        if state is None:
+            state = np.zeros(2, dtype=np.uint32)
+        r0, r1 = region if region is not None else (0, 0)
+        pos, flags, off, names = dbsnp if dbsnp is not None else dbsnp_arrays([])
+        db = BsoDbsnp(len(pos), pos.ctypes.data, flags.ctypes.data, off.ctypes.data, names.ctypes.data)
+        gcv = _c(gc, np.uint8) if gc is not None else None
+        self.lib.bso_stats_block(_p(vcf), C.c_uint32(len(vcf)), _p(refcodes), C.c_uint32(x), C.c_uint32(ctg_end), C.c_int(1 if all_positions else 0),
+                                 C.c_uint32(r0), C.c_uint32(r1), C.byref(db) if len(pos) else None, _p(gcv) if gcv is not None else None,
+                                 C.c_int(len(gcv) if gcv is not None else 0), C.c_uint32(start_pos), _p(stats), _p(state))
+        return stats, state
+
     def profile_enable(self, on=True):
         """--report-file side channels (process-wide in the library); process_block then wants codes for [x, y + 1]"""
         self.lib.bso_profile_enable(C.c_int(1 if on else 0))
@@ -414,6 +462,23 @@ class Reference:
         thread runs them; refcodes covers [x, x + len(vcf) + 1].  Returns (BCF record bytes, number of records)."""
         return _print_block(self.lib.bsref_print_block, vcf, refcodes, x, rid, ctg_end, vcf_ids, all_positions, region, dbsnp,
                             self.lib.bsref_print_block_ann, flat_db=True)
+
+    def writer_stats(self, on=True, gc=None, start_pos=1):
+        """blocks printed from now on count into the reference's bs_stats (src/print_vcf.c:382-526); gc = the contig's GC bins"""
+        self._gc_keep = _c(gc, np.uint8) if gc is not None else None
+        self.lib.bsref_writer_stats(C.c_int(1 if on else 0), _p(self._gc_keep) if self._gc_keep is not None else None,
+                                    C.c_int(len(self._gc_keep) if self._gc_keep is not None else 0), C.c_uint32(start_pos))
+
+    def writer_stats_reset(self):
+        self.lib.bsref_writer_stats_reset()
+
+    def writer_stats_read(self):
+        """(SITE_STATS record array of length 1, per-contig counters u64[6][2] of the block printed last)"""
+        st = np.zeros(1, dtype=SITE_STATS)
+        self.lib.bsref_writer_stats_read(_p(st))
+        cs = np.zeros(12, dtype=np.uint64)
+        self.lib.bsref_writer_ctg_stats_read(_p(cs))
+        return st, cs.reshape(6, 2)
 
     def stats_enable(self, on=True):
         """give the reference a bs_stats (what --report-file does): meth_profile() and the tallies become live"""

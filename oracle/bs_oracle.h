@@ -161,6 +161,30 @@ size_t bso_print_site(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcode
 int bso_print_block(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, int rid, uint32_t ctg_end,
 		const int *vcf_ids, int all_positions, uint8_t *out, size_t cap, size_t *nbytes, size_t *nrec);
 
+/* ---- the writer's --report-file statistics (bs_oracle_stats.c): what _print_vcf_entry() adds to bs_stats for every site it
+ *      is called for (src/print_vcf.c:382-526).  Flat image of the reference's bs_stats fields it touches: the fs / qd / mq
+ *      vectors and the coverage hash become arrays indexed by value (values beyond the array are counted in *_overflow). ---- */
+#define BSO_STATS_FS_MAX 4096
+#define BSO_STATS_COV_MAX 4096
+typedef struct { uint64_t var, CpG[2], CpG_inf[2], all, gc_pcent[101]; } bso_cov_stats;      /* gt_cov_stats, include/bs_call.h:87-95 */
+typedef struct {
+	uint64_t snps[2], multi[2], dbSNP_sites[2], dbSNP_var[2], CpG_ref[2], CpG_nonref[2];
+	uint64_t mut_counts[12][2], dbSNP_mut_counts[12][2];
+	uint64_t qual[4][256];
+	uint64_t filter_counts[2][32];
+	double CpG_ref_meth[2][101], CpG_nonref_meth[2][101];
+	uint64_t qd_stats[256][2], mq_stats[256][2], fs_stats[BSO_STATS_FS_MAX][2];
+	uint64_t fs_overflow, cov_overflow;
+	bso_cov_stats cov[BSO_STATS_COV_MAX];
+} bso_site_stats;
+/* the reference keeps the position and filter state of the last '+' strand CpG in function statics (:107-108) */
+typedef struct { uint32_t prev_cpg_x; int prev_cpg_flt; } bso_stats_state;
+/* gc: GC percentage of every 100-base bin of the contig from start_pos on (ctg_stats->gc, src/read_reference.c:120-123; values
+ * above 100 = not known), or NULL */
+void bso_stats_block(const bso_gt_vcf *vcf, uint32_t sz, const uint8_t *refcodes, uint32_t x, uint32_t ctg_end, int all_positions,
+		uint32_t reg_start, uint32_t reg_stop, const bso_dbsnp *db, const uint8_t *gc, int nbins, uint32_t start_pos,
+		bso_site_stats *st, bso_stats_state *state);
+
 /* host twin of the device generator of per-site count vectors (same draws, same records) */
 void bso_synth_sites(uint64_t seed, uint64_t first, size_t n, double mean_depth, bso_pileup *out, uint8_t *ref, int nthreads);
 

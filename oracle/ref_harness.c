@@ -918,6 +918,65 @@ uint8_t dbSNP_lookup_name(const dbsnp_header_t *const hdr, const dbsnp_ctg_t *c,
 bool load_dbSNP_ctg(const dbsnp_header_t *const hdr, dbsnp_ctg_t *const c) { return true; }
 void unload_dbSNP_ctg(dbsnp_ctg_t *const c) { }
 
+/* ---- the writer's --report-file statistics (src/print_vcf.c:382-526): bsref_writer_stats(1, gc, nbins, start_pos) makes the
+ * blocks printed from then on count into the harness's bs_stats (with the GC bins given as the contig's);
+ * bsref_writer_stats_read() flattens what they left there into a bso_site_stats (vectors and the coverage hash by value) ---- */
+static int pv_stats_on, pv_nbins;
+static const uint8_t *pv_gc;
+static uint32_t pv_start = 1;
+void bsref_writer_stats(int on, const uint8_t *gc, int nbins, uint32_t start_pos) {
+	pv_stats_on = on; pv_gc = gc; pv_nbins = gc ? nbins : 0; pv_start = start_pos ? start_pos : 1;
+}
+void bsref_writer_stats_reset(void) {
+	gt_cov_stats *g, *tmp;
+	HASH_ITER(hh, ref_stats.cov_stats, g, tmp) { HASH_DEL(ref_stats.cov_stats, g); free(g); }
+	gt_vector *keep[4] = { ref_stats.meth_profile, ref_stats.qd_stats, ref_stats.fs_stats, ref_stats.mq_stats };
+	for (int k = 1; k < 4; k++) if (keep[k]) { memset(keep[k]->memory, 0, sizeof(fstats_cts) * keep[k]->elements_allocated); keep[k]->used = 0; }
+	const size_t head = offsetof(bs_stats, qual) + sizeof(ref_stats.qual);      /* snps .. qual; the read-level tallies after them stay */
+	memset(&ref_stats, 0, head);
+	memset(ref_stats.filter_counts, 0, sizeof(ref_stats.filter_counts));
+	memset(ref_stats.CpG_ref_meth, 0, sizeof(ref_stats.CpG_ref_meth));
+	memset(ref_stats.CpG_nonref_meth, 0, sizeof(ref_stats.CpG_nonref_meth));
+}
+static void pv_flat_vec(const gt_vector *v, uint64_t (*out)[2], int n, uint64_t *overflow) {
+	if (!v) return;
+	for (uint64_t i = 0; i < v->used; i++) {
+		const fstats_cts *c = gt_vector_get_elm(v, i, fstats_cts);
+		if (i < (uint64_t)n) { out[i][0] = c->cts[0]; out[i][1] = c->cts[1]; }
+		else if (overflow) *overflow += c->cts[0] + c->cts[1];
+	}
+}
+void bsref_writer_stats_read(bso_site_stats *o) {
+	memset(o, 0, sizeof(*o));
+	memcpy(o->snps, ref_stats.snps, sizeof(o->snps)); memcpy(o->multi, ref_stats.multi, sizeof(o->multi));
+	memcpy(o->dbSNP_sites, ref_stats.dbSNP_sites, sizeof(o->dbSNP_sites)); memcpy(o->dbSNP_var, ref_stats.dbSNP_var, sizeof(o->dbSNP_var));
+	memcpy(o->CpG_ref, ref_stats.CpG_ref, sizeof(o->CpG_ref)); memcpy(o->CpG_nonref, ref_stats.CpG_nonref, sizeof(o->CpG_nonref));
+	memcpy(o->mut_counts, ref_stats.mut_counts, sizeof(o->mut_counts)); memcpy(o->dbSNP_mut_counts, ref_stats.dbSNP_mut_counts, sizeof(o->dbSNP_mut_counts));
+	memcpy(o->qual, ref_stats.qual, sizeof(o->qual));
+	memcpy(o->filter_counts, ref_stats.filter_counts, sizeof(o->filter_counts));
+	memcpy(o->CpG_ref_meth, ref_stats.CpG_ref_meth, sizeof(o->CpG_ref_meth)); memcpy(o->CpG_nonref_meth, ref_stats.CpG_nonref_meth, sizeof(o->CpG_nonref_meth));
+	pv_flat_vec(ref_stats.qd_stats, o->qd_stats, 256, NULL);
+	pv_flat_vec(ref_stats.mq_stats, o->mq_stats, 256, NULL);
+	pv_flat_vec(ref_stats.fs_stats, o->fs_stats, BSO_STATS_FS_MAX, &o->fs_overflow);
+	gt_cov_stats *g, *tmp;
+	HASH_ITER(hh, ref_stats.cov_stats, g, tmp) {
+		if (g->coverage < BSO_STATS_COV_MAX) {
+			bso_cov_stats *d = o->cov + g->coverage;
+			d->var = g->var; d->CpG[0] = g->CpG[0]; d->CpG[1] = g->CpG[1]; d->CpG_inf[0] = g->CpG_inf[0]; d->CpG_inf[1] = g->CpG_inf[1];
+			d->all = g->all; memcpy(d->gc_pcent, g->gc_pcent, sizeof(d->gc_pcent));
+		} else o->cov_overflow += g->all + g->CpG_inf[0] + g->CpG_inf[1];
+	}
+}
+/* per-contig counters of the block printed last (ctg_stats, include/bs_call.h:75-85): snps, multi, dbSNP_sites, dbSNP_var, CpG_ref, CpG_nonref */
+static gt_ctg_stats *pv_last_cstats;
+void bsref_writer_ctg_stats_read(uint64_t out[12]) {
+	memset(out, 0, 12 * sizeof(uint64_t));
+	if (!pv_last_cstats) return;
+	const gt_ctg_stats *c = pv_last_cstats;
+	const uint64_t *src[6] = { c->snps, c->multi, c->dbSNP_sites, c->dbSNP_var, c->CpG_ref, c->CpG_nonref };
+	for (int k = 0; k < 6; k++) { out[2 * k] = src[k][0]; out[2 * k + 1] = src[k][1]; }
+}
+
 void print_vcf_entry(bcf1_t *bcf, ctg_t * const ctg, gt_meth *gtm, const char *rf, const uint32_t x, const uint32_t xstart, bool skip, sr_param * const par);
 void flush_vcf_entries(bcf1_t *bcf, const sr_param * const par);
 
@@ -942,6 +1001,7 @@ int bsref_print_block_ann(const gt_vcf *vcf, uint32_t sz, const uint8_t *refcode
 		uint32_t db_n, const uint32_t *db_pos, const uint8_t *db_flags, const uint32_t *db_name_off, const uint8_t *db_names,
 		uint8_t *out, size_t cap, size_t *nbytes, size_t *nrec) {
 	static ctg_t pv_ctg[2];
+	static gt_ctg_stats pv_cstats[2];
 	static region_t pv_reg;
 	static int flip = 0;
 	static bcf1_t *bcf = NULL;
@@ -955,7 +1015,27 @@ int bsref_print_block_ann(const gt_vcf *vcf, uint32_t sz, const uint8_t *refcode
 	c->name = "ctg"; c->vcf_rid = rid; c->start_pos = 1; c->end_pos = ctg_end; c->curr_reg = NULL;
 	if (reg_start || reg_stop) { pv_reg.ctg = c; pv_reg.start = reg_start; pv_reg.stop = reg_stop; c->curr_reg = &pv_reg; }
 	bs_stats *saved = par.work.stats;
-	par.work.stats = NULL;                     /* the writer's own statistics are not part of this check */
+	par.work.stats = NULL;                     /* the writer's own statistics: only when bsref_writer_stats(1, ..) asked for them */
+	if (pv_stats_on) {
+		/* what init_stats() sets up (src/stats.c:304-318) and the contig's GC bins (src/read_reference.c:120-123); the bins are
+		 * a fresh malloc() per call because _print_vcf_entry() frees those of the contig it saw before (:113-119) */
+		if (!ref_stats.qd_stats) {
+			ref_stats.qd_stats = gt_vector_new(256, sizeof(fstats_cts));
+			ref_stats.fs_stats = gt_vector_new(256, sizeof(fstats_cts));
+			ref_stats.mq_stats = gt_vector_new(256, sizeof(fstats_cts));
+			memset(ref_stats.qd_stats->memory, 0, sizeof(fstats_cts) * ref_stats.qd_stats->elements_allocated);
+			memset(ref_stats.fs_stats->memory, 0, sizeof(fstats_cts) * ref_stats.fs_stats->elements_allocated);
+			memset(ref_stats.mq_stats->memory, 0, sizeof(fstats_cts) * ref_stats.mq_stats->elements_allocated);
+		}
+		gt_ctg_stats *cs = pv_cstats + flip;
+		if (cs->gc) free(cs->gc);
+		memset(cs, 0, sizeof(*cs));
+		if (pv_nbins > 0) { cs->gc = malloc((size_t)pv_nbins); memcpy(cs->gc, pv_gc, (size_t)pv_nbins); cs->nbins = pv_nbins; }
+		c->ctg_stats = cs;
+		pv_last_cstats = cs;
+		c->start_pos = pv_start;
+		par.work.stats = &ref_stats;
+	}
 	par.work.vcf_ctg = c;
 	par.work.dbSNP_hdr = NULL;
 	db_tab.n = 0;

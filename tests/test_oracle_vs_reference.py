@@ -357,3 +357,62 @@ def test_print_block_with_dbsnp_and_regions(oracle, reference, seed):
                     want = reference.print_block(vcf, refw, x, **kw)
                     got = oracle.print_block(vcf, refw, x, **kw)
                     _same_bcf(got, want, "seed %d size %d %r" % (seed, sz, (region, allp, d is not None)))
+
+
+def cpg_rich(rng, vcf, frac=0.2):
+    """make a share of adjacent site pairs a called CpG (CC then GG) with informative counts, so the CpG branches of the
+    writer's statistics see traffic"""
+    g = vcf["gtm"]
+    n = len(vcf)
+    for i in np.flatnonzero(rng.random(max(n - 1, 0)) < frac):
+        for j, gt in ((i, 4), (i + 1, 7)):
+            lp = g["gt_prob"][j].copy()
+            b = int(np.argmax(lp))
+            lp[b], lp[gt] = lp[gt], lp[b]
+            if lp[gt] < lp.max():
+                lp[gt] = lp.max() + 1e-3
+            g["gt_prob"][j] = np.minimum(lp, 0.0)
+            g["max_gt"][j] = gt
+            if rng.random() < 0.9:
+                g["counts"][j, 4:8] = rng.integers(0, [3, 40, 300][int(rng.integers(0, 3))], size=4)
+                vcf["skip"][j] = 0 if g["counts"][j].sum() else 1
+    return vcf
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_writer_statistics(oracle, reference, seed):
+    """the --report-file statistics of the writer (src/print_vcf.c:382-526): the compiled print_vcf.c with a live bs_stats
+    against the restatement, over random records rich in CpGs, with dbSNP, regions, -A and GC bins; counters identical, the
+    methylation posteriors (sums of doubles in the same order) identical too"""
+    from oracle.bindings import SITE_STATS, site_stats_equal
+    rng = np.random.default_rng(2900 + seed)
+    reference.writer_stats_reset()
+    st = np.zeros(1, dtype=SITE_STATS)
+    state = np.zeros(2, dtype=np.uint32)
+    x = 1
+    try:
+        for sz in (1, 2, 5, 60, 700, 4000):
+            vcf = cpg_rich(rng, util.random_gt_vcf(rng, sz, skip_frac=[0.0, 0.2][seed % 2], deep_frac=0.02))
+            refw = rng.integers(1, 5, size=sz + 2).astype(np.uint8)
+            refw[rng.random(sz + 2) < 0.02] = 0
+            for i in np.flatnonzero(rng.random(sz) < 0.3):      # reference CpGs
+                refw[i], refw[i + 1] = 2, 3
+            x += int(rng.integers(1, 500))
+            start_pos = int(rng.integers(1, x + 1))
+            gc = rng.integers(0, 120, size=(x + sz - start_pos) // 100 + int(rng.integers(0, 2))).astype(np.uint8)
+            ctg_end = x + sz - 1 - int(rng.integers(0, 3))
+            db = random_dbsnp(rng, max(1, x - 5), x + sz + 5)
+            for region in (None, (x + sz // 4, x + (3 * sz) // 4)):
+                for allp in (False, True):
+                    for d in (None, db):
+                        reference.writer_stats(True, gc=gc if len(gc) else None, start_pos=start_pos)
+                        kw = dict(ctg_end=ctg_end, all_positions=allp, region=region, dbsnp=d)
+                        reference.print_block(vcf, refw, x, rid=1, **kw)
+                        oracle.stats_block(vcf, refw, x, gc=gc if len(gc) else None, start_pos=start_pos, stats=st, state=state, **kw)
+            x += sz
+        want, _ = reference.writer_stats_read()
+    finally:
+        reference.writer_stats(False)
+    site_stats_equal(st[0], want[0], rtol=1e-13, what="seed %d" % seed)
+    assert want[0]["snps"][0] > 1000 and want[0]["CpG_ref"][0] + want[0]["CpG_nonref"][0] > 50 and want[0]["multi"][0] > 50
+    assert want[0]["CpG_ref_meth"].sum() > 10 and want[0]["cov"]["gc_pcent"].sum() > 1000 and want[0]["dbSNP_sites"][0] > 20
