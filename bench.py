@@ -713,7 +713,7 @@ def main():
     ap.add_argument("--deep-sites", type=float, default=10e6, help="sites of the 500x panel (config 4: 10 Mb)")
     ap.add_argument("--genome-scale", type=int, default=0, help="genome leg: hg38 contig lengths divided by this (0: by the host's free memory)")
     ap.add_argument("--genome-batch-mb", type=int, default=384, help="genome leg: batch size of the streaming session")
-    ap.add_argument("--genome-sessions", type=int, default=1, help="genome leg: sessions (contexts) per GPU, regions dealt out between them (experimental: >1 needs BSGPU_SERIALIZE_SESSIONS=1 today)")
+    ap.add_argument("--genome-sessions", type=int, default=2, help="genome leg: sessions (contexts) per GPU, regions dealt out between them")
     ap.add_argument("--no-genome", action="store_true", help="skip the genome leg")
     ap.add_argument("--legs", default="e2e,block,bam,writer,genome,cpu", help="secondary legs to run (comma separated)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

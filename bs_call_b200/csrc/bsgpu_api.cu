@@ -63,6 +63,8 @@ static_assert(sizeof(bsgpu_record) == 56, "record descriptor layout");
 static_assert(sizeof(bsgpu_block) == 32, "block layout");
 
 static thread_local char g_err[512] = "";
+// contexts alive per device: with more than one, kernels of different contexts share the SMs (see launch_call_sites)
+static std::atomic<int> g_ctx_on_device[64];
 
 static int fail(const char *fmt, ...) {
 	va_list ap;
@@ -149,6 +151,7 @@ struct bsgpu_ctx {
 	std::vector<uint32_t> off_tmp;
 	std::vector<uint8_t> ref_tmp;
 	bool fused = false;                          // BSGPU_FUSED=1: one fused pileup+model kernel instead of two kernels
+	bool overlap_kernels = false;                // the context runs kernels on more than one stream (decode stream of the reader stage)
 	std::vector<cudaEvent_t> win_events;         // output ring
 	uint32_t ring_pos = 0;                       // next output ring slot of the deferred runs
 	bool ring_busy[3] = {false, false, false};   // output ring slot may still be copying out (deferred block_run)
@@ -224,6 +227,7 @@ int bsgpu_init(const bsgpu_params *p, bsgpu_ctx **out) {
 	bsgpu_ctx *c = new bsgpu_ctx();
 	c->device = p->device;
 	c->params = *p;
+	g_ctx_on_device[c->device & 63].fetch_add(1);
 	memset(&c->stats, 0, sizeof(c->stats));
 	// host-side tables, computed with the C library exactly as the reference does
 	std::vector<DevConst> hbuf(1);          // (48 KB: not on the stack, not shared between threads that initialise contexts)
@@ -277,6 +281,7 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaDeviceSynchronize();
+	g_ctx_on_device[c->device & 63].fetch_sub(1);
 	for (int i = 0; i < 2; i++) {
 		c->slot[i].in.release(); c->slot[i].ref.release(); c->slot[i].out.release(); c->slot[i].skip.release();
 		if (c->slot[i].stream) cudaStreamDestroy(c->slot[i].stream);
@@ -336,12 +341,16 @@ void bsgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
 // ------------------------------------------------------------------------------------------------
 // device-pointer entry points
 // ------------------------------------------------------------------------------------------------
+// does a likelihood-kernel launch of this context have to expect other kernels on its SMs?  `own`: the caller itself runs
+// kernels on more than one stream
+static bool overlap_expected(const bsgpu_ctx *c, bool own) { return own || c->overlap_kernels || g_ctx_on_device[c->device & 63].load() > 1; }
+
 int bsgpu_call_sites_dev(bsgpu_ctx *c, const void *d_pileup, const void *d_ref, size_t n, void *d_out, void *d_skip, void *stream) {
 	if (!c) return fail("bsgpu_call_sites_dev: null context");
 	if (n && (!d_pileup || !d_ref || !d_out || !d_skip)) return fail("bsgpu_call_sites_dev: null buffer");
 	if (((uintptr_t)d_pileup | (uintptr_t)d_out) & 7u) return fail("bsgpu_call_sites_dev: record arrays must be 8-byte aligned");
 	CU(cudaSetDevice(c->device));
-	CU(launch_call_sites(d_pileup, d_ref, n, d_out, d_skip, false, c->d_const, c->d_counters, stream ? (cudaStream_t)stream : c->stream, &c->launches));
+	CU(launch_call_sites(d_pileup, d_ref, n, d_out, d_skip, false, c->d_const, c->d_counters, stream ? (cudaStream_t)stream : c->stream, &c->launches, 0, overlap_expected(c, false)));
 	__atomic_fetch_add(&c->stats.sites, (uint64_t)(n), __ATOMIC_RELAXED);
 	return BSGPU_OK;
 }
@@ -351,7 +360,7 @@ int bsgpu_call_sites_vcf_dev(bsgpu_ctx *c, const void *d_pileup, const void *d_r
 	if (n && (!d_pileup || !d_ref || !d_vcf)) return fail("bsgpu_call_sites_vcf_dev: null buffer");
 	if (((uintptr_t)d_pileup | (uintptr_t)d_vcf) & 7u) return fail("bsgpu_call_sites_vcf_dev: record arrays must be 8-byte aligned");
 	CU(cudaSetDevice(c->device));
-	CU(launch_call_sites(d_pileup, d_ref, n, d_vcf, nullptr, true, c->d_const, c->d_counters, stream ? (cudaStream_t)stream : c->stream, &c->launches));
+	CU(launch_call_sites(d_pileup, d_ref, n, d_vcf, nullptr, true, c->d_const, c->d_counters, stream ? (cudaStream_t)stream : c->stream, &c->launches, 0, overlap_expected(c, false)));
 	__atomic_fetch_add(&c->stats.sites, (uint64_t)(n), __ATOMIC_RELAXED);
 	return BSGPU_OK;
 }
@@ -500,7 +509,7 @@ int bsgpu_call_sites(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t *re
 		CU(s.skip.reserve(m));
 		CU(cudaMemcpyAsync(s.in.p, pileup + first, m * sizeof(bsgpu_pileup), cudaMemcpyHostToDevice, s.stream));
 		CU(cudaMemcpyAsync(s.ref.p, ref + first, m, cudaMemcpyHostToDevice, s.stream));
-		CU(launch_call_sites(s.in.p, s.ref.p, m, s.out.p, s.skip.p, false, c->d_const, c->d_counters, s.stream, &c->launches, first));
+		CU(launch_call_sites(s.in.p, s.ref.p, m, s.out.p, s.skip.p, false, c->d_const, c->d_counters, s.stream, &c->launches, first, true));      // two chunk streams
 		CU(cudaMemcpyAsync(out + first, s.out.p, m * sizeof(bsgpu_gt_meth), cudaMemcpyDeviceToHost, s.stream));
 		CU(cudaMemcpyAsync(skip + first, s.skip.p, m, cudaMemcpyDeviceToHost, s.stream));
 		__atomic_fetch_add(&c->stats.h2d_bytes, (uint64_t)(m * (sizeof(bsgpu_pileup) + 1)), __ATOMIC_RELAXED);
@@ -535,7 +544,7 @@ static int call_bins(bsgpu_ctx *c, size_t nseg, const void *d_bases, const void 
 		uint8_t *pile = (uint8_t *)c->pile.p + (sub ? (size_t)(k & 1) * step * kPileTileSites * sizeof(bsgpu_pileup) : 0);
 		CU(launch_pileup_tiles(c->scratch.p, nseg, d_bases, d_ref, x, sz, ta, m, pile, 0, c->d_const, c->d_counters, st, &c->launches));
 		CU(launch_call_sites(pile, (const uint8_t *)d_ref + site0, nsite, (uint8_t *)dout + (site0 - (size_t)t0 * kPileTileSites) * sizeof(bsgpu_gt_vcf), nullptr, true,
-				c->d_const, c->d_counters, st, &c->launches, (unsigned long long)x + site0));
+				c->d_const, c->d_counters, st, &c->launches, (unsigned long long)x + site0, overlap_expected(c, false)));
 	}
 	return BSGPU_OK;
 }
@@ -916,7 +925,7 @@ int bsgpu_call_sites_bcf(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t
 		__atomic_fetch_add(&c->stats.h2d_bytes, (uint64_t)(m * (sizeof(bsgpu_pileup) + 1)), __ATOMIC_RELAXED);
 		CU(cudaStreamWaitEvent(st, E(k, 0), 0));
 		CU(launch_call_sites(c->slot[k & 1].in.p, (const uint8_t *)c->wr_ref.p + lo, m, (uint8_t *)c->wr_vcf.p + (k & 1) * chunk * sizeof(bsgpu_gt_vcf),
-				nullptr, true, c->d_const, c->d_counters, st, &c->launches));
+				nullptr, true, c->d_const, c->d_counters, st, &c->launches, 0, overlap_expected(c, false)));
 		CU(cudaEventRecord(E(k, 1), st));
 		j.d_vcf = (const uint8_t *)c->wr_vcf.p + (k & 1) * chunk * sizeof(bsgpu_gt_vcf) - lo * sizeof(bsgpu_gt_vcf);
 		// the records of chunk k - 1 look at the calls of the first two sites of this chunk (the rest of this chunk's calls are
@@ -1001,8 +1010,12 @@ static int decode_queue(bsgpu_ctx *c, bsgpu_ctx::ReaderSet &R, const uint8_t *ba
 	// debugging switches: BSGPU_ONE_STREAM=1 puts upload, decode and the windows on one stream (no kernel of the reader stage
 	// overlaps a kernel of the window stage); BSGPU_NO_NAME_JOIN=1 leaves the QNAME join to the host
 	static const bool one_stream = getenv("BSGPU_ONE_STREAM") != nullptr, no_join = getenv("BSGPU_NO_NAME_JOIN") != nullptr;
-	static const bool dec_own = getenv("BSGPU_DECODE_STREAM") != nullptr;      // decode kernels on a stream of their own (round-1 behaviour)
-	cudaStream_t up = one_stream ? c->stream : R.up, dec = one_stream || !dec_own || pipelined ? c->stream : c->slot[1].stream;
+	// the decode / name-join kernels run on a stream of their own, next to the window kernels of the pieces (and, in a session,
+	// of the batch) before: the context then launches its likelihood kernel in the overlap-safe form (launch_call_sites).
+	// BSGPU_DECODE_STREAM=0 queues them on the context stream instead.
+	static const bool dec_own = [] { const char *e = getenv("BSGPU_DECODE_STREAM"); return !e || atoi(e) != 0; }();
+	cudaStream_t up = one_stream ? c->stream : R.up, dec = one_stream || !dec_own ? c->stream : c->slot[1].stream;
+	if (dec != c->stream) c->overlap_kernels = true;
 	if (!pipelined) {
 		// nothing of an earlier call is in flight any more.  (A pipelined run of a session starts while the run before it is
 		// still at its window stage: its reader set was last used two runs ago, and the session has waited for that one.)

@@ -58,7 +58,14 @@ __device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, u
 	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 16-byte asynchronous copies global -> shared through the load / store units (LDGSTS), grouped per thread
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // shared-memory copy of the lookup tables (q -> {k, ln k, ln(1/2+k), ln(1+k)}, log/exp reduction tables)
@@ -126,7 +133,7 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 	auto tile_bulk = [&](size_t tile) {          // can this tile's input travel by the bulk engine?
 		const size_t first = tile * kCallTile;
 		const uint32_t bytes = (uint32_t)min((size_t)kCallTile, n - first) * 104u;
-		return bulk_ok && (bytes & 15u) == 0;
+		return (bulk_ok & 1) && (bytes & 15u) == 0;
 	};
 	auto issue = [&](size_t tile) {
 		const size_t first = tile * kCallTile;
@@ -134,8 +141,24 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 		mbar_expect_tx(&bar, bytes);
 		tma_load_1d(inbuf, pileup + first * 104, bytes, &bar);
 	};
+	// the same prefetch without the bulk-copy engine (bulk_ok & 8): every thread copies its share of the tile, 16 bytes at a time
+	const bool ldgsts = (bulk_ok & 8) != 0;
+	auto tile_async = [&](size_t tile) {
+		const size_t first = tile * kCallTile;
+		const uint32_t bytes = (uint32_t)min((size_t)kCallTile, n - first) * 104u;
+		return ldgsts && (bytes & 15u) == 0;
+	};
+	auto issue_async = [&](size_t tile) {
+		const size_t first = tile * kCallTile;
+		const uint32_t chunks = (uint32_t)min((size_t)kCallTile, n - first) * 104u / 16u;
+		const uint8_t *src = pileup + first * 104;
+		const uint32_t dst = smem_u32(inbuf);
+		for (uint32_t k = tid; k < chunks; k += kCallTile) cp_async16(dst + 16u * k, src + 16u * (size_t)k);
+		cp_async_commit();
+	};
 	size_t tile = blockIdx.x;
 	if (tile < ntiles && tid == 0 && tile_bulk(tile)) issue(tile);
+	if (tile < ntiles && tile_async(tile)) issue_async(tile);
 	uint32_t phase = 0, ncalled = 0;
 	for (; tile < ntiles; tile += gridDim.x) {
 		const size_t first = tile * kCallTile;
@@ -144,6 +167,9 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 		if (tile_bulk(tile)) {
 			mbar_wait(&bar, phase);
 			phase ^= 1;
+		} else if (tile_async(tile)) {
+			cp_async_wait();
+			__syncthreads();
 		} else {
 			const uint32_t *g = (const uint32_t *)(pileup + first * 104);
 			uint32_t *sm = (uint32_t *)inbuf;
@@ -166,10 +192,11 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 			s.n = 0;
 			s.mapq2 = 0.0f;
 		}
-		if (tid == 0) tma_store_wait();        // the previous tile's output has left the staging buffer
+		if (tid == 0) { if (bulk_ok & 4) tma_store_wait_all(); else tma_store_wait(); }        // the previous tile's output has left the staging buffer
 		__syncthreads();                       // every thread holds its input; staging buffer free
 		const size_t next = tile + gridDim.x;
 		if (next < ntiles && tid == 0 && tile_bulk(next)) issue(next);
+		if (next < ntiles && tile_async(next)) issue_async(next);
 		uint64_t *rec = stage + tid * RW;
 		// pooled-argument list of this warp: the (not yet written) output rows of its own 32 sites
 		double *wbuf = (double *)(stage + (tid & ~31) * RW);
@@ -181,9 +208,9 @@ k_call_sites(const uint8_t *__restrict__ pileup, const uint8_t *__restrict__ ref
 		}
 		if (VCF) rec[25] = 1ull | ((called ? 0ull : 1ull) << 8);
 		else if (tid < nrec) skip[first + tid] = called ? 0 : 1;
-		store_tile<REC>(out + first * REC, stage, nrec, bulk_ok, tid, kCallTile);
+		store_tile<REC>(out + first * REC, stage, nrec, (bulk_ok & 2) != 0, tid, kCallTile);
 	}
-	if (tid == 0) tma_store_wait();
+	if (tid == 0) { if (bulk_ok & 4) tma_store_wait_all(); else tma_store_wait(); }
 	ncalled = __reduce_add_sync(0xffffffffu, ncalled);
 	if ((tid & 31) == 0 && ncalled) atomicAdd(counters, (unsigned long long)ncalled);
 }
@@ -920,10 +947,18 @@ cudaError_t configure_kernels() {
 }
 
 cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, void *out, void *skip, bool vcf,
-		const DevConst *dc, unsigned long long *counters, cudaStream_t stream, int *launches, unsigned long long guard_base) {
+		const DevConst *dc, unsigned long long *counters, cudaStream_t stream, int *launches, unsigned long long guard_base, bool overlap_safe) {
 	if (!n) return cudaSuccess;
-	static const bool no_bulk = getenv("BSGPU_NO_BULK") != nullptr;      // debugging: plain loads / stores instead of the bulk-copy engine
-	const bool bulk_ok = !no_bulk && (((uintptr_t)pileup | (uintptr_t)out) & 15u) == 0;
+	// How a tile comes in and goes out, as bits: 1 input by one bulk copy (cp.async.bulk + mbarrier), 2 output by one bulk copy,
+	// 4 wait for the completion of the output copy instead of for its reads of shared memory, 8 (without 1) input by 16-byte
+	// cp.async copies of every thread.  Default 3.  overlap_safe (the caller runs other kernels next to this one: a second
+	// context on the device, decode kernels on their own stream, two chunk streams) asks for 10: on B200 the bulk LOAD of this
+	// persistent kernel ends in "illegal memory access" when CTAs of other kernels share its SMs (bisected on the genome leg
+	// with two sessions per GPU: bits 1, 3, 7 fault within seconds, 0, 2, 10 never did; profiles/r02c_fault_bisect.md), and the
+	// cp.async prefetch costs 6 % of the kernel (12.0 against 12.8 G sites/s).  BSGPU_BULK=<bits> / BSGPU_NO_BULK=1 override both.
+	static const int env_bits = [] { if (getenv("BSGPU_NO_BULK")) return 0; const char *e = getenv("BSGPU_BULK"); return e ? atoi(e) & 15 : -1; }();
+	const int bulk_bits = env_bits >= 0 ? env_bits : overlap_safe ? 10 : 3;
+	const int bulk_ok = (((uintptr_t)pileup | (uintptr_t)out) & 15u) == 0 ? bulk_bits : 0;
 	const size_t ntiles = (n + kCallTile - 1) / kCallTile;
 	const int five = g_call_minb == 5;
 	const size_t resident = (size_t)g_sms * (size_t)(g_call_ctas[five][vcf] > 0 ? g_call_ctas[five][vcf] : 1);

@@ -17,7 +17,8 @@ cudaError_t configure_kernels();
 
 // guard_base: id of site 0 of this launch in the guard list (bsgpu_guard_read)
 cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, void *out, void *skip, bool vcf,
-		const DevConst *dc, unsigned long long *counters, cudaStream_t stream, int *launches, unsigned long long guard_base = 0);
+		const DevConst *dc, unsigned long long *counters, cudaStream_t stream, int *launches, unsigned long long guard_base = 0,
+		bool overlap_safe = false);      // overlap_safe: other kernels may run next to this one (see the launcher)
 
 // scratch needed by the segment binning of one block
 size_t pileup_scratch_bytes(size_t nseg, uint32_t sz);

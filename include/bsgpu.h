@@ -171,6 +171,31 @@ typedef struct {
 	uint64_t filter_bases[15];               /* [0] = mates / bases that reached normalisation (+ the bases of src/get_template_vector.c:363) */
 } bsgpu_profile;
 
+/* The site-level side channels of --report-file: what _print_vcf_entry() adds to bs_stats for every site it visits
+ * (src/print_vcf.c:382-526; bs_stats, include/bs_call.h:124-146).  Flat image of the fields it touches: the fs / qd / mq
+ * vectors (add_flt_counts, :22-27) and the coverage hash (gt_cov_stats, include/bs_call.h:87-95) are arrays indexed by value;
+ * values beyond an array are counted in fs_overflow / cov_overflow.  The writer entry points (bsgpu_*_bcf, sessions that return
+ * records) gather it on the device while bsgpu_site_stats_enable is on; a host that replaces the print thread (seam D) folds
+ * it into stats the way bsgpu_seam_reader.c does.  All counters are exact; the two methylation posteriors are sums of
+ * doubles accumulated in device order (equal to the reference's to ~1e-12 relative).  As compiled, the reference counts a
+ * homozygous reference call as "multi" and every other written site as "snp" (the test at :400-402 reads one byte past a
+ * string literal's terminator); that is what is reproduced. */
+#define BSGPU_STATS_FS_MAX 4096
+#define BSGPU_STATS_COV_MAX 4096
+typedef struct { uint64_t var, CpG[2], CpG_inf[2], all, gc_pcent[101]; } bsgpu_cov_stats;
+typedef struct {
+	uint64_t snps[2], multi[2], dbSNP_sites[2], dbSNP_var[2], CpG_ref[2], CpG_nonref[2];      /* [stats_all, stats_passed] */
+	uint64_t mut_counts[12][2], dbSNP_mut_counts[12][2];    /* stats_mut order: AC AG AT CA CG CT GA GC GT TA TC TG */
+	uint64_t qual[4][256];                                  /* all_sites, variant_sites, CpG_ref_sites, CpG_nonref_sites by QUAL */
+	uint64_t filter_counts[2][32];                          /* [het call][filter bits q20 qd2 fs60 mq40] */
+	double CpG_ref_meth[2][101], CpG_nonref_meth[2][101];   /* summed posterior of the methylation level, 1 % steps */
+	uint64_t qd_stats[256][2], mq_stats[256][2], fs_stats[BSGPU_STATS_FS_MAX][2];      /* [value][het call] */
+	uint64_t fs_overflow, cov_overflow;
+	bsgpu_cov_stats cov[BSGPU_STATS_COV_MAX];               /* by depth (CpG_inf: by informative depth) */
+} bsgpu_site_stats;
+/* the per-contig copy of the first six counters (gt_ctg_stats, include/bs_call.h:75-85) */
+typedef struct { uint64_t snps[2], multi[2], dbSNP_sites[2], dbSNP_var[2], CpG_ref[2], CpG_nonref[2]; } bsgpu_ctg_site_stats;
+
 /* ---- writer side: what the print thread needs besides the records to serialise a site (src/print_vcf.c) ---- */
 #define BSGPU_BCF_MAX_RECORD 384
 #define BSGPU_DBSNP_MAX_ID 96
@@ -272,6 +297,14 @@ int bsgpu_process_block(bsgpu_ctx *ctx, const bsgpu_template *t, size_t n, const
  * starts again from zero. */
 int bsgpu_profile_enable(bsgpu_ctx *ctx, int on);
 int bsgpu_profile_read(bsgpu_ctx *ctx, bsgpu_profile *out, int reset);
+
+/* Site-level side channels (bsgpu_site_stats above).  n_contigs sizes the per-contig table; a record's contig is the CHROM the
+ * writer gives it (bsgpu_bcf_params.rid, vcf_rid[tid]).  bsgpu_set_contig_gc hands over ctg_stats->gc of a contig: the GC
+ * percentage of every 100-base bin counted from start_pos (src/read_reference.c:120-123; values above 100 = unknown); without
+ * it the gc_pcent histograms stay empty.  _read waits for the queued work; ctg may be NULL. */
+int bsgpu_site_stats_enable(bsgpu_ctx *ctx, int on, int n_contigs);
+int bsgpu_set_contig_gc(bsgpu_ctx *ctx, int rid, uint32_t start_pos, const uint8_t *gc, uint32_t nbins);
+int bsgpu_site_stats_read(bsgpu_ctx *ctx, bsgpu_site_stats *out, bsgpu_ctg_site_stats *ctg, int n_contigs, int reset);
 
 /* ---- writer side: a block of gt_vcf records -> the BCF records print_thread would hand to bcf_write()
  *      (print_vcf_entry / flush_vcf_entries / _print_vcf_entry, src/print_vcf.c:32-381, 535-594, driven per block by
