@@ -160,6 +160,12 @@ struct bsgpu_ctx {
 	struct DbDev { DevBuf mask, fq, cum, off, names; uint32_t words = 0; uint32_t reg_start = 0, reg_stop = 0; uint64_t key[4] = {0, 0, 0, 0}; };
 	std::map<int, DbDev *> contig_ann;
 	DbDev call_db;
+	// --report-file statistics of the sites (bsgpu_site_stats_enable): device image, per-contig table, GC bins per contig (by rid)
+	bool site_stats_on = false;
+	DevBuf st_main, st_ctg;
+	uint32_t st_nctg = 0;
+	struct GcDev { DevBuf bins; uint32_t n = 0, start = 1; };
+	std::map<int, GcDev *> contig_gc;
 	bool zero_decoded = false;                   // bsgpu_decode_records hands the decoded arrays out: slots of dropped records are cleared
 	uint64_t guard_base[4] = {0, 0, 0, 0};      // guard counters of the device before the last bsgpu_guard_read(reset)
 	int launches = 0;
@@ -282,6 +288,9 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 	cudaSetDevice(c->device);
 	cudaDeviceSynchronize();
 	g_ctx_on_device[c->device & 63].fetch_sub(1);
+	c->st_main.release(); c->st_ctg.release();
+	for (auto &kv : c->contig_gc) if (kv.second) { kv.second->bins.release(); delete kv.second; }
+	c->contig_gc.clear();
 	for (int i = 0; i < 2; i++) {
 		c->slot[i].in.release(); c->slot[i].ref.release(); c->slot[i].out.release(); c->slot[i].skip.release();
 		if (c->slot[i].stream) cudaStreamDestroy(c->slot[i].stream);
@@ -768,6 +777,65 @@ int bsgpu_set_contig_annotation(bsgpu_ctx *c, int tid, uint32_t reg_start, uint3
 	return db_upload(c, db, *d, "bsgpu_set_contig_annotation");
 }
 
+// the statistics side channel of a writer job: where the counters live and the GC bins of the job's contig (j.p.rid is set)
+static void job_stats(bsgpu_ctx *c, BcfJob &j) {
+	if (!c->site_stats_on) return;
+	j.stats = c->st_main.p; j.ctg_stats = c->st_nctg ? c->st_ctg.p : nullptr; j.n_ctg = c->st_nctg;
+	j.stats_carry = (uint32_t *)((uint8_t *)c->st_main.p + sizeof(bsgpu_site_stats));
+	const auto it = c->contig_gc.find((int)j.p.rid);
+	if (it != c->contig_gc.end() && it->second->n) { j.gc = (const uint8_t *)it->second->bins.p; j.gc_bins = it->second->n; j.gc_start = it->second->start; }
+}
+
+int bsgpu_site_stats_enable(bsgpu_ctx *c, int on, int n_contigs) {
+	if (!c || n_contigs < 0) return fail("bsgpu_site_stats_enable: bad argument");
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());
+	if (on) {
+		CU(c->st_main.reserve(sizeof(bsgpu_site_stats) + 16));          // + the carry word of chunked launches
+		CU(cudaMemset(c->st_main.p, 0, sizeof(bsgpu_site_stats) + 16));
+		if (n_contigs) {
+			CU(c->st_ctg.reserve((size_t)n_contigs * sizeof(bsgpu_ctg_site_stats)));
+			CU(cudaMemset(c->st_ctg.p, 0, (size_t)n_contigs * sizeof(bsgpu_ctg_site_stats)));
+		}
+		c->st_nctg = (uint32_t)n_contigs;
+	}
+	c->site_stats_on = on != 0;
+	return BSGPU_OK;
+}
+
+int bsgpu_set_contig_gc(bsgpu_ctx *c, int rid, uint32_t start_pos, const uint8_t *gc, uint32_t nbins) {
+	if (!c || rid < 0 || (nbins && !gc)) return fail("bsgpu_set_contig_gc: bad argument");
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());              // the old bins may still be in use
+	bsgpu_ctx::GcDev *&d = c->contig_gc[rid];
+	if (!d) d = new bsgpu_ctx::GcDev();
+	d->n = 0; d->start = start_pos ? start_pos : 1;
+	if (nbins) {
+		CU(d->bins.reserve(nbins));
+		CU(cudaMemcpy(d->bins.p, gc, nbins, cudaMemcpyHostToDevice));
+		__atomic_fetch_add(&c->stats.h2d_bytes, (uint64_t)nbins, __ATOMIC_RELAXED);
+		d->n = nbins;
+	}
+	return BSGPU_OK;
+}
+
+int bsgpu_site_stats_read(bsgpu_ctx *c, bsgpu_site_stats *out, bsgpu_ctg_site_stats *ctg, int n_contigs, int reset) {
+	if (!c || !out || n_contigs < 0 || (n_contigs && !ctg)) return fail("bsgpu_site_stats_read: bad argument");
+	if (!c->st_main.p) return fail("bsgpu_site_stats_read: bsgpu_site_stats_enable was never called");
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());
+	CU(cudaMemcpy(out, c->st_main.p, sizeof(bsgpu_site_stats), cudaMemcpyDeviceToHost));
+	const size_t nc = std::min<size_t>((size_t)n_contigs, c->st_nctg);
+	if (n_contigs) memset(ctg, 0, (size_t)n_contigs * sizeof(bsgpu_ctg_site_stats));
+	if (nc) CU(cudaMemcpy(ctg, c->st_ctg.p, nc * sizeof(bsgpu_ctg_site_stats), cudaMemcpyDeviceToHost));
+	__atomic_fetch_add(&c->stats.d2h_bytes, (uint64_t)(sizeof(bsgpu_site_stats) + nc * sizeof(bsgpu_ctg_site_stats)), __ATOMIC_RELAXED);
+	if (reset) {
+		CU(cudaMemset(c->st_main.p, 0, sizeof(bsgpu_site_stats)));
+		if (c->st_nctg) CU(cudaMemset(c->st_ctg.p, 0, (size_t)c->st_nctg * sizeof(bsgpu_ctg_site_stats)));
+	}
+	return BSGPU_OK;
+}
+
 // one block, everything resident: records into d_out, sizes back through the pinned totals (slot 0); waits for `st`
 static int bcf_run(bsgpu_ctx *c, const void *d_vcf, const void *d_ref, uint32_t x, uint32_t sz, const bsgpu_bcf_params *p,
 		void *d_out, size_t out_cap, size_t *nbytes, size_t *nrec, cudaStream_t st, const char *who) {
@@ -778,6 +846,7 @@ static int bcf_run(bsgpu_ctx *c, const void *d_vcf, const void *d_ref, uint32_t 
 	j.d_vcf = d_vcf; j.d_ref = d_ref; j.x = x; j.sz = sz; j.d_blocks = nullptr; j.nblocks = 0; j.p = *p; j.dc = c->d_const; j.guard = c->d_counters;
 	j.site_scratch = c->wr_site.p;
 	if (job_annotate(c, p, j, who) != BSGPU_OK) return BSGPU_FAIL;
+	job_stats(c, j);
 	CU(launch_bcf_records(j, 0, sz, c->wr_cta.p, d_out, out_cap, c->d_wr_totals, st, &c->launches));
 	CU(cudaMemcpyAsync(c->h_wr_totals, c->d_wr_totals, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
@@ -891,6 +960,7 @@ int bsgpu_call_sites_bcf(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t
 	j.d_ref = c->wr_ref.p; j.x = x; j.sz = (uint32_t)n; j.d_blocks = nullptr; j.nblocks = 0; j.p = *p; j.dc = c->d_const; j.guard = c->d_counters;
 	j.site_scratch = c->wr_site.p;
 	if (job_annotate(c, p, j, "bsgpu_call_sites_bcf") != BSGPU_OK) return BSGPU_FAIL;
+	job_stats(c, j);
 	CU(cudaMemcpyAsync(c->wr_ref.p, ref, n + 2, cudaMemcpyHostToDevice, up));
 	size_t at = 0, recs = 0;
 	int ret = BSGPU_OK;
@@ -900,6 +970,7 @@ int bsgpu_call_sites_bcf(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t
 		if (k >= 2) CU(cudaStreamWaitEvent(st, E(k - 2, 3), 0));      // the output buffer of chunk k - 2 has left
 		// a.vcf + i must address the ring slot of chunk k for the sites of chunk k (no other site's record is read)
 		j.d_vcf = (const uint8_t *)c->wr_vcf.p + (k & 1) * chunk * sizeof(bsgpu_gt_vcf) - lo * sizeof(bsgpu_gt_vcf);
+		j.stats_carry_flip = (uint32_t)(k & 1);
 		CU(launch_bcf_records(j, (uint32_t)lo, (uint32_t)m, (uint8_t *)c->wr_cta.p + (k & 1) * bcf_cta_scratch_bytes((uint32_t)chunk),
 				(uint8_t *)c->wr_out.p + (k & 1) * ocap, ocap, c->d_wr_totals + 3 * (k & 7), st, &c->launches));
 		CU(cudaMemcpyAsync(c->h_wr_totals + 3 * (k & 7), c->d_wr_totals + 3 * (k & 7), 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1380,6 +1451,7 @@ static int call_window(bsgpu_ctx *c, bsgpu_ctx::ReaderSet &R, const TmSpan *span
 		const auto it = c->contig_ann.find((int)tid);
 		if (it != c->contig_ann.end() && it->second) { j.db = db_view(*it->second); j.reg_start = it->second->reg_start; j.reg_stop = it->second->reg_stop; }
 	}
+	job_stats(c, j);
 	if (sink->queued >= 3) CU(cudaStreamWaitEvent(c->stream, c->wr_copied[rslot], 0));      // the slot's previous records have left
 	CU(launch_bcf_records(j, 0, sz, c->wr_cta.p, c->wr_ring[rslot].p, rcap, c->d_wr_totals + 3 * (sink->queued & 7), c->stream, &c->launches));
 	CU(cudaMemcpyAsync(c->h_wr_totals + 3 * (sink->queued & 7), c->d_wr_totals + 3 * (sink->queued & 7), 3 * sizeof(unsigned long long),

@@ -91,6 +91,14 @@ struct BcfJob {
 	DbView db;                       // dbSNP entries of the window's contig
 	uint32_t reg_start = 0, reg_stop = 0;    // ctg->curr_reg (0, 0: none -> the contig end clips)
 	unsigned long long *guard = nullptr;      // the context's counters: sites whose QUAL / FS sit inside their guard band are counted and listed
+	// --report-file statistics of the sites (bsgpu_site_stats_enable): device image of bsgpu_site_stats, the per-contig table
+	// (entry j.p.rid is used when it is below n_ctg) and the GC bins of the contig
+	void *stats = nullptr, *ctg_stats = nullptr;
+	uint32_t *stats_carry = nullptr;         // chunked launches over one window: what the last site of the chunk before left (see k_bcf_stats)
+	uint32_t stats_carry_flip = 0;           // ... alternating between the two carry words: chunk number & 1
+	uint32_t n_ctg = 0;
+	const uint8_t *gc = nullptr;
+	uint32_t gc_bins = 0, gc_start = 1;
 };
 size_t bcf_site_scratch_bytes(uint32_t sz);
 size_t bcf_cta_scratch_bytes(uint32_t cnt);

@@ -15,6 +15,7 @@
 //   k_bcf_emit      records built in shared memory at their offsets inside the CTA, copied out as aligned words
 //
 // The byte encoding is BCF2 (VCF/BCF specification v4.3 section 6.3) as htslib's bcf_enc_* helpers produce it.
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "bsgpu.h"
@@ -116,6 +117,13 @@ struct WrArgs {
 	unsigned long long *guard;       // the context's counters (guard bands), or NULL
 	DbView db;                       // dbSNP entries of the contig (words == 0: none)
 	uint32_t reg_start, reg_stop;    // ctg->curr_reg (0, 0: none)
+	// site statistics (k_bcf_stats)
+	bsgpu_site_stats *stats;
+	bsgpu_ctg_site_stats *ctg_stats; // this contig's entry, or NULL
+	uint32_t *stats_carry;           // two words, written in turn (carry_flip) by successive launches over one window: 0 / 1 / 2 =
+	uint32_t carry_flip;             // the last site of the launch was not counted / counted unfiltered / counted with a filter set
+	const uint8_t *gc;
+	uint32_t gc_bins, gc_start;
 };
 
 __device__ __forceinline__ void guard_note(unsigned long long *counters, int kind, unsigned long long id) {
@@ -455,6 +463,261 @@ __global__ void __launch_bounds__(kWrThreads) k_bcf_emit(const WrArgs a) {
 	if (threadIdx.x < total - tail0) dst[tail0 + threadIdx.x] = stage[tail0 + threadIdx.x];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// --report-file statistics of the sites (src/print_vcf.c:382-526; restated in oracle/bs_oracle_stats.c, which is pinned
+// against the compiled print_vcf.c).  One thread per site re-derives what the record builder derives (call window, reference
+// context, dbSNP hit, skip, QUAL, QD, FS, filter bits); counters that many sites share go through per-CTA histograms in shared
+// memory, the sparse ones (coverage table, FS beyond 63) straight to global memory, lanes with equal keys combined first.
+// The only state the reference carries from site to site -- position and filter state of the last '+' strand CpG
+// (prev_cpg_x, prev_cpg_flt, :107-108) -- is a function of the site before: a '-' strand CpG at x is called GG behind a call
+// CC at x - 1, which is then a '+' strand CpG itself and set that state iff it was visited and not skipped.
+// The methylation posteriors of the CpG strands (101 exponentials each) are pooled per CTA and evaluated one entry per warp.
+// ---------------------------------------------------------------------------------------------------------------
+struct SiteDer { uint32_t rc[5]; int gt, rfix; uint32_t rs_found; bool skip; int phred, fs; uint32_t qd, flt, dp1, dinf; };
+
+// false: the writer does not visit the site (not called, no depth)
+__device__ bool derive_site(const WrArgs &a, uint32_t i, uint32_t first, uint32_t last, const int g[5], SiteDer &d) {
+	if (!g[2]) return false;
+	const GtVcf *v = a.vcf + i;
+	d.dp1 = d.dinf = 0;
+#pragma unroll
+	for (int k = 0; k < 4; k++) { d.dp1 += (uint32_t)v->counts[k]; d.dinf += (uint32_t)v->counts[4 + k]; }
+	if (!(d.dp1 + d.dinf)) return false;
+	{
+		const int64_t ii = i, f = first, l = last;
+		const int64_t wstart = ii + 2 <= l ? ii - 2 : l - 4;
+		bool wiped = false;
+		for (int64_t j = wstart < f ? f : wstart; j < ii - 2; j++) wiped |= a.ref[j] == 0;
+#pragma unroll
+		for (int k = 0; k < 5; k++) {
+			const int64_t j = ii + k - 2;
+			const uint32_t c = j >= f && !wiped ? a.ref[j] : 0u;
+			if (c == 0 && j >= f) wiped = true;
+			d.rc[k] = c;
+		}
+	}
+	d.rfix = (int)d.rc[2]; d.gt = g[2] - 1;
+	const uint32_t pos = a.x + i;
+	d.rs_found = 0;
+	if ((pos >> 6) < a.db.words) {
+		const unsigned long long bit = 1ull << (pos & 63);
+		if (a.db.mask[pos >> 6] & bit) d.rs_found = (a.db.fq[pos >> 6] & bit) ? 3u : 1u;
+	}
+	d.skip = !a.all_positions && !(d.rs_found & 2u) && ((d.gt == 0 && d.rfix == 1) || (d.gt == 9 && d.rfix == 4));
+	const MathTables *mt = &a.dc->tab.math;
+	const double lp = v->gt_prob[d.gt] * kLn10;
+	const double z1 = lp == 0.0 ? 1.0 : fast_exp(lp < -700.0 ? -700.0 : lp, mt);
+	if (z1 >= 1.0) d.phred = 255;
+	else { d.phred = (int)(-10.0 * fast_log(1.0 - z1, mt) / kLn10); if (d.phred > 255) d.phred = 255; }
+	d.fs = (int)(-v->fisher_strand * 10.0 + 0.5);
+	d.qd = d.dp1 > 0 ? (uint32_t)d.phred / d.dp1 : (uint32_t)d.phred;
+	if (!d.skip) {
+		if (a.reg_start | a.reg_stop) d.skip = pos < a.reg_start || pos > a.reg_stop;
+		else d.skip = pos > a.ctg_end;
+	}
+	d.flt = 0;
+	if (!d.skip) {
+		if (d.phred < 20) d.flt |= 1;
+		if (d.qd < 2) d.flt |= 2;
+		if (d.fs > 60) d.flt |= 4;
+		if (v->mq < 40) d.flt |= 8;
+		if (!d.flt) {
+			const unsigned long long *c = v->counts;
+			bool mac1 = false;
+			switch (d.gt) {
+			case 1: mac1 = c[1] + c[5] + c[7] <= 1 || c[0] + c[4] <= 1; break;
+			case 2: mac1 = c[2] + c[6] <= 1 || c[0] <= 1; break;
+			case 3: mac1 = c[3] + c[7] <= 1 || c[0] + c[4] <= 1; break;
+			case 5: mac1 = c[2] + c[6] + c[4] <= 1 || c[1] + c[5] + c[7] <= 1; break;
+			case 6: mac1 = c[3] <= 1 || c[1] + c[5] <= 1; break;
+			case 8: mac1 = c[3] + c[7] <= 1 || c[2] + c[6] + c[4] <= 1; break;
+			}
+			if (mac1) d.flt |= 128;
+		}
+	}
+	return true;
+}
+
+// layout of the per-CTA histograms (32-bit counters: a CTA has 128 sites)
+enum { H_MISC = 0, H_MUT = 12, H_DBMUT = 36, H_QUAL = 60, H_FLT = H_QUAL + 1024, H_QD = H_FLT + 64, H_MQ = H_QD + 512, H_FS = H_MQ + 512, H_END = H_FS + 128 };
+constexpr int kFsShared = 64;            // FS values below this are counted in shared memory (0 for every homozygous call)
+
+__device__ __forceinline__ void add_u64(uint64_t *p, uint32_t v) { atomicAdd((unsigned long long *)p, (unsigned long long)v); }
+
+__global__ void __launch_bounds__(kWrThreads) k_bcf_stats(const WrArgs a) {
+	__shared__ uint32_t h[H_END];
+	__shared__ double meth[4][101];          // [ref all, ref passed, nonref all, nonref passed]
+	__shared__ uint32_t cg_a[kWrThreads], cg_b[kWrThreads], cg_w[kWrThreads], cg_n;
+	__shared__ double logp[100];
+	const int tid = threadIdx.x, lane = tid & 31;
+	for (int k = tid; k < H_END; k += kWrThreads) h[k] = 0;
+	for (int k = tid; k < 404; k += kWrThreads) (&meth[0][0])[k] = 0.0;
+	if (tid == 0) cg_n = 0;
+	__syncthreads();
+	const uint32_t i = a.i0 + blockIdx.x * kWrThreads + tid;
+	bsgpu_site_stats *st = a.stats;
+	bool visited = false;
+	SiteDer d;
+	uint32_t first = 0, last = 0;
+	int g[5] = { 0, 0, 0, 0, 0 };
+	if (i < a.i1 && block_of(a, i, first, last)) {
+		window_calls(a, i, first, last, g);
+		visited = derive_site(a, i, first, last, g, d);
+	}
+	// coverage table: cov[dp].all and the GC histogram of the depth (:385-398), lanes with the same key combined
+	{
+		const uint32_t dp = visited ? d.dp1 + d.dinf : 0xffffffffu;
+		uint32_t gcv = 0xffu;
+		if (visited && a.gc) {
+			const int bn = (int)((a.x + i - a.gc_start) / 100u);
+			if (bn >= 0 && (uint32_t)bn < a.gc_bins) gcv = a.gc[bn];
+		}
+		const uint32_t m1 = __match_any_sync(0xffffffffu, dp);
+		if (visited && lane == __ffs(m1) - 1) {
+			if (dp < (uint32_t)BSGPU_STATS_COV_MAX) add_u64(&st->cov[dp].all, __popc(m1)); else add_u64(&st->cov_overflow, __popc(m1));
+		}
+		const uint32_t key = visited && gcv <= 100u && dp < (uint32_t)BSGPU_STATS_COV_MAX ? dp << 7 | gcv : 0xffffffffu;
+		const uint32_t m2 = __match_any_sync(0xffffffffu, key);
+		if (key != 0xffffffffu && lane == __ffs(m2) - 1) add_u64(&st->cov[dp].gc_pcent[gcv], __popc(m2));
+	}
+	if (visited && !d.skip) {
+		const GtVcf *v = a.vcf + i;
+		const uint32_t dp = d.dp1 + d.dinf;
+		const bool het = is_het(d.gt), pass = d.flt == 0;
+		int a0, a1;
+		alleles_of(d.gt, a0, a1);
+		// "variant": every written site; as compiled the reference files a homozygous reference call under multi (bsgpu.h)
+		const int var_slot = (a0 == a1 && a0 == d.rfix) ? 2 : 0;
+		atomicAdd(&h[H_MISC + var_slot], 1u);
+		if (pass) atomicAdd(&h[H_MISC + var_slot + 1], 1u);
+		atomicAdd(&h[H_QUAL + 256 + d.phred], 1u);
+		atomicAdd(&h[H_QUAL + d.phred], 1u);
+		if (dp < (uint32_t)BSGPU_STATS_COV_MAX) add_u64(&st->cov[dp].var, 1u);
+		atomicAdd(&h[H_QD + 2 * min(d.qd, 255u) + het], 1u);
+		{
+			const int mq = v->mq;
+			if (mq >= 0 && mq < 256) atomicAdd(&h[H_MQ + 2 * mq + het], 1u);
+		}
+		if (d.fs >= 0 && d.fs < kFsShared) atomicAdd(&h[H_FS + 2 * d.fs + het], 1u);
+		else if (d.fs >= 0 && d.fs < BSGPU_STATS_FS_MAX) add_u64(&st->fs_stats[d.fs][het], 1u);
+		else add_u64(&st->fs_overflow, 1u);
+		atomicAdd(&h[H_FLT + 32 * het + (d.flt & 31u)], 1u);
+		if (d.rs_found) {
+			atomicAdd(&h[H_MISC + 4], 1u); atomicAdd(&h[H_MISC + 6], 1u);
+			if (pass) { atomicAdd(&h[H_MISC + 5], 1u); atomicAdd(&h[H_MISC + 7], 1u); }
+		}
+		if ((g[2] == 5 && g[3] == 8) || (g[2] == 8 && g[1] == 5)) {      // a called CpG (:229-232, 444)
+			bool ref_cpg, ok = false;
+			uint32_t ca = 0, cb = 0;
+			if (d.gt == 4) {                       // '+' strand
+				ref_cpg = d.rc[2] == 2 && d.rc[3] == 3;
+				ca = (uint32_t)v->counts[5]; cb = (uint32_t)v->counts[7];
+				ok = true;
+			} else {                               // '-' strand (gt == 7): pairs with the '+' site before it when that one was counted
+				ref_cpg = d.rc[1] == 2 && d.rc[2] == 3;
+				// (a launch over a later chunk of the window cannot read the record of the site before its first one any more:
+				// the launch before left what is needed in stats_carry)
+				uint32_t prev;
+				if (i > a.i0) {
+					int gp[5];
+					SiteDer dpv;
+					window_calls(a, i - 1, first, last, gp);
+					prev = derive_site(a, i - 1, first, last, gp, dpv) && !dpv.skip ? (dpv.flt ? 2u : 1u) : 0u;
+				} else prev = a.i0 ? a.stats_carry[a.carry_flip ^ 1u] : 0u;
+				if (prev) {
+					atomicAdd(&h[H_MISC + (ref_cpg ? 8 : 10)], 1u);
+					if (!(prev == 2u || d.flt)) atomicAdd(&h[H_MISC + (ref_cpg ? 9 : 11)], 1u);
+				}
+				ca = (uint32_t)v->counts[6]; cb = (uint32_t)v->counts[4];
+				ok = true;
+			}
+			if (ok) {
+				atomicAdd(&h[H_QUAL + (ref_cpg ? 512 : 768) + d.phred], 1u);
+				if (dp < (uint32_t)BSGPU_STATS_COV_MAX) add_u64(&st->cov[dp].CpG[ref_cpg ? 0 : 1], 1u);
+				if (d.dinf < (uint32_t)BSGPU_STATS_COV_MAX) add_u64(&st->cov[d.dinf].CpG_inf[ref_cpg ? 0 : 1], 1u); else add_u64(&st->cov_overflow, 1u);
+				if (ca + cb) {
+					const uint32_t e = atomicAdd(&cg_n, 1u);
+					cg_a[e] = ca; cg_b[e] = cb; cg_w[e] = (ref_cpg ? 0u : 2u) | (pass ? 4u : 0u);
+				}
+			}
+		}
+		// mutation spectrum (mut_type, :47-58): the call's non-reference allele(s) against the reference base
+		if (d.rfix) {
+			int mut = -1;
+			const int alt = a0 != d.rfix ? (a1 != d.rfix && a1 != a0 ? -1 : a0) : (a1 != d.rfix ? a1 : -1);
+			// the table has an entry where exactly one allele differs from the reference base, or both are the same other base
+			// stats_mut order (include/bs_call.h:46): reference base major, the three other bases in base order
+			if (alt > 0) mut = 3 * (d.rfix - 1) + (alt - 1) - (alt > d.rfix ? 1 : 0);
+			if (mut >= 0) {
+				atomicAdd(&h[H_MUT + 2 * mut], 1u);
+				if (pass) atomicAdd(&h[H_MUT + 2 * mut + 1], 1u);
+				if (d.rs_found) { atomicAdd(&h[H_DBMUT + 2 * mut], 1u); if (pass) atomicAdd(&h[H_DBMUT + 2 * mut + 1], 1u); }
+			}
+		}
+	}
+	if (i + 1 == a.i1 && a.stats_carry) a.stats_carry[a.carry_flip] = visited && !d.skip ? (d.flt ? 2u : 1u) : 0u;
+	__syncthreads();
+	// methylation posterior of every pooled CpG strand (:484-514): one warp per entry, lanes over the 101 levels
+	const uint32_t ncg = cg_n;
+	if (ncg) {
+		if (tid < 100) logp[tid] = log(0.01 * (double)(tid + 1));
+		__syncthreads();
+		for (uint32_t e = tid >> 5; e < ncg; e += kWrThreads / 32) {
+			const uint32_t ca = cg_a[e], cb = cg_b[e], w = cg_w[e];
+			const double konst = lgamma((double)(ca + cb + 1) + 1.0) - lgamma((double)ca + 1.0) - lgamma((double)cb + 1.0);
+			const double da = (double)ca, db = (double)cb;
+			double m[4], sum = 0.0;
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const int k = lane + 32 * q;
+				double z = 0.0;
+				if (k == 0) z = ca ? 0.0 : exp(konst);
+				else if (k == 100) z = cb ? 0.0 : exp(konst);
+				else if (k < 100) z = exp(konst + logp[k - 1] * da + logp[99 - k] * db);
+				m[q] = z; sum += z;
+			}
+#pragma unroll
+			for (int s = 16; s; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const int k = lane + 32 * q;
+				if (k <= 100 && m[q] != 0.0) {
+					const double z = m[q] / sum;
+					atomicAdd(&meth[w & 2u][k], z);
+					if (w & 4u) atomicAdd(&meth[(w & 2u) + 1][k], z);
+				}
+			}
+		}
+		__syncthreads();
+		for (int k = tid; k < 404; k += kWrThreads) {
+			const double z = (&meth[0][0])[k];
+			if (z != 0.0) {
+				const int row = k / 101, col = k - row * 101;
+				atomicAdd(row < 2 ? &st->CpG_ref_meth[row][col] : &st->CpG_nonref_meth[row - 2][col], z);
+			}
+		}
+	}
+	// flush the histograms
+	for (int k = tid; k < H_END; k += kWrThreads) {
+		const uint32_t c = h[k];
+		if (!c) continue;
+		uint64_t *dst;
+		if (k < H_MUT) {
+			static_assert(offsetof(bsgpu_site_stats, multi) == 16 && offsetof(bsgpu_site_stats, CpG_nonref) == 80, "bsgpu_site_stats layout");
+			// misc slots: snps 0-1, multi 2-3, dbSNP_sites 4-5, dbSNP_var 6-7, CpG_ref 8-9, CpG_nonref 10-11 = the first twelve words
+			dst = (uint64_t *)st + k;
+			if (a.ctg_stats) add_u64((uint64_t *)a.ctg_stats + k, c);
+		} else if (k < H_DBMUT) dst = &st->mut_counts[0][0] + (k - H_MUT);
+		else if (k < H_QUAL) dst = &st->dbSNP_mut_counts[0][0] + (k - H_DBMUT);
+		else if (k < H_FLT) dst = &st->qual[0][0] + (k - H_QUAL);
+		else if (k < H_QD) dst = &st->filter_counts[0][0] + (k - H_FLT);
+		else if (k < H_MQ) dst = &st->qd_stats[0][0] + (k - H_QD);
+		else if (k < H_FS) dst = &st->mq_stats[0][0] + (k - H_MQ);
+		else dst = &st->fs_stats[0][0] + (k - H_FS);
+		add_u64(dst, c);
+	}
+}
+
 }  // namespace
 
 // per-site scratch of a window (calls, lengths) and per-CTA scratch of one launch over `cnt` sites
@@ -479,6 +742,9 @@ static WrArgs writer_args(const BcfJob &j, uint32_t i0, uint32_t cnt) {
 	a.cta_bytes = nullptr; a.cta_recs = nullptr; a.totals = nullptr; a.out = nullptr; a.out_cap = 0;
 	a.guard = j.guard;
 	a.db = j.db; a.reg_start = j.reg_start; a.reg_stop = j.reg_stop;
+	a.stats = (bsgpu_site_stats *)j.stats;
+	a.ctg_stats = j.ctg_stats && j.p.rid >= 0 && (uint32_t)j.p.rid < j.n_ctg ? (bsgpu_ctg_site_stats *)j.ctg_stats + j.p.rid : nullptr;
+	a.gc = j.gc; a.gc_bins = j.gc_bins; a.gc_start = j.gc_start; a.stats_carry = j.stats_carry; a.carry_flip = j.stats_carry_flip & 1u;
 	return a;
 }
 
@@ -505,6 +771,10 @@ cudaError_t launch_bcf_records(const BcfJob &j, uint32_t i0, uint32_t cnt, void 
 	k_bcf_offsets<<<1, 1024, 0, stream>>>(a.cta_bytes, a.cta_recs, nctas, d_totals);
 	k_bcf_emit<<<nctas, kWrThreads, kStageBytes + 16, stream>>>(a);
 	__atomic_fetch_add(launches, 3, __ATOMIC_RELAXED);
+	if (a.stats) {                  // the calls of the sites and of their neighbours exist now
+		k_bcf_stats<<<nctas, kWrThreads, 0, stream>>>(a);
+		__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
+	}
 	return cudaGetLastError();
 }
 
