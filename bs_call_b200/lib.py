@@ -23,6 +23,7 @@ EXPORTS = [
     "bsgpu_sync", "bsgpu_guard_read", "bsgpu_host_alloc", "bsgpu_host_free",
     "bsgpu_call_sites", "bsgpu_pileup_block", "bsgpu_call_block", "bsgpu_stage_bound", "bsgpu_stage_templates",
     "bsgpu_process_block", "bsgpu_profile_enable", "bsgpu_profile_read", "bsgpu_build_blocks_tally",
+    "bsgpu_site_stats_enable", "bsgpu_set_contig_gc", "bsgpu_site_stats_read",
     "bsgpu_call_bam_bcf", "bsgpu_default_bcf_params", "bsgpu_set_contig_annotation", "bsgpu_bcf_block", "bsgpu_bcf_block_dev", "bsgpu_call_block_bcf", "bsgpu_call_sites_bcf",
     "bsgpu_default_reader_params", "bsgpu_decode_records", "bsgpu_build_blocks", "bsgpu_call_bam",
     "bsgpu_bam_open", "bsgpu_bam_set_contig", "bsgpu_bam_feed", "bsgpu_bam_reserve", "bsgpu_bam_commit", "bsgpu_bam_finish", "bsgpu_bam_cut", "bsgpu_bam_rewind", "bsgpu_bam_drain",
@@ -330,6 +331,23 @@ class BsGpu:
         conv = np.ctypeslib.as_array(pr.conv_cts).reshape(PROFILE_MAX, 4)
         return dict(used=int(pr.used), conv=conv[:pr.used].copy(), base_filter=np.array(list(pr.base_filter), dtype=np.uint64),
                     filter_cts=np.array(list(pr.filter_cts), dtype=np.uint64), filter_bases=np.array(list(pr.filter_bases), dtype=np.uint64))
+
+    def site_stats_enable(self, on=True, n_contigs=0):
+        """gather the writer's --report-file statistics (src/print_vcf.c:382-526) in every entry point that writes BCF records"""
+        self._check(self.lib.bsgpu_site_stats_enable(self.ctx, C.c_int(1 if on else 0), C.c_int(int(n_contigs))))
+
+    def set_contig_gc(self, rid, gc, start_pos=1):
+        """GC percentage of every 100-base bin of contig `rid` from start_pos on (ctg_stats->gc)"""
+        gc = np.ascontiguousarray(gc, dtype=np.uint8)
+        self._check(self.lib.bsgpu_set_contig_gc(self.ctx, C.c_int(int(rid)), C.c_uint32(int(start_pos)), _ptr(gc), C.c_uint32(len(gc))))
+
+    def site_stats_read(self, n_contigs=0, reset=False):
+        """-> (SITE_STATS record array of length 1, CTG_SITE_STATS[n_contigs])"""
+        from .records import SITE_STATS, CTG_SITE_STATS
+        st = np.zeros(1, dtype=SITE_STATS)
+        ctg = np.zeros(max(int(n_contigs), 1), dtype=CTG_SITE_STATS)
+        self._check(self.lib.bsgpu_site_stats_read(self.ctx, _ptr(st), _ptr(ctg) if n_contigs else None, C.c_int(int(n_contigs)), C.c_int(1 if reset else 0)))
+        return st, ctg[:int(n_contigs)]
 
     # ---- reader side ----------------------------------------------------------------------------
     def decode_records(self, bam, rp=None, want_reads=True):

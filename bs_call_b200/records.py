@@ -30,3 +30,17 @@ assert TEMPLATE.itemsize == 56
 assert MISMS.itemsize == 12
 
 GENOTYPES = ("AA", "AC", "AG", "AT", "CC", "CG", "CT", "GG", "GT", "TT")
+
+
+# bsgpu_site_stats (include/bsgpu.h): the writer's --report-file statistics, flat
+STATS_FS_MAX = 4096
+STATS_COV_MAX = 4096
+COV_STATS = np.dtype([("var", "<u8"), ("CpG", "<u8", (2,)), ("CpG_inf", "<u8", (2,)), ("all", "<u8"), ("gc_pcent", "<u8", (101,))])
+SITE_STATS = np.dtype([
+    ("snps", "<u8", (2,)), ("multi", "<u8", (2,)), ("dbSNP_sites", "<u8", (2,)), ("dbSNP_var", "<u8", (2,)), ("CpG_ref", "<u8", (2,)), ("CpG_nonref", "<u8", (2,)),
+    ("mut_counts", "<u8", (12, 2)), ("dbSNP_mut_counts", "<u8", (12, 2)), ("qual", "<u8", (4, 256)), ("filter_counts", "<u8", (2, 32)),
+    ("CpG_ref_meth", "<f8", (2, 101)), ("CpG_nonref_meth", "<f8", (2, 101)),
+    ("qd_stats", "<u8", (256, 2)), ("mq_stats", "<u8", (256, 2)), ("fs_stats", "<u8", (STATS_FS_MAX, 2)),
+    ("fs_overflow", "<u8"), ("cov_overflow", "<u8"), ("cov", COV_STATS, (STATS_COV_MAX,))])
+CTG_SITE_STATS = np.dtype([("snps", "<u8", (2,)), ("multi", "<u8", (2,)), ("dbSNP_sites", "<u8", (2,)), ("dbSNP_var", "<u8", (2,)),
+                           ("CpG_ref", "<u8", (2,)), ("CpG_nonref", "<u8", (2,))])
