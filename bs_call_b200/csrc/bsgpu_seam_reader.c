@@ -36,6 +36,8 @@
 
 static bsgpu_ctx *g_ctx;
 static int g_profile;
+static int g_site_stats;         /* seam D with --report-file: the statistics of print_vcf.c:382-526 are gathered on the device too */
+static int g_site_ctgs;
 
 static void die(const char *what) {
 	gt_fatal_error_msg("bsgpu: %s: %s\n", what, bsgpu_last_error());
@@ -88,10 +90,68 @@ static void fold_profile(bs_stats * const stats) {
 	free(pr);
 }
 
+/* what _print_vcf_entry() would have added to bs_stats and the contigs' ctg_stats for the sites the device wrote (seam D) */
+static void add_vec(gt_vector * const v, const uint64_t (*src)[2], const int n) {
+	int top = -1;
+	for (int i = 0; i < n; i++) if (src[i][0] | src[i][1]) top = i;
+	if (top < 0) return;
+	if ((uint64_t)top >= v->elements_allocated) gt_vector_reserve(v, top + 1, true);
+	if ((uint64_t)top >= v->used) v->used = top + 1;
+	for (int i = 0; i <= top; i++) { fstats_cts * const c = gt_vector_get_elm(v, i, fstats_cts); c->cts[0] += src[i][0]; c->cts[1] += src[i][1]; }
+}
+
+static void fold_site_stats(sr_param * const param) {
+	work_t * const work = &param->work;
+	bs_stats * const stats = work->stats;
+	bsgpu_site_stats *ss = malloc(sizeof(bsgpu_site_stats));
+	bsgpu_ctg_site_stats *cs = calloc((size_t)(g_site_ctgs > 0 ? g_site_ctgs : 1), sizeof(bsgpu_ctg_site_stats));
+	if (ss == NULL || cs == NULL || bsgpu_site_stats_read(g_ctx, ss, cs, g_site_ctgs, 1) != BSGPU_OK) die("bsgpu_site_stats_read");
+	for (int k = 0; k < 2; k++) {
+		stats->snps[k] += ss->snps[k]; stats->multi[k] += ss->multi[k]; stats->dbSNP_sites[k] += ss->dbSNP_sites[k]; stats->dbSNP_var[k] += ss->dbSNP_var[k];
+		stats->CpG_ref[k] += ss->CpG_ref[k]; stats->CpG_nonref[k] += ss->CpG_nonref[k];
+		for (int m = 0; m < 12; m++) { stats->mut_counts[m][k] += ss->mut_counts[m][k]; stats->dbSNP_mut_counts[m][k] += ss->dbSNP_mut_counts[m][k]; }
+		for (int i = 0; i < 101; i++) { stats->CpG_ref_meth[k][i] += ss->CpG_ref_meth[k][i]; stats->CpG_nonref_meth[k][i] += ss->CpG_nonref_meth[k][i]; }
+		for (int f = 0; f < 32; f++) stats->filter_counts[k][f] += ss->filter_counts[k][f];
+	}
+	for (int q = 0; q < 4; q++) for (int i = 0; i < 256; i++) stats->qual[q][i] += ss->qual[q][i];
+	add_vec(stats->qd_stats, ss->qd_stats, 256);
+	add_vec(stats->mq_stats, ss->mq_stats, 256);
+	add_vec(stats->fs_stats, ss->fs_stats, BSGPU_STATS_FS_MAX);
+	for (uint32_t c = 0; c < BSGPU_STATS_COV_MAX; c++) {
+		const bsgpu_cov_stats * const g = ss->cov + c;
+		if (!(g->all | g->var | g->CpG[0] | g->CpG[1] | g->CpG_inf[0] | g->CpG_inf[1])) continue;
+		gt_cov_stats *gcov;
+		HASH_FIND(hh, stats->cov_stats, &c, sizeof(uint32_t), gcov);
+		if (gcov == NULL) {
+			gcov = calloc((size_t)1, sizeof(gt_cov_stats));
+			gcov->coverage = c;
+			HASH_ADD(hh, stats->cov_stats, coverage, sizeof(uint32_t), gcov);
+		}
+		gcov->all += g->all; gcov->var += g->var;
+		for (int k = 0; k < 2; k++) { gcov->CpG[k] += g->CpG[k]; gcov->CpG_inf[k] += g->CpG_inf[k]; }
+		for (int i = 0; i < 101; i++) gcov->gc_pcent[i] += g->gc_pcent[i];
+	}
+	if (ss->fs_overflow | ss->cov_overflow)
+		fprintf(stderr, "bsgpu: %" PRIu64 " site(s) with FS >= %d and %" PRIu64 " with a depth >= %d are missing from the report's histograms\n",
+				ss->fs_overflow, BSGPU_STATS_FS_MAX, ss->cov_overflow, BSGPU_STATS_COV_MAX);
+	for (int k = 0; k < (int)work->n_contigs; k++) {
+		ctg_t * const ctg = work->contigs[k];
+		if (ctg->ctg_stats == NULL || ctg->vcf_rid < 0 || ctg->vcf_rid >= g_site_ctgs) continue;
+		const bsgpu_ctg_site_stats * const c = cs + ctg->vcf_rid;
+		for (int j = 0; j < 2; j++) {
+			ctg->ctg_stats->snps[j] += c->snps[j]; ctg->ctg_stats->multi[j] += c->multi[j]; ctg->ctg_stats->dbSNP_sites[j] += c->dbSNP_sites[j];
+			ctg->ctg_stats->dbSNP_var[j] += c->dbSNP_var[j]; ctg->ctg_stats->CpG_ref[j] += c->CpG_ref[j]; ctg->ctg_stats->CpG_nonref[j] += c->CpG_nonref[j];
+		}
+	}
+	free(ss); free(cs);
+}
+
 void join_calc_threads(sr_param * const param) {
 	work_t * const work = &param->work;
 	work->calc_end = true;
 	if (g_profile && work->stats != NULL) fold_profile(work->stats);
+	if (g_site_stats && work->stats != NULL) fold_site_stats(param);
+	g_site_stats = 0;
 	bsgpu_destroy(g_ctx);
 	g_ctx = NULL;
 	pthread_mutex_lock(&work->vcf_mutex);
@@ -253,6 +313,14 @@ gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param
 	if (work->stats != NULL) {
 		if (bsgpu_profile_enable(g_ctx, 1) != BSGPU_OK) die("bsgpu_profile_enable");
 		g_profile = 1;
+		if (tk.records && !g_site_stats) {
+			/* seam D: no gt_vcf record reaches the reference's writer, so its per-site statistics are gathered where the
+			 * records are built (per-contig counters by vcf_rid) */
+			g_site_ctgs = 0;
+			for (int k = 0; k < (int)work->n_contigs; k++) if (work->contigs[k]->vcf_rid >= g_site_ctgs) g_site_ctgs = work->contigs[k]->vcf_rid + 1;
+			if (bsgpu_site_stats_enable(g_ctx, 1, g_site_ctgs) != BSGPU_OK) die("bsgpu_site_stats_enable");
+			g_site_stats = 1;
+		}
 	}
 	bsgpu_bcf_params bp;
 	int32_t *rid = NULL;
@@ -317,6 +385,8 @@ gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param
 				}
 				prev_ctg = ctg;
 				if (bsgpu_bam_set_contig(tk.sess, curr_tid, tk.codes[curr_tid]) != BSGPU_OK) die("bsgpu_bam_set_contig");
+				if (g_site_stats && ctg->ctg_stats != NULL && ctg->ctg_stats->gc != NULL
+						&& bsgpu_set_contig_gc(g_ctx, ctg->vcf_rid, ctg->start_pos, ctg->ctg_stats->gc, (uint32_t)ctg->ctg_stats->nbins) != BSGPU_OK) die("bsgpu_set_contig_gc");
 			}
 		}
 		if (chr_skip || c->tid < 0) continue;               /* records without a wanted contig never reach a block */

@@ -684,6 +684,7 @@ static uint8_t *pv_out;
 static size_t pv_cap, pv_len, pv_nrec;
 static int pv_overflow;
 static struct { bsref_block *blocks; size_t cap, n; gt_vcf *vcf; size_t vcf_cap, nvcf; int err; } seam;
+static gt_ctg_stats *seam_ctg_sum;       /* sum of the contigs' ctg_stats after the last run with statistics */
 
 static void *seam_print_thread(void *arg) {
 	work_t * const w = &par.work;
@@ -760,6 +761,27 @@ int bsref_seam_read_input(const uint8_t *bam, size_t nbytes, int n_targets, cons
 		ctgs[i].start_pos = 1; ctgs[i].end_pos = len; ctgs[i].seq_len = len;
 		w->contigs[i] = ctgs + i;
 		w->tid2id[i] = i;
+		if (w->stats != NULL) {
+			/* --report-file: the contig's statistics block with GC bins (src/read_reference.c:120-123 computes them while it loads
+			 * the sequence; here: percentage of C / G among the known bases of every 100-base bin) */
+			gt_ctg_stats *cs = calloc(1, sizeof(gt_ctg_stats));
+			cs->nbins = (int)((len + 99) / 100);
+			cs->gc = malloc((size_t)cs->nbins + 1);
+			for (int b = 0; b < cs->nbins; b++) {
+				uint32_t known = 0, gcn = 0;
+				for (uint32_t j = (uint32_t)b * 100; j < len && j < (uint32_t)b * 100 + 100; j++) { const int c = ctg_codes[i][j] & 7; known += c != 0; gcn += c == 2 || c == 3; }
+				cs->gc[b] = known ? (uint8_t)(100 * gcn / known) : 255;
+			}
+			ctgs[i].ctg_stats = cs;
+		}
+	}
+	if (w->stats != NULL && w->stats->qd_stats == NULL) {          /* what init_stats() sets up (src/stats.c:304-318) */
+		w->stats->qd_stats = gt_vector_new(256, sizeof(fstats_cts));
+		w->stats->fs_stats = gt_vector_new(256, sizeof(fstats_cts));
+		w->stats->mq_stats = gt_vector_new(256, sizeof(fstats_cts));
+		memset(w->stats->qd_stats->memory, 0, sizeof(fstats_cts) * w->stats->qd_stats->elements_allocated);
+		memset(w->stats->fs_stats->memory, 0, sizeof(fstats_cts) * w->stats->fs_stats->elements_allocated);
+		memset(w->stats->mq_stats->memory, 0, sizeof(fstats_cts) * w->stats->mq_stats->elements_allocated);
 	}
 	w->n_contigs = n_targets; w->n_regions = 0; w->sam_idx = NULL; w->sam_header = &hdr; w->curr_region = NULL;
 	w->process_end = false; w->print_end = false; w->vcf_n = 0; w->vcf_ctg = NULL;
@@ -780,6 +802,23 @@ int bsref_seam_read_input(const uint8_t *bam, size_t nbytes, int n_targets, cons
 	pthread_join(thr, NULL);
 	*nblocks = seam.n; *nvcf = seam.nvcf; *bcf_bytes = pv_len; *bcf_nrec = pv_nrec;
 	w->vcf = saved_vcf; w->vcf_size = saved_size;          /* work->vcf pointed into the session's results: gone now */
+	if (w->stats != NULL) {
+		/* end of the run as far as the side channels go: the seam folds what the device gathered into bs_stats and the contigs'
+		 * ctg_stats (main() calls join_calc_threads before it writes the report); keep the last contig's counters readable */
+		static gt_ctg_stats seam_last;
+		join_calc_threads(&par);
+		init_calc_threads(&par);
+		memset(&seam_last, 0, sizeof(seam_last));
+		for (int i = 0; i < n_targets; i++) {
+			const gt_ctg_stats *c = ctgs[i].ctg_stats;
+			for (int k = 0; k < 2; k++) {
+				seam_last.snps[k] += c->snps[k]; seam_last.multi[k] += c->multi[k]; seam_last.dbSNP_sites[k] += c->dbSNP_sites[k];
+				seam_last.dbSNP_var[k] += c->dbSNP_var[k]; seam_last.CpG_ref[k] += c->CpG_ref[k]; seam_last.CpG_nonref[k] += c->CpG_nonref[k];
+			}
+		}
+		seam_ctg_sum = &seam_last;
+		for (int i = 0; i < n_targets; i++) { if (ctgs[i].ctg_stats->gc) free(ctgs[i].ctg_stats->gc); free(ctgs[i].ctg_stats); }
+	}
 	for (int i = 0; i < n_targets; i++) { free(hdr.target_name[i]); free(ctgs[i].seq); }
 	free(hdr.target_name); free(w->contigs); free(w->tid2id); free(ctgs);
 	w->contigs = NULL; w->tid2id = NULL; w->sam_header = NULL;
@@ -971,6 +1010,9 @@ void bsref_writer_stats_read(bso_site_stats *o) {
 static gt_ctg_stats *pv_last_cstats;
 void bsref_writer_ctg_stats_read(uint64_t out[12]) {
 	memset(out, 0, 12 * sizeof(uint64_t));
+#ifdef BSREF_SEAM_READER
+	if (seam_ctg_sum) pv_last_cstats = seam_ctg_sum;
+#endif
 	if (!pv_last_cstats) return;
 	const gt_ctg_stats *c = pv_last_cstats;
 	const uint64_t *src[6] = { c->snps, c->multi, c->dbSNP_sites, c->dbSNP_var, c->CpG_ref, c->CpG_nonref };

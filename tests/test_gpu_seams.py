@@ -128,3 +128,41 @@ def test_seam_c_oracle_streams(seam_c, oracle, seed, monkeypatch):
         assert (b["tid"], b["x"], b["y"]) == (w["tid"], w["x"], w["y"])
         sz = int(w["y"]) - int(w["x"]) + 1
         util.assert_vcf_close(vcf[int(b["vcf_off"]):int(b["vcf_off"]) + sz], wv[int(w["vcf_off"]):int(w["vcf_off"]) + sz])
+
+
+def test_seam_d_statistics_reach_the_report(seam_c, oracle, monkeypatch):
+    """seam D with --report-file: no gt_vcf record reaches the reference's writer, so what it would have added to bs_stats and
+    to the contigs' ctg_stats (src/print_vcf.c:382-526) is gathered on the device and folded in by join_calc_threads -- against
+    the pinned restatement over the blocks a seam C run of the same stream hands to the print thread"""
+    from oracle.bindings import SITE_STATS, site_stats_equal
+    from tests import blockgen
+    bam, n, tl, refs = bamgen.make_stream(640, n_contigs=3, dup=0.15, contig_len=9000)
+    o = dict(mapq_thresh=20, max_template_len=1000, keep_unmatched=False, ignore_duplicates=False, keep_duplicates=False)
+    monkeypatch.setenv("BSGPU_BATCH_BYTES", "70000")
+    monkeypatch.delenv("BSGPU_SEAM_RECORDS", raising=False)
+    blocks, vcf, _, _ = seam_c.seam_read_input(bam, tl, refs, **o)
+    want = np.zeros(1, dtype=SITE_STATS)
+    state = np.zeros(2, dtype=np.uint32)
+    for b in blocks:
+        x, y, tid = int(b["x"]), int(b["y"]), int(b["tid"])
+        codes = np.asarray(refs[tid], dtype=np.uint8) & 7
+        nb = (len(codes) + 99) // 100
+        pad = np.zeros(nb * 100, dtype=np.uint8)
+        pad[:len(codes)] = codes
+        known = (pad != 0).reshape(nb, 100).sum(axis=1)
+        gcn = ((pad == 2) | (pad == 3)).reshape(nb, 100).sum(axis=1)
+        gc = np.where(known > 0, 100 * gcn // np.maximum(known, 1), 255).astype(np.uint8)
+        v = vcf[int(b["vcf_off"]):int(b["vcf_off"]) + y - x + 1]
+        oracle.stats_block(v, blockgen.window_codes(refs[tid], x, y + 2), x, ctg_end=int(tl[tid]), gc=gc, start_pos=1, stats=want, state=state)
+    monkeypatch.setenv("BSGPU_SEAM_RECORDS", "1")
+    seam_c.stats_enable(True)
+    seam_c.writer_stats_reset()
+    try:
+        _, _, rec, nrec = seam_c.seam_read_input(bam, tl, refs, **o)
+        got, ctg = seam_c.writer_stats_read()
+    finally:
+        seam_c.stats_enable(False)
+    site_stats_equal(got[0], want[0], rtol=1e-9, what="seam D")
+    assert nrec > 300 and int(want[0]["snps"][0] + want[0]["multi"][0]) == nrec
+    assert np.array_equal(ctg[:, 0], [want[0][f][0] for f in ("snps", "multi", "dbSNP_sites", "dbSNP_var", "CpG_ref", "CpG_nonref")])
+    assert want[0]["cov"]["gc_pcent"].sum() > 1000
