@@ -23,6 +23,7 @@
 #include "bsgpu_device.cuh"
 #include "bsgpu_launch.h"
 #include "bsgpu_session.h"
+#include "bsgpu_wire.h"
 
 static_assert(sizeof(bsgpu_pileup) == 104, "pileup layout (include/bs_call.h:174-182)");
 static_assert(sizeof(bsgpu_gt_meth) == 200, "gt_meth layout (include/bs_call.h:152-160)");
@@ -118,7 +119,7 @@ struct PinBuf {                // grow-on-demand page-locked host buffer
 struct Slot {                  // one stage of the host-buffer pipelines
 	cudaStream_t stream = nullptr;
 	cudaEvent_t done = nullptr;
-	DevBuf in, ref, out, skip;
+	DevBuf in, ref, out, skip, wire;
 };
 
 struct bsgpu_ctx {
@@ -156,6 +157,11 @@ struct bsgpu_ctx {
 	uint32_t ring_pos = 0;                       // next output ring slot of the deferred runs
 	bool ring_busy[3] = {false, false, false};   // output ring slot may still be copying out (deferred block_run)
 	bsgpu_stats stats;
+	// results of the host-buffer entry points come home as wire records (bsgpu_wire.h): pool of rebuilding threads, pinned landing buffers
+	WireExpander *expander = nullptr;
+	PinBuf wire_pin[6];
+	cudaEvent_t wire_landed[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	int wire_mode = 0;                           // BSGPU_WIRE: 0 full records only (default), 1 adaptive (a chunk goes out in full when no landing buffer is free), 2 wire only
 	// dbSNP / region annotation: per contig (bsgpu_set_contig_annotation) and of the last single-contig call (params->dbsnp)
 	struct DbDev { DevBuf mask, fq, cum, off, names; uint32_t words = 0; uint32_t reg_start = 0, reg_stop = 0; uint64_t key[4] = {0, 0, 0, 0}; };
 	std::map<int, DbDev *> contig_ann;
@@ -292,10 +298,13 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 	for (auto &kv : c->contig_gc) if (kv.second) { kv.second->bins.release(); delete kv.second; }
 	c->contig_gc.clear();
 	for (int i = 0; i < 2; i++) {
-		c->slot[i].in.release(); c->slot[i].ref.release(); c->slot[i].out.release(); c->slot[i].skip.release();
+		c->slot[i].in.release(); c->slot[i].ref.release(); c->slot[i].out.release(); c->slot[i].skip.release(); c->slot[i].wire.release();
 		if (c->slot[i].stream) cudaStreamDestroy(c->slot[i].stream);
 		if (c->slot[i].done) cudaEventDestroy(c->slot[i].done);
 	}
+	delete c->expander;
+	for (PinBuf &b : c->wire_pin) b.release();
+	for (cudaEvent_t ev : c->wire_landed) if (ev) cudaEventDestroy(ev);
 	for (cudaEvent_t ev : c->win_events) cudaEventDestroy(ev);
 	for (bsgpu_ctx::ReaderSet &R : c->rs) {
 		for (cudaEvent_t ev : R.rd_up) cudaEventDestroy(ev);
@@ -471,6 +480,34 @@ int bsgpu_math_probe(const double *x, size_t n, double *out_log, double *out_exp
 	return BSGPU_OK;
 }
 
+// host side of the wire records (bsgpu_wire.h), exported for tests and for hosts that want the rebuilding pass on its own
+int bsgpu_wire_pack(const void *records, size_t n, size_t rec_bytes, const uint8_t *skip, void *wire) {
+	if (rec_bytes != sizeof(bsgpu_gt_meth) && rec_bytes != sizeof(bsgpu_gt_vcf)) return fail("bsgpu_wire_pack: rec_bytes must be 200 or 208");
+	if (n && (!records || !wire || (rec_bytes == sizeof(bsgpu_gt_meth) && !skip))) return fail("bsgpu_wire_pack: null buffer");
+	return wire_pack_host((const uint8_t *)records, n, rec_bytes, skip, (uint64_t *)wire) ? BSGPU_OK : fail("bsgpu_wire_pack: a field does not fit its wire width");
+}
+
+int bsgpu_wire_expand(const void *wire, size_t n, size_t rec_bytes, void *records, uint8_t *skip, int threads) {
+	if (rec_bytes != sizeof(bsgpu_gt_meth) && rec_bytes != sizeof(bsgpu_gt_vcf)) return fail("bsgpu_wire_expand: rec_bytes must be 200 or 208");
+	if (n && (!records || !wire || (rec_bytes == sizeof(bsgpu_gt_meth) && !skip))) return fail("bsgpu_wire_expand: null buffer");
+	if (((uintptr_t)wire | (uintptr_t)records) & 7) return fail("bsgpu_wire_expand: buffers must be 8-byte aligned");
+	if (!n) return BSGPU_OK;
+	if (threads <= 1) { wire_expand((const uint64_t *)wire, n, (uint8_t *)records, rec_bytes, skip); return BSGPU_OK; }
+	// through the pool, as the entry points do: one job per 256 Ki sites
+	WireExpander pool((unsigned)threads);
+	const size_t chunk = (size_t)1 << 18;
+	pool.set_buffers((int)((n + chunk - 1) / chunk));
+	size_t id = 0;
+	for (size_t a = 0; a < n; a += chunk, id++) {
+		WireExpander::Job j;
+		j.wire = (const uint64_t *)wire + a * kWireWords; j.n = n - a < chunk ? n - a : chunk; j.out = (uint8_t *)records + a * rec_bytes;
+		j.skip = skip ? skip + a : nullptr; j.rec_bytes = rec_bytes; j.buf = pool.acquire(); j.chunk_id = id;
+		pool.submit(j);
+	}
+	pool.wait_idle();
+	return BSGPU_OK;
+}
+
 // Sites whose result sits inside a guard band since the last reset: ids[k] = kind << 56 | site id, where the id is the
 // index of the site in the bsgpu_call_sites / _bcf call, or its position for the block and reader entry points.
 int bsgpu_guard_read(bsgpu_ctx *c, uint64_t *ids, size_t cap, size_t *n, int reset) {
@@ -499,16 +536,50 @@ int bsgpu_sync(bsgpu_ctx *c) {
 // ------------------------------------------------------------------------------------------------
 // host-buffer entry points
 // ------------------------------------------------------------------------------------------------
+// The pool that rebuilds records from wire chunks, made on first use: BSGPU_EXPAND_THREADS, else half of the cores (2..12)
+static WireExpander *wire_pool(bsgpu_ctx *c) {
+	if (!c->expander) {
+		const char *e = getenv("BSGPU_EXPAND_THREADS");
+		const int hw = (int)std::thread::hardware_concurrency();
+		int t = e ? atoi(e) : 0;
+		if (t <= 0) t = std::max(2, std::min(hw / 2, 12));
+		c->expander = new WireExpander((unsigned)t);
+		const char *m = getenv("BSGPU_WIRE");
+		c->wire_mode = m ? atoi(m) : 0;
+	}
+	return c->expander;
+}
+
+static void wire_wait_event(void *ev) { cudaEventSynchronize((cudaEvent_t)ev); }      // the pool's watcher thread: a chunk has landed
+
 // pileup[] -> gt_meth[] + skip[]: chunks ping-pong between two slots, each with its own stream, so the H2D of chunk
-// i+1 and the D2H of chunk i-1 overlap the kernel of chunk i (PCIe is full duplex).
+// i+1 and the D2H of chunk i-1 overlap the kernel of chunk i (PCIe is full duplex).  The way home is the narrow one
+// (201 against 105 bytes per site).  BSGPU_WIRE=1|2 sends a chunk's records as 120-byte wire records instead (k_wire_pack):
+// they land in one of a few pinned buffers and are rebuilt in `out` / `skip` by the expander pool while later chunks are
+// under way; with 1, a chunk goes home as full records when every landing buffer is still being rebuilt.
+// Measured (profiles/r02d_wire_ab.txt, 16 M sites, 16-core host of the B200 box): full records 238 - 248 M sites/s
+// (PCIe-bound, 50 GB/s home); wire 220 - 276 M whatever the pool size -- the rebuilding pass alone does 357 M sites/s on 8
+// threads and 464 M on 16 (149 GB/s of host memory traffic), but next to the two DMA streams the host's memory system is
+// the limit: wire records cost it 545 bytes per site (105 read by the H2D DMA, 120 written by the D2H DMA, 120 read and
+// 200 written by the pool) against 306 for full records.  Bit-identical either way; off by default.
 int bsgpu_call_sites(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t *ref, size_t n, bsgpu_gt_meth *out, uint8_t *skip) {
 	if (!c) return fail("bsgpu_call_sites: null context");
 	if (!n) return BSGPU_OK;
 	if (!pileup || !ref || !out || !skip) return fail("bsgpu_call_sites: null buffer");
 	CU(cudaSetDevice(c->device));
 	static const size_t chunk = [] { const char *e = getenv("BSGPU_SITES_CHUNK"); const long long v = e ? atoll(e) : 0; return v > 0 ? (size_t)v : (size_t)1 << 18; }();      // 256 Ki sites: 252 M sites/s against 243 M with 1 Mi (the pipeline fills sooner)
-	size_t ci = 0;
-	for (size_t first = 0; first < n; first += chunk, ci++) {
+	WireExpander *pool = wire_pool(c);
+	const int nland = (int)(sizeof(c->wire_pin) / sizeof(c->wire_pin[0]));
+	const size_t wire_bytes = chunk * kWireBytes + 8;
+	if (c->wire_mode) {
+		pool->wait_idle();
+		for (PinBuf &b : c->wire_pin) CU(b.reserve(wire_bytes));
+		for (cudaEvent_t &ev : c->wire_landed) if (!ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+		pool->set_buffers(nland);
+		pool->failed();
+	}
+	uint64_t wire_sites = 0, d2h = 0;
+	auto run_chunk = [&](size_t ci, size_t first, bool allow_wire) -> int {
 		Slot &s = c->slot[ci & 1];
 		const size_t m = n - first < chunk ? n - first : chunk;
 		CU(cudaStreamSynchronize(s.stream));      // the slot's previous chunk has fully left the device
@@ -516,16 +587,61 @@ int bsgpu_call_sites(bsgpu_ctx *c, const bsgpu_pileup *pileup, const uint8_t *re
 		CU(s.ref.reserve(m));
 		CU(s.out.reserve(m * sizeof(bsgpu_gt_meth)));
 		CU(s.skip.reserve(m));
+		int land = -1;
+		if (allow_wire && c->wire_mode) {
+			land = pool->acquire();
+			while (land < 0 && c->wire_mode == 2) { std::this_thread::yield(); land = pool->acquire(); }
+		}
 		CU(cudaMemcpyAsync(s.in.p, pileup + first, m * sizeof(bsgpu_pileup), cudaMemcpyHostToDevice, s.stream));
 		CU(cudaMemcpyAsync(s.ref.p, ref + first, m, cudaMemcpyHostToDevice, s.stream));
 		CU(launch_call_sites(s.in.p, s.ref.p, m, s.out.p, s.skip.p, false, c->d_const, c->d_counters, s.stream, &c->launches, first, true));      // two chunk streams
-		CU(cudaMemcpyAsync(out + first, s.out.p, m * sizeof(bsgpu_gt_meth), cudaMemcpyDeviceToHost, s.stream));
-		CU(cudaMemcpyAsync(skip + first, s.skip.p, m, cudaMemcpyDeviceToHost, s.stream));
+		if (land >= 0) {
+			cudaError_t e = s.wire.reserve(wire_bytes);
+			if (e == cudaSuccess) e = launch_wire_pack(s.out.p, s.skip.p, m, s.wire.p, s.stream, &c->launches);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(c->wire_pin[land].p, s.wire.p, m * kWireBytes + 8, cudaMemcpyDeviceToHost, s.stream);
+			if (e != cudaSuccess) { pool->give_back(land); return fail("bsgpu_call_sites: wire stage: %s", cudaGetErrorString(e)); }
+			WireExpander::Job job;
+			job.wire = (const uint64_t *)c->wire_pin[land].p;
+			job.flag = job.wire + m * kWireWords;
+			job.n = m;
+			job.out = (uint8_t *)(out + first);
+			job.skip = skip + first;
+			job.rec_bytes = sizeof(bsgpu_gt_meth);
+			job.buf = land;
+			job.chunk_id = ci;
+			job.wait_landed = wire_wait_event;
+			job.wait_arg = c->wire_landed[land];
+			e = cudaEventRecord(c->wire_landed[land], s.stream);
+			if (e != cudaSuccess) { pool->give_back(land); return fail("bsgpu_call_sites: cudaEventRecord: %s", cudaGetErrorString(e)); }
+			pool->submit(job);
+			wire_sites += m;
+			d2h += m * kWireBytes + 8;
+		} else {
+			CU(cudaMemcpyAsync(out + first, s.out.p, m * sizeof(bsgpu_gt_meth), cudaMemcpyDeviceToHost, s.stream));
+			CU(cudaMemcpyAsync(skip + first, s.skip.p, m, cudaMemcpyDeviceToHost, s.stream));
+			d2h += m * (sizeof(bsgpu_gt_meth) + 1);
+		}
 		__atomic_fetch_add(&c->stats.h2d_bytes, (uint64_t)(m * (sizeof(bsgpu_pileup) + 1)), __ATOMIC_RELAXED);
-		__atomic_fetch_add(&c->stats.d2h_bytes, (uint64_t)(m * (sizeof(bsgpu_gt_meth) + 1)), __ATOMIC_RELAXED);
+		return BSGPU_OK;
+	};
+	size_t ci = 0;
+	int rc = BSGPU_OK;
+	for (size_t first = 0; first < n && rc == BSGPU_OK; first += chunk, ci++) rc = run_chunk(ci, first, true);
+	cudaError_t e0 = cudaStreamSynchronize(c->slot[0].stream), e1 = cudaStreamSynchronize(c->slot[1].stream);
+	if (c->wire_mode) pool->wait_idle();          // also on failure: no thread may still be writing into the caller's arrays
+	if (rc != BSGPU_OK) return rc;
+	CU(e0);
+	CU(e1);
+	// chunks with a field too wide for the wire: once more, as full records
+	if (c->wire_mode) for (size_t bad : pool->failed()) {
+		const size_t m = n - bad * chunk < chunk ? n - bad * chunk : chunk;
+		if (run_chunk(bad, bad * chunk, false) != BSGPU_OK) return BSGPU_FAIL;
+		CU(cudaStreamSynchronize(c->slot[bad & 1].stream));
+		wire_sites -= m;
+		__atomic_fetch_add(&c->stats.wire_refetched_chunks, (uint64_t)1, __ATOMIC_RELAXED);
 	}
-	CU(cudaStreamSynchronize(c->slot[0].stream));
-	CU(cudaStreamSynchronize(c->slot[1].stream));
+	__atomic_fetch_add(&c->stats.d2h_bytes, d2h, __ATOMIC_RELAXED);
+	__atomic_fetch_add(&c->stats.wire_sites, wire_sites, __ATOMIC_RELAXED);
 	__atomic_fetch_add(&c->stats.sites, (uint64_t)(n), __ATOMIC_RELAXED);
 	return BSGPU_OK;
 }

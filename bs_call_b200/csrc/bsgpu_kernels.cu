@@ -977,6 +977,58 @@ cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, voi
 	return cudaSuccess;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wire records (bsgpu_wire.h): the 120 informative bytes of each gt_meth / gt_vcf record, for the trip over PCIe.
+// One thread per record; the records were written a moment ago by k_call_sites and are read back from L2.  A field that
+// does not fit its wire width raises the chunk's flag word (wire[n * 15]), which the launcher clears beforehand.
+// ------------------------------------------------------------------------------------------------
+template <int REC>
+__global__ void __launch_bounds__(256) k_wire_pack(const uint64_t *__restrict__ rec, const uint8_t *__restrict__ skip, uint32_t n,
+		uint64_t *__restrict__ wire) {
+	const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+	if (i >= n) return;
+	const uint64_t *r = rec + (size_t)i * (REC / 8);
+	uint64_t *w = wire + (size_t)i * 15;
+	uint64_t c[2] = {0, 0}, q = 0, wide = 0;
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const uint64_t v = r[j];
+		wide |= v >> 16;
+		c[j >> 2] |= (v & 0xffff) << 16 * (j & 3);
+	}
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		const uint64_t v = r[8 + j];
+		wide |= (v & 0xffffff00ffffff00ull);
+		q |= (v & 0xff) << 16 * j | (v >> 32 & 0xff) << (16 * j + 8);
+	}
+#pragma unroll
+	for (int g = 0; g < 11; g++) w[g] = r[12 + g];
+	const uint64_t m = r[23], b = r[24];
+	wide |= (m & 0xffffff00ffffff00ull);
+	uint64_t sk;
+	if constexpr (REC == 208) sk = r[25] >> 8 & 0xff;
+	else sk = skip[i];
+	w[11] = c[0];
+	w[12] = c[1];
+	w[13] = q;
+	w[14] = (m & 0xff) | (m >> 32 & 0xff) << 8 | (b & 0xff) << 16 | sk << 24;
+	if (wide) atomicOr((unsigned long long *)(wire + (size_t)n * 15), 1ull);
+}
+
+// records (gt_meth + skip[], or gt_vcf when skip == NULL) -> wire[n * 15 + 1]; the last word is the chunk's flag
+cudaError_t launch_wire_pack(const void *rec, const void *skip, size_t n, void *wire, cudaStream_t stream, int *launches) {
+	if (!n) return cudaSuccess;
+	cudaError_t e = cudaMemsetAsync((uint64_t *)wire + n * 15, 0, 8, stream);
+	if (e != cudaSuccess) return e;
+	const unsigned grid = (unsigned)((n + 255) / 256);
+	if (skip) k_wire_pack<200><<<grid, 256, 0, stream>>>((const uint64_t *)rec, (const uint8_t *)skip, (uint32_t)n, (uint64_t *)wire);
+	else k_wire_pack<208><<<grid, 256, 0, stream>>>((const uint64_t *)rec, nullptr, (uint32_t)n, (uint64_t *)wire);
+	__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+
 static size_t seg_area(size_t nseg) { return (nseg * sizeof(Cand) + 255) & ~(size_t)255; }
 static uint32_t scan_ctas(uint32_t ntiles) { return (ntiles + 1023) / 1024; }
 

@@ -20,6 +20,9 @@ cudaError_t launch_call_sites(const void *pileup, const void *ref, size_t n, voi
 		const DevConst *dc, unsigned long long *counters, cudaStream_t stream, int *launches, unsigned long long guard_base = 0,
 		bool overlap_safe = false);      // overlap_safe: other kernels may run next to this one (see the launcher)
 
+// n records of gt_meth (+ skip[]) or gt_vcf (skip == NULL) -> n wire records + the chunk's flag word (bsgpu_wire.h)
+cudaError_t launch_wire_pack(const void *rec, const void *skip, size_t n, void *wire, cudaStream_t stream, int *launches);
+
 // scratch needed by the segment binning of one block
 size_t pileup_scratch_bytes(size_t nseg, uint32_t sz);
 

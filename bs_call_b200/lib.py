@@ -31,7 +31,7 @@ EXPORTS = [
     "bsgpu_call_sites_dev", "bsgpu_call_sites_vcf_dev", "bsgpu_pileup_block_dev", "bsgpu_call_block_dev",
     "bsgpu_synth_sites_dev", "bsgpu_synth_block_nseg", "bsgpu_synth_block_dev",
     "bsgpu_synth_bam_bytes", "bsgpu_synth_bam_dev", "bsgpu_synth_ref_dev",
-    "bsgpu_math_probe",
+    "bsgpu_math_probe", "bsgpu_wire_pack", "bsgpu_wire_expand",
 ]
 
 
@@ -56,7 +56,7 @@ class Stats(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("qsum_overflow", C.c_uint64),
                 ("bam_decode_s", C.c_double), ("bam_build_s", C.c_double), ("bam_call_s", C.c_double),
                 ("near_tie_sites", C.c_uint64), ("exact_tie_sites", C.c_uint64), ("near_qual_sites", C.c_uint64), ("near_fs_sites", C.c_uint64),
-                ("long_segments", C.c_uint64)]
+                ("long_segments", C.c_uint64), ("wire_sites", C.c_uint64), ("wire_refetched_chunks", C.c_uint64)]
 
 
 PROFILE_MAX = 1024
@@ -601,6 +601,34 @@ def math_probe(x):
     lo, ex = np.zeros_like(x), np.zeros_like(x)
     lib.bsgpu_math_probe(_ptr(x), C.c_size_t(len(x)), _ptr(lo), _ptr(ex))
     return lo, ex
+
+
+WIRE_BYTES = 120
+
+
+def wire_pack(records, skip=None):
+    """records (GT_METH with skip[], or GT_VCF) -> (wire bytes [n, 120], ok) on the host (bsgpu_wire_pack)"""
+    lib = load()
+    records = np.ascontiguousarray(records)
+    n, rb = len(records), records.dtype.itemsize
+    wire = np.zeros((n, WIRE_BYTES), dtype=np.uint8)
+    rc = lib.bsgpu_wire_pack(_ptr(records), C.c_size_t(n), C.c_size_t(rb), _ptr(skip) if skip is not None else None, _ptr(wire))
+    return wire, rc == BSGPU_OK
+
+
+def wire_expand(wire, dtype, threads=1):
+    """wire bytes -> (records of `dtype`, skip[] or None) on the host, the pass the library runs on its own threads (bsgpu_wire_expand)"""
+    lib = load()
+    wire = np.ascontiguousarray(wire, dtype=np.uint8)
+    n = wire.size // WIRE_BYTES
+    rb = np.dtype(dtype).itemsize
+    out = np.full(n, 0, dtype=dtype)
+    out.view(np.uint8)[:] = 0xa5
+    skip = np.full(n, 0xa5, dtype=np.uint8) if rb == 200 else None
+    rc = lib.bsgpu_wire_expand(_ptr(wire), C.c_size_t(n), C.c_size_t(rb), _ptr(out), _ptr(skip) if skip is not None else None, C.c_int(threads))
+    if rc != BSGPU_OK:
+        raise RuntimeError(last_error(lib))
+    return out, skip
 
 
 def build_blocks(bam, rec, rp=None, tally=False):

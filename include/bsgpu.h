@@ -245,6 +245,10 @@ typedef struct {
 	 * bsgpu_guard_read lists them (up to 65536 between two resets). */
 	uint64_t near_tie_sites, exact_tie_sites, near_qual_sites, near_fs_sites;
 	uint64_t long_segments;    /* segments longer than BSGPU_MAX_SEG_LEN handed to a _dev entry point (contract violation) */
+	/* Host-buffer entry points return results over PCIe as 120-byte wire records and rebuild the reference's 200 / 208-byte
+	 * records in the caller's array on host threads (bs_call_b200/csrc/bsgpu_wire.h): sites that came home that way, and
+	 * chunks fetched again in full because a field did not fit its wire width (a count above 65535, a quality above 255) */
+	uint64_t wire_sites, wire_refetched_chunks;
 } bsgpu_stats;
 
 void bsgpu_default_params(bsgpu_params *p);
@@ -463,6 +467,18 @@ int bsgpu_synth_ref_dev(bsgpu_ctx *ctx, uint64_t seed, uint32_t x, uint32_t sz, 
 /* Evaluates, on the host, the table-driven log / exp the kernels use (same source; both sides are FMA-exact, so
  * these are the device's values).  out_log / out_exp may be NULL.  log: x positive normal; exp: x in [-700, 0]. */
 int bsgpu_math_probe(const double *x, size_t n, double *out_log, double *out_exp);
+
+/* ---- wire records ---- */
+/* What the host-buffer entry points send over PCIe instead of the reference's records (layout in
+ * bs_call_b200/csrc/bsgpu_wire.h: gt_prob[10], fisher_strand, counts as uint16, qualities as uint8, mq, aq, max_gt, skip;
+ * BSGPU_WIRE_BYTES each).  Host-only functions, no device needed:
+ * bsgpu_wire_pack    n records of rec_bytes (200: gt_meth, with skip[]; 208: gt_vcf, skip may be NULL) -> wire; BSGPU_FAIL if a
+ *                    field does not fit its wire width (the device then sends that chunk as full records)
+ * bsgpu_wire_expand  the rebuilding pass the library runs on its own threads: wire -> records (+ skip[] for rec_bytes 200),
+ *                    split over `threads` threads (<= 0: one) */
+#define BSGPU_WIRE_BYTES 120
+int bsgpu_wire_pack(const void *records, size_t n, size_t rec_bytes, const uint8_t *skip, void *wire);
+int bsgpu_wire_expand(const void *wire, size_t n, size_t rec_bytes, void *records, uint8_t *skip, int threads);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,13 @@ t0 = time.perf_counter()
 for _ in range(5):
     gpu.call_sites(hp.array, hr.array, out=ho.array, skip=hs.array)
 dt = (time.perf_counter() - t0) / 5
-print("chunk", os.environ.get("BSGPU_SITES_CHUNK", "default"), "sites/s %.1f M" % (int((hp.array["n"] > 0).sum()) / dt / 1e6), "ms %.2f" % (dt * 1e3), "D2H GB/s %.1f" % (n * 201 / dt / 1e9))
+import zlib
+st = gpu.stats()
+print("chunk", os.environ.get("BSGPU_SITES_CHUNK", "default"), "wire", os.environ.get("BSGPU_WIRE", "default"), "threads", os.environ.get("BSGPU_EXPAND_THREADS", "default"),
+      "cores", os.cpu_count(), "sites/s %.1f M" % (int((hp.array["n"] > 0).sum()) / dt / 1e6), "ms %.2f" % (dt * 1e3),
+      "wire share %.2f" % (st["wire_sites"] / max(1, st["sites"])), "crc", zlib.crc32(ho.array.view(np.uint8)), zlib.crc32(hs.array))
+if os.environ.get("E2E_ONLY_SITES"):
+    sys.exit(0)
 refw = np.concatenate([hr.array, [1, 1]]).astype(np.uint8)
 hrw = bslib.HostBuffer(n + 2, np.uint8); hrw.array[:] = refw
 hb = bslib.HostBuffer(n * 160, np.uint8)

@@ -153,3 +153,41 @@ def test_fast_math_accuracy():
     we = np.exp(xe.astype(np.longdouble))
     assert float(np.abs((ex.astype(np.longdouble) - we) / we).max()) < 2.3e-16      # about 1 ulp
     assert ex[-2] == 1.0
+
+
+def test_wire_records_round_trip():
+    """bsgpu_wire_pack / bsgpu_wire_expand (host side of the compact records the host-buffer entry points can send over PCIe,
+    bs_call_b200/csrc/bsgpu_wire.h): every byte of gt_meth / gt_vcf records comes back, on one thread and through the pool,
+    and a field too wide for the wire is refused."""
+    from bs_call_b200 import lib as bslib
+    from bs_call_b200.records import GT_METH, GT_VCF
+    rng = np.random.default_rng(1)
+    n = 300_001
+    for dt in (GT_METH, GT_VCF):
+        r = np.zeros(n, dtype=dt)
+        g = r if dt is GT_METH else r["gtm"]
+        g["counts"] = rng.integers(0, 65536, (n, 8))
+        g["qual"] = rng.integers(0, 256, (n, 8))
+        g["gt_prob"] = rng.standard_normal((n, 10))
+        g["fisher_strand"] = rng.standard_normal(n)
+        g["mq"] = rng.integers(0, 256, n)
+        g["aq"] = rng.integers(0, 256, n)
+        g["max_gt"] = rng.integers(0, 10, n)
+        sk = rng.integers(0, 2, n).astype(np.uint8)
+        if dt is GT_VCF:
+            r["ready"] = 1
+            r["skip"] = sk
+        w, ok = bslib.wire_pack(r, sk if dt is GT_METH else None)
+        assert ok and w.shape == (n, bslib.WIRE_BYTES)
+        for threads in (1, 3):
+            o, s2 = bslib.wire_expand(w, dt, threads)
+            assert o.tobytes() == r.tobytes()
+            assert s2 is None or (s2 == sk).all()
+        for field, val in (("counts", 65536), ("qual", 256), ("mq", 256), ("aq", -1)):
+            bad = r.copy()
+            gb = bad if dt is GT_METH else bad["gtm"]
+            if gb[field].ndim == 2:
+                gb[field][7, 3] = val
+            else:
+                gb[field][7] = val
+            assert not bslib.wire_pack(bad, sk if dt is GT_METH else None)[1], field

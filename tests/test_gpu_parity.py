@@ -360,3 +360,37 @@ def test_fused_variant_agrees(oracle):
         util.assert_pileup_equal(g.pileup_block(segs, g0["norm_bases"], x, y - x + 1), g0["pileup"])
         util.assert_vcf_close(g.call_block(segs, g0["norm_bases"], g0["ref"], x, y - x + 1), g0["vcf"])
         g.close()
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_call_sites_wire_records(gpu, mode, monkeypatch):
+    """BSGPU_WIRE: results cross PCIe as 120-byte wire records and are rebuilt by host threads (bsgpu_wire.h) -- the caller's
+    arrays must hold the same bytes as with full records, including a chunk that has to be fetched again because a count
+    does not fit the wire's 16 bits."""
+    rng = np.random.default_rng(77)
+    n = 2 * (1 << 18) + 1234                            # three chunks of the default size
+    p = np.zeros(n, dtype=PILEUP)
+    c = rng.poisson(3.0, (n, 2, 8)).astype(np.uint32)
+    c[rng.random(n) < 0.05] = 0
+    p["counts"] = c
+    p["n"] = c.sum(axis=(1, 2))
+    p["quality"] = (c.sum(axis=1) * rng.integers(20, 41, (n, 8))).astype(np.float32)
+    p["mapq2"] = (p["n"] * 3600).astype(np.float32)
+    p["counts"][(1 << 18) + 5, 0, 4] = 70000          # second chunk: too wide for the wire
+    p["n"][(1 << 18) + 5] += 70000
+    ref = rng.integers(0, 5, n).astype(np.uint8)
+    want, want_skip = gpu.call_sites(p, ref)
+    monkeypatch.setenv("BSGPU_WIRE", mode)
+    other = bslib.BsGpu(device=0)
+    try:
+        out = np.full(n, 0, dtype=want.dtype)
+        out.view(np.uint8)[:] = 0x5a
+        skip = np.full(n, 0x5a, dtype=np.uint8)
+        other.call_sites(p, ref, out=out, skip=skip)
+        st = other.stats()
+    finally:
+        other.close()
+    assert out.tobytes() == want.tobytes()
+    assert (skip == want_skip).all()
+    assert st["wire_refetched_chunks"] == 1
+    assert 0 < st["wire_sites"] <= n - (1 << 18)
