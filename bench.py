@@ -438,9 +438,14 @@ def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
     from bs_call_b200 import shard as _shard
     nl = max(1, min(int(args.genome_sessions), len(spans)))
     owner = _shard.lpt_assign([hi - lo for _, lo, hi in spans], nl)
+    # dbSNP annotation of the rank's contigs (configs[4] is specified with it): ids, and known sites that are written whatever was called
+    db = {c: sg.contig_dbsnp(SEED, c, lens[c]) for c in contigs}
+    db_entries = sum(len(v[0]) for v in db.values())
     lanes = []
     for k in range(nl):
         g = gpu if k == 0 else bslib.BsGpu(device=local)
+        for c in contigs:
+            g.set_contig_annotation(c, dbsnp=bslib.dbsnp(*db[c]))
         lanes.append({"gpu": g, "spans": [sp for sp, o in zip(spans, owner) if o == k],
                       "sess": g.bam_session(np.array(lens, dtype=np.uint32), codes, bcf=True, batch_bytes=int(args.genome_batch_mb) << 20)})
     SLICE = 32 << 20
@@ -557,12 +562,13 @@ def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
     split_contigs = sorted({r.contig for lst in plan for r in lst if not (r.start == 1 and r.stop == lens[r.contig])})
     loads = [sum(sg.region_templates(r, lens[r.contig])[1] - sg.region_templates(r, lens[r.contig])[0] for r in lst) for lst in plan]
     out = {"workload": "synthetic hg38-shaped genome, 24 contigs at 1/%d scale (%d positions), 30x paired-end %d-bp WGBS records with 5 %% duplicates and a "
-                       "coverage gap every ~100 kb; BASELINE.json configs[4] shape without dbSNP" % (scale, sum(lens), sg.READ_LEN),
+                       "coverage gap every ~100 kb, dbSNP annotation (one known site per %d positions, one in %d of them always written); BASELINE.json configs[4] shape" % (scale, sum(lens), sg.READ_LEN, sg.DBSNP_EVERY, sg.DBSNP_ALWAYS),
            "scaling": "strong", "value": float(tot[2].item()) / float(tmax[0].item()), "unit": "sites/s",
            "pass_s": float(tmax[0].item()), "pass_s_minmax": [float(tmax[2].item()), float(tmax[1].item())], "passes_timed": steps,
            "merge_s": merge_s, "value_with_merge": float(tot[2].item()) / (float(tmax[0].item()) + merge_s),
            "sites_called": int(tot[2].item()), "records_in_bytes": int(tot[3].item()), "bcf_records": int(tot[1].item()), "bcf_bytes": int(tot[0].item()),
            "result_batches": int(tot[4].item()), "extents_merged": len(merged),
+           "dbsnp_entries_rank0": db_entries,
            "plan": {"regions": sum(len(lst) for lst in plan), "contigs_split_at_block_boundaries": split_contigs,
                     "templates_per_rank": loads, "imbalance": max(loads) / (sum(loads) / len(loads))},
            "invariants": {"crc32_contig_%d" % c: (int(tot[5 + i].item()) if c not in split_contigs else None) for i, c in enumerate(small)},
@@ -593,7 +599,7 @@ def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
             for w in cb:
                 n_ = int(w["y"]) - int(w["x"]) + 1
                 wb_, _ = impl.print_block(cv[int(w["vcf_off"]):int(w["vcf_off"]) + n_], blockgen.window_codes(hc, int(w["x"]), int(w["y"]) + 2),
-                                          int(w["x"]), rid=c, ctg_end=lens[c])
+                                          int(w["x"]), rid=c, ctg_end=lens[c], dbsnp=db[c])
                 want.append(wb_)
             ws = time.perf_counter() - t0
             diff = bcf_diff(np.concatenate(keep_small[c]), np.concatenate(want))
@@ -696,6 +702,44 @@ def writer_path(args, gpu, bslib, torch, np, stream, rank, world, local):
                                "sample": "first %d sites (%d records): %s" % (m, wn, what), "parity_records_checked": wn, "parity_bytes_checked": len(wb)}
     for b in (hp, hr, ho):
         b.free()
+    return out
+
+
+def host_link_probe(torch, dist, world, mb=256, reps=6):
+    """What the box gives the host-buffer paths: pinned host <-> device copies with plain cudaMemcpyAsync
+    (one call per copy, torch's copy_), every rank of the run at the same time: H2D alone, D2H alone, both at once on two streams.
+    GB/s summed over the ranks; the e2e legs move 105 B up and 201 B down per site, so sites/s <= min(up / 105, down / 201)."""
+    n = mb << 20
+    hu = torch.empty(n, dtype=torch.uint8).pin_memory()
+    hd = torch.empty(n, dtype=torch.uint8).pin_memory()
+    du = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dd = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(up, down):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s_up):
+                    du.copy_(hu, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s_dn):
+                    hd.copy_(dd, non_blocking=True)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * reps * n / float(t.item()) / 1e9
+
+    run(True, True)
+    out = {"h2d_alone_gbs": run(True, False), "d2h_alone_gbs": run(False, True)}
+    both = run(True, True)
+    out.update({"h2d_and_d2h_each_gbs": both, "ranks": world, "copy_mb": mb,
+                "e2e_ceiling_sites_per_s": both * 1e9 / 201.0,
+                "note": "pinned host <-> device, one cudaMemcpyAsync per copy, all ranks at once; ceiling = the D2H rate with H2D running / 201 B per site"})
     return out
 
 
@@ -883,6 +927,7 @@ def main():
     assert (hs.array == (hp.array["n"] == 0)).all()
     for b in (hp, hr, ho, hs):
         b.free()
+    e2e["host_link"] = host_link_probe(torch, dist, world)
 
     # ---- block path (segments -> pileup -> model) on a synthetic 30x window (config 3 shape), device resident
     block = None

@@ -17,6 +17,8 @@
 // The byte encoding is BCF2 (VCF/BCF specification v4.3 section 6.3) as htslib's bcf_enc_* helpers produce it.
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <cuda_runtime.h>
 #include "bsgpu.h"
 #include "bsgpu_device.cuh"
@@ -143,48 +145,75 @@ __device__ bool block_of(const WrArgs &a, uint32_t i, uint32_t &first, uint32_t 
 	return true;
 }
 
+// Reference context of site i.  The reference fills its window with strncpy() from a string in which N is the terminator
+// (src/print_vcf.c:572-578), so once an N has been copied everything after it reads as N; the window starts at
+// site - 2, except for the last two sites of a block, which reuse the window of the block's last site
+// (flush_vcf_entries only shifts it, :539-543): an N up to two codes further left wipes them too.  Codes before the
+// block are N.
+__device__ __forceinline__ void ref_context(const WrArgs &a, uint32_t i, uint32_t first, uint32_t last, uint32_t rc[5]) {
+	const int64_t ii = i, f = first, l = last;
+	const int64_t wstart = ii + 2 <= l ? ii - 2 : l - 4;
+	bool wiped = false;
+	for (int64_t j = wstart < f ? f : wstart; j < ii - 2; j++) wiped |= a.ref[j] == 0;
+#pragma unroll
+	for (int k = 0; k < 5; k++) {
+		const int64_t j = ii + k - 2;
+		const uint32_t c = j >= f && !wiped ? a.ref[j] : 0u;
+		if (c == 0 && j >= f) wiped = true;
+		rc[k] = c;
+	}
+}
+
+// dbSNP (src/print_vcf.c:133): what dbSNP_lookup_name() answers for a position -- 0, 1 (known) or 3 (known, always written) and the ID
+__device__ __forceinline__ uint32_t dbsnp_lookup(const WrArgs &a, uint32_t pos, const uint8_t *&rs, uint32_t &rs_len) {
+	rs = nullptr;
+	rs_len = 0;
+	if ((pos >> 6) >= a.db.words) return 0;
+	const unsigned long long m = a.db.mask[pos >> 6], bit = 1ull << (pos & 63);
+	if (!(m & bit)) return 0;
+	const uint32_t k = a.db.cum[pos >> 6] + (uint32_t)__popcll(m & (bit - 1));
+	rs = a.db.names + a.db.off[k];
+	rs_len = a.db.off[k + 1] - a.db.off[k];
+	return (a.db.fq[pos >> 6] & bit) ? 3u : 1u;
+}
+
+// Does site i get a record?  `own` = its call (0: skipped).  The tests build_record() makes before it starts to write
+// (src/print_vcf.c:139, 154-157), on their own so that a CTA can gather its writing sites before it builds anything.
+__device__ __forceinline__ bool site_writes(const WrArgs &a, const GtVcf *v, uint32_t i, uint32_t first, uint32_t last, int own) {
+	if (!own) return false;
+	uint32_t dp = 0;
+#pragma unroll
+	for (int k = 0; k < 8; k++) dp += (uint32_t)v->counts[k];
+	if (!dp) return false;
+	const uint32_t pos = a.x + i;
+	if (a.reg_start | a.reg_stop) { if (pos < a.reg_start || pos > a.reg_stop) return false; }
+	else if (pos > a.ctg_end) return false;
+	if (a.all_positions) return true;
+	const int gt = own - 1;
+	if (gt != 0 && gt != 9) return true;
+	uint32_t rc[5];
+	ref_context(a, i, first, last, rc);
+	if (!((gt == 0 && rc[2] == 1) || (gt == 9 && rc[2] == 4))) return true;
+	const uint8_t *rs;
+	uint32_t rs_len;
+	return (dbsnp_lookup(a, pos, rs, rs_len) & 2u) != 0;
+}
+
 // One record.  `g` = calls of sites i-2 .. i+2 as the writer's window holds them.  Returns bytes written (0: no record).
 template <class W>
-__device__ __forceinline__ uint32_t build_record(const WrArgs &a, uint32_t i, uint32_t first, uint32_t last, const int g[5], W &w) {
+__device__ __forceinline__ uint32_t build_record(const WrArgs &a, const GtVcf *v, uint32_t i, uint32_t first, uint32_t last, const int g[5], W &w) {
 	if (!g[2]) return 0;
-	const GtVcf *v = a.vcf + i;
 	uint32_t dp1 = 0, dinf = 0;
 #pragma unroll
 	for (int k = 0; k < 4; k++) { dp1 += (uint32_t)v->counts[k]; dinf += (uint32_t)v->counts[4 + k]; }
 	if (!(dp1 + dinf)) return 0;
-	// Reference context.  The reference fills its window with strncpy() from a string in which N is the terminator
-	// (src/print_vcf.c:572-578), so once an N has been copied everything after it reads as N; the window starts at
-	// site - 2, except for the last two sites of a block, which reuse the window of the block's last site
-	// (flush_vcf_entries only shifts it, :539-543): an N up to two codes further left wipes them too.  Codes before the
-	// block are N.
 	uint32_t rc[5];
-	{
-		const int64_t ii = i, f = first, l = last;
-		const int64_t wstart = ii + 2 <= l ? ii - 2 : l - 4;
-		bool wiped = false;
-		for (int64_t j = wstart < f ? f : wstart; j < ii - 2; j++) wiped |= a.ref[j] == 0;
-#pragma unroll
-		for (int k = 0; k < 5; k++) {
-			const int64_t j = ii + k - 2;
-			const uint32_t c = j >= f && !wiped ? a.ref[j] : 0u;
-			if (c == 0 && j >= f) wiped = true;
-			rc[k] = c;
-		}
-	}
+	ref_context(a, i, first, last, rc);
 	const int rfix = (int)rc[2], gt = g[2] - 1;
-	// dbSNP (:133): what dbSNP_lookup_name() answers for this position -- 0, 1 (known) or 3 (known, always written) and the ID
 	const uint32_t pos = a.x + i;
-	uint32_t rs_found = 0, rs_len = 0;
-	const uint8_t *rs = nullptr;
-	if ((pos >> 6) < a.db.words) {
-		const unsigned long long m = a.db.mask[pos >> 6], bit = 1ull << (pos & 63);
-		if (m & bit) {
-			rs_found = (a.db.fq[pos >> 6] & bit) ? 3u : 1u;
-			const uint32_t k = a.db.cum[pos >> 6] + (uint32_t)__popcll(m & (bit - 1));
-			rs = a.db.names + a.db.off[k];
-			rs_len = a.db.off[k + 1] - a.db.off[k];
-		}
-	}
+	const uint8_t *rs;
+	uint32_t rs_len;
+	const uint32_t rs_found = dbsnp_lookup(a, pos, rs, rs_len);
 	if (!a.all_positions && !(rs_found & 2u) && ((gt == 0 && rfix == 1) || (gt == 9 && rfix == 4))) return 0;      // hom-ref A / T (gt_flag, :91-102, 139)
 	if (a.reg_start | a.reg_stop) { if (pos < a.reg_start || pos > a.reg_stop) return 0; }      // ctg->curr_reg clips, else the contig end (:154-157)
 	else if (pos > a.ctg_end) return 0;
@@ -356,23 +385,50 @@ __device__ __forceinline__ void window_calls(const WrArgs &a, uint32_t i, uint32
 	}
 }
 
+// The writing sites of the CTA, gathered: `mine` = this thread's site writes.  Returns their number; list[k] = thread index of
+// the k-th one, in site order.  Roughly 40 % of the sites of a WGBS window write a record: building records one thread per site
+// leaves most lanes of every warp idle through the ~1500 instructions of a record, building them from the list does not.
+__device__ __forceinline__ uint32_t gather_writers(bool mine, uint16_t *list, uint32_t *wcnt) {
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+	if (lane == 0) wcnt[wid] = __popc(bal);
+	__syncthreads();
+	uint32_t base = 0, total = 0;
+#pragma unroll
+	for (int k = 0; k < kWrThreads / 32; k++) { if (k < wid) base += wcnt[k]; total += wcnt[k]; }
+	if (mine) list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)threadIdx.x;
+	__syncthreads();
+	return total;
+}
+
 __global__ void __launch_bounds__(kWrThreads) k_bcf_measure(const WrArgs a) {
 	__shared__ uint32_t wsum[kWrThreads / 32][2];
-	const uint32_t i = a.i0 + blockIdx.x * kWrThreads + threadIdx.x;
-	uint32_t n = 0;
+	__shared__ uint32_t wcnt[kWrThreads / 32];
+	__shared__ uint16_t list[kWrThreads];
+	__shared__ uint2 blk[kWrThreads];
+	const uint32_t i0 = a.i0 + blockIdx.x * kWrThreads, i = i0 + threadIdx.x;
+	bool mine = false;
 	if (i < a.i1) {
-		// the site's own call is made here (and kept for the neighbours' records); a record's LENGTH does not depend on
-		// the calls around it, so the window is left empty for the count
+		// the site's own call is made here (and kept for the neighbours' records)
 		const int own = site_call(a.vcf + i);
 		a.calls[i] = (uint8_t)own;
 		uint32_t first, last;
 		if (block_of(a, i, first, last)) {
-			const int g[5] = { 0, 0, own, 0, 0 };
-			Count w;
-			n = build_record(a, i, first, last, g, w);
-			if (n > (uint32_t)kMaxRec) { atomicAdd(a.totals + 2, 1ull); n = 0; }
+			blk[threadIdx.x] = make_uint2(first, last);
+			mine = site_writes(a, a.vcf + i, i, first, last, own);
 		}
-		a.len[i] = (uint16_t)n;
+		if (!mine) a.len[i] = 0;
+	}
+	const uint32_t nw = gather_writers(mine, list, wcnt);
+	uint32_t n = 0;
+	if (threadIdx.x < nw) {
+		// a record's LENGTH does not depend on the calls around it, so the window is left empty for the count
+		const uint32_t t = list[threadIdx.x], j = i0 + t;
+		const int g[5] = { 0, 0, (int)a.calls[j], 0, 0 };
+		Count w;
+		n = build_record(a, a.vcf + j, j, blk[t].x, blk[t].y, g, w);
+		if (n > (uint32_t)kMaxRec) { atomicAdd(a.totals + 2, 1ull); n = 0; }
+		a.len[j] = (uint16_t)n;
 	}
 	const uint32_t bytes = __reduce_add_sync(0xffffffffu, n), recs = __reduce_add_sync(0xffffffffu, n ? 1u : 0u);
 	if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5][0] = bytes; wsum[threadIdx.x >> 5][1] = recs; }
@@ -419,35 +475,9 @@ __global__ void __launch_bounds__(1024) k_bcf_offsets(unsigned long long *cta_by
 	}
 }
 
-__global__ void __launch_bounds__(kWrThreads) k_bcf_emit(const WrArgs a) {
-	extern __shared__ __align__(16) uint8_t stage[];          // the CTA's records, back to back
-	__shared__ uint32_t wsum[kWrThreads / 32];
-	const uint32_t i = a.i0 + blockIdx.x * kWrThreads + threadIdx.x;
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const uint32_t n = i < a.i1 ? a.len[i] : 0u;
-	uint32_t inc = n;
-	for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
-	if (lane == 31) wsum[wid] = inc;
-	__syncthreads();
-	uint32_t off = inc - n, total = 0;
-	for (int k = 0; k < kWrThreads / 32; k++) { if (k < wid) off += wsum[k]; total += wsum[k]; }
-	const unsigned long long dst0 = a.cta_bytes[blockIdx.x];
-	if (dst0 + total > a.out_cap) return;                   // the host compares totals[0] with the capacity and reports
-	uint8_t *dst = a.out + dst0;
-	const bool staged = total <= (uint32_t)kStageBytes;
-	if (n) {
-		uint32_t first, last;
-		block_of(a, i, first, last);
-		int g[5];
-		window_calls(a, i, first, last, g);
-		// two instances on purpose: with the destination's address space known the byte stores are STS / STG, not generic
-		if (staged) { Store w; w.p = stage + off; build_record(a, i, first, last, g, w); }
-		else { Store w; w.p = dst + off; build_record(a, i, first, last, g, w); }
-	}
-	if (!staged) return;
-	__syncthreads();
-	// copy out: bytes up to the first aligned word of the destination, aligned words (each stitched from two staged
-	// words), bytes after the last one
+// copy a CTA's staged records out: bytes up to the first aligned word of the destination, aligned words (each stitched
+// from two staged words), bytes after the last one
+__device__ __forceinline__ void copy_stage_out(uint8_t *dst, const uint8_t *stage, uint32_t total) {
 	const uint32_t head = min(total, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
 	if (threadIdx.x < head) dst[threadIdx.x] = stage[threadIdx.x];
 	const uint32_t nwords = (total - head) >> 2;
@@ -461,6 +491,169 @@ __global__ void __launch_bounds__(kWrThreads) k_bcf_emit(const WrArgs a) {
 	}
 	const uint32_t tail0 = head + 4 * nwords;
 	if (threadIdx.x < total - tail0) dst[tail0 + threadIdx.x] = stage[tail0 + threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kWrThreads) k_bcf_emit(const WrArgs a) {
+	extern __shared__ __align__(16) uint8_t stage[];          // the CTA's records, back to back
+	__shared__ uint32_t wsum[kWrThreads / 32];
+	__shared__ uint32_t wcnt[kWrThreads / 32];
+	__shared__ uint16_t list[kWrThreads];
+	__shared__ uint32_t offs[kWrThreads];
+	const uint32_t i = a.i0 + blockIdx.x * kWrThreads + threadIdx.x;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t n = i < a.i1 ? a.len[i] : 0u;
+	uint32_t inc = n;
+	for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+	if (lane == 31) wsum[wid] = inc;
+	__syncthreads();
+	uint32_t off = inc - n, total = 0;
+	for (int k = 0; k < kWrThreads / 32; k++) { if (k < wid) off += wsum[k]; total += wsum[k]; }
+	const unsigned long long dst0 = a.cta_bytes[blockIdx.x];
+	if (dst0 + total > a.out_cap) return;                   // the host compares totals[0] with the capacity and reports
+	uint8_t *dst = a.out + dst0;
+	const bool staged = total <= (uint32_t)kStageBytes;
+	// the writing sites gathered (gather_writers), each with the offset of its record inside the CTA
+	offs[threadIdx.x] = off;
+	const uint32_t nw = gather_writers(n != 0, list, wcnt);
+	if (threadIdx.x < nw) {
+		const uint32_t t = list[threadIdx.x], j = a.i0 + blockIdx.x * kWrThreads + t, o = offs[t];
+		uint32_t first, last;
+		block_of(a, j, first, last);
+		int g[5];
+		window_calls(a, j, first, last, g);
+		// two instances on purpose: with the destination's address space known the byte stores are STS / STG, not generic
+		if (staged) { Store w; w.p = stage + o; build_record(a, a.vcf + j, j, first, last, g, w); }
+		else { Store w; w.p = dst + o; build_record(a, a.vcf + j, j, first, last, g, w); }
+	}
+	if (!staged) return;
+	__syncthreads();
+	copy_stage_out(dst, stage, total);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One pass: the three kernels above read every 208-byte record twice, one thread per record (a quarter of every sector
+// fetched is used, and the two passes together move almost twice the algorithmic bytes).  Here a CTA takes the next tile of
+// 128 sites (ticket), pulls its records into shared memory with coalesced 16-byte loads, makes the calls (its own and the
+// two either side), gathers the writing sites, sizes their records, builds them into the stage, and finds where its bytes go
+// by a decoupled look-back over the tiles before it (tile_state: 2 status bits | bytes; tiles are handed out in order, so
+// every tile a CTA waits for is already running).  Same bytes as the split kernels.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kFusedStage = 16 * 1024;
+constexpr unsigned long long kTileMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long *p) { return *(const volatile unsigned long long *)p; }
+
+__global__ void __launch_bounds__(kWrThreads) k_bcf_fused(const WrArgs a, unsigned long long *tile_state, unsigned int *ticket, uint32_t ntiles) {
+	extern __shared__ __align__(16) uint8_t dyn[];
+	GtVcf *recs = (GtVcf *)dyn;
+	uint8_t *stage = dyn + kWrThreads * sizeof(GtVcf);
+	__shared__ uint32_t wsum[kWrThreads / 32], wcnt[kWrThreads / 32];
+	__shared__ uint16_t list[kWrThreads];
+	__shared__ uint2 blk[kWrThreads];
+	__shared__ uint8_t calls_s[kWrThreads + 4];
+	__shared__ uint32_t s_tile;
+	__shared__ unsigned long long s_excl;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	if (tile >= ntiles) return;
+	const uint32_t i0 = a.i0 + tile * kWrThreads, cnt = min((uint32_t)kWrThreads, a.i1 - i0);
+	{
+		const uint4 *src = (const uint4 *)(a.vcf + i0);
+		uint4 *dst = (uint4 *)recs;
+		for (uint32_t k = tid; k < cnt * 13u; k += kWrThreads) dst[k] = __ldg(src + k);
+	}
+	if (tid < 4) {      // the calls two sites either side of the tile: made here while their records are in reach, else from the calls array
+		const int64_t j = tid < 2 ? (int64_t)i0 - 2 + tid : (int64_t)i0 + kWrThreads + (tid - 2);
+		uint8_t c = 0;
+		if (j >= 0 && j < (int64_t)a.sz) c = (j >= (int64_t)a.i0 && j < (int64_t)a.i1) ? (uint8_t)site_call(a.vcf + j) : a.calls[j];
+		calls_s[tid < 2 ? tid : kWrThreads + tid] = c;
+	}
+	__syncthreads();
+	bool mine = false;
+	if ((uint32_t)tid < cnt) {
+		const int own = site_call(recs + tid);
+		calls_s[2 + tid] = (uint8_t)own;
+		a.calls[i0 + tid] = (uint8_t)own;
+		uint32_t first, last;
+		if (block_of(a, i0 + tid, first, last)) {
+			blk[tid] = make_uint2(first, last);
+			mine = site_writes(a, recs + tid, i0 + tid, first, last, own);
+		}
+	} else calls_s[2 + tid] = 0;
+	const uint32_t nw = gather_writers(mine, list, wcnt);
+	// lengths of the records, dense: thread k sizes the k-th writing site
+	uint32_t n = 0, t = 0;
+	if ((uint32_t)tid < nw) {
+		t = list[tid];
+		const int g[5] = { 0, 0, (int)calls_s[2 + t], 0, 0 };
+		Count w;
+		n = build_record(a, recs + t, i0 + t, blk[t].x, blk[t].y, g, w);
+		if (n > (uint32_t)kMaxRec) { atomicAdd(a.totals + 2, 1ull); n = 0; }
+	}
+	uint32_t inc = n;
+	for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+	const uint32_t nrec_w = __popc(__ballot_sync(0xffffffffu, n != 0));
+	if (lane == 31) wsum[wid] = inc;
+	if (lane == 0) wcnt[wid] = nrec_w;       // (gather_writers is done with wcnt)
+	__syncthreads();
+	uint32_t off = inc - n, total = 0, nrec = 0;
+#pragma unroll
+	for (int k = 0; k < kWrThreads / 32; k++) { if (k < wid) off += wsum[k]; total += wsum[k]; nrec += wcnt[k]; }
+	// let the tiles behind this one see its bytes as early as possible
+	if (tid == 0) {
+		atomicExch(tile_state + tile, (tile ? 1ull : 2ull) << 62 | (unsigned long long)total);
+		if (nrec) atomicAdd(a.totals + 1, (unsigned long long)nrec);
+	}
+	auto look_back = [&]() {            // warp 0: bytes of all tiles before this one
+		if (wid != 0) return;
+		unsigned long long excl = 0;
+		for (int64_t p = (int64_t)tile - 1; p >= 0; p -= 32) {
+			const int64_t q = p - lane;
+			unsigned long long v = q >= 0 ? ld_state(tile_state + q) : 2ull << 62;
+			while (__any_sync(0xffffffffu, (v >> 62) == 0)) { if ((v >> 62) == 0) v = ld_state(tile_state + q); }
+			const uint32_t pref = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+			const int stop = pref ? __ffs(pref) - 1 : 31;
+			unsigned long long c = lane <= stop ? (v & kTileMask) : 0ull;
+			for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+			excl += c;
+			if (pref) break;
+		}
+		if (lane == 0) {
+			s_excl = excl;
+			if (tile) atomicExch(tile_state + tile, 2ull << 62 | (excl + total));
+			if (tile == ntiles - 1) a.totals[0] = excl + total;
+		}
+	};
+	auto window = [&](uint32_t tt, int g[5]) {      // window_calls() from the tile's own calls
+		const int64_t i = (int64_t)i0 + tt, first = blk[tt].x, last = blk[tt].y;
+#pragma unroll
+		for (int k = 0; k < 5; k++) {
+			const int64_t j = i + k - 2;
+			g[k] = j < first ? 0 : (int)calls_s[(j <= last ? j : last) - (int64_t)i0 + 2];
+		}
+	};
+	if (total <= (uint32_t)kFusedStage) {
+		if (n) {
+			int g[5];
+			window(t, g);
+			Store w; w.p = stage + off;
+			build_record(a, recs + t, i0 + t, blk[t].x, blk[t].y, g, w);
+		}
+		look_back();
+		__syncthreads();
+		if (s_excl + total <= a.out_cap) copy_stage_out(a.out + s_excl, stage, total);      // else: the host compares totals[0] with the capacity and reports
+	} else {                            // more bytes than the stage holds: straight to where they go
+		look_back();
+		__syncthreads();
+		if (n && s_excl + total <= a.out_cap) {
+			int g[5];
+			window(t, g);
+			Store w; w.p = a.out + s_excl + off;
+			build_record(a, recs + t, i0 + t, blk[t].x, blk[t].y, g, w);
+		}
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -727,7 +920,10 @@ size_t bcf_cta_scratch_bytes(uint32_t cnt) {
 	return nctas * 8 + ((nctas * 4 + 15) & ~(size_t)15) + 16;
 }
 
+constexpr size_t kFusedSmem = kWrThreads * sizeof(GtVcf) + kFusedStage + 16;
 cudaError_t configure_writer() {
+	cudaError_t e = cudaFuncSetAttribute(k_bcf_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
+	if (e != cudaSuccess) return e;
 	return cudaFuncSetAttribute(k_bcf_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes + 16);
 }
 
@@ -767,10 +963,24 @@ cudaError_t launch_bcf_records(const BcfJob &j, uint32_t i0, uint32_t cnt, void 
 	a.cta_bytes = (unsigned long long *)cta_scratch;
 	a.cta_recs = (uint32_t *)((uint8_t *)cta_scratch + (size_t)nctas * 8);
 	a.totals = d_totals; a.out = (uint8_t *)d_out; a.out_cap = out_cap;
-	k_bcf_measure<<<nctas, kWrThreads, 0, stream>>>(a);
-	k_bcf_offsets<<<1, 1024, 0, stream>>>(a.cta_bytes, a.cta_recs, nctas, d_totals);
-	k_bcf_emit<<<nctas, kWrThreads, kStageBytes + 16, stream>>>(a);
-	__atomic_fetch_add(launches, 3, __ATOMIC_RELAXED);
+	// Default: three kernels (sizes, offsets, records).  BSGPU_WRITER=fused: the single pass (k_bcf_fused) -- it moves half the
+	// bytes (every record read once, coalesced) and is still slower, 1.32 against 1.19 ms per 8 M sites: neither is bound by
+	// memory traffic but by the latency of the ~1500 dependent instructions of a record's serialisation with few warps at work,
+	// and staging the records in shared memory leaves the fused kernel fewer of them (profiles/r02d_writer_ab.txt).
+	const char *wenv = getenv("BSGPU_WRITER");
+	const bool split = !(wenv && !strcmp(wenv, "fused"));
+	if (split || (((uintptr_t)(a.vcf + i0)) & 15u)) {
+		k_bcf_measure<<<nctas, kWrThreads, 0, stream>>>(a);
+		k_bcf_offsets<<<1, 1024, 0, stream>>>(a.cta_bytes, a.cta_recs, nctas, d_totals);
+		k_bcf_emit<<<nctas, kWrThreads, kStageBytes + 16, stream>>>(a);
+		__atomic_fetch_add(launches, 3, __ATOMIC_RELAXED);
+	} else {
+		// tile states + the ticket counter live where the split kernels keep their per-CTA totals
+		e = cudaMemsetAsync(cta_scratch, 0, (size_t)nctas * 8 + 16, stream);
+		if (e != cudaSuccess) return e;
+		k_bcf_fused<<<nctas, kWrThreads, kFusedSmem, stream>>>(a, a.cta_bytes, (unsigned int *)a.cta_recs, nctas);
+		__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
+	}
 	if (a.stats) {                  // the calls of the sites and of their neighbours exist now
 		k_bcf_stats<<<nctas, kWrThreads, 0, stream>>>(a);
 		__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);

@@ -86,3 +86,31 @@ def patch_contig(view, contig, record_bytes):
     v[:, 5] = (contig >> 8) & 0xff
     v[:, 24] = contig & 0xff
     v[:, 25] = (contig >> 8) & 0xff
+
+
+DBSNP_EVERY, DBSNP_ALWAYS = 100, 20
+
+
+def contig_dbsnp(seed, contig, length):
+    """Synthetic dbSNP annotation of a contig (BASELINE.json configs[4]: "with dbSNP annotation"): one known position in
+    every DBSNP_EVERY (at a pseudo-random offset inside its stride), one in DBSNP_ALWAYS of them flagged "always written"
+    (flag 3, else 1: what dbSNP_lookup_name() answers, src/print_vcf.c:133), ids "rs" + nine digits.  A pure function of
+    (seed, contig), so every rank and the CPU check build the same table.  -> (pos u32[], flags u8[], name_off u32[n + 1],
+    names u8[]) as bsgpu_dbsnp / oracle.bindings.dbsnp_arrays lay it out."""
+    import numpy as np
+    n = max((int(length) - 1) // DBSNP_EVERY, 0)
+    k = np.arange(n, dtype=np.uint64)
+    h = (k + np.uint64(contig) * np.uint64(0x9E3779B1) + np.uint64(seed)) * np.uint64(0x9E3779B97F4A7C15)
+    h ^= h >> np.uint64(29)
+    h *= np.uint64(0xBF58476D1CE4E5B9)
+    h ^= h >> np.uint64(32)
+    pos = (1 + k * np.uint64(DBSNP_EVERY) + h % np.uint64(DBSNP_EVERY)).astype(np.uint32)
+    flags = np.where((h >> np.uint64(20)) % np.uint64(DBSNP_ALWAYS) == 0, 3, 1).astype(np.uint8)
+    num = ((h >> np.uint64(33)) % np.uint64(10 ** 9)).astype(np.int64)
+    names = np.empty((n, 11), dtype=np.uint8)
+    names[:, 0], names[:, 1] = ord("r"), ord("s")
+    for d in range(9):
+        names[:, 10 - d] = 48 + num % 10
+        num //= 10
+    off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(11)).astype(np.uint32)
+    return pos, flags, off, np.concatenate([names.reshape(-1), np.zeros(1, dtype=np.uint8)])

@@ -22,6 +22,16 @@ def gpu():
     g.close()
 
 
+@pytest.fixture(autouse=True, params=["split", "fused"])
+def writer_mode(request, monkeypatch):
+    """every test of the module runs with the three-kernel writer (default) and with the single-pass kernel k_bcf_fused"""
+    if request.param == "fused":
+        monkeypatch.setenv("BSGPU_WRITER", "fused")
+    else:
+        monkeypatch.delenv("BSGPU_WRITER", raising=False)
+    return request.param
+
+
 def same_bcf(got, want, what):
     gb, gn = got
     wb, wn = want

@@ -159,3 +159,18 @@ def test_two_rank_gloo_bam_stream_sharded_by_contig(tmp_path):
                          capture_output=True, text=True, timeout=300, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert "BAM_MERGE_OK 2" in res.stdout
+
+
+def test_synthetic_dbsnp_table():
+    """bench.py's genome leg annotates every contig (configs[4]: "with dbSNP annotation"): the table is a pure function of
+    (seed, contig), sorted, one entry per stride, laid out as bsgpu_dbsnp wants it"""
+    from bs_call_b200 import synthgenome as sg
+    pos, flags, off, names = sg.contig_dbsnp(7, 3, 1_000_000)
+    pos2 = sg.contig_dbsnp(7, 3, 1_000_000)[0]
+    assert (pos == pos2).all() and (sg.contig_dbsnp(7, 4, 1_000_000)[0] != pos).any()
+    n = len(pos)
+    assert n == 999_999 // sg.DBSNP_EVERY and (np.diff(pos.astype(np.int64)) > 0).all() and pos[0] >= 1 and pos[-1] < 1_000_000
+    assert set(np.unique(flags)) == {1, 3} and 0.02 < (flags == 3).mean() < 0.1
+    assert len(off) == n + 1 and off[-1] == 11 * n and len(names) == 11 * n + 1
+    nm = names[:-1].reshape(n, 11)
+    assert (nm[:, 0] == ord("r")).all() and (nm[:, 1] == ord("s")).all() and ((nm[:, 2:] >= 48) & (nm[:, 2:] <= 57)).all()
