@@ -386,8 +386,7 @@ __device__ __forceinline__ void window_calls(const WrArgs &a, uint32_t i, uint32
 }
 
 // The writing sites of the CTA, gathered: `mine` = this thread's site writes.  Returns their number; list[k] = thread index of
-// the k-th one, in site order.  Roughly 40 % of the sites of a WGBS window write a record: building records one thread per site
-// leaves most lanes of every warp idle through the ~1500 instructions of a record, building them from the list does not.
+// the k-th one, in site order (roughly 40 % of the sites of a WGBS window write a record).
 __device__ __forceinline__ uint32_t gather_writers(bool mine, uint16_t *list, uint32_t *wcnt) {
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t bal = __ballot_sync(0xffffffffu, mine);
@@ -403,32 +402,23 @@ __device__ __forceinline__ uint32_t gather_writers(bool mine, uint16_t *list, ui
 
 __global__ void __launch_bounds__(kWrThreads) k_bcf_measure(const WrArgs a) {
 	__shared__ uint32_t wsum[kWrThreads / 32][2];
-	__shared__ uint32_t wcnt[kWrThreads / 32];
-	__shared__ uint16_t list[kWrThreads];
-	__shared__ uint2 blk[kWrThreads];
-	const uint32_t i0 = a.i0 + blockIdx.x * kWrThreads, i = i0 + threadIdx.x;
-	bool mine = false;
+	const uint32_t i = a.i0 + blockIdx.x * kWrThreads + threadIdx.x;
+	uint32_t n = 0;
 	if (i < a.i1) {
-		// the site's own call is made here (and kept for the neighbours' records)
+		// the site's own call is made here (and kept for the neighbours' records); a record's LENGTH does not depend on
+		// the calls around it, so the window is left empty for the count.  (Gathering the writing sites first, as the single
+		// pass below does, was measured here too: 1.19 against 1.15 ms per 8 M sites -- the lanes it frees were hiding the
+		// latency of the scattered record loads.)
 		const int own = site_call(a.vcf + i);
 		a.calls[i] = (uint8_t)own;
 		uint32_t first, last;
 		if (block_of(a, i, first, last)) {
-			blk[threadIdx.x] = make_uint2(first, last);
-			mine = site_writes(a, a.vcf + i, i, first, last, own);
+			const int g[5] = { 0, 0, own, 0, 0 };
+			Count w;
+			n = build_record(a, a.vcf + i, i, first, last, g, w);
+			if (n > (uint32_t)kMaxRec) { atomicAdd(a.totals + 2, 1ull); n = 0; }
 		}
-		if (!mine) a.len[i] = 0;
-	}
-	const uint32_t nw = gather_writers(mine, list, wcnt);
-	uint32_t n = 0;
-	if (threadIdx.x < nw) {
-		// a record's LENGTH does not depend on the calls around it, so the window is left empty for the count
-		const uint32_t t = list[threadIdx.x], j = i0 + t;
-		const int g[5] = { 0, 0, (int)a.calls[j], 0, 0 };
-		Count w;
-		n = build_record(a, a.vcf + j, j, blk[t].x, blk[t].y, g, w);
-		if (n > (uint32_t)kMaxRec) { atomicAdd(a.totals + 2, 1ull); n = 0; }
-		a.len[j] = (uint16_t)n;
+		a.len[i] = (uint16_t)n;
 	}
 	const uint32_t bytes = __reduce_add_sync(0xffffffffu, n), recs = __reduce_add_sync(0xffffffffu, n ? 1u : 0u);
 	if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5][0] = bytes; wsum[threadIdx.x >> 5][1] = recs; }
@@ -496,9 +486,6 @@ __device__ __forceinline__ void copy_stage_out(uint8_t *dst, const uint8_t *stag
 __global__ void __launch_bounds__(kWrThreads) k_bcf_emit(const WrArgs a) {
 	extern __shared__ __align__(16) uint8_t stage[];          // the CTA's records, back to back
 	__shared__ uint32_t wsum[kWrThreads / 32];
-	__shared__ uint32_t wcnt[kWrThreads / 32];
-	__shared__ uint16_t list[kWrThreads];
-	__shared__ uint32_t offs[kWrThreads];
 	const uint32_t i = a.i0 + blockIdx.x * kWrThreads + threadIdx.x;
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t n = i < a.i1 ? a.len[i] : 0u;
@@ -512,18 +499,14 @@ __global__ void __launch_bounds__(kWrThreads) k_bcf_emit(const WrArgs a) {
 	if (dst0 + total > a.out_cap) return;                   // the host compares totals[0] with the capacity and reports
 	uint8_t *dst = a.out + dst0;
 	const bool staged = total <= (uint32_t)kStageBytes;
-	// the writing sites gathered (gather_writers), each with the offset of its record inside the CTA
-	offs[threadIdx.x] = off;
-	const uint32_t nw = gather_writers(n != 0, list, wcnt);
-	if (threadIdx.x < nw) {
-		const uint32_t t = list[threadIdx.x], j = a.i0 + blockIdx.x * kWrThreads + t, o = offs[t];
+	if (n) {
 		uint32_t first, last;
-		block_of(a, j, first, last);
+		block_of(a, i, first, last);
 		int g[5];
-		window_calls(a, j, first, last, g);
+		window_calls(a, i, first, last, g);
 		// two instances on purpose: with the destination's address space known the byte stores are STS / STG, not generic
-		if (staged) { Store w; w.p = stage + o; build_record(a, a.vcf + j, j, first, last, g, w); }
-		else { Store w; w.p = dst + o; build_record(a, a.vcf + j, j, first, last, g, w); }
+		if (staged) { Store w; w.p = stage + off; build_record(a, a.vcf + i, i, first, last, g, w); }
+		else { Store w; w.p = dst + off; build_record(a, a.vcf + i, i, first, last, g, w); }
 	}
 	if (!staged) return;
 	__syncthreads();
