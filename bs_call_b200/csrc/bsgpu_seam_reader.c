@@ -272,15 +272,23 @@ static void *taker_thread(void *arg) {
 	return NULL;
 }
 
-/* codes 0..4 of a whole contig from the reference's own sequence store (src/get_sequence.c:20-55) */
-static uint8_t *contig_codes(ctg_t * const ctg, ctg_t * const prev, sr_param * const param) {
+/* codes 0..4 of a whole contig from the reference's own sequence store (src/get_sequence.c:20-55).  The length is the
+ * header's / index's (ctg->seq_len, src/process_sam_header.c:188,221-224): end_pos is only set once load_sequence() has run
+ * (src/read_reference.c:112).  No previous contig is handed to get_sequence_string(): it would free_sequence() it, which also
+ * zeroes that contig's end_pos (src/read_reference.c:35-42) -- and the print thread, blocks behind this reader, still clips
+ * every record against end_pos (src/print_vcf.c:157).  The packed copy this call made load_sequence() allocate is released
+ * here instead, end_pos / start_pos stay. */
+static uint8_t *contig_codes(ctg_t * const ctg, sr_param * const param) {
 	gt_string *s = gt_string_new(1024);
-	const uint32_t len = ctg->end_pos;
+	const uint32_t len = ctg->end_pos ? ctg->end_pos : ctg->seq_len;
+	if (len == 0) { gt_string_delete(s); return NULL; }
 	gt_string_resize(s, (uint64_t)len + 8);
-	if (get_sequence_string(ctg, 1, len, prev, s, param)) { gt_string_delete(s); return NULL; }
+	const bool loaded_here = ctg->seq == NULL;
+	if (get_sequence_string(ctg, 1, len, NULL, s, param)) { gt_string_delete(s); return NULL; }
 	uint8_t *codes = malloc((size_t)len + 8);
 	if (codes != NULL) memcpy(codes, s->buffer, len);
 	gt_string_delete(s);
+	if (loaded_here && ctg->seq != NULL) { free(ctg->seq); ctg->seq = NULL; }
 	return codes;
 }
 
@@ -349,7 +357,6 @@ gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param
 	bam1_t *b = bam_init1();
 	int curr_tid = -1;
 	bool chr_skip = false;
-	ctg_t *prev_ctg = NULL;
 	gt_status st = GT_STATUS_OK;
 	uint8_t *dst = NULL;
 	size_t avail = 0, used = 0;
@@ -377,13 +384,12 @@ gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param
 			if (!chr_skip) {
 				ctg_t * const ctg = work->contigs[k];
 				ctg->curr_reg = work->curr_region;
-				if (tk.codes[curr_tid] == NULL) tk.codes[curr_tid] = contig_codes(ctg, prev_ctg, param);
+				if (tk.codes[curr_tid] == NULL) tk.codes[curr_tid] = contig_codes(ctg, param);
 				if (tk.codes[curr_tid] == NULL) {
 					fprintf(stderr, "Problem loading reference sequence for contig '%s'\n", ctg->name);
 					st = GT_STATUS_FAIL;
 					break;
 				}
-				prev_ctg = ctg;
 				if (bsgpu_bam_set_contig(tk.sess, curr_tid, tk.codes[curr_tid]) != BSGPU_OK) die("bsgpu_bam_set_contig");
 				if (g_site_stats && ctg->ctg_stats != NULL && ctg->ctg_stats->gc != NULL
 						&& bsgpu_set_contig_gc(g_ctx, ctg->vcf_rid, ctg->start_pos, ctg->ctg_stats->gc, (uint32_t)ctg->ctg_stats->nbins) != BSGPU_OK) die("bsgpu_set_contig_gc");

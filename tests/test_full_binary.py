@@ -1,0 +1,156 @@
+"""The whole program: the reference's unmodified bs_call binary
+(oracle/_ref/bs_call: every file of src/Makefile:15-17 over oracle/minihts, this repository's stand-in for htslib) run from
+the command line on a BAM file and a FASTA file, against the checkers everything else in tests/ is pinned to.
+
+CPU part (this file, `reference` marker): the records of the BCF file the binary writes equal the compiled chain
+read_input -> process_template_vector -> call_genotypes_ML -> print_vcf_entry of oracle/_ref/libbsref.so driven block by
+block through the harness -- i.e. the file-level run and the in-memory harness are the same function, so a result that
+holds against the harness holds against the program.  The GPU part is tests/test_gpu_full_binary.py.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bs_call_b200 import hostio
+from tests import bamgen, blockgen
+
+pytestmark = pytest.mark.reference
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BIN = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "bs_call")
+
+# dictionary ids of PASS fail mac1 CX GT FT GL GQ DP MQ QD MC8 AMQ CS CG FS in the header print_vcf_header() writes
+# (src/print_vcf.c:712-733: PASS first, then ids in order of first appearance: CX(INFO) fail q20 qd2 fs60 mq40 mac1 GT FT ...)
+HEADER_IDS = (0, 2, 7, 1, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19)
+
+
+def write_case(tmp, bam, tl, refs):
+    names = ["ctg%d" % i for i in range(len(tl))]
+    fa, bf = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "in.bam")
+    hostio.write_fasta(fa, names, refs)
+    hostio.write_bam(bf, names, tl, bam)
+    return names, fa, bf
+
+
+def run_binary(binary, fa, bf, out, otype="u", extra=(), threads="3", env=None):
+    cmd = [binary, "-r", fa, "-n", "S", "--benchmark-mode", "-O", otype, "-o", out, "-t", threads, *extra, bf]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, "%s\n%s" % (" ".join(cmd), r.stderr[-3000:])
+    return r.stderr
+
+
+def chain_records(impl, bam, tl, refs, all_positions=False, **opts):
+    """the BCF records of the harness-driven chain, block by block"""
+    blocks, _, _, _, vcf = impl.read_input(bam, tl, refs, run_chain=True, **opts)
+    want = []
+    for w in blocks:
+        c = int(w["tid"])
+        n = int(w["y"]) - int(w["x"]) + 1
+        rec, _ = impl.print_block(vcf[int(w["vcf_off"]):int(w["vcf_off"]) + n], blockgen.window_codes(refs[c], int(w["x"]), int(w["y"]) + 2),
+                                  int(w["x"]), rid=c, ctg_end=int(tl[c]), vcf_ids=HEADER_IDS, all_positions=all_positions)
+        want.append(rec)
+    return np.concatenate(want) if want else np.zeros(0, dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def binary():
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/bs_call not built (reference tree absent at build time)")
+    return BIN
+
+
+@pytest.mark.parametrize("seed,extra,opts", [
+    (3, (), {}),
+    (11, ("-k",), {"keep_unmatched": True}),
+    (12, ("-d",), {"keep_duplicates": True}),
+    (13, ("-q", "5", "-l", "400"), {"mapq_thresh": 5, "max_template_len": 400}),
+])
+def test_binary_matches_harness_chain(binary, reference, tmp_path, seed, extra, opts):
+    from oracle.bindings import bcf_diff
+    bam, n, tl, refs = bamgen.make_stream(seed, n_contigs=1, contig_len=30000)
+    names, fa, bf = write_case(str(tmp_path), bam, tl, refs)
+    out = os.path.join(str(tmp_path), "cpu.bcf")
+    run_binary(binary, fa, bf, out, extra=extra)
+    text, got = hostio.read_bcf(out)
+    assert "##contig=<ID=ctg0,length=%d>" % int(tl[0]) in text and text.rstrip().endswith("FORMAT\tS")
+    want = chain_records(reference, bam, tl, refs, **opts)
+    d = bcf_diff(got, want)
+    assert d["records_a"] == d["records_b"] == d["identical"] and d["records_a"] > 100 and d["order_violations"] == 0, d
+
+
+def _keyed(buf):
+    from tests.util import split_bcf
+    out = {}
+    for r in split_bcf(buf):
+        h = np.frombuffer(r[:32], dtype=np.uint32)
+        out[(int(h[2]), int(h[3]) + 1)] = r
+    return out
+
+
+def contig_tail_race(got, want, blocks):
+    """Several contigs: the reference binary has a race at contig ends.  process_thread fetches the next contig's sequence as
+    soon as call_genotypes_ML has handed the last block of the old one to the calc threads (src/process_template.c:30 ->
+    src/get_sequence.c:24 -> free_sequence, src/read_reference.c:35-42: end_pos = 0) while print_thread is still writing that
+    block and clips every record against end_pos (src/print_vcf.c:157): records of the LAST block of a contig that is not the
+    last one can be missing from the file, nothing else.  -> number of records lost that way; asserts everything else."""
+    g, w = _keyed(got), _keyed(want)
+    assert set(g) <= set(w)
+    assert all(g[k] == w[k] for k in g)
+    last = {}
+    for b in blocks:
+        last[int(b["tid"])] = (int(b["x"]), int(b["y"]))
+    final_ctg = max(last)
+    for (c, pos) in set(w) - set(g):
+        assert c != final_ctg and last[c][0] <= pos <= last[c][1] + 2, (c, pos, last[c])
+    return len(w) - len(g)
+
+
+def test_binary_on_several_contigs(binary, reference, tmp_path):
+    bam, n, tl, refs = bamgen.make_stream(3, n_contigs=3)
+    names, fa, bf = write_case(str(tmp_path), bam, tl, refs)
+    out = os.path.join(str(tmp_path), "cpu.bcf")
+    run_binary(binary, fa, bf, out)
+    _, got = hostio.read_bcf(out)
+    blocks = reference.read_input(bam, tl, refs)[0]
+    want = chain_records(reference, bam, tl, refs)
+    lost = contig_tail_race(got, want, blocks)
+    print("records lost to the reference's end-of-contig race: %d of %d" % (lost, len(_keyed(want))))
+
+
+def test_binary_all_positions_and_vcf_text(binary, reference, tmp_path):
+    """-A writes every site; -O v is the same records as text (one line per BCF record, same positions)"""
+    from oracle.bindings import bcf_diff
+    bam, n, tl, refs = bamgen.make_stream(5, n_contigs=1, contig_len=20000)
+    names, fa, bf = write_case(str(tmp_path), bam, tl, refs)
+    out_b, out_v = os.path.join(str(tmp_path), "a.bcf"), os.path.join(str(tmp_path), "a.vcf")
+    run_binary(binary, fa, bf, out_b, extra=("-A",))
+    run_binary(binary, fa, bf, out_v, otype="v", extra=("-A",))
+    _, got = hostio.read_bcf(out_b)
+    want = chain_records(reference, bam, tl, refs, all_positions=True)
+    d = bcf_diff(got, want)
+    assert d["records_a"] == d["records_b"] == d["identical"] and d["order_violations"] == 0, d
+    lines = [l for l in open(out_v).read().split("\n") if l and not l.startswith("#")]
+    assert len(lines) == d["records_a"]
+    # positions and contigs of the text lines follow the BCF records
+    from tests.util import split_bcf
+    recs = split_bcf(got)
+    for ln, r in list(zip(lines, recs))[::97]:
+        f = ln.split("\t")
+        hdr = np.frombuffer(r[:32], dtype=np.uint32)
+        assert f[0] == names[int(hdr[2])] and int(f[1]) == int(hdr[3]) + 1
+        assert f[8].startswith("GT:FT:") or f[8].startswith("GT:")
+
+
+def test_compressed_bcf_is_the_same_stream(binary, tmp_path):
+    """-O b (BGZF level 6) and -O u (BGZF level 0) hold the same bytes"""
+    bam, n, tl, refs = bamgen.make_stream(7, n_contigs=1)
+    names, fa, bf = write_case(str(tmp_path), bam, tl, refs)
+    a, b = os.path.join(str(tmp_path), "u.bcf"), os.path.join(str(tmp_path), "b.bcf")
+    run_binary(binary, fa, bf, a, otype="u")
+    run_binary(binary, fa, bf, b, otype="b")
+    assert os.path.getsize(b) < os.path.getsize(a)
+    ta, ra = hostio.read_bcf(a)
+    tb, rb = hostio.read_bcf(b)
+    assert ta == tb and ra.tobytes() == rb.tobytes() and len(ra) > 0
