@@ -622,6 +622,111 @@ def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
     return out
 
 
+def full_binary_path(args, gpu, bslib, torch, np, stream, local):
+    """The whole program: the reference's unmodified bs_call binary and the same program with the product's
+    seam files (oracle/_ref/bs_call, bs_call_gpu: oracle/Makefile, over oracle/minihts as htslib stand-in), both run from the
+    command line on a BAM file + FASTA file of the config-1 shape; wall clock of the processes, options as SURVEY.md 8d states
+    them, BCF outputs compared.  rank 0, N = 1 only."""
+    import subprocess, tempfile, shutil
+    from bs_call_b200 import hostio
+    from oracle.bindings import bcf_diff
+    here = os.path.dirname(os.path.abspath(__file__))
+    refdir = os.path.join(here, "oracle", "_ref")
+    bins = {k: os.path.join(refdir, k) for k in ("bs_call", "bs_call_gpu")}
+    for b in bins.values():
+        if not os.path.exists(b):
+            raise RuntimeError("%s not built (the reference tree was absent when oracle/Makefile ran)" % b)
+    L, depth, frag, tpb, gap = 150, 30.0, 300, 10000, 400
+    sz = int(args.binary_sites)
+    nt = int(sz * depth / (2 * L))
+    step = 2 * L / depth
+    dev = torch.device("cuda", local)
+    t = torch.arange(nt, device=dev, dtype=torch.int64)
+    p = 101 + torch.floor(t.double() * step).long() + (t // tpb) * gap
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + 29)
+    dup = (torch.rand(nt, device=dev, generator=g) < 0.05) & (t > 0)
+    src = torch.where(dup, t - 1, t)
+    dlen = (frag - L) + ((src * 2654435761) >> 7) % 41 - 20
+    pos_f = p[src]
+    pos_r = pos_f + dlen
+    order = torch.argsort(torch.cat([pos_f, pos_r]), stable=True)
+    rank_of = torch.empty_like(order)
+    rank_of[order] = torch.arange(2 * nt, device=dev)
+    ctg_len = int(pos_r.max().item()) + L + 600
+    nbytes = gpu.synth_bam_bytes(nt, L)
+    d_bam = torch.empty(nbytes + 16, dtype=torch.uint8, device=dev)
+    d_ref = torch.empty(ctg_len + 16, dtype=torch.uint8, device=dev)
+    u32 = lambda a: a.to(torch.int32).contiguous()
+    a_f, a_r, a_s, a_k = u32(pos_f), u32(pos_r), u32(src), u32(rank_of)
+    gpu.synth_bam_dev(SEED, nt, L, a_f.data_ptr(), a_r.data_ptr(), a_s.data_ptr(), a_k.data_ptr(), d_bam.data_ptr(), stream)
+    gpu.synth_ref_dev(SEED, 1, ctg_len, d_ref.data_ptr(), stream)
+    torch.cuda.synchronize()
+    hbam = d_bam[:nbytes].cpu().numpy()
+    href = d_ref[:ctg_len].cpu().numpy()
+    del d_bam, d_ref
+    tl = np.array([ctg_len], dtype=np.uint32)
+    # sites called on this stream (pileup.n > 0): the library's own counter over one in-memory pass
+    hbcf = bslib.HostBuffer(ctg_len * 96 + 4096, np.uint8)
+    s0 = gpu.stats()
+    gpu.call_bam_bcf(hbam, tl, [href], out=hbcf.array)
+    called = gpu.stats()["sites_called"] - s0["sites_called"]
+    del hbcf
+    tmp = tempfile.mkdtemp(prefix="bsgpu_fullbin_", dir=os.environ.get("BENCH_TMPDIR"))
+    try:
+        fa, bf = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "in.bam")
+        t0 = time.perf_counter()
+        hostio.write_fasta(fa, ["ctg0"], [href])
+        hostio.write_bam(bf, ["ctg0"], tl, hbam, level=0)
+        prep = time.perf_counter() - t0
+        ncores = os.cpu_count() or 1
+
+        def run(tag, binary, env_extra):
+            outp = os.path.join(tmp, tag + ".bcf")
+            cmd = [binary, "-r", fa, "-n", "S", "--benchmark-mode", "-O", "u", "-o", outp, "-t", "%d,0,0" % max(1, ncores - 1), bf]
+            env = dict(os.environ)
+            env.update(env_extra)
+            env["BSGPU_DEVICE"] = str(local)
+            t0 = time.perf_counter()
+            pr = subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
+            err = pr.stderr.read().decode(errors="replace")
+            _, status, ru = os.wait4(pr.pid, 0)
+            wall = time.perf_counter() - t0
+            pr.returncode = os.waitstatus_to_exitcode(status)
+            if pr.returncode != 0:
+                raise RuntimeError("%s failed (%d): %s" % (tag, pr.returncode, err[-600:]))
+            thr = [ln for ln in err.split("\n") if ln.startswith("Additional threads:")]
+            return {"value": called / wall, "unit": "sites/s", "wall_s": wall, "user_s": ru.ru_utime, "sys_s": ru.ru_stime,
+                    "maxrss_mb": ru.ru_maxrss / 1024.0, "additional_threads_calc_input_output": thr[0].split(":")[1].split() if thr else None,
+                    "cmd": " ".join(os.path.basename(c) if c.startswith(tmp) or c.startswith(refdir) else c for c in cmd)}, outp
+
+        out = {"workload": "config-1 shape at %d sites: synthetic 30x paired-end 150-bp WGBS, %d records (%.2f GB of BAM records, BGZF level 0), one contig of %d bp, 5 %% duplicates, coverage gap every ~100 kb; FASTA + .fai; output uncompressed BCF" % (
+                   sz, 2 * nt, nbytes / 1e9, ctg_len),
+               "sites_called": int(called), "host_cores": ncores, "file_prep_s": prep,
+               "htslib": "oracle/minihts (this repository's stand-in: no htslib in the image; single-threaded BGZF, BAM, faidx, BCF2), so every additional thread goes to the calc threads (-t n,0,0; src/parse_args.c:191-213 would give 3/7 of them to BGZF input threads the stand-in does not have)"}
+        log("full binary: reference bs_call on %d cores ..." % ncores)
+        out["cpu_reference_binary"], f_cpu = run("cpu", bins["bs_call"], {})
+        log("full binary: bs_call_gpu (seam C, then seam D) ...")
+        out["gpu_seam_C"], f_c = run("gpu_c", bins["bs_call_gpu"], {})
+        out["gpu_seam_D"], f_d = run("gpu_d", bins["bs_call_gpu"], {"BSGPU_SEAM_RECORDS": "1"})
+        out["gpu_seam_C"]["note"] = "read_input / process_template_vector / call_genotypes_ML on the device, the reference's print thread writes (src/print_vcf.c on one host thread)"
+        out["gpu_seam_D"]["note"] = "additionally print_vcf_entry's work on the device: BCF records handed to bcf_write"
+        _, rc_ = hostio.read_bcf(f_cpu)
+        par = {}
+        for tag, f in (("seam_C", f_c), ("seam_D", f_d)):
+            _, rg_ = hostio.read_bcf(f)
+            d = bcf_diff(rg_, rc_)
+            par[tag] = {"records": d["records_a"], "records_cpu": d["records_b"], "fixed_fields_equal": d["fixed_equal"], "byte_identical": d["identical"]}
+            assert d["records_a"] == d["records_b"] and d["order_violations"] == 0, d
+            assert d["identical"] >= d["records_a"] - max(3, d["records_a"] // 100000), d
+        out["parity"] = par
+        out["speedup_wall"] = {"seam_C": out["cpu_reference_binary"]["wall_s"] / out["gpu_seam_C"]["wall_s"],
+                               "seam_D": out["cpu_reference_binary"]["wall_s"] / out["gpu_seam_D"]["wall_s"]}
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def writer_path(args, gpu, bslib, torch, np, stream, rank, world, local):
     """the writer's per-site derivations on the device.  (a) gt_vcf[] resident -> BCF records
     resident (the three writer kernels alone); (b) count vectors on the host -> BCF records on the host
@@ -759,7 +864,8 @@ def main():
     ap.add_argument("--genome-batch-mb", type=int, default=384, help="genome leg: batch size of the streaming session")
     ap.add_argument("--genome-sessions", type=int, default=2, help="genome leg: sessions (contexts) per GPU, regions dealt out between them")
     ap.add_argument("--no-genome", action="store_true", help="skip the genome leg")
-    ap.add_argument("--legs", default="e2e,block,bam,writer,genome,cpu", help="secondary legs to run (comma separated)")
+    ap.add_argument("--binary-sites", type=float, default=20e6, help="whole-program leg: sites of the BAM file both bs_call binaries read (config 1 is 50 M)")
+    ap.add_argument("--legs", default="e2e,block,bam,writer,genome,binary,cpu", help="secondary legs to run (comma separated)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -1122,6 +1228,17 @@ def main():
             import traceback
             genome = {"error": repr(e), "trace": traceback.format_exc()[-1200:]}
 
+    # ---- the whole program: the reference's bs_call binary against the same program with the seam files, from files
+    fullbin = None
+    if rank == 0 and world == 1 and "binary" in legs:
+        log("whole-program leg (config 1 shape) ...")
+        try:
+            torch.cuda.empty_cache()
+            fullbin = full_binary_path(args, gpu, bslib, torch, np, stream, local)
+        except Exception as e:
+            import traceback
+            fullbin = {"error": repr(e), "trace": traceback.format_exc()[-1200:]}
+
     cpu = None
     log("cpu baseline of the headline ...")
     if rank == 0 and world == 1 and not args.no_cpu and "cpu" in legs:
@@ -1139,7 +1256,7 @@ def main():
                            "parallelism": "sites sharded over %d rank(s), no collective" % world, "host": numa_note,
                            "l2": "inputs larger than L2: each step streams %.1f GB of distinct records" % (n_sites * 105 / 1e9)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "block_path": block, "bam_path": bam, "writer_path": writer, "genome_path": genome, "guard_bands": guard, "parity_spot_check": parity}
+                "block_path": block, "bam_path": bam, "writer_path": writer, "genome_path": genome, "full_binary": fullbin, "guard_bands": guard, "parity_spot_check": parity}
         print(json.dumps(line))
     gpu.close()
     if world > 1:
