@@ -696,7 +696,8 @@ def full_binary_path(args, gpu, bslib, torch, np, stream, local):
             if pr.returncode != 0:
                 raise RuntimeError("%s failed (%d): %s" % (tag, pr.returncode, err[-600:]))
             thr = [ln for ln in err.split("\n") if ln.startswith("Additional threads:")]
-            return {"value": called / wall, "unit": "sites/s", "wall_s": wall, "user_s": ru.ru_utime, "sys_s": ru.ru_stime,
+            stamps = [ln[len("bsgpu seam:"):].strip() for ln in err.split("\n") if ln.startswith("bsgpu seam:")]      # BSGPU_SEAM_TIMING=1
+            return {**({"seam_timing": stamps} if stamps else {}),"value": called / wall, "unit": "sites/s", "wall_s": wall, "user_s": ru.ru_utime, "sys_s": ru.ru_stime,
                     "maxrss_mb": ru.ru_maxrss / 1024.0, "additional_threads_calc_input_output": thr[0].split(":")[1].split() if thr else None,
                     "cmd": " ".join(os.path.basename(c) if c.startswith(tmp) or c.startswith(refdir) else c for c in cmd)}, outp
 

@@ -27,6 +27,7 @@
 #include <string.h>
 #include <time.h>
 #include <pthread.h>
+#include <sys/stat.h>
 #include <htslib/sam.h>
 #include <htslib/vcf.h>
 
@@ -52,6 +53,15 @@ static void timed_wait(pthread_cond_t *c, pthread_mutex_t *m) {
 
 static bsgpu_params g_params;
 
+/* BSGPU_SEAM_TIMING=1: wall-clock stamps of the seam's phases on stderr (start-up cost against streaming time) */
+static int g_timing = -1;
+static double g_t0;
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+static void stamp(const char *what) {
+	if (g_timing < 0) { const char *e = getenv("BSGPU_SEAM_TIMING"); g_timing = e != NULL && atoi(e) != 0; g_t0 = now_s(); }
+	if (g_timing) fprintf(stderr, "bsgpu seam: %8.3f s  %s\n", now_s() - g_t0, what);
+}
+
 static void params_of(const sr_param * const param, bsgpu_params * const p) {
 	bsgpu_default_params(p);
 	p->under_conv = param->under_conv;
@@ -66,7 +76,9 @@ static void params_of(const sr_param * const param, bsgpu_params * const p) {
 void init_calc_threads(sr_param * const param) {
 	work_t * const work = &param->work;
 	params_of(param, &g_params);
+	stamp("init_calc_threads");
 	if (bsgpu_init(&g_params, &g_ctx) != BSGPU_OK) die("bsgpu_init");
+	stamp("bsgpu_init done");
 	g_profile = 0;
 	work->calc_end = false;
 	work->n_calc_threads = 0;
@@ -152,7 +164,9 @@ void join_calc_threads(sr_param * const param) {
 	if (g_profile && work->stats != NULL) fold_profile(work->stats);
 	if (g_site_stats && work->stats != NULL) fold_site_stats(param);
 	g_site_stats = 0;
+	stamp("join_calc_threads");
 	bsgpu_destroy(g_ctx);
+	stamp("bsgpu_destroy done");
 	g_ctx = NULL;
 	pthread_mutex_lock(&work->vcf_mutex);
 	pthread_cond_signal(&work->vcf_cond);
@@ -340,7 +354,22 @@ gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param
 		for (int t = 0; t < nt; t++) { const int k = work->tid2id[t]; rid[t] = k >= 0 ? work->contigs[k]->vcf_rid : 0; }
 	}
 	const uint8_t **codes0 = calloc((size_t)nt, sizeof(uint8_t *));
-	if (bsgpu_bam_open(g_ctx, nt, hdr->target_len, codes0, &rp, tk.records ? &bp : NULL, rid, 0, &tk.sess) != BSGPU_OK) die("bsgpu_bam_open");
+	/* Batch size: the library's default (384 MiB) suits a genome; a small input would spend longer page-locking the two
+	 * stages and three results of that size than streaming through them, and its first results would only leave when a third
+	 * of it had been read.  For a regular file an eighth of its size, between 32 MiB and the default (BGZF level 0 ... 6 inflate
+	 * to 1 ... 4 times the file); BSGPU_BATCH_BYTES overrides. */
+	size_t batch = 0;
+	if (getenv("BSGPU_BATCH_BYTES") == NULL && param->input_file != NULL) {
+		struct stat sb;
+		if (stat(param->input_file, &sb) == 0 && S_ISREG(sb.st_mode)) {
+			batch = (size_t)sb.st_size / 8;
+			if (batch < ((size_t)32 << 20)) batch = (size_t)32 << 20;
+			if (batch >= ((size_t)384 << 20)) batch = 0;
+		}
+	}
+	stamp("read_input: opening the session");
+	if (bsgpu_bam_open(g_ctx, nt, hdr->target_len, codes0, &rp, tk.records ? &bp : NULL, rid, batch, &tk.sess) != BSGPU_OK) die("bsgpu_bam_open");
+	stamp("session open");
 	free(codes0);
 	pthread_t taker;
 	pthread_create(&taker, NULL, taker_thread, &tk);
@@ -433,10 +462,13 @@ gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param
 		if (tk.failed) { st = GT_STATUS_FAIL; break; }
 	}
 	if (dst != NULL && bsgpu_bam_commit(tk.sess, used) != BSGPU_OK) die("bsgpu_bam_commit");
+	stamp("last record fed");
 	if (bsgpu_bam_finish(tk.sess) != BSGPU_OK) { fprintf(stderr, "bsgpu: %s\n", bsgpu_last_error()); st = GT_STATUS_FAIL; }
 	pthread_join(taker, NULL);
+	stamp("last result written");
 	if (tk.failed) st = GT_STATUS_FAIL;
 	bsgpu_bam_close(tk.sess);
+	stamp("session closed");
 	bam_destroy1(b);
 	for (int t = 0; t < nt; t++) free(tk.codes[t]);
 	free(tk.codes);
