@@ -17,8 +17,9 @@
  *   seam C (default): gt_vcf[] of every block, published to the reference's print thread by the protocol of
  *       src/call_genotypes.c:228-258 -- work->vcf points INTO the session's page-locked result, nothing is copied;
  *   seam D (BSGPU_SEAM_RECORDS=1): the BCF records of every block (print_vcf_entry's work done on the device), handed to
- *       htslib's bcf_write() one by one -- which writes BCF as it is and formats VCF text for -O v / z.  No dbSNP ids and no
- *       --report-file site statistics on this path yet (src/print_vcf.c:167, 382-526): use seam C with -D / --report-file.
+ *       htslib's bcf_write() one by one -- which writes BCF as it is and formats VCF text for -O v / z.  -D: the contig's dbSNP
+ *       entries go to the device writer when the contig starts (contig_annotation); --report-file: the site statistics of
+ *       src/print_vcf.c:382-526 are gathered on the device and folded into bs_stats at join_calc_threads.
  * Contig sequences: the session wants the codes 0..4 of a whole contig; they are taken from the reference's own
  * get_sequence_string() when the first record of a contig arrives and kept to the end of the run (one byte per position).
  */
@@ -306,6 +307,50 @@ static uint8_t *contig_codes(ctg_t * const ctg, sr_param * const param) {
 	return codes;
 }
 
+/* seam D with -D: the print thread, which loads a contig's dbSNP entries when its first site arrives (src/print_vcf.c:552-561),
+ * never sees a site, so the reader does it when the contig's first record arrives: the reference's own index reader loads the
+ * contig (src/dbSNP.c:157-304), every known position is asked for through dbSNP_lookup_name() (:305-350) and the answers -- flags
+ * and id bytes -- go to the device writer together with the contig's region (src/print_vcf.c:133,139,154-157,163-167). */
+static void contig_annotation(sr_param * const param, ctg_t * const ctg, const int tid) {
+	work_t * const work = &param->work;
+	const uint32_t r0 = ctg->curr_reg ? ctg->curr_reg->start : 0, r1 = ctg->curr_reg ? ctg->curr_reg->stop : 0;
+	dbsnp_ctg_t *dc = NULL;
+	if (work->dbSNP_hdr != NULL) HASH_FIND(hh, work->dbSNP_hdr->dbSNP, ctg->name, strlen(ctg->name), dc);
+	if (dc != NULL && !load_dbSNP_ctg(work->dbSNP_hdr, dc)) dc = NULL;
+	if (dc == NULL) {
+		if ((r0 | r1) && bsgpu_set_contig_annotation(g_ctx, tid, r0, r1, NULL) != BSGPU_OK) die("bsgpu_set_contig_annotation");
+		return;
+	}
+	size_t n = 0, cap = 1024, nb = 0, bcap = 16384;
+	uint32_t *pos = malloc(cap * sizeof(uint32_t)), *off = malloc((cap + 1) * sizeof(uint32_t));
+	uint8_t *flags = malloc(cap), *names = malloc(bcap);
+	char rs[512];
+	for (int bn = dc->min_bin; bn <= dc->max_bin; bn++) {
+		const dbsnp_bin_t * const b = dc->bins + (bn - dc->min_bin);
+		for (int ix = 0; ix < 64; ix++) {
+			if (!(b->mask >> ix & 1)) continue;
+			const uint32_t x = (uint32_t)bn << 6 | (uint32_t)ix;
+			size_t len = 0;
+			const uint8_t f = dbSNP_lookup_name(work->dbSNP_hdr, dc, rs, &len, x);
+			if (!f) continue;
+			if (len > BSGPU_DBSNP_MAX_ID) len = BSGPU_DBSNP_MAX_ID;
+			if (n == cap) {
+				cap *= 2;
+				pos = realloc(pos, cap * sizeof(uint32_t)); off = realloc(off, (cap + 1) * sizeof(uint32_t)); flags = realloc(flags, cap);
+			}
+			if (nb + len > bcap) { bcap = 2 * (nb + len); names = realloc(names, bcap); }
+			pos[n] = x; flags[n] = f; off[n] = (uint32_t)nb;
+			memcpy(names + nb, rs, len);
+			nb += len; n++;
+		}
+	}
+	off[n] = (uint32_t)nb;
+	bsgpu_dbsnp db = {(uint32_t)n, pos, flags, off, names};
+	if (bsgpu_set_contig_annotation(g_ctx, tid, r0, r1, &db) != BSGPU_OK) die("bsgpu_set_contig_annotation");
+	free(pos); free(off); free(flags); free(names);
+	unload_dbSNP_ctg(dc);
+}
+
 gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param) {
 	work_t * const work = &param->work;
 	bam_hdr_t * const hdr = work->sam_header;
@@ -419,6 +464,7 @@ gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param
 					st = GT_STATUS_FAIL;
 					break;
 				}
+				if (tk.records) contig_annotation(param, ctg, curr_tid);
 				if (bsgpu_bam_set_contig(tk.sess, curr_tid, tk.codes[curr_tid]) != BSGPU_OK) die("bsgpu_bam_set_contig");
 				if (g_site_stats && ctg->ctg_stats != NULL && ctg->ctg_stats->gc != NULL
 						&& bsgpu_set_contig_gc(g_ctx, ctg->vcf_rid, ctg->start_pos, ctg->ctg_stats->gc, (uint32_t)ctg->ctg_stats->nbins) != BSGPU_OK) die("bsgpu_set_contig_gc");

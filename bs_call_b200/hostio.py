@@ -115,3 +115,71 @@ def read_bcf(path):
     l_text = struct.unpack_from("<I", data, 5)[0]
     text = data[9:9 + l_text].rstrip(b"\0").decode()
     return text, np.frombuffer(data, dtype=np.uint8, offset=9 + l_text).copy()
+
+
+def write_dbsnp_index(path, contigs, prefixes=("rs",), header="name=dbSNP_synthetic", bins_per_block=4096):
+    """A dbSNP index file in the format src/dbSNP.c:27-304 reads (written by the reference's dbSNP_idx tool,
+    src/dbSNP_output.c:139-300): magic, offsets, per contig a chain of zlib-compressed blocks of 64-position bins, and a
+    compressed directory at the end.  contigs: {name: [(position (1-based), prefix index, digits (str of decimal digits),
+    always_written (bool)), ...]}; at most 64 entries fall into a bin by construction (one per position)."""
+    magic = 0xd7278434
+    body = bytearray()
+    body += struct.pack("<II", magic, 0)
+    body += b"\0" * 24                                # directory offset, buffer size, compressed directory size: patched below
+    directory = []
+    bufsize = 4096
+    for name, ents in contigs.items():
+        ents = sorted(ents, key=lambda e: e[0])
+        if not ents:
+            continue
+        bins = {}
+        for pos, pfx, digits, always in ents:
+            bins.setdefault(pos >> 6, []).append((pos & 63, pfx, digits, always))
+        order = sorted(bins)
+        min_bin, max_bin = order[0], order[-1]
+        offset = len(body)
+        curr = min_bin
+        for s0 in range(0, len(order), bins_per_block):
+            blk = bytearray()
+            for b in order[s0:s0 + bins_per_block]:
+                inc = b - curr
+                curr = b
+                if inc < 64:
+                    blk.append(inc << 2)
+                elif inc < 256:
+                    blk += bytes([1, inc])
+                elif inc < 65536:
+                    blk += bytes([2]) + struct.pack("<H", inc)
+                else:
+                    blk += bytes([3]) + struct.pack("<I", inc)
+                items = bins[b]
+                for k, (ix, pfx, digits, always) in enumerate(items):
+                    if pfx < 3:
+                        blk.append(((pfx + 1) << 6) | ix)              # prefixes 0..2 ride in the entry byte
+                    else:
+                        blk.append(ix)
+                        blk += struct.pack(">H", pfx)
+                    d = [int(c) for c in digits]
+                    for i in range(0, len(d) - 1, 2):
+                        blk.append(0x21 + 10 * d[i] + d[i + 1])
+                    if len(d) & 1:
+                        blk.append(0x85 + d[-1])
+                    blk.append((2 if always else 0) | (1 if k == len(items) - 1 else 0))
+            bufsize = max(bufsize, len(blk) + 64)
+            comp = zlib.compress(bytes(blk))
+            body += struct.pack("<Q", len(comp)) + comp
+        body += struct.pack("<Q", 0)
+        directory.append((min_bin, max_bin, offset, name))
+    d = bytearray(b"\0\0") + struct.pack("<HI", len(prefixes), len(directory))
+    d += b"track " + header.encode() + b"\0"
+    for p in prefixes:
+        d += p.encode() + b"\0"
+    for mn, mx, off, name in directory:
+        d += struct.pack("<IIQ", mn, mx, off) + name.encode() + b"\0"
+    d += b"\0" * 8                                    # the reader wants bytes behind the last name (src/dbSNP.c:113)
+    bufsize = max(bufsize, len(d) + 64)
+    comp = zlib.compress(bytes(d))
+    struct.pack_into("<QQQ", body, 8, len(body), bufsize, len(comp))
+    body += comp + struct.pack("<I", magic)
+    with open(path, "wb") as f:
+        f.write(bytes(body))

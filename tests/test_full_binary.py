@@ -41,15 +41,16 @@ def run_binary(binary, fa, bf, out, otype="u", extra=(), threads="3", env=None):
     return r.stderr
 
 
-def chain_records(impl, bam, tl, refs, all_positions=False, **opts):
-    """the BCF records of the harness-driven chain, block by block"""
+def chain_records(impl, bam, tl, refs, all_positions=False, dbsnp=None, **opts):
+    """the BCF records of the harness-driven chain, block by block; dbsnp: per contig dbsnp_arrays(...) or None"""
     blocks, _, _, _, vcf = impl.read_input(bam, tl, refs, run_chain=True, **opts)
     want = []
     for w in blocks:
         c = int(w["tid"])
         n = int(w["y"]) - int(w["x"]) + 1
         rec, _ = impl.print_block(vcf[int(w["vcf_off"]):int(w["vcf_off"]) + n], blockgen.window_codes(refs[c], int(w["x"]), int(w["y"]) + 2),
-                                  int(w["x"]), rid=c, ctg_end=int(tl[c]), vcf_ids=HEADER_IDS, all_positions=all_positions)
+                                  int(w["x"]), rid=c, ctg_end=int(tl[c]), vcf_ids=HEADER_IDS, all_positions=all_positions,
+                                  dbsnp=None if dbsnp is None else dbsnp[c])
         want.append(rec)
     return np.concatenate(want) if want else np.zeros(0, dtype=np.uint8)
 
@@ -154,3 +155,43 @@ def test_compressed_bcf_is_the_same_stream(binary, tmp_path):
     ta, ra = hostio.read_bcf(a)
     tb, rb = hostio.read_bcf(b)
     assert ta == tb and ra.tobytes() == rb.tobytes() and len(ra) > 0
+
+
+def synthetic_dbsnp(rng, tl, frac=0.02):
+    """-> ({contig name: entries for hostio.write_dbsnp_index}, [per contig dbsnp_arrays(...)]): known sites on `frac` of the
+    positions, a fifth of them flagged "always written" (src/dbSNP.c:278-279), ids rs + 6 or 8 digits, a second prefix"""
+    from oracle.bindings import dbsnp_arrays
+    files, arrays = {}, []
+    for c, L in enumerate(tl):
+        pos = np.unique(rng.integers(1, int(L) + 1, size=max(4, int(frac * int(L)))))
+        ents, flat = [], []
+        for p_ in pos:
+            pfx = int(rng.integers(0, 2))
+            digits = "%0*d" % (6 if rng.random() < 0.3 else 8, int(rng.integers(0, 999999)))
+            always = bool(rng.random() < 0.2)
+            ents.append((int(p_), pfx, digits, always))
+            flat.append((int(p_), 3 if always else 1, (("rs", "ss")[pfx] + digits).encode()))
+        files["ctg%d" % c] = ents
+        arrays.append(dbsnp_arrays(flat))
+    return files, arrays
+
+
+def test_binary_with_dbsnp_index(binary, reference, tmp_path):
+    """-D: the reference's own index reader (src/dbSNP.c, never run by the harness, which serves dbSNP_lookup_name from a
+    table) over an index file written in its format; ids, "always written" sites and everything else as the harness chain
+    gives them with the same table"""
+    from oracle.bindings import bcf_diff
+    rng = np.random.default_rng(77)
+    bam, n, tl, refs = bamgen.make_stream(31, n_contigs=1, contig_len=30000)
+    names, fa, bf = write_case(str(tmp_path), bam, tl, refs)
+    files, arrays = synthetic_dbsnp(rng, tl)
+    idx = os.path.join(str(tmp_path), "db.idx")
+    hostio.write_dbsnp_index(idx, files, prefixes=("rs", "ss"), bins_per_block=50)
+    out = os.path.join(str(tmp_path), "cpu.bcf")
+    run_binary(binary, fa, bf, out, extra=("-D", idx))
+    _, got = hostio.read_bcf(out)
+    want = chain_records(reference, bam, tl, refs, dbsnp=arrays)
+    d = bcf_diff(got, want)
+    assert d["records_a"] == d["records_b"] == d["identical"] and d["order_violations"] == 0, d
+    plain = chain_records(reference, bam, tl, refs)
+    assert len(want) > len(plain)                      # ids and always-written sites are in there

@@ -98,11 +98,13 @@ def test_gpu_binary_all_positions_vcf_text(tmp_path):
     assert len(bad) <= max(3, len(lc) // 500), [(lc[i], lg[i]) for i in bad[:3]]
 
 
-def test_gpu_binary_report_file(tmp_path):
-    """--report-file: the JSON statistics of the GPU binary (seam C: the reference's writer over the device's gt_vcf[]; the
-    read-level tallies and the conversion profile from the device) against the CPU binary's"""
+@pytest.mark.parametrize("variant", ["seamC", "seamD"])
+def test_gpu_binary_report_file(tmp_path, variant):
+    """--report-file: the JSON statistics of the GPU binary against the CPU binary's.  Seam C: the reference's writer over the
+    device's gt_vcf[], the read-level tallies and the conversion profile from the device.  Seam D: the site statistics of
+    src/print_vcf.c:382-526 from the device too (k_bcf_stats), folded into bs_stats at join_calc_threads"""
     import json
-    path, env = gpu_binary("seamC")
+    path, env = gpu_binary(variant)
     bam, n, tl, refs = bamgen.make_stream(21, n_contigs=1, contig_len=30000, dup=0.1, junk=0.05)
     names, fa, bf = write_case(str(tmp_path), bam, tl, refs)
     out = {}
@@ -140,3 +142,28 @@ def test_gpu_binary_report_file(tmp_path):
     assert abs(c["totalStats"]["SNPS"]["All"] - g["totalStats"]["SNPS"]["All"]) <= 3
     hard = [k for k in bad if "ReadLevel/Passed" not in k and not k.startswith("/date")]
     assert len(hard) <= max(10, len(lc) // 50), hard[:10]
+
+
+@pytest.mark.parametrize("variant", ["seamC", "seamD"])
+def test_gpu_binary_with_dbsnp_index(tmp_path, variant):
+    """-D: the reference's index reader over a synthetic index file (tests/test_full_binary.py::test_binary_with_dbsnp_index).
+    Seam C keeps the reference's writer, which looks every site up; on seam D the reader loads the contig's entries and hands
+    them to the device writer (bsgpu_set_contig_annotation): ids and always-written sites as in the CPU binary's file"""
+    from tests.test_full_binary import synthetic_dbsnp
+    path, env = gpu_binary(variant)
+    rng = np.random.default_rng(77)
+    bam, n, tl, refs = bamgen.make_stream(31, n_contigs=1, contig_len=30000)
+    names, fa, bf = write_case(str(tmp_path), bam, tl, refs)
+    files, arrays = synthetic_dbsnp(rng, tl)
+    idx = os.path.join(str(tmp_path), "db.idx")
+    hostio.write_dbsnp_index(idx, files, prefixes=("rs", "ss"), bins_per_block=50)
+    cpu, gpu = os.path.join(str(tmp_path), "cpu.bcf"), os.path.join(str(tmp_path), "gpu.bcf")
+    run_binary(BIN, fa, bf, cpu, extra=("-D", idx))
+    run_binary(path, fa, bf, gpu, extra=("-D", idx), env=env)
+    plain = os.path.join(str(tmp_path), "plain.bcf")
+    run_binary(BIN, fa, bf, plain)
+    _, rc = hostio.read_bcf(cpu)
+    _, rg = hostio.read_bcf(gpu)
+    _, rp = hostio.read_bcf(plain)
+    assert len(_keyed(rc)) > len(_keyed(rp))         # the index added always-written sites
+    compare(rg, rc, variant + " with -D")
