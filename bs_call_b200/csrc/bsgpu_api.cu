@@ -86,20 +86,61 @@ static const char *g_sync_after = getenv("BSGPU_SYNC_AFTER");
 	if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 // grow-on-demand device / pinned buffers
+//
+// BSGPU_REDZONE=1 (debugging aid; compute-sanitizer is not available on every box): every device buffer of the library is
+// allocated at exactly the size asked for (rounded up to 16 bytes) instead of with 12.5 % head-room, followed by a 4-KiB red
+// zone filled with 0xC3.  bsgpu_debug_redzones() -- and every release of a buffer -- reads the zones back and counts the ones a
+// kernel or copy wrote into, so out-of-bounds WRITES of any kernel into library-owned memory are caught without a tool.
+static const bool g_redzone = getenv("BSGPU_REDZONE") != nullptr;
+constexpr size_t kRedZone = 4096;
+struct DevBuf;
+static std::mutex g_red_mu;
+static std::set<DevBuf *> g_red_live;
+static unsigned long long g_red_checked = 0, g_red_corrupt = 0, g_red_first_bytes = 0;
 struct DevBuf {
 	void *p = nullptr;
 	size_t cap = 0;
+	bool zone_intact() const {           // red-zone mode only; caller holds g_red_mu
+		static std::vector<uint8_t> h(kRedZone);
+		if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(h.data(), (const uint8_t *)p + cap, kRedZone, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+		g_red_checked++;
+		for (size_t i = 0; i < kRedZone; i++) if (h[i] != 0xC3) { g_red_corrupt++; if (!g_red_first_bytes) g_red_first_bytes = cap; return false; }
+		return true;
+	}
 	cudaError_t reserve(size_t bytes) {
 		if (bytes <= cap) return cudaSuccess;
-		if (p) cudaFree(p);
-		p = nullptr; cap = 0;
-		size_t want = bytes + bytes / 8 + 256;
-		cudaError_t e = cudaMalloc(&p, want);
-		if (e == cudaSuccess) cap = want;
-		return e;
+		release();
+		size_t want = g_redzone ? ((bytes + 15) & ~(size_t)15) : bytes + bytes / 8 + 256;
+		cudaError_t e = cudaMalloc(&p, want + (g_redzone ? kRedZone : 0));
+		if (e != cudaSuccess) { p = nullptr; return e; }
+		cap = want;
+		if (g_redzone) {
+			if ((e = cudaMemset((uint8_t *)p + want, 0xC3, kRedZone)) != cudaSuccess || (e = cudaDeviceSynchronize()) != cudaSuccess) return e;
+			std::lock_guard<std::mutex> lk(g_red_mu);
+			g_red_live.insert(this);
+		}
+		return cudaSuccess;
 	}
-	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	void release() {
+		if (p) {
+			if (g_redzone) { std::lock_guard<std::mutex> lk(g_red_mu); zone_intact(); g_red_live.erase(this); }
+			cudaFree(p);
+		}
+		p = nullptr; cap = 0;
+	}
 };
+
+// red zones of all live device buffers of the process: *checked zones looked at so far (live ones now + every buffer released
+// before), *corrupt the ones found written into.  Returns BSGPU_OK when none was, BSGPU_FAIL otherwise (or without BSGPU_REDZONE).
+extern "C" int bsgpu_debug_redzones(unsigned long long *checked, unsigned long long *corrupt) {
+	if (!g_redzone) { if (checked) *checked = 0; if (corrupt) *corrupt = 0; return BSGPU_FAIL; }
+	std::lock_guard<std::mutex> lk(g_red_mu);
+	for (DevBuf *b : g_red_live) b->zone_intact();
+	if (checked) *checked = g_red_checked;
+	if (corrupt) *corrupt = g_red_corrupt;
+	if (g_red_corrupt) fprintf(stderr, "bsgpu: %llu red zone(s) written into (first: behind a buffer of %llu bytes)\n", g_red_corrupt, g_red_first_bytes);
+	return g_red_corrupt ? BSGPU_FAIL : BSGPU_OK;
+}
 
 struct PinBuf {                // grow-on-demand page-locked host buffer
 	void *p = nullptr;

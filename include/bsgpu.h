@@ -177,9 +177,11 @@ typedef struct {
  * values beyond an array are counted in fs_overflow / cov_overflow.  The writer entry points (bsgpu_*_bcf, sessions that return
  * records) gather it on the device while bsgpu_site_stats_enable is on; a host that replaces the print thread (seam D) folds
  * it into stats the way bsgpu_seam_reader.c does.  All counters are exact; the two methylation posteriors are sums of
- * doubles accumulated in device order (equal to the reference's to ~1e-12 relative).  As compiled, the reference counts a
- * homozygous reference call as "multi" and every other written site as "snp" (the test at :400-402 reads one byte past a
- * string literal's terminator); that is what is reproduced. */
+ * doubles accumulated in device order (equal to the reference's to ~1e-12 relative).  `multi` holds the written sites whose
+ * call is homozygous reference, `snps` every other written site: which of the two the reference's own counters `snps` / `multi`
+ * receive depends on the byte its test at :400-402 finds behind a string literal's terminator -- undefined behaviour that
+ * comes out differently in different links of the same sources (hom-ref -> multi in oracle/_ref/libbsref.so, everything ->
+ * snps in oracle/_ref/bs_call); the host folds accordingly (bsgpu_seam_reader.c: homref_is_multi). */
 #define BSGPU_STATS_FS_MAX 4096
 #define BSGPU_STATS_COV_MAX 4096
 typedef struct { uint64_t var, CpG[2], CpG_inf[2], all, gc_pcent[101]; } bsgpu_cov_stats;
