@@ -13,6 +13,7 @@
 #include <vector>
 #include <unordered_map>
 #include <map>
+#include <set>
 #include <deque>
 #include <mutex>
 #include <condition_variable>

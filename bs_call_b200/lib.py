@@ -20,7 +20,7 @@ BSGPU_FAIL = -1
 # every symbol include/bsgpu.h declares (tests/test_abi.py checks the header and this list against the .so)
 EXPORTS = [
     "bsgpu_default_params", "bsgpu_init", "bsgpu_destroy", "bsgpu_last_error", "bsgpu_get_stats", "bsgpu_version",
-    "bsgpu_sync", "bsgpu_guard_read", "bsgpu_host_alloc", "bsgpu_host_free",
+    "bsgpu_sync", "bsgpu_guard_read", "bsgpu_debug_redzones", "bsgpu_host_alloc", "bsgpu_host_free",
     "bsgpu_call_sites", "bsgpu_pileup_block", "bsgpu_call_block", "bsgpu_stage_bound", "bsgpu_stage_templates",
     "bsgpu_process_block", "bsgpu_profile_enable", "bsgpu_profile_read", "bsgpu_build_blocks_tally",
     "bsgpu_site_stats_enable", "bsgpu_set_contig_gc", "bsgpu_site_stats_read",
@@ -211,6 +211,12 @@ class BsGpu:
         self._check(self.lib.bsgpu_guard_read(self.ctx, _ptr(ids), C.c_size_t(len(ids)), C.byref(n), C.c_int(1 if reset else 0)))
         ids = ids[:n.value]
         return (ids >> np.uint64(56)).astype(np.int64), (ids & np.uint64((1 << 56) - 1)).astype(np.int64)
+
+    def debug_redzones(self):
+        """-> (ok, zones checked, zones written into); only meaningful with BSGPU_REDZONE=1 set before the library was loaded"""
+        a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+        rc = self.lib.bsgpu_debug_redzones(C.byref(a), C.byref(b))
+        return rc == 1, a.value, b.value
 
     def stats(self):
         s = Stats()

@@ -263,6 +263,12 @@ int bsgpu_sync(bsgpu_ctx *ctx);              /* wait for everything queued on th
 /* the flagged sites since the last reset: ids[k] = kind << 56 | id; kind 1 near tie of the call, 2 QUAL / GQ, 3 FS; id = index
  * of the site within the bsgpu_call_sites[_bcf] call, or its position for the block / reader entry points.  *n <= cap. */
 int bsgpu_guard_read(bsgpu_ctx *ctx, uint64_t *ids, size_t cap, size_t *n, int reset);
+/* Debugging aid (no counterpart in the reference; compute-sanitizer is not available everywhere): with BSGPU_REDZONE=1 in the
+ * environment when the library is loaded, every device buffer the library owns is allocated at exactly the size asked for and
+ * followed by a 4-KiB zone of a known pattern.  This reads the zones of all live buffers back (after a device synchronise) and
+ * reports how many zones were looked at so far -- buffers released earlier included -- and how many were written into by a kernel
+ * or a copy.  BSGPU_OK when none was; BSGPU_FAIL otherwise, and always without BSGPU_REDZONE. */
+int bsgpu_debug_redzones(unsigned long long *checked, unsigned long long *corrupt);
 
 /* page-locked host memory: arrays handed to the host-buffer entry points copy at full PCIe rate when they
  * come from here (any host pointer is accepted, pageable ones just copy slower) */

@@ -25,3 +25,18 @@ def reference():
     if not reference_available():
         pytest.skip("oracle/_ref/libbsref.so not built (reference tree absent)")
     return Reference(calc_threads=2)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """BSGPU_REDZONE=1 (tests/test_gpu_redzones.py runs the parity modules like that in a child process): after the last test
+    every red zone behind a device buffer of the library is read back; a zone a kernel wrote into fails the run."""
+    if not os.environ.get("BSGPU_REDZONE"):
+        return
+    import ctypes as C
+    so = os.path.join(ROOT, "bs_call_b200", "libbsgpu.so")
+    lib = C.CDLL(os.environ.get("BSGPU_LIB_PATH", so))
+    a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+    rc = lib.bsgpu_debug_redzones(C.byref(a), C.byref(b))
+    print("\nredzones: checked %d corrupt %d rc %d" % (a.value, b.value, rc))
+    if b.value or rc != 1:
+        session.exitstatus = 1
