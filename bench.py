@@ -38,6 +38,9 @@ BYTES_PER_SITE = 104 + 1 + 200 + 1
 _T0 = time.time()
 
 
+BLOCK_OVERLAP_DEFAULT = False          # what libbsgpu does without BSGPU_BLOCK_OVERLAP in the environment
+
+
 def log(msg):
     """progress on stderr (the JSON line is the only thing on stdout)"""
     if os.environ.get("RANK", "0") == "0":
@@ -1074,6 +1077,16 @@ def main():
         del os.environ["BSGPU_FUSED"]
         fms = timed(lambda: gfused.call_block_dev(d_seg.data_ptr(), ns, d_b.data_ptr(), d_r.data_ptr(), 1000, fsz, d_v.data_ptr(), stream))
         gfused.close()
+        # the gather of part k + 1 on its own stream next to the model of part k (BSGPU_BLOCK_OVERLAP): same kernels, same bytes
+        d_v2 = torch.empty(fsz * 208 + 16, dtype=torch.uint8, device="cuda")
+        os.environ["BSGPU_BLOCK_OVERLAP"] = "0" if BLOCK_OVERLAP_DEFAULT else "1"
+        galt = bslib.BsGpu(device=local)
+        del os.environ["BSGPU_BLOCK_OVERLAP"]
+        oms = timed(lambda: galt.call_block_dev(d_seg.data_ptr(), ns, d_b.data_ptr(), d_r.data_ptr(), 1000, fsz, d_v2.data_ptr(), stream))
+        torch.cuda.synchronize()
+        alt_same = bool(torch.equal(d_v[:fsz * 208], d_v2[:fsz * 208]))
+        galt.close()
+        del d_v2
         in_bytes = ns * (L + 16)
 
         def roof(nbytes, ms_):
@@ -1089,7 +1102,12 @@ def main():
                  "pileup_only": {"kernels": "k_bin_* + k_pileup_tile<pileup>", "ms": pms, "sites_per_s": fcalled / (pms * 1e-3),
                                  "roofline": roof(in_bytes + fsz * 104, pms)},
                  "fused_variant": {"kernels": "k_bin_* + k_pileup_tile<fused> (BSGPU_FUSED=1)", "ms": fms, "sites_per_s": fcalled / (fms * 1e-3),
-                                   "roofline": roof(in_bytes + fsz * (1 + 208), fms)}}
+                                   "roofline": roof(in_bytes + fsz * (1 + 208), fms)},
+                 ("serial_variant" if BLOCK_OVERLAP_DEFAULT else "overlapped_variant"): {
+                     "kernels": "the same two kernels, " + ("one after the other on one stream (BSGPU_BLOCK_OVERLAP=0)" if BLOCK_OVERLAP_DEFAULT else
+                                                            "window in parts of 2 Mi sites, gather of part k + 1 on its own stream next to the model of part k (BSGPU_BLOCK_OVERLAP=1)"),
+                     "ms": oms, "sites_per_s": fcalled / (oms * 1e-3), "roofline": roof(in_bytes + fsz * (1 + 208), oms),
+                     "gt_vcf_bytes_identical_to_default": alt_same}}
         # deep targeted panel (config 4: 500x single-end 150-bp reads over 10 Mb), the stress case for pileup accumulation.  One
         # window holds at most 4 Gi bases (32-bit offsets into bases[]), so the 10 Mb go through as windows of 2.5 Mb that
         # share the device buffers; times are summed over the windows.

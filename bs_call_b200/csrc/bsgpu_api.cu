@@ -194,7 +194,14 @@ struct bsgpu_ctx {
 	std::vector<uint32_t> off_tmp;
 	std::vector<uint8_t> ref_tmp;
 	bool fused = false;                          // BSGPU_FUSED=1: one fused pileup+model kernel instead of two kernels
+	bool block_overlap = false;                  // BSGPU_BLOCK_OVERLAP=1: gather of part k + 1 on its own stream next to the model of part k
 	bool overlap_kernels = false;                // the context runs kernels on more than one stream (decode stream of the reader stage)
+	// overlapped block path (BSGPU_BLOCK_OVERLAP): the pileup of slab i + 1 on its own stream under the model of slab i
+	cudaStream_t pile_stream = nullptr;
+	cudaEvent_t pile_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};      // piled[2], consumed[2], binned
+	DevBuf pile2;
+	uint32_t pile_pos = 0;
+	bool pile_used[2] = {false, false};
 	std::vector<cudaEvent_t> win_events;         // output ring
 	uint32_t ring_pos = 0;                       // next output ring slot of the deferred runs
 	bool ring_busy[3] = {false, false, false};   // output ring slot may still be copying out (deferred block_run)
@@ -326,6 +333,7 @@ int bsgpu_init(const bsgpu_params *p, bsgpu_ctx **out) {
 	CUI(cudaMalloc(&c->d_wr_totals, 8 * 3 * sizeof(unsigned long long)));
 	CUI(cudaHostAlloc(&c->h_wr_totals, 8 * 3 * sizeof(unsigned long long), cudaHostAllocDefault));
 	{ const char *e = getenv("BSGPU_FUSED"); c->fused = e && atoi(e) == 1; }
+	{ const char *e = getenv("BSGPU_BLOCK_OVERLAP"); c->block_overlap = e && atoi(e) != 0; }
 #undef CUI
 	*out = c;
 	return BSGPU_OK;
@@ -348,6 +356,9 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 	for (PinBuf &b : c->wire_pin) b.release();
 	for (cudaEvent_t ev : c->wire_landed) if (ev) cudaEventDestroy(ev);
 	for (cudaEvent_t ev : c->win_events) cudaEventDestroy(ev);
+	for (cudaEvent_t ev : c->pile_ev) if (ev) cudaEventDestroy(ev);
+	if (c->pile_stream) cudaStreamDestroy(c->pile_stream);
+	c->pile2.release();
 	for (bsgpu_ctx::ReaderSet &R : c->rs) {
 		for (cudaEvent_t ev : R.rd_up) cudaEventDestroy(ev);
 		for (cudaEvent_t ev : R.rd_done) cudaEventDestroy(ev);
@@ -702,6 +713,32 @@ static int call_bins(bsgpu_ctx *c, size_t nseg, const void *d_bases, const void 
 	// one launch each 5.54 ms, n = 8192: 6.59, 4096: 7.31, 2048: 8.95 -- the tails of the smaller launches cost more than the
 	// cached read-back saves (neither kernel is HBM-bound), so the default is 0: one launch each.
 	static const uint32_t sub = [] { const char *e = getenv("BSGPU_SUBSLAB_TILES"); const long v = e ? atol(e) : 0; return (uint32_t)(v < 0 ? 0 : v); }();
+	// BSGPU_BLOCK_OVERLAP=1 (see block_run): a window that comes in one piece (the _dev entry points; c->pile then holds the count
+	// vectors of the whole window) is cut into parts of 16 Ki tiles; the gather of part k + 1 runs on the context's pile stream
+	// next to the model of part k.
+	const uint32_t part = (2u << 20) / kPileTileSites;
+	if (c->block_overlap && !sub && nt > part && c->pile.cap >= ((size_t)nt * kPileTileSites) * sizeof(bsgpu_pileup)) {
+		if (!c->pile_stream) {
+			CU(cudaStreamCreateWithFlags(&c->pile_stream, cudaStreamNonBlocking));
+			for (cudaEvent_t &ev : c->pile_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+		}
+		CU(cudaEventRecord(c->pile_ev[4], st));
+		CU(cudaStreamWaitEvent(c->pile_stream, c->pile_ev[4], 0));
+		for (uint32_t k = 0, a = 0; a < nt; a += part, k++) {
+			const uint32_t m = nt - a < part ? nt - a : part, ta = t0 + a;
+			const size_t site0 = (size_t)ta * kPileTileSites, rel0 = (size_t)a * kPileTileSites;
+			const size_t nsite = (size_t)sz - site0 < (size_t)m * kPileTileSites ? (size_t)sz - site0 : (size_t)m * kPileTileSites;
+			uint8_t *pile = (uint8_t *)c->pile.p + rel0 * sizeof(bsgpu_pileup);
+			CU(launch_pileup_tiles(c->scratch.p, nseg, d_bases, d_ref, x, sz, ta, m, pile, 0, c->d_const, c->d_counters, c->pile_stream, &c->launches));
+			CU(cudaEventRecord(c->pile_ev[k & 1], c->pile_stream));
+			CU(cudaStreamWaitEvent(st, c->pile_ev[k & 1], 0));
+			CU(launch_call_sites(pile, (const uint8_t *)d_ref + site0, nsite, (uint8_t *)dout + rel0 * sizeof(bsgpu_gt_vcf), nullptr, true,
+					c->d_const, c->d_counters, st, &c->launches, (unsigned long long)x + site0, true));
+		}
+		// whatever is queued on `st` next (the next window's binning rewrites the scratch the gather reads) comes after the last model
+		// launch, which waited for the last gather
+		return BSGPU_OK;
+	}
 	const uint32_t step = sub ? sub : nt;
 	for (uint32_t k = 0, a = 0; a < nt; a += step, k++) {
 		const uint32_t m = nt - a < step ? nt - a : step, ta = t0 + a;
@@ -734,6 +771,21 @@ static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *
 	const uint32_t slab_tiles = defer ? slab : (ntiles < slab ? ntiles : slab);
 	CU(c->vcf.reserve((size_t)resident * slab_tiles * kPileTileSites * rec));
 	if (mode && !c->fused) CU(c->pile.reserve((size_t)(defer || ntiles >= slab ? slab : ntiles) * kPileTileSites * sizeof(bsgpu_pileup) + 16));
+	// BSGPU_BLOCK_OVERLAP=1: the gather of slab i + 1 runs on a stream of its own next to the model of slab i (two count-vector
+	// scratches, ping-pong).  The two kernels stall on different things -- the gather on instruction issue of integer / shared-memory
+	// work, the model on the latency of dependent FP64 chains -- so CTAs of both on one SM fill each other's gaps.  The model
+	// then takes its tiles by cp.async (launch_call_sites, overlap_safe).
+	static const bool no_sub = getenv("BSGPU_SUBSLAB_TILES") == nullptr;
+	const bool overlap = c->block_overlap && no_sub && mode && !c->fused && nslab > 1;
+	if (overlap) {
+		if (!c->pile_stream) {
+			CU(cudaStreamCreateWithFlags(&c->pile_stream, cudaStreamNonBlocking));
+			for (cudaEvent_t &ev : c->pile_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+		}
+		CU(c->pile2.reserve((size_t)slab * kPileTileSites * sizeof(bsgpu_pileup) + 16));
+		CU(cudaEventRecord(c->pile_ev[4], c->stream));              // inputs uploaded, segments binned
+		CU(cudaStreamWaitEvent(c->pile_stream, c->pile_ev[4], 0));
+	}
 	while (c->win_events.size() < 6) {
 		cudaEvent_t ev;
 		CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -748,7 +800,18 @@ static int block_run(bsgpu_ctx *c, const void *d_segs, size_t nseg, const void *
 		uint8_t *dslab = (uint8_t *)c->vcf.p + (size_t)r * slab_tiles * kPileTileSites * rec;
 		// ring slot drained: by this run, or by an earlier deferred run whose copy may still be in flight
 		if (si >= resident || c->ring_busy[r]) CU(cudaStreamWaitEvent(c->stream, copied, 0));
-		if (mode) { if (call_bins(c, nseg, d_bases, d_ref, x, sz, t0, nt, dslab, c->stream) != BSGPU_OK) return BSGPU_FAIL; }
+		if (overlap) {
+			const uint32_t b = c->pile_pos++ & 1;
+			uint8_t *pile = (uint8_t *)(b ? c->pile2.p : c->pile.p);
+			if (c->pile_used[b]) CU(cudaStreamWaitEvent(c->pile_stream, c->pile_ev[2 + b], 0));      // the model two slabs back has read this scratch
+			CU(launch_pileup_tiles(c->scratch.p, nseg, d_bases, d_ref, x, sz, t0, nt, pile, 0, c->d_const, c->d_counters, c->pile_stream, &c->launches));
+			CU(cudaEventRecord(c->pile_ev[b], c->pile_stream));
+			CU(cudaStreamWaitEvent(c->stream, c->pile_ev[b], 0));
+			CU(launch_call_sites(pile, (const uint8_t *)d_ref + site0, nsite, dslab, nullptr, true, c->d_const, c->d_counters, c->stream, &c->launches,
+					(unsigned long long)x + site0, true));
+			CU(cudaEventRecord(c->pile_ev[2 + b], c->stream));
+			c->pile_used[b] = true;
+		} else if (mode) { if (call_bins(c, nseg, d_bases, d_ref, x, sz, t0, nt, dslab, c->stream) != BSGPU_OK) return BSGPU_FAIL; }
 		else CU(launch_pileup_tiles(c->scratch.p, nseg, d_bases, d_ref, x, sz, t0, nt, dslab, 0, c->d_const, c->d_counters, c->stream, &c->launches));
 		CU(cudaEventRecord(computed, c->stream));
 		CU(cudaStreamWaitEvent(c->copy_stream, computed, 0));
