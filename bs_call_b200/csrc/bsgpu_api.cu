@@ -1537,6 +1537,9 @@ struct BamRunOpts {
 	// holds the first `keep` bytes of the old one (no copy into the old one is in flight when it is called)
 	uint8_t *(*grow)(void *user, size_t keep, size_t need, size_t *new_cap) = nullptr;
 	void *user = nullptr;
+	// a contig whose codes are missing when its first window is due (bsgpu_bam_on_contig): asks the host, then looks again
+	int (*need_contig)(void *user, int tid) = nullptr;
+	void *contig_user = nullptr;
 };
 
 // templates [tm, tm + nt) of ONE contig (their reads and events are resident from the decode) -> gt_vcf[] of window [x, y]
@@ -1796,6 +1799,8 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 				while (b1 < gb.size() && gb[b1].tid == gb[b0].tid) b1++;
 				const uint32_t tid = gb[b0].tid;
 				if ((int)tid >= n_targets) return fail("bsgpu_call_bam: record on contig %u, only %d contigs given", tid, n_targets);
+				if (!ctg_codes[tid] && opts && opts->need_contig && opts->need_contig(opts->contig_user, (int)tid) != BSGPU_OK)
+					return fail("bsgpu_bam: the host's contig callback failed for contig %u", tid);
 				if (!ctg_codes[tid]) return fail("bsgpu_call_bam: no reference codes were given for contig %u", tid);
 				if ((int)tid != cur_tid) { cur_tid = (int)tid; ctg_x0 = gb[b0].x; ctg_end = ctg_x0 - 1; ctg_ov = ov; }
 				// windows tile the contig; a block may begin ON the last site of the block before it (its x is two before its
@@ -1985,6 +1990,9 @@ struct bsgpu_bam_session {
 	bool bcf = false;
 	bsgpu_bcf_params bp;
 	std::vector<int32_t> rid;
+	int (*on_contig)(void *user, int tid) = nullptr;
+	void *on_contig_user = nullptr;
+	std::mutex contig_mu;
 	Session core;
 };
 
@@ -2003,6 +2011,14 @@ static int sess_run(void *user, const uint8_t *data, size_t len, bool whole, Ses
 	struct Told { void (*f)(void *, uint64_t, size_t, size_t); void *sess; uint64_t seq; } told{scanned, sess, seq};
 	BamRunOpts o;
 	o.partial = !whole; o.blocks_vec = &r->blocks; o.grow = Session::grow; o.user = &g;
+	if (s->on_contig) {
+		o.need_contig = [](void *u, int tid) {
+			bsgpu_bam_session *ss = (bsgpu_bam_session *)u;
+			std::lock_guard<std::mutex> lk(ss->contig_mu);
+			return ss->codes[tid] ? (int)BSGPU_OK : ss->on_contig(ss->on_contig_user, tid);
+		};
+		o.contig_user = s;
+	}
 	// runs of a session overlap: reader stage of this one under the window stage of the one before (BSGPU_SESSION_PIPELINE=0: one at a time)
 	static const bool pipeline = [] { const char *e = getenv("BSGPU_SESSION_PIPELINE"); return !e || atoi(e) != 0; }();
 	o.pipelined = true;
@@ -2062,6 +2078,12 @@ int bsgpu_bam_open(bsgpu_ctx *c, int n_targets, const uint32_t *target_len, cons
 int bsgpu_bam_set_contig(bsgpu_bam_session *s, int tid, const uint8_t *codes) {
 	if (!s || tid < 0 || tid >= s->n_targets) return fail("bsgpu_bam_set_contig: contig %d out of range", tid);
 	s->codes[tid] = codes;               // read by the worker only for contigs whose records are in a batch
+	return BSGPU_OK;
+}
+
+int bsgpu_bam_on_contig(bsgpu_bam_session *s, int (*fn)(void *user, int tid), void *user) {
+	if (!s) return fail("bsgpu_bam_on_contig: null session");
+	s->on_contig = fn; s->on_contig_user = user;
 	return BSGPU_OK;
 }
 

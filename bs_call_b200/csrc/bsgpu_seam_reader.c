@@ -31,6 +31,9 @@
 #include <sys/stat.h>
 #include <htslib/sam.h>
 #include <htslib/vcf.h>
+#ifdef BSGPU_SEAM_BULK_IO
+#include <htslib/bgzf.h>
+#endif
 
 #include "gem_tools.h"
 #include "bs_call.h"
@@ -379,6 +382,30 @@ static void contig_annotation(sr_param * const param, ctg_t * const ctg, const i
 	unload_dbSNP_ctg(dc);
 }
 
+/* A contig begins (src/get_template_vector.c:111-124): its region, its sequence, on seam D its dbSNP entries and GC bins.  Called by
+ * the reader when the first record of the contig arrives, or -- when the reader hands over inflated bytes without looking at the
+ * records -- by the session's worker before the contig's first results are computed (bsgpu_bam_on_contig). */
+static int start_contig(void * const user, const int tid) {
+	taker_t * const tk = user;
+	sr_param * const param = tk->param;
+	work_t * const work = &param->work;
+	const int k = tid >= 0 && tid < tk->n_targets ? work->tid2id[tid] : -1;
+	if (k < 0) return BSGPU_FAIL;
+	ctg_t * const ctg = work->contigs[k];
+	fprintf(stderr, "Processing chromosome %s (OK)\n", ctg->name);
+	ctg->curr_reg = work->curr_region;
+	if (tk->codes[tid] == NULL) tk->codes[tid] = contig_codes(ctg, param);
+	if (tk->codes[tid] == NULL) {
+		fprintf(stderr, "Problem loading reference sequence for contig '%s'\n", ctg->name);
+		return BSGPU_FAIL;
+	}
+	if (tk->records) contig_annotation(param, ctg, tid);
+	if (bsgpu_bam_set_contig(tk->sess, tid, tk->codes[tid]) != BSGPU_OK) die("bsgpu_bam_set_contig");
+	if (g_site_stats && ctg->ctg_stats != NULL && ctg->ctg_stats->gc != NULL
+			&& bsgpu_set_contig_gc(g_ctx, ctg->vcf_rid, ctg->start_pos, ctg->ctg_stats->gc, (uint32_t)ctg->ctg_stats->nbins) != BSGPU_OK) die("bsgpu_set_contig_gc");
+	return BSGPU_OK;
+}
+
 gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param) {
 	work_t * const work = &param->work;
 	bam_hdr_t * const hdr = work->sam_header;
@@ -456,6 +483,44 @@ gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param
 		fprintf(stderr, "Processing region %s:%u-%u\n", reg->ctg->name, reg->start, reg->stop);
 		work->curr_region = reg;
 	}
+#ifdef BSGPU_SEAM_BULK_IO
+	/* Bulk input: when every contig of the header is wanted and no index region restricts the run, the record bytes need not be
+	 * looked at on the host at all -- the session frames, filters and decodes them on the device.  bgzf_read() inflates
+	 * straight into the session's page-locked stage (bsgpu_bam_reserve / _commit, no copy), and the contig bookkeeping of
+	 * src/get_template_vector.c:111-124 happens when the session reaches the contig (bsgpu_bam_on_contig -> start_contig).
+	 * sam_read1() + one copy per record was 2.8 of the 5.9 s of a config-1 run.  BSGPU_SEAM_BULK=0 keeps the record loop. */
+	{
+		const char *e = getenv("BSGPU_SEAM_BULK");
+		bool bulk = (e == NULL || atoi(e) != 0) && itr == NULL && n_reg == 0 && sam_input->format.format == bam;
+		for (int t = 0; t < nt && bulk; t++) if (work->tid2id[t] < 0) bulk = false;
+		if (bulk) {
+			if (bsgpu_bam_on_contig(tk.sess, start_contig, &tk) != BSGPU_OK) die("bsgpu_bam_on_contig");
+			gt_status st = GT_STATUS_OK;
+			for (;;) {
+				uint8_t *dst = NULL;
+				size_t avail = 0;
+				if (bsgpu_bam_reserve(tk.sess, &dst, &avail, 1) != BSGPU_OK) { fprintf(stderr, "bsgpu: %s\n", bsgpu_last_error()); st = GT_STATUS_FAIL; break; }
+				if (avail > ((size_t)4 << 20)) avail = (size_t)4 << 20;       /* an open reservation holds the stage: a few MB at a time */
+				const ssize_t got = bgzf_read(sam_input->fp.bgzf, dst, avail);
+				if (bsgpu_bam_commit(tk.sess, got > 0 ? (size_t)got : 0) != BSGPU_OK) { fprintf(stderr, "bsgpu: %s\n", bsgpu_last_error()); st = GT_STATUS_FAIL; break; }
+				if (got < 0) { st = GT_STATUS_FAIL; break; }
+				if (got == 0) break;
+				if (tk.failed) { st = GT_STATUS_FAIL; break; }
+			}
+			stamp("last byte fed (bulk)");
+			if (bsgpu_bam_finish(tk.sess) != BSGPU_OK) { fprintf(stderr, "bsgpu: %s\n", bsgpu_last_error()); st = GT_STATUS_FAIL; }
+			pthread_join(taker, NULL);
+			stamp("last result written");
+			if (tk.failed) st = GT_STATUS_FAIL;
+			bsgpu_bam_close(tk.sess);
+			stamp("session closed");
+			for (int t = 0; t < nt; t++) free(tk.codes[t]);
+			free(tk.codes);
+			free(rid);
+			return st;
+		}
+	}
+#endif
 	bam1_t *b = bam_init1();
 	int curr_tid = -1;
 	bool chr_skip = false;
@@ -482,21 +547,8 @@ gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param
 			curr_tid = c->tid;
 			const int k = c->tid < nt ? work->tid2id[curr_tid] : -1;
 			chr_skip = k < 0;
-			fprintf(stderr, "Processing chromosome %s (%s)\n", hdr->target_name[curr_tid], chr_skip ? "SKIP" : "OK");
-			if (!chr_skip) {
-				ctg_t * const ctg = work->contigs[k];
-				ctg->curr_reg = work->curr_region;
-				if (tk.codes[curr_tid] == NULL) tk.codes[curr_tid] = contig_codes(ctg, param);
-				if (tk.codes[curr_tid] == NULL) {
-					fprintf(stderr, "Problem loading reference sequence for contig '%s'\n", ctg->name);
-					st = GT_STATUS_FAIL;
-					break;
-				}
-				if (tk.records) contig_annotation(param, ctg, curr_tid);
-				if (bsgpu_bam_set_contig(tk.sess, curr_tid, tk.codes[curr_tid]) != BSGPU_OK) die("bsgpu_bam_set_contig");
-				if (g_site_stats && ctg->ctg_stats != NULL && ctg->ctg_stats->gc != NULL
-						&& bsgpu_set_contig_gc(g_ctx, ctg->vcf_rid, ctg->start_pos, ctg->ctg_stats->gc, (uint32_t)ctg->ctg_stats->nbins) != BSGPU_OK) die("bsgpu_set_contig_gc");
-			}
+			if (chr_skip) fprintf(stderr, "Processing chromosome %s (SKIP)\n", hdr->target_name[curr_tid]);
+			else if (start_contig(&tk, curr_tid) != BSGPU_OK) { st = GT_STATUS_FAIL; break; }
 		}
 		if (chr_skip || c->tid < 0) continue;               /* records without a wanted contig never reach a block */
 		/* the record as it lies in a BAM file: block_size, the 32 fixed bytes, then qname | cigar | seq | qual | aux */

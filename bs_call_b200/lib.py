@@ -20,7 +20,7 @@ BSGPU_FAIL = -1
 # every symbol include/bsgpu.h declares (tests/test_abi.py checks the header and this list against the .so)
 EXPORTS = [
     "bsgpu_default_params", "bsgpu_init", "bsgpu_destroy", "bsgpu_last_error", "bsgpu_get_stats", "bsgpu_version",
-    "bsgpu_sync", "bsgpu_guard_read", "bsgpu_debug_redzones", "bsgpu_host_alloc", "bsgpu_host_free",
+    "bsgpu_sync", "bsgpu_guard_read", "bsgpu_debug_redzones", "bsgpu_bam_on_contig", "bsgpu_host_alloc", "bsgpu_host_free",
     "bsgpu_call_sites", "bsgpu_pileup_block", "bsgpu_call_block", "bsgpu_stage_bound", "bsgpu_stage_templates",
     "bsgpu_process_block", "bsgpu_profile_enable", "bsgpu_profile_read", "bsgpu_build_blocks_tally",
     "bsgpu_site_stats_enable", "bsgpu_set_contig_gc", "bsgpu_site_stats_read",

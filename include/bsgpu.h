@@ -412,6 +412,12 @@ int bsgpu_bam_open(bsgpu_ctx *ctx, int n_targets, const uint32_t *target_len, co
 /* the reference codes of a contig that was NULL at bsgpu_bam_open (a host that loads contigs as the stream reaches them):
  * call it before the first record of that contig is fed; the array must stay valid until the session is closed */
 int bsgpu_bam_set_contig(bsgpu_bam_session *s, int tid, const uint8_t *codes);
+/* For a host that feeds bytes without looking at the records (BGZF blocks inflated straight into bsgpu_bam_reserve's buffer):
+ * `fn(user, tid)` is called by the session's worker when the results of contig `tid` are about to be computed and no codes
+ * were set for it -- once per contig, in stream order, never concurrently with itself.  It may call bsgpu_bam_set_contig,
+ * bsgpu_set_contig_annotation and bsgpu_set_contig_gc; a return value other than BSGPU_OK (or codes still missing) fails the
+ * session.  Counterpart of the contig change in read_input (src/get_template_vector.c:111-124). */
+int bsgpu_bam_on_contig(bsgpu_bam_session *s, int (*fn)(void *user, int tid), void *user);
 /* copies the slice into the session's staging.  accepted == NULL: blocks while both staging buffers are full;
  * accepted != NULL: never blocks, *accepted <= nbytes says how much was taken (drain, then offer the rest again) */
 int bsgpu_bam_feed(bsgpu_bam_session *s, const uint8_t *bytes, size_t nbytes, size_t *accepted);

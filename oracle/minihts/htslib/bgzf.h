@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <sys/types.h>
 typedef struct BGZF BGZF;
+ssize_t bgzf_read(BGZF *fp, void *data, size_t length);      /* bytes read (less than length only at the end of the file), < 0 on error */
 int bgzf_getc(BGZF *fp);
 int bgzf_useek(BGZF *fp, off_t uoffset, int where);
 #endif

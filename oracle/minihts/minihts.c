@@ -130,6 +130,8 @@ static long bgzf_read_bytes(BGZF *b, void *dst, size_t n) {
 	return (long)got;
 }
 
+ssize_t bgzf_read(BGZF *b, void *data, size_t length) { return (ssize_t)bgzf_read_bytes(b, data, length); }
+
 int bgzf_getc(BGZF *b) {
 	if (b->upos == b->ulen) { if (bgzf_fill(b) != 0) return -1; }
 	return b->ubuf[b->upos++];

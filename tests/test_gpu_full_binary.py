@@ -28,6 +28,10 @@ VARIANTS = {
     "seamC": ("bs_call_gpu", {}),
     "seamD": ("bs_call_gpu", {"BSGPU_SEAM_RECORDS": "1"}),
     "narrow": ("bs_call_gpu_narrow", {}),
+    # the record loop (sam_read1 per record) instead of the bulk input (bgzf_read straight into the session's stage), which is
+    # what seams C / D use when every contig of the header is wanted
+    "seamC_loop": ("bs_call_gpu", {"BSGPU_SEAM_BULK": "0"}),
+    "seamD_loop": ("bs_call_gpu", {"BSGPU_SEAM_RECORDS": "1", "BSGPU_SEAM_BULK": "0"}),
 }
 
 
@@ -52,7 +56,7 @@ def compare(got, want, what, tol=0.002):
     return len(only), len(differ)
 
 
-@pytest.mark.parametrize("variant", ["seamC", "seamD", "narrow"])
+@pytest.mark.parametrize("variant", ["seamC", "seamD", "narrow", "seamD_loop"])
 @pytest.mark.parametrize("seed,extra", [(3, ()), (11, ("-k",)), (12, ("-d",)), (13, ("-q", "5", "-l", "400", "-L", "3", "-R", "2,4"))])
 def test_gpu_binary_writes_the_cpu_binarys_records(tmp_path, variant, seed, extra):
     path, env = gpu_binary(variant)
@@ -67,7 +71,7 @@ def test_gpu_binary_writes_the_cpu_binarys_records(tmp_path, variant, seed, extr
     compare(rg, rc, "%s seed %d %s" % (variant, seed, " ".join(extra)))
 
 
-@pytest.mark.parametrize("variant", ["seamC", "seamD"])
+@pytest.mark.parametrize("variant", ["seamC", "seamD", "seamC_loop", "seamD_loop"])
 def test_gpu_binary_on_several_contigs(reference, tmp_path, variant):
     """three contigs: the wide seams keep every contig's end (the reader does not free a contig under the print thread), so the
     file holds what the harness-driven chain produces -- the CPU binary itself loses records of contig ends to its race
@@ -98,7 +102,7 @@ def test_gpu_binary_all_positions_vcf_text(tmp_path):
     assert len(bad) <= max(3, len(lc) // 500), [(lc[i], lg[i]) for i in bad[:3]]
 
 
-@pytest.mark.parametrize("variant", ["seamC", "seamD"])
+@pytest.mark.parametrize("variant", ["seamC", "seamD", "seamD_loop"])
 def test_gpu_binary_report_file(tmp_path, variant):
     """--report-file: the JSON statistics of the GPU binary against the CPU binary's.  Seam C: the reference's writer over the
     device's gt_vcf[], the read-level tallies and the conversion profile from the device.  Seam D: the site statistics of
@@ -144,7 +148,7 @@ def test_gpu_binary_report_file(tmp_path, variant):
     assert len(hard) <= max(10, len(lc) // 50), hard[:10]
 
 
-@pytest.mark.parametrize("variant", ["seamC", "seamD"])
+@pytest.mark.parametrize("variant", ["seamC", "seamD", "seamD_loop"])
 def test_gpu_binary_with_dbsnp_index(tmp_path, variant):
     """-D: the reference's index reader over a synthetic index file (tests/test_full_binary.py::test_binary_with_dbsnp_index).
     Seam C keeps the reference's writer, which looks every site up; on seam D the reader loads the contig's entries and hands
@@ -167,3 +171,22 @@ def test_gpu_binary_with_dbsnp_index(tmp_path, variant):
     _, rp = hostio.read_bcf(plain)
     assert len(_keyed(rc)) > len(_keyed(rp))         # the index added always-written sites
     compare(rg, rc, variant + " with -D")
+
+
+@pytest.mark.parametrize("variant", ["seamD", "seamD_loop"])
+def test_gpu_binary_several_contigs_with_dbsnp(reference, tmp_path, variant):
+    """three contigs with -D on seam D: every contig's entries reach the device writer when the session gets to the contig (bulk
+    input: from the session's worker through bsgpu_bam_on_contig), against the harness chain with the same table"""
+    from tests.test_full_binary import synthetic_dbsnp
+    path, env = gpu_binary(variant)
+    rng = np.random.default_rng(5)
+    bam, n, tl, refs = bamgen.make_stream(3, n_contigs=3)
+    names, fa, bf = write_case(str(tmp_path), bam, tl, refs)
+    files, arrays = synthetic_dbsnp(rng, tl, frac=0.03)
+    idx = os.path.join(str(tmp_path), "db.idx")
+    hostio.write_dbsnp_index(idx, files, prefixes=("rs", "ss"), bins_per_block=20)
+    gpu = os.path.join(str(tmp_path), "gpu.bcf")
+    run_binary(path, fa, bf, gpu, extra=("-D", idx), env=env)
+    _, rg = hostio.read_bcf(gpu)
+    want = chain_records(reference, bam, tl, refs, dbsnp=arrays)
+    compare(rg, want, variant + " three contigs with -D")
