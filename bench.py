@@ -709,10 +709,17 @@ def full_binary_path(args, gpu, bslib, torch, np, stream, local):
                "sites_called": int(called), "host_cores": ncores, "file_prep_s": prep,
                "htslib": "oracle/minihts (this repository's stand-in: no htslib in the image; single-threaded BGZF, BAM, faidx, BCF2), so every additional thread goes to the calc threads (-t n,0,0; src/parse_args.c:191-213 would give 3/7 of them to BGZF input threads the stand-in does not have)"}
         log("full binary: reference bs_call on %d cores ..." % ncores)
-        out["cpu_reference_binary"], f_cpu = run("cpu", bins["bs_call"], {})
+        def best_of(n, *a):
+            # process start-up (CUDA context, page cache) varies by seconds from run to run: the faster of n runs, all walls reported
+            runs = [run(*a) for _ in range(n)]
+            best = min(runs, key=lambda r: r[0]["wall_s"])
+            best[0]["wall_s_all_runs"] = [r[0]["wall_s"] for r in runs]
+            return best
+
+        out["cpu_reference_binary"], f_cpu = best_of(2, "cpu", bins["bs_call"], {})
         log("full binary: bs_call_gpu (seam C, then seam D) ...")
-        out["gpu_seam_C"], f_c = run("gpu_c", bins["bs_call_gpu"], {})
-        out["gpu_seam_D"], f_d = run("gpu_d", bins["bs_call_gpu"], {"BSGPU_SEAM_RECORDS": "1"})
+        out["gpu_seam_C"], f_c = best_of(2, "gpu_c", bins["bs_call_gpu"], {})
+        out["gpu_seam_D"], f_d = best_of(2, "gpu_d", bins["bs_call_gpu"], {"BSGPU_SEAM_RECORDS": "1"})
         out["gpu_seam_C"]["note"] = "read_input / process_template_vector / call_genotypes_ML on the device, the reference's print thread writes (src/print_vcf.c on one host thread)"
         out["gpu_seam_D"]["note"] = "additionally print_vcf_entry's work on the device: BCF records handed to bcf_write"
         _, rc_ = hostio.read_bcf(f_cpu)

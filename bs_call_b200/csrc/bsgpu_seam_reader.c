@@ -496,12 +496,21 @@ gt_status read_input(htsFile *sam_input, gt_vector * align_list, sr_param *param
 		if (bulk) {
 			if (bsgpu_bam_on_contig(tk.sess, start_contig, &tk) != BSGPU_OK) die("bsgpu_bam_on_contig");
 			gt_status st = GT_STATUS_OK;
+			bool first_slice = true;
 			for (;;) {
 				uint8_t *dst = NULL;
 				size_t avail = 0;
 				if (bsgpu_bam_reserve(tk.sess, &dst, &avail, 1) != BSGPU_OK) { fprintf(stderr, "bsgpu: %s\n", bsgpu_last_error()); st = GT_STATUS_FAIL; break; }
 				if (avail > ((size_t)4 << 20)) avail = (size_t)4 << 20;       /* an open reservation holds the stage: a few MB at a time */
 				const ssize_t got = bgzf_read(sam_input->fp.bgzf, dst, avail);
+				if (first_slice && got >= 8) {
+					/* the first contig's sequence now, before the pipeline has anything to wait for (the later ones when the
+					 * session reaches them, under the batches already queued) */
+					int32_t tid0;
+					memcpy(&tid0, dst + 4, 4);
+					if (tid0 >= 0 && tid0 < nt && start_contig(&tk, tid0) != BSGPU_OK) { bsgpu_bam_commit(tk.sess, 0); st = GT_STATUS_FAIL; break; }
+				}
+				first_slice = false;
 				if (bsgpu_bam_commit(tk.sess, got > 0 ? (size_t)got : 0) != BSGPU_OK) { fprintf(stderr, "bsgpu: %s\n", bsgpu_last_error()); st = GT_STATUS_FAIL; break; }
 				if (got < 0) { st = GT_STATUS_FAIL; break; }
 				if (got == 0) break;
