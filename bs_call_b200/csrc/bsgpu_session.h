@@ -62,6 +62,7 @@ public:
 	Stage stage[2];
 	int w = 0;                               // staging buffer the caller fills
 	bool filling = false;                    // the caller is writing into stage[w] outside the lock
+	int carry_waiters = 0;                   // runs waiting for the caller's reservation to close so that they can move their carry
 	std::mutex mu;
 	std::condition_variable cv;
 	struct Run { std::thread th; int buf = 0; bool final = false, whole = false, scanned = false, returned = false; uint64_t seq = 0; size_t len = 0; const uint8_t *data = nullptr; };
@@ -110,6 +111,7 @@ public:
 		if (filling) { *err = "bsgpu_bam_feed: a reservation is open"; return false; }
 		size_t off = 0;
 		while (off < nbytes) {
+			if (carry_waiters) cv.wait(lk, [&] { return carry_waiters == 0 || failed || closing; });
 			if (!room(lk, nowait)) break;
 			Stage &st = stage[w];
 			const size_t m = std::min(nbytes - off, batch_bytes - (st.fill - st.head));
@@ -135,6 +137,7 @@ public:
 		*ptr = nullptr; *avail = 0;
 		if (finishing) { *err = "bsgpu_bam_reserve: the stream was finished"; return false; }
 		if (filling) { *err = "bsgpu_bam_reserve: the previous reservation was not committed"; return false; }
+		if (carry_waiters) cv.wait(lk, [&] { return carry_waiters == 0 || failed || closing; });
 		if (!room(lk, !wait)) { if (failed) { *err = errmsg; return false; } return true; }
 		Stage &st = stage[w];
 		*ptr = st.p + st.fill;
@@ -340,7 +343,11 @@ private:
 		const size_t carry = r->len - consumed;
 		Stage &nx = stage[r->buf ^ 1];
 		if (carry && !failed) {
+			// a caller that reserves again the moment it has committed (bulk input) would win the mutex every time: it yields
+			// to waiting carries in reserve() / feed()
+			carry_waiters++;
 			cv.wait(lk, [&] { return !filling || closing; });
+			carry_waiters--;
 			if (carry > nx.start && !stage_fit(r->buf ^ 1, carry + (nx.head - nx.start))) { failed = true; errmsg = "bsgpu_bam: cannot allocate staging memory for the carried records"; }
 			if (!failed) { memcpy(nx.p + nx.start - carry, r->data + consumed, carry); nx.start -= carry; }
 		}
