@@ -875,7 +875,7 @@ def main():
     ap.add_argument("--genome-batch-mb", type=int, default=384, help="genome leg: batch size of the streaming session")
     ap.add_argument("--genome-sessions", type=int, default=2, help="genome leg: sessions (contexts) per GPU, regions dealt out between them")
     ap.add_argument("--no-genome", action="store_true", help="skip the genome leg")
-    ap.add_argument("--binary-sites", type=float, default=20e6, help="whole-program leg: sites of the BAM file both bs_call binaries read (config 1 is 50 M)")
+    ap.add_argument("--binary-sites", type=float, default=50e6, help="whole-program leg: sites of the BAM file both bs_call binaries read (config 1 = configs[0] is 50 M)")
     ap.add_argument("--legs", default="e2e,block,bam,writer,genome,binary,cpu", help="secondary legs to run (comma separated)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
