@@ -196,26 +196,6 @@ def test_device_scan_of_certain_block_starts(monkeypatch, seed):
         g.close()
 
 
-@pytest.mark.parametrize("name", ["reader_pe", "reader_mixed"])
-def test_host_scan_of_certain_block_starts(monkeypatch, name):
-    """BSGPU_HOST_SCAN=1: the keys come home and host threads mark the certain block starts (the default before the device's
-    mask became it): same blocks as the golden"""
-    monkeypatch.setenv("BSGPU_HOST_SCAN", "1")
-    monkeypatch.setenv("BSGPU_READER_CHUNK_MIN_BYTES", "1")
-    monkeypatch.setenv("BSGPU_BUILDER_MIN_RECORDS", "1")
-    g = util.load_golden(name)
-    refs = [g["ref%d" % i] for i in range(len(g["target_len"]))]
-    gpu = bslib.BsGpu()
-    try:
-        rp = _rp({k: (bool(g[k]) if k.startswith(("keep", "ignore")) else int(g[k])) for k in ("mapq_thresh", "max_template_len", "keep_unmatched", "ignore_duplicates", "keep_duplicates")})
-        blocks, vcf = gpu.call_bam(g["bam"], g["target_len"], refs, rp)
-        assert len(blocks) == len(g["blocks"])
-        for f in ("tid", "x", "y", "n_templates"):
-            assert (blocks[f] == g["blocks"][f]).all(), f
-    finally:
-        gpu.close()
-
-
 def test_exact_offset_table_path(monkeypatch):
     """windows whose mates get exact offsets instead of uniform slots (what a piece with a very long reference span falls
     back to; BSGPU_EXACT_SLOTS forces it): same records"""
