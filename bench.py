@@ -628,8 +628,9 @@ def genome_path(args, gpu, bslib, torch, np, stream, rank, world, local):
 def full_binary_path(args, gpu, bslib, torch, np, stream, local):
     """The whole program: the reference's unmodified bs_call binary and the same program with the product's
     seam files (oracle/_ref/bs_call, bs_call_gpu: oracle/Makefile, over oracle/minihts as htslib stand-in), both run from the
-    command line on a BAM file + FASTA file of the config-1 shape; wall clock of the processes, options as SURVEY.md 8d states
-    them, BCF outputs compared.  rank 0, N = 1 only."""
+    command line on a BAM file + FASTA file of the config-1 shape (BASELINE.json configs[0] and [2]: "bs_call -L5", the same BAM
+    end to end on one B200, BCF diffed against the CPU run); wall clock of the processes, options as SURVEY.md 8d states them.
+    rank 0, N = 1 only."""
     import subprocess, tempfile, shutil
     from bs_call_b200 import hostio
     from oracle.bindings import bcf_diff
@@ -686,7 +687,7 @@ def full_binary_path(args, gpu, bslib, torch, np, stream, local):
 
         def run(tag, binary, env_extra):
             outp = os.path.join(tmp, tag + ".bcf")
-            cmd = [binary, "-r", fa, "-n", "S", "--benchmark-mode", "-O", "u", "-o", outp, "-t", "%d,0,0" % max(1, ncores - 1), bf]
+            cmd = [binary, "-r", fa, "-n", "S", "-L", "5", "--benchmark-mode", "-O", "u", "-o", outp, "-t", "%d,0,0" % max(1, ncores - 1), bf]
             env = dict(os.environ)
             env.update(env_extra)
             env["BSGPU_DEVICE"] = str(local)
