@@ -186,7 +186,10 @@ static int bgzf_close_file(BGZF *b) {
 	int r = 0;
 	if (b->is_write) {
 		if (b->ulen) r |= bgzf_flush_block(b);
-		if (b->compressed) r |= bgzf_flush_block(b);       /* the empty EOF block */
+		if (b->compressed) {                               /* the canonical 28-byte empty block that marks the end of a BGZF file */
+			static const uint8_t eof_block[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+			if (fwrite(eof_block, 1, 28, b->f) != 28) r = -1;
+		}
 		r |= fflush(b->f);
 	}
 	if (b->f != stdout && b->f != stdin) fclose(b->f);

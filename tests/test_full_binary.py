@@ -195,3 +195,28 @@ def test_binary_with_dbsnp_index(binary, reference, tmp_path):
     assert d["records_a"] == d["records_b"] == d["identical"] and d["order_violations"] == 0, d
     plain = chain_records(reference, bam, tl, refs)
     assert len(want) > len(plain)                      # ids and always-written sites are in there
+
+
+def test_bgzf_files_are_plain_multi_member_gzip(binary, tmp_path):
+    """BGZF is a series of gzip members (SAM specification 4.1): what hostio writes as input and what the stand-in writes as
+    output (-O b: deflated, -O u: stored blocks) must decompress with an independent gzip implementation to the same payload
+    the BGZF-aware reader sees, and end with the 28-byte empty EOF block"""
+    import gzip
+    bam, n, tl, refs = bamgen.make_stream(9, n_contigs=1)
+    names, fa, bf = write_case(str(tmp_path), bam, tl, refs)
+    raw = open(bf, "rb").read()
+    payload = gzip.decompress(raw)
+    assert payload == hostio.read_bgzf(bf) and payload.startswith(b"BAM\x01") and payload.endswith(bytes(bam[-64:]))
+    eof = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    assert raw.endswith(eof)
+    for ot in ("u", "b"):
+        out = os.path.join(str(tmp_path), "o_%s.bcf" % ot)
+        run_binary(binary, fa, bf, out, otype=ot)
+        r = open(out, "rb").read()
+        assert r.endswith(eof)
+        assert gzip.decompress(r) == hostio.read_bgzf(out)
+    vz = os.path.join(str(tmp_path), "o.vcf.gz")
+    run_binary(binary, fa, bf, vz, otype="z")
+    vt = os.path.join(str(tmp_path), "o.vcf")
+    run_binary(binary, fa, bf, vt, otype="v")
+    assert gzip.decompress(open(vz, "rb").read()) == open(vt, "rb").read()
