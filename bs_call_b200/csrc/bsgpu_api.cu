@@ -177,7 +177,7 @@ struct bsgpu_ctx {
 	// Two sets, so that a streaming session can have the reader stage of batch k + 1 under way (framing, upload, decode,
 	// certain-start scan, block builder) while the windows of batch k are still being queued and run.
 	struct ReaderSet {
-		DevBuf rd_bam, rd_recoff, rd_readoff, rd_mmoff, rd_rec, rd_bases, rd_misms, rd_key, rd_mask, rd_names, rd_nameid;
+		DevBuf rd_bam, rd_recoff, rd_readoff, rd_mmoff, rd_rec, rd_bases, rd_misms, rd_key, rd_mask, rd_scan, rd_names, rd_nameid;
 		PinBuf h_nameid;                         // name ids of the records coming home (QNAME join on the device)
 		std::vector<size_t> mask_off;            // word offset of every chunk's certain-start mask in rd_mask / h_mask
 		std::vector<uint64_t> rec_off;           // framing of the stream
@@ -363,7 +363,7 @@ void bsgpu_destroy(bsgpu_ctx *c) {
 		for (cudaEvent_t ev : R.rd_up) cudaEventDestroy(ev);
 		for (cudaEvent_t ev : R.rd_done) cudaEventDestroy(ev);
 		if (R.frame_scratch) frame_scratch_free(R.frame_scratch);
-		R.h_rec.release(); R.h_off.release(); R.h_tmpl.release(); R.h_key.release(); R.rd_key.release(); R.h_mask.release(); R.rd_mask.release();
+		R.h_rec.release(); R.h_off.release(); R.h_tmpl.release(); R.h_key.release(); R.rd_key.release(); R.h_mask.release(); R.rd_mask.release(); R.rd_scan.release();
 		R.rd_names.release(); R.rd_nameid.release(); R.h_nameid.release();
 		R.rd_bam.release(); R.rd_recoff.release(); R.rd_readoff.release(); R.rd_mmoff.release(); R.rd_rec.release(); R.rd_bases.release(); R.rd_misms.release();
 		if (R.up && R.up != c->slot[0].stream) cudaStreamDestroy(R.up);
@@ -1373,6 +1373,7 @@ static int decode_queue(bsgpu_ctx *c, bsgpu_ctx::ReaderSet &R, const uint8_t *ba
 	CU(cudaMemsetAsync(R.rd_names.p, 0, name_table_bytes(n), dec));
 	CU(cudaMemsetAsync((uint32_t *)R.rd_nameid.p + n, 0, 4, dec));
 	CU(R.rd_mask.reserve((n / 32 + 2 * K + 8) * 4 + 16));
+	if (dev_scan) CU(R.rd_scan.reserve(certain_scratch_bytes(n)));
 	CU(R.h_mask.reserve((n / 32 + 2 * K + 8) * 4));
 	R.mask_off.assign(K + 1, 0);
 	uint32_t *d_carry = (uint32_t *)R.rd_mask.p;          // first four words of the buffer: {last contig, running end}
@@ -1426,7 +1427,7 @@ static int decode_queue(bsgpu_ctx *c, bsgpu_ctx::ReaderSet &R, const uint8_t *ba
 			if (host_scan) CU(cudaMemcpyAsync((uint8_t *)R.h_key.p + r0 * 16, (const uint8_t *)R.rd_key.p + r0 * 16, (r1 - r0) * 16, cudaMemcpyDeviceToHost, dec));
 			if (dev_scan) {
 				const size_t words = (r1 - r0 + 31) / 32;
-				CU(launch_certain_starts((const uint8_t *)R.rd_key.p + r0 * 16, (uint32_t)(r1 - r0), d_carry, (uint32_t *)R.rd_mask.p + mask_words, dec, &c->launches));
+				CU(launch_certain_starts((const uint8_t *)R.rd_key.p + r0 * 16, (uint32_t)(r1 - r0), d_carry, (uint32_t *)R.rd_mask.p + mask_words, R.rd_scan.p, dec, &c->launches));
 				CU(cudaMemcpyAsync((uint32_t *)R.h_mask.p + mask_words, (const uint32_t *)R.rd_mask.p + mask_words, words * 4, cudaMemcpyDeviceToHost, dec));
 				R.mask_off[k] = mask_words;
 				mask_words += words;

@@ -122,7 +122,8 @@ cudaError_t launch_name_ids(const void *bam, const void *rec_off, const void *re
 		void *name_id, cudaStream_t stream, int *launches);
 
 // certain block starts of a chunk of records as a bit mask, from the keys launch_decode_records wrote (bsgpu_reader.cu)
-cudaError_t launch_certain_starts(const void *keys, uint32_t n, void *carry, void *mask, cudaStream_t stream, int *launches);
+cudaError_t launch_certain_starts(const void *keys, uint32_t n, void *carry, void *mask, void *scratch, cudaStream_t stream, int *launches);
+size_t certain_scratch_bytes(size_t n);       // scratch of launch_certain_starts for n records
 
 constexpr int kPileTileSites = 128;      // sites per tile of the gather kernel (= its CTA size)
 constexpr int kMaxSegLen = 256;          // BSGPU_MAX_SEG_LEN

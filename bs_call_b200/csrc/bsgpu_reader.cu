@@ -281,93 +281,134 @@ k_decode_records(const uint8_t *__restrict__ bam, const uint64_t *__restrict__ r
 
 // ---------------------------------------------------------------------------------------------------------------
 // device: certain block starts (see certain_block_starts below for what they are) as a bit per record.
-// The host formulation is a running maximum that is reset at every contig change: a segmented max-scan.  One CTA walks
-// the chunk in tiles of 4096 keys (four consecutive records per thread): a take-right scan gives every thread the contig
+// The host formulation is a running maximum that is reset at every contig change: a segmented max-scan over tiles of 4096
+// keys (four consecutive records per thread), one CTA per tile: a take-right scan gives every thread the contig
 // of the last kept record before its own, which decides where segments begin; a segmented max-scan of the records' ends
 // gives it the running end before its records; with those it replays its four records exactly as the host loop would.
 // The state at the end of a chunk is carried to the next launch through `carry` ({last contig, running end}).
-// One CTA on purpose: the chunk is 6 MB of keys, the scan runs beside the decode of the next chunk and off the host's
-// critical path; ~0.1 us per 1000 records.
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 constexpr uint32_t kNoTid = 0xffffffffu;
 struct SegMax { uint32_t flag; uint32_t m; };      // flag: a segment begins inside; m: maximum since the last begin
 __device__ __forceinline__ SegMax seg_combine(SegMax a, SegMax b) { return SegMax{a.flag | b.flag, b.flag ? b.m : max(a.m, b.m)}; }
 
-__global__ void __launch_bounds__(1024) k_certain_starts(const uint4 *__restrict__ keys, uint32_t n, uint32_t *__restrict__ carry, uint32_t *__restrict__ mask) {
-	__shared__ uint32_t w_tid[32];
+// Three phases so that the scan fills the device instead of one SM (the first version was ONE CTA walking the chunk: 56 ms per
+// 10 M records in the reader stage against 13 ms for four host threads):
+//   k_certain_tile<false>  every 4096-key tile summarises itself as if the stream simply continued into it: first / last kept
+//                          contig, "a contig change inside", running end since the last change (or since the tile began);
+//   k_certain_combine      one CTA chains the summaries from the carried state: the state every tile starts from;
+//   k_certain_tile<true>   every tile replays its records from that state and writes its 128 mask words.
+// tests/test_cpu_reader.py emulates the three phases against the sequential scan; BSGPU_CHECK_SCAN=1 compares on the device.
+struct TileAgg { uint32_t first, last, flag, m; };
+
+template <bool FINAL>
+__global__ void __launch_bounds__(1024) k_certain_tile(const uint4 *__restrict__ keys, uint32_t n, const uint2 *__restrict__ tile_in,
+		TileAgg *__restrict__ tile_agg, uint32_t *__restrict__ mask) {
+	__shared__ uint32_t w_tid[32], w_first[32];
 	__shared__ SegMax w_seg[32];
-	__shared__ uint32_t c_tid, c_m;
 	const int tid_x = threadIdx.x, lane = tid_x & 31, wid = tid_x >> 5;
-	if (tid_x == 0) { c_tid = carry[0]; c_m = carry[1]; }
+	const uint32_t i0 = blockIdx.x * 4096u + 4u * (uint32_t)tid_x;
+	uint4 k[4];
+#pragma unroll
+	for (int e = 0; e < 4; e++) k[e] = i0 + e < n ? keys[i0 + e] : make_uint4(kNoTid, 0, 0, 0);
+	// ---- contig of the last kept record before my four: take-right scan; first kept contig of the tile: take-left
+	uint32_t mine = kNoTid, mine_first = kNoTid;
+#pragma unroll
+	for (int e = 0; e < 4; e++) if (k[e].x != kNoTid) { if (mine_first == kNoTid) mine_first = k[e].x; mine = k[e].x; }
+	uint32_t inc = mine;
+	for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d && inc == kNoTid) inc = o; }
+	if (lane == 31) w_tid[wid] = inc;
+	{
+		const uint32_t have = __ballot_sync(0xffffffffu, mine_first != kNoTid);
+		const uint32_t f = __shfl_sync(0xffffffffu, mine_first, have ? __ffs(have) - 1 : 0);
+		if (lane == 0) w_first[wid] = have ? f : kNoTid;
+	}
 	__syncthreads();
-	for (uint32_t base = 0; base < n; base += 4096) {
-		const uint32_t i0 = base + 4 * tid_x;
-		uint4 k[4];
+	uint32_t tile_first = kNoTid, tile_last = kNoTid;
+	for (int w = 0; w < 32 && tile_first == kNoTid; w++) tile_first = w_first[w];
+	for (int w = 31; w >= 0 && tile_last == kNoTid; w--) tile_last = w_tid[w];
+	// the state the tile starts from: phase 3 knows it; phase 1 pretends the stream continues (its own first contig, no end yet)
+	const uint32_t c_tid = FINAL ? tile_in[blockIdx.x].x : tile_first, c_m = FINAL ? tile_in[blockIdx.x].y : 0u;
+	uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
+	if (lane == 0) prev = kNoTid;
+	if (prev == kNoTid) { for (int w = wid - 1; w >= 0 && prev == kNoTid; w--) prev = w_tid[w]; }
+	if (prev == kNoTid) prev = c_tid;
+	// ---- my four records: where segments begin, and the running end since the last begin
+	SegMax agg{0u, 0u};
+	uint32_t pt = prev;
 #pragma unroll
-		for (int e = 0; e < 4; e++) k[e] = i0 + e < n ? keys[i0 + e] : make_uint4(kNoTid, 0, 0, 0);
-		// ---- contig of the last kept record before my four: take-right scan
-		uint32_t mine = kNoTid;
-#pragma unroll
-		for (int e = 0; e < 4; e++) if (k[e].x != kNoTid) mine = k[e].x;
-		uint32_t inc = mine;
-		for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d && inc == kNoTid) inc = o; }
-		if (lane == 31) w_tid[wid] = inc;
-		__syncthreads();
-		uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
-		if (lane == 0) prev = kNoTid;
-		if (prev == kNoTid) { for (int w = wid - 1; w >= 0 && prev == kNoTid; w--) prev = w_tid[w]; }
-		if (prev == kNoTid) prev = c_tid;
-		uint32_t tile_last = kNoTid;
-		if (tid_x == 1023) { tile_last = inc; for (int w = 30; w >= 0 && tile_last == kNoTid; w--) tile_last = w_tid[w]; }
-		// ---- my four records: where segments begin, and the running end since the last begin
-		SegMax agg{0u, 0u};
-		uint32_t pt = prev;
-#pragma unroll
-		for (int e = 0; e < 4; e++) {
-			if (k[e].x == kNoTid) continue;
-			const uint32_t f = k[e].x != pt;
-			agg = seg_combine(agg, SegMax{f, k[e].z});
-			pt = k[e].x;
-		}
-		SegMax sinc = agg;
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t of = __shfl_up_sync(0xffffffffu, sinc.flag, d), om = __shfl_up_sync(0xffffffffu, sinc.m, d);
-			if (lane >= d) sinc = seg_combine(SegMax{of, om}, sinc);
-		}
-		if (lane == 31) w_seg[wid] = sinc;
-		__syncthreads();
-		SegMax before{0u, c_m};                                   // everything before my records, the carry included
-		for (int w = 0; w < wid; w++) before = seg_combine(before, w_seg[w]);
-		{
-			const uint32_t of = __shfl_up_sync(0xffffffffu, sinc.flag, 1), om = __shfl_up_sync(0xffffffffu, sinc.m, 1);
-			if (lane) before = seg_combine(before, SegMax{of, om});
-		}
-		// ---- replay (src/get_template_vector.c:111-149 as certain_scan_seq has it)
-		uint32_t m = before.m, bits = 0;
-		pt = prev;
-#pragma unroll
-		for (int e = 0; e < 4; e++) {
-			if (k[e].x == kNoTid) continue;
-			if (k[e].x != pt) { bits |= 1u << e; m = 0; pt = k[e].x; }
-			else if (k[e].y && (unsigned long long)k[e].y > (unsigned long long)m + 1) bits |= 1u << e;
-			m = max(m, k[e].z);
-		}
-		// eight threads make one word of the mask
-		uint32_t word = bits << (4 * (lane & 7));
-		word |= __shfl_xor_sync(0xffffffffu, word, 1);
-		word |= __shfl_xor_sync(0xffffffffu, word, 2);
-		word |= __shfl_xor_sync(0xffffffffu, word, 4);
-		if ((lane & 7) == 0 && i0 < n) mask[i0 >> 5] = word;
-		__syncthreads();
+	for (int e = 0; e < 4; e++) {
+		if (k[e].x == kNoTid) continue;
+		const uint32_t f = k[e].x != pt;
+		agg = seg_combine(agg, SegMax{f, k[e].z});
+		pt = k[e].x;
+	}
+	SegMax sinc = agg;
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t of = __shfl_up_sync(0xffffffffu, sinc.flag, d), om = __shfl_up_sync(0xffffffffu, sinc.m, d);
+		if (lane >= d) sinc = seg_combine(SegMax{of, om}, sinc);
+	}
+	if (lane == 31) w_seg[wid] = sinc;
+	__syncthreads();
+	SegMax before{0u, c_m};                                   // everything before my records, the incoming state included
+	for (int w = 0; w < wid; w++) before = seg_combine(before, w_seg[w]);
+	{
+		const uint32_t of = __shfl_up_sync(0xffffffffu, sinc.flag, 1), om = __shfl_up_sync(0xffffffffu, sinc.m, 1);
+		if (lane) before = seg_combine(before, SegMax{of, om});
+	}
+	if (!FINAL) {
 		if (tid_x == 1023) {
 			const SegMax total = seg_combine(before, agg);
-			c_m = total.m;
-			if (tile_last != kNoTid) c_tid = tile_last;
+			tile_agg[blockIdx.x] = TileAgg{tile_first, tile_last, total.flag, total.m};
+		}
+		return;
+	}
+	// ---- replay (src/get_template_vector.c:111-149 as certain_scan_seq has it)
+	uint32_t m = before.m, bits = 0;
+	pt = prev;
+#pragma unroll
+	for (int e = 0; e < 4; e++) {
+		if (k[e].x == kNoTid) continue;
+		if (k[e].x != pt) { bits |= 1u << e; m = 0; pt = k[e].x; }
+		else if (k[e].y && (unsigned long long)k[e].y > (unsigned long long)m + 1) bits |= 1u << e;
+		m = max(m, k[e].z);
+	}
+	// eight threads make one word of the mask
+	uint32_t word = bits << (4 * (lane & 7));
+	word |= __shfl_xor_sync(0xffffffffu, word, 1);
+	word |= __shfl_xor_sync(0xffffffffu, word, 2);
+	word |= __shfl_xor_sync(0xffffffffu, word, 4);
+	if ((lane & 7) == 0 && i0 < n) mask[i0 >> 5] = word;
+}
+
+__global__ void __launch_bounds__(1024) k_certain_combine(const TileAgg *__restrict__ tile_agg, uint32_t ntiles, uint32_t *__restrict__ carry,
+		uint2 *__restrict__ tile_in) {
+	__shared__ TileAgg s[1024];
+	__shared__ uint2 o[1024];
+	__shared__ uint32_t c_tid, c_m;
+	const uint32_t t = threadIdx.x;
+	if (t == 0) { c_tid = carry[0]; c_m = carry[1]; }
+	__syncthreads();
+	for (uint32_t base = 0; base < ntiles; base += 1024) {
+		if (base + t < ntiles) s[t] = tile_agg[base + t];
+		__syncthreads();
+		if (t == 0) {
+			uint32_t tid = c_tid, m = c_m;
+			const uint32_t cnt = min(1024u, ntiles - base);
+			for (uint32_t i = 0; i < cnt; i++) {
+				o[i] = make_uint2(tid, m);
+				const TileAgg a = s[i];
+				if (a.first == kNoTid) continue;             // no kept record in the tile: the state passes through
+				m = (a.flag || a.first != tid) ? a.m : max(m, a.m);
+				tid = a.last;
+			}
+			c_tid = tid; c_m = m;
 		}
 		__syncthreads();
+		if (base + t < ntiles) tile_in[base + t] = o[t];
+		__syncthreads();
 	}
-	if (tid_x == 0) { carry[0] = c_tid; carry[1] = c_m; }
+	if (t == 0) { carry[0] = c_tid; carry[1] = c_m; }
 }
 // name_id[i] = the smallest record index of the batch whose read name is that of record i (i itself when it is the first), for
 // kept paired records; 0xffffffff for the others.  rec_off / rec / name_id are indexed by the batch-wide record number.
@@ -418,12 +459,19 @@ cudaError_t launch_name_ids(const void *bam, const void *rec_off, const void *re
 }
 
 // mask: one bit per record of the chunk (bit i of word i / 32), (n + 31) / 32 words, 4096-record tiles start on word boundaries
-cudaError_t launch_certain_starts(const void *keys, uint32_t n, void *carry, void *mask, cudaStream_t stream, int *launches) {
+cudaError_t launch_certain_starts(const void *keys, uint32_t n, void *carry, void *mask, void *scratch, cudaStream_t stream, int *launches) {
 	if (!n) return cudaSuccess;
-	k_certain_starts<<<1, 1024, 0, stream>>>((const uint4 *)keys, n, (uint32_t *)carry, (uint32_t *)mask);
-	__atomic_fetch_add(launches, 1, __ATOMIC_RELAXED);
+	// scratch: certain_scratch_bytes(n) = per tile a 16-byte summary and the 8-byte state it starts from
+	const uint32_t ntiles = (n + 4095u) / 4096u;
+	TileAgg *agg = (TileAgg *)scratch;
+	uint2 *tin = (uint2 *)((uint8_t *)scratch + (size_t)ntiles * sizeof(TileAgg));
+	k_certain_tile<false><<<ntiles, 1024, 0, stream>>>((const uint4 *)keys, n, nullptr, agg, nullptr);
+	k_certain_combine<<<1, 1024, 0, stream>>>(agg, ntiles, (uint32_t *)carry, tin);
+	k_certain_tile<true><<<ntiles, 1024, 0, stream>>>((const uint4 *)keys, n, tin, nullptr, (uint32_t *)mask);
+	__atomic_fetch_add(launches, 3, __ATOMIC_RELAXED);
 	return cudaGetLastError();
 }
+size_t certain_scratch_bytes(size_t n) { return ((n + 4095) / 4096 + 1) * 24 + 16; }
 
 cudaError_t launch_decode_records(const void *bam, const void *rec_off, const void *read_off, const void *mm_off, size_t nrec,
 		uint32_t mapq_thresh, uint32_t max_tlen, int keep_unmatched, int ignore_dup, void *out, void *bases, void *misms,

@@ -158,3 +158,79 @@ def test_streams_the_reference_aborts_on_are_errors(oracle, seed, code):
     rec = descriptors_from_oracle(orec, ob, bam)
     with pytest.raises(lib.BsGpuError, match=code):
         lib.build_blocks(bam, rec, lib.reader_params(**o))
+
+
+def test_three_phase_certain_start_scan_equals_the_sequential_one():
+    """The device marks certain block starts (bs_call_b200/csrc/bsgpu_reader.cu: k_certain_tile / k_certain_combine) tile by
+    tile: phase 1 summarises every tile as if the stream continued into it (first / last kept contig, "a contig change inside",
+    running end since that change), phase 2 chains the summaries from the carried state, phase 3 replays every tile from its
+    incoming state.  Emulated here in Python over random key streams with tiny tiles (every boundary case: empty tiles, tiles
+    of dropped records only, contig changes on tile edges) against the sequential scan (certain_scan_seq)."""
+    NO = 0xffffffff
+    rng = np.random.default_rng(4)
+
+    def seq(keys, st):
+        tid, m = st
+        out = []
+        for i, (t, mn, e) in enumerate(keys):
+            if t == NO:
+                continue
+            if t != tid:
+                tid, m = t, 0
+                out.append(i)
+            elif mn and mn > m + 1:
+                out.append(i)
+            m = max(m, e)
+        return out, (tid, m)
+
+    def three(keys, st, T):
+        nt = (len(keys) + T - 1) // T
+        agg = []
+        for t in range(nt):
+            tile = [k for k in keys[t * T:(t + 1) * T] if k[0] != NO]
+            if not tile:
+                agg.append((NO, NO, 0, 0))
+                continue
+            pt, m, flag = tile[0][0], 0, 0
+            for (td, mn, e) in tile:
+                if td != pt:
+                    flag, m, pt = 1, 0, td
+                m = max(m, e)
+            agg.append((tile[0][0], tile[-1][0], flag, m))
+        tid, m = st
+        tin = []
+        for (first, last, flag, am) in agg:
+            tin.append((tid, m))
+            if first == NO:
+                continue
+            f = flag or first != tid
+            m = am if f else max(m, am)
+            tid = last
+        out = []
+        for t in range(nt):
+            o, _ = seq(keys[t * T:(t + 1) * T], tin[t])
+            out += [t * T + i for i in o]
+        return out, (tid, m)
+
+    for trial in range(300):
+        n = int(rng.integers(0, 120))
+        T = int(rng.choice([1, 2, 3, 4, 8, 16]))
+        keys, tid, pos = [], int(rng.integers(0, 3)), 10
+        for _ in range(n):
+            r = rng.random()
+            if r < 0.25:
+                keys.append((NO, 0, 0))
+                continue
+            if r < 0.33:
+                tid += 1
+                pos = int(rng.integers(1, 50))
+            pos += int(rng.integers(0, 40))
+            keys.append((tid, pos if rng.random() < 0.7 else 0, pos + int(rng.integers(1, 60))))
+        st = (int(rng.choice([-1 & NO, 0, 1, tid])), int(rng.integers(0, 200)))
+        # a stream in two chunks, state carried
+        cut = int(rng.integers(0, n + 1))
+        a1, s1 = seq(keys[:cut], st)
+        a2, s2 = seq(keys[cut:], s1)
+        b1, t1 = three(keys[:cut], st, T)
+        b2, t2 = three(keys[cut:], t1, T)
+        assert a1 == b1 and a2 == b2 and s1 == t1 and s2 == t2, (trial, T, keys, st)
