@@ -1358,10 +1358,11 @@ static int decode_queue(bsgpu_ctx *c, bsgpu_ctx::ReaderSet &R, const uint8_t *ba
 		CU(cudaMemsetAsync(R.rd_bases.p, 0, *nb + 16, dec));
 		CU(cudaMemsetAsync(R.rd_misms.p, 0, (*nm + 1) * sizeof(bsgpu_misms), dec));
 	}
-	// certain block starts: the keys the decode kernel writes come home and host threads scan them; BSGPU_DEVICE_SCAN=1
-	// uses the bit mask of the scan on the device instead, BSGPU_CHECK_SCAN=1 does both and compares
-	const bool dev_scan = getenv("BSGPU_DEVICE_SCAN") != nullptr || getenv("BSGPU_CHECK_SCAN") != nullptr;
-	const bool host_scan = getenv("BSGPU_DEVICE_SCAN") == nullptr || getenv("BSGPU_CHECK_SCAN") != nullptr;
+	// certain block starts: the device scans the keys the decode kernel writes (launch_certain_starts: three phases over all
+	// SMs) and one bit per record comes home; BSGPU_HOST_SCAN=1 brings the keys home instead (16 bytes per record) and host
+	// threads scan them -- the default before the device scan was spread over the SMs --, BSGPU_CHECK_SCAN=1 does both and compares
+	const bool dev_scan = getenv("BSGPU_HOST_SCAN") == nullptr || getenv("BSGPU_CHECK_SCAN") != nullptr;
+	const bool host_scan = getenv("BSGPU_HOST_SCAN") != nullptr || getenv("BSGPU_CHECK_SCAN") != nullptr;
 	CU(R.rd_key.reserve(n * 16));
 	if (host_scan) CU(R.h_key.reserve(n * 16));
 	// QNAME join: table of kept paired records by name hash, name ids per record (+ one word: the overflow flag)
@@ -1853,7 +1854,7 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 	std::atomic<int> scan_state{0};                      // 0 running, 1 done, -1 a CUDA call failed
 	double sc_rd = 0, sc_cert = 0;
 	cudaError_t scan_err = cudaSuccess;
-	const bool check_scan = getenv("BSGPU_CHECK_SCAN") != nullptr, use_host_scan = check_scan || getenv("BSGPU_DEVICE_SCAN") == nullptr;
+	const bool check_scan = getenv("BSGPU_CHECK_SCAN") != nullptr, use_host_scan = check_scan || getenv("BSGPU_HOST_SCAN") != nullptr;
 	std::atomic<int> scan_mismatch{0};
 	std::unordered_map<std::string, uint32_t> host_names;
 	size_t host_names_done = 0, name_fallbacks = 0;

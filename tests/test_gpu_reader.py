@@ -2,6 +2,8 @@
 descriptors, and the whole chain raw records -> gt_vcf[] (bsgpu_call_bam), against the goldens captured from the
 reference's own get_next_align_details / read_input / process_template_vector / call_genotypes_ML and against the
 oracle on seeded streams.  Everything on the reader side is integer / byte work: bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -54,7 +56,8 @@ def test_decode_records_golden(gpu, name):
     g = util.load_golden(name)
     before = gpu.stats()["kernel_launches"]
     rec, bases, misms = gpu.decode_records(g["bam"], _rp(_golden_opts(g)))
-    assert gpu.stats()["kernel_launches"] == before + 2          # k_decode_records + k_name_ids
+    # k_decode_records + k_name_ids, and the three launches of the certain-start scan unless the host scans (BSGPU_HOST_SCAN)
+    assert gpu.stats()["kernel_launches"] == before + (2 if os.environ.get("BSGPU_HOST_SCAN") else 5)
     _check_records(rec, bases, misms, g["rec"], g["rec_bases"], g["rec_misms"])
 
 
@@ -194,6 +197,25 @@ def test_device_scan_of_certain_block_starts(monkeypatch, seed):
             assert len(blocks) > 3
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("name", ["reader_pe", "reader_mixed"])
+def test_host_scan_of_certain_block_starts(monkeypatch, name):
+    """BSGPU_HOST_SCAN=1: the keys come home and host threads mark the certain block starts (the default before the device's
+    scan was spread over the SMs): same blocks as the golden"""
+    monkeypatch.setenv("BSGPU_HOST_SCAN", "1")
+    monkeypatch.setenv("BSGPU_READER_CHUNK_MIN_BYTES", "1")
+    monkeypatch.setenv("BSGPU_BUILDER_MIN_RECORDS", "1")
+    g = util.load_golden(name)
+    refs = [g["ref%d" % i] for i in range(len(g["target_len"]))]
+    gpu = bslib.BsGpu()
+    try:
+        blocks, vcf = gpu.call_bam(g["bam"], g["target_len"], refs, _rp(_golden_opts(g)))
+        assert len(blocks) == len(g["blocks"])
+        for f in ("tid", "x", "y", "n_templates"):
+            assert (blocks[f] == g["blocks"][f]).all(), f
+    finally:
+        gpu.close()
 
 
 def test_exact_offset_table_path(monkeypatch):
