@@ -148,6 +148,39 @@ static void drive_threads(Session &s, const std::vector<uint8_t> &v, std::mt1993
 	printer.join();
 }
 
+// the bulk-input pattern of bsgpu_seam_reader.c: the feeder reserves (blocking), fills a slice in place, commits and reserves again
+// at once -- without a pause in which a run waiting to move its carry could get the session's mutex (reserve() yields to it)
+static void drive_threads_reserve(Session &s, const std::vector<uint8_t> &v, std::mt19937 &rng, size_t max_slice, const std::vector<size_t> &cuts, Collected &c) {
+	std::thread printer([&] {
+		std::string err;
+		for (;;) {
+			SessResult *r; bool done;
+			CHECK(s.drain(true, &r, &done, &err), "drain: %s", err.c_str());
+			if (r) take(s, r, c);
+			else if (!done) usleep(200);
+			if (done) break;
+		}
+		c.done = true;
+	});
+	std::string err;
+	size_t at = 0, ci = 0;
+	while (at < v.size()) {
+		size_t lim = v.size();
+		if (ci < cuts.size()) lim = cuts[ci];
+		if (at == lim) { CHECK(s.mark(false, &err), "cut: %s", err.c_str()); ci++; continue; }
+		uint8_t *p = nullptr;
+		size_t avail = 0;
+		CHECK(s.reserve(&p, &avail, true, &err), "reserve: %s", err.c_str());
+		CHECK(p != nullptr && avail > 0, "a blocking reserve came back without room");
+		const size_t m = std::min(std::min(lim - at, avail), (size_t)(1 + rng() % max_slice));
+		memcpy(p, v.data() + at, m);
+		CHECK(s.commit(m, &err), "commit: %s", err.c_str());
+		at += m;
+	}
+	CHECK(s.mark(true, &err), "finish: %s", err.c_str());
+	printer.join();
+}
+
 int main(int argc, char **argv) {
 	const int rounds = argc > 1 ? atoi(argv[1]) : 60;
 	alarm(240);                               // a deadlock ends the test instead of hanging it
@@ -169,7 +202,8 @@ int main(int argc, char **argv) {
 		CHECK(s.open(hk, batch, it % 2 ? 0.01 : 1.0), "open");
 		Collected c;
 		const size_t max_slice = (it % 3 == 0) ? 700 : (it % 3 == 1) ? 20000 : 1000000;
-		if (it % 2) drive_threads(s, v, rng, max_slice, cuts, c);
+		if (it % 4 == 3) drive_threads_reserve(s, v, rng, max_slice, cuts, c);
+		else if (it % 2) drive_threads(s, v, rng, max_slice, cuts, c);
 		else drive_single(s, v, rng, max_slice, cuts, c, it % 4 == 2);
 		CHECK(c.bytes.size() == v.size(), "round %d: %zu bytes back, %zu fed", it, c.bytes.size(), v.size());
 		CHECK(!memcmp(c.bytes.data(), v.data(), v.size()), "round %d: results differ from the stream", it);

@@ -1,6 +1,7 @@
 """Host logic of the streaming session (bs_call_b200/csrc/bsgpu_session.h) on the CPU: tests/session_harness.cpp drives it
 with a stand-in for the device run of a batch -- random streams, batch sizes, slicings, one thread (non-blocking feeds,
-reserve / commit) and two threads (feeder + printer, as in the reference), cuts, rewind, truncated streams.  The results
+reserve / commit) and two threads (feeder + printer, as in the reference; blocking feeds, and the bulk-input pattern: blocking
+reserve, fill in place, commit, reserve again at once), cuts, rewind, truncated streams.  The results
 of a session, concatenated, must be the stream; a deadlock ends the run through alarm()."""
 import os
 import subprocess
