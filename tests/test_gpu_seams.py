@@ -134,6 +134,9 @@ def test_seam_d_statistics_reach_the_report(seam_c, oracle, monkeypatch):
     """seam D with --report-file: no gt_vcf record reaches the reference's writer, so what it would have added to bs_stats and
     to the contigs' ctg_stats (src/print_vcf.c:382-526) is gathered on the device and folded in by join_calc_threads -- against
     the pinned restatement over the blocks a seam C run of the same stream hands to the print thread"""
+    # snps / multi: the restatement is pinned to what oracle/_ref/libbsref.so does (a hom-ref call counts as "multi"); which of the
+    # two the seam's own link would do is a property of its string pool (bsgpu_seam_reader.c: homref_is_multi), so say it here
+    monkeypatch.setenv("BSGPU_STATS_HOMREF_MULTI", "1")
     from oracle.bindings import SITE_STATS, site_stats_equal
     from tests import blockgen
     bam, n, tl, refs = bamgen.make_stream(640, n_contigs=3, dup=0.15, contig_len=9000)
