@@ -16,8 +16,7 @@
  *                 encoders and the record layout of the VCF/BCF specification v4.3 section 6.3; bcf_write() writes BCF
  *                 records as they are, or formats the same record as a VCF text line (-O v / z).
  *
- * Not provided: SAM text and CRAM input, BAM indices (sam_index_load returns NULL -> the reference reads sequentially,
- * src/get_template_vector.c:69,93), multi-threaded (de)compression (hts_set_threads is accepted and ignored).  Number
+ * Not provided: SAM text and CRAM input, .bai files (regions are served by scanning, see sam_itr_queryi), multi-threaded (de)compression (hts_set_threads is accepted and ignored).  Number
  * formatting of VCF text (QUAL, GL) is C's "%g", which is not guaranteed to be htslib's digit for digit; BCF output is
  * byte-exact by construction (the record bytes are the encoders' output).
  *
@@ -56,6 +55,7 @@ struct BGZF {
 	int ulen, upos;
 	uint8_t *cbuf;
 	uint64_t upos_total;             /* uncompressed offset of ubuf[0] (plain files) */
+	off_t block_off;                 /* file offset at which the current block (ubuf) begins: bgzf_rewind_to() */
 };
 
 static BGZF *bgzf_from_file(FILE *f, int is_write, int level) {
@@ -77,6 +77,7 @@ static BGZF *bgzf_from_file(FILE *f, int is_write, int level) {
 static int bgzf_fill(BGZF *b) {
 	b->upos_total += (uint64_t)b->ulen;
 	b->upos = b->ulen = 0;
+	b->block_off = ftello(b->f);
 	if (!b->compressed) {
 		const size_t n = fread(b->ubuf, 1, BLOCK_MAX, b->f);
 		if (n == 0) { b->eof = 1; return ferror(b->f) ? -1 : 1; }
@@ -104,7 +105,7 @@ static int bgzf_fill(BGZF *b) {
 		if (fread(b->cbuf, 1, (size_t)clen, b->f) != (size_t)clen || fread(tail, 1, 8, b->f) != 8) return -1;
 		const uint32_t isize = (uint32_t)tail[4] | (uint32_t)tail[5] << 8 | (uint32_t)tail[6] << 16 | (uint32_t)tail[7] << 24;
 		if (isize > BLOCK_MAX) return -1;
-		if (isize == 0) continue;          /* empty block (the EOF marker, or padding) */
+		if (isize == 0) { b->block_off = ftello(b->f); continue; }          /* empty block (the EOF marker, or padding) */
 		z_stream zs;
 		memset(&zs, 0, sizeof zs);
 		if (inflateInit2(&zs, -15) != Z_OK) return -1;
@@ -200,6 +201,8 @@ static int bgzf_close_file(BGZF *b) {
 /* ------------------------------------------------------------------------------------------------------------------
  * htsFile
  * ------------------------------------------------------------------------------------------------------------------ */
+static void scan_state_free(void *state);          /* the region scanner's state hangs off htsFile.state (below) */
+
 static htsFile *hts_wrap(FILE *f, const char *fn, const char *mode) {
 	htsFile *fp = calloc(1, sizeof(htsFile));
 	if (!fp) return NULL;
@@ -243,17 +246,146 @@ htsFile *hts_hopen(hFILE *h, const char *fn, const char *mode) {
 int hts_close(htsFile *fp) {
 	if (!fp) return 0;
 	const int r = bgzf_close_file(fp->fp.bgzf);
+	if (fp->state) scan_state_free(fp->state);
 	free(fp->fn); free(fp->fn_aux); free(fp->line.s); free(fp);
 	return r;
 }
 
 int hts_set_threads(htsFile *fp, int n) { (void)fp; (void)n; return 0; }
 int hts_set_fai_filename(htsFile *fp, const char *fn_aux) { free(fp->fn_aux); fp->fn_aux = strdup(fn_aux); return 0; }
-hts_idx_t *sam_index_load(htsFile *fp, const char *fn) { (void)fp; (void)fn; return NULL; }
-void hts_idx_destroy(hts_idx_t *idx) { (void)idx; }
-hts_itr_t *sam_itr_queryi(const hts_idx_t *idx, int tid, hts_pos_t beg, hts_pos_t end) { (void)idx; (void)tid; (void)beg; (void)end; return NULL; }
-int sam_itr_next(htsFile *fp, hts_itr_t *itr, bam1_t *b) { (void)fp; (void)itr; (void)b; return -1; }
-void hts_itr_destroy(hts_itr_t *itr) { (void)itr; }
+/* ---- regions without a .bai: a scanning stand-in for the index.  sam_index_load() hands out a handle for any seekable BAM
+ * file; sam_itr_queryi() / sam_itr_next() then return, in file order, the records of contig tid that overlap [beg, end) --
+ * htslib's contract -- by reading on from where the file stands when the region lies ahead (regions of a coordinate-sorted
+ * file asked for in ascending order: one pass over the file), and from the first record again otherwise.  Records already read
+ * that reach beyond the end of a region are kept, because they also overlap a region that begins there. ---- */
+typedef struct {
+	bam1_t *pend;                    /* a record read from the file that lies beyond the region that was being served */
+	int has_pend;
+	bam1_t **keep;                   /* records served or skipped that end beyond the last region's end */
+	int nkeep, mkeep;
+	int last_tid;                    /* the last region served: the next one may go forward iff it begins at or beyond its end */
+	hts_pos_t last_end;
+	off_t rec0_off;                  /* where the first alignment record lies: block start in the file, offset inside the block */
+	int rec0_upos;
+} scan_state;
+struct hts_idx_t { htsFile *fp; };
+struct hts_itr_t { htsFile *fp; int tid; hts_pos_t beg, end; bam1_t **serve; int nserve, iserve; };
+
+static hts_pos_t rec_endpos(const bam1_t *b) {
+	const uint32_t *cig = bam_get_cigar(b);
+	hts_pos_t len = 0;
+	for (uint32_t i = 0; i < b->core.n_cigar; i++) {
+		const int op = bam_cigar_op(cig[i]);
+		if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) len += bam_cigar_oplen(cig[i]);       /* M D N = X consume the reference */
+	}
+	return b->core.pos + (len ? len : 1);
+}
+static bam1_t *rec_dup(const bam1_t *b) {
+	bam1_t *c = calloc(1, sizeof(bam1_t));
+	*c = *b;
+	c->data = malloc((size_t)b->l_data + 1);
+	memcpy(c->data, b->data, (size_t)b->l_data);
+	c->m_data = (uint32_t)b->l_data + 1;
+	return c;
+}
+static void rec_copy(bam1_t *dst, const bam1_t *src) {
+	if ((uint32_t)src->l_data > dst->m_data) { dst->data = realloc(dst->data, (size_t)src->l_data + 1); dst->m_data = (uint32_t)src->l_data + 1; }
+	uint8_t *d = dst->data;
+	const uint32_t m = dst->m_data;
+	*dst = *src;
+	dst->data = d; dst->m_data = m;
+	memcpy(dst->data, src->data, (size_t)src->l_data);
+}
+static void keep_push(scan_state *st, bam1_t *r) {
+	if (st->nkeep == st->mkeep) { st->mkeep = st->mkeep ? 2 * st->mkeep : 64; st->keep = realloc(st->keep, sizeof(bam1_t *) * (size_t)st->mkeep); }
+	st->keep[st->nkeep++] = r;
+}
+
+static void scan_state_free(void *state) {
+	scan_state *st = state;
+	for (int i = 0; i < st->nkeep; i++) bam_destroy1(st->keep[i]);
+	free(st->keep);
+	if (st->pend) bam_destroy1(st->pend);
+	free(st);
+}
+
+hts_idx_t *sam_index_load(htsFile *fp, const char *fn) {
+	(void)fn;
+	if (!fp || fp->format.format != bam || fp->fp.bgzf->f == stdin) return NULL;      /* (the scanner's state is made by sam_hdr_read) */
+	hts_idx_t *idx = calloc(1, sizeof(hts_idx_t));
+	idx->fp = fp;
+	return idx;
+}
+void hts_idx_destroy(hts_idx_t *idx) { free(idx); }
+
+hts_itr_t *sam_itr_queryi(const hts_idx_t *idx, int tid, hts_pos_t beg, hts_pos_t end) {
+	if (!idx || !idx->fp->state) return NULL;
+	htsFile *fp = idx->fp;
+	scan_state *st = fp->state;
+	hts_itr_t *it = calloc(1, sizeof(hts_itr_t));
+	it->fp = fp; it->tid = tid; it->beg = beg; it->end = end;
+	const int forward = st->last_tid < 0 || tid > st->last_tid || (tid == st->last_tid && beg >= st->last_end);
+	if (!forward) {
+		/* from the first record again */
+		BGZF *b = fp->fp.bgzf;
+		for (int i = 0; i < st->nkeep; i++) bam_destroy1(st->keep[i]);
+		st->nkeep = 0; st->has_pend = 0;
+		fseeko(b->f, st->rec0_off, SEEK_SET);
+		b->ulen = b->upos = 0; b->eof = 0;
+		if (bgzf_fill(b) == 0) b->upos = st->rec0_upos;
+	}
+	/* kept records that overlap this region are served first; those that end beyond it stay for the next one */
+	it->serve = calloc((size_t)st->nkeep + 1, sizeof(bam1_t *));
+	int nk = 0;
+	for (int i = 0; i < st->nkeep; i++) {
+		bam1_t *r = st->keep[i];
+		const int mine = r->core.tid == tid && r->core.pos < end && rec_endpos(r) > beg;
+		const int later = r->core.tid > tid || (r->core.tid == tid && rec_endpos(r) > end);
+		if (mine) it->serve[it->nserve++] = later ? rec_dup(r) : r;
+		if (later) st->keep[nk++] = r;
+		else if (!mine) bam_destroy1(r);
+	}
+	st->nkeep = nk;
+	st->last_tid = tid; st->last_end = end;
+	return it;
+}
+
+int sam_itr_next(htsFile *fp, hts_itr_t *it, bam1_t *b) {
+	if (!it) return -1;
+	scan_state *st = fp->state;
+	if (it->iserve < it->nserve) {
+		bam1_t *r = it->serve[it->iserve++];
+		rec_copy(b, r);
+		bam_destroy1(r);
+		return b->l_data + 36;
+	}
+	for (;;) {
+		int ret;
+		if (st->has_pend) { rec_copy(b, st->pend); st->has_pend = 0; ret = b->l_data + 36; }
+		else ret = sam_read1(fp, NULL, b);
+		if (ret < 0) return ret;
+		const bam1_core_t *c = &b->core;
+		if (c->tid < 0 || c->tid > it->tid || (c->tid == it->tid && c->pos >= it->end)) {
+			/* beyond the region (unmapped records sort last): keep it for the region that may follow */
+			if (!st->pend) st->pend = bam_init1();
+			rec_copy(st->pend, b);
+			st->has_pend = 1;
+			return -1;
+		}
+		if (c->tid < it->tid) continue;
+		const hts_pos_t e = rec_endpos(b);
+		if (e > it->end) keep_push(st, rec_dup(b));
+		if (e <= it->beg) continue;
+		return ret;
+	}
+}
+
+void hts_itr_destroy(hts_itr_t *it) {
+	if (!it) return;
+	for (int i = it->iserve; i < it->nserve; i++) bam_destroy1(it->serve[i]);
+	free(it->serve);
+	free(it);
+}
 
 /* ------------------------------------------------------------------------------------------------------------------
  * BAM input
@@ -280,6 +412,12 @@ sam_hdr_t *sam_hdr_read(htsFile *fp) {
 		h->target_name[i] = calloc((size_t)l_name + 1, 1);
 		if (bgzf_read_bytes(b, h->target_name[i], (size_t)l_name) != l_name || rd_i32(b, &l_ref)) return NULL;
 		h->target_len[i] = (uint32_t)l_ref;
+	}
+	{   /* where the first alignment record lies (regions without an index read from here) */
+		scan_state *st = calloc(1, sizeof(scan_state));
+		if (b->upos == b->ulen && bgzf_fill(b) < 0) { free(st); return NULL; }
+		st->rec0_off = b->block_off; st->rec0_upos = b->upos; st->last_tid = -1;
+		fp->state = st;
 	}
 	return h;
 }

@@ -220,3 +220,73 @@ def test_bgzf_files_are_plain_multi_member_gzip(binary, tmp_path):
     vt = os.path.join(str(tmp_path), "o.vcf")
     run_binary(binary, fa, bf, vt, otype="v")
     assert gzip.decompress(open(vz, "rb").read()) == open(vt, "rb").read()
+
+
+def test_binary_region_runs_concatenate_to_the_whole_run(binary, reference, tmp_path):
+    """Level-2 sharding as the reference documents it (src/process_sam_header.c:52-70, 108-169: one run per -C region, outputs
+    concatenated): a contig cut between two blocks, each half called by its own process through the region machinery
+    (sam_itr_queryi / sam_itr_next, src/get_template_vector.c:69-74,93-97; the writer clips to the region, src/print_vcf.c:154-157)
+    -- the two files hold exactly the records of the one-process run.  Also: regions asked for out of order, and a region whose
+    first reads begin before it."""
+    bam, n, tl, refs = bamgen.make_stream(41, n_contigs=1, contig_len=40000)
+    names, fa, bf = write_case(str(tmp_path), bam, tl, refs)
+    blocks = reference.read_input(bam, tl, refs)[0]
+    assert len(blocks) >= 4
+    k = len(blocks) // 2
+    assert int(blocks[k]["x"]) - int(blocks[k - 1]["y"]) > 6
+    cut = (int(blocks[k - 1]["y"]) + int(blocks[k]["x"])) // 2
+    L = int(tl[0])
+    whole = os.path.join(str(tmp_path), "whole.bcf")
+    run_binary(binary, fa, bf, whole)
+    _, rw = hostio.read_bcf(whole)
+    parts = []
+    for tag, (a, b) in (("a", (0, cut)), ("b", (cut, L))):
+        bed = os.path.join(str(tmp_path), tag + ".bed")
+        open(bed, "w").write("ctg0\t%d\t%d\n" % (a, b))
+        out = os.path.join(str(tmp_path), tag + ".bcf")
+        err = run_binary(binary, fa, bf, out, extra=("-C", bed))
+        assert "Processing region ctg0:%d-%d" % (a + 1, b) in err and "(Index)" in err
+        parts.append(hostio.read_bcf(out)[1])
+    assert len(parts[0]) > 0 and len(parts[1]) > 0
+    assert np.concatenate(parts).tobytes() == rw.tobytes()
+    # a region that begins inside a block: reads that start before it but reach into it are part of it (htslib's overlap rule),
+    # so the sites of the region get the same records as in the whole run
+    x, y = int(blocks[k]["x"]) + 40, int(blocks[k]["y"]) - 40
+    bed = os.path.join(str(tmp_path), "in.bed")
+    open(bed, "w").write("ctg0\t%d\t%d\n" % (x - 1, y))
+    out = os.path.join(str(tmp_path), "in.bcf")
+    run_binary(binary, fa, bf, out, extra=("-C", bed))
+    gi, gw = _keyed(hostio.read_bcf(out)[1]), _keyed(rw)
+    inside = {kk: v for kk, v in gw.items() if x <= kk[1] <= y}
+    assert set(gi) == set(inside) and len(gi) > 20
+    # interior sites (more than a read length from the region's edges, where every read that covers them is in the region) are identical
+    deep = [kk for kk in gi if x + 150 <= kk[1] <= y - 150]
+    assert deep and all(gi[kk] == gw[kk] for kk in deep)
+
+
+def test_binary_regions_out_of_file_order(binary, reference, tmp_path):
+    """-C with two contigs named in the opposite of their order in the file: the scanning stand-in for the index starts over
+    from the first record for the second region; the third contig is never read into a block"""
+    bam, n, tl, refs = bamgen.make_stream(3, n_contigs=3)
+    names, fa, bf = write_case(str(tmp_path), bam, tl, refs)
+    bed = os.path.join(str(tmp_path), "r.bed")
+    open(bed, "w").write("ctg2\t0\t%d\nctg0\t0\t%d\n" % (int(tl[2]), int(tl[0])))
+    out = os.path.join(str(tmp_path), "r.bcf")
+    err = run_binary(binary, fa, bf, out, extra=("-C", bed))
+    assert err.index("Processing region ctg2") < err.index("Processing region ctg0")
+    text, got = hostio.read_bcf(out)
+    assert "##contig=<ID=ctg1" not in text
+    # the header lists the wanted contigs in the file's order: CHROM 0 = ctg0, 1 = ctg2
+    g = _keyed(got)
+    blocks = reference.read_input(bam, tl, refs)[0]
+    want = _keyed(chain_records(reference, bam, tl, refs))
+    w0 = {(0, p): v for (c, p), v in want.items() if c == 0}
+    w2 = {(1, p): v[:8] + np.array([1], dtype="<i4").tobytes() + v[12:] for (c, p), v in want.items() if c == 2}      # CHROM field renumbered
+    g0 = {k: v for k, v in g.items() if k[0] == 0}
+    g2 = {k: v for k, v in g.items() if k[0] == 1}
+    assert len(g0) + len(g2) == len(g)
+    assert g0 == w0                                            # processed last: complete
+    last2 = [b for b in blocks if int(b["tid"]) == 2][-1]
+    assert set(g2) <= set(w2) and all(g2[k] == w2[k] for k in g2)
+    for (c, p) in set(w2) - set(g2):                           # processed first: its last block may lose records to the reference's race
+        assert int(last2["x"]) <= p <= int(last2["y"]) + 2
