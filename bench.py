@@ -675,7 +675,7 @@ def full_binary_path(args, gpu, bslib, torch, np, stream, local):
     s0 = gpu.stats()
     gpu.call_bam_bcf(hbam, tl, [href], out=hbcf.array)
     called = gpu.stats()["sites_called"] - s0["sites_called"]
-    del hbcf
+    hbcf.free()                                     # page-locked: give it back before the child processes lock their own
     tmp = tempfile.mkdtemp(prefix="bsgpu_fullbin_", dir=os.environ.get("BENCH_TMPDIR"))
     try:
         fa, bf = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "in.bam")
