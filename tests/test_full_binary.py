@@ -290,3 +290,29 @@ def test_binary_regions_out_of_file_order(binary, reference, tmp_path):
     assert set(g2) <= set(w2) and all(g2[k] == w2[k] for k in g2)
     for (c, p) in set(w2) - set(g2):                           # processed first: its last block may lose records to the reference's race
         assert int(last2["x"]) <= p <= int(last2["y"]) + 2
+
+
+def test_dbsnp_index_with_explicit_prefix_ids(binary, reference, tmp_path):
+    """index entries whose name prefix does not fit the two bits of the entry byte carry a two-byte prefix id
+    (src/dbSNP.c:235-243, 326-331): five prefixes, ids of 4 to 10 digits, several compressed blocks per contig"""
+    from oracle.bindings import bcf_diff, dbsnp_arrays
+    rng = np.random.default_rng(8)
+    bam, n, tl, refs = bamgen.make_stream(33, n_contigs=1, contig_len=25000)
+    names, fa, bf = write_case(str(tmp_path), bam, tl, refs)
+    prefixes = ("rs", "ss", "esv", "nsv", "x")
+    ents, flat = [], []
+    for p_ in np.unique(rng.integers(1, int(tl[0]) + 1, size=900)):
+        pfx = int(rng.integers(0, 5))
+        digits = "%0*d" % (int(rng.choice([4, 6, 8, 10])), int(rng.integers(0, 9999)))
+        always = bool(rng.random() < 0.25)
+        ents.append((int(p_), pfx, digits, always))
+        flat.append((int(p_), 3 if always else 1, (prefixes[pfx] + digits).encode()))
+    idx = os.path.join(str(tmp_path), "db.idx")
+    hostio.write_dbsnp_index(idx, {"ctg0": ents}, prefixes=prefixes, bins_per_block=7)
+    out = os.path.join(str(tmp_path), "cpu.bcf")
+    run_binary(binary, fa, bf, out, extra=("-D", idx))
+    _, got = hostio.read_bcf(out)
+    want = chain_records(reference, bam, tl, refs, dbsnp=[dbsnp_arrays(flat)])
+    d = bcf_diff(got, want)
+    assert d["records_a"] == d["records_b"] == d["identical"] and d["order_violations"] == 0, d
+    assert any(b"esv" in r or b"nsv" in r for r in _keyed(got).values())
