@@ -871,6 +871,10 @@ int bsgpu_process_block(bsgpu_ctx *c, const bsgpu_template *t, size_t n, const u
 	uint32_t maxcap = 1;
 	for (size_t i = 0; i < n; i++) for (int k = 0; k < 2; k++) {
 		off[2 * i + k] = (uint32_t)tot;
+		{   // the smaller position of a template must lie inside the window, read or no read there (src/call_genotypes.c:182-186)
+			const uint32_t pk = k ? t[i].reverse_position : t[i].forward_position;
+			if (pk && pk < x && !t[i].present[k]) return fail("bsgpu_process_block: template %zu: its absent mate lies before the window (%u < %u); the reference asserts there", i, pk, x);
+		}
 		if (!t[i].present[k]) continue;
 		if ((size_t)t[i].read_off[k] + t[i].read_len[k] > nbases) return fail("bsgpu_process_block: template %zu read outside bases[]", i);
 		if ((size_t)t[i].mm_off[k] + t[i].mm_n[k] > nmisms) return fail("bsgpu_process_block: template %zu events outside misms[]", i);
@@ -1500,7 +1504,8 @@ int bsgpu_build_blocks_tally(const uint8_t *bam, size_t nbytes, const bsgpu_reco
 	bsgpu_template *t = tmpl_cap >= nrec ? tmpl : (bsgpu_template *)malloc((nrec + 1) * sizeof(bsgpu_template));      // build in place when there is room
 	if (!t) return fail("bsgpu_build_blocks: out of memory");
 	size_t nt = 0;
-	const int rc = build_blocks_host(bam, rec_off.data(), rec, nrec, rp->keep_unmatched, rp->keep_duplicates, b, t, &nt, filter_cts ? tally : nullptr);
+	int rc = build_blocks_host(bam, rec_off.data(), rec, nrec, rp->keep_unmatched, rp->keep_duplicates, b, t, &nt, filter_cts ? tally : nullptr);
+	if (rc == -6) rc = 0;       // a template whose absent mate lies before its block: read_input itself succeeds (the callers of the blocks refuse)
 	if (!rc && filter_cts) for (int k = 0; k < 15; k++) { filter_cts[k] += tally[k]; filter_bases[k] += tally[15 + k]; }
 	int ret = BSGPU_OK;
 	if (rc == -4) ret = fail("bsgpu_build_blocks: duplicate read name among waiting mates");
@@ -1783,6 +1788,7 @@ static int call_bam_impl(bsgpu_ctx *c, const uint8_t *bam, size_t nbytes, int n_
 				tm_piece += now() - w0;
 				if (rc == -4) return fail("bsgpu_call_bam: duplicate read name among waiting mates");
 				if (rc == -5) return fail("bsgpu_call_bam: the two mates of a template disagree about their positions");
+				if (rc == -6) return fail("bsgpu_call_bam: a template's absent mate lies before its block's window (-k with -d): the reference asserts there (src/call_genotypes.c:186)");
 				if (rc) return fail("bsgpu_call_bam: block builder failed (%d)", rc);
 				if (const uint64_t *pt = build_blocks_piece_tally(job, p)) for (int k = 0; k < 30; k++) c->reader_tally[k] += pt[k];
 				for (bsgpu_block o : *pb) { o.first_template += (uint32_t)gnt; gb.push_back(o); }

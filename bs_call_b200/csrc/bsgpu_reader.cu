@@ -710,6 +710,7 @@ struct BlockBuilder {
 	bsgpu_template *out = nullptr;       // templates of this builder, in publication order (room for one per record)
 	size_t nout = 0;
 	uint32_t maxcap = 1;                 // largest read_len + reference span of a published mate: bounds a mate in reference coordinates
+	bool before_window = false;          // a published template's absent mate lies before its block's window: the reference aborts (publish)
 	uint64_t *tally = nullptr;           // --report-file: filter_cts[15] then filter_bases[15] of read_input, or none
 	void count(int reason_cts, uint64_t cts, int reason_bases, uint64_t bases) { tally[reason_cts] += cts; tally[15 + reason_bases] += bases; }
 	uint32_t read_len_of(const Tmpl &t, int k) const { return t.rec[k] >= 0 ? rec[t.rec[k]].read_len : 0; }
@@ -739,6 +740,11 @@ struct BlockBuilder {
 		blocks->push_back(b);
 		for (size_t i = 0; i < used; i++) {
 			const Tmpl &t = list[i];
+			// call_genotypes_ML asserts that the smaller position of every template lies inside the window, read or no read there
+			// (src/call_genotypes.c:182-186).  With -k and -d together a lone mate is kept with the position its absent partner
+			// claimed (src/get_template_vector.c:247-268), which may lie before the block: the reference aborts on such a stream.
+			// (A PRESENT mate cannot start before the window of a coordinate-sorted stream.)
+			for (int k = 0; k < 2; k++) { const uint32_t pk = k ? t.rev : t.fwd; if (pk && pk < b.x && t.rec[k] < 0) before_window = true; }
 			bsgpu_template d;
 			memset(&d, 0, sizeof(d));
 			d.forward_position = t.fwd; d.reverse_position = t.rev; d.orientation = t.orientation; d.bs_strand = t.bs_strand;
@@ -897,7 +903,7 @@ struct BlockBuilder {
 			}
 		}
 		if (curr_tid >= 0) publish((uint32_t)curr_tid, max_pos);
-		return 0;
+		return before_window ? -6 : 0;       // -6: the blocks are complete (read_input itself succeeds), the reference aborts when it calls them
 	}
 };
 
@@ -1176,12 +1182,13 @@ int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_r
 	BuildJob *job = build_blocks_start(bam, rec_off, rec, name_id.data(), nrec, keep_unmatched, keep_duplicates, tmpl, 1, tally != nullptr);
 	const size_t np = build_blocks_pieces(job);
 	size_t at = 0;
-	int rc = 0;
+	int rc = 0, soft = 0;                 // soft (-6): the blocks are complete, but the reference would abort when it calls one of them
 	for (size_t p = 0; p < np; p++) {
 		const std::vector<bsgpu_block> *pb;
 		size_t base, n;
 		const int r = build_blocks_piece(job, p, &pb, &base, &n);
-		if (r && !rc) rc = r;
+		if (r == -6) soft = r;
+		else if (r && !rc) rc = r;
 		if (rc) continue;
 		if (tally) { const uint64_t *pt = build_blocks_piece_tally(job, p); for (int k = 0; k < 30; k++) tally[k] += pt[k]; }
 		for (bsgpu_block b : *pb) { b.first_template += (uint32_t)at; blocks.push_back(b); }
@@ -1190,7 +1197,7 @@ int build_blocks_host(const uint8_t *bam, const uint64_t *rec_off, const bsgpu_r
 	}
 	build_blocks_finish(job);
 	*ntmpl = at;
-	return rc;
+	return rc ? rc : soft;
 }
 
 }  // namespace bsgpu

@@ -757,6 +757,16 @@ int bso_process_block(const bso_template *t, size_t n, const uint8_t *bases, con
 	prof_ref = refcodes; prof_x = x;              /* with the profile on, refcodes holds one more code (y + 1) */
 	int ret = bso_normalise_block(t, n, bases, mm, p, nt, nb, cap + 16, &used);
 	prof_ref = NULL;
+	/* call_genotypes_ML asserts that no template begins before the window -- the smaller of its two positions, whether or not
+	 * a read lies there (src/call_genotypes.c:182-186; the reference's build keeps its asserts).  It happens with -k and -d
+	 * together: a lone mate is then kept with the position its absent partner claimed, which may lie before the block
+	 * (src/get_template_vector.c:247-268).  The reference aborts; the restatement refuses the block. */
+	for (size_t i = 0; !ret && i < n; i++) {
+		uint32_t x1 = nt[i].forward_position;
+		if (x1 == 0) x1 = nt[i].reverse_position;
+		else if (nt[i].reverse_position > 0 && nt[i].reverse_position < x1) x1 = nt[i].reverse_position;
+		if (x1 < x) ret = -7;
+	}
 	if (!ret) {
 		bso_pileup *pl = pile_out ? pile_out : malloc(sizeof(bso_pileup) * sz);
 		bso_pileup_block(nt, n, nb, x, y, p, pl);

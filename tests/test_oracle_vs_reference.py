@@ -4,6 +4,8 @@
 Both run on the same CPU with the same libm, so every field -- including the doubles -- must be
 bit-identical.  Skipped where the prebuilt reference library is absent.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -416,3 +418,35 @@ def test_writer_statistics(oracle, reference, seed):
     site_stats_equal(st[0], want[0], rtol=1e-13, what="seed %d" % seed)
     assert want[0]["snps"][0] > 1000 and want[0]["CpG_ref"][0] + want[0]["CpG_nonref"][0] > 50 and want[0]["multi"][0] > 50
     assert want[0]["CpG_ref_meth"].sum() > 10 and want[0]["cov"]["gc_pcent"].sum() > 1000 and want[0]["dbSNP_sites"][0] > 20
+
+
+@pytest.mark.parametrize("seed", [5007, 5080])
+def test_lone_mate_before_its_block_aborts_the_reference(oracle, seed):
+    """-k with -d: a lone mate is kept with the position its absent partner claimed (src/get_template_vector.c:247-268), which
+    may lie before the block; read_input hands the block on, call_genotypes_ML asserts `x1 >= x` on it (src/call_genotypes.c:186;
+    the reference is built with its asserts) and the process dies.  Found by tests/fuzz_cpu.py.  The restatement's read_input
+    succeeds on the same stream with the same blocks as the product's host builder, and its chain refuses it; the compiled
+    reference is run in a child process, because it takes the process down."""
+    import subprocess
+    import sys
+    from bs_call_b200 import lib
+    from tests import bamgen
+    from tests.test_cpu_reader import descriptors_from_oracle
+    rng = np.random.default_rng(seed)
+    bam, n, tl, refs = bamgen.make_stream(seed, dup=float(rng.choice([0.0, 0.1, 0.3])), junk=float(rng.choice([0.0, 0.1, 0.3])))
+    o = dict(mapq_thresh=int(rng.integers(0, 40)), max_template_len=int(rng.integers(200, 1500)), keep_unmatched=bool(rng.random() < 0.3),
+             ignore_duplicates=bool(rng.random() < 0.3), keep_duplicates=bool(rng.random() < 0.3))
+    assert o["keep_unmatched"] and o["keep_duplicates"]
+    wbk = oracle.read_input(bam, tl, refs, **o)[0]
+    with pytest.raises(RuntimeError):
+        oracle.read_input(bam, tl, refs, run_chain=True, **o)
+    orec, ob, om = oracle.decode_records(bam, o["mapq_thresh"], o["max_template_len"], o["keep_unmatched"], o["ignore_duplicates"])
+    hb, ht = lib.build_blocks(bam, descriptors_from_oracle(orec, ob, bam), lib.reader_params(keep_unmatched=True, keep_duplicates=True))
+    assert len(hb) == len(wbk) and all((hb[f] == wbk[f]).all() for f in ("tid", "x", "y", "n_templates"))
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from oracle.bindings import Reference; from tests import bamgen; "
+            "rng = np.random.default_rng(%d); "
+            "bam, n, tl, refs = bamgen.make_stream(%d, dup=float(rng.choice([0.0, 0.1, 0.3])), junk=float(rng.choice([0.0, 0.1, 0.3]))); "
+            "Reference(calc_threads=1).read_input(bam, tl, refs, run_chain=True, **%r); print('survived')"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), seed, seed, o))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "survived" not in r.stdout and "x1 >= x" in r.stderr, (r.returncode, r.stderr[-300:])
