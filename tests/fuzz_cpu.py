@@ -18,13 +18,17 @@ from tests.test_cpu_reader import descriptors_from_oracle  # noqa: E402
 
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
 count = int(sys.argv[2]) if len(sys.argv) > 2 else 60
-oracle, ref = Oracle(), Reference(calc_threads=2)
 sites = refused = programs = 0
 for seed in range(first, first + count):
     rng = np.random.default_rng(seed)
     bam, n, tl, refs = bamgen.make_stream(seed, dup=float(rng.choice([0.0, 0.1, 0.3])), junk=float(rng.choice([0.0, 0.1, 0.3])))
     o = dict(mapq_thresh=int(rng.integers(0, 40)), max_template_len=int(rng.integers(200, 1500)), keep_unmatched=bool(rng.random() < 0.3),
              ignore_duplicates=bool(rng.random() < 0.3), keep_duplicates=bool(rng.random() < 0.3))
+    # model / normalisation parameters: the defaults on even seeds (what the whole-program runs and the child process use), random ones on odd seeds
+    mp = dict() if seed % 2 == 0 else dict(under_conv=float(rng.choice([0.0, 0.01, 0.05])), over_conv=float(rng.choice([0.0, 0.05, 0.1])),
+                                           ref_bias=float(rng.choice([1.0, 2.0, 5.0])), min_qual=int(rng.integers(5, 35)),
+                                           left_trim=(int(rng.integers(0, 8)), int(rng.integers(0, 8))), right_trim=(int(rng.integers(0, 8)), int(rng.integers(0, 8))))
+    oracle, ref = Oracle(**mp), Reference(calc_threads=2, **mp)
     try:
         wbk, wt, wb, wm, wv = oracle.read_input(bam, tl, refs, run_chain=True, **o)
     except RuntimeError:
