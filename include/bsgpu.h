@@ -359,7 +359,9 @@ int bsgpu_decode_records(bsgpu_ctx *ctx, const uint8_t *bam, size_t nbytes, cons
 
 /* read_input(): mate pairing, positional duplicate removal, block cutting (src/get_template_vector.c:49-389) over the
  * descriptors of bsgpu_decode_records.  Host side (order dependent over the sorted stream); templates refer to the
- * decoded arrays by offset. */
+ * decoded arrays by offset.  Streams on which the reference's read_input ends the process are refused (BSGPU_FAIL, the text says
+ * which): a read name that is already waiting for its mate (:327-328, fatal error) and a mate that disagrees with its waiting
+ * partner about their positions (:239, assert). */
 int bsgpu_build_blocks(const uint8_t *bam, size_t nbytes, const bsgpu_record *rec, size_t nrec, const bsgpu_reader_params *rp,
 		bsgpu_block *blocks, size_t block_cap, size_t *nblocks, bsgpu_template *tmpl, size_t tmpl_cap, size_t *ntmpl);
 /* same, also adding read_input's per-reason tallies (filtered records, mates whose partner never came, duplicates) to
@@ -370,7 +372,10 @@ int bsgpu_build_blocks_tally(const uint8_t *bam, size_t nbytes, const bsgpu_reco
 
 /* The whole path: BAM records -> decode -> blocks -> normalisation -> pileup -> model.  ctg_codes[tid] holds the
  * reference codes 0..4 of positions 1..target_len[tid].  vcf receives, per contig that has blocks, one gt_vcf record for
- * every position from the first block's x to the last block's y; blocks[b].vcf_off locates block b's window in it. */
+ * every position from the first block's x to the last block's y; blocks[b].vcf_off locates block b's window in it.
+ * Besides the streams bsgpu_build_blocks refuses, this (and the sessions, and bsgpu_process_block on raw templates) refuses a
+ * stream on which call_genotypes_ML dies on its assert that no template begins before its block's window
+ * (src/call_genotypes.c:186): a lone mate kept by -k and -d together whose absent partner's position lies before the block. */
 int bsgpu_call_bam(bsgpu_ctx *ctx, const uint8_t *bam, size_t nbytes, int n_targets, const uint32_t *target_len,
 		const uint8_t *const *ctg_codes, const bsgpu_reader_params *rp, bsgpu_block *blocks, size_t block_cap, size_t *nblocks,
 		bsgpu_gt_vcf *vcf, size_t vcf_cap, size_t *nvcf);
