@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Randomised CPU stress (not collected by pytest; needs oracle/_ref): seeded record streams with random reader options through
 (1) the compiled reference chain and the oracle restatement -- blocks, templates and every gt_vcf field bit-identical, or both
-refuse the stream --, (2) the product's host block builder over the oracle's descriptors, and (3) every 8th seed the whole
-reference program from files against the harness chain.   usage: python tests/fuzz_cpu.py [first_seed] [n_seeds]"""
+refuse the stream --, (2) the product's host block builder over the oracle's descriptors, and (3) every 4th seed with one contig the whole
+reference program from files (random -q -l -k -e -d -A, -D with a synthetic index) against the harness chain.   usage: python tests/fuzz_cpu.py [first_seed] [n_seeds]"""
 import os
 import subprocess
 import sys
@@ -13,7 +13,7 @@ import numpy as np  # noqa: E402
 from bs_call_b200 import hostio, lib as bslib  # noqa: E402
 from oracle.bindings import Oracle, Reference, bcf_diff  # noqa: E402
 from tests import bamgen, util  # noqa: E402
-from tests.test_full_binary import BIN, chain_records, run_binary, write_case  # noqa: E402
+from tests.test_full_binary import BIN, chain_records, run_binary, synthetic_dbsnp, write_case  # noqa: E402
 from tests.test_cpu_reader import descriptors_from_oracle  # noqa: E402
 
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
@@ -51,14 +51,21 @@ for seed in range(first, first + count):
     hb, ht = bslib.build_blocks(bam, descriptors_from_oracle(orec, ob, bam), bslib.reader_params(keep_unmatched=o["keep_unmatched"], keep_duplicates=o["keep_duplicates"]))
     assert len(hb) == len(wbk) and all((hb[f] == wbk[f]).all() for f in ("tid", "x", "y", "n_templates", "first_template")), seed
     assert bamgen.template_keys(ht, ob, om) == bamgen.template_keys(wt, wb, wm), seed
-    if seed % 8 == 0 and len(tl) == 1 and os.path.exists(BIN):
+    if seed % 4 == 0 and len(tl) == 1 and os.path.exists(BIN):
         with tempfile.TemporaryDirectory() as tmp:
             names, fa, bf = write_case(tmp, bam, tl, refs)
             extra = ["-q", str(o["mapq_thresh"]), "-l", str(o["max_template_len"])] + (["-k"] if o["keep_unmatched"] else []) + \
                     (["-e"] if o["ignore_duplicates"] else []) + (["-d"] if o["keep_duplicates"] else [])
+            allp, db = bool(rng.random() < 0.3), None
+            if allp:
+                extra.append("-A")
+            if rng.random() < 0.5:                       # -D: an index file in the reference's format through its own reader
+                files, db = synthetic_dbsnp(rng, tl, frac=0.03)
+                hostio.write_dbsnp_index(os.path.join(tmp, "db.idx"), files, prefixes=("rs", "ss"), bins_per_block=int(rng.integers(1, 40)))
+                extra += ["-D", os.path.join(tmp, "db.idx")]
             out = os.path.join(tmp, "o.bcf")
             run_binary(BIN, fa, bf, out, extra=tuple(extra))
-            d = bcf_diff(hostio.read_bcf(out)[1], chain_records(ref, bam, tl, refs, **o))
+            d = bcf_diff(hostio.read_bcf(out)[1], chain_records(ref, bam, tl, refs, all_positions=allp, dbsnp=db, **o))
             assert d["records_a"] == d["records_b"] == d["identical"], (seed, d)
             programs += 1
 print("cpu fuzz ok: seeds %d..%d, %d called sites bit-identical between the reference chain and the restatement, host builder = oracle blocks, "
