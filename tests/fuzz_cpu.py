@@ -29,6 +29,9 @@ for seed in range(first, first + count):
                                            ref_bias=float(rng.choice([1.0, 2.0, 5.0])), min_qual=int(rng.integers(5, 35)),
                                            left_trim=(int(rng.integers(0, 8)), int(rng.integers(0, 8))), right_trim=(int(rng.integers(0, 8)), int(rng.integers(0, 8))))
     oracle, ref = Oracle(**mp), Reference(calc_threads=2, **mp)
+    # --report-file's counters live on both sides (read_input's tallies, the conversion profile, the normalisation tallies)
+    ref.stats_enable(True); ref.stats_reset()
+    oracle.profile_enable(True); oracle.profile_reset()
     try:
         wbk, wt, wb, wm, wv = oracle.read_input(bam, tl, refs, run_chain=True, **o)
     except RuntimeError:
@@ -41,8 +44,11 @@ for seed in range(first, first + count):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
         assert r.returncode != 0 and "survived" not in r.stdout, "seed %d: the oracle refuses the stream, the reference does not" % seed
         refused += 1
+        ref.stats_enable(False); oracle.profile_enable(False)
         continue
     rbk, rt, rb, rm, rv = ref.read_input(bam, tl, refs, run_chain=True, **o)
+    util.same_profile(oracle.profile_read(), ref.stats_read(), "seed %d" % seed, recycled_vectors=True)
+    ref.stats_enable(False); oracle.profile_enable(False)
     assert len(rbk) == len(wbk) and all((rbk[f] == wbk[f]).all() for f in ("tid", "x", "y", "first_template", "n_templates", "vcf_off")), seed
     assert bamgen.template_keys(rt, rb, rm) == bamgen.template_keys(wt, wb, wm), seed
     util.assert_gt_meth_close(wv["gtm"], wv["skip"], rv["gtm"], rv["skip"], exact_doubles=True)
