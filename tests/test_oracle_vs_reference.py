@@ -450,3 +450,31 @@ def test_lone_mate_before_its_block_aborts_the_reference(oracle, seed):
             % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), seed, seed, o))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "survived" not in r.stdout and "x1 >= x" in r.stderr, (r.returncode, r.stderr[-300:])
+
+
+def test_block_at_the_very_start_of_a_contig_is_where_the_restatement_leaves_the_reference(oracle, reference):
+    """Known, deliberate deviation (found by running test_print_block_on_random_records over a thousand more seeds): the
+    reference's writer keeps its five-site window in file statics (gt_store, store_x; src/print_vcf.c:529-533) and clears it at a
+    block start only when the block begins at position 5 or later (`l = x - store_x`, :563-570).  A block that begins at
+    position 2 therefore sees a call of whatever block was printed BEFORE it -- another contig -- in the context fields of its
+    first record (from position 3 on the stale calls have left the window before a site is printed), and one that begins at
+    position 1 makes the writer print the stale site `x - 2` = 2^32 - 1, after which `x <= old_x` (:120-121) discards every site
+    of the contig.  Only contigs whose first read begins within their first four bases (x = first read - 2) are affected.  The restatement -- and the device writer pinned to it -- starts every block from a clean window: it writes the
+    contig, with the context a first block has."""
+    rng = np.random.default_rng(2010)
+    stale = util.random_gt_vcf(rng, 50, skip_frac=0.0)
+    refs = rng.integers(1, 5, size=52).astype(np.uint8)
+    vcf = util.random_gt_vcf(rng, 60, skip_frac=0.0)
+    refw = rng.integers(1, 5, size=62).astype(np.uint8)
+    for x, what in ((1, "nothing"), (2, "context"), (3, "same"), (5, "same")):
+        reference.print_block(stale, refs, 700, ctg_end=10000)                 # the block "before": leaves its last calls behind
+        want = reference.print_block(vcf, refw, x, ctg_end=10000)
+        got = oracle.print_block(vcf, refw, x, ctg_end=10000)
+        assert got[1] > 20
+        if what == "nothing":
+            assert want[1] == 0
+        elif what == "context":
+            a, b = util.split_bcf(got[0]), util.split_bcf(want[0])
+            assert len(a) == len(b) and a[0] != b[0] and a[1:] == b[1:]        # only the first record's context fields differ
+        else:
+            assert got[0].tobytes() == want[0].tobytes()
