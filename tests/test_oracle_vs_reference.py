@@ -453,7 +453,7 @@ def test_lone_mate_before_its_block_aborts_the_reference(oracle, seed):
 
 
 def test_block_at_the_very_start_of_a_contig_is_where_the_restatement_leaves_the_reference(oracle, reference):
-    """Known, deliberate deviation (found by running test_print_block_on_random_records over a thousand more seeds): the
+    """Known, deliberate deviation (found by running test_print_block_on_random_records over several hundred more seeds): the
     reference's writer keeps its five-site window in file statics (gt_store, store_x; src/print_vcf.c:529-533) and clears it at a
     block start only when the block begins at position 5 or later (`l = x - store_x`, :563-570).  A block that begins at
     position 2 therefore sees a call of whatever block was printed BEFORE it -- another contig -- in the context fields of its
